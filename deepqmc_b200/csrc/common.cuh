@@ -1,0 +1,119 @@
+// Shared device helpers for the local-energy engine (sm_100a).
+// Compiles under nvcc (product) and, with -DDQMC_EMU, under g++ against
+// tools/cuda_emu/cuda_emu.h (development-time logic checks only, never shipped).
+#pragma once
+#ifdef DQMC_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#define DQMC_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define DQMC_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+#include <cmath>
+#include <cstdint>
+
+namespace dq {
+
+template <class T> struct Num;
+template <> struct Num<double> {
+  // eps of the eps-safe norm: jnp.finfo(dtype).eps (reference: src/deepqmc/utils.py:79-85)
+  static __host__ __device__ __forceinline__ double eps() { return 2.220446049250313e-16; }
+};
+template <> struct Num<float> {
+  static __host__ __device__ __forceinline__ float eps() { return 1.1920928955078125e-07f; }
+};
+
+__host__ __device__ __forceinline__ double m_exp(double x) { return ::exp(x); }
+__host__ __device__ __forceinline__ float m_exp(float x) { return ::expf(x); }
+__host__ __device__ __forceinline__ double m_log(double x) { return ::log(x); }
+__host__ __device__ __forceinline__ float m_log(float x) { return ::logf(x); }
+__host__ __device__ __forceinline__ double m_log1p(double x) { return ::log1p(x); }
+__host__ __device__ __forceinline__ float m_log1p(float x) { return ::log1pf(x); }
+__host__ __device__ __forceinline__ double m_tanh(double x) { return ::tanh(x); }
+__host__ __device__ __forceinline__ float m_tanh(float x) { return ::tanhf(x); }
+__host__ __device__ __forceinline__ double m_sqrt(double x) { return ::sqrt(x); }
+__host__ __device__ __forceinline__ float m_sqrt(float x) { return ::sqrtf(x); }
+__host__ __device__ __forceinline__ double m_abs(double x) { return ::fabs(x); }
+__host__ __device__ __forceinline__ float m_abs(float x) { return ::fabsf(x); }
+__host__ __device__ __forceinline__ double m_cos(double x) { return ::cos(x); }
+__host__ __device__ __forceinline__ float m_cos(float x) { return ::cosf(x); }
+__host__ __device__ __forceinline__ double m_sin(double x) { return ::sin(x); }
+__host__ __device__ __forceinline__ float m_sin(float x) { return ::sinf(x); }
+
+template <class T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the whole block; result valid in every thread. scratch: >= 33 T's of shared memory.
+// Requires blockDim.x % 32 == 0 and all threads to call it.
+template <class T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect scratch from a previous use
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    T x = lane < nw ? scratch[lane] : T(0);
+    x = warp_sum(x);
+    if (lane == 0) scratch[32] = x;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+template <class T>
+__device__ __forceinline__ void block_sum2(T& a, T& b, T* scratch) {
+  // scratch: >= 66 T's
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  a = warp_sum(a);
+  b = warp_sum(b);
+  __syncthreads();
+  if (lane == 0) { scratch[w] = a; scratch[33 + w] = b; }
+  __syncthreads();
+  if (w == 0) {
+    T x = lane < nw ? scratch[lane] : T(0);
+    T y = lane < nw ? scratch[33 + lane] : T(0);
+    x = warp_sum(x);
+    y = warp_sum(y);
+    if (lane == 0) { scratch[32] = x; scratch[65] = y; }
+  }
+  __syncthreads();
+  a = scratch[32];
+  b = scratch[65];
+}
+
+
+// ---- Philox4x32-10 counter-based generator (Salmon et al. 2011), hand-written ---------
+struct Philox {
+  static __host__ __device__ __forceinline__ void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+    uint64_t p = (uint64_t)a * b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+  }
+  static __host__ __device__ __forceinline__ void gen(uint64_t key, uint64_t ctr_lo, uint64_t ctr_hi, uint32_t out[4]) {
+    uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+    uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t h0, l0, h1, l1;
+      mulhilo(0xD2511F53u, c0, h0, l0);
+      mulhilo(0xCD9E8D57u, c2, h1, l1);
+      uint32_t n0 = h1 ^ c1 ^ k0, n1 = l1, n2 = h0 ^ c3 ^ k1, n3 = l0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+  }
+  // uniform in (0,1)
+  static __host__ __device__ __forceinline__ double u01(uint32_t a, uint32_t b) {
+    uint64_t x = ((uint64_t)a << 21) ^ (uint64_t)(b >> 11);  // 53 bits
+    x &= ((1ull << 53) - 1);
+    return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
+  }
+};
+
+}  // namespace dq

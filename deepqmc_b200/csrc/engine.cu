@@ -1,0 +1,452 @@
+// Host side of libdqmc_b200.so: engine object, parameter table, workspace planning, kernel
+// sequencing, C ABI (include/dqmc_b200.h).  Built by nvcc for sm_100a; with -DDQMC_EMU the same
+// file builds against tools/cuda_emu for CPU-side logic checks during development (never shipped).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dqmc_b200.h"
+#include "kernels_mcmc.cuh"
+#include "kernels_slater.cuh"
+#include "kernels_trunk.cuh"
+#if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
+#include "gemm_tcgen05.cuh"
+#endif
+
+namespace dq {
+
+struct ParamEntry {
+  std::string name;
+  int64_t offset;
+  int rows, cols;
+};
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct EngineBase {
+  dqmc_config cfg;
+  int device = 0;
+  std::string err;
+  int64_t launches = 0;
+  std::vector<ParamEntry> entries;
+  int64_t total = 0;
+  virtual ~EngineBase() {}
+  virtual int set_params(const double* host, int64_t n, cudaStream_t st) = 0;
+  virtual int64_t ws_bytes(int B, int mode) = 0;
+  virtual int forward(const void* r, const void* R, int Rb, int B, void* sign, void* logp, void* ws, int64_t wsb,
+                      cudaStream_t st) = 0;
+  virtual int local_energy(const void* r, const void* R, int Rb, int B, uint64_t seed, const void* twist, void* E,
+                           void* stats, void* sign, void* logp, void* grad, void* ws, int64_t wsb,
+                           cudaStream_t st) = 0;
+  virtual int mcmc(void* r, void* sign, void* logp, int32_t* age, void* tau, const void* R, int Rb, int B, int n_sub,
+                   double target, int max_age, uint64_t seed, uint64_t step0, uint64_t woff, const void* nn,
+                   const void* nu, void* stats, void* ws, int64_t wsb, cudaStream_t st) = 0;
+
+  void add(const std::string& n, int rows, int cols) {
+    entries.push_back({n, total, rows, cols});
+    total += (int64_t)rows * cols;
+  }
+  void build_layout() {
+    const int N = cfg.n_up + cfg.n_down, M = cfg.n_nuc, d = cfg.embedding_dim, K = cfg.n_determinants;
+    if (cfg.kind == DQMC_PSIFORMER) {
+      add("emb.w", 4 * M + 1, d);
+      for (int l = 0; l < cfg.n_layers; ++l) {
+        std::string p = "L" + std::to_string(l) + ".";
+        add(p + "wqkv", d, 3 * d);
+        add(p + "wo", d, d);
+        add(p + "w1", d, d);
+        add(p + "b1", 1, d);
+        add(p + "w2", d, d);
+        add(p + "b2", 1, d);
+      }
+    }
+    add("bf.up", d, K * N);
+    add("bf.dn", d, K * N);
+    add("env.pi_up", K * N, M);
+    add("env.pi_dn", K * N, M);
+    add("env.zeta_up", K * N, M);
+    add("env.zeta_dn", K * N, M);
+    add("cusp.alpha", 1, 2);
+  }
+  int64_t off(const std::string& n) const {
+    for (auto& e : entries)
+      if (e.name == n) return e.offset;
+    return -1;
+  }
+};
+
+template <class T>
+__global__ void convert_kernel(const double* __restrict__ src, T* __restrict__ dst, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (T)src[i];
+}
+
+#define DQ_CHECK(call)                                                             \
+  do {                                                                             \
+    cudaError_t e_ = (call);                                                       \
+    if (e_ != cudaSuccess) {                                                       \
+      err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+      return 1;                                                                    \
+    }                                                                              \
+  } while (0)
+
+#define DQ_LAUNCH(kern, grid, block, smem, stream, ...)          \
+  do {                                                           \
+    auto kfn_ = kern;                                            \
+    DQMC_LAUNCH(kfn_, grid, block, smem, stream, __VA_ARGS__);   \
+    ++launches;                                                  \
+  } while (0)
+
+template <class T>
+struct Engine : EngineBase {
+  T* d_params = nullptr;
+  double* d_stage = nullptr;
+  T* d_zval = nullptr;
+  int* d_ecp_mask = nullptr;
+  T* d_ecp_loc = nullptr;
+  T* d_nl_params = nullptr;
+  int* d_nl_nuc = nullptr;
+  int J = 0;  // nuclei with a non-local channel
+  int N, M, d, K, KN, H, dh, T3;
+  size_t max_smem = 0;
+
+  int init() {
+    N = cfg.n_up + cfg.n_down; M = cfg.n_nuc; d = cfg.embedding_dim; K = cfg.n_determinants;
+    KN = K * N; H = cfg.n_heads; dh = d / H; T3 = 3 * N;
+    if (cfg.kind != DQMC_PSIFORMER) { err = "only DQMC_PSIFORMER is implemented in this build"; return 2; }
+    if (M > DQMC_MAX_NUC || d % H != 0 || N < 2) { err = "bad config"; return 2; }
+    build_layout();
+    DQ_CHECK(cudaSetDevice(device));
+    DQ_CHECK(cudaMalloc((void**)&d_params, sizeof(T) * total));
+    DQ_CHECK(cudaMalloc((void**)&d_stage, sizeof(double) * total));
+    std::vector<T> z(M);
+    for (int m = 0; m < M; ++m) z[m] = (T)cfg.z_valence[m];
+    DQ_CHECK(cudaMalloc((void**)&d_zval, sizeof(T) * M));
+    DQ_CHECK(cudaMemcpy(d_zval, z.data(), sizeof(T) * M, cudaMemcpyHostToDevice));
+    DQ_CHECK(cudaMalloc((void**)&d_ecp_mask, sizeof(int) * M));
+    DQ_CHECK(cudaMemcpy(d_ecp_mask, cfg.ecp_mask, sizeof(int) * M, cudaMemcpyHostToDevice));
+    const int Tm = cfg.ecp_loc_terms;
+    if (Tm > 0) {
+      std::vector<T> lp((size_t)M * 6 * Tm);
+      for (int m = 0; m < M; ++m)
+        for (int n = 0; n < 3; ++n)
+          for (int ab = 0; ab < 2; ++ab)
+            for (int t = 0; t < Tm; ++t) lp[(((size_t)m * 3 + n) * 2 + ab) * Tm + t] = (T)cfg.ecp_loc[m][n][ab][t];
+      DQ_CHECK(cudaMalloc((void**)&d_ecp_loc, sizeof(T) * lp.size()));
+      DQ_CHECK(cudaMemcpy(d_ecp_loc, lp.data(), sizeof(T) * lp.size(), cudaMemcpyHostToDevice));
+    }
+    const int L = cfg.ecp_nl_lmax_p1, Tn = cfg.ecp_nl_terms;
+    if (L > 0 && Tn > 0) {
+      std::vector<T> np((size_t)M * L * 2 * Tn);
+      std::vector<int> nuc;
+      for (int m = 0; m < M; ++m) {
+        bool any = false;
+        for (int l = 0; l < L; ++l)
+          for (int ab = 0; ab < 2; ++ab)
+            for (int t = 0; t < Tn; ++t) {
+              double v = cfg.ecp_nl[m][l][ab][t];
+              np[(((size_t)m * L + l) * 2 + ab) * Tn + t] = (T)v;
+              any = any || v != 0.0;
+            }
+        if (any) nuc.push_back(m);  // nuc_with_nl_pot, gaussian_type_ecp.py:120
+      }
+      J = (int)nuc.size();
+      if (J > 0) {
+        DQ_CHECK(cudaMalloc((void**)&d_nl_params, sizeof(T) * np.size()));
+        DQ_CHECK(cudaMemcpy(d_nl_params, np.data(), sizeof(T) * np.size(), cudaMemcpyHostToDevice));
+        DQ_CHECK(cudaMalloc((void**)&d_nl_nuc, sizeof(int) * J));
+        DQ_CHECK(cudaMemcpy(d_nl_nuc, nuc.data(), sizeof(int) * J, cudaMemcpyHostToDevice));
+      }
+    }
+    // opt in to large dynamic shared memory
+    size_t s_attn = attn_smem_bytes<T>(N, dh), s_sl = slater_smem_bytes<T>(N);
+    max_smem = s_attn > s_sl ? s_attn : s_sl;
+    if (max_smem > 227 * 1024) { err = "system too large for the shared-memory tiling (N)"; return 2; }
+    DQ_CHECK(cudaFuncSetAttribute(attn_fl_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_attn));
+    DQ_CHECK(cudaFuncSetAttribute(slater_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_sl));
+    return 0;
+  }
+  ~Engine() override {
+    cudaFree(d_params); cudaFree(d_stage); cudaFree(d_zval); cudaFree(d_ecp_mask);
+    if (d_ecp_loc) cudaFree(d_ecp_loc);
+    if (d_nl_params) cudaFree(d_nl_params);
+    if (d_nl_nuc) cudaFree(d_nl_nuc);
+  }
+  const T* P(const std::string& n) const { return d_params + off(n); }
+
+  int set_params(const double* host, int64_t n, cudaStream_t st) override {
+    if (n != total) { err = "parameter count mismatch"; return 2; }
+    DQ_CHECK(cudaMemcpyAsync(d_stage, host, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    DQ_LAUNCH(convert_kernel<T>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, (const double*)d_stage, d_params, n);
+    DQ_CHECK(cudaGetLastError());
+    return 0;
+  }
+
+  // ---- workspace ---------------------------------------------------------------------------
+  struct Ws {
+    T *X, *O, *A, *M1, *QKV, *BF, *dsign, *dlog, *dlap, *dgrad;
+    size_t bytes;
+  };
+  size_t per_walker_elems(int S) const {
+    size_t rows = (size_t)N * S;
+    return rows * (size_t)(4 * d + 3 * d + KN) + (size_t)K * (3 + (S > 1 ? T3 : 0));
+  }
+  size_t chunk_bytes(int Bc, int S) const { return sizeof(T) * per_walker_elems(S) * Bc + 16 * 256; }
+  Ws carve(void* base, int Bc, int S) const {
+    Ws w;
+    size_t rows = (size_t)Bc * N * S;
+    char* p = (char*)base;
+    auto take = [&](size_t n) { T* q = (T*)p; p += align_up(sizeof(T) * n); return q; };
+    w.X = take(rows * d); w.O = take(rows * d); w.A = take(rows * d); w.M1 = take(rows * d);
+    w.QKV = take(rows * 3 * d); w.BF = take(rows * KN);
+    w.dsign = take((size_t)Bc * K); w.dlog = take((size_t)Bc * K); w.dlap = take((size_t)Bc * K);
+    w.dgrad = take((size_t)Bc * K * (S > 1 ? T3 : 1));
+    w.bytes = p - (char*)base;
+    return w;
+  }
+  int max_chunk(int64_t wsb, int S, int B) const {
+    int64_t per = (int64_t)(sizeof(T) * per_walker_elems(S));
+    int64_t c = (wsb - 16 * 256) / per;
+    int64_t row_cap = (int64_t)2000000000 / ((int64_t)N * S * 3 * d);  // keep 32-bit row*ld products safe
+    if (c > row_cap) c = row_cap;
+    if (c > B) c = B;
+    return (int)c;
+  }
+  int64_t ws_bytes(int B, int mode) override {
+    int S = mode == DQMC_MODE_FORWARD ? 1 : T3 + 2;
+    int64_t need = (int64_t)chunk_bytes(B, S);
+    if (mode == DQMC_MODE_LOCAL_ENERGY && J > 0) {
+      int64_t V = (int64_t)B * J * N * 12;
+      int64_t e = (int64_t)sizeof(T) * V * (3 * N + 2) + 1024 + (int64_t)chunk_bytes((int)std::min<int64_t>(V, 1 << 20), 1);
+      if (e > need) need = e;
+    }
+    return need;
+  }
+
+  // ---- GEMM dispatch ------------------------------------------------------------------------
+  int gemm(const T* A, int lda, const T* W0, const T* W1, int zsplit, int ldw, const T* bias, const T* Res, int ldr,
+           T* C, int ldc, int Mr, int Nc, int Kc, int S, int sliced, int Nel, cudaStream_t st) {
+    GemmArgs<T> g;
+    g.A = A; g.lda = lda; g.W0 = W0; g.W1 = W1; g.z_split = zsplit; g.ldw = ldw; g.bias = bias; g.Res = Res;
+    g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = Mr; g.N = Nc; g.K = Kc; g.S = S; g.sliced = sliced; g.Nel = Nel;
+    constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
+    dim3 grid((Nc + BN - 1) / BN, (Mr + BM - 1) / BM, sliced ? Nel : 1);
+    DQ_LAUNCH((gemm_kernel<T, BM, BN, BK, TM, TN>), grid, dim3(256), 0, st, g);
+    return 0;
+  }
+
+  // ---- one chunk of the wave-function pipeline ---------------------------------------------
+  int run_chunk(const T* r, const T* R, int Rb, int Bc, int S, int Bstat, T* sign, T* logp, T* E, T* stats, T* grad,
+                void* wsbase, cudaStream_t st) {
+    Ws w = carve(wsbase, Bc, S);
+    const int rows = Bc * N * S;
+    const int F = 4 * M + 1;
+    DQ_LAUNCH(embed_kernel<T>, dim3(Bc * N), dim3(128), sizeof(T) * 5 * F, st, r, R, Rb, N, M, cfg.n_up, S, 1, 1,
+              P("emb.w"), d, w.X);
+    T* X = w.X;
+    T* O = w.O;
+    const T scale = (T)(1.0 / std::sqrt((double)dh));
+    for (int l = 0; l < cfg.n_layers; ++l) {
+      std::string p = "L" + std::to_string(l) + ".";
+      gemm(X, d, P(p + "wqkv"), nullptr, 0, 3 * d, nullptr, nullptr, 0, w.QKV, 3 * d, rows, 3 * d, d, S, 0, N, st);
+      DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh), st, (const T*)w.QKV, 3 * d, O, d,
+                N, S, dh, d, scale);
+      gemm(O, d, P(p + "wo"), nullptr, 0, d, nullptr, X, d, w.A, d, rows, d, d, S, 0, N, st);
+      gemm(w.A, d, P(p + "w1"), nullptr, 0, d, P(p + "b1"), nullptr, 0, w.M1, d, rows, d, d, S, 0, N, st);
+      DQ_LAUNCH(tanh_fl_kernel<T>, dim3(Bc * N, (d + 127) / 128), dim3(128), 0, st, w.M1, d, (const T*)nullptr, 0, S, d,
+                T(1));
+      gemm(w.M1, d, P(p + "w2"), nullptr, 0, d, P(p + "b2"), nullptr, 0, O, d, rows, d, d, S, 0, N, st);
+      DQ_LAUNCH(tanh_fl_kernel<T>, dim3(Bc * N, (d + 127) / 128), dim3(128), 0, st, O, d, (const T*)w.A, d, S, d, T(1));
+      T* tmp = X; X = O; O = tmp;
+    }
+    // per-spin backflow heads: rows of electron e across walkers, weights by spin
+    gemm(X, d, P("bf.up"), P("bf.dn"), cfg.n_up, KN, nullptr, nullptr, 0, w.BF, KN, Bc * S, KN, d, S, 1, N, st);
+    DQ_LAUNCH(slater_kernel<T>, dim3(Bc, K), dim3(128), slater_smem_bytes<T>(N), st, r, R, Rb, N, M, cfg.n_up, K, S,
+              P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog,
+              w.dgrad, w.dlap);
+    FinalizeCfg fc;
+    fc.N = N; fc.M = M; fc.n_up = cfg.n_up; fc.K = K; fc.S = S; fc.cusp_kind = cfg.cusp_kind;
+    fc.cusp_same_scale = cfg.cusp_same_scale; fc.cusp_anti_scale = cfg.cusp_anti_scale;
+    fc.ecp_terms = cfg.ecp_loc_terms;
+    DQ_LAUNCH(finalize_kernel<T>, dim3(Bc), dim3(128), finalize_smem_bytes<T>(N, K), st, fc, r, R, Rb,
+              (const T*)w.dsign, (const T*)w.dlog, (const T*)w.dgrad, (const T*)w.dlap, P("cusp.alpha"),
+              (const T*)d_zval, (const T*)d_ecp_loc, (const int*)d_ecp_mask, Bstat, sign, logp, E, stats, grad);
+    return 0;
+  }
+
+  int run_batched(const T* r, const T* R, int Rb, int B, int S, T* sign, T* logp, T* E, T* stats, T* grad, void* ws,
+                  int64_t wsb, cudaStream_t st) {
+    int Bc = max_chunk(wsb, S, B);
+    if (Bc < 1) { err = "workspace too small for a single walker"; return 3; }
+    for (int b0 = 0; b0 < B; b0 += Bc) {
+      int nb = std::min(Bc, B - b0);
+      int rc = run_chunk(r + (size_t)b0 * 3 * N, R + (Rb ? (size_t)b0 * 3 * M : 0), Rb, nb, S, B, sign + b0, logp + b0,
+                         E ? E + b0 : nullptr, stats ? stats + b0 : nullptr, grad ? grad + (size_t)b0 * T3 : nullptr, ws,
+                         st);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+
+  int forward(const void* r, const void* R, int Rb, int B, void* sign, void* logp, void* ws, int64_t wsb,
+              cudaStream_t st) override {
+    int rc = run_batched((const T*)r, (const T*)R, Rb, B, 1, (T*)sign, (T*)logp, nullptr, nullptr, nullptr, ws, wsb, st);
+    if (rc) return rc;
+    DQ_CHECK(cudaGetLastError());
+    return 0;
+  }
+
+  int local_energy(const void* r_, const void* R_, int Rb, int B, uint64_t seed, const void* twist, void* E,
+                   void* stats, void* sign, void* logp, void* grad, void* ws, int64_t wsb, cudaStream_t st) override {
+    const T* r = (const T*)r_;
+    const T* R = (const T*)R_;
+    int rc = run_batched(r, R, Rb, B, T3 + 2, (T*)sign, (T*)logp, (T*)E, (T*)stats, (T*)grad, ws, wsb, st);
+    if (rc) return rc;
+    if (J > 0) {
+      // non-local ECP: virtual walkers (12 quadrature points x electrons x ECP nuclei)
+      const int64_t vper = (int64_t)J * N * 12;
+      const int64_t per = (int64_t)sizeof(T) * vper * (3 * N + 2) + (int64_t)sizeof(T) * per_walker_elems(1) * vper;
+      int64_t Be = (wsb - 64 * 256) / per;
+      if (Be < 1) { err = "workspace too small for the non-local ECP pass"; return 3; }
+      if (Be > B) Be = B;
+      for (int b0 = 0; b0 < B; b0 += (int)Be) {
+        int nb = (int)std::min<int64_t>(Be, B - b0);
+        int64_t V = (int64_t)nb * vper;
+        char* p = (char*)ws;
+        T* rv = (T*)p; p += align_up(sizeof(T) * V * 3 * N);
+        T* sv = (T*)p; p += align_up(sizeof(T) * V);
+        T* lv = (T*)p; p += align_up(sizeof(T) * V);
+        const T* rb = r + (size_t)b0 * 3 * N;
+        const T* Rbp = R + (Rb ? (size_t)b0 * 3 * M : 0);
+        const T* tw = twist ? (const T*)twist + (size_t)b0 * J * N : nullptr;
+        DQ_LAUNCH(ecp_points_kernel<T>, dim3(nb * J * N), dim3(64), 0, st, rb, Rbp, Rb, N, M, J, (const int*)d_nl_nuc, tw,
+                  seed, (uint64_t)b0, rv);
+        if (Rb) { err = "non-local ECP with per-walker nuclei is not supported"; return 2; }
+        rc = run_batched(rv, R, 0, (int)V, 1, sv, lv, nullptr, nullptr, nullptr, p, wsb - (p - (char*)ws), st);
+        if (rc) return rc;
+        DQ_LAUNCH(ecp_accumulate_kernel<T>, dim3((nb + 127) / 128), dim3(128), 0, st, rb, Rbp, Rb, N, M, J,
+                  (const int*)d_nl_nuc, (const T*)d_nl_params, cfg.ecp_nl_lmax_p1, cfg.ecp_nl_terms,
+                  (const T*)sign + b0, (const T*)logp + b0, (const T*)sv, (const T*)lv, nb, B, (T*)E + b0,
+                  (T*)stats + b0);
+      }
+    }
+    DQ_CHECK(cudaGetLastError());
+    return 0;
+  }
+
+  int mcmc(void* r_, void* sign_, void* logp_, int32_t* age, void* tau_, const void* R_, int Rb, int B, int n_sub,
+           double target, int max_age, uint64_t seed, uint64_t step0, uint64_t woff, const void* nn, const void* nu,
+           void* stats_, void* ws, int64_t wsb, cudaStream_t st) override {
+    T* r = (T*)r_; T* sign = (T*)sign_; T* logp = (T*)logp_; T* tau = (T*)tau_; T* stats = (T*)stats_;
+    const T* R = (const T*)R_;
+    char* p = (char*)ws;
+    T* rp = (T*)p; p += align_up(sizeof(T) * (size_t)B * 3 * N);
+    T* sp = (T*)p; p += align_up(sizeof(T) * (size_t)B);
+    T* lp = (T*)p; p += align_up(sizeof(T) * (size_t)B);
+    int* cnt = (int*)p; p += 256;
+    int64_t rest = wsb - (p - (char*)ws);
+    DQ_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int), st));
+    const int ne = B * 3 * N;
+    for (int s = 0; s < n_sub; ++s) {
+      const T* nns = nn ? (const T*)nn + (size_t)s * ne : nullptr;
+      const T* nus = nu ? (const T*)nu + (size_t)s * B : nullptr;
+      DQ_LAUNCH(propose_kernel<T>, dim3((ne / 2 + 1 + 127) / 128), dim3(128), 0, st, (const T*)r, rp, (const T*)tau, nns,
+                seed, step0 + (uint64_t)s, woff * (uint64_t)(3 * N), ne);
+      int rc = run_batched(rp, R, Rb, B, 1, sp, lp, nullptr, nullptr, nullptr, p, rest, st);
+      if (rc) return rc;
+      DQ_LAUNCH(accept_kernel<T>, dim3((B + 127) / 128), dim3(128), 0, st, r, (const T*)rp, sign, (const T*)sp, logp,
+                (const T*)lp, age, nus, seed, step0 + (uint64_t)s, woff, max_age, B, N, cnt);
+      DQ_LAUNCH(tau_kernel<T>, dim3(1), dim3(32), 0, st, tau, cnt, B, (T)target, stats);
+    }
+    DQ_LAUNCH(sampler_stats_kernel<T>, dim3(1), dim3(256), 0, st, (const T*)r, (const T*)logp, (const int*)age,
+              (const T*)tau, B, N, stats);
+    DQ_CHECK(cudaGetLastError());
+    return 0;
+  }
+};
+
+}  // namespace dq
+
+// ================================= C ABI ======================================================
+struct dqmc_engine {
+  dq::EngineBase* e;
+};
+
+extern "C" {
+
+const char* dqmc_version(void) { return "dqmc_b200 0.1 (sm_100a)"; }
+
+int dqmc_create(const dqmc_config* cfg, int device, dqmc_handle* out) {
+  if (!cfg || !out) return 2;
+  dq::EngineBase* e = nullptr;
+  int rc = 0;
+  if (cfg->dtype == DQMC_F64) {
+    auto* x = new dq::Engine<double>();
+    x->cfg = *cfg; x->device = device; rc = x->init(); e = x;
+  } else if (cfg->dtype == DQMC_F32) {
+    auto* x = new dq::Engine<float>();
+    x->cfg = *cfg; x->device = device; rc = x->init(); e = x;
+  } else {
+    return 2;
+  }
+  if (rc) {
+    std::fprintf(stderr, "dqmc_create failed: %s\n", e->err.c_str());
+    delete e;
+    return rc;
+  }
+  *out = new dqmc_engine{e};
+  return 0;
+}
+int dqmc_destroy(dqmc_handle h) {
+  if (!h) return 2;
+  delete h->e;
+  delete h;
+  return 0;
+}
+const char* dqmc_last_error(dqmc_handle h) { return h ? h->e->err.c_str() : "null handle"; }
+int dqmc_param_count(dqmc_handle h) { return h ? (int)h->e->entries.size() : -1; }
+int64_t dqmc_param_total(dqmc_handle h) { return h ? h->e->total : -1; }
+int dqmc_param_entry(dqmc_handle h, int idx, char* name, int name_len, int64_t* offset, int32_t* rows, int32_t* cols) {
+  if (!h || idx < 0 || idx >= (int)h->e->entries.size()) return 2;
+  auto& en = h->e->entries[idx];
+  if (name && name_len > 0) {
+    std::strncpy(name, en.name.c_str(), name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  if (offset) *offset = en.offset;
+  if (rows) *rows = en.rows;
+  if (cols) *cols = en.cols;
+  return 0;
+}
+int dqmc_set_params(dqmc_handle h, const double* host_params, int64_t n, void* stream) {
+  if (!h) return 2;
+  return h->e->set_params(host_params, n, (cudaStream_t)stream);
+}
+int64_t dqmc_workspace_bytes(dqmc_handle h, int32_t n_walkers, int32_t mode) {
+  return h ? h->e->ws_bytes(n_walkers, mode) : -1;
+}
+int dqmc_wf_forward(dqmc_handle h, const void* r, const void* R, int32_t R_batched, int32_t n_walkers, void* out_sign,
+                    void* out_log, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!h) return 2;
+  return h->e->forward(r, R, R_batched, n_walkers, out_sign, out_log, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int dqmc_local_energy(dqmc_handle h, const void* r, const void* R, int32_t R_batched, int32_t n_walkers, uint64_t seed,
+                      const void* ecp_twist, void* out_E, void* out_stats, void* out_sign, void* out_log,
+                      void* out_grad, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!h) return 2;
+  return h->e->local_energy(r, R, R_batched, n_walkers, seed, ecp_twist, out_E, out_stats, out_sign, out_log, out_grad,
+                            workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int dqmc_mcmc_sweep(dqmc_handle h, void* r, void* sign, void* log, int32_t* age, void* tau, const void* R,
+                    int32_t R_batched, int32_t n_walkers, int32_t n_sub, double target_acceptance, int32_t max_age,
+                    uint64_t seed, uint64_t step0, uint64_t walker_offset, const void* noise_normal,
+                    const void* noise_uniform, void* out_stats, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!h) return 2;
+  return h->e->mcmc(r, sign, log, age, tau, R, R_batched, n_walkers, n_sub, target_acceptance, max_age, seed, step0,
+                    walker_offset, noise_normal, noise_uniform, out_stats, workspace, workspace_bytes,
+                    (cudaStream_t)stream);
+}
+int64_t dqmc_launch_count(dqmc_handle h) { return h ? h->e->launches : -1; }
+
+}  // extern "C"

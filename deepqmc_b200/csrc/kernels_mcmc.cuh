@@ -1,0 +1,234 @@
+// Metropolis walker update and non-local ECP quadrature kernels.
+#pragma once
+#include "common.cuh"
+
+namespace dq {
+
+// Gaussian proposal r' = r + tau * N(0,1), all electrons at once.
+// reference: src/deepqmc/sampling/electron_samplers.py:102-104.
+// noise != nullptr: injected standard normals (parity tests); else Philox keyed by
+// (seed; global element pair index, step).
+template <class T>
+__global__ void propose_kernel(const T* __restrict__ r, T* __restrict__ r_prop, const T* __restrict__ tau,
+                               const T* __restrict__ noise, uint64_t seed, uint64_t step, uint64_t elem_offset,
+                               int n_elem) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;  // pair index
+  const int e0 = 2 * p;
+  if (e0 >= n_elem) return;
+  const T t = tau[0];
+  T z0, z1;
+  if (noise) {
+    z0 = noise[e0];
+    z1 = e0 + 1 < n_elem ? noise[e0 + 1] : T(0);
+  } else {
+    uint32_t w[4];
+    Philox::gen(seed, elem_offset / 2 + (uint64_t)p, step, w);
+    double u1 = Philox::u01(w[0], w[1]), u2 = Philox::u01(w[2], w[3]);
+    double rad = ::sqrt(-2.0 * ::log(u1)), ang = 6.283185307179586 * u2;
+    z0 = (T)(rad * ::cos(ang));
+    z1 = (T)(rad * ::sin(ang));
+  }
+  r_prop[e0] = r[e0] + t * z0;
+  if (e0 + 1 < n_elem) r_prop[e0 + 1] = r[e0 + 1] + t * z1;
+}
+
+// Accept/reject, one thread per walker.  reference: electron_samplers.py:106-138
+// (2 dlog|psi| > log u, max_age override, age bookkeeping, per-walker select of r/psi/age).
+template <class T>
+__global__ void accept_kernel(T* __restrict__ r, const T* __restrict__ r_prop, T* __restrict__ sign,
+                              const T* __restrict__ sign_p, T* __restrict__ logp, const T* __restrict__ logp_p,
+                              int* __restrict__ age, const T* __restrict__ unoise, uint64_t seed, uint64_t step,
+                              uint64_t walker_offset, int max_age, int B, int N, int* __restrict__ acc_count) {
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    double u;
+    if (unoise) u = (double)unoise[b];
+    else {
+      uint32_t w[4];
+      Philox::gen(seed ^ 0x9E3779B97F4A7C15ull, walker_offset + (uint64_t)b, step, w);
+      u = Philox::u01(w[0], w[1]);
+    }
+    double lp = 2.0 * ((double)logp_p[b] - (double)logp[b]);
+    bool acc = lp > ::log(u);
+    if (max_age >= 0) acc = acc || (age[b] >= max_age);
+    if (acc) {
+      for (int e = 0; e < 3 * N; ++e) r[(size_t)b * 3 * N + e] = r_prop[(size_t)b * 3 * N + e];
+      sign[b] = sign_p[b];
+      logp[b] = logp_p[b];
+      age[b] = 0;
+      atomicAdd(&s_cnt, 1);
+    } else {
+      age[b] += 1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cnt) atomicAdd(acc_count, s_cnt);
+}
+
+// tau <- tau * max(acceptance, 0.05) / target   (reference: electron_samplers.py:121-126)
+template <class T>
+__global__ void tau_kernel(T* tau, int* acc_count, int B, T target, T* acc_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    T acc = (T)acc_count[0] / (T)B;
+    if (target > T(0)) {
+      T a = acc > T(0.05) ? acc : T(0.05);
+      tau[0] = tau[0] / (target / a);
+    }
+    acc_out[0] = acc;
+    acc_count[0] = 0;
+  }
+}
+
+// Sampler statistics of the final sub-step (reference: electron_samplers.py:154-163):
+// out[0]=acceptance (written by tau_kernel), [1]=tau, [2]=age mean, [3]=age max,
+// [4]=log|psi| mean, [5]=log|psi| std (population), [6]=mean e-e distance.  Single block.
+template <class T>
+__global__ void sampler_stats_kernel(const T* __restrict__ r, const T* __restrict__ logp, const int* __restrict__ age,
+                                     const T* __restrict__ tau, int B, int N, T* __restrict__ out) {
+  __shared__ T scratch[66];
+  __shared__ int s_max;
+  if (threadIdx.x == 0) s_max = 0;
+  __syncthreads();
+  T sa = 0, sl = 0, sd = 0;
+  int amax = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    sa += (T)age[b];
+    amax = age[b] > amax ? age[b] : amax;
+    sl += logp[b];
+    const T* rb = r + (size_t)b * 3 * N;
+    for (int i = 0; i < N; ++i)
+      for (int j = i + 1; j < N; ++j) {
+        T d0 = rb[3 * i] - rb[3 * j], d1 = rb[3 * i + 1] - rb[3 * j + 1], d2 = rb[3 * i + 2] - rb[3 * j + 2];
+        sd += m_sqrt(Num<T>::eps() + d0 * d0 + d1 * d1 + d2 * d2);
+      }
+  }
+  atomicMax(&s_max, amax);
+  block_sum2(sa, sl, scratch);
+  T mean_l = sl / (T)B;
+  T dummy = 0, sv = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    T dl = logp[b] - mean_l;
+    sv += dl * dl;
+  }
+  block_sum2(sd, sv, scratch);
+  (void)dummy;
+  if (threadIdx.x == 0) {
+    out[1] = tau[0];
+    out[2] = sa / (T)B;
+    out[3] = (T)s_max;
+    out[4] = mean_l;
+    out[5] = m_sqrt(sv / (T)B);
+    int npair = N * (N - 1) / 2;
+    out[6] = sd / ((T)B * (T)(npair > 0 ? npair : 1));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Non-local ECP: 12-point icosahedron quadrature, rotated onto r_i - R_I with a random twist
+// about the local z axis.  reference: src/deepqmc/ecp/ecp_utils.py:24-60,
+// gaussian_type_ecp.py:161-255.  One block per (walker b, ecp nucleus slot j, electron i);
+// writes 12 virtual walkers r_virt[v][N][3], v = ((b*J + j)*N + i)*12 + q.
+// phi: injected twists [B][J][N] in [0, pi/5) or nullptr -> Philox.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ico_vertex(int q, double& th, double& ph) {
+  const double pi = 3.141592653589793, at2 = 1.1071487177940904;  // atan(2)
+  if (q == 0) { th = 0; ph = 0; }
+  else if (q == 1) { th = pi; ph = 0; }
+  else {
+    int j = (q - 2) / 2;
+    if ((q & 1) == 0) { th = at2; ph = pi / 5 * 2 * j; }
+    else { th = pi - at2; ph = pi / 5 * (2 * j - 1); }
+  }
+}
+
+template <class T>
+__global__ void ecp_points_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M,
+                                  int J, const int* __restrict__ nl_nuc, const T* __restrict__ phi, uint64_t seed,
+                                  uint64_t walker_offset, T* __restrict__ r_virt) {
+  __shared__ double pts[12][3];
+  const int blk = blockIdx.x;
+  const int i = blk % N, j = (blk / N) % J, b = blk / (N * J);
+  const T* rb = r + (size_t)b * 3 * N;
+  const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
+  const int I = nl_nuc[j];
+  if (threadIdx.x < 12) {
+    const int q = threadIdx.x;
+    double dx = (double)rb[3 * i] - (double)Rb[3 * I], dy = (double)rb[3 * i + 1] - (double)Rb[3 * I + 1],
+           dz = (double)rb[3 * i + 2] - (double)Rb[3 * I + 2];
+    double radius = ::sqrt(dx * dx + dy * dy + dz * dz);
+    double cz = dz / radius;
+    cz = cz > 1.0 ? 1.0 : (cz < -1.0 ? -1.0 : cz);
+    double theta = ::acos(cz), ph0 = ::atan2(dy, dx);
+    double pr;
+    if (phi) pr = (double)phi[((size_t)b * J + j) * N + i];
+    else {
+      uint32_t w[4];
+      Philox::gen(seed ^ 0xD1B54A32D192ED03ull, (walker_offset + (uint64_t)b) * (uint64_t)(J * N) + (uint64_t)(j * N + i), 0, w);
+      pr = Philox::u01(w[0], w[1]) * (3.141592653589793 / 5);
+    }
+    double th, ph;
+    ico_vertex(q, th, ph);
+    double ux = ::sin(th) * ::cos(ph), uy = ::sin(th) * ::sin(ph), uz = ::cos(th);
+    // rot_z(pr)
+    double ax = ::cos(pr) * ux - ::sin(pr) * uy, ay = ::sin(pr) * ux + ::cos(pr) * uy, az = uz;
+    // rot_y(theta)
+    double bx = ::cos(theta) * ax + ::sin(theta) * az, by = ay, bz = -::sin(theta) * ax + ::cos(theta) * az;
+    // rot_z(ph0)
+    double cx = ::cos(ph0) * bx - ::sin(ph0) * by, cy = ::sin(ph0) * bx + ::cos(ph0) * by;
+    pts[q][0] = radius * cx + (double)Rb[3 * I];
+    pts[q][1] = radius * cy + (double)Rb[3 * I + 1];
+    pts[q][2] = radius * bz + (double)Rb[3 * I + 2];
+  }
+  __syncthreads();
+  T* out = r_virt + (size_t)blk * 12 * 3 * N;
+  for (int idx = threadIdx.x; idx < 12 * 3 * N; idx += blockDim.x) {
+    int q = idx / (3 * N), e = idx % (3 * N);
+    out[idx] = (e / 3 == i) ? (T)pts[q][e % 3] : rb[e];
+  }
+}
+
+// V_nl[b] = sum_{j,i,l} (2l+1)/12 v_l(|r_i - R_I|) sum_q P_l(cos th_q) psi(r_i->q)/psi(r)
+// one thread per walker; adds V_nl to E_loc and to stats[3].
+template <class T>
+__global__ void ecp_accumulate_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M,
+                                      int J, const int* __restrict__ nl_nuc, const T* __restrict__ nl_params,
+                                      int L, int Tm, const T* __restrict__ sign0, const T* __restrict__ log0,
+                                      const T* __restrict__ sign_v, const T* __restrict__ log_v, int B, int Bstat,
+                                      T* __restrict__ out_E, T* __restrict__ out_stats) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const T* rb = r + (size_t)b * 3 * N;
+  const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
+  double total = 0.0;
+  for (int j = 0; j < J; ++j) {
+    const int I = nl_nuc[j];
+    const T* nl = nl_params + (size_t)I * L * 2 * Tm;
+    for (int i = 0; i < N; ++i) {
+      double dx = (double)rb[3 * i] - (double)Rb[3 * I], dy = (double)rb[3 * i + 1] - (double)Rb[3 * I + 1],
+             dz = (double)rb[3 * i + 2] - (double)Rb[3 * I + 2];
+      double d2 = dx * dx + dy * dy + dz * dz;
+      double integ[4] = {0, 0, 0, 0};
+      for (int q = 0; q < 12; ++q) {
+        size_t v = (((size_t)b * J + j) * N + i) * 12 + q;
+        double ratio = ::exp((double)log_v[v] - (double)log0[b]) * (double)sign_v[v] * (double)sign0[b];
+        double th, ph;
+        ico_vertex(q, th, ph);
+        double x = ::cos(th);
+        double pl[4] = {1.0, x, 0.5 * (3 * x * x - 1), 0.5 * (5 * x * x * x - 3 * x)};
+        for (int l = 0; l < L; ++l) integ[l] += ratio * pl[l];
+      }
+      for (int l = 0; l < L; ++l) {
+        double vl = 0.0;
+        for (int t = 0; t < Tm; ++t) vl += (double)nl[(l * 2 + 1) * Tm + t] * ::exp(-(double)nl[(l * 2 + 0) * Tm + t] * d2);
+        total += vl * (2 * l + 1) / 12.0 * integ[l];
+      }
+    }
+  }
+  out_E[b] += (T)total;
+  out_stats[3 * (size_t)Bstat + b] = (T)total;
+}
+
+}  // namespace dq

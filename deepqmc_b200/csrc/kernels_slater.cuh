@@ -1,0 +1,314 @@
+// Determinant tail of the wave function with forward-Laplacian propagation:
+// envelopes (x) backflow -> K signed log-determinants (+ gradient, Laplacian) -> exp-normalised
+// determinant sum, e-e cusp, Coulomb / local-ECP potentials, local-energy assembly.
+#pragma once
+#include "common.cuh"
+
+namespace dq {
+
+// ------------------------------------------------------------------------------------------
+// One block per (walker b, determinant k).
+//   A[i][mu] = env_k[i][mu] * bf_k[i][mu]
+//   reference: src/deepqmc/wf/env.py:57-75 (phi = sum_m pi exp(-|zeta| |r_i - R_m|), eps-safe
+//   norm), wf/nn_wave_function.py:111-151 (multiplicative backflow with mult_act = identity,
+//   full determinant, jnp.linalg.slogdet = partial-pivot LU sign/log convention).
+//   d_t log|det A| = tr(A^-1 A^t);  lap log|det A| = tr(A^-1 A^L) - sum_t tr((A^-1 A^t)^2)
+// BF: augmented rows [b][i][s][K*N] (orbital index k*N + mu, wf/omni.py:78-88).
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M, int n_up,
+                              int K, int S, const T* __restrict__ pi_up, const T* __restrict__ pi_dn,
+                              const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn,
+                              const T* __restrict__ BF, int ldb, T* __restrict__ det_sign, T* __restrict__ det_log,
+                              T* __restrict__ det_grad, T* __restrict__ det_lap) {
+  DQMC_DYN_SMEM(smem_raw);
+  const int NP = N + 1, N2 = 2 * N + 1;
+  T* env = reinterpret_cast<T*>(smem_raw);  // [N][NP]
+  T* denv = env + N * NP;                    // [3][N][NP]
+  T* bfv = denv + 3 * N * NP;                // [N][NP]
+  T* AL = bfv + N * NP;                      // [N][NP]
+  T* At = AL + N * NP;                       // [N][NP]
+  T* Bt = At + N * NP;                       // [N][NP]
+  T* aug = Bt + N * NP;                      // [N][N2]
+  T* fcol = aug + N * N2;                    // [N]
+  T* scratch = fcol + N;                     // [66]
+  T* misc = scratch + 66;                    // [4]: logdet, sign, pivot row (as T)
+  const int b = blockIdx.x, k = blockIdx.y;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int T3 = S > 1 ? S - 2 : 0;
+  const T* rb = r + (size_t)b * N * 3;
+  const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
+  const size_t brow0 = (size_t)b * N * S;
+  const int KN = K * N;
+
+  for (int idx = tid; idx < N * N; idx += nt) {
+    const int i = idx / N, mu = idx % N;
+    const T* pi = (i < n_up ? pi_up : pi_dn) + (size_t)(k * N + mu) * M;
+    const T* ze = (i < n_up ? zeta_up : zeta_dn) + (size_t)(k * N + mu) * M;
+    T e = 0, de0 = 0, de1 = 0, de2 = 0, le = 0;
+    for (int m = 0; m < M; ++m) {
+      T dx0 = rb[3 * i] - Rb[3 * m], dx1 = rb[3 * i + 1] - Rb[3 * m + 1], dx2 = rb[3 * i + 2] - Rb[3 * m + 2];
+      T d2 = dx0 * dx0 + dx1 * dx1 + dx2 * dx2;
+      T rho2 = Num<T>::eps() + d2, rho = m_sqrt(rho2);
+      T a = m_abs(ze[m]);
+      T ex = pi[m] * m_exp(-a * rho);
+      e += ex;
+      if (S > 1) {
+        T c = -a * ex / rho;
+        de0 += c * dx0; de1 += c * dx1; de2 += c * dx2;
+        le += ex * (a * a * d2 / rho2 - a * (T(3) / rho - d2 / (rho2 * rho)));
+      }
+    }
+    const T* bfrow = BF + (brow0 + (size_t)i * S) * ldb + k * N + mu;
+    T bf0 = bfrow[0];
+    env[i * NP + mu] = e;
+    bfv[i * NP + mu] = bf0;
+    T a0 = e * bf0;
+    aug[i * N2 + mu] = a0;
+    aug[i * N2 + N + mu] = (i == mu) ? T(1) : T(0);
+    if (S > 1) {
+      denv[(0 * N + i) * NP + mu] = de0;
+      denv[(1 * N + i) * NP + mu] = de1;
+      denv[(2 * N + i) * NP + mu] = de2;
+      T bfl = bfrow[(size_t)(1 + T3) * ldb];
+      T x0 = bfrow[(size_t)(1 + 3 * i) * ldb], x1 = bfrow[(size_t)(2 + 3 * i) * ldb], x2 = bfrow[(size_t)(3 + 3 * i) * ldb];
+      AL[i * NP + mu] = le * bf0 + e * bfl + T(2) * (de0 * x0 + de1 * x1 + de2 * x2);
+    }
+  }
+  if (tid == 0) { misc[0] = T(0); misc[1] = T(1); }
+  __syncthreads();
+
+  // ---- Gauss-Jordan with partial pivoting on [A | I] ------------------------------------
+  for (int c = 0; c < N; ++c) {
+    if (tid < 32) {
+      T best = T(-1);
+      int bi = c;
+      for (int rr = c + tid; rr < N; rr += 32) {
+        T v = m_abs(aug[rr * N2 + c]);
+        if (v > best) { best = v; bi = rr; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        T ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (tid == 0) misc[2] = (T)bi;
+    }
+    __syncthreads();
+    const int prow = (int)misc[2];
+    if (prow != c) {
+      for (int j = tid; j < 2 * N; j += nt) {
+        T t0 = aug[c * N2 + j];
+        aug[c * N2 + j] = aug[prow * N2 + j];
+        aug[prow * N2 + j] = t0;
+      }
+    }
+    __syncthreads();
+    const T pv = aug[c * N2 + c];
+    if (tid == 0) {
+      misc[0] += m_log(m_abs(pv));
+      T sg = pv > T(0) ? T(1) : (pv < T(0) ? T(-1) : T(0));
+      misc[1] *= (prow != c ? -sg : sg);
+    }
+    for (int rr = tid; rr < N; rr += nt) fcol[rr] = aug[rr * N2 + c];
+    __syncthreads();
+    const T ipv = T(1) / pv;
+    for (int j = tid; j < 2 * N; j += nt) aug[c * N2 + j] *= ipv;
+    __syncthreads();
+    for (int idx = tid; idx < N * 2 * N; idx += nt) {
+      int rr = idx / (2 * N), j = idx % (2 * N);
+      if (rr != c) aug[rr * N2 + j] -= fcol[rr] * aug[c * N2 + j];
+    }
+    __syncthreads();
+  }
+  const size_t bk = (size_t)b * K + k;
+  if (tid == 0) { det_log[bk] = misc[0]; det_sign[bk] = misc[1]; }
+  if (S == 1) return;
+
+  // Ainv[mu][i] = aug[mu][N + i]
+  T lap_part = T(0), dummy = T(0);
+  for (int idx = tid; idx < N * N; idx += nt) {
+    int i = idx / N, mu = idx % N;
+    lap_part += aug[mu * N2 + N + i] * AL[i * NP + mu];
+  }
+  block_sum2(lap_part, dummy, scratch);
+  T lap = lap_part;
+  for (int t = 0; t < T3; ++t) {
+    const int it = t / 3, ct = t % 3;
+    for (int idx = tid; idx < N * N; idx += nt) {
+      int i = idx / N, mu = idx % N;
+      T bft = BF[(brow0 + (size_t)i * S + 1 + t) * ldb + k * N + mu];
+      T a = env[i * NP + mu] * bft;
+      if (i == it) a += denv[(ct * N + i) * NP + mu] * bfv[i * NP + mu];
+      At[i * NP + mu] = a;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < N * N; idx += nt) {
+      int mu = idx / N, nu = idx % N;
+      T a = T(0);
+      for (int i = 0; i < N; ++i) a += aug[mu * N2 + N + i] * At[i * NP + nu];
+      Bt[mu * NP + nu] = a;
+    }
+    __syncthreads();
+    T tr2 = T(0), gt = T(0);
+    for (int idx = tid; idx < N * N; idx += nt) {
+      int mu = idx / N, nu = idx % N;
+      tr2 += Bt[mu * NP + nu] * Bt[nu * NP + mu];
+      if (mu == nu) gt += Bt[mu * NP + mu];
+    }
+    block_sum2(tr2, gt, scratch);
+    lap -= tr2;
+    if (tid == 0) det_grad[bk * T3 + t] = gt;
+  }
+  if (tid == 0) det_lap[bk] = lap;
+}
+
+template <class T>
+inline size_t slater_smem_bytes(int N) {
+  return sizeof(T) * ((size_t)8 * N * (N + 1) + (size_t)N * (2 * N + 1) + N + 66 + 4);
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-walker assembly.  reference: wf/nn_wave_function.py:152-171 (exp-normalised sum with
+// stop-gradient shift, SumPool conf_coeff, cusp), wf/cusp.py:17-26 (PsiformerCusp),
+// physics.py:79-141 (kinetic term, Coulomb terms, eps-safe e-e and n-n distances, plain e-n
+// distance), ecp/gaussian_type_ecp.py:127-159 (local ECP), hamil.py:165-180 (sum + 6 stats).
+// One block per walker.  stats layout: [6][B] in the order V_el, E_kin, V_loc, V_nl, lap, qf2.
+// ------------------------------------------------------------------------------------------
+struct FinalizeCfg {
+  int N, M, n_up, K, S;
+  int cusp_kind;  // 0 none, 1 psiformer
+  double cusp_same_scale, cusp_anti_scale;
+  int ecp_terms;  // Tmax of loc params (0: plain Coulomb)
+};
+
+template <class T>
+__global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T* __restrict__ R, int R_batched,
+                                const T* __restrict__ det_sign, const T* __restrict__ det_log,
+                                const T* __restrict__ det_grad, const T* __restrict__ det_lap,
+                                const T* __restrict__ cusp_alpha /*[2] same, anti*/,
+                                const T* __restrict__ z_val /*[M]*/, const T* __restrict__ ecp_loc /*[M][3][2][Tm]*/,
+                                const int* __restrict__ ecp_mask, int B, T* __restrict__ out_sign,
+                                T* __restrict__ out_log, T* __restrict__ out_E, T* __restrict__ out_stats,
+                                T* __restrict__ out_grad) {
+  DQMC_DYN_SMEM(smem_raw);
+  const int N = c.N, M = c.M, K = c.K, S = c.S;
+  const int T3 = S > 1 ? S - 2 : 0;
+  T* pk = reinterpret_cast<T*>(smem_raw);  // [K]
+  T* grad = pk + K;                         // [3N]
+  T* scratch = grad + 3 * N;                // [66]
+  T* misc = scratch + 66;                   // [4]
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const T* rb = r + (size_t)b * N * 3;
+  const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
+  const T* ds = det_sign + (size_t)b * K;
+  const T* dl = det_log + (size_t)b * K;
+  if (tid == 0) {
+    T shift = dl[0];
+    for (int k = 1; k < K; ++k) shift = dl[k] > shift ? dl[k] : shift;
+    if ((shift - shift) != T(0)) shift = T(0);  // +-inf shift -> 0 (nn_wave_function.py:154)
+    T psi = T(0);
+    for (int k = 0; k < K; ++k) { pk[k] = ds[k] * m_exp(dl[k] - shift); psi += pk[k]; }
+    for (int k = 0; k < K; ++k) pk[k] /= psi;
+    misc[0] = m_log(m_abs(psi)) + shift;
+    misc[1] = psi > T(0) ? T(1) : (psi < T(0) ? T(-1) : T(0));
+  }
+  __syncthreads();
+  // ---- cusp + e-e repulsion: thread i handles electron i ---------------------------------
+  T cusp_v = T(0), cusp_l = T(0), vel = T(0), vloc = T(0), enuc = T(0);
+  T as_ = T(1), aa_ = T(1);
+  if (c.cusp_kind == 1) { as_ = cusp_alpha[0]; aa_ = cusp_alpha[1]; }
+  for (int i = tid; i < N; i += nt) {
+    T g0 = 0, g1 = 0, g2 = 0;
+    for (int j = 0; j < N; ++j) {
+      if (j == i) continue;
+      T dx0 = rb[3 * i] - rb[3 * j], dx1 = rb[3 * i + 1] - rb[3 * j + 1], dx2 = rb[3 * i + 2] - rb[3 * j + 2];
+      T d2 = dx0 * dx0 + dx1 * dx1 + dx2 * dx2;
+      T rho2 = Num<T>::eps() + d2, rho = m_sqrt(rho2);
+      vel += T(0.5) / rho;
+      if (c.cusp_kind == 1) {
+        bool same = (i < c.n_up) == (j < c.n_up);
+        T al = same ? as_ : aa_;
+        T sc = (T)(same ? c.cusp_same_scale : c.cusp_anti_scale) * al * al;
+        T den = al + rho;
+        T f = -sc / den, fp = sc / (den * den), fpp = T(-2) * sc / (den * den * den);
+        cusp_v += T(0.5) * f;
+        if (S > 1) {
+          T cc = fp / rho;
+          g0 += cc * dx0; g1 += cc * dx1; g2 += cc * dx2;
+          cusp_l += fpp * d2 / rho2 + fp * (T(3) / rho - d2 / (rho2 * rho));
+        }
+      }
+    }
+    if (S > 1) { grad[3 * i] = g0; grad[3 * i + 1] = g1; grad[3 * i + 2] = g2; }
+    // electron-nucleus attraction (plain norm) + local ECP
+    for (int m = 0; m < M; ++m) {
+      T dx0 = rb[3 * i] - Rb[3 * m], dx1 = rb[3 * i + 1] - Rb[3 * m + 1], dx2 = rb[3 * i + 2] - Rb[3 * m + 2];
+      T d2 = dx0 * dx0 + dx1 * dx1 + dx2 * dx2;
+      T dist = m_sqrt(d2);
+      vloc -= z_val[m] / dist;
+      if (c.ecp_terms > 0 && ecp_mask[m]) {
+        const T* lp = ecp_loc + (size_t)m * 6 * c.ecp_terms;
+        for (int tt = 0; tt < c.ecp_terms; ++tt) {
+          vloc += lp[(0 * 2 + 1) * c.ecp_terms + tt] / dist * m_exp(-lp[(0 * 2 + 0) * c.ecp_terms + tt] * d2);
+          vloc += lp[(1 * 2 + 1) * c.ecp_terms + tt] * m_exp(-lp[(1 * 2 + 0) * c.ecp_terms + tt] * d2);
+          vloc += lp[(2 * 2 + 1) * c.ecp_terms + tt] * dist * m_exp(-lp[(2 * 2 + 0) * c.ecp_terms + tt] * d2);
+        }
+      }
+    }
+  }
+  for (int idx = tid; idx < M * M; idx += nt) {
+    int I = idx / M, J = idx % M;
+    if (I < J) {
+      T dx0 = Rb[3 * I] - Rb[3 * J], dx1 = Rb[3 * I + 1] - Rb[3 * J + 1], dx2 = Rb[3 * I + 2] - Rb[3 * J + 2];
+      enuc += z_val[I] * z_val[J] / m_sqrt(Num<T>::eps() + dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
+    }
+  }
+  block_sum2(cusp_v, cusp_l, scratch);
+  block_sum2(vel, vloc, scratch);
+  T dummy = T(0);
+  block_sum2(enuc, dummy, scratch);
+  if (tid == 0) {
+    out_sign[b] = misc[1];
+    out_log[b] = misc[0] + cusp_v;
+  }
+  if (S == 1) return;
+  // ---- determinant sum: gradient and Laplacian -------------------------------------------
+  const T* dg = det_grad + (size_t)b * K * T3;
+  T sum_pg2 = T(0), sum_g2 = T(0);
+  for (int t = tid; t < T3; t += nt) {
+    T gd = T(0), pg2 = T(0);
+    for (int k = 0; k < K; ++k) {
+      T gk = dg[(size_t)k * T3 + t];
+      gd += pk[k] * gk;
+      pg2 += pk[k] * gk * gk;
+    }
+    sum_pg2 += pg2 - gd * gd;  // contributes sum_k p_k g_k^2 - (sum_k p_k g_k)^2
+    T gtot = gd + grad[t];
+    grad[t] = gtot;
+    sum_g2 += gtot * gtot;
+    if (out_grad) out_grad[(size_t)b * T3 + t] = gtot;
+  }
+  block_sum2(sum_pg2, sum_g2, scratch);
+  if (tid == 0) {
+    T lap = sum_pg2 + cusp_l;
+    for (int k = 0; k < K; ++k) lap += pk[k] * det_lap[(size_t)b * K + k];
+    T ekin = T(-0.5) * (lap + sum_g2);
+    T e = ekin + vloc + vel + enuc;  // V_nl added by the non-local ECP pass
+    out_E[b] = e;
+    out_stats[0 * (size_t)B + b] = vel;
+    out_stats[1 * (size_t)B + b] = ekin;
+    out_stats[2 * (size_t)B + b] = vloc;
+    out_stats[3 * (size_t)B + b] = T(0);
+    out_stats[4 * (size_t)B + b] = lap;
+    out_stats[5 * (size_t)B + b] = sum_g2;
+  }
+}
+
+template <class T>
+inline size_t finalize_smem_bytes(int N, int K) {
+  return sizeof(T) * ((size_t)K + 3 * N + 66 + 4);
+}
+
+}  // namespace dq

@@ -1,0 +1,368 @@
+// Trunk kernels of the forward-Laplacian engine: electron embedding, row GEMM, tanh
+// propagation, self-attention propagation.
+//
+// Activation layout ("augmented rows"): X[b][i][s][f], f fastest, for walker b, electron i and
+// slot s in [0, S).  S == 1: plain forward (value only).  S == T+2, T = 3*N: slot 0 = value,
+// slot 1+t = d/dx_t (t = 3*j + c, coordinate c of electron j), slot T+1 = Laplacian
+// sum_t d^2/dx_t^2.  A dense layer acts on all slots alike (linearity), an elementwise
+// nonlinearity mixes slot 0 with the others, attention mixes electrons -- the same propagation
+// rules folx applies in the reference's CLI default (conf/hamil/qc_forward_laplacian.yaml).
+#pragma once
+#include "common.cuh"
+
+namespace dq {
+
+// ------------------------------------------------------------------------------------------
+// Electron embedding: nucleus-electron features (+ spin) -> optional projection.
+// reference: src/deepqmc/gnn/electron_gnn.py:596-619, gnn/edge_features.py:21-78,
+//            conf/ansatz/psiformer.yaml:53-67, ferminet.yaml:45-56.
+// grid = B*N blocks, dynamic smem = 5*F*sizeof(T), F = 4*M + use_spin.
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void embed_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M,
+                             int n_up, int S, int log_rescale, int use_spin, const T* __restrict__ W, int d,
+                             T* __restrict__ X) {
+  DQMC_DYN_SMEM(smem_raw);
+  const int F = 4 * M + use_spin;
+  T* feat = reinterpret_cast<T*>(smem_raw);  // [F]
+  T* dfeat = feat + F;                        // [3][F]
+  T* lfeat = dfeat + 3 * F;                   // [F]
+  const int bi = blockIdx.x, b = bi / N, i = bi % N;
+  const T* ri = r + (size_t)bi * 3;
+  const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    T dx[3] = {ri[0] - Rb[3 * m], ri[1] - Rb[3 * m + 1], ri[2] - Rb[3 * m + 2]};
+    T d2 = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+    T rho2 = Num<T>::eps() + d2, rho = m_sqrt(rho2);
+    T gr2 = d2 / rho2;                     // |grad rho|^2
+    T lr = T(3) / rho - d2 / (rho2 * rho);  // laplacian rho
+    T f0, f0p, f0pp, s, sp, spp;
+    if (log_rescale) {
+      T g = m_log1p(rho), gp = T(1) / (T(1) + rho), gpp = -gp * gp;
+      f0 = g; f0p = gp; f0pp = gpp;
+      s = g / rho;
+      sp = gp / rho - g / rho2;
+      spp = gpp / rho - T(2) * gp / rho2 + T(2) * g / (rho2 * rho);
+    } else {
+      f0 = rho; f0p = T(1); f0pp = T(0);
+      s = T(1); sp = T(0); spp = T(0);
+    }
+    const int k0 = 4 * m;
+    feat[k0] = f0;
+    lfeat[k0] = f0pp * gr2 + f0p * lr;
+    T ls = spp * gr2 + sp * lr;  // laplacian of s(rho)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      dfeat[c * F + k0] = f0p * dx[c] / rho;
+      feat[k0 + 1 + c] = dx[c] * s;
+      lfeat[k0 + 1 + c] = T(2) * sp * dx[c] / rho + dx[c] * ls;
+#pragma unroll
+      for (int e = 0; e < 3; ++e)
+        dfeat[e * F + k0 + 1 + c] = (c == e ? s : T(0)) + dx[c] * sp * dx[e] / rho;
+    }
+  }
+  if (use_spin && threadIdx.x == 0) {
+    feat[F - 1] = i < n_up ? T(1) : T(-1);
+    dfeat[F - 1] = dfeat[F + F - 1] = dfeat[2 * F + F - 1] = T(0);
+    lfeat[F - 1] = T(0);
+  }
+  __syncthreads();
+  const int T3 = S - 2;
+  T* Xg = X + (size_t)bi * S * d;
+  for (int f = threadIdx.x; f < d; f += blockDim.x) {
+    T y0 = 0, y1 = 0, y2 = 0, y3 = 0, yl = 0;
+    if (W) {
+      for (int k = 0; k < F; ++k) {
+        T w = W[(size_t)k * d + f];
+        y0 += feat[k] * w;
+        y1 += dfeat[k] * w;
+        y2 += dfeat[F + k] * w;
+        y3 += dfeat[2 * F + k] * w;
+        yl += lfeat[k] * w;
+      }
+    } else {  // identity projection (d == F)
+      y0 = feat[f]; y1 = dfeat[f]; y2 = dfeat[F + f]; y3 = dfeat[2 * F + f]; yl = lfeat[f];
+    }
+    Xg[f] = y0;
+    if (S > 1) {
+      for (int t = 0; t < T3; ++t) {
+        T v = T(0);
+        if (t == 3 * i) v = y1;
+        else if (t == 3 * i + 1) v = y2;
+        else if (t == 3 * i + 2) v = y3;
+        Xg[(size_t)(1 + t) * d + f] = v;
+      }
+      Xg[(size_t)(1 + T3) * d + f] = yl;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Row GEMM  C[row(m), :] = (Res[row(m), :]) + A[row(m), :] @ W + (bias on value rows)
+// Plain SIMT tiling (CUDA cores), used for the fp64 parity mode and as the reference
+// implementation the tcgen05 fp32 path is validated against.
+// sliced == 1: blockIdx.z = electron e, rows m = (b, s) -> physical row (b*Nel + e)*S + s,
+//              weights W0 for e < z_split else W1 (per-spin backflow heads, wf/omni.py:43-88).
+// ------------------------------------------------------------------------------------------
+template <class T>
+struct GemmArgs {
+  const T* A; int lda;
+  const T* W0; const T* W1; int z_split; int ldw;
+  const T* bias;
+  const T* Res; int ldr;
+  T* C; int ldc;
+  int M, N, K;
+  int S;
+  int sliced, Nel;
+};
+
+template <class T, int BM, int BN, int BK, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(GemmArgs<T> g) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  __shared__ T As[BK][BM + 1];
+  __shared__ T Ws[BK][BN];
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int z = blockIdx.z;
+  const T* W = (g.sliced && z >= g.z_split) ? g.W1 : g.W0;
+  auto phys_row = [&](int m) -> size_t {
+    if (!g.sliced) return (size_t)m;
+    int b = m / g.S, s = m % g.S;
+    return ((size_t)b * g.Nel + z) * g.S + s;
+  };
+  T acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = T(0);
+
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+    for (int idx = tid; idx < BM * BK; idx += NT) {
+      int mm = idx / BK, kk = idx % BK;
+      int m = m0 + mm, k = k0 + kk;
+      T v = T(0);
+      if (m < g.M && k < g.K) v = g.A[phys_row(m) * g.lda + k];
+      As[kk][mm] = v;
+    }
+    for (int idx = tid; idx < BK * BN; idx += NT) {
+      int kk = idx / BN, nn = idx % BN;
+      int k = k0 + kk, n = n0 + nn;
+      T v = T(0);
+      if (k < g.K && n < g.N) v = W[(size_t)k * g.ldw + n];
+      Ws[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      T a[TM], w[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) w[j] = Ws[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] += a[i] * w[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m0 + ty * TM + i;
+    if (m >= g.M) continue;
+    size_t pr = phys_row(m);
+    bool value_row = (pr % g.S) == 0;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int n = n0 + tx * TN + j;
+      if (n >= g.N) continue;
+      T v = acc[i][j];
+      if (g.bias && value_row) v += g.bias[n];
+      if (g.Res) v += g.Res[pr * g.ldr + n];
+      g.C[pr * g.ldc + n] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// tanh propagation: y = tanh(z); y_t = y' z_t; y_lap = y' z_lap + y'' sum_t z_t^2
+// optional residual (all slots): out = res_scale * (Res + y)
+// grid = (G groups, ceil(d/blockDim)); in place on Z.
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void tanh_fl_kernel(T* __restrict__ Z, int ldz, const T* __restrict__ Res, int ldr, int S, int d,
+                               T out_scale) {
+  const int g = blockIdx.x;
+  const int f = blockIdx.y * blockDim.x + threadIdx.x;
+  if (f >= d) return;
+  T* z = Z + (size_t)g * S * ldz + f;
+  const T* rs = Res ? Res + (size_t)g * S * ldr + f : nullptr;
+  T y = m_tanh(z[0]);
+  T y1 = T(1) - y * y, y2 = T(-2) * y * y1;
+  z[0] = out_scale * ((rs ? rs[0] : T(0)) + y);
+  if (S > 1) {
+    const int T3 = S - 2;
+    T ss = T(0);
+    for (int t = 1; t <= T3; ++t) {
+      T zt = z[(size_t)t * ldz];
+      ss += zt * zt;
+      z[(size_t)t * ldz] = out_scale * ((rs ? rs[(size_t)t * ldr] : T(0)) + y1 * zt);
+    }
+    T zl = z[(size_t)(T3 + 1) * ldz];
+    z[(size_t)(T3 + 1) * ldz] = out_scale * ((rs ? rs[(size_t)(T3 + 1) * ldr] : T(0)) + y1 * zl + y2 * ss);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Self-attention with forward-Laplacian propagation, one block per (walker, head).
+// value algebra: hk.MultiHeadAttention (restated in reference src/deepqmc/hkext.py:215-253,
+// folxext.py:7-17): logits = q k^T / sqrt(dh), softmax over keys, out = P v.
+// derivative algebra: dense-Jacobian generalisation of reference src/deepqmc/folxext.py:70-171.
+//   s^t  = c (q^t k + q k^t)            p^t  = p (s^t - m^t),  m^t = sum_j p s^t
+//   s^L  = c (q^L k + q k^L + 2 sum_t q^t k^t)
+//   lap p = p (u - V + s^L - sum_j p s^L),  u = sum_t (s^t - m^t)^2,  V = sum_j p u
+//   o^t  = p^t v + p v^t ;  o^L = (lap p) v + 2 sum_t p^t v^t + p v^L
+// QKV: [rows][ldq] with q at col h*dh, k at dmodel + h*dh, v at 2*dmodel + h*dh.
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict__ O, int ldo, int N, int S, int dh,
+                               int dmodel, T scale) {
+  DQMC_DYN_SMEM(smem_raw);
+  const int dhp = dh + 1;
+  T* q = reinterpret_cast<T*>(smem_raw);
+  T* k = q + N * dhp;
+  T* v = k + N * dhp;
+  T* qt = v + N * dhp;
+  T* kt = qt + N * dhp;
+  T* vt = kt + N * dhp;
+  T* p = vt + N * dhp;  // [N][N]
+  T* st = p + N * N;
+  T* u = st + N * N;
+  T* qk = u + N * N;
+  T* olap = qk + N * N;  // [N][dh]
+  T* mrow = olap + N * dh;  // [N]
+  T* vrow = mrow + N;       // [N]
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int T3 = S > 1 ? S - 2 : 0;
+  const size_t row0 = (size_t)b * N * S;
+  auto load3 = [&](int slot, T* dq_, T* dk_, T* dv_) {
+    for (int idx = tid; idx < N * dh; idx += nt) {
+      int i = idx / dh, e = idx % dh;
+      const T* src = QKV + (row0 + (size_t)i * S + slot) * ldq + h * dh + e;
+      dq_[i * dhp + e] = src[0];
+      dk_[i * dhp + e] = src[dmodel];
+      dv_[i * dhp + e] = src[2 * dmodel];
+    }
+  };
+  load3(0, q, k, v);
+  __syncthreads();
+  for (int idx = tid; idx < N * N; idx += nt) {
+    int i = idx / N, j = idx % N;
+    T a = T(0);
+    for (int e = 0; e < dh; ++e) a += q[i * dhp + e] * k[j * dhp + e];
+    p[idx] = a * scale;
+    u[idx] = T(0);
+    qk[idx] = T(0);
+  }
+  for (int idx = tid; idx < N * dh; idx += nt) olap[idx] = T(0);
+  __syncthreads();
+  for (int i = tid; i < N; i += nt) {  // softmax row i
+    T mx = p[i * N];
+    for (int j = 1; j < N; ++j) mx = p[i * N + j] > mx ? p[i * N + j] : mx;
+    T sum = T(0);
+    for (int j = 0; j < N; ++j) {
+      T e = m_exp(p[i * N + j] - mx);
+      p[i * N + j] = e;
+      sum += e;
+    }
+    T inv = T(1) / sum;
+    for (int j = 0; j < N; ++j) p[i * N + j] *= inv;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < N * dh; idx += nt) {
+    int i = idx / dh, e = idx % dh;
+    T a = T(0);
+    for (int j = 0; j < N; ++j) a += p[i * N + j] * v[j * dhp + e];
+    O[(row0 + (size_t)i * S) * ldo + h * dh + e] = a;
+  }
+  if (S == 1) return;
+  for (int t = 0; t < T3; ++t) {
+    __syncthreads();  // previous iteration done with qt/kt/vt/st
+    load3(1 + t, qt, kt, vt);
+    __syncthreads();
+    for (int idx = tid; idx < N * N; idx += nt) {
+      int i = idx / N, j = idx % N;
+      T a = T(0), c = T(0);
+      for (int e = 0; e < dh; ++e) {
+        a += qt[i * dhp + e] * k[j * dhp + e] + q[i * dhp + e] * kt[j * dhp + e];
+        c += qt[i * dhp + e] * kt[j * dhp + e];
+      }
+      st[idx] = a * scale;
+      qk[idx] += c;
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += nt) {
+      T m = T(0);
+      for (int j = 0; j < N; ++j) m += p[i * N + j] * st[i * N + j];
+      mrow[i] = m;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < N * N; idx += nt) {
+      int i = idx / N;
+      T dv_ = st[idx] - mrow[i];
+      u[idx] += dv_ * dv_;
+      st[idx] = p[idx] * dv_;  // p^t
+    }
+    __syncthreads();
+    for (int idx = tid; idx < N * dh; idx += nt) {
+      int i = idx / dh, e = idx % dh;
+      T a = T(0), c = T(0);
+      for (int j = 0; j < N; ++j) {
+        a += st[i * N + j] * v[j * dhp + e] + p[i * N + j] * vt[j * dhp + e];
+        c += st[i * N + j] * vt[j * dhp + e];
+      }
+      olap[idx] += T(2) * c;
+      O[(row0 + (size_t)i * S + 1 + t) * ldo + h * dh + e] = a;
+    }
+  }
+  __syncthreads();
+  load3(1 + T3, qt, kt, vt);
+  __syncthreads();
+  for (int idx = tid; idx < N * N; idx += nt) {
+    int i = idx / N, j = idx % N;
+    T a = T(0);
+    for (int e = 0; e < dh; ++e) a += qt[i * dhp + e] * k[j * dhp + e] + q[i * dhp + e] * kt[j * dhp + e];
+    st[idx] = scale * (a + T(2) * qk[idx]);
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += nt) {
+    T m = T(0), V = T(0);
+    for (int j = 0; j < N; ++j) {
+      m += p[i * N + j] * st[i * N + j];
+      V += p[i * N + j] * u[i * N + j];
+    }
+    mrow[i] = m;
+    vrow[i] = V;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < N * N; idx += nt) {
+    int i = idx / N;
+    st[idx] = p[idx] * (u[idx] - vrow[i] + st[idx] - mrow[i]);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < N * dh; idx += nt) {
+    int i = idx / dh, e = idx % dh;
+    T a = olap[idx];
+    for (int j = 0; j < N; ++j) a += st[i * N + j] * v[j * dhp + e] + p[i * N + j] * vt[j * dhp + e];
+    O[(row0 + (size_t)i * S + 1 + T3) * ldo + h * dh + e] = a;
+  }
+}
+
+template <class T>
+inline size_t attn_smem_bytes(int N, int dh) {
+  return sizeof(T) * ((size_t)6 * N * (dh + 1) + 4 * N * N + (size_t)N * dh + 2 * N);
+}
+
+}  // namespace dq

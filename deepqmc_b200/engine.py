@@ -1,0 +1,218 @@
+"""Thin Python owner of one ``dqmc_handle``: config marshalling, parameter packing, workspace.
+
+Everything numerical happens inside libdqmc_b200.so; this module only moves pointers.  torch is
+used for device memory and streams (plumbing).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import params as PN
+from .spec import AnsatzSpec
+
+MODE_FORWARD, MODE_LOCAL_ENERGY = 0, 1
+_TORCH_DTYPE = {0: torch.float64, 1: torch.float32}
+
+
+def _pack_haiku_params(spec: AnsatzSpec, params: dict) -> dict[str, np.ndarray]:
+    """Haiku-named tree (deepqmc_b200.params) -> the engine's packed entries."""
+    g = lambda k: np.asarray(params[k], dtype=np.float64)
+    out = {}
+    if spec.kind == 'psiformer':
+        out['emb.w'] = g(PN.GNN + 'electron_embedding/linear:w')
+        for l in range(spec.n_layers):
+            a = PN.attn_prefix(l)
+            out[f'L{l}.wqkv'] = np.concatenate(
+                [g(a + f'multi_head_attention/{n}:w') for n in ('query', 'key', 'value')], axis=1
+            )
+            out[f'L{l}.wo'] = g(a + 'multi_head_attention/linear:w')
+            out[f'L{l}.w1'], out[f'L{l}.b1'] = g(a + 'mlp/linear_0:w'), g(a + 'mlp/linear_0:b')[None]
+            out[f'L{l}.w2'], out[f'L{l}.b2'] = g(a + 'mlp/linear_1:w'), g(a + 'mlp/linear_1:b')[None]
+    else:
+        raise NotImplementedError(spec.kind)
+    out['bf.up'], out['bf.dn'] = g(PN.BF_UP + ':w'), g(PN.BF_DN + ':w')
+    for s, t in (('up', 'up'), ('down', 'dn')):
+        out[f'env.pi_{t}'] = g(f'{PN.ENV}:pi_{s}')
+        out[f'env.zeta_{t}'] = g(f'{PN.ENV}:zetas_{s}')
+    if spec.cusp == 'psiformer':
+        out['cusp.alpha'] = np.array([[g(f'{PN.CUSP}:same_alpha'), g(f'{PN.CUSP}:anti_alpha')]], dtype=np.float64)
+    else:
+        out['cusp.alpha'] = np.ones((1, 2))
+    return out
+
+
+class Engine:
+    """One engine per (ansatz spec, Hamiltonian constants, dtype, device)."""
+
+    def __init__(self, spec: AnsatzSpec, hamil, dtype: str = 'float64', device: int | None = None,
+                 gemm_backend: int = 0, _lib_path: str | None = None):
+        self._host = _lib_path is not None  # emulator build: "device" pointers are host pointers
+        self.lib = _lib.load(_lib_path)
+        if not self._host and not torch.cuda.is_available():
+            raise RuntimeError('deepqmc_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
+        self.spec, self.hamil = spec, hamil
+        self.dtype_code = {'float64': 0, 'float32': 1}[dtype]
+        self.dtype = _TORCH_DTYPE[self.dtype_code]
+        self.device_index = 0 if self._host else (torch.cuda.current_device() if device is None else device)
+        self.device = torch.device('cpu') if self._host else torch.device('cuda', self.device_index)
+        cfg = _lib.DqmcConfig()
+        cfg.kind = {'psiformer': 0, 'ferminet': 1}[spec.kind]
+        cfg.dtype, cfg.gemm_backend = self.dtype_code, gemm_backend
+        cfg.n_up, cfg.n_down, cfg.n_nuc = spec.n_up, spec.n_down, spec.n_nuc
+        cfg.embedding_dim, cfg.n_layers, cfg.n_heads = spec.embedding_dim, spec.n_layers, spec.n_heads
+        cfg.n_determinants, cfg.edge_dim = spec.n_determinants, spec.edge_dim
+        cfg.cusp_kind = 1 if spec.cusp == 'psiformer' else 0
+        cfg.cusp_same_scale, cfg.cusp_anti_scale = spec.cusp_same_scale, spec.cusp_anti_scale
+        M = spec.n_nuc
+        assert M <= _lib.MAX_NUC
+        for m in range(M):
+            cfg.z_valence[m] = float(hamil.ns_valence[m])
+            cfg.ecp_mask[m] = int(hamil.ecp_mask[m])
+        lp, nl = getattr(hamil, 'loc_params', None), getattr(hamil, 'nl_params', None)
+        if lp is not None and lp.shape[-1] > 0:
+            Tm = lp.shape[-1]
+            assert Tm <= _lib.MAX_T
+            cfg.ecp_loc_terms = Tm
+            arr = np.zeros((_lib.MAX_NUC, 3, 2, _lib.MAX_T))
+            arr[:M, :, :, :Tm] = lp
+            cfg.ecp_loc[:] = arr.ravel().tolist()
+        if nl is not None and nl.size > 0:
+            L, Tn = nl.shape[1], nl.shape[3]
+            assert L <= _lib.MAX_L and Tn <= _lib.MAX_T
+            cfg.ecp_nl_lmax_p1, cfg.ecp_nl_terms = L, Tn
+            arr = np.zeros((_lib.MAX_NUC, _lib.MAX_L, 2, _lib.MAX_T))
+            arr[:M, :L, :, :Tn] = nl
+            cfg.ecp_nl[:] = arr.ravel().tolist()
+        self._cfg = cfg
+        h = C.c_void_p()
+        rc = self.lib.dqmc_create(C.byref(cfg), self.device_index, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f'dqmc_create failed with status {rc}')
+        self.h = h
+        self.entries = {}
+        name = C.create_string_buffer(64)
+        off, rows, cols = C.c_int64(), C.c_int32(), C.c_int32()
+        for i in range(self.lib.dqmc_param_count(h)):
+            self.lib.dqmc_param_entry(h, i, name, 64, C.byref(off), C.byref(rows), C.byref(cols))
+            self.entries[name.value.decode()] = (off.value, rows.value, cols.value)
+        self.n_packed = self.lib.dqmc_param_total(h)
+        self._ws = None
+        self._params_version = None
+
+    # ------------------------------------------------------------------------------------
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f'{what} failed ({rc}): {self.lib.dqmc_last_error(self.h).decode()}')
+
+    def _stream(self):
+        return C.c_void_p(0 if self._host else torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_params(self, params: dict):
+        packed = _pack_haiku_params(self.spec, params)
+        flat = np.zeros(self.n_packed, dtype=np.float64)
+        for k, (off, rows, cols) in self.entries.items():
+            v = packed[k]
+            assert v.shape == (rows, cols), (k, v.shape, rows, cols)
+            flat[off:off + rows * cols] = v.ravel()
+        self._flat = flat  # keep alive until the async copy is done
+        rc = self.lib.dqmc_set_params(self.h, flat.ctypes.data_as(C.POINTER(C.c_double)), self.n_packed, self._stream())
+        self._check(rc, 'dqmc_set_params')
+        if not self._host:
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def workspace(self, n_walkers: int, mode: int, max_bytes: int | None = None):
+        need = self.lib.dqmc_workspace_bytes(self.h, n_walkers, mode)
+        if max_bytes is not None:
+            need = min(need, max(max_bytes, self.lib.dqmc_workspace_bytes(self.h, 1, mode)))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _prep(self, x):
+        x = torch.as_tensor(x, dtype=self.dtype, device=self.device)
+        return x.contiguous()
+
+    def _R(self, R, B):
+        R = self._prep(R)
+        batched = 1 if R.dim() == 3 else 0
+        if batched:
+            assert R.shape[0] == B
+        return R, batched
+
+    # ------------------------------------------------------------------------------------
+    def wf_forward(self, r, R, max_ws_bytes=None):
+        r = self._prep(r)
+        B = r.shape[0]
+        R, Rb = self._R(R, B)
+        sign = torch.empty(B, dtype=self.dtype, device=self.device)
+        log = torch.empty(B, dtype=self.dtype, device=self.device)
+        ws = self.workspace(B, MODE_FORWARD, max_ws_bytes)
+        rc = self.lib.dqmc_wf_forward(self.h, r.data_ptr(), R.data_ptr(), Rb, B, sign.data_ptr(), log.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), self._stream())
+        self._check(rc, 'dqmc_wf_forward')
+        return sign, log
+
+    def local_energy(self, r, R, seed=0, ecp_twist=None, want_grad=False, max_ws_bytes=None):
+        r = self._prep(r)
+        B, N = r.shape[0], r.shape[1]
+        R, Rb = self._R(R, B)
+        mk = lambda *s: torch.empty(*s, dtype=self.dtype, device=self.device)
+        E, stats, sign, log = mk(B), mk(6, B), mk(B), mk(B)
+        grad = mk(B, 3 * N) if want_grad else None
+        tw = self._prep(ecp_twist) if ecp_twist is not None else None
+        ws = self.workspace(B, MODE_LOCAL_ENERGY, max_ws_bytes)
+        rc = self.lib.dqmc_local_energy(
+            self.h, r.data_ptr(), R.data_ptr(), Rb, B, seed, tw.data_ptr() if tw is not None else None,
+            E.data_ptr(), stats.data_ptr(), sign.data_ptr(), log.data_ptr(),
+            grad.data_ptr() if grad is not None else None, ws.data_ptr(), ws.numel(), self._stream())
+        self._check(rc, 'dqmc_local_energy')
+        return E, stats, sign, log, grad
+
+    def mcmc_sweep(self, state, R, n_sub, target_acceptance=0.57, max_age=None, seed=0, step0=0, walker_offset=0,
+                   noise_normal=None, noise_uniform=None, max_ws_bytes=None):
+        """state: dict(r[B,N,3], sign[B], log[B], age[B] int32, tau[1]) -- updated IN PLACE."""
+        r = state['r']
+        B = r.shape[0]
+        for k in ('r', 'sign', 'log', 'tau'):
+            assert state[k].dtype == self.dtype and state[k].is_contiguous() and state[k].device == self.device, k
+        assert state['age'].dtype == torch.int32
+        R, Rb = self._R(R, B)
+        nn = self._prep(noise_normal) if noise_normal is not None else None
+        nu = self._prep(noise_uniform) if noise_uniform is not None else None
+        stats = torch.zeros(7, dtype=self.dtype, device=self.device)
+        ws = self.workspace(B, MODE_FORWARD, max_ws_bytes)
+        extra = (B * (r.shape[1] * 3 + 2)) * r.element_size() + 4096
+        if ws.numel() < self.lib.dqmc_workspace_bytes(self.h, 1, MODE_FORWARD) + extra:
+            self._ws = None
+            ws = self.workspace(B, MODE_FORWARD)
+        if self._ws.numel() < self.lib.dqmc_workspace_bytes(self.h, B, MODE_FORWARD) + extra and max_ws_bytes is None:
+            self._ws = torch.empty(self.lib.dqmc_workspace_bytes(self.h, B, MODE_FORWARD) + extra, dtype=torch.uint8,
+                                   device=self.device)
+            ws = self._ws
+        rc = self.lib.dqmc_mcmc_sweep(
+            self.h, r.data_ptr(), state['sign'].data_ptr(), state['log'].data_ptr(), state['age'].data_ptr(),
+            state['tau'].data_ptr(), R.data_ptr(), Rb, B, n_sub, float(target_acceptance if target_acceptance else 0.0),
+            -1 if max_age is None else int(max_age), seed, step0, walker_offset,
+            nn.data_ptr() if nn is not None else None, nu.data_ptr() if nu is not None else None,
+            stats.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
+        self._check(rc, 'dqmc_mcmc_sweep')
+        return stats
+
+    @property
+    def launch_count(self):
+        return self.lib.dqmc_launch_count(self.h)
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.dqmc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

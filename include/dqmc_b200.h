@@ -1,0 +1,108 @@
+/* dqmc_b200.h -- C ABI of the B200-native local-energy engine (libdqmc_b200.so).
+ *
+ * Drop-in boundary for the per-walker local-energy hot path of deepqmc/deepqmc.  The
+ * reference has no FFI of its own (pure JAX); each entry point below names the reference
+ * interface it stands in for (paths relative to the reference repo).  Conventions follow
+ * what an XLA-FFI / ctypes binding needs: caller-owned DEVICE pointers,
+ * no allocation on the call path except the caller-provided workspace, work is enqueued on
+ * the caller's cudaStream_t, every call returns an int status (0 = ok) and never throws,
+ * handles are re-entrant per stream-ordered use.  Array dtype is the handle's compute dtype
+ * (cfg.dtype): double for the fp64 parity mode, float for the production mode
+ * (reference: src/deepqmc/__init__.py:9-34 fp32, tests/conftest.py:20 fp64).
+ */
+#ifndef DQMC_B200_H
+#define DQMC_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DQMC_MAX_NUC 32
+#define DQMC_MAX_ECP_TERMS 4
+#define DQMC_MAX_ECP_L 4
+
+enum { DQMC_PSIFORMER = 0, DQMC_FERMINET = 1 };
+enum { DQMC_F64 = 0, DQMC_F32 = 1 };
+enum { DQMC_GEMM_SIMT = 0, DQMC_GEMM_TCGEN05 = 1 };
+enum { DQMC_MODE_FORWARD = 0, DQMC_MODE_LOCAL_ENERGY = 1 };
+
+/* Ansatz + Hamiltonian constants that fix the kernel shapes.
+ * reference: src/deepqmc/conf/ansatz/psiformer.yaml, ferminet.yaml;
+ *            src/deepqmc/hamil.py:97-154 (n_up, n_down, ns_valence, ecp_mask);
+ *            src/deepqmc/ecp/gaussian_type_ecp.py:32-95 (loc/nl parameter layout). */
+typedef struct dqmc_config {
+  int32_t kind;            /* DQMC_PSIFORMER | DQMC_FERMINET */
+  int32_t dtype;           /* DQMC_F64 | DQMC_F32 */
+  int32_t gemm_backend;    /* DQMC_GEMM_SIMT | DQMC_GEMM_TCGEN05 (f32 only) */
+  int32_t n_up, n_down, n_nuc;
+  int32_t embedding_dim, n_layers, n_heads, n_determinants, edge_dim;
+  int32_t cusp_kind;       /* 0 none, 1 PsiformerCusp (wf/cusp.py:17-26) */
+  double cusp_same_scale, cusp_anti_scale;
+  double z_valence[DQMC_MAX_NUC];                                   /* pot.ns_valence */
+  int32_t ecp_mask[DQMC_MAX_NUC];
+  int32_t ecp_loc_terms;                                            /* 0: plain Coulomb */
+  double ecp_loc[DQMC_MAX_NUC][3][2][DQMC_MAX_ECP_TERMS];           /* [I][r^-1,r^0,r^1][alpha,beta][term] */
+  int32_t ecp_nl_lmax_p1, ecp_nl_terms;
+  double ecp_nl[DQMC_MAX_NUC][DQMC_MAX_ECP_L][2][DQMC_MAX_ECP_TERMS]; /* [I][l][alpha,beta][term] */
+} dqmc_config;
+
+typedef struct dqmc_engine* dqmc_handle;
+
+/* Build / tear down an engine bound to one CUDA device.
+ * replaces: app.py:82-105 instantiate_ansatz + hamil.py:97-154 MolecularHamiltonian.__init__ */
+int dqmc_create(const dqmc_config* cfg, int device, dqmc_handle* out);
+int dqmc_destroy(dqmc_handle h);
+const char* dqmc_last_error(dqmc_handle h);
+const char* dqmc_version(void);
+
+/* Parameter table: the engine's packed layout (one fp64 host buffer, converted on upload).
+ * replaces: the Haiku params pytree passed to Ansatz.apply (types.py:133-150). */
+int dqmc_param_count(dqmc_handle h);
+int dqmc_param_entry(dqmc_handle h, int idx, char* name, int name_len, int64_t* offset, int32_t* rows,
+                     int32_t* cols);
+int64_t dqmc_param_total(dqmc_handle h);
+int dqmc_set_params(dqmc_handle h, const double* host_params, int64_t n, void* stream);
+
+/* Workspace the caller must provide for n_walkers in one call (bytes). The engine chunks
+ * walkers internally if given less (>= dqmc_workspace_bytes(h, 1, mode) required).
+ * replaces: XLA buffer assignment / loss/energy.py:44-48 local_energy_batch_size chunking. */
+int64_t dqmc_workspace_bytes(dqmc_handle h, int32_t n_walkers, int32_t mode);
+
+/* psi(r) for a batch of walkers.  r[B][N][3], R[M][3] (R_batched = 0) or R[B][M][3].
+ * replaces: vmap(ansatz.apply)(params, phys_conf) -> Psi(sign, log)
+ *           (types.py:133-150; wf/nn_wave_function.py:127-173; callers
+ *           sampling/electron_samplers.py:76-81). */
+int dqmc_wf_forward(dqmc_handle h, const void* r, const void* R, int32_t R_batched, int32_t n_walkers,
+                    void* out_sign, void* out_log, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Local energies.  out_stats[6][B] = V_el, E_kin, V_loc, V_nl, lap, quantum_force^2
+ * (hamil.py:172-180 order); out_grad[B][3N] (nullable) = grad log|psi| (quantum force).
+ * ecp_twist (nullable) = injected quadrature twists [B][J][N] in [0, pi/5) replacing the
+ * rng stream (gaussian_type_ecp.py:217-223); otherwise Philox(seed).
+ * replaces: loss/energy.py:19-60 compute_local_energy -> hamil.py:156-184 local_energy
+ *           -> physics.py:79-109 kinetic_term with a forward-Laplacian factory
+ *           (conf/hamil/qc_forward_laplacian.yaml). */
+int dqmc_local_energy(dqmc_handle h, const void* r, const void* R, int32_t R_batched, int32_t n_walkers,
+                      uint64_t seed, const void* ecp_twist, void* out_E, void* out_stats, void* out_sign,
+                      void* out_log, void* out_grad, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* n_sub Metropolis sub-steps on the walker state {r, sign, log, age, tau} (updated in place).
+ * noise_normal[n_sub][B][N][3] / noise_uniform[n_sub][B] (nullable): injected random numbers.
+ * out_stats[7] (device, compute dtype) = acceptance, tau, age mean, age max, log|psi| mean,
+ * log|psi| std, mean e-e distance of the LAST sub-step.
+ * replaces: sampling/electron_samplers.py:140-163 MetropolisSampler.sample inside
+ *           :347-357 DecorrSampler.sample (lax.scan of `length` sub-steps). */
+int dqmc_mcmc_sweep(dqmc_handle h, void* r, void* sign, void* log, int32_t* age, void* tau, const void* R,
+                    int32_t R_batched, int32_t n_walkers, int32_t n_sub, double target_acceptance, int32_t max_age,
+                    uint64_t seed, uint64_t step0, uint64_t walker_offset, const void* noise_normal,
+                    const void* noise_uniform, void* out_stats, void* workspace, int64_t workspace_bytes,
+                    void* stream);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches claim). */
+int64_t dqmc_launch_count(dqmc_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DQMC_B200_H */

@@ -1,0 +1,226 @@
+"""Restatement of MolecularHamiltonian + potentials (TEST INFRASTRUCTURE, see oracle/__init__).
+
+Follows src/deepqmc/hamil.py:31-184, src/deepqmc/physics.py:79-141 and
+src/deepqmc/ecp/gaussian_type_ecp.py:127-255 / ecp_utils.py:12-60 of the reference.
+torch.float64 on CPU, single-walker functions (callers vmap / loop).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+F64 = torch.float64
+
+
+def get_shell(z):
+    # reference: src/deepqmc/hamil.py:31-40 -- number of (partially) occupied shells
+    max_elec, n = 0, 0
+    while True:
+        if z <= max_elec:
+            break
+        max_elec += 2 * (1 + n) ** 2
+        n += 1
+    return n
+
+
+# Gaussian-type ECP tables.  The reference loads them from pyscf (absent here):
+# pyscf.gto.basis.load_ecp('ccECP', 'C').  Values restated from the published ccECP
+# (Bennett et al., J. Chem. Phys. 147, 224106 (2017)); UNVERIFIED against pyscf in this
+# container ("parity unpinned" for the table itself, the algebra is checked independently).
+# layout: n_core, loc[n in (r^-1, r^0, r^1)] = list of (alpha, beta), nl[l] = list of (alpha, beta)
+ECP_TABLES = {
+    ('ccECP', 6): dict(
+        n_core=2,
+        loc=[[(14.43502, 4.00000)], [(7.38188, -25.81955)], [(8.39889, 57.74008)]],
+        nl=[[(7.76079, 52.13345)]],
+    ),
+}
+
+
+def parse_ecp(charges, ecp_type, ecp_mask):
+    """reference: gaussian_type_ecp.py:32-95 -> ns_valence, loc_params[I,3,2,T], nl_params[I,L,2,T]"""
+    ns_valence, locs, nls = [], [], []
+    for z, m in zip(charges, ecp_mask):
+        if m:
+            tab = ECP_TABLES[(ecp_type, int(z))]
+            ns_valence.append(z - tab['n_core'])
+            locs.append(tab['loc'])
+            nls.append(tab['nl'])
+        else:
+            ns_valence.append(z)
+            locs.append([[], [], []])
+            nls.append([])
+    pad = max((len(t) for loc in locs for t in loc), default=0)
+    loc_params = np.zeros((len(charges), 3, 2, pad))
+    for i, loc in enumerate(locs):
+        for n, terms in enumerate(loc):
+            for t, (a, b) in enumerate(terms):
+                loc_params[i, n, 0, t], loc_params[i, n, 1, t] = a, b
+    lmax = max((len(nl) for nl in nls), default=0)
+    tmax = max((len(t) for nl in nls for t in nl), default=0)
+    nl_params = np.zeros((len(charges), lmax, 2, tmax))
+    for i, nl in enumerate(nls):
+        for l, terms in enumerate(nl):
+            for t, (a, b) in enumerate(terms):
+                nl_params[i, l, 0, t], nl_params[i, l, 1, t] = a, b
+    return np.asarray(ns_valence, dtype=np.float64), loc_params, nl_params
+
+
+def safe_norm(d, eps=None):
+    # reference: src/deepqmc/utils.py:79-85
+    eps = torch.finfo(d.dtype).eps if eps is None else eps
+    return torch.sqrt(eps + (d * d).sum(-1))
+
+
+def pairwise_self_distance(x):
+    # reference: src/deepqmc/geom/general.py:30-43 (upper triangle, eps-safe)
+    n = x.shape[-2]
+    i, j = torch.triu_indices(n, n, 1)
+    return safe_norm(x[..., i, :] - x[..., j, :])
+
+
+def icosahedron():
+    # reference: src/deepqmc/ecp/ecp_utils.py:24-32
+    sph = [[0.0, 0.0], [math.pi, 0.0]]
+    for j in range(5):
+        sph.append([math.atan(2), math.pi / 5 * 2 * j])
+        sph.append([math.pi - math.atan(2), math.pi / 5 * (2 * j - 1)])
+    sph = np.asarray(sph)
+    th, ph = sph[:, 0], sph[:, 1]
+    cart = np.stack([np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)], -1)
+    return th, cart
+
+
+def rot_y(t):
+    c, s = math.cos(t), math.sin(t)
+    return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+
+
+def rot_z(p):
+    c, s = math.cos(p), math.sin(p)
+    return np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])
+
+
+def legendre_values(lmax_p1, x):
+    out = [np.ones_like(x), x, 0.5 * (3 * x**2 - 1), 0.5 * (5 * x**3 - 3 * x)]
+    return np.stack(out[:lmax_p1], -1)
+
+
+class OracleHamiltonian:
+    """reference: src/deepqmc/hamil.py:70-184"""
+
+    def __init__(self, mol, ecp_type=None, ecp_mask=None):
+        self.mol = mol
+        charges = mol.charges
+        if ecp_type is None:
+            ecp_mask = [False] * len(charges)
+        elif ecp_mask is None:
+            ecp_mask = list(charges > 2)
+        self.ecp_type, self.ecp_mask = ecp_type, np.asarray(ecp_mask, dtype=bool)
+        if self.ecp_mask.any():
+            self.ns_valence, self.loc_params, self.nl_params = parse_ecp(charges, ecp_type, self.ecp_mask)
+        else:
+            self.ns_valence, self.loc_params, self.nl_params = charges.copy(), None, None
+        n_elec = int(self.ns_valence.sum() - mol.charge)
+        assert not (n_elec + mol.spin) % 2 and n_elec > 1
+        self.n_nuc = len(charges)
+        self.n_up = (n_elec + mol.spin) // 2
+        self.n_down = (n_elec - mol.spin) // 2
+        self.mol_shells = [get_shell(z) for z in charges]
+        self.mol_ecp_shells = [get_shell(z + 1) - 1 for z in charges - self.ns_valence]
+
+    # ---- potentials (single walker r[N,3]) --------------------------------------
+    def nuclear_energy(self, R):
+        # reference: physics.py:112-116
+        z = torch.as_tensor(self.ns_valence, dtype=F64)
+        n = len(z)
+        if n < 2:
+            return torch.zeros((), dtype=F64)
+        i, j = torch.triu_indices(n, n, 1)
+        return (z[i] * z[j] / pairwise_self_distance(R)).sum()
+
+    def electronic_potential(self, r):
+        # reference: physics.py:119-121
+        return (1 / pairwise_self_distance(r)).sum(-1)
+
+    def local_potential(self, r, R):
+        d = torch.linalg.norm(r[:, None] - R[None], dim=-1)  # pairwise_distance: plain norm
+        z = torch.as_tensor(self.ns_valence, dtype=F64)
+        v = -(z / d).sum()
+        if self.loc_params is None:
+            return v  # NuclearCoulombPotential, physics.py:131-133
+        # reference: gaussian_type_ecp.py:127-159
+        lp = torch.as_tensor(self.loc_params, dtype=F64)
+        for I in np.nonzero(self.ecp_mask)[0]:
+            ren = d[:, I][:, None]  # [N,1]
+            a, b = lp[I, :, 0, :], lp[I, :, 1, :]
+            v = v + (b[0] / ren * torch.exp(-a[0] * ren**2)).sum()
+            v = v + (b[1] * torch.exp(-a[1] * ren**2)).sum()
+            v = v + (b[2] * ren * torch.exp(-a[2] * ren**2)).sum()
+        return v
+
+    def quadrature_points(self, r_i, R_I, phi_random):
+        """reference: ecp_utils.py:34-60 -> [12,3] positions for electron i around nucleus I"""
+        _, ico = icosahedron()
+        diff = (r_i - R_I).detach().numpy()
+        radius = np.linalg.norm(diff)
+        theta = math.acos(np.clip(diff[2] / radius, -1.0, 1.0))
+        phi = math.atan2(diff[1], diff[0])
+        rot = rot_z(phi) @ rot_y(theta) @ rot_z(phi_random)
+        return torch.as_tensor(radius * (ico @ rot.T) + R_I.numpy())
+
+    def nonloc_potential(self, r, R, wf, phi_random):
+        """reference: gaussian_type_ecp.py:161-255.  ``phi_random[j, i]`` replaces the
+        jax.random.uniform(0, pi/5) draw keyed by fold_in(fold_in(rng, j), i)."""
+        if self.nl_params is None:
+            return torch.zeros((), dtype=F64)
+        nlp = self.nl_params
+        nuc_with_nl = np.unique(np.nonzero(nlp)[0])
+        thetas, _ = icosahedron()
+        s0, l0 = wf(r)
+        total = torch.zeros((), dtype=F64)
+        for j, I in enumerate(nuc_with_nl):
+            lmax_p1 = nlp.shape[1]
+            leg = torch.as_tensor(legendre_values(lmax_p1, np.cos(thetas)))  # [12, L]
+            coefs = torch.as_tensor((np.arange(lmax_p1) * 2 + 1) / 12.0)
+            a = torch.as_tensor(nlp[I, :, 0, :])
+            b = torch.as_tensor(nlp[I, :, 1, :])
+            for i in range(r.shape[0]):
+                dist = torch.linalg.norm(r[i] - R[I])
+                v_l = (b * torch.exp(-a * dist**2)).sum(-1)  # [L]
+                pts = self.quadrature_points(r[i], R[I], float(phi_random[j, i]))
+                ratios = []
+                for q in range(12):
+                    rq = r.clone()
+                    rq[i] = pts[q]
+                    sq, lq = wf(rq)
+                    ratios.append(torch.exp(lq - l0) * sq * s0)
+                ratios = torch.stack(ratios)  # [12]
+                integ = (ratios[:, None] * leg).sum(0)  # [L]
+                total = total + (v_l * coefs * integ).sum()
+        return total
+
+    def local_energy(self, wf_single, r, R, phi_random=None):
+        """reference: hamil.py:156-184.  ``wf_single(r[N,3]) -> (sign, log)``.
+        Returns (E_loc, stats dict with the reference's 6 keys)."""
+        from .laplacian import laplacian_hessian
+
+        lap, grad = laplacian_hessian(lambda x: wf_single(x.reshape(-1, 3))[1], r.reshape(-1))
+        qf2 = (grad**2).sum()
+        e_kin = -0.5 * (lap + qf2)
+        e_nuc = self.nuclear_energy(R)
+        v_el = self.electronic_potential(r)
+        v_loc = self.local_potential(r, R)
+        v_nl = (
+            self.nonloc_potential(r, R, wf_single, phi_random)
+            if self.nl_params is not None
+            else torch.zeros((), dtype=F64)
+        )
+        e_loc = e_kin + v_loc + v_nl + v_el + e_nuc
+        stats = {
+            'hamil/V_el': v_el, 'hamil/E_kin': e_kin, 'hamil/V_loc': v_loc,
+            'hamil/V_nl': v_nl, 'hamil/lap': lap, 'hamil/quantum_force': qf2,
+        }
+        return e_loc, stats

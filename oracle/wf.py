@@ -1,0 +1,148 @@
+"""Restatement of the reference's neural wave functions (TEST INFRASTRUCTURE).
+
+Single-walker, functional, torch.float64; differentiable so the Laplacian can be taken by
+autograd (oracle/laplacian.py).  Follows
+  src/deepqmc/wf/nn_wave_function.py:127-173  (assembly, slogdet, exp-normalised det sum, cusp)
+  src/deepqmc/wf/env.py:57-108                (ExponentialEnvelopes, isotropic per-orbital)
+  src/deepqmc/wf/omni.py:43-88                (Backflow reshape/swap order)
+  src/deepqmc/wf/cusp.py:17-26,49-78          (PsiformerCusp)
+  src/deepqmc/gnn/electron_gnn.py:596-619     (positional embedding + spin + projection)
+  src/deepqmc/gnn/update_features.py:241-286  (attention + MLP, residuals) with
+  hk.MultiHeadAttention's algebra (restated in src/deepqmc/hkext.py:215-253)
+  src/deepqmc/gnn/update_features.py:47-159, electron_gnn.py:160-259 (FermiNet layer)
+  src/deepqmc/gnn/edge_features.py:21-78, gnn/graph.py:23-31 (features, receiver - sender)
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from deepqmc_b200 import params as P  # names/shapes only (data)
+
+from .hamil import safe_norm
+
+
+def _t(params, name):
+    return params[name]
+
+
+def ne_features(r, R, log_rescale):
+    diffs = r[:, None] - R[None]  # receiver(electron) - sender(nucleus)
+    rr = safe_norm(diffs)
+    if log_rescale:
+        lg = torch.log1p(rr)
+        feats = torch.cat([lg[..., None], diffs * (lg / rr)[..., None]], -1)
+    else:
+        feats = torch.cat([rr[..., None], diffs], -1)
+    return feats.reshape(r.shape[0], -1), rr
+
+
+def psiformer_embeddings(spec, params, r, R):
+    N, d, H = spec.n_elec, spec.embedding_dim, spec.n_heads
+    dh = d // H
+    feats, _ = ne_features(r, R, True)
+    spins = torch.cat([torch.ones(spec.n_up), -torch.ones(spec.n_down)]).to(r.dtype)[:, None]
+    x = torch.cat([feats, spins], 1) @ _t(params, P.GNN + 'electron_embedding/linear:w')
+    for l in range(spec.n_layers):
+        a = P.attn_prefix(l)
+        q = (x @ _t(params, a + 'multi_head_attention/query:w')).reshape(N, H, dh)
+        k = (x @ _t(params, a + 'multi_head_attention/key:w')).reshape(N, H, dh)
+        v = (x @ _t(params, a + 'multi_head_attention/value:w')).reshape(N, H, dh)
+        logits = torch.einsum('thd,Thd->htT', q, k) / math.sqrt(dh)
+        w = torch.softmax(logits, -1)
+        o = torch.einsum('htT,Thd->thd', w, v).reshape(N, d)
+        att = x + o @ _t(params, a + 'multi_head_attention/linear:w')
+        m = torch.tanh(att @ _t(params, a + 'mlp/linear_0:w') + _t(params, a + 'mlp/linear_0:b'))
+        m = torch.tanh(m @ _t(params, a + 'mlp/linear_1:w') + _t(params, a + 'mlp/linear_1:b'))
+        x = att + m
+    return x
+
+
+def ferminet_embeddings(spec, params, r, R):
+    n_up = spec.n_up
+    x, _ = ne_features(r, R, False)  # [N, 4M], no projection
+
+    def edge_feats(sender):
+        d = r[None, :, :] - sender[:, None, :]  # [S, N, 3] receiver - sender
+        return torch.cat([safe_norm(d)[..., None], d], -1)
+
+    e_up, e_dn = edge_feats(r[:n_up]), edge_feats(r[n_up:])
+    sq2 = math.sqrt(2.0)
+    for l in range(spec.n_layers):
+        lp = P.layer_prefix(l)
+        f = torch.cat(
+            [
+                x,
+                x[:n_up].mean(0, keepdim=True).expand(x.shape[0], -1),
+                x[n_up:].mean(0, keepdim=True).expand(x.shape[0], -1),
+                e_up.mean(0),
+                e_dn.mean(0),
+            ],
+            -1,
+        )
+        upd = torch.tanh(f @ _t(params, lp + 'g/linear_0:w') + _t(params, lp + 'g/linear_0:b'))
+        x_new = (x + upd) / sq2 if upd.shape == x.shape else upd
+        if l < spec.n_layers - 1:
+            wu, bu = _t(params, lp + 'u/linear_0:w'), _t(params, lp + 'u/linear_0:b')
+            nu, nd = torch.tanh(e_up @ wu + bu), torch.tanh(e_dn @ wu + bu)
+            if nu.shape == e_up.shape:
+                nu, nd = (e_up + nu) / sq2, (e_dn + nd) / sq2
+            e_up, e_dn = nu, nd
+        x = x_new
+    return x
+
+
+def orbitals(spec, params, emb, r, R):
+    """envelopes (*) backflow -> A[K, N, N] (electron i, orbital mu)."""
+    N, K, n_up = spec.n_elec, spec.n_determinants, spec.n_up
+    dist = safe_norm(r[:, None] - R[None])  # [N, M]
+
+    def env(spin, sl):
+        zeta, pi = _t(params, f'{P.ENV}:zetas_{spin}'), _t(params, f'{P.ENV}:pi_{spin}')
+        ex = torch.abs(zeta[None] * dist[sl][:, None, :])  # [n, K*N, M]
+        orb = (pi[None] * torch.exp(-ex)).sum(-1)  # [n, K*N]
+        return orb.reshape(-1, K, N).permute(1, 0, 2)  # [K, n, N]
+
+    def bf(w, sl):
+        return (emb[sl] @ w).reshape(-1, K, N).permute(1, 0, 2)
+
+    up, dn = slice(None, n_up), slice(n_up, None)
+    a_up = env('up', up) * bf(_t(params, P.BF_UP + ':w'), up)
+    a_dn = env('down', dn) * bf(_t(params, P.BF_DN + ':w'), dn)
+    return torch.cat([a_up, a_dn], 1)
+
+
+def psiformer_cusp(spec, params, r):
+    n_up, N = spec.n_up, spec.n_elec
+    a_s, a_a = _t(params, f'{P.CUSP}:same_alpha'), _t(params, f'{P.CUSP}:anti_alpha')
+    out = torch.zeros((), dtype=r.dtype)
+    for i in range(N):
+        for j in range(i + 1, N):
+            dij = safe_norm(r[i] - r[j])
+            same = (i < n_up) == (j < n_up)
+            if same:
+                out = out - spec.cusp_same_scale * a_s**2 / (a_s + dij)
+            else:
+                out = out - spec.cusp_anti_scale * a_a**2 / (a_a + dij)
+    return out
+
+
+def log_psi(spec, params, r, R):
+    """ansatz.apply for one walker -> (sign, log|psi|); reference nn_wave_function.py:127-173"""
+    emb = (psiformer_embeddings if spec.kind == 'psiformer' else ferminet_embeddings)(spec, params, r, R)
+    A = orbitals(spec, params, emb, r, R)
+    sign, ld = torch.linalg.slogdet(A)
+    shift = ld.max().detach()
+    if torch.isinf(shift):
+        shift = torch.zeros_like(shift)
+    psi = (sign * torch.exp(ld - shift)).sum()
+    log = torch.log(torch.abs(psi)) + shift
+    sgn = torch.sign(psi).detach()
+    if spec.cusp == 'psiformer':
+        log = log + psiformer_cusp(spec, params, r)
+    return sgn, log
+
+
+def to_torch(params, dtype=torch.float64):
+    return {k: torch.as_tensor(v, dtype=dtype) for k, v in params.items()}
