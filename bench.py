@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""Benchmark of the local-energy hot path (contract in the task statement / DESIGN.md).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA engine)
+  python bench.py --impl reference --steps K --warmup W    # reference arm: CPU oracle port
+
+metric: walker.local-energies / second.  A "step" = one local-energy evaluation of every walker
+of the batch (Psiformer forward + forward-Laplacian + potentials) followed, for N > 1, by the
+fused statistics all-reduce.  Workload at N=1: BASELINE.json configs[1], LiH Psiformer
+(d=256, L=4, H=4, K=16), 4096 walkers per GPU, synthetic walkers (atom-centred Gaussians,
+equilibrated by 200 Metropolis sub-steps, untimed) and random-init weights.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+WORKLOADS = {
+    'lih_psiformer': dict(mol='LiH', ecp=None, walkers=4096, hyper={}),
+    'n2_psiformer': dict(mol='N2', ecp=None, walkers=4096, hyper={}),
+    'benzene_psiformer': dict(mol='benzene', ecp='ccECP', walkers=4096, hyper={}),
+}
+
+
+def algorithmic_flops_per_eloc(N, M, d=256, L=4, K=16):
+    """F_lap with dense 3N tangents (forward-Laplacian)."""
+    T = 3 * N
+    return (5 * 2 * N * (4 * M + 1) * d + (T + 2) * (L * 12 * N * d * d + 2 * K * N * N * d + 6 * K * N * N * M)
+            + (3 * T + 3) * L * 4 * N * N * d + K * (2 / 3 + 2) * N**3 + 2 * K * T * N**3)
+
+
+def make_problem(wl, B, seed):
+    from deepqmc_b200 import params as PN
+    from deepqmc_b200.hamil import MolecularHamiltonian
+    from deepqmc_b200.molecule import Molecule
+
+    mol = Molecule.from_name(wl['mol'])
+    hamil = MolecularHamiltonian(mol=mol, ecp_type=wl['ecp'])
+    rng = np.random.default_rng(seed)
+    N = hamil.n_up + hamil.n_down
+    p = hamil.ns_valence / hamil.ns_valence.sum()
+    centers = rng.choice(len(mol.coords), size=(B, N), p=p)
+    r = mol.coords[centers] + rng.normal(size=(B, N, 3)) * 0.7
+    return mol, hamil, r, PN
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith('active')})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def time_oracle(wl, n_sample, steps, warmup, seed=0):
+    """CPU arm: the oracle (torch fp64 restatement of the reference path) on the host cores."""
+    from oracle import wf
+    from oracle.hamil import OracleHamiltonian
+
+    mol, hamil, r, PN = make_problem(wl, n_sample * (steps + warmup), seed)
+    from deepqmc_b200.spec import psiformer_spec
+
+    oh = OracleHamiltonian(mol, ecp_type=wl['ecp'])
+    spec = psiformer_spec(oh, **wl['hyper'])
+    pt = wf.to_torch(PN.perturb_params(PN.init_params(spec, 0)))
+    R = torch.as_tensor(mol.coords)
+    rt = torch.as_tensor(r)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    J = 0 if oh.nl_params is None else len(np.unique(np.nonzero(oh.nl_params)[0]))
+    tw = torch.zeros(max(J, 1), spec.n_elec) + 0.1
+    times = []
+    for s in range(steps + warmup):
+        t0 = time.perf_counter()
+        for b in range(n_sample):
+            f = lambda x: wf.log_psi(spec, pt, x, R)
+            oh.local_energy(f, rt[s * n_sample + b], R, phi_random=tw if J else None)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    return n_sample * len(times) / sum(times), cores, 1e3 * float(np.mean(times))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='lih_psiformer', choices=sorted(WORKLOADS))
+    ap.add_argument('--dtype', default='float32', choices=['float32', 'float64'])
+    ap.add_argument('--walkers', type=int, default=None, help='walkers per GPU (default: workload)')
+    ap.add_argument('--cpu-sample', type=int, default=None)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == 'ours' else a.warmup
+    wl = WORKLOADS[a.workload]
+    B = a.walkers or wl['walkers']
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    unit = 'walker.local-energies/s'
+    metric = 'walker.local-energies/sec'
+    workload_name = f"{wl['mol']} Psiformer d256 L4 H4 K16{' ' + wl['ecp'] if wl['ecp'] else ''}, {B} walkers/GPU"
+
+    if a.impl == 'reference':
+        if rank != 0:
+            return 0
+        n_sample = a.cpu_sample or (16 if wl['mol'] == 'LiH' else 1)
+        val, cores, ms = time_oracle(wl, n_sample, a.steps, a.warmup)
+        out = {
+            'impl': 'reference', 'metric': metric, 'value': val, 'unit': unit, 'n_gpus': a.gpus, 'steps': a.steps,
+            'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': workload_name, 'note': 'CPU oracle port of the reference JAX path (JAX not installable here)'},
+            'cpu_baseline': {'value': val, 'unit': unit, 'cores': cores, 'kind': 'port',
+                             'sample': f'{n_sample} walkers per step x {a.steps} steps (autograd-Hessian Laplacian, fp64)'},
+            'e2e': {'value': val, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        }
+        print(json.dumps(out))
+        return 0
+
+    # ------------------------------- our arm -------------------------------------------------
+    from deepqmc_b200 import parallel
+    from deepqmc_b200.ansatz import B200Ansatz
+    from deepqmc_b200.types import PhysicalConfiguration
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device; there is no CPU fallback (use --impl reference)'
+    rank, world = parallel.init_from_env()
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    mol, hamil, r_np, PN = make_problem(wl, B, seed=1000 + rank)
+    ansatz = B200Ansatz(hamil, 'psiformer', dtype=a.dtype, device=local, **wl['hyper'])
+    params = PN.perturb_params(ansatz.init(0))
+    tdt = torch.float32 if a.dtype == 'float32' else torch.float64
+    N, M = hamil.n_up + hamil.n_down, hamil.n_nuc
+    R = torch.as_tensor(mol.coords, dtype=tdt, device=dev)
+    r = torch.as_tensor(r_np, dtype=tdt, device=dev)
+    eng = ansatz.engine_for(hamil, params)
+    # equilibrate the synthetic walkers (untimed): 20 sweeps x 10 Metropolis sub-steps
+    sign, log = eng.wf_forward(r, R)
+    state = dict(r=r.clone(), sign=sign, log=log, age=torch.zeros(B, dtype=torch.int32, device=dev),
+                 tau=torch.tensor([0.5], dtype=tdt, device=dev))
+    for it in range(20):
+        eng.mcmc_sweep(state, R, 10, seed=parallel.rank_seed(7), step0=10 * it, walker_offset=rank * B)
+    r = state['r'].clone()
+    pc = PhysicalConfiguration(R, r, torch.zeros(B, device=dev))
+    loc_ene = hamil.local_energy(ansatz.apply)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(seed):
+        E, st = loc_ene(seed, params, pc)
+        return parallel.energy_statistics(E, st), E
+
+    for w in range(a.warmup):
+        step(w)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = eng.launch_count
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for s in range(a.steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the per-step events)
+        evs[s][0].record()
+        stats, E = step(100 + s)
+        evs[s][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = eng.launch_count - l0
+    clk = clocks.stop() if rank == 0 else None
+    ms = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in evs)], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    total_ms = ms.item()
+    value = B * world * a.steps / (total_ms / 1e3)
+
+    # ---- e2e: host buffers through the plugin API, H2D + D2H inside the timed region ----------
+    r_host = r.cpu().pin_memory()
+    R_host = R.cpu().pin_memory()
+    def e2e_step(seed):
+        pc_h = PhysicalConfiguration(R_host.to(dev, non_blocking=True), r_host.to(dev, non_blocking=True),
+                                     torch.zeros(B, device=dev))
+        E, st = loc_ene(seed, params, pc_h)
+        parallel.energy_statistics(E, st)
+        return E.cpu()
+    for w in range(3):
+        e2e_step(w)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    for s in range(a.steps):
+        e2e_step(s)
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
+    e2e_val = B * world * a.steps / te.item()
+    esz = r_host.element_size()
+
+    # ---- roofline of the dominant kernel (dense-layer GEMMs), timed live with CUDA events ------
+    roof = None
+    if rank == 0:
+        eng.profile_begin()
+        for s in range(3):
+            step(s)
+        gemm_ms, gemm_flops, n_gemm = eng.profile_end()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = peaks.get('bf16_tflops_sustained', 1590.0 * 0.88)
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        roof = {'bound': 'tensor', 'kernel': 'dense-layer row GEMM (dqmc gemm_kernel)', 'achieved': achieved,
+                'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+                'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback',
+                'traffic': None, 'gemm_share_of_step': (gemm_ms / 3) / (total_ms / a.steps),
+                'gemm_launches_per_step': n_gemm // 3,
+                'algorithmic_flops_per_eloc': algorithmic_flops_per_eloc(N, M),
+                'whole_step_tflops': algorithmic_flops_per_eloc(N, M) * B * a.steps / (total_ms / 1e3) / 1e12}
+    if rank != 0:
+        return 0
+    cpu = None
+    if not a.no_cpu_baseline and world == 1:
+        n_sample = a.cpu_sample or (64 if wl['mol'] == 'LiH' else 1)
+        cv, cores, cms = time_oracle(wl, n_sample, 2, 1)
+        cpu = {'value': cv, 'unit': unit, 'cores': cores, 'kind': 'port',
+               'sample': f'{n_sample} walkers x 2 steps of the same workload, oracle (torch fp64, autograd Hessian)'}
+    out = {
+        'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+        'ms_per_step': total_ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32' if a.dtype == 'float32' else 'f64', 'data': 'synthetic',
+        'config': {'workload': workload_name, 'global_batch': B * world, 'parallelism': f'walker-shard x{world}',
+                   'l2': 'flushed between timed iterations (256 MiB memset) and activations >> L2',
+                   'step': 'E_loc of all walkers (+ fused stats all-reduce for N>1)'},
+        'clocks': clk, 'e2e': {'value': e2e_val, 'unit': unit, 'h2d_bytes_per_step': (B * N * 3 + M * 3) * esz,
+                               'd2h_bytes_per_step': B * esz},
+        'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu,
+        'energy_mean': float(stats['energy/mean']), 'wall_s_timed_region': t_wall,
+    }
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,52 @@
+"""Host-side mirror of the reference's ``Ansatz`` protocol (reference: src/deepqmc/types.py:107-150).
+
+``B200Ansatz(hamil, kind='psiformer', ...)`` stands where the reference has
+``hk.without_apply_rng(hk.transform(NeuralNetworkWaveFunction(...)))`` (app.py:82-105):
+``init(rng, phys_conf) -> params`` and ``apply(params, phys_conf, return_mos=False) -> Psi``.
+``apply`` accepts a single sample (r[N,3]) or a batch (r[B,N,3]); the walker loop the reference
+gets from ``jax.vmap`` lives inside the CUDA engine.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import params as PN
+from .engine import Engine
+from .spec import AnsatzSpec, ferminet_spec, psiformer_spec
+from .types import PhysicalConfiguration, Psi
+
+
+class B200Ansatz:
+    def __init__(self, hamil, kind='psiformer', dtype='float64', device=None, gemm_backend=0, **hyper):
+        self.hamil = hamil
+        self.spec: AnsatzSpec = {'psiformer': psiformer_spec, 'ferminet': ferminet_spec}[kind](hamil, **hyper)
+        self.dtype, self.device, self.gemm_backend = dtype, device, gemm_backend
+        self._engine = None
+        self._uploaded = None
+
+    # -- reference: Ansatz.init(rng, phys_conf) -> Params (types.py:119-131)
+    def init(self, rng, phys_conf: PhysicalConfiguration | None = None):
+        seed = int(rng) if rng is not None else 0
+        return PN.init_params(self.spec, seed)
+
+    def engine_for(self, hamil, params) -> Engine:
+        if self._engine is None:
+            self._engine = Engine(self.spec, hamil, dtype=self.dtype, device=self.device,
+                                  gemm_backend=self.gemm_backend)
+        if self._uploaded is not params:
+            self._engine.set_params(params)
+            self._uploaded = params
+        return self._engine
+
+    # -- reference: Ansatz.apply(params, phys_conf, return_mos=False) -> Psi (types.py:133-150)
+    def apply(self, params, phys_conf: PhysicalConfiguration, return_mos: bool = False) -> Psi:
+        if return_mos:
+            raise NotImplementedError('return_mos is only used by pretraining (out of scope, SURVEY.md 2 #17)')
+        eng = self.engine_for(self.hamil, params)
+        r, R = phys_conf.r, phys_conf.R
+        single = r.dim() == 2
+        if single:
+            r = r[None]
+        sign, log = eng.wf_forward(r, R)
+        return Psi(sign[0], log[0]) if single else Psi(sign, log)

@@ -31,6 +31,13 @@ struct EngineBase {
   int64_t launches = 0;
   std::vector<ParamEntry> entries;
   int64_t total = 0;
+  // optional per-launch timing of the dominant (GEMM) kernels with CUDA events on the caller's stream
+  bool prof = false;
+  double prof_flops = 0;
+  int64_t prof_n = 0;
+#ifndef DQMC_EMU
+  std::vector<cudaEvent_t> prof_ev;
+#endif
   virtual ~EngineBase() {}
   virtual int set_params(const double* host, int64_t n, cudaStream_t st) = 0;
   virtual int64_t ws_bytes(int B, int mode) = 0;
@@ -232,7 +239,19 @@ struct Engine : EngineBase {
     g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = Mr; g.N = Nc; g.K = Kc; g.S = S; g.sliced = sliced; g.Nel = Nel;
     constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
     dim3 grid((Nc + BN - 1) / BN, (Mr + BM - 1) / BM, sliced ? Nel : 1);
+#ifndef DQMC_EMU
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (prof) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+#endif
     DQ_LAUNCH((gemm_kernel<T, BM, BN, BK, TM, TN>), grid, dim3(256), 0, st, g);
+#ifndef DQMC_EMU
+    if (prof) {
+      cudaEventRecord(e1, st);
+      prof_ev.push_back(e0); prof_ev.push_back(e1);
+      prof_flops += 2.0 * (double)Mr * (sliced ? Nel : 1) * (double)Nc * (double)Kc;
+      ++prof_n;
+    }
+#endif
     return 0;
   }
 
@@ -448,5 +467,30 @@ int dqmc_mcmc_sweep(dqmc_handle h, void* r, void* sign, void* log, int32_t* age,
                     (cudaStream_t)stream);
 }
 int64_t dqmc_launch_count(dqmc_handle h) { return h ? h->e->launches : -1; }
+
+int dqmc_profile_begin(dqmc_handle h) {
+  if (!h) return 2;
+  h->e->prof = true; h->e->prof_flops = 0; h->e->prof_n = 0;
+  return 0;
+}
+int dqmc_profile_end(dqmc_handle h, double* gemm_ms, double* gemm_flops, int64_t* n_gemm) {
+  if (!h) return 2;
+  double ms = 0;
+#ifndef DQMC_EMU
+  for (size_t i = 0; i + 1 < h->e->prof_ev.size(); i += 2) {
+    cudaEventSynchronize(h->e->prof_ev[i + 1]);
+    float t = 0;
+    cudaEventElapsedTime(&t, h->e->prof_ev[i], h->e->prof_ev[i + 1]);
+    ms += t;
+    cudaEventDestroy(h->e->prof_ev[i]); cudaEventDestroy(h->e->prof_ev[i + 1]);
+  }
+  h->e->prof_ev.clear();
+#endif
+  h->e->prof = false;
+  if (gemm_ms) *gemm_ms = ms;
+  if (gemm_flops) *gemm_flops = h->e->prof_flops;
+  if (n_gemm) *n_gemm = h->e->prof_n;
+  return 0;
+}
 
 }  // extern "C"

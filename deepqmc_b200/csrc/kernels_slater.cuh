@@ -39,7 +39,6 @@ __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, 
   const T* rb = r + (size_t)b * N * 3;
   const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
   const size_t brow0 = (size_t)b * N * S;
-  const int KN = K * N;
 
   for (int idx = tid; idx < N * N; idx += nt) {
     const int i = idx / N, mu = idx % N;

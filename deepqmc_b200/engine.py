@@ -202,6 +202,14 @@ class Engine:
         self._check(rc, 'dqmc_mcmc_sweep')
         return stats
 
+    def profile_begin(self):
+        self.lib.dqmc_profile_begin(self.h)
+
+    def profile_end(self):
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+        self.lib.dqmc_profile_end(self.h, C.byref(ms), C.byref(fl), C.byref(n))
+        return ms.value, fl.value, n.value
+
     @property
     def launch_count(self):
         return self.lib.dqmc_launch_count(self.h)

@@ -1,0 +1,123 @@
+"""Host-side mirror of the reference's Hamiltonian plugin interface.
+
+``MolecularHamiltonian`` keeps the reference's constructor arguments, attributes
+(mol, n_up, n_down, n_nuc, ns_valence, ecp_mask, pot, mol_shells, mol_ecp_shells) and the
+``local_energy(ansatz_apply) -> f(rng, params, phys_conf) -> (E_loc, stats)`` factory
+(reference: src/deepqmc/hamil.py:44-67,70-184); the arithmetic runs in libdqmc_b200.so.
+Difference to the reference: the returned function is *batched* (leading walker axis) instead
+of single-sample + vmap, because the CUDA engine owns the walker loop.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .molecule import Molecule
+from .types import PhysicalConfiguration
+
+STAT_KEYS = ('hamil/V_el', 'hamil/E_kin', 'hamil/V_loc', 'hamil/V_nl', 'hamil/lap', 'hamil/quantum_force')
+
+# Gaussian-type ECP tables (the reference reads them from pyscf: gaussian_type_ecp.py:57).
+# ccECP carbon, Bennett et al. JCP 147, 224106 (2017); see DESIGN.md ("parity unpinned" table).
+ECP_TABLES = {
+    ('ccECP', 6): dict(
+        n_core=2,
+        loc=[[(14.43502, 4.00000)], [(7.38188, -25.81955)], [(8.39889, 57.74008)]],
+        nl=[[(7.76079, 52.13345)]],
+    ),
+}
+
+
+def get_shell(z):
+    """Number of (partially) occupied shells for z electrons (reference: hamil.py:31-40)."""
+    filled, n = 0, 0
+    while z > filled:
+        filled += 2 * (n + 1) ** 2
+        n += 1
+    return n
+
+
+class _Potential:
+    """Potential record (reference: physics.py:36-141, ecp/gaussian_type_ecp.py:98-125)."""
+
+    def __init__(self, charges, ecp_type, ecp_mask):
+        M = len(charges)
+        nsv, locs, nls = [], [], []
+        for z, m in zip(charges, ecp_mask):
+            if m:
+                key = (ecp_type, int(z))
+                if key not in ECP_TABLES:
+                    raise ValueError(f'Effective core potential {ecp_type} not tabulated for Z={int(z)}')
+                t = ECP_TABLES[key]
+                nsv.append(z - t['n_core']); locs.append(t['loc']); nls.append(t['nl'])
+            else:
+                nsv.append(z); locs.append([[], [], []]); nls.append([])
+        self.ns_valence = np.asarray(nsv, dtype=np.float64)
+        tm = max((len(t) for loc in locs for t in loc), default=0)
+        self.loc_params = np.zeros((M, 3, 2, tm))
+        for i, loc in enumerate(locs):
+            for n, terms in enumerate(loc):
+                for t, (a, b) in enumerate(terms):
+                    self.loc_params[i, n, :, t] = (a, b)
+        lm = max((len(nl) for nl in nls), default=0)
+        tn = max((len(t) for nl in nls for t in nl), default=0)
+        self.nl_params = np.zeros((M, lm, 2, tn))
+        for i, nl in enumerate(nls):
+            for l, terms in enumerate(nl):
+                for t, (a, b) in enumerate(terms):
+                    self.nl_params[i, l, :, t] = (a, b)
+        self.nuc_with_nl_pot = np.unique(np.nonzero(self.nl_params)[0])
+
+
+class MolecularHamiltonian:
+    def __init__(self, *, mol: Molecule, ecp_type=None, ecp_mask=None, elec_std=1.0, laplacian_factory=None):
+        self.mol, self.elec_std, self.ecp_type = mol, elec_std, ecp_type
+        # The engine implements the forward-Laplacian factory (conf/hamil/qc_forward_laplacian.yaml);
+        # the argument is accepted for signature compatibility.
+        self.lap_factory = laplacian_factory
+        if ecp_type is None:
+            ecp_mask = [False] * len(mol.charges)
+        elif ecp_mask is None:
+            ecp_mask = list(mol.charges > 2)
+        assert len(ecp_mask) == len(mol.charges), "Incompatible shape of 'ecp_mask'!"
+        self.ecp_mask = np.asarray(ecp_mask, dtype=bool)
+        if self.ecp_mask.any():
+            assert ecp_type is not None, 'ECP type must be specified if ECPs are used.'
+            if 'PH' in str(ecp_type):
+                raise NotImplementedError('PseudoHamiltonian is outside the hot-path scope (SURVEY.md 8f N3)')
+        self.pot = _Potential(mol.charges, ecp_type, self.ecp_mask)
+        n_elec = int(sum(self.pot.ns_valence) - mol.charge)
+        assert not (n_elec + mol.spin) % 2
+        assert n_elec > 1, 'The system must contain at least two active electrons.'
+        self.n_nuc = len(mol.charges)
+        self.n_up = (n_elec + mol.spin) // 2
+        self.n_down = (n_elec - mol.spin) // 2
+        self.ns_valence = self.pot.ns_valence
+        self.loc_params = self.pot.loc_params if self.ecp_mask.any() else None
+        self.nl_params = self.pot.nl_params if self.ecp_mask.any() else None
+        self.mol_shells = [get_shell(z) for z in mol.charges]
+        self.mol_ecp_shells = [get_shell(z + 1) - 1 for z in mol.charges - self.ns_valence]
+
+    def local_energy(self, ansatz_apply):
+        """-> loc_ene(rng, params, phys_conf) -> (E_loc[B], stats{6 keys: [B]})"""
+        ansatz = getattr(ansatz_apply, '__self__', None)
+        if ansatz is None or not hasattr(ansatz, 'engine_for'):
+            raise TypeError('local_energy expects the bound .apply of a deepqmc_b200 B200Ansatz')
+
+        def loc_ene(rng, params, phys_conf: PhysicalConfiguration, ecp_twist=None, return_grad=False):
+            eng = ansatz.engine_for(self, params)
+            if self.nl_params is not None and len(self.pot.nuc_with_nl_pot) and rng is None and ecp_twist is None:
+                raise AssertionError('rng is required for the non-local ECP quadrature')  # gaussian_type_ecp.py:176
+            r, R = phys_conf.r, phys_conf.R
+            single = r.dim() == 2
+            if single:
+                r, R = r[None], R
+            if R.dim() == 3 and self.nl_params is not None:
+                R = R[0]
+            seed = int(rng) if isinstance(rng, (int, np.integer)) else 0
+            E, stats, sign, log, grad = eng.local_energy(r, R, seed=seed, ecp_twist=ecp_twist, want_grad=return_grad)
+            sd = {k: (stats[i, 0] if single else stats[i]) for i, k in enumerate(STAT_KEYS)}
+            out = (E[0] if single else E, sd)
+            return out + (grad,) if return_grad else out
+
+        return loc_ene

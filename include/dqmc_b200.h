@@ -102,6 +102,13 @@ int dqmc_mcmc_sweep(dqmc_handle h, void* r, void* sign, void* log, int32_t* age,
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches claim). */
 int64_t dqmc_launch_count(dqmc_handle h);
 
+/* Measurement aid (bench.py roofline): between begin/end every dense-layer GEMM launch is
+ * bracketed by CUDA events on the caller's stream; end() returns their summed duration [ms],
+ * the algorithmic flops they performed (2*M*N*K each) and their count.  No reference analogue
+ * (the reference ships no profiler hooks). */
+int dqmc_profile_begin(dqmc_handle h);
+int dqmc_profile_end(dqmc_handle h, double* gemm_ms, double* gemm_flops, int64_t* n_gemm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,245 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs, plus size-independent properties at the benchmark's full walker count.
+
+Tolerances: fp64 mode |dE_loc| <= 1e-8 max(1,|E_loc|), |dlog|psi|| <= 1e-10;
+fp32 mode <= 2e-4 relative (the reference's own E_loc regression tolerance, tests/test_hamil.py:37-40).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from deepqmc_b200 import params as PN
+from deepqmc_b200.ansatz import B200Ansatz
+from deepqmc_b200.hamil import STAT_KEYS, MolecularHamiltonian
+from deepqmc_b200.molecule import Molecule
+from deepqmc_b200.types import PhysicalConfiguration
+
+DEV = 'cuda:0'
+
+
+def make(mol_name, ecp=None, dtype='float64', seed=0, B=4, **hyper):
+    from oracle.hamil import OracleHamiltonian
+
+    mol = Molecule.from_name(mol_name)
+    hamil = MolecularHamiltonian(mol=mol, ecp_type=ecp)
+    ansatz = B200Ansatz(hamil, 'psiformer', dtype=dtype, **hyper)
+    params = PN.perturb_params(ansatz.init(seed))
+    rng = np.random.default_rng(seed)
+    N = hamil.n_up + hamil.n_down
+    r = mol.coords[rng.integers(0, len(mol.coords), size=(B, N))] + rng.normal(size=(B, N, 3))
+    r = torch.as_tensor(r, device=DEV)
+    R = torch.as_tensor(mol.coords, device=DEV)
+    return mol, hamil, OracleHamiltonian(mol, ecp_type=ecp), ansatz, params, r, R
+
+
+def oracle_eval(ansatz, ohamil, params, r, R, twist=None):
+    from oracle import wf
+
+    pt = wf.to_torch(params)
+    Rc = R.cpu()
+    out = []
+    for b in range(r.shape[0]):
+        f = lambda x: wf.log_psi(ansatz.spec, pt, x, Rc)
+        s, l = f(r[b].cpu())
+        e, st = ohamil.local_energy(f, r[b].cpu(), Rc, phi_random=None if twist is None else twist[b].cpu())
+        out.append((s.item(), l.item(), e.item(), {k: v.item() for k, v in st.items()}))
+    return out
+
+
+SMALL = dict(embedding_dim=32, n_layers=2, n_heads=4, n_determinants=4)
+
+
+@pytest.mark.parametrize('mol_name,hyper,B', [
+    ('LiH', SMALL, 4),
+    ('LiH', dict(), 2),  # full Psiformer: d=256, L=4, H=4, K=16 (BASELINE configs[1])
+    ('N2', dict(embedding_dim=32, n_layers=2, n_heads=2, n_determinants=3), 2),
+    ('H2O', dict(embedding_dim=64, n_layers=1, n_heads=4, n_determinants=2), 3),
+])
+def test_local_energy_fp64(mol_name, hyper, B):
+    mol, hamil, oh, ansatz, params, r, R = make(mol_name, B=B, **hyper)
+    pc = PhysicalConfiguration(R, r, torch.zeros(B, device=DEV))
+    psi = ansatz.apply(params, pc)
+    E, stats, grad = hamil.local_energy(ansatz.apply)(None, params, pc, return_grad=True)
+    assert set(stats) == set(STAT_KEYS)
+    ref = oracle_eval(ansatz, oh, params, r, R)
+    for b, (s, l, e, st) in enumerate(ref):
+        assert psi.sign[b].item() == s
+        assert abs(psi.log[b].item() - l) <= 1e-10 * max(1, abs(l))
+        assert abs(E[b].item() - e) <= 1e-8 * max(1, abs(e)), (b, E[b].item(), e)
+        for k in STAT_KEYS:
+            assert abs(stats[k][b].item() - st[k]) <= 1e-8 * max(1, abs(st[k])), (k, stats[k][b].item(), st[k])
+    # quantum force = grad log|psi| against autograd
+    from oracle import wf
+
+    pt = wf.to_torch(params)
+    g = torch.func.grad(lambda x: wf.log_psi(ansatz.spec, pt, x.reshape(-1, 3), R.cpu())[1])(r[0].cpu().reshape(-1))
+    assert torch.allclose(grad[0].cpu(), g, rtol=1e-8, atol=1e-9)
+
+
+def test_single_sample_signature():
+    """The reference's Ansatz/Hamiltonian act on one sample (types.py:107-150); the mirror accepts that too."""
+    mol, hamil, oh, ansatz, params, r, R = make('LiH', B=2, **SMALL)
+    pc1 = PhysicalConfiguration(R, r[0], torch.zeros((), device=DEV))
+    psi = ansatz.apply(params, pc1)
+    assert psi.log.dim() == 0
+    E, stats = hamil.local_energy(ansatz.apply)(None, params, pc1)
+    Eb, _ = hamil.local_energy(ansatz.apply)(None, params, PhysicalConfiguration(R, r, torch.zeros(2, device=DEV)))
+    assert E.dim() == 0 and abs(E.item() - Eb[0].item()) < 1e-12
+
+
+def test_ecp_local_and_nonlocal_fp64():
+    """ccECP carbon atom: local + non-local (12-point quadrature, injected twists) parity."""
+    mol, hamil, oh, ansatz, params, r, R = make('C', ecp='ccECP', B=3, **SMALL)
+    assert (hamil.n_up, hamil.n_down) == (3, 1)
+    N = 4
+    tw = torch.as_tensor(np.random.default_rng(5).uniform(0, np.pi / 5, size=(3, 1, N)), device=DEV)
+    pc = PhysicalConfiguration(R, r, torch.zeros(3, device=DEV))
+    E, stats = hamil.local_energy(ansatz.apply)(None, params, pc, ecp_twist=tw)
+    ref = oracle_eval(ansatz, oh, params, r, R, twist=tw)
+    for b, (s, l, e, st) in enumerate(ref):
+        assert abs(stats['hamil/V_nl'][b].item() - st['hamil/V_nl']) <= 1e-8 * max(1, abs(st['hamil/V_nl']))
+        assert abs(stats['hamil/V_loc'][b].item() - st['hamil/V_loc']) <= 1e-9 * max(1, abs(st['hamil/V_loc']))
+        assert abs(E[b].item() - e) <= 1e-8 * max(1, abs(e))
+    with pytest.raises(AssertionError):  # rng is mandatory with a non-local ECP (gaussian_type_ecp.py:176)
+        hamil.local_energy(ansatz.apply)(None, params, pc)
+    # Philox twists: valid, deterministic per seed, different across seeds
+    E1, s1 = hamil.local_energy(ansatz.apply)(7, params, pc)
+    E2, s2 = hamil.local_energy(ansatz.apply)(7, params, pc)
+    E3, s3 = hamil.local_energy(ansatz.apply)(8, params, pc)
+    assert torch.equal(E1, E2) and not torch.equal(E1, E3)
+    assert torch.all(torch.isfinite(E1))
+
+
+def test_determinism_rng_independence_and_chunking():
+    """reference tests/test_energy.py:38-92: determinism, rng-independence without ECP,
+    batch_size chunking == unbatched."""
+    mol, hamil, oh, ansatz, params, r, R = make('LiH', B=7, **SMALL)
+    pc = PhysicalConfiguration(R, r, torch.zeros(7, device=DEV))
+    f = hamil.local_energy(ansatz.apply)
+    E1, _ = f(1, params, pc)
+    E2, _ = f(1, params, pc)
+    E3, _ = f(2, params, pc)
+    assert torch.equal(E1, E2) and torch.equal(E1, E3)
+    eng = ansatz.engine_for(hamil, params)
+    one = eng.lib.dqmc_workspace_bytes(eng.h, 1, 1)
+    eng._ws = None
+    Ec, *_ = eng.local_energy(r, R, max_ws_bytes=3 * one)  # chunks of <= 3 walkers
+    eng._ws = None
+    assert torch.allclose(Ec, E1, rtol=0, atol=1e-12)
+
+
+def test_batched_nuclei_equals_shared():
+    mol, hamil, oh, ansatz, params, r, R = make('LiH', B=3, **SMALL)
+    eng = ansatz.engine_for(hamil, params)
+    E0, *_ = eng.local_energy(r, R)
+    E1, *_ = eng.local_energy(r, R[None].expand(3, -1, -1).contiguous())
+    assert torch.equal(E0, E1)
+    # translation invariance: shift electrons and nuclei of walker 1 together
+    Rb = R[None].repeat(3, 1, 1)
+    shift = torch.tensor([0.3, -1.1, 0.7], device=DEV, dtype=torch.float64)
+    Rb[1] += shift
+    rs = r.clone()
+    rs[1] += shift
+    E2, *_ = eng.local_energy(rs, Rb)
+    assert torch.allclose(E2, E0, rtol=1e-9, atol=1e-9)
+
+
+def test_fp32_mode_within_reference_tolerance():
+    mol, hamil, oh, ansatz, params, r, R = make('LiH', B=4, dtype='float32')
+    pc = PhysicalConfiguration(R.float(), r.float(), torch.zeros(4, device=DEV))
+    E, stats = hamil.local_energy(ansatz.apply)(None, params, pc)
+    ref = oracle_eval(ansatz, oh, params, r.double(), R.double())
+    for b, (s, l, e, st) in enumerate(ref):
+        assert abs(E[b].item() - e) <= 2e-4 * max(1, abs(e), abs(st['hamil/E_kin'])), (E[b].item(), e)
+
+
+def test_metropolis_injected_noise_matches_oracle():
+    """reference electron_samplers.py:102-163 with identical (injected) random numbers."""
+    from oracle import wf
+    from oracle.sampling import metropolis_step
+
+    mol, hamil, oh, ansatz, params, r, R = make('LiH', B=6, **SMALL)
+    eng = ansatz.engine_for(hamil, params)
+    sign, log = eng.wf_forward(r, R)
+    rng = np.random.default_rng(3)
+    nsub, B, N = 5, 6, 4
+    nn = torch.as_tensor(rng.normal(size=(nsub, B, N, 3)), device=DEV)
+    nu = torch.as_tensor(rng.uniform(size=(nsub, B)), device=DEV)
+    state = dict(r=r.clone(), sign=sign.clone(), log=log.clone(), age=torch.zeros(B, dtype=torch.int32, device=DEV),
+                 tau=torch.tensor([0.4], dtype=torch.float64, device=DEV))
+    stats = eng.mcmc_sweep(state, R, nsub, target_acceptance=0.57, max_age=2, noise_normal=nn, noise_uniform=nu)
+    pt = wf.to_torch(params)
+    Rc = R.cpu()
+    wfb = lambda rr: tuple(torch.stack(x) for x in zip(*[wf.log_psi(ansatz.spec, pt, rr[b], Rc) for b in range(B)]))
+    ost = dict(r=r.cpu().clone(), sign=sign.cpu().clone(), log=log.cpu().clone(), age=torch.zeros(B, dtype=torch.int32),
+               tau=torch.tensor(0.4, dtype=torch.float64))
+    for s in range(nsub):
+        ost, acc = metropolis_step(wfb, ost, nn[s].cpu(), nu[s].cpu(), 0.57, 2)
+    assert torch.allclose(state['r'].cpu(), ost['r'], atol=1e-12)
+    assert torch.allclose(state['log'].cpu(), ost['log'], atol=1e-10)
+    assert torch.equal(state['age'].cpu(), ost['age'])
+    assert abs(state['tau'].item() - ost['tau'].item()) < 1e-12
+    assert abs(stats[0].item() - acc.item()) < 1e-12
+    assert abs(stats[4].item() - ost['log'].mean().item()) < 1e-10
+    assert abs(stats[5].item() - ost['log'].std(unbiased=False).item()) < 1e-10
+
+
+def test_metropolis_philox_statistics():
+    """In-kernel Philox stream: acceptance in (0,1), tau adapts toward the target, walkers move,
+    sampled log|psi| rises from the initial guess (equilibration)."""
+    mol, hamil, oh, ansatz, params, r, R = make('LiH', B=512, **SMALL)
+    eng = ansatz.engine_for(hamil, params)
+    sign, log = eng.wf_forward(r, R)
+    state = dict(r=r.clone(), sign=sign.clone(), log=log.clone(), age=torch.zeros(512, dtype=torch.int32, device=DEV),
+                 tau=torch.tensor([1.0], dtype=torch.float64, device=DEV))
+    accs = []
+    for it in range(10):
+        st = eng.mcmc_sweep(state, R, 10, seed=11, step0=10 * it)
+        accs.append(st[0].item())
+    assert 0.35 < accs[-1] < 0.8, accs
+    assert state['log'].mean().item() > log.mean().item()
+    s2, l2 = eng.wf_forward(state['r'], R)
+    assert torch.allclose(l2, state['log'], atol=1e-9)  # state psi consistent with state r
+    # different seeds -> different chains; same seed/step -> identical
+    a = dict((k, v.clone()) for k, v in state.items())
+    b = dict((k, v.clone()) for k, v in state.items())
+    eng.mcmc_sweep(a, R, 2, seed=1, step0=0)
+    eng.mcmc_sweep(b, R, 2, seed=1, step0=0)
+    assert torch.equal(a['r'], b['r'])
+    c = dict((k, v.clone()) for k, v in state.items())
+    eng.mcmc_sweep(c, R, 2, seed=2, step0=0)
+    assert not torch.equal(a['r'], c['r'])
+
+
+def test_full_size_properties_4096_walkers():
+    """BASELINE configs[1] size (LiH Psiformer d=256 L=4 K=16, 4096 walkers), fp32 production mode:
+    size-independent properties instead of an oracle run.
+      * exchange of two same-spin electrons: sign flips, log|psi| and E_loc unchanged
+      * E_loc finite, E_kin + V_loc + V_el + E_nuc == E_loc (assembly identity, hamil.py:165-172)
+      * fp32 result agrees with the fp64 engine on the same walkers to 2e-4
+    """
+    mol, hamil, oh, ansatz, params, r, R = make('LiH', B=4096, dtype='float32')
+    r = (torch.as_tensor(mol.coords, device=DEV)[torch.randint(0, 2, (4096, 4), device=DEV)]
+         + 0.8 * torch.randn(4096, 4, 3, device=DEV, dtype=torch.float64))
+    pc = PhysicalConfiguration(R.float(), r.float(), torch.zeros(4096, device=DEV))
+    f = hamil.local_energy(ansatz.apply)
+    E, st = f(None, params, pc)
+    psi = ansatz.apply(params, pc)
+    assert torch.isfinite(E).all()
+    perm = torch.tensor([1, 0, 2, 3], device=DEV)
+    pcx = PhysicalConfiguration(R.float(), r.float()[:, perm], torch.zeros(4096, device=DEV))
+    Ex, _ = f(None, params, pcx)
+    psix = ansatz.apply(params, pcx)
+    assert torch.equal(psix.sign, -psi.sign)
+    assert torch.allclose(psix.log, psi.log, rtol=1e-4, atol=1e-4)
+    scale = torch.maximum(E.abs(), st['hamil/E_kin'].abs()).clamp(min=1)
+    assert ((Ex - E).abs() / scale).max().item() < 5e-3
+    e_nuc = 3.0 * 1.0 / np.linalg.norm(mol.coords[0] - mol.coords[1])
+    asm = st['hamil/E_kin'] + st['hamil/V_loc'] + st['hamil/V_el'] + st['hamil/V_nl'] + e_nuc
+    assert ((asm - E).abs() / scale).max().item() < 1e-5
+    a64 = B200Ansatz(hamil, 'psiformer', dtype='float64')
+    E64, st64 = hamil.local_energy(a64.apply)(None, params, PhysicalConfiguration(R, r, torch.zeros(4096, device=DEV)))
+    rel = ((E.double() - E64).abs() / torch.maximum(E64.abs(), st64['hamil/E_kin'].abs()).clamp(min=1))
+    assert rel.median().item() < 2e-5 and rel.quantile(0.99).item() < 2e-4, (rel.median().item(), rel.max().item())

@@ -1,0 +1,134 @@
+"""CPU: pin the oracle (and the host-side Hamiltonian mirror) against every param-free golden
+of the reference's own test-suite (tests/golden/reference_goldens.json)."""
+import numpy as np
+import pytest
+import torch
+
+from deepqmc_b200.hamil import MolecularHamiltonian
+from deepqmc_b200.molecule import Molecule
+from oracle import wf as owf
+from oracle.hamil import OracleHamiltonian, pairwise_self_distance
+from oracle.laplacian import laplacian_hessian, laplacian_jvp_loop
+
+
+@pytest.mark.parametrize('name', ['LiH', 'C', 'H2O'])
+def test_molecule_geometry(goldens, name):
+    # reference: tests/test_molecule.py (from_name) -- angstrom -> bohr conversion
+    g = goldens['molecule'][name]
+    mol = Molecule.from_name(name)
+    np.testing.assert_allclose(mol.coords, np.asarray(g['coords']).reshape(-1, 3), rtol=0, atol=1e-8)
+    np.testing.assert_allclose(mol.charges, g['charges'])
+    assert mol.charge == g['charge'] and mol.spin == g['spin']
+
+
+@pytest.mark.parametrize('cls', [OracleHamiltonian, lambda mol, ecp_type=None: MolecularHamiltonian(mol=mol, ecp_type=ecp_type)])
+def test_hamil_init(goldens, cls):
+    # reference: tests/test_hamil.py:16-26 (n_up, n_down, ns_valence, pp_mask)
+    g = goldens['hamil_init']['Molecular']
+    h = cls(Molecule.from_name('LiH'))
+    assert (h.n_up, h.n_down) == (g['n_up'], g['n_down'])
+    np.testing.assert_allclose(h.ns_valence, g['ns_valence'])
+    np.testing.assert_array_equal(h.ecp_mask, g['pp_mask'])
+
+
+def _lih_walker(goldens):
+    # r = ne[0] because R_Li = 0 and edges are receiver - sender (reference gnn/graph.py:24)
+    ne = np.asarray(goldens['edge_builder_LiH']['ne'])
+    return ne[0], ne
+
+
+def test_edge_convention_and_walker(goldens):
+    r, ne = _lih_walker(goldens)
+    R = Molecule.from_name('LiH').coords
+    np.testing.assert_allclose(ne[1] + R[1], r, atol=1e-14)
+    same = np.asarray(goldens['edge_builder_LiH']['same'])
+    np.testing.assert_allclose(same[0], r[0] - r[1], atol=1e-14)  # receiver - sender, uu block
+    anti = np.asarray(goldens['edge_builder_LiH']['anti'])
+    # du block first: senders = down electrons, receivers = up electrons (graph.py:146-149)
+    np.testing.assert_allclose(anti[0], r[0] - r[2], atol=1e-14)
+
+
+def test_graph_edge_builder_goldens(goldens):
+    # reference: tests/test_gnn.py:7-9,20-32; compute_edges = receiver - sender, optional diagonal filter
+    nodes = np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 2.0], [0.0, 0.0, 6.0]])
+    full = nodes[None, :, :] - nodes[:, None, :]  # [sender, receiver]
+    np.testing.assert_allclose(full, np.asarray(goldens['graph_edge_builder_mask_self_False']['graph_edges']))
+    n = 3
+    sender_idx = (np.arange(n)[None, :] <= np.arange(n - 1)[:, None]) + np.arange(n - 1)[:, None]
+    recv_idx = np.broadcast_to(np.arange(n)[None], (n - 1, n))
+    np.testing.assert_allclose(full[sender_idx, recv_idx], np.asarray(goldens['graph_edge_builder_mask_self_True']['graph_edges']))
+
+
+def test_coulomb_known_answers(goldens):
+    # reference: tests/test_physics.py:7-17, tests/test_geom.py:8-18
+    k = goldens['coulomb_kat']
+    mol = Molecule(coords=k['R'], charges=[1, 1], charge=0, spin=0)
+    h = OracleHamiltonian(mol)
+    R, r = torch.as_tensor(k['R'], dtype=torch.float64), torch.as_tensor(k['r'], dtype=torch.float64)
+    assert abs(h.nuclear_energy(R).item() - k['nuclear_energy']) < 1e-12
+    assert abs(h.electronic_potential(r).item() - k['electronic_potential']) < 1e-12
+    np.testing.assert_allclose(pairwise_self_distance(R).numpy(), [1.4], atol=1e-12)
+    d = torch.linalg.norm(r[:, None] - R[None], dim=-1).numpy()
+    np.testing.assert_allclose(d, k['pairwise_distance'], atol=1e-12)
+
+
+def test_lih_potentials_and_eloc_assembly(goldens):
+    """V_loc is bit-comparable to the reference golden; the four goldens together pin the
+    E_loc assembly (hamil.py:165-172, physics.py:108)."""
+    r, _ = _lih_walker(goldens)
+    mol = Molecule.from_name('LiH')
+    h = OracleHamiltonian(mol)
+    rt, Rt = torch.as_tensor(r), torch.as_tensor(mol.coords)
+    v_loc = h.local_potential(rt, Rt).item()
+    assert abs(v_loc - goldens['potential_LiH_None']['local_potential']) < 1e-11
+    v_el, e_nuc = h.electronic_potential(rt).item(), h.nuclear_energy(Rt).item()
+    lap = goldens['wf_laplace']['lap_log_psis']
+    qf = np.asarray(goldens['wf_laplace']['quantum_force'])
+    e_kin = -0.5 * (lap + (qf**2).sum())
+    assert abs(e_kin + v_loc + v_el + e_nuc - goldens['local_energy_Molecular']['E_loc']) < 1e-11
+
+
+def test_oracle_laplacian_two_ways():
+    """Hessian trace == jvp-of-grad loop (reference physics.py:144-156) for both ansatz families."""
+    from deepqmc_b200 import params as PN
+    from deepqmc_b200.spec import ferminet_spec, psiformer_spec
+
+    mol = Molecule.from_name('LiH')
+    h = OracleHamiltonian(mol)
+    R = torch.as_tensor(mol.coords)
+    torch.manual_seed(1)
+    r = torch.randn(4, 3, dtype=torch.float64)
+    for mk in (psiformer_spec, ferminet_spec):
+        spec = mk(h, embedding_dim=16, n_layers=2, n_heads=2, n_determinants=2)
+        p = owf.to_torch(PN.perturb_params(PN.init_params(spec, 0)))
+        f = lambda x: owf.log_psi(spec, p, x.reshape(-1, 3), R)[1]
+        a, ga = laplacian_hessian(f, r.reshape(-1))
+        b, gb = laplacian_jvp_loop(f, r.reshape(-1))
+        assert abs(a.item() - b.item()) < 1e-9 * max(1, abs(a.item()))
+        assert torch.allclose(ga, gb, atol=1e-12)
+
+
+def test_psiformer_param_count():
+    # reference logs 1 610 498 parameters for LiH Psiformer (doc/examples/ground_state_lih.ipynb:67)
+    from deepqmc_b200 import params as PN
+    from deepqmc_b200.spec import psiformer_spec
+
+    h = OracleHamiltonian(Molecule.from_name('LiH'))
+    assert PN.n_params(psiformer_spec(h)) == 1610498
+
+
+def test_antisymmetry_of_oracle():
+    """Exchange of two same-spin electrons flips the sign and keeps log|psi| (fermionic WF)."""
+    from deepqmc_b200 import params as PN
+    from deepqmc_b200.spec import psiformer_spec
+
+    mol = Molecule.from_name('LiH')
+    h = OracleHamiltonian(mol)
+    spec = psiformer_spec(h, embedding_dim=16, n_layers=1, n_heads=2, n_determinants=2)
+    p = owf.to_torch(PN.perturb_params(PN.init_params(spec, 0)))
+    R = torch.as_tensor(mol.coords)
+    torch.manual_seed(0)
+    r = torch.randn(4, 3, dtype=torch.float64)
+    s0, l0 = owf.log_psi(spec, p, r, R)
+    s1, l1 = owf.log_psi(spec, p, r[[1, 0, 2, 3]], R)
+    assert s0.item() == -s1.item() and abs(l0.item() - l1.item()) < 1e-10

@@ -1,0 +1,52 @@
+"""Extract the PARAM-FREE goldens of the reference's own test-suite into a small JSON fixture.
+
+Run in the build container (reads /root/reference/tests/**/*.npz, which do not travel to the
+GPU box):   python tools/extract_reference_goldens.py
+Only numbers are extracted (regression *data*), no reference source.  See SURVEY.md 8(c) for
+why the parameter-dependent goldens (psi, Laplacian, E_loc of the Haiku-initialised test
+ansatz) cannot be re-derived without JAX: they are stored here only to pin the E_loc assembly
+identity  E_kin + V_loc + V_el + E_nuc == E_loc.
+"""
+import json
+import os
+
+import numpy as np
+
+REF = '/root/reference/tests'
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'reference_goldens.json')
+
+
+def npz(path):
+    d = np.load(os.path.join(REF, path))
+    return {k: d[k].tolist() for k in d.files}
+
+
+def main():
+    g = {
+        'source': 'deepqmc/deepqmc v1.3.0 tests/*.npz (ndarrays_regression fixtures)',
+        'molecule': {n: npz(f'test_molecule/test_from_name_{n}_.npz') for n in ('LiH', 'C', 'H2O')},
+        'hamil_init': {
+            'Molecular': npz('test_hamil/test_init_Molecular_.npz'),
+            'Molecular_PP': npz('test_hamil/test_init_Molecular_PP_.npz'),
+        },
+        'edge_builder_LiH': npz('test_gnn/test_molecular_graph_edge_builder.npz'),
+        'graph_edge_builder_mask_self_True': npz('test_gnn/test_graph_edge_builder_mask_self_True_.npz'),
+        'graph_edge_builder_mask_self_False': npz('test_gnn/test_graph_edge_builder_mask_self_False_.npz'),
+        'potential_LiH_None': npz('test_potential/test_pseudo_potentials_LiH_None_.npz'),
+        'potential_C_None': npz('test_potential/test_pseudo_potentials_C_None_.npz'),
+        'wf_psi': npz('test_wf/test_psi.npz'),
+        'wf_laplace': npz('test_wf/test_laplace_psi.npz'),
+        'local_energy_Molecular': npz('test_hamil/test_local_energy_Molecular_.npz'),
+        # reference tests/test_physics.py:7-17 and tests/test_geom.py:8-18 (inline known answers)
+        'coulomb_kat': {'R': [[0, 0, 0], [0, 0, 1.4]], 'r': [[0, 0, 0], [0, 0, 1.0]], 'ns_valence': [1.0, 1.0],
+                        'nuclear_energy': 1 / 1.4, 'electronic_potential': 1.0,
+                        'pairwise_distance': [[0.0, 1.4], [1.0, 0.4]]},
+    }
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    with open(OUT, 'w') as f:
+        json.dump(g, f, indent=1)
+    print('wrote', OUT)
+
+
+if __name__ == '__main__':
+    main()
