@@ -89,8 +89,9 @@ class ClockSampler:
                 'reasons': reasons, 'samples': len(sm)}
 
 
-def time_oracle(wl, n_sample, steps, warmup, seed=0):
-    """CPU arm: the oracle (torch fp64 restatement of the reference path) on the host cores."""
+def time_oracle(wl, n_sample, steps, warmup, seed=0, budget_s=None):
+    """CPU arm: the oracle (torch fp64 restatement of the reference path) on the host cores.
+    budget_s: stop adding walkers to a step once the step has used this many seconds (bounded sample)."""
     from oracle import wf
     from oracle.hamil import OracleHamiltonian
 
@@ -106,16 +107,21 @@ def time_oracle(wl, n_sample, steps, warmup, seed=0):
     torch.set_num_threads(cores)
     J = 0 if oh.nl_params is None else len(np.unique(np.nonzero(oh.nl_params)[0]))
     tw = torch.zeros(max(J, 1), spec.n_elec) + 0.1
-    times = []
+    times, done = [], []
     for s in range(steps + warmup):
         t0 = time.perf_counter()
+        nb = 0
         for b in range(n_sample):
             f = lambda x: wf.log_psi(spec, pt, x, R)
             oh.local_energy(f, rt[s * n_sample + b], R, phi_random=tw if J else None)
+            nb += 1
+            if budget_s is not None and time.perf_counter() - t0 > budget_s:
+                break
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
-    return n_sample * len(times) / sum(times), cores, 1e3 * float(np.mean(times))
+            done.append(nb)
+    return sum(done) / sum(times), cores, 1e3 * float(np.mean(times)), int(np.mean(done))
 
 
 def main():
@@ -129,6 +135,8 @@ def main():
     ap.add_argument('--walkers', type=int, default=None, help='walkers per GPU (default: workload)')
     ap.add_argument('--cpu-sample', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--gemm-backend', default='tcgen05', choices=['simt', 'tcgen05'])
+    ap.add_argument('--equil-sweeps', type=int, default=20)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == 'ours' else a.warmup
     wl = WORKLOADS[a.workload]
@@ -143,7 +151,7 @@ def main():
         if rank != 0:
             return 0
         n_sample = a.cpu_sample or (16 if wl['mol'] == 'LiH' else 1)
-        val, cores, ms = time_oracle(wl, n_sample, a.steps, a.warmup)
+        val, cores, ms, n_sample = time_oracle(wl, n_sample, a.steps, a.warmup, budget_s=120.0 / max(1, a.steps + a.warmup))
         out = {
             'impl': 'reference', 'metric': metric, 'value': val, 'unit': unit, 'n_gpus': a.gpus, 'steps': a.steps,
             'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -167,7 +175,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     mol, hamil, r_np, PN = make_problem(wl, B, seed=1000 + rank)
-    ansatz = B200Ansatz(hamil, 'psiformer', dtype=a.dtype, device=local, **wl['hyper'])
+    backend = 1 if (a.gemm_backend == 'tcgen05' and a.dtype == 'float32') else 0
+    ansatz = B200Ansatz(hamil, 'psiformer', dtype=a.dtype, device=local, gemm_backend=backend, **wl['hyper'])
     params = PN.perturb_params(ansatz.init(0))
     tdt = torch.float32 if a.dtype == 'float32' else torch.float64
     N, M = hamil.n_up + hamil.n_down, hamil.n_nuc
@@ -178,7 +187,7 @@ def main():
     sign, log = eng.wf_forward(r, R)
     state = dict(r=r.clone(), sign=sign, log=log, age=torch.zeros(B, dtype=torch.int32, device=dev),
                  tau=torch.tensor([0.5], dtype=tdt, device=dev))
-    for it in range(20):
+    for it in range(a.equil_sweeps):
         eng.mcmc_sweep(state, R, 10, seed=parallel.rank_seed(7), step0=10 * it, walker_offset=rank * B)
     r = state['r'].clone()
     pc = PhysicalConfiguration(R, r, torch.zeros(B, device=dev))
@@ -256,7 +265,7 @@ def main():
             pass
         peak = peaks.get('bf16_tflops_sustained', 1590.0 * 0.88)
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-        roof = {'bound': 'tensor', 'kernel': 'dense-layer row GEMM (dqmc gemm_kernel)', 'achieved': achieved,
+        roof = {'bound': 'tensor', 'kernel': 'dense-layer row GEMM (' + ('tcgen05 3xTF32 gemm3xtf32_kernel' if backend else 'CUDA-core gemm_kernel') + ')', 'achieved': achieved,
                 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback',
                 'traffic': None, 'gemm_share_of_step': (gemm_ms / 3) / (total_ms / a.steps),
@@ -268,16 +277,17 @@ def main():
     cpu = None
     if not a.no_cpu_baseline and world == 1:
         n_sample = a.cpu_sample or (64 if wl['mol'] == 'LiH' else 1)
-        cv, cores, cms = time_oracle(wl, n_sample, 2, 1)
+        cv, cores, cms, n_done = time_oracle(wl, n_sample, 2, 1, budget_s=8.0)
         cpu = {'value': cv, 'unit': unit, 'cores': cores, 'kind': 'port',
-               'sample': f'{n_sample} walkers x 2 steps of the same workload, oracle (torch fp64, autograd Hessian)'}
+               'sample': f'{n_done} walkers x 2 steps of the same workload (<= 8 s per step), oracle (torch fp64, autograd Hessian)'}
     out = {
         'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
         'ms_per_step': total_ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32' if a.dtype == 'float32' else 'f64', 'data': 'synthetic',
         'config': {'workload': workload_name, 'global_batch': B * world, 'parallelism': f'walker-shard x{world}',
                    'l2': 'flushed between timed iterations (256 MiB memset) and activations >> L2',
-                   'step': 'E_loc of all walkers (+ fused stats all-reduce for N>1)'},
+                   'step': 'E_loc of all walkers (+ fused stats all-reduce for N>1)',
+                   'gemm_backend': 'tcgen05-3xTF32' if backend else 'cuda-core'},
         'clocks': clk, 'e2e': {'value': e2e_val, 'unit': unit, 'h2d_bytes_per_step': (B * N * 3 + M * 3) * esz,
                                'd2h_bytes_per_step': B * esz},
         'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu,

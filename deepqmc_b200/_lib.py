@@ -18,7 +18,7 @@ SYMBOLS = [
     'dqmc_create', 'dqmc_destroy', 'dqmc_last_error', 'dqmc_version', 'dqmc_param_count',
     'dqmc_param_entry', 'dqmc_param_total', 'dqmc_set_params', 'dqmc_workspace_bytes',
     'dqmc_wf_forward', 'dqmc_local_energy', 'dqmc_mcmc_sweep', 'dqmc_launch_count',
-    'dqmc_profile_begin', 'dqmc_profile_end',
+    'dqmc_profile_begin', 'dqmc_profile_end', 'dqmc_debug_gemm',
 ]
 
 
@@ -72,6 +72,7 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dqmc_launch_count.argtypes = [vp]
     lib.dqmc_launch_count.restype = i64
     lib.dqmc_profile_begin.argtypes = [vp]
+    lib.dqmc_debug_gemm.argtypes = [vp, C.c_char_p, C.c_char_p, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.dqmc_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
     _cache[path] = lib
     return lib

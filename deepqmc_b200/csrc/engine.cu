@@ -3,7 +3,9 @@
 // file builds against tools/cuda_emu for CPU-side logic checks during development (never shipped).
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "dqmc_b200.h"
@@ -46,6 +48,8 @@ struct EngineBase {
   virtual int local_energy(const void* r, const void* R, int Rb, int B, uint64_t seed, const void* twist, void* E,
                            void* stats, void* sign, void* logp, void* grad, void* ws, int64_t wsb,
                            cudaStream_t st) = 0;
+  virtual int debug_gemm(const char* wname, const char* bname, const void* A, const void* Res, void* C, int Mr, int S,
+                         int sliced, int backend, cudaStream_t st) = 0;
   virtual int mcmc(void* r, void* sign, void* logp, int32_t* age, void* tau, const void* R, int Rb, int B, int n_sub,
                    double target, int max_age, uint64_t seed, uint64_t step0, uint64_t woff, const void* nn,
                    const void* nu, void* stats, void* ws, int64_t wsb, cudaStream_t st) = 0;
@@ -89,6 +93,22 @@ __global__ void convert_kernel(const double* __restrict__ src, T* __restrict__ d
   if (i < n) dst[i] = (T)src[i];
 }
 
+// W[K][N] (row-major) -> W^T hi/lo [N][K]: hi = top 19 bits (exact TF32), lo = w - hi
+__global__ void split_transpose_kernel(const float* __restrict__ W, int K, int N, float* __restrict__ hi,
+                                       float* __restrict__ lo) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * N) return;
+  int n = idx / K, k = idx % K;
+  float w = W[(size_t)k * N + n];
+#ifndef DQMC_EMU
+  float h = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+#else
+  float h = w;
+#endif
+  hi[idx] = h;
+  lo[idx] = w - h;
+}
+
 #define DQ_CHECK(call)                                                             \
   do {                                                                             \
     cudaError_t e_ = (call);                                                       \
@@ -117,6 +137,28 @@ struct Engine : EngineBase {
   int J = 0;  // nuclei with a non-local channel
   int N, M, d, K, KN, H, dh, T3;
   size_t max_smem = 0;
+  int n_sms = 148;
+#if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
+  struct TcWeight { float* hi = nullptr; float* lo = nullptr; CUtensorMap mh, ml; int N = 0, K = 0, BN = 0; };
+  std::map<std::string, TcWeight> tcw;
+  bool use_tc() const { return std::is_same<T, float>::value && cfg.gemm_backend == DQMC_GEMM_TCGEN05; }
+  int prepare_tc_weight(const std::string& name, const float* W, int Kc, int Nc, cudaStream_t st) {
+    TcWeight& w = tcw[name];
+    if (!w.hi) {
+      DQ_CHECK(cudaMalloc((void**)&w.hi, sizeof(float) * (size_t)Kc * Nc));
+      DQ_CHECK(cudaMalloc((void**)&w.lo, sizeof(float) * (size_t)Kc * Nc));
+      w.N = Nc; w.K = Kc; w.BN = tc::pick_bn(Nc);
+      if (tc::make_weight_map(&w.mh, w.hi, Nc, Kc, w.BN) || tc::make_weight_map(&w.ml, w.lo, Nc, Kc, w.BN)) {
+        err = "cuTensorMapEncodeTiled failed for " + name;
+        return 4;
+      }
+    }
+    DQ_LAUNCH(split_transpose_kernel, dim3((Kc * Nc + 255) / 256), dim3(256), 0, st, W, Kc, Nc, w.hi, w.lo);
+    return 0;
+  }
+#else
+  bool use_tc() const { return false; }
+#endif
 
   int init() {
     N = cfg.n_up + cfg.n_down; M = cfg.n_nuc; d = cfg.embedding_dim; K = cfg.n_determinants;
@@ -172,6 +214,19 @@ struct Engine : EngineBase {
     if (max_smem > 227 * 1024) { err = "system too large for the shared-memory tiling (N)"; return 2; }
     DQ_CHECK(cudaFuncSetAttribute(attn_fl_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_attn));
     DQ_CHECK(cudaFuncSetAttribute(slater_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_sl));
+    if (cfg.gemm_backend == DQMC_GEMM_TCGEN05) {
+#if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
+      if (!std::is_same<T, float>::value) { err = "DQMC_GEMM_TCGEN05 needs dtype DQMC_F32"; return 2; }
+      if (d % 32 != 0) { err = "DQMC_GEMM_TCGEN05 needs embedding_dim % 32 == 0"; return 2; }
+      DQ_CHECK(cudaFuncSetAttribute(tc::gemm3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    tc::SmemLayout::total(256)));
+      cudaDeviceProp prop;
+      DQ_CHECK(cudaGetDeviceProperties(&prop, device));
+      n_sms = prop.multiProcessorCount;
+#else
+      err = "this build has no tcgen05 backend"; return 2;
+#endif
+    }
     return 0;
   }
   ~Engine() override {
@@ -186,6 +241,16 @@ struct Engine : EngineBase {
     if (n != total) { err = "parameter count mismatch"; return 2; }
     DQ_CHECK(cudaMemcpyAsync(d_stage, host, sizeof(double) * n, cudaMemcpyHostToDevice, st));
     DQ_LAUNCH(convert_kernel<T>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, (const double*)d_stage, d_params, n);
+#if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
+    if (use_tc()) {
+      for (auto& e : entries) {
+        bool is_w = e.name.find(".w") != std::string::npos || e.name.rfind("bf.", 0) == 0;
+        if (!is_w || e.name == "emb.w") continue;
+        int rc = prepare_tc_weight(e.name, (const float*)(d_params + e.offset), e.rows, e.cols, st);
+        if (rc) return rc;
+      }
+    }
+#endif
     DQ_CHECK(cudaGetLastError());
     return 0;
   }
@@ -232,8 +297,35 @@ struct Engine : EngineBase {
   }
 
   // ---- GEMM dispatch ------------------------------------------------------------------------
-  int gemm(const T* A, int lda, const T* W0, const T* W1, int zsplit, int ldw, const T* bias, const T* Res, int ldr,
-           T* C, int ldc, int Mr, int Nc, int Kc, int S, int sliced, int Nel, cudaStream_t st) {
+  int gemm(const T* A, int lda, const char* w0, const char* w1, int zsplit, int ldw, const T* bias, const T* Res,
+           int ldr, T* C, int ldc, int Mr, int Nc, int Kc, int S, int sliced, int Nel, cudaStream_t st) {
+    const T* W0 = P(w0);
+    const T* W1 = w1 ? P(w1) : nullptr;
+#if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
+    if constexpr (std::is_same<T, float>::value) {
+      if (use_tc() && Kc % 32 == 0 && lda % 4 == 0 && ldc % 4 == 0) {
+        const TcWeight& t0 = tcw.at(w0);
+        const TcWeight& t1 = w1 ? tcw.at(w1) : t0;
+        tc::Params p;
+        p.A = A; p.lda = lda; p.bias = bias; p.Res = Res; p.ldr = ldr; p.C = C; p.ldc = ldc; p.M = Mr; p.N = Nc;
+        p.K = Kc; p.S = S; p.sliced = sliced; p.Nel = Nel; p.z_split = zsplit; p.BN = t0.BN; p.err_flag = nullptr;
+        int MT = (Mr + tc::kBM - 1) / tc::kBM, NT = (Nc + p.BN - 1) / p.BN;
+        int n_tiles = (sliced ? Nel : 1) * MT * NT;
+        int grid = n_tiles < n_sms ? n_tiles : n_sms;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (prof) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+        tc::gemm3xtf32_kernel<<<grid, tc::kThreads, tc::SmemLayout::total(p.BN), st>>>(t0.mh, t0.ml, t1.mh, t1.ml, p);
+        ++launches;
+        if (prof) {
+          cudaEventRecord(e1, st);
+          prof_ev.push_back(e0); prof_ev.push_back(e1);
+          prof_flops += 2.0 * (double)Mr * (sliced ? Nel : 1) * (double)Nc * (double)Kc;
+          ++prof_n;
+        }
+        return 0;
+      }
+    }
+#endif
     GemmArgs<T> g;
     g.A = A; g.lda = lda; g.W0 = W0; g.W1 = W1; g.z_split = zsplit; g.ldw = ldw; g.bias = bias; g.Res = Res;
     g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = Mr; g.N = Nc; g.K = Kc; g.S = S; g.sliced = sliced; g.Nel = Nel;
@@ -255,6 +347,22 @@ struct Engine : EngineBase {
     return 0;
   }
 
+  int debug_gemm(const char* wname, const char* bname, const void* A, const void* Res, void* C, int Mr, int S,
+                 int sliced, int backend, cudaStream_t st) override {
+    int64_t o = off(wname);
+    if (o < 0) { err = "unknown weight"; return 2; }
+    int rows = 0, cols = 0;
+    for (auto& e : entries) if (e.name == wname) { rows = e.rows; cols = e.cols; }
+    int saved = cfg.gemm_backend;
+    cfg.gemm_backend = backend;
+    int rc = gemm((const T*)A, rows, wname, sliced ? "bf.dn" : nullptr, cfg.n_up, cols, bname ? P(bname) : nullptr,
+                  (const T*)Res, cols, (T*)C, cols, Mr, cols, rows, S, sliced, N, st);
+    cfg.gemm_backend = saved;
+    if (rc) return rc;
+    DQ_CHECK(cudaGetLastError());
+    return 0;
+  }
+
   // ---- one chunk of the wave-function pipeline ---------------------------------------------
   int run_chunk(const T* r, const T* R, int Rb, int Bc, int S, int Bstat, T* sign, T* logp, T* E, T* stats, T* grad,
                 void* wsbase, cudaStream_t st) {
@@ -268,19 +376,19 @@ struct Engine : EngineBase {
     const T scale = (T)(1.0 / std::sqrt((double)dh));
     for (int l = 0; l < cfg.n_layers; ++l) {
       std::string p = "L" + std::to_string(l) + ".";
-      gemm(X, d, P(p + "wqkv"), nullptr, 0, 3 * d, nullptr, nullptr, 0, w.QKV, 3 * d, rows, 3 * d, d, S, 0, N, st);
+      gemm(X, d, (p + "wqkv").c_str(), nullptr, 0, 3 * d, nullptr, nullptr, 0, w.QKV, 3 * d, rows, 3 * d, d, S, 0, N, st);
       DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh), st, (const T*)w.QKV, 3 * d, O, d,
                 N, S, dh, d, scale);
-      gemm(O, d, P(p + "wo"), nullptr, 0, d, nullptr, X, d, w.A, d, rows, d, d, S, 0, N, st);
-      gemm(w.A, d, P(p + "w1"), nullptr, 0, d, P(p + "b1"), nullptr, 0, w.M1, d, rows, d, d, S, 0, N, st);
+      gemm(O, d, (p + "wo").c_str(), nullptr, 0, d, nullptr, X, d, w.A, d, rows, d, d, S, 0, N, st);
+      gemm(w.A, d, (p + "w1").c_str(), nullptr, 0, d, P(p + "b1"), nullptr, 0, w.M1, d, rows, d, d, S, 0, N, st);
       DQ_LAUNCH(tanh_fl_kernel<T>, dim3(Bc * N, (d + 127) / 128), dim3(128), 0, st, w.M1, d, (const T*)nullptr, 0, S, d,
                 T(1));
-      gemm(w.M1, d, P(p + "w2"), nullptr, 0, d, P(p + "b2"), nullptr, 0, O, d, rows, d, d, S, 0, N, st);
+      gemm(w.M1, d, (p + "w2").c_str(), nullptr, 0, d, P(p + "b2"), nullptr, 0, O, d, rows, d, d, S, 0, N, st);
       DQ_LAUNCH(tanh_fl_kernel<T>, dim3(Bc * N, (d + 127) / 128), dim3(128), 0, st, O, d, (const T*)w.A, d, S, d, T(1));
       T* tmp = X; X = O; O = tmp;
     }
     // per-spin backflow heads: rows of electron e across walkers, weights by spin
-    gemm(X, d, P("bf.up"), P("bf.dn"), cfg.n_up, KN, nullptr, nullptr, 0, w.BF, KN, Bc * S, KN, d, S, 1, N, st);
+    gemm(X, d, "bf.up", "bf.dn", cfg.n_up, KN, nullptr, nullptr, 0, w.BF, KN, Bc * S, KN, d, S, 1, N, st);
     DQ_LAUNCH(slater_kernel<T>, dim3(Bc, K), dim3(128), slater_smem_bytes<T>(N), st, r, R, Rb, N, M, cfg.n_up, K, S,
               P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog,
               w.dgrad, w.dlap);
@@ -467,6 +575,12 @@ int dqmc_mcmc_sweep(dqmc_handle h, void* r, void* sign, void* log, int32_t* age,
                     (cudaStream_t)stream);
 }
 int64_t dqmc_launch_count(dqmc_handle h) { return h ? h->e->launches : -1; }
+
+int dqmc_debug_gemm(dqmc_handle h, const char* weight, const char* bias, const void* A, const void* Res, void* C,
+                    int32_t rows, int32_t S, int32_t sliced, int32_t backend, void* stream) {
+  if (!h) return 2;
+  return h->e->debug_gemm(weight, bias, A, Res, C, rows, S, sliced, backend, (cudaStream_t)stream);
+}
 
 int dqmc_profile_begin(dqmc_handle h) {
   if (!h) return 2;

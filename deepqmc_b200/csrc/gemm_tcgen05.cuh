@@ -1,0 +1,377 @@
+// fp32-accurate dense-layer GEMM on the 5th-gen tensor cores (sm_100a): 3xTF32 split
+//   C[row(m), :] = (Res) + A[row(m), :] @ W + (bias on value rows),  A, W, C fp32 in HBM.
+//
+//   a = a_hi + a_lo, w = w_hi + w_lo with *_hi = top 19 bits (exactly representable in TF32);
+//   acc(fp32, TMEM) = a_hi w_lo + a_lo w_hi + a_hi w_hi        -> ~2^-21 relative per product,
+//   i.e. the accuracy class the reference demands (jax_default_matmul_precision='highest',
+//   NVIDIA_TF32_OVERRIDE=0: src/deepqmc/__init__.py:9-34) at 1/3 of the TF32 tensor peak.
+//
+// Persistent warp-specialised kernel, one CTA per SM, tile = 128 rows x BN columns x K:
+//   warps 0-3  epilogue      : TMEM -> registers (tcgen05.ld) -> +bias/+residual -> global
+//   warps 4-7  A producers   : global fp32 rows -> split hi/lo -> 128B-swizzled K-major smem
+//   warp  8    W producer    : TMA (cp.async.bulk.tensor) of the pre-split W^T hi/lo tiles
+//   warp  9    MMA issuer    : tcgen05.mma.kind::tf32 (one elected lane), commits to mbarriers
+// smem ring of kStages k-blocks (32 fp32 = one 128B swizzle row), 2 accumulators in TMEM so the
+// epilogue of tile i overlaps the main loop of tile i+1.  W^T (N x K, K contiguous) is split into
+// hi/lo once per parameter upload (engine.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace dq {
+namespace tc {
+
+constexpr int kBM = 128;          // rows per tile (UMMA_M)
+constexpr int kBK = 32;           // fp32 per k-block = 128 bytes = one swizzle row
+constexpr int kStages = 2;
+constexpr int kUmmaK = 8;         // tf32: 32 bytes per MMA k-step
+constexpr int kThreads = 320;
+constexpr uint32_t kTmemCols = 512;
+
+struct Params {
+  const float* A; int lda;
+  const float* bias;
+  const float* Res; int ldr;
+  float* C; int ldc;
+  int M, N, K;
+  int S;
+  int sliced, Nel, z_split;
+  int BN;            // 64 | 128 | 256
+  int* err_flag;     // device int: set to non-zero if a barrier wait times out
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must not hang the GPU box -> flag + trap after ~2 s.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) {
+      if (err_flag) atomicExch(err_flag, 1);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) = 1024B/16
+// | version=1 [46,48) | layout_type=SWIZZLE_128B(2) [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): c_format=F32 (1) [4,6),
+// a_format=b_format=TF32 (2) [7,10),[10,13), a/b K-major (0), n>>3 [17,23), m>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ size_t phys_row(const Params& p, int m, int z) {
+  if (!p.sliced) return (size_t)m;
+  int b = m / p.S, s = m % p.S;
+  return ((size_t)b * p.Nel + z) * p.S + s;
+}
+
+struct SmemLayout {
+  // byte offsets from the 1024B-aligned base
+  static __host__ __device__ int a_hi(int s, int BN) { return s * stage_bytes(BN); }
+  static __host__ __device__ int a_lo(int s, int BN) { return s * stage_bytes(BN) + kBM * 128; }
+  static __host__ __device__ int w_hi(int s, int BN) { return s * stage_bytes(BN) + 2 * kBM * 128; }
+  static __host__ __device__ int w_lo(int s, int BN) { return s * stage_bytes(BN) + 2 * kBM * 128 + BN * 128; }
+  static __host__ __device__ int stage_bytes(int BN) { return 2 * kBM * 128 + 2 * BN * 128; }
+  static __host__ __device__ int bars(int BN) { return kStages * stage_bytes(BN); }
+  static __host__ __device__ int total(int BN) { return bars(BN) + 256 + 1024; }  // + barriers + alignment slack
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_constant__ CUtensorMap map_lo0,
+                  const __grid_constant__ CUtensorMap map_hi1, const __grid_constant__ CUtensorMap map_lo1, Params p) {
+  extern __shared__ unsigned char smem_raw_[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw_ + 1023) & ~(uintptr_t)1023);
+  const int BN = p.BN;
+  uint64_t* bars = (uint64_t*)(smem + SmemLayout::bars(BN));
+  uint64_t* full_a = bars;                 // [kStages] count 128 (producer threads)
+  uint64_t* full_w = bars + kStages;       // [kStages] count 1 + tx bytes
+  uint64_t* empty = bars + 2 * kStages;    // [kStages] count 1 (tcgen05.commit)
+  uint64_t* tmem_full = bars + 3 * kStages;       // [2] count 1 (commit)
+  uint64_t* tmem_empty = bars + 3 * kStages + 2;  // [2] count 128 (epilogue threads)
+  uint32_t* tmem_base_slot = (uint32_t*)(bars + 3 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int MT = (p.M + kBM - 1) / kBM, NT = (p.N + BN - 1) / BN;
+  const int Z = p.sliced ? p.Nel : 1;
+  const int n_tiles = Z * MT * NT;
+  const int KB = p.K / kBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_a[s], 128);
+      mbar_init(&full_w[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 9) {  // TMEM allocation (whole warp), address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&map_hi0); tma_prefetch_desc(&map_lo0);
+    if (p.sliced) { tma_prefetch_desc(&map_hi1); tma_prefetch_desc(&map_lo1); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp >= 4 && warp < 8) {
+    // ===================== A producers: one thread per tile row =============================
+    const int trow = threadIdx.x - 128;
+    uint32_t it = 0;  // running k-block counter (ring position)
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int nt = tile % NT, mt = (tile / NT) % MT, z = tile / (NT * MT);
+      (void)nt;
+      const int m = mt * kBM + trow;
+      const bool valid = m < p.M;
+      const float* arow = valid ? p.A + phys_row(p, m, z) * p.lda : p.A;
+      float4 cur[8], nxt[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) cur[c] = valid ? __ldg((const float4*)(arow) + c) : make_float4(0, 0, 0, 0);
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        if (kb + 1 < KB) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            nxt[c] = valid ? __ldg((const float4*)(arow + (kb + 1) * kBK) + c) : make_float4(0, 0, 0, 0);
+        }
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1, p.err_flag);
+        unsigned char* ah = smem + SmemLayout::a_hi(s, BN);
+        unsigned char* al = smem + SmemLayout::a_lo(s, BN);
+        const int rbase = (trow >> 3) * 1024 + (trow & 7) * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 v = cur[c], h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+          const int off = rbase + ((c ^ (trow & 7)) << 4);
+          *(float4*)(ah + off) = h;
+          *(float4*)(al + off) = l;
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
+        mbar_arrive(&full_a[s]);
+        if (kb + 1 < KB) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) cur[c] = nxt[c];
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ===================== W producer: TMA of the pre-split weight tiles ====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int nt = tile % NT, z = tile / (NT * MT);
+        const bool second = p.sliced && z >= p.z_split;
+        const CUtensorMap* mh = second ? &map_hi1 : &map_hi0;
+        const CUtensorMap* ml = second ? &map_lo1 : &map_lo0;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1, p.err_flag);
+          mbar_expect_tx(&full_w[s], 2u * BN * 128u);
+          tma_load_2d(mh, &full_w[s], smem + SmemLayout::w_hi(s, BN), kb * kBK, nt * BN);
+          tma_load_2d(ml, &full_w[s], smem + SmemLayout::w_lo(s, BN), kb * kBK, nt * BN);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer ========================================================
+    const uint32_t idesc = make_idesc(kBM, BN);
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      const int acc = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], aph ^ 1, p.err_flag);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&full_a[s], ph, p.err_flag);
+        mbar_wait(&full_w[s], ph, p.err_flag);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t ah = smem_u32(smem + SmemLayout::a_hi(s, BN)), al = smem_u32(smem + SmemLayout::a_lo(s, BN));
+          const uint32_t wh = smem_u32(smem + SmemLayout::w_hi(s, BN)), wl = smem_u32(smem + SmemLayout::w_lo(s, BN));
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint32_t ko = k * kUmmaK * 4;  // byte offset inside the 128B swizzle row
+            umma_tf32(d_tmem, make_desc(ah + ko), make_desc(wl + ko), idesc, (kb | k) ? 1u : 0u);
+            umma_tf32(d_tmem, make_desc(al + ko), make_desc(wh + ko), idesc, 1u);
+            umma_tf32(d_tmem, make_desc(ah + ko), make_desc(wh + ko), idesc, 1u);
+          }
+          umma_commit(&empty[s]);                         // frees the smem stage when the MMAs retire
+          if (kb == KB - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue: warps 0-3 <-> TMEM lanes 32*warp .. +31 ================
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      const int nt = tile % NT, mt = (tile / NT) % MT, z = tile / (NT * MT);
+      const int acc = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      const int m = mt * kBM + warp * 32 + lane;
+      const bool valid = m < p.M;
+      const size_t pr = valid ? phys_row(p, m, z) : 0;
+      const bool value_row = (pr % (size_t)p.S) == 0;
+      mbar_wait(&tmem_full[acc], aph, p.err_flag);
+      tc_fence_after();
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
+        tmem_ld_wait();
+        const int n0 = nt * BN + c0;
+        if (valid && n0 < p.N) {
+          float* crow = p.C + pr * p.ldc + n0;
+          const float* rrow = p.Res ? p.Res + pr * p.ldr + n0 : nullptr;
+          if (n0 + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                     __uint_as_float(v[j + 3]));
+              if (p.bias && value_row) {
+                float4 bb = __ldg((const float4*)(p.bias + n0 + j));
+                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+              }
+              if (rrow) {
+                float4 rr = *(const float4*)(rrow + j);
+                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+              }
+              *(float4*)(crow + j) = o;
+            }
+          } else {
+            for (int j = 0; j < 32 && n0 + j < p.N; ++j) {
+              float o = __uint_as_float(v[j]);
+              if (p.bias && value_row) o += p.bias[n0 + j];
+              if (rrow) o += rrow[j];
+              crow[j] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && ptr)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// W^T split tensors: [Nrows][K] fp32, K contiguous.  Box = 32 fp32 (128 B) x BN rows, 128B swizzle.
+inline int make_weight_map(CUtensorMap* map, const float* wt, int Nrows, int K, int BN) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return 1;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)Nrows};
+  cuuint64_t gstr[1] = {(cuuint64_t)K * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wt, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2;
+}
+
+inline int pick_bn(int N) { return N > 128 ? 256 : (N > 64 ? 128 : 64); }
+
+}  // namespace tc
+}  // namespace dq

@@ -202,6 +202,20 @@ class Engine:
         self._check(rc, 'dqmc_mcmc_sweep')
         return stats
 
+    def debug_gemm(self, weight, A, bias=None, Res=None, S=1, sliced=False, backend=0):
+        off, K, Nc = self.entries[weight]
+        A = self._prep(A)
+        rows = A.shape[0]
+        out_rows = rows
+        Cout = torch.zeros(out_rows, Nc, dtype=self.dtype, device=self.device)
+        Res = self._prep(Res) if Res is not None else None
+        rc = self.lib.dqmc_debug_gemm(self.h, weight.encode(), bias.encode() if bias else None, A.data_ptr(),
+                                      Res.data_ptr() if Res is not None else None, Cout.data_ptr(),
+                                      rows // self.spec.n_elec if sliced else rows, S, int(sliced),
+                                      backend, self._stream())
+        self._check(rc, 'dqmc_debug_gemm')
+        return Cout
+
     def profile_begin(self):
         self.lib.dqmc_profile_begin(self.h)
 

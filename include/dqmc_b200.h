@@ -102,6 +102,15 @@ int dqmc_mcmc_sweep(dqmc_handle h, void* r, void* sign, void* log, int32_t* age,
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches claim). */
 int64_t dqmc_launch_count(dqmc_handle h);
 
+/* Self-test hook: run ONE dense-layer row GEMM  C = (Res) + A @ W[weight] (+ bias on value rows)
+ * with the named weight of the handle's parameter table, on the requested backend
+ * (DQMC_GEMM_SIMT | DQMC_GEMM_TCGEN05).  A[rows][K], Res/C[rows][N] device arrays in the compute
+ * dtype; sliced = 1 exercises the per-spin backflow mapping (weight "bf.up"/"bf.dn", rows = B*S).
+ * Used by tests to validate the tcgen05 3xTF32 kernel against the CUDA-core kernel and fp64.
+ * No reference analogue (the reference's dense layers are hk.Linear -> XLA dot). */
+int dqmc_debug_gemm(dqmc_handle h, const char* weight, const char* bias, const void* A, const void* Res, void* C,
+                    int32_t rows, int32_t S, int32_t sliced, int32_t backend, void* stream);
+
 /* Measurement aid (bench.py roofline): between begin/end every dense-layer GEMM launch is
  * bracketed by CUDA events on the caller's stream; end() returns their summed duration [ms],
  * the algorithmic flops they performed (2*M*N*K each) and their count.  No reference analogue

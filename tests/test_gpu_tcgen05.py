@@ -1,0 +1,94 @@
+"""GPU: the tcgen05 3xTF32 dense-layer GEMM (gemm_tcgen05.cuh) against fp64 matmul and the
+CUDA-core kernel, then the whole fp32 engine with the tensor-core backend against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from deepqmc_b200 import params as PN
+from deepqmc_b200.ansatz import B200Ansatz
+from deepqmc_b200.hamil import MolecularHamiltonian
+from deepqmc_b200.molecule import Molecule
+from deepqmc_b200.types import PhysicalConfiguration
+
+DEV = 'cuda:0'
+
+
+def _engine(backend, mol='LiH', **hyper):
+    hamil = MolecularHamiltonian(mol=Molecule.from_name(mol))
+    a = B200Ansatz(hamil, 'psiformer', dtype='float32', gemm_backend=backend, **hyper)
+    params = PN.perturb_params(a.init(0))
+    return hamil, a, params, a.engine_for(hamil, params)
+
+
+@pytest.mark.parametrize('rows,S', [(128, 1), (1000, 14), (56 * 300 + 5, 14), (77, 1)])
+@pytest.mark.parametrize('weight,bias', [('L0.wqkv', None), ('L1.w1', 'L1.b1'), ('L2.wo', None)])
+def test_gemm_3xtf32_matches_fp64(rows, S, weight, bias):
+    hamil, a, params, eng = _engine(1)
+    g = torch.Generator(device='cpu').manual_seed(rows + S)
+    A = (torch.randn(rows, 256, generator=g) * torch.exp(2 * torch.randn(rows, 1, generator=g))).to(DEV)
+    off, K, Nc = eng.entries[weight]
+    flat = torch.as_tensor(eng._flat, device=DEV)
+    W = flat[off:off + K * Nc].reshape(K, Nc).float().double()
+    Res = torch.randn(rows, Nc, generator=g).to(DEV) if weight.endswith('wo') else None
+    ref = A.double() @ W
+    if bias:
+        boff, _, bn = eng.entries[bias]
+        bvec = flat[boff:boff + bn].float().double()
+        ref[torch.arange(rows, device=DEV) % S == 0] += bvec
+    if Res is not None:
+        ref += Res.double()
+    C_tc = eng.debug_gemm(weight, A, bias=bias, Res=Res, S=S, backend=1)
+    C_sm = eng.debug_gemm(weight, A, bias=bias, Res=Res, S=S, backend=0)
+    torch.cuda.synchronize()
+    scale = (A.double().abs() @ W.abs()) + 1e-30  # per-element magnitude of the accumulated products
+    err_tc = ((C_tc.double() - ref).abs() / scale).max().item()
+    err_sm = ((C_sm.double() - ref).abs() / scale).max().item()
+    assert err_sm < 5e-7, err_sm
+    assert err_tc < 2e-6, (err_tc, err_sm)  # 3xTF32: ~2^-21 per product, fp32 accumulation
+
+
+def test_gemm_sliced_backflow_heads():
+    hamil, a, params, eng = _engine(1)
+    B, N, S = 37, 4, 14
+    A = torch.randn(B * N * S, 256, device=DEV)
+    C_tc = eng.debug_gemm('bf.up', A, S=S, sliced=True, backend=1)
+    C_sm = eng.debug_gemm('bf.up', A, S=S, sliced=True, backend=0)
+    flat = torch.as_tensor(eng._flat, device=DEV)
+    ws = []
+    for nm in ('bf.up', 'bf.dn'):
+        off, K, Nc = eng.entries[nm]
+        ws.append(flat[off:off + K * Nc].reshape(K, Nc).float().double())
+    A4 = A.double().reshape(B, N, S, 256)
+    ref = torch.stack([A4[:, i] @ ws[0 if i < hamil.n_up else 1] for i in range(N)], 1).reshape(B * N * S, -1)
+    assert (C_sm.double() - ref).abs().max().item() < 1e-4
+    assert (C_tc.double() - ref).abs().max().item() < 1e-4
+
+
+def test_engine_tcgen05_backend_parity():
+    """fp32 engine, tensor-core backend: agrees with the CUDA-core fp32 engine and with the fp64
+    oracle within the reference's fp32 tolerance (2e-4, tests/test_hamil.py:37-40)."""
+    from oracle import wf
+    from oracle.hamil import OracleHamiltonian
+
+    hamil, a1, params, e1 = _engine(1)
+    _, a0, _, e0 = _engine(0)
+    e0.set_params(params)
+    mol = hamil.mol
+    rng = np.random.default_rng(0)
+    B = 64
+    r = torch.as_tensor(mol.coords[rng.integers(0, 2, size=(B, 4))] + rng.normal(size=(B, 4, 3)), device=DEV).float()
+    R = torch.as_tensor(mol.coords, device=DEV).float()
+    E1, st1, s1, l1, _ = e1.local_energy(r, R)
+    E0, st0, s0, l0, _ = e0.local_energy(r, R)
+    assert torch.equal(s0, s1)
+    scale = torch.maximum(E0.abs(), st0[1].abs()).clamp(min=1)
+    assert ((E1 - E0).abs() / scale).max().item() < 1e-4
+    oh = OracleHamiltonian(mol)
+    pt = wf.to_torch(params)
+    Rc = R.double().cpu()
+    for b in range(3):
+        f = lambda x: wf.log_psi(a1.spec, pt, x, Rc)
+        eo, st = oh.local_energy(f, r[b].double().cpu(), Rc)
+        assert abs(E1[b].item() - eo.item()) <= 2e-4 * max(1, abs(eo.item()), abs(st['hamil/E_kin'].item()))
