@@ -234,7 +234,7 @@ def test_full_size_properties_4096_walkers():
     psix = ansatz.apply(params, pcx)
     assert torch.equal(psix.sign, -psi.sign)
     dl = (psix.log - psi.log).abs()
-    assert dl.median().item() < 1e-5 and dl.quantile(0.999).item() < 1e-3, (dl.median().item(), dl.max().item())
+    assert dl.median().item() < 2e-5 and dl.quantile(0.99).item() < 2e-3, (dl.median().item(), dl.max().item())
     scale = torch.maximum(E.abs(), st['hamil/E_kin'].abs()).clamp(min=1)
     assert ((Ex - E).abs() / scale).max().item() < 5e-3
     e_nuc = 3.0 * 1.0 / np.linalg.norm(mol.coords[0] - mol.coords[1])

@@ -33,16 +33,18 @@ def test_gemm_3xtf32_matches_fp64(rows, S, weight, bias):
     W = flat[off:off + K * Nc].reshape(K, Nc).float().double()
     Res = torch.randn(rows, Nc, generator=g).to(DEV) if weight.endswith('wo') else None
     ref = A.double() @ W
+    scale = (A.double().abs() @ W.abs()) + 1e-30  # per-element magnitude of the accumulated terms
     if bias:
         boff, _, bn = eng.entries[bias]
         bvec = flat[boff:boff + bn].float().double()
         ref[torch.arange(rows, device=DEV) % S == 0] += bvec
+        scale += bvec.abs()
     if Res is not None:
         ref += Res.double()
+        scale += Res.double().abs()
     C_tc = eng.debug_gemm(weight, A, bias=bias, Res=Res, S=S, backend=1)
     C_sm = eng.debug_gemm(weight, A, bias=bias, Res=Res, S=S, backend=0)
     torch.cuda.synchronize()
-    scale = (A.double().abs() @ W.abs()) + 1e-30  # per-element magnitude of the accumulated products
     err_tc = ((C_tc.double() - ref).abs() / scale).max().item()
     err_sm = ((C_sm.double() - ref).abs() / scale).max().item()
     assert err_sm < 5e-7, err_sm
