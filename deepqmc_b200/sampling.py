@@ -1,0 +1,158 @@
+"""Host-side mirror of the reference's electron samplers (reference:
+src/deepqmc/sampling/base.py:14-79 ElectronSampler protocol, electron_samplers.py:32-173
+MetropolisSampler, :333-357 DecorrSampler, electron_sample_initializers.py:43-288 initialiser).
+
+``sampler.init(rng, params, n, R)``, ``sampler.sample(rng, state, params, R) -> (state,
+phys_conf, stats)`` and ``sampler.update(state, params, R)`` keep the reference's meaning; the
+sweep itself (proposal, wave-function forward, accept/reject, age, tau adaptation, statistics)
+runs in ``dqmc_mcmc_sweep``.  State dict: r[B,N,3], psi=Psi(sign[B], log[B]), age[B] int32, tau.
+``rng`` is an integer seed (Philox key) instead of a JAX key.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .types import PhysicalConfiguration, Psi
+
+STAT_NAMES = ('sampling/acceptance', 'sampling/tau', 'sampling/age/mean', 'sampling/age/max',
+              'sampling/log_psi/mean', 'sampling/log_psi/std', 'sampling/dists/mean')
+
+
+class ShellBasedDistribution:
+    """|r| ~ Exp / (2 zeta), zeta = Z * shell factor, uniform direction
+    (reference: electron_sample_initializers.py:196-255)."""
+
+    @staticmethod
+    def shell_factor(spin_idx):
+        return np.where(spin_idx < 1, 1.0, np.where(spin_idx < 5, 0.5, np.where(spin_idx < 9, 1 / 3, 0.25)))
+
+    def __call__(self, rng: np.random.Generator, charges, counts_per_nucleus):
+        total = len(charges)
+        # index of each electron among the same-spin electrons of its nucleus
+        spin_idx = np.concatenate([np.arange(c) for c in counts_per_nucleus if c > 0]) if total else np.zeros(0)
+        zetas = np.asarray(charges) * self.shell_factor(spin_idx)
+        dist = rng.exponential(size=total) / (2 * zetas)
+        v = rng.normal(size=(total, 3))
+        v /= np.linalg.norm(v, axis=-1, keepdims=True)
+        return dist[:, None] * v
+
+
+class AtomCenteredElectronInitializer:
+    """Places electrons around nuclei (reference: electron_sample_initializers.py:258-288 with the
+    assignment heuristics of :43-160: electrons per nucleus by valence charge, electron pairs
+    first, remaining spins alternating between nearest neighbours)."""
+
+    def __init__(self, atom_centered_distribution=None):
+        self.dist = atom_centered_distribution or ShellBasedDistribution()
+
+    @staticmethod
+    def assign_electrons(rng, ns_valence, n_up, n_down):
+        ns_valence = np.asarray(ns_valence, dtype=float)
+        charge = ns_valence.sum() - n_up - n_down
+        valence = ns_valence - charge / len(ns_valence)
+        el = np.floor(valence).astype(int)
+        while ns_valence.sum() - charge - el.sum() > 0:
+            logits = valence - el
+            p = np.exp(logits - logits.max())
+            el[rng.choice(len(el), p=p / p.sum())] += 1
+        return el
+
+    @staticmethod
+    def assign_spins(rng, el, coords, n_up, n_down):
+        up, down = np.zeros_like(el), np.zeros_like(el)
+        for i in range(int(el.max()) if len(el) else 0):
+            mask = el >= 2 * (i + 1)
+            inc = np.where(mask & (mask.sum() + down.sum() <= n_down), 1, 0)
+            up, down = up + inc, down + inc
+        d = np.linalg.norm(coords[:, None] - coords[None], axis=-1)
+        np.fill_diagonal(d, np.inf)
+        nn = np.argsort(d, axis=-1)
+        rem = el - up - down
+        if (rem > 0).any():
+            cands = np.flatnonzero(rem == rem.max())
+            center = int(rng.choice(cands))
+            i = 0
+            while (up + down < el).any():
+                is_down = (i % 2) and (down.sum() < n_down)
+                if is_down:
+                    down[center] += 1
+                else:
+                    up[center] += 1
+                order = nn[center]
+                has = (el - up - down)[order] > 0
+                center = int(order[int(np.argmax(has))])
+                i += 1
+        return up, down
+
+    def __call__(self, rng, charges, ns_valence, nuclear_coordinates, n_up, n_down):
+        coords = np.asarray(nuclear_coordinates)
+        el = self.assign_electrons(rng, ns_valence, n_up, n_down)
+        up, down = self.assign_spins(rng, el, coords, n_up, n_down)
+        up_idx, dn_idx = np.repeat(np.arange(len(el)), up)[:n_up], np.repeat(np.arange(len(el)), down)[:n_down]
+        ch = np.asarray(charges)
+        r_up = coords[up_idx] + self.dist(rng, ch[up_idx], up)
+        r_dn = coords[dn_idx] + self.dist(rng, ch[dn_idx], down)
+        return np.concatenate([r_up, r_dn])
+
+
+class MetropolisSampler:
+    """reference: sampling/electron_samplers.py:32-173."""
+
+    WALKER_STATE = ['r', 'psi', 'age']
+
+    def __init__(self, hamil, wf, *, sample_initializer=None, tau=1.0, target_acceptance=0.57, max_age=None):
+        self.hamil = hamil
+        self.wf = wf  # bound B200Ansatz.apply
+        self.ansatz = wf.__self__
+        self.sample_initializer = sample_initializer or AtomCenteredElectronInitializer()
+        self.initial_tau, self.target_acceptance, self.max_age = tau, target_acceptance, max_age
+        self.length = 1
+        self._step = 0
+
+    def phys_conf(self, R, r):
+        if r.dim() == 2:
+            return PhysicalConfiguration(R, r, torch.zeros((), device=r.device))
+        return PhysicalConfiguration(R, r, torch.zeros(len(r), dtype=torch.int32, device=r.device))
+
+    def _engine(self, params):
+        return self.ansatz.engine_for(self.hamil, params)
+
+    def update(self, state, params, R):
+        eng = self._engine(params)
+        sign, log = eng.wf_forward(state['r'], R)
+        return {**state, 'psi': Psi(sign, log)}
+
+    def init(self, rng, params, n, R):
+        eng = self._engine(params)
+        g = np.random.default_rng(int(rng))
+        h = self.hamil
+        Rn = np.asarray(R.detach().cpu() if torch.is_tensor(R) else R, dtype=np.float64)
+        r = np.stack([self.sample_initializer(g, h.mol.charges, h.ns_valence, Rn, h.n_up, h.n_down) for _ in range(n)])
+        state = {
+            'r': torch.as_tensor(r, dtype=eng.dtype, device=eng.device),
+            'age': torch.zeros(n, dtype=torch.int32, device=eng.device),
+            'tau': torch.tensor([self.initial_tau], dtype=eng.dtype, device=eng.device),
+        }
+        return self.update(state, params, torch.as_tensor(Rn, dtype=eng.dtype, device=eng.device))
+
+    def sample(self, rng, state, params, R, *, walker_offset=0, noise_normal=None, noise_uniform=None):
+        eng = self._engine(params)
+        st = {'r': state['r'], 'sign': state['psi'].sign, 'log': state['psi'].log, 'age': state['age'], 'tau': state['tau']}
+        stats = eng.mcmc_sweep(st, R, self.length, target_acceptance=self.target_acceptance, max_age=self.max_age,
+                               seed=int(rng), step0=self._step, walker_offset=walker_offset,
+                               noise_normal=noise_normal, noise_uniform=noise_uniform)
+        self._step += self.length
+        new = {'r': st['r'], 'psi': Psi(st['sign'], st['log']), 'age': st['age'], 'tau': st['tau']}
+        return new, self.phys_conf(R, new['r']), dict(zip(STAT_NAMES, stats))
+
+
+class DecorrSampler(MetropolisSampler):
+    """DecorrSampler(length) chained in front of MetropolisSampler (reference:
+    electron_samplers.py:333-357; `chain(DecorrSampler(length=30), MetropolisSampler(...))` in
+    conf/task/sampler_factory/elec_sampler/decorr_metropolis_psiformer.yaml): `length` sub-steps per
+    sample(), statistics of the last one.  The whole scan is one dqmc_mcmc_sweep call."""
+
+    def __init__(self, hamil, wf, *, length, **kw):
+        super().__init__(hamil, wf, **kw)
+        self.length = int(length)

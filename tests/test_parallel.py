@@ -1,0 +1,89 @@
+"""CPU, gloo, world_size = 2: walker sharding and the fused per-step statistics exchange
+(deepqmc_b200/parallel.py; reference: src/deepqmc/parallel.py, loss/energy.py:63-74)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from deepqmc_b200 import parallel
+
+    r, w = parallel.init_from_env('gloo')
+    assert (r, w) == (rank, world)
+    B = 12
+    g = torch.Generator().manual_seed(0)
+    E_all = torch.randn(B, generator=g, dtype=torch.float64)
+    stats_all = {'hamil/E_kin': torch.randn(B, generator=g, dtype=torch.float64),
+                 'hamil/V_el': torch.randn(B, generator=g, dtype=torch.float64)}
+    lo, hi = parallel.shard_bounds(B)
+    out = parallel.energy_statistics(E_all[lo:hi], {k: v[lo:hi] for k, v in stats_all.items()})
+    gathered = parallel.all_gather_walkers(E_all[lo:hi])
+    ok = (
+        abs(out['energy/mean'].item() - E_all.mean().item()) < 1e-12
+        and abs(out['energy/var'].item() - E_all.var(unbiased=False).item()) < 1e-12
+        and abs(out['energy/max'].item() - E_all.max().item()) < 1e-15
+        and abs(out['energy/min'].item() - E_all.min().item()) < 1e-15
+        and abs(out['hamil/E_kin'].item() - stats_all['hamil/E_kin'].mean().item()) < 1e-12
+        and torch.equal(gathered, E_all)
+        and parallel.rank_seed(5) == 5 + rank
+    )
+    q.put((rank, bool(ok)))
+    torch.distributed.destroy_process_group()
+
+
+def test_sharded_statistics_gloo_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_shard_bounds_contract():
+    from deepqmc_b200 import parallel
+
+    assert parallel.shard_bounds(4096, 3, 8) == (1536, 2048)
+    with pytest.raises(ValueError):  # electron_batch_size % device_count == 0 (validate_kwargs.py:45-48)
+        parallel.shard_bounds(10, 0, 4)
+    E = torch.arange(6, dtype=torch.float64)
+    out = parallel.energy_statistics(E)  # single process: no collective
+    assert out['energy/mean'].item() == 2.5 and out['energy/count'].item() == 6
+
+
+def test_initializer_and_host_hamiltonian():
+    """Walker initialiser (host, one-off): right shapes, spins on the right atoms, charge-neutral
+    assignment (reference: electron_sample_initializers.py:43-160; tests/test_hamil.py:28-31)."""
+    import numpy as np
+
+    from deepqmc_b200.hamil import MolecularHamiltonian
+    from deepqmc_b200.molecule import Molecule
+    from deepqmc_b200.sampling import AtomCenteredElectronInitializer
+
+    for name, ecp in (('LiH', None), ('N2', None), ('benzene', 'ccECP'), ('C', 'ccECP')):
+        h = MolecularHamiltonian(mol=Molecule.from_name(name), ecp_type=ecp)
+        init = AtomCenteredElectronInitializer()
+        g = np.random.default_rng(0)
+        r = init(g, h.mol.charges, h.ns_valence, h.mol.coords, h.n_up, h.n_down)
+        assert r.shape == (h.n_up + h.n_down, 3) and np.isfinite(r).all()
+        el = init.assign_electrons(g, h.ns_valence, h.n_up, h.n_down)
+        assert el.sum() == h.n_up + h.n_down
+        up, dn = init.assign_spins(g, el, h.mol.coords, h.n_up, h.n_down)
+        assert up.sum() == h.n_up and dn.sum() == h.n_down and ((up + dn) == el).all()
+    hb = MolecularHamiltonian(mol=Molecule.from_name('benzene'), ecp_type='ccECP')
+    assert (hb.n_up, hb.n_down) == (15, 15) and list(hb.ns_valence) == [4.0] * 6 + [1.0] * 6
+    assert list(hb.pot.nuc_with_nl_pot) == [0, 1, 2, 3, 4, 5]
