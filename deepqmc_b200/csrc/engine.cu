@@ -2,6 +2,7 @@
 // sequencing, C ABI (include/dqmc_b200.h).  Built by nvcc for sm_100a; with -DDQMC_EMU the same
 // file builds against tools/cuda_emu for CPU-side logic checks during development (never shipped).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -135,6 +136,7 @@ struct Engine : EngineBase {
   T* d_nl_params = nullptr;
   int* d_nl_nuc = nullptr;
   int J = 0;  // nuclei with a non-local channel
+  int attn_tb = 1, attn_tb1 = 1;
   int N, M, d, K, KN, H, dh, T3;
   size_t max_smem = 0;
   int n_sms = 148;
@@ -209,7 +211,9 @@ struct Engine : EngineBase {
       }
     }
     // opt in to large dynamic shared memory
-    size_t s_attn = attn_smem_bytes<T>(N, dh), s_sl = slater_smem_bytes<T>(N);
+    attn_tb = attn_pick_tb<T>(N, dh, T3, 100 * 1024);
+    if (const char* ev = std::getenv("DQMC_ATTN_TB")) { int x = std::atoi(ev); if (x >= 1 && x <= T3) attn_tb = x; }
+    size_t s_attn = attn_smem_bytes<T>(N, dh, attn_tb), s_sl = slater_smem_bytes<T>(N);
     max_smem = s_attn > s_sl ? s_attn : s_sl;
     if (max_smem > 227 * 1024) { err = "system too large for the shared-memory tiling (N)"; return 2; }
     DQ_CHECK(cudaFuncSetAttribute(attn_fl_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_attn));
@@ -377,8 +381,11 @@ struct Engine : EngineBase {
     for (int l = 0; l < cfg.n_layers; ++l) {
       std::string p = "L" + std::to_string(l) + ".";
       gemm(X, d, (p + "wqkv").c_str(), nullptr, 0, 3 * d, nullptr, nullptr, 0, w.QKV, 3 * d, rows, 3 * d, d, S, 0, N, st);
-      DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh), st, (const T*)w.QKV, 3 * d, O, d,
-                N, S, dh, d, scale);
+      {
+        const int tb = S > 1 ? attn_tb : 1;
+        DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh, tb), st, (const T*)w.QKV, 3 * d, O,
+                  d, N, S, dh, d, scale, tb);
+      }
       gemm(O, d, (p + "wo").c_str(), nullptr, 0, d, nullptr, X, d, w.A, d, rows, d, d, S, 0, N, st);
       gemm(w.A, d, (p + "w1").c_str(), nullptr, 0, d, P(p + "b1"), nullptr, 0, w.M1, d, rows, d, d, S, 0, N, st);
       DQ_LAUNCH(tanh_fl_kernel<T>, dim3(Bc * N, (d + 127) / 128), dim3(128), 0, st, w.M1, d, (const T*)nullptr, 0, S, d,
@@ -389,8 +396,9 @@ struct Engine : EngineBase {
     }
     // per-spin backflow heads: rows of electron e across walkers, weights by spin
     gemm(X, d, "bf.up", "bf.dn", cfg.n_up, KN, nullptr, nullptr, 0, w.BF, KN, Bc * S, KN, d, S, 1, N, st);
-    DQ_LAUNCH(slater_kernel<T>, dim3(Bc, K), dim3(128), slater_smem_bytes<T>(N), st, r, R, Rb, N, M, cfg.n_up, K, S,
-              P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog,
+    const int sl_wpb = slater_warps_per_block<T>(N);
+    DQ_LAUNCH(slater_kernel<T>, dim3((Bc * K + sl_wpb - 1) / sl_wpb), dim3(32 * sl_wpb), slater_smem_bytes<T>(N), st, r, R,
+              Rb, N, M, cfg.n_up, K, S, Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog,
               w.dgrad, w.dlap);
     FinalizeCfg fc;
     fc.N = N; fc.M = M; fc.n_up = cfg.n_up; fc.K = K; fc.S = S; fc.cusp_kind = cfg.cusp_kind;

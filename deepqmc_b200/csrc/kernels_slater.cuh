@@ -17,30 +17,32 @@ namespace dq {
 // ------------------------------------------------------------------------------------------
 template <class T>
 __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M, int n_up,
-                              int K, int S, const T* __restrict__ pi_up, const T* __restrict__ pi_dn,
+                              int K, int S, int total, const T* __restrict__ pi_up, const T* __restrict__ pi_dn,
                               const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn,
                               const T* __restrict__ BF, int ldb, T* __restrict__ det_sign, T* __restrict__ det_log,
                               T* __restrict__ det_grad, T* __restrict__ det_lap) {
+  // One WARP per (walker b, determinant k): all phases are lane-strided loops separated by
+  // __syncwarp, reductions are warp shuffles (no block barriers: N <= ~40 electrons).
   DQMC_DYN_SMEM(smem_raw);
   const int NP = N + 1, N2 = 2 * N + 1;
-  T* env = reinterpret_cast<T*>(smem_raw);  // [N][NP]
-  T* denv = env + N * NP;                    // [3][N][NP]
-  T* bfv = denv + 3 * N * NP;                // [N][NP]
-  T* AL = bfv + N * NP;                      // [N][NP]
-  T* At = AL + N * NP;                       // [N][NP]
-  T* Bt = At + N * NP;                       // [N][NP]
-  T* aug = Bt + N * NP;                      // [N][N2]
-  T* fcol = aug + N * N2;                    // [N]
-  T* scratch = fcol + N;                     // [66]
-  T* misc = scratch + 66;                    // [4]: logdet, sign, pivot row (as T)
-  const int b = blockIdx.x, k = blockIdx.y;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int gw = blockIdx.x * wpb + wib;
+  const size_t per_warp = (size_t)7 * N * NP + (size_t)N * N2 + N;
+  T* env = reinterpret_cast<T*>(smem_raw) + per_warp * wib;  // [N][NP]
+  T* denv = env + N * NP;                                     // [3][N][NP]
+  T* bfv = denv + 3 * N * NP;                                 // [N][NP]
+  T* AL = bfv + N * NP;                                       // [N][NP]  (reused as B^t)
+  T* At = AL + N * NP;                                        // [N][NP]
+  T* aug = At + N * NP;                                       // [N][N2]
+  T* fcol = aug + N * N2;                                     // [N]
+  if (gw >= total) return;
+  const int b = gw / K, k = gw % K;
   const int T3 = S > 1 ? S - 2 : 0;
   const T* rb = r + (size_t)b * N * 3;
   const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
   const size_t brow0 = (size_t)b * N * S;
 
-  for (int idx = tid; idx < N * N; idx += nt) {
+  for (int idx = lane; idx < N * N; idx += 32) {
     const int i = idx / N, mu = idx % N;
     const T* pi = (i < n_up ? pi_up : pi_dn) + (size_t)(k * N + mu) * M;
     const T* ze = (i < n_up ? zeta_up : zeta_dn) + (size_t)(k * N + mu) * M;
@@ -62,8 +64,7 @@ __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, 
     T bf0 = bfrow[0];
     env[i * NP + mu] = e;
     bfv[i * NP + mu] = bf0;
-    T a0 = e * bf0;
-    aug[i * N2 + mu] = a0;
+    aug[i * N2 + mu] = e * bf0;
     aug[i * N2 + N + mu] = (i == mu) ? T(1) : T(0);
     if (S > 1) {
       denv[(0 * N + i) * NP + mu] = de0;
@@ -74,98 +75,105 @@ __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, 
       AL[i * NP + mu] = le * bf0 + e * bfl + T(2) * (de0 * x0 + de1 * x1 + de2 * x2);
     }
   }
-  if (tid == 0) { misc[0] = T(0); misc[1] = T(1); }
-  __syncthreads();
+  __syncwarp();
 
-  // ---- Gauss-Jordan with partial pivoting on [A | I] ------------------------------------
+  // ---- Gauss-Jordan with partial pivoting on [A | I] (pivots == LU with partial pivoting) -----
+  T logdet = T(0), sgn = T(1);
   for (int c = 0; c < N; ++c) {
-    if (tid < 32) {
-      T best = T(-1);
-      int bi = c;
-      for (int rr = c + tid; rr < N; rr += 32) {
-        T v = m_abs(aug[rr * N2 + c]);
-        if (v > best) { best = v; bi = rr; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        T ob = __shfl_xor_sync(0xffffffffu, best, o);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-      }
-      if (tid == 0) misc[2] = (T)bi;
+    T best = T(-1);
+    int bi = c;
+    for (int rr = c + lane; rr < N; rr += 32) {
+      T vv = m_abs(aug[rr * N2 + c]);
+      if (vv > best) { best = vv; bi = rr; }
     }
-    __syncthreads();
-    const int prow = (int)misc[2];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      T ob = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    const int prow = bi;
     if (prow != c) {
-      for (int j = tid; j < 2 * N; j += nt) {
+      for (int j = lane; j < 2 * N; j += 32) {
         T t0 = aug[c * N2 + j];
         aug[c * N2 + j] = aug[prow * N2 + j];
         aug[prow * N2 + j] = t0;
       }
     }
-    __syncthreads();
+    __syncwarp();
     const T pv = aug[c * N2 + c];
-    if (tid == 0) {
-      misc[0] += m_log(m_abs(pv));
-      T sg = pv > T(0) ? T(1) : (pv < T(0) ? T(-1) : T(0));
-      misc[1] *= (prow != c ? -sg : sg);
-    }
-    for (int rr = tid; rr < N; rr += nt) fcol[rr] = aug[rr * N2 + c];
-    __syncthreads();
+    logdet += m_log(m_abs(pv));
+    T sg = pv > T(0) ? T(1) : (pv < T(0) ? T(-1) : T(0));
+    sgn *= (prow != c ? -sg : sg);
+    for (int rr = lane; rr < N; rr += 32) fcol[rr] = aug[rr * N2 + c];
+    __syncwarp();
     const T ipv = T(1) / pv;
-    for (int j = tid; j < 2 * N; j += nt) aug[c * N2 + j] *= ipv;
-    __syncthreads();
-    for (int idx = tid; idx < N * 2 * N; idx += nt) {
+    for (int j = lane; j < 2 * N; j += 32) aug[c * N2 + j] *= ipv;
+    __syncwarp();
+    for (int idx = lane; idx < N * 2 * N; idx += 32) {
       int rr = idx / (2 * N), j = idx % (2 * N);
       if (rr != c) aug[rr * N2 + j] -= fcol[rr] * aug[c * N2 + j];
     }
-    __syncthreads();
+    __syncwarp();
   }
   const size_t bk = (size_t)b * K + k;
-  if (tid == 0) { det_log[bk] = misc[0]; det_sign[bk] = misc[1]; }
+  if (lane == 0) { det_log[bk] = logdet; det_sign[bk] = sgn; }
   if (S == 1) return;
 
   // Ainv[mu][i] = aug[mu][N + i]
-  T lap_part = T(0), dummy = T(0);
-  for (int idx = tid; idx < N * N; idx += nt) {
+  T lap = T(0);
+  for (int idx = lane; idx < N * N; idx += 32) {
     int i = idx / N, mu = idx % N;
-    lap_part += aug[mu * N2 + N + i] * AL[i * NP + mu];
+    lap += aug[mu * N2 + N + i] * AL[i * NP + mu];
   }
-  block_sum2(lap_part, dummy, scratch);
-  T lap = lap_part;
+  lap = warp_sum(lap);
+  T* Bt = AL;  // A^L no longer needed
   for (int t = 0; t < T3; ++t) {
     const int it = t / 3, ct = t % 3;
-    for (int idx = tid; idx < N * N; idx += nt) {
+    __syncwarp();
+    for (int idx = lane; idx < N * N; idx += 32) {
       int i = idx / N, mu = idx % N;
       T bft = BF[(brow0 + (size_t)i * S + 1 + t) * ldb + k * N + mu];
       T a = env[i * NP + mu] * bft;
       if (i == it) a += denv[(ct * N + i) * NP + mu] * bfv[i * NP + mu];
       At[i * NP + mu] = a;
     }
-    __syncthreads();
-    for (int idx = tid; idx < N * N; idx += nt) {
+    __syncwarp();
+    for (int idx = lane; idx < N * N; idx += 32) {
       int mu = idx / N, nu = idx % N;
       T a = T(0);
       for (int i = 0; i < N; ++i) a += aug[mu * N2 + N + i] * At[i * NP + nu];
       Bt[mu * NP + nu] = a;
     }
-    __syncthreads();
+    __syncwarp();
     T tr2 = T(0), gt = T(0);
-    for (int idx = tid; idx < N * N; idx += nt) {
+    for (int idx = lane; idx < N * N; idx += 32) {
       int mu = idx / N, nu = idx % N;
       tr2 += Bt[mu * NP + nu] * Bt[nu * NP + mu];
       if (mu == nu) gt += Bt[mu * NP + mu];
     }
-    block_sum2(tr2, gt, scratch);
+    tr2 = warp_sum(tr2);
+    gt = warp_sum(gt);
     lap -= tr2;
-    if (tid == 0) det_grad[bk * T3 + t] = gt;
+    if (lane == 0) det_grad[bk * T3 + t] = gt;
   }
-  if (tid == 0) det_lap[bk] = lap;
+  if (lane == 0) det_lap[bk] = lap;
 }
 
 template <class T>
+inline size_t slater_smem_per_warp(int N) {
+  return sizeof(T) * ((size_t)7 * N * (N + 1) + (size_t)N * (2 * N + 1) + N);
+}
+// warps per block: as many as fit ~96 KB (two blocks per SM), at most 8
+template <class T>
+inline int slater_warps_per_block(int N) {
+  size_t pw = slater_smem_per_warp<T>(N);
+  int w = (int)((96 * 1024) / pw);
+  return w < 1 ? 1 : (w > 8 ? 8 : w);
+}
+template <class T>
 inline size_t slater_smem_bytes(int N) {
-  return sizeof(T) * ((size_t)8 * N * (N + 1) + (size_t)N * (2 * N + 1) + N + 66 + 4);
+  return slater_smem_per_warp<T>(N) * slater_warps_per_block<T>(N);
 }
 
 // ------------------------------------------------------------------------------------------

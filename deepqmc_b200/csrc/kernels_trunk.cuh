@@ -227,38 +227,41 @@ __global__ void tanh_fl_kernel(T* __restrict__ Z, int ldz, const T* __restrict__
 // ------------------------------------------------------------------------------------------
 template <class T>
 __global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict__ O, int ldo, int N, int S, int dh,
-                               int dmodel, T scale) {
+                               int dmodel, T scale, int TB) {
+  // Tangent slots are processed in chunks of TB so that every phase has (TB x N x N) or (N x dh)
+  // independent work items (small molecules: all 3N tangents in one chunk).
   DQMC_DYN_SMEM(smem_raw);
-  const int dhp = dh + 1;
+  const int dhp = dh + 1, NN = N * N;
   T* q = reinterpret_cast<T*>(smem_raw);
   T* k = q + N * dhp;
   T* v = k + N * dhp;
-  T* qt = v + N * dhp;
-  T* kt = qt + N * dhp;
-  T* vt = kt + N * dhp;
-  T* p = vt + N * dhp;  // [N][N]
-  T* st = p + N * N;
-  T* u = st + N * N;
-  T* qk = u + N * N;
-  T* olap = qk + N * N;  // [N][dh]
-  T* mrow = olap + N * dh;  // [N]
-  T* vrow = mrow + N;       // [N]
+  T* qt = v + N * dhp;            // [TB][N][dhp]
+  T* kt = qt + (size_t)TB * N * dhp;
+  T* vt = kt + (size_t)TB * N * dhp;
+  T* p = vt + (size_t)TB * N * dhp;  // [N][N]
+  T* st = p + NN;                 // [TB][N][N]
+  T* u = st + (size_t)TB * NN;    // [N][N]
+  T* qk = u + NN;                 // [N][N]
+  T* olap = qk + NN;              // [N][dh]
+  T* mrow = olap + N * dh;        // [TB][N]
+  T* vrow = mrow + TB * N;        // [N]
   const int b = blockIdx.x, h = blockIdx.y;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int T3 = S > 1 ? S - 2 : 0;
   const size_t row0 = (size_t)b * N * S;
-  auto load3 = [&](int slot, T* dq_, T* dk_, T* dv_) {
-    for (int idx = tid; idx < N * dh; idx += nt) {
-      int i = idx / dh, e = idx % dh;
-      const T* src = QKV + (row0 + (size_t)i * S + slot) * ldq + h * dh + e;
-      dq_[i * dhp + e] = src[0];
-      dk_[i * dhp + e] = src[dmodel];
-      dv_[i * dhp + e] = src[2 * dmodel];
+  auto load3 = [&](int slot0, int nslot, T* dq_, T* dk_, T* dv_) {
+    for (int idx = tid; idx < nslot * N * dh; idx += nt) {
+      int e = idx % dh, i = (idx / dh) % N, t = idx / (dh * N);
+      const T* src = QKV + (row0 + (size_t)i * S + slot0 + t) * ldq + h * dh + e;
+      int o = (t * N + i) * dhp + e;
+      dq_[o] = src[0];
+      dk_[o] = src[dmodel];
+      dv_[o] = src[2 * dmodel];
     }
   };
-  load3(0, q, k, v);
+  load3(0, 1, q, k, v);
   __syncthreads();
-  for (int idx = tid; idx < N * N; idx += nt) {
+  for (int idx = tid; idx < NN; idx += nt) {
     int i = idx / N, j = idx % N;
     T a = T(0);
     for (int e = 0; e < dh; ++e) a += q[i * dhp + e] * k[j * dhp + e];
@@ -288,49 +291,71 @@ __global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict
     O[(row0 + (size_t)i * S) * ldo + h * dh + e] = a;
   }
   if (S == 1) return;
-  for (int t = 0; t < T3; ++t) {
-    __syncthreads();  // previous iteration done with qt/kt/vt/st
-    load3(1 + t, qt, kt, vt);
+  for (int t0 = 0; t0 < T3; t0 += TB) {
+    const int tc = T3 - t0 < TB ? T3 - t0 : TB;
+    __syncthreads();  // previous chunk done with qt/kt/vt/st
+    load3(1 + t0, tc, qt, kt, vt);
     __syncthreads();
-    for (int idx = tid; idx < N * N; idx += nt) {
-      int i = idx / N, j = idx % N;
-      T a = T(0), c = T(0);
-      for (int e = 0; e < dh; ++e) {
-        a += qt[i * dhp + e] * k[j * dhp + e] + q[i * dhp + e] * kt[j * dhp + e];
-        c += qt[i * dhp + e] * kt[j * dhp + e];
-      }
+    for (int idx = tid; idx < tc * NN; idx += nt) {
+      int j = idx % N, i = (idx / N) % N, t = idx / NN;
+      const T* qti = qt + (t * N + i) * dhp;
+      const T* ktj = kt + (t * N + j) * dhp;
+      T a = T(0);
+      for (int e = 0; e < dh; ++e) a += qti[e] * k[j * dhp + e] + q[i * dhp + e] * ktj[e];
       st[idx] = a * scale;
+    }
+    for (int idx = tid; idx < NN; idx += nt) {
+      int i = idx / N, j = idx % N;
+      T c = T(0);
+      for (int t = 0; t < tc; ++t) {
+        const T* qti = qt + (t * N + i) * dhp;
+        const T* ktj = kt + (t * N + j) * dhp;
+        for (int e = 0; e < dh; ++e) c += qti[e] * ktj[e];
+      }
       qk[idx] += c;
     }
     __syncthreads();
-    for (int i = tid; i < N; i += nt) {
+    for (int idx = tid; idx < tc * N; idx += nt) {  // (t, i)
+      const T* pr = p + (idx % N) * N;
+      const T* sr = st + (size_t)idx * N;
       T m = T(0);
-      for (int j = 0; j < N; ++j) m += p[i * N + j] * st[i * N + j];
-      mrow[i] = m;
+      for (int j = 0; j < N; ++j) m += pr[j] * sr[j];
+      mrow[idx] = m;
     }
     __syncthreads();
-    for (int idx = tid; idx < N * N; idx += nt) {
+    for (int idx = tid; idx < NN; idx += nt) {
       int i = idx / N;
-      T dv_ = st[idx] - mrow[i];
-      u[idx] += dv_ * dv_;
-      st[idx] = p[idx] * dv_;  // p^t
+      T uu = T(0), pp = p[idx];
+      for (int t = 0; t < tc; ++t) {
+        T dv_ = st[t * NN + idx] - mrow[t * N + i];
+        uu += dv_ * dv_;
+        st[t * NN + idx] = pp * dv_;  // p^t
+      }
+      u[idx] += uu;
     }
     __syncthreads();
     for (int idx = tid; idx < N * dh; idx += nt) {
       int i = idx / dh, e = idx % dh;
-      T a = T(0), c = T(0);
-      for (int j = 0; j < N; ++j) {
-        a += st[i * N + j] * v[j * dhp + e] + p[i * N + j] * vt[j * dhp + e];
-        c += st[i * N + j] * vt[j * dhp + e];
+      T c2 = T(0);
+      for (int t = 0; t < tc; ++t) {
+        const T* sr = st + t * NN + i * N;
+        const T* vtt = vt + (size_t)t * N * dhp + e;
+        T a = T(0), c = T(0);
+        for (int j = 0; j < N; ++j) {
+          T vtj = vtt[j * dhp];
+          a += sr[j] * v[j * dhp + e] + p[i * N + j] * vtj;
+          c += sr[j] * vtj;
+        }
+        c2 += c;
+        O[(row0 + (size_t)i * S + 1 + t0 + t) * ldo + h * dh + e] = a;
       }
-      olap[idx] += T(2) * c;
-      O[(row0 + (size_t)i * S + 1 + t) * ldo + h * dh + e] = a;
+      olap[idx] += T(2) * c2;
     }
   }
   __syncthreads();
-  load3(1 + T3, qt, kt, vt);
+  load3(1 + T3, 1, qt, kt, vt);
   __syncthreads();
-  for (int idx = tid; idx < N * N; idx += nt) {
+  for (int idx = tid; idx < NN; idx += nt) {
     int i = idx / N, j = idx % N;
     T a = T(0);
     for (int e = 0; e < dh; ++e) a += qt[i * dhp + e] * k[j * dhp + e] + q[i * dhp + e] * kt[j * dhp + e];
@@ -347,7 +372,7 @@ __global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict
     vrow[i] = V;
   }
   __syncthreads();
-  for (int idx = tid; idx < N * N; idx += nt) {
+  for (int idx = tid; idx < NN; idx += nt) {
     int i = idx / N;
     st[idx] = p[idx] * (u[idx] - vrow[i] + st[idx] - mrow[i]);
   }
@@ -361,8 +386,16 @@ __global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict
 }
 
 template <class T>
-inline size_t attn_smem_bytes(int N, int dh) {
-  return sizeof(T) * ((size_t)6 * N * (dh + 1) + 4 * N * N + (size_t)N * dh + 2 * N);
+inline size_t attn_smem_bytes(int N, int dh, int TB) {
+  return sizeof(T) * ((size_t)3 * N * (dh + 1) + (size_t)3 * TB * N * (dh + 1) + (size_t)N * N * (3 + TB) +
+                      (size_t)N * dh + (size_t)TB * N + N);
+}
+// largest tangent chunk whose working set fits `budget` bytes of shared memory
+template <class T>
+inline int attn_pick_tb(int N, int dh, int T3, size_t budget) {
+  int tb = T3 > 0 ? T3 : 1;
+  while (tb > 1 && attn_smem_bytes<T>(N, dh, tb) > budget) --tb;
+  return tb;
 }
 
 }  // namespace dq
