@@ -141,7 +141,8 @@ struct SmemLayout {
   static __host__ __device__ int w_lo(int s, int BN) { return s * stage_bytes(BN) + 2 * kBM * 128 + BN * 128; }
   static __host__ __device__ int stage_bytes(int BN) { return 2 * kBM * 128 + 2 * BN * 128; }
   static __host__ __device__ int bars(int BN) { return kStages * stage_bytes(BN); }
-  static __host__ __device__ int total(int BN) { return bars(BN) + 256 + 1024; }  // + barriers + alignment slack
+  static __host__ __device__ int epi(int BN) { return bars(BN) + 256; }              // 4 warps x 32 x 33 floats
+  static __host__ __device__ int total(int BN) { return epi(BN) + 4 * 32 * 33 * 4 + 1024; }  // + alignment slack
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -190,38 +191,43 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
   const uint32_t tmem_base = *tmem_base_slot;
 
   if (warp >= 4 && warp < 8) {
-    // ===================== A producers: one thread per tile row =============================
-    const int trow = threadIdx.x - 128;
+    // ===================== A producers ======================================================
+    // warp pw owns tile rows [32 pw, 32 pw + 32); instruction j of a k-block loads rows
+    // 32 pw + 4 j + (lane >> 3), 16-byte chunk (lane & 7): every LDG covers 4 full 128-byte lines.
+    const int pw = warp - 4;
+    const int chunk = lane & 7, rsub = lane >> 3;
     uint32_t it = 0;  // running k-block counter (ring position)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int nt = tile % NT, mt = (tile / NT) % MT, z = tile / (NT * MT);
-      (void)nt;
-      const int m = mt * kBM + trow;
-      const bool valid = m < p.M;
-      const float* arow = valid ? p.A + phys_row(p, m, z) * p.lda : p.A;
+      const int mt = (tile / NT) % MT, z = tile / (NT * MT);
+      const float* rowp[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int m = mt * kBM + pw * 32 + 4 * j + rsub;
+        rowp[j] = m < p.M ? p.A + phys_row(p, m, z) * p.lda + chunk * 4 : nullptr;
+      }
       float4 cur[8], nxt[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) cur[c] = valid ? __ldg((const float4*)(arow) + c) : make_float4(0, 0, 0, 0);
+      for (int j = 0; j < 8; ++j) cur[j] = rowp[j] ? __ldg((const float4*)rowp[j]) : make_float4(0, 0, 0, 0);
       for (int kb = 0; kb < KB; ++kb, ++it) {
         if (kb + 1 < KB) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            nxt[c] = valid ? __ldg((const float4*)(arow + (kb + 1) * kBK) + c) : make_float4(0, 0, 0, 0);
+          for (int j = 0; j < 8; ++j)
+            nxt[j] = rowp[j] ? __ldg((const float4*)(rowp[j] + (kb + 1) * kBK)) : make_float4(0, 0, 0, 0);
         }
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
         mbar_wait(&empty[s], ph ^ 1, p.err_flag);
         unsigned char* ah = smem + SmemLayout::a_hi(s, BN);
         unsigned char* al = smem + SmemLayout::a_lo(s, BN);
-        const int rbase = (trow >> 3) * 1024 + (trow & 7) * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float4 v = cur[c], h, l;
+        for (int j = 0; j < 8; ++j) {
+          const int trow = pw * 32 + 4 * j + rsub;
+          float4 v = cur[j], h, l;
           h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
           h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
           h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
           h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-          const int off = rbase + ((c ^ (trow & 7)) << 4);
+          const int off = (trow >> 3) * 1024 + (trow & 7) * 128 + ((chunk ^ (trow & 7)) << 4);
           *(float4*)(ah + off) = h;
           *(float4*)(al + off) = l;
         }
@@ -229,7 +235,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
         mbar_arrive(&full_a[s]);
         if (kb + 1 < KB) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) cur[c] = nxt[c];
+          for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
         }
       }
     }
@@ -286,48 +292,43 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
     }
   } else {
     // ===================== epilogue: warps 0-3 <-> TMEM lanes 32*warp .. +31 ================
+    // tcgen05.ld hands each lane one accumulator ROW; a 32x33 shared-memory transpose per warp turns
+    // that into one 128-byte coalesced global store (and residual load) per row and chunk.
+    float* stage = (float*)(smem + SmemLayout::epi(BN)) + warp * 32 * 33;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const int nt = tile % NT, mt = (tile / NT) % MT, z = tile / (NT * MT);
       const int acc = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
       const int m = mt * kBM + warp * 32 + lane;
-      const bool valid = m < p.M;
-      const size_t pr = valid ? phys_row(p, m, z) : 0;
-      const bool value_row = (pr % (size_t)p.S) == 0;
+      const int my_valid = m < p.M ? 1 : 0;
+      const unsigned long long my_pr = my_valid ? (unsigned long long)phys_row(p, m, z) : 0ull;
+      const int my_value_row = (my_pr % (unsigned long long)p.S) == 0 ? 1 : 0;
       mbar_wait(&tmem_full[acc], aph, p.err_flag);
       tc_fence_after();
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
         tmem_ld_wait();
-        const int n0 = nt * BN + c0;
-        if (valid && n0 < p.N) {
-          float* crow = p.C + pr * p.ldc + n0;
-          const float* rrow = p.Res ? p.Res + pr * p.ldr + n0 : nullptr;
-          if (n0 + 32 <= p.N) {
+        const int col = nt * BN + c0 + lane;
+        if (nt * BN + c0 < p.N) {  // warp-uniform
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                     __uint_as_float(v[j + 3]));
-              if (p.bias && value_row) {
-                float4 bb = __ldg((const float4*)(p.bias + n0 + j));
-                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-              }
-              if (rrow) {
-                float4 rr = *(const float4*)(rrow + j);
-                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-              }
-              *(float4*)(crow + j) = o;
-            }
-          } else {
-            for (int j = 0; j < 32 && n0 + j < p.N; ++j) {
-              float o = __uint_as_float(v[j]);
-              if (p.bias && value_row) o += p.bias[n0 + j];
-              if (rrow) o += rrow[j];
-              crow[j] = o;
+          for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(v[j]);
+          __syncwarp();
+          const float bcol = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.f;
+#pragma unroll 4
+          for (int j = 0; j < 32; ++j) {
+            const int vj = __shfl_sync(0xffffffffu, my_valid, j);
+            const unsigned long long prj = __shfl_sync(0xffffffffu, my_pr, j);
+            const int valj = __shfl_sync(0xffffffffu, my_value_row, j);
+            if (vj && col < p.N) {
+              float o = stage[j * 33 + lane];
+              if (valj) o += bcol;
+              if (p.Res) o += p.Res[prj * p.ldr + col];
+              p.C[prj * p.ldc + col] = o;
             }
           }
+          __syncwarp();
         }
       }
       tc_fence_before();
