@@ -137,6 +137,7 @@ struct Engine : EngineBase {
   int* d_nl_nuc = nullptr;
   int J = 0;  // nuclei with a non-local channel
   int attn_tb = 1, attn_tb1 = 1;
+  bool attn_f32 = false;
   int N, M, d, K, KN, H, dh, T3;
   size_t max_smem = 0;
   int n_sms = 148;
@@ -212,11 +213,17 @@ struct Engine : EngineBase {
     }
     // opt in to large dynamic shared memory
     attn_tb = attn_pick_tb<T>(N, dh, T3, 100 * 1024);
+    attn_f32 = std::is_same<T, float>::value && dh % 16 == 0 && !std::getenv("DQMC_ATTN_GENERIC");
+    if (attn_f32) attn_tb = attn_f32_pick_tb(N, dh, T3, 48 * 1024);
     if (const char* ev = std::getenv("DQMC_ATTN_TB")) { int x = std::atoi(ev); if (x >= 1 && x <= T3) attn_tb = x; }
-    size_t s_attn = attn_smem_bytes<T>(N, dh, attn_tb), s_sl = slater_smem_bytes<T>(N);
+    size_t s_attn = attn_f32 ? attn_f32_smem_bytes(N, dh, attn_tb) : attn_smem_bytes<T>(N, dh, attn_tb);
+    size_t s_sl = slater_smem_bytes<T>(N);
     max_smem = s_attn > s_sl ? s_attn : s_sl;
     if (max_smem > 227 * 1024) { err = "system too large for the shared-memory tiling (N)"; return 2; }
-    DQ_CHECK(cudaFuncSetAttribute(attn_fl_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_attn));
+    if (attn_f32)
+      DQ_CHECK(cudaFuncSetAttribute(attn_fl_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_attn));
+    else
+      DQ_CHECK(cudaFuncSetAttribute(attn_fl_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_attn));
     DQ_CHECK(cudaFuncSetAttribute(slater_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_sl));
     if (cfg.gemm_backend == DQMC_GEMM_TCGEN05) {
 #if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
@@ -383,8 +390,18 @@ struct Engine : EngineBase {
       gemm(X, d, (p + "wqkv").c_str(), nullptr, 0, 3 * d, nullptr, nullptr, 0, w.QKV, 3 * d, rows, 3 * d, d, S, 0, N, st);
       {
         const int tb = S > 1 ? attn_tb : 1;
-        DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh, tb), st, (const T*)w.QKV, 3 * d, O,
-                  d, N, S, dh, d, scale, tb);
+        if constexpr (std::is_same<T, float>::value) {
+          if (attn_f32) {
+            DQ_LAUNCH(attn_fl_f32_kernel, dim3(Bc, H), dim3(128), attn_f32_smem_bytes(N, dh, tb), st,
+                      (const float*)w.QKV, 3 * d, (float*)O, d, N, S, dh, d, (float)scale, tb);
+          } else {
+            DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh, tb), st, (const T*)w.QKV,
+                      3 * d, O, d, N, S, dh, d, scale, tb);
+          }
+        } else {
+          DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh, tb), st, (const T*)w.QKV, 3 * d,
+                    O, d, N, S, dh, d, scale, tb);
+        }
       }
       gemm(O, d, (p + "wo").c_str(), nullptr, 0, d, nullptr, X, d, w.A, d, rows, d, d, S, 0, N, st);
       gemm(w.A, d, (p + "w1").c_str(), nullptr, 0, d, P(p + "b1"), nullptr, 0, w.M1, d, rows, d, d, S, 0, N, st);

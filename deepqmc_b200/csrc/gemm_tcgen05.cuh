@@ -142,7 +142,7 @@ struct SmemLayout {
   static __host__ __device__ int stage_bytes(int BN) { return 2 * kBM * 128 + 2 * BN * 128; }
   static __host__ __device__ int bars(int BN) { return kStages * stage_bytes(BN); }
   static __host__ __device__ int epi(int BN) { return bars(BN) + 256; }              // 4 warps x 32 x 33 floats
-  static __host__ __device__ int total(int BN) { return epi(BN) + 4 * 32 * 33 * 4 + 1024; }  // + alignment slack
+  static __host__ __device__ int total(int BN) { return epi(BN) + 4 * 32 * 33 * 4 + 4 * 32 * 8 + 1024; }  // + row info + alignment slack
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -205,15 +205,16 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
         const int m = mt * kBM + pw * 32 + 4 * j + rsub;
         rowp[j] = m < p.M ? p.A + phys_row(p, m, z) * p.lda + chunk * 4 : nullptr;
       }
-      float4 cur[8], nxt[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) cur[j] = rowp[j] ? __ldg((const float4*)rowp[j]) : make_float4(0, 0, 0, 0);
-      for (int kb = 0; kb < KB; ++kb, ++it) {
-        if (kb + 1 < KB) {
+      // register ring of 3 k-blocks: loads run two k-blocks ahead of the conversion
+      float4 b0[8], b1[8], b2[8];
+      auto load_kb = [&](float4(&buf)[8], int kbi) {
+        if (kbi < KB) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            nxt[j] = rowp[j] ? __ldg((const float4*)(rowp[j] + (kb + 1) * kBK)) : make_float4(0, 0, 0, 0);
+            buf[j] = rowp[j] ? __ldg((const float4*)(rowp[j] + kbi * kBK)) : make_float4(0, 0, 0, 0);
         }
+      };
+      auto process = [&](const float4(&buf)[8]) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
         mbar_wait(&empty[s], ph ^ 1, p.err_flag);
@@ -222,7 +223,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int trow = pw * 32 + 4 * j + rsub;
-          float4 v = cur[j], h, l;
+          float4 v = buf[j], h, l;
           h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
           h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
           h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
@@ -233,10 +234,15 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
         }
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
         mbar_arrive(&full_a[s]);
-        if (kb + 1 < KB) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
-        }
+        ++it;
+      };
+      load_kb(b0, 0);
+      load_kb(b1, 1);
+      for (int kb = 0; kb < KB; kb += 3) {
+        load_kb(b2, kb + 2);
+        process(b0);
+        if (kb + 1 < KB) { load_kb(b0, kb + 3); process(b1); }
+        if (kb + 2 < KB) { load_kb(b1, kb + 4); process(b2); }
       }
     }
   } else if (warp == 8) {
@@ -293,17 +299,29 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
   } else {
     // ===================== epilogue: warps 0-3 <-> TMEM lanes 32*warp .. +31 ================
     // tcgen05.ld hands each lane one accumulator ROW; a 32x33 shared-memory transpose per warp turns
-    // that into one 128-byte coalesced global store (and residual load) per row and chunk.
+    // that into one 128-byte coalesced global store (and residual load) per row and chunk.  Row
+    // descriptors live in shared memory (one broadcast LDS.64 per row); all residual loads of a
+    // chunk are issued before the first store so 32 loads are in flight per warp.
     float* stage = (float*)(smem + SmemLayout::epi(BN)) + warp * 32 * 33;
+    long long* rowinfo = (long long*)(smem + SmemLayout::epi(BN) + 4 * 32 * 33 * 4) + warp * 32;
+    const float* __restrict__ Resp = p.Res;
+    float* __restrict__ Cp = p.C;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const int nt = tile % NT, mt = (tile / NT) % MT, z = tile / (NT * MT);
       const int acc = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
       const int m = mt * kBM + warp * 32 + lane;
-      const int my_valid = m < p.M ? 1 : 0;
-      const unsigned long long my_pr = my_valid ? (unsigned long long)phys_row(p, m, z) : 0ull;
-      const int my_value_row = (my_pr % (unsigned long long)p.S) == 0 ? 1 : 0;
+      {
+        long long info = -1;  // invalid row
+        if (m < p.M) {
+          const long long pr = (long long)phys_row(p, m, z);
+          info = (pr << 1) | ((pr % p.S) == 0 ? 1 : 0);
+        }
+        __syncwarp();
+        rowinfo[lane] = info;
+        __syncwarp();
+      }
       mbar_wait(&tmem_full[acc], aph, p.err_flag);
       tc_fence_after();
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -312,21 +330,28 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
         tmem_ld_wait();
         const int col = nt * BN + c0 + lane;
         if (nt * BN + c0 < p.N) {  // warp-uniform
+          const bool colok = col < p.N;
 #pragma unroll
           for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(v[j]);
           __syncwarp();
-          const float bcol = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.f;
-#pragma unroll 4
-          for (int j = 0; j < 32; ++j) {
-            const int vj = __shfl_sync(0xffffffffu, my_valid, j);
-            const unsigned long long prj = __shfl_sync(0xffffffffu, my_pr, j);
-            const int valj = __shfl_sync(0xffffffffu, my_value_row, j);
-            if (vj && col < p.N) {
-              float o = stage[j * 33 + lane];
-              if (valj) o += bcol;
-              if (p.Res) o += p.Res[prj * p.ldr + col];
-              p.C[prj * p.ldc + col] = o;
+          const float bcol = (p.bias && colok) ? __ldg(p.bias + col) : 0.f;
+          float res[32];
+          if (Resp) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const long long info = rowinfo[j];
+              res[j] = (info >= 0 && colok) ? __ldg(Resp + (size_t)(info >> 1) * p.ldr + col) : 0.f;
             }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) res[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const long long info = rowinfo[j];
+            float o = stage[j * 33 + lane] + res[j];
+            if (info & 1) o += bcol;
+            if (info >= 0 && colok) Cp[(size_t)(info >> 1) * p.ldc + col] = o;
           }
           __syncwarp();
         }

@@ -398,4 +398,230 @@ inline int attn_pick_tb(int N, int dh, int T3, size_t budget) {
   return tb;
 }
 
+// ------------------------------------------------------------------------------------------
+// fp32 production variant of attn_fl_kernel: same algebra, but shared-memory rows are padded to
+// dh+4 floats so that every operand is fetched with 128-bit LDS (own rows conflict-free, shared
+// rows as broadcasts), the e-range of each dot product is split over 4 adjacent lanes and reduced
+// with shuffles, and global traffic is float4.  Requires dh % 16 == 0.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+}
+__device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
+  acc.x += s * v.x; acc.y += s * v.y; acc.z += s * v.z; acc.w += s * v.w;
+}
+
+__global__ void attn_fl_f32_kernel(const float* __restrict__ QKV, int ldq, float* __restrict__ O, int ldo, int N,
+                                   int S, int dh, int dmodel, float scale, int TB) {
+  DQMC_DYN_SMEM(smem_raw);
+  const int PQ = dh + 4, NN = N * N, d4 = dh / 4;
+  float* q = reinterpret_cast<float*>(smem_raw);
+  float* k = q + N * PQ;
+  float* v = k + N * PQ;
+  float* qt = v + N * PQ;                    // [TB][N][PQ]
+  float* kt = qt + (size_t)TB * N * PQ;
+  float* vt = kt + (size_t)TB * N * PQ;
+  float* olap = vt + (size_t)TB * N * PQ;    // [N][dh]   (16B aligned: all sizes above are multiples of 4 floats)
+  float* p = olap + N * dh;                  // [N][N]
+  float* st = p + NN;                        // [TB][N][N]
+  float* ctp = st + (size_t)TB * NN;         // [TB][N][N]
+  float* u = ctp + (size_t)TB * NN;          // [N][N]
+  float* qk = u + NN;                        // [N][N]
+  float* mrow = qk + NN;                     // [TB][N]
+  float* vrow = mrow + TB * N;               // [N]
+  const int b = blockIdx.x, h = blockIdx.y;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int T3 = S > 1 ? S - 2 : 0;
+  const size_t row0 = (size_t)b * N * S;
+  auto load3 = [&](int slot0, int nslot, float* dq_, float* dk_, float* dv_) {
+    for (int idx = tid; idx < nslot * N * d4; idx += nt) {
+      int e4 = idx % d4, i = (idx / d4) % N, t = idx / (d4 * N);
+      const float4* src = (const float4*)(QKV + (row0 + (size_t)i * S + slot0 + t) * ldq + h * dh) + e4;
+      int o = (t * N + i) * PQ + 4 * e4;
+      *(float4*)(dq_ + o) = __ldg(src);
+      *(float4*)(dk_ + o) = __ldg(src + dmodel / 4);
+      *(float4*)(dv_ + o) = __ldg(src + dmodel / 2);
+    }
+  };
+  load3(0, 1, q, k, v);
+  __syncthreads();
+  for (int idx = tid; idx < NN; idx += nt) {
+    int i = idx / N, j = idx % N;
+    float a = 0.f;
+    for (int e4 = 0; e4 < d4; ++e4) a += dot4(*(const float4*)(q + i * PQ + 4 * e4), *(const float4*)(k + j * PQ + 4 * e4));
+    p[idx] = a * scale;
+    u[idx] = 0.f;
+    qk[idx] = 0.f;
+  }
+  for (int idx = tid; idx < N * dh; idx += nt) olap[idx] = 0.f;
+  __syncthreads();
+  for (int i = tid; i < N; i += nt) {  // softmax row i
+    float mx = p[i * N];
+    for (int j = 1; j < N; ++j) mx = fmaxf(mx, p[i * N + j]);
+    float sum = 0.f;
+    for (int j = 0; j < N; ++j) {
+      float e = m_exp(p[i * N + j] - mx);
+      p[i * N + j] = e;
+      sum += e;
+    }
+    float inv = 1.f / sum;
+    for (int j = 0; j < N; ++j) p[i * N + j] *= inv;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < N * d4; idx += nt) {
+    int i = idx / d4, e4 = idx % d4;
+    float4 a = make_float4(0, 0, 0, 0);
+    for (int j = 0; j < N; ++j) fma4(a, p[i * N + j], *(const float4*)(v + j * PQ + 4 * e4));
+    *(float4*)(O + (row0 + (size_t)i * S) * ldo + h * dh + 4 * e4) = a;
+  }
+  if (S == 1) return;
+  const int e4_per = d4 / 4;  // each of the 4 cooperating lanes covers dh/4 floats = d4/4 float4
+  for (int t0 = 0; t0 < T3; t0 += TB) {
+    const int tc = T3 - t0 < TB ? T3 - t0 : TB;
+    __syncthreads();  // previous chunk done with qt/kt/vt/st
+    load3(1 + t0, tc, qt, kt, vt);
+    __syncthreads();
+    // ---- (t,i) x 4 lanes: a_j = q^t_i . k_j,  c_j = q^t_i . k^t_j ----------------------------
+    {
+      const int nitem = tc * N * 4;
+      const int nround = (nitem + nt - 1) / nt;
+      for (int rd = 0; rd < nround; ++rd) {
+        const int idx = rd * nt + tid;
+        const bool act = idx < nitem;
+        const int eq = idx & 3, ti = act ? idx >> 2 : 0;  // ti = t*N + i
+        const int t = ti / N;
+        const float* own = qt + (size_t)ti * PQ + eq * (dh / 4);
+        for (int j = 0; j < N; ++j) {
+          const float* kj = k + j * PQ + eq * (dh / 4);
+          const float* ktj = kt + (size_t)(t * N + j) * PQ + eq * (dh / 4);
+          float a = 0.f, c = 0.f;
+          if (act) {
+            for (int e4 = 0; e4 < e4_per; ++e4) {
+              float4 x = *(const float4*)(own + 4 * e4);
+              a += dot4(x, *(const float4*)(kj + 4 * e4));
+              c += dot4(x, *(const float4*)(ktj + 4 * e4));
+            }
+          }
+          a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
+          c += __shfl_xor_sync(0xffffffffu, c, 1); c += __shfl_xor_sync(0xffffffffu, c, 2);
+          if (act && eq == 0) { st[(size_t)ti * N + j] = a; ctp[(size_t)ti * N + j] = c; }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- (t,j) x 4 lanes: b_i = k^t_j . q_i ; st = scale (a + b) -------------------------------
+    {
+      const int nitem = tc * N * 4;
+      const int nround = (nitem + nt - 1) / nt;
+      for (int rd = 0; rd < nround; ++rd) {
+        const int idx = rd * nt + tid;
+        const bool act = idx < nitem;
+        const int eq = idx & 3, tj = act ? idx >> 2 : 0;
+        const int t = tj / N, j = tj % N;
+        const float* own = kt + (size_t)tj * PQ + eq * (dh / 4);
+        for (int i = 0; i < N; ++i) {
+          const float* qi = q + i * PQ + eq * (dh / 4);
+          float bsum = 0.f;
+          if (act)
+            for (int e4 = 0; e4 < e4_per; ++e4) bsum += dot4(*(const float4*)(own + 4 * e4), *(const float4*)(qi + 4 * e4));
+          bsum += __shfl_xor_sync(0xffffffffu, bsum, 1); bsum += __shfl_xor_sync(0xffffffffu, bsum, 2);
+          if (act && eq == 0) {
+            const size_t o = ((size_t)t * N + i) * N + j;
+            st[o] = scale * (st[o] + bsum);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < tc * N; idx += nt) {  // (t, i)
+      const float* pr = p + (idx % N) * N;
+      const float* sr = st + (size_t)idx * N;
+      float m = 0.f;
+      for (int j = 0; j < N; ++j) m += pr[j] * sr[j];
+      mrow[idx] = m;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < NN; idx += nt) {
+      int i = idx / N;
+      float uu = 0.f, cc = 0.f, pp = p[idx];
+      for (int t = 0; t < tc; ++t) {
+        float dv_ = st[t * NN + idx] - mrow[t * N + i];
+        uu += dv_ * dv_;
+        cc += ctp[t * NN + idx];
+        st[t * NN + idx] = pp * dv_;  // p^t
+      }
+      u[idx] += uu;
+      qk[idx] += cc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < N * d4; idx += nt) {
+      int i = idx / d4, e4 = idx % d4;
+      float4 c2 = make_float4(0, 0, 0, 0);
+      for (int t = 0; t < tc; ++t) {
+        const float* sr = st + t * NN + i * N;
+        float4 a = make_float4(0, 0, 0, 0);
+        for (int j = 0; j < N; ++j) {
+          float4 vtj = *(const float4*)(vt + (size_t)(t * N + j) * PQ + 4 * e4);
+          float4 vj = *(const float4*)(v + j * PQ + 4 * e4);
+          float sj = sr[j];
+          fma4(a, sj, vj);
+          fma4(a, p[i * N + j], vtj);
+          fma4(c2, sj, vtj);
+        }
+        *(float4*)(O + (row0 + (size_t)i * S + 1 + t0 + t) * ldo + h * dh + 4 * e4) = a;
+      }
+      float4* ol = (float4*)(olap + i * dh + 4 * e4);
+      float4 o = *ol;
+      o.x += 2.f * c2.x; o.y += 2.f * c2.y; o.z += 2.f * c2.z; o.w += 2.f * c2.w;
+      *ol = o;
+    }
+  }
+  __syncthreads();
+  load3(1 + T3, 1, qt, kt, vt);
+  __syncthreads();
+  for (int idx = tid; idx < NN; idx += nt) {
+    int i = idx / N, j = idx % N;
+    float a = 0.f;
+    for (int e4 = 0; e4 < d4; ++e4)
+      a += dot4(*(const float4*)(qt + i * PQ + 4 * e4), *(const float4*)(k + j * PQ + 4 * e4)) +
+           dot4(*(const float4*)(q + i * PQ + 4 * e4), *(const float4*)(kt + j * PQ + 4 * e4));
+    st[idx] = scale * (a + 2.f * qk[idx]);
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += nt) {
+    float m = 0.f, V = 0.f;
+    for (int j = 0; j < N; ++j) {
+      m += p[i * N + j] * st[i * N + j];
+      V += p[i * N + j] * u[i * N + j];
+    }
+    mrow[i] = m;
+    vrow[i] = V;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < NN; idx += nt) {
+    int i = idx / N;
+    st[idx] = p[idx] * (u[idx] - vrow[i] + st[idx] - mrow[i]);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < N * d4; idx += nt) {
+    int i = idx / d4, e4 = idx % d4;
+    float4 a = *(const float4*)(olap + i * dh + 4 * e4);
+    for (int j = 0; j < N; ++j) {
+      fma4(a, st[i * N + j], *(const float4*)(v + j * PQ + 4 * e4));
+      fma4(a, p[i * N + j], *(const float4*)(vt + j * PQ + 4 * e4));
+    }
+    *(float4*)(O + (row0 + (size_t)i * S + 1 + T3) * ldo + h * dh + 4 * e4) = a;
+  }
+}
+
+inline size_t attn_f32_smem_bytes(int N, int dh, int TB) {
+  return sizeof(float) * ((size_t)3 * N * (dh + 4) + (size_t)3 * TB * N * (dh + 4) + (size_t)N * dh +
+                          (size_t)N * N * (3 + 2 * TB) + (size_t)TB * N + N + 8);
+}
+inline int attn_f32_pick_tb(int N, int dh, int T3, size_t budget) {
+  int tb = T3 > 0 ? T3 : 1;
+  while (tb > 1 && attn_f32_smem_bytes(N, dh, tb) > budget) --tb;
+  return tb;
+}
+
 }  // namespace dq

@@ -158,6 +158,10 @@ inline void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> bod
 }
 }  // namespace emu
 
+struct alignas(16) float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+template <class T> inline T __ldg(const T* p) { return *p; }
+
 #define __global__
 #define __device__
 #define __host__
