@@ -148,8 +148,10 @@ struct SmemLayout {
 __global__ void __launch_bounds__(kThreads, 1)
 gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_constant__ CUtensorMap map_lo0,
                   const __grid_constant__ CUtensorMap map_hi1, const __grid_constant__ CUtensorMap map_lo1, Params p) {
-  extern __shared__ unsigned char smem_raw_[];
-  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw_ + 1023) & ~(uintptr_t)1023);
+  // 1024-byte aligned dynamic shared memory (SWIZZLE_128B atoms).  No integer round-up of the
+  // pointer: that would drop the shared address space and turn every access into a generic LD/ST.
+  extern __shared__ __align__(1024) unsigned char smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int BN = p.BN;
   uint64_t* bars = (uint64_t*)(smem + SmemLayout::bars(BN));
   uint64_t* full_a = bars;                 // [kStages] count 128 (producer threads)
