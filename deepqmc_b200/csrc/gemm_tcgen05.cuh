@@ -141,8 +141,8 @@ struct SmemLayout {
   static __host__ __device__ int w_lo(int s, int BN) { return s * stage_bytes(BN) + 2 * kBM * 128 + BN * 128; }
   static __host__ __device__ int stage_bytes(int BN) { return 2 * kBM * 128 + 2 * BN * 128; }
   static __host__ __device__ int bars(int BN) { return kStages * stage_bytes(BN); }
-  static __host__ __device__ int epi(int BN) { return bars(BN) + 256; }              // 4 warps x 32 x 33 floats
-  static __host__ __device__ int total(int BN) { return epi(BN) + 4 * 32 * 33 * 4 + 4 * 32 * 8 + 1024; }  // + row info + alignment slack
+  static __host__ __device__ int epi(int BN) { return bars(BN) + 256; }              // 4 warps x 32 x 36 floats
+  static __host__ __device__ int total(int BN) { return epi(BN) + 4 * 32 * 36 * 4 + 4 * 32 * 8 + 64; }  // + row info
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -300,14 +300,16 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
     }
   } else {
     // ===================== epilogue: warps 0-3 <-> TMEM lanes 32*warp .. +31 ================
-    // tcgen05.ld hands each lane one accumulator ROW; a 32x33 shared-memory transpose per warp turns
-    // that into one 128-byte coalesced global store (and residual load) per row and chunk.  Row
-    // descriptors live in shared memory (one broadcast LDS.64 per row); all residual loads of a
-    // chunk are issued before the first store so 32 loads are in flight per warp.
-    float* stage = (float*)(smem + SmemLayout::epi(BN)) + warp * 32 * 33;
-    long long* rowinfo = (long long*)(smem + SmemLayout::epi(BN) + 4 * 32 * 33 * 4) + warp * 32;
+    // tcgen05.ld hands each lane one accumulator ROW (32 columns per chunk).  A 32x36-float
+    // shared-memory transpose per warp re-maps that to "8 lanes x float4 per row", so one warp
+    // instruction stores (and loads the residual of) 4 complete 128-byte row segments.  Bias and
+    // residual loads are issued before the data they are added to is needed.
+    constexpr int kPitch = 36;
+    float* stage = (float*)(smem + SmemLayout::epi(BN)) + warp * 32 * kPitch;
+    long long* rowinfo = (long long*)(smem + SmemLayout::epi(BN) + 4 * 32 * kPitch * 4) + warp * 32;
     const float* __restrict__ Resp = p.Res;
     float* __restrict__ Cp = p.C;
+    const int rsub = lane >> 3, cq = lane & 7;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const int nt = tile % NT, mt = (tile / NT) % MT, z = tile / (NT * MT);
@@ -324,42 +326,67 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
         rowinfo[lane] = info;
         __syncwarp();
       }
+      long long inf[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) inf[jj] = rowinfo[4 * jj + rsub];
+      const int nchunk = BN / 32;
+      const bool vec_ok = (p.N % 4) == 0;
       mbar_wait(&tmem_full[acc], aph, p.err_flag);
       tc_fence_after();
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
-        tmem_ld_wait();
-        const int col = nt * BN + c0 + lane;
-        if (nt * BN + c0 < p.N) {  // warp-uniform
-          const bool colok = col < p.N;
+      for (int c = 0; c < nchunk; ++c) {
+        const int col = nt * BN + c * 32 + 4 * cq;  // first of this lane's 4 columns
+        const bool chunk_on = nt * BN + c * 32 < p.N;  // warp-uniform
+        float4 bq = make_float4(0, 0, 0, 0);
+        float4 res[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(v[j]);
-          __syncwarp();
-          const float bcol = (p.bias && colok) ? __ldg(p.bias + col) : 0.f;
-          float res[32];
+        for (int jj = 0; jj < 8; ++jj) res[jj] = make_float4(0, 0, 0, 0);
+        if (chunk_on && vec_ok && col < p.N) {
+          if (p.bias) bq = __ldg((const float4*)(p.bias + col));
           if (Resp) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const long long info = rowinfo[j];
-              res[j] = (info >= 0 && colok) ? __ldg(Resp + (size_t)(info >> 1) * p.ldr + col) : 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) res[j] = 0.f;
+            for (int jj = 0; jj < 8; ++jj)
+              if (inf[jj] >= 0) res[jj] = __ldg((const float4*)(Resp + (size_t)(inf[jj] >> 1) * p.ldr + col));
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const long long info = rowinfo[j];
-            float o = stage[j * 33 + lane] + res[j];
-            if (info & 1) o += bcol;
-            if (info >= 0 && colok) Cp[(size_t)(info >> 1) * p.ldc + col] = o;
-          }
-          __syncwarp();
         }
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 256 + c * 32), v);
+        tmem_ld_wait();
+        if (c == nchunk - 1) {  // accumulator fully read: hand it back to the MMA warp early
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[acc]);
+        }
+        if (!chunk_on) continue;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4)
+          *(float4*)(stage + lane * kPitch + 4 * q4) =
+              make_float4(__uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1]), __uint_as_float(v[4 * q4 + 2]),
+                          __uint_as_float(v[4 * q4 + 3]));
+        __syncwarp();
+        if (vec_ok) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            float4 o = *(const float4*)(stage + (4 * jj + rsub) * kPitch + 4 * cq);
+            o.x += res[jj].x; o.y += res[jj].y; o.z += res[jj].z; o.w += res[jj].w;
+            if (inf[jj] & 1) { o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w; }
+            if (inf[jj] >= 0 && col < p.N) *(float4*)(Cp + (size_t)(inf[jj] >> 1) * p.ldc + col) = o;
+          }
+        } else {  // ragged N: scalar tail path
+#pragma unroll 1
+          for (int jj = 0; jj < 8; ++jj) {
+            const long long inj = rowinfo[4 * jj + rsub];
+            if (inj < 0) continue;
+            const size_t pr = (size_t)(inj >> 1);
+            for (int e = 0; e < 4; ++e) {
+              if (col + e >= p.N) break;
+              float o = stage[(4 * jj + rsub) * kPitch + 4 * cq + e];
+              if (p.bias && (inj & 1)) o += p.bias[col + e];
+              if (Resp) o += Resp[pr * p.ldr + col + e];
+              Cp[pr * p.ldc + col + e] = o;
+            }
+          }
+        }
+        __syncwarp();
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
     }
   }
   tc_fence_before();
