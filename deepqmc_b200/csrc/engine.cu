@@ -308,8 +308,15 @@ struct Engine : EngineBase {
   }
 
   // ---- GEMM dispatch ------------------------------------------------------------------------
+  // dense layers can absorb the tanh propagation in the tensor-core epilogue when whole slot
+  // groups fit a 128-row tile with little padding
+  bool can_fuse_act(int S) const {
+    if (!use_tc() || std::getenv("DQMC_NO_FUSE_TANH")) return false;
+    if (S == 1) return true;
+    return S <= 128 && (128 / S) * S >= 112;
+  }
   int gemm(const T* A, int lda, const char* w0, const char* w1, int zsplit, int ldw, const T* bias, const T* Res,
-           int ldr, T* C, int ldc, int Mr, int Nc, int Kc, int S, int sliced, int Nel, cudaStream_t st) {
+           int ldr, T* C, int ldc, int Mr, int Nc, int Kc, int S, int sliced, int Nel, cudaStream_t st, int act = 0) {
     const T* W0 = P(w0);
     const T* W1 = w1 ? P(w1) : nullptr;
 #if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
@@ -320,7 +327,9 @@ struct Engine : EngineBase {
         tc::Params p;
         p.A = A; p.lda = lda; p.bias = bias; p.Res = Res; p.ldr = ldr; p.C = C; p.ldc = ldc; p.M = Mr; p.N = Nc;
         p.K = Kc; p.S = S; p.sliced = sliced; p.Nel = Nel; p.z_split = zsplit; p.BN = t0.BN; p.err_flag = nullptr;
-        int MT = (Mr + tc::kBM - 1) / tc::kBM, NT = (Nc + p.BN - 1) / p.BN;
+        p.act = act;
+        p.rpt = (act && S > 1) ? (128 / S) * S : tc::kBM;
+        int MT = (Mr + p.rpt - 1) / p.rpt, NT = (Nc + p.BN - 1) / p.BN;
         int n_tiles = (sliced ? Nel : 1) * MT * NT;
         int grid = n_tiles < n_sms ? n_tiles : n_sms;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -337,6 +346,7 @@ struct Engine : EngineBase {
       }
     }
 #endif
+    if (act) { err = "internal: fused activation requested on the CUDA-core GEMM"; return 5; }
     GemmArgs<T> g;
     g.A = A; g.lda = lda; g.W0 = W0; g.W1 = W1; g.z_split = zsplit; g.ldw = ldw; g.bias = bias; g.Res = Res;
     g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = Mr; g.N = Nc; g.K = Kc; g.S = S; g.sliced = sliced; g.Nel = Nel;
@@ -404,11 +414,17 @@ struct Engine : EngineBase {
         }
       }
       gemm(O, d, (p + "wo").c_str(), nullptr, 0, d, nullptr, X, d, w.A, d, rows, d, d, S, 0, N, st);
-      gemm(w.A, d, (p + "w1").c_str(), nullptr, 0, d, P(p + "b1"), nullptr, 0, w.M1, d, rows, d, d, S, 0, N, st);
-      DQ_LAUNCH(tanh_fl_kernel<T>, dim3(Bc * N, (d + 127) / 128), dim3(128), 0, st, w.M1, d, (const T*)nullptr, 0, S, d,
-                T(1));
-      gemm(w.M1, d, (p + "w2").c_str(), nullptr, 0, d, P(p + "b2"), nullptr, 0, O, d, rows, d, d, S, 0, N, st);
-      DQ_LAUNCH(tanh_fl_kernel<T>, dim3(Bc * N, (d + 127) / 128), dim3(128), 0, st, O, d, (const T*)w.A, d, S, d, T(1));
+      if (can_fuse_act(S)) {
+        // MLP with the tanh (and its Jacobian/Laplacian propagation) inside the GEMM epilogues
+        gemm(w.A, d, (p + "w1").c_str(), nullptr, 0, d, P(p + "b1"), nullptr, 0, w.M1, d, rows, d, d, S, 0, N, st, 1);
+        gemm(w.M1, d, (p + "w2").c_str(), nullptr, 0, d, P(p + "b2"), w.A, d, O, d, rows, d, d, S, 0, N, st, 1);
+      } else {
+        gemm(w.A, d, (p + "w1").c_str(), nullptr, 0, d, P(p + "b1"), nullptr, 0, w.M1, d, rows, d, d, S, 0, N, st);
+        DQ_LAUNCH(tanh_fl_kernel<T>, dim3(Bc * N, (d + 127) / 128), dim3(128), 0, st, w.M1, d, (const T*)nullptr, 0, S, d,
+                  T(1));
+        gemm(w.M1, d, (p + "w2").c_str(), nullptr, 0, d, P(p + "b2"), nullptr, 0, O, d, rows, d, d, S, 0, N, st);
+        DQ_LAUNCH(tanh_fl_kernel<T>, dim3(Bc * N, (d + 127) / 128), dim3(128), 0, st, O, d, (const T*)w.A, d, S, d, T(1));
+      }
       T* tmp = X; X = O; O = tmp;
     }
     // per-spin backflow heads: rows of electron e across walkers, weights by spin

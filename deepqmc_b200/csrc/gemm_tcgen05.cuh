@@ -39,6 +39,8 @@ struct Params {
   int S;
   int sliced, Nel, z_split;
   int BN;            // 64 | 128 | 256
+  int act;           // 0: none, 1: tanh with forward-Laplacian propagation fused into the epilogue
+  int rpt;           // rows per tile (<= 128): G*S for act = 1 so that slot groups never straddle tiles
   int* err_flag;     // device int: set to non-zero if a barrier wait times out
 };
 
@@ -142,7 +144,8 @@ struct SmemLayout {
   static __host__ __device__ int stage_bytes(int BN) { return 2 * kBM * 128 + 2 * BN * 128; }
   static __host__ __device__ int bars(int BN) { return kStages * stage_bytes(BN); }
   static __host__ __device__ int epi(int BN) { return bars(BN) + 256; }              // 4 warps x 32 x 36 floats
-  static __host__ __device__ int total(int BN) { return epi(BN) + 4 * 32 * 36 * 4 + 4 * 32 * 8 + 64; }  // + row info
+  static __host__ __device__ int side(int BN) { return epi(BN) + 4 * 32 * 36 * 4 + 4 * 32 * 8; }  // y', y'' [2][32 groups][32]
+  static __host__ __device__ int total(int BN) { return side(BN) + 2 * 32 * 32 * 4 + 64; }
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -162,7 +165,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
   uint32_t* tmem_base_slot = (uint32_t*)(bars + 3 * kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int MT = (p.M + kBM - 1) / kBM, NT = (p.N + BN - 1) / BN;
+  const int RPT = p.rpt;
+  const int MT = (p.M + RPT - 1) / RPT, NT = (p.N + BN - 1) / BN;
   const int Z = p.sliced ? p.Nel : 1;
   const int n_tiles = Z * MT * NT;
   const int KB = p.K / kBK;
@@ -204,8 +208,9 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
       const float* rowp[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int m = mt * kBM + pw * 32 + 4 * j + rsub;
-        rowp[j] = m < p.M ? p.A + phys_row(p, m, z) * p.lda + chunk * 4 : nullptr;
+        const int lrow = pw * 32 + 4 * j + rsub;
+        const int m = mt * RPT + lrow;
+        rowp[j] = (lrow < RPT && m < p.M) ? p.A + phys_row(p, m, z) * p.lda + chunk * 4 : nullptr;
       }
       // register ring of 3 k-blocks: loads run two k-blocks ahead of the conversion
       float4 b0[8], b1[8], b2[8];
@@ -305,22 +310,28 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
     // instruction stores (and loads the residual of) 4 complete 128-byte row segments.  Bias and
     // residual loads are issued before the data they are added to is needed.
     constexpr int kPitch = 36;
-    float* stage = (float*)(smem + SmemLayout::epi(BN)) + warp * 32 * kPitch;
-    long long* rowinfo = (long long*)(smem + SmemLayout::epi(BN) + 4 * 32 * kPitch * 4) + warp * 32;
+    float* stage_all = (float*)(smem + SmemLayout::epi(BN));          // [128][kPitch]
+    float* stage = stage_all + warp * 32 * kPitch;
+    long long* rowinfo_all = (long long*)(smem + SmemLayout::epi(BN) + 4 * 32 * kPitch * 4);
+    long long* rowinfo = rowinfo_all + warp * 32;
+    float* side1 = (float*)(smem + SmemLayout::side(BN));              // y'  [group][32]
+    float* side2 = side1 + 32 * 32;                                    // y'' [group][32]
     const float* __restrict__ Resp = p.Res;
     float* __restrict__ Cp = p.C;
     const int rsub = lane >> 3, cq = lane & 7;
+    const int S = p.S;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const int nt = tile % NT, mt = (tile / NT) % MT, z = tile / (NT * MT);
       const int acc = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
-      const int m = mt * kBM + warp * 32 + lane;
       {
+        const int lrow = warp * 32 + lane;
+        const int m = mt * RPT + lrow;
         long long info = -1;  // invalid row
-        if (m < p.M) {
+        if (lrow < RPT && m < p.M) {
           const long long pr = (long long)phys_row(p, m, z);
-          info = (pr << 1) | ((pr % p.S) == 0 ? 1 : 0);
+          info = (pr << 8) | (long long)(pr % S);  // physical row, slot
         }
         __syncwarp();
         rowinfo[lane] = info;
@@ -345,7 +356,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
           if (Resp) {
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj)
-              if (inf[jj] >= 0) res[jj] = __ldg((const float4*)(Resp + (size_t)(inf[jj] >> 1) * p.ldr + col));
+              if (inf[jj] >= 0) res[jj] = __ldg((const float4*)(Resp + (size_t)(inf[jj] >> 8) * p.ldr + col));
           }
         }
         uint32_t v[32];
@@ -361,25 +372,74 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
           *(float4*)(stage + lane * kPitch + 4 * q4) =
               make_float4(__uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1]), __uint_as_float(v[4 * q4 + 2]),
                           __uint_as_float(v[4 * q4 + 3]));
+        if (p.act) {
+          // ---- tanh + forward-Laplacian propagation (reference: hkext.py:104-113 MLP activation; rule
+          // y_t = y' z_t, y_L = y' z_L + y'' sum_t z_t^2).  Tiles hold whole slot groups (rpt = G*S).
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            if (inf[jj] >= 0 && (inf[jj] & 255) == 0) {  // value row: y, y', y''
+              const int lrow = warp * 32 + 4 * jj + rsub;
+              float4* zp = (float4*)(stage_all + lrow * kPitch + 4 * cq);
+              float4 zz = *zp;
+              float4 y = make_float4(tanhf(zz.x + bq.x), tanhf(zz.y + bq.y), tanhf(zz.z + bq.z), tanhf(zz.w + bq.w));
+              float4 y1 = make_float4(1.f - y.x * y.x, 1.f - y.y * y.y, 1.f - y.z * y.z, 1.f - y.w * y.w);
+              float4 y2 = make_float4(-2.f * y.x * y1.x, -2.f * y.y * y1.y, -2.f * y.z * y1.z, -2.f * y.w * y1.w);
+              *zp = y;
+              if (S > 1) {
+                const int g = lrow / S;
+                *(float4*)(side1 + g * 32 + 4 * cq) = y1;
+                *(float4*)(side2 + g * 32 + 4 * cq) = y2;
+              }
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            if (inf[jj] < 0) continue;
+            const int slot = (int)(inf[jj] & 255);
+            const int lrow = warp * 32 + 4 * jj + rsub;
+            const int g = lrow / S;
+            float4 o = *(const float4*)(stage_all + lrow * kPitch + 4 * cq);
+            if (slot > 0) {
+              const float4 y1 = *(const float4*)(side1 + g * 32 + 4 * cq);
+              o.x *= y1.x; o.y *= y1.y; o.z *= y1.z; o.w *= y1.w;
+              if (slot == S - 1 && S > 2) {
+                float4 ss = make_float4(0, 0, 0, 0);
+                const float* zt = stage_all + (lrow - (S - 2)) * kPitch + 4 * cq;
+                for (int t = 0; t < S - 2; ++t) {
+                  const float4 a = *(const float4*)(zt + t * kPitch);
+                  ss.x += a.x * a.x; ss.y += a.y * a.y; ss.z += a.z * a.z; ss.w += a.w * a.w;
+                }
+                const float4 y2 = *(const float4*)(side2 + g * 32 + 4 * cq);
+                o.x += y2.x * ss.x; o.y += y2.y * ss.y; o.z += y2.z * ss.z; o.w += y2.w * ss.w;
+              }
+            }
+            o.x += res[jj].x; o.y += res[jj].y; o.z += res[jj].z; o.w += res[jj].w;
+            if (col < p.N) *(float4*)(Cp + (size_t)(inf[jj] >> 8) * p.ldc + col) = o;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // stage / side buffers reused by the next chunk
+          continue;
+        }
         __syncwarp();
         if (vec_ok) {
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
             float4 o = *(const float4*)(stage + (4 * jj + rsub) * kPitch + 4 * cq);
             o.x += res[jj].x; o.y += res[jj].y; o.z += res[jj].z; o.w += res[jj].w;
-            if (inf[jj] & 1) { o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w; }
-            if (inf[jj] >= 0 && col < p.N) *(float4*)(Cp + (size_t)(inf[jj] >> 1) * p.ldc + col) = o;
+            if ((inf[jj] & 255) == 0) { o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w; }
+            if (inf[jj] >= 0 && col < p.N) *(float4*)(Cp + (size_t)(inf[jj] >> 8) * p.ldc + col) = o;
           }
         } else {  // ragged N: scalar tail path
 #pragma unroll 1
           for (int jj = 0; jj < 8; ++jj) {
             const long long inj = rowinfo[4 * jj + rsub];
             if (inj < 0) continue;
-            const size_t pr = (size_t)(inj >> 1);
+            const size_t pr = (size_t)(inj >> 8);
             for (int e = 0; e < 4; ++e) {
               if (col + e >= p.N) break;
               float o = stage[(4 * jj + rsub) * kPitch + 4 * cq + e];
-              if (p.bias && (inj & 1)) o += p.bias[col + e];
+              if (p.bias && (inj & 255) == 0) o += p.bias[col + e];
               if (Resp) o += Resp[pr * p.ldr + col + e];
               Cp[pr * p.ldc + col + e] = o;
             }
