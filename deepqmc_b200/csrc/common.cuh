@@ -40,6 +40,21 @@ __host__ __device__ __forceinline__ float m_cos(float x) { return ::cosf(x); }
 __host__ __device__ __forceinline__ double m_sin(double x) { return ::sin(x); }
 __host__ __device__ __forceinline__ float m_sin(float x) { return ::sinf(x); }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS, bypasses L1 and registers)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+#ifdef DQMC_EMU
+  *reinterpret_cast<float4*>(smem_dst) = *reinterpret_cast<const float4*>(gmem_src);
+#else
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+#ifndef DQMC_EMU
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 template <class T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

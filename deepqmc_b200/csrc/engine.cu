@@ -220,9 +220,9 @@ struct Engine : EngineBase {
     size_t s_sl = slater_smem_bytes<T>(N);
     max_smem = s_attn > s_sl ? s_attn : s_sl;
     if (max_smem > 227 * 1024) { err = "system too large for the shared-memory tiling (N)"; return 2; }
-    if (attn_f32)
-      DQ_CHECK(cudaFuncSetAttribute(attn_fl_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_attn));
-    else
+    if (attn_f32) {
+      if (launch_attn_f32(nullptr, nullptr, 0, 0, 0, 0.f, 0, (int)s_attn, nullptr, true)) return 1;
+    } else
       DQ_CHECK(cudaFuncSetAttribute(attn_fl_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_attn));
     DQ_CHECK(cudaFuncSetAttribute(slater_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_sl));
     if (cfg.gemm_backend == DQMC_GEMM_TCGEN05) {
@@ -384,6 +384,31 @@ struct Engine : EngineBase {
     return 0;
   }
 
+  // fp32 attention: pick the <N, dh> specialisation (compile-time index arithmetic) when there is one
+  template <int NE, int DH>
+  int attn_f32_go(const float* QKV, float* O, int Bc, int S, int tb, float scale, int smem, cudaStream_t st, bool setup) {
+    if (setup) {
+      DQ_CHECK(cudaFuncSetAttribute(attn_fl_f32_kernel<NE, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      return 0;
+    }
+    DQ_LAUNCH((attn_fl_f32_kernel<NE, DH>), dim3(Bc, H), dim3(128), smem, st, QKV, 3 * d, O, d, N, S, dh, d, scale, tb);
+    return 0;
+  }
+  int launch_attn_f32(const float* QKV, float* O, int Bc, int S, int tb, float scale, int, int smem, cudaStream_t st,
+                      bool setup) {
+    if (dh == 64) {
+      switch (N) {
+        case 4: return attn_f32_go<4, 64>(QKV, O, Bc, S, tb, scale, smem, st, setup);
+        case 10: return attn_f32_go<10, 64>(QKV, O, Bc, S, tb, scale, smem, st, setup);
+        case 14: return attn_f32_go<14, 64>(QKV, O, Bc, S, tb, scale, smem, st, setup);
+        case 28: return attn_f32_go<28, 64>(QKV, O, Bc, S, tb, scale, smem, st, setup);
+        case 30: return attn_f32_go<30, 64>(QKV, O, Bc, S, tb, scale, smem, st, setup);
+        default: return attn_f32_go<0, 64>(QKV, O, Bc, S, tb, scale, smem, st, setup);
+      }
+    }
+    return attn_f32_go<0, 0>(QKV, O, Bc, S, tb, scale, smem, st, setup);
+  }
+
   // ---- one chunk of the wave-function pipeline ---------------------------------------------
   int run_chunk(const T* r, const T* R, int Rb, int Bc, int S, int Bstat, T* sign, T* logp, T* E, T* stats, T* grad,
                 void* wsbase, cudaStream_t st) {
@@ -402,8 +427,9 @@ struct Engine : EngineBase {
         const int tb = S > 1 ? attn_tb : 1;
         if constexpr (std::is_same<T, float>::value) {
           if (attn_f32) {
-            DQ_LAUNCH(attn_fl_f32_kernel, dim3(Bc, H), dim3(128), attn_f32_smem_bytes(N, dh, tb), st,
-                      (const float*)w.QKV, 3 * d, (float*)O, d, N, S, dh, d, (float)scale, tb);
+            if (launch_attn_f32((const float*)w.QKV, (float*)O, Bc, S, tb, (float)scale, 0,
+                                (int)attn_f32_smem_bytes(N, dh, tb), st, false))
+              return 1;
           } else {
             DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh, tb), st, (const T*)w.QKV,
                       3 * d, O, d, N, S, dh, d, scale, tb);

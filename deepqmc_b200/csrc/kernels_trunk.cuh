@@ -411,9 +411,14 @@ __device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
   acc.x += s * v.x; acc.y += s * v.y; acc.z += s * v.z; acc.w += s * v.w;
 }
 
-__global__ void attn_fl_f32_kernel(const float* __restrict__ QKV, int ldq, float* __restrict__ O, int ldo, int N,
-                                   int S, int dh, int dmodel, float scale, int TB) {
+// NE / DH: compile-time electron count / head dim (0 = use the runtime value): with constants the
+// index arithmetic (div/mod by N, dh/4) folds away and the j-loops unroll.
+template <int NE, int DH>
+__global__ void attn_fl_f32_kernel(const float* __restrict__ QKV, int ldq, float* __restrict__ O, int ldo, int N_rt,
+                                   int S, int dh_rt, int dmodel, float scale, int TB) {
   DQMC_DYN_SMEM(smem_raw);
+  const int N = NE ? NE : N_rt;
+  const int dh = DH ? DH : dh_rt;
   const int PQ = dh + 4, NN = N * N, d4 = dh / 4;
   float* q = reinterpret_cast<float*>(smem_raw);
   float* k = q + N * PQ;
@@ -433,15 +438,17 @@ __global__ void attn_fl_f32_kernel(const float* __restrict__ QKV, int ldq, float
   const int tid = threadIdx.x, nt = blockDim.x;
   const int T3 = S > 1 ? S - 2 : 0;
   const size_t row0 = (size_t)b * N * S;
+  // global -> shared with cp.async (16 B, L2 only): all copies of a chunk are in flight at once
   auto load3 = [&](int slot0, int nslot, float* dq_, float* dk_, float* dv_) {
     for (int idx = tid; idx < nslot * N * d4; idx += nt) {
       int e4 = idx % d4, i = (idx / d4) % N, t = idx / (d4 * N);
       const float4* src = (const float4*)(QKV + (row0 + (size_t)i * S + slot0 + t) * ldq + h * dh) + e4;
       int o = (t * N + i) * PQ + 4 * e4;
-      *(float4*)(dq_ + o) = __ldg(src);
-      *(float4*)(dk_ + o) = __ldg(src + dmodel / 4);
-      *(float4*)(dv_ + o) = __ldg(src + dmodel / 2);
+      cp_async16(dq_ + o, src);
+      cp_async16(dk_ + o, src + dmodel / 4);
+      cp_async16(dv_ + o, src + dmodel / 2);
     }
+    cp_async_wait_all();
   };
   load3(0, 1, q, k, v);
   __syncthreads();
