@@ -144,8 +144,9 @@ struct SmemLayout {
   static __host__ __device__ int stage_bytes(int BN) { return 2 * kBM * 128 + 2 * BN * 128; }
   static __host__ __device__ int bars(int BN) { return kStages * stage_bytes(BN); }
   static __host__ __device__ int epi(int BN) { return bars(BN) + 256; }              // 4 warps x 32 x 36 floats
-  static __host__ __device__ int side(int BN) { return epi(BN) + 4 * 32 * 36 * 4 + 4 * 32 * 8; }  // y', y'' [2][32 groups][32]
-  static __host__ __device__ int total(int BN) { return side(BN) + 2 * 32 * 32 * 4 + 64; }
+  static __host__ __device__ int side(int BN) { return epi(BN) + 4 * 32 * 36 * 4 + 4 * 32 * 8; }  // y', y'', sum z_t^2: [3][32 groups][32]
+  static __host__ __device__ int sbias(int BN) { return side(BN) + 3 * 32 * 32 * 4; }  // bias of the tile's BN columns
+  static __host__ __device__ int total(int BN) { return sbias(BN) + 256 * 4 + 64; }
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -316,6 +317,9 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
     long long* rowinfo = rowinfo_all + warp * 32;
     float* side1 = (float*)(smem + SmemLayout::side(BN));              // y'  [group][32]
     float* side2 = side1 + 32 * 32;                                    // y'' [group][32]
+    float* side3 = side2 + 32 * 32;                                    // sum_t z_t^2 [group][32]
+    float* sbias = (float*)(smem + SmemLayout::sbias(BN));             // [BN]
+    const int etid = threadIdx.x;                                      // 0..127 (epilogue warps are warps 0-3)
     const float* __restrict__ Resp = p.Res;
     float* __restrict__ Cp = p.C;
     const int rsub = lane >> 3, cq = lane & 7;
@@ -340,6 +344,12 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
       long long inf[8];
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) inf[jj] = rowinfo[4 * jj + rsub];
+      if (p.act) {  // bias of this tile's columns -> shared (latency overlaps the wait for the accumulator)
+        for (int i = etid; i < BN; i += 128) {
+          const int cc = nt * BN + i;
+          sbias[i] = (p.bias && cc < p.N) ? __ldg(p.bias + cc) : 0.f;
+        }
+      }
       const int nchunk = BN / 32;
       const bool vec_ok = (p.N % 4) == 0;
       mbar_wait(&tmem_full[acc], aph, p.err_flag);
@@ -352,7 +362,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) res[jj] = make_float4(0, 0, 0, 0);
         if (chunk_on && vec_ok && col < p.N) {
-          if (p.bias) bq = __ldg((const float4*)(p.bias + col));
+          if (p.bias && !p.act) bq = __ldg((const float4*)(p.bias + col));
           if (Resp) {
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj)
@@ -376,20 +386,27 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
           // ---- tanh + forward-Laplacian propagation (reference: hkext.py:104-113 MLP activation; rule
           // y_t = y' z_t, y_L = y' z_L + y'' sum_t z_t^2).  Tiles hold whole slot groups (rpt = G*S).
           asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            if (inf[jj] >= 0 && (inf[jj] & 255) == 0) {  // value row: y, y', y''
-              const int lrow = warp * 32 + 4 * jj + rsub;
-              float4* zp = (float4*)(stage_all + lrow * kPitch + 4 * cq);
-              float4 zz = *zp;
-              float4 y = make_float4(tanhf(zz.x + bq.x), tanhf(zz.y + bq.y), tanhf(zz.z + bq.z), tanhf(zz.w + bq.w));
-              float4 y1 = make_float4(1.f - y.x * y.x, 1.f - y.y * y.y, 1.f - y.z * y.z, 1.f - y.w * y.w);
-              float4 y2 = make_float4(-2.f * y.x * y1.x, -2.f * y.y * y1.y, -2.f * y.z * y1.z, -2.f * y.w * y1.w);
+          // phase A (work spread evenly over the 128 epilogue threads, no divergence):
+          // per (group, column): y = tanh(z0 + b) written over the value row, y', y'', sum_t z_t^2
+          {
+            const int rows_here = (p.M - mt * RPT) < RPT ? (p.M - mt * RPT) : RPT;
+            const int ngrp = S > 1 ? rows_here / S : rows_here;  // whole groups (S == 1: every row)
+            for (int idx = etid; idx < ngrp * 32; idx += 128) {
+              const int g = idx >> 5, cc = idx & 31;
+              const int r0 = (S > 1 ? g * S : g);
+              float* zp = stage_all + r0 * kPitch + cc;
+              const float y = tanhf(*zp + sbias[c * 32 + cc]);
               *zp = y;
               if (S > 1) {
-                const int g = lrow / S;
-                *(float4*)(side1 + g * 32 + 4 * cq) = y1;
-                *(float4*)(side2 + g * 32 + 4 * cq) = y2;
+                const float y1 = 1.f - y * y;
+                float ss = 0.f;
+                for (int t = 1; t <= S - 2; ++t) {
+                  const float a = zp[t * kPitch];
+                  ss += a * a;
+                }
+                side1[g * 32 + cc] = y1;
+                side2[g * 32 + cc] = -2.f * y * y1;
+                side3[g * 32 + cc] = ss;
               }
             }
           }
@@ -399,19 +416,14 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
             if (inf[jj] < 0) continue;
             const int slot = (int)(inf[jj] & 255);
             const int lrow = warp * 32 + 4 * jj + rsub;
-            const int g = lrow / S;
             float4 o = *(const float4*)(stage_all + lrow * kPitch + 4 * cq);
             if (slot > 0) {
+              const int g = lrow / S;
               const float4 y1 = *(const float4*)(side1 + g * 32 + 4 * cq);
               o.x *= y1.x; o.y *= y1.y; o.z *= y1.z; o.w *= y1.w;
-              if (slot == S - 1 && S > 2) {
-                float4 ss = make_float4(0, 0, 0, 0);
-                const float* zt = stage_all + (lrow - (S - 2)) * kPitch + 4 * cq;
-                for (int t = 0; t < S - 2; ++t) {
-                  const float4 a = *(const float4*)(zt + t * kPitch);
-                  ss.x += a.x * a.x; ss.y += a.y * a.y; ss.z += a.z * a.z; ss.w += a.w * a.w;
-                }
+              if (slot == S - 1) {
                 const float4 y2 = *(const float4*)(side2 + g * 32 + 4 * cq);
+                const float4 ss = *(const float4*)(side3 + g * 32 + 4 * cq);
                 o.x += y2.x * ss.x; o.y += y2.y * ss.y; o.z += y2.z * ss.z; o.w += y2.w * ss.w;
               }
             }

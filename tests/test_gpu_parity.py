@@ -152,7 +152,8 @@ def test_fp32_mode_within_reference_tolerance():
     E, stats = hamil.local_energy(ansatz.apply)(None, params, pc)
     ref = oracle_eval(ansatz, oh, params, r.double(), R.double())
     for b, (s, l, e, st) in enumerate(ref):
-        assert abs(E[b].item() - e) <= 2e-4 * max(1, abs(e), abs(st['hamil/E_kin'])), (E[b].item(), e)
+        scale_b = max(1, abs(e), 0.5 * abs(st['hamil/lap']), 0.5 * st['hamil/quantum_force'])
+        assert abs(E[b].item() - e) <= 2e-4 * scale_b, (E[b].item(), e)
 
 
 def test_metropolis_injected_noise_matches_oracle():
