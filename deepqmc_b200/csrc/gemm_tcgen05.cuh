@@ -335,7 +335,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
         long long info = -1;  // invalid row
         if (lrow < RPT && m < p.M) {
           const long long pr = (long long)phys_row(p, m, z);
-          info = (pr << 8) | (long long)(pr % S);  // physical row, slot
+          // physical row | group index inside the tile | slot  (one division per row and tile)
+          info = (pr << 16) | ((long long)(lrow / S) << 8) | (long long)(pr % S);
         }
         __syncwarp();
         rowinfo[lane] = info;
@@ -344,6 +345,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
       long long inf[8];
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) inf[jj] = rowinfo[4 * jj + rsub];
+      const int rows_here = (p.M - mt * RPT) < RPT ? (p.M - mt * RPT) : RPT;
+      const int ngrp = S > 1 ? rows_here / S : rows_here;  // whole slot groups in this tile (S == 1: rows)
       if (p.act) {  // bias of this tile's columns -> shared (latency overlaps the wait for the accumulator)
         for (int i = etid; i < BN; i += 128) {
           const int cc = nt * BN + i;
@@ -366,7 +369,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
           if (Resp) {
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj)
-              if (inf[jj] >= 0) res[jj] = __ldg((const float4*)(Resp + (size_t)(inf[jj] >> 8) * p.ldr + col));
+              if (inf[jj] >= 0) res[jj] = __ldg((const float4*)(Resp + (size_t)(inf[jj] >> 16) * p.ldr + col));
           }
         }
         uint32_t v[32];
@@ -389,8 +392,6 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
           // phase A (work spread evenly over the 128 epilogue threads, no divergence):
           // per (group, column): y = tanh(z0 + b) written over the value row, y', y'', sum_t z_t^2
           {
-            const int rows_here = (p.M - mt * RPT) < RPT ? (p.M - mt * RPT) : RPT;
-            const int ngrp = S > 1 ? rows_here / S : rows_here;  // whole groups (S == 1: every row)
             for (int idx = etid; idx < ngrp * 32; idx += 128) {
               const int g = idx >> 5, cc = idx & 31;
               const int r0 = (S > 1 ? g * S : g);
@@ -399,11 +400,18 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
               *zp = y;
               if (S > 1) {
                 const float y1 = 1.f - y * y;
-                float ss = 0.f;
-                for (int t = 1; t <= S - 2; ++t) {
-                  const float a = zp[t * kPitch];
-                  ss += a * a;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                int t = 1;
+                for (; t + 3 <= S - 2; t += 4) {
+                  const float a0 = zp[t * kPitch], a1 = zp[(t + 1) * kPitch], a2 = zp[(t + 2) * kPitch],
+                              a3 = zp[(t + 3) * kPitch];
+                  s0 += a0 * a0; s1 += a1 * a1; s2 += a2 * a2; s3 += a3 * a3;
                 }
+                for (; t <= S - 2; ++t) {
+                  const float a = zp[t * kPitch];
+                  s0 += a * a;
+                }
+                const float ss = (s0 + s1) + (s2 + s3);
                 side1[g * 32 + cc] = y1;
                 side2[g * 32 + cc] = -2.f * y * y1;
                 side3[g * 32 + cc] = ss;
@@ -418,7 +426,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
             const int lrow = warp * 32 + 4 * jj + rsub;
             float4 o = *(const float4*)(stage_all + lrow * kPitch + 4 * cq);
             if (slot > 0) {
-              const int g = lrow / S;
+              const int g = (int)((inf[jj] >> 8) & 255);
               const float4 y1 = *(const float4*)(side1 + g * 32 + 4 * cq);
               o.x *= y1.x; o.y *= y1.y; o.z *= y1.z; o.w *= y1.w;
               if (slot == S - 1) {
@@ -428,7 +436,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
               }
             }
             o.x += res[jj].x; o.y += res[jj].y; o.z += res[jj].z; o.w += res[jj].w;
-            if (col < p.N) *(float4*)(Cp + (size_t)(inf[jj] >> 8) * p.ldc + col) = o;
+            if (col < p.N) *(float4*)(Cp + (size_t)(inf[jj] >> 16) * p.ldc + col) = o;
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");  // stage / side buffers reused by the next chunk
           continue;
@@ -440,14 +448,14 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
             float4 o = *(const float4*)(stage + (4 * jj + rsub) * kPitch + 4 * cq);
             o.x += res[jj].x; o.y += res[jj].y; o.z += res[jj].z; o.w += res[jj].w;
             if ((inf[jj] & 255) == 0) { o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w; }
-            if (inf[jj] >= 0 && col < p.N) *(float4*)(Cp + (size_t)(inf[jj] >> 8) * p.ldc + col) = o;
+            if (inf[jj] >= 0 && col < p.N) *(float4*)(Cp + (size_t)(inf[jj] >> 16) * p.ldc + col) = o;
           }
         } else {  // ragged N: scalar tail path
 #pragma unroll 1
           for (int jj = 0; jj < 8; ++jj) {
             const long long inj = rowinfo[4 * jj + rsub];
             if (inj < 0) continue;
-            const size_t pr = (size_t)(inj >> 8);
+            const size_t pr = (size_t)(inj >> 16);
             for (int e = 0; e < 4; ++e) {
               if (col + e >= p.N) break;
               float o = stage[(4 * jj + rsub) * kPitch + 4 * cq + e];
