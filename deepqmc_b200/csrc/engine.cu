@@ -214,7 +214,7 @@ struct Engine : EngineBase {
     // opt in to large dynamic shared memory
     attn_tb = attn_pick_tb<T>(N, dh, T3, 100 * 1024);
     attn_f32 = std::is_same<T, float>::value && dh % 16 == 0 && !std::getenv("DQMC_ATTN_GENERIC");
-    if (attn_f32) attn_tb = attn_f32_pick_tb(N, dh, T3, 48 * 1024);
+    if (attn_f32) attn_tb = attn_f32_pick_tb(N, dh, T3, 32 * 1024);  // ~7 blocks/SM for small molecules
     if (const char* ev = std::getenv("DQMC_ATTN_TB")) { int x = std::atoi(ev); if (x >= 1 && x <= T3) attn_tb = x; }
     size_t s_attn = attn_f32 ? attn_f32_smem_bytes(N, dh, attn_tb) : attn_smem_bytes<T>(N, dh, attn_tb);
     size_t s_sl = slater_smem_bytes<T>(N);

@@ -628,6 +628,14 @@ inline size_t attn_f32_smem_bytes(int N, int dh, int TB) {
 inline int attn_f32_pick_tb(int N, int dh, int T3, size_t budget) {
   int tb = T3 > 0 ? T3 : 1;
   while (tb > 1 && attn_f32_smem_bytes(N, dh, tb) > budget) --tb;
+  if (tb < 4 && T3 >= 4) {  // large molecules: allow up to ~200 KB for at least 4 tangents per chunk
+    tb = 4;
+    while (tb > 1 && attn_f32_smem_bytes(N, dh, tb) > (size_t)200 * 1024) --tb;
+  }
+  if (T3 > 0) {  // balance the chunks
+    int nchunk = (T3 + tb - 1) / tb;
+    tb = (T3 + nchunk - 1) / nchunk;
+  }
   return tb;
 }
 
