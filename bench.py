@@ -272,7 +272,7 @@ def main():
     if rank == 0:
         eng.profile_begin()
         for s in range(3):
-            step(s)
+            loc_ene(s, params, pc)  # rank-local: no collective here (the other ranks are already done)
         gemm_ms, gemm_flops, n_gemm = eng.profile_end()
         peaks = {}
         try:
@@ -288,6 +288,9 @@ def main():
                 'gemm_launches_per_step': n_gemm // 3,
                 'algorithmic_flops_per_eloc': algorithmic_flops_per_eloc(N, M),
                 'whole_step_tflops': algorithmic_flops_per_eloc(N, M) * B * a.steps / (total_ms / 1e3) / 1e12}
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return 0
     cpu = None
