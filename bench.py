@@ -31,11 +31,13 @@ WORKLOADS = {
 }
 
 
-def algorithmic_flops_per_eloc(N, M, d=256, L=4, K=16):
-    """F_lap with dense 3N tangents (forward-Laplacian)."""
+def algorithmic_flops_per_eloc(N, M, d=256, L=4, K=16, n_ecp=0):
+    """F_lap with dense 3N tangents (forward-Laplacian) + 12 N N_ecp plain forwards."""
     T = 3 * N
-    return (5 * 2 * N * (4 * M + 1) * d + (T + 2) * (L * 12 * N * d * d + 2 * K * N * N * d + 6 * K * N * N * M)
-            + (3 * T + 3) * L * 4 * N * N * d + K * (2 / 3 + 2) * N**3 + 2 * K * T * N**3)
+    f_lap = (5 * 2 * N * (4 * M + 1) * d + (T + 2) * (L * 12 * N * d * d + 2 * K * N * N * d + 6 * K * N * N * M)
+             + (3 * T + 3) * L * 4 * N * N * d + K * (2 / 3 + 2) * N**3 + 2 * K * T * N**3)
+    f_fwd = 2 * N * (4 * M + 1) * d + L * (12 * N * d * d + 4 * N * N * d) + 2 * K * N * N * d + 6 * K * N * N * M + 2 / 3 * K * N**3
+    return f_lap + 12 * N * n_ecp * f_fwd
 
 
 def make_problem(wl, B, seed):
@@ -196,6 +198,7 @@ def main():
     params = PN.perturb_params(ansatz.init(0))
     tdt = torch.float32 if a.dtype == 'float32' else torch.float64
     N, M = hamil.n_up + hamil.n_down, hamil.n_nuc
+    n_ecp = len(hamil.pot.nuc_with_nl_pot)
     R = torch.as_tensor(mol.coords, dtype=tdt, device=dev)
     r = torch.as_tensor(r_np, dtype=tdt, device=dev)
     eng = ansatz.engine_for(hamil, params)
@@ -286,8 +289,8 @@ def main():
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback',
                 'traffic': None, 'gemm_share_of_step': (gemm_ms / 3) / (total_ms / a.steps),
                 'gemm_launches_per_step': n_gemm // 3,
-                'algorithmic_flops_per_eloc': algorithmic_flops_per_eloc(N, M),
-                'whole_step_tflops': algorithmic_flops_per_eloc(N, M) * B * a.steps / (total_ms / 1e3) / 1e12}
+                'algorithmic_flops_per_eloc': algorithmic_flops_per_eloc(N, M, n_ecp=n_ecp),
+                'whole_step_tflops': algorithmic_flops_per_eloc(N, M, n_ecp=n_ecp) * B * a.steps / (total_ms / 1e3) / 1e12}
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

@@ -248,3 +248,39 @@ def test_full_size_properties_4096_walkers():
     # median at fp32 round-off; the tail are walkers next to a node / nucleus where E_kin cancels badly
     assert rel.median().item() < 2e-5 and rel.quantile(0.9).item() < 2e-4 and rel.quantile(0.99).item() < 2e-3, (
         rel.median().item(), rel.quantile(0.99).item(), rel.max().item())
+
+
+def test_benzene_ccecp_small_hyper_vs_oracle():
+    """BASELINE configs[3] geometry (benzene, ccECP, N = 30 valence electrons, M = 12, 6 non-local
+    centres): full E_loc including the 12-point non-local quadrature, reduced widths so the oracle's
+    autograd Hessian (90 coordinates) and 2160 forwards stay in seconds."""
+    hyper = dict(embedding_dim=32, n_layers=1, n_heads=2, n_determinants=2)
+    mol, hamil, oh, ansatz, params, r, R = make('benzene', ecp='ccECP', B=1, **hyper)
+    assert (hamil.n_up, hamil.n_down) == (15, 15)
+    tw = torch.as_tensor(np.random.default_rng(2).uniform(0, np.pi / 5, size=(1, 6, 30)), device=DEV)
+    pc = PhysicalConfiguration(R, r, torch.zeros(1, device=DEV))
+    E, stats = hamil.local_energy(ansatz.apply)(None, params, pc, ecp_twist=tw)
+    (s, l, e, st), = oracle_eval(ansatz, oh, params, r, R, twist=tw)
+    for k in STAT_KEYS:
+        assert abs(stats[k][0].item() - st[k]) <= 1e-7 * max(1, abs(st[k])), (k, stats[k][0].item(), st[k])
+    assert abs(E[0].item() - e) <= 1e-7 * max(1, abs(e))
+
+
+def test_benzene_full_psiformer_fp32_tensor_core_vs_fp64():
+    """Full-width benzene Psiformer (d=256, L=4, K=16): fp32 tensor-core engine against the fp64
+    CUDA-core engine on the same walkers and quadrature twists (the oracle is too slow here)."""
+    mol, hamil, oh, a64, params, r, R = make('benzene', ecp='ccECP', B=3)
+    a32 = B200Ansatz(hamil, 'psiformer', dtype='float32', gemm_backend=1)
+    tw = torch.as_tensor(np.random.default_rng(2).uniform(0, np.pi / 5, size=(3, 6, 30)), device=DEV)
+    f64 = hamil.local_energy(a64.apply)
+    f32 = hamil.local_energy(a32.apply)
+    E64, s64 = f64(None, params, PhysicalConfiguration(R, r, torch.zeros(3, device=DEV)), ecp_twist=tw)
+    E32, s32 = f32(None, params, PhysicalConfiguration(R.float(), r.float(), torch.zeros(3, device=DEV)), ecp_twist=tw.float())
+    psi64 = a64.apply(params, PhysicalConfiguration(R, r, torch.zeros(3, device=DEV)))
+    psi32 = a32.apply(params, PhysicalConfiguration(R.float(), r.float(), torch.zeros(3, device=DEV)))
+    assert torch.equal(psi64.sign.float(), psi32.sign)
+    assert (psi64.log - psi32.log.double()).abs().max().item() < 2e-3
+    for b in range(3):
+        scale = max(1.0, abs(E64[b].item()), 0.5 * abs(s64['hamil/lap'][b].item()), 0.5 * s64['hamil/quantum_force'][b].item())
+        assert abs(E32[b].item() - E64[b].item()) <= 1e-3 * scale, (b, E32[b].item(), E64[b].item())
+        assert abs(s32['hamil/V_nl'][b].item() - s64['hamil/V_nl'][b].item()) <= 2e-3 * max(1, abs(s64['hamil/V_nl'][b].item()))
