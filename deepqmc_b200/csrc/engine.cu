@@ -296,14 +296,17 @@ struct Engine : EngineBase {
     if (c > B) c = B;
     return (int)c;
   }
+  // non-local ECP pass for nb walkers: virtual walkers r_virt[V][N][3], sign[V], log[V] + one
+  // forward chunk over all V = nb * J * N * 12 virtual walkers
+  int64_t ecp_bytes(int64_t nb) const {
+    const int64_t V = nb * J * N * 12;
+    return (int64_t)align_up(sizeof(T) * V * 3 * N) + 2 * (int64_t)align_up(sizeof(T) * V) +
+           (int64_t)(sizeof(T) * per_walker_elems(1)) * V + 32 * 256;
+  }
   int64_t ws_bytes(int B, int mode) override {
     int S = mode == DQMC_MODE_FORWARD ? 1 : T3 + 2;
     int64_t need = (int64_t)chunk_bytes(B, S);
-    if (mode == DQMC_MODE_LOCAL_ENERGY && J > 0) {
-      int64_t V = (int64_t)B * J * N * 12;
-      int64_t e = (int64_t)sizeof(T) * V * (3 * N + 2) + 1024 + (int64_t)chunk_bytes((int)std::min<int64_t>(V, 1 << 20), 1);
-      if (e > need) need = e;
-    }
+    if (mode == DQMC_MODE_LOCAL_ENERGY && J > 0) need = std::max<int64_t>(need, ecp_bytes(B));
     return need;
   }
 
@@ -500,10 +503,18 @@ struct Engine : EngineBase {
     if (J > 0) {
       // non-local ECP: virtual walkers (12 quadrature points x electrons x ECP nuclei)
       const int64_t vper = (int64_t)J * N * 12;
-      const int64_t per = (int64_t)sizeof(T) * vper * (3 * N + 2) + (int64_t)sizeof(T) * per_walker_elems(1) * vper;
-      int64_t Be = (wsb - 64 * 256) / per;
+      int64_t Be = B;
+      if (ecp_bytes(Be) > wsb) {  // largest walker group whose virtual walkers fit the workspace
+        int64_t lo = 0, hi = B;
+        while (hi - lo > 1) {
+          int64_t mid = (lo + hi) / 2;
+          if (ecp_bytes(mid) <= wsb) lo = mid; else hi = mid;
+        }
+        Be = lo;
+      }
       if (Be < 1) { err = "workspace too small for the non-local ECP pass"; return 3; }
-      if (Be > B) Be = B;
+      const int64_t vcap = 2000000000LL / ((int64_t)N * 3 * d);  // keep 32-bit row counts safe
+      if (Be * vper > vcap) Be = std::max<int64_t>(1, vcap / vper);
       for (int b0 = 0; b0 < B; b0 += (int)Be) {
         int nb = (int)std::min<int64_t>(Be, B - b0);
         int64_t V = (int64_t)nb * vper;

@@ -126,6 +126,10 @@ class Engine:
 
     def workspace(self, n_walkers: int, mode: int, max_bytes: int | None = None):
         need = self.lib.dqmc_workspace_bytes(self.h, n_walkers, mode)
+        if max_bytes is None and not self._host:
+            # never ask for more than ~60 % of the free HBM: the engine chunks the walkers internally
+            free = torch.cuda.mem_get_info(self.device)[0] + (self._ws.numel() if self._ws is not None else 0)
+            max_bytes = int(0.6 * free)
         if max_bytes is not None:
             need = min(need, max(max_bytes, self.lib.dqmc_workspace_bytes(self.h, 1, mode)))
         if self._ws is None or self._ws.numel() < need:
@@ -184,15 +188,18 @@ class Engine:
         nn = self._prep(noise_normal) if noise_normal is not None else None
         nu = self._prep(noise_uniform) if noise_uniform is not None else None
         stats = torch.zeros(7, dtype=self.dtype, device=self.device)
-        ws = self.workspace(B, MODE_FORWARD, max_ws_bytes)
-        extra = (B * (r.shape[1] * 3 + 2)) * r.element_size() + 4096
-        if ws.numel() < self.lib.dqmc_workspace_bytes(self.h, 1, MODE_FORWARD) + extra:
+        # proposal buffers (r', sign', log', counter) + the forward-pass workspace
+        extra = (B * (r.shape[1] * 3 + 2)) * r.element_size() + 8192
+        fw = self.lib.dqmc_workspace_bytes(self.h, B, MODE_FORWARD)
+        if max_ws_bytes is not None:
+            fw = min(fw, max(max_ws_bytes, self.lib.dqmc_workspace_bytes(self.h, 1, MODE_FORWARD)))
+        elif not self._host:
+            free = torch.cuda.mem_get_info(self.device)[0] + (self._ws.numel() if self._ws is not None else 0)
+            fw = min(fw, max(int(0.6 * free), self.lib.dqmc_workspace_bytes(self.h, 1, MODE_FORWARD)))
+        if self._ws is None or self._ws.numel() < fw + extra:
             self._ws = None
-            ws = self.workspace(B, MODE_FORWARD)
-        if self._ws.numel() < self.lib.dqmc_workspace_bytes(self.h, B, MODE_FORWARD) + extra and max_ws_bytes is None:
-            self._ws = torch.empty(self.lib.dqmc_workspace_bytes(self.h, B, MODE_FORWARD) + extra, dtype=torch.uint8,
-                                   device=self.device)
-            ws = self._ws
+            self._ws = torch.empty(fw + extra, dtype=torch.uint8, device=self.device)
+        ws = self._ws
         rc = self.lib.dqmc_mcmc_sweep(
             self.h, r.data_ptr(), state['sign'].data_ptr(), state['log'].data_ptr(), state['age'].data_ptr(),
             state['tau'].data_ptr(), R.data_ptr(), Rb, B, n_sub, float(target_acceptance if target_acceptance else 0.0),
