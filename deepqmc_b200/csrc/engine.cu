@@ -418,8 +418,9 @@ struct Engine : EngineBase {
     Ws w = carve(wsbase, Bc, S);
     const int rows = Bc * N * S;
     const int F = 4 * M + 1;
-    DQ_LAUNCH(embed_kernel<T>, dim3(Bc * N), dim3(128), sizeof(T) * 5 * F, st, r, R, Rb, N, M, cfg.n_up, S, 1, 1,
-              P("emb.w"), d, w.X);
+    const int epb = S == 1 ? 8 : 1;  // plain forwards: several electrons per block (tiny per-electron work)
+    DQ_LAUNCH(embed_kernel<T>, dim3((Bc * N + epb - 1) / epb), dim3(128), sizeof(T) * 5 * F, st, r, R, Rb, N, M, cfg.n_up,
+              S, 1, 1, P("emb.w"), d, w.X, Bc * N, epb);
     T* X = w.X;
     T* O = w.O;
     const T scale = (T)(1.0 / std::sqrt((double)dh));
@@ -459,6 +460,11 @@ struct Engine : EngineBase {
     // per-spin backflow heads: rows of electron e across walkers, weights by spin
     gemm(X, d, "bf.up", "bf.dn", cfg.n_up, KN, nullptr, nullptr, 0, w.BF, KN, Bc * S, KN, d, S, 1, N, st);
     const int sl_wpb = slater_warps_per_block<T>(N);
+    if (S == 1 && N <= 32 && !std::getenv("DQMC_SLATER_GENERIC")) {
+      const int wpb = K < 8 ? K : 8;
+      DQ_LAUNCH(slater_fwd_reg_kernel<T>, dim3(Bc), dim3(32 * wpb), sizeof(T) * N * M, st, r, R, Rb, N, M, cfg.n_up, K,
+                P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog);
+    } else
     DQ_LAUNCH(slater_kernel<T>, dim3((Bc * K + sl_wpb - 1) / sl_wpb), dim3(32 * sl_wpb), slater_smem_bytes<T>(N), st, r, R,
               Rb, N, M, cfg.n_up, K, S, Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog,
               w.dgrad, w.dlap);

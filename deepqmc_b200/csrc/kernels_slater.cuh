@@ -15,6 +15,18 @@ namespace dq {
 //   d_t log|det A| = tr(A^-1 A^t);  lap log|det A| = tr(A^-1 A^L) - sum_t tr((A^-1 A^t)^2)
 // BF: augmented rows [b][i][s][K*N] (orbital index k*N + mu, wf/omni.py:78-88).
 // ------------------------------------------------------------------------------------------
+// lane-strided walk over a rows x cols index space without per-item division
+struct LaneWalk {
+  int i, j, qi, qj, cols;
+  __device__ __forceinline__ LaneWalk(int lane, int cols_) : cols(cols_) {
+    i = lane / cols_; j = lane - i * cols_; qi = 32 / cols_; qj = 32 - qi * cols_;
+  }
+  __device__ __forceinline__ void next() {
+    j += qj; i += qi;
+    if (j >= cols) { j -= cols; ++i; }
+  }
+};
+
 template <class T>
 __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M, int n_up,
                               int K, int S, int total, const T* __restrict__ pi_up, const T* __restrict__ pi_dn,
@@ -42,8 +54,8 @@ __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, 
   const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
   const size_t brow0 = (size_t)b * N * S;
 
-  for (int idx = lane; idx < N * N; idx += 32) {
-    const int i = idx / N, mu = idx % N;
+  for (LaneWalk w(lane, N); w.i < N; w.next()) {
+    const int i = w.i, mu = w.j;
     const T* pi = (i < n_up ? pi_up : pi_dn) + (size_t)(k * N + mu) * M;
     const T* ze = (i < n_up ? zeta_up : zeta_dn) + (size_t)(k * N + mu) * M;
     T e = 0, de0 = 0, de1 = 0, de2 = 0, le = 0;
@@ -110,8 +122,8 @@ __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, 
     const T ipv = T(1) / pv;
     for (int j = lane; j < 2 * N; j += 32) aug[c * N2 + j] *= ipv;
     __syncwarp();
-    for (int idx = lane; idx < N * 2 * N; idx += 32) {
-      int rr = idx / (2 * N), j = idx % (2 * N);
+    for (LaneWalk w(lane, 2 * N); w.i < N; w.next()) {
+      const int rr = w.i, j = w.j;
       if (rr != c) aug[rr * N2 + j] -= fcol[rr] * aug[c * N2 + j];
     }
     __syncwarp();
@@ -122,8 +134,8 @@ __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, 
 
   // Ainv[mu][i] = aug[mu][N + i]
   T lap = T(0);
-  for (int idx = lane; idx < N * N; idx += 32) {
-    int i = idx / N, mu = idx % N;
+  for (LaneWalk w(lane, N); w.i < N; w.next()) {
+    const int i = w.i, mu = w.j;
     lap += aug[mu * N2 + N + i] * AL[i * NP + mu];
   }
   lap = warp_sum(lap);
@@ -131,24 +143,24 @@ __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, 
   for (int t = 0; t < T3; ++t) {
     const int it = t / 3, ct = t % 3;
     __syncwarp();
-    for (int idx = lane; idx < N * N; idx += 32) {
-      int i = idx / N, mu = idx % N;
+    for (LaneWalk w(lane, N); w.i < N; w.next()) {
+      const int i = w.i, mu = w.j;
       T bft = BF[(brow0 + (size_t)i * S + 1 + t) * ldb + k * N + mu];
       T a = env[i * NP + mu] * bft;
       if (i == it) a += denv[(ct * N + i) * NP + mu] * bfv[i * NP + mu];
       At[i * NP + mu] = a;
     }
     __syncwarp();
-    for (int idx = lane; idx < N * N; idx += 32) {
-      int mu = idx / N, nu = idx % N;
+    for (LaneWalk w(lane, N); w.i < N; w.next()) {
+      const int mu = w.i, nu = w.j;
       T a = T(0);
       for (int i = 0; i < N; ++i) a += aug[mu * N2 + N + i] * At[i * NP + nu];
       Bt[mu * NP + nu] = a;
     }
     __syncwarp();
     T tr2 = T(0), gt = T(0);
-    for (int idx = lane; idx < N * N; idx += 32) {
-      int mu = idx / N, nu = idx % N;
+    for (LaneWalk w(lane, N); w.i < N; w.next()) {
+      const int mu = w.i, nu = w.j;
       tr2 += Bt[mu * NP + nu] * Bt[nu * NP + mu];
       if (mu == nu) gt += Bt[mu * NP + mu];
     }
@@ -174,6 +186,103 @@ inline int slater_warps_per_block(int N) {
 template <class T>
 inline size_t slater_smem_bytes(int N) {
   return slater_smem_per_warp<T>(N) * slater_warps_per_block<T>(N);
+}
+
+// ------------------------------------------------------------------------------------------
+// Forward-only (S = 1) Slater kernel for N <= 32: the hot kernel of the Metropolis sweep and of
+// the non-local ECP quadrature (12 N N_ecp plain forwards per walker).  One block per walker,
+// one warp per determinant (looping), lane r owns matrix ROW r entirely in registers:
+//   * electron-nucleus distances are computed once per walker into shared memory,
+//   * A[r][mu] = (sum_m pi exp(-|zeta| rho[r][m])) * bf[r][k N + mu]  built row-wise,
+//   * LU with implicit partial pivoting: per column one warp arg-max, one broadcast per remaining
+//     column (shuffle) and one FMA per lane -- no shared memory, no barriers;
+//   * sign = parity(pivot order) * prod sign(pivot)  (== LAPACK getrf convention of slogdet).
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void slater_fwd_reg_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M,
+                                      int n_up, int K, const T* __restrict__ pi_up, const T* __restrict__ pi_dn,
+                                      const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn,
+                                      const T* __restrict__ BF, int ldb, T* __restrict__ det_sign,
+                                      T* __restrict__ det_log) {
+  constexpr int NM = 32;
+  DQMC_DYN_SMEM(smem_raw);
+  T* rho = reinterpret_cast<T*>(smem_raw);  // [N][M]
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const T* rb = r + (size_t)b * N * 3;
+  const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
+  for (int idx = threadIdx.x; idx < N * M; idx += blockDim.x) {
+    const int i = idx / M, m = idx - i * M;
+    T dx0 = rb[3 * i] - Rb[3 * m], dx1 = rb[3 * i + 1] - Rb[3 * m + 1], dx2 = rb[3 * i + 2] - Rb[3 * m + 2];
+    rho[idx] = m_sqrt(Num<T>::eps() + dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
+  }
+  __syncthreads();
+  const bool rowok = lane < N;
+  const T* pi = (lane < n_up ? pi_up : pi_dn);
+  const T* ze = (lane < n_up ? zeta_up : zeta_dn);
+  for (int k = wib; k < K; k += wpb) {
+    T a[NM];
+#pragma unroll
+    for (int mu = 0; mu < NM; ++mu) {
+      T v = (mu == lane) ? T(1) : T(0);  // padding rows/columns: identity
+      if (rowok && mu < N) {
+        const T* pk = pi + (size_t)(k * N + mu) * M;
+        const T* zk = ze + (size_t)(k * N + mu) * M;
+        T e = T(0);
+        for (int m = 0; m < M; ++m) e += pk[m] * m_exp(-m_abs(zk[m]) * rho[lane * M + m]);
+        v = e * BF[((size_t)b * N + lane) * ldb + k * N + mu];
+      }
+      a[mu] = v;
+    }
+    T logdet = T(0), sgn = T(1);
+    unsigned used = 0u;       // rows already chosen as pivots (same value in every lane)
+    unsigned long long order0 = 0, order1 = 0, order2 = 0;  // pivot row of step c, 5 bits each, 12 steps per word
+#pragma unroll
+    for (int c = 0; c < NM; ++c) {
+      const bool mine_used = (used >> lane) & 1u;
+      T best = mine_used ? T(-1) : m_abs(a[c]);
+      int bi = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        T ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      const int prow = bi;
+      used |= 1u << prow;
+      if (c < 12) order0 |= (unsigned long long)prow << (5 * c);
+      else if (c < 24) order1 |= (unsigned long long)prow << (5 * (c - 12));
+      else order2 |= (unsigned long long)prow << (5 * (c - 24));
+      const T pv = __shfl_sync(0xffffffffu, a[c], prow);
+      logdet += m_log(m_abs(pv));
+      sgn *= pv > T(0) ? T(1) : (pv < T(0) ? T(-1) : T(0));
+      const bool elim = !((used >> lane) & 1u);  // rows not yet used (prow itself is used now)
+      const T f = elim ? a[c] / pv : T(0);
+#pragma unroll
+      for (int j = c + 1; j < NM; ++j) {
+        const T pj = __shfl_sync(0xffffffffu, a[j], prow);
+        a[j] -= f * pj;
+      }
+    }
+    if (lane == 0) {
+      // parity of the permutation c -> pivot row(c) by cycle counting
+      int perm[NM];
+#pragma unroll
+      for (int c = 0; c < NM; ++c)
+        perm[c] = (int)((c < 12 ? (order0 >> (5 * c)) : c < 24 ? (order1 >> (5 * (c - 12))) : (order2 >> (5 * (c - 24)))) & 31ull);
+      unsigned seen = 0u;
+      int transp = 0;
+      for (int c = 0; c < NM; ++c) {
+        if ((seen >> c) & 1u) continue;
+        int len = 0, x = c;
+        while (!((seen >> x) & 1u)) { seen |= 1u << x; x = perm[x]; ++len; }
+        transp += len - 1;
+      }
+      if (transp & 1) sgn = -sgn;
+      det_log[(size_t)b * K + k] = logdet;
+      det_sign[(size_t)b * K + k] = sgn;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -16,18 +16,21 @@ namespace dq {
 // Electron embedding: nucleus-electron features (+ spin) -> optional projection.
 // reference: src/deepqmc/gnn/electron_gnn.py:596-619, gnn/edge_features.py:21-78,
 //            conf/ansatz/psiformer.yaml:53-67, ferminet.yaml:45-56.
-// grid = B*N blocks, dynamic smem = 5*F*sizeof(T), F = 4*M + use_spin.
+// grid = ceil(B*N / epb) blocks, each handling epb consecutive (walker, electron) pairs;
+// dynamic smem = 5*F*sizeof(T), F = 4*M + use_spin.
 // ------------------------------------------------------------------------------------------
 template <class T>
 __global__ void embed_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M,
                              int n_up, int S, int log_rescale, int use_spin, const T* __restrict__ W, int d,
-                             T* __restrict__ X) {
+                             T* __restrict__ X, int total, int epb) {
   DQMC_DYN_SMEM(smem_raw);
   const int F = 4 * M + use_spin;
   T* feat = reinterpret_cast<T*>(smem_raw);  // [F]
   T* dfeat = feat + F;                        // [3][F]
   T* lfeat = dfeat + 3 * F;                   // [F]
-  const int bi = blockIdx.x, b = bi / N, i = bi % N;
+  for (int bi = blockIdx.x * epb; bi < total && bi < (blockIdx.x + 1) * epb; ++bi) {
+  __syncthreads();  // shared feature buffers are reused per electron
+  const int b = bi / N, i = bi % N;
   const T* ri = r + (size_t)bi * 3;
   const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
@@ -94,6 +97,7 @@ __global__ void embed_kernel(const T* __restrict__ r, const T* __restrict__ R, i
       }
       Xg[(size_t)(1 + T3) * d + f] = yl;
     }
+  }
   }
 }
 
