@@ -25,9 +25,10 @@ import numpy as np
 import torch
 
 WORKLOADS = {
-    'lih_psiformer': dict(mol='LiH', ecp=None, walkers=4096, hyper={}),
-    'n2_psiformer': dict(mol='N2', ecp=None, walkers=4096, hyper={}),
-    'benzene_psiformer': dict(mol='benzene', ecp='ccECP', walkers=4096, hyper={}),
+    'lih_psiformer': dict(mol='LiH', ecp=None, walkers=4096, hyper={}, kind='psiformer'),
+    'n2_psiformer': dict(mol='N2', ecp=None, walkers=4096, hyper={}, kind='psiformer'),
+    'n2_ferminet': dict(mol='N2', ecp=None, walkers=4096, hyper={}, kind='ferminet'),
+    'benzene_psiformer': dict(mol='benzene', ecp='ccECP', walkers=4096, hyper={}, kind='psiformer'),
 }
 
 
@@ -97,14 +98,14 @@ _ORACLE = {}
 def _oracle_init(wl_name, seed):
     """Pool initialiser: one single-threaded oracle per worker process."""
     torch.set_num_threads(1)
-    from deepqmc_b200.spec import psiformer_spec
+    from deepqmc_b200.spec import ferminet_spec, psiformer_spec
     from oracle import wf
     from oracle.hamil import OracleHamiltonian
 
     wl = WORKLOADS[wl_name]
     mol, hamil, r, PN = make_problem(wl, 1, seed)
     oh = OracleHamiltonian(mol, ecp_type=wl['ecp'])
-    spec = psiformer_spec(oh, **wl['hyper'])
+    spec = (psiformer_spec if wl['kind'] == 'psiformer' else ferminet_spec)(oh, **wl['hyper'])
     pt = wf.to_torch(PN.perturb_params(PN.init_params(spec, 0)))
     J = 0 if oh.nl_params is None else len(np.unique(np.nonzero(oh.nl_params)[0]))
     _ORACLE.update(wl=wl, oh=oh, spec=spec, pt=pt, R=torch.as_tensor(mol.coords), J=J, wf=wf)
@@ -163,7 +164,7 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     unit = 'walker.local-energies/s'
     metric = 'walker.local-energies/sec'
-    workload_name = f"{wl['mol']} Psiformer d256 L4 H4 K16{' ' + wl['ecp'] if wl['ecp'] else ''}, {B} walkers/GPU"
+    workload_name = f"{wl['mol']} {'Psiformer d256 L4 H4 K16' if wl['kind'] == 'psiformer' else 'FermiNet d256 L4 e32 K16'}{' ' + wl['ecp'] if wl['ecp'] else ''}, {B} walkers/GPU"
 
     if a.impl == 'reference':
         if rank != 0:
@@ -194,7 +195,7 @@ def main():
     dev = torch.device('cuda', local)
     mol, hamil, r_np, PN = make_problem(wl, B, seed=1000 + rank)
     backend = 1 if (a.gemm_backend == 'tcgen05' and a.dtype == 'float32') else 0
-    ansatz = B200Ansatz(hamil, 'psiformer', dtype=a.dtype, device=local, gemm_backend=backend, **wl['hyper'])
+    ansatz = B200Ansatz(hamil, wl['kind'], dtype=a.dtype, device=local, gemm_backend=backend, **wl['hyper'])
     params = PN.perturb_params(ansatz.init(0))
     tdt = torch.float32 if a.dtype == 'float32' else torch.float64
     N, M = hamil.n_up + hamil.n_down, hamil.n_nuc

@@ -73,6 +73,20 @@ struct EngineBase {
         add(p + "b2", 1, d);
       }
     }
+    if (cfg.kind == DQMC_FERMINET) {
+      const int de = cfg.edge_dim;
+      int din = 4 * M, ein = 4;
+      for (int l = 0; l < cfg.n_layers; ++l) {
+        std::string p = "F" + std::to_string(l) + ".";
+        add(p + "wg", 3 * din + 2 * ein, d);
+        add(p + "bg", 1, d);
+        if (l < cfg.n_layers - 1) {
+          add(p + "wu", ein, de);
+          add(p + "bu", 1, de);
+        }
+        din = d; ein = de;
+      }
+    }
     add("bf.up", d, K * N);
     add("bf.dn", d, K * N);
     add("env.pi_up", K * N, M);
@@ -166,7 +180,9 @@ struct Engine : EngineBase {
   int init() {
     N = cfg.n_up + cfg.n_down; M = cfg.n_nuc; d = cfg.embedding_dim; K = cfg.n_determinants;
     KN = K * N; H = cfg.n_heads; dh = d / H; T3 = 3 * N;
-    if (cfg.kind != DQMC_PSIFORMER) { err = "only DQMC_PSIFORMER is implemented in this build"; return 2; }
+    if (cfg.kind != DQMC_PSIFORMER && cfg.kind != DQMC_FERMINET) { err = "unknown ansatz kind"; return 2; }
+    if (H < 1) H = 1;
+    if (cfg.kind == DQMC_FERMINET) { H = 1; dh = d; }
     if (M > DQMC_MAX_NUC || d % H != 0 || N < 2) { err = "bad config"; return 2; }
     build_layout();
     DQ_CHECK(cudaSetDevice(device));
@@ -212,17 +228,18 @@ struct Engine : EngineBase {
       }
     }
     // opt in to large dynamic shared memory
+    const bool psif = cfg.kind == DQMC_PSIFORMER;
     attn_tb = attn_pick_tb<T>(N, dh, T3, 100 * 1024);
-    attn_f32 = std::is_same<T, float>::value && dh % 16 == 0 && !std::getenv("DQMC_ATTN_GENERIC");
+    attn_f32 = psif && std::is_same<T, float>::value && dh % 16 == 0 && !std::getenv("DQMC_ATTN_GENERIC");
     if (attn_f32) attn_tb = attn_f32_pick_tb(N, dh, T3, 32 * 1024);  // ~7 blocks/SM for small molecules
     if (const char* ev = std::getenv("DQMC_ATTN_TB")) { int x = std::atoi(ev); if (x >= 1 && x <= T3) attn_tb = x; }
-    size_t s_attn = attn_f32 ? attn_f32_smem_bytes(N, dh, attn_tb) : attn_smem_bytes<T>(N, dh, attn_tb);
+    size_t s_attn = !psif ? 0 : attn_f32 ? attn_f32_smem_bytes(N, dh, attn_tb) : attn_smem_bytes<T>(N, dh, attn_tb);
     size_t s_sl = slater_smem_bytes<T>(N);
     max_smem = s_attn > s_sl ? s_attn : s_sl;
     if (max_smem > 227 * 1024) { err = "system too large for the shared-memory tiling (N)"; return 2; }
     if (attn_f32) {
       if (launch_attn_f32(nullptr, nullptr, 0, 0, 0, 0.f, 0, (int)s_attn, nullptr, true)) return 1;
-    } else
+    } else if (psif)
       DQ_CHECK(cudaFuncSetAttribute(attn_fl_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_attn));
     DQ_CHECK(cudaFuncSetAttribute(slater_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_sl));
     if (cfg.gemm_backend == DQMC_GEMM_TCGEN05) {
@@ -256,7 +273,7 @@ struct Engine : EngineBase {
     if (use_tc()) {
       for (auto& e : entries) {
         bool is_w = e.name.find(".w") != std::string::npos || e.name.rfind("bf.", 0) == 0;
-        if (!is_w || e.name == "emb.w") continue;
+        if (!is_w || e.name == "emb.w" || e.rows % 32 != 0 || e.cols < 64) continue;
         int rc = prepare_tc_weight(e.name, (const float*)(d_params + e.offset), e.rows, e.cols, st);
         if (rc) return rc;
       }
@@ -273,7 +290,12 @@ struct Engine : EngineBase {
   };
   size_t per_walker_elems(int S) const {
     size_t rows = (size_t)N * S;
-    return rows * (size_t)(4 * d + 3 * d + KN) + (size_t)K * (3 + (S > 1 ? T3 : 0));
+    size_t dets = (size_t)K * (3 + (S > 1 ? T3 : 0));
+    if (cfg.kind == DQMC_FERMINET) {
+      const size_t de = cfg.edge_dim, fin = 3 * (size_t)d + 2 * de;
+      return rows * (2 * (size_t)d + fin + KN) + (size_t)N * rows * 2 * de + dets;
+    }
+    return rows * (size_t)(4 * d + 3 * d + KN) + dets;
   }
   size_t chunk_bytes(int Bc, int S) const { return sizeof(T) * per_walker_elems(S) * Bc + 16 * 256; }
   Ws carve(void* base, int Bc, int S) const {
@@ -281,8 +303,15 @@ struct Engine : EngineBase {
     size_t rows = (size_t)Bc * N * S;
     char* p = (char*)base;
     auto take = [&](size_t n) { T* q = (T*)p; p += align_up(sizeof(T) * n); return q; };
-    w.X = take(rows * d); w.O = take(rows * d); w.A = take(rows * d); w.M1 = take(rows * d);
-    w.QKV = take(rows * 3 * d); w.BF = take(rows * KN);
+    if (cfg.kind == DQMC_FERMINET) {
+      const size_t de = cfg.edge_dim, fin = 3 * (size_t)d + 2 * de;
+      w.X = take(rows * d); w.O = take(rows * d); w.QKV = take(rows * fin);    // H, H2, F
+      w.A = take(rows * N * de); w.M1 = take(rows * N * de);                   // E, E2
+      w.BF = take(rows * KN);
+    } else {
+      w.X = take(rows * d); w.O = take(rows * d); w.A = take(rows * d); w.M1 = take(rows * d);
+      w.QKV = take(rows * 3 * d); w.BF = take(rows * KN);
+    }
     w.dsign = take((size_t)Bc * K); w.dlog = take((size_t)Bc * K); w.dlap = take((size_t)Bc * K);
     w.dgrad = take((size_t)Bc * K * (S > 1 ? T3 : 1));
     w.bytes = p - (char*)base;
@@ -292,6 +321,7 @@ struct Engine : EngineBase {
     int64_t per = (int64_t)(sizeof(T) * per_walker_elems(S));
     int64_t c = (wsb - 16 * 256) / per;
     int64_t row_cap = (int64_t)2000000000 / ((int64_t)N * S * 3 * d);  // keep 32-bit row*ld products safe
+    if (cfg.kind == DQMC_FERMINET) row_cap = (int64_t)2000000000 / ((int64_t)N * N * S * (3 * d + 64));
     if (c > row_cap) c = row_cap;
     if (c > B) c = B;
     return (int)c;
@@ -324,7 +354,7 @@ struct Engine : EngineBase {
     const T* W1 = w1 ? P(w1) : nullptr;
 #if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
     if constexpr (std::is_same<T, float>::value) {
-      if (use_tc() && Kc % 32 == 0 && lda % 4 == 0 && ldc % 4 == 0) {
+      if (use_tc() && Kc % 32 == 0 && lda % 4 == 0 && ldc % 4 == 0 && tcw.count(w0) && (!w1 || tcw.count(w1))) {
         const TcWeight& t0 = tcw.at(w0);
         const TcWeight& t1 = w1 ? tcw.at(w1) : t0;
         tc::Params p;
@@ -413,10 +443,51 @@ struct Engine : EngineBase {
   }
 
   // ---- one chunk of the wave-function pipeline ---------------------------------------------
+  // FermiNet trunk (reference: conf/ansatz/ferminet.yaml; gnn/electron_gnn.py:160-259 with
+  // Residual / NodeSum / EdgeSum update features and a shared edge MLP): leaves the final electron
+  // embeddings in *Xout.
+  int ferminet_trunk(const T* r, const T* R, int Rb, int Bc, int S, Ws& w, T** Xout, cudaStream_t st) {
+    const int rows = Bc * N * S, rowsE = Bc * N * N * S, de = cfg.edge_dim, d0 = 4 * M;
+    const T isq2 = (T)0.70710678118654752440;
+    DQ_LAUNCH(embed_kernel<T>, dim3(Bc * N), dim3(128), sizeof(T) * 5 * d0, st, r, R, Rb, N, M, cfg.n_up, S, 0, 0,
+              (const T*)nullptr, d0, w.X, Bc * N, 1);
+    DQ_LAUNCH(edge_feat_kernel<T>, dim3((Bc * N * N + 127) / 128), dim3(128), 0, st, r, N, S, w.A, Bc * N * N);
+    T* Hc = w.X; T* Hn = w.O; T* Ec = w.A; T* En = w.M1;
+    int dcur = d0, ecur = 4;
+    for (int l = 0; l < cfg.n_layers; ++l) {
+      std::string p = "F" + std::to_string(l) + ".";
+      const int fin = 3 * dcur + 2 * ecur;
+      DQ_LAUNCH(fermi_agg_kernel<T>, dim3(Bc * S, N), dim3(128), 0, st, (const T*)Hc, dcur, (const T*)Ec, ecur, N, cfg.n_up,
+                S, w.QKV);
+      int rc = gemm(w.QKV, fin, (p + "wg").c_str(), nullptr, 0, d, P(p + "bg"), nullptr, 0, Hn, d, rows, d, fin, S, 0, N, st);
+      if (rc) return rc;
+      DQ_LAUNCH(tanh_fl_kernel<T>, dim3(Bc * N, (d + 127) / 128), dim3(128), 0, st, Hn, d,
+                (const T*)(dcur == d ? Hc : nullptr), dcur, S, d, dcur == d ? isq2 : T(1));
+      if (l < cfg.n_layers - 1) {
+        rc = gemm(Ec, ecur, (p + "wu").c_str(), nullptr, 0, de, P(p + "bu"), nullptr, 0, En, de, rowsE, de, ecur, S, 0, N, st);
+        if (rc) return rc;
+        DQ_LAUNCH(tanh_fl_kernel<T>, dim3(Bc * N * N, 1), dim3(32), 0, st, En, de, (const T*)(ecur == de ? Ec : nullptr),
+                  ecur, S, de, ecur == de ? isq2 : T(1));
+        T* t2 = Ec; Ec = En; En = t2;
+        ecur = de;
+      }
+      T* t1 = Hc; Hc = Hn; Hn = t1;
+      dcur = d;
+    }
+    *Xout = Hc;
+    return 0;
+  }
+
   int run_chunk(const T* r, const T* R, int Rb, int Bc, int S, int Bstat, T* sign, T* logp, T* E, T* stats, T* grad,
                 void* wsbase, cudaStream_t st) {
     Ws w = carve(wsbase, Bc, S);
     const int rows = Bc * N * S;
+    if (cfg.kind == DQMC_FERMINET) {
+      T* Xf = nullptr;
+      int rc = ferminet_trunk(r, R, Rb, Bc, S, w, &Xf, st);
+      if (rc) return rc;
+      return tail(r, R, Rb, Bc, S, Bstat, sign, logp, E, stats, grad, w, Xf, st);
+    }
     const int F = 4 * M + 1;
     const int epb = S == 1 ? 8 : 1;  // plain forwards: several electrons per block (tiny per-electron work)
     DQ_LAUNCH(embed_kernel<T>, dim3((Bc * N + epb - 1) / epb), dim3(128), sizeof(T) * 5 * F, st, r, R, Rb, N, M, cfg.n_up,
@@ -457,6 +528,12 @@ struct Engine : EngineBase {
       }
       T* tmp = X; X = O; O = tmp;
     }
+    return tail(r, R, Rb, Bc, S, Bstat, sign, logp, E, stats, grad, w, X, st);
+  }
+
+  // backflow heads -> Slater determinants -> det sum / cusp / potentials (shared by all trunks)
+  int tail(const T* r, const T* R, int Rb, int Bc, int S, int Bstat, T* sign, T* logp, T* E, T* stats, T* grad, Ws& w,
+           T* X, cudaStream_t st) {
     // per-spin backflow heads: rows of electron e across walkers, weights by spin
     gemm(X, d, "bf.up", "bf.dn", cfg.n_up, KN, nullptr, nullptr, 0, w.BF, KN, Bc * S, KN, d, S, 1, N, st);
     const int sl_wpb = slater_warps_per_block<T>(N);

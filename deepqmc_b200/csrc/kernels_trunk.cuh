@@ -644,3 +644,79 @@ inline int attn_f32_pick_tb(int N, int dh, int T3, size_t budget) {
 }
 
 }  // namespace dq
+
+namespace dq {
+
+// ------------------------------------------------------------------------------------------
+// FermiNet two-electron stream, initial features.  reference: src/deepqmc/gnn/graph.py:23-31
+// (edges = receiver - sender), :197-215 'up'/'down' builders (senders = spin-up / spin-down
+// electrons, receivers = all electrons, self-interaction kept), gnn/edge_features.py:42-78
+// ([|d| eps-safe, d]), conf/ansatz/ferminet.yaml:58-72.
+// E[b][j][i][s][4]: sender j (0..N-1; j < n_up are the 'up' senders), receiver i, slot s.
+// One thread per (b, j, i).
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void edge_feat_kernel(const T* __restrict__ r, int N, int S, T* __restrict__ E, int total) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int i = idx % N, j = (idx / N) % N, b = idx / (N * N);
+  const T* rb = r + (size_t)b * N * 3;
+  T* e = E + (size_t)idx * S * 4;
+  T dx[3] = {rb[3 * i] - rb[3 * j], rb[3 * i + 1] - rb[3 * j + 1], rb[3 * i + 2] - rb[3 * j + 2]};
+  T d2 = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+  T rho2 = Num<T>::eps() + d2, rho = m_sqrt(rho2);
+  e[0] = rho; e[1] = dx[0]; e[2] = dx[1]; e[3] = dx[2];
+  if (S == 1) return;
+  const int T3 = S - 2;
+  for (int t = 0; t < T3; ++t) {
+    const int el = t / 3, c = t % 3;
+    T sgn = T(0);
+    if (i != j) sgn = el == i ? T(1) : (el == j ? T(-1) : T(0));
+    T* et = e + (size_t)(1 + t) * 4;
+    et[0] = sgn * dx[c] / rho;
+    et[1] = c == 0 ? sgn : T(0);
+    et[2] = c == 1 ? sgn : T(0);
+    et[3] = c == 2 ? sgn : T(0);
+  }
+  T* el = e + (size_t)(1 + T3) * 4;
+  el[0] = i != j ? T(2) * (T(3) / rho - d2 / (rho2 * rho)) : T(0);
+  el[1] = el[2] = el[3] = T(0);
+}
+
+// ------------------------------------------------------------------------------------------
+// FermiNet node-update input: F[b][i][s][:] = [h_i, mean_up h, mean_down h, mean_{j in up} e_ji,
+// mean_{j in down} e_ji]  (reference: gnn/update_features.py:47-159 Residual / NodeSum / EdgeSum
+// features with normalize = true, electron_gnn.py:243-259 'concatenate').  All linear, so it acts
+// slot-wise on the augmented rows.  grid = (B*S, N), block over features.
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void fermi_agg_kernel(const T* __restrict__ H, int dh, const T* __restrict__ E, int de, int N, int n_up,
+                                 int S, T* __restrict__ F) {
+  const int bs = blockIdx.x, b = bs / S, s = bs % S, i = blockIdx.y;
+  const int ldf = 3 * dh + 2 * de;
+  T* f = F + ((size_t)(b * N + i) * S + s) * ldf;
+  const int n_dn = N - n_up;
+  for (int k = threadIdx.x; k < ldf; k += blockDim.x) {
+    T v;
+    if (k < dh) {
+      v = H[((size_t)(b * N + i) * S + s) * dh + k];
+    } else if (k < 3 * dh) {
+      const bool up = k < 2 * dh;
+      const int kk = up ? k - dh : k - 2 * dh;
+      const int j0 = up ? 0 : n_up, j1 = up ? n_up : N;
+      T acc = T(0);
+      for (int j = j0; j < j1; ++j) acc += H[((size_t)(b * N + j) * S + s) * dh + kk];
+      v = acc / (T)(up ? n_up : n_dn);
+    } else {
+      const bool up = k < 3 * dh + de;
+      const int kk = up ? k - 3 * dh : k - 3 * dh - de;
+      const int j0 = up ? 0 : n_up, j1 = up ? n_up : N;
+      T acc = T(0);
+      for (int j = j0; j < j1; ++j) acc += E[(((size_t)(b * N + j) * N + i) * S + s) * de + kk];
+      v = acc / (T)(up ? n_up : n_dn);
+    }
+    f[k] = v;
+  }
+}
+
+}  // namespace dq

@@ -32,6 +32,12 @@ def _pack_haiku_params(spec: AnsatzSpec, params: dict) -> dict[str, np.ndarray]:
             out[f'L{l}.wo'] = g(a + 'multi_head_attention/linear:w')
             out[f'L{l}.w1'], out[f'L{l}.b1'] = g(a + 'mlp/linear_0:w'), g(a + 'mlp/linear_0:b')[None]
             out[f'L{l}.w2'], out[f'L{l}.b2'] = g(a + 'mlp/linear_1:w'), g(a + 'mlp/linear_1:b')[None]
+    elif spec.kind == 'ferminet':
+        for l in range(spec.n_layers):
+            lp = PN.layer_prefix(l)
+            out[f'F{l}.wg'], out[f'F{l}.bg'] = g(lp + 'g/linear_0:w'), g(lp + 'g/linear_0:b')[None]
+            if l < spec.n_layers - 1:
+                out[f'F{l}.wu'], out[f'F{l}.bu'] = g(lp + 'u/linear_0:w'), g(lp + 'u/linear_0:b')[None]
     else:
         raise NotImplementedError(spec.kind)
     out['bf.up'], out['bf.dn'] = g(PN.BF_UP + ':w'), g(PN.BF_DN + ':w')

@@ -19,12 +19,12 @@ from deepqmc_b200.types import PhysicalConfiguration
 DEV = 'cuda:0'
 
 
-def make(mol_name, ecp=None, dtype='float64', seed=0, B=4, **hyper):
+def make(mol_name, ecp=None, dtype='float64', seed=0, B=4, kind='psiformer', **hyper):
     from oracle.hamil import OracleHamiltonian
 
     mol = Molecule.from_name(mol_name)
     hamil = MolecularHamiltonian(mol=mol, ecp_type=ecp)
-    ansatz = B200Ansatz(hamil, 'psiformer', dtype=dtype, **hyper)
+    ansatz = B200Ansatz(hamil, kind, dtype=dtype, **hyper)
     params = PN.perturb_params(ansatz.init(seed))
     rng = np.random.default_rng(seed)
     N = hamil.n_up + hamil.n_down
@@ -284,3 +284,32 @@ def test_benzene_full_psiformer_fp32_tensor_core_vs_fp64():
         scale = max(1.0, abs(E64[b].item()), 0.5 * abs(s64['hamil/lap'][b].item()), 0.5 * s64['hamil/quantum_force'][b].item())
         assert abs(E32[b].item() - E64[b].item()) <= 1e-3 * scale, (b, E32[b].item(), E64[b].item())
         assert abs(s32['hamil/V_nl'][b].item() - s64['hamil/V_nl'][b].item()) <= 2e-3 * max(1, abs(s64['hamil/V_nl'][b].item()))
+
+
+@pytest.mark.parametrize('mol_name,hyper,B', [
+    ('LiH', dict(embedding_dim=32, n_layers=3, n_determinants=4), 3),
+    ('N2', dict(embedding_dim=32, n_layers=2, n_determinants=2), 2),  # BASELINE configs[2] geometry
+])
+def test_ferminet_local_energy_fp64(mol_name, hyper, B):
+    """FermiNet trunk (reference conf/ansatz/ferminet.yaml: one- and two-electron streams, shared edge
+    MLP, residual/sqrt2, no cusp) through the same engine: psi, E_loc, stats against the oracle."""
+    mol, hamil, oh, ansatz, params, r, R = make(mol_name, B=B, kind='ferminet', **hyper)
+    pc = PhysicalConfiguration(R, r, torch.zeros(B, device=DEV))
+    psi = ansatz.apply(params, pc)
+    E, stats = hamil.local_energy(ansatz.apply)(None, params, pc)
+    for b, (s, l, e, st) in enumerate(oracle_eval(ansatz, oh, params, r, R)):
+        assert psi.sign[b].item() == s and abs(psi.log[b].item() - l) <= 1e-10 * max(1, abs(l))
+        assert abs(E[b].item() - e) <= 1e-8 * max(1, abs(e))
+        for k in STAT_KEYS:
+            assert abs(stats[k][b].item() - st[k]) <= 1e-8 * max(1, abs(st[k])), (k, stats[k][b].item(), st[k])
+
+
+def test_ferminet_n2_full_fp32_tensor_core_vs_fp64():
+    """N2 FermiNet at full width (d=256, L=4, K=16, 32-wide edge stream): fp32 tensor-core engine vs fp64."""
+    mol, hamil, oh, a64, params, r, R = make('N2', B=4, kind='ferminet')
+    a32 = B200Ansatz(hamil, 'ferminet', dtype='float32', gemm_backend=1)
+    E64, s64 = hamil.local_energy(a64.apply)(None, params, PhysicalConfiguration(R, r, torch.zeros(4, device=DEV)))
+    E32, s32 = hamil.local_energy(a32.apply)(None, params, PhysicalConfiguration(R.float(), r.float(), torch.zeros(4, device=DEV)))
+    for b in range(4):
+        scale = max(1.0, abs(E64[b].item()), 0.5 * abs(s64['hamil/lap'][b].item()), 0.5 * s64['hamil/quantum_force'][b].item())
+        assert abs(E32[b].item() - E64[b].item()) <= 1e-3 * scale, (b, E32[b].item(), E64[b].item())

@@ -31,6 +31,7 @@ def main():
     ap.add_argument('--K', type=int, default=3)
     ap.add_argument('--B', type=int, default=3)
     ap.add_argument('--ecp', default=None)
+    ap.add_argument('--kind', default='psiformer')
     ap.add_argument('--dtype', default='float64')
     ap.add_argument('--nobuild', action='store_true')
     a = ap.parse_args()
@@ -38,13 +39,14 @@ def main():
     from deepqmc_b200 import params as PN
     from deepqmc_b200.engine import Engine
     from deepqmc_b200.molecule import Molecule
-    from deepqmc_b200.spec import psiformer_spec
+    from deepqmc_b200.spec import ferminet_spec, psiformer_spec
     from oracle import wf
     from oracle.hamil import OracleHamiltonian
 
     mol = Molecule.from_name(a.mol)
     h = OracleHamiltonian(mol, ecp_type=a.ecp)
-    spec = psiformer_spec(h, embedding_dim=a.d, n_layers=a.layers, n_heads=a.heads, n_determinants=a.K)
+    mk = psiformer_spec if a.kind == 'psiformer' else ferminet_spec
+    spec = mk(h, embedding_dim=a.d, n_layers=a.layers, n_heads=a.heads, n_determinants=a.K)
     params = PN.perturb_params(PN.init_params(spec, 0))
     pt = wf.to_torch(params)
     rng = np.random.default_rng(0)
