@@ -537,7 +537,21 @@ struct Engine : EngineBase {
     // per-spin backflow heads: rows of electron e across walkers, weights by spin
     gemm(X, d, "bf.up", "bf.dn", cfg.n_up, KN, nullptr, nullptr, 0, w.BF, KN, Bc * S, KN, d, S, 1, N, st);
     const int sl_wpb = slater_warps_per_block<T>(N);
-    if (S == 1 && N <= 32 && !std::getenv("DQMC_SLATER_GENERIC")) {
+    if ((N <= 4 || (N <= 6 && std::is_same<T, float>::value)) && !std::getenv("DQMC_SLATER_GENERIC")) {
+      const int tot = Bc * K;
+#define DQ_SL_SMALL(NS_)                                                                                           \
+  DQ_LAUNCH((slater_small_kernel<T, NS_>), dim3((tot + 63) / 64), dim3(64), 0, st, r, R, Rb, M, cfg.n_up, K, S, tot,    \
+            P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog, \
+            w.dgrad, w.dlap)
+      switch (N) {
+        case 2: DQ_SL_SMALL(2); break;
+        case 3: DQ_SL_SMALL(3); break;
+        case 4: DQ_SL_SMALL(4); break;
+        case 5: DQ_SL_SMALL(5); break;
+        default: DQ_SL_SMALL(6); break;
+      }
+#undef DQ_SL_SMALL
+    } else if (S == 1 && N <= 32 && !std::getenv("DQMC_SLATER_GENERIC")) {
       const int wpb = K < 8 ? K : 8;
       DQ_LAUNCH(slater_fwd_reg_kernel<T>, dim3(Bc), dim3(32 * wpb), sizeof(T) * N * M, st, r, R, Rb, N, M, cfg.n_up, K,
                 P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog);

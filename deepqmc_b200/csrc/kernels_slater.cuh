@@ -189,6 +189,141 @@ inline size_t slater_smem_bytes(int N) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Small molecules (N = NS <= 6 electrons, compile time): ONE THREAD per (walker, determinant),
+// the NS x NS matrix, its inverse and all per-tangent products live in registers (fully unrolled).
+// Same algebra as slater_kernel (envelopes, Gauss-Jordan with partial pivoting, tr(A^-1 dA),
+// tr((A^-1 dA)^2)); used for both S = 1 and the forward-Laplacian pass.
+// ------------------------------------------------------------------------------------------
+template <class T, int NS>
+__global__ void slater_small_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int M, int n_up,
+                                    int K, int S, int total, const T* __restrict__ pi_up, const T* __restrict__ pi_dn,
+                                    const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn,
+                                    const T* __restrict__ BF, int ldb, T* __restrict__ det_sign,
+                                    T* __restrict__ det_log, T* __restrict__ det_grad, T* __restrict__ det_lap) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int b = gid / K, k = gid % K;
+  const int T3 = S > 1 ? S - 2 : 0;
+  const T* rb = r + (size_t)b * NS * 3;
+  const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
+  const size_t brow0 = (size_t)b * NS * S;
+  T env[NS][NS], de[3][NS][NS], bf0[NS][NS], A[NS][NS], Ai[NS][NS], AL[NS][NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    const T* pi_s = i < n_up ? pi_up : pi_dn;
+    const T* ze_s = i < n_up ? zeta_up : zeta_dn;
+#pragma unroll
+    for (int mu = 0; mu < NS; ++mu) {
+      const T* pi = pi_s + (size_t)(k * NS + mu) * M;
+      const T* ze = ze_s + (size_t)(k * NS + mu) * M;
+      T e = 0, d0 = 0, d1 = 0, d2_ = 0, le = 0;
+      for (int m = 0; m < M; ++m) {
+        T dx0 = rb[3 * i] - Rb[3 * m], dx1 = rb[3 * i + 1] - Rb[3 * m + 1], dx2 = rb[3 * i + 2] - Rb[3 * m + 2];
+        T dd = dx0 * dx0 + dx1 * dx1 + dx2 * dx2;
+        T rho2 = Num<T>::eps() + dd, rho = m_sqrt(rho2);
+        T a = m_abs(ze[m]);
+        T ex = pi[m] * m_exp(-a * rho);
+        e += ex;
+        if (S > 1) {
+          T c = -a * ex / rho;
+          d0 += c * dx0; d1 += c * dx1; d2_ += c * dx2;
+          le += ex * (a * a * dd / rho2 - a * (T(3) / rho - dd / (rho2 * rho)));
+        }
+      }
+      const T* bfrow = BF + (brow0 + (size_t)i * S) * ldb + k * NS + mu;
+      const T b0 = bfrow[0];
+      env[i][mu] = e; bf0[i][mu] = b0;
+      de[0][i][mu] = d0; de[1][i][mu] = d1; de[2][i][mu] = d2_;
+      A[i][mu] = e * b0;
+      Ai[i][mu] = (i == mu) ? T(1) : T(0);
+      AL[i][mu] = T(0);
+      if (S > 1) {
+        const T bfl = bfrow[(size_t)(1 + T3) * ldb];
+        const T x0 = bfrow[(size_t)(1 + 3 * i) * ldb], x1 = bfrow[(size_t)(2 + 3 * i) * ldb], x2 = bfrow[(size_t)(3 + 3 * i) * ldb];
+        AL[i][mu] = le * b0 + e * bfl + T(2) * (d0 * x0 + d1 * x1 + d2_ * x2);
+      }
+    }
+  }
+  // Gauss-Jordan with partial pivoting on [A | I]
+  T logdet = T(0), sgn = T(1);
+#pragma unroll
+  for (int c = 0; c < NS; ++c) {
+    int prow = c;
+    T best = m_abs(A[c][c]);
+#pragma unroll
+    for (int rr = c + 1; rr < NS; ++rr) {
+      T v = m_abs(A[rr][c]);
+      if (v > best) { best = v; prow = rr; }
+    }
+#pragma unroll
+    for (int rr = c + 1; rr < NS; ++rr) {
+      if (rr == prow) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          T t0 = A[c][j]; A[c][j] = A[rr][j]; A[rr][j] = t0;
+          T t1 = Ai[c][j]; Ai[c][j] = Ai[rr][j]; Ai[rr][j] = t1;
+        }
+      }
+    }
+    const T pv = A[c][c];
+    logdet += m_log(m_abs(pv));
+    const T sg = pv > T(0) ? T(1) : (pv < T(0) ? T(-1) : T(0));
+    sgn *= (prow != c ? -sg : sg);
+    const T ipv = T(1) / pv;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) { A[c][j] *= ipv; Ai[c][j] *= ipv; }
+#pragma unroll
+    for (int rr = 0; rr < NS; ++rr) {
+      if (rr != c) {
+        const T f = A[rr][c];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) { A[rr][j] -= f * A[c][j]; Ai[rr][j] -= f * Ai[c][j]; }
+      }
+    }
+  }
+  const size_t bk = (size_t)b * K + k;
+  det_log[bk] = logdet;
+  det_sign[bk] = sgn;
+  if (S == 1) return;
+  T lap = T(0);
+#pragma unroll
+  for (int i = 0; i < NS; ++i)
+#pragma unroll
+    for (int mu = 0; mu < NS; ++mu) lap += Ai[mu][i] * AL[i][mu];
+  for (int t = 0; t < T3; ++t) {
+    const int it = t / 3, ct = t % 3;
+    T At[NS][NS], Bt[NS][NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+#pragma unroll
+      for (int mu = 0; mu < NS; ++mu) {
+        T a = env[i][mu] * BF[(brow0 + (size_t)i * S + 1 + t) * ldb + k * NS + mu];
+        if (i == it) a += (ct == 0 ? de[0][i][mu] : ct == 1 ? de[1][i][mu] : de[2][i][mu]) * bf0[i][mu];
+        At[i][mu] = a;
+      }
+    T gt = T(0), tr2 = T(0);
+#pragma unroll
+    for (int mu = 0; mu < NS; ++mu)
+#pragma unroll
+      for (int nu = 0; nu < NS; ++nu) {
+        T a = T(0);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) a += Ai[mu][i] * At[i][nu];
+        Bt[mu][nu] = a;
+      }
+#pragma unroll
+    for (int mu = 0; mu < NS; ++mu) {
+      gt += Bt[mu][mu];
+#pragma unroll
+      for (int nu = 0; nu < NS; ++nu) tr2 += Bt[mu][nu] * Bt[nu][mu];
+    }
+    lap -= tr2;
+    det_grad[bk * T3 + t] = gt;
+  }
+  det_lap[bk] = lap;
+}
+
+// ------------------------------------------------------------------------------------------
 // Forward-only (S = 1) Slater kernel for N <= 32: the hot kernel of the Metropolis sweep and of
 // the non-local ECP quadrature (12 N N_ecp plain forwards per walker).  One block per walker,
 // one warp per determinant (looping), lane r owns matrix ROW r entirely in registers:
