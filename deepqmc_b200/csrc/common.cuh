@@ -55,6 +55,26 @@ __device__ __forceinline__ void cp_async_wait_all() {
 #endif
 }
 
+// 4 consecutive elements with ONE memory instruction where the type allows it (float: 128-bit).
+// The pointer must be 16-byte aligned for T = float.
+template <class T>
+__device__ __forceinline__ void ld4(const T* p, T (&v)[4]) {
+  if constexpr (sizeof(T) == 4) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  } else {
+    v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3];
+  }
+}
+template <class T>
+__device__ __forceinline__ void st4(T* p, const T (&v)[4]) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    p[0] = v[0]; p[1] = v[1]; p[2] = v[2]; p[3] = v[3];
+  }
+}
+
 template <class T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

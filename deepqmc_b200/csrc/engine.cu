@@ -152,6 +152,9 @@ struct Engine : EngineBase {
   int J = 0;  // nuclei with a non-local channel
   int attn_tb = 1, attn_tb1 = 1;
   bool attn_f32 = false;
+  bool embed_fwd_ok = false;
+  bool attn_fwd_ok = false;
+  bool slater_fwd2_ok = false;
   int N, M, d, K, KN, H, dh, T3;
   size_t max_smem = 0;
   int n_sms = 148;
@@ -227,6 +230,13 @@ struct Engine : EngineBase {
         DQ_CHECK(cudaMemcpy(d_nl_nuc, nuc.data(), sizeof(int) * J, cudaMemcpyHostToDevice));
       }
     }
+#ifndef DQMC_EMU
+    {
+      int v = 0;
+      DQ_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+      if (v > 0) n_sms = v;
+    }
+#endif
     // opt in to large dynamic shared memory
     const bool psif = cfg.kind == DQMC_PSIFORMER;
     attn_tb = attn_pick_tb<T>(N, dh, T3, 100 * 1024);
@@ -242,15 +252,32 @@ struct Engine : EngineBase {
     } else if (psif)
       DQ_CHECK(cudaFuncSetAttribute(attn_fl_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_attn));
     DQ_CHECK(cudaFuncSetAttribute(slater_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_sl));
+    slater_fwd2_ok = N <= 32 && slater_fwd2_smem_bytes<T>(N, M, K) <= 110 * 1024 && !std::getenv("DQMC_SLATER_GENERIC") &&
+                     !std::getenv("DQMC_SLATER_FWD1");
+    if (slater_fwd2_ok) {
+      DQ_CHECK(cudaFuncSetAttribute(slater_fwd2_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)slater_fwd2_smem_bytes<T>(N, M, K)));
+      DQ_CHECK(cudaFuncSetAttribute(slater_fwd2_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)slater_fwd2_smem_bytes<T>(N, M, K)));
+    }
+    attn_fwd_ok = psif && std::is_same<T, float>::value && dh == 64 && N <= 32 && d % 4 == 0 &&
+                  !std::getenv("DQMC_ATTN_GENERIC") && !std::getenv("DQMC_ATTN_FWD_OLD");
+    if (attn_fwd_ok) {
+      const int smem = 4 * 2 * N * 64 * (int)sizeof(float);
+      DQ_CHECK(cudaFuncSetAttribute(attn_fwd_f32_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      DQ_CHECK(cudaFuncSetAttribute(attn_fwd_f32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      DQ_CHECK(cudaFuncSetAttribute(attn_fwd_f32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+    embed_fwd_ok = psif && d % 4 == 0 && embed_fwd_smem_bytes<T>(M, d) <= 200 * 1024 && !std::getenv("DQMC_EMBED_GENERIC");
+    if (embed_fwd_ok)
+      DQ_CHECK(cudaFuncSetAttribute(embed_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)embed_fwd_smem_bytes<T>(M, d)));
     if (cfg.gemm_backend == DQMC_GEMM_TCGEN05) {
 #if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
       if (!std::is_same<T, float>::value) { err = "DQMC_GEMM_TCGEN05 needs dtype DQMC_F32"; return 2; }
       if (d % 32 != 0) { err = "DQMC_GEMM_TCGEN05 needs embedding_dim % 32 == 0"; return 2; }
       DQ_CHECK(cudaFuncSetAttribute(tc::gemm3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     tc::SmemLayout::total(256)));
-      cudaDeviceProp prop;
-      DQ_CHECK(cudaGetDeviceProperties(&prop, device));
-      n_sms = prop.multiProcessorCount;
 #else
       err = "this build has no tcgen05 backend"; return 2;
 #endif
@@ -489,9 +516,18 @@ struct Engine : EngineBase {
       return tail(r, R, Rb, Bc, S, Bstat, sign, logp, E, stats, grad, w, Xf, st);
     }
     const int F = 4 * M + 1;
-    const int epb = S == 1 ? 8 : 1;  // plain forwards: several electrons per block (tiny per-electron work)
-    DQ_LAUNCH(embed_kernel<T>, dim3((Bc * N + epb - 1) / epb), dim3(128), sizeof(T) * 5 * F, st, r, R, Rb, N, M, cfg.n_up,
-              S, 1, 1, P("emb.w"), d, w.X, Bc * N, epb);
+    if (S == 1 && embed_fwd_ok) {
+      // plain forwards (Metropolis, ECP quadrature): register-tiled projection, W staged per block
+      const int tot = Bc * N;
+      int epb = (tot / (2 * n_sms)) / 32 * 32;
+      epb = epb < 32 ? 32 : (epb > 512 ? 512 : epb);
+      DQ_LAUNCH(embed_fwd_kernel<T>, dim3((tot + epb - 1) / epb), dim3(256), embed_fwd_smem_bytes<T>(M, d), st, r, R, Rb, N,
+                M, cfg.n_up, 1, P("emb.w"), d, w.X, tot, epb);
+    } else {
+      const int epb = S == 1 ? 8 : 1;  // plain forwards: several electrons per block (tiny per-electron work)
+      DQ_LAUNCH(embed_kernel<T>, dim3((Bc * N + epb - 1) / epb), dim3(128), sizeof(T) * 5 * F, st, r, R, Rb, N, M,
+                cfg.n_up, S, 1, 1, P("emb.w"), d, w.X, Bc * N, epb);
+    }
     T* X = w.X;
     T* O = w.O;
     const T scale = (T)(1.0 / std::sqrt((double)dh));
@@ -501,7 +537,20 @@ struct Engine : EngineBase {
       {
         const int tb = S > 1 ? attn_tb : 1;
         if constexpr (std::is_same<T, float>::value) {
-          if (attn_f32) {
+          if (S == 1 && attn_fwd_ok) {
+            const int n_pairs = Bc * H;
+            const int smem = 4 * 2 * N * 64 * (int)sizeof(float);
+            const dim3 grid((n_pairs + 3) / 4), block(128);
+            if (N <= 8)
+              DQ_LAUNCH(attn_fwd_f32_kernel<8>, grid, block, smem, st, (const float*)w.QKV, 3 * d, (float*)O, d, N, H, d,
+                        (float)scale, n_pairs);
+            else if (N <= 16)
+              DQ_LAUNCH(attn_fwd_f32_kernel<16>, grid, block, smem, st, (const float*)w.QKV, 3 * d, (float*)O, d, N, H, d,
+                        (float)scale, n_pairs);
+            else
+              DQ_LAUNCH(attn_fwd_f32_kernel<32>, grid, block, smem, st, (const float*)w.QKV, 3 * d, (float*)O, d, N, H, d,
+                        (float)scale, n_pairs);
+          } else if (attn_f32) {
             if (launch_attn_f32((const float*)w.QKV, (float*)O, Bc, S, tb, (float)scale, 0,
                                 (int)attn_f32_smem_bytes(N, dh, tb), st, false))
               return 1;
@@ -551,6 +600,17 @@ struct Engine : EngineBase {
         default: DQ_SL_SMALL(6); break;
       }
 #undef DQ_SL_SMALL
+    } else if (S == 1 && N <= 32 && slater_fwd2_ok) {
+      const int nthr = 32 * K < 256 ? 32 * K : 256;
+      const int grid = Bc < 3 * n_sms ? Bc : 3 * n_sms;
+      if (N <= 16)
+        DQ_LAUNCH((slater_fwd2_kernel<T, 16>), dim3(grid), dim3(nthr), slater_fwd2_smem_bytes<T>(N, M, K), st, r, R, Rb, N,
+                  M, cfg.n_up, K, Bc, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF,
+                  KN, w.dsign, w.dlog);
+      else
+        DQ_LAUNCH((slater_fwd2_kernel<T, 32>), dim3(grid), dim3(nthr), slater_fwd2_smem_bytes<T>(N, M, K), st, r, R, Rb, N,
+                  M, cfg.n_up, K, Bc, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF,
+                  KN, w.dsign, w.dlog);
     } else if (S == 1 && N <= 32 && !std::getenv("DQMC_SLATER_GENERIC")) {
       const int wpb = K < 8 ? K : 8;
       DQ_LAUNCH(slater_fwd_reg_kernel<T>, dim3(Bc), dim3(32 * wpb), sizeof(T) * N * M, st, r, R, Rb, N, M, cfg.n_up, K,

@@ -129,6 +129,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// tanh for the plain-forward epilogue: odd polynomial below |x| = 0.15, 1 - 2 / (1 + e^{2x})
+// (ex2.approx + fast division) above; absolute error <= ~3e-7.  The forward-Laplacian epilogue
+// keeps tanhf (derivative slots amplify the error); plain forwards only feed log|psi| ratios.
+__device__ __forceinline__ float tanh_fwd(float x) {
+  const float x2 = x * x;
+  const float poly = x + x * x2 * (-0.33333333333f + x2 * (0.13333333333f + x2 * (-0.05396825397f)));
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+  const float big = 1.f - __fdividef(2.f, 1.f + e);
+  return fabsf(x) < 0.15f ? poly : big;
+}
+
 __device__ __forceinline__ size_t phys_row(const Params& p, int m, int z) {
   if (!p.sliced) return (size_t)m;
   int b = m / p.S, s = m % p.S;
@@ -348,10 +360,12 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
       const int rows_here = (p.M - mt * RPT) < RPT ? (p.M - mt * RPT) : RPT;
       const int ngrp = S > 1 ? rows_here / S : rows_here;  // whole slot groups in this tile (S == 1: rows)
       if (p.act) {  // bias of this tile's columns -> shared (latency overlaps the wait for the accumulator)
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // every epilogue warp is done with the previous tile's bias
         for (int i = etid; i < BN; i += 128) {
           const int cc = nt * BN + i;
           sbias[i] = (p.bias && cc < p.N) ? __ldg(p.bias + cc) : 0.f;
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       const int nchunk = BN / 32;
       const bool vec_ok = (p.N % 4) == 0;
@@ -380,12 +394,17 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
           mbar_arrive(&tmem_empty[acc]);
         }
         if (!chunk_on) continue;
+        const bool act_rows = p.act && S == 1;  // plain forward: every row is a value row -> tanh in registers
+        if (act_rows) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(tanh_fwd(__uint_as_float(v[i]) + sbias[c * 32 + i]));
+        }
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4)
           *(float4*)(stage + lane * kPitch + 4 * q4) =
               make_float4(__uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1]), __uint_as_float(v[4 * q4 + 2]),
                           __uint_as_float(v[4 * q4 + 3]));
-        if (p.act) {
+        if (p.act && !act_rows) {
           // ---- tanh + forward-Laplacian propagation (reference: hkext.py:104-113 MLP activation; rule
           // y_t = y' z_t, y_L = y' z_L + y'' sum_t z_t^2).  Tiles hold whole slot groups (rpt = G*S).
           asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -459,7 +478,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
             for (int e = 0; e < 4; ++e) {
               if (col + e >= p.N) break;
               float o = stage[(4 * jj + rsub) * kPitch + 4 * cq + e];
-              if (p.bias && (inj & 255) == 0) o += p.bias[col + e];
+              if (p.bias && !p.act && (inj & 255) == 0) o += p.bias[col + e];
               if (Resp) o += Resp[pr * p.ldr + col + e];
               Cp[pr * p.ldc + col + e] = o;
             }

@@ -421,6 +421,148 @@ __global__ void slater_fwd_reg_kernel(const T* __restrict__ r, const T* __restri
 }
 
 // ------------------------------------------------------------------------------------------
+// Forward-only (S = 1) Slater kernel, second generation (N <= 32): persistent blocks, one walker
+// per iteration, two phases per walker.
+//   phase 1, thread <-> orbital o = k N + mu (coalesced over the backflow row): envelopes
+//     phi_o(r_i) = sum_m pi_o,m exp(-|zeta_o,m| rho_i,m) for 8 electrons at a time (parameters are
+//     loaded once per 8 electrons, rho comes from shared memory as a broadcast), times the
+//     backflow entry -> A[k][i][mu] in shared memory (odd row pitch: conflict-free row reads).
+//   phase 2, warp <-> determinant k, lane <-> matrix row held in registers: LU with implicit
+//     partial pivoting.  Pivot search is ONE redux.sync (max over the integer image of |a|, fp32)
+//     plus a ballot; the pivot row reaches the other lanes by shuffles; the permutation parity
+//     is accumulated as an inversion count (popc), so nothing leaves the register file.
+// Same reference lines as slater_kernel; slogdet sign/log convention = LAPACK getrf.
+// dynamic smem = sizeof(T) * (K N NP + N M), NP = N | 1.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_argmax_abs(float v, bool excluded, int lane) {
+#ifndef DQMC_EMU
+  const unsigned key = excluded ? 0u : __float_as_uint(fabsf(v)) + 1u;
+  const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+  const unsigned bal = __ballot_sync(0xffffffffu, key == kmax);
+  return __ffs(bal) - 1;
+#else
+  float best = excluded ? -1.f : fabsf(v);
+  int bi = lane;
+  for (int o = 16; o > 0; o >>= 1) {
+    float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  return bi;
+#endif
+}
+__device__ __forceinline__ int warp_argmax_abs(double v, bool excluded, int lane) {
+  double best = excluded ? -1.0 : fabs(v);
+  int bi = lane;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  return bi;
+}
+
+template <class T, int NM>
+__global__ void __launch_bounds__(256, 3)
+slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M, int n_up, int K,
+                   int B, const T* __restrict__ pi_up, const T* __restrict__ pi_dn, const T* __restrict__ zeta_up,
+                   const T* __restrict__ zeta_dn, const T* __restrict__ BF, int ldb, T* __restrict__ det_sign,
+                   T* __restrict__ det_log) {
+  DQMC_DYN_SMEM(smem_raw);
+  const int NP = N | 1, KN = K * N;
+  T* As = reinterpret_cast<T*>(smem_raw);  // [K][N][NP]
+  T* rho = As + (size_t)KN * NP;           // [N][M]
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, wib = tid >> 5, nw = nt >> 5;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const T* rb = r + (size_t)b * N * 3;
+    const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
+    __syncthreads();  // previous walker's determinants are in registers / written
+    for (int idx = tid; idx < N * M; idx += nt) {
+      const int i = idx / M, m = idx - i * M;
+      const T dx0 = rb[3 * i] - Rb[3 * m], dx1 = rb[3 * i + 1] - Rb[3 * m + 1], dx2 = rb[3 * i + 2] - Rb[3 * m + 2];
+      rho[idx] = m_sqrt(Num<T>::eps() + dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
+    }
+    __syncthreads();
+    // ---- phase 1 ---------------------------------------------------------------------------
+    for (int o = tid; o < KN; o += nt) {
+      const int k = o / N, mu = o - k * N;
+      const T* bfp = BF + (size_t)b * N * ldb + o;
+      T* arow = As + (size_t)k * N * NP + mu;
+#pragma unroll 1
+      for (int sb = 0; sb < 2; ++sb) {
+        const int ib = sb ? n_up : 0, ie = sb ? N : n_up;
+        const T* pi = (sb ? pi_dn : pi_up) + (size_t)o * M;
+        const T* ze = (sb ? zeta_dn : zeta_up) + (size_t)o * M;
+#pragma unroll 1
+        for (int i0 = ib; i0 < ie; i0 += 8) {
+          T e[8], bf[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            e[j] = T(0);
+            bf[j] = i0 + j < ie ? bfp[(size_t)(i0 + j) * ldb] : T(0);
+          }
+          for (int m = 0; m < M; ++m) {
+            const T p = pi[m], z = -m_abs(ze[m]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int ii = i0 + j < ie ? i0 + j : ie - 1;
+              e[j] += p * m_exp(z * rho[ii * M + m]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (i0 + j < ie) arow[(i0 + j) * NP] = e[j] * bf[j];
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase 2 ---------------------------------------------------------------------------
+    for (int k = wib; k < K; k += nw) {
+      T a[NM];
+      const T* arow = As + ((size_t)k * N + (lane < N ? lane : 0)) * NP;
+#pragma unroll
+      for (int mu = 0; mu < NM; ++mu) {
+        T v = (mu == lane) ? T(1) : T(0);  // padding rows / columns: identity
+        if (lane < N && mu < N) v = arow[mu];
+        a[mu] = v;
+      }
+      T logdet = T(0), sgn = T(1);
+      unsigned used = 0u;  // rows already chosen as pivots (warp-uniform)
+      int inv = 0;         // inversion count of the pivot order
+#pragma unroll
+      for (int c = 0; c < NM; ++c) {
+        if (c < N) {
+          const int prow = warp_argmax_abs(a[c], (used >> lane) & 1u, lane);
+          inv += __popc(~used & ((1u << prow) - 1u));
+          used |= 1u << prow;
+          const T pv = __shfl_sync(0xffffffffu, a[c], prow);
+          logdet += m_log(m_abs(pv));
+          sgn = pv < T(0) ? -sgn : (pv == T(0) ? T(0) : sgn);
+          const bool elim = !((used >> lane) & 1u);
+          const T f = (elim && pv != T(0)) ? a[c] / pv : T(0);  // exactly singular: (sign 0, log -inf) like slogdet
+#pragma unroll
+          for (int j = c + 1; j < NM; ++j) {  // padding columns (j >= N) hold zeros in the live rows
+            const T pj = __shfl_sync(0xffffffffu, a[j], prow);
+            a[j] -= f * pj;
+          }
+        }
+      }
+      if (lane == 0) {
+        det_log[(size_t)b * K + k] = logdet;
+        det_sign[(size_t)b * K + k] = (inv & 1) ? -sgn : sgn;
+      }
+    }
+  }
+}
+
+template <class T>
+inline size_t slater_fwd2_smem_bytes(int N, int M, int K) {
+  return sizeof(T) * ((size_t)K * N * (N | 1) + (size_t)N * M);
+}
+
+// ------------------------------------------------------------------------------------------
 // Per-walker assembly.  reference: wf/nn_wave_function.py:152-171 (exp-normalised sum with
 // stop-gradient shift, SumPool conf_coeff, cusp), wf/cusp.py:17-26 (PsiformerCusp),
 // physics.py:79-141 (kinetic term, Coulomb terms, eps-safe e-e and n-n distances, plain e-n

@@ -102,6 +102,107 @@ __global__ void embed_kernel(const T* __restrict__ r, const T* __restrict__ R, i
 }
 
 // ------------------------------------------------------------------------------------------
+// Plain-forward (S == 1) electron embedding with projection: the first kernel of every Metropolis
+// sub-step and of every non-local-ECP quadrature forward (12 N N_ecp per walker), so it is written
+// as a small register-tiled GEMM  X[e, :] = feat[e, 0:F] @ W[F, d]  with the features computed in
+// the block.  Same reference lines as embed_kernel (electron_gnn.py:596-619, edge_features.py:21-78).
+// Block = 256 threads; W (F x d) is staged once per block in shared memory and reused for `epb`
+// electrons (persistent over tiles of 32 electrons); thread tile = 8 electrons x 4 features.
+// dynamic smem = sizeof(T) * (F * d + FP * 32), FP = F rounded up to a multiple of 4.
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256)
+embed_fwd_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M, int n_up,
+                 int log_rescale, const T* __restrict__ W, int d, T* __restrict__ X, int total, int epb) {
+  DQMC_DYN_SMEM(smem_raw);
+  const int F = 4 * M + 1;
+  T* Ws = reinterpret_cast<T*>(smem_raw);  // [F][d]
+  T* ft = Ws + (size_t)F * d;              // [F][32]  feature k of the tile's 32 electrons
+  const int tid = threadIdx.x;
+  for (int i = tid; i < F * d; i += 256) Ws[i] = W[i];
+  const int e_begin = blockIdx.x * epb;
+  const int e_end = e_begin + epb < total ? e_begin + epb : total;
+  const int te = tid >> 6, tf = tid & 63;  // electron group (8 electrons), feature group (4 features)
+  for (int e0 = e_begin; e0 < e_end; e0 += 32) {
+    __syncthreads();  // previous tile done with ft (and Ws staged)
+    for (int idx = tid; idx < 32 * M; idx += 256) {
+      const int el = idx / M, m = idx - el * M;
+      const int bi = e0 + el;
+      T f0 = T(0), g0 = T(0), g1 = T(0), g2 = T(0);
+      if (bi < e_end) {
+        const int b = bi / N;
+        const T* ri = r + (size_t)bi * 3;
+        const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
+        const T dx0 = ri[0] - Rb[3 * m], dx1 = ri[1] - Rb[3 * m + 1], dx2 = ri[2] - Rb[3 * m + 2];
+        const T rho = m_sqrt(Num<T>::eps() + dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
+        T s = T(1);
+        f0 = rho;
+        if (log_rescale) { f0 = m_log1p(rho); s = f0 / rho; }
+        g0 = dx0 * s; g1 = dx1 * s; g2 = dx2 * s;
+      }
+      ft[(4 * m) * 32 + el] = f0;
+      ft[(4 * m + 1) * 32 + el] = g0;
+      ft[(4 * m + 2) * 32 + el] = g1;
+      ft[(4 * m + 3) * 32 + el] = g2;
+    }
+    if (tid < 32) {
+      const int bi = e0 + tid;
+      ft[(F - 1) * 32 + tid] = (bi < e_end && (bi % N) < n_up) ? T(1) : T(-1);
+    }
+    __syncthreads();
+    for (int f0 = 4 * tf; f0 < d; f0 += 256) {
+      T acc[8][4];
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[e][j] = T(0);
+      const bool full = f0 + 3 < d;
+      for (int k = 0; k < F; ++k) {
+        T w[4], x[8];
+        const T* wr = Ws + (size_t)k * d + f0;
+        if (full) {
+          ld4(wr, w);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) w[j] = f0 + j < d ? wr[j] : T(0);
+        }
+        const T* xr = ft + k * 32 + te * 8;
+        {
+          T xa[4], xb[4];
+          ld4(xr, xa);
+          ld4(xr + 4, xb);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { x[e] = xa[e]; x[4 + e] = xb[e]; }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[e][j] += x[e] * w[j];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int bi = e0 + te * 8 + e;
+        if (bi >= e_end) continue;
+        T* xo = X + (size_t)bi * d + f0;
+        if (full) {
+          st4(xo, acc[e]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (f0 + j < d) xo[j] = acc[e][j];
+        }
+      }
+    }
+  }
+}
+
+template <class T>
+inline size_t embed_fwd_smem_bytes(int M, int d) {
+  const int F = 4 * M + 1;
+  return sizeof(T) * ((size_t)F * d + (size_t)F * 32);
+}
+
+// ------------------------------------------------------------------------------------------
 // Row GEMM  C[row(m), :] = (Res[row(m), :]) + A[row(m), :] @ W + (bias on value rows)
 // Plain SIMT tiling (CUDA cores), used for the fp64 parity mode and as the reference
 // implementation the tcgen05 fp32 path is validated against.
@@ -622,6 +723,88 @@ __global__ void attn_fl_f32_kernel(const float* __restrict__ QKV, int ldq, float
       fma4(a, p[i * N + j], *(const float4*)(vt + j * PQ + 4 * e4));
     }
     *(float4*)(O + (row0 + (size_t)i * S + 1 + T3) * ldo + h * dh + 4 * e4) = a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Plain-forward (S == 1) self-attention, fp32, N <= NMAX <= 32 electrons, head dim 64: the
+// attention of every Metropolis sub-step and non-local-ECP quadrature forward.
+// One WARP per (walker, head); lane i owns QUERY i: its q row, its full score row s[i][:] and its
+// output row live in registers, so the softmax is lane-local (no shuffles, no barriers); K and V
+// of the head are staged once in shared memory (cp.async, coalesced) and read as 128-bit
+// broadcasts.  Same algebra / reference lines as attn_fl_kernel (value part).
+// dynamic smem = warps_per_block * 2 * N * 64 * 4 bytes.
+// ------------------------------------------------------------------------------------------
+template <int NMAX>
+__global__ void __launch_bounds__(128)
+attn_fwd_f32_kernel(const float* __restrict__ QKV, int ldq, float* __restrict__ O, int ldo, int N, int H, int dmodel,
+                    float scale, int n_pairs) {
+  constexpr int DH = 64;
+  DQMC_DYN_SMEM(smem_raw);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int pair = blockIdx.x * wpb + wib;
+  if (pair >= n_pairs) return;
+  const int b = pair / H, h = pair - b * H;
+  float* ks = reinterpret_cast<float*>(smem_raw) + (size_t)wib * 2 * N * DH;  // [N][64]
+  float* vs = ks + N * DH;                                                     // [N][64]
+  const float* base = QKV + (size_t)b * N * ldq + h * DH;
+  for (int idx = lane; idx < N * (DH / 4); idx += 32) {
+    const int j = idx >> 4, c4 = idx & 15;
+    const float* src = base + (size_t)j * ldq + 4 * c4;
+    cp_async16(ks + j * DH + 4 * c4, src + dmodel);
+    cp_async16(vs + j * DH + 4 * c4, src + 2 * dmodel);
+  }
+  const int i = lane < N ? lane : N - 1;  // idle lanes shadow the last query (no divergence)
+  float4 q[DH / 4];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(base + (size_t)i * ldq);
+#pragma unroll
+    for (int c = 0; c < DH / 4; ++c) q[c] = __ldg(qp + c);
+  }
+  cp_async_wait_all();
+  __syncwarp();
+  float sc[NMAX];
+  float mx = -3.0e38f;
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) {
+    sc[j] = -3.0e38f;
+    if (j < N) {
+      const float4* kp = reinterpret_cast<const float4*>(ks + j * DH);
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < DH / 4; c += 2) {
+        a0 += dot4(q[c], kp[c]);
+        a1 += dot4(q[c + 1], kp[c + 1]);
+      }
+      sc[j] = (a0 + a1) * scale;
+      mx = fmaxf(mx, sc[j]);
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) {
+    if (j < N) {
+      sc[j] = m_exp(sc[j] - mx);
+      sum += sc[j];
+    }
+  }
+  const float inv = 1.f / sum;
+  float4 o[DH / 4];
+#pragma unroll
+  for (int c = 0; c < DH / 4; ++c) o[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) {
+    if (j < N) {
+      const float pj = sc[j] * inv;
+      const float4* vp = reinterpret_cast<const float4*>(vs + j * DH);
+#pragma unroll
+      for (int c = 0; c < DH / 4; ++c) fma4(o[c], pj, vp[c]);
+    }
+  }
+  if (lane < N) {
+    float4* op = reinterpret_cast<float4*>(O + ((size_t)b * N + lane) * ldo + h * DH);
+#pragma unroll
+    for (int c = 0; c < DH / 4; ++c) op[c] = o[c];
   }
 }
 

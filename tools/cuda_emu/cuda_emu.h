@@ -183,6 +183,7 @@ template <class T> inline T __shfl_down_sync(unsigned, T v, int d) {
   int lane = emu::S().fibers[emu::S().cur].lin & 31;
   return emu::shfl_idx(v, lane + d < 32 ? lane + d : lane);
 }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
 template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
 
