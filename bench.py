@@ -5,10 +5,13 @@
   python bench.py --impl reference --steps K --warmup W    # reference arm: CPU oracle port
 
 metric: walker.local-energies / second.  A "step" = one local-energy evaluation of every walker
-of the batch (Psiformer forward + forward-Laplacian + potentials) followed, for N > 1, by the
-fused statistics all-reduce.  Workload at N=1: BASELINE.json configs[1], LiH Psiformer
-(d=256, L=4, H=4, K=16), 4096 walkers per GPU, synthetic walkers (atom-centred Gaussians,
-equilibrated by 200 Metropolis sub-steps, untimed) and random-init weights.
+of the batch (Psiformer forward + forward-Laplacian + potentials, incl. the non-local ECP
+quadrature) followed, for N > 1, by the fused statistics all-reduce.  Default workload = the
+configuration BASELINE.json's metric is quoted on: benzene (ccECP, 30 valence electrons)
+Psiformer (d=256, L=4, H=4, K=16), 4096 walkers per GPU (the engine chunks the walkers through
+its workspace, so it fits one B200); ``--workload lih_psiformer`` = BASELINE configs[1],
+``n2_ferminet`` = configs[2].  Synthetic walkers (atom-centred Gaussians, equilibrated by
+Metropolis sub-steps, untimed) and random-init weights.
 """
 import argparse
 import json
@@ -92,6 +95,10 @@ class ClockSampler:
                 'reasons': reasons, 'samples': len(sm)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from one
+# `ncu --set full` capture of the same command (profiles/, B200_PROFILING.md); None = not captured.
+TRAFFIC = {}
+
 _ORACLE = {}
 
 
@@ -119,27 +126,76 @@ def _oracle_eval(r_np):
     return float(e)
 
 
+def _oracle_task(task):
+    """One slice of ONE walker's local energy (heavy workloads: a single benzene walker costs about
+    a minute of one core, so its 3N Hessian rows and its 12 N N_ecp quadrature forwards are spread
+    over the worker processes).  kind 'lap': Hessian rows [lo, hi) (+ gradient and the local
+    potentials with the first slice); kind 'ecp': (nucleus, electron) pairs [lo, hi)."""
+    r_np, kind, lo, hi = task
+    o = _ORACLE
+    r = torch.as_tensor(r_np)
+    f = lambda x: o['wf'].log_psi(o['spec'], o['pt'], x, o['R'])
+    if kind == 'lap':
+        x = r.reshape(-1)
+        grad_f = torch.func.grad(lambda xx: f(xx.reshape(-1, 3))[1])
+        eye = torch.eye(x.numel(), dtype=x.dtype)[lo:hi]
+        rows = torch.func.vmap(lambda v: torch.func.jvp(grad_f, (x,), (v,))[1])(eye)
+        out = float(rows[torch.arange(hi - lo), torch.arange(lo, hi)].sum())
+        if lo == 0:  # E_loc = -(lap + |g|^2)/2 + potentials (oracle/hamil.py local_energy)
+            g = grad_f(x)
+            oh = o['oh']
+            out = -0.5 * (out + float((g * g).sum())) + float(oh.nuclear_energy(o['R']) + oh.electronic_potential(r)
+                                                               + oh.local_potential(r, o['R']))
+        else:
+            out = -0.5 * out
+        return out
+    tw = torch.zeros(max(o['J'], 1), o['spec'].n_elec) + 0.1
+    N = o['spec'].n_elec
+    pairs = {(p // N, p % N) for p in range(lo, hi)}
+    return float(o['oh'].nonloc_potential(r, o['R'], f, tw, pairs=pairs))
+
+
 def time_oracle(wl_name, per_worker, steps, warmup, seed=0):
-    """CPU arm: the oracle (torch fp64 restatement of the reference path) on the host cores, walkers
-    spread over one single-threaded process per core (the walker axis is embarrassingly parallel,
-    which is also how XLA:CPU would spread the reference's vmap).  Returns walkers/s, workers,
+    """CPU arm: the oracle (torch fp64 restatement of the reference path) on the host cores, one
+    single-threaded process per core.  Light workloads: whole walkers per worker (the walker axis
+    is embarrassingly parallel, which is also how XLA:CPU would spread the reference's vmap).
+    Heavy workloads (non-local ECP): a step is a bounded sample of `per_worker` walkers whose
+    Hessian rows / quadrature pairs are spread over all workers.  Returns walkers/s, workers,
     ms/step, walkers per step."""
     import multiprocessing as mp
 
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 64))
     wl = WORKLOADS[wl_name]
-    n = workers * per_worker
-    _, _, r, _ = make_problem(wl, n * (steps + warmup), seed)
+    heavy = wl['ecp'] is not None
+    n = per_worker if heavy else workers * per_worker
+    _, hamil, r, _ = make_problem(wl, n * (steps + warmup), seed)
     times = []
     with mp.get_context('fork').Pool(workers, initializer=_oracle_init, initargs=(wl_name, seed)) as pool:
-        pool.map(_oracle_eval, [r[i] for i in range(workers)])  # import / first-call cost, untimed
-        for s in range(steps + warmup):
-            t0 = time.perf_counter()
-            pool.map(_oracle_eval, [r[s * n + i] for i in range(n)], chunksize=per_worker)
-            dt = time.perf_counter() - t0
-            if s >= warmup:
-                times.append(dt)
+        if heavy:
+            N = hamil.n_up + hamil.n_down
+            n_pairs = N * len(hamil.pot.nuc_with_nl_pot)
+
+            def tasks(rw):
+                t = [(rw, 'lap', lo, min(lo + 6, 3 * N)) for lo in range(0, 3 * N, 6)]
+                return t + [(rw, 'ecp', lo, min(lo + 2, n_pairs)) for lo in range(0, n_pairs, 2)]
+
+            pool.map(_oracle_task, [(r[0], 'ecp', i % n_pairs, i % n_pairs + 1) for i in range(workers)])  # first-call cost
+            for s in range(steps + warmup):
+                t0 = time.perf_counter()
+                todo = [t for i in range(n) for t in tasks(r[s * n + i])]
+                pool.map(_oracle_task, todo, chunksize=1)
+                dt = time.perf_counter() - t0
+                if s >= warmup:
+                    times.append(dt)
+        else:
+            pool.map(_oracle_eval, [r[i] for i in range(workers)])  # import / first-call cost, untimed
+            for s in range(steps + warmup):
+                t0 = time.perf_counter()
+                pool.map(_oracle_eval, [r[s * n + i] for i in range(n)], chunksize=per_worker)
+                dt = time.perf_counter() - t0
+                if s >= warmup:
+                    times.append(dt)
     return n * len(times) / sum(times), workers, 1e3 * float(np.mean(times)), n
 
 
@@ -149,13 +205,13 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='lih_psiformer', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='benzene_psiformer', choices=sorted(WORKLOADS))
     ap.add_argument('--dtype', default='float32', choices=['float32', 'float64'])
     ap.add_argument('--walkers', type=int, default=None, help='walkers per GPU (default: workload)')
     ap.add_argument('--cpu-sample', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--gemm-backend', default='tcgen05', choices=['simt', 'tcgen05'])
-    ap.add_argument('--equil-sweeps', type=int, default=20)
+    ap.add_argument('--equil-sweeps', type=int, default=None)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == 'ours' else a.warmup
     wl = WORKLOADS[a.workload]
@@ -169,15 +225,18 @@ def main():
     if a.impl == 'reference':
         if rank != 0:
             return 0
-        per_worker = a.cpu_sample or (8 if wl['mol'] == 'LiH' else 1)
+        heavy = wl['ecp'] is not None
+        per_worker = a.cpu_sample or (8 if wl['mol'] == 'LiH' else (2 if heavy else 1))
         val, cores, ms, n_sample = time_oracle(a.workload, per_worker, a.steps, a.warmup)
+        how = ('Hessian rows and ECP quadrature pairs of each walker spread over one single-threaded process per core'
+               if heavy else 'one single-threaded process per core')
         out = {
             'impl': 'reference', 'metric': metric, 'value': val, 'unit': unit, 'n_gpus': a.gpus, 'steps': a.steps,
             'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': workload_name, 'note': 'CPU oracle port of the reference JAX path (JAX not installable here)'},
             'cpu_baseline': {'value': val, 'unit': unit, 'cores': cores, 'kind': 'port',
-                             'sample': f'{n_sample} walkers per step x {a.steps} steps, one single-threaded process per core (autograd-Hessian Laplacian, fp64)'},
+                             'sample': f'{n_sample} walkers per step x {a.steps} steps, {how} (autograd-Hessian Laplacian, fp64)'},
             'e2e': {'value': val, 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         }
         print(json.dumps(out))
@@ -207,7 +266,9 @@ def main():
     sign, log = eng.wf_forward(r, R)
     state = dict(r=r.clone(), sign=sign, log=log, age=torch.zeros(B, dtype=torch.int32, device=dev),
                  tau=torch.tensor([0.5], dtype=tdt, device=dev))
-    for it in range(a.equil_sweeps):
+    heavy = wl['ecp'] is not None
+    n_equil = a.equil_sweeps if a.equil_sweeps is not None else (5 if heavy else 20)
+    for it in range(n_equil):
         eng.mcmc_sweep(state, R, 10, seed=parallel.rank_seed(7), step0=10 * it, walker_offset=rank * B)
     r = state['r'].clone()
     pc = PhysicalConfiguration(R, r, torch.zeros(B, device=dev))
@@ -218,14 +279,15 @@ def main():
         E, st = loc_ene(seed, params, pc)
         return parallel.energy_statistics(E, st), E
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()  # started before the warm-up: NVML start-up must not overlap the timed region
     for w in range(a.warmup):
         step(w)
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
+    clocks.rows.clear()  # keep only the samples taken during the timed region
     l0 = eng.launch_count
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     torch.cuda.synchronize()
@@ -241,7 +303,8 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     launches = eng.launch_count - l0
     clk = clocks.stop() if rank == 0 else None
-    ms = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in evs)], device=dev, dtype=torch.float64)
+    per_step = [e0.elapsed_time(e1) for e0, e1 in evs]
+    ms = torch.tensor([sum(per_step)], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
     total_ms = ms.item()
@@ -256,26 +319,30 @@ def main():
         E, st = loc_ene(seed, params, pc_h)
         parallel.energy_statistics(E, st)
         return E.cpu()
-    for w in range(3):
+    # long steps (seconds): the pipeline is warm already, bound the e2e leg to a few steps
+    slow = total_ms / a.steps > 500.0
+    e2e_warm, e2e_steps = (1, max(1, min(a.steps, 3))) if slow else (3, a.steps)
+    for w in range(e2e_warm):
         e2e_step(w)
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
     t0 = time.perf_counter()
-    for s in range(a.steps):
+    for s in range(e2e_steps):
         e2e_step(s)
     torch.cuda.synchronize()
     te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
-    e2e_val = B * world * a.steps / te.item()
+    e2e_val = B * world * e2e_steps / te.item()
     esz = r_host.element_size()
 
     # ---- roofline of the dominant kernel (dense-layer GEMMs), timed live with CUDA events ------
     roof = None
     if rank == 0:
+        n_prof = 1 if slow else 3
         eng.profile_begin()
-        for s in range(3):
+        for s in range(n_prof):
             loc_ene(s, params, pc)  # rank-local: no collective here (the other ranks are already done)
         gemm_ms, gemm_flops, n_gemm = eng.profile_end()
         peaks = {}
@@ -288,8 +355,8 @@ def main():
         roof = {'bound': 'tensor', 'kernel': 'dense-layer row GEMM (' + ('tcgen05 3xTF32 gemm3xtf32_kernel' if backend else 'CUDA-core gemm_kernel') + ')', 'achieved': achieved,
                 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback',
-                'traffic': None, 'gemm_share_of_step': (gemm_ms / 3) / (total_ms / a.steps),
-                'gemm_launches_per_step': n_gemm // 3,
+                'traffic': TRAFFIC.get(a.workload), 'gemm_share_of_step': (gemm_ms / n_prof) / (total_ms / a.steps),
+                'gemm_launches_per_step': n_gemm // n_prof,
                 'algorithmic_flops_per_eloc': algorithmic_flops_per_eloc(N, M, n_ecp=n_ecp),
                 'whole_step_tflops': algorithmic_flops_per_eloc(N, M, n_ecp=n_ecp) * B * a.steps / (total_ms / 1e3) / 1e12}
     if world > 1:
@@ -302,20 +369,21 @@ def main():
         # the CPU leg runs in a fresh process (fork-based worker pool; this process holds a CUDA context)
         try:
             cp = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--workload', a.workload,
-                                 '--steps', '2', '--warmup', '1'], capture_output=True, text=True, timeout=900)
+                                 '--steps', '2', '--warmup', '1'], capture_output=True, text=True, timeout=1200)
             cpu = json.loads(cp.stdout.strip().splitlines()[-1])['cpu_baseline']
         except Exception as exc:  # the baseline is a reported number, never the thing measured
             cpu = {'value': None, 'unit': unit, 'cores': os.cpu_count(), 'kind': 'port', 'sample': f'failed: {exc!r}'}
     out = {
         'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
-        'ms_per_step': total_ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'ms_per_step': total_ms / a.steps, 'ms_per_step_min': min(per_step), 'ms_per_step_median': float(np.median(per_step)),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32' if a.dtype == 'float32' else 'f64', 'data': 'synthetic',
         'config': {'workload': workload_name, 'global_batch': B * world, 'parallelism': f'walker-shard x{world}',
                    'l2': 'flushed between timed iterations (256 MiB memset) and activations >> L2',
                    'step': 'E_loc of all walkers (+ fused stats all-reduce for N>1)',
                    'gemm_backend': 'tcgen05-3xTF32' if backend else 'cuda-core'},
         'clocks': clk, 'e2e': {'value': e2e_val, 'unit': unit, 'h2d_bytes_per_step': (B * N * 3 + M * 3) * esz,
-                               'd2h_bytes_per_step': B * esz},
+                               'd2h_bytes_per_step': B * esz, 'steps': e2e_steps},
         'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu,
         'energy_mean': float(stats['energy/mean']), 'wall_s_timed_region': t_wall,
     }

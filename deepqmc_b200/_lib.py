@@ -33,6 +33,7 @@ class DqmcConfig(C.Structure):
         ('ecp_loc_terms', C.c_int32), ('ecp_loc', C.c_double * (MAX_NUC * 3 * 2 * MAX_T)),
         ('ecp_nl_lmax_p1', C.c_int32), ('ecp_nl_terms', C.c_int32),
         ('ecp_nl', C.c_double * (MAX_NUC * MAX_L * 2 * MAX_T)),
+        ('n_env_per_nuc', C.c_int32), ('n_nuc_tokens', C.c_int32),
     ]
 
 

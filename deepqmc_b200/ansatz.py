@@ -13,14 +13,15 @@ import torch
 
 from . import params as PN
 from .engine import Engine
-from .spec import AnsatzSpec, ferminet_spec, psiformer_spec
+from .spec import AnsatzSpec, ferminet_spec, psiformer_spec, transpsiformer_spec
 from .types import PhysicalConfiguration, Psi
 
 
 class B200Ansatz:
     def __init__(self, hamil, kind='psiformer', dtype='float64', device=None, gemm_backend=0, **hyper):
         self.hamil = hamil
-        self.spec: AnsatzSpec = {'psiformer': psiformer_spec, 'ferminet': ferminet_spec}[kind](hamil, **hyper)
+        self.spec: AnsatzSpec = {'psiformer': psiformer_spec, 'ferminet': ferminet_spec,
+                                 'transpsiformer': transpsiformer_spec}[kind](hamil, **hyper)
         self.dtype, self.device, self.gemm_backend = dtype, device, gemm_backend
         self._engine = None
         self._uploaded = None

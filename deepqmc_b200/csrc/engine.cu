@@ -61,7 +61,8 @@ struct EngineBase {
   }
   void build_layout() {
     const int N = cfg.n_up + cfg.n_down, M = cfg.n_nuc, d = cfg.embedding_dim, K = cfg.n_determinants;
-    if (cfg.kind == DQMC_PSIFORMER) {
+    const int rep = cfg.n_env_per_nuc > 1 ? cfg.n_env_per_nuc : 1;
+    if (cfg.kind == DQMC_PSIFORMER || cfg.kind == DQMC_TRANSPSIFORMER) {
       add("emb.w", 4 * M + 1, d);
       for (int l = 0; l < cfg.n_layers; ++l) {
         std::string p = "L" + std::to_string(l) + ".";
@@ -71,6 +72,10 @@ struct EngineBase {
         add(p + "b1", 1, d);
         add(p + "w2", d, d);
         add(p + "b2", 1, d);
+        if (cfg.kind == DQMC_TRANSPSIFORMER && cfg.n_nuc_tokens > 0) {
+          add(p + "kn", cfg.n_nuc_tokens, d);  // key / value rows of the nuclear tokens (host-evaluated stream)
+          add(p + "vn", cfg.n_nuc_tokens, d);
+        }
       }
     }
     if (cfg.kind == DQMC_FERMINET) {
@@ -89,10 +94,10 @@ struct EngineBase {
     }
     add("bf.up", d, K * N);
     add("bf.dn", d, K * N);
-    add("env.pi_up", K * N, M);
-    add("env.pi_dn", K * N, M);
-    add("env.zeta_up", K * N, M);
-    add("env.zeta_dn", K * N, M);
+    add("env.pi_up", K * N, M * rep);
+    add("env.pi_dn", K * N, M * rep);
+    add("env.zeta_up", K * N, M * rep);
+    add("env.zeta_dn", K * N, M * rep);
     add("cusp.alpha", 1, 2);
   }
   int64_t off(const std::string& n) const {
@@ -156,6 +161,8 @@ struct Engine : EngineBase {
   bool attn_fwd_ok = false;
   bool slater_fwd2_ok = false;
   int N, M, d, K, KN, H, dh, T3;
+  bool trans = false;  // TransPsiformer: nuclear attention tokens + nucleus-dependent envelopes
+  int Mn = 0, env_rep = 1;
   size_t max_smem = 0;
   int n_sms = 148;
 #if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
@@ -183,7 +190,13 @@ struct Engine : EngineBase {
   int init() {
     N = cfg.n_up + cfg.n_down; M = cfg.n_nuc; d = cfg.embedding_dim; K = cfg.n_determinants;
     KN = K * N; H = cfg.n_heads; dh = d / H; T3 = 3 * N;
-    if (cfg.kind != DQMC_PSIFORMER && cfg.kind != DQMC_FERMINET) { err = "unknown ansatz kind"; return 2; }
+    if (cfg.kind != DQMC_PSIFORMER && cfg.kind != DQMC_FERMINET && cfg.kind != DQMC_TRANSPSIFORMER) {
+      err = "unknown ansatz kind"; return 2;
+    }
+    trans = cfg.kind == DQMC_TRANSPSIFORMER;
+    Mn = trans ? cfg.n_nuc_tokens : 0;
+    env_rep = cfg.n_env_per_nuc > 1 ? cfg.n_env_per_nuc : 1;
+    if (M * env_rep > 4 * DQMC_MAX_NUC || Mn < 0 || Mn > DQMC_MAX_NUC) { err = "bad config (envelope terms / nuclear tokens)"; return 2; }
     if (H < 1) H = 1;
     if (cfg.kind == DQMC_FERMINET) { H = 1; dh = d; }
     if (M > DQMC_MAX_NUC || d % H != 0 || N < 2) { err = "bad config"; return 2; }
@@ -238,12 +251,13 @@ struct Engine : EngineBase {
     }
 #endif
     // opt in to large dynamic shared memory
-    const bool psif = cfg.kind == DQMC_PSIFORMER;
-    attn_tb = attn_pick_tb<T>(N, dh, T3, 100 * 1024);
-    attn_f32 = psif && std::is_same<T, float>::value && dh % 16 == 0 && !std::getenv("DQMC_ATTN_GENERIC");
+    const bool psif = cfg.kind == DQMC_PSIFORMER || trans;
+    attn_tb = attn_pick_tb<T>(N, dh, T3, 100 * 1024, Mn);
+    // the specialised fp32 attention kernels do not take extra tokens yet: TransPsiformer runs the generic one
+    attn_f32 = psif && !trans && std::is_same<T, float>::value && dh % 16 == 0 && !std::getenv("DQMC_ATTN_GENERIC");
     if (attn_f32) attn_tb = attn_f32_pick_tb(N, dh, T3, 32 * 1024);  // ~7 blocks/SM for small molecules
     if (const char* ev = std::getenv("DQMC_ATTN_TB")) { int x = std::atoi(ev); if (x >= 1 && x <= T3) attn_tb = x; }
-    size_t s_attn = !psif ? 0 : attn_f32 ? attn_f32_smem_bytes(N, dh, attn_tb) : attn_smem_bytes<T>(N, dh, attn_tb);
+    size_t s_attn = !psif ? 0 : attn_f32 ? attn_f32_smem_bytes(N, dh, attn_tb) : attn_smem_bytes<T>(N, dh, attn_tb, Mn);
     size_t s_sl = slater_smem_bytes<T>(N);
     max_smem = s_attn > s_sl ? s_attn : s_sl;
     if (max_smem > 227 * 1024) { err = "system too large for the shared-memory tiling (N)"; return 2; }
@@ -260,7 +274,7 @@ struct Engine : EngineBase {
       DQ_CHECK(cudaFuncSetAttribute(slater_fwd2_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)slater_fwd2_smem_bytes<T>(N, M, K)));
     }
-    attn_fwd_ok = psif && std::is_same<T, float>::value && dh == 64 && N <= 32 && d % 4 == 0 &&
+    attn_fwd_ok = psif && !trans && std::is_same<T, float>::value && dh == 64 && N <= 32 && d % 4 == 0 &&
                   !std::getenv("DQMC_ATTN_GENERIC") && !std::getenv("DQMC_ATTN_FWD_OLD");
     if (attn_fwd_ok) {
       const int smem = 4 * 2 * N * 64 * (int)sizeof(float);
@@ -536,6 +550,8 @@ struct Engine : EngineBase {
       gemm(X, d, (p + "wqkv").c_str(), nullptr, 0, 3 * d, nullptr, nullptr, 0, w.QKV, 3 * d, rows, 3 * d, d, S, 0, N, st);
       {
         const int tb = S > 1 ? attn_tb : 1;
+        const T* kn = Mn > 0 ? P(p + "kn") : nullptr;
+        const T* vn = Mn > 0 ? P(p + "vn") : nullptr;
         if constexpr (std::is_same<T, float>::value) {
           if (S == 1 && attn_fwd_ok) {
             const int n_pairs = Bc * H;
@@ -555,12 +571,12 @@ struct Engine : EngineBase {
                                 (int)attn_f32_smem_bytes(N, dh, tb), st, false))
               return 1;
           } else {
-            DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh, tb), st, (const T*)w.QKV,
-                      3 * d, O, d, N, S, dh, d, scale, tb);
+            DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh, tb, Mn), st, (const T*)w.QKV,
+                      3 * d, O, d, N, S, dh, d, scale, tb, kn, vn, Mn);
           }
         } else {
-          DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh, tb), st, (const T*)w.QKV, 3 * d,
-                    O, d, N, S, dh, d, scale, tb);
+          DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh, tb, Mn), st, (const T*)w.QKV,
+                    3 * d, O, d, N, S, dh, d, scale, tb, kn, vn, Mn);
         }
       }
       gemm(O, d, (p + "wo").c_str(), nullptr, 0, d, nullptr, X, d, w.A, d, rows, d, d, S, 0, N, st);
@@ -591,7 +607,7 @@ struct Engine : EngineBase {
 #define DQ_SL_SMALL(NS_)                                                                                           \
   DQ_LAUNCH((slater_small_kernel<T, NS_>), dim3((tot + 63) / 64), dim3(64), 0, st, r, R, Rb, M, cfg.n_up, K, S, tot,    \
             P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog, \
-            w.dgrad, w.dlap)
+            w.dgrad, w.dlap, env_rep)
       switch (N) {
         case 2: DQ_SL_SMALL(2); break;
         case 3: DQ_SL_SMALL(3); break;
@@ -606,19 +622,20 @@ struct Engine : EngineBase {
       if (N <= 16)
         DQ_LAUNCH((slater_fwd2_kernel<T, 16>), dim3(grid), dim3(nthr), slater_fwd2_smem_bytes<T>(N, M, K), st, r, R, Rb, N,
                   M, cfg.n_up, K, Bc, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF,
-                  KN, w.dsign, w.dlog);
+                  KN, w.dsign, w.dlog, env_rep);
       else
         DQ_LAUNCH((slater_fwd2_kernel<T, 32>), dim3(grid), dim3(nthr), slater_fwd2_smem_bytes<T>(N, M, K), st, r, R, Rb, N,
                   M, cfg.n_up, K, Bc, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF,
-                  KN, w.dsign, w.dlog);
+                  KN, w.dsign, w.dlog, env_rep);
     } else if (S == 1 && N <= 32 && !std::getenv("DQMC_SLATER_GENERIC")) {
       const int wpb = K < 8 ? K : 8;
       DQ_LAUNCH(slater_fwd_reg_kernel<T>, dim3(Bc), dim3(32 * wpb), sizeof(T) * N * M, st, r, R, Rb, N, M, cfg.n_up, K,
-                P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog);
+                P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog,
+                env_rep);
     } else
     DQ_LAUNCH(slater_kernel<T>, dim3((Bc * K + sl_wpb - 1) / sl_wpb), dim3(32 * sl_wpb), slater_smem_bytes<T>(N), st, r, R,
               Rb, N, M, cfg.n_up, K, S, Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog,
-              w.dgrad, w.dlap);
+              w.dgrad, w.dlap, env_rep);
     FinalizeCfg fc;
     fc.N = N; fc.M = M; fc.n_up = cfg.n_up; fc.K = K; fc.S = S; fc.cusp_kind = cfg.cusp_kind;
     fc.cusp_same_scale = cfg.cusp_same_scale; fc.cusp_anti_scale = cfg.cusp_anti_scale;

@@ -32,7 +32,9 @@ __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, 
                               int K, int S, int total, const T* __restrict__ pi_up, const T* __restrict__ pi_dn,
                               const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn,
                               const T* __restrict__ BF, int ldb, T* __restrict__ det_sign, T* __restrict__ det_log,
-                              T* __restrict__ det_grad, T* __restrict__ det_lap) {
+                              T* __restrict__ det_grad, T* __restrict__ det_lap, int rep) {
+  // rep = envelope terms per nucleus (1: ExponentialEnvelopes; 3: SimplifiedNucleusDependentEnvelopes,
+  // reference wf/env.py:111-226): parameter rows are [K N][M rep], term m rep + e sits on nucleus m.
   // One WARP per (walker b, determinant k): all phases are lane-strided loops separated by
   // __syncwarp, reductions are warp shuffles (no block barriers: N <= ~40 electrons).
   DQMC_DYN_SMEM(smem_raw);
@@ -56,20 +58,22 @@ __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, 
 
   for (LaneWalk w(lane, N); w.i < N; w.next()) {
     const int i = w.i, mu = w.j;
-    const T* pi = (i < n_up ? pi_up : pi_dn) + (size_t)(k * N + mu) * M;
-    const T* ze = (i < n_up ? zeta_up : zeta_dn) + (size_t)(k * N + mu) * M;
+    const T* pi = (i < n_up ? pi_up : pi_dn) + (size_t)(k * N + mu) * M * rep;
+    const T* ze = (i < n_up ? zeta_up : zeta_dn) + (size_t)(k * N + mu) * M * rep;
     T e = 0, de0 = 0, de1 = 0, de2 = 0, le = 0;
     for (int m = 0; m < M; ++m) {
       T dx0 = rb[3 * i] - Rb[3 * m], dx1 = rb[3 * i + 1] - Rb[3 * m + 1], dx2 = rb[3 * i + 2] - Rb[3 * m + 2];
       T d2 = dx0 * dx0 + dx1 * dx1 + dx2 * dx2;
       T rho2 = Num<T>::eps() + d2, rho = m_sqrt(rho2);
-      T a = m_abs(ze[m]);
-      T ex = pi[m] * m_exp(-a * rho);
-      e += ex;
-      if (S > 1) {
-        T c = -a * ex / rho;
-        de0 += c * dx0; de1 += c * dx1; de2 += c * dx2;
-        le += ex * (a * a * d2 / rho2 - a * (T(3) / rho - d2 / (rho2 * rho)));
+      for (int et = 0; et < rep; ++et) {
+        T a = m_abs(ze[m * rep + et]);
+        T ex = pi[m * rep + et] * m_exp(-a * rho);
+        e += ex;
+        if (S > 1) {
+          T c = -a * ex / rho;
+          de0 += c * dx0; de1 += c * dx1; de2 += c * dx2;
+          le += ex * (a * a * d2 / rho2 - a * (T(3) / rho - d2 / (rho2 * rho)));
+        }
       }
     }
     const T* bfrow = BF + (brow0 + (size_t)i * S) * ldb + k * N + mu;
@@ -199,7 +203,8 @@ __global__ void slater_small_kernel(const T* __restrict__ r, const T* __restrict
                                     int K, int S, int total, const T* __restrict__ pi_up, const T* __restrict__ pi_dn,
                                     const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn,
                                     const T* __restrict__ BF, int ldb, T* __restrict__ det_sign,
-                                    T* __restrict__ det_log, T* __restrict__ det_grad, T* __restrict__ det_lap) {
+                                    T* __restrict__ det_log, T* __restrict__ det_grad, T* __restrict__ det_lap,
+                                    int rep) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
   const int b = gid / K, k = gid % K;
@@ -214,20 +219,22 @@ __global__ void slater_small_kernel(const T* __restrict__ r, const T* __restrict
     const T* ze_s = i < n_up ? zeta_up : zeta_dn;
 #pragma unroll
     for (int mu = 0; mu < NS; ++mu) {
-      const T* pi = pi_s + (size_t)(k * NS + mu) * M;
-      const T* ze = ze_s + (size_t)(k * NS + mu) * M;
+      const T* pi = pi_s + (size_t)(k * NS + mu) * M * rep;
+      const T* ze = ze_s + (size_t)(k * NS + mu) * M * rep;
       T e = 0, d0 = 0, d1 = 0, d2_ = 0, le = 0;
       for (int m = 0; m < M; ++m) {
         T dx0 = rb[3 * i] - Rb[3 * m], dx1 = rb[3 * i + 1] - Rb[3 * m + 1], dx2 = rb[3 * i + 2] - Rb[3 * m + 2];
         T dd = dx0 * dx0 + dx1 * dx1 + dx2 * dx2;
         T rho2 = Num<T>::eps() + dd, rho = m_sqrt(rho2);
-        T a = m_abs(ze[m]);
-        T ex = pi[m] * m_exp(-a * rho);
-        e += ex;
-        if (S > 1) {
-          T c = -a * ex / rho;
-          d0 += c * dx0; d1 += c * dx1; d2_ += c * dx2;
-          le += ex * (a * a * dd / rho2 - a * (T(3) / rho - dd / (rho2 * rho)));
+        for (int et = 0; et < rep; ++et) {
+          T a = m_abs(ze[m * rep + et]);
+          T ex = pi[m * rep + et] * m_exp(-a * rho);
+          e += ex;
+          if (S > 1) {
+            T c = -a * ex / rho;
+            d0 += c * dx0; d1 += c * dx1; d2_ += c * dx2;
+            le += ex * (a * a * dd / rho2 - a * (T(3) / rho - dd / (rho2 * rho)));
+          }
         }
       }
       const T* bfrow = BF + (brow0 + (size_t)i * S) * ldb + k * NS + mu;
@@ -338,7 +345,7 @@ __global__ void slater_fwd_reg_kernel(const T* __restrict__ r, const T* __restri
                                       int n_up, int K, const T* __restrict__ pi_up, const T* __restrict__ pi_dn,
                                       const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn,
                                       const T* __restrict__ BF, int ldb, T* __restrict__ det_sign,
-                                      T* __restrict__ det_log) {
+                                      T* __restrict__ det_log, int rep) {
   constexpr int NM = 32;
   DQMC_DYN_SMEM(smem_raw);
   T* rho = reinterpret_cast<T*>(smem_raw);  // [N][M]
@@ -361,10 +368,11 @@ __global__ void slater_fwd_reg_kernel(const T* __restrict__ r, const T* __restri
     for (int mu = 0; mu < NM; ++mu) {
       T v = (mu == lane) ? T(1) : T(0);  // padding rows/columns: identity
       if (rowok && mu < N) {
-        const T* pk = pi + (size_t)(k * N + mu) * M;
-        const T* zk = ze + (size_t)(k * N + mu) * M;
+        const T* pk = pi + (size_t)(k * N + mu) * M * rep;
+        const T* zk = ze + (size_t)(k * N + mu) * M * rep;
         T e = T(0);
-        for (int m = 0; m < M; ++m) e += pk[m] * m_exp(-m_abs(zk[m]) * rho[lane * M + m]);
+        for (int m = 0; m < M; ++m)
+          for (int et = 0; et < rep; ++et) e += pk[m * rep + et] * m_exp(-m_abs(zk[m * rep + et]) * rho[lane * M + m]);
         v = e * BF[((size_t)b * N + lane) * ldb + k * N + mu];
       }
       a[mu] = v;
@@ -468,7 +476,7 @@ __global__ void __launch_bounds__(256, 3)
 slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M, int n_up, int K,
                    int B, const T* __restrict__ pi_up, const T* __restrict__ pi_dn, const T* __restrict__ zeta_up,
                    const T* __restrict__ zeta_dn, const T* __restrict__ BF, int ldb, T* __restrict__ det_sign,
-                   T* __restrict__ det_log) {
+                   T* __restrict__ det_log, int rep) {
   DQMC_DYN_SMEM(smem_raw);
   const int NP = N | 1, KN = K * N;
   T* As = reinterpret_cast<T*>(smem_raw);  // [K][N][NP]
@@ -493,8 +501,8 @@ slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batch
 #pragma unroll 1
       for (int sb = 0; sb < 2; ++sb) {
         const int ib = sb ? n_up : 0, ie = sb ? N : n_up;
-        const T* pi = (sb ? pi_dn : pi_up) + (size_t)o * M;
-        const T* ze = (sb ? zeta_dn : zeta_up) + (size_t)o * M;
+        const T* pi = (sb ? pi_dn : pi_up) + (size_t)o * M * rep;
+        const T* ze = (sb ? zeta_dn : zeta_up) + (size_t)o * M * rep;
 #pragma unroll 1
         for (int i0 = ib; i0 < ie; i0 += 8) {
           T e[8], bf[8];
@@ -503,8 +511,9 @@ slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batch
             e[j] = T(0);
             bf[j] = i0 + j < ie ? bfp[(size_t)(i0 + j) * ldb] : T(0);
           }
-          for (int m = 0; m < M; ++m) {
-            const T p = pi[m], z = -m_abs(ze[m]);
+          for (int mt = 0; mt < M * rep; ++mt) {
+            const T p = pi[mt], z = -m_abs(ze[mt]);
+            const int m = rep == 1 ? mt : mt / rep;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int ii = i0 + j < ie ? i0 + j : ie - 1;

@@ -332,21 +332,26 @@ __global__ void tanh_fl_kernel(T* __restrict__ Z, int ldz, const T* __restrict__
 // ------------------------------------------------------------------------------------------
 template <class T>
 __global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict__ O, int ldo, int N, int S, int dh,
-                               int dmodel, T scale, int TB) {
-  // Tangent slots are processed in chunks of TB so that every phase has (TB x N x N) or (N x dh)
+                               int dmodel, T scale, int TB, const T* __restrict__ Kn, const T* __restrict__ Vn, int Mn) {
+  // Tangent slots are processed in chunks of TB so that every phase has (TB x N x NK) or (N x dh)
   // independent work items (small molecules: all 3N tangents in one chunk).
+  // Kn / Vn [Mn][dmodel] (nullable): key / value rows of Mn walker-independent extra tokens (the
+  // nuclei of the TransPsiformer, reference gnn/update_features.py:385-451 with elec_to_nuc =
+  // false); they sit behind the N electron keys (softmax is order-independent) and carry zero
+  // tangents, so every derivative term with k^t_j, v^t_j, k^L_j, v^L_j vanishes for j >= N.
   DQMC_DYN_SMEM(smem_raw);
-  const int dhp = dh + 1, NN = N * N;
-  T* q = reinterpret_cast<T*>(smem_raw);
-  T* k = q + N * dhp;
-  T* v = k + N * dhp;
-  T* qt = v + N * dhp;            // [TB][N][dhp]
+  const int NK = N + Mn;
+  const int dhp = dh + 1, NN = N * NK;
+  T* q = reinterpret_cast<T*>(smem_raw);   // [N][dhp]
+  T* k = q + N * dhp;                      // [NK][dhp]
+  T* v = k + NK * dhp;                     // [NK][dhp]
+  T* qt = v + NK * dhp;                    // [TB][N][dhp]
   T* kt = qt + (size_t)TB * N * dhp;
   T* vt = kt + (size_t)TB * N * dhp;
-  T* p = vt + (size_t)TB * N * dhp;  // [N][N]
-  T* st = p + NN;                 // [TB][N][N]
-  T* u = st + (size_t)TB * NN;    // [N][N]
-  T* qk = u + NN;                 // [N][N]
+  T* p = vt + (size_t)TB * N * dhp;  // [N][NK]
+  T* st = p + NN;                 // [TB][N][NK]
+  T* u = st + (size_t)TB * NN;    // [N][NK]
+  T* qk = u + NN;                 // [N][NK]
   T* olap = qk + NN;              // [N][dh]
   T* mrow = olap + N * dh;        // [TB][N]
   T* vrow = mrow + TB * N;        // [N]
@@ -365,9 +370,14 @@ __global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict
     }
   };
   load3(0, 1, q, k, v);
+  for (int idx = tid; idx < Mn * dh; idx += nt) {
+    int e = idx % dh, m = idx / dh;
+    k[(N + m) * dhp + e] = Kn[(size_t)m * dmodel + h * dh + e];
+    v[(N + m) * dhp + e] = Vn[(size_t)m * dmodel + h * dh + e];
+  }
   __syncthreads();
   for (int idx = tid; idx < NN; idx += nt) {
-    int i = idx / N, j = idx % N;
+    int i = idx / NK, j = idx % NK;
     T a = T(0);
     for (int e = 0; e < dh; ++e) a += q[i * dhp + e] * k[j * dhp + e];
     p[idx] = a * scale;
@@ -377,22 +387,22 @@ __global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict
   for (int idx = tid; idx < N * dh; idx += nt) olap[idx] = T(0);
   __syncthreads();
   for (int i = tid; i < N; i += nt) {  // softmax row i
-    T mx = p[i * N];
-    for (int j = 1; j < N; ++j) mx = p[i * N + j] > mx ? p[i * N + j] : mx;
+    T mx = p[i * NK];
+    for (int j = 1; j < NK; ++j) mx = p[i * NK + j] > mx ? p[i * NK + j] : mx;
     T sum = T(0);
-    for (int j = 0; j < N; ++j) {
-      T e = m_exp(p[i * N + j] - mx);
-      p[i * N + j] = e;
+    for (int j = 0; j < NK; ++j) {
+      T e = m_exp(p[i * NK + j] - mx);
+      p[i * NK + j] = e;
       sum += e;
     }
     T inv = T(1) / sum;
-    for (int j = 0; j < N; ++j) p[i * N + j] *= inv;
+    for (int j = 0; j < NK; ++j) p[i * NK + j] *= inv;
   }
   __syncthreads();
   for (int idx = tid; idx < N * dh; idx += nt) {
     int i = idx / dh, e = idx % dh;
     T a = T(0);
-    for (int j = 0; j < N; ++j) a += p[i * N + j] * v[j * dhp + e];
+    for (int j = 0; j < NK; ++j) a += p[i * NK + j] * v[j * dhp + e];
     O[(row0 + (size_t)i * S) * ldo + h * dh + e] = a;
   }
   if (S == 1) return;
@@ -402,15 +412,20 @@ __global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict
     load3(1 + t0, tc, qt, kt, vt);
     __syncthreads();
     for (int idx = tid; idx < tc * NN; idx += nt) {
-      int j = idx % N, i = (idx / N) % N, t = idx / NN;
+      int j = idx % NK, i = (idx / NK) % N, t = idx / NN;
       const T* qti = qt + (t * N + i) * dhp;
-      const T* ktj = kt + (t * N + j) * dhp;
       T a = T(0);
-      for (int e = 0; e < dh; ++e) a += qti[e] * k[j * dhp + e] + q[i * dhp + e] * ktj[e];
+      if (j < N) {
+        const T* ktj = kt + (t * N + j) * dhp;
+        for (int e = 0; e < dh; ++e) a += qti[e] * k[j * dhp + e] + q[i * dhp + e] * ktj[e];
+      } else {
+        for (int e = 0; e < dh; ++e) a += qti[e] * k[j * dhp + e];
+      }
       st[idx] = a * scale;
     }
     for (int idx = tid; idx < NN; idx += nt) {
-      int i = idx / N, j = idx % N;
+      int i = idx / NK, j = idx % NK;
+      if (j >= N) continue;
       T c = T(0);
       for (int t = 0; t < tc; ++t) {
         const T* qti = qt + (t * N + i) * dhp;
@@ -421,15 +436,15 @@ __global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict
     }
     __syncthreads();
     for (int idx = tid; idx < tc * N; idx += nt) {  // (t, i)
-      const T* pr = p + (idx % N) * N;
-      const T* sr = st + (size_t)idx * N;
+      const T* pr = p + (idx % N) * NK;
+      const T* sr = st + (size_t)idx * NK;
       T m = T(0);
-      for (int j = 0; j < N; ++j) m += pr[j] * sr[j];
+      for (int j = 0; j < NK; ++j) m += pr[j] * sr[j];
       mrow[idx] = m;
     }
     __syncthreads();
     for (int idx = tid; idx < NN; idx += nt) {
-      int i = idx / N;
+      int i = idx / NK;
       T uu = T(0), pp = p[idx];
       for (int t = 0; t < tc; ++t) {
         T dv_ = st[t * NN + idx] - mrow[t * N + i];
@@ -443,14 +458,15 @@ __global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict
       int i = idx / dh, e = idx % dh;
       T c2 = T(0);
       for (int t = 0; t < tc; ++t) {
-        const T* sr = st + t * NN + i * N;
+        const T* sr = st + t * NN + i * NK;
         const T* vtt = vt + (size_t)t * N * dhp + e;
         T a = T(0), c = T(0);
         for (int j = 0; j < N; ++j) {
           T vtj = vtt[j * dhp];
-          a += sr[j] * v[j * dhp + e] + p[i * N + j] * vtj;
+          a += sr[j] * v[j * dhp + e] + p[i * NK + j] * vtj;
           c += sr[j] * vtj;
         }
+        for (int j = N; j < NK; ++j) a += sr[j] * v[j * dhp + e];
         c2 += c;
         O[(row0 + (size_t)i * S + 1 + t0 + t) * ldo + h * dh + e] = a;
       }
@@ -461,45 +477,51 @@ __global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict
   load3(1 + T3, 1, qt, kt, vt);
   __syncthreads();
   for (int idx = tid; idx < NN; idx += nt) {
-    int i = idx / N, j = idx % N;
+    int i = idx / NK, j = idx % NK;
     T a = T(0);
-    for (int e = 0; e < dh; ++e) a += qt[i * dhp + e] * k[j * dhp + e] + q[i * dhp + e] * kt[j * dhp + e];
+    if (j < N) {
+      for (int e = 0; e < dh; ++e) a += qt[i * dhp + e] * k[j * dhp + e] + q[i * dhp + e] * kt[j * dhp + e];
+    } else {
+      for (int e = 0; e < dh; ++e) a += qt[i * dhp + e] * k[j * dhp + e];
+    }
     st[idx] = scale * (a + T(2) * qk[idx]);
   }
   __syncthreads();
   for (int i = tid; i < N; i += nt) {
     T m = T(0), V = T(0);
-    for (int j = 0; j < N; ++j) {
-      m += p[i * N + j] * st[i * N + j];
-      V += p[i * N + j] * u[i * N + j];
+    for (int j = 0; j < NK; ++j) {
+      m += p[i * NK + j] * st[i * NK + j];
+      V += p[i * NK + j] * u[i * NK + j];
     }
     mrow[i] = m;
     vrow[i] = V;
   }
   __syncthreads();
   for (int idx = tid; idx < NN; idx += nt) {
-    int i = idx / N;
+    int i = idx / NK;
     st[idx] = p[idx] * (u[idx] - vrow[i] + st[idx] - mrow[i]);
   }
   __syncthreads();
   for (int idx = tid; idx < N * dh; idx += nt) {
     int i = idx / dh, e = idx % dh;
     T a = olap[idx];
-    for (int j = 0; j < N; ++j) a += st[i * N + j] * v[j * dhp + e] + p[i * N + j] * vt[j * dhp + e];
+    for (int j = 0; j < N; ++j) a += st[i * NK + j] * v[j * dhp + e] + p[i * NK + j] * vt[j * dhp + e];
+    for (int j = N; j < NK; ++j) a += st[i * NK + j] * v[j * dhp + e];
     O[(row0 + (size_t)i * S + 1 + T3) * ldo + h * dh + e] = a;
   }
 }
 
 template <class T>
-inline size_t attn_smem_bytes(int N, int dh, int TB) {
-  return sizeof(T) * ((size_t)3 * N * (dh + 1) + (size_t)3 * TB * N * (dh + 1) + (size_t)N * N * (3 + TB) +
-                      (size_t)N * dh + (size_t)TB * N + N);
+inline size_t attn_smem_bytes(int N, int dh, int TB, int Mn = 0) {
+  const size_t NK = N + Mn;
+  return sizeof(T) * ((size_t)N * (dh + 1) + 2 * NK * (dh + 1) + (size_t)3 * TB * N * (dh + 1) +
+                      (size_t)N * NK * (3 + TB) + (size_t)N * dh + (size_t)TB * N + N);
 }
 // largest tangent chunk whose working set fits `budget` bytes of shared memory
 template <class T>
-inline int attn_pick_tb(int N, int dh, int T3, size_t budget) {
+inline int attn_pick_tb(int N, int dh, int T3, size_t budget, int Mn = 0) {
   int tb = T3 > 0 ? T3 : 1;
-  while (tb > 1 && attn_smem_bytes<T>(N, dh, tb) > budget) --tb;
+  while (tb > 1 && attn_smem_bytes<T>(N, dh, tb, Mn) > budget) --tb;
   return tb;
 }
 

@@ -18,14 +18,14 @@ MODE_FORWARD, MODE_LOCAL_ENERGY = 0, 1
 _TORCH_DTYPE = {0: torch.float64, 1: torch.float32}
 
 
-def _pack_haiku_params(spec: AnsatzSpec, params: dict) -> dict[str, np.ndarray]:
+def _pack_haiku_params(spec: AnsatzSpec, params: dict, R=None) -> dict[str, np.ndarray]:
     """Haiku-named tree (deepqmc_b200.params) -> the engine's packed entries."""
     g = lambda k: np.asarray(params[k], dtype=np.float64)
     out = {}
-    if spec.kind == 'psiformer':
+    if spec.kind in ('psiformer', 'transpsiformer'):
         out['emb.w'] = g(PN.GNN + 'electron_embedding/linear:w')
         for l in range(spec.n_layers):
-            a = PN.attn_prefix(l)
+            a = PN.attn_prefix(l) if spec.kind == 'psiformer' else PN.comb_prefix(l)
             out[f'L{l}.wqkv'] = np.concatenate(
                 [g(a + f'multi_head_attention/{n}:w') for n in ('query', 'key', 'value')], axis=1
             )
@@ -41,9 +41,23 @@ def _pack_haiku_params(spec: AnsatzSpec, params: dict) -> dict[str, np.ndarray]:
     else:
         raise NotImplementedError(spec.kind)
     out['bf.up'], out['bf.dn'] = g(PN.BF_UP + ':w'), g(PN.BF_DN + ':w')
-    for s, t in (('up', 'up'), ('down', 'dn')):
-        out[f'env.pi_{t}'] = g(f'{PN.ENV}:pi_{s}')
-        out[f'env.zeta_{t}'] = g(f'{PN.ENV}:zetas_{s}')
+    if spec.kind == 'transpsiformer':
+        # walker-independent nuclear stream (deepqmc_b200/nuclear.py): per-layer key/value rows of the
+        # nuclear tokens and the envelope exponents zetas[M, K, E] -> engine layout [K N][M E], pi = 1
+        from .nuclear import nuclear_stream
+
+        ns = nuclear_stream(spec, params, R)
+        N, K, M, E = spec.n_elec, spec.n_determinants, spec.n_nuc, spec.n_env_per_nuc
+        for l in range(spec.n_layers):
+            out[f'L{l}.kn'], out[f'L{l}.vn'] = ns['kn'][l], ns['vn'][l]
+        for s, t in (('up', 'up'), ('down', 'dn')):
+            z = np.transpose(ns[f'zetas_{s}'], (1, 0, 2)).reshape(K, 1, M * E)  # [K][m E + e]
+            out[f'env.zeta_{t}'] = np.broadcast_to(z, (K, N, M * E)).reshape(K * N, M * E).copy()
+            out[f'env.pi_{t}'] = np.ones((K * N, M * E))
+    else:
+        for s, t in (('up', 'up'), ('down', 'dn')):
+            out[f'env.pi_{t}'] = g(f'{PN.ENV}:pi_{s}')
+            out[f'env.zeta_{t}'] = g(f'{PN.ENV}:zetas_{s}')
     if spec.cusp == 'psiformer':
         out['cusp.alpha'] = np.array([[g(f'{PN.CUSP}:same_alpha'), g(f'{PN.CUSP}:anti_alpha')]], dtype=np.float64)
     else:
@@ -66,11 +80,13 @@ class Engine:
         self.device_index = 0 if self._host else (torch.cuda.current_device() if device is None else device)
         self.device = torch.device('cpu') if self._host else torch.device('cuda', self.device_index)
         cfg = _lib.DqmcConfig()
-        cfg.kind = {'psiformer': 0, 'ferminet': 1}[spec.kind]
+        cfg.kind = {'psiformer': 0, 'ferminet': 1, 'transpsiformer': 2}[spec.kind]
         cfg.dtype, cfg.gemm_backend = self.dtype_code, gemm_backend
         cfg.n_up, cfg.n_down, cfg.n_nuc = spec.n_up, spec.n_down, spec.n_nuc
         cfg.embedding_dim, cfg.n_layers, cfg.n_heads = spec.embedding_dim, spec.n_layers, spec.n_heads
         cfg.n_determinants, cfg.edge_dim = spec.n_determinants, spec.edge_dim
+        cfg.n_env_per_nuc = spec.n_env_per_nuc
+        cfg.n_nuc_tokens = spec.n_nuc if spec.kind == 'transpsiformer' else 0
         cfg.cusp_kind = 1 if spec.cusp == 'psiformer' else 0
         cfg.cusp_same_scale, cfg.cusp_anti_scale = spec.cusp_same_scale, spec.cusp_anti_scale
         M = spec.n_nuc
@@ -117,8 +133,15 @@ class Engine:
     def _stream(self):
         return C.c_void_p(0 if self._host else torch.cuda.current_stream(self.device).cuda_stream)
 
-    def set_params(self, params: dict):
-        packed = _pack_haiku_params(self.spec, params)
+    def set_params(self, params: dict, R=None):
+        """Upload a parameter tree.  TransPsiformer: ``R`` (default: the Hamiltonian's geometry) fixes
+        the walker-independent nuclear stream that is uploaded with the parameters."""
+        if self.spec.kind == 'transpsiformer':
+            R = self.hamil.mol.coords if R is None else R
+            R = np.asarray(R.detach().cpu() if torch.is_tensor(R) else R, dtype=np.float64)
+            self._nuc_R, self._nuc_key = R, None
+        self._params = params
+        packed = _pack_haiku_params(self.spec, params, R)
         flat = np.zeros(self.n_packed, dtype=np.float64)
         for k, (off, rows, cols) in self.entries.items():
             v = packed[k]
@@ -151,6 +174,15 @@ class Engine:
         batched = 1 if R.dim() == 3 else 0
         if batched:
             assert R.shape[0] == B
+        if self.spec.kind == 'transpsiformer':
+            if batched:
+                raise NotImplementedError('TransPsiformer engine: one geometry per call (unbatched R)')
+            key = (R.data_ptr(), R._version)
+            if key != self._nuc_key:  # geometry may have changed: the nuclear stream depends on it
+                Rh = R.detach().cpu().double().numpy()
+                if not np.allclose(Rh, self._nuc_R, rtol=0, atol=1e-12):
+                    self.set_params(self._params, Rh)
+                self._nuc_key = key
         return R, batched
 
     # ------------------------------------------------------------------------------------

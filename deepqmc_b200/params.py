@@ -24,6 +24,14 @@ BF_UP = P + 'omni_net/~/Backflow/~/mlp/linear_0'
 BF_DN = P + 'omni_net/~/Backflow_1/~/mlp/linear_0'
 
 
+NUC_EMB = GNN + 'nuclei_embedding/'
+HEAD = P + 'omni_net/~/nuclear_gnn_head/'
+
+
+def comb_prefix(l):
+    return layer_prefix(l) + 'combined_node_attention_update_feature/'
+
+
 def layer_prefix(l):
     return GNN + ('electron_gnn_layer' if l == 0 else f'electron_gnn_layer_{l}') + '/~/'
 
@@ -35,8 +43,9 @@ def attn_prefix(l):
 def param_shapes(spec: AnsatzSpec) -> dict[str, tuple[int, ...]]:
     N, M, d, K = spec.n_elec, spec.n_nuc, spec.embedding_dim, spec.n_determinants
     s: dict[str, tuple[int, ...]] = {}
-    for nm in ('pi_up', 'pi_down', 'zetas_up', 'zetas_down'):
-        s[f'{ENV}:{nm}'] = (K * N, M)
+    if spec.kind != 'transpsiformer':
+        for nm in ('pi_up', 'pi_down', 'zetas_up', 'zetas_down'):
+            s[f'{ENV}:{nm}'] = (K * N, M)
     if spec.cusp == 'psiformer':
         s[f'{CUSP}:same_alpha'] = ()
         s[f'{CUSP}:anti_alpha'] = ()
@@ -60,6 +69,27 @@ def param_shapes(spec: AnsatzSpec) -> dict[str, tuple[int, ...]]:
                 s[lp + 'u/linear_0:w'] = (e_in, de)
                 s[lp + 'u/linear_0:b'] = (de,)
             d_in, e_in = d, de
+    elif spec.kind == 'transpsiformer':
+        # reference: conf/ansatz/transpsiformer.yaml; gnn/electron_gnn.py:435-537 NucleiEmbedding,
+        # gnn/update_features.py:385-451 CombinedNodeAttentionUpdateFeature, wf/omni.py:181-211 head
+        de, E = spec.nuc_edge_dim, spec.n_env_per_nuc
+        s[GNN + 'electron_embedding/linear:w'] = (spec.n_feat_in, d)
+        for nm, (i, o) in (('edge_mlp/linear_0', (4 + M, de)), ('edge_mlp/linear_1', (de, de)),
+                           ('embed_mlp/linear_0', (de, d)), ('embed_mlp/linear_1', (d, d))):
+            s[NUC_EMB + nm + ':w'] = (i, o)
+            s[NUC_EMB + nm + ':b'] = (o,)
+        for l in range(spec.n_layers):
+            a = comb_prefix(l)
+            for nm in ('query', 'key', 'value', 'linear'):
+                s[a + f'multi_head_attention/{nm}:w'] = (d, d)
+            for i in range(2):
+                s[a + f'mlp/linear_{i}:w'] = (d, d)
+                s[a + f'mlp/linear_{i}:b'] = (d,)
+        for glu, spin in (('zetas_readout_glu', 'up'), ('zetas_readout_glu_1', 'down')):
+            for lin in ('W', 'V'):
+                s[HEAD + f'{glu}/{lin}:w'] = (d, K * E)
+                s[HEAD + f'{glu}/{lin}:b'] = (K * E,)
+            s[HEAD + f':zetas_bias_{spin}'] = (M, K, E)
     else:
         raise ValueError(spec.kind)
     s[BF_UP + ':w'] = (d, K * N)
@@ -77,6 +107,8 @@ def init_params(spec: AnsatzSpec, seed: int = 0) -> dict[str, np.ndarray]:
             v = np.ones(shape)
         elif name.startswith(CUSP):
             v = np.ones(shape)
+        elif leaf.startswith('zetas_bias'):
+            v = 2 * np.ones(shape)  # wf/omni.py:199-203
         elif leaf == 'w':
             v = rng.standard_normal(shape) / np.sqrt(shape[0])
         elif leaf == 'b':
@@ -93,7 +125,7 @@ def perturb_params(params, seed=1, scale=0.2):
     rng = np.random.default_rng(seed)
     out = dict(params)
     for k, v in params.items():
-        if k.startswith(ENV) or k.startswith(CUSP):
+        if k.startswith(ENV) or k.startswith(CUSP) or 'zetas_bias' in k:
             out[k] = v * (1 + scale * rng.uniform(-1, 1, size=v.shape))
     return out
 

@@ -22,7 +22,7 @@ extern "C" {
 #define DQMC_MAX_ECP_TERMS 4
 #define DQMC_MAX_ECP_L 4
 
-enum { DQMC_PSIFORMER = 0, DQMC_FERMINET = 1 };
+enum { DQMC_PSIFORMER = 0, DQMC_FERMINET = 1, DQMC_TRANSPSIFORMER = 2 };
 enum { DQMC_F64 = 0, DQMC_F32 = 1 };
 enum { DQMC_GEMM_SIMT = 0, DQMC_GEMM_TCGEN05 = 1 };
 enum { DQMC_MODE_FORWARD = 0, DQMC_MODE_LOCAL_ENERGY = 1 };
@@ -32,7 +32,7 @@ enum { DQMC_MODE_FORWARD = 0, DQMC_MODE_LOCAL_ENERGY = 1 };
  *            src/deepqmc/hamil.py:97-154 (n_up, n_down, ns_valence, ecp_mask);
  *            src/deepqmc/ecp/gaussian_type_ecp.py:32-95 (loc/nl parameter layout). */
 typedef struct dqmc_config {
-  int32_t kind;            /* DQMC_PSIFORMER | DQMC_FERMINET */
+  int32_t kind;            /* DQMC_PSIFORMER | DQMC_FERMINET | DQMC_TRANSPSIFORMER */
   int32_t dtype;           /* DQMC_F64 | DQMC_F32 */
   int32_t gemm_backend;    /* DQMC_GEMM_SIMT | DQMC_GEMM_TCGEN05 (f32 only) */
   int32_t n_up, n_down, n_nuc;
@@ -45,6 +45,12 @@ typedef struct dqmc_config {
   double ecp_loc[DQMC_MAX_NUC][3][2][DQMC_MAX_ECP_TERMS];           /* [I][r^-1,r^0,r^1][alpha,beta][term] */
   int32_t ecp_nl_lmax_p1, ecp_nl_terms;
   double ecp_nl[DQMC_MAX_NUC][DQMC_MAX_ECP_L][2][DQMC_MAX_ECP_TERMS]; /* [I][l][alpha,beta][term] */
+  /* DQMC_TRANSPSIFORMER (conf/ansatz/transpsiformer.yaml): envelope terms per nucleus
+   * (SimplifiedNucleusDependentEnvelopes.n_envelope_per_nucleus, wf/env.py:111-226; 0/1 otherwise) and the
+   * number of walker-independent nuclear attention tokens (gnn/update_features.py:385-451, elec_to_nuc =
+   * false), whose per-layer key/value rows are entries "L<l>.kn" / "L<l>.vn" of the parameter table. */
+  int32_t n_env_per_nuc;
+  int32_t n_nuc_tokens;
 } dqmc_config;
 
 typedef struct dqmc_engine* dqmc_handle;

@@ -171,9 +171,11 @@ class OracleHamiltonian:
         rot = rot_z(phi) @ rot_y(theta) @ rot_z(phi_random)
         return torch.as_tensor(radius * (ico @ rot.T) + R_I.numpy())
 
-    def nonloc_potential(self, r, R, wf, phi_random):
+    def nonloc_potential(self, r, R, wf, phi_random, pairs=None):
         """reference: gaussian_type_ecp.py:161-255.  ``phi_random[j, i]`` replaces the
-        jax.random.uniform(0, pi/5) draw keyed by fold_in(fold_in(rng, j), i)."""
+        jax.random.uniform(0, pi/5) draw keyed by fold_in(fold_in(rng, j), i).
+        ``pairs`` (optional set of (j, i)) restricts the double sum to a subset so that callers can
+        spread one walker's quadrature over several processes (bench.py CPU arm)."""
         if self.nl_params is None:
             return torch.zeros((), dtype=F64)
         nlp = self.nl_params
@@ -188,6 +190,8 @@ class OracleHamiltonian:
             a = torch.as_tensor(nlp[I, :, 0, :])
             b = torch.as_tensor(nlp[I, :, 1, :])
             for i in range(r.shape[0]):
+                if pairs is not None and (j, i) not in pairs:
+                    continue
                 dist = torch.linalg.norm(r[i] - R[I])
                 v_l = (b * torch.exp(-a * dist**2)).sum(-1)  # [L]
                 pts = self.quadrature_points(r[i], R[I], float(phi_random[j, i]))

@@ -93,6 +93,93 @@ def ferminet_embeddings(spec, params, r, R):
     return x
 
 
+def layer_norm(x, eps=1e-5):
+    # hk.LayerNorm(-1, create_scale=False, create_offset=False) (reference: hkext.py:200-201)
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps)
+
+
+def nuclei_embedding(spec, params, R):
+    """reference: gnn/electron_gnn.py:435-537 (edge_features given, 'nn' edges with
+    self-interaction, receiver - sender), edge features gnn/edge_features.py:21-78 log-rescaled."""
+    M = spec.n_nuc
+    d = R[None, :, :] - R[:, None, :]  # [sender, receiver, 3]
+    rr = safe_norm(d)
+    lg = torch.log1p(rr)
+    feats = torch.cat([lg[..., None], d * (lg / rr)[..., None]], -1)  # [M, M, 4]
+    ch = torch.as_tensor(spec.charges, dtype=R.dtype)
+    inv = torch.unique(ch, return_inverse=True)[1]
+    onehot = torch.nn.functional.one_hot(inv, M).to(R.dtype)  # type of the SENDER (axis 0)
+    x = torch.cat([feats, onehot[:, None, :].expand(M, M, M)], -1)
+    silu = torch.nn.functional.silu
+    g = lambda nm: (_t(params, P.NUC_EMB + nm + ':w'), _t(params, P.NUC_EMB + nm + ':b'))
+    w0, b0 = g('edge_mlp/linear_0'); w1, b1 = g('edge_mlp/linear_1')
+    e = silu(x @ w0 + b0) @ w1 + b1
+    v0, c0 = g('embed_mlp/linear_0'); v1, c1 = g('embed_mlp/linear_1')
+    return silu(e.sum(0) @ v0 + c0) @ v1 + c1  # [M, d]
+
+
+def transpsiformer_embeddings(spec, params, r, R):
+    """Electron AND nucleus embeddings (reference: gnn/update_features.py:385-451: attention over
+    [nuclei; electrons] tokens, nuclei masked from attending electrons; residual, tanh MLP, residual)."""
+    N, M, d, H = spec.n_elec, spec.n_nuc, spec.embedding_dim, spec.n_heads
+    dh = d // H
+    feats, _ = ne_features(r, R, True)
+    spins = torch.cat([torch.ones(spec.n_up), -torch.ones(spec.n_down)]).to(r.dtype)[:, None]
+    xe = torch.cat([feats, spins], 1) @ _t(params, P.GNN + 'electron_embedding/linear:w')
+    h = torch.cat([nuclei_embedding(spec, params, R), xe], 0)  # [M + N, d]
+    mask = torch.ones(M + N, M + N, dtype=torch.bool)
+    mask[:M, M:] = False
+    for l in range(spec.n_layers):
+        a = P.comb_prefix(l)
+        q = (h @ _t(params, a + 'multi_head_attention/query:w')).reshape(M + N, H, dh)
+        k = (h @ _t(params, a + 'multi_head_attention/key:w')).reshape(M + N, H, dh)
+        v = (h @ _t(params, a + 'multi_head_attention/value:w')).reshape(M + N, H, dh)
+        logits = torch.einsum('thd,Thd->htT', q, k) / math.sqrt(dh)
+        logits = torch.where(mask[None], logits, torch.full_like(logits, -1e30))
+        w = torch.softmax(logits, -1)
+        o = torch.einsum('htT,Thd->thd', w, v).reshape(M + N, d)
+        att = h + o @ _t(params, a + 'multi_head_attention/linear:w')
+        m = torch.tanh(att @ _t(params, a + 'mlp/linear_0:w') + _t(params, a + 'mlp/linear_0:b'))
+        m = torch.tanh(m @ _t(params, a + 'mlp/linear_1:w') + _t(params, a + 'mlp/linear_1:b'))
+        h = att + m
+    return h[M:], h[:M]
+
+
+def nuclear_head_zetas(spec, params, nuc_emb):
+    """reference: wf/omni.py:181-211 NuclearGNNHead + hkext.py:165-202 GLU (LayerNorm before,
+    sigmoid gate) + bias initialised to 2 -> zetas_{up,down}[M, K, E]."""
+    K, E = spec.n_determinants, spec.n_env_per_nuc
+    x = layer_norm(nuc_emb)
+    out = {}
+    for glu, spin in (('zetas_readout_glu', 'up'), ('zetas_readout_glu_1', 'down')):
+        W, bW = _t(params, P.HEAD + glu + '/W:w'), _t(params, P.HEAD + glu + '/W:b')
+        V, bV = _t(params, P.HEAD + glu + '/V:w'), _t(params, P.HEAD + glu + '/V:b')
+        y = torch.sigmoid(x @ W + bW) * (x @ V + bV)
+        out[spin] = y.reshape(-1, K, E) + _t(params, P.HEAD + f':zetas_bias_{spin}')
+    return out
+
+
+def orbitals_nucdep(spec, params, emb, zetas, r, R):
+    """SimplifiedNucleusDependentEnvelopes (reference: wf/env.py:111-226; fixed pi = 1,
+    per_orbital_exponent = false: the envelope does not depend on the orbital index) (*) backflow."""
+    N, K, n_up = spec.n_elec, spec.n_determinants, spec.n_up
+    dist = safe_norm(r[:, None] - R[None])  # [N, M]
+
+    def env(spin, sl):
+        ex = torch.abs(dist[sl][:, :, None, None] * zetas[spin][None])  # [n, M, K, E]
+        return torch.exp(-ex).sum((1, 3)).permute(1, 0)[:, :, None]  # [K, n, 1]
+
+    def bf(w, sl):
+        return (emb[sl] @ w).reshape(-1, K, N).permute(1, 0, 2)
+
+    up, dn = slice(None, n_up), slice(n_up, None)
+    a_up = env('up', up) * bf(_t(params, P.BF_UP + ':w'), up)
+    a_dn = env('down', dn) * bf(_t(params, P.BF_DN + ':w'), dn)
+    return torch.cat([a_up, a_dn], 1)
+
+
 def orbitals(spec, params, emb, r, R):
     """envelopes (*) backflow -> A[K, N, N] (electron i, orbital mu)."""
     N, K, n_up = spec.n_elec, spec.n_determinants, spec.n_up
@@ -130,8 +217,12 @@ def psiformer_cusp(spec, params, r):
 
 def log_psi(spec, params, r, R):
     """ansatz.apply for one walker -> (sign, log|psi|); reference nn_wave_function.py:127-173"""
-    emb = (psiformer_embeddings if spec.kind == 'psiformer' else ferminet_embeddings)(spec, params, r, R)
-    A = orbitals(spec, params, emb, r, R)
+    if spec.kind == 'transpsiformer':
+        emb, nuc = transpsiformer_embeddings(spec, params, r, R)
+        A = orbitals_nucdep(spec, params, emb, nuclear_head_zetas(spec, params, nuc), r, R)
+    else:
+        emb = (psiformer_embeddings if spec.kind == 'psiformer' else ferminet_embeddings)(spec, params, r, R)
+        A = orbitals(spec, params, emb, r, R)
     sign, ld = torch.linalg.slogdet(A)
     shift = ld.max().detach()
     if torch.isinf(shift):

@@ -313,3 +313,45 @@ def test_ferminet_n2_full_fp32_tensor_core_vs_fp64():
     for b in range(4):
         scale = max(1.0, abs(E64[b].item()), 0.5 * abs(s64['hamil/lap'][b].item()), 0.5 * s64['hamil/quantum_force'][b].item())
         assert abs(E32[b].item() - E64[b].item()) <= 1e-3 * scale, (b, E32[b].item(), E64[b].item())
+
+
+@pytest.mark.parametrize('mol_name,hyper,B', [
+    ('LiH', SMALL, 3),
+    ('H2O', dict(embedding_dim=32, n_layers=2, n_heads=2, n_determinants=3), 2),
+    ('cyclobutadiene_square', dict(embedding_dim=32, n_layers=1, n_heads=2, n_determinants=2), 1),  # BASELINE configs[4] geometry
+])
+def test_transpsiformer_local_energy_fp64(mol_name, hyper, B):
+    """TransPsiformer (reference conf/ansatz/transpsiformer.yaml): nuclear attention tokens, envelope
+    exponents from the NuclearGNNHead -- wave function, E_loc and the 6 stats
+    against the oracle; fp32 engine within the reference's 2e-4 tolerance."""
+    mol, hamil, oh, ansatz, params, r, R = make(mol_name, B=B, kind='transpsiformer', **hyper)
+    pc = PhysicalConfiguration(R, r, torch.zeros(B, device=DEV))
+    psi = ansatz.apply(params, pc)
+    E, stats = hamil.local_energy(ansatz.apply)(None, params, pc)
+    ref = oracle_eval(ansatz, oh, params, r, R)
+    for b, (s, l, e, st) in enumerate(ref):
+        assert psi.sign[b].item() == s
+        assert abs(psi.log[b].item() - l) <= 1e-10 * max(1, abs(l))
+        assert abs(E[b].item() - e) <= 1e-8 * max(1, abs(e)), (b, E[b].item(), e)
+        for k in STAT_KEYS:
+            assert abs(stats[k][b].item() - st[k]) <= 1e-8 * max(1, abs(st[k])), (k, stats[k][b].item(), st[k])
+    a32 = B200Ansatz(hamil, 'transpsiformer', dtype='float32', **hyper)
+    E32, _ = hamil.local_energy(a32.apply)(None, params, PhysicalConfiguration(R.float(), r.float(), torch.zeros(B, device=DEV)))
+    for b, (_, _, e, _) in enumerate(ref):
+        assert abs(E32[b].item() - e) <= 2e-4 * max(1, abs(e)) + 2e-3, (b, E32[b].item(), e)
+
+
+def test_transpsiformer_geometry_change_refreshes_nuclear_stream():
+    """The nuclear stream (keys/values of the nuclear tokens, envelope exponents) is a function of R:
+    a call with another geometry must not reuse the uploaded one."""
+    mol, hamil, oh, ansatz, params, r, R = make('LiH', B=2, kind='transpsiformer', **SMALL)
+    from oracle import wf
+
+    pt = wf.to_torch(params)
+    R2 = R.clone()
+    R2[1, 0] += 0.3
+    for Rx in (R, R2, R):
+        psi = ansatz.apply(params, PhysicalConfiguration(Rx, r, torch.zeros(2, device=DEV)))
+        for b in range(2):
+            _, l = wf.log_psi(ansatz.spec, pt, r[b].cpu(), Rx.cpu())
+            assert abs(psi.log[b].item() - l.item()) <= 1e-10 * max(1, abs(l.item()))

@@ -132,3 +132,40 @@ def test_antisymmetry_of_oracle():
     s0, l0 = owf.log_psi(spec, p, r, R)
     s1, l1 = owf.log_psi(spec, p, r[[1, 0, 2, 3]], R)
     assert s0.item() == -s1.item() and abs(l0.item() - l1.item()) < 1e-10
+
+
+def test_transpsiformer_nuclear_stream_matches_oracle():
+    """Host-side nuclear stream of the product (numpy, deepqmc_b200/nuclear.py) against the oracle's
+    independent torch restatement: final nuclear embeddings -> envelope exponents, and antisymmetry
+    of the resulting wave function (reference: conf/ansatz/transpsiformer.yaml)."""
+    import numpy as np
+    import torch
+
+    from deepqmc_b200 import params as PN
+    from deepqmc_b200.hamil import MolecularHamiltonian
+    from deepqmc_b200.molecule import Molecule
+    from deepqmc_b200.nuclear import nuclear_stream
+    from deepqmc_b200.spec import transpsiformer_spec
+    from oracle import wf
+
+    mol = Molecule.from_name('H2O')
+    h = MolecularHamiltonian(mol=mol)
+    spec = transpsiformer_spec(h, embedding_dim=16, n_layers=2, n_heads=2, n_determinants=3)
+    params = PN.perturb_params(PN.init_params(spec, 0))
+    pt = wf.to_torch(params)
+    rng = np.random.default_rng(0)
+    R = torch.as_tensor(mol.coords)
+    r = torch.as_tensor(mol.coords[rng.integers(0, 3, size=10)] + rng.normal(size=(10, 3)))
+    _, nuc = wf.transpsiformer_embeddings(spec, pt, r, R)
+    z = wf.nuclear_head_zetas(spec, pt, nuc)
+    ns = nuclear_stream(spec, params, mol.coords)
+    for s in ('up', 'down'):
+        assert np.allclose(ns[f'zetas_{s}'], z[s].numpy(), rtol=1e-12, atol=1e-13)
+    assert len(ns['kn']) == spec.n_layers and ns['kn'][0].shape == (3, 16)
+    s0, l0 = wf.log_psi(spec, pt, r, R)
+    perm = list(range(10))
+    perm[0], perm[1] = 1, 0
+    s1, l1 = wf.log_psi(spec, pt, r[perm], R)
+    assert s0.item() == -s1.item() and abs(l0.item() - l1.item()) < 1e-10
+    # parameter count of the full-size cyclobutadiene ansatz is finite and the table is consistent
+    assert PN.n_params(spec) == sum(int(np.prod(v.shape)) for v in params.values())
