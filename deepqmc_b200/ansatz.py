@@ -25,6 +25,9 @@ class B200Ansatz:
         self.dtype, self.device, self.gemm_backend = dtype, device, gemm_backend
         self._engine = None
         self._uploaded = None
+        self._engines = []  # [(params, Engine)], most recent first: one resident engine per parameter tree
+        self.max_engines = 4  # electronic states kept resident (excited-state runs evaluate every state's
+                              # wave function on every state's walkers, reference loss/overlap.py:19-49)
 
     # -- reference: Ansatz.init(rng, phys_conf) -> Params (types.py:119-131)
     def init(self, rng, phys_conf: PhysicalConfiguration | None = None):
@@ -32,13 +35,20 @@ class B200Ansatz:
         return PN.init_params(self.spec, seed)
 
     def engine_for(self, hamil, params) -> Engine:
-        if self._engine is None:
-            self._engine = Engine(self.spec, hamil, dtype=self.dtype, device=self.device,
-                                  gemm_backend=self.gemm_backend)
-        if self._uploaded is not params:
-            self._engine.set_params(params)
-            self._uploaded = params
-        return self._engine
+        for i, (p, e) in enumerate(self._engines):
+            if p is params:
+                if i:
+                    self._engines.insert(0, self._engines.pop(i))
+                self._engine, self._uploaded = e, params
+                return e
+        if len(self._engines) < self.max_engines:
+            e = Engine(self.spec, hamil, dtype=self.dtype, device=self.device, gemm_backend=self.gemm_backend)
+        else:
+            _, e = self._engines.pop()  # least recently used handle is re-targeted
+        e.set_params(params)
+        self._engines.insert(0, (params, e))
+        self._engine, self._uploaded = e, params
+        return e
 
     # -- reference: Ansatz.apply(params, phys_conf, return_mos=False) -> Psi (types.py:133-150)
     def apply(self, params, phys_conf: PhysicalConfiguration, return_mos: bool = False) -> Psi:

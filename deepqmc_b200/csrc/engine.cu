@@ -704,7 +704,7 @@ struct Engine : EngineBase {
         if (Rb) { err = "non-local ECP with per-walker nuclei is not supported"; return 2; }
         rc = run_batched(rv, R, 0, (int)V, 1, sv, lv, nullptr, nullptr, nullptr, p, wsb - (p - (char*)ws), st);
         if (rc) return rc;
-        DQ_LAUNCH(ecp_accumulate_kernel<T>, dim3((nb + 127) / 128), dim3(128), 0, st, rb, Rbp, Rb, N, M, J,
+        DQ_LAUNCH(ecp_accumulate_kernel<T>, dim3((nb + 3) / 4), dim3(128), 0, st, rb, Rbp, Rb, N, M, J,
                   (const int*)d_nl_nuc, (const T*)d_nl_params, cfg.ecp_nl_lmax_p1, cfg.ecp_nl_terms,
                   (const T*)sign + b0, (const T*)logp + b0, (const T*)sv, (const T*)lv, nb, B, (T*)E + b0,
                   (T*)stats + b0);

@@ -191,44 +191,50 @@ __global__ void ecp_points_kernel(const T* __restrict__ r, const T* __restrict__
 }
 
 // V_nl[b] = sum_{j,i,l} (2l+1)/12 v_l(|r_i - R_I|) sum_q P_l(cos th_q) psi(r_i->q)/psi(r)
-// one thread per walker; adds V_nl to E_loc and to stats[3].
+// (reference: ecp/gaussian_type_ecp.py:161-255).  One WARP per walker: lanes stride over the
+// (nucleus, electron) pairs, 12 quadrature ratios each, warp-shuffle reduction; accumulation in
+// double.  Adds V_nl to E_loc and to stats[3].
 template <class T>
 __global__ void ecp_accumulate_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M,
                                       int J, const int* __restrict__ nl_nuc, const T* __restrict__ nl_params,
                                       int L, int Tm, const T* __restrict__ sign0, const T* __restrict__ log0,
                                       const T* __restrict__ sign_v, const T* __restrict__ log_v, int B, int Bstat,
                                       T* __restrict__ out_E, T* __restrict__ out_stats) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;  // warp-uniform
   const T* rb = r + (size_t)b * 3 * N;
   const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
+  const double l0 = (double)log0[b], s0 = (double)sign0[b];
   double total = 0.0;
-  for (int j = 0; j < J; ++j) {
+  for (int p = lane; p < J * N; p += 32) {
+    const int j = p / N, i = p - j * N;
     const int I = nl_nuc[j];
     const T* nl = nl_params + (size_t)I * L * 2 * Tm;
-    for (int i = 0; i < N; ++i) {
-      double dx = (double)rb[3 * i] - (double)Rb[3 * I], dy = (double)rb[3 * i + 1] - (double)Rb[3 * I + 1],
-             dz = (double)rb[3 * i + 2] - (double)Rb[3 * I + 2];
-      double d2 = dx * dx + dy * dy + dz * dz;
-      double integ[4] = {0, 0, 0, 0};
-      for (int q = 0; q < 12; ++q) {
-        size_t v = (((size_t)b * J + j) * N + i) * 12 + q;
-        double ratio = ::exp((double)log_v[v] - (double)log0[b]) * (double)sign_v[v] * (double)sign0[b];
-        double th, ph;
-        ico_vertex(q, th, ph);
-        double x = ::cos(th);
-        double pl[4] = {1.0, x, 0.5 * (3 * x * x - 1), 0.5 * (5 * x * x * x - 3 * x)};
-        for (int l = 0; l < L; ++l) integ[l] += ratio * pl[l];
-      }
-      for (int l = 0; l < L; ++l) {
-        double vl = 0.0;
-        for (int t = 0; t < Tm; ++t) vl += (double)nl[(l * 2 + 1) * Tm + t] * ::exp(-(double)nl[(l * 2 + 0) * Tm + t] * d2);
-        total += vl * (2 * l + 1) / 12.0 * integ[l];
-      }
+    double dx = (double)rb[3 * i] - (double)Rb[3 * I], dy = (double)rb[3 * i + 1] - (double)Rb[3 * I + 1],
+           dz = (double)rb[3 * i + 2] - (double)Rb[3 * I + 2];
+    double d2 = dx * dx + dy * dy + dz * dz;
+    double integ[4] = {0, 0, 0, 0};
+    for (int q = 0; q < 12; ++q) {
+      size_t v = ((size_t)b * J * N + p) * 12 + q;
+      double ratio = ::exp((double)log_v[v] - l0) * (double)sign_v[v] * s0;
+      double th, ph;
+      ico_vertex(q, th, ph);
+      double x = ::cos(th);
+      double pl[4] = {1.0, x, 0.5 * (3 * x * x - 1), 0.5 * (5 * x * x * x - 3 * x)};
+      for (int l = 0; l < L; ++l) integ[l] += ratio * pl[l];
+    }
+    for (int l = 0; l < L; ++l) {
+      double vl = 0.0;
+      for (int t = 0; t < Tm; ++t) vl += (double)nl[(l * 2 + 1) * Tm + t] * ::exp(-(double)nl[(l * 2 + 0) * Tm + t] * d2);
+      total += vl * (2 * l + 1) / 12.0 * integ[l];
     }
   }
-  out_E[b] += (T)total;
-  out_stats[3 * (size_t)Bstat + b] = (T)total;
+  total = warp_sum(total);
+  if (lane == 0) {
+    out_E[b] += (T)total;
+    out_stats[3 * (size_t)Bstat + b] = (T)total;
+  }
 }
 
 }  // namespace dq

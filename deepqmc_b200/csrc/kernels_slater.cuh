@@ -32,7 +32,9 @@ __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, 
                               int K, int S, int total, const T* __restrict__ pi_up, const T* __restrict__ pi_dn,
                               const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn,
                               const T* __restrict__ BF, int ldb, T* __restrict__ det_sign, T* __restrict__ det_log,
-                              T* __restrict__ det_grad, T* __restrict__ det_lap, int rep) {
+                              T* __restrict__ det_grad, T* __restrict__ det_lap, int rep, int full_det) {
+  // full_det == 0: spin-factorised determinants det_up(n_up x n_up) det_down(n_down x n_down) (reference
+  // wf/nn_wave_function.py:143-151) = determinant of the matrix with the spin-off-diagonal blocks zeroed.
   // rep = envelope terms per nucleus (1: ExponentialEnvelopes; 3: SimplifiedNucleusDependentEnvelopes,
   // reference wf/env.py:111-226): parameter rows are [K N][M rep], term m rep + e sits on nucleus m.
   // One WARP per (walker b, determinant k): all phases are lane-strided loops separated by
@@ -76,6 +78,7 @@ __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, 
         }
       }
     }
+    if (!full_det && ((i < n_up) != (mu < n_up))) { e = T(0); de0 = T(0); de1 = T(0); de2 = T(0); le = T(0); }
     const T* bfrow = BF + (brow0 + (size_t)i * S) * ldb + k * N + mu;
     T bf0 = bfrow[0];
     env[i * NP + mu] = e;
@@ -204,7 +207,7 @@ __global__ void slater_small_kernel(const T* __restrict__ r, const T* __restrict
                                     const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn,
                                     const T* __restrict__ BF, int ldb, T* __restrict__ det_sign,
                                     T* __restrict__ det_log, T* __restrict__ det_grad, T* __restrict__ det_lap,
-                                    int rep) {
+                                    int rep, int full_det) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
   const int b = gid / K, k = gid % K;
@@ -237,6 +240,7 @@ __global__ void slater_small_kernel(const T* __restrict__ r, const T* __restrict
           }
         }
       }
+      if (!full_det && ((i < n_up) != (mu < n_up))) { e = T(0); d0 = T(0); d1 = T(0); d2_ = T(0); le = T(0); }
       const T* bfrow = BF + (brow0 + (size_t)i * S) * ldb + k * NS + mu;
       const T b0 = bfrow[0];
       env[i][mu] = e; bf0[i][mu] = b0;
@@ -345,7 +349,7 @@ __global__ void slater_fwd_reg_kernel(const T* __restrict__ r, const T* __restri
                                       int n_up, int K, const T* __restrict__ pi_up, const T* __restrict__ pi_dn,
                                       const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn,
                                       const T* __restrict__ BF, int ldb, T* __restrict__ det_sign,
-                                      T* __restrict__ det_log, int rep) {
+                                      T* __restrict__ det_log, int rep, int full_det) {
   constexpr int NM = 32;
   DQMC_DYN_SMEM(smem_raw);
   T* rho = reinterpret_cast<T*>(smem_raw);  // [N][M]
@@ -373,6 +377,7 @@ __global__ void slater_fwd_reg_kernel(const T* __restrict__ r, const T* __restri
         T e = T(0);
         for (int m = 0; m < M; ++m)
           for (int et = 0; et < rep; ++et) e += pk[m * rep + et] * m_exp(-m_abs(zk[m * rep + et]) * rho[lane * M + m]);
+        if (!full_det && ((lane < n_up) != (mu < n_up))) e = T(0);
         v = e * BF[((size_t)b * N + lane) * ldb + k * N + mu];
       }
       a[mu] = v;
@@ -442,6 +447,60 @@ __global__ void slater_fwd_reg_kernel(const T* __restrict__ r, const T* __restri
 // Same reference lines as slater_kernel; slogdet sign/log convention = LAPACK getrf.
 // dynamic smem = sizeof(T) * (K N NP + N M), NP = N | 1.
 // ------------------------------------------------------------------------------------------
+// exp for the envelope sums of the plain-forward kernel: ex2.approx on a Cody-Waite reduced
+// argument (the product x log2(e) is split into its rounded value and the exact FMA remainder),
+// ~2 ulp like expf at a third of the instructions.
+__device__ __forceinline__ float env_exp(float x) {
+#ifndef DQMC_EMU
+  const float t = x * 1.4426950216293335f;
+  float e = fmaf(x, 1.4426950216293335f, -t);
+  e = fmaf(x, 1.925963033500011e-8f, e);
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t));
+  return fmaf(y * e, 0.6931471805599453f, y);
+#else
+  return ::expf(x);
+#endif
+}
+__device__ __forceinline__ double env_exp(double x) { return ::exp(x); }
+
+// log|det| = sum of log|pivot|: fp32 keeps a running mantissa product and an integer exponent sum
+// (one logf at the end instead of one per pivot); pivots outside the normal range take the plain path.
+template <class T>
+struct LogProd {
+  T acc = T(0);
+  __device__ __forceinline__ void mul(T apv) { acc += m_log(apv); }
+  __device__ __forceinline__ T value() const { return acc; }
+};
+#ifndef DQMC_EMU
+template <>
+struct LogProd<float> {
+  float mant = 1.f, extra = 0.f;
+  int esum = 0;
+  __device__ __forceinline__ void mul(float apv) {
+    if (apv > 1e-30f && apv < 1e30f) {  // warp-uniform (the pivot is a broadcast value)
+      mant *= apv;
+      const int bits = __float_as_int(mant);
+      esum += (bits >> 23) - 127;
+      mant = __int_as_float((bits & 0x007fffff) | 0x3f800000);
+    } else {
+      extra += logf(apv);
+    }
+  }
+  __device__ __forceinline__ float value() const { return fmaf((float)esum, 0.6931471805599453f, logf(mant)) + extra; }
+};
+#endif
+__device__ __forceinline__ float pivot_rcp(float pv) {
+#ifndef DQMC_EMU
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(pv));
+  return y;
+#else
+  return 1.f / pv;
+#endif
+}
+__device__ __forceinline__ double pivot_rcp(double pv) { return 1.0 / pv; }
+
 __device__ __forceinline__ int warp_argmax_abs(float v, bool excluded, int lane) {
 #ifndef DQMC_EMU
   const unsigned key = excluded ? 0u : __float_as_uint(fabsf(v)) + 1u;
@@ -476,7 +535,7 @@ __global__ void __launch_bounds__(256, 3)
 slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M, int n_up, int K,
                    int B, const T* __restrict__ pi_up, const T* __restrict__ pi_dn, const T* __restrict__ zeta_up,
                    const T* __restrict__ zeta_dn, const T* __restrict__ BF, int ldb, T* __restrict__ det_sign,
-                   T* __restrict__ det_log, int rep) {
+                   T* __restrict__ det_log, int rep, int full_det) {
   DQMC_DYN_SMEM(smem_raw);
   const int NP = N | 1, KN = K * N;
   T* As = reinterpret_cast<T*>(smem_raw);  // [K][N][NP]
@@ -517,12 +576,13 @@ slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batch
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int ii = i0 + j < ie ? i0 + j : ie - 1;
-              e[j] += p * m_exp(z * rho[ii * M + m]);
+              e[j] += p * env_exp(z * rho[ii * M + m]);
             }
           }
+          const bool off_block = !full_det && ((sb == 0) != (mu < n_up));  // spin-factorised determinants
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (i0 + j < ie) arow[(i0 + j) * NP] = e[j] * bf[j];
+            if (i0 + j < ie) arow[(i0 + j) * NP] = off_block ? T(0) : e[j] * bf[j];
         }
       }
     }
@@ -537,7 +597,8 @@ slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batch
         if (lane < N && mu < N) v = arow[mu];
         a[mu] = v;
       }
-      T logdet = T(0), sgn = T(1);
+      LogProd<T> logdet;
+      T sgn = T(1);
       unsigned used = 0u;  // rows already chosen as pivots (warp-uniform)
       int inv = 0;         // inversion count of the pivot order
 #pragma unroll
@@ -547,10 +608,10 @@ slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batch
           inv += __popc(~used & ((1u << prow) - 1u));
           used |= 1u << prow;
           const T pv = __shfl_sync(0xffffffffu, a[c], prow);
-          logdet += m_log(m_abs(pv));
+          logdet.mul(m_abs(pv));
           sgn = pv < T(0) ? -sgn : (pv == T(0) ? T(0) : sgn);
           const bool elim = !((used >> lane) & 1u);
-          const T f = (elim && pv != T(0)) ? a[c] / pv : T(0);  // exactly singular: (sign 0, log -inf) like slogdet
+          const T f = (elim && pv != T(0)) ? a[c] * pivot_rcp(pv) : T(0);  // exactly singular: (sign 0, log -inf) like slogdet
 #pragma unroll
           for (int j = c + 1; j < NM; ++j) {  // padding columns (j >= N) hold zeros in the live rows
             const T pj = __shfl_sync(0xffffffffu, a[j], prow);
@@ -559,7 +620,7 @@ slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batch
         }
       }
       if (lane == 0) {
-        det_log[(size_t)b * K + k] = logdet;
+        det_log[(size_t)b * K + k] = logdet.value();
         det_sign[(size_t)b * K + k] = (inv & 1) ? -sgn : sgn;
       }
     }
@@ -580,7 +641,7 @@ inline size_t slater_fwd2_smem_bytes(int N, int M, int K) {
 // ------------------------------------------------------------------------------------------
 struct FinalizeCfg {
   int N, M, n_up, K, S;
-  int cusp_kind;  // 0 none, 1 psiformer
+  int cusp_kind;  // 0 none, 1 psiformer -s a^2 / (a + r), 2 deepqmc -s / (a (1 + a r)) (wf/cusp.py:5-26)
   double cusp_same_scale, cusp_anti_scale;
   int ecp_terms;  // Tmax of loc params (0: plain Coulomb)
 };
@@ -593,7 +654,8 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
                                 const T* __restrict__ z_val /*[M]*/, const T* __restrict__ ecp_loc /*[M][3][2][Tm]*/,
                                 const int* __restrict__ ecp_mask, int B, T* __restrict__ out_sign,
                                 T* __restrict__ out_log, T* __restrict__ out_E, T* __restrict__ out_stats,
-                                T* __restrict__ out_grad) {
+                                T* __restrict__ out_grad, const T* __restrict__ conf_w /*[K] or null: SumPool*/,
+                                const T* __restrict__ jastrow /*[B][S] augmented scalar rows or null*/) {
   DQMC_DYN_SMEM(smem_raw);
   const int N = c.N, M = c.M, K = c.K, S = c.S;
   const int T3 = S > 1 ? S - 2 : 0;
@@ -611,7 +673,10 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
     for (int k = 1; k < K; ++k) shift = dl[k] > shift ? dl[k] : shift;
     if ((shift - shift) != T(0)) shift = T(0);  // +-inf shift -> 0 (nn_wave_function.py:154)
     T psi = T(0);
-    for (int k = 0; k < K; ++k) { pk[k] = ds[k] * m_exp(dl[k] - shift); psi += pk[k]; }
+    for (int k = 0; k < K; ++k) {  // conf_coeff: SumPool or hk.Linear(1, no bias) (nn_wave_function.py:158)
+      pk[k] = (conf_w ? conf_w[k] : T(1)) * ds[k] * m_exp(dl[k] - shift);
+      psi += pk[k];
+    }
     for (int k = 0; k < K; ++k) pk[k] /= psi;
     misc[0] = m_log(m_abs(psi)) + shift;
     misc[1] = psi > T(0) ? T(1) : (psi < T(0) ? T(-1) : T(0));
@@ -620,7 +685,7 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
   // ---- cusp + e-e repulsion: thread i handles electron i ---------------------------------
   T cusp_v = T(0), cusp_l = T(0), vel = T(0), vloc = T(0), enuc = T(0);
   T as_ = T(1), aa_ = T(1);
-  if (c.cusp_kind == 1) { as_ = cusp_alpha[0]; aa_ = cusp_alpha[1]; }
+  if (c.cusp_kind != 0) { as_ = cusp_alpha[0]; aa_ = cusp_alpha[1]; }
   for (int i = tid; i < N; i += nt) {
     T g0 = 0, g1 = 0, g2 = 0;
     for (int j = 0; j < N; ++j) {
@@ -629,11 +694,12 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
       T d2 = dx0 * dx0 + dx1 * dx1 + dx2 * dx2;
       T rho2 = Num<T>::eps() + d2, rho = m_sqrt(rho2);
       vel += T(0.5) / rho;
-      if (c.cusp_kind == 1) {
+      if (c.cusp_kind != 0) {
         bool same = (i < c.n_up) == (j < c.n_up);
         T al = same ? as_ : aa_;
-        T sc = (T)(same ? c.cusp_same_scale : c.cusp_anti_scale) * al * al;
-        T den = al + rho;
+        // both cusp functions are -sc / (den0 + r): psiformer sc = s a^2, den0 = a; deepqmc sc = s / a^2, den0 = 1 / a
+        T sc = (T)(same ? c.cusp_same_scale : c.cusp_anti_scale) * (c.cusp_kind == 1 ? al * al : T(1) / (al * al));
+        T den = (c.cusp_kind == 1 ? al : T(1) / al) + rho;
         T f = -sc / den, fp = sc / (den * den), fpp = T(-2) * sc / (den * den * den);
         cusp_v += T(0.5) * f;
         if (S > 1) {
@@ -671,9 +737,10 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
   block_sum2(vel, vloc, scratch);
   T dummy = T(0);
   block_sum2(enuc, dummy, scratch);
+  const T* jr = jastrow ? jastrow + (size_t)b * S : nullptr;
   if (tid == 0) {
     out_sign[b] = misc[1];
-    out_log[b] = misc[0] + cusp_v;
+    out_log[b] = misc[0] + cusp_v + (jr ? jr[0] : T(0));
   }
   if (S == 1) return;
   // ---- determinant sum: gradient and Laplacian -------------------------------------------
@@ -687,14 +754,14 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
       pg2 += pk[k] * gk * gk;
     }
     sum_pg2 += pg2 - gd * gd;  // contributes sum_k p_k g_k^2 - (sum_k p_k g_k)^2
-    T gtot = gd + grad[t];
+    T gtot = gd + grad[t] + (jr ? jr[1 + t] : T(0));
     grad[t] = gtot;
     sum_g2 += gtot * gtot;
     if (out_grad) out_grad[(size_t)b * T3 + t] = gtot;
   }
   block_sum2(sum_pg2, sum_g2, scratch);
   if (tid == 0) {
-    T lap = sum_pg2 + cusp_l;
+    T lap = sum_pg2 + cusp_l + (jr ? jr[T3 + 1] : T(0));
     for (int k = 0; k < K; ++k) lap += pk[k] * det_lap[(size_t)b * K + k];
     T ekin = T(-0.5) * (lap + sum_g2);
     T e = ekin + vloc + vel + enuc;  // V_nl added by the non-local ECP pass

@@ -219,6 +219,7 @@ struct GemmArgs {
   int M, N, K;
   int S;
   int sliced, Nel;
+  const T* bias1 = nullptr;  // sliced: bias of the second weight (z >= z_split); null: `bias` for both
 };
 
 template <class T, int BM, int BN, int BK, int TM, int TN>
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(GemmArgs<T>
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int z = blockIdx.z;
   const T* W = (g.sliced && z >= g.z_split) ? g.W1 : g.W0;
+  const T* bias = (g.sliced && z >= g.z_split && g.bias1) ? g.bias1 : g.bias;
   auto phys_row = [&](int m) -> size_t {
     if (!g.sliced) return (size_t)m;
     int b = m / g.S, s = m % g.S;
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(GemmArgs<T>
       int n = n0 + tx * TN + j;
       if (n >= g.N) continue;
       T v = acc[i][j];
-      if (g.bias && value_row) v += g.bias[n];
+      if (bias && value_row) v += bias[n];
       if (g.Res) v += g.Res[pr * g.ldr + n];
       g.C[pr * g.ldc + n] = v;
     }

@@ -1,0 +1,67 @@
+"""Excited-state overlap estimates on top of the CUDA wave-function forward.
+
+Mirror of the value-level part of the reference's ``loss/overlap.py``: all wave functions on the
+samples of all wave functions (``compute_wave_function_values`` :19-49), sample-wise ratios
+(:52-74), their batch version (:77-99), the clipped-geometric-mean symmetrisation (:102-121) and
+the mean overlap / penalty (:124-150).  ``params`` is a sequence with one parameter tree per
+electronic state, ``phys_conf`` carries a leading state axis ``[n_wfs, B, ...]``.  Each
+``Psi_i(r ~ Psi_j^2)`` block is one ``dqmc_wf_forward`` call (plain-forward kernels); the small
+[n_wfs, n_wfs, B] algebra that follows is elementwise torch on the device.  The parameter
+tangent of the overlap (:182-229) needs d log|psi| / d params (row N1) and is not built.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import parallel
+from .types import PhysicalConfiguration, Psi
+
+
+def compute_wave_function_values(ansatz, params, phys_conf: PhysicalConfiguration):
+    """-> Psi with sign/log [n_wfs (i), n_wfs (j), B]:  Psi_i(r ~ Psi_j^2)"""
+    n = len(params)
+    assert phys_conf.r.shape[0] == n, 'leading axis of phys_conf must run over the electronic states'
+    signs, logs = [], []
+    for i in range(n):
+        R = phys_conf.R[0] if phys_conf.R.dim() == 4 else phys_conf.R
+        R = R[0] if R.dim() == 3 else R
+        B = phys_conf.r.shape[1]
+        flat = PhysicalConfiguration(R, phys_conf.r.reshape(n * B, *phys_conf.r.shape[2:]),
+                                     torch.zeros(n * B, device=phys_conf.r.device))
+        psi = ansatz.apply(params[i], flat)  # one forward over the samples of ALL states
+        signs.append(psi.sign.reshape(n, B))
+        logs.append(psi.log.reshape(n, B))
+    return Psi(torch.stack(signs), torch.stack(logs)), {}
+
+
+def compute_psi_ratio(ansatz, params, phys_conf):
+    """ratio[i, j, b] = Psi_i(r_b ~ Psi_j^2) / Psi_j(r_b ~ Psi_j^2)  (reference :52-99; the mean
+    log magnitude of each wave function is subtracted before exponentiating)."""
+    psi, stats = compute_wave_function_values(ansatz, params, phys_conf)
+    mean_log = psi.log.mean(dim=(-1, -2))  # [n_wfs]
+    shifted = psi.log - mean_log[:, None, None]
+    diag_log = torch.diagonal(shifted, dim1=0, dim2=1).transpose(0, 1)    # [j, b] -> log|Psi_j(r~j)| shifted
+    diag_sign = torch.diagonal(psi.sign, dim1=0, dim2=1).transpose(0, 1)
+    ratio = psi.sign * diag_sign[None] * torch.exp(shifted - diag_log[None])
+    return ratio, stats
+
+
+def symmetrize_overlap_with_clipped_geometric_mean(x):
+    """y_ij = sign(x_ij) sqrt(max(0, x_ij x_ji))  (reference :102-121)"""
+    return torch.sign(x) * torch.sqrt(torch.clamp(x * x.transpose(-1, -2), min=0.0))
+
+
+def compute_mean_overlap(psi_ratio, weight=None):
+    """-> (overlap penalty = sum_{i<j} S_ij^2, {'overlap/pairwise/mean': S[n_wfs, n_wfs]}); the sample mean
+    is the all-device mean (one all-reduce, reference parallel.py all_device_mean)."""
+    w = torch.ones_like(psi_ratio[0]) if weight is None else weight
+    local = (w[None] * psi_ratio).double()
+    packed = torch.cat([local.sum(-1).reshape(-1), torch.tensor([float(local.shape[-1])], device=local.device,
+                                                                dtype=torch.float64)])
+    if parallel.world()[1] > 1:
+        torch.distributed.all_reduce(packed, op=torch.distributed.ReduceOp.SUM)
+    n = psi_ratio.shape[0]
+    mean = (packed[:-1] / packed[-1]).reshape(n, n)
+    symm = symmetrize_overlap_with_clipped_geometric_mean(mean)
+    iu = torch.triu_indices(n, n, 1)
+    return (symm[iu[0], iu[1]] ** 2).sum(), {'overlap/pairwise/mean': symm}

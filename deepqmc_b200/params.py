@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .spec import AnsatzSpec
+from .spec import AnsatzSpec, log_dims
 
 P = 'neural_network_wave_function/~/'
 ENV = P + 'exponential_envelopes'
@@ -26,6 +26,20 @@ BF_DN = P + 'omni_net/~/Backflow_1/~/mlp/linear_0'
 
 NUC_EMB = GNN + 'nuclei_embedding/'
 HEAD = P + 'omni_net/~/nuclear_gnn_head/'
+
+
+JASTROW = P + 'omni_net/~/Jastrow/~/mlp/'
+CONF = P + 'conf_coeff'
+EDGE_TYPES = ('same', 'anti', 'ne')
+
+
+def conv_prefix(l):
+    return layer_prefix(l) + 'convolution_electron_update_feature/~single_edge_type_update/'
+
+
+def backflow_dims(spec, n_spin):
+    n_orb = spec.n_elec if spec.full_determinant else n_spin
+    return log_dims(spec.embedding_dim, spec.n_determinants * n_orb, spec.backflow_layers)
 
 
 def comb_prefix(l):
@@ -43,6 +57,35 @@ def attn_prefix(l):
 def param_shapes(spec: AnsatzSpec) -> dict[str, tuple[int, ...]]:
     N, M, d, K = spec.n_elec, spec.n_nuc, spec.embedding_dim, spec.n_determinants
     s: dict[str, tuple[int, ...]] = {}
+    if spec.kind == 'paulinet':
+        # reference: tests/conf/ansatz.yaml; wf/env.py:10-75 (per_shell, shared zetas, spin-restricted)
+        n_env, e = len(spec.env_centers), spec.edge_dim
+        s[f'{ENV}:pi'] = (K * N, n_env)
+        s[f'{ENV}:zetas'] = (n_env,)
+        s[GNN + 'electron_embedding/ElectronicEmbedding:embeddings'] = (1 if spec.n_up == spec.n_down else 2, d)
+        s[GNN + 'nuclei_embedding/~/embed:embeddings'] = (M, d)
+        for l in range(spec.n_layers):
+            c = conv_prefix(l)
+            for t in EDGE_TYPES:
+                s[c + f'w_{t}/linear_0:w'] = (4, e)
+                s[c + f'h_{t}/linear_0:w'] = (d, e)
+                s[c + f'h_{t}/linear_0:b'] = (e,)
+                s[layer_prefix(l) + f'g_conv_{t}/linear_0:w'] = (e, d)
+                s[layer_prefix(l) + f'g_conv_{t}/linear_0:b'] = (d,)
+        dj = [d] + log_dims(d, 1, spec.jastrow_layers) if spec.jastrow_layers else []
+        for i in range(len(dj) - 1):
+            s[JASTROW + f'linear_{i}:w'] = (dj[i], dj[i + 1])
+            if i < len(dj) - 2:  # bias: 'not_last'
+                s[JASTROW + f'linear_{i}:b'] = (dj[i + 1],)
+        for pre, n_spin in ((BF_UP, spec.n_up), (BF_DN, spec.n_down)):
+            db = [d] + backflow_dims(spec, n_spin)
+            base = pre.rsplit('linear_0', 1)[0]
+            for i in range(len(db) - 1):
+                s[base + f'linear_{i}:w'] = (db[i], db[i + 1])
+                s[base + f'linear_{i}:b'] = (db[i + 1],)
+        if spec.conf_coeff == 'linear':
+            s[CONF + ':w'] = (K, 1)
+        return s
     if spec.kind != 'transpsiformer':
         for nm in ('pi_up', 'pi_down', 'zetas_up', 'zetas_down'):
             s[f'{ENV}:{nm}'] = (K * N, M)
@@ -103,7 +146,15 @@ def init_params(spec: AnsatzSpec, seed: int = 0) -> dict[str, np.ndarray]:
     out = {}
     for name, shape in param_shapes(spec).items():
         leaf = name.rsplit(':', 1)[1]
-        if name.startswith(ENV):
+        if name == f'{ENV}:zetas' and spec.kind == 'paulinet':
+            v = np.asarray(spec.env_zeta_init, dtype=np.float64)  # init_to_ones = false: z / (k + 1)
+        elif name == f'{ENV}:pi' and spec.kind == 'paulinet':
+            v = 1.0 + rng.standard_normal(shape) / np.sqrt(shape[0])
+        elif name == CONF + ':w':
+            v = np.ones(shape)  # w_init = jnp.ones
+        elif leaf == 'embeddings':
+            v = rng.standard_normal(shape)  # hk.Embed default: truncated normal
+        elif name.startswith(ENV):
             v = np.ones(shape)
         elif name.startswith(CUSP):
             v = np.ones(shape)
@@ -125,7 +176,7 @@ def perturb_params(params, seed=1, scale=0.2):
     rng = np.random.default_rng(seed)
     out = dict(params)
     for k, v in params.items():
-        if k.startswith(ENV) or k.startswith(CUSP) or 'zetas_bias' in k:
+        if k.startswith(ENV) or k.startswith(CUSP) or 'zetas_bias' in k or k == CONF + ':w':
             out[k] = v * (1 + scale * rng.uniform(-1, 1, size=v.shape))
     return out
 

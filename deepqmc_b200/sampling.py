@@ -156,3 +156,30 @@ class DecorrSampler(MetropolisSampler):
     def __init__(self, hamil, wf, *, length, **kw):
         super().__init__(hamil, wf, **kw)
         self.length = int(length)
+
+
+class MultiElectronicStateSampler:
+    """Sample from several electronic states side by side (reference:
+    sampling/combined_samplers.py:58-90: vmap of the underlying sampler over the state axis).
+    ``params`` is a sequence with one parameter tree per state; the state dicts are kept in a list;
+    the returned PhysicalConfiguration has a leading state axis [n_state, B, ...]."""
+
+    def __init__(self, sampler: MetropolisSampler, n_state: int):
+        self.sampler, self.n_state = sampler, n_state
+
+    def init(self, rng, params, electron_batch_size, R):
+        assert len(params) == self.n_state
+        return [self.sampler.init(int(rng) * self.n_state + s, params[s], electron_batch_size, R)
+                for s in range(self.n_state)]
+
+    def update(self, state, params, R):
+        return [self.sampler.update(state[s], params[s], R) for s in range(self.n_state)]
+
+    def sample(self, rng, state, params, R, **kw):
+        new, rs, stats = [], [], []
+        for s in range(self.n_state):
+            st, pc, stt = self.sampler.sample(int(rng) * self.n_state + s, state[s], params[s], R, **kw)
+            new.append(st); rs.append(pc.r); stats.append(stt)
+        r = torch.stack(rs)
+        pc = PhysicalConfiguration(R, r, torch.zeros(r.shape[:2], dtype=torch.int32, device=r.device))
+        return new, pc, {k: torch.stack([s[k] for s in stats]) for k in stats[0]}

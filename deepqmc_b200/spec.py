@@ -8,12 +8,12 @@ from __future__ import annotations
 
 import dataclasses
 
-__all__ = ['AnsatzSpec', 'psiformer_spec', 'ferminet_spec', 'transpsiformer_spec']
+__all__ = ['AnsatzSpec', 'psiformer_spec', 'ferminet_spec', 'transpsiformer_spec', 'paulinet_spec', 'log_dims']
 
 
 @dataclasses.dataclass(frozen=True)
 class AnsatzSpec:
-    kind: str  # 'psiformer' | 'ferminet' | 'transpsiformer'
+    kind: str  # 'psiformer' | 'ferminet' | 'transpsiformer' | 'paulinet'
     n_up: int
     n_down: int
     n_nuc: int
@@ -31,6 +31,15 @@ class AnsatzSpec:
     n_env_per_nuc: int = 1  # SimplifiedNucleusDependentEnvelopes.n_envelope_per_nucleus (3)
     nuc_edge_dim: int = 32  # NucleiEmbedding edge_mlp width (gnn/electron_gnn.py:476-484)
     charges: tuple = ()     # nuclear charges (atom-type one-hot of the nuclear embedding)
+    # conv-GNN family ("PauliNet" of the reference's tests, tests/conf/ansatz.yaml = BASELINE configs[0]):
+    full_determinant: bool = True   # False: det_up(n_up x n_up) * det_down(n_down x n_down)
+    conf_coeff: str = 'sum'         # 'sum' = SumPool | 'linear' = hk.Linear(1, no bias, init ones)
+    cusp_alpha: float = 10.0        # fixed alpha of the DeepQMCCusp (wf/cusp.py:5-14)
+    mult_act: str = 'identity'      # 'identity' | 'default' = 1 + 2 tanh(x / 4) (wf/nn_wave_function.py:17)
+    jastrow_layers: int = 0         # hidden_layers ['log', n] of the Jastrow MLP on sum_i x_i; 0 = no Jastrow
+    backflow_layers: int = 1        # hidden_layers ['log', n] of the per-spin backflow MLPs
+    env_centers: tuple = ()         # per_shell envelopes: nucleus index of every envelope (wf/env.py:26-33)
+    env_zeta_init: tuple = ()       # their initial exponents z / (k + 1)
 
     @property
     def n_elec(self):
@@ -62,3 +71,32 @@ def transpsiformer_spec(hamil, **kw):
     kw.setdefault('n_env_per_nuc', 3)
     kw.setdefault('charges', tuple(float(z) for z in hamil.mol.charges))
     return AnsatzSpec('transpsiformer', hamil.n_up, hamil.n_down, hamil.n_nuc, **kw)
+
+
+def log_dims(d_in, d_out, n):
+    """hidden_layers ['log', n] of the reference's MLP (hkext.py:95-99): n layer widths ending in d_out."""
+    return [round(d_in ** (1 - k / n) * d_out ** (k / n)) for k in range(1, n + 1)]
+
+
+def paulinet_spec(hamil, **kw):
+    """reference: tests/conf/ansatz.yaml (the conv-GNN 'PauliNet' ansatz of the reference's own CPU tests,
+    BASELINE configs[0]): embedding lookup, one featurewise convolution layer over same / anti / ne edges,
+    ssp Jastrow and backflow MLPs, per-shell spin-restricted envelopes, spin-factorised determinants,
+    hk.Linear determinant combination, DeepQMCCusp."""
+    shells = []
+    for i, (z, n_shell, n_ecp) in enumerate(zip(hamil.mol.charges, hamil.mol_shells, hamil.mol_ecp_shells)):
+        for k in range(n_ecp, n_shell):  # per_shell = true (wf/env.py:26-33)
+            shells.append((i, float(z) / (k + 1)))
+    kw.setdefault('embedding_dim', 8)
+    kw.setdefault('n_layers', 1)
+    kw.setdefault('n_determinants', 2)
+    kw.setdefault('edge_dim', 8)
+    kw.setdefault('cusp', 'deepqmc')
+    kw.setdefault('full_determinant', False)
+    kw.setdefault('conf_coeff', 'linear')
+    kw.setdefault('mult_act', 'default')
+    kw.setdefault('jastrow_layers', 3)
+    kw.setdefault('backflow_layers', 3)
+    kw.setdefault('env_centers', tuple(c for c, _ in shells))
+    kw.setdefault('env_zeta_init', tuple(z for _, z in shells))
+    return AnsatzSpec('paulinet', hamil.n_up, hamil.n_down, hamil.n_nuc, **kw)

@@ -180,6 +180,94 @@ def orbitals_nucdep(spec, params, emb, zetas, r, R):
     return torch.cat([a_up, a_dn], 1)
 
 
+def ssp(x):
+    # reference: hkext.py:11-19 shifted softplus
+    return torch.nn.functional.softplus(x) + math.log(0.5)
+
+
+def paulinet_embeddings(spec, params, r, R):
+    """conv-GNN of the reference's test ansatz (tests/conf/ansatz.yaml): embedding lookup
+    (gnn/electron_gnn.py:620-624; one electron type if n_up == n_down, :337-343), nuclear hk.Embed
+    (:514), per layer conv_t(i) = sum_senders w_t(e) * h_t(x_sender) for t in same / anti / ne
+    (gnn/update_features.py:162-238, graph.py:226-335; edges = receiver - sender, no
+    self-interaction; features [|d| eps-safe, d], edge_features.py:21-78), 'featurewise' update
+    sum_t g_t(conv_t) and residual (electron_gnn.py:243-259)."""
+    N, n_up = spec.n_elec, spec.n_up
+    emb = _t(params, P.GNN + 'electron_embedding/ElectronicEmbedding:embeddings')
+    types = [0] * n_up + [int(spec.n_up != spec.n_down)] * spec.n_down
+    x = emb[types]  # [N, d]
+    xn = _t(params, P.GNN + 'nuclei_embedding/~/embed:embeddings')  # [M, d]
+
+    def feats(d):
+        return torch.cat([safe_norm(d)[..., None], d], -1)
+
+    up = torch.arange(N) < n_up
+    same = (up[:, None] == up[None, :]) & ~torch.eye(N, dtype=torch.bool)  # [sender j, receiver i]
+    anti = up[:, None] != up[None, :]
+    e_ee = feats(r[None, :, :] - r[:, None, :])  # [j, i, 4] receiver - sender
+    e_ne = feats(r[None, :, :] - R[:, None, :])  # [I, i, 4]
+    for l in range(spec.n_layers):
+        c, lp = P.conv_prefix(l), P.layer_prefix(l)
+        upd = 0
+        for t, edges, mask, send in (('same', e_ee, same, x), ('anti', e_ee, anti, x), ('ne', e_ne, None, xn)):
+            we = torch.tanh(edges @ _t(params, c + f'w_{t}/linear_0:w'))  # [senders, N, e]
+            hx = torch.tanh(send @ _t(params, c + f'h_{t}/linear_0:w') + _t(params, c + f'h_{t}/linear_0:b'))
+            prod = we * hx[:, None, :]
+            if mask is not None:
+                prod = prod * mask[:, :, None].to(prod.dtype)
+            conv = prod.sum(0)  # [N, e]
+            upd = upd + torch.tanh(conv @ _t(params, lp + f'g_conv_{t}/linear_0:w') + _t(params, lp + f'g_conv_{t}/linear_0:b'))
+        x = x + upd if upd.shape == x.shape else upd  # ResidualConnection(normalize=False), hkext.py:116-137
+    return x
+
+
+def paulinet_log_psi(spec, params, r, R):
+    """reference: wf/nn_wave_function.py:127-173 with full_determinant = False, mult backflow with the
+    default mult_act, hk.Linear conf_coeff, DeepQMCCusp, Jastrow (wf/omni.py:13-40, sum_first)."""
+    N, K, n_up, n_dn = spec.n_elec, spec.n_determinants, spec.n_up, spec.n_down
+    x = paulinet_embeddings(spec, params, r, R)
+
+    def mlp(base, h, n_lin, act, bias_last):
+        for i in range(n_lin):
+            h = h @ _t(params, base + f'linear_{i}:w')
+            if i < n_lin - 1 or bias_last:
+                h = h + _t(params, base + f'linear_{i}:b')
+            if i < n_lin - 1:
+                h = act(h)
+        return h
+
+    jastrow = mlp(P.JASTROW, x.sum(0), spec.jastrow_layers, ssp, False).squeeze(-1) if spec.jastrow_layers else 0.0
+    # envelopes (wf/env.py:57-75: per_shell, shared exponents, spin-restricted) -> [K, N_el, N_orb]
+    centers = list(spec.env_centers)
+    dist = safe_norm(r[:, None] - R[None])[:, centers]  # [N, n_env]
+    zeta, pi = _t(params, f'{P.ENV}:zetas'), _t(params, f'{P.ENV}:pi')
+    orb = (pi[None] * torch.exp(-torch.abs(zeta * dist))[:, None, :]).sum(-1)  # [N, K*N]
+    orb = orb.reshape(N, K, N).permute(1, 0, 2)
+    mult = (lambda v: 1 + 2 * torch.tanh(v / 4)) if spec.mult_act == 'default' else (lambda v: v)
+    signs, logs = 1.0, 0.0
+    for sl, osl, pre, n in ((slice(0, n_up), slice(0, n_up), P.BF_UP, n_up), (slice(n_up, N), slice(n_up, N), P.BF_DN, n_dn)):
+        base = pre.rsplit('linear_0', 1)[0]
+        f = mlp(base, x[sl], spec.backflow_layers, ssp, True)  # [n, K * n]
+        f = f.reshape(n, K, n).permute(1, 0, 2)  # wf/omni.py:78-88
+        a = orb[:, sl, osl] * mult(f)
+        s, l = torch.linalg.slogdet(a) if n > 0 else (torch.ones(K, dtype=r.dtype), torch.zeros(K, dtype=r.dtype))
+        signs, logs = signs * s, logs + l
+    shift = logs.max().detach()
+    if torch.isinf(shift):
+        shift = torch.zeros_like(shift)
+    xs = signs * torch.exp(logs - shift)
+    psi = (xs @ _t(params, P.CONF + ':w')).squeeze() if spec.conf_coeff == 'linear' else xs.sum()
+    log = torch.log(torch.abs(psi)) + shift
+    sgn = torch.sign(psi).detach()
+    if spec.cusp == 'deepqmc':  # wf/cusp.py:5-14
+        al = spec.cusp_alpha
+        for i in range(N):
+            for j in range(i + 1, N):
+                sc = spec.cusp_same_scale if (i < n_up) == (j < n_up) else spec.cusp_anti_scale
+                log = log - sc / (al * (1 + al * safe_norm(r[i] - r[j])))
+    return sgn, log + jastrow
+
+
 def orbitals(spec, params, emb, r, R):
     """envelopes (*) backflow -> A[K, N, N] (electron i, orbital mu)."""
     N, K, n_up = spec.n_elec, spec.n_determinants, spec.n_up
@@ -217,6 +305,8 @@ def psiformer_cusp(spec, params, r):
 
 def log_psi(spec, params, r, R):
     """ansatz.apply for one walker -> (sign, log|psi|); reference nn_wave_function.py:127-173"""
+    if spec.kind == 'paulinet':
+        return paulinet_log_psi(spec, params, r, R)
     if spec.kind == 'transpsiformer':
         emb, nuc = transpsiformer_embeddings(spec, params, r, R)
         A = orbitals_nucdep(spec, params, emb, nuclear_head_zetas(spec, params, nuc), r, R)

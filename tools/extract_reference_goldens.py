@@ -34,6 +34,11 @@ def main():
         'graph_edge_builder_mask_self_False': npz('test_gnn/test_graph_edge_builder_mask_self_False_.npz'),
         'potential_LiH_None': npz('test_potential/test_pseudo_potentials_LiH_None_.npz'),
         'potential_C_None': npz('test_potential/test_pseudo_potentials_C_None_.npz'),
+        # parameter-tree names and shapes of the reference's test ansatz (tests/conf/ansatz.yaml on LiH): the keys of
+        # tests/test_wf/test_grad_psi.npz are the Haiku paths (values are gradients, which need the Haiku-initialised
+        # parameters and are not reproducible here)
+        'test_ansatz_param_shapes': {k: list(np.load(os.path.join(REF, 'test_wf/test_grad_psi.npz'))[k].shape)
+                                     for k in np.load(os.path.join(REF, 'test_wf/test_grad_psi.npz')).files},
         'wf_psi': npz('test_wf/test_psi.npz'),
         'wf_laplace': npz('test_wf/test_laplace_psi.npz'),
         'local_energy_Molecular': npz('test_hamil/test_local_energy_Molecular_.npz'),
