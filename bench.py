@@ -32,6 +32,7 @@ WORKLOADS = {
     'n2_psiformer': dict(mol='N2', ecp=None, walkers=4096, hyper={}, kind='psiformer'),
     'n2_ferminet': dict(mol='N2', ecp=None, walkers=4096, hyper={}, kind='ferminet'),
     'benzene_psiformer': dict(mol='benzene', ecp='ccECP', walkers=4096, hyper={}, kind='psiformer'),
+    'lih_paulinet': dict(mol='LiH', ecp=None, walkers=256, hyper={}, kind='paulinet'),  # BASELINE configs[0]
 }
 
 
@@ -97,7 +98,14 @@ class ClockSampler:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from one
 # `ncu --set full` capture of the same command (profiles/, B200_PROFILING.md); None = not captured.
-TRAFFIC = {}
+TRAFFIC = {
+    # profiles/r01_ncu_full_fwd_kernels_v1.csv, launch 1: QKV row GEMM of one non-local-ECP forward chunk
+    # (518400 rows x K=256 -> N=768): dram read 0.5326 GB + write 1.5352 GB; algorithmic bytes of that launch
+    # = 518400 * (256 + 768) * 4 + weights 0.79 MB = 2.124 GB
+    'benzene_psiformer': {'bytes_per_launch': 2.0678e9, 'algorithmic_bytes_per_launch': 2.1241e9,
+                          'launch': 'QKV GEMM, 518400 rows x 256 -> 768 (8 walkers x 2160 quadrature forwards x 30 electrons)',
+                          'source': 'profiles/r01_ncu_full_fwd_kernels_v1.csv'},
+}
 
 _ORACLE = {}
 
@@ -105,14 +113,14 @@ _ORACLE = {}
 def _oracle_init(wl_name, seed):
     """Pool initialiser: one single-threaded oracle per worker process."""
     torch.set_num_threads(1)
-    from deepqmc_b200.spec import ferminet_spec, psiformer_spec
+    from deepqmc_b200.spec import ferminet_spec, paulinet_spec, psiformer_spec
     from oracle import wf
     from oracle.hamil import OracleHamiltonian
 
     wl = WORKLOADS[wl_name]
     mol, hamil, r, PN = make_problem(wl, 1, seed)
     oh = OracleHamiltonian(mol, ecp_type=wl['ecp'])
-    spec = (psiformer_spec if wl['kind'] == 'psiformer' else ferminet_spec)(oh, **wl['hyper'])
+    spec = {'psiformer': psiformer_spec, 'ferminet': ferminet_spec, 'paulinet': paulinet_spec}[wl['kind']](oh, **wl['hyper'])
     pt = wf.to_torch(PN.perturb_params(PN.init_params(spec, 0)))
     J = 0 if oh.nl_params is None else len(np.unique(np.nonzero(oh.nl_params)[0]))
     _ORACLE.update(wl=wl, oh=oh, spec=spec, pt=pt, R=torch.as_tensor(mol.coords), J=J, wf=wf)
@@ -220,7 +228,9 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     unit = 'walker.local-energies/s'
     metric = 'walker.local-energies/sec'
-    workload_name = f"{wl['mol']} {'Psiformer d256 L4 H4 K16' if wl['kind'] == 'psiformer' else 'FermiNet d256 L4 e32 K16'}{' ' + wl['ecp'] if wl['ecp'] else ''}, {B} walkers/GPU"
+    arch = {'psiformer': 'Psiformer d256 L4 H4 K16', 'ferminet': 'FermiNet d256 L4 e32 K16',
+            'paulinet': 'PauliNet test ansatz (tests/conf/ansatz.yaml) d8 L1 K2'}[wl['kind']]
+    workload_name = f"{wl['mol']} {arch}{' ' + wl['ecp'] if wl['ecp'] else ''}, {B} walkers/GPU"
 
     if a.impl == 'reference':
         if rank != 0:
@@ -357,8 +367,9 @@ def main():
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback',
                 'traffic': TRAFFIC.get(a.workload), 'gemm_share_of_step': (gemm_ms / n_prof) / (total_ms / a.steps),
                 'gemm_launches_per_step': n_gemm // n_prof,
-                'algorithmic_flops_per_eloc': algorithmic_flops_per_eloc(N, M, n_ecp=n_ecp),
-                'whole_step_tflops': algorithmic_flops_per_eloc(N, M, n_ecp=n_ecp) * B * a.steps / (total_ms / 1e3) / 1e12}
+                'algorithmic_flops_per_eloc': algorithmic_flops_per_eloc(N, M, n_ecp=n_ecp) if wl['kind'] == 'psiformer' else None,
+                'whole_step_tflops': (algorithmic_flops_per_eloc(N, M, n_ecp=n_ecp) * B * a.steps / (total_ms / 1e3) / 1e12
+                                      if wl['kind'] == 'psiformer' else None)}
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

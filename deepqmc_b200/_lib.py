@@ -34,6 +34,9 @@ class DqmcConfig(C.Structure):
         ('ecp_nl_lmax_p1', C.c_int32), ('ecp_nl_terms', C.c_int32),
         ('ecp_nl', C.c_double * (MAX_NUC * MAX_L * 2 * MAX_T)),
         ('n_env_per_nuc', C.c_int32), ('n_nuc_tokens', C.c_int32),
+        ('factorized_det', C.c_int32), ('conf_linear', C.c_int32), ('mult_act', C.c_int32),
+        ('n_elec_types', C.c_int32), ('jastrow_n', C.c_int32), ('jastrow_dims', C.c_int32 * 8),
+        ('backflow_n', C.c_int32), ('backflow_dims', C.c_int32 * 8),
     ]
 
 

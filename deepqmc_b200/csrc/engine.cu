@@ -13,6 +13,7 @@
 #include "kernels_mcmc.cuh"
 #include "kernels_slater.cuh"
 #include "kernels_trunk.cuh"
+#include "kernels_gnn.cuh"
 #if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
 #include "gemm_tcgen05.cuh"
 #endif
@@ -78,6 +79,35 @@ struct EngineBase {
         }
       }
     }
+    int bf_in = d;  // input width of the final backflow layer
+    if (cfg.kind == DQMC_PAULINET) {
+      // reference tests/conf/ansatz.yaml; names of the engine entries mirror the Haiku modules
+      const int e = cfg.edge_dim;
+      add("emb.table", cfg.n_elec_types > 0 ? cfg.n_elec_types : 1, d);
+      for (int l = 0; l < cfg.n_layers; ++l) {
+        std::string p = "G" + std::to_string(l) + ".";
+        for (const char* t : {"same", "anti", "ne"}) add(p + "w_" + t, 4, e);
+        for (const char* t : {"same", "anti"}) { add(p + "h_" + t + ".w", d, e); add(p + "h_" + t + ".b", 1, e); }
+        add(p + "hne", M, e);  // tanh(h_ne(nuclear embedding)): walker-independent, evaluated on the host
+        for (const char* t : {"same", "anti", "ne"}) { add(p + "g_" + t + ".w", e, d); add(p + "g_" + t + ".b", 1, d); }
+      }
+      int din = d;
+      for (int i = 0; i < cfg.jastrow_n; ++i) {
+        add("J" + std::to_string(i) + ".w", din, cfg.jastrow_dims[i]);
+        if (i < cfg.jastrow_n - 1) add("J" + std::to_string(i) + ".b", 1, cfg.jastrow_dims[i]);
+        din = cfg.jastrow_dims[i];
+      }
+      din = d;
+      for (int i = 0; i < cfg.backflow_n; ++i) {
+        const std::string q = std::to_string(i);
+        add("bfh" + q + ".up", din, cfg.backflow_dims[i]); add("bfh" + q + ".dn", din, cfg.backflow_dims[i]);
+        add("bfb" + q + ".up", 1, cfg.backflow_dims[i]); add("bfb" + q + ".dn", 1, cfg.backflow_dims[i]);
+        din = cfg.backflow_dims[i];
+      }
+      bf_in = din;
+      add("bfb.up", 1, K * N); add("bfb.dn", 1, K * N);
+      if (cfg.conf_linear) add("conf.w", 1, K);
+    }
     if (cfg.kind == DQMC_FERMINET) {
       const int de = cfg.edge_dim;
       int din = 4 * M, ein = 4;
@@ -92,8 +122,8 @@ struct EngineBase {
         din = d; ein = de;
       }
     }
-    add("bf.up", d, K * N);
-    add("bf.dn", d, K * N);
+    add("bf.up", bf_in, K * N);
+    add("bf.dn", bf_in, K * N);
     add("env.pi_up", K * N, M * rep);
     add("env.pi_dn", K * N, M * rep);
     add("env.zeta_up", K * N, M * rep);
@@ -161,6 +191,8 @@ struct Engine : EngineBase {
   bool attn_fwd_ok = false;
   bool slater_fwd2_ok = false;
   int N, M, d, K, KN, H, dh, T3;
+  bool gnn = false;    // conv-GNN ("PauliNet" test ansatz)
+  int bf_in = 0;       // input width of the final backflow layer
   bool trans = false;  // TransPsiformer: nuclear attention tokens + nucleus-dependent envelopes
   int Mn = 0, env_rep = 1;
   size_t max_smem = 0;
@@ -190,7 +222,8 @@ struct Engine : EngineBase {
   int init() {
     N = cfg.n_up + cfg.n_down; M = cfg.n_nuc; d = cfg.embedding_dim; K = cfg.n_determinants;
     KN = K * N; H = cfg.n_heads; dh = d / H; T3 = 3 * N;
-    if (cfg.kind != DQMC_PSIFORMER && cfg.kind != DQMC_FERMINET && cfg.kind != DQMC_TRANSPSIFORMER) {
+    if (cfg.kind != DQMC_PSIFORMER && cfg.kind != DQMC_FERMINET && cfg.kind != DQMC_TRANSPSIFORMER &&
+        cfg.kind != DQMC_PAULINET) {
       err = "unknown ansatz kind"; return 2;
     }
     trans = cfg.kind == DQMC_TRANSPSIFORMER;
@@ -198,7 +231,11 @@ struct Engine : EngineBase {
     env_rep = cfg.n_env_per_nuc > 1 ? cfg.n_env_per_nuc : 1;
     if (M * env_rep > 4 * DQMC_MAX_NUC || Mn < 0 || Mn > DQMC_MAX_NUC) { err = "bad config (envelope terms / nuclear tokens)"; return 2; }
     if (H < 1) H = 1;
-    if (cfg.kind == DQMC_FERMINET) { H = 1; dh = d; }
+    if (cfg.kind == DQMC_FERMINET || cfg.kind == DQMC_PAULINET) { H = 1; dh = d; }
+    gnn = cfg.kind == DQMC_PAULINET;
+    if (gnn && (cfg.jastrow_n > 8 || cfg.backflow_n > 8 || cfg.jastrow_n < 0 || cfg.backflow_n < 0)) { err = "bad MLP depth"; return 2; }
+    bf_in = d;
+    if (gnn && cfg.backflow_n > 0) bf_in = cfg.backflow_dims[cfg.backflow_n - 1];
     if (M > DQMC_MAX_NUC || d % H != 0 || N < 2) { err = "bad config"; return 2; }
     build_layout();
     DQ_CHECK(cudaSetDevice(device));
@@ -327,11 +364,28 @@ struct Engine : EngineBase {
   // ---- workspace ---------------------------------------------------------------------------
   struct Ws {
     T *X, *O, *A, *M1, *QKV, *BF, *dsign, *dlog, *dlap, *dgrad;
+    T *G0 = nullptr, *G1 = nullptr, *G2 = nullptr, *Hs = nullptr, *Ha = nullptr, *C = nullptr, *Wc = nullptr,
+      *Y0 = nullptr, *Y1 = nullptr, *Jb = nullptr;  // conv-GNN trunk
     size_t bytes;
   };
+  int gnn_hmax() const {
+    int h = 1;
+    for (int i = 0; i < cfg.backflow_n; ++i) h = cfg.backflow_dims[i] > h ? cfg.backflow_dims[i] : h;
+    return h;
+  }
+  int gnn_jsum() const {
+    int j = d;
+    for (int i = 0; i < cfg.jastrow_n; ++i) j += cfg.jastrow_dims[i];
+    return j;
+  }
   size_t per_walker_elems(int S) const {
     size_t rows = (size_t)N * S;
     size_t dets = (size_t)K * (3 + (S > 1 ? T3 : 0));
+    if (gnn) {
+      const size_t e = cfg.edge_dim;
+      return rows * (5 * (size_t)d + 5 * e + 2 * (size_t)gnn_hmax() + KN) + (size_t)N * (N + M) * 8 * e +
+             (size_t)S * gnn_jsum() + dets;
+    }
     if (cfg.kind == DQMC_FERMINET) {
       const size_t de = cfg.edge_dim, fin = 3 * (size_t)d + 2 * de;
       return rows * (2 * (size_t)d + fin + KN) + (size_t)N * rows * 2 * de + dets;
@@ -344,7 +398,15 @@ struct Engine : EngineBase {
     size_t rows = (size_t)Bc * N * S;
     char* p = (char*)base;
     auto take = [&](size_t n) { T* q = (T*)p; p += align_up(sizeof(T) * n); return q; };
-    if (cfg.kind == DQMC_FERMINET) {
+    if (gnn) {
+      const size_t e = cfg.edge_dim, hm = gnn_hmax();
+      w.X = take(rows * d); w.O = take(rows * d); w.G0 = take(rows * d); w.G1 = take(rows * d); w.G2 = take(rows * d);
+      w.Hs = take(rows * e); w.Ha = take(rows * e); w.C = take(rows * 3 * e);
+      w.Wc = take((size_t)Bc * N * (N + M) * 8 * e);
+      w.Y0 = take(rows * hm); w.Y1 = take(rows * hm); w.Jb = take((size_t)Bc * S * gnn_jsum());
+      w.A = w.M1 = w.QKV = nullptr;
+      w.BF = take(rows * KN);
+    } else if (cfg.kind == DQMC_FERMINET) {
       const size_t de = cfg.edge_dim, fin = 3 * (size_t)d + 2 * de;
       w.X = take(rows * d); w.O = take(rows * d); w.QKV = take(rows * fin);    // H, H2, F
       w.A = take(rows * N * de); w.M1 = take(rows * N * de);                   // E, E2
@@ -363,6 +425,7 @@ struct Engine : EngineBase {
     int64_t c = (wsb - 16 * 256) / per;
     int64_t row_cap = (int64_t)2000000000 / ((int64_t)N * S * 3 * d);  // keep 32-bit row*ld products safe
     if (cfg.kind == DQMC_FERMINET) row_cap = (int64_t)2000000000 / ((int64_t)N * N * S * (3 * d + 64));
+    if (gnn) row_cap = (int64_t)2000000000 / ((int64_t)N * (N + M + S) * (8 * cfg.edge_dim + 3 * d + KN));
     if (c > row_cap) c = row_cap;
     if (c > B) c = B;
     return (int)c;
@@ -390,12 +453,13 @@ struct Engine : EngineBase {
     return S <= 128 && (128 / S) * S >= 112;
   }
   int gemm(const T* A, int lda, const char* w0, const char* w1, int zsplit, int ldw, const T* bias, const T* Res,
-           int ldr, T* C, int ldc, int Mr, int Nc, int Kc, int S, int sliced, int Nel, cudaStream_t st, int act = 0) {
+           int ldr, T* C, int ldc, int Mr, int Nc, int Kc, int S, int sliced, int Nel, cudaStream_t st, int act = 0,
+           const T* bias1 = nullptr) {
     const T* W0 = P(w0);
     const T* W1 = w1 ? P(w1) : nullptr;
 #if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
     if constexpr (std::is_same<T, float>::value) {
-      if (use_tc() && Kc % 32 == 0 && lda % 4 == 0 && ldc % 4 == 0 && tcw.count(w0) && (!w1 || tcw.count(w1))) {
+      if (use_tc() && !bias1 && Kc % 32 == 0 && lda % 4 == 0 && ldc % 4 == 0 && tcw.count(w0) && (!w1 || tcw.count(w1))) {
         const TcWeight& t0 = tcw.at(w0);
         const TcWeight& t1 = w1 ? tcw.at(w1) : t0;
         tc::Params p;
@@ -424,6 +488,7 @@ struct Engine : EngineBase {
     GemmArgs<T> g;
     g.A = A; g.lda = lda; g.W0 = W0; g.W1 = W1; g.z_split = zsplit; g.ldw = ldw; g.bias = bias; g.Res = Res;
     g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = Mr; g.N = Nc; g.K = Kc; g.S = S; g.sliced = sliced; g.Nel = Nel;
+    g.bias1 = bias1;
     constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
     dim3 grid((Nc + BN - 1) / BN, (Mr + BM - 1) / BM, sliced ? Nel : 1);
 #ifndef DQMC_EMU
@@ -519,10 +584,88 @@ struct Engine : EngineBase {
     return 0;
   }
 
+  // conv-GNN trunk (reference tests/conf/ansatz.yaml): embedding lookup, per layer edge filters w_t, node
+  // transforms h_t, convolution over same / anti / ne edges, featurewise update sum_t g_t(conv_t) + residual;
+  // then the Jastrow MLP on sum_i x_i and the hidden layers of the per-spin backflow MLPs (ssp).
+  int paulinet_trunk(const T* r, const T* R, int Rb, int Bc, int S, Ws& w, T** Xbf, const T** jastrow, cudaStream_t st) {
+    const int rows = Bc * N * S, e = cfg.edge_dim, groups = Bc * N;
+    DQ_LAUNCH(gnn_embed_kernel<T>, dim3((Bc * N * d + 127) / 128), dim3(128), 0, st, P("emb.table"),
+              cfg.n_elec_types > 0 ? cfg.n_elec_types : 1, N, cfg.n_up, S, d, w.X, Bc * N);
+    T* X = w.X;
+    T* Xn = w.O;
+    for (int l = 0; l < cfg.n_layers; ++l) {
+      const std::string p = "G" + std::to_string(l) + ".";
+      const int tot = Bc * N * (N + M);
+      DQ_LAUNCH(gnn_edge_w_kernel<T>, dim3((tot + 63) / 64), dim3(64), 0, st, r, R, Rb, N, M, cfg.n_up, P(p + "w_same"),
+                P(p + "w_anti"), P(p + "w_ne"), e, w.Wc, tot);
+      int rc = gemm(X, d, (p + "h_same.w").c_str(), nullptr, 0, e, P(p + "h_same.b"), nullptr, 0, w.Hs, e, rows, e, d, S, 0, N, st);
+      if (rc) return rc;
+      rc = gemm(X, d, (p + "h_anti.w").c_str(), nullptr, 0, e, P(p + "h_anti.b"), nullptr, 0, w.Ha, e, rows, e, d, S, 0, N, st);
+      if (rc) return rc;
+      DQ_LAUNCH(act_fl_kernel<T>, dim3(groups, (e + 63) / 64), dim3(64), 0, st, w.Hs, e, (const T*)nullptr, 0, S, e, T(1), 0);
+      DQ_LAUNCH(act_fl_kernel<T>, dim3(groups, (e + 63) / 64), dim3(64), 0, st, w.Ha, e, (const T*)nullptr, 0, S, e, T(1), 0);
+      DQ_LAUNCH(gnn_conv_kernel<T>, dim3(groups), dim3(128), 0, st, (const T*)w.Wc, (const T*)w.Hs, (const T*)w.Ha,
+                P(p + "hne"), N, M, cfg.n_up, S, e, w.C);
+      // featurewise update: x <- x + sum_t tanh(g_t(conv_t))   (electron_gnn.py:243-259, residual hkext.py:116-137)
+      T* G[3] = {w.G0, w.G1, w.G2};
+      const char* tn[3] = {"same", "anti", "ne"};
+      const T* res = X;
+      for (int t = 0; t < 3; ++t) {
+        rc = gemm(w.C + t * e, 3 * e, (p + "g_" + tn[t] + ".w").c_str(), nullptr, 0, d, P(p + "g_" + tn[t] + ".b"), nullptr, 0,
+                  G[t], d, rows, d, e, S, 0, N, st);
+        if (rc) return rc;
+        DQ_LAUNCH(act_fl_kernel<T>, dim3(groups, (d + 63) / 64), dim3(64), 0, st, G[t], d, res, d, S, d, T(1), 0);
+        res = G[t];
+      }
+      // G2 now holds x + sum_t ...; ping-pong it with the X buffers
+      T* tmp = X; X = w.G2; w.G2 = Xn; Xn = tmp;
+    }
+    *jastrow = nullptr;
+    if (cfg.jastrow_n > 0) {
+      const int jr = Bc * S;
+      T* cur = w.Jb;
+      int din = d;
+      DQ_LAUNCH(sum_electrons_kernel<T>, dim3((jr * d + 127) / 128), dim3(128), 0, st, (const T*)X, N, S, d, cur, jr * d);
+      for (int i = 0; i < cfg.jastrow_n; ++i) {
+        const int dout = cfg.jastrow_dims[i];
+        T* nxt = cur + (size_t)jr * din;
+        const bool last = i == cfg.jastrow_n - 1;
+        const std::string q = "J" + std::to_string(i);
+        int rc = gemm(cur, din, (q + ".w").c_str(), nullptr, 0, dout, last ? nullptr : P(q + ".b"), nullptr, 0, nxt, dout, jr,
+                      dout, din, S, 0, 1, st);
+        if (rc) return rc;
+        if (!last) DQ_LAUNCH(act_fl_kernel<T>, dim3(Bc, (dout + 31) / 32), dim3(32), 0, st, nxt, dout, (const T*)nullptr, 0, S, dout, T(1), 1);
+        cur = nxt; din = dout;
+      }
+      *jastrow = cur;  // [Bc][S] scalar rows
+    }
+    T* Y = X;
+    int din = d;
+    for (int i = 0; i < cfg.backflow_n; ++i) {
+      const int dout = cfg.backflow_dims[i];
+      const std::string q = std::to_string(i);
+      T* out = (i & 1) ? w.Y1 : w.Y0;
+      int rc = gemm(Y, din, ("bfh" + q + ".up").c_str(), ("bfh" + q + ".dn").c_str(), cfg.n_up, dout, P("bfb" + q + ".up"),
+                    nullptr, 0, out, dout, Bc * S, dout, din, S, 1, N, st, 0, P("bfb" + q + ".dn"));
+      if (rc) return rc;
+      DQ_LAUNCH(act_fl_kernel<T>, dim3(groups, (dout + 31) / 32), dim3(32), 0, st, out, dout, (const T*)nullptr, 0, S, dout, T(1), 1);
+      Y = out; din = dout;
+    }
+    *Xbf = Y;
+    return 0;
+  }
+
   int run_chunk(const T* r, const T* R, int Rb, int Bc, int S, int Bstat, T* sign, T* logp, T* E, T* stats, T* grad,
                 void* wsbase, cudaStream_t st) {
     Ws w = carve(wsbase, Bc, S);
     const int rows = Bc * N * S;
+    if (gnn) {
+      T* Xbf = nullptr;
+      const T* jas = nullptr;
+      int rc = paulinet_trunk(r, R, Rb, Bc, S, w, &Xbf, &jas, st);
+      if (rc) return rc;
+      return tail(r, R, Rb, Bc, S, Bstat, sign, logp, E, stats, grad, w, Xbf, st, jas);
+    }
     if (cfg.kind == DQMC_FERMINET) {
       T* Xf = nullptr;
       int rc = ferminet_trunk(r, R, Rb, Bc, S, w, &Xf, st);
@@ -598,16 +741,20 @@ struct Engine : EngineBase {
 
   // backflow heads -> Slater determinants -> det sum / cusp / potentials (shared by all trunks)
   int tail(const T* r, const T* R, int Rb, int Bc, int S, int Bstat, T* sign, T* logp, T* E, T* stats, T* grad, Ws& w,
-           T* X, cudaStream_t st) {
+           T* X, cudaStream_t st, const T* jastrow = nullptr) {
     // per-spin backflow heads: rows of electron e across walkers, weights by spin
-    gemm(X, d, "bf.up", "bf.dn", cfg.n_up, KN, nullptr, nullptr, 0, w.BF, KN, Bc * S, KN, d, S, 1, N, st);
+    gemm(X, bf_in, "bf.up", "bf.dn", cfg.n_up, KN, gnn ? P("bfb.up") : nullptr, nullptr, 0, w.BF, KN, Bc * S, KN, bf_in, S, 1, N,
+         st, 0, gnn ? P("bfb.dn") : nullptr);
+    if (cfg.mult_act == 1)  // default mult_act 1 + 2 tanh(x / 4) of the BackflowOp (nn_wave_function.py:14-33)
+      DQ_LAUNCH(act_fl_kernel<T>, dim3(Bc * N, (KN + 127) / 128), dim3(128), 0, st, w.BF, KN, (const T*)nullptr, 0, S, KN, T(1), 2);
+    const int full_det = cfg.factorized_det ? 0 : 1;
     const int sl_wpb = slater_warps_per_block<T>(N);
     if ((N <= 4 || (N <= 6 && std::is_same<T, float>::value)) && !std::getenv("DQMC_SLATER_GENERIC")) {
       const int tot = Bc * K;
 #define DQ_SL_SMALL(NS_)                                                                                           \
   DQ_LAUNCH((slater_small_kernel<T, NS_>), dim3((tot + 63) / 64), dim3(64), 0, st, r, R, Rb, M, cfg.n_up, K, S, tot,    \
             P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog, \
-            w.dgrad, w.dlap, env_rep)
+            w.dgrad, w.dlap, env_rep, full_det)
       switch (N) {
         case 2: DQ_SL_SMALL(2); break;
         case 3: DQ_SL_SMALL(3); break;
@@ -622,27 +769,28 @@ struct Engine : EngineBase {
       if (N <= 16)
         DQ_LAUNCH((slater_fwd2_kernel<T, 16>), dim3(grid), dim3(nthr), slater_fwd2_smem_bytes<T>(N, M, K), st, r, R, Rb, N,
                   M, cfg.n_up, K, Bc, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF,
-                  KN, w.dsign, w.dlog, env_rep);
+                  KN, w.dsign, w.dlog, env_rep, full_det);
       else
         DQ_LAUNCH((slater_fwd2_kernel<T, 32>), dim3(grid), dim3(nthr), slater_fwd2_smem_bytes<T>(N, M, K), st, r, R, Rb, N,
                   M, cfg.n_up, K, Bc, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF,
-                  KN, w.dsign, w.dlog, env_rep);
+                  KN, w.dsign, w.dlog, env_rep, full_det);
     } else if (S == 1 && N <= 32 && !std::getenv("DQMC_SLATER_GENERIC")) {
       const int wpb = K < 8 ? K : 8;
       DQ_LAUNCH(slater_fwd_reg_kernel<T>, dim3(Bc), dim3(32 * wpb), sizeof(T) * N * M, st, r, R, Rb, N, M, cfg.n_up, K,
                 P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog,
-                env_rep);
+                env_rep, full_det);
     } else
     DQ_LAUNCH(slater_kernel<T>, dim3((Bc * K + sl_wpb - 1) / sl_wpb), dim3(32 * sl_wpb), slater_smem_bytes<T>(N), st, r, R,
               Rb, N, M, cfg.n_up, K, S, Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog,
-              w.dgrad, w.dlap, env_rep);
+              w.dgrad, w.dlap, env_rep, full_det);
     FinalizeCfg fc;
     fc.N = N; fc.M = M; fc.n_up = cfg.n_up; fc.K = K; fc.S = S; fc.cusp_kind = cfg.cusp_kind;
     fc.cusp_same_scale = cfg.cusp_same_scale; fc.cusp_anti_scale = cfg.cusp_anti_scale;
     fc.ecp_terms = cfg.ecp_loc_terms;
     DQ_LAUNCH(finalize_kernel<T>, dim3(Bc), dim3(128), finalize_smem_bytes<T>(N, K), st, fc, r, R, Rb,
               (const T*)w.dsign, (const T*)w.dlog, (const T*)w.dgrad, (const T*)w.dlap, P("cusp.alpha"),
-              (const T*)d_zval, (const T*)d_ecp_loc, (const int*)d_ecp_mask, Bstat, sign, logp, E, stats, grad);
+              (const T*)d_zval, (const T*)d_ecp_loc, (const int*)d_ecp_mask, Bstat, sign, logp, E, stats, grad,
+              cfg.conf_linear ? P("conf.w") : (const T*)nullptr, jastrow);
     return 0;
   }
 

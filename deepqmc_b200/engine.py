@@ -18,6 +18,17 @@ MODE_FORWARD, MODE_LOCAL_ENERGY = 0, 1
 _TORCH_DTYPE = {0: torch.float64, 1: torch.float32}
 
 
+def paulinet_backflow_hidden(spec: AnsatzSpec) -> list[int]:
+    """Hidden widths of the per-spin backflow MLPs, padded to the wider spin."""
+    du, dd = PN.backflow_dims(spec, spec.n_up)[:-1], PN.backflow_dims(spec, spec.n_down)[:-1]
+    return [max(a, b) for a, b in zip(du, dd)]
+
+
+def paulinet_env_rep(spec: AnsatzSpec) -> int:
+    """Envelope terms per nucleus in the engine layout = the largest number of shells on one nucleus."""
+    return max(max((spec.env_centers.count(c) for c in set(spec.env_centers)), default=1), 1)
+
+
 def _pack_haiku_params(spec: AnsatzSpec, params: dict, R=None) -> dict[str, np.ndarray]:
     """Haiku-named tree (deepqmc_b200.params) -> the engine's packed entries."""
     g = lambda k: np.asarray(params[k], dtype=np.float64)
@@ -32,6 +43,56 @@ def _pack_haiku_params(spec: AnsatzSpec, params: dict, R=None) -> dict[str, np.n
             out[f'L{l}.wo'] = g(a + 'multi_head_attention/linear:w')
             out[f'L{l}.w1'], out[f'L{l}.b1'] = g(a + 'mlp/linear_0:w'), g(a + 'mlp/linear_0:b')[None]
             out[f'L{l}.w2'], out[f'L{l}.b2'] = g(a + 'mlp/linear_1:w'), g(a + 'mlp/linear_1:b')[None]
+    elif spec.kind == 'paulinet':
+        N, K, M, d, n_up = spec.n_elec, spec.n_determinants, spec.n_nuc, spec.embedding_dim, spec.n_up
+        out['emb.table'] = g(PN.GNN + 'electron_embedding/ElectronicEmbedding:embeddings')
+        xn = g(PN.GNN + 'nuclei_embedding/~/embed:embeddings')
+        for l in range(spec.n_layers):
+            c, lp = PN.conv_prefix(l), PN.layer_prefix(l)
+            for t in PN.EDGE_TYPES:
+                out[f'G{l}.w_{t}'] = g(c + f'w_{t}/linear_0:w')
+                out[f'G{l}.g_{t}.w'] = g(lp + f'g_conv_{t}/linear_0:w')
+                out[f'G{l}.g_{t}.b'] = g(lp + f'g_conv_{t}/linear_0:b')[None]
+            for t in ('same', 'anti'):
+                out[f'G{l}.h_{t}.w'] = g(c + f'h_{t}/linear_0:w')
+                out[f'G{l}.h_{t}.b'] = g(c + f'h_{t}/linear_0:b')[None]
+            # nuclear embeddings are an hk.Embed lookup (gnn/electron_gnn.py:514): h_ne of them is walker-independent
+            out[f'G{l}.hne'] = np.tanh(xn @ g(c + 'h_ne/linear_0:w') + g(c + 'h_ne/linear_0:b'))
+        for i in range(spec.jastrow_layers):
+            out[f'J{i}.w'] = g(PN.JASTROW + f'linear_{i}:w')
+            if i < spec.jastrow_layers - 1:
+                out[f'J{i}.b'] = g(PN.JASTROW + f'linear_{i}:b')[None]
+        hid = paulinet_backflow_hidden(spec)
+        dims_pad = [d] + hid
+        for tag, pre, n_spin, off in (('up', PN.BF_UP, n_up, 0), ('dn', PN.BF_DN, spec.n_down, 0 if spec.full_determinant else n_up)):
+            base = pre.rsplit('linear_0', 1)[0]
+            nl = spec.backflow_layers
+            for i in range(nl - 1):  # hidden layers, zero-padded to the wider spin (ssp(0) = 0 keeps the padding inert)
+                w, b = g(base + f'linear_{i}:w'), g(base + f'linear_{i}:b')
+                wp, bp = np.zeros((dims_pad[i], dims_pad[i + 1])), np.zeros((1, dims_pad[i + 1]))
+                wp[:w.shape[0], :w.shape[1]], bp[0, :b.shape[0]] = w, b
+                out[f'bfh{i}.{tag}'], out[f'bfb{i}.{tag}'] = wp, bp
+            w, b = g(base + f'linear_{nl - 1}:w'), g(base + f'linear_{nl - 1}:b')
+            n_orb = N if spec.full_determinant else n_spin
+            cols = (np.arange(K)[:, None] * N + off + np.arange(n_orb)[None, :]).ravel()  # (k, mu') -> k N + mu
+            wp, bp = np.zeros((dims_pad[-1], K * N)), np.zeros((1, K * N))
+            wp[:w.shape[0], cols], bp[0, cols] = w, b
+            out[f'bf.{tag}'], out[f'bfb.{tag}'] = wp, bp
+        # per-shell spin-restricted envelopes (wf/env.py:26-75) -> engine layout [K N][M rep], unused terms pi = 0
+        rep = paulinet_env_rep(spec)
+        pi, zeta = g(f'{PN.ENV}:pi'), g(f'{PN.ENV}:zetas')
+        pe, ze = np.zeros((K * N, M * rep)), np.ones((K * N, M * rep))
+        seen = {}
+        for j, c in enumerate(spec.env_centers):
+            sh = seen.get(c, 0)
+            seen[c] = sh + 1
+            pe[:, c * rep + sh], ze[:, c * rep + sh] = pi[:, j], zeta[j]
+        for t in ('up', 'dn'):
+            out[f'env.pi_{t}'], out[f'env.zeta_{t}'] = pe, ze
+        out['cusp.alpha'] = np.array([[spec.cusp_alpha, spec.cusp_alpha]], dtype=np.float64)
+        if spec.conf_coeff == 'linear':
+            out['conf.w'] = g(PN.CONF + ':w').reshape(1, K)
+        return out
     elif spec.kind == 'ferminet':
         for l in range(spec.n_layers):
             lp = PN.layer_prefix(l)
@@ -60,6 +121,8 @@ def _pack_haiku_params(spec: AnsatzSpec, params: dict, R=None) -> dict[str, np.n
             out[f'env.zeta_{t}'] = g(f'{PN.ENV}:zetas_{s}')
     if spec.cusp == 'psiformer':
         out['cusp.alpha'] = np.array([[g(f'{PN.CUSP}:same_alpha'), g(f'{PN.CUSP}:anti_alpha')]], dtype=np.float64)
+    elif spec.cusp == 'deepqmc':
+        out['cusp.alpha'] = np.array([[spec.cusp_alpha, spec.cusp_alpha]], dtype=np.float64)
     else:
         out['cusp.alpha'] = np.ones((1, 2))
     return out
@@ -80,14 +143,28 @@ class Engine:
         self.device_index = 0 if self._host else (torch.cuda.current_device() if device is None else device)
         self.device = torch.device('cpu') if self._host else torch.device('cuda', self.device_index)
         cfg = _lib.DqmcConfig()
-        cfg.kind = {'psiformer': 0, 'ferminet': 1, 'transpsiformer': 2}[spec.kind]
+        cfg.kind = {'psiformer': 0, 'ferminet': 1, 'transpsiformer': 2, 'paulinet': 3}[spec.kind]
         cfg.dtype, cfg.gemm_backend = self.dtype_code, gemm_backend
         cfg.n_up, cfg.n_down, cfg.n_nuc = spec.n_up, spec.n_down, spec.n_nuc
         cfg.embedding_dim, cfg.n_layers, cfg.n_heads = spec.embedding_dim, spec.n_layers, spec.n_heads
         cfg.n_determinants, cfg.edge_dim = spec.n_determinants, spec.edge_dim
         cfg.n_env_per_nuc = spec.n_env_per_nuc
         cfg.n_nuc_tokens = spec.n_nuc if spec.kind == 'transpsiformer' else 0
-        cfg.cusp_kind = 1 if spec.cusp == 'psiformer' else 0
+        if spec.kind == 'paulinet':
+            cfg.n_env_per_nuc = paulinet_env_rep(spec)
+            cfg.factorized_det = 0 if spec.full_determinant else 1
+            cfg.conf_linear = 1 if spec.conf_coeff == 'linear' else 0
+            cfg.mult_act = 1 if spec.mult_act == 'default' else 0
+            cfg.n_elec_types = 1 if spec.n_up == spec.n_down else 2
+            jd = PN.log_dims(spec.embedding_dim, 1, spec.jastrow_layers) if spec.jastrow_layers else []
+            cfg.jastrow_n = len(jd)
+            for i, v in enumerate(jd):
+                cfg.jastrow_dims[i] = v
+            hid = paulinet_backflow_hidden(spec)
+            cfg.backflow_n = len(hid)
+            for i, v in enumerate(hid):
+                cfg.backflow_dims[i] = v
+        cfg.cusp_kind = {'psiformer': 1, 'deepqmc': 2}.get(spec.cusp, 0)
         cfg.cusp_same_scale, cfg.cusp_anti_scale = spec.cusp_same_scale, spec.cusp_anti_scale
         M = spec.n_nuc
         assert M <= _lib.MAX_NUC

@@ -22,7 +22,7 @@ extern "C" {
 #define DQMC_MAX_ECP_TERMS 4
 #define DQMC_MAX_ECP_L 4
 
-enum { DQMC_PSIFORMER = 0, DQMC_FERMINET = 1, DQMC_TRANSPSIFORMER = 2 };
+enum { DQMC_PSIFORMER = 0, DQMC_FERMINET = 1, DQMC_TRANSPSIFORMER = 2, DQMC_PAULINET = 3 };
 enum { DQMC_F64 = 0, DQMC_F32 = 1 };
 enum { DQMC_GEMM_SIMT = 0, DQMC_GEMM_TCGEN05 = 1 };
 enum { DQMC_MODE_FORWARD = 0, DQMC_MODE_LOCAL_ENERGY = 1 };
@@ -32,12 +32,12 @@ enum { DQMC_MODE_FORWARD = 0, DQMC_MODE_LOCAL_ENERGY = 1 };
  *            src/deepqmc/hamil.py:97-154 (n_up, n_down, ns_valence, ecp_mask);
  *            src/deepqmc/ecp/gaussian_type_ecp.py:32-95 (loc/nl parameter layout). */
 typedef struct dqmc_config {
-  int32_t kind;            /* DQMC_PSIFORMER | DQMC_FERMINET | DQMC_TRANSPSIFORMER */
+  int32_t kind;            /* DQMC_PSIFORMER | DQMC_FERMINET | DQMC_TRANSPSIFORMER | DQMC_PAULINET */
   int32_t dtype;           /* DQMC_F64 | DQMC_F32 */
   int32_t gemm_backend;    /* DQMC_GEMM_SIMT | DQMC_GEMM_TCGEN05 (f32 only) */
   int32_t n_up, n_down, n_nuc;
   int32_t embedding_dim, n_layers, n_heads, n_determinants, edge_dim;
-  int32_t cusp_kind;       /* 0 none, 1 PsiformerCusp (wf/cusp.py:17-26) */
+  int32_t cusp_kind;       /* 0 none, 1 PsiformerCusp (wf/cusp.py:17-26), 2 DeepQMCCusp (wf/cusp.py:5-14) */
   double cusp_same_scale, cusp_anti_scale;
   double z_valence[DQMC_MAX_NUC];                                   /* pot.ns_valence */
   int32_t ecp_mask[DQMC_MAX_NUC];
@@ -51,6 +51,16 @@ typedef struct dqmc_config {
    * false), whose per-layer key/value rows are entries "L<l>.kn" / "L<l>.vn" of the parameter table. */
   int32_t n_env_per_nuc;
   int32_t n_nuc_tokens;
+  /* DQMC_PAULINET = the conv-GNN ansatz of the reference's own CPU tests (tests/conf/ansatz.yaml; BASELINE
+   * configs[0]).  All zero for the other kinds. */
+  int32_t factorized_det;   /* 1: det_up(n_up x n_up) det_down(n_down x n_down) (wf/nn_wave_function.py:143-151) */
+  int32_t conf_linear;      /* 1: hk.Linear(1, no bias) determinant combination, entry "conf.w" (else SumPool) */
+  int32_t mult_act;         /* 0 identity, 1: 1 + 2 tanh(x / 4) on the backflow (wf/nn_wave_function.py:17) */
+  int32_t n_elec_types;     /* rows of the electron embedding table (gnn/electron_gnn.py:337-343) */
+  int32_t jastrow_n;        /* layers of the Jastrow MLP on sum_i x_i (wf/omni.py:13-40); 0: none */
+  int32_t jastrow_dims[8];  /* their widths (the last one is 1) */
+  int32_t backflow_n;       /* HIDDEN layers of the per-spin backflow MLPs (wf/omni.py:43-88), ssp activation */
+  int32_t backflow_dims[8]; /* their widths, padded to the larger of the two spins */
 } dqmc_config;
 
 typedef struct dqmc_engine* dqmc_handle;

@@ -356,3 +356,49 @@ def test_transpsiformer_geometry_change_refreshes_nuclear_stream():
         for b in range(2):
             _, l = wf.log_psi(ansatz.spec, pt, r[b].cpu(), Rx.cpu())
             assert abs(psi.log[b].item() - l.item()) <= 1e-10 * max(1, abs(l.item()))
+
+
+@pytest.mark.parametrize('mol_name,hyper,B', [
+    ('LiH', dict(), 4),               # the reference's own test ansatz on LiH (BASELINE configs[0])
+    ('LiH', dict(n_layers=2), 2),     # second layer: dense tangents through the convolution
+    ('C', dict(), 2),                 # n_up != n_down: two electron types, per-spin backflow widths differ
+    ('H2O', dict(n_layers=2, n_determinants=3), 2),
+])
+def test_paulinet_test_ansatz_local_energy_fp64(mol_name, hyper, B):
+    """conv-GNN 'PauliNet' ansatz of the reference's CPU tests (tests/conf/ansatz.yaml; SURVEY.md 8a rows
+    a9, a10, a12-a14): embedding lookup, same/anti/ne convolutions, ssp Jastrow + backflow, default mult_act,
+    per-shell envelopes, spin-factorised determinants, hk.Linear conf_coeff, DeepQMCCusp."""
+    mol, hamil, oh, ansatz, params, r, R = make(mol_name, B=B, kind='paulinet', **hyper)
+    pc = PhysicalConfiguration(R, r, torch.zeros(B, device=DEV))
+    psi = ansatz.apply(params, pc)
+    E, stats = hamil.local_energy(ansatz.apply)(None, params, pc)
+    ref = oracle_eval(ansatz, oh, params, r, R)
+    for b, (s, l, e, st) in enumerate(ref):
+        assert psi.sign[b].item() == s
+        assert abs(psi.log[b].item() - l) <= 1e-10 * max(1, abs(l))
+        assert abs(E[b].item() - e) <= 1e-8 * max(1, abs(e)), (b, E[b].item(), e)
+        for k in STAT_KEYS:
+            assert abs(stats[k][b].item() - st[k]) <= 1e-8 * max(1, abs(st[k])), (k, stats[k][b].item(), st[k])
+
+
+def test_paulinet_256_walkers_fp32_and_sampler():
+    """BASELINE configs[0]: LiH, PauliNet test ansatz, 256 walkers -- fp32 engine against fp64 engine on
+    Metropolis-equilibrated walkers, plus one decorrelated sampling step through the sampler mirror."""
+    from deepqmc_b200.sampling import DecorrSampler
+
+    mol = Molecule.from_name('LiH')
+    hamil = MolecularHamiltonian(mol=mol)
+    a64 = B200Ansatz(hamil, 'paulinet', dtype='float64')
+    a32 = B200Ansatz(hamil, 'paulinet', dtype='float32')
+    params = PN.perturb_params(a64.init(0))
+    R = torch.as_tensor(mol.coords, device=DEV)
+    smp = DecorrSampler(hamil, a64.apply, length=20, tau=0.1, max_age=20)
+    state = smp.init(3, params, 256, R)
+    for it in range(3):
+        state, pc, stats = smp.sample(it, state, params, R)
+    assert 0.05 < stats['sampling/acceptance'].item() <= 1.0
+    E64, s64 = hamil.local_energy(a64.apply)(None, params, pc)
+    E32, _ = hamil.local_energy(a32.apply)(None, params, PhysicalConfiguration(R.float(), pc.r.float(), torch.zeros(256, device=DEV)))
+    scale = torch.maximum(torch.maximum(E64.abs(), 0.5 * s64['hamil/lap'].abs()), 0.5 * s64['hamil/quantum_force']).clamp(min=1)
+    assert torch.isfinite(E64).all()
+    assert ((E32.double() - E64).abs() <= 2e-4 * scale).float().mean().item() > 0.99

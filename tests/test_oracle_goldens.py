@@ -169,3 +169,51 @@ def test_transpsiformer_nuclear_stream_matches_oracle():
     assert s0.item() == -s1.item() and abs(l0.item() - l1.item()) < 1e-10
     # parameter count of the full-size cyclobutadiene ansatz is finite and the table is consistent
     assert PN.n_params(spec) == sum(int(np.prod(v.shape)) for v in params.values())
+
+
+def test_test_ansatz_parameter_table_matches_reference_golden():
+    """The parameter tree of the 'paulinet' mirror (names AND shapes) equals the Haiku tree of the reference's
+    test ansatz on LiH, read off the keys of tests/test_wf/test_grad_psi.npz (tests/golden/reference_goldens.json):
+    pins the embedding tables, the three w/h/g convolution subnets, the 'log'-width Jastrow (8-4-2-1) and backflow
+    (8-6-5-4) MLPs, the per-shell envelope count (3 for LiH) and the hk.Linear conf_coeff."""
+    import json
+    import os
+
+    from deepqmc_b200 import params as PN
+    from deepqmc_b200.hamil import MolecularHamiltonian
+    from deepqmc_b200.molecule import Molecule
+    from deepqmc_b200.spec import paulinet_spec
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_goldens.json')))
+    ref = {k: tuple(v) for k, v in g['test_ansatz_param_shapes'].items()}
+    h = MolecularHamiltonian(mol=Molecule.from_name('LiH'))
+    mine = {k: tuple(v) for k, v in PN.param_shapes(paulinet_spec(h)).items()}
+    assert mine == ref
+
+
+def test_paulinet_oracle_antisymmetry_and_laplacian_self_check():
+    import numpy as np
+    import torch
+
+    from deepqmc_b200 import params as PN
+    from deepqmc_b200.hamil import MolecularHamiltonian
+    from deepqmc_b200.molecule import Molecule
+    from deepqmc_b200.spec import paulinet_spec
+    from oracle import wf
+    from oracle.laplacian import laplacian_hessian, laplacian_jvp_loop
+
+    mol = Molecule.from_name('C')
+    h = MolecularHamiltonian(mol=mol)
+    spec = paulinet_spec(h)
+    pt = wf.to_torch(PN.perturb_params(PN.init_params(spec, 0)))
+    rng = np.random.default_rng(1)
+    R = torch.as_tensor(mol.coords)
+    r = torch.as_tensor(rng.normal(size=(6, 3)))
+    s0, l0 = wf.log_psi(spec, pt, r, R)
+    perm = [1, 0, 2, 3, 4, 5]
+    s1, l1 = wf.log_psi(spec, pt, r[perm], R)
+    assert s0.item() == -s1.item() and abs(l0.item() - l1.item()) < 1e-10
+    f = lambda x: wf.log_psi(spec, pt, x.reshape(-1, 3), R)[1]
+    la, ga = laplacian_hessian(f, r.reshape(-1))
+    lb, gb = laplacian_jvp_loop(f, r.reshape(-1))
+    assert abs(la.item() - lb.item()) < 1e-8 * max(1, abs(la.item())) and torch.allclose(ga, gb)
