@@ -210,7 +210,7 @@ def time_oracle(wl_name, per_worker, steps, warmup, seed=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='benzene_psiformer', choices=sorted(WORKLOADS))
@@ -263,7 +263,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     mol, hamil, r_np, PN = make_problem(wl, B, seed=1000 + rank)
-    backend = 1 if (a.gemm_backend == 'tcgen05' and a.dtype == 'float32') else 0
+    backend = 1 if (a.gemm_backend == 'tcgen05' and a.dtype == 'float32' and wl['kind'] != 'paulinet') else 0  # d = 8: CUDA cores
     ansatz = B200Ansatz(hamil, wl['kind'], dtype=a.dtype, device=local, gemm_backend=backend, **wl['hyper'])
     params = PN.perturb_params(ansatz.init(0))
     tdt = torch.float32 if a.dtype == 'float32' else torch.float64

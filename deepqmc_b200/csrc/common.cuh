@@ -75,6 +75,20 @@ __device__ __forceinline__ void st4(T* p, const T (&v)[4]) {
   }
 }
 
+// cp.async group control for software pipelines: commit the copies issued so far as one group;
+// wait until at most `N` groups are still in flight.
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef DQMC_EMU
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+#ifndef DQMC_EMU
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
 template <class T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

@@ -189,6 +189,7 @@ struct Engine : EngineBase {
   bool attn_f32 = false;
   bool embed_fwd_ok = false;
   bool attn_fwd_ok = false;
+  bool attn_fwd_pipelined = false;
   bool slater_fwd2_ok = false;
   int N, M, d, K, KN, H, dh, T3;
   bool gnn = false;    // conv-GNN ("PauliNet" test ansatz)
@@ -287,6 +288,7 @@ struct Engine : EngineBase {
       if (v > 0) n_sms = v;
     }
 #endif
+    if (const char* ev = std::getenv("DQMC_NSMS")) { int x = std::atoi(ev); if (x >= 1) n_sms = x; }  // test hook
     // opt in to large dynamic shared memory
     const bool psif = cfg.kind == DQMC_PSIFORMER || trans;
     attn_tb = attn_pick_tb<T>(N, dh, T3, 100 * 1024, Mn);
@@ -313,11 +315,23 @@ struct Engine : EngineBase {
     }
     attn_fwd_ok = psif && !trans && std::is_same<T, float>::value && dh == 64 && N <= 32 && d % 4 == 0 &&
                   !std::getenv("DQMC_ATTN_GENERIC") && !std::getenv("DQMC_ATTN_FWD_OLD");
+    attn_fwd_pipelined = attn_fwd_ok && std::getenv("DQMC_ATTN_FWD2");  // measured slower than the block-per-walker kernel
+    if (attn_fwd_pipelined) {
+      const int smem2 = 6 * 4 * N * 64 * (int)sizeof(float);
+      DQ_CHECK(cudaFuncSetAttribute(attn_fwd2_f32_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      DQ_CHECK(cudaFuncSetAttribute(attn_fwd2_f32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      DQ_CHECK(cudaFuncSetAttribute(attn_fwd2_f32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    }
     if (attn_fwd_ok) {
       const int smem = 4 * 2 * N * 64 * (int)sizeof(float);
-      DQ_CHECK(cudaFuncSetAttribute(attn_fwd_f32_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      DQ_CHECK(cudaFuncSetAttribute(attn_fwd_f32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      DQ_CHECK(cudaFuncSetAttribute(attn_fwd_f32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<8, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<16, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<32, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<4, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<10, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<14, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<28, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<30, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     embed_fwd_ok = psif && d % 4 == 0 && embed_fwd_smem_bytes<T>(M, d) <= 200 * 1024 && !std::getenv("DQMC_EMBED_GENERIC");
     if (embed_fwd_ok)
@@ -696,19 +710,40 @@ struct Engine : EngineBase {
         const T* kn = Mn > 0 ? P(p + "kn") : nullptr;
         const T* vn = Mn > 0 ? P(p + "vn") : nullptr;
         if constexpr (std::is_same<T, float>::value) {
-          if (S == 1 && attn_fwd_ok) {
+          if (S == 1 && attn_fwd_ok && attn_fwd_pipelined) {
+            // persistent blocks (one per SM), 6 warps each, K / V of the next pair prefetched by cp.async
+            const int n_pairs = Bc * H, wpb = 6;
+            const int smem = wpb * 4 * N * 64 * (int)sizeof(float);
+            const int nblk = (n_pairs + wpb - 1) / wpb;
+            const dim3 grid(nblk < n_sms ? nblk : n_sms), block(32 * wpb);
+            if (N <= 8)
+              DQ_LAUNCH(attn_fwd2_f32_kernel<8>, grid, block, smem, st, (const float*)w.QKV, 3 * d, (float*)O, d, N, H, d,
+                        (float)scale, n_pairs);
+            else if (N <= 16)
+              DQ_LAUNCH(attn_fwd2_f32_kernel<16>, grid, block, smem, st, (const float*)w.QKV, 3 * d, (float*)O, d, N, H, d,
+                        (float)scale, n_pairs);
+            else
+              DQ_LAUNCH(attn_fwd2_f32_kernel<32>, grid, block, smem, st, (const float*)w.QKV, 3 * d, (float*)O, d, N, H, d,
+                        (float)scale, n_pairs);
+          } else if (S == 1 && attn_fwd_ok) {
             const int n_pairs = Bc * H;
             const int smem = 4 * 2 * N * 64 * (int)sizeof(float);
             const dim3 grid((n_pairs + 3) / 4), block(128);
-            if (N <= 8)
-              DQ_LAUNCH(attn_fwd_f32_kernel<8>, grid, block, smem, st, (const float*)w.QKV, 3 * d, (float*)O, d, N, H, d,
-                        (float)scale, n_pairs);
-            else if (N <= 16)
-              DQ_LAUNCH(attn_fwd_f32_kernel<16>, grid, block, smem, st, (const float*)w.QKV, 3 * d, (float*)O, d, N, H, d,
-                        (float)scale, n_pairs);
-            else
-              DQ_LAUNCH(attn_fwd_f32_kernel<32>, grid, block, smem, st, (const float*)w.QKV, 3 * d, (float*)O, d, N, H, d,
-                        (float)scale, n_pairs);
+#define DQ_ATTN_FWD(NM_, EX_)                                                                                          \
+  DQ_LAUNCH((attn_fwd_f32_kernel<NM_, EX_>), grid, block, smem, st, (const float*)w.QKV, 3 * d, (float*)O, d, N, H, d, \
+            (float)scale, n_pairs)
+            switch (N) {  // exact-size instances for the benchmark molecules, padded generic ones otherwise
+              case 4: DQ_ATTN_FWD(4, true); break;
+              case 10: DQ_ATTN_FWD(10, true); break;
+              case 14: DQ_ATTN_FWD(14, true); break;
+              case 28: DQ_ATTN_FWD(28, true); break;
+              case 30: DQ_ATTN_FWD(30, true); break;
+              default:
+                if (N <= 8) DQ_ATTN_FWD(8, false);
+                else if (N <= 16) DQ_ATTN_FWD(16, false);
+                else DQ_ATTN_FWD(32, false);
+            }
+#undef DQ_ATTN_FWD
           } else if (attn_f32) {
             if (launch_attn_f32((const float*)w.QKV, (float*)O, Bc, S, tb, (float)scale, 0,
                                 (int)attn_f32_smem_bytes(N, dh, tb), st, false))

@@ -402,3 +402,43 @@ def test_paulinet_256_walkers_fp32_and_sampler():
     scale = torch.maximum(torch.maximum(E64.abs(), 0.5 * s64['hamil/lap'].abs()), 0.5 * s64['hamil/quantum_force']).clamp(min=1)
     assert torch.isfinite(E64).all()
     assert ((E32.double() - E64).abs() <= 2e-4 * scale).float().mean().item() > 0.99
+
+
+def test_excited_state_overlap_two_states_vs_oracle():
+    """BASELINE configs[4] shape (two electronic states, TransPsiformer): Psi_i(r ~ Psi_j^2) blocks, sample-wise
+    ratios and the symmetrised mean overlap (reference loss/overlap.py:19-150) against the oracle."""
+    from deepqmc_b200.overlap import compute_mean_overlap, compute_psi_ratio
+    from deepqmc_b200.sampling import MetropolisSampler, MultiElectronicStateSampler
+    from oracle import wf
+
+    hyper = dict(embedding_dim=32, n_layers=1, n_heads=2, n_determinants=2)
+    mol = Molecule.from_name('LiH')
+    hamil = MolecularHamiltonian(mol=mol)
+    ansatz = B200Ansatz(hamil, 'transpsiformer', dtype='float64', **hyper)
+    params = [PN.perturb_params(ansatz.init(s), seed=10 + s) for s in range(2)]
+    R = torch.as_tensor(mol.coords, device=DEV)
+    smp = MultiElectronicStateSampler(MetropolisSampler(hamil, ansatz.apply, tau=0.3), 2)
+    state = smp.init(5, params, 6, R)
+    state, pc, stats = smp.sample(6, state, params, R)
+    assert pc.r.shape == (2, 6, 4, 3) and stats['sampling/acceptance'].shape == (2,)
+    ratio, _ = compute_psi_ratio(ansatz, params, pc)
+    pts = [wf.to_torch(p) for p in params]
+    Rc = R.cpu()
+    ref = torch.zeros(2, 2, 6, dtype=torch.float64)
+    logs = torch.zeros(2, 2, 6, dtype=torch.float64)
+    signs = torch.zeros(2, 2, 6, dtype=torch.float64)
+    for i in range(2):
+        for j in range(2):
+            for b in range(6):
+                s, l = wf.log_psi(ansatz.spec, pts[i], pc.r[j, b].cpu(), Rc)
+                signs[i, j, b], logs[i, j, b] = s, l
+    for i in range(2):
+        for j in range(2):
+            ref[i, j] = signs[i, j] * signs[j, j] * torch.exp(logs[i, j] - logs[j, j])
+    assert torch.allclose(ratio.cpu(), ref, rtol=1e-8, atol=1e-10)
+    assert torch.allclose(ratio[0, 0].cpu(), torch.ones(6, dtype=torch.float64)) and torch.allclose(ratio[1, 1].cpu(), torch.ones(6, dtype=torch.float64))
+    loss, ostats = compute_mean_overlap(ratio)
+    S = ostats['overlap/pairwise/mean'].cpu()
+    x = ref.mean(-1)
+    expect = torch.sign(x) * torch.sqrt(torch.clamp(x * x.T, min=0))
+    assert torch.allclose(S, expect, rtol=1e-8, atol=1e-10) and abs(loss.item() - expect[0, 1].item() ** 2) < 1e-10
