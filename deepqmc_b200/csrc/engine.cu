@@ -199,7 +199,8 @@ struct Engine : EngineBase {
   size_t max_smem = 0;
   int n_sms = 148;
 #if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
-  struct TcWeight { float* hi = nullptr; float* lo = nullptr; CUtensorMap mh, ml; int N = 0, K = 0, BN = 0; };
+  struct TcWeight { float* hi = nullptr; float* lo = nullptr; CUtensorMap mh, ml, mh2, ml2; int N = 0, K = 0, BN = 0; };
+  bool gemm_2cta = false;  // CTA-pair (cta_group::2) variant of the dense-layer GEMM
   std::map<std::string, TcWeight> tcw;
   bool use_tc() const { return std::is_same<T, float>::value && cfg.gemm_backend == DQMC_GEMM_TCGEN05; }
   int prepare_tc_weight(const std::string& name, const float* W, int Kc, int Nc, cudaStream_t st) {
@@ -208,7 +209,8 @@ struct Engine : EngineBase {
       DQ_CHECK(cudaMalloc((void**)&w.hi, sizeof(float) * (size_t)Kc * Nc));
       DQ_CHECK(cudaMalloc((void**)&w.lo, sizeof(float) * (size_t)Kc * Nc));
       w.N = Nc; w.K = Kc; w.BN = tc::pick_bn(Nc);
-      if (tc::make_weight_map(&w.mh, w.hi, Nc, Kc, w.BN) || tc::make_weight_map(&w.ml, w.lo, Nc, Kc, w.BN)) {
+      if (tc::make_weight_map(&w.mh, w.hi, Nc, Kc, w.BN) || tc::make_weight_map(&w.ml, w.lo, Nc, Kc, w.BN) ||
+          tc::make_weight_map(&w.mh2, w.hi, Nc, Kc, w.BN / 2) || tc::make_weight_map(&w.ml2, w.lo, Nc, Kc, w.BN / 2)) {
         err = "cuTensorMapEncodeTiled failed for " + name;
         return 4;
       }
@@ -341,8 +343,11 @@ struct Engine : EngineBase {
 #if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
       if (!std::is_same<T, float>::value) { err = "DQMC_GEMM_TCGEN05 needs dtype DQMC_F32"; return 2; }
       if (d % 32 != 0) { err = "DQMC_GEMM_TCGEN05 needs embedding_dim % 32 == 0"; return 2; }
-      DQ_CHECK(cudaFuncSetAttribute(tc::gemm3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      DQ_CHECK(cudaFuncSetAttribute(tc::gemm3xtf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     tc::SmemLayout::total(256)));
+      DQ_CHECK(cudaFuncSetAttribute(tc::gemm3xtf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    tc::SmemLayoutT<true>::total(256)));
+      gemm_2cta = std::getenv("DQMC_GEMM_2CTA") != nullptr;
 #else
       err = "this build has no tcgen05 backend"; return 2;
 #endif
@@ -486,7 +491,23 @@ struct Engine : EngineBase {
         int grid = n_tiles < n_sms ? n_tiles : n_sms;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (prof) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
-        tc::gemm3xtf32_kernel<<<grid, tc::kThreads, tc::SmemLayout::total(p.BN), st>>>(t0.mh, t0.ml, t1.mh, t1.ml, p);
+        if (gemm_2cta && n_sms >= 2) {
+          // CTA pairs: clusters of 2, each pair owns 256-row tiles; weight maps with half-tile boxes
+          const int MT2 = (MT + 1) / 2;
+          const int n_pt = (sliced ? Nel : 1) * MT2 * NT;
+          int pairs = n_sms / 2;
+          if (n_pt < pairs) pairs = n_pt;
+          cudaLaunchConfig_t lc = {};
+          lc.gridDim = dim3(2 * pairs); lc.blockDim = dim3(tc::kThreads);
+          lc.dynamicSmemBytes = tc::SmemLayoutT<true>::total(p.BN); lc.stream = st;
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeClusterDimension;
+          at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+          lc.attrs = at; lc.numAttrs = 1;
+          DQ_CHECK(cudaLaunchKernelEx(&lc, tc::gemm3xtf32_kernel<true>, t0.mh2, t0.ml2, t1.mh2, t1.ml2, p));
+        } else {
+          tc::gemm3xtf32_kernel<false><<<grid, tc::kThreads, tc::SmemLayout::total(p.BN), st>>>(t0.mh, t0.ml, t1.mh, t1.ml, p);
+        }
         ++launches;
         if (prof) {
           cudaEventRecord(e1, st);

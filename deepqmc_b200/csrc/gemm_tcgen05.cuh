@@ -85,6 +85,47 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers: instruction forms as in CUTLASS' cute/arch/copy_sm100_tma.hpp
+// (SM100_TMA_2SM_LOAD_2D), cutlass/arch/barrier.h (ClusterBarrier::arrive, umma_arrive_multicast_2x1SM) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared-memory object of THIS CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of one CTA's half of a CTA-pair operand; completes on the mbarrier at cluster address `bar_cluster`
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t bar_cluster, void* dst, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// commit the MMAs issued so far; the arrival lands on the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+      ::"r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -147,20 +188,27 @@ __device__ __forceinline__ size_t phys_row(const Params& p, int m, int z) {
   return ((size_t)b * p.Nel + z) * p.S + s;
 }
 
-struct SmemLayout {
+// TWO = CTA pair (cta_group::2): every CTA stages its own 128 activation rows and HALF of the weight tile, so a
+// stage is 64 KB instead of 96 KB and the ring gets a third stage.
+template <bool TWO>
+struct SmemLayoutT {
+  static constexpr int kSt = TWO ? 3 : 2;
   // byte offsets from the 1024B-aligned base
+  static __host__ __device__ int wrows(int BN) { return TWO ? BN / 2 : BN; }
   static __host__ __device__ int a_hi(int s, int BN) { return s * stage_bytes(BN); }
   static __host__ __device__ int a_lo(int s, int BN) { return s * stage_bytes(BN) + kBM * 128; }
   static __host__ __device__ int w_hi(int s, int BN) { return s * stage_bytes(BN) + 2 * kBM * 128; }
-  static __host__ __device__ int w_lo(int s, int BN) { return s * stage_bytes(BN) + 2 * kBM * 128 + BN * 128; }
-  static __host__ __device__ int stage_bytes(int BN) { return 2 * kBM * 128 + 2 * BN * 128; }
-  static __host__ __device__ int bars(int BN) { return kStages * stage_bytes(BN); }
+  static __host__ __device__ int w_lo(int s, int BN) { return s * stage_bytes(BN) + 2 * kBM * 128 + wrows(BN) * 128; }
+  static __host__ __device__ int stage_bytes(int BN) { return 2 * kBM * 128 + 2 * wrows(BN) * 128; }
+  static __host__ __device__ int bars(int BN) { return kSt * stage_bytes(BN); }
   static __host__ __device__ int epi(int BN) { return bars(BN) + 256; }              // 4 warps x 32 x 36 floats
   static __host__ __device__ int side(int BN) { return epi(BN) + 4 * 32 * 36 * 4 + 4 * 32 * 8; }  // y', y'', sum z_t^2: [3][32 groups][32]
   static __host__ __device__ int sbias(int BN) { return side(BN) + 3 * 32 * 32 * 4; }  // bias of the tile's BN columns
   static __host__ __device__ int total(int BN) { return sbias(BN) + 256 * 4 + 64; }
 };
+using SmemLayout = SmemLayoutT<false>;
 
+template <bool TWO>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_constant__ CUtensorMap map_lo0,
                   const __grid_constant__ CUtensorMap map_hi1, const __grid_constant__ CUtensorMap map_lo1, Params p) {
@@ -168,37 +216,52 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
   // pointer: that would drop the shared address space and turn every access into a generic LD/ST.
   extern __shared__ __align__(1024) unsigned char smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  using SmemLayout = SmemLayoutT<TWO>;
+  constexpr int kStages = SmemLayout::kSt;
   const int BN = p.BN;
   uint64_t* bars = (uint64_t*)(smem + SmemLayout::bars(BN));
-  uint64_t* full_a = bars;                 // [kStages] count 128 (producer threads)
-  uint64_t* full_w = bars + kStages;       // [kStages] count 1 + tx bytes
-  uint64_t* empty = bars + 2 * kStages;    // [kStages] count 1 (tcgen05.commit)
+  uint64_t* full_a = bars;                 // [kStages] count 128 producer threads per CTA (pair: both CTAs -> the leader's)
+  uint64_t* full_w = bars + kStages;       // [kStages] count 1 + tx bytes (pair: both halves land on the leader's)
+  uint64_t* empty = bars + 2 * kStages;    // [kStages] count 1 (tcgen05.commit; pair: multicast to both CTAs)
   uint64_t* tmem_full = bars + 3 * kStages;       // [2] count 1 (commit)
-  uint64_t* tmem_empty = bars + 3 * kStages + 2;  // [2] count 128 (epilogue threads)
+  uint64_t* tmem_empty = bars + 3 * kStages + 2;  // [2] count 128 epilogue threads per CTA (pair: leader's collects both)
   uint32_t* tmem_base_slot = (uint32_t*)(bars + 3 * kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int RPT = p.rpt;
   const int MT = (p.M + RPT - 1) / RPT, NT = (p.N + BN - 1) / BN;
   const int Z = p.sliced ? p.Nel : 1;
-  const int n_tiles = Z * MT * NT;
   const int KB = p.K / kBK;
+  // work distribution: single CTA: tile = (z, mt, nt); pair: the two CTAs of a cluster take the M tiles 2 mt2 + rank
+  // of a pair tile (z, mt2, nt) -- an M tile index >= MT simply has no valid rows
+  const uint32_t crank = TWO ? cluster_ctarank() : 0u;
+  const bool leader = crank == 0u;
+  const int MTX = TWO ? (MT + 1) / 2 : MT;
+  const int n_tiles = Z * MTX * NT;
+  const int tile0 = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tstep = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr uint32_t kPer = TWO ? 256u : 128u;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_a[s], 128);
+      mbar_init(&full_a[s], kPer);
       mbar_init(&full_w[s], 1);
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], kPer);
     }
     fence_barrier_init();
   }
   if (warp == 9) {  // TMEM allocation (whole warp), address lands in shared memory
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(kTmemCols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if constexpr (TWO) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(kTmemCols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(kTmemCols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&map_hi0); tma_prefetch_desc(&map_lo0);
@@ -206,6 +269,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (TWO) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -216,8 +280,9 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
     const int pw = warp - 4;
     const int chunk = lane & 7, rsub = lane >> 3;
     uint32_t it = 0;  // running k-block counter (ring position)
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int mt = (tile / NT) % MT, z = tile / (NT * MT);
+    const uint32_t full_a_leader = TWO ? mapa_u32(full_a, 0) : 0u;  // cluster address of the leader's full_a[0]
+    for (int tile = tile0; tile < n_tiles; tile += tstep) {
+      const int mt = TWO ? 2 * ((tile / NT) % MTX) + (int)crank : (tile / NT) % MT, z = tile / (NT * MTX);
       const float* rowp[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -253,7 +318,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
           *(float4*)(al + off) = l;
         }
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
-        mbar_arrive(&full_a[s]);
+        if (TWO && !leader) mbar_arrive_cluster(full_a_leader + 8u * (uint32_t)s);
+        else mbar_arrive(&full_a[s]);
         ++it;
       };
       load_kb(b0, 0);
@@ -269,8 +335,9 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
     // ===================== W producer: TMA of the pre-split weight tiles ====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int nt = tile % NT, z = tile / (NT * MT);
+      const uint32_t full_w_leader = TWO ? mapa_u32(full_w, 0) : 0u;
+      for (int tile = tile0; tile < n_tiles; tile += tstep) {
+        const int nt = tile % NT, z = tile / (NT * MTX);
         const bool second = p.sliced && z >= p.z_split;
         const CUtensorMap* mh = second ? &map_hi1 : &map_hi0;
         const CUtensorMap* ml = second ? &map_lo1 : &map_lo0;
@@ -278,17 +345,25 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&empty[s], ph ^ 1, p.err_flag);
-          mbar_expect_tx(&full_w[s], 2u * BN * 128u);
-          tma_load_2d(mh, &full_w[s], smem + SmemLayout::w_hi(s, BN), kb * kBK, nt * BN);
-          tma_load_2d(ml, &full_w[s], smem + SmemLayout::w_lo(s, BN), kb * kBK, nt * BN);
+          if constexpr (TWO) {
+            // each CTA fetches its half of the weight tile (BN / 2 rows of W^T); both halves complete on the leader's barrier
+            if (leader) mbar_expect_tx(&full_w[s], 2u * BN * 128u);
+            const int y = nt * BN + (int)crank * (BN / 2);
+            tma_load_2d_2sm(mh, full_w_leader + 8u * (uint32_t)s, smem + SmemLayout::w_hi(s, BN), kb * kBK, y);
+            tma_load_2d_2sm(ml, full_w_leader + 8u * (uint32_t)s, smem + SmemLayout::w_lo(s, BN), kb * kBK, y);
+          } else {
+            mbar_expect_tx(&full_w[s], 2u * BN * 128u);
+            tma_load_2d(mh, &full_w[s], smem + SmemLayout::w_hi(s, BN), kb * kBK, nt * BN);
+            tma_load_2d(ml, &full_w[s], smem + SmemLayout::w_lo(s, BN), kb * kBK, nt * BN);
+          }
         }
       }
     }
   } else if (warp == 9) {
     // ===================== MMA issuer ========================================================
-    const uint32_t idesc = make_idesc(kBM, BN);
+    const uint32_t idesc = make_idesc(TWO ? 2 * kBM : kBM, BN);
     uint32_t it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+    for (int tile = tile0; tile < n_tiles && leader; tile += tstep, ++tcount) {  // pair: only the leader issues
       const int acc = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
       mbar_wait(&tmem_empty[acc], aph ^ 1, p.err_flag);
@@ -306,12 +381,23 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             const uint32_t ko = k * kUmmaK * 4;  // byte offset inside the 128B swizzle row
-            umma_tf32(d_tmem, make_desc(ah + ko), make_desc(wl + ko), idesc, (kb | k) ? 1u : 0u);
-            umma_tf32(d_tmem, make_desc(al + ko), make_desc(wh + ko), idesc, 1u);
-            umma_tf32(d_tmem, make_desc(ah + ko), make_desc(wh + ko), idesc, 1u);
+            if constexpr (TWO) {
+              umma_tf32_2sm(d_tmem, make_desc(ah + ko), make_desc(wl + ko), idesc, (kb | k) ? 1u : 0u);
+              umma_tf32_2sm(d_tmem, make_desc(al + ko), make_desc(wh + ko), idesc, 1u);
+              umma_tf32_2sm(d_tmem, make_desc(ah + ko), make_desc(wh + ko), idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, make_desc(ah + ko), make_desc(wl + ko), idesc, (kb | k) ? 1u : 0u);
+              umma_tf32(d_tmem, make_desc(al + ko), make_desc(wh + ko), idesc, 1u);
+              umma_tf32(d_tmem, make_desc(ah + ko), make_desc(wh + ko), idesc, 1u);
+            }
           }
-          umma_commit(&empty[s]);                         // frees the smem stage when the MMAs retire
-          if (kb == KB - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
+          if constexpr (TWO) {
+            umma_commit_2sm(&empty[s]);                         // frees the stage in BOTH CTAs when the MMAs retire
+            if (kb == KB - 1) umma_commit_2sm(&tmem_full[acc]);  // accumulator complete (both epilogues)
+          } else {
+            umma_commit(&empty[s]);                         // frees the smem stage when the MMAs retire
+            if (kb == KB - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
+          }
         }
         __syncwarp();
       }
@@ -337,8 +423,9 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
     const int rsub = lane >> 3, cq = lane & 7;
     const int S = p.S;
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-      const int nt = tile % NT, mt = (tile / NT) % MT, z = tile / (NT * MT);
+    const uint32_t tmem_empty_leader = TWO ? mapa_u32(tmem_empty, 0) : 0u;
+    for (int tile = tile0; tile < n_tiles; tile += tstep, ++tcount) {
+      const int nt = tile % NT, mt = TWO ? 2 * ((tile / NT) % MTX) + (int)crank : (tile / NT) % MT, z = tile / (NT * MTX);
       const int acc = tcount & 1;
       const uint32_t aph = (tcount >> 1) & 1;
       {
@@ -391,7 +478,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
         tmem_ld_wait();
         if (c == nchunk - 1) {  // accumulator fully read: hand it back to the MMA warp early
           tc_fence_before();
-          mbar_arrive(&tmem_empty[acc]);
+          if (TWO && !leader) mbar_arrive_cluster(tmem_empty_leader + 8u * (uint32_t)acc);
+          else mbar_arrive(&tmem_empty[acc]);
         }
         if (!chunk_on) continue;
         const bool act_rows = p.act && S == 1;  // plain forward: every row is a value row -> tanh in registers
@@ -490,9 +578,13 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (TWO) cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer can still reach into it
   if (warp == 9) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    if constexpr (TWO)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
   }
 }
 

@@ -200,6 +200,8 @@ class Engine:
             self.entries[name.value.decode()] = (off.value, rows.value, cols.value)
         self.n_packed = self.lib.dqmc_param_total(h)
         self._ws = None
+        self._ws_ok = set()  # (n_walkers, mode, cap) requests the current workspace is known to satisfy
+        self._mcmc_fw = {}
         self._params_version = None
 
     # ------------------------------------------------------------------------------------
@@ -231,6 +233,9 @@ class Engine:
             torch.cuda.current_stream(self.device).synchronize()
 
     def workspace(self, n_walkers: int, mode: int, max_bytes: int | None = None):
+        key = (n_walkers, mode, max_bytes)
+        if self._ws is not None and key in self._ws_ok:  # hot path: no driver queries per call
+            return self._ws
         need = self.lib.dqmc_workspace_bytes(self.h, n_walkers, mode)
         if max_bytes is None and not self._host:
             # never ask for more than ~60 % of the free HBM: the engine chunks the walkers internally
@@ -239,7 +244,10 @@ class Engine:
         if max_bytes is not None:
             need = min(need, max(max_bytes, self.lib.dqmc_workspace_bytes(self.h, 1, mode)))
         if self._ws is None or self._ws.numel() < need:
+            self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws_ok = set()
+        self._ws_ok.add(key)
         return self._ws
 
     def _prep(self, x):
@@ -305,15 +313,20 @@ class Engine:
         stats = torch.zeros(7, dtype=self.dtype, device=self.device)
         # proposal buffers (r', sign', log', counter) + the forward-pass workspace
         extra = (B * (r.shape[1] * 3 + 2)) * r.element_size() + 8192
-        fw = self.lib.dqmc_workspace_bytes(self.h, B, MODE_FORWARD)
-        if max_ws_bytes is not None:
-            fw = min(fw, max(max_ws_bytes, self.lib.dqmc_workspace_bytes(self.h, 1, MODE_FORWARD)))
-        elif not self._host:
-            free = torch.cuda.mem_get_info(self.device)[0] + (self._ws.numel() if self._ws is not None else 0)
-            fw = min(fw, max(int(0.6 * free), self.lib.dqmc_workspace_bytes(self.h, 1, MODE_FORWARD)))
+        fkey = (B, max_ws_bytes)
+        fw = self._mcmc_fw.get(fkey)
+        if fw is None:  # decided once per batch size (cudaMemGetInfo is a slow driver query)
+            fw = self.lib.dqmc_workspace_bytes(self.h, B, MODE_FORWARD)
+            if max_ws_bytes is not None:
+                fw = min(fw, max(max_ws_bytes, self.lib.dqmc_workspace_bytes(self.h, 1, MODE_FORWARD)))
+            elif not self._host:
+                free = torch.cuda.mem_get_info(self.device)[0] + (self._ws.numel() if self._ws is not None else 0)
+                fw = min(fw, max(int(0.6 * free), self.lib.dqmc_workspace_bytes(self.h, 1, MODE_FORWARD)))
+            self._mcmc_fw[fkey] = fw
         if self._ws is None or self._ws.numel() < fw + extra:
             self._ws = None
             self._ws = torch.empty(fw + extra, dtype=torch.uint8, device=self.device)
+            self._ws_ok = set()
         ws = self._ws
         rc = self.lib.dqmc_mcmc_sweep(
             self.h, r.data_ptr(), state['sign'].data_ptr(), state['log'].data_ptr(), state['age'].data_ptr(),

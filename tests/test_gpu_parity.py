@@ -432,9 +432,10 @@ def test_excited_state_overlap_two_states_vs_oracle():
             for b in range(6):
                 s, l = wf.log_psi(ansatz.spec, pts[i], pc.r[j, b].cpu(), Rc)
                 signs[i, j, b], logs[i, j, b] = s, l
+    mean_log = logs.mean(dim=(-1, -2))  # per wave function over the samples of all states (loss/overlap.py:93-95)
     for i in range(2):
         for j in range(2):
-            ref[i, j] = signs[i, j] * signs[j, j] * torch.exp(logs[i, j] - logs[j, j])
+            ref[i, j] = signs[i, j] * signs[j, j] * torch.exp((logs[i, j] - mean_log[i]) - (logs[j, j] - mean_log[j]))
     assert torch.allclose(ratio.cpu(), ref, rtol=1e-8, atol=1e-10)
     assert torch.allclose(ratio[0, 0].cpu(), torch.ones(6, dtype=torch.float64)) and torch.allclose(ratio[1, 1].cpu(), torch.ones(6, dtype=torch.float64))
     loss, ostats = compute_mean_overlap(ratio)
