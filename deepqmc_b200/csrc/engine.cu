@@ -315,9 +315,9 @@ struct Engine : EngineBase {
       DQ_CHECK(cudaFuncSetAttribute(slater_fwd2_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)slater_fwd2_smem_bytes<T>(N, M, K)));
     }
-    attn_fwd_ok = psif && !trans && std::is_same<T, float>::value && dh == 64 && N <= 32 && d % 4 == 0 &&
+    attn_fwd_ok = psif && std::is_same<T, float>::value && dh == 64 && N <= 32 && N + Mn <= 48 && d % 4 == 0 &&
                   !std::getenv("DQMC_ATTN_GENERIC") && !std::getenv("DQMC_ATTN_FWD_OLD");
-    attn_fwd_pipelined = attn_fwd_ok && std::getenv("DQMC_ATTN_FWD2");  // measured slower than the block-per-walker kernel
+    attn_fwd_pipelined = attn_fwd_ok && !trans && std::getenv("DQMC_ATTN_FWD2");  // measured slower than the block-per-walker kernel
     if (attn_fwd_pipelined) {
       const int smem2 = 6 * 4 * N * 64 * (int)sizeof(float);
       DQ_CHECK(cudaFuncSetAttribute(attn_fwd2_f32_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
@@ -325,7 +325,8 @@ struct Engine : EngineBase {
       DQ_CHECK(cudaFuncSetAttribute(attn_fwd2_f32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
     }
     if (attn_fwd_ok) {
-      const int smem = 4 * 2 * N * 64 * (int)sizeof(float);
+      const int smem = 4 * 2 * (N + Mn) * 64 * (int)sizeof(float);
+      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<48, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<8, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<16, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<32, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -748,21 +749,22 @@ struct Engine : EngineBase {
                         (float)scale, n_pairs);
           } else if (S == 1 && attn_fwd_ok) {
             const int n_pairs = Bc * H;
-            const int smem = 4 * 2 * N * 64 * (int)sizeof(float);
+            const int smem = 4 * 2 * (N + Mn) * 64 * (int)sizeof(float);
             const dim3 grid((n_pairs + 3) / 4), block(128);
 #define DQ_ATTN_FWD(NM_, EX_)                                                                                          \
   DQ_LAUNCH((attn_fwd_f32_kernel<NM_, EX_>), grid, block, smem, st, (const float*)w.QKV, 3 * d, (float*)O, d, N, H, d, \
-            (float)scale, n_pairs)
-            switch (N) {  // exact-size instances for the benchmark molecules, padded generic ones otherwise
+            (float)scale, n_pairs, (const float*)kn, (const float*)vn, Mn)
+            switch (Mn > 0 ? -1 : N) {  // exact-size instances for the benchmark molecules, padded generic ones otherwise
               case 4: DQ_ATTN_FWD(4, true); break;
               case 10: DQ_ATTN_FWD(10, true); break;
               case 14: DQ_ATTN_FWD(14, true); break;
               case 28: DQ_ATTN_FWD(28, true); break;
               case 30: DQ_ATTN_FWD(30, true); break;
               default:
-                if (N <= 8) DQ_ATTN_FWD(8, false);
-                else if (N <= 16) DQ_ATTN_FWD(16, false);
-                else DQ_ATTN_FWD(32, false);
+                if (N + Mn <= 8) DQ_ATTN_FWD(8, false);
+                else if (N + Mn <= 16) DQ_ATTN_FWD(16, false);
+                else if (N + Mn <= 32) DQ_ATTN_FWD(32, false);
+                else DQ_ATTN_FWD(48, false);
             }
 #undef DQ_ATTN_FWD
           } else if (attn_f32) {

@@ -759,26 +759,37 @@ __global__ void attn_fl_f32_kernel(const float* __restrict__ QKV, int ldq, float
 // broadcasts.  Same algebra / reference lines as attn_fl_kernel (value part).
 // dynamic smem = warps_per_block * 2 * N * 64 * 4 bytes.
 // ------------------------------------------------------------------------------------------
-// EXACT: N == NMAX is known at compile time -> the per-key loops carry no branches, so the compiler can
-// hoist the shared-memory loads of several keys above the FMAs that consume them (latency hiding by ILP).
+// EXACT: the key count N == NMAX is known at compile time (and there are no extra tokens) -> the per-key
+// loops carry no branches, so the compiler can hoist the shared-memory loads of several keys above the
+// FMAs that consume them (latency hiding by ILP).
+// Kn / Vn [Mn][dmodel] (nullable): key / value rows of Mn walker-independent extra tokens (TransPsiformer
+// nuclei, see attn_fl_kernel); they sit behind the N electron keys, N + Mn <= NMAX.
 template <int NMAX, bool EXACT>
 __global__ void __launch_bounds__(128)
 attn_fwd_f32_kernel(const float* __restrict__ QKV, int ldq, float* __restrict__ O, int ldo, int N, int H, int dmodel,
-                    float scale, int n_pairs) {
+                    float scale, int n_pairs, const float* __restrict__ Kn, const float* __restrict__ Vn, int Mn) {
   constexpr int DH = 64;
   DQMC_DYN_SMEM(smem_raw);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int pair = blockIdx.x * wpb + wib;
   if (pair >= n_pairs) return;
   const int b = pair / H, h = pair - b * H;
-  float* ks = reinterpret_cast<float*>(smem_raw) + (size_t)wib * 2 * N * DH;  // [N][64]
-  float* vs = ks + N * DH;                                                     // [N][64]
+  const int NK = EXACT ? NMAX : N + Mn;
+  float* ks = reinterpret_cast<float*>(smem_raw) + (size_t)wib * 2 * NK * DH;  // [NK][64]
+  float* vs = ks + NK * DH;                                                     // [NK][64]
   const float* base = QKV + (size_t)b * N * ldq + h * DH;
   for (int idx = lane; idx < N * (DH / 4); idx += 32) {
     const int j = idx >> 4, c4 = idx & 15;
     const float* src = base + (size_t)j * ldq + 4 * c4;
     cp_async16(ks + j * DH + 4 * c4, src + dmodel);
     cp_async16(vs + j * DH + 4 * c4, src + 2 * dmodel);
+  }
+  if (!EXACT) {
+    for (int idx = lane; idx < Mn * (DH / 4); idx += 32) {
+      const int m = idx >> 4, c4 = idx & 15;
+      cp_async16(ks + (N + m) * DH + 4 * c4, Kn + (size_t)m * dmodel + h * DH + 4 * c4);
+      cp_async16(vs + (N + m) * DH + 4 * c4, Vn + (size_t)m * dmodel + h * DH + 4 * c4);
+    }
   }
   const int i = lane < N ? lane : N - 1;  // idle lanes shadow the last query (no divergence)
   float4 q[DH / 4];
@@ -794,7 +805,7 @@ attn_fwd_f32_kernel(const float* __restrict__ QKV, int ldq, float* __restrict__ 
 #pragma unroll
   for (int j = 0; j < NMAX; ++j) {
     sc[j] = -3.0e38f;
-    if (EXACT || j < N) {
+    if (EXACT || j < NK) {
       const float4* kp = reinterpret_cast<const float4*>(ks + j * DH);
       float a0 = 0.f, a1 = 0.f;
 #pragma unroll
@@ -809,7 +820,7 @@ attn_fwd_f32_kernel(const float* __restrict__ QKV, int ldq, float* __restrict__ 
   float sum = 0.f;
 #pragma unroll
   for (int j = 0; j < NMAX; ++j) {
-    if (EXACT || j < N) {
+    if (EXACT || j < NK) {
       sc[j] = m_exp(sc[j] - mx);
       sum += sc[j];
     }
@@ -820,7 +831,7 @@ attn_fwd_f32_kernel(const float* __restrict__ QKV, int ldq, float* __restrict__ 
   for (int c = 0; c < DH / 4; ++c) o[c] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int j = 0; j < NMAX; ++j) {
-    if (EXACT || j < N) {
+    if (EXACT || j < NK) {
       const float pj = sc[j] * inv;
       const float4* vp = reinterpret_cast<const float4*>(vs + j * DH);
 #pragma unroll
