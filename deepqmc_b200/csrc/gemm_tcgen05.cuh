@@ -281,67 +281,56 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
     const int chunk = lane & 7, rsub = lane >> 3;
     uint32_t it = 0;  // running k-block counter (ring position)
     const uint32_t full_a_leader = TWO ? mapa_u32(full_a, 0) : 0u;  // cluster address of the leader's full_a[0]
-    // The loads form ONE stream over all k-blocks of all tiles of this CTA (register ring of kRing k-blocks): the
-    // first k-blocks of the next tile are already in flight while the last ones of the current tile are converted,
-    // so HBM latency is exposed once per kernel, not once per tile.
-    int ltile = tile0, lkb = 0;  // load cursor
-    const float* rowp[8];
-    auto set_rows = [&](int tile) {
+    for (int tile = tile0; tile < n_tiles; tile += tstep) {
       const int mt = TWO ? 2 * ((tile / NT) % MTX) + (int)crank : (tile / NT) % MT, z = tile / (NT * MTX);
+      const float* rowp[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int lrow = pw * 32 + 4 * j + rsub;
         const int m = mt * RPT + lrow;
         rowp[j] = (lrow < RPT && m < p.M) ? p.A + phys_row(p, m, z) * p.lda + chunk * 4 : nullptr;
       }
-    };
-    if (ltile < n_tiles) set_rows(ltile);
-    auto load_next = [&](float4(&buf)[8]) {
-      if (ltile < n_tiles) {
+      // register ring of 3 k-blocks: loads run two k-blocks ahead of the conversion.  (A single load stream
+      // across tiles with a 4-deep ring was measured 20-30 % SLOWER: round-1 profile notes.)
+      float4 b0[8], b1[8], b2[8];
+      auto load_kb = [&](float4(&buf)[8], int kbi) {
+        if (kbi < KB) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          buf[j] = rowp[j] ? __ldg((const float4*)(rowp[j] + lkb * kBK)) : make_float4(0, 0, 0, 0);
-        if (++lkb == KB) {
-          lkb = 0;
-          ltile += tstep;
-          if (ltile < n_tiles) set_rows(ltile);
+          for (int j = 0; j < 8; ++j)
+            buf[j] = rowp[j] ? __ldg((const float4*)(rowp[j] + kbi * kBK)) : make_float4(0, 0, 0, 0);
         }
-      }
-    };
-    auto process = [&](const float4(&buf)[8]) {
-      const int s = it % kStages;
-      const uint32_t ph = (it / kStages) & 1;
-      mbar_wait(&empty[s], ph ^ 1, p.err_flag);
-      unsigned char* ah = smem + SmemLayout::a_hi(s, BN);
-      unsigned char* al = smem + SmemLayout::a_lo(s, BN);
+      };
+      auto process = [&](const float4(&buf)[8]) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1, p.err_flag);
+        unsigned char* ah = smem + SmemLayout::a_hi(s, BN);
+        unsigned char* al = smem + SmemLayout::a_lo(s, BN);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int trow = pw * 32 + 4 * j + rsub;
-        float4 v = buf[j], h, l;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-        const int off = (trow >> 3) * 1024 + (trow & 7) * 128 + ((chunk ^ (trow & 7)) << 4);
-        *(float4*)(ah + off) = h;
-        *(float4*)(al + off) = l;
+        for (int j = 0; j < 8; ++j) {
+          const int trow = pw * 32 + 4 * j + rsub;
+          float4 v = buf[j], h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+          const int off = (trow >> 3) * 1024 + (trow & 7) * 128 + ((chunk ^ (trow & 7)) << 4);
+          *(float4*)(ah + off) = h;
+          *(float4*)(al + off) = l;
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
+        if (TWO && !leader) mbar_arrive_cluster(full_a_leader + 8u * (uint32_t)s);
+        else mbar_arrive(&full_a[s]);
+        ++it;
+      };
+      load_kb(b0, 0);
+      load_kb(b1, 1);
+      for (int kb = 0; kb < KB; kb += 3) {
+        load_kb(b2, kb + 2);
+        process(b0);
+        if (kb + 1 < KB) { load_kb(b0, kb + 3); process(b1); }
+        if (kb + 2 < KB) { load_kb(b1, kb + 4); process(b2); }
       }
-      fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
-      if (TWO && !leader) mbar_arrive_cluster(full_a_leader + 8u * (uint32_t)s);
-      else mbar_arrive(&full_a[s]);
-      ++it;
-    };
-    const int my_tiles = tile0 < n_tiles ? (n_tiles - tile0 + tstep - 1) / tstep : 0;
-    const int G = my_tiles * KB;  // k-blocks this CTA converts
-    float4 b0[8], b1[8], b2[8], b3[8];
-    load_next(b0);
-    load_next(b1);
-    load_next(b2);
-    for (int g = 0; g < G; g += 4) {
-      load_next(b3); process(b0);
-      if (g + 1 < G) { load_next(b0); process(b1); }
-      if (g + 2 < G) { load_next(b1); process(b2); }
-      if (g + 3 < G) { load_next(b2); process(b3); }
     }
   } else if (warp == 8) {
     // ===================== W producer: TMA of the pre-split weight tiles ====================
@@ -468,22 +457,33 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
       }
       const int nchunk = BN / 32;
       const bool vec_ok = (p.N % 4) == 0;
+      // residual rows are fetched ONE CHUNK AHEAD (the first chunk before the accumulator wait): their HBM
+      // latency overlaps the TMEM read / transpose / store of the previous chunk instead of stalling every chunk
+      float4 res[8], resn[8];
+      auto load_res = [&](float4(&dst)[8], int cc) {
+        const int colc = nt * BN + cc * 32 + 4 * cq;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) dst[jj] = make_float4(0, 0, 0, 0);
+        if (Resp && vec_ok && colc < p.N) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            if (inf[jj] >= 0) dst[jj] = __ldg((const float4*)(Resp + (size_t)(inf[jj] >> 16) * p.ldr + colc));
+        }
+      };
+      load_res(res, 0);
       mbar_wait(&tmem_full[acc], aph, p.err_flag);
       tc_fence_after();
       for (int c = 0; c < nchunk; ++c) {
         const int col = nt * BN + c * 32 + 4 * cq;  // first of this lane's 4 columns
         const bool chunk_on = nt * BN + c * 32 < p.N;  // warp-uniform
         float4 bq = make_float4(0, 0, 0, 0);
-        float4 res[8];
+        if (c > 0) {
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) res[jj] = make_float4(0, 0, 0, 0);
+          for (int jj = 0; jj < 8; ++jj) res[jj] = resn[jj];
+        }
+        if (c + 1 < nchunk) load_res(resn, c + 1);
         if (chunk_on && vec_ok && col < p.N) {
           if (p.bias && !p.act) bq = __ldg((const float4*)(p.bias + col));
-          if (Resp) {
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj)
-              if (inf[jj] >= 0) res[jj] = __ldg((const float4*)(Resp + (size_t)(inf[jj] >> 16) * p.ldr + col));
-          }
         }
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 256 + c * 32), v);

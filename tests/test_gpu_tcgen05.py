@@ -101,3 +101,32 @@ def test_engine_tcgen05_backend_parity():
         # fp32 tolerance relative to the magnitudes that cancel in E_kin = -(lap + |grad|^2)/2
         scale_b = max(1, abs(eo.item()), 0.5 * abs(st['hamil/lap'].item()), 0.5 * st['hamil/quantum_force'].item())
         assert abs(E1[b].item() - eo.item()) <= 2e-4 * scale_b
+
+
+def test_cta_pair_variant_matches_single_cta(monkeypatch):
+    """The cta_group::2 variant of the kernel (clusters of 2 CTAs, 256-row pair tiles, half weight tile per CTA,
+    multicast commits; engine switch DQMC_GEMM_2CTA read at handle creation) gives the same result as the
+    single-CTA kernel: dense GEMM incl. ragged row count and residual, sliced backflow heads, and one fp32
+    local-energy evaluation."""
+    hamil, a1, params, eng1 = _engine(1)
+    monkeypatch.setenv('DQMC_GEMM_2CTA', '1')
+    hamil2, a2, _, eng2 = _engine(1)
+    g = torch.Generator(device='cpu').manual_seed(5)
+    for rows, S, weight, bias in [(56 * 300 + 5, 14, 'L0.wqkv', None), (1000, 14, 'L1.w1', 'L1.b1'), (77, 1, 'L2.wo', None)]:
+        A = torch.randn(rows, 256, generator=g).to(DEV)
+        Res = torch.randn(rows, 256, generator=g).to(DEV) if weight.endswith('wo') else None
+        C1 = eng1.debug_gemm(weight, A, bias=bias, Res=Res, S=S, backend=1)
+        C2 = eng2.debug_gemm(weight, A, bias=bias, Res=Res, S=S, backend=1)
+        torch.cuda.synchronize()
+        assert torch.allclose(C1, C2, rtol=1e-6, atol=1e-5), (weight, (C1 - C2).abs().max().item())
+    A = torch.randn(37 * 4 * 14, 256, device=DEV)
+    assert torch.allclose(eng1.debug_gemm('bf.up', A, S=14, sliced=True, backend=1),
+                          eng2.debug_gemm('bf.up', A, S=14, sliced=True, backend=1), rtol=1e-6, atol=1e-5)
+    rng = np.random.default_rng(0)
+    mol = hamil.mol
+    r = torch.as_tensor(mol.coords[rng.integers(0, 2, size=(64, 4))] + rng.normal(size=(64, 4, 3)), device=DEV, dtype=torch.float32)
+    R = torch.as_tensor(mol.coords, device=DEV, dtype=torch.float32)
+    pc = PhysicalConfiguration(R, r, torch.zeros(64, device=DEV))
+    E1, _ = hamil.local_energy(a1.apply)(None, params, pc)
+    E2, _ = hamil2.local_energy(a2.apply)(None, params, pc)
+    assert torch.allclose(E1, E2, rtol=1e-5, atol=1e-4)
