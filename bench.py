@@ -365,7 +365,8 @@ def main():
         roof = {'bound': 'tensor', 'kernel': 'dense-layer row GEMM (' + ('tcgen05 3xTF32 gemm3xtf32_kernel' if backend else 'CUDA-core gemm_kernel') + ')', 'achieved': achieved,
                 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback',
-                'traffic': TRAFFIC.get(a.workload), 'gemm_share_of_step': (gemm_ms / n_prof) / (total_ms / a.steps),
+                'traffic': (TRAFFIC.get(a.workload) or {}).get('bytes_per_launch'), 'traffic_detail': TRAFFIC.get(a.workload),
+                'gemm_share_of_step': (gemm_ms / n_prof) / (total_ms / a.steps),
                 'gemm_launches_per_step': n_gemm // n_prof,
                 'algorithmic_flops_per_eloc': algorithmic_flops_per_eloc(N, M, n_ecp=n_ecp) if wl['kind'] == 'psiformer' else None,
                 'whole_step_tflops': (algorithmic_flops_per_eloc(N, M, n_ecp=n_ecp) * B * a.steps / (total_ms / 1e3) / 1e12

@@ -70,6 +70,66 @@ __global__ void gnn_edge_w_kernel(const T* __restrict__ r, const T* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// Raw edge features [|d|, d] in the compact 8-slot layout (same conventions as gnn_edge_w_kernel):
+// E[b][i][jj][8][4]; the edge MLPs (w_t, u) then run on these rows with the ordinary row GEMM and
+// act_fl_kernel with S = 8 (slots 1..6 are the tangents, slot 7 the Laplacian).  One thread per (b, i, jj).
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void gnn_edge_feat_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M,
+                                     int Mne, T* __restrict__ E, int total) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int NS = N + Mne;
+  const int jj = idx % NS, i = (idx / NS) % N, b = idx / (NS * N);
+  T* out = E + (size_t)idx * 32;
+  for (int k = 0; k < 32; ++k) out[k] = T(0);
+  if (jj == i) return;
+  const T* ri = r + ((size_t)b * N + i) * 3;
+  const bool nuc = jj >= N;
+  const T* pj = nuc ? R + (R_batched ? (size_t)b * M * 3 : 0) + (size_t)(jj - N) * 3 : r + ((size_t)b * N + jj) * 3;
+  const T d[3] = {ri[0] - pj[0], ri[1] - pj[1], ri[2] - pj[2]};
+  const T dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+  const T rho2 = Num<T>::eps() + dd, rho = m_sqrt(rho2);
+  const T sj = nuc ? T(0) : T(-1), np = nuc ? T(1) : T(2);
+  out[0] = rho; out[1] = d[0]; out[2] = d[1]; out[3] = d[2];
+  for (int c = 0; c < 3; ++c) {
+    T* gi = out + (1 + c) * 4;  // d / d r_i,c
+    gi[0] = d[c] / rho; gi[1 + c] = T(1);
+    T* gj = out + (4 + c) * 4;  // d / d r_j,c
+    gj[0] = sj * d[c] / rho; gj[1 + c] = sj;
+  }
+  out[7 * 4] = np * (T(3) / rho - dd / (rho2 * rho));
+}
+
+// Node-update input of the 'concatenate' rule (reference gnn/update_features.py:47-121 Residual / NodeSum with
+// normalize = true, then the convolutions): F[b][i][s][:] = [x_i, mean_up x, mean_down x, conv_*(i)].  Linear, so it
+// acts slot-wise.  grid = (B * S, N), block over features.
+template <class T>
+__global__ void gnn_concat_kernel(const T* __restrict__ X, int dx, const T* __restrict__ C, int dc, int N, int n_up,
+                                  int S, T* __restrict__ F) {
+  const int bs = blockIdx.x, b = bs / S, s = bs % S, i = blockIdx.y;
+  const int ldf = 3 * dx + dc;
+  T* f = F + ((size_t)(b * N + i) * S + s) * ldf;
+  const int n_dn = N - n_up;
+  for (int k = threadIdx.x; k < ldf; k += blockDim.x) {
+    T v;
+    if (k < dx) {
+      v = X[((size_t)(b * N + i) * S + s) * dx + k];
+    } else if (k < 3 * dx) {
+      const bool up = k < 2 * dx;
+      const int kk = up ? k - dx : k - 2 * dx;
+      const int j0 = up ? 0 : n_up, j1 = up ? n_up : N;
+      T acc = T(0);
+      for (int j = j0; j < j1; ++j) acc += X[((size_t)(b * N + j) * S + s) * dx + kk];
+      v = acc / (T)(up ? n_up : n_dn);
+    } else {
+      v = C[((size_t)(b * N + i) * S + s) * dc + (k - 3 * dx)];
+    }
+    f[k] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Convolution  conv_t(i) = sum_{senders j of type t} w_t(e_ji) * h_t(x_j)  (update_features.py:
 // 196-209; no normalisation) with the product rule on the augmented rows:
 //   value   sum_j w h
@@ -78,13 +138,17 @@ __global__ void gnn_edge_w_kernel(const T* __restrict__ r, const T* __restrict__
 // Hs / Ha: h_same(x_j) / h_anti(x_j) augmented rows [b][j][s][e]; Hne[M][e]: h_ne of the (constant)
 // nuclear embeddings.  C[b][i][s][3 e] = [conv_same | conv_anti | conv_ne].  Block per (b, i).
 // ------------------------------------------------------------------------------------------
+// Wsame / Wanti / Wne: the filters of the three edge types evaluated on ALL (i, jj) pairs (compact layout, M = number
+// of nuclear senders in it, 0 without 'ne' edges); the kernel reads the one matching the pair.  C has nt * e columns.
 template <class T>
-__global__ void gnn_conv_kernel(const T* __restrict__ Wc, const T* __restrict__ Hs, const T* __restrict__ Ha,
+__global__ void gnn_conv_kernel(const T* __restrict__ Wsame, const T* __restrict__ Wanti, const T* __restrict__ Wne,
+                                const T* __restrict__ Hs, const T* __restrict__ Ha,
                                 const T* __restrict__ Hne, int N, int M, int n_up, int S, int e,
                                 T* __restrict__ C) {
   const int bi = blockIdx.x, b = bi / N, i = bi - b * N;
   const int NS = N + M, T3 = S > 1 ? S - 2 : 0;
-  const T* wrow = Wc + (size_t)bi * NS * 8 * e;
+  const int nt = M > 0 ? 3 : 2;
+  const size_t wbase = (size_t)bi * NS * 8 * e;
   for (int idx = threadIdx.x; idx < S * e; idx += blockDim.x) {
     const int s = idx / e, f = idx - s * e;
     T acc_same = T(0), acc_anti = T(0), acc_ne = T(0);
@@ -92,8 +156,8 @@ __global__ void gnn_conv_kernel(const T* __restrict__ Wc, const T* __restrict__ 
     const int te = t / 3, tc = t - 3 * te;
     for (int j = 0; j < N; ++j) {
       if (j == i) continue;
-      const T* w = wrow + (size_t)j * 8 * e + f;
       const bool same = (i < n_up) == (j < n_up);
+      const T* w = (same ? Wsame : Wanti) + wbase + (size_t)j * 8 * e + f;
       const T* h = (same ? Hs : Ha) + ((size_t)(b * N + j) * S) * e + f;
       T v;
       if (s == 0) {
@@ -112,14 +176,15 @@ __global__ void gnn_conv_kernel(const T* __restrict__ Wc, const T* __restrict__ 
       if (same) acc_same += v; else acc_anti += v;
     }
     for (int m = 0; m < M; ++m) {
-      const T* w = wrow + (size_t)(N + m) * 8 * e + f;
+      const T* w = Wne + wbase + (size_t)(N + m) * 8 * e + f;
       const T h0 = Hne[m * e + f];
       if (s == 0) acc_ne += w[0] * h0;
       else if (s <= T3) { if (te == i) acc_ne += w[(1 + tc) * e] * h0; }
       else acc_ne += w[7 * e] * h0;
     }
-    T* c = C + ((size_t)bi * S + s) * 3 * e;
-    c[f] = acc_same; c[e + f] = acc_anti; c[2 * e + f] = acc_ne;
+    T* c = C + ((size_t)bi * S + s) * nt * e;
+    c[f] = acc_same; c[e + f] = acc_anti;
+    if (nt == 3) c[2 * e + f] = acc_ne;
   }
 }
 

@@ -58,20 +58,45 @@ def param_shapes(spec: AnsatzSpec) -> dict[str, tuple[int, ...]]:
     N, M, d, K = spec.n_elec, spec.n_nuc, spec.embedding_dim, spec.n_determinants
     s: dict[str, tuple[int, ...]] = {}
     if spec.kind == 'paulinet':
-        # reference: tests/conf/ansatz.yaml; wf/env.py:10-75 (per_shell, shared zetas, spin-restricted)
+        # reference: tests/conf/ansatz.yaml / conf/ansatz/default.yaml; wf/env.py:10-75
         n_env, e = len(spec.env_centers), spec.edge_dim
-        s[f'{ENV}:pi'] = (K * N, n_env)
-        s[f'{ENV}:zetas'] = (n_env,)
-        s[GNN + 'electron_embedding/ElectronicEmbedding:embeddings'] = (1 if spec.n_up == spec.n_down else 2, d)
-        s[GNN + 'nuclei_embedding/~/embed:embeddings'] = (M, d)
+        if spec.env_per_shell:  # per_shell, shared zetas, spin-restricted
+            s[f'{ENV}:pi'] = (K * N, n_env)
+            s[f'{ENV}:zetas'] = (n_env,)
+        else:
+            for nm in ('pi_up', 'pi_down', 'zetas_up', 'zetas_down'):
+                s[f'{ENV}:{nm}'] = (K * N, M)
+        if spec.gnn_embedding == 'embed':
+            s[GNN + 'electron_embedding/ElectronicEmbedding:embeddings'] = (1 if spec.n_up == spec.n_down else 2, d)
+        if spec.gnn_conv_ne:
+            s[GNN + 'nuclei_embedding/~/embed:embeddings'] = (M, d)
+        types = EDGE_TYPES if spec.gnn_conv_ne else EDGE_TYPES[:2]
+        d_in, e_in = (d if spec.gnn_embedding == 'embed' else 4 * M), 4
         for l in range(spec.n_layers):
-            c = conv_prefix(l)
-            for t in EDGE_TYPES:
-                s[c + f'w_{t}/linear_0:w'] = (4, e)
-                s[c + f'h_{t}/linear_0:w'] = (d, e)
-                s[c + f'h_{t}/linear_0:b'] = (e,)
-                s[layer_prefix(l) + f'g_conv_{t}/linear_0:w'] = (e, d)
-                s[layer_prefix(l) + f'g_conv_{t}/linear_0:b'] = (d,)
+            c, lp = conv_prefix(l), layer_prefix(l)
+            for t in types:
+                dw = [e_in] + log_dims(e_in, e, spec.gnn_subnet_layers)   # w: edges -> two_particle_stream_dim
+                dh = [d_in if t != 'ne' else d] + log_dims(d_in if t != 'ne' else d, e, spec.gnn_subnet_layers)
+                for i in range(spec.gnn_subnet_layers):
+                    s[c + f'w_{t}/linear_{i}:w'] = (dw[i], dw[i + 1])
+                    if spec.gnn_update == 'concatenate':  # default.yaml: w_factory bias true; test ansatz: false
+                        s[c + f'w_{t}/linear_{i}:b'] = (dw[i + 1],)
+                    s[c + f'h_{t}/linear_{i}:w'] = (dh[i], dh[i + 1])
+                    s[c + f'h_{t}/linear_{i}:b'] = (dh[i + 1],)
+                if spec.gnn_update == 'featurewise':
+                    s[lp + f'g_conv_{t}/linear_0:w'] = (e, d)
+                    s[lp + f'g_conv_{t}/linear_0:b'] = (d,)
+            if spec.gnn_update == 'concatenate':
+                s[lp + 'g/linear_0:w'] = (3 * d_in + len(types) * e, d)
+                if spec.gnn_g_bias:
+                    s[lp + 'g/linear_0:b'] = (d,)
+            if spec.gnn_deep_edges and l < spec.n_layers - 1:
+                du = [e_in] + log_dims(e_in, e, spec.gnn_subnet_layers)
+                for i in range(spec.gnn_subnet_layers):
+                    s[lp + f'u/linear_{i}:w'] = (du[i], du[i + 1])
+                    s[lp + f'u/linear_{i}:b'] = (du[i + 1],)
+                e_in = e
+            d_in = d
         dj = [d] + log_dims(d, 1, spec.jastrow_layers) if spec.jastrow_layers else []
         for i in range(len(dj) - 1):
             s[JASTROW + f'linear_{i}:w'] = (dj[i], dj[i + 1])
@@ -82,7 +107,8 @@ def param_shapes(spec: AnsatzSpec) -> dict[str, tuple[int, ...]]:
             base = pre.rsplit('linear_0', 1)[0]
             for i in range(len(db) - 1):
                 s[base + f'linear_{i}:w'] = (db[i], db[i + 1])
-                s[base + f'linear_{i}:b'] = (db[i + 1],)
+                if spec.backflow_bias:
+                    s[base + f'linear_{i}:b'] = (db[i + 1],)
         if spec.conf_coeff == 'linear':
             s[CONF + ':w'] = (K, 1)
         return s

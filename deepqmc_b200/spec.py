@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import dataclasses
 
-__all__ = ['AnsatzSpec', 'psiformer_spec', 'ferminet_spec', 'transpsiformer_spec', 'paulinet_spec', 'log_dims']
+__all__ = ['AnsatzSpec', 'psiformer_spec', 'ferminet_spec', 'transpsiformer_spec', 'paulinet_spec', 'paulinet_default_spec', 'log_dims']
 
 
 @dataclasses.dataclass(frozen=True)
@@ -40,6 +40,16 @@ class AnsatzSpec:
     backflow_layers: int = 1        # hidden_layers ['log', n] of the per-spin backflow MLPs
     env_centers: tuple = ()         # per_shell envelopes: nucleus index of every envelope (wf/env.py:26-33)
     env_zeta_init: tuple = ()       # their initial exponents z / (k + 1)
+    # conv-GNN variants (tests/conf/ansatz.yaml vs conf/ansatz/default.yaml):
+    gnn_embedding: str = 'embed'    # 'embed': hk.Embed lookup | 'features': raw [|r_iI|, d_iI] for all nuclei (4 M wide)
+    gnn_update: str = 'featurewise' # 'featurewise': sum_t g_t(conv_t) | 'concatenate': g([h, mean_up h, mean_down h, conv_same, conv_anti])
+    gnn_conv_ne: bool = True        # nucleus -> electron convolution (needs the nuclear hk.Embed table)
+    gnn_subnet_layers: int = 1      # layers of the w / h (and u) MLPs (hidden_layers ['log', n])
+    gnn_deep_edges: bool = False    # deep_features 'shared': edge MLP u + normalised residual between layers
+    gnn_residual_normalize: bool = False  # electron ResidualConnection(normalize=...)
+    gnn_g_bias: bool = True
+    backflow_bias: bool = True
+    env_per_shell: bool = True      # False: one per-orbital exponent per nucleus, spin-unrestricted (as Psiformer)
 
     @property
     def n_elec(self):
@@ -100,3 +110,16 @@ def paulinet_spec(hamil, **kw):
     kw.setdefault('env_centers', tuple(c for c, _ in shells))
     kw.setdefault('env_zeta_init', tuple(z for _, z in shells))
     return AnsatzSpec('paulinet', hamil.n_up, hamil.n_down, hamil.n_nuc, **kw)
+
+
+def paulinet_default_spec(hamil, **kw):
+    """reference: src/deepqmc/conf/ansatz/default.yaml (the "PauliNet" column of SURVEY.md 8(a0)): raw
+    nucleus-electron features, 3 layers of [h, mean_up, mean_down, conv_same, conv_anti] -> Linear+tanh with
+    normalised residuals, two-layer tanh w / h MLPs, shared deep edge MLP, linear Jastrow and backflow,
+    full determinants, per-orbital envelopes, hk.Linear conf_coeff, DeepQMCCusp."""
+    d = dict(embedding_dim=128, n_layers=3, n_determinants=16, edge_dim=32, cusp='deepqmc', full_determinant=True,
+             conf_coeff='linear', mult_act='identity', jastrow_layers=1, backflow_layers=1, backflow_bias=False,
+             gnn_embedding='features', gnn_update='concatenate', gnn_conv_ne=False, gnn_subnet_layers=2,
+             gnn_deep_edges=True, gnn_residual_normalize=True, gnn_g_bias=False, env_per_shell=False)
+    d.update(kw)
+    return AnsatzSpec('paulinet', hamil.n_up, hamil.n_down, hamil.n_nuc, **d)

@@ -186,38 +186,71 @@ def ssp(x):
 
 
 def paulinet_embeddings(spec, params, r, R):
-    """conv-GNN of the reference's test ansatz (tests/conf/ansatz.yaml): embedding lookup
-    (gnn/electron_gnn.py:620-624; one electron type if n_up == n_down, :337-343), nuclear hk.Embed
-    (:514), per layer conv_t(i) = sum_senders w_t(e) * h_t(x_sender) for t in same / anti / ne
-    (gnn/update_features.py:162-238, graph.py:226-335; edges = receiver - sender, no
-    self-interaction; features [|d| eps-safe, d], edge_features.py:21-78), 'featurewise' update
-    sum_t g_t(conv_t) and residual (electron_gnn.py:243-259)."""
+    """conv-GNN of the reference's test ansatz (tests/conf/ansatz.yaml) and of conf/ansatz/default.yaml:
+    initial embeddings = hk.Embed lookup (gnn/electron_gnn.py:620-624; one electron type if n_up == n_down,
+    :337-343) or the raw nucleus-electron features [|d|, d] (:596-611); per layer
+    conv_t(i) = sum_senders w_t(e) * h_t(x_sender) for t in same / anti (/ ne) (gnn/update_features.py:162-238,
+    graph.py:226-335; edges = receiver - sender, no self-interaction; features [|d| eps-safe, d],
+    edge_features.py:21-78); update 'featurewise' sum_t g_t(conv_t) or 'concatenate'
+    g([h, mean_up h, mean_down h, conv_same, conv_anti]) (update_features.py:47-121, electron_gnn.py:243-259) with
+    (normalised) residual (hkext.py:116-137); optional shared edge MLP u with normalised residual between layers
+    (electron_gnn.py:160-192)."""
     N, n_up = spec.n_elec, spec.n_up
-    emb = _t(params, P.GNN + 'electron_embedding/ElectronicEmbedding:embeddings')
-    types = [0] * n_up + [int(spec.n_up != spec.n_down)] * spec.n_down
-    x = emb[types]  # [N, d]
-    xn = _t(params, P.GNN + 'nuclei_embedding/~/embed:embeddings')  # [M, d]
+    if spec.gnn_embedding == 'embed':
+        emb = _t(params, P.GNN + 'electron_embedding/ElectronicEmbedding:embeddings')
+        types = [0] * n_up + [int(spec.n_up != spec.n_down)] * spec.n_down
+        x = emb[types]  # [N, d]
+    else:
+        x, _ = ne_features(r, R, False)  # [N, 4M]
+    xn = _t(params, P.GNN + 'nuclei_embedding/~/embed:embeddings') if spec.gnn_conv_ne else None
 
     def feats(d):
         return torch.cat([safe_norm(d)[..., None], d], -1)
+
+    def mlp(base, h, n, bias=True):
+        for i in range(n):
+            h = h @ _t(params, base + f'linear_{i}:w')
+            if bias:
+                h = h + _t(params, base + f'linear_{i}:b')
+            h = torch.tanh(h)  # last_linear = false
+        return h
 
     up = torch.arange(N) < n_up
     same = (up[:, None] == up[None, :]) & ~torch.eye(N, dtype=torch.bool)  # [sender j, receiver i]
     anti = up[:, None] != up[None, :]
     e_ee = feats(r[None, :, :] - r[:, None, :])  # [j, i, 4] receiver - sender
-    e_ne = feats(r[None, :, :] - R[:, None, :])  # [I, i, 4]
+    e_ne = feats(r[None, :, :] - R[:, None, :]) if spec.gnn_conv_ne else None  # [I, i, 4]
+    nl = spec.gnn_subnet_layers
+    sq2 = math.sqrt(2.0)
     for l in range(spec.n_layers):
         c, lp = P.conv_prefix(l), P.layer_prefix(l)
-        upd = 0
-        for t, edges, mask, send in (('same', e_ee, same, x), ('anti', e_ee, anti, x), ('ne', e_ne, None, xn)):
-            we = torch.tanh(edges @ _t(params, c + f'w_{t}/linear_0:w'))  # [senders, N, e]
-            hx = torch.tanh(send @ _t(params, c + f'h_{t}/linear_0:w') + _t(params, c + f'h_{t}/linear_0:b'))
+        convs = []
+        kinds = [('same', e_ee, same, x), ('anti', e_ee, anti, x)] + ([('ne', e_ne, None, xn)] if spec.gnn_conv_ne else [])
+        for t, edges, mask, send in kinds:
+            we = mlp(c + f'w_{t}/', edges, nl, bias=spec.gnn_update == 'concatenate')  # [senders, N, e]
+            hx = mlp(c + f'h_{t}/', send, nl)
             prod = we * hx[:, None, :]
             if mask is not None:
                 prod = prod * mask[:, :, None].to(prod.dtype)
-            conv = prod.sum(0)  # [N, e]
-            upd = upd + torch.tanh(conv @ _t(params, lp + f'g_conv_{t}/linear_0:w') + _t(params, lp + f'g_conv_{t}/linear_0:b'))
-        x = x + upd if upd.shape == x.shape else upd  # ResidualConnection(normalize=False), hkext.py:116-137
+            convs.append((t, prod.sum(0)))  # [N, e]
+        if spec.gnn_update == 'featurewise':
+            upd = 0
+            for t, cv in convs:
+                upd = upd + torch.tanh(cv @ _t(params, lp + f'g_conv_{t}/linear_0:w') + _t(params, lp + f'g_conv_{t}/linear_0:b'))
+        else:
+            f = torch.cat([x, x[:n_up].mean(0, keepdim=True).expand(N, -1), x[n_up:].mean(0, keepdim=True).expand(N, -1)]
+                          + [cv for _, cv in convs], -1)
+            upd = f @ _t(params, lp + 'g/linear_0:w')
+            if spec.gnn_g_bias:
+                upd = upd + _t(params, lp + 'g/linear_0:b')
+            upd = torch.tanh(upd)
+        if upd.shape == x.shape:
+            x = (x + upd) / sq2 if spec.gnn_residual_normalize else x + upd
+        else:
+            x = upd
+        if spec.gnn_deep_edges and l < spec.n_layers - 1:  # shared edge MLP, same + anti edges alike
+            ne_ = mlp(lp + 'u/', e_ee, nl)
+            e_ee = (e_ee + ne_) / sq2 if ne_.shape == e_ee.shape else ne_
     return x
 
 
@@ -227,10 +260,10 @@ def paulinet_log_psi(spec, params, r, R):
     N, K, n_up, n_dn = spec.n_elec, spec.n_determinants, spec.n_up, spec.n_down
     x = paulinet_embeddings(spec, params, r, R)
 
-    def mlp(base, h, n_lin, act, bias_last):
+    def mlp(base, h, n_lin, act, bias_last, bias=True):
         for i in range(n_lin):
             h = h @ _t(params, base + f'linear_{i}:w')
-            if i < n_lin - 1 or bias_last:
+            if bias and (i < n_lin - 1 or bias_last):
                 h = h + _t(params, base + f'linear_{i}:b')
             if i < n_lin - 1:
                 h = act(h)
@@ -238,20 +271,36 @@ def paulinet_log_psi(spec, params, r, R):
 
     jastrow = mlp(P.JASTROW, x.sum(0), spec.jastrow_layers, ssp, False).squeeze(-1) if spec.jastrow_layers else 0.0
     # envelopes (wf/env.py:57-75: per_shell, shared exponents, spin-restricted) -> [K, N_el, N_orb]
-    centers = list(spec.env_centers)
-    dist = safe_norm(r[:, None] - R[None])[:, centers]  # [N, n_env]
-    zeta, pi = _t(params, f'{P.ENV}:zetas'), _t(params, f'{P.ENV}:pi')
-    orb = (pi[None] * torch.exp(-torch.abs(zeta * dist))[:, None, :]).sum(-1)  # [N, K*N]
-    orb = orb.reshape(N, K, N).permute(1, 0, 2)
+    if spec.env_per_shell:
+        centers = list(spec.env_centers)
+        dist = safe_norm(r[:, None] - R[None])[:, centers]  # [N, n_env]
+        zeta, pi = _t(params, f'{P.ENV}:zetas'), _t(params, f'{P.ENV}:pi')
+        orb = (pi[None] * torch.exp(-torch.abs(zeta * dist))[:, None, :]).sum(-1)  # [N, K*N]
+        orb = orb.reshape(N, K, N).permute(1, 0, 2)
+    else:  # per-orbital exponents, one shell per nucleus, spin-unrestricted (conf/ansatz/default.yaml:3-11)
+        dist = safe_norm(r[:, None] - R[None])  # [N, M]
+        rows = []
+        for spin, sl in (('up', slice(0, n_up)), ('down', slice(n_up, N))):
+            zeta, pi = _t(params, f'{P.ENV}:zetas_{spin}'), _t(params, f'{P.ENV}:pi_{spin}')
+            rows.append((pi[None] * torch.exp(-torch.abs(zeta[None] * dist[sl][:, None, :]))).sum(-1))  # [n, K*N]
+        orb = torch.cat(rows, 0).reshape(N, K, N).permute(1, 0, 2)
     mult = (lambda v: 1 + 2 * torch.tanh(v / 4)) if spec.mult_act == 'default' else (lambda v: v)
-    signs, logs = 1.0, 0.0
+    signs, logs, blocks = 1.0, 0.0, []
     for sl, osl, pre, n in ((slice(0, n_up), slice(0, n_up), P.BF_UP, n_up), (slice(n_up, N), slice(n_up, N), P.BF_DN, n_dn)):
         base = pre.rsplit('linear_0', 1)[0]
-        f = mlp(base, x[sl], spec.backflow_layers, ssp, True)  # [n, K * n]
-        f = f.reshape(n, K, n).permute(1, 0, 2)  # wf/omni.py:78-88
+        n_orb = N if spec.full_determinant else n
+        f = mlp(base, x[sl], spec.backflow_layers, ssp, True, bias=spec.backflow_bias)  # [n, K * n_orb]
+        f = f.reshape(n, K, n_orb).permute(1, 0, 2)  # wf/omni.py:78-88
+        if spec.full_determinant:
+            osl = slice(0, N)
         a = orb[:, sl, osl] * mult(f)
+        if spec.full_determinant:
+            blocks.append(a)
+            continue
         s, l = torch.linalg.slogdet(a) if n > 0 else (torch.ones(K, dtype=r.dtype), torch.zeros(K, dtype=r.dtype))
         signs, logs = signs * s, logs + l
+    if spec.full_determinant:
+        signs, logs = torch.linalg.slogdet(torch.cat(blocks, 1))
     shift = logs.max().detach()
     if torch.isinf(shift):
         shift = torch.zeros_like(shift)
