@@ -37,6 +37,9 @@ class DqmcConfig(C.Structure):
         ('factorized_det', C.c_int32), ('conf_linear', C.c_int32), ('mult_act', C.c_int32),
         ('n_elec_types', C.c_int32), ('jastrow_n', C.c_int32), ('jastrow_dims', C.c_int32 * 8),
         ('backflow_n', C.c_int32), ('backflow_dims', C.c_int32 * 8),
+        ('gnn_features', C.c_int32), ('gnn_concat', C.c_int32), ('gnn_conv_ne', C.c_int32), ('gnn_sub_n', C.c_int32),
+        ('gnn_deep_edges', C.c_int32), ('gnn_res_norm', C.c_int32), ('gnn_g_bias', C.c_int32), ('gnn_w_bias', C.c_int32),
+        ('gnn_w_dims', C.c_int32 * 32), ('gnn_h_dims', C.c_int32 * 32), ('gnn_u_dims', C.c_int32 * 32),
     ]
 
 

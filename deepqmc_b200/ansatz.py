@@ -13,7 +13,7 @@ import torch
 
 from . import params as PN
 from .engine import Engine
-from .spec import AnsatzSpec, ferminet_spec, paulinet_spec, psiformer_spec, transpsiformer_spec
+from .spec import AnsatzSpec, ferminet_spec, paulinet_default_spec, paulinet_spec, psiformer_spec, transpsiformer_spec
 from .types import PhysicalConfiguration, Psi
 
 
@@ -21,7 +21,8 @@ class B200Ansatz:
     def __init__(self, hamil, kind='psiformer', dtype='float64', device=None, gemm_backend=0, **hyper):
         self.hamil = hamil
         self.spec: AnsatzSpec = {'psiformer': psiformer_spec, 'ferminet': ferminet_spec,
-                                 'transpsiformer': transpsiformer_spec, 'paulinet': paulinet_spec}[kind](hamil, **hyper)
+                                 'transpsiformer': transpsiformer_spec, 'paulinet': paulinet_spec,
+                                 'paulinet_default': paulinet_default_spec}[kind](hamil, **hyper)
         self.dtype, self.device, self.gemm_backend = dtype, device, gemm_backend
         self._engine = None
         self._uploaded = None

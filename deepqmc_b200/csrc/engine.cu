@@ -81,15 +81,48 @@ struct EngineBase {
     }
     int bf_in = d;  // input width of the final backflow layer
     if (cfg.kind == DQMC_PAULINET) {
-      // reference tests/conf/ansatz.yaml; names of the engine entries mirror the Haiku modules
-      const int e = cfg.edge_dim;
-      add("emb.table", cfg.n_elec_types > 0 ? cfg.n_elec_types : 1, d);
+      // reference tests/conf/ansatz.yaml and conf/ansatz/default.yaml; entry names mirror the Haiku modules
+      const int e = cfg.edge_dim, nl = cfg.gnn_sub_n > 0 ? cfg.gnn_sub_n : 1;
+      if (!cfg.gnn_features) add("emb.table", cfg.n_elec_types > 0 ? cfg.n_elec_types : 1, d);
+      int dcur = cfg.gnn_features ? 4 * M : d, ecur = 4;
+      const int nt = cfg.gnn_conv_ne ? 3 : 2;
+      const char* tn[3] = {"same", "anti", "ne"};
       for (int l = 0; l < cfg.n_layers; ++l) {
         std::string p = "G" + std::to_string(l) + ".";
-        for (const char* t : {"same", "anti", "ne"}) add(p + "w_" + t, 4, e);
-        for (const char* t : {"same", "anti"}) { add(p + "h_" + t + ".w", d, e); add(p + "h_" + t + ".b", 1, e); }
-        add(p + "hne", M, e);  // tanh(h_ne(nuclear embedding)): walker-independent, evaluated on the host
-        for (const char* t : {"same", "anti", "ne"}) { add(p + "g_" + t + ".w", e, d); add(p + "g_" + t + ".b", 1, d); }
+        for (int t = 0; t < nt; ++t) {
+          int din = ecur;
+          for (int i = 0; i < nl; ++i) {
+            const std::string q = p + "w_" + tn[t] + "." + std::to_string(i);
+            add(q + ".w", din, cfg.gnn_w_dims[l][i]);
+            if (cfg.gnn_w_bias) add(q + ".b", 1, cfg.gnn_w_dims[l][i]);
+            din = cfg.gnn_w_dims[l][i];
+          }
+          if (t < 2) {
+            din = dcur;
+            for (int i = 0; i < nl; ++i) {
+              const std::string q = p + "h_" + tn[t] + "." + std::to_string(i);
+              add(q + ".w", din, cfg.gnn_h_dims[l][i]); add(q + ".b", 1, cfg.gnn_h_dims[l][i]);
+              din = cfg.gnn_h_dims[l][i];
+            }
+          } else {
+            add(p + "hne", M, e);  // h_ne(nuclear embedding table): walker-independent, evaluated on the host
+          }
+          if (!cfg.gnn_concat) { add(p + "g_" + tn[t] + ".w", e, d); add(p + "g_" + tn[t] + ".b", 1, d); }
+        }
+        if (cfg.gnn_concat) {
+          add(p + "g.w", 3 * dcur + nt * e, d);
+          if (cfg.gnn_g_bias) add(p + "g.b", 1, d);
+        }
+        if (cfg.gnn_deep_edges && l < cfg.n_layers - 1) {
+          int din = ecur;
+          for (int i = 0; i < nl; ++i) {
+            const std::string q = p + "u." + std::to_string(i);
+            add(q + ".w", din, cfg.gnn_u_dims[l][i]); add(q + ".b", 1, cfg.gnn_u_dims[l][i]);
+            din = cfg.gnn_u_dims[l][i];
+          }
+          ecur = e;
+        }
+        dcur = d;
       }
       int din = d;
       for (int i = 0; i < cfg.jastrow_n; ++i) {
@@ -384,7 +417,8 @@ struct Engine : EngineBase {
   // ---- workspace ---------------------------------------------------------------------------
   struct Ws {
     T *X, *O, *A, *M1, *QKV, *BF, *dsign, *dlog, *dlap, *dgrad;
-    T *G0 = nullptr, *G1 = nullptr, *G2 = nullptr, *Hs = nullptr, *Ha = nullptr, *C = nullptr, *Wc = nullptr,
+    T *G0 = nullptr, *G1 = nullptr, *G2 = nullptr, *Hs = nullptr, *Ha = nullptr, *C = nullptr, *Fc = nullptr, *HT = nullptr,
+      *E0 = nullptr, *E1 = nullptr, *ET0 = nullptr, *ET1 = nullptr, *W3 = nullptr,
       *Y0 = nullptr, *Y1 = nullptr, *Jb = nullptr;  // conv-GNN trunk
     size_t bytes;
   };
@@ -392,6 +426,22 @@ struct Engine : EngineBase {
     int h = 1;
     for (int i = 0; i < cfg.backflow_n; ++i) h = cfg.backflow_dims[i] > h ? cfg.backflow_dims[i] : h;
     return h;
+  }
+  int gnn_dmax() const { return cfg.gnn_features && 4 * M > d ? 4 * M : d; }
+  int gnn_emax() const {  // widest edge-side row (raw features, w / u hidden and output widths)
+    int m = cfg.edge_dim > 4 ? cfg.edge_dim : 4;
+    for (int l = 0; l < cfg.n_layers && l < 8; ++l)
+      for (int i = 0; i < cfg.gnn_sub_n && i < 4; ++i) {
+        m = cfg.gnn_w_dims[l][i] > m ? cfg.gnn_w_dims[l][i] : m;
+        m = cfg.gnn_u_dims[l][i] > m ? cfg.gnn_u_dims[l][i] : m;
+      }
+    return m;
+  }
+  int gnn_hnode_max() const {
+    int m = cfg.edge_dim;
+    for (int l = 0; l < cfg.n_layers && l < 8; ++l)
+      for (int i = 0; i < cfg.gnn_sub_n && i < 4; ++i) m = cfg.gnn_h_dims[l][i] > m ? cfg.gnn_h_dims[l][i] : m;
+    return m;
   }
   int gnn_jsum() const {
     int j = d;
@@ -402,9 +452,10 @@ struct Engine : EngineBase {
     size_t rows = (size_t)N * S;
     size_t dets = (size_t)K * (3 + (S > 1 ? T3 : 0));
     if (gnn) {
-      const size_t e = cfg.edge_dim;
-      return rows * (5 * (size_t)d + 5 * e + 2 * (size_t)gnn_hmax() + KN) + (size_t)N * (N + M) * 8 * e +
-             (size_t)S * gnn_jsum() + dets;
+      const size_t e = cfg.edge_dim, dm = gnn_dmax(), em = gnn_emax(), hn = gnn_hnode_max();
+      const size_t pairs8 = (size_t)N * (N + (cfg.gnn_conv_ne ? M : 0)) * 8;
+      return rows * (2 * dm + 3 * (size_t)d + (3 * dm + 3 * e) + 2 * e + hn + 3 * e + 2 * (size_t)gnn_hmax() + KN) +
+             pairs8 * (4 * em + 3 * e) + (size_t)S * gnn_jsum() + dets;
     }
     if (cfg.kind == DQMC_FERMINET) {
       const size_t de = cfg.edge_dim, fin = 3 * (size_t)d + 2 * de;
@@ -419,10 +470,13 @@ struct Engine : EngineBase {
     char* p = (char*)base;
     auto take = [&](size_t n) { T* q = (T*)p; p += align_up(sizeof(T) * n); return q; };
     if (gnn) {
-      const size_t e = cfg.edge_dim, hm = gnn_hmax();
-      w.X = take(rows * d); w.O = take(rows * d); w.G0 = take(rows * d); w.G1 = take(rows * d); w.G2 = take(rows * d);
-      w.Hs = take(rows * e); w.Ha = take(rows * e); w.C = take(rows * 3 * e);
-      w.Wc = take((size_t)Bc * N * (N + M) * 8 * e);
+      const size_t e = cfg.edge_dim, hm = gnn_hmax(), dm = gnn_dmax(), em = gnn_emax(), hn = gnn_hnode_max();
+      const size_t pairs8 = (size_t)Bc * N * (N + (cfg.gnn_conv_ne ? M : 0)) * 8;
+      w.X = take(rows * dm); w.O = take(rows * dm); w.G0 = take(rows * d); w.G1 = take(rows * d); w.G2 = take(rows * d);
+      w.Fc = take(rows * (3 * dm + 3 * e)); w.Hs = take(rows * e); w.Ha = take(rows * e); w.HT = take(rows * hn);
+      w.C = take(rows * 3 * e);
+      w.E0 = take(pairs8 * em); w.E1 = take(pairs8 * em); w.ET0 = take(pairs8 * em); w.ET1 = take(pairs8 * em);
+      w.W3 = take(pairs8 * 3 * e);
       w.Y0 = take(rows * hm); w.Y1 = take(rows * hm); w.Jb = take((size_t)Bc * S * gnn_jsum());
       w.A = w.M1 = w.QKV = nullptr;
       w.BF = take(rows * KN);
@@ -445,7 +499,7 @@ struct Engine : EngineBase {
     int64_t c = (wsb - 16 * 256) / per;
     int64_t row_cap = (int64_t)2000000000 / ((int64_t)N * S * 3 * d);  // keep 32-bit row*ld products safe
     if (cfg.kind == DQMC_FERMINET) row_cap = (int64_t)2000000000 / ((int64_t)N * N * S * (3 * d + 64));
-    if (gnn) row_cap = (int64_t)2000000000 / ((int64_t)N * (N + M + S) * (8 * cfg.edge_dim + 3 * d + KN));
+    if (gnn) row_cap = (int64_t)2000000000 / ((int64_t)N * (N + M + S) * (8 * gnn_emax() + 3 * gnn_dmax() + 3 * cfg.edge_dim + KN));
     if (c > row_cap) c = row_cap;
     if (c > B) c = B;
     return (int)c;
@@ -623,38 +677,106 @@ struct Engine : EngineBase {
   // conv-GNN trunk (reference tests/conf/ansatz.yaml): embedding lookup, per layer edge filters w_t, node
   // transforms h_t, convolution over same / anti / ne edges, featurewise update sum_t g_t(conv_t) + residual;
   // then the Jastrow MLP on sum_i x_i and the hidden layers of the per-spin backflow MLPs (ssp).
+  // MLP of `nl` Linear(+bias)+tanh layers on augmented rows (groups of Sg slots): in -> out, ping-pong through tmp
+  int gnn_mlp(const T* in, int din, const std::string& base, const int* dims, int nl, bool bias, T* tmp, T* out, int rows_,
+              int Sg, cudaStream_t st) {
+    const T* cur = in;
+    int dc = din;
+    for (int i = 0; i < nl; ++i) {
+      T* dst = (i == nl - 1) ? out : tmp;
+      const std::string q = base + "." + std::to_string(i);
+      int rc = gemm(cur, dc, (q + ".w").c_str(), nullptr, 0, dims[i], bias ? P(q + ".b") : nullptr, nullptr, 0, dst, dims[i], rows_,
+                    dims[i], dc, Sg, 0, 1, st);
+      if (rc) return rc;
+      DQ_LAUNCH(act_fl_kernel<T>, dim3(rows_ / Sg, (dims[i] + 63) / 64), dim3(64), 0, st, dst, dims[i], (const T*)nullptr, 0, Sg,
+                dims[i], T(1), 0);
+      cur = dst; dc = dims[i];
+    }
+    return 0;
+  }
+
   int paulinet_trunk(const T* r, const T* R, int Rb, int Bc, int S, Ws& w, T** Xbf, const T** jastrow, cudaStream_t st) {
-    const int rows = Bc * N * S, e = cfg.edge_dim, groups = Bc * N;
-    DQ_LAUNCH(gnn_embed_kernel<T>, dim3((Bc * N * d + 127) / 128), dim3(128), 0, st, P("emb.table"),
-              cfg.n_elec_types > 0 ? cfg.n_elec_types : 1, N, cfg.n_up, S, d, w.X, Bc * N);
+    const int rows = Bc * N * S, e = cfg.edge_dim, groups = Bc * N, nl = cfg.gnn_sub_n > 0 ? cfg.gnn_sub_n : 1;
+    const int Mne = cfg.gnn_conv_ne ? M : 0, NS = N + Mne, nt = cfg.gnn_conv_ne ? 3 : 2;
+    const int pairs = Bc * N * NS, prow = pairs * 8;  // compact edge rows: 8 slots per (receiver, sender) pair
+    const T isq2 = (T)0.70710678118654752440;
+    int dcur = d, ecur = 4;
+    if (cfg.gnn_features) {
+      dcur = 4 * M;
+      DQ_LAUNCH(embed_kernel<T>, dim3(Bc * N), dim3(128), sizeof(T) * 5 * dcur, st, r, R, Rb, N, M, cfg.n_up, S, 0, 0,
+                (const T*)nullptr, dcur, w.X, Bc * N, 1);
+    } else {
+      DQ_LAUNCH(gnn_embed_kernel<T>, dim3((Bc * N * d + 127) / 128), dim3(128), 0, st, P("emb.table"),
+                cfg.n_elec_types > 0 ? cfg.n_elec_types : 1, N, cfg.n_up, S, d, w.X, Bc * N);
+    }
+    DQ_LAUNCH(gnn_edge_feat_kernel<T>, dim3((pairs + 63) / 64), dim3(64), 0, st, r, R, Rb, N, M, Mne, w.E0, pairs);
     T* X = w.X;
     T* Xn = w.O;
+    T* E = w.E0;
+    T* En = w.E1;
+    const char* tn[3] = {"same", "anti", "ne"};
     for (int l = 0; l < cfg.n_layers; ++l) {
       const std::string p = "G" + std::to_string(l) + ".";
-      const int tot = Bc * N * (N + M);
-      DQ_LAUNCH(gnn_edge_w_kernel<T>, dim3((tot + 63) / 64), dim3(64), 0, st, r, R, Rb, N, M, cfg.n_up, P(p + "w_same"),
-                P(p + "w_anti"), P(p + "w_ne"), e, w.Wc, tot);
-      int rc = gemm(X, d, (p + "h_same.w").c_str(), nullptr, 0, e, P(p + "h_same.b"), nullptr, 0, w.Hs, e, rows, e, d, S, 0, N, st);
-      if (rc) return rc;
-      rc = gemm(X, d, (p + "h_anti.w").c_str(), nullptr, 0, e, P(p + "h_anti.b"), nullptr, 0, w.Ha, e, rows, e, d, S, 0, N, st);
-      if (rc) return rc;
-      DQ_LAUNCH(act_fl_kernel<T>, dim3(groups, (e + 63) / 64), dim3(64), 0, st, w.Hs, e, (const T*)nullptr, 0, S, e, T(1), 0);
-      DQ_LAUNCH(act_fl_kernel<T>, dim3(groups, (e + 63) / 64), dim3(64), 0, st, w.Ha, e, (const T*)nullptr, 0, S, e, T(1), 0);
-      DQ_LAUNCH(gnn_conv_kernel<T>, dim3(groups), dim3(128), 0, st, (const T*)w.Wc, (const T*)w.Hs, (const T*)w.Ha,
-                P(p + "hne"), N, M, cfg.n_up, S, e, w.C);
-      // featurewise update: x <- x + sum_t tanh(g_t(conv_t))   (electron_gnn.py:243-259, residual hkext.py:116-137)
-      T* G[3] = {w.G0, w.G1, w.G2};
-      const char* tn[3] = {"same", "anti", "ne"};
-      const T* res = X;
-      for (int t = 0; t < 3; ++t) {
-        rc = gemm(w.C + t * e, 3 * e, (p + "g_" + tn[t] + ".w").c_str(), nullptr, 0, d, P(p + "g_" + tn[t] + ".b"), nullptr, 0,
-                  G[t], d, rows, d, e, S, 0, N, st);
+      // edge filters of every type on all pairs (compact rows), node transforms h_same / h_anti
+      for (int t = 0; t < nt; ++t) {
+        int rc = gnn_mlp(E, ecur, p + "w_" + tn[t], cfg.gnn_w_dims[l], nl, cfg.gnn_w_bias != 0, w.ET0, w.W3 + (size_t)t * prow * e,
+                         prow, 8, st);
         if (rc) return rc;
-        DQ_LAUNCH(act_fl_kernel<T>, dim3(groups, (d + 63) / 64), dim3(64), 0, st, G[t], d, res, d, S, d, T(1), 0);
-        res = G[t];
       }
-      // G2 now holds x + sum_t ...; ping-pong it with the X buffers
-      T* tmp = X; X = w.G2; w.G2 = Xn; Xn = tmp;
+      int rc = gnn_mlp(X, dcur, p + "h_same", cfg.gnn_h_dims[l], nl, true, w.HT, w.Hs, rows, S, st);
+      if (rc) return rc;
+      rc = gnn_mlp(X, dcur, p + "h_anti", cfg.gnn_h_dims[l], nl, true, w.HT, w.Ha, rows, S, st);
+      if (rc) return rc;
+      DQ_LAUNCH(gnn_conv_kernel<T>, dim3(groups), dim3(128), 0, st, (const T*)w.W3, (const T*)(w.W3 + (size_t)prow * e),
+                (const T*)(w.W3 + (size_t)2 * prow * e), (const T*)w.Hs, (const T*)w.Ha,
+                cfg.gnn_conv_ne ? P(p + "hne") : (const T*)nullptr, N, Mne, cfg.n_up, S, e, w.C);
+      T* Xout;
+      if (cfg.gnn_concat) {
+        // x <- [(x +) tanh(g([x, mean_up x, mean_down x, conv_*]))] (/ sqrt 2)   (electron_gnn.py:243-259)
+        const int fin = 3 * dcur + nt * e;
+        DQ_LAUNCH(gnn_concat_kernel<T>, dim3(Bc * S, N), dim3(128), 0, st, (const T*)X, dcur, (const T*)w.C, nt * e, N, cfg.n_up,
+                  S, w.Fc);
+        rc = gemm(w.Fc, fin, (p + "g.w").c_str(), nullptr, 0, d, cfg.gnn_g_bias ? P(p + "g.b") : nullptr, nullptr, 0, Xn, d, rows,
+                  d, fin, S, 0, N, st);
+        if (rc) return rc;
+        const bool res = dcur == d;
+        DQ_LAUNCH(act_fl_kernel<T>, dim3(groups, (d + 63) / 64), dim3(64), 0, st, Xn, d, res ? (const T*)X : (const T*)nullptr,
+                  d, S, d, (res && cfg.gnn_res_norm) ? isq2 : T(1), 0);
+        Xout = Xn; Xn = X;
+      } else {
+        // featurewise update: x <- x + sum_t tanh(g_t(conv_t))   (residual hkext.py:116-137)
+        T* G[3] = {w.G0, w.G1, w.G2};
+        const T* res = dcur == d ? X : nullptr;
+        for (int t = 0; t < nt; ++t) {
+          rc = gemm(w.C + t * e, nt * e, (p + "g_" + tn[t] + ".w").c_str(), nullptr, 0, d, P(p + "g_" + tn[t] + ".b"), nullptr,
+                    0, G[t], d, rows, d, e, S, 0, N, st);
+          if (rc) return rc;
+          const bool last = t == nt - 1;
+          DQ_LAUNCH(act_fl_kernel<T>, dim3(groups, (d + 63) / 64), dim3(64), 0, st, G[t], d, res, d, S, d,
+                    (last && res && cfg.gnn_res_norm) ? isq2 : T(1), 0);
+          res = G[t];
+        }
+        Xout = G[nt - 1];
+        // the accumulated buffer becomes the new x; hand the old x buffer to the G slot
+        T* old = X;
+        if (nt == 3) w.G2 = old; else w.G1 = old;
+      }
+      X = Xout;
+      dcur = d;
+      if (cfg.gnn_deep_edges && l < cfg.n_layers - 1) {
+        // shared edge MLP u on the compact rows + normalised residual (electron_gnn.py:160-192)
+        rc = gnn_mlp(E, ecur, p + "u", cfg.gnn_u_dims[l], nl, true, w.ET0, w.ET1, prow, 8, st);
+        if (rc) return rc;
+        if (ecur == e) {
+          // (e + u(e)) / sqrt 2: u's last tanh already applied -> plain scaled add on all slots
+          DQ_LAUNCH((axpby_kernel<T>), dim3((unsigned)(((size_t)prow * e + 255) / 256)), dim3(256), 0, st, (const T*)E,
+                    (const T*)w.ET1, isq2, En, (size_t)prow * e);
+          T* tmp = E; E = En; En = tmp;
+        } else {
+          T* tmp = E; E = w.ET1; w.ET1 = tmp;
+        }
+        ecur = e;
+      }
     }
     *jastrow = nullptr;
     if (cfg.jastrow_n > 0) {

@@ -228,6 +228,13 @@ __global__ void act_fl_kernel(T* __restrict__ Z, int ldz, const T* __restrict__ 
   }
 }
 
+// out = scale * (a + b), elementwise (normalised residual of the edge stream)
+template <class T>
+__global__ void axpby_kernel(const T* __restrict__ a, const T* __restrict__ b, T scale, T* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = scale * (a[i] + b[i]);
+}
+
 // Sum over the electrons of a walker, slot-wise (Jastrow with sum_first, wf/omni.py:35-37):
 // Y[b][s][f] = sum_i X[b][i][s][f].  One thread per (b, s, f).
 template <class T>

@@ -45,19 +45,40 @@ def _pack_haiku_params(spec: AnsatzSpec, params: dict, R=None) -> dict[str, np.n
             out[f'L{l}.w2'], out[f'L{l}.b2'] = g(a + 'mlp/linear_1:w'), g(a + 'mlp/linear_1:b')[None]
     elif spec.kind == 'paulinet':
         N, K, M, d, n_up = spec.n_elec, spec.n_determinants, spec.n_nuc, spec.embedding_dim, spec.n_up
-        out['emb.table'] = g(PN.GNN + 'electron_embedding/ElectronicEmbedding:embeddings')
-        xn = g(PN.GNN + 'nuclei_embedding/~/embed:embeddings')
+        nl = spec.gnn_subnet_layers
+        if spec.gnn_embedding == 'embed':
+            out['emb.table'] = g(PN.GNN + 'electron_embedding/ElectronicEmbedding:embeddings')
+        types = PN.EDGE_TYPES if spec.gnn_conv_ne else PN.EDGE_TYPES[:2]
+        xn = g(PN.GNN + 'nuclei_embedding/~/embed:embeddings') if spec.gnn_conv_ne else None
+        w_bias = spec.gnn_update == 'concatenate'
         for l in range(spec.n_layers):
             c, lp = PN.conv_prefix(l), PN.layer_prefix(l)
-            for t in PN.EDGE_TYPES:
-                out[f'G{l}.w_{t}'] = g(c + f'w_{t}/linear_0:w')
-                out[f'G{l}.g_{t}.w'] = g(lp + f'g_conv_{t}/linear_0:w')
-                out[f'G{l}.g_{t}.b'] = g(lp + f'g_conv_{t}/linear_0:b')[None]
-            for t in ('same', 'anti'):
-                out[f'G{l}.h_{t}.w'] = g(c + f'h_{t}/linear_0:w')
-                out[f'G{l}.h_{t}.b'] = g(c + f'h_{t}/linear_0:b')[None]
-            # nuclear embeddings are an hk.Embed lookup (gnn/electron_gnn.py:514): h_ne of them is walker-independent
-            out[f'G{l}.hne'] = np.tanh(xn @ g(c + 'h_ne/linear_0:w') + g(c + 'h_ne/linear_0:b'))
+            for t in types:
+                for i in range(nl):
+                    out[f'G{l}.w_{t}.{i}.w'] = g(c + f'w_{t}/linear_{i}:w')
+                    if w_bias:
+                        out[f'G{l}.w_{t}.{i}.b'] = g(c + f'w_{t}/linear_{i}:b')[None]
+                if t != 'ne':
+                    for i in range(nl):
+                        out[f'G{l}.h_{t}.{i}.w'] = g(c + f'h_{t}/linear_{i}:w')
+                        out[f'G{l}.h_{t}.{i}.b'] = g(c + f'h_{t}/linear_{i}:b')[None]
+                else:
+                    # nuclear embeddings are an hk.Embed lookup (gnn/electron_gnn.py:514): h_ne of them is walker-independent
+                    hn = xn
+                    for i in range(nl):
+                        hn = np.tanh(hn @ g(c + f'h_ne/linear_{i}:w') + g(c + f'h_ne/linear_{i}:b'))
+                    out[f'G{l}.hne'] = hn
+                if spec.gnn_update == 'featurewise':
+                    out[f'G{l}.g_{t}.w'] = g(lp + f'g_conv_{t}/linear_0:w')
+                    out[f'G{l}.g_{t}.b'] = g(lp + f'g_conv_{t}/linear_0:b')[None]
+            if spec.gnn_update == 'concatenate':
+                out[f'G{l}.g.w'] = g(lp + 'g/linear_0:w')
+                if spec.gnn_g_bias:
+                    out[f'G{l}.g.b'] = g(lp + 'g/linear_0:b')[None]
+            if spec.gnn_deep_edges and l < spec.n_layers - 1:
+                for i in range(nl):
+                    out[f'G{l}.u.{i}.w'] = g(lp + f'u/linear_{i}:w')
+                    out[f'G{l}.u.{i}.b'] = g(lp + f'u/linear_{i}:b')[None]
         for i in range(spec.jastrow_layers):
             out[f'J{i}.w'] = g(PN.JASTROW + f'linear_{i}:w')
             if i < spec.jastrow_layers - 1:
@@ -67,28 +88,36 @@ def _pack_haiku_params(spec: AnsatzSpec, params: dict, R=None) -> dict[str, np.n
         for tag, pre, n_spin, off in (('up', PN.BF_UP, n_up, 0), ('dn', PN.BF_DN, spec.n_down, 0 if spec.full_determinant else n_up)):
             base = pre.rsplit('linear_0', 1)[0]
             nl = spec.backflow_layers
+            zb = lambda k, n: g(k) if spec.backflow_bias else np.zeros(n)
             for i in range(nl - 1):  # hidden layers, zero-padded to the wider spin (ssp(0) = 0 keeps the padding inert)
-                w, b = g(base + f'linear_{i}:w'), g(base + f'linear_{i}:b')
+                w = g(base + f'linear_{i}:w')
+                b = zb(base + f'linear_{i}:b', w.shape[1])
                 wp, bp = np.zeros((dims_pad[i], dims_pad[i + 1])), np.zeros((1, dims_pad[i + 1]))
                 wp[:w.shape[0], :w.shape[1]], bp[0, :b.shape[0]] = w, b
                 out[f'bfh{i}.{tag}'], out[f'bfb{i}.{tag}'] = wp, bp
-            w, b = g(base + f'linear_{nl - 1}:w'), g(base + f'linear_{nl - 1}:b')
+            w = g(base + f'linear_{nl - 1}:w')
+            b = zb(base + f'linear_{nl - 1}:b', w.shape[1])
             n_orb = N if spec.full_determinant else n_spin
             cols = (np.arange(K)[:, None] * N + off + np.arange(n_orb)[None, :]).ravel()  # (k, mu') -> k N + mu
             wp, bp = np.zeros((dims_pad[-1], K * N)), np.zeros((1, K * N))
             wp[:w.shape[0], cols], bp[0, cols] = w, b
             out[f'bf.{tag}'], out[f'bfb.{tag}'] = wp, bp
-        # per-shell spin-restricted envelopes (wf/env.py:26-75) -> engine layout [K N][M rep], unused terms pi = 0
-        rep = paulinet_env_rep(spec)
-        pi, zeta = g(f'{PN.ENV}:pi'), g(f'{PN.ENV}:zetas')
-        pe, ze = np.zeros((K * N, M * rep)), np.ones((K * N, M * rep))
-        seen = {}
-        for j, c in enumerate(spec.env_centers):
-            sh = seen.get(c, 0)
-            seen[c] = sh + 1
-            pe[:, c * rep + sh], ze[:, c * rep + sh] = pi[:, j], zeta[j]
-        for t in ('up', 'dn'):
-            out[f'env.pi_{t}'], out[f'env.zeta_{t}'] = pe, ze
+        if spec.env_per_shell:
+            # per-shell spin-restricted envelopes (wf/env.py:26-75) -> engine layout [K N][M rep], unused terms pi = 0
+            rep = paulinet_env_rep(spec)
+            pi, zeta = g(f'{PN.ENV}:pi'), g(f'{PN.ENV}:zetas')
+            pe, ze = np.zeros((K * N, M * rep)), np.ones((K * N, M * rep))
+            seen = {}
+            for j, c in enumerate(spec.env_centers):
+                sh = seen.get(c, 0)
+                seen[c] = sh + 1
+                pe[:, c * rep + sh], ze[:, c * rep + sh] = pi[:, j], zeta[j]
+            for t in ('up', 'dn'):
+                out[f'env.pi_{t}'], out[f'env.zeta_{t}'] = pe, ze
+        else:
+            for s_, t in (('up', 'up'), ('down', 'dn')):
+                out[f'env.pi_{t}'] = g(f'{PN.ENV}:pi_{s_}')
+                out[f'env.zeta_{t}'] = g(f'{PN.ENV}:zetas_{s_}')
         out['cusp.alpha'] = np.array([[spec.cusp_alpha, spec.cusp_alpha]], dtype=np.float64)
         if spec.conf_coeff == 'linear':
             out['conf.w'] = g(PN.CONF + ':w').reshape(1, K)
@@ -151,7 +180,26 @@ class Engine:
         cfg.n_env_per_nuc = spec.n_env_per_nuc
         cfg.n_nuc_tokens = spec.n_nuc if spec.kind == 'transpsiformer' else 0
         if spec.kind == 'paulinet':
-            cfg.n_env_per_nuc = paulinet_env_rep(spec)
+            cfg.n_env_per_nuc = paulinet_env_rep(spec) if spec.env_per_shell else 1
+            cfg.gnn_features = 1 if spec.gnn_embedding == 'features' else 0
+            cfg.gnn_concat = 1 if spec.gnn_update == 'concatenate' else 0
+            cfg.gnn_conv_ne = 1 if spec.gnn_conv_ne else 0
+            cfg.gnn_sub_n = spec.gnn_subnet_layers
+            cfg.gnn_deep_edges = 1 if spec.gnn_deep_edges else 0
+            cfg.gnn_res_norm = 1 if spec.gnn_residual_normalize else 0
+            cfg.gnn_g_bias = 1 if spec.gnn_g_bias else 0
+            cfg.gnn_w_bias = 1 if spec.gnn_update == 'concatenate' else 0
+            assert spec.n_layers <= 8 and spec.gnn_subnet_layers <= 4
+            d_in, e_in = (spec.embedding_dim if spec.gnn_embedding == 'embed' else 4 * spec.n_nuc), 4
+            for l in range(spec.n_layers):
+                for i, v in enumerate(PN.log_dims(e_in, spec.edge_dim, spec.gnn_subnet_layers)):
+                    cfg.gnn_w_dims[l * 4 + i] = v
+                    cfg.gnn_u_dims[l * 4 + i] = v
+                for i, v in enumerate(PN.log_dims(d_in, spec.edge_dim, spec.gnn_subnet_layers)):
+                    cfg.gnn_h_dims[l * 4 + i] = v
+                if spec.gnn_deep_edges and l < spec.n_layers - 1:
+                    e_in = spec.edge_dim
+                d_in = spec.embedding_dim
             cfg.factorized_det = 0 if spec.full_determinant else 1
             cfg.conf_linear = 1 if spec.conf_coeff == 'linear' else 0
             cfg.mult_act = 1 if spec.mult_act == 'default' else 0

@@ -61,6 +61,17 @@ typedef struct dqmc_config {
   int32_t jastrow_dims[8];  /* their widths (the last one is 1) */
   int32_t backflow_n;       /* HIDDEN layers of the per-spin backflow MLPs (wf/omni.py:43-88), ssp activation */
   int32_t backflow_dims[8]; /* their widths, padded to the larger of the two spins */
+  /* conv-GNN variants (tests/conf/ansatz.yaml vs conf/ansatz/default.yaml) */
+  int32_t gnn_features;     /* 0: hk.Embed lookup; 1: raw nucleus-electron features [|d|, d] (4 M wide) */
+  int32_t gnn_concat;       /* 0: 'featurewise' update; 1: 'concatenate' of [h, mean_up, mean_down, conv_*] */
+  int32_t gnn_conv_ne;      /* nucleus -> electron convolution present */
+  int32_t gnn_sub_n;        /* layers of the w / h / u MLPs (1..4) */
+  int32_t gnn_deep_edges;   /* shared edge MLP u + normalised residual between layers */
+  int32_t gnn_res_norm;     /* electron residual divided by sqrt(2) */
+  int32_t gnn_g_bias, gnn_w_bias;
+  int32_t gnn_w_dims[8][4]; /* per layer: widths of the w MLP layers (last = edge_dim) */
+  int32_t gnn_h_dims[8][4]; /* per layer: widths of the h MLP layers (last = edge_dim) */
+  int32_t gnn_u_dims[8][4]; /* per layer: widths of the u MLP layers (last = edge_dim) */
 } dqmc_config;
 
 typedef struct dqmc_engine* dqmc_handle;

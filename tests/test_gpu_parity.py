@@ -443,3 +443,25 @@ def test_excited_state_overlap_two_states_vs_oracle():
     x = ref.mean(-1)
     expect = torch.sign(x) * torch.sqrt(torch.clamp(x * x.T, min=0))
     assert torch.allclose(S, expect, rtol=1e-8, atol=1e-10) and abs(loss.item() - expect[0, 1].item() ** 2) < 1e-10
+
+
+@pytest.mark.parametrize('mol_name,hyper,B', [
+    ('LiH', dict(embedding_dim=32, n_determinants=4, edge_dim=8), 3),
+    ('H2O', dict(embedding_dim=16, n_determinants=3, edge_dim=8, n_layers=2), 2),
+    ('C', dict(embedding_dim=16, n_determinants=2, edge_dim=16), 2),   # n_up != n_down
+])
+def test_paulinet_default_yaml_local_energy_fp64(mol_name, hyper, B):
+    """'PauliNet' of conf/ansatz/default.yaml (SURVEY.md 8(a0) column 3): raw nucleus-electron features, concatenate
+    update of [h, mean_up, mean_down, conv_same, conv_anti], two-layer tanh w / h MLPs, shared deep edge MLP with
+    normalised residuals, linear Jastrow / backflow, full determinants, hk.Linear conf_coeff, DeepQMCCusp."""
+    mol, hamil, oh, ansatz, params, r, R = make(mol_name, B=B, kind='paulinet_default', **hyper)
+    pc = PhysicalConfiguration(R, r, torch.zeros(B, device=DEV))
+    psi = ansatz.apply(params, pc)
+    E, stats = hamil.local_energy(ansatz.apply)(None, params, pc)
+    ref = oracle_eval(ansatz, oh, params, r, R)
+    for b, (s, l, e, st) in enumerate(ref):
+        assert psi.sign[b].item() == s
+        assert abs(psi.log[b].item() - l) <= 1e-10 * max(1, abs(l))
+        assert abs(E[b].item() - e) <= 1e-8 * max(1, abs(e)), (b, E[b].item(), e)
+        for k in STAT_KEYS:
+            assert abs(stats[k][b].item() - st[k]) <= 1e-8 * max(1, abs(st[k])), (k, stats[k][b].item(), st[k])

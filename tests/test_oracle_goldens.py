@@ -217,3 +217,34 @@ def test_paulinet_oracle_antisymmetry_and_laplacian_self_check():
     la, ga = laplacian_hessian(f, r.reshape(-1))
     lb, gb = laplacian_jvp_loop(f, r.reshape(-1))
     assert abs(la.item() - lb.item()) < 1e-8 * max(1, abs(la.item())) and torch.allclose(ga, gb)
+
+
+def test_paulinet_default_yaml_parameter_count_and_antisymmetry():
+    """conf/ansatz/default.yaml on LiH: layer widths from the 'log' rule (w: 4-11-32 then 32-32-32; h: 8-16-32 then
+    128-64-32; g: 88->128 then 448->128) and antisymmetry of the oracle restatement."""
+    import numpy as np
+    import torch
+
+    from deepqmc_b200 import params as PN
+    from deepqmc_b200.hamil import MolecularHamiltonian
+    from deepqmc_b200.molecule import Molecule
+    from deepqmc_b200.spec import paulinet_default_spec
+    from oracle import wf
+
+    mol = Molecule.from_name('LiH')
+    h = MolecularHamiltonian(mol=mol)
+    spec = paulinet_default_spec(h)
+    sh = PN.param_shapes(spec)
+    c0 = PN.conv_prefix(0)
+    assert sh[c0 + 'w_same/linear_0:w'] == (4, 11) and sh[c0 + 'w_same/linear_1:w'] == (11, 32)
+    assert sh[c0 + 'h_anti/linear_0:w'] == (8, 16) and sh[PN.conv_prefix(1) + 'h_anti/linear_0:w'] == (128, 64)
+    assert sh[PN.layer_prefix(0) + 'g/linear_0:w'] == (88, 128) and sh[PN.layer_prefix(2) + 'g/linear_0:w'] == (448, 128)
+    assert PN.layer_prefix(2) + 'u/linear_0:w' not in sh  # no edge update in the last layer
+    small = paulinet_default_spec(h, embedding_dim=16, n_determinants=3, edge_dim=8)
+    pt = wf.to_torch(PN.perturb_params(PN.init_params(small, 0)))
+    rng = np.random.default_rng(2)
+    R = torch.as_tensor(mol.coords)
+    r = torch.as_tensor(rng.normal(size=(4, 3)))
+    s0, l0 = wf.log_psi(small, pt, r, R)
+    s1, l1 = wf.log_psi(small, pt, r[[1, 0, 2, 3]], R)
+    assert s0.item() == -s1.item() and abs(l0.item() - l1.item()) < 1e-10

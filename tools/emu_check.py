@@ -39,14 +39,14 @@ def main():
     from deepqmc_b200 import params as PN
     from deepqmc_b200.engine import Engine
     from deepqmc_b200.molecule import Molecule
-    from deepqmc_b200.spec import ferminet_spec, paulinet_spec, psiformer_spec, transpsiformer_spec
+    from deepqmc_b200.spec import ferminet_spec, paulinet_default_spec, paulinet_spec, psiformer_spec, transpsiformer_spec
     from oracle import wf
     from oracle.hamil import OracleHamiltonian
 
     mol = Molecule.from_name(a.mol)
     h = OracleHamiltonian(mol, ecp_type=a.ecp)
-    mk = {'psiformer': psiformer_spec, 'ferminet': ferminet_spec, 'transpsiformer': transpsiformer_spec, 'paulinet': paulinet_spec}[a.kind]
-    spec = mk(h, n_layers=a.layers) if a.kind == 'paulinet' else mk(h, embedding_dim=a.d, n_layers=a.layers, n_heads=a.heads, n_determinants=a.K)
+    mk = {'psiformer': psiformer_spec, 'ferminet': ferminet_spec, 'transpsiformer': transpsiformer_spec, 'paulinet': paulinet_spec, 'paulinet_default': paulinet_default_spec}[a.kind]
+    spec = (mk(h, n_layers=a.layers) if a.kind == 'paulinet' else mk(h, n_layers=a.layers, embedding_dim=a.d, n_determinants=a.K, edge_dim=8)) if a.kind.startswith('paulinet') else mk(h, embedding_dim=a.d, n_layers=a.layers, n_heads=a.heads, n_determinants=a.K)
     params = PN.perturb_params(PN.init_params(spec, 0))
     pt = wf.to_torch(params)
     rng = np.random.default_rng(0)
