@@ -162,6 +162,7 @@ struct EngineBase {
     add("env.zeta_up", K * N, M * rep);
     add("env.zeta_dn", K * N, M * rep);
     add("cusp.alpha", 1, 2);
+    if (cfg.nuc_cusp_kind) add("cusp.nuc", 1, 1 + M);  // alpha_nuc, nuclear charges
   }
   int64_t off(const std::string& n) const {
     for (auto& e : entries)
@@ -967,10 +968,12 @@ struct Engine : EngineBase {
     fc.N = N; fc.M = M; fc.n_up = cfg.n_up; fc.K = K; fc.S = S; fc.cusp_kind = cfg.cusp_kind;
     fc.cusp_same_scale = cfg.cusp_same_scale; fc.cusp_anti_scale = cfg.cusp_anti_scale;
     fc.ecp_terms = cfg.ecp_loc_terms;
+    fc.nuc_cusp_kind = cfg.nuc_cusp_kind;
     DQ_LAUNCH(finalize_kernel<T>, dim3(Bc), dim3(128), finalize_smem_bytes<T>(N, K), st, fc, r, R, Rb,
               (const T*)w.dsign, (const T*)w.dlog, (const T*)w.dgrad, (const T*)w.dlap, P("cusp.alpha"),
               (const T*)d_zval, (const T*)d_ecp_loc, (const int*)d_ecp_mask, Bstat, sign, logp, E, stats, grad,
-              cfg.conf_linear ? P("conf.w") : (const T*)nullptr, jastrow);
+              cfg.conf_linear ? P("conf.w") : (const T*)nullptr, jastrow,
+              cfg.nuc_cusp_kind ? P("cusp.nuc") : (const T*)nullptr);
     return 0;
   }
 

@@ -644,6 +644,7 @@ struct FinalizeCfg {
   int cusp_kind;  // 0 none, 1 psiformer -s a^2 / (a + r), 2 deepqmc -s / (a (1 + a r)) (wf/cusp.py:5-26)
   double cusp_same_scale, cusp_anti_scale;
   int ecp_terms;  // Tmax of loc params (0: plain Coulomb)
+  int nuc_cusp_kind = 0;  // NuclearCuspAsymptotic (wf/cusp.py:81-101): 0 none, 1 psiformer, 2 deepqmc form, scale = Z_I
 };
 
 template <class T>
@@ -655,7 +656,8 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
                                 const int* __restrict__ ecp_mask, int B, T* __restrict__ out_sign,
                                 T* __restrict__ out_log, T* __restrict__ out_E, T* __restrict__ out_stats,
                                 T* __restrict__ out_grad, const T* __restrict__ conf_w /*[K] or null: SumPool*/,
-                                const T* __restrict__ jastrow /*[B][S] augmented scalar rows or null*/) {
+                                const T* __restrict__ jastrow /*[B][S] augmented scalar rows or null*/,
+                                const T* __restrict__ nuc_cusp /*[1 + M]: alpha, nuclear charges; or null*/) {
   DQMC_DYN_SMEM(smem_raw);
   const int N = c.N, M = c.M, K = c.K, S = c.S;
   const int T3 = S > 1 ? S - 2 : 0;
@@ -709,13 +711,25 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
         }
       }
     }
-    if (S > 1) { grad[3 * i] = g0; grad[3 * i + 1] = g1; grad[3 * i + 2] = g2; }
-    // electron-nucleus attraction (plain norm) + local ECP
+    // electron-nucleus attraction (plain norm) + local ECP (+ nuclear cusp factor on the plain distances,
+    // reference wf/nn_wave_function.py:129,169-170)
     for (int m = 0; m < M; ++m) {
       T dx0 = rb[3 * i] - Rb[3 * m], dx1 = rb[3 * i + 1] - Rb[3 * m + 1], dx2 = rb[3 * i + 2] - Rb[3 * m + 2];
       T d2 = dx0 * dx0 + dx1 * dx1 + dx2 * dx2;
       T dist = m_sqrt(d2);
       vloc -= z_val[m] / dist;
+      if (c.nuc_cusp_kind != 0) {
+        const T al = nuc_cusp[0], zn = nuc_cusp[1 + m];
+        const T sc = zn * (c.nuc_cusp_kind == 1 ? al * al : T(1) / (al * al));
+        const T den = (c.nuc_cusp_kind == 1 ? al : T(1) / al) + dist;
+        const T f = -sc / den, fp = sc / (den * den), fpp = T(-2) * sc / (den * den * den);
+        cusp_v += f;
+        if (S > 1) {
+          const T cc = fp / dist;
+          g0 += cc * dx0; g1 += cc * dx1; g2 += cc * dx2;
+          cusp_l += fpp + T(2) * fp / dist;
+        }
+      }
       if (c.ecp_terms > 0 && ecp_mask[m]) {
         const T* lp = ecp_loc + (size_t)m * 6 * c.ecp_terms;
         for (int tt = 0; tt < c.ecp_terms; ++tt) {
@@ -725,6 +739,7 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
         }
       }
     }
+    if (S > 1) { grad[3 * i] = g0; grad[3 * i + 1] = g1; grad[3 * i + 2] = g2; }
   }
   for (int idx = tid; idx < M * M; idx += nt) {
     int I = idx / M, J = idx % M;

@@ -213,6 +213,9 @@ class Engine:
             for i, v in enumerate(hid):
                 cfg.backflow_dims[i] = v
         cfg.cusp_kind = {'psiformer': 1, 'deepqmc': 2}.get(spec.cusp, 0)
+        cfg.nuc_cusp_kind = {'psiformer': 1, 'deepqmc': 2}.get(spec.cusp_nuclei, 0)
+        for m in range(spec.n_nuc):
+            cfg.z_nuclear[m] = float(hamil.mol.charges[m])
         cfg.cusp_same_scale, cfg.cusp_anti_scale = spec.cusp_same_scale, spec.cusp_anti_scale
         M = spec.n_nuc
         assert M <= _lib.MAX_NUC
@@ -269,6 +272,10 @@ class Engine:
             self._nuc_R, self._nuc_key = R, None
         self._params = params
         packed = _pack_haiku_params(self.spec, params, R)
+        if self.spec.cusp_nuclei != 'none':  # NuclearCuspAsymptotic: alpha (trainable or fixed) + the nuclear charges
+            al = (float(np.asarray(params[f'{PN.NUC_CUSP}:nuc_alpha'])) if self.spec.cusp_nuclei_trainable
+                  else self.spec.cusp_nuclei_alpha)
+            packed['cusp.nuc'] = np.array([[al, *[float(z) for z in self.hamil.mol.charges]]], dtype=np.float64)
         flat = np.zeros(self.n_packed, dtype=np.float64)
         for k, (off, rows, cols) in self.entries.items():
             v = packed[k]

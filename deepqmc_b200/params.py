@@ -19,6 +19,7 @@ from .spec import AnsatzSpec, log_dims
 P = 'neural_network_wave_function/~/'
 ENV = P + 'exponential_envelopes'
 CUSP = P + 'electronic_cusp_asymptotic'
+NUC_CUSP = P + 'nuclear_cusp_asymptotic'
 GNN = P + 'omni_net/~/electron_gnn/~/'
 BF_UP = P + 'omni_net/~/Backflow/~/mlp/linear_0'
 BF_DN = P + 'omni_net/~/Backflow_1/~/mlp/linear_0'
@@ -118,6 +119,8 @@ def param_shapes(spec: AnsatzSpec) -> dict[str, tuple[int, ...]]:
     if spec.cusp == 'psiformer':
         s[f'{CUSP}:same_alpha'] = ()
         s[f'{CUSP}:anti_alpha'] = ()
+    if spec.cusp_nuclei != 'none' and spec.cusp_nuclei_trainable:
+        s[f'{NUC_CUSP}:nuc_alpha'] = ()
     if spec.kind == 'psiformer':
         s[GNN + 'electron_embedding/linear:w'] = (spec.n_feat_in, d)
         for l in range(spec.n_layers):
@@ -182,6 +185,8 @@ def init_params(spec: AnsatzSpec, seed: int = 0) -> dict[str, np.ndarray]:
             v = rng.standard_normal(shape)  # hk.Embed default: truncated normal
         elif name.startswith(ENV):
             v = np.ones(shape)
+        elif name.startswith(NUC_CUSP):
+            v = spec.cusp_nuclei_alpha * np.ones(shape)
         elif name.startswith(CUSP):
             v = np.ones(shape)
         elif leaf.startswith('zetas_bias'):
@@ -202,7 +207,7 @@ def perturb_params(params, seed=1, scale=0.2):
     rng = np.random.default_rng(seed)
     out = dict(params)
     for k, v in params.items():
-        if k.startswith(ENV) or k.startswith(CUSP) or 'zetas_bias' in k or k == CONF + ':w':
+        if k.startswith(ENV) or k.startswith(CUSP) or k.startswith(NUC_CUSP) or 'zetas_bias' in k or k == CONF + ':w':
             out[k] = v * (1 + scale * rng.uniform(-1, 1, size=v.shape))
     return out
 

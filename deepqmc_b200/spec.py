@@ -26,6 +26,10 @@ class AnsatzSpec:
     cusp: str = 'psiformer'
     cusp_same_scale: float = 0.25
     cusp_anti_scale: float = 0.5
+    # nuclear cusp factor (reference wf/cusp.py:81-101; `cusp_nuclei: false` in every shipped ansatz yaml)
+    cusp_nuclei: str = 'none'  # 'none' | 'psiformer' | 'deepqmc'
+    cusp_nuclei_alpha: float = 1.0
+    cusp_nuclei_trainable: bool = True
     # TransPsiformer (reference: conf/ansatz/transpsiformer.yaml): nuclei are extra attention tokens
     # (elec_to_nuc = false) and the envelope exponents are read out of the nuclear embeddings
     n_env_per_nuc: int = 1  # SimplifiedNucleusDependentEnvelopes.n_envelope_per_nucleus (3)
@@ -67,12 +71,14 @@ class AnsatzSpec:
 
 def psiformer_spec(hamil, **kw):
     """reference: src/deepqmc/conf/ansatz/psiformer.yaml"""
+    kw.setdefault('charges', tuple(float(z) for z in hamil.mol.charges))
     return AnsatzSpec('psiformer', hamil.n_up, hamil.n_down, hamil.n_nuc, **kw)
 
 
 def ferminet_spec(hamil, **kw):
     """reference: src/deepqmc/conf/ansatz/ferminet.yaml"""
     kw.setdefault('cusp', 'none')
+    kw.setdefault('charges', tuple(float(z) for z in hamil.mol.charges))
     return AnsatzSpec('ferminet', hamil.n_up, hamil.n_down, hamil.n_nuc, **kw)
 
 
@@ -109,6 +115,7 @@ def paulinet_spec(hamil, **kw):
     kw.setdefault('backflow_layers', 3)
     kw.setdefault('env_centers', tuple(c for c, _ in shells))
     kw.setdefault('env_zeta_init', tuple(z for _, z in shells))
+    kw.setdefault('charges', tuple(float(z) for z in hamil.mol.charges))
     return AnsatzSpec('paulinet', hamil.n_up, hamil.n_down, hamil.n_nuc, **kw)
 
 
@@ -122,4 +129,5 @@ def paulinet_default_spec(hamil, **kw):
              gnn_embedding='features', gnn_update='concatenate', gnn_conv_ne=False, gnn_subnet_layers=2,
              gnn_deep_edges=True, gnn_residual_normalize=True, gnn_g_bias=False, env_per_shell=False)
     d.update(kw)
+    d.setdefault('charges', tuple(float(z) for z in hamil.mol.charges))
     return AnsatzSpec('paulinet', hamil.n_up, hamil.n_down, hamil.n_nuc, **d)

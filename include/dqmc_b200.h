@@ -72,6 +72,10 @@ typedef struct dqmc_config {
   int32_t gnn_w_dims[8][4]; /* per layer: widths of the w MLP layers (last = edge_dim) */
   int32_t gnn_h_dims[8][4]; /* per layer: widths of the h MLP layers (last = edge_dim) */
   int32_t gnn_u_dims[8][4]; /* per layer: widths of the u MLP layers (last = edge_dim) */
+  /* NuclearCuspAsymptotic (wf/cusp.py:81-101): 0 none, 1 PsiformerCusp, 2 DeepQMCCusp form with scale = nuclear
+   * charge; alpha is entry "cusp.alpha_nuc", the charges are z_nuclear (all kinds) */
+  int32_t nuc_cusp_kind;
+  double z_nuclear[DQMC_MAX_NUC];
 } dqmc_config;
 
 typedef struct dqmc_engine* dqmc_handle;

@@ -352,8 +352,25 @@ def psiformer_cusp(spec, params, r):
     return out
 
 
+def nuclear_cusp(spec, params, r, R):
+    """reference: wf/cusp.py:81-101 on dists_nuc = plain norm (wf/nn_wave_function.py:129,169-170)"""
+    if spec.cusp_nuclei == 'none':
+        return 0.0
+    al = _t(params, f'{P.NUC_CUSP}:nuc_alpha') if spec.cusp_nuclei_trainable else spec.cusp_nuclei_alpha
+    z = torch.as_tensor(spec.charges, dtype=r.dtype)
+    dist = torch.sqrt(((r[:, None] - R[None]) ** 2).sum(-1))  # [N, M]
+    if spec.cusp_nuclei == 'psiformer':
+        return -((z[None] * al**2) / (al + dist)).sum()
+    return -(z[None] / (al * (1 + al * dist))).sum()
+
+
 def log_psi(spec, params, r, R):
     """ansatz.apply for one walker -> (sign, log|psi|); reference nn_wave_function.py:127-173"""
+    s, l = _log_psi(spec, params, r, R)
+    return s, l + nuclear_cusp(spec, params, r, R)
+
+
+def _log_psi(spec, params, r, R):
     if spec.kind == 'paulinet':
         return paulinet_log_psi(spec, params, r, R)
     if spec.kind == 'transpsiformer':

@@ -465,3 +465,18 @@ def test_paulinet_default_yaml_local_energy_fp64(mol_name, hyper, B):
         assert abs(E[b].item() - e) <= 1e-8 * max(1, abs(e)), (b, E[b].item(), e)
         for k in STAT_KEYS:
             assert abs(stats[k][b].item() - st[k]) <= 1e-8 * max(1, abs(st[k])), (k, stats[k][b].item(), st[k])
+
+
+@pytest.mark.parametrize('form', ['psiformer', 'deepqmc'])
+def test_nuclear_cusp_factor_fp64(form):
+    """NuclearCuspAsymptotic (reference wf/cusp.py:81-101; off in the shipped yamls): value, gradient and Laplacian
+    contributions on the plain electron-nucleus distances."""
+    hyper = dict(SMALL, cusp_nuclei=form, cusp_nuclei_alpha=0.7)
+    mol, hamil, oh, ansatz, params, r, R = make('H2O', B=2, **hyper)
+    pc = PhysicalConfiguration(R, r, torch.zeros(2, device=DEV))
+    psi = ansatz.apply(params, pc)
+    E, stats = hamil.local_energy(ansatz.apply)(None, params, pc)
+    for b, (s, l, e, st) in enumerate(oracle_eval(ansatz, oh, params, r, R)):
+        assert abs(psi.log[b].item() - l) <= 1e-10 * max(1, abs(l))
+        assert abs(E[b].item() - e) <= 1e-8 * max(1, abs(e)), (b, E[b].item(), e)
+        assert abs(stats['hamil/lap'][b].item() - st['hamil/lap']) <= 1e-8 * max(1, abs(st['hamil/lap']))
