@@ -62,3 +62,12 @@ class B200Ansatz:
             r = r[None]
         sign, log = eng.wf_forward(r, R)
         return Psi(sign[0], log[0]) if single else Psi(sign, log)
+
+    # -- reference: jax.grad / jvp of ansatz.apply w.r.t. params (loss/loss_function.py:53-82), SURVEY.md 8(f) N1
+    def log_psi_vjp(self, params, phys_conf: PhysicalConfiguration, weights):
+        """-> (Psi, grads): grads[name] = d/d params[name] sum_b weights[b] log|psi(r_b)| (Psiformer only so far).
+        With weights = 2 (E_loc - mean E_loc) / B this is the gradient of the variational energy
+        (loss/energy.py:77-102)."""
+        eng = self.engine_for(self.hamil, params)
+        sign, log, grads = eng.vjp_params(phys_conf.r, phys_conf.R, weights)
+        return Psi(sign, log), grads

@@ -14,6 +14,7 @@
 #include "kernels_slater.cuh"
 #include "kernels_trunk.cuh"
 #include "kernels_gnn.cuh"
+#include "kernels_bwd.cuh"
 #if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
 #include "gemm_tcgen05.cuh"
 #endif
@@ -50,6 +51,8 @@ struct EngineBase {
   virtual int local_energy(const void* r, const void* R, int Rb, int B, uint64_t seed, const void* twist, void* E,
                            void* stats, void* sign, void* logp, void* grad, void* ws, int64_t wsb,
                            cudaStream_t st) = 0;
+  virtual int vjp_params(const void* r, const void* R, int Rb, int B, const void* weights, void* sign, void* logp,
+                         void* grad_params, void* ws, int64_t wsb, cudaStream_t st) = 0;
   virtual int debug_gemm(const char* wname, const char* bname, const void* A, const void* Res, void* C, int Mr, int S,
                          int sliced, int backend, cudaStream_t st) = 0;
   virtual int mcmc(void* r, void* sign, void* logp, int32_t* age, void* tau, const void* R, int Rb, int B, int n_sub,
@@ -212,6 +215,7 @@ __global__ void split_transpose_kernel(const float* __restrict__ W, int K, int N
 template <class T>
 struct Engine : EngineBase {
   T* d_params = nullptr;
+  T* d_params_t = nullptr;  // every entry transposed ([cols][rows]): operands of the dA = dY W^T products of the reverse pass
   double* d_stage = nullptr;
   T* d_zval = nullptr;
   int* d_ecp_mask = nullptr;
@@ -277,6 +281,7 @@ struct Engine : EngineBase {
     build_layout();
     DQ_CHECK(cudaSetDevice(device));
     DQ_CHECK(cudaMalloc((void**)&d_params, sizeof(T) * total));
+    DQ_CHECK(cudaMalloc((void**)&d_params_t, sizeof(T) * total));
     DQ_CHECK(cudaMalloc((void**)&d_stage, sizeof(double) * total));
     std::vector<T> z(M);
     for (int m = 0; m < M; ++m) z[m] = (T)cfg.z_valence[m];
@@ -390,7 +395,7 @@ struct Engine : EngineBase {
     return 0;
   }
   ~Engine() override {
-    cudaFree(d_params); cudaFree(d_stage); cudaFree(d_zval); cudaFree(d_ecp_mask);
+    cudaFree(d_params); cudaFree(d_params_t); cudaFree(d_stage); cudaFree(d_zval); cudaFree(d_ecp_mask);
     if (d_ecp_loc) cudaFree(d_ecp_loc);
     if (d_nl_params) cudaFree(d_nl_params);
     if (d_nl_nuc) cudaFree(d_nl_nuc);
@@ -401,6 +406,10 @@ struct Engine : EngineBase {
     if (n != total) { err = "parameter count mismatch"; return 2; }
     DQ_CHECK(cudaMemcpyAsync(d_stage, host, sizeof(double) * n, cudaMemcpyHostToDevice, st));
     DQ_LAUNCH(convert_kernel<T>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, (const double*)d_stage, d_params, n);
+    for (auto& e : entries)
+      if (e.rows > 1 && e.cols > 1)
+        DQ_LAUNCH(transpose_kernel<T>, dim3((e.rows * e.cols + 255) / 256), dim3(256), 0, st, (const T*)(d_params + e.offset),
+                  e.rows, e.cols, d_params_t + e.offset);
 #if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
     if (use_tc()) {
       for (auto& e : entries) {
@@ -513,6 +522,7 @@ struct Engine : EngineBase {
            (int64_t)(sizeof(T) * per_walker_elems(1)) * V + 32 * 256;
   }
   int64_t ws_bytes(int B, int mode) override {
+    if (mode == DQMC_MODE_VJP) return (int64_t)(sizeof(T) * vjp_per_walker_elems()) * B + 64 * 256;
     int S = mode == DQMC_MODE_FORWARD ? 1 : T3 + 2;
     int64_t need = (int64_t)chunk_bytes(B, S);
     if (mode == DQMC_MODE_LOCAL_ENERGY && J > 0) need = std::max<int64_t>(need, ecp_bytes(B));
@@ -991,6 +1001,148 @@ struct Engine : EngineBase {
     return 0;
   }
 
+  // ---- parameter VJP of the plain forward (Psiformer): SURVEY.md 8(f) N1 ------------------------
+  const T* PT(const std::string& n) const { return d_params_t + off(n); }
+  size_t vjp_per_walker_elems() const {
+    const size_t L = cfg.n_layers, F = 4 * M + 1;
+    return (size_t)N * ((7 * L + 1) * d + 9 * (size_t)d + 2 * (size_t)KN + F) + (size_t)K * 4;
+  }
+  // C = (Res) + A @ W with a raw weight pointer (CUDA-core kernel; used by the reverse pass with transposed weights)
+  int gemm_raw(const T* A, int lda, const T* W0, const T* W1, int zsplit, int ldw, const T* Res, int ldr, T* C, int ldc,
+               int Mr, int Nc, int Kc, int sliced, cudaStream_t st) {
+    GemmArgs<T> g;
+    g.A = A; g.lda = lda; g.W0 = W0; g.W1 = W1; g.z_split = zsplit; g.ldw = ldw; g.bias = nullptr; g.Res = Res;
+    g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = Mr; g.N = Nc; g.K = Kc; g.S = 1; g.sliced = sliced; g.Nel = N;
+    constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
+    dim3 grid((Nc + BN - 1) / BN, (Mr + BM - 1) / BM, sliced ? N : 1);
+    DQ_LAUNCH((gemm_kernel<T, BM, BN, BK, TM, TN>), grid, dim3(256), 0, st, g);
+    return 0;
+  }
+  // dW += A^T dY over `rows` rows (optionally only electrons lo <= i < hi of every walker), db += column sums
+  void wgrad(const T* A, int lda, const T* dY, int ldy, int rows, int Kc, int Nc, T* dW, int lo, int hi, cudaStream_t st) {
+    int nz = (rows + 4095) / 4096;
+    if (nz > 256) nz = 256;
+    if (nz < 1) nz = 1;
+    const int rpb = ((rows + nz - 1) / nz + 31) / 32 * 32;
+    DQ_LAUNCH(gemm_tn_kernel<T>, dim3((Nc + 31) / 32, (Kc + 31) / 32, (rows + rpb - 1) / rpb), dim3(256), 0, st, A, lda, dY, ldy,
+              rows, Kc, Nc, rpb, hi > lo ? N : 0, lo, hi, dW, Nc);
+  }
+  void bgrad(const T* dZ, int ld, int rows, int Nc, T* db, cudaStream_t st) {
+    int ny = (rows + 2047) / 2048;
+    if (ny > 128) ny = 128;
+    if (ny < 1) ny = 1;
+    const int rpb = (rows + ny - 1) / ny;
+    DQ_LAUNCH(colsum_kernel<T>, dim3((Nc + 127) / 128, (rows + rpb - 1) / rpb), dim3(128), 0, st, dZ, ld, rows, Nc, rpb, db);
+  }
+
+  int vjp_chunk(const T* r, const T* R, int Rb, int Bc, const T* wts, T* sign, T* logp, T* G, void* wsbase, cudaStream_t st) {
+    const int L = cfg.n_layers, rows = Bc * N, F = 4 * M + 1;
+    char* p = (char*)wsbase;
+    auto take = [&](size_t n) { T* q = (T*)p; p += align_up(sizeof(T) * n); return q; };
+    std::vector<T*> X(L + 1), QKV(L), O(L), A(L), M1(L);
+    for (int l = 0; l <= L; ++l) X[l] = take((size_t)rows * d);
+    for (int l = 0; l < L; ++l) { QKV[l] = take((size_t)rows * 3 * d); O[l] = take((size_t)rows * d); A[l] = take((size_t)rows * d); M1[l] = take((size_t)rows * d); }
+    T* BF = take((size_t)rows * KN); T* dBF = take((size_t)rows * KN);
+    T* dsign = take((size_t)Bc * K); T* dlog = take((size_t)Bc * K); T* dld = take((size_t)Bc * K);
+    T* dXn = take((size_t)rows * d); T* dZ = take((size_t)rows * d); T* dM1 = take((size_t)rows * d);
+    T* dA = take((size_t)rows * d); T* dO = take((size_t)rows * d); T* dQKV = take((size_t)rows * 3 * d);
+    T* dX = take((size_t)rows * d); T* Feat = take((size_t)rows * F);
+    const T scale = (T)(1.0 / std::sqrt((double)dh));
+    // ---- forward with every layer's activations kept --------------------------------------------------------
+    DQ_LAUNCH(embed_kernel<T>, dim3((rows + 7) / 8), dim3(128), sizeof(T) * 5 * F, st, r, R, Rb, N, M, cfg.n_up, 1, 1, 1,
+              P("emb.w"), d, X[0], rows, 8);
+    for (int l = 0; l < L; ++l) {
+      const std::string q = "L" + std::to_string(l) + ".";
+      gemm(X[l], d, (q + "wqkv").c_str(), nullptr, 0, 3 * d, nullptr, nullptr, 0, QKV[l], 3 * d, rows, 3 * d, d, 1, 0, N, st);
+      DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh, 1, 0), st, (const T*)QKV[l], 3 * d, O[l], d, N,
+                1, dh, d, scale, 1, (const T*)nullptr, (const T*)nullptr, 0);
+      gemm(O[l], d, (q + "wo").c_str(), nullptr, 0, d, nullptr, X[l], d, A[l], d, rows, d, d, 1, 0, N, st);
+      gemm(A[l], d, (q + "w1").c_str(), nullptr, 0, d, P(q + "b1"), nullptr, 0, M1[l], d, rows, d, d, 1, 0, N, st);
+      DQ_LAUNCH(tanh_fl_kernel<T>, dim3(rows, (d + 127) / 128), dim3(128), 0, st, M1[l], d, (const T*)nullptr, 0, 1, d, T(1));
+      gemm(M1[l], d, (q + "w2").c_str(), nullptr, 0, d, P(q + "b2"), nullptr, 0, X[l + 1], d, rows, d, d, 1, 0, N, st);
+      DQ_LAUNCH(tanh_fl_kernel<T>, dim3(rows, (d + 127) / 128), dim3(128), 0, st, X[l + 1], d, (const T*)A[l], d, 1, d, T(1));
+    }
+    gemm(X[L], d, "bf.up", "bf.dn", cfg.n_up, KN, nullptr, nullptr, 0, BF, KN, Bc, KN, d, 1, 1, N, st);
+    const int sl_wpb = slater_warps_per_block<T>(N);
+    DQ_LAUNCH(slater_kernel<T>, dim3((Bc * K + sl_wpb - 1) / sl_wpb), dim3(32 * sl_wpb), slater_smem_bytes<T>(N), st, r, R, Rb, N,
+              M, cfg.n_up, K, 1, Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)BF, KN,
+              dsign, dlog, (T*)nullptr, (T*)nullptr, 1, 1);
+    FinalizeCfg fc;
+    fc.N = N; fc.M = M; fc.n_up = cfg.n_up; fc.K = K; fc.S = 1; fc.cusp_kind = cfg.cusp_kind;
+    fc.cusp_same_scale = cfg.cusp_same_scale; fc.cusp_anti_scale = cfg.cusp_anti_scale; fc.ecp_terms = 0;
+    DQ_LAUNCH(finalize_kernel<T>, dim3(Bc), dim3(128), finalize_smem_bytes<T>(N, K), st, fc, r, R, Rb, (const T*)dsign,
+              (const T*)dlog, (const T*)nullptr, (const T*)nullptr, P("cusp.alpha"), (const T*)d_zval, (const T*)nullptr,
+              (const int*)d_ecp_mask, Bc, sign, logp, (T*)nullptr, (T*)nullptr, (T*)nullptr, (const T*)nullptr, (const T*)nullptr,
+              (const T*)nullptr);
+    // ---- reverse ------------------------------------------------------------------------------------------------
+    DQ_LAUNCH(finalize_bwd_kernel<T>, dim3((Bc + 127) / 128), dim3(128), 0, st, r, N, cfg.n_up, K, Bc, (const T*)dsign,
+              (const T*)dlog, wts, cfg.cusp_kind, (T)cfg.cusp_same_scale, (T)cfg.cusp_anti_scale, P("cusp.alpha"), dld,
+              G + off("cusp.alpha"));
+    {
+      const size_t pw = slater_bwd_smem_per_warp<T>(N);
+      int wpb = (int)((96 * 1024) / pw);
+      wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
+      DQ_LAUNCH(slater_bwd_kernel<T>, dim3((Bc * K + wpb - 1) / wpb), dim3(32 * wpb), pw * wpb, st, r, R, Rb, N, M, cfg.n_up, K,
+                Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)BF, KN, (const T*)dld, dBF,
+                G + off("env.pi_up"), G + off("env.pi_dn"), G + off("env.zeta_up"), G + off("env.zeta_dn"));
+    }
+    // backflow heads: dX_L = dBF W_spin^T, dW_spin += X_L[spin rows]^T dBF[spin rows]
+    gemm_raw(dBF, KN, PT("bf.up"), PT("bf.dn"), cfg.n_up, d, nullptr, 0, dXn, d, Bc, d, KN, 1, st);
+    wgrad(X[L], d, dBF, KN, rows, d, KN, G + off("bf.up"), 0, cfg.n_up, st);
+    wgrad(X[L], d, dBF, KN, rows, d, KN, G + off("bf.dn"), cfg.n_up, N, st);
+    const size_t nel = (size_t)rows * d;
+    for (int l = L - 1; l >= 0; --l) {
+      const std::string q = "L" + std::to_string(l) + ".";
+      // X_{l+1} = A + tanh(M1 W2 + b2)
+      DQ_LAUNCH(tanh_bwd_kernel<T>, dim3((unsigned)((nel + 255) / 256)), dim3(256), 0, st, (const T*)dXn, (const T*)X[l + 1],
+                (const T*)A[l], dZ, nel);
+      bgrad(dZ, d, rows, d, G + off(q + "b2"), st);
+      wgrad(M1[l], d, dZ, d, rows, d, d, G + off(q + "w2"), 0, 0, st);
+      gemm_raw(dZ, d, PT(q + "w2"), nullptr, 0, d, nullptr, 0, dM1, d, rows, d, d, 0, st);
+      // M1 = tanh(A W1 + b1)
+      DQ_LAUNCH(tanh_bwd_kernel<T>, dim3((unsigned)((nel + 255) / 256)), dim3(256), 0, st, (const T*)dM1, (const T*)M1[l],
+                (const T*)nullptr, dZ, nel);
+      bgrad(dZ, d, rows, d, G + off(q + "b1"), st);
+      wgrad(A[l], d, dZ, d, rows, d, d, G + off(q + "w1"), 0, 0, st);
+      gemm_raw(dZ, d, PT(q + "w1"), nullptr, 0, d, dXn, d, dA, d, rows, d, d, 0, st);  // dA = dX_{l+1} + dZ1 W1^T
+      // A = X + O Wo
+      wgrad(O[l], d, dA, d, rows, d, d, G + off(q + "wo"), 0, 0, st);
+      gemm_raw(dA, d, PT(q + "wo"), nullptr, 0, d, nullptr, 0, dO, d, rows, d, d, 0, st);
+      DQ_LAUNCH(attn_bwd_kernel<T>, dim3(Bc, H), dim3(128), attn_bwd_smem_bytes<T>(N, dh), st, (const T*)QKV[l], 3 * d, (const T*)dO,
+                d, N, dh, d, scale, dQKV);
+      wgrad(X[l], d, dQKV, 3 * d, rows, d, 3 * d, G + off(q + "wqkv"), 0, 0, st);
+      gemm_raw(dQKV, 3 * d, PT(q + "wqkv"), nullptr, 0, d, dA, d, dX, d, rows, d, 3 * d, 0, st);  // dX_l = dA + dQKV Wqkv^T
+      T* t = dXn; dXn = dX; dX = t;
+    }
+    DQ_LAUNCH(embed_feat_kernel<T>, dim3((rows * M + 127) / 128), dim3(128), 0, st, r, R, Rb, N, M, cfg.n_up, Feat, rows);
+    wgrad(Feat, F, dXn, d, rows, F, d, G + off("emb.w"), 0, 0, st);
+    return 0;
+  }
+
+  int vjp_params(const void* r_, const void* R_, int Rb, int B, const void* weights, void* sign, void* logp,
+                 void* grad_params, void* ws, int64_t wsb, cudaStream_t st) override {
+    if (cfg.kind != DQMC_PSIFORMER) { err = "dqmc_wf_vjp_params: only the Psiformer ansatz has a reverse pass so far"; return 2; }
+    const T* r = (const T*)r_;
+    const T* R = (const T*)R_;
+    DQ_CHECK(cudaMemsetAsync(grad_params, 0, sizeof(T) * total, st));
+    const int64_t per = (int64_t)(sizeof(T) * vjp_per_walker_elems()) + 64 * 256 / (B > 0 ? 1 : 1);
+    int64_t Bc = (wsb - 64 * 256) / (int64_t)(sizeof(T) * vjp_per_walker_elems());
+    if (Bc > B) Bc = B;
+    if (Bc < 1) { err = "workspace too small for a single walker (vjp)"; return 3; }
+    (void)per;
+    DQ_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_bwd_smem_bytes<T>(N, dh)));
+    DQ_CHECK(cudaFuncSetAttribute(slater_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(slater_bwd_smem_per_warp<T>(N) * 4)));
+    for (int b0 = 0; b0 < B; b0 += (int)Bc) {
+      const int nb = (int)std::min<int64_t>(Bc, B - b0);
+      int rc = vjp_chunk(r + (size_t)b0 * 3 * N, R + (Rb ? (size_t)b0 * 3 * M : 0), Rb, nb, (const T*)weights + b0, (T*)sign + b0,
+                         (T*)logp + b0, (T*)grad_params, ws, st);
+      if (rc) return rc;
+    }
+    DQ_CHECK(cudaGetLastError());
+    return 0;
+  }
+
   int forward(const void* r, const void* R, int Rb, int B, void* sign, void* logp, void* ws, int64_t wsb,
               cudaStream_t st) override {
     int rc = run_batched((const T*)r, (const T*)R, Rb, B, 1, (T*)sign, (T*)logp, nullptr, nullptr, nullptr, ws, wsb, st);
@@ -1156,6 +1308,13 @@ int dqmc_mcmc_sweep(dqmc_handle h, void* r, void* sign, void* log, int32_t* age,
   return h->e->mcmc(r, sign, log, age, tau, R, R_batched, n_walkers, n_sub, target_acceptance, max_age, seed, step0,
                     walker_offset, noise_normal, noise_uniform, out_stats, workspace, workspace_bytes,
                     (cudaStream_t)stream);
+}
+int dqmc_wf_vjp_params(dqmc_handle h, const void* r, const void* R, int32_t R_batched, int32_t n_walkers, const void* weights,
+                       void* out_sign, void* out_log, void* out_grad_params, void* workspace, int64_t workspace_bytes,
+                       void* stream) {
+  if (!h) return 2;
+  return h->e->vjp_params(r, R, R_batched, n_walkers, weights, out_sign, out_log, out_grad_params, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
 }
 int64_t dqmc_launch_count(dqmc_handle h) { return h ? h->e->launches : -1; }
 

@@ -1,0 +1,303 @@
+// Reverse pass of the plain forward (S = 1): d/dparams sum_b w_b log|psi(r_b)| for the Psiformer.
+// This is the parameter VJP the reference's loss takes through `jvp`/`grad` of ansatz.apply
+// (reference src/deepqmc/loss/loss_function.py:53-82 compute_log_psi_tangent, loss/energy.py:77-102:
+// grad E = 2 < (E_loc - <E_loc>) d log|psi| / d theta >), SURVEY.md 8(f) row N1.
+// Parameter gradients are ACCUMULATED (atomicAdd) into a caller-zeroed buffer with the engine's
+// packed layout.  Kernels are SIMT and generic in T (fp64 parity / fp32).
+#pragma once
+#include "common.cuh"
+
+namespace dq {
+
+template <class T>
+__device__ __forceinline__ void atomic_add(T* p, T v) { atomicAdd(p, v); }
+
+// ------------------------------------------------------------------------------------------
+// dW[k][n] += sum_rows A[row][k] * dY[row][n]  (weight gradient of Y = A W).  Tile 32 x 32 of dW per block,
+// the row range is split over blockIdx.z; partial tiles are added atomically.
+// Row selection for the per-spin backflow heads: rows are (b, i) with i = row % Nel; only i in [lo, hi) counts.
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void gemm_tn_kernel(const T* __restrict__ A, int lda, const T* __restrict__ dY, int ldy, int rows, int K,
+                               int Nc, int rows_per_block, int Nel, int lo, int hi, T* __restrict__ dW, int ldw) {
+  __shared__ T As[32][33];
+  __shared__ T Ys[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads, 4 k-rows each
+  const int r_begin = blockIdx.z * rows_per_block;
+  const int r_end = r_begin + rows_per_block < rows ? r_begin + rows_per_block : rows;
+  T acc[4] = {T(0), T(0), T(0), T(0)};
+  for (int r0 = r_begin; r0 < r_end; r0 += 32) {
+    __syncthreads();
+    for (int rr = ty; rr < 32; rr += 8) {
+      const int row = r0 + rr;
+      bool ok = row < r_end;
+      if (ok && Nel > 0) { const int i = row % Nel; ok = i >= lo && i < hi; }
+      As[rr][tx] = (ok && k0 + tx < K) ? A[(size_t)row * lda + k0 + tx] : T(0);
+      Ys[rr][tx] = (ok && n0 + tx < Nc) ? dY[(size_t)row * ldy + n0 + tx] : T(0);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int rr = 0; rr < 32; ++rr) {
+      const T y = Ys[rr][tx];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] += As[rr][ty * 4 + q] * y;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int k = k0 + ty * 4 + q, n = n0 + tx;
+    if (k < K && n < Nc && acc[q] != T(0)) atomic_add(dW + (size_t)k * ldw + n, acc[q]);
+  }
+}
+
+// db[n] += sum_rows dZ[row][n]
+template <class T>
+__global__ void colsum_kernel(const T* __restrict__ dZ, int ld, int rows, int Nc, int rows_per_block, T* __restrict__ db) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= Nc) return;
+  const int r_begin = blockIdx.y * rows_per_block;
+  const int r_end = r_begin + rows_per_block < rows ? r_begin + rows_per_block : rows;
+  T acc = T(0);
+  for (int r = r_begin; r < r_end; ++r) acc += dZ[(size_t)r * ld + n];
+  atomic_add(db + n, acc);
+}
+
+// dZ = dY * (1 - y^2) with y = Y - Ysub (Ysub nullable): backward of y = tanh(z) given the stored outputs.
+template <class T>
+__global__ void tanh_bwd_kernel(const T* __restrict__ dY, const T* __restrict__ Y, const T* __restrict__ Ysub,
+                                T* __restrict__ dZ, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const T y = Y[i] - (Ysub ? Ysub[i] : T(0));
+  dZ[i] = dY[i] * (T(1) - y * y);
+}
+
+// W[rows][cols] -> Wt[cols][rows]
+template <class T>
+__global__ void transpose_kernel(const T* __restrict__ W, int rows, int cols, T* __restrict__ Wt) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const int r = idx / cols, c = idx - r * cols;
+  Wt[(size_t)c * rows + r] = W[idx];
+}
+
+// ------------------------------------------------------------------------------------------
+// Attention backward (plain forward), one block per (walker, head):  P = softmax(c q k^T), o = P v;
+//   dV = P^T dO;  dP = dO V^T;  dS = P (dP - rowsum(dP P));  dq = c dS k;  dk = c dS^T q.
+// QKV / dQKV rows [b][i][3 dmodel]; dO rows [b][i][dmodel].
+// dynamic smem = sizeof(T) * (4 N (dh + 1) + 2 N N).
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void attn_bwd_kernel(const T* __restrict__ QKV, int ldq, const T* __restrict__ dO, int ldo, int N, int dh,
+                                int dmodel, T scale, T* __restrict__ dQKV) {
+  DQMC_DYN_SMEM(smem_raw);
+  const int dhp = dh + 1, NN = N * N;
+  T* q = reinterpret_cast<T*>(smem_raw);
+  T* k = q + N * dhp;
+  T* v = k + N * dhp;
+  T* go = v + N * dhp;   // dO
+  T* p = go + N * dhp;   // [N][N]
+  T* ds = p + NN;        // [N][N]
+  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+  const size_t row0 = (size_t)b * N;
+  for (int idx = tid; idx < N * dh; idx += nt) {
+    const int i = idx / dh, e = idx - i * dh;
+    const T* src = QKV + (row0 + i) * ldq + h * dh + e;
+    q[i * dhp + e] = src[0]; k[i * dhp + e] = src[dmodel]; v[i * dhp + e] = src[2 * dmodel];
+    go[i * dhp + e] = dO[(row0 + i) * ldo + h * dh + e];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < NN; idx += nt) {
+    const int i = idx / N, j = idx - i * N;
+    T a = T(0), c = T(0);
+    for (int e = 0; e < dh; ++e) { a += q[i * dhp + e] * k[j * dhp + e]; c += go[i * dhp + e] * v[j * dhp + e]; }
+    p[idx] = a * scale;
+    ds[idx] = c;  // dP
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += nt) {
+    T mx = p[i * N];
+    for (int j = 1; j < N; ++j) mx = p[i * N + j] > mx ? p[i * N + j] : mx;
+    T sum = T(0);
+    for (int j = 0; j < N; ++j) { T ex = m_exp(p[i * N + j] - mx); p[i * N + j] = ex; sum += ex; }
+    T inv = T(1) / sum, dot = T(0);
+    for (int j = 0; j < N; ++j) { p[i * N + j] *= inv; dot += p[i * N + j] * ds[i * N + j]; }
+    for (int j = 0; j < N; ++j) ds[i * N + j] = p[i * N + j] * (ds[i * N + j] - dot) * scale;  // c dS
+  }
+  __syncthreads();
+  for (int idx = tid; idx < N * dh; idx += nt) {
+    const int i = idx / dh, e = idx - i * dh;
+    T dq = T(0), dk = T(0), dv = T(0);
+    for (int j = 0; j < N; ++j) {
+      dq += ds[i * N + j] * k[j * dhp + e];
+      dk += ds[j * N + i] * q[j * dhp + e];
+      dv += p[j * N + i] * go[j * dhp + e];
+    }
+    T* dst = dQKV + (row0 + i) * ldq + h * dh + e;
+    dst[0] = dq; dst[dmodel] = dk; dst[2 * dmodel] = dv;
+  }
+}
+
+template <class T>
+inline size_t attn_bwd_smem_bytes(int N, int dh) { return sizeof(T) * ((size_t)4 * N * (dh + 1) + (size_t)2 * N * N); }
+
+// ------------------------------------------------------------------------------------------
+// Determinant-sum backward: dlogdet[b][k] = w_b p_k,  p_k = c_k s_k e^{l_k - shift} / psi  (d log|psi| / d logdet_k),
+// plus the trainable cusp exponents (PsiformerCusp: -s a^2 / (a + r)) accumulated into dalpha[2].
+// One thread per walker.
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void finalize_bwd_kernel(const T* __restrict__ r, int N, int n_up, int K, int B,
+                                    const T* __restrict__ det_sign, const T* __restrict__ det_log,
+                                    const T* __restrict__ weights, int cusp_kind, T same_scale, T anti_scale,
+                                    const T* __restrict__ cusp_alpha, T* __restrict__ dlogdet, T* __restrict__ dalpha) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const T w = weights[b];
+  const T* ds = det_sign + (size_t)b * K;
+  const T* dl = det_log + (size_t)b * K;
+  T shift = dl[0];
+  for (int k = 1; k < K; ++k) shift = dl[k] > shift ? dl[k] : shift;
+  if ((shift - shift) != T(0)) shift = T(0);
+  T psi = T(0);
+  for (int k = 0; k < K; ++k) psi += ds[k] * m_exp(dl[k] - shift);
+  for (int k = 0; k < K; ++k) dlogdet[(size_t)b * K + k] = w * ds[k] * m_exp(dl[k] - shift) / psi;
+  if (cusp_kind == 1 && dalpha) {
+    const T as_ = cusp_alpha[0], aa_ = cusp_alpha[1];
+    T gs = T(0), ga = T(0);
+    const T* rb = r + (size_t)b * N * 3;
+    for (int i = 0; i < N; ++i)
+      for (int j = i + 1; j < N; ++j) {
+        const T dx0 = rb[3 * i] - rb[3 * j], dx1 = rb[3 * i + 1] - rb[3 * j + 1], dx2 = rb[3 * i + 2] - rb[3 * j + 2];
+        const T rho = m_sqrt(Num<T>::eps() + dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
+        const bool same = (i < n_up) == (j < n_up);
+        const T al = same ? as_ : aa_, sc = same ? same_scale : anti_scale;
+        const T g = -sc * al * (al + T(2) * rho) / ((al + rho) * (al + rho));  // d/dalpha of -s a^2 / (a + rho)
+        if (same) gs += g; else ga += g;
+      }
+    atomic_add(dalpha, w * gs);
+    atomic_add(dalpha + 1, w * ga);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Slater backward, one warp per (walker, determinant): rebuild A = env * bf, invert it (Gauss-Jordan with partial
+// pivoting), G = dlogdet A^-T;  dBF[b][i][k N + mu] = G[i][mu] env[i][mu];  envelope parameters:
+//   dpi[o][m] += G bf e^{-|zeta| rho},  dzeta[o][m] += G bf pi e^{-|zeta| rho} (-rho sign(zeta))   (o = k N + mu).
+// dynamic smem per warp: sizeof(T) * (N (2N + 1) + 2 N (N + 1)).
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void slater_bwd_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M,
+                                  int n_up, int K, int total, const T* __restrict__ pi_up, const T* __restrict__ pi_dn,
+                                  const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn,
+                                  const T* __restrict__ BF, int ldb, const T* __restrict__ dlogdet, T* __restrict__ dBF,
+                                  T* __restrict__ dpi_up, T* __restrict__ dpi_dn, T* __restrict__ dzeta_up,
+                                  T* __restrict__ dzeta_dn) {
+  DQMC_DYN_SMEM(smem_raw);
+  const int NP = N + 1, N2 = 2 * N + 1;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int gw = blockIdx.x * wpb + wib;
+  const size_t per_warp = (size_t)N * N2 + (size_t)2 * N * NP;
+  T* aug = reinterpret_cast<T*>(smem_raw) + per_warp * wib;  // [N][N2]
+  T* env = aug + N * N2;                                      // [N][NP]
+  T* bfv = env + N * NP;                                      // [N][NP]
+  if (gw >= total) return;
+  const int b = gw / K, k = gw % K;
+  const T* rb = r + (size_t)b * N * 3;
+  const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
+  for (int idx = lane; idx < N * N; idx += 32) {
+    const int i = idx / N, mu = idx - i * N;
+    const T* pi = (i < n_up ? pi_up : pi_dn) + (size_t)(k * N + mu) * M;
+    const T* ze = (i < n_up ? zeta_up : zeta_dn) + (size_t)(k * N + mu) * M;
+    T e = T(0);
+    for (int m = 0; m < M; ++m) {
+      const T dx0 = rb[3 * i] - Rb[3 * m], dx1 = rb[3 * i + 1] - Rb[3 * m + 1], dx2 = rb[3 * i + 2] - Rb[3 * m + 2];
+      const T rho = m_sqrt(Num<T>::eps() + dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
+      e += pi[m] * m_exp(-m_abs(ze[m]) * rho);
+    }
+    const T bf0 = BF[((size_t)b * N + i) * ldb + k * N + mu];
+    env[i * NP + mu] = e;
+    bfv[i * NP + mu] = bf0;
+    aug[i * N2 + mu] = e * bf0;
+    aug[i * N2 + N + mu] = (i == mu) ? T(1) : T(0);
+  }
+  __syncwarp();
+  for (int c = 0; c < N; ++c) {
+    T best = T(-1);
+    int bi = c;
+    for (int rr = c + lane; rr < N; rr += 32) {
+      T vv = m_abs(aug[rr * N2 + c]);
+      if (vv > best) { best = vv; bi = rr; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      T ob = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    const int prow = bi;
+    if (prow != c) {
+      for (int j = lane; j < 2 * N; j += 32) {
+        T t0 = aug[c * N2 + j];
+        aug[c * N2 + j] = aug[prow * N2 + j];
+        aug[prow * N2 + j] = t0;
+      }
+    }
+    __syncwarp();
+    const T ipv = T(1) / aug[c * N2 + c];
+    __syncwarp();
+    for (int j = lane; j < 2 * N; j += 32) aug[c * N2 + j] *= ipv;
+    __syncwarp();
+    for (int rr = 0; rr < N; ++rr) {
+      if (rr == c) continue;
+      const T f = aug[rr * N2 + c];
+      __syncwarp();
+      for (int j = lane; j < 2 * N; j += 32) aug[rr * N2 + j] -= f * aug[c * N2 + j];
+      __syncwarp();
+    }
+  }
+  // A^-1[mu][i] = aug[mu][N + i];  G[i][mu] = dlogdet * A^-1[mu][i]
+  const T dl = dlogdet[(size_t)b * K + k];
+  for (int idx = lane; idx < N * N; idx += 32) {
+    const int i = idx / N, mu = idx - i * N;
+    const T G = dl * aug[mu * N2 + N + i];
+    dBF[((size_t)b * N + i) * ldb + k * N + mu] = G * env[i * NP + mu];
+    const T gb = G * bfv[i * NP + mu];  // d / d env[i][mu]
+    const bool up = i < n_up;
+    const T* pi = (up ? pi_up : pi_dn) + (size_t)(k * N + mu) * M;
+    const T* ze = (up ? zeta_up : zeta_dn) + (size_t)(k * N + mu) * M;
+    T* dpi = (up ? dpi_up : dpi_dn) + (size_t)(k * N + mu) * M;
+    T* dze = (up ? dzeta_up : dzeta_dn) + (size_t)(k * N + mu) * M;
+    for (int m = 0; m < M; ++m) {
+      const T dx0 = rb[3 * i] - Rb[3 * m], dx1 = rb[3 * i + 1] - Rb[3 * m + 1], dx2 = rb[3 * i + 2] - Rb[3 * m + 2];
+      const T rho = m_sqrt(Num<T>::eps() + dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
+      const T z = ze[m], ex = m_exp(-m_abs(z) * rho);
+      atomic_add(dpi + m, gb * ex);
+      atomic_add(dze + m, gb * pi[m] * ex * (-rho) * (z > T(0) ? T(1) : (z < T(0) ? T(-1) : T(0))));
+    }
+  }
+}
+
+template <class T>
+inline size_t slater_bwd_smem_per_warp(int N) { return sizeof(T) * ((size_t)N * (2 * N + 1) + (size_t)2 * N * (N + 1)); }
+
+// Electron-nucleus features of the plain forward as a row matrix Feat[rows][F] (for dW_emb = Feat^T dX0).
+template <class T>
+__global__ void embed_feat_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M, int n_up,
+                                  T* __restrict__ Feat, int total) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total * M) return;
+  const int bi = idx / M, m = idx - bi * M, b = bi / N, i = bi - b * N;
+  const int F = 4 * M + 1;
+  const T* ri = r + (size_t)bi * 3;
+  const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
+  const T dx0 = ri[0] - Rb[3 * m], dx1 = ri[1] - Rb[3 * m + 1], dx2 = ri[2] - Rb[3 * m + 2];
+  const T rho = m_sqrt(Num<T>::eps() + dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
+  const T g = m_log1p(rho), s = g / rho;
+  T* f = Feat + (size_t)bi * F;
+  f[4 * m] = g; f[4 * m + 1] = dx0 * s; f[4 * m + 2] = dx1 * s; f[4 * m + 3] = dx2 * s;
+  if (m == 0) f[F - 1] = i < n_up ? T(1) : T(-1);
+}
+
+}  // namespace dq

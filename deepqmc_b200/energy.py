@@ -33,3 +33,42 @@ def compute_mean_energy(local_energy, weight=None):
     """all-device mean (reference: loss/energy.py:63-74 -> parallel.all_device_mean)."""
     x = local_energy if weight is None else local_energy * weight
     return parallel.energy_statistics(x.reshape(-1))['energy/mean']
+
+
+def median_clip_and_mask(x, clip_width: float, median_center: bool = True, exclude_width: float = float('inf')):
+    """Hard-clip local energies to `clip_width` mean absolute deviations around the (all-device) median / mean and
+    flag outliers beyond `exclude_width` MADs (reference: loss/clip.py:73-98; the median needs the all-gather of
+    E_loc, parallel.py:185-192)."""
+    allx = parallel.all_gather_walkers(x.reshape(-1))
+    center = allx.median() if median_center else allx.mean()
+    abs_all = (allx - center).abs()
+    mad = abs_all.mean()
+    x_clip = torch.clamp(x, center - clip_width * mad, center + clip_width * mad)
+    return x_clip, (x - center).abs() < exclude_width
+
+
+def compute_mean_energy_tangent(local_energy, weight, gradient_mask, ansatz, params, phys_conf):
+    """Gradient of the mean energy w.r.t. the ansatz parameters: the reference contracts
+    (E_loc - <E_loc>) * weight * mask / n_mask with the parameter tangent of log|psi|
+    (loss/energy.py:77-102 with loss/loss_function.py:53-82); here the same per-walker factors are the cotangent of
+    ONE reverse pass through the CUDA engine (dqmc_wf_vjp_params).  Returns {haiku name: gradient} summed over all
+    ranks (all-reduce of the packed gradient, reference optimizer.py:142 pmean)."""
+    E = local_energy.reshape(-1)
+    w = torch.ones_like(E) if weight is None else weight.reshape(-1)
+    mask = torch.ones_like(E, dtype=torch.bool) if gradient_mask is None else gradient_mask.reshape(-1)
+    stats = parallel.energy_statistics(E * w)
+    n_mask = mask.sum().double()
+    if parallel.world()[1] > 1:
+        torch.distributed.all_reduce(n_mask)
+    cot = ((E - stats['energy/mean'].to(E.dtype)) * w * mask.to(E.dtype) / n_mask.to(E.dtype)).contiguous()
+    _, grads = ansatz.log_psi_vjp(params, phys_conf, cot)
+    if parallel.world()[1] > 1:
+        keys = sorted(grads)
+        flat = torch.cat([grads[k].reshape(-1) for k in keys])
+        torch.distributed.all_reduce(flat)
+        o = 0
+        for k in keys:
+            n = grads[k].numel()
+            grads[k] = flat[o:o + n].reshape(grads[k].shape)
+            o += n
+    return grads

@@ -14,7 +14,7 @@ from . import _lib
 from . import params as PN
 from .spec import AnsatzSpec
 
-MODE_FORWARD, MODE_LOCAL_ENERGY = 0, 1
+MODE_FORWARD, MODE_LOCAL_ENERGY, MODE_VJP = 0, 1, 2
 _TORCH_DTYPE = {0: torch.float64, 1: torch.float32}
 
 
@@ -154,6 +154,32 @@ def _pack_haiku_params(spec: AnsatzSpec, params: dict, R=None) -> dict[str, np.n
         out['cusp.alpha'] = np.array([[spec.cusp_alpha, spec.cusp_alpha]], dtype=np.float64)
     else:
         out['cusp.alpha'] = np.ones((1, 2))
+    return out
+
+
+def _unpack_psiformer_grads(spec: AnsatzSpec, entries: dict, flat) -> dict:
+    """Engine-layout gradient vector -> Haiku-named tree (inverse of _pack_haiku_params for the Psiformer)."""
+    def e(name):
+        off, rows, cols = entries[name]
+        return flat[off:off + rows * cols].reshape(rows, cols)
+
+    d = spec.embedding_dim
+    out = {PN.GNN + 'electron_embedding/linear:w': e('emb.w')}
+    for l in range(spec.n_layers):
+        a = PN.attn_prefix(l)
+        qkv = e(f'L{l}.wqkv')
+        for j, n in enumerate(('query', 'key', 'value')):
+            out[a + f'multi_head_attention/{n}:w'] = qkv[:, j * d:(j + 1) * d]
+        out[a + 'multi_head_attention/linear:w'] = e(f'L{l}.wo')
+        out[a + 'mlp/linear_0:w'], out[a + 'mlp/linear_0:b'] = e(f'L{l}.w1'), e(f'L{l}.b1')[0]
+        out[a + 'mlp/linear_1:w'], out[a + 'mlp/linear_1:b'] = e(f'L{l}.w2'), e(f'L{l}.b2')[0]
+    out[PN.BF_UP + ':w'], out[PN.BF_DN + ':w'] = e('bf.up'), e('bf.dn')
+    for s_, t in (('up', 'up'), ('down', 'dn')):
+        out[f'{PN.ENV}:pi_{s_}'] = e(f'env.pi_{t}')
+        out[f'{PN.ENV}:zetas_{s_}'] = e(f'env.zeta_{t}')
+    if spec.cusp == 'psiformer':
+        ca = e('cusp.alpha')
+        out[f'{PN.CUSP}:same_alpha'], out[f'{PN.CUSP}:anti_alpha'] = ca[0, 0], ca[0, 1]
     return out
 
 
@@ -353,6 +379,23 @@ class Engine:
             grad.data_ptr() if grad is not None else None, ws.data_ptr(), ws.numel(), self._stream())
         self._check(rc, 'dqmc_local_energy')
         return E, stats, sign, log, grad
+
+    def vjp_params(self, r, R, weights, max_ws_bytes=None):
+        """-> (sign[B], log[B], grads): grads = d/dparams sum_b weights[b] log|psi(r_b)| as a Haiku-named dict
+        (reference: loss/loss_function.py:53-82).  Psiformer only."""
+        r = self._prep(r)
+        B = r.shape[0]
+        R, Rb = self._R(R, B)
+        w = self._prep(weights)
+        assert w.shape == (B,)
+        sign = torch.empty(B, dtype=self.dtype, device=self.device)
+        log = torch.empty(B, dtype=self.dtype, device=self.device)
+        flat = torch.empty(self.n_packed, dtype=self.dtype, device=self.device)
+        ws = self.workspace(B, MODE_VJP, max_ws_bytes)
+        rc = self.lib.dqmc_wf_vjp_params(self.h, r.data_ptr(), R.data_ptr(), Rb, B, w.data_ptr(), sign.data_ptr(), log.data_ptr(),
+                                         flat.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
+        self._check(rc, 'dqmc_wf_vjp_params')
+        return sign, log, _unpack_psiformer_grads(self.spec, self.entries, flat)
 
     def mcmc_sweep(self, state, R, n_sub, target_acceptance=0.57, max_age=None, seed=0, step0=0, walker_offset=0,
                    noise_normal=None, noise_uniform=None, max_ws_bytes=None):

@@ -25,7 +25,7 @@ extern "C" {
 enum { DQMC_PSIFORMER = 0, DQMC_FERMINET = 1, DQMC_TRANSPSIFORMER = 2, DQMC_PAULINET = 3 };
 enum { DQMC_F64 = 0, DQMC_F32 = 1 };
 enum { DQMC_GEMM_SIMT = 0, DQMC_GEMM_TCGEN05 = 1 };
-enum { DQMC_MODE_FORWARD = 0, DQMC_MODE_LOCAL_ENERGY = 1 };
+enum { DQMC_MODE_FORWARD = 0, DQMC_MODE_LOCAL_ENERGY = 1, DQMC_MODE_VJP = 2 };
 
 /* Ansatz + Hamiltonian constants that fix the kernel shapes.
  * reference: src/deepqmc/conf/ansatz/psiformer.yaml, ferminet.yaml;
@@ -129,6 +129,15 @@ int dqmc_mcmc_sweep(dqmc_handle h, void* r, void* sign, void* log, int32_t* age,
                     uint64_t seed, uint64_t step0, uint64_t walker_offset, const void* noise_normal,
                     const void* noise_uniform, void* out_stats, void* workspace, int64_t workspace_bytes,
                     void* stream);
+
+/* Parameter VJP of the wave function: out_grad_params[dqmc_param_total] (compute dtype, the packed layout of
+ * dqmc_param_entry) = d/dparams sum_b weights[b] log|psi(r_b)|; also returns sign/log of the batch.
+ * With weights = 2 (E_loc - <E_loc>) / B this is the energy gradient (Psiformer only so far).
+ * replaces: loss/loss_function.py:53-82 compute_log_psi_tangent / jax.grad through ansatz.apply,
+ *           loss/energy.py:77-102 compute_mean_energy_tangent. */
+int dqmc_wf_vjp_params(dqmc_handle h, const void* r, const void* R, int32_t R_batched, int32_t n_walkers,
+                       const void* weights, void* out_sign, void* out_log, void* out_grad_params, void* workspace,
+                       int64_t workspace_bytes, void* stream);
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches claim). */
 int64_t dqmc_launch_count(dqmc_handle h);

@@ -480,3 +480,50 @@ def test_nuclear_cusp_factor_fp64(form):
         assert abs(psi.log[b].item() - l) <= 1e-10 * max(1, abs(l))
         assert abs(E[b].item() - e) <= 1e-8 * max(1, abs(e)), (b, E[b].item(), e)
         assert abs(stats['hamil/lap'][b].item() - st['hamil/lap']) <= 1e-8 * max(1, abs(st['hamil/lap']))
+
+
+def test_parameter_vjp_matches_autograd_fp64():
+    """dqmc_wf_vjp_params: d/dparams sum_b w_b log|psi(r_b)| for the Psiformer against torch
+    autograd through the oracle, every parameter group (envelopes, cusp exponents, embedding, attention, MLP,
+    backflow heads)."""
+    from oracle import wf
+
+    mol, hamil, oh, ansatz, params, r, R = make('H2O', B=3, embedding_dim=32, n_layers=2, n_heads=2, n_determinants=3)
+    w = torch.as_tensor(np.random.default_rng(3).normal(size=3), device=DEV)
+    psi, grads = ansatz.log_psi_vjp(params, PhysicalConfiguration(R, r, torch.zeros(3, device=DEV)), w)
+    pt = {k: torch.as_tensor(v, dtype=torch.float64).requires_grad_(True) for k, v in params.items()}
+    tot = 0
+    for b in range(3):
+        s, l = wf.log_psi(ansatz.spec, pt, r[b].cpu(), R.cpu())
+        assert psi.sign[b].item() == s.item() and abs(psi.log[b].item() - l.item()) <= 1e-10 * max(1, abs(l.item()))
+        tot = tot + w[b].cpu() * l
+    tot.backward()
+    assert set(grads) == set(pt)
+    for k, v in pt.items():
+        ref = v.grad
+        assert torch.allclose(grads[k].cpu().reshape(ref.shape), ref, rtol=1e-8, atol=1e-9 * max(1.0, ref.abs().max().item())), k
+
+
+def test_energy_gradient_fp32_close_to_fp64():
+    """Energy gradient = one local-energy pass + one reverse pass with cotangent (E_loc - <E>) / B
+    (reference loss/energy.py:77-102): the fp32 engine (tcgen05 forward GEMMs) agrees with the fp64 engine."""
+    from deepqmc_b200.energy import compute_mean_energy_tangent, median_clip_and_mask
+
+    mol = Molecule.from_name('LiH')
+    hamil = MolecularHamiltonian(mol=mol)
+    hyper = dict(embedding_dim=64, n_layers=2, n_heads=2, n_determinants=4)
+    a64 = B200Ansatz(hamil, 'psiformer', dtype='float64', **hyper)
+    a32 = B200Ansatz(hamil, 'psiformer', dtype='float32', gemm_backend=1, **hyper)
+    params = PN.perturb_params(a64.init(0))
+    rng = np.random.default_rng(0)
+    r = torch.as_tensor(mol.coords[rng.integers(0, 2, size=(64, 4))] + 0.7 * rng.normal(size=(64, 4, 3)), device=DEV)
+    R = torch.as_tensor(mol.coords, device=DEV)
+    out = {}
+    for name, a, dt in (('f64', a64, torch.float64), ('f32', a32, torch.float32)):
+        pc = PhysicalConfiguration(R.to(dt), r.to(dt), torch.zeros(64, device=DEV))
+        E, _ = hamil.local_energy(a.apply)(None, params, pc)
+        Ec, mask = median_clip_and_mask(E, 5.0)
+        out[name] = compute_mean_energy_tangent(Ec, None, mask, a, params, pc)
+    for k in out['f64']:
+        g64, g32 = out['f64'][k].double(), out['f32'][k].double()
+        assert (g64 - g32).abs().max().item() <= 2e-3 * max(1e-3, g64.abs().max().item()), k

@@ -37,6 +37,26 @@ def _worker(rank, world, port, q):
         and torch.equal(gathered, E_all)
         and parallel.rank_seed(5) == 5 + rank
     )
+    # global-median clipping + energy-gradient cotangents / gradient all-reduce (loss/clip.py:73-98, loss/energy.py:77-102)
+    from deepqmc_b200.energy import compute_mean_energy_tangent, median_clip_and_mask
+    from deepqmc_b200.types import PhysicalConfiguration, Psi
+
+    Ec, mask = median_clip_and_mask(E_all[lo:hi], 1.0, exclude_width=2.0)
+    center = E_all.median()
+    mad = (E_all - center).abs().mean()
+    ok = ok and torch.allclose(Ec, torch.clamp(E_all[lo:hi], center - mad, center + mad))
+    ok = ok and torch.equal(mask, (E_all[lo:hi] - center).abs() < 2.0)
+
+    class FakeAnsatz:  # d log psi_b / d theta = feature vector f_b: the VJP is sum_b cot_b f_b
+        def log_psi_vjp(self, params, pc, cot):
+            return Psi(torch.ones_like(cot), torch.zeros_like(cot)), {'theta': (cot[:, None] * pc.r).sum(0)}
+
+    feats = torch.randn(B, 3, generator=g, dtype=torch.float64)
+    pc = PhysicalConfiguration(torch.zeros(1, 3), feats[lo:hi], torch.zeros(hi - lo))
+    grads = compute_mean_energy_tangent(E_all[lo:hi], None, mask, FakeAnsatz(), None, pc)
+    mask_all = (E_all - center).abs() < 2.0
+    ref = (((E_all - E_all.mean()) * mask_all)[:, None] * feats).sum(0) / mask_all.sum()
+    ok = ok and torch.allclose(grads['theta'], ref)
     q.put((rank, bool(ok)))
     torch.distributed.destroy_process_group()
 
