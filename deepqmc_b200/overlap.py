@@ -65,3 +65,57 @@ def compute_mean_overlap(psi_ratio, weight=None):
     symm = symmetrize_overlap_with_clipped_geometric_mean(mean)
     iu = torch.triu_indices(n, n, 1)
     return (symm[iu[0], iu[1]] ** 2).sum(), {'overlap/pairwise/mean': symm}
+
+
+def compute_mean_overlap_tangent(psi_ratio, weight, ratio_gradient_mask, ansatz, params, phys_conf, scale=None,
+                                 ordering=None):
+    """Parameter gradient of the overlap penalty sum_{i<j} S_ij^2 (reference loss/overlap.py:182-229, Eq. 16 of
+    Entwistle et al. 2023 restricted -- like the reference -- to the parameters of the SECOND state of every ordered
+    pair).  For state j the reference contracts
+
+        2 <ratio_ji> (ratio_ij[b] - <ratio_ij>) w_b mask_b / n_mask * scale_ij      summed over the pairs i < j
+
+    with the parameter tangent of log|psi_j| on state j's own samples; here these factors are the cotangent of one
+    reverse pass per state (dqmc_wf_vjp_params).  psi_ratio[i, j, b] as returned by compute_psi_ratio;
+    `ordering`: permutation of the states that defines "i < j" (reference permute_matrix with data['ordering']).
+    Returns a list with one {haiku name: gradient} dict per state (None for a state that is never the second one)."""
+    n, _, B = psi_ratio.shape
+    w = torch.ones(n, B, dtype=psi_ratio.dtype, device=psi_ratio.device) if weight is None else weight
+    mask = torch.ones(n, n, B, dtype=torch.bool, device=psi_ratio.device) if ratio_gradient_mask is None else ratio_gradient_mask
+    local = (w[None] * psi_ratio).double()
+    packed = torch.cat([local.sum(-1).reshape(-1), mask.double().sum(-1).reshape(-1),
+                        torch.tensor([float(B)], device=local.device, dtype=torch.float64)])
+    if parallel.world()[1] > 1:
+        torch.distributed.all_reduce(packed)
+    mean_ratio = (packed[:n * n] / packed[-1]).reshape(n, n).to(psi_ratio.dtype)
+    n_mask = packed[n * n:2 * n * n].reshape(n, n).to(psi_ratio.dtype)
+    sc = torch.ones(n, n, dtype=psi_ratio.dtype, device=psi_ratio.device) if scale is None else scale
+    order = list(range(n)) if ordering is None else [int(x) for x in ordering]
+    pos = {s: k for k, s in enumerate(order)}  # position of every state in the ordering
+    grads = []
+    for j in range(n):
+        cot = torch.zeros(B, dtype=psi_ratio.dtype, device=psi_ratio.device)
+        used = False
+        for i in range(n):
+            if pos[i] < pos[j]:  # (i, j) is in the upper triangle of the permuted matrix
+                cot = cot + (2 * mean_ratio[j, i] * (psi_ratio[i, j] - mean_ratio[i, j]) * w[j] * mask[i, j].to(cot.dtype)
+                             / n_mask[i, j] * sc[i, j])
+                used = True
+        if not used:
+            grads.append(None)
+            continue
+        R = phys_conf.R[0] if phys_conf.R.dim() == 4 else phys_conf.R
+        R = R[0] if R.dim() == 3 else R
+        pc_j = PhysicalConfiguration(R, phys_conf.r[j], torch.zeros(B, device=cot.device))
+        _, g = ansatz.log_psi_vjp(params[j], pc_j, cot.contiguous())
+        if parallel.world()[1] > 1:
+            keys = sorted(g)
+            flat = torch.cat([g[k].reshape(-1) for k in keys])
+            torch.distributed.all_reduce(flat)
+            o = 0
+            for k in keys:
+                m = g[k].numel()
+                g[k] = flat[o:o + m].reshape(g[k].shape)
+                o += m
+        grads.append(g)
+    return grads

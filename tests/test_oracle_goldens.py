@@ -248,3 +248,32 @@ def test_paulinet_default_yaml_parameter_count_and_antisymmetry():
     s0, l0 = wf.log_psi(small, pt, r, R)
     s1, l1 = wf.log_psi(small, pt, r[[1, 0, 2, 3]], R)
     assert s0.item() == -s1.item() and abs(l0.item() - l1.item()) < 1e-10
+
+
+def test_overlap_tangent_cotangents_match_autograd_of_the_penalty():
+    """compute_mean_overlap_tangent (reference loss/overlap.py:182-229): with a toy 'ansatz' whose log|psi| is linear
+    in the parameters the returned gradient must equal the reference's tangent formula evaluated directly:
+    d/d theta_j of  sum_{i<j} 2 <ratio_ji> < (ratio_ij - <ratio_ij>) d log psi_j > ."""
+    import torch
+
+    from deepqmc_b200.overlap import compute_mean_overlap_tangent
+    from deepqmc_b200.types import PhysicalConfiguration, Psi
+
+    g = torch.Generator().manual_seed(0)
+    n, B, P = 3, 7, 4
+    ratio = torch.randn(n, n, B, generator=g, dtype=torch.float64)
+    feats = torch.randn(n, B, P, generator=g, dtype=torch.float64)  # d log psi_j(r_b) / d theta_j
+
+    class Toy:
+        def log_psi_vjp(self, params, pc, cot):
+            return Psi(torch.ones_like(cot), torch.zeros_like(cot)), {'theta': (cot[:, None] * pc.r).sum(0)}
+
+    pc = PhysicalConfiguration(torch.zeros(1, 3), feats, torch.zeros(n, B))
+    grads = compute_mean_overlap_tangent(ratio, None, None, Toy(), [None] * n, pc)
+    assert grads[0] is None
+    mean = ratio.mean(-1)
+    for j in (1, 2):
+        ref = torch.zeros(P, dtype=torch.float64)
+        for i in range(j):
+            ref += 2 * mean[j, i] * ((ratio[i, j] - mean[i, j])[:, None] * feats[j]).mean(0)
+        assert torch.allclose(grads[j]['theta'], ref)
