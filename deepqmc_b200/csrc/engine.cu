@@ -1125,11 +1125,10 @@ struct Engine : EngineBase {
     const T* r = (const T*)r_;
     const T* R = (const T*)R_;
     DQ_CHECK(cudaMemsetAsync(grad_params, 0, sizeof(T) * total, st));
-    const int64_t per = (int64_t)(sizeof(T) * vjp_per_walker_elems()) + 64 * 256 / (B > 0 ? 1 : 1);
+    // walkers per chunk: activations of every layer stay resident for the reverse pass (64 buffers, 256 B alignment each)
     int64_t Bc = (wsb - 64 * 256) / (int64_t)(sizeof(T) * vjp_per_walker_elems());
     if (Bc > B) Bc = B;
     if (Bc < 1) { err = "workspace too small for a single walker (vjp)"; return 3; }
-    (void)per;
     DQ_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_bwd_smem_bytes<T>(N, dh)));
     DQ_CHECK(cudaFuncSetAttribute(slater_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(slater_bwd_smem_per_warp<T>(N) * 4)));

@@ -26,53 +26,13 @@ __global__ void gnn_embed_kernel(const T* __restrict__ emb, int n_types, int N, 
 }
 
 // ------------------------------------------------------------------------------------------
-// Edge filters  w_t(e_ji) = tanh(W_t^T [|d|, d]),  d = r_i - p_j (receiver - sender, graph.py:24;
-// eps-safe norm, edge_features.py:42-78), t = same / anti (sender electron j != i) or ne (sender
-// nucleus).  An edge depends on r_i and r_j only, so its forward-Laplacian state is COMPACT:
+// Raw edge features [|d|, d],  d = r_i - p_j (receiver - sender, graph.py:24; eps-safe norm,
+// edge_features.py:42-78), sender = electron j != i (same / anti edges) or nucleus (ne edges).  An edge
+// depends on r_i and r_j only, so its forward-Laplacian state is COMPACT:
 //   slot 0 value | 1..3 d/dr_i | 4..6 d/dr_j (zero for nuclei) | 7 Laplacian over both particles.
-// Layout Wc[b][i][jj][8][e], jj < N: electron sender, jj >= N: nucleus jj - N; (i, i) is zero.
-// One thread per (b, i, jj).
-// ------------------------------------------------------------------------------------------
-template <class T>
-__global__ void gnn_edge_w_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M,
-                                  int n_up, const T* __restrict__ Wsame, const T* __restrict__ Wanti,
-                                  const T* __restrict__ Wne, int e, T* __restrict__ Wc, int total) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int NS = N + M;
-  const int jj = idx % NS, i = (idx / NS) % N, b = idx / (NS * N);
-  T* out = Wc + (size_t)idx * 8 * e;
-  if (jj == i) {
-    for (int k = 0; k < 8 * e; ++k) out[k] = T(0);
-    return;
-  }
-  const T* ri = r + ((size_t)b * N + i) * 3;
-  const bool nuc = jj >= N;
-  const T* pj = nuc ? R + (R_batched ? (size_t)b * M * 3 : 0) + (size_t)(jj - N) * 3 : r + ((size_t)b * N + jj) * 3;
-  const T* W = nuc ? Wne : (((i < n_up) == (jj < n_up)) ? Wsame : Wanti);
-  const T d0 = ri[0] - pj[0], d1 = ri[1] - pj[1], d2 = ri[2] - pj[2];
-  const T dd = d0 * d0 + d1 * d1 + d2 * d2;
-  const T rho2 = Num<T>::eps() + dd, rho = m_sqrt(rho2);
-  const T lap_rho = T(3) / rho - dd / (rho2 * rho);  // Laplacian of rho w.r.t. one particle
-  const T np = nuc ? T(1) : T(2);                    // particles the edge depends on
-  for (int f = 0; f < e; ++f) {
-    const T w0 = W[f], w1 = W[e + f], w2 = W[2 * e + f], w3 = W[3 * e + f];
-    const T z = w0 * rho + w1 * d0 + w2 * d1 + w3 * d2;
-    const T g0 = w0 * d0 / rho + w1, g1 = w0 * d1 / rho + w2, g2 = w0 * d2 / rho + w3;  // dz / dr_i
-    const T zl = np * w0 * lap_rho;
-    const T y = m_tanh(z), y1 = T(1) - y * y, y2 = T(-2) * y * y1;
-    out[f] = y;
-    out[e + f] = y1 * g0; out[2 * e + f] = y1 * g1; out[3 * e + f] = y1 * g2;
-    const T sj = nuc ? T(0) : T(-1);
-    out[4 * e + f] = sj * y1 * g0; out[5 * e + f] = sj * y1 * g1; out[6 * e + f] = sj * y1 * g2;
-    out[7 * e + f] = y1 * zl + y2 * np * (g0 * g0 + g1 * g1 + g2 * g2);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Raw edge features [|d|, d] in the compact 8-slot layout (same conventions as gnn_edge_w_kernel):
-// E[b][i][jj][8][4]; the edge MLPs (w_t, u) then run on these rows with the ordinary row GEMM and
-// act_fl_kernel with S = 8 (slots 1..6 are the tangents, slot 7 the Laplacian).  One thread per (b, i, jj).
+// Layout E[b][i][jj][8][4], jj < N: electron sender, jj >= N: nucleus jj - N; (i, i) is zero.  The edge MLPs
+// (w_t, u) run on these rows with the ordinary row GEMM and act_fl_kernel with S = 8 (slots 1..6 are the
+// tangents, slot 7 the Laplacian).  One thread per (b, i, jj).
 // ------------------------------------------------------------------------------------------
 template <class T>
 __global__ void gnn_edge_feat_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M,
