@@ -51,6 +51,9 @@ struct EngineBase {
   virtual int local_energy(const void* r, const void* R, int Rb, int B, uint64_t seed, const void* twist, void* E,
                            void* stats, void* sign, void* logp, void* grad, void* ws, int64_t wsb,
                            cudaStream_t st) = 0;
+  virtual int langevin(void* r, void* sign, void* logp, void* force, int32_t* age, void* tau, const void* R, int Rb, int B,
+                       int n_sub, double target, int max_age, uint64_t seed, uint64_t step0, uint64_t woff, const void* nn,
+                       const void* nu, void* stats, void* ws, int64_t wsb, cudaStream_t st) = 0;
   virtual int vjp_params(const void* r, const void* R, int Rb, int B, const void* weights, void* sign, void* logp,
                          void* grad_params, void* ws, int64_t wsb, cudaStream_t st) = 0;
   virtual int debug_gemm(const char* wname, const char* bname, const void* A, const void* Res, void* C, int Mr, int S,
@@ -218,6 +221,7 @@ struct Engine : EngineBase {
   T* d_params_t = nullptr;  // every entry transposed ([cols][rows]): operands of the dA = dY W^T products of the reverse pass
   double* d_stage = nullptr;
   T* d_zval = nullptr;
+  T* d_znuc = nullptr;  // full nuclear charges (Langevin clean_force)
   int* d_ecp_mask = nullptr;
   T* d_ecp_loc = nullptr;
   T* d_nl_params = nullptr;
@@ -287,6 +291,12 @@ struct Engine : EngineBase {
     for (int m = 0; m < M; ++m) z[m] = (T)cfg.z_valence[m];
     DQ_CHECK(cudaMalloc((void**)&d_zval, sizeof(T) * M));
     DQ_CHECK(cudaMemcpy(d_zval, z.data(), sizeof(T) * M, cudaMemcpyHostToDevice));
+    {
+      std::vector<T> zn(M);
+      for (int m = 0; m < M; ++m) zn[m] = (T)cfg.z_nuclear[m];
+      DQ_CHECK(cudaMalloc((void**)&d_znuc, sizeof(T) * M));
+      DQ_CHECK(cudaMemcpy(d_znuc, zn.data(), sizeof(T) * M, cudaMemcpyHostToDevice));
+    }
     DQ_CHECK(cudaMalloc((void**)&d_ecp_mask, sizeof(int) * M));
     DQ_CHECK(cudaMemcpy(d_ecp_mask, cfg.ecp_mask, sizeof(int) * M, cudaMemcpyHostToDevice));
     const int Tm = cfg.ecp_loc_terms;
@@ -395,7 +405,7 @@ struct Engine : EngineBase {
     return 0;
   }
   ~Engine() override {
-    cudaFree(d_params); cudaFree(d_params_t); cudaFree(d_stage); cudaFree(d_zval); cudaFree(d_ecp_mask);
+    cudaFree(d_params); cudaFree(d_params_t); cudaFree(d_stage); cudaFree(d_znuc); cudaFree(d_zval); cudaFree(d_ecp_mask);
     if (d_ecp_loc) cudaFree(d_ecp_loc);
     if (d_nl_params) cudaFree(d_nl_params);
     if (d_nl_nuc) cudaFree(d_nl_nuc);
@@ -1001,6 +1011,60 @@ struct Engine : EngineBase {
     return 0;
   }
 
+  // ---- Metropolis-adjusted Langevin sweep: value + drift from the forward-Laplacian pass ----
+  // state = {r, sign, log, force}; force == clean_force(grad log|psi|) with the CURRENT tau (electron_samplers.py:197-211)
+  int value_and_force(const T* r, const T* R, int Rb, int B, const T* tau, T* sign, T* logp, T* force, char* p, int64_t rest,
+                      cudaStream_t st) {
+    T* E = (T*)p; p += align_up(sizeof(T) * (size_t)B);
+    T* stt = (T*)p; p += align_up(sizeof(T) * (size_t)6 * B);
+    T* grad = (T*)p; p += align_up(sizeof(T) * (size_t)B * T3);
+    rest -= (int64_t)(align_up(sizeof(T) * (size_t)B) + align_up(sizeof(T) * (size_t)6 * B) + align_up(sizeof(T) * (size_t)B * T3));
+    int rc = run_batched(r, R, Rb, B, T3 + 2, sign, logp, E, stt, grad, p, rest, st);
+    if (rc) return rc;
+    DQ_LAUNCH(langevin_force_kernel<T>, dim3((B * N + 127) / 128), dim3(128), 0, st, (const T*)grad, r, R, Rb, (const T*)d_znuc, tau,
+              N, M, B * N, force);
+    return 0;
+  }
+  int langevin(void* r_, void* sign_, void* logp_, void* force_, int32_t* age, void* tau_, const void* R_, int Rb, int B, int n_sub,
+               double target, int max_age, uint64_t seed, uint64_t step0, uint64_t woff, const void* nn, const void* nu,
+               void* stats_, void* ws, int64_t wsb, cudaStream_t st) override {
+    T* r = (T*)r_; T* sign = (T*)sign_; T* logp = (T*)logp_; T* force = (T*)force_; T* tau = (T*)tau_; T* stats = (T*)stats_;
+    const T* R = (const T*)R_;
+    if (n_sub == 0) return langevin_update(r, R, Rb, B, tau, sign, logp, force, ws, wsb, st);
+    char* p = (char*)ws;
+    T* rp = (T*)p; p += align_up(sizeof(T) * (size_t)B * 3 * N);
+    T* fp = (T*)p; p += align_up(sizeof(T) * (size_t)B * 3 * N);
+    T* sp = (T*)p; p += align_up(sizeof(T) * (size_t)B);
+    T* lp = (T*)p; p += align_up(sizeof(T) * (size_t)B);
+    int* cnt = (int*)p; p += 256;
+    int64_t rest = wsb - (p - (char*)ws);
+    DQ_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int), st));
+    const int ne = B * 3 * N;
+    for (int s = 0; s < n_sub; ++s) {
+      const T* nns = nn ? (const T*)nn + (size_t)s * ne : nullptr;
+      const T* nus = nu ? (const T*)nu + (size_t)s * B : nullptr;
+      DQ_LAUNCH(langevin_propose_kernel<T>, dim3((ne / 2 + 1 + 127) / 128), dim3(128), 0, st, (const T*)r, (const T*)force, rp,
+                (const T*)tau, nns, seed, step0 + (uint64_t)s, woff * (uint64_t)(3 * N), ne);
+      int rc = value_and_force(rp, R, Rb, B, tau, sp, lp, fp, p, rest, st);
+      if (rc) return rc;
+      DQ_LAUNCH(langevin_accept_kernel<T>, dim3((B + 127) / 128), dim3(128), 0, st, r, (const T*)rp, force, (const T*)fp, sign,
+                (const T*)sp, logp, (const T*)lp, age, (const T*)tau, nus, seed, step0 + (uint64_t)s, woff, max_age, B, N, cnt);
+      DQ_LAUNCH(tau_kernel<T>, dim3(1), dim3(32), 0, st, tau, cnt, B, (T)target, stats);
+    }
+    DQ_LAUNCH(sampler_stats_kernel<T>, dim3(1), dim3(256), 0, st, (const T*)r, (const T*)logp, (const int*)age, (const T*)tau, B,
+              N, stats);
+    DQ_CHECK(cudaGetLastError());
+    return 0;
+  }
+  // n_sub == 0 with force output: (re)compute psi and the drift of the current walkers (sampler.update)
+  int langevin_update(const T* r, const T* R, int Rb, int B, const T* tau, T* sign, T* logp, T* force, void* ws, int64_t wsb,
+                      cudaStream_t st) {
+    int rc = value_and_force(r, R, Rb, B, tau, sign, logp, force, (char*)ws, wsb, st);
+    if (rc) return rc;
+    DQ_CHECK(cudaGetLastError());
+    return 0;
+  }
+
   // ---- parameter VJP of the plain forward (Psiformer): SURVEY.md 8(f) N1 ------------------------
   const T* PT(const std::string& n) const { return d_params_t + off(n); }
   size_t vjp_per_walker_elems() const {
@@ -1307,6 +1371,14 @@ int dqmc_mcmc_sweep(dqmc_handle h, void* r, void* sign, void* log, int32_t* age,
   return h->e->mcmc(r, sign, log, age, tau, R, R_batched, n_walkers, n_sub, target_acceptance, max_age, seed, step0,
                     walker_offset, noise_normal, noise_uniform, out_stats, workspace, workspace_bytes,
                     (cudaStream_t)stream);
+}
+int dqmc_langevin_sweep(dqmc_handle h, void* r, void* sign, void* log, void* force, int32_t* age, void* tau, const void* R,
+                        int32_t R_batched, int32_t n_walkers, int32_t n_sub, double target_acceptance, int32_t max_age,
+                        uint64_t seed, uint64_t step0, uint64_t walker_offset, const void* noise_normal,
+                        const void* noise_uniform, void* out_stats, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!h) return 2;
+  return h->e->langevin(r, sign, log, force, age, tau, R, R_batched, n_walkers, n_sub, target_acceptance, max_age, seed, step0,
+                        walker_offset, noise_normal, noise_uniform, out_stats, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 int dqmc_wf_vjp_params(dqmc_handle h, const void* r, const void* R, int32_t R_batched, int32_t n_walkers, const void* weights,
                        void* out_sign, void* out_log, void* out_grad_params, void* workspace, int64_t workspace_bytes,

@@ -68,6 +68,115 @@ __global__ void accept_kernel(T* __restrict__ r, const T* __restrict__ r_prop, T
   if (threadIdx.x == 0 && s_cnt) atomicAdd(acc_count, s_cnt);
 }
 
+// ---- Metropolis-adjusted Langevin sampler (reference: sampling/electron_samplers.py:176-232) --------------------
+// clean_force (sampling_utils.py:71-101): damp the drift near the nuclei.  grad[B][3N] = d log|psi| / dr from the
+// forward-Laplacian pass; z = r_i - R_nearest (plain distances), a = (1 + f^.z^)/2 + Z^2 z^2 / (10 (4 + Z^2 z^2)),
+// f <- f 2 / (sqrt(1 + 2 a |f|^2 tau) + 1), then |f| limited to |z| / tau.  One thread per (walker, electron).
+template <class T>
+__global__ void langevin_force_kernel(const T* __restrict__ grad, const T* __restrict__ r, const T* __restrict__ R,
+                                      int R_batched, const T* __restrict__ charges, const T* __restrict__ tau, int N,
+                                      int M, int total, T* __restrict__ force) {
+  const int bi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bi >= total) return;
+  const int b = bi / N;
+  const T* ri = r + (size_t)bi * 3;
+  const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
+  T z0 = 0, z1 = 0, z2 = 0, zz = T(-1), zch = 0;
+  for (int m = 0; m < M; ++m) {
+    const T d0 = ri[0] - Rb[3 * m], d1 = ri[1] - Rb[3 * m + 1], d2 = ri[2] - Rb[3 * m + 2];
+    const T dd = d0 * d0 + d1 * d1 + d2 * d2;
+    if (zz < T(0) || dd < zz) { zz = dd; z0 = d0; z1 = d1; z2 = d2; zch = charges[m]; }  // argmin: first minimum
+  }
+  T f0 = grad[(size_t)bi * 3], f1 = grad[(size_t)bi * 3 + 1], f2 = grad[(size_t)bi * 3 + 2];
+  const T eps = Num<T>::eps(), t = tau[0];
+  const T zn = m_sqrt(zz);
+  T fn = m_sqrt(f0 * f0 + f1 * f1 + f2 * f2);
+  const T fc = fn > eps ? fn : eps;
+  const T cosfz = (f0 * z0 + f1 * z1 + f2 * z2) / (fc * zn);
+  const T Z2z2 = zch * zch * zz;
+  const T a = (T(1) + cosfz) / T(2) + Z2z2 / (T(10) * (T(4) + Z2z2));
+  const T factor = T(2) / (m_sqrt(T(1) + T(2) * a * fn * fn * t) + T(1));
+  f0 *= factor; f1 *= factor; f2 *= factor;
+  fn = m_sqrt(f0 * f0 + f1 * f1 + f2 * f2);
+  const T lim = zn / (t * (fn > eps ? fn : eps));
+  const T nf = lim < T(1) ? lim : T(1);
+  force[(size_t)bi * 3] = f0 * nf; force[(size_t)bi * 3 + 1] = f1 * nf; force[(size_t)bi * 3 + 2] = f2 * nf;
+}
+
+// proposal r' = r + tau F + sqrt(tau) N(0, 1)  (electron_samplers.py:213-220); noise / Philox as propose_kernel
+template <class T>
+__global__ void langevin_propose_kernel(const T* __restrict__ r, const T* __restrict__ force, T* __restrict__ r_prop,
+                                        const T* __restrict__ tau, const T* __restrict__ noise, uint64_t seed,
+                                        uint64_t step, uint64_t elem_offset, int n_elem) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e0 = 2 * p;
+  if (e0 >= n_elem) return;
+  const T t = tau[0], st = m_sqrt(t);
+  T z0, z1;
+  if (noise) {
+    z0 = noise[e0];
+    z1 = e0 + 1 < n_elem ? noise[e0 + 1] : T(0);
+  } else {
+    uint32_t w[4];
+    Philox::gen(seed, elem_offset / 2 + (uint64_t)p, step, w);
+    double u1 = Philox::u01(w[0], w[1]), u2 = Philox::u01(w[2], w[3]);
+    double rad = ::sqrt(-2.0 * ::log(u1)), ang = 6.283185307179586 * u2;
+    z0 = (T)(rad * ::cos(ang));
+    z1 = (T)(rad * ::sin(ang));
+  }
+  r_prop[e0] = r[e0] + t * force[e0] + st * z0;
+  if (e0 + 1 < n_elem) r_prop[e0 + 1] = r[e0 + 1] + t * force[e0 + 1] + st * z1;
+}
+
+// accept with log G ratio = sum (F + F') . ((r - r') + tau / 2 (F - F')) plus 2 dlog|psi| (electron_samplers.py:222-232);
+// the force travels with the walker state.  One thread per walker.
+template <class T>
+__global__ void langevin_accept_kernel(T* __restrict__ r, const T* __restrict__ r_prop, T* __restrict__ force,
+                                       const T* __restrict__ force_p, T* __restrict__ sign, const T* __restrict__ sign_p,
+                                       T* __restrict__ logp, const T* __restrict__ logp_p, int* __restrict__ age,
+                                       const T* __restrict__ tau, const T* __restrict__ unoise, uint64_t seed,
+                                       uint64_t step, uint64_t walker_offset, int max_age, int B, int N,
+                                       int* __restrict__ acc_count) {
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    double u;
+    if (unoise) u = (double)unoise[b];
+    else {
+      uint32_t w[4];
+      Philox::gen(seed ^ 0x9E3779B97F4A7C15ull, walker_offset + (uint64_t)b, step, w);
+      u = Philox::u01(w[0], w[1]);
+    }
+    const double t = (double)tau[0];
+    double lg = 0.0;
+    for (int e = 0; e < 3 * N; ++e) {
+      const size_t k = (size_t)b * 3 * N + e;
+      const double f = (double)force[k], fp = (double)force_p[k];
+      lg += (f + fp) * (((double)r[k] - (double)r_prop[k]) + 0.5 * t * (f - fp));
+    }
+    const double lp = lg + 2.0 * ((double)logp_p[b] - (double)logp[b]);
+    bool acc = lp > ::log(u);
+    if (max_age >= 0) acc = acc || (age[b] >= max_age);
+    if (acc) {
+      for (int e = 0; e < 3 * N; ++e) {
+        const size_t k = (size_t)b * 3 * N + e;
+        r[k] = r_prop[k];
+        force[k] = force_p[k];
+      }
+      sign[b] = sign_p[b];
+      logp[b] = logp_p[b];
+      age[b] = 0;
+      atomicAdd(&s_cnt, 1);
+    } else {
+      age[b] += 1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cnt) atomicAdd(acc_count, s_cnt);
+}
+
 // tau <- tau * max(acceptance, 0.05) / target   (reference: electron_samplers.py:121-126)
 template <class T>
 __global__ void tau_kernel(T* tau, int* acc_count, int B, T target, T* acc_out) {

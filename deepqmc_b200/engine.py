@@ -435,6 +435,38 @@ class Engine:
         self._check(rc, 'dqmc_mcmc_sweep')
         return stats
 
+    def langevin_sweep(self, state, R, n_sub, target_acceptance=0.57, max_age=None, seed=0, step0=0, walker_offset=0,
+                       noise_normal=None, noise_uniform=None):
+        """state: dict(r[B,N,3], sign[B], log[B], force[B,N,3], age[B] int32, tau[1]) -- updated IN PLACE.
+        n_sub = 0: recompute sign / log / force of the current walkers (sampler update)."""
+        r = state['r']
+        B, N = r.shape[0], r.shape[1]
+        for k in ('r', 'sign', 'log', 'force', 'tau'):
+            assert state[k].dtype == self.dtype and state[k].is_contiguous() and state[k].device == self.device, k
+        assert state['age'].dtype == torch.int32
+        R, Rb = self._R(R, B)
+        nn = self._prep(noise_normal) if noise_normal is not None else None
+        nu = self._prep(noise_uniform) if noise_uniform is not None else None
+        stats = torch.zeros(7, dtype=self.dtype, device=self.device)
+        extra = (B * (2 * N * 3 + 2 + 7 + 3 * N)) * r.element_size() + 16384
+        need = self.lib.dqmc_workspace_bytes(self.h, B, MODE_LOCAL_ENERGY) + extra
+        if not self._host:
+            free = torch.cuda.mem_get_info(self.device)[0] + (self._ws.numel() if self._ws is not None else 0)
+            need = min(need, max(int(0.6 * free), self.lib.dqmc_workspace_bytes(self.h, 1, MODE_LOCAL_ENERGY) + extra))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws_ok = set()
+        ws = self._ws
+        rc = self.lib.dqmc_langevin_sweep(
+            self.h, r.data_ptr(), state['sign'].data_ptr(), state['log'].data_ptr(), state['force'].data_ptr(),
+            state['age'].data_ptr(), state['tau'].data_ptr(), R.data_ptr(), Rb, B, n_sub,
+            float(target_acceptance if target_acceptance else 0.0), -1 if max_age is None else int(max_age), seed, step0,
+            walker_offset, nn.data_ptr() if nn is not None else None, nu.data_ptr() if nu is not None else None,
+            stats.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
+        self._check(rc, 'dqmc_langevin_sweep')
+        return stats
+
     def debug_gemm(self, weight, A, bias=None, Res=None, S=1, sliced=False, backend=0):
         off, K, Nc = self.entries[weight]
         A = self._prep(A)

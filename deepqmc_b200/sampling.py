@@ -183,3 +183,36 @@ class MultiElectronicStateSampler:
         r = torch.stack(rs)
         pc = PhysicalConfiguration(R, r, torch.zeros(r.shape[:2], dtype=torch.int32, device=r.device))
         return new, pc, {k: torch.stack([s[k] for s in stats]) for k in stats[0]}
+
+
+class LangevinSampler(MetropolisSampler):
+    """Metropolis-adjusted Langevin sampler (reference: sampling/electron_samplers.py:176-232): the walker state
+    carries the drift ``force`` = clean_force(grad log|psi|) (sampling_utils.py:71-101); proposal, Green's-function
+    acceptance and the force clean-up run in ``dqmc_langevin_sweep``; every sub-step costs one forward-Laplacian
+    pass.  ``length`` sub-steps per sample() (use ``length > 1`` for a Decorr-chained sampler)."""
+
+    WALKER_STATE = MetropolisSampler.WALKER_STATE + ['force']
+
+    def __init__(self, hamil, wf, *, length=1, **kw):
+        super().__init__(hamil, wf, **kw)
+        self.length = int(length)
+
+    def update(self, state, params, R):
+        eng = self._engine(params)
+        r = state['r']
+        st = {'r': r, 'sign': torch.empty(len(r), dtype=eng.dtype, device=eng.device),
+              'log': torch.empty(len(r), dtype=eng.dtype, device=eng.device), 'force': torch.empty_like(r),
+              'age': state['age'], 'tau': state['tau']}
+        eng.langevin_sweep(st, R, 0)
+        return {**state, 'psi': Psi(st['sign'], st['log']), 'force': st['force']}
+
+    def sample(self, rng, state, params, R, *, walker_offset=0, noise_normal=None, noise_uniform=None):
+        eng = self._engine(params)
+        st = {'r': state['r'], 'sign': state['psi'].sign, 'log': state['psi'].log, 'force': state['force'],
+              'age': state['age'], 'tau': state['tau']}
+        stats = eng.langevin_sweep(st, R, self.length, target_acceptance=self.target_acceptance, max_age=self.max_age,
+                                   seed=int(rng), step0=self._step, walker_offset=walker_offset, noise_normal=noise_normal,
+                                   noise_uniform=noise_uniform)
+        self._step += self.length
+        new = {'r': st['r'], 'psi': Psi(st['sign'], st['log']), 'force': st['force'], 'age': st['age'], 'tau': st['tau']}
+        return new, self.phys_conf(R, new['r']), dict(zip(STAT_NAMES, stats))

@@ -130,6 +130,16 @@ int dqmc_mcmc_sweep(dqmc_handle h, void* r, void* sign, void* log, int32_t* age,
                     const void* noise_uniform, void* out_stats, void* workspace, int64_t workspace_bytes,
                     void* stream);
 
+/* Metropolis-adjusted Langevin sweep: like dqmc_mcmc_sweep with the drift force[B][N][3] (= clean_force of
+ * grad log|psi|, sampling_utils.py:71-101) as an extra piece of walker state; proposals r + tau F + sqrt(tau) N(0,1),
+ * acceptance with the Green's-function ratio.  Every sub-step costs one forward-Laplacian pass (value + gradient).
+ * n_sub = 0 recomputes sign / log / force of the walkers in place (ElectronSampler.update).
+ * replaces: sampling/electron_samplers.py:176-232 LangevinSampler (inside DecorrSampler). */
+int dqmc_langevin_sweep(dqmc_handle h, void* r, void* sign, void* log, void* force, int32_t* age, void* tau, const void* R,
+                        int32_t R_batched, int32_t n_walkers, int32_t n_sub, double target_acceptance, int32_t max_age,
+                        uint64_t seed, uint64_t step0, uint64_t walker_offset, const void* noise_normal,
+                        const void* noise_uniform, void* out_stats, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Parameter VJP of the wave function: out_grad_params[dqmc_param_total] (compute dtype, the packed layout of
  * dqmc_param_entry) = d/dparams sum_b weights[b] log|psi(r_b)|; also returns sign/log of the batch.
  * With weights = 2 (E_loc - <E_loc>) / B this is the energy gradient (Psiformer only so far).
