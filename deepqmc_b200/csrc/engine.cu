@@ -1118,8 +1118,10 @@ struct Engine : EngineBase {
     for (int l = 0; l < L; ++l) {
       const std::string q = "L" + std::to_string(l) + ".";
       gemm(X[l], d, (q + "wqkv").c_str(), nullptr, 0, 3 * d, nullptr, nullptr, 0, QKV[l], 3 * d, rows, 3 * d, d, 1, 0, N, st);
-      DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh, 1, 0), st, (const T*)QKV[l], 3 * d, O[l], d, N,
-                1, dh, d, scale, 1, (const T*)nullptr, (const T*)nullptr, 0);
+      const T* kn = Mn > 0 ? P(q + "kn") : nullptr;
+      const T* vn = Mn > 0 ? P(q + "vn") : nullptr;
+      DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh, 1, Mn), st, (const T*)QKV[l], 3 * d, O[l], d, N,
+                1, dh, d, scale, 1, kn, vn, Mn);
       gemm(O[l], d, (q + "wo").c_str(), nullptr, 0, d, nullptr, X[l], d, A[l], d, rows, d, d, 1, 0, N, st);
       gemm(A[l], d, (q + "w1").c_str(), nullptr, 0, d, P(q + "b1"), nullptr, 0, M1[l], d, rows, d, d, 1, 0, N, st);
       DQ_LAUNCH(tanh_fl_kernel<T>, dim3(rows, (d + 127) / 128), dim3(128), 0, st, M1[l], d, (const T*)nullptr, 0, 1, d, T(1));
@@ -1130,7 +1132,7 @@ struct Engine : EngineBase {
     const int sl_wpb = slater_warps_per_block<T>(N);
     DQ_LAUNCH(slater_kernel<T>, dim3((Bc * K + sl_wpb - 1) / sl_wpb), dim3(32 * sl_wpb), slater_smem_bytes<T>(N), st, r, R, Rb, N,
               M, cfg.n_up, K, 1, Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)BF, KN,
-              dsign, dlog, (T*)nullptr, (T*)nullptr, 1, 1);
+              dsign, dlog, (T*)nullptr, (T*)nullptr, env_rep, 1);
     FinalizeCfg fc;
     fc.N = N; fc.M = M; fc.n_up = cfg.n_up; fc.K = K; fc.S = 1; fc.cusp_kind = cfg.cusp_kind;
     fc.cusp_same_scale = cfg.cusp_same_scale; fc.cusp_anti_scale = cfg.cusp_anti_scale; fc.ecp_terms = 0;
@@ -1148,7 +1150,7 @@ struct Engine : EngineBase {
       wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
       DQ_LAUNCH(slater_bwd_kernel<T>, dim3((Bc * K + wpb - 1) / wpb), dim3(32 * wpb), pw * wpb, st, r, R, Rb, N, M, cfg.n_up, K,
                 Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)BF, KN, (const T*)dld, dBF,
-                G + off("env.pi_up"), G + off("env.pi_dn"), G + off("env.zeta_up"), G + off("env.zeta_dn"));
+                G + off("env.pi_up"), G + off("env.pi_dn"), G + off("env.zeta_up"), G + off("env.zeta_dn"), env_rep);
     }
     // backflow heads: dX_L = dBF W_spin^T, dW_spin += X_L[spin rows]^T dBF[spin rows]
     gemm_raw(dBF, KN, PT("bf.up"), PT("bf.dn"), cfg.n_up, d, nullptr, 0, dXn, d, Bc, d, KN, 1, st);
@@ -1172,8 +1174,10 @@ struct Engine : EngineBase {
       // A = X + O Wo
       wgrad(O[l], d, dA, d, rows, d, d, G + off(q + "wo"), 0, 0, st);
       gemm_raw(dA, d, PT(q + "wo"), nullptr, 0, d, nullptr, 0, dO, d, rows, d, d, 0, st);
-      DQ_LAUNCH(attn_bwd_kernel<T>, dim3(Bc, H), dim3(128), attn_bwd_smem_bytes<T>(N, dh), st, (const T*)QKV[l], 3 * d, (const T*)dO,
-                d, N, dh, d, scale, dQKV);
+      DQ_LAUNCH(attn_bwd_kernel<T>, dim3(Bc, H), dim3(128), attn_bwd_smem_bytes<T>(N, dh, Mn), st, (const T*)QKV[l], 3 * d,
+                (const T*)dO, d, N, dh, d, scale, dQKV, Mn > 0 ? P(q + "kn") : (const T*)nullptr,
+                Mn > 0 ? P(q + "vn") : (const T*)nullptr, Mn, Mn > 0 ? G + off(q + "kn") : (T*)nullptr,
+                Mn > 0 ? G + off(q + "vn") : (T*)nullptr);
       wgrad(X[l], d, dQKV, 3 * d, rows, d, 3 * d, G + off(q + "wqkv"), 0, 0, st);
       gemm_raw(dQKV, 3 * d, PT(q + "wqkv"), nullptr, 0, d, dA, d, dX, d, rows, d, 3 * d, 0, st);  // dX_l = dA + dQKV Wqkv^T
       T* t = dXn; dXn = dX; dX = t;
@@ -1185,7 +1189,11 @@ struct Engine : EngineBase {
 
   int vjp_params(const void* r_, const void* R_, int Rb, int B, const void* weights, void* sign, void* logp,
                  void* grad_params, void* ws, int64_t wsb, cudaStream_t st) override {
-    if (cfg.kind != DQMC_PSIFORMER) { err = "dqmc_wf_vjp_params: only the Psiformer ansatz has a reverse pass so far"; return 2; }
+    if (cfg.kind != DQMC_PSIFORMER && cfg.kind != DQMC_TRANSPSIFORMER) {
+      err = "dqmc_wf_vjp_params: only the Psiformer / TransPsiformer ansatzes have a reverse pass so far";
+      return 2;
+    }
+    if (cfg.nuc_cusp_kind) { err = "dqmc_wf_vjp_params: nuclear cusp exponent gradient not implemented"; return 2; }
     const T* r = (const T*)r_;
     const T* R = (const T*)R_;
     DQ_CHECK(cudaMemsetAsync(grad_params, 0, sizeof(T) * total, st));
@@ -1193,7 +1201,7 @@ struct Engine : EngineBase {
     int64_t Bc = (wsb - 64 * 256) / (int64_t)(sizeof(T) * vjp_per_walker_elems());
     if (Bc > B) Bc = B;
     if (Bc < 1) { err = "workspace too small for a single walker (vjp)"; return 3; }
-    DQ_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_bwd_smem_bytes<T>(N, dh)));
+    DQ_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_bwd_smem_bytes<T>(N, dh, Mn)));
     DQ_CHECK(cudaFuncSetAttribute(slater_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(slater_bwd_smem_per_warp<T>(N) * 4)));
     for (int b0 = 0; b0 < B; b0 += (int)Bc) {

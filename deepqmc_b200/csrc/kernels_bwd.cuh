@@ -90,15 +90,19 @@ __global__ void transpose_kernel(const T* __restrict__ W, int rows, int cols, T*
 // ------------------------------------------------------------------------------------------
 template <class T>
 __global__ void attn_bwd_kernel(const T* __restrict__ QKV, int ldq, const T* __restrict__ dO, int ldo, int N, int dh,
-                                int dmodel, T scale, T* __restrict__ dQKV) {
+                                int dmodel, T scale, T* __restrict__ dQKV, const T* __restrict__ Kn,
+                                const T* __restrict__ Vn, int Mn, T* __restrict__ dKn, T* __restrict__ dVn) {
+  // Kn / Vn [Mn][dmodel] (nullable): keys / values of Mn walker-independent extra tokens behind the N electron
+  // keys (TransPsiformer nuclei); their cotangents are accumulated over walkers into dKn / dVn (atomicAdd).
   DQMC_DYN_SMEM(smem_raw);
-  const int dhp = dh + 1, NN = N * N;
-  T* q = reinterpret_cast<T*>(smem_raw);
-  T* k = q + N * dhp;
-  T* v = k + N * dhp;
-  T* go = v + N * dhp;   // dO
-  T* p = go + N * dhp;   // [N][N]
-  T* ds = p + NN;        // [N][N]
+  const int NK = N + Mn;
+  const int dhp = dh + 1, NN = N * NK;
+  T* q = reinterpret_cast<T*>(smem_raw);  // [N][dhp]
+  T* go = q + N * dhp;                    // [N][dhp]  dO
+  T* k = go + N * dhp;                    // [NK][dhp]
+  T* v = k + NK * dhp;                    // [NK][dhp]
+  T* p = v + NK * dhp;                    // [N][NK]
+  T* ds = p + NN;                         // [N][NK]
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
   const size_t row0 = (size_t)b * N;
   for (int idx = tid; idx < N * dh; idx += nt) {
@@ -107,9 +111,14 @@ __global__ void attn_bwd_kernel(const T* __restrict__ QKV, int ldq, const T* __r
     q[i * dhp + e] = src[0]; k[i * dhp + e] = src[dmodel]; v[i * dhp + e] = src[2 * dmodel];
     go[i * dhp + e] = dO[(row0 + i) * ldo + h * dh + e];
   }
+  for (int idx = tid; idx < Mn * dh; idx += nt) {
+    const int m = idx / dh, e = idx - m * dh;
+    k[(N + m) * dhp + e] = Kn[(size_t)m * dmodel + h * dh + e];
+    v[(N + m) * dhp + e] = Vn[(size_t)m * dmodel + h * dh + e];
+  }
   __syncthreads();
   for (int idx = tid; idx < NN; idx += nt) {
-    const int i = idx / N, j = idx - i * N;
+    const int i = idx / NK, j = idx - i * NK;
     T a = T(0), c = T(0);
     for (int e = 0; e < dh; ++e) { a += q[i * dhp + e] * k[j * dhp + e]; c += go[i * dhp + e] * v[j * dhp + e]; }
     p[idx] = a * scale;
@@ -117,30 +126,42 @@ __global__ void attn_bwd_kernel(const T* __restrict__ QKV, int ldq, const T* __r
   }
   __syncthreads();
   for (int i = tid; i < N; i += nt) {
-    T mx = p[i * N];
-    for (int j = 1; j < N; ++j) mx = p[i * N + j] > mx ? p[i * N + j] : mx;
+    T mx = p[i * NK];
+    for (int j = 1; j < NK; ++j) mx = p[i * NK + j] > mx ? p[i * NK + j] : mx;
     T sum = T(0);
-    for (int j = 0; j < N; ++j) { T ex = m_exp(p[i * N + j] - mx); p[i * N + j] = ex; sum += ex; }
+    for (int j = 0; j < NK; ++j) { T ex = m_exp(p[i * NK + j] - mx); p[i * NK + j] = ex; sum += ex; }
     T inv = T(1) / sum, dot = T(0);
-    for (int j = 0; j < N; ++j) { p[i * N + j] *= inv; dot += p[i * N + j] * ds[i * N + j]; }
-    for (int j = 0; j < N; ++j) ds[i * N + j] = p[i * N + j] * (ds[i * N + j] - dot) * scale;  // c dS
+    for (int j = 0; j < NK; ++j) { p[i * NK + j] *= inv; dot += p[i * NK + j] * ds[i * NK + j]; }
+    for (int j = 0; j < NK; ++j) ds[i * NK + j] = p[i * NK + j] * (ds[i * NK + j] - dot) * scale;  // c dS
   }
   __syncthreads();
   for (int idx = tid; idx < N * dh; idx += nt) {
     const int i = idx / dh, e = idx - i * dh;
     T dq = T(0), dk = T(0), dv = T(0);
+    for (int j = 0; j < NK; ++j) dq += ds[i * NK + j] * k[j * dhp + e];
     for (int j = 0; j < N; ++j) {
-      dq += ds[i * N + j] * k[j * dhp + e];
-      dk += ds[j * N + i] * q[j * dhp + e];
-      dv += p[j * N + i] * go[j * dhp + e];
+      dk += ds[j * NK + i] * q[j * dhp + e];
+      dv += p[j * NK + i] * go[j * dhp + e];
     }
     T* dst = dQKV + (row0 + i) * ldq + h * dh + e;
     dst[0] = dq; dst[dmodel] = dk; dst[2 * dmodel] = dv;
   }
+  for (int idx = tid; idx < Mn * dh; idx += nt) {
+    const int m = idx / dh, e = idx - m * dh;
+    T dk = T(0), dv = T(0);
+    for (int j = 0; j < N; ++j) {
+      dk += ds[j * NK + N + m] * q[j * dhp + e];
+      dv += p[j * NK + N + m] * go[j * dhp + e];
+    }
+    atomic_add(dKn + (size_t)m * dmodel + h * dh + e, dk);
+    atomic_add(dVn + (size_t)m * dmodel + h * dh + e, dv);
+  }
 }
 
 template <class T>
-inline size_t attn_bwd_smem_bytes(int N, int dh) { return sizeof(T) * ((size_t)4 * N * (dh + 1) + (size_t)2 * N * N); }
+inline size_t attn_bwd_smem_bytes(int N, int dh, int Mn = 0) {
+  return sizeof(T) * ((size_t)2 * N * (dh + 1) + (size_t)2 * (N + Mn) * (dh + 1) + (size_t)2 * N * (N + Mn));
+}
 
 // ------------------------------------------------------------------------------------------
 // Determinant-sum backward: dlogdet[b][k] = w_b p_k,  p_k = c_k s_k e^{l_k - shift} / psi  (d log|psi| / d logdet_k),
@@ -193,7 +214,7 @@ __global__ void slater_bwd_kernel(const T* __restrict__ r, const T* __restrict__
                                   const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn,
                                   const T* __restrict__ BF, int ldb, const T* __restrict__ dlogdet, T* __restrict__ dBF,
                                   T* __restrict__ dpi_up, T* __restrict__ dpi_dn, T* __restrict__ dzeta_up,
-                                  T* __restrict__ dzeta_dn) {
+                                  T* __restrict__ dzeta_dn, int rep) {
   DQMC_DYN_SMEM(smem_raw);
   const int NP = N + 1, N2 = 2 * N + 1;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -208,13 +229,13 @@ __global__ void slater_bwd_kernel(const T* __restrict__ r, const T* __restrict__
   const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
   for (int idx = lane; idx < N * N; idx += 32) {
     const int i = idx / N, mu = idx - i * N;
-    const T* pi = (i < n_up ? pi_up : pi_dn) + (size_t)(k * N + mu) * M;
-    const T* ze = (i < n_up ? zeta_up : zeta_dn) + (size_t)(k * N + mu) * M;
+    const T* pi = (i < n_up ? pi_up : pi_dn) + (size_t)(k * N + mu) * M * rep;
+    const T* ze = (i < n_up ? zeta_up : zeta_dn) + (size_t)(k * N + mu) * M * rep;
     T e = T(0);
     for (int m = 0; m < M; ++m) {
       const T dx0 = rb[3 * i] - Rb[3 * m], dx1 = rb[3 * i + 1] - Rb[3 * m + 1], dx2 = rb[3 * i + 2] - Rb[3 * m + 2];
       const T rho = m_sqrt(Num<T>::eps() + dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
-      e += pi[m] * m_exp(-m_abs(ze[m]) * rho);
+      for (int et = 0; et < rep; ++et) e += pi[m * rep + et] * m_exp(-m_abs(ze[m * rep + et]) * rho);
     }
     const T bf0 = BF[((size_t)b * N + i) * ldb + k * N + mu];
     env[i * NP + mu] = e;
@@ -265,16 +286,18 @@ __global__ void slater_bwd_kernel(const T* __restrict__ r, const T* __restrict__
     dBF[((size_t)b * N + i) * ldb + k * N + mu] = G * env[i * NP + mu];
     const T gb = G * bfv[i * NP + mu];  // d / d env[i][mu]
     const bool up = i < n_up;
-    const T* pi = (up ? pi_up : pi_dn) + (size_t)(k * N + mu) * M;
-    const T* ze = (up ? zeta_up : zeta_dn) + (size_t)(k * N + mu) * M;
-    T* dpi = (up ? dpi_up : dpi_dn) + (size_t)(k * N + mu) * M;
-    T* dze = (up ? dzeta_up : dzeta_dn) + (size_t)(k * N + mu) * M;
+    const T* pi = (up ? pi_up : pi_dn) + (size_t)(k * N + mu) * M * rep;
+    const T* ze = (up ? zeta_up : zeta_dn) + (size_t)(k * N + mu) * M * rep;
+    T* dpi = (up ? dpi_up : dpi_dn) + (size_t)(k * N + mu) * M * rep;
+    T* dze = (up ? dzeta_up : dzeta_dn) + (size_t)(k * N + mu) * M * rep;
     for (int m = 0; m < M; ++m) {
       const T dx0 = rb[3 * i] - Rb[3 * m], dx1 = rb[3 * i + 1] - Rb[3 * m + 1], dx2 = rb[3 * i + 2] - Rb[3 * m + 2];
       const T rho = m_sqrt(Num<T>::eps() + dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
-      const T z = ze[m], ex = m_exp(-m_abs(z) * rho);
-      atomic_add(dpi + m, gb * ex);
-      atomic_add(dze + m, gb * pi[m] * ex * (-rho) * (z > T(0) ? T(1) : (z < T(0) ? T(-1) : T(0))));
+      for (int et = 0; et < rep; ++et) {
+        const T z = ze[m * rep + et], ex = m_exp(-m_abs(z) * rho);
+        atomic_add(dpi + m * rep + et, gb * ex);
+        atomic_add(dze + m * rep + et, gb * pi[m * rep + et] * ex * (-rho) * (z > T(0) ? T(1) : (z < T(0) ? T(-1) : T(0))));
+      }
     }
   }
 }

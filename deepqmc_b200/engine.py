@@ -166,7 +166,7 @@ def _unpack_psiformer_grads(spec: AnsatzSpec, entries: dict, flat) -> dict:
     d = spec.embedding_dim
     out = {PN.GNN + 'electron_embedding/linear:w': e('emb.w')}
     for l in range(spec.n_layers):
-        a = PN.attn_prefix(l)
+        a = PN.attn_prefix(l) if spec.kind == 'psiformer' else PN.comb_prefix(l)
         qkv = e(f'L{l}.wqkv')
         for j, n in enumerate(('query', 'key', 'value')):
             out[a + f'multi_head_attention/{n}:w'] = qkv[:, j * d:(j + 1) * d]
@@ -174,9 +174,10 @@ def _unpack_psiformer_grads(spec: AnsatzSpec, entries: dict, flat) -> dict:
         out[a + 'mlp/linear_0:w'], out[a + 'mlp/linear_0:b'] = e(f'L{l}.w1'), e(f'L{l}.b1')[0]
         out[a + 'mlp/linear_1:w'], out[a + 'mlp/linear_1:b'] = e(f'L{l}.w2'), e(f'L{l}.b2')[0]
     out[PN.BF_UP + ':w'], out[PN.BF_DN + ':w'] = e('bf.up'), e('bf.dn')
-    for s_, t in (('up', 'up'), ('down', 'dn')):
-        out[f'{PN.ENV}:pi_{s_}'] = e(f'env.pi_{t}')
-        out[f'{PN.ENV}:zetas_{s_}'] = e(f'env.zeta_{t}')
+    if spec.kind == 'psiformer':
+        for s_, t in (('up', 'up'), ('down', 'dn')):
+            out[f'{PN.ENV}:pi_{s_}'] = e(f'env.pi_{t}')
+            out[f'{PN.ENV}:zetas_{s_}'] = e(f'env.zeta_{t}')
     if spec.cusp == 'psiformer':
         ca = e('cusp.alpha')
         out[f'{PN.CUSP}:same_alpha'], out[f'{PN.CUSP}:anti_alpha'] = ca[0, 0], ca[0, 1]
@@ -395,7 +396,26 @@ class Engine:
         rc = self.lib.dqmc_wf_vjp_params(self.h, r.data_ptr(), R.data_ptr(), Rb, B, w.data_ptr(), sign.data_ptr(), log.data_ptr(),
                                          flat.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
         self._check(rc, 'dqmc_wf_vjp_params')
-        return sign, log, _unpack_psiformer_grads(self.spec, self.entries, flat)
+        grads = _unpack_psiformer_grads(self.spec, self.entries, flat)
+        if self.spec.kind == 'transpsiformer':
+            # the walker-independent nuclear stream is differentiated on the host: the engine accumulated the
+            # cotangents of its outputs (keys / values of the nuclear tokens, envelope exponents)
+            from .nuclear import nuclear_stream_vjp
+
+            def e(name):
+                off, rows, cols = self.entries[name]
+                return flat[off:off + rows * cols].reshape(rows, cols).detach().cpu().double().numpy()
+
+            N, K, M, E = self.spec.n_elec, self.spec.n_determinants, self.spec.n_nuc, self.spec.n_env_per_nuc
+            cot = {'kn': [e(f'L{l}.kn') for l in range(self.spec.n_layers)],
+                   'vn': [e(f'L{l}.vn') for l in range(self.spec.n_layers)]}
+            for s_, t in (('up', 'up'), ('down', 'dn')):  # engine [K N][M E] -> zetas[M, K, E] (shared by the orbitals)
+                cot[f'zetas_{s_}'] = e(f'env.zeta_{t}').reshape(K, N, M, E).sum(1).transpose(1, 0, 2)
+            host = nuclear_stream_vjp(self.spec, self._params, self._nuc_R, cot)
+            for k, v in host.items():
+                v = v.to(device=self.device, dtype=self.dtype)
+                grads[k] = grads[k] + v.reshape(grads[k].shape) if k in grads else v
+        return sign, log, grads
 
     def mcmc_sweep(self, state, R, n_sub, target_acceptance=0.57, max_age=None, seed=0, step0=0, walker_offset=0,
                    noise_normal=None, noise_uniform=None, max_ws_bytes=None):

@@ -83,3 +83,54 @@ def nuclear_stream(spec: AnsatzSpec, params: dict, R) -> dict:
             x @ g(PN.HEAD + glu + '/V:w') + g(PN.HEAD + glu + '/V:b'))
         out[f'zetas_{spin}'] = y.reshape(M, K, E) + g(PN.HEAD + f':zetas_bias_{spin}')
     return out
+
+
+def nuclear_stream_vjp(spec: AnsatzSpec, params: dict, R, cot: dict) -> dict:
+    """Parameter gradient contribution of the nuclear stream: `cot` holds the cotangents the CUDA reverse pass
+    accumulated for the stream's outputs ({'kn': [L][M, d], 'vn': [L][M, d], 'zetas_up', 'zetas_down': [M, K, E]});
+    the stream itself (O(M^2 d), walker-independent) is differentiated on the host with torch autograd in float64.
+    Returns {haiku name: gradient} for every parameter the stream touches."""
+    import torch
+
+    R_t = torch.as_tensor(np.asarray(R, dtype=np.float64))
+    pt = {k: torch.as_tensor(np.asarray(v, dtype=np.float64)).requires_grad_(True) for k, v in params.items()}
+    g = lambda k: pt[k]
+    M, d, H = spec.n_nuc, spec.embedding_dim, spec.n_heads
+    dh = d // H
+    dd = R_t[None, :, :] - R_t[:, None, :]
+    rr = torch.sqrt(torch.finfo(torch.float64).eps + (dd * dd).sum(-1))
+    lg = torch.log1p(rr)
+    feats = torch.cat([lg[..., None], dd * (lg / rr)[..., None]], -1)
+    inv = np.unique(np.asarray(spec.charges), return_inverse=True)[1]
+    onehot = torch.eye(M, dtype=torch.float64)[torch.as_tensor(inv)]
+    x = torch.cat([feats, onehot[:, None, :].expand(M, M, M)], -1)
+    silu = torch.nn.functional.silu
+    e = silu(x @ g(PN.NUC_EMB + 'edge_mlp/linear_0:w') + g(PN.NUC_EMB + 'edge_mlp/linear_0:b'))
+    e = e @ g(PN.NUC_EMB + 'edge_mlp/linear_1:w') + g(PN.NUC_EMB + 'edge_mlp/linear_1:b')
+    h = silu(e.sum(0) @ g(PN.NUC_EMB + 'embed_mlp/linear_0:w') + g(PN.NUC_EMB + 'embed_mlp/linear_0:b'))
+    h = h @ g(PN.NUC_EMB + 'embed_mlp/linear_1:w') + g(PN.NUC_EMB + 'embed_mlp/linear_1:b')
+    total = torch.zeros((), dtype=torch.float64)
+    as_t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
+    for l in range(spec.n_layers):
+        a = PN.comb_prefix(l)
+        q = (h @ g(a + 'multi_head_attention/query:w')).reshape(M, H, dh)
+        k = h @ g(a + 'multi_head_attention/key:w')
+        v = h @ g(a + 'multi_head_attention/value:w')
+        total = total + (k * as_t(cot['kn'][l])).sum() + (v * as_t(cot['vn'][l])).sum()
+        logits = torch.einsum('thd,Thd->htT', q, k.reshape(M, H, dh)) / np.sqrt(dh)
+        w = torch.softmax(logits, -1)
+        o = torch.einsum('htT,Thd->thd', w, v.reshape(M, H, dh)).reshape(M, d)
+        att = h + o @ g(a + 'multi_head_attention/linear:w')
+        m = torch.tanh(att @ g(a + 'mlp/linear_0:w') + g(a + 'mlp/linear_0:b'))
+        m = torch.tanh(m @ g(a + 'mlp/linear_1:w') + g(a + 'mlp/linear_1:b'))
+        h = att + m
+    mu = h.mean(-1, keepdim=True)
+    xn = (h - mu) / torch.sqrt(((h - mu) ** 2).mean(-1, keepdim=True) + 1e-5)
+    K, E = spec.n_determinants, spec.n_env_per_nuc
+    for glu, spin in (('zetas_readout_glu', 'up'), ('zetas_readout_glu_1', 'down')):
+        y = torch.sigmoid(xn @ g(PN.HEAD + glu + '/W:w') + g(PN.HEAD + glu + '/W:b')) * (
+            xn @ g(PN.HEAD + glu + '/V:w') + g(PN.HEAD + glu + '/V:b'))
+        z = y.reshape(M, K, E) + g(PN.HEAD + f':zetas_bias_{spin}')
+        total = total + (z * as_t(cot[f'zetas_{spin}'])).sum()
+    total.backward()
+    return {k: v.grad for k, v in pt.items() if v.grad is not None}

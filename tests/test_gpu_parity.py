@@ -573,3 +573,26 @@ def test_langevin_injected_noise_matches_oracle():
     assert torch.allclose(new['force'].cpu(), ost['force'], rtol=1e-8, atol=1e-9)
     assert new['age'].cpu().tolist() == ost['age'].tolist()
     assert abs(new['tau'].item() - ost['tau'].item()) < 1e-12 and abs(stats['sampling/acceptance'].item() - acc.item()) < 1e-12
+
+
+def test_parameter_vjp_transpsiformer_matches_autograd_fp64():
+    """Reverse pass of the TransPsiformer: electron stream in the CUDA engine (attention with nuclear tokens, cotangents
+    of their keys / values and of the envelope exponents accumulated over walkers), nuclear stream differentiated on the
+    host -- every parameter against torch autograd through the oracle."""
+    from oracle import wf
+
+    mol, hamil, oh, ansatz, params, r, R = make('H2O', B=3, kind='transpsiformer', embedding_dim=32, n_layers=2, n_heads=2,
+                                                n_determinants=3)
+    w = torch.as_tensor(np.random.default_rng(5).normal(size=3), device=DEV)
+    psi, grads = ansatz.log_psi_vjp(params, PhysicalConfiguration(R, r, torch.zeros(3, device=DEV)), w)
+    pt = {k: torch.as_tensor(v, dtype=torch.float64).requires_grad_(True) for k, v in params.items()}
+    tot = 0
+    for b in range(3):
+        s, l = wf.log_psi(ansatz.spec, pt, r[b].cpu(), R.cpu())
+        assert abs(psi.log[b].item() - l.item()) <= 1e-10 * max(1, abs(l.item()))
+        tot = tot + w[b].cpu() * l
+    tot.backward()
+    assert set(grads) == set(pt)
+    for k, v in pt.items():
+        ref = v.grad
+        assert torch.allclose(grads[k].cpu().reshape(ref.shape), ref, rtol=1e-8, atol=1e-9 * max(1.0, ref.abs().max().item())), k
