@@ -527,72 +527,3 @@ def test_energy_gradient_fp32_close_to_fp64():
     for k in out['f64']:
         g64, g32 = out['f64'][k].double(), out['f32'][k].double()
         assert (g64 - g32).abs().max().item() <= 2e-3 * max(1e-3, g64.abs().max().item()), k
-
-
-def test_langevin_injected_noise_matches_oracle():
-    """LangevinSampler (reference electron_samplers.py:176-232, clean_force sampling_utils.py:71-101; SURVEY.md 8(f)
-    N3) with identical injected random numbers: update (value + cleaned drift), three sub-steps with rejections,
-    age / tau bookkeeping."""
-    from deepqmc_b200.sampling import LangevinSampler
-    from oracle import wf
-    from oracle.sampling import clean_force, langevin_step
-
-    mol, hamil, oh, ansatz, params, r, R = make('H2O', B=5, embedding_dim=32, n_layers=1, n_heads=2, n_determinants=2)
-    pt = wf.to_torch(params)
-    Rc = R.cpu()
-    B, N = 5, 10
-
-    def wfg(rr):
-        ss, ll, gg = [], [], []
-        for b in range(len(rr)):
-            x = rr[b].clone().requires_grad_(True)
-            s, l = wf.log_psi(ansatz.spec, pt, x, Rc)
-            g, = torch.autograd.grad(l, x)
-            ss.append(s.detach()); ll.append(l.detach()); gg.append(g)
-        return torch.stack(ss), torch.stack(ll), torch.stack(gg)
-
-    tau0 = 1.5
-    smp = LangevinSampler(hamil, ansatz.apply, tau=tau0, max_age=2, length=3)
-    state = {'r': r.clone(), 'age': torch.zeros(B, dtype=torch.int32, device=DEV),
-             'tau': torch.tensor([tau0], dtype=torch.float64, device=DEV)}
-    state = smp.update(state, params, R)
-    s0, l0, g0 = wfg(r.cpu())
-    f0 = clean_force(g0, r.cpu(), Rc, mol.charges, torch.tensor(tau0, dtype=torch.float64))
-    assert torch.allclose(state['psi'].log.cpu(), l0, rtol=0, atol=1e-9)
-    assert torch.allclose(state['force'].cpu(), f0, rtol=1e-8, atol=1e-9)
-    rng = np.random.default_rng(4)
-    nn = torch.as_tensor(rng.normal(size=(3, B, N, 3)), device=DEV)
-    nu = torch.as_tensor(rng.uniform(size=(3, B)), device=DEV)
-    new, pc, stats = smp.sample(0, state, params, R, noise_normal=nn, noise_uniform=nu)
-    ost = dict(r=r.cpu().clone(), sign=s0, log=l0, force=f0, age=torch.zeros(B, dtype=torch.int32),
-               tau=torch.tensor(tau0, dtype=torch.float64))
-    for s in range(3):
-        ost, acc = langevin_step(wfg, Rc, mol.charges, ost, nn[s].cpu(), nu[s].cpu(), 0.57, 2)
-    assert torch.allclose(new['r'].cpu(), ost['r'], rtol=0, atol=1e-9)
-    assert torch.allclose(new['psi'].log.cpu(), ost['log'], rtol=0, atol=1e-9)
-    assert torch.allclose(new['force'].cpu(), ost['force'], rtol=1e-8, atol=1e-9)
-    assert new['age'].cpu().tolist() == ost['age'].tolist()
-    assert abs(new['tau'].item() - ost['tau'].item()) < 1e-12 and abs(stats['sampling/acceptance'].item() - acc.item()) < 1e-12
-
-
-def test_parameter_vjp_transpsiformer_matches_autograd_fp64():
-    """Reverse pass of the TransPsiformer: electron stream in the CUDA engine (attention with nuclear tokens, cotangents
-    of their keys / values and of the envelope exponents accumulated over walkers), nuclear stream differentiated on the
-    host -- every parameter against torch autograd through the oracle."""
-    from oracle import wf
-
-    mol, hamil, oh, ansatz, params, r, R = make('H2O', B=3, kind='transpsiformer', embedding_dim=32, n_layers=2, n_heads=2,
-                                                n_determinants=3)
-    w = torch.as_tensor(np.random.default_rng(5).normal(size=3), device=DEV)
-    psi, grads = ansatz.log_psi_vjp(params, PhysicalConfiguration(R, r, torch.zeros(3, device=DEV)), w)
-    pt = {k: torch.as_tensor(v, dtype=torch.float64).requires_grad_(True) for k, v in params.items()}
-    tot = 0
-    for b in range(3):
-        s, l = wf.log_psi(ansatz.spec, pt, r[b].cpu(), R.cpu())
-        assert abs(psi.log[b].item() - l.item()) <= 1e-10 * max(1, abs(l.item()))
-        tot = tot + w[b].cpu() * l
-    tot.backward()
-    assert set(grads) == set(pt)
-    for k, v in pt.items():
-        ref = v.grad
-        assert torch.allclose(grads[k].cpu().reshape(ref.shape), ref, rtol=1e-8, atol=1e-9 * max(1.0, ref.abs().max().item())), k
