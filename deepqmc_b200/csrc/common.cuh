@@ -136,6 +136,96 @@ __device__ __forceinline__ void block_sum2(T& a, T& b, T* scratch) {
 }
 
 
+// ---- Pseudo-Hamiltonian helpers (reference ecp/pseudo_hamiltonian.py:165-278) -------------
+// The PH replaces -1/2 Laplacian by  sum_i [ A(r_i) : Hess_i + b(r_i) . grad_i ]  with a symmetric positive
+// 3x3 matrix A per electron.  The reference evaluates it as a plain Laplacian in coordinates v = Q^-1 r,
+// A = Q Q^T; the forward-Laplacian engine does the same by seeding the tangent slots of electron i with the
+// columns of Q_i and weighting the second derivatives of every function of r_i with A_i.
+// Per (walker, electron) record of PH_STRIDE values: Q lower triangle (q00 q10 q11 q20 q21 q22),
+// A (a00 a01 a02 a11 a12 a22), b (3).
+constexpr int PH_STRIDE = 16;
+
+template <class T>
+struct PhMetric {  // second-derivative weights of a radial function of d = r_i - c, rho = |d| (or its eps-safe version)
+  T q[6], a[6];
+  __device__ __forceinline__ void load(const T* rec) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { q[k] = rec[k]; a[k] = rec[6 + k]; }
+  }
+  __device__ __forceinline__ T trace() const { return a[0] + a[3] + a[5]; }
+  // (A u)
+  __device__ __forceinline__ void mul(T u0, T u1, T u2, T& o0, T& o1, T& o2) const {
+    o0 = a[0] * u0 + a[1] * u1 + a[2] * u2;
+    o1 = a[1] * u0 + a[3] * u1 + a[4] * u2;
+    o2 = a[2] * u0 + a[4] * u1 + a[5] * u2;
+  }
+  // gradient w.r.t. r -> gradient w.r.t. v (Q^T g)
+  __device__ __forceinline__ void to_v(T& g0, T& g1, T& g2) const {
+    g0 = q[0] * g0 + q[1] * g1 + q[3] * g2;
+    g1 = q[2] * g1 + q[4] * g2;
+    g2 = q[5] * g2;
+  }
+  // gradient w.r.t. v -> gradient w.r.t. r (solve Q^T x = g)
+  __device__ __forceinline__ void to_r(T& g0, T& g1, T& g2) const {
+    g2 = g2 / q[5];
+    g1 = (g1 - q[4] * g2) / q[2];
+    g0 = (g0 - q[1] * g1 - q[3] * g2) / q[0];
+  }
+};
+
+// linear interpolation on the uniform grid [0, rmax] with G points, 0 outside
+// (jax.scipy.interpolate.RegularGridInterpolator(method='linear', fill_value=0), pseudo_hamiltonian.py:95-101)
+template <class T>
+__device__ __forceinline__ T ph_interp(const T* __restrict__ tab, int G, T rmax, T x) {
+  if (!(x >= T(0) && x <= rmax)) return T(0);
+  const T t = x * (T(G - 1) / rmax);
+  int i0 = (int)t;
+  if (i0 > G - 2) i0 = G - 2;
+  const T w = t - T(i0);
+  return tab[i0] + w * (tab[i0 + 1] - tab[i0]);
+}
+
+template <class T>
+struct PhArgs {  // all null / 0: no pseudo-Hamiltonian
+  const T* QA = nullptr;          // [walkers][N][PH_STRIDE]
+  const T* tabs = nullptr;        // [n_tab][2][G]: r V_loc, r V_L2
+  const int* tab_of_nuc = nullptr;  // [M] table index or -1
+  int G = 0;
+  T rmax = T(0);
+};
+
+// A, b, Q of every (walker, electron): compute_coefficients_of_differential_operators + Cholesky
+// (pseudo_hamiltonian.py:198-233,254-259).  One thread per electron.
+template <class T>
+__global__ void ph_coeff_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M,
+                                PhArgs<T> ph, T* __restrict__ QA, int total) {
+  const int bi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bi >= total) return;
+  const int b = bi / N;
+  const T* ri = r + (size_t)bi * 3;
+  const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
+  T a00 = T(0.5), a01 = T(0), a02 = T(0), a11 = T(0.5), a12 = T(0), a22 = T(0.5), b0 = T(0), b1 = T(0), b2 = T(0);
+  for (int m = 0; m < M; ++m) {
+    const int tb = ph.tab_of_nuc[m];
+    if (tb < 0) continue;
+    const T d0 = ri[0] - Rb[3 * m], d1 = ri[1] - Rb[3 * m + 1], d2 = ri[2] - Rb[3 * m + 2];
+    const T dd = d0 * d0 + d1 * d1 + d2 * d2, dist = m_sqrt(dd);
+    const T rv = ph_interp(ph.tabs + ((size_t)tb * 2 + 1) * ph.G, ph.G, ph.rmax, dist);
+    const T v = rv / dist;  // V_L2
+    b0 += T(2) * v * d0; b1 += T(2) * v * d1; b2 += T(2) * v * d2;
+    const T dg = rv * dist;
+    a00 += dg - v * d0 * d0; a11 += dg - v * d1 * d1; a22 += dg - v * d2 * d2;
+    a01 -= v * d0 * d1; a02 -= v * d0 * d2; a12 -= v * d1 * d2;
+  }
+  T* o = QA + (size_t)bi * PH_STRIDE;
+  const T q00 = m_sqrt(a00), q10 = a01 / q00, q20 = a02 / q00;
+  const T q11 = m_sqrt(a11 - q10 * q10), q21 = (a12 - q20 * q10) / q11;
+  const T q22 = m_sqrt(a22 - q20 * q20 - q21 * q21);
+  o[0] = q00; o[1] = q10; o[2] = q11; o[3] = q20; o[4] = q21; o[5] = q22;
+  o[6] = a00; o[7] = a01; o[8] = a02; o[9] = a11; o[10] = a12; o[11] = a22;
+  o[12] = b0; o[13] = b1; o[14] = b2; o[15] = T(0);
+}
+
 // ---- Philox4x32-10 counter-based generator (Salmon et al. 2011), hand-written ---------
 struct Philox {
   static __host__ __device__ __forceinline__ void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {

@@ -56,6 +56,7 @@ struct EngineBase {
                        const void* nu, void* stats, void* ws, int64_t wsb, cudaStream_t st) = 0;
   virtual int vjp_params(const void* r, const void* R, int Rb, int B, const void* weights, void* sign, void* logp,
                          void* grad_params, void* ws, int64_t wsb, cudaStream_t st) = 0;
+  virtual int set_ph(int n_tab, int n_grid, double r_max, const double* tables, const int32_t* tab_of_nuc) = 0;
   virtual int debug_gemm(const char* wname, const char* bname, const void* A, const void* Res, void* C, int Mr, int S,
                          int sliced, int backend, cudaStream_t st) = 0;
   virtual int mcmc(void* r, void* sign, void* logp, int32_t* age, void* tau, const void* R, int Rb, int B, int n_sub,
@@ -227,6 +228,13 @@ struct Engine : EngineBase {
   T* d_nl_params = nullptr;
   int* d_nl_nuc = nullptr;
   int J = 0;  // nuclei with a non-local channel
+  // pseudo-Hamiltonian (reference ecp/pseudo_hamiltonian.py): tables r V_loc / r V_L2 per element on a uniform grid
+  T* d_ph_tabs = nullptr;
+  int* d_ph_nuc = nullptr;
+  int ph_G = 0;
+  double ph_rmax = 0;
+  bool ph_on = false;      // tables uploaded
+  bool ph_active = false;  // set around the forward-Laplacian pass of local_energy only
   int attn_tb = 1, attn_tb1 = 1;
   bool attn_f32 = false;
   bool embed_fwd_ok = false;
@@ -409,8 +417,36 @@ struct Engine : EngineBase {
     if (d_ecp_loc) cudaFree(d_ecp_loc);
     if (d_nl_params) cudaFree(d_nl_params);
     if (d_nl_nuc) cudaFree(d_nl_nuc);
+    if (d_ph_tabs) cudaFree(d_ph_tabs);
+    if (d_ph_nuc) cudaFree(d_ph_nuc);
   }
   const T* P(const std::string& n) const { return d_params + off(n); }
+
+  int set_ph(int n_tab, int n_grid, double r_max, const double* tables, const int32_t* tab_of_nuc) override {
+    if (cfg.kind != DQMC_PSIFORMER && cfg.kind != DQMC_TRANSPSIFORMER) {
+      err = "the pseudo-Hamiltonian kinetic term is implemented for the Psiformer-family trunks only";
+      return 2;
+    }
+    if (J > 0 || cfg.ecp_loc_terms > 0) { err = "pseudo-Hamiltonian and Gaussian-type ECP are mutually exclusive"; return 2; }
+    if (n_tab < 1 || n_grid < 2 || !(r_max > 0) || !tables || !tab_of_nuc) { err = "bad pseudo-Hamiltonian tables"; return 2; }
+    for (int m = 0; m < M; ++m)
+      if (tab_of_nuc[m] >= n_tab) { err = "pseudo-Hamiltonian table index out of range"; return 2; }
+    std::vector<T> h((size_t)n_tab * 2 * n_grid);
+    for (size_t i = 0; i < h.size(); ++i) h[i] = (T)tables[i];
+    if (d_ph_tabs) cudaFree(d_ph_tabs);
+    if (d_ph_nuc) cudaFree(d_ph_nuc);
+    DQ_CHECK(cudaMalloc((void**)&d_ph_tabs, sizeof(T) * h.size()));
+    DQ_CHECK(cudaMemcpy(d_ph_tabs, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+    DQ_CHECK(cudaMalloc((void**)&d_ph_nuc, sizeof(int) * M));
+    DQ_CHECK(cudaMemcpy(d_ph_nuc, tab_of_nuc, sizeof(int) * M, cudaMemcpyHostToDevice));
+    ph_G = n_grid; ph_rmax = r_max; ph_on = true;
+    return 0;
+  }
+  PhArgs<T> ph_args(const T* QA) const {
+    PhArgs<T> a;
+    a.QA = QA; a.tabs = d_ph_tabs; a.tab_of_nuc = d_ph_nuc; a.G = ph_G; a.rmax = (T)ph_rmax;
+    return a;
+  }
 
   int set_params(const double* host, int64_t n, cudaStream_t st) override {
     if (n != total) { err = "parameter count mismatch"; return 2; }
@@ -437,6 +473,7 @@ struct Engine : EngineBase {
   // ---- workspace ---------------------------------------------------------------------------
   struct Ws {
     T *X, *O, *A, *M1, *QKV, *BF, *dsign, *dlog, *dlap, *dgrad;
+    T* QA = nullptr;  // pseudo-Hamiltonian records [Bc][N][PH_STRIDE]
     T *G0 = nullptr, *G1 = nullptr, *G2 = nullptr, *Hs = nullptr, *Ha = nullptr, *C = nullptr, *Fc = nullptr, *HT = nullptr,
       *E0 = nullptr, *E1 = nullptr, *ET0 = nullptr, *ET1 = nullptr, *W3 = nullptr,
       *Y0 = nullptr, *Y1 = nullptr, *Jb = nullptr;  // conv-GNN trunk
@@ -470,7 +507,7 @@ struct Engine : EngineBase {
   }
   size_t per_walker_elems(int S) const {
     size_t rows = (size_t)N * S;
-    size_t dets = (size_t)K * (3 + (S > 1 ? T3 : 0));
+    size_t dets = (size_t)K * (3 + (S > 1 ? T3 : 0)) + (ph_on && S > 1 ? (size_t)N * PH_STRIDE : 0);
     if (gnn) {
       const size_t e = cfg.edge_dim, dm = gnn_dmax(), em = gnn_emax(), hn = gnn_hnode_max();
       const size_t pairs8 = (size_t)N * (N + (cfg.gnn_conv_ne ? M : 0)) * 8;
@@ -511,6 +548,7 @@ struct Engine : EngineBase {
     }
     w.dsign = take((size_t)Bc * K); w.dlog = take((size_t)Bc * K); w.dlap = take((size_t)Bc * K);
     w.dgrad = take((size_t)Bc * K * (S > 1 ? T3 : 1));
+    if (ph_on && S > 1) w.QA = take((size_t)Bc * N * PH_STRIDE);
     w.bytes = p - (char*)base;
     return w;
   }
@@ -667,7 +705,7 @@ struct Engine : EngineBase {
     const int rows = Bc * N * S, rowsE = Bc * N * N * S, de = cfg.edge_dim, d0 = 4 * M;
     const T isq2 = (T)0.70710678118654752440;
     DQ_LAUNCH(embed_kernel<T>, dim3(Bc * N), dim3(128), sizeof(T) * 5 * d0, st, r, R, Rb, N, M, cfg.n_up, S, 0, 0,
-              (const T*)nullptr, d0, w.X, Bc * N, 1);
+              (const T*)nullptr, d0, w.X, Bc * N, 1, (const T*)nullptr);
     DQ_LAUNCH(edge_feat_kernel<T>, dim3((Bc * N * N + 127) / 128), dim3(128), 0, st, r, N, S, w.A, Bc * N * N);
     T* Hc = w.X; T* Hn = w.O; T* Ec = w.A; T* En = w.M1;
     int dcur = d0, ecur = 4;
@@ -725,7 +763,7 @@ struct Engine : EngineBase {
     if (cfg.gnn_features) {
       dcur = 4 * M;
       DQ_LAUNCH(embed_kernel<T>, dim3(Bc * N), dim3(128), sizeof(T) * 5 * dcur, st, r, R, Rb, N, M, cfg.n_up, S, 0, 0,
-                (const T*)nullptr, dcur, w.X, Bc * N, 1);
+                (const T*)nullptr, dcur, w.X, Bc * N, 1, (const T*)nullptr);
     } else {
       DQ_LAUNCH(gnn_embed_kernel<T>, dim3((Bc * N * d + 127) / 128), dim3(128), 0, st, P("emb.table"),
                 cfg.n_elec_types > 0 ? cfg.n_elec_types : 1, N, cfg.n_up, S, d, w.X, Bc * N);
@@ -838,6 +876,12 @@ struct Engine : EngineBase {
                 void* wsbase, cudaStream_t st) {
     Ws w = carve(wsbase, Bc, S);
     const int rows = Bc * N * S;
+    const T* qa = nullptr;  // pseudo-Hamiltonian: per-electron metric of the forward-Laplacian pass
+    if (ph_on && ph_active && S > 1) {
+      DQ_LAUNCH(ph_coeff_kernel<T>, dim3((Bc * N + 127) / 128), dim3(128), 0, st, r, R, Rb, N, M, ph_args(nullptr), w.QA,
+                Bc * N);
+      qa = w.QA;
+    }
     if (gnn) {
       T* Xbf = nullptr;
       const T* jas = nullptr;
@@ -862,7 +906,7 @@ struct Engine : EngineBase {
     } else {
       const int epb = S == 1 ? 8 : 1;  // plain forwards: several electrons per block (tiny per-electron work)
       DQ_LAUNCH(embed_kernel<T>, dim3((Bc * N + epb - 1) / epb), dim3(128), sizeof(T) * 5 * F, st, r, R, Rb, N, M,
-                cfg.n_up, S, 1, 1, P("emb.w"), d, w.X, Bc * N, epb);
+                cfg.n_up, S, 1, 1, P("emb.w"), d, w.X, Bc * N, epb, qa);
     }
     T* X = w.X;
     T* O = w.O;
@@ -937,12 +981,12 @@ struct Engine : EngineBase {
       }
       T* tmp = X; X = O; O = tmp;
     }
-    return tail(r, R, Rb, Bc, S, Bstat, sign, logp, E, stats, grad, w, X, st);
+    return tail(r, R, Rb, Bc, S, Bstat, sign, logp, E, stats, grad, w, X, st, nullptr, qa);
   }
 
   // backflow heads -> Slater determinants -> det sum / cusp / potentials (shared by all trunks)
   int tail(const T* r, const T* R, int Rb, int Bc, int S, int Bstat, T* sign, T* logp, T* E, T* stats, T* grad, Ws& w,
-           T* X, cudaStream_t st, const T* jastrow = nullptr) {
+           T* X, cudaStream_t st, const T* jastrow = nullptr, const T* qa = nullptr) {
     // per-spin backflow heads: rows of electron e across walkers, weights by spin
     gemm(X, bf_in, "bf.up", "bf.dn", cfg.n_up, KN, gnn ? P("bfb.up") : nullptr, nullptr, 0, w.BF, KN, Bc * S, KN, bf_in, S, 1, N,
          st, 0, gnn ? P("bfb.dn") : nullptr);
@@ -950,7 +994,7 @@ struct Engine : EngineBase {
       DQ_LAUNCH(act_fl_kernel<T>, dim3(Bc * N, (KN + 127) / 128), dim3(128), 0, st, w.BF, KN, (const T*)nullptr, 0, S, KN, T(1), 2);
     const int full_det = cfg.factorized_det ? 0 : 1;
     const int sl_wpb = slater_warps_per_block<T>(N);
-    if ((N <= 4 || (N <= 6 && std::is_same<T, float>::value)) && !std::getenv("DQMC_SLATER_GENERIC")) {
+    if ((N <= 4 || (N <= 6 && std::is_same<T, float>::value)) && !qa && !std::getenv("DQMC_SLATER_GENERIC")) {
       const int tot = Bc * K;
 #define DQ_SL_SMALL(NS_)                                                                                           \
   DQ_LAUNCH((slater_small_kernel<T, NS_>), dim3((tot + 63) / 64), dim3(64), 0, st, r, R, Rb, M, cfg.n_up, K, S, tot,    \
@@ -983,7 +1027,7 @@ struct Engine : EngineBase {
     } else
     DQ_LAUNCH(slater_kernel<T>, dim3((Bc * K + sl_wpb - 1) / sl_wpb), dim3(32 * sl_wpb), slater_smem_bytes<T>(N), st, r, R,
               Rb, N, M, cfg.n_up, K, S, Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog,
-              w.dgrad, w.dlap, env_rep, full_det);
+              w.dgrad, w.dlap, env_rep, full_det, qa);
     FinalizeCfg fc;
     fc.N = N; fc.M = M; fc.n_up = cfg.n_up; fc.K = K; fc.S = S; fc.cusp_kind = cfg.cusp_kind;
     fc.cusp_same_scale = cfg.cusp_same_scale; fc.cusp_anti_scale = cfg.cusp_anti_scale;
@@ -993,7 +1037,7 @@ struct Engine : EngineBase {
               (const T*)w.dsign, (const T*)w.dlog, (const T*)w.dgrad, (const T*)w.dlap, P("cusp.alpha"),
               (const T*)d_zval, (const T*)d_ecp_loc, (const int*)d_ecp_mask, Bstat, sign, logp, E, stats, grad,
               cfg.conf_linear ? P("conf.w") : (const T*)nullptr, jastrow,
-              cfg.nuc_cusp_kind ? P("cusp.nuc") : (const T*)nullptr);
+              cfg.nuc_cusp_kind ? P("cusp.nuc") : (const T*)nullptr, qa ? ph_args(qa) : PhArgs<T>());
     return 0;
   }
 
@@ -1114,7 +1158,7 @@ struct Engine : EngineBase {
     const T scale = (T)(1.0 / std::sqrt((double)dh));
     // ---- forward with every layer's activations kept --------------------------------------------------------
     DQ_LAUNCH(embed_kernel<T>, dim3((rows + 7) / 8), dim3(128), sizeof(T) * 5 * F, st, r, R, Rb, N, M, cfg.n_up, 1, 1, 1,
-              P("emb.w"), d, X[0], rows, 8);
+              P("emb.w"), d, X[0], rows, 8, (const T*)nullptr);
     for (int l = 0; l < L; ++l) {
       const std::string q = "L" + std::to_string(l) + ".";
       gemm(X[l], d, (q + "wqkv").c_str(), nullptr, 0, 3 * d, nullptr, nullptr, 0, QKV[l], 3 * d, rows, 3 * d, d, 1, 0, N, st);
@@ -1132,14 +1176,14 @@ struct Engine : EngineBase {
     const int sl_wpb = slater_warps_per_block<T>(N);
     DQ_LAUNCH(slater_kernel<T>, dim3((Bc * K + sl_wpb - 1) / sl_wpb), dim3(32 * sl_wpb), slater_smem_bytes<T>(N), st, r, R, Rb, N,
               M, cfg.n_up, K, 1, Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)BF, KN,
-              dsign, dlog, (T*)nullptr, (T*)nullptr, env_rep, 1);
+              dsign, dlog, (T*)nullptr, (T*)nullptr, env_rep, 1, (const T*)nullptr);
     FinalizeCfg fc;
     fc.N = N; fc.M = M; fc.n_up = cfg.n_up; fc.K = K; fc.S = 1; fc.cusp_kind = cfg.cusp_kind;
     fc.cusp_same_scale = cfg.cusp_same_scale; fc.cusp_anti_scale = cfg.cusp_anti_scale; fc.ecp_terms = 0;
     DQ_LAUNCH(finalize_kernel<T>, dim3(Bc), dim3(128), finalize_smem_bytes<T>(N, K), st, fc, r, R, Rb, (const T*)dsign,
               (const T*)dlog, (const T*)nullptr, (const T*)nullptr, P("cusp.alpha"), (const T*)d_zval, (const T*)nullptr,
               (const int*)d_ecp_mask, Bc, sign, logp, (T*)nullptr, (T*)nullptr, (T*)nullptr, (const T*)nullptr, (const T*)nullptr,
-              (const T*)nullptr);
+              (const T*)nullptr, PhArgs<T>());
     // ---- reverse ------------------------------------------------------------------------------------------------
     DQ_LAUNCH(finalize_bwd_kernel<T>, dim3((Bc + 127) / 128), dim3(128), 0, st, r, N, cfg.n_up, K, Bc, (const T*)dsign,
               (const T*)dlog, wts, cfg.cusp_kind, (T)cfg.cusp_same_scale, (T)cfg.cusp_anti_scale, P("cusp.alpha"), dld,
@@ -1226,7 +1270,9 @@ struct Engine : EngineBase {
                    void* stats, void* sign, void* logp, void* grad, void* ws, int64_t wsb, cudaStream_t st) override {
     const T* r = (const T*)r_;
     const T* R = (const T*)R_;
+    ph_active = ph_on;
     int rc = run_batched(r, R, Rb, B, T3 + 2, (T*)sign, (T*)logp, (T*)E, (T*)stats, (T*)grad, ws, wsb, st);
+    ph_active = false;
     if (rc) return rc;
     if (J > 0) {
       // non-local ECP: virtual walkers (12 quadrature points x electrons x ECP nuclei)
@@ -1394,6 +1440,12 @@ int dqmc_wf_vjp_params(dqmc_handle h, const void* r, const void* R, int32_t R_ba
   if (!h) return 2;
   return h->e->vjp_params(r, R, R_batched, n_walkers, weights, out_sign, out_log, out_grad_params, workspace, workspace_bytes,
                           (cudaStream_t)stream);
+}
+int dqmc_set_pseudo_hamiltonian(dqmc_handle h, int32_t n_tab, int32_t n_grid, double r_max, const double* tables,
+                                const int32_t* tab_of_nuc) {
+  if (!h) return 2;
+  cudaSetDevice(h->e->device);
+  return h->e->set_ph(n_tab, n_grid, r_max, tables, tab_of_nuc);
 }
 int64_t dqmc_launch_count(dqmc_handle h) { return h ? h->e->launches : -1; }
 

@@ -32,7 +32,9 @@ __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, 
                               int K, int S, int total, const T* __restrict__ pi_up, const T* __restrict__ pi_dn,
                               const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn,
                               const T* __restrict__ BF, int ldb, T* __restrict__ det_sign, T* __restrict__ det_log,
-                              T* __restrict__ det_grad, T* __restrict__ det_lap, int rep, int full_det) {
+                              T* __restrict__ det_grad, T* __restrict__ det_lap, int rep, int full_det,
+                              const T* __restrict__ QA) {
+  // QA != null: pseudo-Hamiltonian metric per electron (common.cuh PhMetric; tangent slots are v-coordinates)
   // full_det == 0: spin-factorised determinants det_up(n_up x n_up) det_down(n_down x n_down) (reference
   // wf/nn_wave_function.py:143-151) = determinant of the matrix with the spin-off-diagonal blocks zeroed.
   // rep = envelope terms per nucleus (1: ExponentialEnvelopes; 3: SimplifiedNucleusDependentEnvelopes,
@@ -63,10 +65,19 @@ __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, 
     const T* pi = (i < n_up ? pi_up : pi_dn) + (size_t)(k * N + mu) * M * rep;
     const T* ze = (i < n_up ? zeta_up : zeta_dn) + (size_t)(k * N + mu) * M * rep;
     T e = 0, de0 = 0, de1 = 0, de2 = 0, le = 0;
+    PhMetric<T> pm;
+    if (QA) pm.load(QA + ((size_t)b * N + i) * PH_STRIDE);
     for (int m = 0; m < M; ++m) {
       T dx0 = rb[3 * i] - Rb[3 * m], dx1 = rb[3 * i + 1] - Rb[3 * m + 1], dx2 = rb[3 * i + 2] - Rb[3 * m + 2];
       T d2 = dx0 * dx0 + dx1 * dx1 + dx2 * dx2;
       T rho2 = Num<T>::eps() + d2, rho = m_sqrt(rho2);
+      T gr2 = d2 / rho2, lr = T(3) / rho - d2 / (rho2 * rho);  // |grad rho|^2, laplacian rho
+      if (QA && S > 1) {
+        T a0, a1, a2;
+        pm.mul(dx0 / rho, dx1 / rho, dx2 / rho, a0, a1, a2);
+        gr2 = (dx0 * a0 + dx1 * a1 + dx2 * a2) / rho;
+        lr = (pm.trace() - gr2) / rho;
+      }
       for (int et = 0; et < rep; ++et) {
         T a = m_abs(ze[m * rep + et]);
         T ex = pi[m * rep + et] * m_exp(-a * rho);
@@ -74,10 +85,11 @@ __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, 
         if (S > 1) {
           T c = -a * ex / rho;
           de0 += c * dx0; de1 += c * dx1; de2 += c * dx2;
-          le += ex * (a * a * d2 / rho2 - a * (T(3) / rho - d2 / (rho2 * rho)));
+          le += ex * (a * a * gr2 - a * lr);
         }
       }
     }
+    if (QA && S > 1) pm.to_v(de0, de1, de2);
     if (!full_det && ((i < n_up) != (mu < n_up))) { e = T(0); de0 = T(0); de1 = T(0); de2 = T(0); le = T(0); }
     const T* bfrow = BF + (brow0 + (size_t)i * S) * ldb + k * N + mu;
     T bf0 = bfrow[0];
@@ -657,9 +669,11 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
                                 T* __restrict__ out_log, T* __restrict__ out_E, T* __restrict__ out_stats,
                                 T* __restrict__ out_grad, const T* __restrict__ conf_w /*[K] or null: SumPool*/,
                                 const T* __restrict__ jastrow /*[B][S] augmented scalar rows or null*/,
-                                const T* __restrict__ nuc_cusp /*[1 + M]: alpha, nuclear charges; or null*/) {
+                                const T* __restrict__ nuc_cusp /*[1 + M]: alpha, nuclear charges; or null*/,
+                                PhArgs<T> ph /*pseudo-Hamiltonian (common.cuh); all null: none*/) {
   DQMC_DYN_SMEM(smem_raw);
   const int N = c.N, M = c.M, K = c.K, S = c.S;
+  const T* QA = S > 1 ? ph.QA : nullptr;
   const int T3 = S > 1 ? S - 2 : 0;
   T* pk = reinterpret_cast<T*>(smem_raw);  // [K]
   T* grad = pk + K;                         // [3N]
@@ -690,6 +704,8 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
   if (c.cusp_kind != 0) { as_ = cusp_alpha[0]; aa_ = cusp_alpha[1]; }
   for (int i = tid; i < N; i += nt) {
     T g0 = 0, g1 = 0, g2 = 0;
+    PhMetric<T> pm;
+    if (QA) pm.load(QA + ((size_t)b * N + i) * PH_STRIDE);
     for (int j = 0; j < N; ++j) {
       if (j == i) continue;
       T dx0 = rb[3 * i] - rb[3 * j], dx1 = rb[3 * i + 1] - rb[3 * j + 1], dx2 = rb[3 * i + 2] - rb[3 * j + 2];
@@ -707,6 +723,12 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
         if (S > 1) {
           T cc = fp / rho;
           g0 += cc * dx0; g1 += cc * dx1; g2 += cc * dx2;
+          if (QA) {  // tr(A_i Hess_i f): the pair (i, j) carries electron i's metric, (j, i) electron j's
+            T a0, a1, a2;
+            pm.mul(dx0 / rho, dx1 / rho, dx2 / rho, a0, a1, a2);
+            const T uau = (dx0 * a0 + dx1 * a1 + dx2 * a2) / rho;
+            cusp_l += fpp * uau + fp * (pm.trace() - uau) / rho;
+          } else
           cusp_l += fpp * d2 / rho2 + fp * (T(3) / rho - d2 / (rho2 * rho));
         }
       }
@@ -727,9 +749,17 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
         if (S > 1) {
           const T cc = fp / dist;
           g0 += cc * dx0; g1 += cc * dx1; g2 += cc * dx2;
+          if (QA) {
+            T a0, a1, a2;
+            pm.mul(dx0 / dist, dx1 / dist, dx2 / dist, a0, a1, a2);
+            const T uau = (dx0 * a0 + dx1 * a1 + dx2 * a2) / dist;
+            cusp_l += fpp * uau + fp * (pm.trace() - uau) / dist;
+          } else
           cusp_l += fpp + T(2) * fp / dist;
         }
       }
+      if (ph.tabs && ph.tab_of_nuc[m] >= 0)  // local pseudo-Hamiltonian term r V_loc(r) / r (pseudo_hamiltonian.py:180-196)
+        vloc += ph_interp(ph.tabs + (size_t)ph.tab_of_nuc[m] * 2 * ph.G, ph.G, ph.rmax, dist) / dist;
       if (c.ecp_terms > 0 && ecp_mask[m]) {
         const T* lp = ecp_loc + (size_t)m * 6 * c.ecp_terms;
         for (int tt = 0; tt < c.ecp_terms; ++tt) {
@@ -739,7 +769,10 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
         }
       }
     }
-    if (S > 1) { grad[3 * i] = g0; grad[3 * i + 1] = g1; grad[3 * i + 2] = g2; }
+    if (S > 1) {
+      if (QA) pm.to_v(g0, g1, g2);
+      grad[3 * i] = g0; grad[3 * i + 1] = g1; grad[3 * i + 2] = g2;
+    }
   }
   for (int idx = tid; idx < M * M; idx += nt) {
     int I = idx / M, J = idx % M;
@@ -772,13 +805,31 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
     T gtot = gd + grad[t] + (jr ? jr[1 + t] : T(0));
     grad[t] = gtot;
     sum_g2 += gtot * gtot;
-    if (out_grad) out_grad[(size_t)b * T3 + t] = gtot;
+    if (out_grad && !QA) out_grad[(size_t)b * T3 + t] = gtot;
   }
   block_sum2(sum_pg2, sum_g2, scratch);
+  T first = T(0);
+  if (QA) {  // first-order term sum_i b_i . grad_{r_i} log|psi|, grad_r = Q^-T grad_v (pseudo_hamiltonian.py:268-274)
+    for (int i = tid; i < N; i += nt) {
+      PhMetric<T> pm;
+      const T* rec = QA + ((size_t)b * N + i) * PH_STRIDE;
+      pm.load(rec);
+      T g0 = grad[3 * i], g1 = grad[3 * i + 1], g2 = grad[3 * i + 2];
+      pm.to_r(g0, g1, g2);
+      first += rec[12] * g0 + rec[13] * g1 + rec[14] * g2;
+      if (out_grad) {
+        T* og = out_grad + (size_t)b * T3 + 3 * i;
+        og[0] = g0; og[1] = g1; og[2] = g2;
+      }
+    }
+    T dummy2 = T(0);
+    block_sum2(first, dummy2, scratch);
+  }
   if (tid == 0) {
     T lap = sum_pg2 + cusp_l + (jr ? jr[T3 + 1] : T(0));
     for (int k = 0; k < K; ++k) lap += pk[k] * det_lap[(size_t)b * K + k];
-    T ekin = T(-0.5) * (lap + sum_g2);
+    // A already contains the 1/2 of the kinetic energy when a pseudo-Hamiltonian is active
+    T ekin = QA ? first - (lap + sum_g2) : T(-0.5) * (lap + sum_g2);
     T e = ekin + vloc + vel + enuc;  // V_nl added by the non-local ECP pass
     out_E[b] = e;
     out_stats[0 * (size_t)B + b] = vel;

@@ -22,7 +22,7 @@ namespace dq {
 template <class T>
 __global__ void embed_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M,
                              int n_up, int S, int log_rescale, int use_spin, const T* __restrict__ W, int d,
-                             T* __restrict__ X, int total, int epb) {
+                             T* __restrict__ X, int total, int epb, const T* __restrict__ QA /*pseudo-Hamiltonian metric or null*/) {
   DQMC_DYN_SMEM(smem_raw);
   const int F = 4 * M + use_spin;
   T* feat = reinterpret_cast<T*>(smem_raw);  // [F]
@@ -39,6 +39,15 @@ __global__ void embed_kernel(const T* __restrict__ r, const T* __restrict__ R, i
     T rho2 = Num<T>::eps() + d2, rho = m_sqrt(rho2);
     T gr2 = d2 / rho2;                     // |grad rho|^2
     T lr = T(3) / rho - d2 / (rho2 * rho);  // laplacian rho
+    T au[3] = {dx[0] / rho, dx[1] / rho, dx[2] / rho};  // (A grad rho); A = 1 without a pseudo-Hamiltonian
+    if (QA) {  // second derivatives weighted by A(r_i): u^T A u and tr(A Hess rho) (common.cuh, PhMetric)
+      PhMetric<T> pm;
+      pm.load(QA + (size_t)bi * PH_STRIDE);
+      const T u0 = au[0], u1 = au[1], u2 = au[2];
+      pm.mul(u0, u1, u2, au[0], au[1], au[2]);
+      gr2 = u0 * au[0] + u1 * au[1] + u2 * au[2];
+      lr = (pm.trace() - gr2) / rho;
+    }
     T f0, f0p, f0pp, s, sp, spp;
     if (log_rescale) {
       T g = m_log1p(rho), gp = T(1) / (T(1) + rho), gpp = -gp * gp;
@@ -58,7 +67,7 @@ __global__ void embed_kernel(const T* __restrict__ r, const T* __restrict__ R, i
     for (int c = 0; c < 3; ++c) {
       dfeat[c * F + k0] = f0p * dx[c] / rho;
       feat[k0 + 1 + c] = dx[c] * s;
-      lfeat[k0 + 1 + c] = T(2) * sp * dx[c] / rho + dx[c] * ls;
+      lfeat[k0 + 1 + c] = T(2) * sp * au[c] + dx[c] * ls;
 #pragma unroll
       for (int e = 0; e < 3; ++e)
         dfeat[e * F + k0 + 1 + c] = (c == e ? s : T(0)) + dx[c] * sp * dx[e] / rho;
@@ -88,6 +97,11 @@ __global__ void embed_kernel(const T* __restrict__ r, const T* __restrict__ R, i
     }
     Xg[f] = y0;
     if (S > 1) {
+      if (QA) {  // tangent seeds = columns of Q_i
+        PhMetric<T> pm;
+        pm.load(QA + (size_t)bi * PH_STRIDE);
+        pm.to_v(y1, y2, y3);
+      }
       for (int t = 0; t < T3; ++t) {
         T v = T(0);
         if (t == 3 * i) v = y1;

@@ -270,6 +270,13 @@ class Engine:
         if rc != 0:
             raise RuntimeError(f'dqmc_create failed with status {rc}')
         self.h = h
+        ph = getattr(hamil, 'ph', None)
+        if ph is not None:  # pseudo-Hamiltonian tables (deepqmc_b200/ph.py) -> device
+            n_tab, _, G = ph.tables.shape
+            rc = self.lib.dqmc_set_pseudo_hamiltonian(h, n_tab, G, float(ph.r_max),
+                                                      ph.tables.ctypes.data_as(C.POINTER(C.c_double)),
+                                                      ph.tab_of_nuc.ctypes.data_as(C.POINTER(C.c_int32)))
+            self._check(rc, 'dqmc_set_pseudo_hamiltonian')
         self.entries = {}
         name = C.create_string_buffer(64)
         off, rows, cols = C.c_int64(), C.c_int32(), C.c_int32()

@@ -70,7 +70,8 @@ class _Potential:
 
 
 class MolecularHamiltonian:
-    def __init__(self, *, mol: Molecule, ecp_type=None, ecp_mask=None, elec_std=1.0, laplacian_factory=None):
+    def __init__(self, *, mol: Molecule, ecp_type=None, ecp_mask=None, elec_std=1.0, laplacian_factory=None,
+                 ph_data_dir=None):
         self.mol, self.elec_std, self.ecp_type = mol, elec_std, ecp_type
         # The engine implements the forward-Laplacian factory (conf/hamil/qc_forward_laplacian.yaml);
         # the argument is accepted for signature compatibility.
@@ -83,9 +84,13 @@ class MolecularHamiltonian:
         self.ecp_mask = np.asarray(ecp_mask, dtype=bool)
         if self.ecp_mask.any():
             assert ecp_type is not None, 'ECP type must be specified if ECPs are used.'
-            if 'PH' in str(ecp_type):
-                raise NotImplementedError('PseudoHamiltonian is outside the hot-path scope (SURVEY.md 8f N3)')
-        self.pot = _Potential(mol.charges, ecp_type, self.ecp_mask)
+        self.ph = None
+        if self.ecp_mask.any() and 'PH' in str(ecp_type):  # hamil.py:134-135 -> ecp/pseudo_hamiltonian.py
+            from .ph import PseudoHamiltonianPotential
+
+            self.pot = self.ph = PseudoHamiltonianPotential(mol.charges, ecp_type, self.ecp_mask, ph_data_dir)
+        else:
+            self.pot = _Potential(mol.charges, ecp_type, self.ecp_mask)
         n_elec = int(sum(self.pot.ns_valence) - mol.charge)
         assert not (n_elec + mol.spin) % 2
         assert n_elec > 1, 'The system must contain at least two active electrons.'
@@ -93,8 +98,9 @@ class MolecularHamiltonian:
         self.n_up = (n_elec + mol.spin) // 2
         self.n_down = (n_elec - mol.spin) // 2
         self.ns_valence = self.pot.ns_valence
-        self.loc_params = self.pot.loc_params if self.ecp_mask.any() else None
-        self.nl_params = self.pot.nl_params if self.ecp_mask.any() else None
+        gaussian = self.ecp_mask.any() and self.ph is None
+        self.loc_params = self.pot.loc_params if gaussian else None
+        self.nl_params = self.pot.nl_params if gaussian else None
         self.mol_shells = [get_shell(z) for z in mol.charges]
         self.mol_ecp_shells = [get_shell(z + 1) - 1 for z in mol.charges - self.ns_valence]
 

@@ -149,6 +149,18 @@ int dqmc_wf_vjp_params(dqmc_handle h, const void* r, const void* R, int32_t R_ba
                        const void* weights, void* out_sign, void* out_log, void* out_grad_params, void* workspace,
                        int64_t workspace_bytes, void* stream);
 
+/* Switch the handle's Hamiltonian to a pseudo-Hamiltonian (fully local replacement of the semi-local ECP):
+ * tables[n_tab][2][n_grid] (host, fp64) = r V_loc(r) and r V_L2(r) per tabulated element on the uniform grid
+ * [0, r_max]; tab_of_nuc[n_nuc] = table index of each nucleus or -1.  z_valence of the config carries the
+ * effective charges.  dqmc_local_energy then evaluates  sum_i [A(r_i) : Hess_i + b(r_i) . grad_i] psi / psi  with
+ * A = 1/2 + sum_I (r V_L2 |d| 1 - V_L2 d d^T), b = 2 sum_I V_L2 d  by seeding the forward-Laplacian tangents with
+ * the Cholesky factor of A, and adds r V_loc / r to V_loc; stats lap / quantum_force are those of the transformed
+ * coordinates as in the reference.  Psiformer-family trunks; call once after dqmc_create (changes the workspace size).
+ * replaces: ecp/pseudo_hamiltonian.py:165-278 PseudoHamiltonian.{local_potential, kinetic_term},
+ *           :71-112 load_PH_functions (RegularGridInterpolator tables). */
+int dqmc_set_pseudo_hamiltonian(dqmc_handle h, int32_t n_tab, int32_t n_grid, double r_max, const double* tables,
+                                const int32_t* tab_of_nuc);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches claim). */
 int64_t dqmc_launch_count(dqmc_handle h);
 

@@ -111,7 +111,7 @@ def legendre_values(lmax_p1, x):
 class OracleHamiltonian:
     """reference: src/deepqmc/hamil.py:70-184"""
 
-    def __init__(self, mol, ecp_type=None, ecp_mask=None):
+    def __init__(self, mol, ecp_type=None, ecp_mask=None, ph_dir=None):
         self.mol = mol
         charges = mol.charges
         if ecp_type is None:
@@ -119,7 +119,13 @@ class OracleHamiltonian:
         elif ecp_mask is None:
             ecp_mask = list(charges > 2)
         self.ecp_type, self.ecp_mask = ecp_type, np.asarray(ecp_mask, dtype=bool)
-        if self.ecp_mask.any():
+        self.ph = None
+        if self.ecp_mask.any() and 'PH' in str(ecp_type):  # hamil.py:134-135
+            from .ph import OraclePseudoHamiltonian
+
+            self.ph = OraclePseudoHamiltonian(charges, ecp_type, self.ecp_mask, ph_dir)
+            self.ns_valence, self.loc_params, self.nl_params = self.ph.ns_valence, None, None
+        elif self.ecp_mask.any():
             self.ns_valence, self.loc_params, self.nl_params = parse_ecp(charges, ecp_type, self.ecp_mask)
         else:
             self.ns_valence, self.loc_params, self.nl_params = charges.copy(), None, None
@@ -211,12 +217,16 @@ class OracleHamiltonian:
         Returns (E_loc, stats dict with the reference's 6 keys)."""
         from .laplacian import laplacian_hessian
 
-        lap, grad = laplacian_hessian(lambda x: wf_single(x.reshape(-1, 3))[1], r.reshape(-1))
-        qf2 = (grad**2).sum()
-        e_kin = -0.5 * (lap + qf2)
+        if self.ph is not None:  # pseudo-Hamiltonian: kinetic-like term with position-dependent mass tensor
+            e_kin, lap, qf2 = self.ph.kinetic_term(lambda x: wf_single(x)[1], r, R)
+            v_loc = self.ph.local_potential(r, R)
+        else:
+            lap, grad = laplacian_hessian(lambda x: wf_single(x.reshape(-1, 3))[1], r.reshape(-1))
+            qf2 = (grad**2).sum()
+            e_kin = -0.5 * (lap + qf2)
+            v_loc = self.local_potential(r, R)
         e_nuc = self.nuclear_energy(R)
         v_el = self.electronic_potential(r)
-        v_loc = self.local_potential(r, R)
         v_nl = (
             self.nonloc_potential(r, R, wf_single, phi_random)
             if self.nl_params is not None

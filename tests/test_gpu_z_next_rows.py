@@ -77,3 +77,54 @@ def test_parameter_vjp_transpsiformer_matches_autograd_fp64():
     for k, v in pt.items():
         ref = v.grad
         assert torch.allclose(grads[k].cpu().reshape(ref.shape), ref, rtol=1e-8, atol=1e-9 * max(1.0, ref.abs().max().item())), k
+
+
+@pytest.mark.parametrize('kind,charges,spin,dtype', [
+    ('psiformer', [17, 1], 0, 'float64'),        # HCl-like: one pseudo-Hamiltonian centre, 8 valence electrons
+    ('psiformer', [15, 17], 0, 'float64'),       # two centres with different tables, 12 electrons
+    ('transpsiformer', [16, 1, 1], 0, 'float64'),
+    ('psiformer', [16, 1, 1], 0, 'float32'),
+])
+def test_pseudo_hamiltonian_local_energy(tmp_path, kind, charges, spin, dtype):
+    """PseudoHamiltonian (reference ecp/pseudo_hamiltonian.py:165-278): mass-tensor kinetic term
+    through Cholesky-seeded forward-Laplacian tangents, first-order term, tabulated local potential -- E_loc, all six
+    statistics and grad_r log|psi| against the oracle (autograd Hessian in the transformed coordinates).  Tables:
+    synthetic files in the reference's XML layout (tests/ph_fixture.py)."""
+    from deepqmc_b200.hamil import STAT_KEYS, MolecularHamiltonian
+    from deepqmc_b200.molecule import Molecule
+    from deepqmc_b200 import params as PN
+    from deepqmc_b200.ansatz import B200Ansatz
+    from oracle import wf
+    from oracle.hamil import OracleHamiltonian
+    from ph_fixture import write_synthetic_ph
+
+    d = write_synthetic_ph(str(tmp_path))
+    coords = [[0.0, 0.0, 0.0], [2.4, 0.0, 0.0], [0.0, 2.6, 0.3]][:len(charges)]
+    mol = Molecule(coords=coords, charges=charges, charge=0, spin=spin)
+    hamil = MolecularHamiltonian(mol=mol, ecp_type='PH', ph_data_dir=d)
+    oh = OracleHamiltonian(mol, ecp_type='PH', ph_dir=d)
+    ansatz = B200Ansatz(hamil, kind, dtype=dtype, embedding_dim=32, n_layers=2, n_heads=2, n_determinants=3)
+    params = PN.perturb_params(ansatz.init(0))
+    pt = wf.to_torch(params)
+    B, N = 3, hamil.n_up + hamil.n_down
+    rng = np.random.default_rng(0)
+    r64 = torch.as_tensor(mol.coords[rng.integers(0, len(mol.coords), size=(B, N))] + 0.8 * rng.normal(size=(B, N, 3)))
+    tdt = torch.float64 if dtype == 'float64' else torch.float32
+    R = torch.as_tensor(mol.coords, dtype=tdt, device=DEV)
+    pc = PhysicalConfiguration(R, r64.to(tdt).to(DEV), torch.zeros(B, device=DEV))
+    E, st, grad = hamil.local_energy(ansatz.apply)(None, params, pc, return_grad=True)
+    for b in range(B):
+        f = lambda x: wf.log_psi(ansatz.spec, pt, x, R.cpu().double())
+        eo, so = oh.local_energy(f, r64[b], R.cpu().double())
+        x = r64[b].clone().requires_grad_(True)
+        g, = torch.autograd.grad(f(x)[1], x)
+        if dtype == 'float64':
+            tol = 1e-8 * max(1.0, abs(eo.item()), 0.5 * abs(so['hamil/lap'].item()))
+            gtol = 1e-8 * max(1.0, g.abs().max().item())
+        else:  # the reference's own fp32 regression tolerance (tests/test_hamil.py:37-40) on the largest term
+            tol = 2e-4 * max(1.0, abs(eo.item()), abs(so['hamil/lap'].item()), abs(so['hamil/quantum_force'].item()))
+            gtol = 2e-4 * max(1.0, g.abs().max().item())
+        assert abs(E[b].item() - eo.item()) <= tol
+        for k in STAT_KEYS:
+            assert abs(st[k][b].item() - so[k].item()) <= tol * (10 if k in ('hamil/lap', 'hamil/quantum_force') else 1), k
+        assert (grad[b].reshape(N, 3).cpu().double() - g).abs().max().item() <= gtol
