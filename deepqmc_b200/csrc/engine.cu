@@ -570,7 +570,8 @@ struct Engine : EngineBase {
            (int64_t)(sizeof(T) * per_walker_elems(1)) * V + 32 * 256;
   }
   int64_t ws_bytes(int B, int mode) override {
-    if (mode == DQMC_MODE_VJP) return (int64_t)(sizeof(T) * vjp_per_walker_elems()) * B + 64 * 256;
+    if (mode == DQMC_MODE_VJP)
+      return (int64_t)(sizeof(T) * (cfg.kind == DQMC_FERMINET ? vjp_per_walker_elems_ferminet() : vjp_per_walker_elems())) * B + 64 * 256;
     int S = mode == DQMC_MODE_FORWARD ? 1 : T3 + 2;
     int64_t need = (int64_t)chunk_bytes(B, S);
     if (mode == DQMC_MODE_LOCAL_ENERGY && J > 0) need = std::max<int64_t>(need, ecp_bytes(B));
@@ -1231,10 +1232,124 @@ struct Engine : EngineBase {
     return 0;
   }
 
+  // FermiNet reverse pass (conf/ansatz/ferminet.yaml): node update g on concat[h, spin means of h, spin means of the
+  // incoming edges], shared edge MLP u, residuals / sqrt(2).  The raw input features carry no parameters, so the
+  // chain stops at the first layer's weights.
+  int vjp_chunk_ferminet(const T* r, const T* R, int Rb, int Bc, const T* wts, T* sign, T* logp, T* G, void* wsbase,
+                         cudaStream_t st) {
+    const int L = cfg.n_layers, rows = Bc * N, rowsE = Bc * N * N, de = cfg.edge_dim, d0 = 4 * M;
+    const T isq2 = (T)0.70710678118654752440;
+    char* p = (char*)wsbase;
+    auto take = [&](size_t n) { T* q = (T*)p; p += align_up(sizeof(T) * n); return q; };
+    std::vector<T*> Hs(L + 1), Es(L), Fs(L);
+    std::vector<int> dH(L + 1), dEd(L);
+    dH[0] = d0;
+    for (int l = 1; l <= L; ++l) dH[l] = d;
+    for (int l = 0; l < L; ++l) dEd[l] = l == 0 ? 4 : de;
+    for (int l = 0; l <= L; ++l) Hs[l] = take((size_t)rows * dH[l]);
+    for (int l = 0; l < L; ++l) { Es[l] = take((size_t)rowsE * dEd[l]); Fs[l] = take((size_t)rows * (3 * dH[l] + 2 * dEd[l])); }
+    const int fmax = 3 * (d > d0 ? d : d0) + 2 * (de > 4 ? de : 4);
+    T* BF = take((size_t)rows * KN); T* dBF = take((size_t)rows * KN);
+    T* dsign = take((size_t)Bc * K); T* dlog = take((size_t)Bc * K); T* dld = take((size_t)Bc * K);
+    T* dXa = take((size_t)rows * d); T* dXb = take((size_t)rows * d); T* dZ = take((size_t)rows * d);
+    T* dF = take((size_t)rows * fmax);
+    T* dEa = take((size_t)rowsE * de); T* dEb = take((size_t)rowsE * de); T* dZe = take((size_t)rowsE * de);
+    // ---- forward, activations kept -----------------------------------------------------------------------------
+    DQ_LAUNCH(embed_kernel<T>, dim3(Bc * N), dim3(128), sizeof(T) * 5 * d0, st, r, R, Rb, N, M, cfg.n_up, 1, 0, 0,
+              (const T*)nullptr, d0, Hs[0], Bc * N, 1, (const T*)nullptr);
+    DQ_LAUNCH(edge_feat_kernel<T>, dim3((rowsE + 127) / 128), dim3(128), 0, st, r, N, 1, Es[0], rowsE);
+    for (int l = 0; l < L; ++l) {
+      const std::string q = "F" + std::to_string(l) + ".";
+      const int dc = dH[l], ec = dEd[l], fin = 3 * dc + 2 * ec;
+      DQ_LAUNCH(fermi_agg_kernel<T>, dim3(Bc, N), dim3(128), 0, st, (const T*)Hs[l], dc, (const T*)Es[l], ec, N, cfg.n_up, 1, Fs[l]);
+      int rc = gemm(Fs[l], fin, (q + "wg").c_str(), nullptr, 0, d, P(q + "bg"), nullptr, 0, Hs[l + 1], d, rows, d, fin, 1, 0, N, st);
+      if (rc) return rc;
+      DQ_LAUNCH(tanh_fl_kernel<T>, dim3(rows, (d + 127) / 128), dim3(128), 0, st, Hs[l + 1], d,
+                (const T*)(dc == d ? Hs[l] : nullptr), dc, 1, d, dc == d ? isq2 : T(1));
+      if (l < L - 1) {
+        rc = gemm(Es[l], ec, (q + "wu").c_str(), nullptr, 0, de, P(q + "bu"), nullptr, 0, Es[l + 1], de, rowsE, de, ec, 1, 0, N, st);
+        if (rc) return rc;
+        DQ_LAUNCH(tanh_fl_kernel<T>, dim3(rowsE, 1), dim3(32), 0, st, Es[l + 1], de, (const T*)(ec == de ? Es[l] : nullptr), ec,
+                  1, de, ec == de ? isq2 : T(1));
+      }
+    }
+    gemm(Hs[L], d, "bf.up", "bf.dn", cfg.n_up, KN, nullptr, nullptr, 0, BF, KN, Bc, KN, d, 1, 1, N, st);
+    const int sl_wpb = slater_warps_per_block<T>(N);
+    DQ_LAUNCH(slater_kernel<T>, dim3((Bc * K + sl_wpb - 1) / sl_wpb), dim3(32 * sl_wpb), slater_smem_bytes<T>(N), st, r, R, Rb, N,
+              M, cfg.n_up, K, 1, Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)BF, KN,
+              dsign, dlog, (T*)nullptr, (T*)nullptr, env_rep, 1, (const T*)nullptr);
+    FinalizeCfg fc;
+    fc.N = N; fc.M = M; fc.n_up = cfg.n_up; fc.K = K; fc.S = 1; fc.cusp_kind = cfg.cusp_kind;
+    fc.cusp_same_scale = cfg.cusp_same_scale; fc.cusp_anti_scale = cfg.cusp_anti_scale; fc.ecp_terms = 0;
+    DQ_LAUNCH(finalize_kernel<T>, dim3(Bc), dim3(128), finalize_smem_bytes<T>(N, K), st, fc, r, R, Rb, (const T*)dsign,
+              (const T*)dlog, (const T*)nullptr, (const T*)nullptr, P("cusp.alpha"), (const T*)d_zval, (const T*)nullptr,
+              (const int*)d_ecp_mask, Bc, sign, logp, (T*)nullptr, (T*)nullptr, (T*)nullptr, (const T*)nullptr, (const T*)nullptr,
+              (const T*)nullptr, PhArgs<T>());
+    // ---- reverse -------------------------------------------------------------------------------------------------
+    DQ_LAUNCH(finalize_bwd_kernel<T>, dim3((Bc + 127) / 128), dim3(128), 0, st, r, N, cfg.n_up, K, Bc, (const T*)dsign,
+              (const T*)dlog, wts, cfg.cusp_kind, (T)cfg.cusp_same_scale, (T)cfg.cusp_anti_scale, P("cusp.alpha"), dld,
+              G + off("cusp.alpha"));
+    {
+      const size_t pw = slater_bwd_smem_per_warp<T>(N);
+      int wpb = (int)((96 * 1024) / pw);
+      wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
+      DQ_LAUNCH(slater_bwd_kernel<T>, dim3((Bc * K + wpb - 1) / wpb), dim3(32 * wpb), pw * wpb, st, r, R, Rb, N, M, cfg.n_up, K,
+                Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)BF, KN, (const T*)dld, dBF,
+                G + off("env.pi_up"), G + off("env.pi_dn"), G + off("env.zeta_up"), G + off("env.zeta_dn"), env_rep);
+    }
+    T* dHn = dXa;   // gradient w.r.t. H_{l+1}
+    T* dHc = dXb;   // gradient w.r.t. H_l (being built)
+    T* dEn = dEa;   // gradient w.r.t. E_{l+1} (valid for l < L - 1)
+    T* dEc = dEb;
+    gemm_raw(dBF, KN, PT("bf.up"), PT("bf.dn"), cfg.n_up, d, nullptr, 0, dHn, d, Bc, d, KN, 1, st);
+    wgrad(Hs[L], d, dBF, KN, rows, d, KN, G + off("bf.up"), 0, cfg.n_up, st);
+    wgrad(Hs[L], d, dBF, KN, rows, d, KN, G + off("bf.dn"), cfg.n_up, N, st);
+    for (int l = L - 1; l >= 0; --l) {
+      const std::string q = "F" + std::to_string(l) + ".";
+      const int dc = dH[l], ec = dEd[l], fin = 3 * dc + 2 * ec;
+      const bool res_h = dc == d, res_e = ec == de;
+      const size_t nel = (size_t)rows * d;
+      // H_{l+1} = s (H_l + tanh(F Wg + bg))  |  tanh(F Wg + bg)
+      DQ_LAUNCH(tanh_res_bwd_kernel<T>, dim3((unsigned)((nel + 255) / 256)), dim3(256), 0, st, (const T*)dHn, (const T*)Hs[l + 1],
+                (const T*)(res_h ? Hs[l] : nullptr), res_h ? isq2 : T(1), dZ, nel);
+      bgrad(dZ, d, rows, d, G + off(q + "bg"), st);
+      wgrad(Fs[l], fin, dZ, d, rows, fin, d, G + off(q + "wg"), 0, 0, st);
+      if (l > 0) {
+        gemm_raw(dZ, d, PT(q + "wg"), nullptr, 0, fin, nullptr, 0, dF, fin, rows, fin, d, 0, st);
+        DQ_LAUNCH(fermi_agg_bwd_kernel<T>, dim3(Bc, N), dim3(128), 0, st, (const T*)dF, dc, ec, N, cfg.n_up,
+                  (const T*)(res_h ? dHn : nullptr), isq2, dHc, dEc);
+      }
+      if (l < L - 1) {
+        // E_{l+1} = s (E_l + tanh(E_l Wu + bu))  |  tanh(E_l Wu + bu)
+        const size_t nee = (size_t)rowsE * de;
+        DQ_LAUNCH(tanh_res_bwd_kernel<T>, dim3((unsigned)((nee + 255) / 256)), dim3(256), 0, st, (const T*)dEn, (const T*)Es[l + 1],
+                  (const T*)(res_e ? Es[l] : nullptr), res_e ? isq2 : T(1), dZe, nee);
+        bgrad(dZe, de, rowsE, de, G + off(q + "bu"), st);
+        wgrad(Es[l], ec, dZe, de, rowsE, ec, de, G + off(q + "wu"), 0, 0, st);
+        if (l > 0) {
+          gemm_raw(dZe, de, PT(q + "wu"), nullptr, 0, ec, dEc, ec, dEc, ec, rowsE, ec, de, 0, st);  // dE_l += dZe Wu^T
+          if (res_e) {
+            const size_t ne2 = (size_t)rowsE * ec;
+            DQ_LAUNCH(axpy_kernel<T>, dim3((unsigned)((ne2 + 255) / 256)), dim3(256), 0, st, (const T*)dEn, isq2, dEc, ne2);
+          }
+        }
+      }
+      T* t1 = dHn; dHn = dHc; dHc = t1;
+      T* t2 = dEn; dEn = dEc; dEc = t2;
+    }
+    return 0;
+  }
+  size_t vjp_per_walker_elems_ferminet() const {
+    const size_t L = cfg.n_layers, de = cfg.edge_dim, d0 = 4 * M, dm = (size_t)d > d0 ? d : d0, em = de > 4 ? de : 4;
+    const size_t rowsN = N, rowsE = (size_t)N * N;
+    return rowsN * (d0 + L * d + L * (3 * dm + 2 * em) + 2 * (size_t)KN + 3 * (size_t)d + 3 * dm + 2 * em) + rowsE * (4 + L * de + 3 * de) +
+           (size_t)K * 4;
+  }
+
   int vjp_params(const void* r_, const void* R_, int Rb, int B, const void* weights, void* sign, void* logp,
                  void* grad_params, void* ws, int64_t wsb, cudaStream_t st) override {
-    if (cfg.kind != DQMC_PSIFORMER && cfg.kind != DQMC_TRANSPSIFORMER) {
-      err = "dqmc_wf_vjp_params: only the Psiformer / TransPsiformer ansatzes have a reverse pass so far";
+    if (cfg.kind != DQMC_PSIFORMER && cfg.kind != DQMC_TRANSPSIFORMER && cfg.kind != DQMC_FERMINET) {
+      err = "dqmc_wf_vjp_params: only the Psiformer / TransPsiformer / FermiNet ansatzes have a reverse pass so far";
       return 2;
     }
     if (cfg.nuc_cusp_kind) { err = "dqmc_wf_vjp_params: nuclear cusp exponent gradient not implemented"; return 2; }
@@ -1242,16 +1357,20 @@ struct Engine : EngineBase {
     const T* R = (const T*)R_;
     DQ_CHECK(cudaMemsetAsync(grad_params, 0, sizeof(T) * total, st));
     // walkers per chunk: activations of every layer stay resident for the reverse pass (64 buffers, 256 B alignment each)
-    int64_t Bc = (wsb - 64 * 256) / (int64_t)(sizeof(T) * vjp_per_walker_elems());
+    const bool fermi = cfg.kind == DQMC_FERMINET;
+    int64_t Bc = (wsb - 64 * 256) / (int64_t)(sizeof(T) * (fermi ? vjp_per_walker_elems_ferminet() : vjp_per_walker_elems()));
     if (Bc > B) Bc = B;
     if (Bc < 1) { err = "workspace too small for a single walker (vjp)"; return 3; }
+    if (!fermi)
     DQ_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_bwd_smem_bytes<T>(N, dh, Mn)));
     DQ_CHECK(cudaFuncSetAttribute(slater_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(slater_bwd_smem_per_warp<T>(N) * 4)));
     for (int b0 = 0; b0 < B; b0 += (int)Bc) {
       const int nb = (int)std::min<int64_t>(Bc, B - b0);
-      int rc = vjp_chunk(r + (size_t)b0 * 3 * N, R + (Rb ? (size_t)b0 * 3 * M : 0), Rb, nb, (const T*)weights + b0, (T*)sign + b0,
-                         (T*)logp + b0, (T*)grad_params, ws, st);
+      const T* rc_ = r + (size_t)b0 * 3 * N;
+      const T* Rc_ = R + (Rb ? (size_t)b0 * 3 * M : 0);
+      int rc = fermi ? vjp_chunk_ferminet(rc_, Rc_, Rb, nb, (const T*)weights + b0, (T*)sign + b0, (T*)logp + b0, (T*)grad_params, ws, st)
+                     : vjp_chunk(rc_, Rc_, Rb, nb, (const T*)weights + b0, (T*)sign + b0, (T*)logp + b0, (T*)grad_params, ws, st);
       if (rc) return rc;
     }
     DQ_CHECK(cudaGetLastError());

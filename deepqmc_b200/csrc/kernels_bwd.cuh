@@ -73,6 +73,51 @@ __global__ void tanh_bwd_kernel(const T* __restrict__ dY, const T* __restrict__ 
   dZ[i] = dY[i] * (T(1) - y * y);
 }
 
+// Backward of y = scale * (res + tanh(z)) (FermiNet residual / sqrt(2), hkext.py:116-137) or y = tanh(z) (Res null,
+// scale 1) from the stored outputs: dZ = dY scale (1 - t^2), t = Y / scale - res.
+template <class T>
+__global__ void tanh_res_bwd_kernel(const T* __restrict__ dY, const T* __restrict__ Y, const T* __restrict__ Res, T scale,
+                                    T* __restrict__ dZ, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const T t = Y[i] / scale - (Res ? Res[i] : T(0));
+  dZ[i] = dY[i] * scale * (T(1) - t * t);
+}
+
+// Backward of fermi_agg_kernel (kernels_trunk.cuh) for the plain forward: from dF[b][i][3 dh + 2 de]
+//   dH[b][j][k]    = dF[b][j][k] + (1 / n_spin(j)) sum_i dF[b][i][dh (1 + down(j)) + k]  (+ res_scale * dRes[b][j][k])
+//   dE[b][j][i][k] = dF[b][i][3 dh + de down(j) + k] / n_spin(j)
+// One block per (walker, electron j).  dH / dE may be null (first layer: nothing upstream has parameters).
+template <class T>
+__global__ void fermi_agg_bwd_kernel(const T* __restrict__ dF, int dh, int de, int N, int n_up, const T* __restrict__ dRes,
+                                     T res_scale, T* __restrict__ dH, T* __restrict__ dE) {
+  const int b = blockIdx.x, j = blockIdx.y;
+  const int ldf = 3 * dh + 2 * de;
+  const bool down = j >= n_up;
+  const T inv = T(1) / (T)(down ? N - n_up : n_up);
+  const T* dFb = dF + (size_t)b * N * ldf;
+  if (dH)
+    for (int k = threadIdx.x; k < dh; k += blockDim.x) {
+      T acc = T(0);
+      for (int i = 0; i < N; ++i) acc += dFb[(size_t)i * ldf + dh * (down ? 2 : 1) + k];
+      T v = dFb[(size_t)j * ldf + k] + inv * acc;
+      if (dRes) v += res_scale * dRes[((size_t)b * N + j) * dh + k];
+      dH[((size_t)b * N + j) * dh + k] = v;
+    }
+  if (dE)
+    for (int idx = threadIdx.x; idx < N * de; idx += blockDim.x) {
+      const int i = idx / de, k = idx - i * de;
+      dE[(((size_t)b * N + j) * N + i) * de + k] = inv * dFb[(size_t)i * ldf + 3 * dh + (down ? de : 0) + k];
+    }
+}
+
+// y += a x
+template <class T>
+__global__ void axpy_kernel(const T* __restrict__ x, T a, T* __restrict__ y, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += a * x[i];
+}
+
 // W[rows][cols] -> Wt[cols][rows]
 template <class T>
 __global__ void transpose_kernel(const T* __restrict__ W, int rows, int cols, T* __restrict__ Wt) {

@@ -184,6 +184,28 @@ def _unpack_psiformer_grads(spec: AnsatzSpec, entries: dict, flat) -> dict:
     return out
 
 
+def _unpack_ferminet_grads(spec: AnsatzSpec, entries: dict, flat) -> dict:
+    """Engine-layout gradient vector -> Haiku-named tree for the FermiNet (inverse of _pack_haiku_params)."""
+    def e(name):
+        off, rows, cols = entries[name]
+        return flat[off:off + rows * cols].reshape(rows, cols)
+
+    out = {}
+    for l in range(spec.n_layers):
+        lp = PN.layer_prefix(l)
+        out[lp + 'g/linear_0:w'], out[lp + 'g/linear_0:b'] = e(f'F{l}.wg'), e(f'F{l}.bg')[0]
+        if l < spec.n_layers - 1:
+            out[lp + 'u/linear_0:w'], out[lp + 'u/linear_0:b'] = e(f'F{l}.wu'), e(f'F{l}.bu')[0]
+    out[PN.BF_UP + ':w'], out[PN.BF_DN + ':w'] = e('bf.up'), e('bf.dn')
+    for s_, t in (('up', 'up'), ('down', 'dn')):
+        out[f'{PN.ENV}:pi_{s_}'] = e(f'env.pi_{t}')
+        out[f'{PN.ENV}:zetas_{s_}'] = e(f'env.zeta_{t}')
+    if spec.cusp == 'psiformer':
+        ca = e('cusp.alpha')
+        out[f'{PN.CUSP}:same_alpha'], out[f'{PN.CUSP}:anti_alpha'] = ca[0, 0], ca[0, 1]
+    return out
+
+
 class Engine:
     """One engine per (ansatz spec, Hamiltonian constants, dtype, device)."""
 
@@ -390,7 +412,7 @@ class Engine:
 
     def vjp_params(self, r, R, weights, max_ws_bytes=None):
         """-> (sign[B], log[B], grads): grads = d/dparams sum_b weights[b] log|psi(r_b)| as a Haiku-named dict
-        (reference: loss/loss_function.py:53-82).  Psiformer only."""
+        (reference: loss/loss_function.py:53-82).  Psiformer, TransPsiformer, FermiNet."""
         r = self._prep(r)
         B = r.shape[0]
         R, Rb = self._R(R, B)
@@ -403,7 +425,8 @@ class Engine:
         rc = self.lib.dqmc_wf_vjp_params(self.h, r.data_ptr(), R.data_ptr(), Rb, B, w.data_ptr(), sign.data_ptr(), log.data_ptr(),
                                          flat.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
         self._check(rc, 'dqmc_wf_vjp_params')
-        grads = _unpack_psiformer_grads(self.spec, self.entries, flat)
+        unpack = _unpack_ferminet_grads if self.spec.kind == 'ferminet' else _unpack_psiformer_grads
+        grads = unpack(self.spec, self.entries, flat)
         if self.spec.kind == 'transpsiformer':
             # the walker-independent nuclear stream is differentiated on the host: the engine accumulated the
             # cotangents of its outputs (keys / values of the nuclear tokens, envelope exponents)
