@@ -423,10 +423,6 @@ struct Engine : EngineBase {
   const T* P(const std::string& n) const { return d_params + off(n); }
 
   int set_ph(int n_tab, int n_grid, double r_max, const double* tables, const int32_t* tab_of_nuc) override {
-    if (cfg.kind != DQMC_PSIFORMER && cfg.kind != DQMC_TRANSPSIFORMER) {
-      err = "the pseudo-Hamiltonian kinetic term is implemented for the Psiformer-family trunks only";
-      return 2;
-    }
     if (J > 0 || cfg.ecp_loc_terms > 0) { err = "pseudo-Hamiltonian and Gaussian-type ECP are mutually exclusive"; return 2; }
     if (n_tab < 1 || n_grid < 2 || !(r_max > 0) || !tables || !tab_of_nuc) { err = "bad pseudo-Hamiltonian tables"; return 2; }
     for (int m = 0; m < M; ++m)
@@ -702,12 +698,12 @@ struct Engine : EngineBase {
   // FermiNet trunk (reference: conf/ansatz/ferminet.yaml; gnn/electron_gnn.py:160-259 with
   // Residual / NodeSum / EdgeSum update features and a shared edge MLP): leaves the final electron
   // embeddings in *Xout.
-  int ferminet_trunk(const T* r, const T* R, int Rb, int Bc, int S, Ws& w, T** Xout, cudaStream_t st) {
+  int ferminet_trunk(const T* r, const T* R, int Rb, int Bc, int S, Ws& w, T** Xout, cudaStream_t st, const T* qa = nullptr) {
     const int rows = Bc * N * S, rowsE = Bc * N * N * S, de = cfg.edge_dim, d0 = 4 * M;
     const T isq2 = (T)0.70710678118654752440;
     DQ_LAUNCH(embed_kernel<T>, dim3(Bc * N), dim3(128), sizeof(T) * 5 * d0, st, r, R, Rb, N, M, cfg.n_up, S, 0, 0,
-              (const T*)nullptr, d0, w.X, Bc * N, 1, (const T*)nullptr);
-    DQ_LAUNCH(edge_feat_kernel<T>, dim3((Bc * N * N + 127) / 128), dim3(128), 0, st, r, N, S, w.A, Bc * N * N);
+              (const T*)nullptr, d0, w.X, Bc * N, 1, qa);
+    DQ_LAUNCH(edge_feat_kernel<T>, dim3((Bc * N * N + 127) / 128), dim3(128), 0, st, r, N, S, w.A, Bc * N * N, qa);
     T* Hc = w.X; T* Hn = w.O; T* Ec = w.A; T* En = w.M1;
     int dcur = d0, ecur = 4;
     for (int l = 0; l < cfg.n_layers; ++l) {
@@ -755,7 +751,8 @@ struct Engine : EngineBase {
     return 0;
   }
 
-  int paulinet_trunk(const T* r, const T* R, int Rb, int Bc, int S, Ws& w, T** Xbf, const T** jastrow, cudaStream_t st) {
+  int paulinet_trunk(const T* r, const T* R, int Rb, int Bc, int S, Ws& w, T** Xbf, const T** jastrow, cudaStream_t st,
+                     const T* qa = nullptr) {
     const int rows = Bc * N * S, e = cfg.edge_dim, groups = Bc * N, nl = cfg.gnn_sub_n > 0 ? cfg.gnn_sub_n : 1;
     const int Mne = cfg.gnn_conv_ne ? M : 0, NS = N + Mne, nt = cfg.gnn_conv_ne ? 3 : 2;
     const int pairs = Bc * N * NS, prow = pairs * 8;  // compact edge rows: 8 slots per (receiver, sender) pair
@@ -764,12 +761,12 @@ struct Engine : EngineBase {
     if (cfg.gnn_features) {
       dcur = 4 * M;
       DQ_LAUNCH(embed_kernel<T>, dim3(Bc * N), dim3(128), sizeof(T) * 5 * dcur, st, r, R, Rb, N, M, cfg.n_up, S, 0, 0,
-                (const T*)nullptr, dcur, w.X, Bc * N, 1, (const T*)nullptr);
+                (const T*)nullptr, dcur, w.X, Bc * N, 1, qa);
     } else {
       DQ_LAUNCH(gnn_embed_kernel<T>, dim3((Bc * N * d + 127) / 128), dim3(128), 0, st, P("emb.table"),
                 cfg.n_elec_types > 0 ? cfg.n_elec_types : 1, N, cfg.n_up, S, d, w.X, Bc * N);
     }
-    DQ_LAUNCH(gnn_edge_feat_kernel<T>, dim3((pairs + 63) / 64), dim3(64), 0, st, r, R, Rb, N, M, Mne, w.E0, pairs);
+    DQ_LAUNCH(gnn_edge_feat_kernel<T>, dim3((pairs + 63) / 64), dim3(64), 0, st, r, R, Rb, N, M, Mne, w.E0, pairs, S > 1 ? qa : (const T*)nullptr);
     T* X = w.X;
     T* Xn = w.O;
     T* E = w.E0;
@@ -886,15 +883,15 @@ struct Engine : EngineBase {
     if (gnn) {
       T* Xbf = nullptr;
       const T* jas = nullptr;
-      int rc = paulinet_trunk(r, R, Rb, Bc, S, w, &Xbf, &jas, st);
+      int rc = paulinet_trunk(r, R, Rb, Bc, S, w, &Xbf, &jas, st, qa);
       if (rc) return rc;
-      return tail(r, R, Rb, Bc, S, Bstat, sign, logp, E, stats, grad, w, Xbf, st, jas);
+      return tail(r, R, Rb, Bc, S, Bstat, sign, logp, E, stats, grad, w, Xbf, st, jas, qa);
     }
     if (cfg.kind == DQMC_FERMINET) {
       T* Xf = nullptr;
-      int rc = ferminet_trunk(r, R, Rb, Bc, S, w, &Xf, st);
+      int rc = ferminet_trunk(r, R, Rb, Bc, S, w, &Xf, st, qa);
       if (rc) return rc;
-      return tail(r, R, Rb, Bc, S, Bstat, sign, logp, E, stats, grad, w, Xf, st);
+      return tail(r, R, Rb, Bc, S, Bstat, sign, logp, E, stats, grad, w, Xf, st, nullptr, qa);
     }
     const int F = 4 * M + 1;
     if (S == 1 && embed_fwd_ok) {
@@ -1257,7 +1254,7 @@ struct Engine : EngineBase {
     // ---- forward, activations kept -----------------------------------------------------------------------------
     DQ_LAUNCH(embed_kernel<T>, dim3(Bc * N), dim3(128), sizeof(T) * 5 * d0, st, r, R, Rb, N, M, cfg.n_up, 1, 0, 0,
               (const T*)nullptr, d0, Hs[0], Bc * N, 1, (const T*)nullptr);
-    DQ_LAUNCH(edge_feat_kernel<T>, dim3((rowsE + 127) / 128), dim3(128), 0, st, r, N, 1, Es[0], rowsE);
+    DQ_LAUNCH(edge_feat_kernel<T>, dim3((rowsE + 127) / 128), dim3(128), 0, st, r, N, 1, Es[0], rowsE, (const T*)nullptr);
     for (int l = 0; l < L; ++l) {
       const std::string q = "F" + std::to_string(l) + ".";
       const int dc = dH[l], ec = dEd[l], fin = 3 * dc + 2 * ec;

@@ -36,7 +36,8 @@ __global__ void gnn_embed_kernel(const T* __restrict__ emb, int n_types, int N, 
 // ------------------------------------------------------------------------------------------
 template <class T>
 __global__ void gnn_edge_feat_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M,
-                                     int Mne, T* __restrict__ E, int total) {
+                                     int Mne, T* __restrict__ E, int total,
+                                     const T* __restrict__ QA /*pseudo-Hamiltonian metric or null*/) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int NS = N + Mne;
@@ -59,6 +60,26 @@ __global__ void gnn_edge_feat_kernel(const T* __restrict__ r, const T* __restric
     gj[0] = sj * d[c] / rho; gj[1 + c] = sj;
   }
   out[7 * 4] = np * (T(3) / rho - dd / (rho2 * rho));
+  if (QA) {
+    // pseudo-Hamiltonian: tangents w.r.t. v_n = Q_n^-1 r_n (columns of Q_n), second derivatives weighted by A_n
+    PhMetric<T> pm;
+    const T u0 = d[0] / rho, u1 = d[1] / rho, u2 = d[2] / rho;
+    T lap = T(0);
+    for (int side = 0; side < (nuc ? 1 : 2); ++side) {
+      pm.load(QA + ((size_t)b * N + (side == 0 ? i : jj)) * PH_STRIDE);
+      const T sg = side == 0 ? T(1) : T(-1);
+      const T qc[3][3] = {{pm.q[0], pm.q[1], pm.q[3]}, {T(0), pm.q[2], pm.q[4]}, {T(0), T(0), pm.q[5]}};  // column c of Q
+      for (int c = 0; c < 3; ++c) {
+        T* g = out + (1 + 3 * side + c) * 4;
+        g[0] = sg * (u0 * qc[c][0] + u1 * qc[c][1] + u2 * qc[c][2]);
+        g[1] = sg * qc[c][0]; g[2] = sg * qc[c][1]; g[3] = sg * qc[c][2];
+      }
+      T a0, a1, a2;
+      pm.mul(u0, u1, u2, a0, a1, a2);
+      lap += (pm.trace() - (u0 * a0 + u1 * a1 + u2 * a2)) / rho;
+    }
+    out[7 * 4] = lap;
+  }
 }
 
 // Node-update input of the 'concatenate' rule (reference gnn/update_features.py:47-121 Residual / NodeSum with

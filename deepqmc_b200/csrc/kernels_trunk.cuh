@@ -992,7 +992,8 @@ namespace dq {
 // One thread per (b, j, i).
 // ------------------------------------------------------------------------------------------
 template <class T>
-__global__ void edge_feat_kernel(const T* __restrict__ r, int N, int S, T* __restrict__ E, int total) {
+__global__ void edge_feat_kernel(const T* __restrict__ r, int N, int S, T* __restrict__ E, int total,
+                                 const T* __restrict__ QA /*pseudo-Hamiltonian metric or null*/) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int i = idx % N, j = (idx / N) % N, b = idx / (N * N);
@@ -1004,6 +1005,40 @@ __global__ void edge_feat_kernel(const T* __restrict__ r, int N, int S, T* __res
   e[0] = rho; e[1] = dx[0]; e[2] = dx[1]; e[3] = dx[2];
   if (S == 1) return;
   const int T3 = S - 2;
+  if (QA) {
+    // pseudo-Hamiltonian: the tangent slots of electron n are the columns of Q_n, second derivatives carry A_n
+    // (common.cuh PhMetric): d/dv_{n,c} d = +-Q_n[:, c], Lap rho = sum_{n in (i, j)} (tr A_n - u^T A_n u) / rho
+    PhMetric<T> pi, pj;
+    pi.load(QA + ((size_t)b * N + i) * PH_STRIDE);
+    pj.load(QA + ((size_t)b * N + j) * PH_STRIDE);
+    const T u0 = dx[0] / rho, u1 = dx[1] / rho, u2 = dx[2] / rho;
+    for (int t = 0; t < T3; ++t) {
+      const int el = t / 3, c = t % 3;
+      T* et = e + (size_t)(1 + t) * 4;
+      T q0 = T(0), q1 = T(0), q2 = T(0);  // +-column c of Q_el (lower triangular: q00 q10 q11 q20 q21 q22)
+      if (i != j && (el == i || el == j)) {
+        const PhMetric<T>& pm = el == i ? pi : pj;
+        const T sg = el == i ? T(1) : T(-1);
+        q0 = c == 0 ? sg * pm.q[0] : T(0);
+        q1 = c == 0 ? sg * pm.q[1] : (c == 1 ? sg * pm.q[2] : T(0));
+        q2 = c == 0 ? sg * pm.q[3] : (c == 1 ? sg * pm.q[4] : sg * pm.q[5]);
+      }
+      et[0] = u0 * q0 + u1 * q1 + u2 * q2;
+      et[1] = q0; et[2] = q1; et[3] = q2;
+    }
+    T* el = e + (size_t)(1 + T3) * 4;
+    T lap = T(0);
+    if (i != j) {
+      T a0, a1, a2;
+      pi.mul(u0, u1, u2, a0, a1, a2);
+      lap += (pi.trace() - (u0 * a0 + u1 * a1 + u2 * a2)) / rho;
+      pj.mul(u0, u1, u2, a0, a1, a2);
+      lap += (pj.trace() - (u0 * a0 + u1 * a1 + u2 * a2)) / rho;
+    }
+    el[0] = lap;
+    el[1] = el[2] = el[3] = T(0);
+    return;
+  }
   for (int t = 0; t < T3; ++t) {
     const int el = t / 3, c = t % 3;
     T sgn = T(0);

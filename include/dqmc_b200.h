@@ -155,7 +155,7 @@ int dqmc_wf_vjp_params(dqmc_handle h, const void* r, const void* R, int32_t R_ba
  * effective charges.  dqmc_local_energy then evaluates  sum_i [A(r_i) : Hess_i + b(r_i) . grad_i] psi / psi  with
  * A = 1/2 + sum_I (r V_L2 |d| 1 - V_L2 d d^T), b = 2 sum_I V_L2 d  by seeding the forward-Laplacian tangents with
  * the Cholesky factor of A, and adds r V_loc / r to V_loc; stats lap / quantum_force are those of the transformed
- * coordinates as in the reference.  Psiformer-family trunks; call once after dqmc_create (changes the workspace size).
+ * coordinates as in the reference.  Call once after dqmc_create (changes the workspace size).
  * replaces: ecp/pseudo_hamiltonian.py:165-278 PseudoHamiltonian.{local_potential, kinetic_term},
  *           :71-112 load_PH_functions (RegularGridInterpolator tables). */
 int dqmc_set_pseudo_hamiltonian(dqmc_handle h, int32_t n_tab, int32_t n_grid, double r_max, const double* tables,

@@ -84,6 +84,9 @@ def test_parameter_vjp_transpsiformer_matches_autograd_fp64():
     ('psiformer', [15, 17], 0, 'float64'),       # two centres with different tables, 12 electrons
     ('transpsiformer', [16, 1, 1], 0, 'float64'),
     ('psiformer', [16, 1, 1], 0, 'float32'),
+    ('ferminet', [16, 1, 1], 0, 'float64'),      # edge features carry the metrics of both electrons of a pair
+    ('paulinet', [16, 1, 1], 0, 'float64'),      # compact (value, d/dv_i, d/dv_j, Laplacian) edge state
+    ('paulinet_default', [17, 1], 0, 'float64'),
 ])
 def test_pseudo_hamiltonian_local_energy(tmp_path, kind, charges, spin, dtype):
     """PseudoHamiltonian (reference ecp/pseudo_hamiltonian.py:165-278): mass-tensor kinetic term
@@ -103,7 +106,10 @@ def test_pseudo_hamiltonian_local_energy(tmp_path, kind, charges, spin, dtype):
     mol = Molecule(coords=coords, charges=charges, charge=0, spin=spin)
     hamil = MolecularHamiltonian(mol=mol, ecp_type='PH', ph_data_dir=d)
     oh = OracleHamiltonian(mol, ecp_type='PH', ph_dir=d)
-    ansatz = B200Ansatz(hamil, kind, dtype=dtype, embedding_dim=32, n_layers=2, n_heads=2, n_determinants=3)
+    hyper = {'ferminet': dict(embedding_dim=32, n_layers=2, n_determinants=3, edge_dim=8), 'paulinet': dict(n_layers=2),
+             'paulinet_default': dict(embedding_dim=16, n_layers=2, n_determinants=3, edge_dim=8)}.get(
+                 kind, dict(embedding_dim=32, n_layers=2, n_determinants=3, n_heads=2))
+    ansatz = B200Ansatz(hamil, kind, dtype=dtype, **hyper)
     params = PN.perturb_params(ansatz.init(0))
     pt = wf.to_torch(params)
     B, N = 3, hamil.n_up + hamil.n_down

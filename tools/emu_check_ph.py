@@ -27,7 +27,7 @@ def main():
     from deepqmc_b200.engine import Engine
     from deepqmc_b200.hamil import MolecularHamiltonian
     from deepqmc_b200.molecule import Molecule
-    from deepqmc_b200.spec import psiformer_spec, transpsiformer_spec
+    from deepqmc_b200.spec import ferminet_spec, paulinet_default_spec, paulinet_spec, psiformer_spec, transpsiformer_spec
     from oracle import wf
     from oracle.hamil import OracleHamiltonian
 
@@ -38,8 +38,13 @@ def main():
     hamil = MolecularHamiltonian(mol=mol, ecp_type='PH', ph_data_dir=d)
     oh = OracleHamiltonian(mol, ecp_type='PH', ph_dir=d)
     assert np.allclose(hamil.ns_valence, oh.ns_valence)
-    mk = {'psiformer': psiformer_spec, 'transpsiformer': transpsiformer_spec}[a.kind]
-    spec = mk(oh, embedding_dim=16, n_layers=2, n_heads=2, n_determinants=3)
+    if a.kind == 'paulinet':
+        spec = paulinet_spec(oh, n_layers=2)
+    elif a.kind == 'paulinet_default':
+        spec = paulinet_default_spec(oh, n_layers=2, embedding_dim=16, n_determinants=3, edge_dim=8)
+    else:
+        mk = {'psiformer': psiformer_spec, 'transpsiformer': transpsiformer_spec, 'ferminet': ferminet_spec}[a.kind]
+        spec = mk(oh, embedding_dim=16, n_layers=2, n_heads=2, n_determinants=3)
     params = PN.perturb_params(PN.init_params(spec, 0))
     pt = wf.to_torch(params)
     rng = np.random.default_rng(0)
