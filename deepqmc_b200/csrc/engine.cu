@@ -1353,6 +1353,7 @@ struct Engine : EngineBase {
     const T* r = (const T*)r_;
     const T* R = (const T*)R_;
     DQ_CHECK(cudaMemsetAsync(grad_params, 0, sizeof(T) * total, st));
+    if (B == 0) return 0;  // empty batch: zero gradient
     // walkers per chunk: activations of every layer stay resident for the reverse pass (64 buffers, 256 B alignment each)
     const bool fermi = cfg.kind == DQMC_FERMINET;
     int64_t Bc = (wsb - 64 * 256) / (int64_t)(sizeof(T) * (fermi ? vjp_per_walker_elems_ferminet() : vjp_per_walker_elems()));
@@ -1524,12 +1525,16 @@ int64_t dqmc_workspace_bytes(dqmc_handle h, int32_t n_walkers, int32_t mode) {
 int dqmc_wf_forward(dqmc_handle h, const void* r, const void* R, int32_t R_batched, int32_t n_walkers, void* out_sign,
                     void* out_log, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!h) return 2;
+  if (n_walkers < 0) { h->e->err = "negative walker count"; return 2; }
+  if (n_walkers == 0) return 0;  // empty batch: nothing to evaluate
   return h->e->forward(r, R, R_batched, n_walkers, out_sign, out_log, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 int dqmc_local_energy(dqmc_handle h, const void* r, const void* R, int32_t R_batched, int32_t n_walkers, uint64_t seed,
                       const void* ecp_twist, void* out_E, void* out_stats, void* out_sign, void* out_log,
                       void* out_grad, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!h) return 2;
+  if (n_walkers < 0) { h->e->err = "negative walker count"; return 2; }
+  if (n_walkers == 0) return 0;  // empty batch: nothing to evaluate
   return h->e->local_energy(r, R, R_batched, n_walkers, seed, ecp_twist, out_E, out_stats, out_sign, out_log, out_grad,
                             workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -1538,6 +1543,7 @@ int dqmc_mcmc_sweep(dqmc_handle h, void* r, void* sign, void* log, int32_t* age,
                     uint64_t seed, uint64_t step0, uint64_t walker_offset, const void* noise_normal,
                     const void* noise_uniform, void* out_stats, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!h) return 2;
+  if (n_walkers < 1) { h->e->err = "the sampler needs at least one walker"; return 2; }
   return h->e->mcmc(r, sign, log, age, tau, R, R_batched, n_walkers, n_sub, target_acceptance, max_age, seed, step0,
                     walker_offset, noise_normal, noise_uniform, out_stats, workspace, workspace_bytes,
                     (cudaStream_t)stream);
@@ -1547,6 +1553,7 @@ int dqmc_langevin_sweep(dqmc_handle h, void* r, void* sign, void* log, void* for
                         uint64_t seed, uint64_t step0, uint64_t walker_offset, const void* noise_normal,
                         const void* noise_uniform, void* out_stats, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!h) return 2;
+  if (n_walkers < 1) { h->e->err = "the sampler needs at least one walker"; return 2; }
   return h->e->langevin(r, sign, log, force, age, tau, R, R_batched, n_walkers, n_sub, target_acceptance, max_age, seed, step0,
                         walker_offset, noise_normal, noise_uniform, out_stats, workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -1554,6 +1561,7 @@ int dqmc_wf_vjp_params(dqmc_handle h, const void* r, const void* R, int32_t R_ba
                        void* out_sign, void* out_log, void* out_grad_params, void* workspace, int64_t workspace_bytes,
                        void* stream) {
   if (!h) return 2;
+  if (n_walkers < 0) { h->e->err = "negative walker count"; return 2; }
   return h->e->vjp_params(r, R, R_batched, n_walkers, weights, out_sign, out_log, out_grad_params, workspace, workspace_bytes,
                           (cudaStream_t)stream);
 }

@@ -9,6 +9,9 @@
  * handles are re-entrant per stream-ordered use.  Array dtype is the handle's compute dtype
  * (cfg.dtype): double for the fp64 parity mode, float for the production mode
  * (reference: src/deepqmc/__init__.py:9-34 fp32, tests/conftest.py:20 fp64).
+ * Empty batches: n_walkers = 0 is a no-op for dqmc_wf_forward / dqmc_local_energy and yields a zero gradient from
+ * dqmc_wf_vjp_params; the samplers need at least one walker (status 2).  Status 2 = bad argument / unsupported
+ * configuration, 3 = workspace too small, other non-zero = CUDA error; dqmc_last_error gives the text.
  */
 #ifndef DQMC_B200_H
 #define DQMC_B200_H

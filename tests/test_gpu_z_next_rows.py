@@ -160,3 +160,25 @@ def test_parameter_vjp_ferminet_matches_autograd_fp64(mol_name, hyper):
     for k, v in pt.items():
         ref = v.grad
         assert torch.allclose(grads[k].cpu().reshape(ref.shape), ref, rtol=1e-8, atol=1e-9 * max(1.0, ref.abs().max().item())), k
+
+
+def test_empty_and_single_walker_batches():
+    """Edge cases of the batched entry points: an empty batch is a no-op (empty outputs, zero parameter gradient),
+    a single walker equals its row of a larger batch (walkers are independent), and the samplers
+    refuse an empty walker set."""
+    mol, hamil, oh, ansatz, params, r, R = make('LiH', B=3, embedding_dim=32, n_layers=2, n_heads=4, n_determinants=4)
+    eng = ansatz.engine_for(hamil, params)
+    E3, st3, s3, l3, g3 = eng.local_energy(r, R, want_grad=True)
+    E1, st1, s1, l1, g1 = eng.local_energy(r[1:2], R, want_grad=True)
+    same = lambda a, b: torch.allclose(a, b, rtol=1e-11, atol=1e-11)
+    assert same(E1, E3[1:2]) and same(st1, st3[:, 1:2]) and same(l1, l3[1:2]) and same(g1, g3[1:2])
+    E0, st0, s0, l0, g0 = eng.local_energy(r[:0], R, want_grad=True)
+    assert E0.shape == (0,) and st0.shape == (6, 0) and l0.shape == (0,) and g0.shape == (0, 12)
+    sf, lf = eng.wf_forward(r[:0], R)
+    assert sf.shape == (0,) and lf.shape == (0,)
+    _, _, grads = eng.vjp_params(r[:0], R, torch.zeros(0, dtype=r.dtype, device=DEV))
+    assert all(float(v.abs().sum()) == 0.0 for v in grads.values())
+    state = dict(r=r[:0].clone(), sign=s3[:0].clone(), log=l3[:0].clone(), age=torch.zeros(0, dtype=torch.int32, device=DEV),
+                 tau=torch.tensor([0.1], dtype=r.dtype, device=DEV))
+    with pytest.raises(RuntimeError):
+        eng.mcmc_sweep(state, R, 2)
