@@ -40,11 +40,43 @@ def median_clip_and_mask(x, clip_width: float, median_center: bool = True, exclu
     flag outliers beyond `exclude_width` MADs (reference: loss/clip.py:73-98; the median needs the all-gather of
     E_loc, parallel.py:185-192)."""
     allx = parallel.all_gather_walkers(x.reshape(-1))
-    center = allx.median() if median_center else allx.mean()
+    center = all_walker_median(allx) if median_center else allx.mean()
     abs_all = (allx - center).abs()
     mad = abs_all.mean()
     x_clip = torch.clamp(x, center - clip_width * mad, center + clip_width * mad)
     return x_clip, (x - center).abs() < exclude_width
+
+
+def all_walker_median(allx):
+    """jnp.median convention (mean of the two middle values for an even count; torch.median would return the lower
+    one) on the already gathered walkers (reference parallel.py:185-192)."""
+    return torch.quantile(allx.reshape(-1), 0.5)
+
+
+def log_squeeze(x):
+    """reference utils.py:186-188"""
+    sgn, a = torch.sign(x), x.abs()
+    return sgn * torch.log1p((a + 0.5 * a**2 + a**3) / (1 + a**2))
+
+
+def median_log_squeeze_and_mask(x, clip_width: float = 1.0, quantile: float = 0.95, exclude_width: float = float('inf')):
+    """Soft squeeze toward the (all-device) median: x_med + 2w log_squeeze((x - x_med) / 2w), w = clip_width times the
+    `quantile`-th quantile of |x - x_med| over all walkers (reference: loss/clip.py:101-141)."""
+    allx = parallel.all_gather_walkers(x.reshape(-1))
+    med = all_walker_median(allx)
+    q = torch.quantile((allx - med).abs(), quantile)
+    width = clip_width * q
+    diff = x - med
+    return med + 2 * width * log_squeeze(diff / (2 * width)), diff.abs() / q < exclude_width
+
+
+def clip_local_energy(clip_mask_fn, local_energy):
+    """Apply `clip_mask_fn` to every (molecule, electronic state) electron batch of local_energy[..., B]
+    (reference: loss/clip.py:32-48; vmap over the two leading axes)."""
+    lead = local_energy.shape[:-1]
+    flat = local_energy.reshape(-1, local_energy.shape[-1])
+    out = [clip_mask_fn(row) for row in flat]
+    return (torch.stack([o[0] for o in out]).reshape(*lead, -1), torch.stack([o[1] for o in out]).reshape(*lead, -1))
 
 
 def compute_mean_energy_tangent(local_energy, weight, gradient_mask, ansatz, params, phys_conf):

@@ -7,7 +7,8 @@ the mean overlap / penalty (:124-150).  ``params`` is a sequence with one parame
 electronic state, ``phys_conf`` carries a leading state axis ``[n_wfs, B, ...]``.  Each
 ``Psi_i(r ~ Psi_j^2)`` block is one ``dqmc_wf_forward`` call (plain-forward kernels); the small
 [n_wfs, n_wfs, B] algebra that follows is elementwise torch on the device.  The parameter
-tangent of the overlap (:182-229) needs d log|psi| / d params (row N1) and is not built.
+tangent of the overlap (:182-229) is one reverse pass (``dqmc_wf_vjp_params``, row N1) per state;
+ratio clipping follows loss/clip.py:51-70,144-174.
 """
 from __future__ import annotations
 
@@ -119,3 +120,26 @@ def compute_mean_overlap_tangent(psi_ratio, weight, ratio_gradient_mask, ansatz,
                 o += m
         grads.append(g)
     return grads
+
+
+def psi_ratio_clip_and_mask(psi_ratio, *, clip_width: float = 10.0, exclude_width: float = float('inf')):
+    """Clip the wave-function ratios of ONE electron batch to `clip_width` median absolute deviations around the
+    (all-device) median and flag outliers beyond `exclude_width` (reference: loss/clip.py:144-174)."""
+    from . import parallel
+    from .energy import all_walker_median
+
+    allr = parallel.all_gather_walkers(psi_ratio.reshape(-1))
+    center = all_walker_median(allr)
+    sigma = all_walker_median((allr - center).abs())
+    clipped = torch.clamp(psi_ratio, center - clip_width * sigma, center + clip_width * sigma)
+    return clipped, (psi_ratio - center).abs() < exclude_width
+
+
+def clip_psi_ratio(clip_mask_fn, psi_ratio):
+    """Apply `clip_mask_fn` to every [molecule, state i, state j] electron batch of psi_ratio[..., B]
+    (reference: loss/clip.py:51-70; vmap over the three leading axes)."""
+    lead = psi_ratio.shape[:-1]
+    flat = psi_ratio.reshape(-1, psi_ratio.shape[-1])
+    out = [clip_mask_fn(row) for row in flat]
+    return (torch.stack([o[0] for o in out]).reshape(*lead, -1), torch.stack([o[1] for o in out]).reshape(*lead, -1))
+

@@ -3,6 +3,7 @@
 import os
 import socket
 
+import numpy as np
 import pytest
 import torch
 import torch.multiprocessing as mp
@@ -42,7 +43,7 @@ def _worker(rank, world, port, q):
     from deepqmc_b200.types import PhysicalConfiguration, Psi
 
     Ec, mask = median_clip_and_mask(E_all[lo:hi], 1.0, exclude_width=2.0)
-    center = E_all.median()
+    center = torch.as_tensor(np.median(E_all.numpy()))  # jnp.median convention: mean of the two middle values
     mad = (E_all - center).abs().mean()
     ok = ok and torch.allclose(Ec, torch.clamp(E_all[lo:hi], center - mad, center + mad))
     ok = ok and torch.equal(mask, (E_all[lo:hi] - center).abs() < 2.0)
@@ -107,3 +108,40 @@ def test_initializer_and_host_hamiltonian():
     hb = MolecularHamiltonian(mol=Molecule.from_name('benzene'), ecp_type='ccECP')
     assert (hb.n_up, hb.n_down) == (15, 15) and list(hb.ns_valence) == [4.0] * 6 + [1.0] * 6
     assert list(hb.pot.nuc_with_nl_pot) == [0, 1, 2, 3, 4, 5]
+
+
+def test_clipping_functions_follow_numpy_median_and_quantile_conventions():
+    """loss/clip.py:73-174 on one process: medians are jnp.median (mean of the two middle values for an even count),
+    quantiles linear-interpolated; restated here with numpy."""
+    from deepqmc_b200.energy import clip_local_energy, median_clip_and_mask, median_log_squeeze_and_mask
+    from deepqmc_b200.overlap import clip_psi_ratio, psi_ratio_clip_and_mask
+
+    rng = np.random.default_rng(0)
+    x = rng.standard_cauchy(size=10)  # even count, heavy tails
+    xt = torch.as_tensor(x)
+    med = np.median(x)
+    assert med != np.sort(x)[4]  # the lower-median convention would differ here
+    mad = np.abs(x - med).mean()
+    xc, m = median_clip_and_mask(xt, 5.0, exclude_width=3.0)
+    assert np.allclose(xc.numpy(), np.clip(x, med - 5 * mad, med + 5 * mad)) and (m.numpy() == (np.abs(x - med) < 3.0)).all()
+    xc, m = median_clip_and_mask(xt, 2.0, median_center=False)
+    mad_mean = np.abs(x - x.mean()).mean()
+    assert np.allclose(xc.numpy(), np.clip(x, x.mean() - 2 * mad_mean, x.mean() + 2 * mad_mean)) and m.all()
+    # log-squeeze
+    q = np.quantile(np.abs(x - med), 0.95)
+    z = (x - med) / (2 * 1.5 * q)
+    ls = np.sign(z) * np.log1p((np.abs(z) + 0.5 * z**2 + np.abs(z) ** 3) / (1 + z**2))
+    xs, m = median_log_squeeze_and_mask(xt, clip_width=1.5, quantile=0.95, exclude_width=0.8)
+    assert np.allclose(xs.numpy(), med + 2 * 1.5 * q * ls) and (m.numpy() == (np.abs(x - med) / q < 0.8)).all()
+    # wave-function ratios: median absolute deviation as sigma
+    sig = np.median(np.abs(x - med))
+    rc, m = psi_ratio_clip_and_mask(xt, clip_width=2.0, exclude_width=4.0)
+    assert np.allclose(rc.numpy(), np.clip(x, med - 2 * sig, med + 2 * sig)) and (m.numpy() == (np.abs(x - med) < 4.0)).all()
+    # batched application over the leading axes
+    E = torch.as_tensor(rng.normal(size=(2, 3, 8)))
+    Ec, M = clip_local_energy(lambda e: median_clip_and_mask(e, 1.0), E)
+    assert Ec.shape == E.shape and M.shape == E.shape
+    assert torch.allclose(Ec[1, 2], median_clip_and_mask(E[1, 2], 1.0)[0])
+    Rr = torch.as_tensor(rng.normal(size=(1, 2, 2, 8)))
+    Rc, Mr = clip_psi_ratio(psi_ratio_clip_and_mask, Rr)
+    assert Rc.shape == Rr.shape and torch.allclose(Rc[0, 1, 0], psi_ratio_clip_and_mask(Rr[0, 1, 0])[0])
