@@ -216,3 +216,133 @@ class LangevinSampler(MetropolisSampler):
         self._step += self.length
         new = {'r': st['r'], 'psi': Psi(st['sign'], st['log']), 'force': st['force'], 'age': st['age'], 'tau': st['tau']}
         return new, self.phys_conf(R, new['r']), dict(zip(STAT_NAMES, stats))
+
+
+class MoleculeIdxSampler:
+    """Cycles through the molecule indices of a transferable run in batches of ``batch_size``, optionally through a
+    random permutation drawn once or after every pass (reference: sampling/combined_samplers.py:17-55)."""
+
+    def __init__(self, rng, n_mols: int, batch_size: int, shuffle=False):
+        assert shuffle in [False, 'once', 'always']
+        self.rng = np.random.default_rng(int(rng))
+        self.n_mols, self.batch_size, self.shuffle, self.state = n_mols, batch_size, shuffle, 0
+        self._once = None
+        self.permutation = self.new_permutation()
+
+    def new_permutation(self):
+        if not self.shuffle:
+            return np.arange(self.n_mols)
+        if self.shuffle == 'once':  # the same permutation after every pass (the reference re-uses its key)
+            if self._once is None:
+                self._once = self.rng.permutation(self.n_mols)
+            return self._once
+        return self.rng.permutation(self.n_mols)
+
+    def sample(self):
+        idx = np.arange(self.state, min(self.state + self.batch_size, self.n_mols))
+        value = [self.permutation[idx]]
+        if len(idx) < self.batch_size:  # wrap around into the next pass
+            self.permutation = self.new_permutation()
+            value.append(self.permutation[np.arange(self.batch_size - len(idx))])
+        self.state = (self.state + self.batch_size) % self.n_mols
+        return np.concatenate(value)
+
+
+class IdleNucleiSampler:
+    """Keeps the nuclei where they are (reference: sampling/nuclei_samplers.py:16-36)."""
+
+    def __init__(self, charges=None):
+        pass
+
+    def init(self, nuc_coords, *args, **kwargs):
+        return {'R': nuc_coords}
+
+    def sample(self, rng, state):
+        return state, torch.zeros_like(state['R']), {}
+
+
+def no_elec_warp(rng, R, dR, smpl_state):
+    """reference: sampling/nuclei_samplers.py:175-190"""
+    return smpl_state
+
+
+def nn_elec_warp(rng, R, dR, smpl_state):
+    """Move every electron with its nearest nucleus (reference: sampling/nuclei_samplers.py:193-213).  ``smpl_state`` is
+    the state list of a MultiElectronicStateSampler (or a single sampler state)."""
+    states = smpl_state if isinstance(smpl_state, list) else [smpl_state]
+    R_old = R - dR
+    for st in states:
+        nearest = torch.cdist(st['r'], R_old.to(st['r'])[None].expand(len(st['r']), -1, -1)).argmin(-1)  # [B, N]
+        st['r'] = st['r'] + dR.to(st['r'])[nearest]
+    return smpl_state
+
+
+class MultiNuclearGeometrySampler:
+    """Electron samplers of several nuclear geometries side by side (reference: sampling/combined_samplers.py:93-214).
+
+    The reference vmaps one sampler over the molecule axis; here every geometry keeps its own electron-sampler state
+    (a list, like the state axis of ``MultiElectronicStateSampler``) and each (geometry, state) block is one sweep of
+    the CUDA engine with that geometry's ``R``.  ``sample`` returns the reference's batch layout
+    ``[mol_batch, n_state, B, ...]`` with ``R`` tiled per walker and ``mol_idx`` filled in.
+    State: ``{'nuc': [nuc state per molecule], 'elec': [elec state per molecule], 'update_nuc_counter': int64[n_mol]}``.
+    """
+
+    def __init__(self, elec_sampler, nuc_sampler=None, warp_elec_fn=None, update_nuc_period=None,
+                 elec_equilibration_steps=None):
+        self.elec_sampler = elec_sampler
+        self.nuc_sampler = nuc_sampler or IdleNucleiSampler()
+        self.warp_elec_fn = warp_elec_fn or no_elec_warp
+        self.update_nuc_period, self.elec_equilibration_steps = update_nuc_period, elec_equilibration_steps
+
+    def init(self, rng, params, electron_batch_size, R):
+        R = torch.as_tensor(np.asarray(R, dtype=np.float64)) if not torch.is_tensor(R) else R
+        n_mol = len(R)
+        return {
+            'nuc': [self.nuc_sampler.init(R[m]) for m in range(n_mol)],
+            'elec': [self.elec_sampler.init(int(rng) * n_mol + m, params, electron_batch_size, R[m]) for m in range(n_mol)],
+            'update_nuc_counter': torch.zeros(n_mol, dtype=torch.int64),
+        }
+
+    def _R_dev(self, elec_state, R):
+        st0 = elec_state[0] if isinstance(elec_state, list) else elec_state
+        return R.to(device=st0['r'].device, dtype=st0['r'].dtype)
+
+    def update_nuc(self, rng, nuc_state, elec_state, params):
+        """One molecule: propose new nuclei, warp the electrons along, refresh psi, re-equilibrate (:130-160)."""
+        nuc_state, dR, stats = self.nuc_sampler.sample(int(rng), nuc_state)
+        R = nuc_state['R']
+        elec_state = self.warp_elec_fn(int(rng) + 1, R, dR, elec_state)
+        Rd = self._R_dev(elec_state, R)
+        elec_state = self.elec_sampler.update(elec_state, params, Rd)
+        for i in range(self.elec_equilibration_steps or 0):
+            elec_state = self.elec_sampler.sample(int(rng) * 7919 + i, elec_state, params, Rd)[0]
+        return nuc_state, elec_state, stats
+
+    def sample(self, rng, smpl_state, params, mol_idxs):
+        mol_idxs = [int(m) for m in np.asarray(mol_idxs).reshape(-1)]
+        counter = smpl_state['update_nuc_counter']
+        rs, Rs, stats = [], [], []
+        for k, m in enumerate(mol_idxs):
+            if self.update_nuc_period is not None:
+                if int(counter[m]) == self.update_nuc_period - 1:
+                    smpl_state['nuc'][m], smpl_state['elec'][m], _ = self.update_nuc(
+                        int(rng) * 104729 + k, smpl_state['nuc'][m], smpl_state['elec'][m], params)
+                    counter[m] = 0
+                else:
+                    counter[m] += 1
+            Rd = self._R_dev(smpl_state['elec'][m], smpl_state['nuc'][m]['R'])
+            smpl_state['elec'][m], pc, st = self.elec_sampler.sample(int(rng) * len(mol_idxs) + k, smpl_state['elec'][m], params, Rd)
+            r = pc.r if pc.r.dim() == 4 else pc.r[None]  # [n_state, B, N, 3]
+            rs.append(r)
+            Rs.append(Rd[None, None].expand(*r.shape[:2], *Rd.shape))
+            stats.append(st)
+        r, R = torch.stack(rs), torch.stack(Rs)
+        mol_idx = torch.as_tensor(mol_idxs, dtype=torch.int32, device=r.device)[:, None, None].expand(r.shape[:3])
+        out_stats = {k: torch.stack([torch.as_tensor(s[k]) for s in stats]) for k in stats[0]} if stats else {}
+        return smpl_state, PhysicalConfiguration(R, r, mol_idx), out_stats
+
+    def update(self, smpl_state, params):
+        for m in range(len(smpl_state['elec'])):
+            smpl_state['elec'][m] = self.elec_sampler.update(
+                smpl_state['elec'][m], params, self._R_dev(smpl_state['elec'][m], smpl_state['nuc'][m]['R']))
+        return smpl_state

@@ -182,3 +182,38 @@ def test_empty_and_single_walker_batches():
                  tau=torch.tensor([0.1], dtype=r.dtype, device=DEV))
     with pytest.raises(RuntimeError):
         eng.mcmc_sweep(state, R, 2)
+
+
+def test_multi_nuclear_geometry_sampler_two_lih_geometries():
+    """MultiNuclearGeometrySampler (reference sampling/combined_samplers.py:93-214) over two bond lengths of LiH with one
+    parameter tree: every geometry's walkers are advanced with that geometry's nuclei, the returned batch has the
+    reference layout [mol, state, walker] with R tiled per walker, and compute_local_energy on it equals the direct
+    evaluation per geometry."""
+    from deepqmc_b200.energy import compute_local_energy
+    from deepqmc_b200.sampling import DecorrSampler, MultiNuclearGeometrySampler
+
+    mol, hamil, oh, ansatz, params, r, R = make('LiH', B=4, embedding_dim=32, n_layers=2, n_heads=4, n_determinants=4)
+    Rs = torch.stack([R.cpu(), R.cpu() * 1.3])
+    smp = MultiNuclearGeometrySampler(DecorrSampler(hamil, ansatz.apply, length=3, tau=0.3))
+    state = smp.init(3, params, 4, Rs)
+    r0 = [state['elec'][m]['r'].clone() for m in range(2)]
+    state, pc, stats = smp.sample(5, state, params, [1, 0])
+    assert pc.batch_shape == (2, 1, 4) and pc.mol_idx[:, 0, 0].tolist() == [1, 0]
+    assert torch.equal(pc.R[0, 0, 2].cpu(), Rs[1]) and torch.equal(pc.R[1, 0, 0].cpu(), Rs[0])
+    assert stats['sampling/acceptance'].shape[0] == 2
+    eng = ansatz.engine_for(hamil, params)
+    for k, m in enumerate([1, 0]):
+        assert not torch.equal(pc.r[k, 0], r0[m])  # walkers moved
+        s, l = eng.wf_forward(pc.r[k, 0], Rs[m].to(DEV))
+        assert torch.allclose(l, state['elec'][m]['psi'].log, rtol=0, atol=1e-10)  # psi of the state belongs to ITS geometry
+    E, st = compute_local_energy(None, hamil, ansatz.apply, params, pc)
+    assert E.shape == (2, 1, 4)
+    for k, m in enumerate([1, 0]):
+        Ed = eng.local_energy(pc.r[k, 0], Rs[m].to(DEV))[0]
+        assert torch.allclose(E[k, 0], Ed, rtol=0, atol=1e-10)
+    from oracle import wf
+
+    pt = wf.to_torch(params)
+    f = lambda x: wf.log_psi(ansatz.spec, pt, x, Rs[1])
+    eo, _ = oh.local_energy(f, pc.r[0, 0, 0].cpu(), Rs[1])
+    assert abs(E[0, 0, 0].item() - eo.item()) <= 1e-8 * max(1.0, abs(eo.item()))

@@ -1,0 +1,77 @@
+"""Host-side sampler orchestration that needs no GPU: molecule index batches, electron warps and the
+multi-geometry sampler's bookkeeping (reference: sampling/combined_samplers.py:17-55,93-214,
+sampling/nuclei_samplers.py:16-36,175-213) with a stand-in electron sampler."""
+import numpy as np
+import torch
+
+from deepqmc_b200.sampling import (IdleNucleiSampler, MoleculeIdxSampler, MultiNuclearGeometrySampler, nn_elec_warp)
+from deepqmc_b200.types import PhysicalConfiguration
+
+
+def test_molecule_idx_sampler_cycles_and_wraps():
+    s = MoleculeIdxSampler(0, n_mols=5, batch_size=2)
+    got = [s.sample().tolist() for _ in range(5)]
+    assert got == [[0, 1], [2, 3], [4, 0], [1, 2], [3, 4]]  # wrap-around fills from the next pass (:37-46)
+    s = MoleculeIdxSampler(3, n_mols=6, batch_size=3, shuffle='once')
+    a, b, c, d = (s.sample().tolist() for _ in range(4))
+    assert sorted(a + b) == list(range(6)) and (a, b) == (c, d)  # 'once': every pass uses the same permutation
+    s = MoleculeIdxSampler(3, n_mols=6, batch_size=6, shuffle='always')
+    assert sorted(s.sample().tolist()) == list(range(6))
+
+
+def test_nn_elec_warp_moves_electrons_with_their_nearest_nucleus():
+    R_old = torch.tensor([[0.0, 0, 0], [4.0, 0, 0]], dtype=torch.float64)
+    dR = torch.tensor([[0.0, 0.5, 0], [1.0, 0, 0]], dtype=torch.float64)
+    r = torch.tensor([[[0.3, 0.1, 0.0], [3.8, -0.2, 0.1], [1.9, 0.0, 0.0]]], dtype=torch.float64)
+    st = nn_elec_warp(0, R_old + dR, dR, {'r': r.clone()})
+    assert torch.allclose(st['r'][0, 0], r[0, 0] + dR[0]) and torch.allclose(st['r'][0, 1], r[0, 1] + dR[1])
+    assert torch.allclose(st['r'][0, 2], r[0, 2] + dR[0])  # 1.9 is closer to the nucleus at 0 than to the one at 4
+
+
+class _FakeElecSampler:
+    """Two 'electronic states', walkers random-walk; records the geometry every call saw."""
+
+    def __init__(self):
+        self.seen, self.updates = [], 0
+
+    def init(self, rng, params, n, R):
+        g = torch.Generator().manual_seed(int(rng))
+        return [{'r': torch.randn(n, 2, 3, generator=g, dtype=torch.float64)} for _ in range(2)]
+
+    def update(self, state, params, R):
+        self.updates += 1
+        return state
+
+    def sample(self, rng, state, params, R):
+        self.seen.append(R.clone())
+        state = [{'r': s['r'] + 0.01} for s in state]
+        r = torch.stack([s['r'] for s in state])
+        pc = PhysicalConfiguration(R, r, torch.zeros(r.shape[:2], dtype=torch.int32))
+        return state, pc, {'sampling/acceptance': torch.tensor([0.5, 0.6])}
+
+
+class _ShiftNuclei(IdleNucleiSampler):
+    def sample(self, rng, state):
+        dR = torch.full_like(state['R'], 0.1)
+        return {'R': state['R'] + dR}, dR, {}
+
+
+def test_multi_nuclear_geometry_sampler_layout_and_update_period():
+    R = torch.tensor([[[0.0, 0, 0], [1.5, 0, 0]], [[0.0, 0, 0], [2.0, 0, 0]], [[0.0, 0, 0], [2.5, 0, 0]]], dtype=torch.float64)
+    es = _FakeElecSampler()
+    smp = MultiNuclearGeometrySampler(es, _ShiftNuclei(), nn_elec_warp, update_nuc_period=2, elec_equilibration_steps=1)
+    state = smp.init(0, None, 4, R)
+    assert len(state['elec']) == 3 and state['update_nuc_counter'].tolist() == [0, 0, 0]
+    state, pc, stats = smp.sample(1, state, None, np.array([2, 0]))
+    assert pc.r.shape == (2, 2, 4, 2, 3) and pc.R.shape == (2, 2, 4, 2, 3) and pc.batch_shape == (2, 2, 4)
+    assert pc.mol_idx[:, 0, 0].tolist() == [2, 0] and torch.equal(pc.R[0, 1, 3], R[2]) and torch.equal(pc.R[1, 0, 0], R[0])
+    assert stats['sampling/acceptance'].shape == (2, 2) and state['update_nuc_counter'].tolist() == [1, 0, 1]
+    assert es.updates == 0
+    # second visit of molecule 2: counter == period - 1 -> nuclei move, electrons are warped, psi refreshed, 1 equilibration sweep
+    r_before = state['elec'][2][0]['r'].clone()
+    state, pc, _ = smp.sample(2, state, None, [2])
+    assert torch.allclose(state['nuc'][2]['R'], R[2] + 0.1) and state['update_nuc_counter'].tolist() == [1, 0, 0]
+    assert es.updates == 1 and torch.allclose(pc.R[0, 0, 0], R[2] + 0.1)
+    assert torch.allclose(state['elec'][2][0]['r'], r_before + 0.1 + 0.02)  # warp + equilibration sweep + sample sweep
+    state = smp.update(state, None)
+    assert es.updates == 4
