@@ -53,13 +53,14 @@ class B200Ansatz:
 
     # -- reference: Ansatz.apply(params, phys_conf, return_mos=False) -> Psi (types.py:133-150)
     def apply(self, params, phys_conf: PhysicalConfiguration, return_mos: bool = False) -> Psi:
-        if return_mos:
-            raise NotImplementedError('return_mos is only used by pretraining (out of scope, SURVEY.md 2 #17)')
         eng = self.engine_for(self.hamil, params)
         r, R = phys_conf.r, phys_conf.R
         single = r.dim() == 2
         if single:
             r = r[None]
+        if return_mos:  # (orb_up, orb_down), what the reference's pretraining fits to the baseline orbitals
+            up, dn = eng.wf_orbitals(r, R)
+            return (up[0], dn[0]) if single else (up, dn)
         sign, log = eng.wf_forward(r, R)
         return Psi(sign[0], log[0]) if single else Psi(sign, log)
 

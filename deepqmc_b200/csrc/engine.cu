@@ -56,6 +56,7 @@ struct EngineBase {
                        const void* nu, void* stats, void* ws, int64_t wsb, cudaStream_t st) = 0;
   virtual int vjp_params(const void* r, const void* R, int Rb, int B, const void* weights, void* sign, void* logp,
                          void* grad_params, void* ws, int64_t wsb, cudaStream_t st) = 0;
+  virtual int orbitals(const void* r, const void* R, int Rb, int B, void* out, void* ws, int64_t wsb, cudaStream_t st) = 0;
   virtual int set_ph(int n_tab, int n_grid, double r_max, const double* tables, const int32_t* tab_of_nuc) = 0;
   virtual int debug_gemm(const char* wname, const char* bname, const void* A, const void* Res, void* C, int Mr, int S,
                          int sliced, int backend, cudaStream_t st) = 0;
@@ -235,6 +236,7 @@ struct Engine : EngineBase {
   double ph_rmax = 0;
   bool ph_on = false;      // tables uploaded
   bool ph_active = false;  // set around the forward-Laplacian pass of local_energy only
+  T* mos_out = nullptr;    // set by orbitals(): the tail writes the orbital matrices of the chunk here and stops
   int attn_tb = 1, attn_tb1 = 1;
   bool attn_f32 = false;
   bool embed_fwd_ok = false;
@@ -991,6 +993,13 @@ struct Engine : EngineBase {
     if (cfg.mult_act == 1)  // default mult_act 1 + 2 tanh(x / 4) of the BackflowOp (nn_wave_function.py:14-33)
       DQ_LAUNCH(act_fl_kernel<T>, dim3(Bc * N, (KN + 127) / 128), dim3(128), 0, st, w.BF, KN, (const T*)nullptr, 0, S, KN, T(1), 2);
     const int full_det = cfg.factorized_det ? 0 : 1;
+    if (mos_out) {  // Ansatz.apply(..., return_mos=True): orbital matrices instead of determinants
+      const size_t tot = (size_t)Bc * K * N * N;
+      DQ_LAUNCH(orbitals_kernel<T>, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, r, R, Rb, N, M, cfg.n_up, K,
+                P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, env_rep, full_det,
+                mos_out, tot);
+      return 0;
+    }
     const int sl_wpb = slater_warps_per_block<T>(N);
     if ((N <= 4 || (N <= 6 && std::is_same<T, float>::value)) && !qa && !std::getenv("DQMC_SLATER_GENERIC")) {
       const int tot = Bc * K;
@@ -1375,6 +1384,25 @@ struct Engine : EngineBase {
     return 0;
   }
 
+  // orbital matrices out[B][K][N][N] (electron i, orbital mu) of a plain forward
+  int orbitals(const void* r_, const void* R_, int Rb, int B, void* out, void* ws, int64_t wsb, cudaStream_t st) override {
+    const T* r = (const T*)r_;
+    const T* R = (const T*)R_;
+    const int Bc = max_chunk(wsb, 1, B);
+    if (Bc < 1) { err = "workspace too small for a single walker"; return 3; }
+    int rc = 0;
+    for (int b0 = 0; b0 < B && !rc; b0 += Bc) {
+      const int nb = std::min(Bc, B - b0);
+      mos_out = (T*)out + (size_t)b0 * K * N * N;
+      rc = run_chunk(r + (size_t)b0 * 3 * N, R + (Rb ? (size_t)b0 * 3 * M : 0), Rb, nb, 1, B, nullptr, nullptr, nullptr, nullptr,
+                     nullptr, ws, st);
+    }
+    mos_out = nullptr;
+    if (rc) return rc;
+    DQ_CHECK(cudaGetLastError());
+    return 0;
+  }
+
   int forward(const void* r, const void* R, int Rb, int B, void* sign, void* logp, void* ws, int64_t wsb,
               cudaStream_t st) override {
     int rc = run_batched((const T*)r, (const T*)R, Rb, B, 1, (T*)sign, (T*)logp, nullptr, nullptr, nullptr, ws, wsb, st);
@@ -1528,6 +1556,13 @@ int dqmc_wf_forward(dqmc_handle h, const void* r, const void* R, int32_t R_batch
   if (n_walkers < 0) { h->e->err = "negative walker count"; return 2; }
   if (n_walkers == 0) return 0;  // empty batch: nothing to evaluate
   return h->e->forward(r, R, R_batched, n_walkers, out_sign, out_log, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int dqmc_wf_orbitals(dqmc_handle h, const void* r, const void* R, int32_t R_batched, int32_t n_walkers, void* out_orbitals,
+                     void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!h) return 2;
+  if (n_walkers < 0) { h->e->err = "negative walker count"; return 2; }
+  if (n_walkers == 0) return 0;
+  return h->e->orbitals(r, R, R_batched, n_walkers, out_orbitals, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 int dqmc_local_energy(dqmc_handle h, const void* r, const void* R, int32_t R_batched, int32_t n_walkers, uint64_t seed,
                       const void* ecp_twist, void* out_E, void* out_stats, void* out_sign, void* out_log,

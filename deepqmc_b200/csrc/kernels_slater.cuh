@@ -639,6 +639,35 @@ slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batch
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Molecular orbitals  A[b][k][i][mu] = envelope_{k mu}(r_i) * backflow[b][i][k N + mu]  -- what Ansatz.apply returns
+// with return_mos = True (reference wf/nn_wave_function.py:131-142; used by pretraining/pretraining.py:73-78).  BF already
+// carries mult_act.  full_det == 0: the spin-off-diagonal blocks are written as zeros (the caller slices the
+// n_up x n_up / n_down x n_down blocks).  One thread per (b, k, i, mu).
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void orbitals_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M, int n_up,
+                                int K, const T* __restrict__ pi_up, const T* __restrict__ pi_dn,
+                                const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn, const T* __restrict__ BF,
+                                int ldb, int rep, int full_det, T* __restrict__ out, size_t total) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int mu = (int)(idx % N), i = (int)((idx / N) % N), k = (int)((idx / ((size_t)N * N)) % K);
+  const size_t b = idx / ((size_t)N * N * K);
+  const T* ri = r + (b * N + i) * 3;
+  const T* Rb = R + (R_batched ? b * M * 3 : 0);
+  const T* pi = (i < n_up ? pi_up : pi_dn) + (size_t)(k * N + mu) * M * rep;
+  const T* ze = (i < n_up ? zeta_up : zeta_dn) + (size_t)(k * N + mu) * M * rep;
+  T e = T(0);
+  for (int m = 0; m < M; ++m) {
+    const T dx0 = ri[0] - Rb[3 * m], dx1 = ri[1] - Rb[3 * m + 1], dx2 = ri[2] - Rb[3 * m + 2];
+    const T rho = m_sqrt(Num<T>::eps() + dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
+    for (int et = 0; et < rep; ++et) e += pi[m * rep + et] * m_exp(-m_abs(ze[m * rep + et]) * rho);
+  }
+  if (!full_det && ((i < n_up) != (mu < n_up))) e = T(0);
+  out[idx] = e * BF[(b * N + i) * ldb + k * N + mu];
+}
+
 template <class T>
 inline size_t slater_fwd2_smem_bytes(int N, int M, int K) {
   return sizeof(T) * ((size_t)K * N * (N | 1) + (size_t)N * M);

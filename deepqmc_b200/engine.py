@@ -394,6 +394,23 @@ class Engine:
         self._check(rc, 'dqmc_wf_forward')
         return sign, log
 
+    def wf_orbitals(self, r, R, max_ws_bytes=None):
+        """-> (orb_up[B, K, n_up, n_orb], orb_down[B, K, n_down, n_orb]): envelope * mult_act(backflow), the matrices whose
+        determinants make up psi; n_orb = N for full determinants, the spin's electron count otherwise
+        (reference: Ansatz.apply(..., return_mos=True), wf/nn_wave_function.py:131-142)."""
+        r = self._prep(r)
+        B, N = r.shape[0], r.shape[1]
+        R, Rb = self._R(R, B)
+        K, n_up = self.spec.n_determinants, self.spec.n_up
+        out = torch.empty(B, K, N, N, dtype=self.dtype, device=self.device)
+        ws = self.workspace(B, MODE_FORWARD, max_ws_bytes)
+        rc = self.lib.dqmc_wf_orbitals(self.h, r.data_ptr(), R.data_ptr(), Rb, B, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       self._stream())
+        self._check(rc, 'dqmc_wf_orbitals')
+        if self.spec.full_determinant:
+            return out[:, :, :n_up, :], out[:, :, n_up:, :]
+        return out[:, :, :n_up, :n_up], out[:, :, n_up:, n_up:]
+
     def local_energy(self, r, R, seed=0, ecp_twist=None, want_grad=False, max_ws_bytes=None):
         r = self._prep(r)
         B, N = r.shape[0], r.shape[1]

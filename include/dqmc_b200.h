@@ -121,6 +121,15 @@ int dqmc_local_energy(dqmc_handle h, const void* r, const void* R, int32_t R_bat
                       uint64_t seed, const void* ecp_twist, void* out_E, void* out_stats, void* out_sign,
                       void* out_log, void* out_grad, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Orbital matrices of a plain forward: out_orbitals[B][K][N][N] (determinant k, electron i, orbital mu) =
+ * envelope * mult_act(backflow), the matrices whose determinants dqmc_wf_forward takes.  With spin-factorised
+ * determinants the spin-off-diagonal blocks are zero; the caller slices the n_up x n_up / n_down x n_down blocks.
+ * Workspace: dqmc_workspace_bytes(h, B, DQMC_MODE_FORWARD).
+ * replaces: Ansatz.apply(params, phys_conf, return_mos=True) (types.py:133-150, wf/nn_wave_function.py:131-142;
+ *           caller pretrain/pretraining.py:73-78). */
+int dqmc_wf_orbitals(dqmc_handle h, const void* r, const void* R, int32_t R_batched, int32_t n_walkers, void* out_orbitals,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
 /* n_sub Metropolis sub-steps on the walker state {r, sign, log, age, tau} (updated in place).
  * noise_normal[n_sub][B][N][3] / noise_uniform[n_sub][B] (nullable): injected random numbers.
  * out_stats[7] (device, compute dtype) = acceptance, tau, age mean, age max, log|psi| mean,

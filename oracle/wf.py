@@ -254,7 +254,7 @@ def paulinet_embeddings(spec, params, r, R):
     return x
 
 
-def paulinet_log_psi(spec, params, r, R):
+def paulinet_log_psi(spec, params, r, R, return_mos=False):
     """reference: wf/nn_wave_function.py:127-173 with full_determinant = False, mult backflow with the
     default mult_act, hk.Linear conf_coeff, DeepQMCCusp, Jastrow (wf/omni.py:13-40, sum_first)."""
     N, K, n_up, n_dn = spec.n_elec, spec.n_determinants, spec.n_up, spec.n_down
@@ -294,11 +294,13 @@ def paulinet_log_psi(spec, params, r, R):
         if spec.full_determinant:
             osl = slice(0, N)
         a = orb[:, sl, osl] * mult(f)
-        if spec.full_determinant:
+        if spec.full_determinant or return_mos:
             blocks.append(a)
             continue
         s, l = torch.linalg.slogdet(a) if n > 0 else (torch.ones(K, dtype=r.dtype), torch.zeros(K, dtype=r.dtype))
         signs, logs = signs * s, logs + l
+    if return_mos:
+        return tuple(blocks)
     if spec.full_determinant:
         signs, logs = torch.linalg.slogdet(torch.cat(blocks, 1))
     shift = logs.max().detach()
@@ -370,15 +372,23 @@ def log_psi(spec, params, r, R):
     return s, l + nuclear_cusp(spec, params, r, R)
 
 
-def _log_psi(spec, params, r, R):
+def molecular_orbitals(spec, params, r, R):
+    """ansatz.apply(..., return_mos=True) for one walker -> (orb_up[K, n_up, n_orb], orb_down[K, n_down, n_orb]);
+    reference nn_wave_function.py:131-142"""
+    return _log_psi(spec, params, r, R, return_mos=True)
+
+
+def _log_psi(spec, params, r, R, return_mos=False):
     if spec.kind == 'paulinet':
-        return paulinet_log_psi(spec, params, r, R)
+        return paulinet_log_psi(spec, params, r, R, return_mos)
     if spec.kind == 'transpsiformer':
         emb, nuc = transpsiformer_embeddings(spec, params, r, R)
         A = orbitals_nucdep(spec, params, emb, nuclear_head_zetas(spec, params, nuc), r, R)
     else:
         emb = (psiformer_embeddings if spec.kind == 'psiformer' else ferminet_embeddings)(spec, params, r, R)
         A = orbitals(spec, params, emb, r, R)
+    if return_mos:
+        return A[:, :spec.n_up], A[:, spec.n_up:]
     sign, ld = torch.linalg.slogdet(A)
     shift = ld.max().detach()
     if torch.isinf(shift):

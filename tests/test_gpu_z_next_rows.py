@@ -217,3 +217,32 @@ def test_multi_nuclear_geometry_sampler_two_lih_geometries():
     f = lambda x: wf.log_psi(ansatz.spec, pt, x, Rs[1])
     eo, _ = oh.local_energy(f, pc.r[0, 0, 0].cpu(), Rs[1])
     assert abs(E[0, 0, 0].item() - eo.item()) <= 1e-8 * max(1.0, abs(eo.item()))
+
+
+@pytest.mark.parametrize('kind,mol_name,hyper', [
+    ('psiformer', 'H2O', dict(embedding_dim=32, n_layers=1, n_heads=2, n_determinants=3)),
+    ('ferminet', 'LiH', dict(embedding_dim=16, n_layers=2, n_determinants=2, edge_dim=8)),
+    ('transpsiformer', 'LiH', dict(embedding_dim=32, n_layers=1, n_heads=2, n_determinants=2)),
+    ('paulinet', 'LiH', dict()),                 # spin-factorised determinants: n_up x n_up and n_down x n_down blocks
+    ('paulinet_default', 'H2O', dict(embedding_dim=16, n_layers=1, n_determinants=2, edge_dim=8)),
+])
+def test_return_mos_matches_oracle(kind, mol_name, hyper):
+    """Ansatz.apply(params, phys_conf, return_mos=True) (reference types.py:133-150, nn_wave_function.py:131-142): the
+    per-spin orbital matrices envelope * mult_act(backflow); their determinants reproduce psi."""
+    from oracle import wf
+
+    mol, hamil, oh, ansatz, params, r, R = make(mol_name, B=3, kind=kind, **hyper)
+    pc = PhysicalConfiguration(R, r, torch.zeros(3, device=DEV))
+    up, dn = ansatz.apply(params, pc, return_mos=True)
+    psi = ansatz.apply(params, pc)
+    pt = wf.to_torch(params)
+    for b in range(3):
+        ou, od = wf.molecular_orbitals(ansatz.spec, pt, r[b].cpu(), R.cpu())
+        assert up[b].shape == ou.shape and dn[b].shape == od.shape
+        assert torch.allclose(up[b].cpu(), ou, rtol=1e-9, atol=1e-11) and torch.allclose(dn[b].cpu(), od, rtol=1e-9, atol=1e-11)
+    su, du = ansatz.apply(params, pc[0], return_mos=True)  # single-sample call, as in the reference
+    assert su.shape == up[0].shape and torch.equal(su, up[0]) and torch.equal(du, dn[0])
+    if ansatz.spec.full_determinant and ansatz.spec.cusp == 'none' and kind == 'ferminet':
+        s, l = torch.linalg.slogdet(torch.cat([up, dn], 2))  # [B, K]
+        tot = (s * torch.exp(l - l.max(-1, keepdim=True).values)).sum(-1)
+        assert torch.allclose(torch.log(tot.abs()) + l.max(-1).values, psi.log, rtol=0, atol=1e-9)
