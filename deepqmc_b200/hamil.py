@@ -104,6 +104,28 @@ class MolecularHamiltonian:
         self.mol_shells = [get_shell(z) for z in mol.charges]
         self.mol_ecp_shells = [get_shell(z + 1) - 1 for z in mol.charges - self.ns_valence]
 
+    def laplacian(self, ansatz_apply):
+        """Mirror of the ``LaplacianFactory`` seam (reference physics.py:24-33: ``f -> (x[3N] -> (lap, grad[3N]))`` applied
+        to ``x -> ansatz(params, r=x).log``, physics.py:79-109): -> ``lap_fn(params, phys_conf) -> (lap[B], grad[B, 3N])``
+        of log|psi| from the engine's forward-Laplacian pass.  The reference's factory takes an arbitrary traced closure;
+        an opaque CUDA engine can only offer it for its own wave function."""
+        ansatz = getattr(ansatz_apply, '__self__', None)
+        if ansatz is None or not hasattr(ansatz, 'engine_for'):
+            raise TypeError('laplacian expects the bound .apply of a deepqmc_b200 B200Ansatz')
+
+        def lap_fn(params, phys_conf: PhysicalConfiguration):
+            eng = ansatz.engine_for(self, params)
+            r, R = phys_conf.r, phys_conf.R
+            single = r.dim() == 2
+            if self.ph is not None:
+                raise NotImplementedError('with a pseudo-Hamiltonian the engine differentiates in the transformed coordinates')
+            # one dqmc_local_energy call; the potentials it computes alongside are discarded (with a Gaussian-type ECP
+            # that includes the quadrature pass: prefer the 'hamil/lap' statistic of local_energy there)
+            _, stats, _, _, grad = eng.local_energy(r[None] if single else r, R, seed=0, want_grad=True)
+            return (stats[4, 0], grad[0]) if single else (stats[4], grad)
+
+        return lap_fn
+
     def local_energy(self, ansatz_apply):
         """-> loc_ene(rng, params, phys_conf) -> (E_loc[B], stats{6 keys: [B]})"""
         ansatz = getattr(ansatz_apply, '__self__', None)

@@ -246,3 +246,21 @@ def test_return_mos_matches_oracle(kind, mol_name, hyper):
         s, l = torch.linalg.slogdet(torch.cat([up, dn], 2))  # [B, K]
         tot = (s * torch.exp(l - l.max(-1, keepdim=True).values)).sum(-1)
         assert torch.allclose(torch.log(tot.abs()) + l.max(-1).values, psi.log, rtol=0, atol=1e-9)
+
+
+def test_laplacian_factory_seam_matches_oracle():
+    """The LaplacianFactory seam (reference physics.py:24-33,144-156): Laplacian and gradient of log|psi| with respect to
+    the 3N electron coordinates, against the oracle's Hessian trace / autograd gradient."""
+    from oracle import wf
+    from oracle.laplacian import laplacian_hessian
+
+    mol, hamil, oh, ansatz, params, r, R = make('H2O', B=3, embedding_dim=32, n_layers=2, n_heads=2, n_determinants=3)
+    lap_fn = hamil.laplacian(ansatz.apply)
+    lap, grad = lap_fn(params, PhysicalConfiguration(R, r, torch.zeros(3, device=DEV)))
+    pt = wf.to_torch(params)
+    for b in range(3):
+        lo, go = laplacian_hessian(lambda x: wf.log_psi(ansatz.spec, pt, x.reshape(-1, 3), R.cpu())[1], r[b].cpu().reshape(-1))
+        assert abs(lap[b].item() - lo.item()) <= 1e-8 * max(1.0, abs(lo.item()))
+        assert torch.allclose(grad[b].cpu(), go, rtol=1e-8, atol=1e-9)
+    l1, g1 = lap_fn(params, PhysicalConfiguration(R, r[1], torch.zeros((), device=DEV)))  # single sample, as the reference calls it
+    assert torch.allclose(l1, lap[1]) and torch.allclose(g1, grad[1])
