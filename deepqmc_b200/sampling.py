@@ -153,9 +153,51 @@ class DecorrSampler(MetropolisSampler):
     conf/task/sampler_factory/elec_sampler/decorr_metropolis_psiformer.yaml): `length` sub-steps per
     sample(), statistics of the last one.  The whole scan is one dqmc_mcmc_sweep call."""
 
-    def __init__(self, hamil, wf, *, length, **kw):
+    def __init__(self, hamil=None, wf=None, *, length, **kw):
+        if hamil is None:  # reference form DecorrSampler(length=...): a link for chain(), not a sampler by itself
+            self.hamil, self.length = None, int(length)
+            return
         super().__init__(hamil, wf, **kw)
         self.length = int(length)
+
+
+def chain(*samplers):
+    """chain(DecorrSampler(length=30), MetropolisSampler(hamil, wf, tau=1.0)) -> a sampler that returns every 30th
+    Metropolis step (reference: sampling/sampling_utils.py:31-54, conf/task/sampler_factory/elec_sampler/*.yaml).  The last
+    link must be a Metropolis or Langevin sampler; the engine runs the whole scan as one sweep call."""
+    last = samplers[-1]
+    assert isinstance(last, MetropolisSampler) and last.hamil is not None, 'the last link must be a Metropolis / Langevin sampler'
+    for link in samplers[:-1]:
+        assert isinstance(link, DecorrSampler) and link.hamil is None, 'only DecorrSampler(length=...) links can be chained in front'
+        last.length = last.length * link.length
+    return last
+
+
+def combine_samplers(samplers, hamil, wf):
+    """reference: sampling/sampling_utils.py:57-69 -- the last entry is a constructor taking (hamil, wf)"""
+    return chain(*samplers[:-1], samplers[-1](hamil, wf))
+
+
+def equilibrate(rng, params, molecule_idx_sampler, sampler, state, criterion, steps, *, block_size, n_blocks=5,
+                allow_early_stopping=True):
+    """Generator: sample until ``criterion(phys_conf)`` has stabilised -- once block_size * n_blocks values are buffered,
+    stop when the means of the first and last block differ by less than the smaller of their standard deviations
+    (reference: sampling/sampling_utils.py:104-162).  Yields (step, state, mol_idxs, stats)."""
+    from statistics import mean, stdev
+
+    buffer_size = block_size * n_blocks
+    buffer: list = []
+    for k, step in enumerate(steps):
+        mol_idxs = molecule_idx_sampler.sample()
+        state, phys_conf, stats = sampler.sample(int(rng) * 1000003 + k, state, params, mol_idxs)
+        yield step, state, mol_idxs, stats
+        if allow_early_stopping:
+            buffer = [*buffer[-buffer_size + 1:], float(criterion(phys_conf))]
+            if len(buffer) < buffer_size:
+                continue
+            b1, b2 = buffer[:block_size], buffer[-block_size:]
+            if abs(mean(b1) - mean(b2)) < min(stdev(b1), stdev(b2)):
+                break
 
 
 class MultiElectronicStateSampler:

@@ -75,3 +75,45 @@ def test_multi_nuclear_geometry_sampler_layout_and_update_period():
     assert torch.allclose(state['elec'][2][0]['r'], r_before + 0.1 + 0.02)  # warp + equilibration sweep + sample sweep
     state = smp.update(state, None)
     assert es.updates == 4
+
+
+def test_chain_and_combine_samplers_follow_the_reference_composition():
+    """chain(DecorrSampler(length), MetropolisSampler(...)) (sampling_utils.py:31-69): the Decorr link only carries the
+    number of sub-steps; the combined sampler is the last link."""
+    from functools import partial
+
+    from deepqmc_b200.sampling import DecorrSampler, LangevinSampler, MetropolisSampler, chain, combine_samplers
+
+    class _Ansatz:
+        def apply(self, *a):
+            raise AssertionError('not evaluated here')
+
+    hamil, wf = object(), _Ansatz().apply
+    s = chain(DecorrSampler(length=30), MetropolisSampler(hamil, wf, tau=1.0, target_acceptance=0.57))
+    assert isinstance(s, MetropolisSampler) and s.length == 30 and s.initial_tau == 1.0
+    s = combine_samplers([DecorrSampler(length=10), partial(LangevinSampler, tau=0.1)], hamil, wf)
+    assert isinstance(s, LangevinSampler) and s.length == 10 and s.hamil is hamil
+    assert DecorrSampler(hamil, wf, length=5).length == 5  # the merged form used elsewhere in this repository
+
+
+def test_equilibrate_stops_when_the_criterion_is_stationary():
+    from deepqmc_b200.sampling import equilibrate
+
+    class _Sampler:
+        def __init__(self):
+            self.n = 0
+
+        def sample(self, rng, state, params, mol_idxs):
+            self.n += 1
+            return state, self.n, {'step': self.n}
+
+    # criterion decays to a noisy plateau: 1/n + alternating ripple
+    crit = lambda n: 1.0 / n + (0.01 if n % 2 else -0.01)
+    smp = _Sampler()
+    mols = MoleculeIdxSampler(0, 3, 1)
+    out = list(equilibrate(0, None, mols, smp, {}, crit, range(1000), block_size=4, n_blocks=3))
+    assert 12 <= len(out) < 1000 and out[0][0] == 0 and out[-1][3]['step'] == len(out)
+    assert [o[2].tolist() for o in out[:4]] == [[0], [1], [2], [0]]
+    smp2 = _Sampler()
+    assert len(list(equilibrate(0, None, MoleculeIdxSampler(0, 3, 1), smp2, {}, crit, range(20), block_size=4, n_blocks=3,
+                                allow_early_stopping=False))) == 20
