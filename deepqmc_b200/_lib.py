@@ -41,7 +41,7 @@ class DqmcConfig(C.Structure):
         ('gnn_features', C.c_int32), ('gnn_concat', C.c_int32), ('gnn_conv_ne', C.c_int32), ('gnn_sub_n', C.c_int32),
         ('gnn_deep_edges', C.c_int32), ('gnn_res_norm', C.c_int32), ('gnn_g_bias', C.c_int32), ('gnn_w_bias', C.c_int32),
         ('gnn_w_dims', C.c_int32 * 32), ('gnn_h_dims', C.c_int32 * 32), ('gnn_u_dims', C.c_int32 * 32),
-        ('nuc_cusp_kind', C.c_int32), ('z_nuclear', C.c_double * MAX_NUC),
+        ('nuc_cusp_kind', C.c_int32), ('z_nuclear', C.c_double * MAX_NUC), ('backflow_add', C.c_int32),
     ]
 
 

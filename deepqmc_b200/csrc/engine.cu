@@ -163,8 +163,8 @@ struct EngineBase {
         din = d; ein = de;
       }
     }
-    add("bf.up", bf_in, K * N);
-    add("bf.dn", bf_in, K * N);
+    add("bf.up", bf_in, K * N * (cfg.backflow_add == 2 ? 2 : 1));
+    add("bf.dn", bf_in, K * N * (cfg.backflow_add == 2 ? 2 : 1));
     add("env.pi_up", K * N, M * rep);
     add("env.pi_dn", K * N, M * rep);
     add("env.zeta_up", K * N, M * rep);
@@ -244,6 +244,8 @@ struct Engine : EngineBase {
   bool attn_fwd_pipelined = false;
   bool slater_fwd2_ok = false;
   int N, M, d, K, KN, H, dh, T3;
+  int BFW = 0;      // row width of the backflow buffer: K N, or 2 K N with multiplicative + additive heads
+  int add_off = 0;  // column offset of the additive head in it
   bool gnn = false;    // conv-GNN ("PauliNet" test ansatz)
   int bf_in = 0;       // input width of the final backflow layer
   bool trans = false;  // TransPsiformer: nuclear attention tokens + nucleus-dependent envelopes
@@ -277,6 +279,9 @@ struct Engine : EngineBase {
   int init() {
     N = cfg.n_up + cfg.n_down; M = cfg.n_nuc; d = cfg.embedding_dim; K = cfg.n_determinants;
     KN = K * N; H = cfg.n_heads; dh = d / H; T3 = 3 * N;
+    BFW = KN * (cfg.backflow_add == 2 ? 2 : 1);
+    add_off = cfg.backflow_add == 2 ? KN : 0;
+    if (cfg.backflow_add && cfg.kind == DQMC_PAULINET) { err = "additive backflow: linear-head ansatz kinds only"; return 2; }
     if (cfg.kind != DQMC_PSIFORMER && cfg.kind != DQMC_FERMINET && cfg.kind != DQMC_TRANSPSIFORMER &&
         cfg.kind != DQMC_PAULINET) {
       err = "unknown ansatz kind"; return 2;
@@ -472,6 +477,7 @@ struct Engine : EngineBase {
   struct Ws {
     T *X, *O, *A, *M1, *QKV, *BF, *dsign, *dlog, *dlap, *dgrad;
     T* QA = nullptr;  // pseudo-Hamiltonian records [Bc][N][PH_STRIDE]
+    T* Gadd = nullptr;  // additive-backflow factor g_i = cutoff * envelope norm with gradient / Laplacian [Bc][N][5]
     T *G0 = nullptr, *G1 = nullptr, *G2 = nullptr, *Hs = nullptr, *Ha = nullptr, *C = nullptr, *Fc = nullptr, *HT = nullptr,
       *E0 = nullptr, *E1 = nullptr, *ET0 = nullptr, *ET1 = nullptr, *W3 = nullptr,
       *Y0 = nullptr, *Y1 = nullptr, *Jb = nullptr;  // conv-GNN trunk
@@ -505,7 +511,8 @@ struct Engine : EngineBase {
   }
   size_t per_walker_elems(int S) const {
     size_t rows = (size_t)N * S;
-    size_t dets = (size_t)K * (3 + (S > 1 ? T3 : 0)) + (ph_on && S > 1 ? (size_t)N * PH_STRIDE : 0);
+    size_t dets = (size_t)K * (3 + (S > 1 ? T3 : 0)) + (ph_on && S > 1 ? (size_t)N * PH_STRIDE : 0) +
+                  (cfg.backflow_add ? (size_t)N * 5 + 64 : 0);
     if (gnn) {
       const size_t e = cfg.edge_dim, dm = gnn_dmax(), em = gnn_emax(), hn = gnn_hnode_max();
       const size_t pairs8 = (size_t)N * (N + (cfg.gnn_conv_ne ? M : 0)) * 8;
@@ -514,9 +521,9 @@ struct Engine : EngineBase {
     }
     if (cfg.kind == DQMC_FERMINET) {
       const size_t de = cfg.edge_dim, fin = 3 * (size_t)d + 2 * de;
-      return rows * (2 * (size_t)d + fin + KN) + (size_t)N * rows * 2 * de + dets;
+      return rows * (2 * (size_t)d + fin + BFW) + (size_t)N * rows * 2 * de + dets;
     }
-    return rows * (size_t)(4 * d + 3 * d + KN) + dets;
+    return rows * (size_t)(4 * d + 3 * d + BFW) + dets;
   }
   size_t chunk_bytes(int Bc, int S) const { return sizeof(T) * per_walker_elems(S) * Bc + 16 * 256; }
   Ws carve(void* base, int Bc, int S) const {
@@ -539,14 +546,15 @@ struct Engine : EngineBase {
       const size_t de = cfg.edge_dim, fin = 3 * (size_t)d + 2 * de;
       w.X = take(rows * d); w.O = take(rows * d); w.QKV = take(rows * fin);    // H, H2, F
       w.A = take(rows * N * de); w.M1 = take(rows * N * de);                   // E, E2
-      w.BF = take(rows * KN);
+      w.BF = take(rows * BFW);
     } else {
       w.X = take(rows * d); w.O = take(rows * d); w.A = take(rows * d); w.M1 = take(rows * d);
-      w.QKV = take(rows * 3 * d); w.BF = take(rows * KN);
+      w.QKV = take(rows * 3 * d); w.BF = take(rows * BFW);
     }
     w.dsign = take((size_t)Bc * K); w.dlog = take((size_t)Bc * K); w.dlap = take((size_t)Bc * K);
     w.dgrad = take((size_t)Bc * K * (S > 1 ? T3 : 1));
     if (ph_on && S > 1) w.QA = take((size_t)Bc * N * PH_STRIDE);
+    if (cfg.backflow_add) w.Gadd = take((size_t)Bc * N * 5);
     w.bytes = p - (char*)base;
     return w;
   }
@@ -988,20 +996,31 @@ struct Engine : EngineBase {
   int tail(const T* r, const T* R, int Rb, int Bc, int S, int Bstat, T* sign, T* logp, T* E, T* stats, T* grad, Ws& w,
            T* X, cudaStream_t st, const T* jastrow = nullptr, const T* qa = nullptr) {
     // per-spin backflow heads: rows of electron e across walkers, weights by spin
-    gemm(X, bf_in, "bf.up", "bf.dn", cfg.n_up, KN, gnn ? P("bfb.up") : nullptr, nullptr, 0, w.BF, KN, Bc * S, KN, bf_in, S, 1, N,
+    gemm(X, bf_in, "bf.up", "bf.dn", cfg.n_up, BFW, gnn ? P("bfb.up") : nullptr, nullptr, 0, w.BF, BFW, Bc * S, BFW, bf_in, S, 1, N,
          st, 0, gnn ? P("bfb.dn") : nullptr);
     if (cfg.mult_act == 1)  // default mult_act 1 + 2 tanh(x / 4) of the BackflowOp (nn_wave_function.py:14-33)
       DQ_LAUNCH(act_fl_kernel<T>, dim3(Bc * N, (KN + 127) / 128), dim3(128), 0, st, w.BF, KN, (const T*)nullptr, 0, S, KN, T(1), 2);
     const int full_det = cfg.factorized_det ? 0 : 1;
+    const int mult_on = cfg.backflow_add == 1 ? 0 : 1;
+    const T* gadd = nullptr;
+    if (cfg.backflow_add) {
+      // additive branch (wf/nn_wave_function.py:26-32): add_act on its head, electron-local factor cutoff * |envelope|
+      if (qa) { err = "additive backflow with a pseudo-Hamiltonian is not supported"; return 2; }
+      DQ_LAUNCH(act_fl_kernel<T>, dim3(Bc * N, (KN + 127) / 128), dim3(128), 0, st, w.BF + add_off, BFW, (const T*)nullptr, 0, S, KN,
+                T(1), 3);
+      DQ_LAUNCH(bf_add_factor_kernel<T>, dim3((Bc * N + 63) / 64), dim3(64), 0, st, r, R, Rb, N, M, cfg.n_up, K, P("env.pi_up"),
+                P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), env_rep, full_det, w.Gadd, Bc * N);
+      gadd = w.Gadd;
+    }
     if (mos_out) {  // Ansatz.apply(..., return_mos=True): orbital matrices instead of determinants
       const size_t tot = (size_t)Bc * K * N * N;
       DQ_LAUNCH(orbitals_kernel<T>, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, r, R, Rb, N, M, cfg.n_up, K,
-                P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, env_rep, full_det,
-                mos_out, tot);
+                P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, BFW, env_rep, full_det,
+                mos_out, tot, gadd, add_off, mult_on);
       return 0;
     }
     const int sl_wpb = slater_warps_per_block<T>(N);
-    if ((N <= 4 || (N <= 6 && std::is_same<T, float>::value)) && !qa && !std::getenv("DQMC_SLATER_GENERIC")) {
+    if ((N <= 4 || (N <= 6 && std::is_same<T, float>::value)) && !qa && !gadd && !std::getenv("DQMC_SLATER_GENERIC")) {
       const int tot = Bc * K;
 #define DQ_SL_SMALL(NS_)                                                                                           \
   DQ_LAUNCH((slater_small_kernel<T, NS_>), dim3((tot + 63) / 64), dim3(64), 0, st, r, R, Rb, M, cfg.n_up, K, S, tot,    \
@@ -1015,7 +1034,7 @@ struct Engine : EngineBase {
         default: DQ_SL_SMALL(6); break;
       }
 #undef DQ_SL_SMALL
-    } else if (S == 1 && N <= 32 && slater_fwd2_ok) {
+    } else if (S == 1 && N <= 32 && slater_fwd2_ok && !gadd) {
       const int nthr = 32 * K < 256 ? 32 * K : 256;
       const int grid = Bc < 3 * n_sms ? Bc : 3 * n_sms;
       if (N <= 16)
@@ -1026,15 +1045,15 @@ struct Engine : EngineBase {
         DQ_LAUNCH((slater_fwd2_kernel<T, 32>), dim3(grid), dim3(nthr), slater_fwd2_smem_bytes<T>(N, M, K), st, r, R, Rb, N,
                   M, cfg.n_up, K, Bc, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF,
                   KN, w.dsign, w.dlog, env_rep, full_det);
-    } else if (S == 1 && N <= 32 && !std::getenv("DQMC_SLATER_GENERIC")) {
+    } else if (S == 1 && N <= 32 && !gadd && !std::getenv("DQMC_SLATER_GENERIC")) {
       const int wpb = K < 8 ? K : 8;
       DQ_LAUNCH(slater_fwd_reg_kernel<T>, dim3(Bc), dim3(32 * wpb), sizeof(T) * N * M, st, r, R, Rb, N, M, cfg.n_up, K,
                 P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog,
                 env_rep, full_det);
     } else
     DQ_LAUNCH(slater_kernel<T>, dim3((Bc * K + sl_wpb - 1) / sl_wpb), dim3(32 * sl_wpb), slater_smem_bytes<T>(N), st, r, R,
-              Rb, N, M, cfg.n_up, K, S, Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, w.dlog,
-              w.dgrad, w.dlap, env_rep, full_det, qa);
+              Rb, N, M, cfg.n_up, K, S, Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, BFW, w.dsign, w.dlog,
+              w.dgrad, w.dlap, env_rep, full_det, qa, gadd, add_off, mult_on);
     FinalizeCfg fc;
     fc.N = N; fc.M = M; fc.n_up = cfg.n_up; fc.K = K; fc.S = S; fc.cusp_kind = cfg.cusp_kind;
     fc.cusp_same_scale = cfg.cusp_same_scale; fc.cusp_anti_scale = cfg.cusp_anti_scale;
@@ -1183,7 +1202,7 @@ struct Engine : EngineBase {
     const int sl_wpb = slater_warps_per_block<T>(N);
     DQ_LAUNCH(slater_kernel<T>, dim3((Bc * K + sl_wpb - 1) / sl_wpb), dim3(32 * sl_wpb), slater_smem_bytes<T>(N), st, r, R, Rb, N,
               M, cfg.n_up, K, 1, Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)BF, KN,
-              dsign, dlog, (T*)nullptr, (T*)nullptr, env_rep, 1, (const T*)nullptr);
+              dsign, dlog, (T*)nullptr, (T*)nullptr, env_rep, 1, (const T*)nullptr, (const T*)nullptr, 0, 1);
     FinalizeCfg fc;
     fc.N = N; fc.M = M; fc.n_up = cfg.n_up; fc.K = K; fc.S = 1; fc.cusp_kind = cfg.cusp_kind;
     fc.cusp_same_scale = cfg.cusp_same_scale; fc.cusp_anti_scale = cfg.cusp_anti_scale; fc.ecp_terms = 0;
@@ -1283,7 +1302,7 @@ struct Engine : EngineBase {
     const int sl_wpb = slater_warps_per_block<T>(N);
     DQ_LAUNCH(slater_kernel<T>, dim3((Bc * K + sl_wpb - 1) / sl_wpb), dim3(32 * sl_wpb), slater_smem_bytes<T>(N), st, r, R, Rb, N,
               M, cfg.n_up, K, 1, Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)BF, KN,
-              dsign, dlog, (T*)nullptr, (T*)nullptr, env_rep, 1, (const T*)nullptr);
+              dsign, dlog, (T*)nullptr, (T*)nullptr, env_rep, 1, (const T*)nullptr, (const T*)nullptr, 0, 1);
     FinalizeCfg fc;
     fc.N = N; fc.M = M; fc.n_up = cfg.n_up; fc.K = K; fc.S = 1; fc.cusp_kind = cfg.cusp_kind;
     fc.cusp_same_scale = cfg.cusp_same_scale; fc.cusp_anti_scale = cfg.cusp_anti_scale; fc.ecp_terms = 0;
@@ -1359,6 +1378,7 @@ struct Engine : EngineBase {
       return 2;
     }
     if (cfg.nuc_cusp_kind) { err = "dqmc_wf_vjp_params: nuclear cusp exponent gradient not implemented"; return 2; }
+    if (cfg.backflow_add) { err = "dqmc_wf_vjp_params: additive backflow branch has no reverse pass"; return 2; }
     const T* r = (const T*)r_;
     const T* R = (const T*)R_;
     DQ_CHECK(cudaMemsetAsync(grad_params, 0, sizeof(T) * total, st));

@@ -173,7 +173,8 @@ __global__ void gnn_conv_kernel(const T* __restrict__ Wsame, const T* __restrict
 // Elementwise activation with forward-Laplacian propagation, in place on groups of S rows:
 //   y = f(z); y_t = f'(z) z_t; y_L = f'(z) z_L + f''(z) sum_t z_t^2; out = out_scale (Res + y).
 // act 0: tanh; 1: ssp = softplus + log(1/2) (reference hkext.py:11-19); 2: the default mult_act of the
-// backflow 1 + 2 tanh(z / 4) (wf/nn_wave_function.py:17).  grid = (groups, ceil(d / blockDim)).
+// backflow 1 + 2 tanh(z / 4) (wf/nn_wave_function.py:17); 3: its default add_act 0.1 tanh(z / 4) (:18).
+// grid = (groups, ceil(d / blockDim)).
 // ------------------------------------------------------------------------------------------
 template <class T>
 __global__ void act_fl_kernel(T* __restrict__ Z, int ldz, const T* __restrict__ Res, int ldr, int S, int d,
@@ -191,9 +192,12 @@ __global__ void act_fl_kernel(T* __restrict__ Z, int ldz, const T* __restrict__ 
     const T sg = T(1) / (T(1) + m_exp(-z0));
     y = (z0 > T(0) ? z0 + m_log1p(m_exp(-z0)) : m_log1p(m_exp(z0))) - T(0.6931471805599453094);
     y1 = sg; y2 = sg * (T(1) - sg);
-  } else {
+  } else if (act == 2) {
     const T th = m_tanh(z0 * T(0.25)), sc = T(1) - th * th;
     y = T(1) + T(2) * th; y1 = T(0.5) * sc; y2 = T(-0.25) * th * sc;
+  } else {  // 3: the default add_act of the backflow 0.1 tanh(z / 4) (wf/nn_wave_function.py:18)
+    const T th = m_tanh(z0 * T(0.25)), sc = T(1) - th * th;
+    y = T(0.1) * th; y1 = T(0.025) * sc; y2 = T(-0.0125) * th * sc;
   }
   z[0] = out_scale * ((rs ? rs[0] : T(0)) + y);
   if (S > 1) {

@@ -27,14 +27,84 @@ struct LaneWalk {
   }
 };
 
+// ------------------------------------------------------------------------------------------
+// Additive backflow branch of the BackflowOp (reference wf/nn_wave_function.py:14-33):
+//   xs <- xs * mult_act(f_mult) + cutoff(r_i) * envel_i * add_act(f_add),
+//   envel_i = sqrt(sum_{k, mu} xs[k, i, mu]^2) over the determinants and the orbitals of electron i's spin block,
+//   cutoff = R^2 (6 - 8 R + 3 R^2) for R = min_I |r_i - R_I| / 0.5 < 1, else 1.
+// This kernel evaluates the electron-local factor g_i = cutoff * envel with its gradient and Laplacian w.r.t. r_i:
+// G[b][i][5] = (g, dg/dx, dg/dy, dg/dz, Lap g).  One thread per (walker, electron).
+// ------------------------------------------------------------------------------------------
+template <class T>
+__global__ void bf_add_factor_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M, int n_up,
+                                     int K, const T* __restrict__ pi_up, const T* __restrict__ pi_dn,
+                                     const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn, int rep, int full_det,
+                                     T* __restrict__ G, int total) {
+  const int bi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bi >= total) return;
+  const int b = bi / N, i = bi - b * N;
+  const T* ri = r + (size_t)bi * 3;
+  const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
+  const bool up = i < n_up;
+  const int mu0 = full_det ? 0 : (up ? 0 : n_up), mu1 = full_det ? N : (up ? n_up : N);
+  T S = T(0), gS0 = T(0), gS1 = T(0), gS2 = T(0), lS = T(0);
+  for (int k = 0; k < K; ++k)
+    for (int mu = mu0; mu < mu1; ++mu) {
+      const T* pi = (up ? pi_up : pi_dn) + (size_t)(k * N + mu) * M * rep;
+      const T* ze = (up ? zeta_up : zeta_dn) + (size_t)(k * N + mu) * M * rep;
+      T e = T(0), d0 = T(0), d1 = T(0), d2 = T(0), le = T(0);
+      for (int m = 0; m < M; ++m) {
+        const T dx0 = ri[0] - Rb[3 * m], dx1 = ri[1] - Rb[3 * m + 1], dx2 = ri[2] - Rb[3 * m + 2];
+        const T dd = dx0 * dx0 + dx1 * dx1 + dx2 * dx2;
+        const T rho2 = Num<T>::eps() + dd, rho = m_sqrt(rho2);
+        for (int et = 0; et < rep; ++et) {
+          const T a = m_abs(ze[m * rep + et]);
+          const T ex = pi[m * rep + et] * m_exp(-a * rho);
+          const T c = -a * ex / rho;
+          e += ex;
+          d0 += c * dx0; d1 += c * dx1; d2 += c * dx2;
+          le += ex * (a * a * dd / rho2 - a * (T(3) / rho - dd / (rho2 * rho)));
+        }
+      }
+      S += e * e;
+      gS0 += T(2) * e * d0; gS1 += T(2) * e * d1; gS2 += T(2) * e * d2;
+      lS += T(2) * (d0 * d0 + d1 * d1 + d2 * d2 + e * le);
+    }
+  const T n = m_sqrt(S);
+  const T n0 = gS0 / (T(2) * n), n1 = gS1 / (T(2) * n), n2 = gS2 / (T(2) * n);
+  const T ln = lS / (T(2) * n) - (gS0 * gS0 + gS1 * gS1 + gS2 * gS2) / (T(4) * S * n);
+  // cutoff on the plain distance to the nearest nucleus
+  T best = T(-1), c0 = T(0), c1 = T(0), c2 = T(0);
+  for (int m = 0; m < M; ++m) {
+    const T dx0 = ri[0] - Rb[3 * m], dx1 = ri[1] - Rb[3 * m + 1], dx2 = ri[2] - Rb[3 * m + 2];
+    const T dd = dx0 * dx0 + dx1 * dx1 + dx2 * dx2;
+    if (best < T(0) || dd < best) { best = dd; c0 = dx0; c1 = dx1; c2 = dx2; }
+  }
+  const T rho = m_sqrt(best), Rr = rho * T(2);
+  T c = T(1), cg0 = T(0), cg1 = T(0), cg2 = T(0), cl = T(0);
+  if (Rr < T(1)) {
+    c = Rr * Rr * (T(6) - T(8) * Rr + T(3) * Rr * Rr);
+    const T cp = T(12) * Rr * (T(1) - Rr) * (T(1) - Rr) * T(2);            // dc/drho
+    const T cpp = (T(12) - T(48) * Rr + T(36) * Rr * Rr) * T(4);           // d2c/drho2
+    cg0 = cp * c0 / rho; cg1 = cp * c1 / rho; cg2 = cp * c2 / rho;
+    cl = cpp + T(2) * cp / rho;
+  }
+  T* g = G + (size_t)bi * 5;
+  g[0] = c * n;
+  g[1] = c * n0 + n * cg0; g[2] = c * n1 + n * cg1; g[3] = c * n2 + n * cg2;
+  g[4] = c * ln + T(2) * (cg0 * n0 + cg1 * n1 + cg2 * n2) + n * cl;
+}
+
 template <class T>
 __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M, int n_up,
                               int K, int S, int total, const T* __restrict__ pi_up, const T* __restrict__ pi_dn,
                               const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn,
                               const T* __restrict__ BF, int ldb, T* __restrict__ det_sign, T* __restrict__ det_log,
                               T* __restrict__ det_grad, T* __restrict__ det_lap, int rep, int full_det,
-                              const T* __restrict__ QA) {
+                              const T* __restrict__ QA, const T* __restrict__ Gadd, int add_off, int mult_on) {
   // QA != null: pseudo-Hamiltonian metric per electron (common.cuh PhMetric; tangent slots are v-coordinates)
+  // Gadd != null: additive backflow branch, A = env * bf_mult (mult_on) + g_i * bf_add with g from bf_add_factor_kernel and
+  // the (already activated) additive head at column offset add_off of BF
   // full_det == 0: spin-factorised determinants det_up(n_up x n_up) det_down(n_down x n_down) (reference
   // wf/nn_wave_function.py:143-151) = determinant of the matrix with the spin-off-diagonal blocks zeroed.
   // rep = envelope terms per nucleus (1: ExponentialEnvelopes; 3: SimplifiedNucleusDependentEnvelopes,
@@ -92,18 +162,31 @@ __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, 
     if (QA && S > 1) pm.to_v(de0, de1, de2);
     if (!full_det && ((i < n_up) != (mu < n_up))) { e = T(0); de0 = T(0); de1 = T(0); de2 = T(0); le = T(0); }
     const T* bfrow = BF + (brow0 + (size_t)i * S) * ldb + k * N + mu;
-    T bf0 = bfrow[0];
+    T bf0 = mult_on ? bfrow[0] : T(1);
+    const bool blocked = !full_det && ((i < n_up) != (mu < n_up));
+    const T* ga = Gadd ? Gadd + ((size_t)b * N + i) * 5 : nullptr;
+    T a0 = e * bf0;
+    if (ga && !blocked) a0 += ga[0] * bfrow[add_off];
     env[i * NP + mu] = e;
     bfv[i * NP + mu] = bf0;
-    aug[i * N2 + mu] = e * bf0;
+    aug[i * N2 + mu] = a0;
     aug[i * N2 + N + mu] = (i == mu) ? T(1) : T(0);
     if (S > 1) {
       denv[(0 * N + i) * NP + mu] = de0;
       denv[(1 * N + i) * NP + mu] = de1;
       denv[(2 * N + i) * NP + mu] = de2;
-      T bfl = bfrow[(size_t)(1 + T3) * ldb];
-      T x0 = bfrow[(size_t)(1 + 3 * i) * ldb], x1 = bfrow[(size_t)(2 + 3 * i) * ldb], x2 = bfrow[(size_t)(3 + 3 * i) * ldb];
-      AL[i * NP + mu] = le * bf0 + e * bfl + T(2) * (de0 * x0 + de1 * x1 + de2 * x2);
+      T al = le * bf0;
+      if (mult_on) {
+        T bfl = bfrow[(size_t)(1 + T3) * ldb];
+        T x0 = bfrow[(size_t)(1 + 3 * i) * ldb], x1 = bfrow[(size_t)(2 + 3 * i) * ldb], x2 = bfrow[(size_t)(3 + 3 * i) * ldb];
+        al += e * bfl + T(2) * (de0 * x0 + de1 * x1 + de2 * x2);
+      }
+      if (ga && !blocked) {
+        const T* yr = bfrow + add_off;
+        al += ga[4] * yr[0] + ga[0] * yr[(size_t)(1 + T3) * ldb] +
+              T(2) * (ga[1] * yr[(size_t)(1 + 3 * i) * ldb] + ga[2] * yr[(size_t)(2 + 3 * i) * ldb] + ga[3] * yr[(size_t)(3 + 3 * i) * ldb]);
+      }
+      AL[i * NP + mu] = al;
     }
   }
   __syncwarp();
@@ -164,9 +247,14 @@ __global__ void slater_kernel(const T* __restrict__ r, const T* __restrict__ R, 
     __syncwarp();
     for (LaneWalk w(lane, N); w.i < N; w.next()) {
       const int i = w.i, mu = w.j;
-      T bft = BF[(brow0 + (size_t)i * S + 1 + t) * ldb + k * N + mu];
-      T a = env[i * NP + mu] * bft;
+      const T* bft_p = BF + (brow0 + (size_t)i * S + 1 + t) * ldb + k * N + mu;
+      T a = mult_on ? env[i * NP + mu] * bft_p[0] : T(0);
       if (i == it) a += denv[(ct * N + i) * NP + mu] * bfv[i * NP + mu];
+      if (Gadd && (full_det || ((i < n_up) == (mu < n_up)))) {
+        const T* ga = Gadd + ((size_t)b * N + i) * 5;
+        a += ga[0] * bft_p[add_off];
+        if (i == it) a += ga[1 + ct] * BF[(brow0 + (size_t)i * S) * ldb + k * N + mu + add_off];
+      }
       At[i * NP + mu] = a;
     }
     __syncwarp();
@@ -649,7 +737,8 @@ template <class T>
 __global__ void orbitals_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M, int n_up,
                                 int K, const T* __restrict__ pi_up, const T* __restrict__ pi_dn,
                                 const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn, const T* __restrict__ BF,
-                                int ldb, int rep, int full_det, T* __restrict__ out, size_t total) {
+                                int ldb, int rep, int full_det, T* __restrict__ out, size_t total,
+                                const T* __restrict__ Gadd, int add_off, int mult_on) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int mu = (int)(idx % N), i = (int)((idx / N) % N), k = (int)((idx / ((size_t)N * N)) % K);
@@ -664,8 +753,12 @@ __global__ void orbitals_kernel(const T* __restrict__ r, const T* __restrict__ R
     const T rho = m_sqrt(Num<T>::eps() + dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
     for (int et = 0; et < rep; ++et) e += pi[m * rep + et] * m_exp(-m_abs(ze[m * rep + et]) * rho);
   }
-  if (!full_det && ((i < n_up) != (mu < n_up))) e = T(0);
-  out[idx] = e * BF[(b * N + i) * ldb + k * N + mu];
+  const bool blocked = !full_det && ((i < n_up) != (mu < n_up));
+  if (blocked) e = T(0);
+  const T* bfp = BF + (b * N + i) * ldb + k * N + mu;
+  T a = mult_on ? e * bfp[0] : e;
+  if (Gadd && !blocked) a += Gadd[(b * N + i) * 5] * bfp[add_off];
+  out[idx] = a;
 }
 
 template <class T>

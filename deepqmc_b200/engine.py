@@ -131,6 +131,9 @@ def _pack_haiku_params(spec: AnsatzSpec, params: dict, R=None) -> dict[str, np.n
     else:
         raise NotImplementedError(spec.kind)
     out['bf.up'], out['bf.dn'] = g(PN.BF_UP + ':w'), g(PN.BF_DN + ':w')
+    if spec.backflow_transform == 'both':  # [multiplicative head | additive head]
+        out['bf.up'] = np.concatenate([out['bf.up'], g(PN.BF_UP_ADD + ':w')], axis=1)
+        out['bf.dn'] = np.concatenate([out['bf.dn'], g(PN.BF_DN_ADD + ':w')], axis=1)
     if spec.kind == 'transpsiformer':
         # walker-independent nuclear stream (deepqmc_b200/nuclear.py): per-layer key/value rows of the
         # nuclear tokens and the envelope exponents zetas[M, K, E] -> engine layout [K N][M E], pi = 1
@@ -262,6 +265,9 @@ class Engine:
             for i, v in enumerate(hid):
                 cfg.backflow_dims[i] = v
         cfg.cusp_kind = {'psiformer': 1, 'deepqmc': 2}.get(spec.cusp, 0)
+        cfg.backflow_add = {'mult': 0, 'add': 1, 'both': 2}[spec.backflow_transform]
+        if cfg.backflow_add and spec.kind not in ('psiformer', 'ferminet'):
+            raise NotImplementedError('additive backflow branch: Psiformer / FermiNet kinds only')
         cfg.nuc_cusp_kind = {'psiformer': 1, 'deepqmc': 2}.get(spec.cusp_nuclei, 0)
         for m in range(spec.n_nuc):
             cfg.z_nuclear[m] = float(hamil.mol.charges[m])

@@ -23,6 +23,9 @@ NUC_CUSP = P + 'nuclear_cusp_asymptotic'
 GNN = P + 'omni_net/~/electron_gnn/~/'
 BF_UP = P + 'omni_net/~/Backflow/~/mlp/linear_0'
 BF_DN = P + 'omni_net/~/Backflow_1/~/mlp/linear_0'
+# second net of Backflow(multi_head=True, n_backflows=2) with backflow_transform = 'both' (wf/omni.py:69-73)
+BF_UP_ADD = P + 'omni_net/~/Backflow/~/mlp_1/linear_0'
+BF_DN_ADD = P + 'omni_net/~/Backflow_1/~/mlp_1/linear_0'
 
 
 NUC_EMB = GNN + 'nuclei_embedding/'
@@ -166,6 +169,9 @@ def param_shapes(spec: AnsatzSpec) -> dict[str, tuple[int, ...]]:
         raise ValueError(spec.kind)
     s[BF_UP + ':w'] = (d, K * N)
     s[BF_DN + ':w'] = (d, K * N)
+    if spec.backflow_transform == 'both':
+        s[BF_UP_ADD + ':w'] = (d, K * N)
+        s[BF_DN_ADD + ':w'] = (d, K * N)
     return s
 
 

@@ -54,6 +54,9 @@ class AnsatzSpec:
     gnn_g_bias: bool = True
     backflow_bias: bool = True
     env_per_shell: bool = True      # False: one per-orbital exponent per nucleus, spin-unrestricted (as Psiformer)
+    # BackflowOp branches (wf/nn_wave_function.py:14-33,111-125): 'mult' in every shipped config; 'add' / 'both' add
+    # cutoff(r_i) * |envelope_i| * 0.1 tanh(f_add / 4) (Psiformer / FermiNet kinds)
+    backflow_transform: str = 'mult'
 
     @property
     def n_elec(self):

@@ -79,6 +79,11 @@ typedef struct dqmc_config {
    * charge; alpha is entry "cusp.alpha_nuc", the charges are z_nuclear (all kinds) */
   int32_t nuc_cusp_kind;
   double z_nuclear[DQMC_MAX_NUC];
+  /* BackflowOp branches (wf/nn_wave_function.py:14-33,111-125 backflow_transform): 0 'mult' (every shipped config),
+   * 1 'add', 2 'both'.  With an additive branch the heads "bf.up" / "bf.dn" are [d][K N] ('add') or
+   * [d][2 K N] ('both': multiplicative head first), add_act = 0.1 tanh(x / 4), with_envelope = true.
+   * Linear-head ansatz kinds (Psiformer, FermiNet, TransPsiformer) only. */
+  int32_t backflow_add;
 } dqmc_config;
 
 typedef struct dqmc_engine* dqmc_handle;

@@ -334,9 +334,33 @@ def orbitals(spec, params, emb, r, R):
         return (emb[sl] @ w).reshape(-1, K, N).permute(1, 0, 2)
 
     up, dn = slice(None, n_up), slice(n_up, None)
-    a_up = env('up', up) * bf(_t(params, P.BF_UP + ':w'), up)
-    a_dn = env('down', dn) * bf(_t(params, P.BF_DN + ':w'), dn)
-    return torch.cat([a_up, a_dn], 1)
+    mode = spec.backflow_transform
+    if mode == 'mult':
+        a_up = env('up', up) * bf(_t(params, P.BF_UP + ':w'), up)
+        a_dn = env('down', dn) * bf(_t(params, P.BF_DN + ':w'), dn)
+        return torch.cat([a_up, a_dn], 1)
+    # additive branch of the BackflowOp (wf/nn_wave_function.py:14-33,111-125); Backflow(multi_head=True) builds one
+    # net per transform: 'mlp' (first) and 'mlp_1' (wf/omni.py:69-73)
+    dists_nuc = torch.sqrt(((r[:, None] - R[None]) ** 2).sum(-1))  # plain norm, nn_wave_function.py:128-129
+    out = []
+    for spin, sl, first, second in (('up', up, P.BF_UP, P.BF_UP_ADD), ('down', dn, P.BF_DN, P.BF_DN_ADD)):
+        f_mult = bf(_t(params, first + ':w'), sl) if mode == 'both' else None
+        f_add = bf(_t(params, (second if mode == 'both' else first) + ':w'), sl)
+        out.append(backflow_op(env(spin, sl), f_mult, f_add, dists_nuc[sl]))
+    return torch.cat(out, 1)
+
+
+def backflow_op(xs, f_mult, f_add, dists_nuc):
+    """reference: wf/nn_wave_function.py:14-33 with the identity mult_act of the Psiformer / FermiNet configs, the default
+    add_act 0.1 tanh(x / 4) and with_envelope = True.  xs[K, n, n_orb], dists_nuc[n, M]."""
+    envel = torch.sqrt((xs ** 2).sum((-1, -3), keepdim=True))
+    if f_mult is not None:
+        xs = xs * f_mult
+    if f_add is not None:
+        Rr = dists_nuc.min(-1).values / 0.5
+        cutoff = torch.where(Rr < 1, Rr ** 2 * (6 - 8 * Rr + 3 * Rr ** 2), torch.ones_like(Rr))
+        xs = xs + cutoff[None, :, None] * envel * (0.1 * torch.tanh(f_add / 4))
+    return xs
 
 
 def psiformer_cusp(spec, params, r):

@@ -264,3 +264,50 @@ def test_laplacian_factory_seam_matches_oracle():
         assert torch.allclose(grad[b].cpu(), go, rtol=1e-8, atol=1e-9)
     l1, g1 = lap_fn(params, PhysicalConfiguration(R, r[1], torch.zeros((), device=DEV)))  # single sample, as the reference calls it
     assert torch.allclose(l1, lap[1]) and torch.allclose(g1, grad[1])
+
+
+@pytest.mark.parametrize('kind,mode,mol_name,dtype', [
+    ('psiformer', 'both', 'H2O', 'float64'),
+    ('psiformer', 'add', 'LiH', 'float64'),
+    ('ferminet', 'both', 'LiH', 'float64'),
+    ('psiformer', 'both', 'H2O', 'float32'),
+])
+def test_additive_backflow_branch(kind, mode, mol_name, dtype):
+    """backflow_transform = 'add' / 'both' of the BackflowOp (reference wf/nn_wave_function.py:14-33,111-125): orbitals
+    = envelope * f_mult + cutoff(nearest-nucleus distance) * |envelope_i| * 0.1 tanh(f_add / 4).  Walkers are drawn close
+    to the nuclei so the cutoff polynomial is active.  Value, orbital matrices and the local energy against the oracle."""
+    from deepqmc_b200.hamil import MolecularHamiltonian
+    from deepqmc_b200.molecule import Molecule
+    from deepqmc_b200 import params as PN
+    from deepqmc_b200.ansatz import B200Ansatz
+    from oracle import wf
+    from oracle.hamil import OracleHamiltonian
+
+    mol = Molecule.from_name(mol_name)
+    hamil, oh = MolecularHamiltonian(mol=mol), OracleHamiltonian(mol)
+    hyper = dict(embedding_dim=16, n_layers=1, n_determinants=3, backflow_transform=mode)
+    hyper.update(dict(n_heads=2) if kind == 'psiformer' else dict(edge_dim=8))
+    ansatz = B200Ansatz(hamil, kind, dtype=dtype, **hyper)
+    params = PN.perturb_params(ansatz.init(0))
+    pt = wf.to_torch(params)
+    B, N = 3, hamil.n_up + hamil.n_down
+    rng = np.random.default_rng(0)
+    r64 = torch.as_tensor(mol.coords[rng.integers(0, len(mol.coords), size=(B, N))] + 0.4 * rng.normal(size=(B, N, 3)))
+    R64 = torch.as_tensor(mol.coords)
+    assert ((r64[:, :, None] - R64[None, None]).norm(dim=-1).min(-1).values < 0.5).any()  # cutoff region is sampled
+    tdt = torch.float64 if dtype == 'float64' else torch.float32
+    pc = PhysicalConfiguration(R64.to(tdt).to(DEV), r64.to(tdt).to(DEV), torch.zeros(B, device=DEV))
+    E, st = hamil.local_energy(ansatz.apply)(None, params, pc)
+    psi = ansatz.apply(params, pc)
+    up, dn = ansatz.apply(params, pc, return_mos=True)
+    tol = 1e-8 if dtype == 'float64' else 2e-4
+    for b in range(B):
+        f = lambda x: wf.log_psi(ansatz.spec, pt, x, R64)
+        so, lo = f(r64[b])
+        eo, sto = oh.local_energy(f, r64[b], R64)
+        ou, od = wf.molecular_orbitals(ansatz.spec, pt, r64[b], R64)
+        scale = max(1.0, abs(eo.item()), 0.5 * abs(sto['hamil/lap'].item()), 0.5 * sto['hamil/quantum_force'].item())
+        assert psi.sign[b].item() == so.item() and abs(psi.log[b].item() - lo.item()) <= (1e-10 if dtype == 'float64' else 2e-4) * max(1, abs(lo.item()))
+        assert abs(E[b].item() - eo.item()) <= tol * scale
+        mt = 1e-10 if dtype == 'float64' else 1e-4
+        assert torch.allclose(up[b].cpu().double(), ou, rtol=mt, atol=mt) and torch.allclose(dn[b].cpu().double(), od, rtol=mt, atol=mt)

@@ -134,6 +134,37 @@ def test_antisymmetry_of_oracle():
     assert s0.item() == -s1.item() and abs(l0.item() - l1.item()) < 1e-10
 
 
+def test_additive_backflow_oracle_antisymmetry_and_mult_limit():
+    """BackflowOp with an additive branch (nn_wave_function.py:14-33): still antisymmetric; with a zero additive head
+    'both' reduces to 'mult'; the cutoff polynomial is C^2 at R = 1 (value 1, zero slope / curvature)."""
+    from deepqmc_b200 import params as PN
+    from deepqmc_b200.spec import psiformer_spec
+
+    mol = Molecule.from_name('LiH')
+    h = OracleHamiltonian(mol)
+    hy = dict(embedding_dim=16, n_layers=1, n_heads=2, n_determinants=2)
+    both, mult = psiformer_spec(h, backflow_transform='both', **hy), psiformer_spec(h, **hy)
+    pb = PN.perturb_params(PN.init_params(both, 0))
+    assert set(pb) - set(PN.init_params(mult, 0)) == {PN.BF_UP_ADD + ':w', PN.BF_DN_ADD + ':w'}
+    p = owf.to_torch(pb)
+    R = torch.as_tensor(mol.coords)
+    torch.manual_seed(0)
+    r = 0.5 * torch.randn(4, 3, dtype=torch.float64)
+    s0, l0 = owf.log_psi(both, p, r, R)
+    s1, l1 = owf.log_psi(both, p, r[[1, 0, 2, 3]], R)
+    assert s0.item() == -s1.item() and abs(l0.item() - l1.item()) < 1e-10
+    sm, lm = owf.log_psi(mult, p, r, R)
+    assert abs(lm.item() - l0.item()) > 1e-6  # the additive head matters ...
+    p0 = {**p, PN.BF_UP_ADD + ':w': torch.zeros_like(p[PN.BF_UP_ADD + ':w']), PN.BF_DN_ADD + ':w': torch.zeros_like(p[PN.BF_DN_ADD + ':w'])}
+    sz, lz = owf.log_psi(both, p0, r, R)
+    assert sz.item() == sm.item() and abs(lz.item() - lm.item()) < 1e-12  # ... and vanishes with it
+    c = lambda x: x**2 * (6 - 8 * x + 3 * x**2)
+    x = torch.tensor(1.0, dtype=torch.float64, requires_grad=True)
+    g, = torch.autograd.grad(c(x), x, create_graph=True)
+    g2, = torch.autograd.grad(g, x)
+    assert c(x).item() == 1.0 and abs(g.item()) < 1e-12 and abs(g2.item()) < 1e-12
+
+
 def test_transpsiformer_nuclear_stream_matches_oracle():
     """Host-side nuclear stream of the product (numpy, deepqmc_b200/nuclear.py) against the oracle's
     independent torch restatement: final nuclear embeddings -> envelope exponents, and antisymmetry
