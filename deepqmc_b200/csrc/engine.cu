@@ -1206,14 +1206,16 @@ struct Engine : EngineBase {
     FinalizeCfg fc;
     fc.N = N; fc.M = M; fc.n_up = cfg.n_up; fc.K = K; fc.S = 1; fc.cusp_kind = cfg.cusp_kind;
     fc.cusp_same_scale = cfg.cusp_same_scale; fc.cusp_anti_scale = cfg.cusp_anti_scale; fc.ecp_terms = 0;
+    fc.nuc_cusp_kind = cfg.nuc_cusp_kind;
     DQ_LAUNCH(finalize_kernel<T>, dim3(Bc), dim3(128), finalize_smem_bytes<T>(N, K), st, fc, r, R, Rb, (const T*)dsign,
               (const T*)dlog, (const T*)nullptr, (const T*)nullptr, P("cusp.alpha"), (const T*)d_zval, (const T*)nullptr,
               (const int*)d_ecp_mask, Bc, sign, logp, (T*)nullptr, (T*)nullptr, (T*)nullptr, (const T*)nullptr, (const T*)nullptr,
-              (const T*)nullptr, PhArgs<T>());
+              cfg.nuc_cusp_kind ? P("cusp.nuc") : (const T*)nullptr, PhArgs<T>());
     // ---- reverse ------------------------------------------------------------------------------------------------
     DQ_LAUNCH(finalize_bwd_kernel<T>, dim3((Bc + 127) / 128), dim3(128), 0, st, r, N, cfg.n_up, K, Bc, (const T*)dsign,
               (const T*)dlog, wts, cfg.cusp_kind, (T)cfg.cusp_same_scale, (T)cfg.cusp_anti_scale, P("cusp.alpha"), dld,
-              G + off("cusp.alpha"));
+              G + off("cusp.alpha"), R, Rb, M, cfg.nuc_cusp_kind, cfg.nuc_cusp_kind ? P("cusp.nuc") : (const T*)nullptr,
+              cfg.nuc_cusp_kind ? G + off("cusp.nuc") : (T*)nullptr);
     {
       const size_t pw = slater_bwd_smem_per_warp<T>(N);
       int wpb = (int)((96 * 1024) / pw);
@@ -1306,14 +1308,16 @@ struct Engine : EngineBase {
     FinalizeCfg fc;
     fc.N = N; fc.M = M; fc.n_up = cfg.n_up; fc.K = K; fc.S = 1; fc.cusp_kind = cfg.cusp_kind;
     fc.cusp_same_scale = cfg.cusp_same_scale; fc.cusp_anti_scale = cfg.cusp_anti_scale; fc.ecp_terms = 0;
+    fc.nuc_cusp_kind = cfg.nuc_cusp_kind;
     DQ_LAUNCH(finalize_kernel<T>, dim3(Bc), dim3(128), finalize_smem_bytes<T>(N, K), st, fc, r, R, Rb, (const T*)dsign,
               (const T*)dlog, (const T*)nullptr, (const T*)nullptr, P("cusp.alpha"), (const T*)d_zval, (const T*)nullptr,
               (const int*)d_ecp_mask, Bc, sign, logp, (T*)nullptr, (T*)nullptr, (T*)nullptr, (const T*)nullptr, (const T*)nullptr,
-              (const T*)nullptr, PhArgs<T>());
+              cfg.nuc_cusp_kind ? P("cusp.nuc") : (const T*)nullptr, PhArgs<T>());
     // ---- reverse -------------------------------------------------------------------------------------------------
     DQ_LAUNCH(finalize_bwd_kernel<T>, dim3((Bc + 127) / 128), dim3(128), 0, st, r, N, cfg.n_up, K, Bc, (const T*)dsign,
               (const T*)dlog, wts, cfg.cusp_kind, (T)cfg.cusp_same_scale, (T)cfg.cusp_anti_scale, P("cusp.alpha"), dld,
-              G + off("cusp.alpha"));
+              G + off("cusp.alpha"), R, Rb, M, cfg.nuc_cusp_kind, cfg.nuc_cusp_kind ? P("cusp.nuc") : (const T*)nullptr,
+              cfg.nuc_cusp_kind ? G + off("cusp.nuc") : (T*)nullptr);
     {
       const size_t pw = slater_bwd_smem_per_warp<T>(N);
       int wpb = (int)((96 * 1024) / pw);
@@ -1377,7 +1381,6 @@ struct Engine : EngineBase {
       err = "dqmc_wf_vjp_params: only the Psiformer / TransPsiformer / FermiNet ansatzes have a reverse pass so far";
       return 2;
     }
-    if (cfg.nuc_cusp_kind) { err = "dqmc_wf_vjp_params: nuclear cusp exponent gradient not implemented"; return 2; }
     if (cfg.backflow_add) { err = "dqmc_wf_vjp_params: additive backflow branch has no reverse pass"; return 2; }
     const T* r = (const T*)r_;
     const T* R = (const T*)R_;

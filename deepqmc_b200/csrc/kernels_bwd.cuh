@@ -217,7 +217,9 @@ template <class T>
 __global__ void finalize_bwd_kernel(const T* __restrict__ r, int N, int n_up, int K, int B,
                                     const T* __restrict__ det_sign, const T* __restrict__ det_log,
                                     const T* __restrict__ weights, int cusp_kind, T same_scale, T anti_scale,
-                                    const T* __restrict__ cusp_alpha, T* __restrict__ dlogdet, T* __restrict__ dalpha) {
+                                    const T* __restrict__ cusp_alpha, T* __restrict__ dlogdet, T* __restrict__ dalpha,
+                                    const T* __restrict__ R, int R_batched, int M, int nuc_cusp_kind,
+                                    const T* __restrict__ nuc_cusp /*[1 + M]: alpha, charges*/, T* __restrict__ dnuc_alpha) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const T w = weights[b];
@@ -244,6 +246,22 @@ __global__ void finalize_bwd_kernel(const T* __restrict__ r, int N, int n_up, in
       }
     atomic_add(dalpha, w * gs);
     atomic_add(dalpha + 1, w * ga);
+  }
+  if (nuc_cusp_kind != 0 && dnuc_alpha) {
+    // NuclearCuspAsymptotic exponent (wf/cusp.py:81-101) on the plain electron-nucleus distances:
+    // psiformer form -Z a^2 / (a + d), deepqmc form -Z / (a (1 + a d))
+    const T al = nuc_cusp[0];
+    const T* rb = r + (size_t)b * N * 3;
+    const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
+    T g = T(0);
+    for (int i = 0; i < N; ++i)
+      for (int m = 0; m < M; ++m) {
+        const T dx0 = rb[3 * i] - Rb[3 * m], dx1 = rb[3 * i + 1] - Rb[3 * m + 1], dx2 = rb[3 * i + 2] - Rb[3 * m + 2];
+        const T dist = m_sqrt(dx0 * dx0 + dx1 * dx1 + dx2 * dx2), z = nuc_cusp[1 + m];
+        if (nuc_cusp_kind == 1) g -= z * al * (al + T(2) * dist) / ((al + dist) * (al + dist));
+        else g += z * (T(1) + T(2) * al * dist) / (al * al * (T(1) + al * dist) * (T(1) + al * dist));
+      }
+    atomic_add(dnuc_alpha, w * g);
   }
 }
 

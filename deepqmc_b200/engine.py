@@ -450,6 +450,8 @@ class Engine:
         self._check(rc, 'dqmc_wf_vjp_params')
         unpack = _unpack_ferminet_grads if self.spec.kind == 'ferminet' else _unpack_psiformer_grads
         grads = unpack(self.spec, self.entries, flat)
+        if self.spec.cusp_nuclei != 'none' and self.spec.cusp_nuclei_trainable:
+            grads[f'{PN.NUC_CUSP}:nuc_alpha'] = flat[self.entries['cusp.nuc'][0]]
         if self.spec.kind == 'transpsiformer':
             # the walker-independent nuclear stream is differentiated on the host: the engine accumulated the
             # cotangents of its outputs (keys / values of the nuclear tokens, envelope exponents)

@@ -311,3 +311,27 @@ def test_additive_backflow_branch(kind, mode, mol_name, dtype):
         assert abs(E[b].item() - eo.item()) <= tol * scale
         mt = 1e-10 if dtype == 'float64' else 1e-4
         assert torch.allclose(up[b].cpu().double(), ou, rtol=mt, atol=mt) and torch.allclose(dn[b].cpu().double(), od, rtol=mt, atol=mt)
+
+
+@pytest.mark.parametrize('kind,form', [('psiformer', 'psiformer'), ('ferminet', 'deepqmc')])
+def test_parameter_vjp_with_trainable_nuclear_cusp(kind, form):
+    """Reverse pass with the NuclearCuspAsymptotic factor switched on (reference wf/cusp.py:81-101): the gradient of its
+    trainable exponent and of every other parameter against torch autograd through the oracle."""
+    from oracle import wf
+
+    hyper = dict(embedding_dim=16, n_layers=1, n_determinants=2, cusp_nuclei=form, cusp_nuclei_alpha=0.7)
+    hyper.update(dict(n_heads=2) if kind == 'psiformer' else dict(edge_dim=8))
+    mol, hamil, oh, ansatz, params, r, R = make('LiH', B=3, kind=kind, **hyper)
+    w = torch.as_tensor(np.random.default_rng(8).normal(size=3), device=DEV)
+    psi, grads = ansatz.log_psi_vjp(params, PhysicalConfiguration(R, r, torch.zeros(3, device=DEV)), w)
+    pt = {k: torch.as_tensor(v, dtype=torch.float64).requires_grad_(True) for k, v in params.items()}
+    tot = 0
+    for b in range(3):
+        s, l = wf.log_psi(ansatz.spec, pt, r[b].cpu(), R.cpu())
+        assert abs(psi.log[b].item() - l.item()) <= 1e-10 * max(1, abs(l.item()))
+        tot = tot + w[b].cpu() * l
+    tot.backward()
+    assert set(grads) == set(pt) and any('nuc_alpha' in k for k in grads)
+    for k, v in pt.items():
+        ref = v.grad
+        assert torch.allclose(grads[k].cpu().reshape(ref.shape), ref, rtol=1e-8, atol=1e-9 * max(1.0, ref.abs().max().item())), k
