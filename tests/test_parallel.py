@@ -48,6 +48,20 @@ def _worker(rank, world, port, q):
     ok = ok and torch.allclose(Ec, torch.clamp(E_all[lo:hi], center - mad, center + mad))
     ok = ok and torch.equal(mask, (E_all[lo:hi] - center).abs() < 2.0)
 
+    # soft squeeze and wave-function-ratio clipping use all-walker medians / quantiles as well (loss/clip.py:101-174)
+    from deepqmc_b200.energy import median_log_squeeze_and_mask
+    from deepqmc_b200.overlap import psi_ratio_clip_and_mask
+
+    xs, ms = median_log_squeeze_and_mask(E_all[lo:hi], clip_width=1.5, quantile=0.9, exclude_width=2.0)
+    qv = torch.quantile((E_all - center).abs(), 0.9)
+    z = (E_all[lo:hi] - center) / (3.0 * qv)
+    ref_sq = center + 3.0 * qv * torch.sign(z) * torch.log1p((z.abs() + 0.5 * z**2 + z.abs() ** 3) / (1 + z**2))
+    ok = ok and torch.allclose(xs, ref_sq) and torch.equal(ms, (E_all[lo:hi] - center).abs() / qv < 2.0)
+    rc, mr = psi_ratio_clip_and_mask(E_all[lo:hi], clip_width=2.0, exclude_width=1.0)
+    sig = torch.as_tensor(np.median((E_all - center).abs().numpy()))
+    ok = ok and torch.allclose(rc, torch.clamp(E_all[lo:hi], center - 2 * sig, center + 2 * sig))
+    ok = ok and torch.equal(mr, (E_all[lo:hi] - center).abs() < 1.0)
+
     class FakeAnsatz:  # d log psi_b / d theta = feature vector f_b: the VJP is sum_b cot_b f_b
         def log_psi_vjp(self, params, pc, cot):
             return Psi(torch.ones_like(cot), torch.zeros_like(cot)), {'theta': (cot[:, None] * pc.r).sum(0)}
