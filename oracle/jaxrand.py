@@ -1,0 +1,222 @@
+"""Numpy restatement of the pieces of jax.random / dm-haiku initialisation that the reference's own tests use to
+create parameters (TEST INFRASTRUCTURE, see oracle/__init__): with it the goldens of /root/reference/tests that depend
+on ``hk.transform(...).init(jax.random.PRNGKey(0), ...)`` parameter VALUES can be regenerated without JAX, which pins
+the network trunk of the oracle against the reference's recorded outputs.
+
+Third-party algorithms restated (neither library is in this image):
+  * Threefry-2x32, 20 rounds (Salmon et al., SC'11) -- jax's default PRNG implementation;
+  * jax.random.split / bits / uniform / normal / truncated_normal with ``jax_threefry_partitionable = True`` (the default
+    since JAX 0.5; the reference's CHANGELOG 1.3.0 "Compatibility with the PRNG key changes in JAX v0.5.0") and, for
+    cross-checking, the older counter layout;
+  * haiku's PRNGSequence (one ``split(key, 2)`` per requested key) and the TruncatedNormal / VarianceScaling initialisers.
+Known answers used to check this file are in tests/test_jaxrand.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.special import erf, erfinv
+
+U32 = np.uint32
+_ROT = ((13, 15, 26, 6), (17, 29, 16, 24))
+
+
+def _rotl(x, d):
+    return ((x << U32(d)) | (x >> U32(32 - d))).astype(U32)
+
+
+def threefry2x32(key, c0, c1):
+    """key: 2 uint32; c0, c1: uint32 arrays of equal shape -> two uint32 arrays."""
+    with np.errstate(over='ignore'):
+        k0, k1 = U32(key[0]), U32(key[1])
+        ks = (k0, k1, U32(k0 ^ k1 ^ U32(0x1BD11BDA)))
+        x0 = (np.asarray(c0, dtype=U32) + ks[0]).astype(U32)
+        x1 = (np.asarray(c1, dtype=U32) + ks[1]).astype(U32)
+        for r in range(5):
+            for d in _ROT[r % 2]:
+                x0 = (x0 + x1).astype(U32)
+                x1 = _rotl(x1, d)
+                x1 = (x1 ^ x0).astype(U32)
+            x0 = (x0 + ks[(r + 1) % 3]).astype(U32)
+            x1 = (x1 + ks[(r + 2) % 3] + U32(r + 1)).astype(U32)
+    return x0, x1
+
+
+def prng_key(seed: int):
+    return np.array([(seed >> 32) & 0xFFFFFFFF, seed & 0xFFFFFFFF], dtype=U32)
+
+
+def _iota_2x32(n):
+    i = np.arange(n, dtype=np.uint64)
+    return (i >> np.uint64(32)).astype(U32), (i & np.uint64(0xFFFFFFFF)).astype(U32)
+
+
+def split(key, num=2, partitionable=True):
+    if partitionable:  # key_i = threefry(key, 64-bit counter i as (hi, lo))
+        b1, b2 = threefry2x32(key, *_iota_2x32(num))
+        return np.stack([b1, b2], -1)
+    cnt = np.arange(2 * num, dtype=U32)  # original layout: counters split in two halves
+    o0, o1 = threefry2x32(key, cnt[:num], cnt[num:])
+    return np.concatenate([o0, o1]).reshape(num, 2)
+
+
+def random_bits(key, bit_width, shape, partitionable=True):
+    size = int(np.prod(shape, dtype=np.int64)) if len(shape) else 1
+    if partitionable:
+        b1, b2 = threefry2x32(key, *_iota_2x32(size))
+        if bit_width == 64:
+            out = (b1.astype(np.uint64) << np.uint64(32)) | b2.astype(np.uint64)
+        else:
+            out = (b1 ^ b2).astype(U32)
+        return out.reshape(shape)
+    n32 = size * (bit_width // 32)
+    pad = n32 % 2
+    cnt = np.concatenate([np.arange(n32, dtype=U32), np.zeros(pad, dtype=U32)])  # odd counts are padded with a 0 counter
+    half = (n32 + pad) // 2
+    o0, o1 = threefry2x32(key, cnt[:half], cnt[half:])
+    bits = np.concatenate([o0, o1])[:n32]
+    if bit_width == 64:
+        out = (bits[:size].astype(np.uint64) << np.uint64(32)) | bits[size:].astype(np.uint64)
+    else:
+        out = bits
+    return out.reshape(shape)
+
+
+def uniform(key, shape, dtype=np.float64, minval=0.0, maxval=1.0, partitionable=True):
+    dtype = np.dtype(dtype)
+    if dtype == np.float64:
+        bits = random_bits(key, 64, shape, partitionable)
+        fb = (bits >> np.uint64(64 - 52)) | np.float64(1.0).view(np.uint64)
+        f = fb.view(np.float64) - 1.0
+    else:
+        bits = random_bits(key, 32, shape, partitionable)
+        fb = (bits >> U32(32 - 23)) | np.float32(1.0).view(U32)
+        f = fb.view(np.float32) - np.float32(1.0)
+    minval, maxval = dtype.type(minval), dtype.type(maxval)
+    return np.maximum(minval, (f * (maxval - minval) + minval).astype(dtype))
+
+
+def _erfinv32(x):
+    """XLA's single-precision erf_inv (Giles 2010 polynomial), evaluated in float32."""
+    x = x.astype(np.float32)
+    w = -np.log((np.float32(1) - x) * (np.float32(1) + x)).astype(np.float32)
+    lt = w < np.float32(5)
+    wa = np.where(lt, w - np.float32(2.5), np.sqrt(np.maximum(w, 0)).astype(np.float32) - np.float32(3)).astype(np.float32)
+    ca = [2.81022636e-08, 3.43273939e-07, -3.5233877e-06, -4.39150654e-06, 0.00021858087, -0.00125372503, -0.00417768164,
+          0.246640727, 1.50140941]
+    cb = [-0.000200214257, 0.000100950558, 0.00134934322, -0.00367342844, 0.00573950773, -0.0076224613, 0.00943887047,
+          1.00167406, 2.83297682]
+    p = np.where(lt, np.float32(ca[0]), np.float32(cb[0])).astype(np.float32)
+    for a, b in zip(ca[1:], cb[1:]):
+        p = (np.where(lt, np.float32(a), np.float32(b)) + p * wa).astype(np.float32)
+    return (p * x).astype(np.float32)
+
+
+def _erfinv(u):
+    return _erfinv32(u) if u.dtype == np.float32 else erfinv(u)
+
+
+def normal(key, shape, dtype=np.float64, partitionable=True):
+    dtype = np.dtype(dtype)
+    lo = np.nextafter(dtype.type(-1), dtype.type(0))
+    u = uniform(key, shape, dtype, lo, 1.0, partitionable)
+    return (dtype.type(np.sqrt(2)) * _erfinv(u)).astype(dtype)
+
+
+def truncated_normal(key, lower, upper, shape, dtype=np.float64, partitionable=True):
+    dtype = np.dtype(dtype)
+    s2 = dtype.type(np.sqrt(2))
+    a, b = dtype.type(erf(dtype.type(lower) / s2)), dtype.type(erf(dtype.type(upper) / s2))
+    u = uniform(key, shape, dtype, a, b, partitionable)
+    out = (s2 * _erfinv(u)).astype(dtype)
+    return np.clip(out, np.nextafter(dtype.type(lower), dtype.type(np.inf)), np.nextafter(dtype.type(upper), dtype.type(-np.inf)))
+
+
+class PRNGSequence:
+    """haiku.PRNGSequence: every requested key costs one split(key, 2) of the running key."""
+
+    def __init__(self, key, partitionable=True):
+        self.key, self.partitionable, self.count = np.asarray(key, dtype=U32), partitionable, 0
+
+    def next(self):
+        new = split(self.key, 2, self.partitionable)
+        self.key = new[0]
+        self.count += 1
+        return new[1]
+
+
+def hk_truncated_normal(seq: PRNGSequence, shape, stddev, dtype=np.float64):
+    """hk.initializers.TruncatedNormal(stddev)(shape, dtype)"""
+    return np.dtype(dtype).type(stddev) * truncated_normal(seq.next(), -2.0, 2.0, shape, dtype, seq.partitionable)
+
+
+def hk_variance_scaling_normal(seq: PRNGSequence, shape, scale=1.0, fan='fan_in', dtype=np.float64):
+    """hk.initializers.VarianceScaling(scale, fan, 'normal')(shape, dtype) for 2-d (fan_in, fan_out) weights and 1-d biases
+    (haiku computes the fans of a 1-d shape as fan_in = fan_out = shape[0])."""
+    fan_in, fan_out = (shape[0], shape[0]) if len(shape) == 1 else (shape[-2], shape[-1])
+    n = {'fan_in': fan_in, 'fan_out': fan_out, 'fan_avg': (fan_in + fan_out) / 2}[fan]
+    return np.dtype(dtype).type(np.sqrt(scale / max(1.0, n))) * normal(seq.next(), shape, dtype, seq.partitionable)
+
+
+def haiku_init_conv_gnn_ansatz(spec, seed: int = 0, partitionable: bool = True):
+    """Parameters of the reference's conv-GNN test ansatz exactly as ``hk.transform(...).init(jax.random.PRNGKey(seed), ...)``
+    creates them under ``jax_enable_x64`` (tests/conftest.py:20,121-136 of the reference), in haiku's creation order:
+
+      1. envelope ``pi`` in the constructor of ExponentialEnvelopes (wf/env.py:37-42,75-81): ones + VarianceScaling(1.0) drawn
+         in float32 (hk.get_parameter's default dtype); ``zetas`` = z / (k + 1), no random numbers;
+      2. on the first call (wf/nn_wave_function.py:127-133 -> wf/omni.py:157-178 -> gnn/electron_gnn.py:374-432):
+         nuclear hk.Embed table, electron hk.Embed table (float32, TruncatedNormal(1));
+      3. per layer, per edge type in the yaml's order same, anti, ne: the filter MLP w_t then the node MLP h_t
+         (gnn/update_features.py:196-209), then g_conv_same / anti / ne (electron_gnn.py:243-259);
+      4. Jastrow MLP, Backflow (up) MLP, Backflow_1 (down) MLP (wf/omni.py:168-177); conf_coeff = ones.
+    hkext.MLP(init='default'): w ~ VarianceScaling(1, fan_in, truncated_normal), b = 0 (hkext.py:63-78).  A hk.Linear
+    takes the dtype of its input, so the h MLPs of the FIRST layer (input: float32 embeddings) draw float32 numbers.
+    ``spec``: deepqmc_b200.spec.paulinet_spec(...) ('featurewise' update, hk.Embed embeddings, no deep edge features).
+    Returns {haiku path: float64 array}.
+    """
+    from deepqmc_b200 import params as PN
+
+    assert spec.kind == 'paulinet' and spec.gnn_update == 'featurewise' and spec.gnn_embedding == 'embed' and not spec.gnn_deep_edges
+    seq = PRNGSequence(prng_key(seed), partitionable)
+    K, N, M, d, e = spec.n_determinants, spec.n_elec, spec.n_nuc, spec.embedding_dim, spec.edge_dim
+
+    def vs(shape, dtype):  # VarianceScaling(1.0, 'fan_in', 'truncated_normal')
+        return hk_truncated_normal(seq, shape, np.sqrt(1.0 / max(1.0, shape[0])) / .87962566103423978, dtype).astype(np.float64)
+
+    n_env = len(spec.env_centers)
+    out = {f'{PN.ENV}:pi': 1.0 + vs((K * N, n_env), np.float32), f'{PN.ENV}:zetas': np.asarray(spec.env_zeta_init, dtype=np.float64)}
+    types = PN.EDGE_TYPES if spec.gnn_conv_ne else PN.EDGE_TYPES[:2]
+    if spec.gnn_conv_ne:
+        out[PN.GNN + 'nuclei_embedding/~/embed:embeddings'] = hk_truncated_normal(seq, (M, d), 1.0, np.float32).astype(np.float64)
+    n_types = 1 if spec.n_up == spec.n_down else 2
+    out[PN.GNN + 'electron_embedding/ElectronicEmbedding:embeddings'] = hk_truncated_normal(seq, (n_types, d), 1.0, np.float32).astype(np.float64)
+    nl = spec.gnn_subnet_layers
+    for l in range(spec.n_layers):
+        c, lp = PN.conv_prefix(l), PN.layer_prefix(l)
+        x_dtype = np.float32 if l == 0 else np.float64  # electron embeddings are float64 after the first residual update
+        for t in types:
+            dw = [4] + PN.log_dims(4, e, nl)
+            for i in range(nl):
+                out[c + f'w_{t}/linear_{i}:w'] = vs((dw[i], dw[i + 1]), np.float64)
+            dh = [d] + PN.log_dims(d, e, nl)
+            h_dtype = np.float32 if t == 'ne' else x_dtype  # nuclear embeddings are never updated: float32 in every layer
+            for i in range(nl):
+                out[c + f'h_{t}/linear_{i}:w'] = vs((dh[i], dh[i + 1]), h_dtype)
+                out[c + f'h_{t}/linear_{i}:b'] = np.zeros(dh[i + 1])
+        for t in types:
+            out[lp + f'g_conv_{t}/linear_0:w'] = vs((e, d), np.float64)
+            out[lp + f'g_conv_{t}/linear_0:b'] = np.zeros(d)
+    dj = [d] + PN.log_dims(d, 1, spec.jastrow_layers) if spec.jastrow_layers else []
+    for i in range(len(dj) - 1):
+        out[PN.JASTROW + f'linear_{i}:w'] = vs((dj[i], dj[i + 1]), np.float64)
+        if i < len(dj) - 2:
+            out[PN.JASTROW + f'linear_{i}:b'] = np.zeros(dj[i + 1])
+    for pre, n_spin in ((PN.BF_UP, spec.n_up), (PN.BF_DN, spec.n_down)):
+        db = [d] + PN.backflow_dims(spec, n_spin)
+        base = pre.rsplit('linear_0', 1)[0]
+        for i in range(len(db) - 1):
+            out[base + f'linear_{i}:w'] = vs((db[i], db[i + 1]), np.float64)
+            if spec.backflow_bias:
+                out[base + f'linear_{i}:b'] = np.zeros(db[i + 1])
+    if spec.conf_coeff == 'linear':
+        out[PN.CONF + ':w'] = np.ones((K, 1))
+    return out

@@ -134,6 +134,42 @@ def test_antisymmetry_of_oracle():
     assert s0.item() == -s1.item() and abs(l0.item() - l1.item()) < 1e-10
 
 
+def test_oracle_reproduces_parameter_dependent_reference_goldens(goldens):
+    """The reference's own regression fixtures for its test ansatz (tests/conf/ansatz.yaml on LiH) with the parameters
+    ``hk.transform(...).init(jax.random.PRNGKey(0), phys_conf)`` creates: test_wf/test_psi.npz, test_grad_psi.npz,
+    test_laplace_psi.npz and test_hamil/test_local_energy_Molecular_.npz.  The parameters are regenerated without JAX by
+    oracle/jaxrand.py (Threefry + haiku initialisers in creation order), the walker comes from the edge-builder golden.
+    Agreement is limited to ~3e-7 by the reference itself: it evaluates the first layer's node MLPs in float32 (hk.Embed
+    tables and the hk.Linear layers fed by them are float32 under jax_enable_x64), the oracle uses float64 throughout.
+    The reference's own tolerances for these fixtures are rtol 1e-4 / atol 1e-6 (grad) and rtol 2e-4 (E_loc)."""
+    from deepqmc_b200 import params as PN
+    from deepqmc_b200.spec import paulinet_spec
+    from oracle import jaxrand
+    from oracle.laplacian import laplacian_hessian
+
+    mol = Molecule.from_name('LiH')
+    oh = OracleHamiltonian(mol)
+    spec = paulinet_spec(oh)
+    p = jaxrand.haiku_init_conv_gnn_ansatz(spec, seed=0)
+    assert {k: list(v.shape) for k, v in p.items()} == goldens['test_ansatz_param_shapes']
+    r = torch.as_tensor(np.asarray(goldens['edge_builder_LiH']['ne'])[0])  # edges are r - R and R_Li = 0
+    R = torch.as_tensor(mol.coords)
+    pt = {k: torch.as_tensor(v).requires_grad_(True) for k, v in p.items()}
+    sign, log = owf.log_psi(spec, pt, r, R)
+    assert sign.item() == goldens['wf_psi']['sign'] and abs(log.item() - goldens['wf_psi']['log']) < 1e-6
+    log.backward()
+    for k, ref in goldens['wf_grad_psi'].items():
+        ref = np.asarray(ref, dtype=np.float64)
+        assert np.allclose(pt[k].grad.numpy(), ref, rtol=1e-5, atol=1e-6 * max(1.0, np.abs(ref).max())), k
+    p64 = owf.to_torch(p)
+    f = lambda x: owf.log_psi(spec, p64, x, R)
+    lap, grad = laplacian_hessian(lambda x: f(x.reshape(-1, 3))[1], r.reshape(-1))
+    assert abs(lap.item() - goldens['wf_laplace']['lap_log_psis']) < 1e-6 * abs(lap.item())
+    assert np.allclose(grad.numpy(), np.asarray(goldens['wf_laplace']['quantum_force']), rtol=1e-5, atol=1e-6)
+    e_loc, _ = oh.local_energy(f, r, R)
+    assert abs(e_loc.item() - goldens['local_energy_Molecular']['E_loc']) < 2e-6
+
+
 def test_additive_backflow_oracle_antisymmetry_and_mult_limit():
     """BackflowOp with an additive branch (nn_wave_function.py:14-33): still antisymmetric; with a zero additive head
     'both' reduces to 'mult'; the cutoff polynomial is C^2 at R = 1 (value 1, zero slope / curvature)."""

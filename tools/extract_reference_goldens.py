@@ -2,10 +2,10 @@
 
 Run in the build container (reads /root/reference/tests/**/*.npz, which do not travel to the
 GPU box):   python tools/extract_reference_goldens.py
-Only numbers are extracted (regression *data*), no reference source.  See SURVEY.md 8(c) for
-why the parameter-dependent goldens (psi, Laplacian, E_loc of the Haiku-initialised test
-ansatz) cannot be re-derived without JAX: they are stored here only to pin the E_loc assembly
-identity  E_kin + V_loc + V_el + E_nuc == E_loc.
+Only numbers are extracted (regression *data*), no reference source.  The parameter-dependent
+goldens (psi, its parameter gradient, Laplacian, E_loc of the Haiku-initialised test ansatz) are
+reproduced in tests/test_oracle_goldens.py by regenerating the Haiku / jax.random initialisation
+in numpy (oracle/jaxrand.py); the walker is recovered from the edge-builder golden.
 """
 import json
 import os
@@ -39,6 +39,8 @@ def main():
         # parameters and are not reproducible here)
         'test_ansatz_param_shapes': {k: list(np.load(os.path.join(REF, 'test_wf/test_grad_psi.npz'))[k].shape)
                                      for k in np.load(os.path.join(REF, 'test_wf/test_grad_psi.npz')).files},
+        # d log|psi| / d params of the test ansatz with its Haiku-initialised parameters (tests/test_wf.py test_grad_psi)
+        'wf_grad_psi': npz('test_wf/test_grad_psi.npz'),
         'wf_psi': npz('test_wf/test_psi.npz'),
         'wf_laplace': npz('test_wf/test_laplace_psi.npz'),
         'local_energy_Molecular': npz('test_hamil/test_local_energy_Molecular_.npz'),
