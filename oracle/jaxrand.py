@@ -157,7 +157,7 @@ def hk_variance_scaling_normal(seq: PRNGSequence, shape, scale=1.0, fan='fan_in'
     return np.dtype(dtype).type(np.sqrt(scale / max(1.0, n))) * normal(seq.next(), shape, dtype, seq.partitionable)
 
 
-def haiku_init_conv_gnn_ansatz(spec, seed: int = 0, partitionable: bool = True):
+def haiku_init_conv_gnn_ansatz(spec, seed: int = 0, partitionable: bool = True, gnn_only: bool = False, g_layers: int = 1):
     """Parameters of the reference's conv-GNN test ansatz exactly as ``hk.transform(...).init(jax.random.PRNGKey(seed), ...)``
     creates them under ``jax_enable_x64`` (tests/conftest.py:20,121-136 of the reference), in haiku's creation order:
 
@@ -171,6 +171,8 @@ def haiku_init_conv_gnn_ansatz(spec, seed: int = 0, partitionable: bool = True):
     hkext.MLP(init='default'): w ~ VarianceScaling(1, fan_in, truncated_normal), b = 0 (hkext.py:63-78).  A hk.Linear
     takes the dtype of its input, so the h MLPs of the FIRST layer (input: float32 embeddings) draw float32 numbers.
     ``spec``: deepqmc_b200.spec.paulinet_spec(...) ('featurewise' update, hk.Embed embeddings, no deep edge features).
+    ``gnn_only`` / ``g_layers``: the bare ElectronGNN of tests/conf/gnn.yaml (tests/test_gnn.py TestGNN.test_embedding):
+    steps 2 and 3 only, g_t MLPs with ['log', g_layers] layers.
     Returns {haiku path: float64 array}.
     """
     from deepqmc_b200 import params as PN
@@ -182,8 +184,11 @@ def haiku_init_conv_gnn_ansatz(spec, seed: int = 0, partitionable: bool = True):
     def vs(shape, dtype):  # VarianceScaling(1.0, 'fan_in', 'truncated_normal')
         return hk_truncated_normal(seq, shape, np.sqrt(1.0 / max(1.0, shape[0])) / .87962566103423978, dtype).astype(np.float64)
 
-    n_env = len(spec.env_centers)
-    out = {f'{PN.ENV}:pi': 1.0 + vs((K * N, n_env), np.float32), f'{PN.ENV}:zetas': np.asarray(spec.env_zeta_init, dtype=np.float64)}
+    out = {}
+    if not gnn_only:
+        n_env = len(spec.env_centers)
+        out[f'{PN.ENV}:pi'] = 1.0 + vs((K * N, n_env), np.float32)
+        out[f'{PN.ENV}:zetas'] = np.asarray(spec.env_zeta_init, dtype=np.float64)
     types = PN.EDGE_TYPES if spec.gnn_conv_ne else PN.EDGE_TYPES[:2]
     if spec.gnn_conv_ne:
         out[PN.GNN + 'nuclei_embedding/~/embed:embeddings'] = hk_truncated_normal(seq, (M, d), 1.0, np.float32).astype(np.float64)
@@ -203,8 +208,12 @@ def haiku_init_conv_gnn_ansatz(spec, seed: int = 0, partitionable: bool = True):
                 out[c + f'h_{t}/linear_{i}:w'] = vs((dh[i], dh[i + 1]), h_dtype)
                 out[c + f'h_{t}/linear_{i}:b'] = np.zeros(dh[i + 1])
         for t in types:
-            out[lp + f'g_conv_{t}/linear_0:w'] = vs((e, d), np.float64)
-            out[lp + f'g_conv_{t}/linear_0:b'] = np.zeros(d)
+            dg = [e] + PN.log_dims(e, d, g_layers)
+            for i in range(g_layers):
+                out[lp + f'g_conv_{t}/linear_{i}:w'] = vs((dg[i], dg[i + 1]), np.float64)
+                out[lp + f'g_conv_{t}/linear_{i}:b'] = np.zeros(dg[i + 1])
+    if gnn_only:
+        return out
     dj = [d] + PN.log_dims(d, 1, spec.jastrow_layers) if spec.jastrow_layers else []
     for i in range(len(dj) - 1):
         out[PN.JASTROW + f'linear_{i}:w'] = vs((dj[i], dj[i + 1]), np.float64)
@@ -219,4 +228,102 @@ def haiku_init_conv_gnn_ansatz(spec, seed: int = 0, partitionable: bool = True):
                 out[base + f'linear_{i}:b'] = np.zeros(db[i + 1])
     if spec.conf_coeff == 'linear':
         out[PN.CONF + ':w'] = np.ones((K, 1))
+    return out
+
+
+# ---- electron initialiser of the reference (sampling/electron_sample_initializers.py) with jax.random streams ----------
+def exponential(key, shape, partitionable=True):
+    return -np.log1p(-uniform(key, shape, np.float64, 0.0, 1.0, partitionable))
+
+
+def gumbel(key, shape, partitionable=True):
+    u = uniform(key, shape, np.float64, np.finfo(np.float64).tiny, 1.0, partitionable)
+    return -np.log(-np.log(u))
+
+
+def categorical(key, logits, partitionable=True):
+    logits = np.asarray(logits, dtype=np.float64)
+    return int(np.argmax(gumbel(key, logits.shape, partitionable) + logits))
+
+
+def orthogonal3(key, partitionable=True):
+    """jax.random.orthogonal(key, 3): QR of a Gaussian matrix, columns signed so that diag(R) > 0 (Haar measure)."""
+    z = normal(key, (3, 3), np.float64, partitionable)
+    q, r = np.linalg.qr(z)
+    d = np.diagonal(r)
+    return q * (d / np.abs(d))[None, :]
+
+
+def _shell_positions(key, charges, counts, partitionable=True):
+    """ShellBasedDistribution.__call__ (:198-251): |r| ~ Exp / (2 zeta), zeta = Z x {1, 1/2, 1/3, 1/4} by shell."""
+    total = len(charges)
+    marks = np.zeros(total + 1)
+    cs = np.cumsum(counts)
+    for c_, n_ in zip(cs, counts):
+        if c_ < total:
+            marks[c_] = n_
+    spin_idx = np.arange(total) - np.cumsum(marks[:total])
+    factor = np.where(spin_idx < 1, 1.0, np.where(spin_idx < 5, 0.5, np.where(spin_idx < 9, 1 / 3, 0.25)))
+    zetas = np.asarray(charges, dtype=np.float64) * factor
+    pos = np.zeros((total, 3))
+    for i, (k, z) in enumerate(zip(split(key, total, partitionable), zetas)):
+        k_r, k_dir = split(k, 2, partitionable)
+        pos[i] = exponential(k_r, (), partitionable) / (2 * z) * orthogonal3(k_dir, partitionable)[:, 0]
+    return pos
+
+
+def atom_centered_initializer(key, charges, ns_valence, R, n_up, n_down, partitionable=True):
+    """AtomCenteredElectronInitializer(ShellBasedDistribution())(rng, ...) (:254-288) -> r[n_up + n_down, 3]."""
+    charges, ns_valence, R = (np.asarray(a, dtype=np.float64) for a in (charges, ns_valence, R))
+    M = len(charges)
+    k_assign, k_spin, k_up, k_dn = split(key, 4, partitionable)
+    # assign_electrons_to_nuclei (:43-81)
+    charge = ns_valence.sum() - n_up - n_down
+    valence = ns_valence - charge / M
+    el = np.floor(valence).astype(int)
+    rng = k_assign
+    while ns_valence.sum() - charge - el.sum() > 0:
+        rng, k_cat = split(rng, 2, partitionable)
+        el[categorical(k_cat, valence - el, partitionable)] += 1
+    # assign_spins_to_nuclei (:84-155)
+    up, down = np.zeros(M, dtype=int), np.zeros(M, dtype=int)
+    for i in range(int(el.max())):
+        mask = el >= 2 * (i + 1)
+        inc = np.where(mask & (mask.sum() + down.sum() <= n_down), 1, 0)
+        up, down = up + inc, down + inc
+    dists = np.linalg.norm(R[:, None] - R[None], axis=-1)
+    np.fill_diagonal(dists, np.inf)
+    nn = np.argsort(dists, axis=-1, kind='stable')
+    rem = el - up - down
+    center = categorical(k_spin, np.where(rem == rem.max(), 0.0, -np.inf), partitionable)
+    i = 0
+    while (up + down < el).any():
+        is_down = (i % 2) & int(down.sum() < n_down)
+        up[center] += 1 - is_down
+        down[center] += is_down
+        ordering = nn[center]
+        has_rem = (el - up - down)[ordering] > 0
+        center = ordering[int(np.argmax(has_rem))]
+        i += 1
+    idx = lambda counts, total: (np.cumsum(counts)[:, None] <= np.arange(total)).sum(0)
+    up_idx, dn_idx = idx(up, n_up), idx(down, n_down)
+    r_up = R[up_idx] + _shell_positions(k_up, charges[up_idx], up, partitionable)
+    r_dn = R[dn_idx] + _shell_positions(k_dn, charges[dn_idx], down, partitionable)
+    return np.concatenate([r_up, r_dn])
+
+
+def fold_in(key, data: int):
+    """jax.random.fold_in(key, data) for 32-bit data: threefry(key, (0, data))."""
+    o0, o1 = threefry2x32(key, np.array([0], dtype=U32), np.array([data & 0xFFFFFFFF], dtype=U32))
+    return np.array([o0[0], o1[0]], dtype=U32)
+
+
+def ecp_quadrature_twists(key, n_nl_nuclei: int, n_elec: int, partitionable=True):
+    """phi_random[j, i] of the reference's non-local ECP quadrature: uniform(fold_in(fold_in(rng, j), i), (), 0, pi / 5)
+    (ecp/gaussian_type_ecp.py:224, ecp/ecp_utils.py:52)."""
+    out = np.zeros((n_nl_nuclei, n_elec))
+    for j in range(n_nl_nuclei):
+        kj = fold_in(key, j)
+        for i in range(n_elec):
+            out[j, i] = uniform(fold_in(kj, i), (), np.float64, 0.0, np.pi / 5, partitionable)
     return out

@@ -235,8 +235,9 @@ def paulinet_embeddings(spec, params, r, R):
             convs.append((t, prod.sum(0)))  # [N, e]
         if spec.gnn_update == 'featurewise':
             upd = 0
-            for t, cv in convs:
-                upd = upd + torch.tanh(cv @ _t(params, lp + f'g_conv_{t}/linear_0:w') + _t(params, lp + f'g_conv_{t}/linear_0:b'))
+            for t, cv in convs:  # g_t: hkext.MLP, last_linear = false (one layer in tests/conf/ansatz.yaml, three in gnn.yaml)
+                n_g = sum(1 for i in range(8) if (lp + f'g_conv_{t}/linear_{i}:w') in params)
+                upd = upd + mlp(lp + f'g_conv_{t}/', cv, n_g)
         else:
             f = torch.cat([x, x[:n_up].mean(0, keepdim=True).expand(N, -1), x[n_up:].mean(0, keepdim=True).expand(N, -1)]
                           + [cv for _, cv in convs], -1)

@@ -1,0 +1,126 @@
+"""The reference's parameter- and random-stream-dependent regression fixtures, reproduced WITHOUT JAX (CPU): oracle +
+oracle/jaxrand.py (numpy restatement of jax.random / haiku initialisation).  Everything here is checked against numbers
+the reference recorded itself (tests/golden/reference_goldens.json, extracted by tools/extract_reference_goldens.py):
+the electron initialiser, the carbon ccECP potentials (which validates the restated ccECP table), and the Metropolis /
+Decorr / Langevin samplers.  The wave-function fixtures (psi, gradient, Laplacian, E_loc) are in test_oracle_goldens.py.
+Agreement beyond ~1e-6 is not expected where the wave function enters: the reference evaluates part of its first GNN
+layer in float32."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from deepqmc_b200.molecule import Molecule
+from deepqmc_b200.spec import paulinet_spec
+from oracle import jaxrand as J
+from oracle import wf
+from oracle.hamil import OracleHamiltonian
+from oracle.sampling import clean_force, langevin_step, metropolis_step
+
+
+@pytest.fixture(scope='module')
+def g():
+    return json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_goldens.json')))
+
+
+@pytest.fixture(scope='module')
+def lih():
+    mol = Molecule.from_name('LiH')
+    oh = OracleHamiltonian(mol)
+    spec = paulinet_spec(oh)
+    pt = wf.to_torch(J.haiku_init_conv_gnn_ansatz(spec, seed=0))
+    R = torch.as_tensor(mol.coords)
+    r0 = np.stack([J.atom_centered_initializer(k, mol.charges, mol.charges, mol.coords, 2, 2) for k in J.split(J.prng_key(0), 10)])
+    return mol, spec, pt, R, r0
+
+
+def test_electron_initializer_reproduces_reference_walkers(g):
+    """AtomCenteredElectronInitializer(ShellBasedDistribution()) (sampling/electron_sample_initializers.py:43-288) driven by
+    the jax.random streams: split, categorical tie-break, exponential radii, Haar-orthogonal directions."""
+    mol = Molecule.from_name('LiH')
+    r = J.atom_centered_initializer(J.prng_key(0), mol.charges, mol.charges, mol.coords, 2, 2)
+    assert np.abs(r - np.asarray(g['edge_builder_LiH']['ne'])[0]).max() < 1e-14  # the walker of every n = 1 fixture
+    rs = np.stack([J.atom_centered_initializer(k, mol.charges, mol.charges, mol.coords, 2, 2) for k in J.split(J.prng_key(0), 5)])
+    assert np.abs(rs - np.asarray(g['init_sample_Molecular']['rs'])).max() < 1e-14
+
+
+def test_carbon_ccecp_potentials_match_reference_fixture(g):
+    """tests/test_potential.py for C: the ccECP table restated in oracle/hamil.py (the reference reads it from pyscf)
+    reproduces the recorded local potential, and -- with the Haiku-initialised ansatz and the fold_in-derived quadrature
+    twists -- the non-local potential (the reference notes that term is 'not particularly numerically stable')."""
+    mol = Molecule.from_name('C')
+    oh0 = OracleHamiltonian(mol)
+    r = J.atom_centered_initializer(J.prng_key(0), mol.charges, oh0.ns_valence, mol.coords, oh0.n_up, oh0.n_down)
+    v = oh0.local_potential(torch.as_tensor(r), torch.as_tensor(mol.coords))
+    assert abs(v.item() - g['potential_C_None']['local_potential']) < 1e-9 * abs(v.item())
+    oh = OracleHamiltonian(mol, ecp_type='ccECP')
+    assert (oh.n_up, oh.n_down) == (3, 1)
+    r = torch.as_tensor(J.atom_centered_initializer(J.prng_key(0), mol.charges, oh.ns_valence, mol.coords, oh.n_up, oh.n_down))
+    R = torch.as_tensor(mol.coords)
+    assert abs(oh.local_potential(r, R).item() - g['potential_C_ccECP']['local_potential']) < 1e-9 * 99.0
+    spec = paulinet_spec(oh)
+    pt = wf.to_torch(J.haiku_init_conv_gnn_ansatz(spec, seed=0))
+    twists = torch.as_tensor(J.ecp_quadrature_twists(J.prng_key(0), 1, spec.n_elec))
+    vnl = oh.nonloc_potential(r, R, lambda x: wf.log_psi(spec, pt, x, R), twists)
+    assert abs(vnl.item() / g['potential_C_ccECP']['nonlocal_potential'] - 1) < 1e-5
+
+
+def _wf_batch(spec, pt, R):
+    return lambda rr: tuple(torch.stack(x) for x in zip(*[wf.log_psi(spec, pt, rr[b], R) for b in range(len(rr))]))
+
+
+@pytest.mark.parametrize('kind', ['Metropolis', 'DecorrMetropolis'])
+def test_metropolis_sampler_reproduces_reference_fixture(g, lih, kind):
+    """tests/test_sampling.py TestSampling: init(PRNGKey(0)) then sample(PRNGKey(step)) for step < 4; Decorr: 20 sub-steps per
+    sample from split(rng, 20), max_age 20.  Proposal / acceptance noise = the reference's jax.random streams."""
+    mol, spec, pt, R, r0 = lih
+    wfb = _wf_batch(spec, pt, R)
+    s0, l0 = wfb(torch.as_tensor(r0))
+    gi = g['sampling']['init_Metropolis']
+    assert np.abs(r0 - np.asarray(gi['r'])).max() < 1e-14 and np.abs(l0.numpy() - np.asarray(gi['psi:log'])).max() < 2e-5
+    st = dict(r=torch.as_tensor(r0), sign=s0, log=l0, age=torch.zeros(10, dtype=torch.int32), tau=torch.tensor(0.1, dtype=torch.float64))
+    decorr = kind == 'DecorrMetropolis'
+    for step in range(4):
+        key = J.prng_key(step)
+        for k in (J.split(key, 20) if decorr else [key]):
+            kp, ka = J.split(k, 2)
+            st, acc = metropolis_step(wfb, st, torch.as_tensor(J.normal(kp, (10, 4, 3))), torch.as_tensor(J.uniform(ka, (10,))),
+                                      0.57, 20 if decorr else None)
+    gs = g['sampling'][f'sample_{kind}']
+    assert np.abs(st['r'].numpy() - np.asarray(gs['smpl_state:r'])).max() < 1e-12  # the same accept / reject history
+    assert st['age'].tolist() == gs['smpl_state:age'] and abs(st['tau'].item() - gs['smpl_state:tau']) < 1e-12
+    assert np.abs(st['log'].numpy() - np.asarray(gs['smpl_state:psi:log'])).max() < 2e-5
+    assert acc.item() == gs['stats:sampling/acceptance']
+    assert abs(st['log'].mean().item() - gs['stats:sampling/log_psi/mean']) < 2e-5
+    assert abs(st['log'].std(unbiased=False).item() - gs['stats:sampling/log_psi/std']) < 2e-5
+    i, j = torch.triu_indices(4, 4, 1)
+    dm = torch.sqrt(torch.finfo(torch.float64).eps + ((st['r'][:, i] - st['r'][:, j]) ** 2).sum(-1)).mean().item()
+    assert abs(dm - gs['stats:sampling/dists/mean']) < 1e-9
+
+
+def test_langevin_sampler_reproduces_reference_fixture(g, lih):
+    mol, spec, pt, R, r0 = lih
+
+    def wfg(rr):
+        out = []
+        for b in range(len(rr)):
+            x = rr[b].clone().requires_grad_(True)
+            s, l = wf.log_psi(spec, pt, x, R)
+            out.append((s.detach(), l.detach(), torch.autograd.grad(l, x)[0]))
+        return tuple(torch.stack(x) for x in zip(*out))
+
+    tau0 = torch.tensor(0.1, dtype=torch.float64)
+    r = torch.as_tensor(r0)
+    s, l, gr = wfg(r)
+    st = dict(r=r, sign=s, log=l, force=clean_force(gr, r, R, mol.charges, tau0), age=torch.zeros(10, dtype=torch.int32), tau=tau0)
+    assert np.abs(st['force'].numpy() - np.asarray(g['sampling']['init_Langevin']['force'])).max() < 5e-5
+    for step in range(4):
+        kp, ka = J.split(J.prng_key(step), 2)
+        st, acc = langevin_step(wfg, R, mol.charges, st, torch.as_tensor(J.normal(kp, (10, 4, 3))), torch.as_tensor(J.uniform(ka, (10,))), 0.57, None)
+    gs = g['sampling']['sample_Langevin']
+    assert np.abs(st['r'].numpy() - np.asarray(gs['smpl_state:r'])).max() < 5e-6  # the float32-tainted force moves the walkers
+    assert np.abs(st['force'].numpy() - np.asarray(gs['smpl_state:force'])).max() < 5e-5
+    assert st['age'].tolist() == gs['smpl_state:age'] and abs(st['tau'].item() - gs['smpl_state:tau']) < 1e-12
+    assert acc.item() == gs['stats:sampling/acceptance']

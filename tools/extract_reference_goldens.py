@@ -42,6 +42,13 @@ def main():
         # d log|psi| / d params of the test ansatz with its Haiku-initialised parameters (tests/test_wf.py test_grad_psi)
         'wf_grad_psi': npz('test_wf/test_grad_psi.npz'),
         'wf_psi': npz('test_wf/test_psi.npz'),
+        # walkers drawn by AtomCenteredElectronInitializer(ShellBasedDistribution()) from split(PRNGKey(0), 5)
+        'init_sample_Molecular': npz('test_hamil/test_init_sample_Molecular_.npz'),
+        # carbon atom: plain Coulomb and ccECP potentials on the PRNGKey(0) walker (tests/test_potential.py)
+        'potential_C_ccECP': npz('test_potential/test_pseudo_potentials_C_ccECP_.npz'),
+        # sampler fixtures (tests/test_sampling.py): state after init(PRNGKey(0)) and after sample(PRNGKey(step)), step < 4
+        'sampling': {k: npz(f'test_sampling/test_sampler_{k}_.npz') for k in
+                     ('init_Metropolis', 'init_Langevin', 'sample_Metropolis', 'sample_DecorrMetropolis', 'sample_Langevin')},
         'wf_laplace': npz('test_wf/test_laplace_psi.npz'),
         'local_energy_Molecular': npz('test_hamil/test_local_energy_Molecular_.npz'),
         # reference tests/test_physics.py:7-17 and tests/test_geom.py:8-18 (inline known answers)
