@@ -18,7 +18,7 @@ from .types import PhysicalConfiguration
 STAT_KEYS = ('hamil/V_el', 'hamil/E_kin', 'hamil/V_loc', 'hamil/V_nl', 'hamil/lap', 'hamil/quantum_force')
 
 # Gaussian-type ECP tables (the reference reads them from pyscf: gaussian_type_ecp.py:57).
-# ccECP carbon, Bennett et al. JCP 147, 224106 (2017); see DESIGN.md ("parity unpinned" table).
+# ccECP carbon, Bennett et al. JCP 147, 224106 (2017); reproduces the reference's recorded C / ccECP potentials.
 ECP_TABLES = {
     ('ccECP', 6): dict(
         n_core=2,

@@ -27,8 +27,9 @@ def get_shell(z):
 
 # Gaussian-type ECP tables.  The reference loads them from pyscf (absent here):
 # pyscf.gto.basis.load_ecp('ccECP', 'C').  Values restated from the published ccECP
-# (Bennett et al., J. Chem. Phys. 147, 224106 (2017)); UNVERIFIED against pyscf in this
-# container ("parity unpinned" for the table itself, the algebra is checked independently).
+# (Bennett et al., J. Chem. Phys. 147, 224106 (2017)); verified against the reference's own fixture
+# tests/test_potential/test_pseudo_potentials_C_ccECP_.npz (local potential to 1e-9 relative, non-local term to
+# 4e-7: tests/test_reference_fixtures.py::test_carbon_ccecp_potentials_match_reference_fixture).
 # layout: n_core, loc[n in (r^-1, r^0, r^1)] = list of (alpha, beta), nl[l] = list of (alpha, beta)
 ECP_TABLES = {
     ('ccECP', 6): dict(

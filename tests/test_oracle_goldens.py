@@ -170,6 +170,22 @@ def test_oracle_reproduces_parameter_dependent_reference_goldens(goldens):
     assert abs(e_loc.item() - goldens['local_energy_Molecular']['E_loc']) < 2e-6
 
 
+def test_oracle_gnn_reproduces_reference_embedding_fixture(goldens):
+    """tests/test_gnn.py TestGNN.test_embedding: the bare ElectronGNN of tests/conf/gnn.yaml (4 interactions, three-layer
+    'log' MLPs for w / h / g) with its Haiku-initialised parameters -- pins the multi-layer message passing of the oracle
+    (layers 2-4 run on float64 embeddings in the reference as well)."""
+    from deepqmc_b200.spec import paulinet_spec
+    from oracle import jaxrand
+
+    mol = Molecule.from_name('LiH')
+    spec = paulinet_spec(OracleHamiltonian(mol), n_layers=4, gnn_subnet_layers=3)
+    p = jaxrand.haiku_init_conv_gnn_ansatz(spec, seed=0, gnn_only=True, g_layers=3)
+    r = torch.as_tensor(np.asarray(goldens['edge_builder_LiH']['ne'])[0])
+    x = owf.paulinet_embeddings(spec, owf.to_torch(p), r, torch.as_tensor(mol.coords))
+    ref = np.asarray(goldens['gnn_embedding']['embedding'])
+    assert x.shape == ref.shape == (4, 8) and np.abs(x.numpy() - ref).max() < 2e-6  # reference tolerance: rtol 1e-4
+
+
 def test_additive_backflow_oracle_antisymmetry_and_mult_limit():
     """BackflowOp with an additive branch (nn_wave_function.py:14-33): still antisymmetric; with a zero additive head
     'both' reduces to 'mult'; the cutoff polynomial is C^2 at R = 1 (value 1, zero slope / curvature)."""

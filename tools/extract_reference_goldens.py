@@ -42,6 +42,8 @@ def main():
         # d log|psi| / d params of the test ansatz with its Haiku-initialised parameters (tests/test_wf.py test_grad_psi)
         'wf_grad_psi': npz('test_wf/test_grad_psi.npz'),
         'wf_psi': npz('test_wf/test_psi.npz'),
+        # electron embeddings of the bare 4-interaction ElectronGNN of tests/conf/gnn.yaml (tests/test_gnn.py TestGNN)
+        'gnn_embedding': npz('test_gnn/test_embedding.npz'),
         # walkers drawn by AtomCenteredElectronInitializer(ShellBasedDistribution()) from split(PRNGKey(0), 5)
         'init_sample_Molecular': npz('test_hamil/test_init_sample_Molecular_.npz'),
         # carbon atom: plain Coulomb and ccECP potentials on the PRNGKey(0) walker (tests/test_potential.py)
