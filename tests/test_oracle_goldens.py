@@ -11,12 +11,12 @@ from oracle.hamil import OracleHamiltonian, pairwise_self_distance
 from oracle.laplacian import laplacian_hessian, laplacian_jvp_loop
 
 
-@pytest.mark.parametrize('name', ['LiH', 'C', 'H2O'])
+@pytest.mark.parametrize('name', ['LiH', 'C', 'H2O', 'NH3', 'H10', 'ScO', 'bicyclobutane'])
 def test_molecule_geometry(goldens, name):
     # reference: tests/test_molecule.py (from_name) -- angstrom -> bohr conversion
     g = goldens['molecule'][name]
     mol = Molecule.from_name(name)
-    np.testing.assert_allclose(mol.coords, np.asarray(g['coords']).reshape(-1, 3), rtol=0, atol=1e-8)
+    np.testing.assert_allclose(mol.coords, np.asarray(g['coords']).reshape(-1, 3), rtol=0, atol=2e-8)
     np.testing.assert_allclose(mol.charges, g['charges'])
     assert mol.charge == g['charge'] and mol.spin == g['spin']
 

@@ -24,7 +24,7 @@ def npz(path):
 def main():
     g = {
         'source': 'deepqmc/deepqmc v1.3.0 tests/*.npz (ndarrays_regression fixtures)',
-        'molecule': {n: npz(f'test_molecule/test_from_name_{n}_.npz') for n in ('LiH', 'C', 'H2O')},
+        'molecule': {n: npz(f'test_molecule/test_from_name_{n}_.npz') for n in ('LiH', 'C', 'H2O', 'NH3', 'H10', 'ScO', 'bicyclobutane')},
         'hamil_init': {
             'Molecular': npz('test_hamil/test_init_Molecular_.npz'),
             'Molecular_PP': npz('test_hamil/test_init_Molecular_PP_.npz'),
