@@ -360,7 +360,9 @@ class MultiNuclearGeometrySampler:
             elec_state = self.elec_sampler.sample(int(rng) * 7919 + i, elec_state, params, Rd)[0]
         return nuc_state, elec_state, stats
 
-    def sample(self, rng, smpl_state, params, mol_idxs):
+    def sample(self, rng, smpl_state, params, mol_idxs, *, noise_normal=None, noise_uniform=None):
+        """``noise_normal`` / ``noise_uniform``: optional per-sampled-molecule lists of injected random numbers handed to the
+        electron sampler (parity tests replay the reference's streams)."""
         mol_idxs = [int(m) for m in np.asarray(mol_idxs).reshape(-1)]
         counter = smpl_state['update_nuc_counter']
         rs, Rs, stats = [], [], []
@@ -373,7 +375,8 @@ class MultiNuclearGeometrySampler:
                 else:
                     counter[m] += 1
             Rd = self._R_dev(smpl_state['elec'][m], smpl_state['nuc'][m]['R'])
-            smpl_state['elec'][m], pc, st = self.elec_sampler.sample(int(rng) * len(mol_idxs) + k, smpl_state['elec'][m], params, Rd)
+            kw = {} if noise_normal is None else {'noise_normal': noise_normal[k], 'noise_uniform': noise_uniform[k]}
+            smpl_state['elec'][m], pc, st = self.elec_sampler.sample(int(rng) * len(mol_idxs) + k, smpl_state['elec'][m], params, Rd, **kw)
             r = pc.r if pc.r.dim() == 4 else pc.r[None]  # [n_state, B, N, 3]
             rs.append(r)
             Rs.append(Rd[None, None].expand(*r.shape[:2], *Rd.shape))

@@ -124,3 +124,26 @@ def test_langevin_sampler_reproduces_reference_fixture(g, lih):
     assert np.abs(st['force'].numpy() - np.asarray(gs['smpl_state:force'])).max() < 5e-5
     assert st['age'].tolist() == gs['smpl_state:age'] and abs(st['tau'].item() - gs['smpl_state:tau']) < 1e-12
     assert acc.item() == gs['stats:sampling/acceptance']
+
+
+def test_multi_nuclear_geometry_sampler_reproduces_reference_fixture(g, lih):
+    """TestMultimoleculeSampling: two copies of LiH; init keys = split(PRNGKey(0), 2), every molecule's walkers from
+    split(key_m, 10); sample keys = split(PRNGKey(step), (2, 2)) -- electron keys first, nuclear keys second
+    (sampling/combined_samplers.py:128-141,173-199)."""
+    mol, spec, pt, R, _ = lih
+    wfb = _wf_batch(spec, pt, R)
+    states = []
+    for m, km in enumerate(J.split(J.prng_key(0), 2)):
+        r0 = np.stack([J.atom_centered_initializer(k, mol.charges, mol.charges, mol.coords, 2, 2) for k in J.split(km, 10)])
+        assert np.abs(r0 - np.asarray(g['sampling_multi']['init']['elec:r'])[m]).max() < 1e-14
+        s, l = wfb(torch.as_tensor(r0))
+        states.append(dict(r=torch.as_tensor(r0), sign=s, log=l, age=torch.zeros(10, dtype=torch.int32), tau=torch.tensor(0.1, dtype=torch.float64)))
+    for step in range(4):
+        ks = J.split(J.prng_key(step), 4)
+        for m in range(2):
+            kp, ka = J.split(ks[m], 2)
+            states[m], _ = metropolis_step(wfb, states[m], torch.as_tensor(J.normal(kp, (10, 4, 3))), torch.as_tensor(J.uniform(ka, (10,))), 0.57, None)
+    gs = g['sampling_multi']['sample']
+    for m in range(2):
+        assert np.abs(states[m]['r'].numpy() - np.asarray(gs['smpl_state:elec:r'])[m]).max() < 1e-12
+        assert states[m]['age'].tolist() == gs['smpl_state:elec:age'][m] and abs(states[m]['tau'].item() - gs['smpl_state:elec:tau'][m]) < 1e-12

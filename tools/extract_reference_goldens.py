@@ -51,6 +51,8 @@ def main():
         # sampler fixtures (tests/test_sampling.py): state after init(PRNGKey(0)) and after sample(PRNGKey(step)), step < 4
         'sampling': {k: npz(f'test_sampling/test_sampler_{k}_.npz') for k in
                      ('init_Metropolis', 'init_Langevin', 'sample_Metropolis', 'sample_DecorrMetropolis', 'sample_Langevin')},
+        # MultiNuclearGeometrySampler over two copies of LiH (tests/test_sampling.py TestMultimoleculeSampling)
+        'sampling_multi': {k: npz(f'test_sampling/test_multi_nuclear_geometry_sampler_{k}_Metropolis_.npz') for k in ('init', 'sample')},
         'wf_laplace': npz('test_wf/test_laplace_psi.npz'),
         'local_energy_Molecular': npz('test_hamil/test_local_energy_Molecular_.npz'),
         # reference tests/test_physics.py:7-17 and tests/test_geom.py:8-18 (inline known answers)
