@@ -1,6 +1,8 @@
 // Host side of libdqmc_b200.so: engine object, parameter table, workspace planning, kernel
 // sequencing, C ABI (include/dqmc_b200.h).  Built by nvcc for sm_100a; with -DDQMC_EMU the same
 // file builds against tools/cuda_emu for CPU-side logic checks during development (never shipped).
+#include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -455,8 +457,8 @@ struct Engine : EngineBase {
     if (n != total) { err = "parameter count mismatch"; return 2; }
     DQ_CHECK(cudaMemcpyAsync(d_stage, host, sizeof(double) * n, cudaMemcpyHostToDevice, st));
     DQ_LAUNCH(convert_kernel<T>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, (const double*)d_stage, d_params, n);
-    for (auto& e : entries)
-      if (e.rows > 1 && e.cols > 1)
+    for (auto& e : entries)  // (vectors included: a [n][1] weight such as the Jastrow's last layer is its own transpose)
+      if (e.rows >= 1 && e.cols >= 1)
         DQ_LAUNCH(transpose_kernel<T>, dim3((e.rows * e.cols + 255) / 256), dim3(256), 0, st, (const T*)(d_params + e.offset),
                   e.rows, e.cols, d_params_t + e.offset);
 #if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
@@ -577,7 +579,8 @@ struct Engine : EngineBase {
   }
   int64_t ws_bytes(int B, int mode) override {
     if (mode == DQMC_MODE_VJP)
-      return (int64_t)(sizeof(T) * (cfg.kind == DQMC_FERMINET ? vjp_per_walker_elems_ferminet() : vjp_per_walker_elems())) * B + 64 * 256;
+      return (int64_t)(sizeof(T) * (gnn ? vjp_per_walker_elems_paulinet()
+                                        : cfg.kind == DQMC_FERMINET ? vjp_per_walker_elems_ferminet() : vjp_per_walker_elems())) * B + 256 * 256;
     int S = mode == DQMC_MODE_FORWARD ? 1 : T3 + 2;
     int64_t need = (int64_t)chunk_bytes(B, S);
     if (mode == DQMC_MODE_LOCAL_ENERGY && J > 0) need = std::max<int64_t>(need, ecp_bytes(B));
@@ -1161,12 +1164,13 @@ struct Engine : EngineBase {
     DQ_LAUNCH(gemm_tn_kernel<T>, dim3((Nc + 31) / 32, (Kc + 31) / 32, (rows + rpb - 1) / rpb), dim3(256), 0, st, A, lda, dY, ldy,
               rows, Kc, Nc, rpb, hi > lo ? N : 0, lo, hi, dW, Nc);
   }
-  void bgrad(const T* dZ, int ld, int rows, int Nc, T* db, cudaStream_t st) {
+  void bgrad(const T* dZ, int ld, int rows, int Nc, T* db, cudaStream_t st, int lo = 0, int hi = 0) {
     int ny = (rows + 2047) / 2048;
     if (ny > 128) ny = 128;
     if (ny < 1) ny = 1;
     const int rpb = (rows + ny - 1) / ny;
-    DQ_LAUNCH(colsum_kernel<T>, dim3((Nc + 127) / 128, (rows + rpb - 1) / rpb), dim3(128), 0, st, dZ, ld, rows, Nc, rpb, db);
+    DQ_LAUNCH(colsum_kernel<T>, dim3((Nc + 127) / 128, (rows + rpb - 1) / rpb), dim3(128), 0, st, dZ, ld, rows, Nc, rpb, db,
+              hi > lo ? N : 0, lo, hi);
   }
 
   int vjp_chunk(const T* r, const T* R, int Rb, int Bc, const T* wts, T* sign, T* logp, T* G, void* wsbase, cudaStream_t st) {
@@ -1215,14 +1219,14 @@ struct Engine : EngineBase {
     DQ_LAUNCH(finalize_bwd_kernel<T>, dim3((Bc + 127) / 128), dim3(128), 0, st, r, N, cfg.n_up, K, Bc, (const T*)dsign,
               (const T*)dlog, wts, cfg.cusp_kind, (T)cfg.cusp_same_scale, (T)cfg.cusp_anti_scale, P("cusp.alpha"), dld,
               G + off("cusp.alpha"), R, Rb, M, cfg.nuc_cusp_kind, cfg.nuc_cusp_kind ? P("cusp.nuc") : (const T*)nullptr,
-              cfg.nuc_cusp_kind ? G + off("cusp.nuc") : (T*)nullptr);
+              cfg.nuc_cusp_kind ? G + off("cusp.nuc") : (T*)nullptr, (const T*)nullptr, (T*)nullptr);
     {
       const size_t pw = slater_bwd_smem_per_warp<T>(N);
       int wpb = (int)((96 * 1024) / pw);
       wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
       DQ_LAUNCH(slater_bwd_kernel<T>, dim3((Bc * K + wpb - 1) / wpb), dim3(32 * wpb), pw * wpb, st, r, R, Rb, N, M, cfg.n_up, K,
                 Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)BF, KN, (const T*)dld, dBF,
-                G + off("env.pi_up"), G + off("env.pi_dn"), G + off("env.zeta_up"), G + off("env.zeta_dn"), env_rep);
+                G + off("env.pi_up"), G + off("env.pi_dn"), G + off("env.zeta_up"), G + off("env.zeta_dn"), env_rep, 1);
     }
     // backflow heads: dX_L = dBF W_spin^T, dW_spin += X_L[spin rows]^T dBF[spin rows]
     gemm_raw(dBF, KN, PT("bf.up"), PT("bf.dn"), cfg.n_up, d, nullptr, 0, dXn, d, Bc, d, KN, 1, st);
@@ -1317,14 +1321,14 @@ struct Engine : EngineBase {
     DQ_LAUNCH(finalize_bwd_kernel<T>, dim3((Bc + 127) / 128), dim3(128), 0, st, r, N, cfg.n_up, K, Bc, (const T*)dsign,
               (const T*)dlog, wts, cfg.cusp_kind, (T)cfg.cusp_same_scale, (T)cfg.cusp_anti_scale, P("cusp.alpha"), dld,
               G + off("cusp.alpha"), R, Rb, M, cfg.nuc_cusp_kind, cfg.nuc_cusp_kind ? P("cusp.nuc") : (const T*)nullptr,
-              cfg.nuc_cusp_kind ? G + off("cusp.nuc") : (T*)nullptr);
+              cfg.nuc_cusp_kind ? G + off("cusp.nuc") : (T*)nullptr, (const T*)nullptr, (T*)nullptr);
     {
       const size_t pw = slater_bwd_smem_per_warp<T>(N);
       int wpb = (int)((96 * 1024) / pw);
       wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
       DQ_LAUNCH(slater_bwd_kernel<T>, dim3((Bc * K + wpb - 1) / wpb), dim3(32 * wpb), pw * wpb, st, r, R, Rb, N, M, cfg.n_up, K,
                 Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)BF, KN, (const T*)dld, dBF,
-                G + off("env.pi_up"), G + off("env.pi_dn"), G + off("env.zeta_up"), G + off("env.zeta_dn"), env_rep);
+                G + off("env.pi_up"), G + off("env.pi_dn"), G + off("env.zeta_up"), G + off("env.zeta_dn"), env_rep, 1);
     }
     T* dHn = dXa;   // gradient w.r.t. H_{l+1}
     T* dHc = dXb;   // gradient w.r.t. H_l (being built)
@@ -1368,6 +1372,240 @@ struct Engine : EngineBase {
     }
     return 0;
   }
+  // ---- conv-GNN reverse pass: the reference's test ansatz (tests/conf/ansatz.yaml: hk.Embed embeddings, 'featurewise'
+  // update over same / anti / ne convolutions, no deep edge features), Jastrow and per-spin backflow MLPs (ssp), default
+  // mult_act, spin-factorised determinants, hk.Linear determinant weights.  Value layouts of kernels_bwd.cuh.
+  struct Tape {
+    std::vector<T*> a;     // a[0] input, a[k] output of layer k (after its activation)
+    std::vector<int> dim;  // widths
+  };
+  template <class Take>
+  int tape_fwd(const T* in, int din, const int* dims, int nl, const std::string& base, bool bias, int act, bool last_linear,
+               int rows_, Take& take, Tape& t, cudaStream_t st) {
+    t.a.assign(1, const_cast<T*>(in));
+    t.dim.assign(1, din);
+    for (int i = 0; i < nl; ++i) {
+      T* out = take((size_t)rows_ * dims[i]);
+      const std::string q = base + std::to_string(i);
+      const bool b_i = bias && (!last_linear || base[0] != 'J' || i < nl - 1);  // Jastrow: bias 'not_last'
+      int rc = gemm(t.a.back(), t.dim.back(), (q + ".w").c_str(), nullptr, 0, dims[i], b_i ? P(q + ".b") : nullptr, nullptr, 0, out,
+                    dims[i], rows_, dims[i], t.dim.back(), 1, 0, 1, st);
+      if (rc) return rc;
+      if (i < nl - 1 || !last_linear)
+        DQ_LAUNCH(act_fl_kernel<T>, dim3(rows_, (dims[i] + 63) / 64), dim3(64), 0, st, out, dims[i], (const T*)nullptr, 0, 1, dims[i],
+                  T(1), act);
+      t.a.push_back(out);
+      t.dim.push_back(dims[i]);
+    }
+    return 0;
+  }
+  // dY = gradient w.r.t. the tape's output (destroyed).  s0 / s1: scratch of rows_ x max width.  dIn (nullable) receives
+  // (accumulate: is increased by) the gradient w.r.t. the tape's input.
+  int tape_bwd(const Tape& t, T* dY, const std::string& base, bool bias, int act, bool last_linear, int rows_, T* s0, T* s1,
+               T* dIn, bool accumulate, T* G, cudaStream_t st) {
+    const int nl = (int)t.a.size() - 1;
+    T* cur = dY;
+    for (int i = nl - 1; i >= 0; --i) {
+      const int dout = t.dim[i + 1], din = t.dim[i];
+      const std::string q = base + std::to_string(i);
+      const size_t n = (size_t)rows_ * dout;
+      if (i < nl - 1 || !last_linear)
+        DQ_LAUNCH(act_bwd_kernel<T>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, cur, (const T*)t.a[i + 1], act, n);
+      const bool b_i = bias && (!last_linear || base[0] != 'J' || i < nl - 1);
+      if (b_i) bgrad(cur, dout, rows_, dout, G + off(q + ".b"), st);
+      wgrad(t.a[i], din, cur, dout, rows_, din, dout, G + off(q + ".w"), 0, 0, st);
+      if (i > 0) {
+        T* nxt = (cur == s0) ? s1 : s0;
+        gemm_raw(cur, dout, PT(q + ".w"), nullptr, 0, din, nullptr, 0, nxt, din, rows_, din, dout, 0, st);
+        cur = nxt;
+      } else if (dIn) {
+        gemm_raw(cur, dout, PT(q + ".w"), nullptr, 0, din, accumulate ? dIn : nullptr, din, dIn, din, rows_, din, dout, 0, st);
+      }
+    }
+    return 0;
+  }
+  size_t vjp_per_walker_elems_paulinet() const {
+    const size_t L = cfg.n_layers, e = cfg.edge_dim, NS = N + (cfg.gnn_conv_ne ? M : 0), pairs = (size_t)N * NS;
+    const size_t nl = cfg.gnn_sub_n > 0 ? cfg.gnn_sub_n : 1, em = gnn_emax(), hn = gnn_hnode_max(), hm = gnn_hmax();
+    size_t jw = d;
+    for (int i = 0; i < cfg.jastrow_n; ++i) jw += cfg.jastrow_dims[i];
+    // every buffer vjp_chunk_paulinet takes, with a factor 2 of head-room (these networks are tiny)
+    return 2 * ((size_t)N * ((L + 1) * d + L * (2 * nl * hn + 3 * e + 3 * (size_t)d) + cfg.backflow_n * hm + 2 * (size_t)KN +
+                             6 * (size_t)d + 4 * hn + 3 * e + 4 * hm) +
+                pairs * (4 + L * 3 * nl * em + 3 * e + 2 * em) + 3 * jw + 6 * (size_t)d + (size_t)K * 4 + 64);
+  }
+  int vjp_chunk_paulinet(const T* r, const T* R, int Rb, int Bc, const T* wts, T* sign, T* logp, T* G, void* wsbase,
+                         cudaStream_t st) {
+    const int L = cfg.n_layers, rows = Bc * N, e = cfg.edge_dim, nl = cfg.gnn_sub_n > 0 ? cfg.gnn_sub_n : 1;
+    const int Mne = cfg.gnn_conv_ne ? M : 0, NS = N + Mne, nt = cfg.gnn_conv_ne ? 3 : 2, pairs = Bc * N * NS;
+    const int n_types = cfg.n_elec_types > 0 ? cfg.n_elec_types : 1;
+    const char* tn[3] = {"same", "anti", "ne"};
+    char* p = (char*)wsbase;
+    auto take = [&](size_t n) { T* q = (T*)p; p += align_up(sizeof(T) * n); return q; };
+    // ---- forward, everything kept --------------------------------------------------------------------------------
+    std::vector<T*> X(L + 1), C(L);
+    std::vector<std::array<T*, 3>> Gt(L);
+    std::vector<std::array<Tape, 3>> Wt(L);
+    std::vector<std::array<Tape, 2>> Ht(L);
+    X[0] = take((size_t)rows * d);
+    DQ_LAUNCH(gnn_embed_kernel<T>, dim3((rows * d + 127) / 128), dim3(128), 0, st, P("emb.table"), n_types, N, cfg.n_up, 1, d, X[0], rows);
+    T* E = take((size_t)pairs * 4);
+    DQ_LAUNCH(gnn_edge_val_kernel<T>, dim3((pairs + 127) / 128), dim3(128), 0, st, r, R, Rb, N, M, Mne, E, pairs);
+    for (int l = 0; l < L; ++l) {
+      const std::string q = "G" + std::to_string(l) + ".";
+      for (int t = 0; t < nt; ++t) {
+        int rc = tape_fwd(E, 4, cfg.gnn_w_dims[l], nl, q + "w_" + tn[t] + ".", false, 0, false, pairs, take, Wt[l][t], st);
+        if (rc) return rc;
+      }
+      for (int t = 0; t < 2; ++t) {
+        int rc = tape_fwd(X[l], d, cfg.gnn_h_dims[l], nl, q + "h_" + tn[t] + ".", true, 0, false, rows, take, Ht[l][t], st);
+        if (rc) return rc;
+      }
+      C[l] = take((size_t)rows * nt * e);
+      DQ_LAUNCH(gnn_conv_val_kernel<T>, dim3(rows), dim3(64), 0, st, (const T*)Wt[l][0].a.back(), (const T*)Wt[l][1].a.back(),
+                (const T*)(nt == 3 ? Wt[l][2].a.back() : nullptr), (const T*)Ht[l][0].a.back(), (const T*)Ht[l][1].a.back(),
+                nt == 3 ? P(q + "hne") : (const T*)nullptr, N, Mne, cfg.n_up, e, C[l]);
+      const T* res = X[l];
+      for (int t = 0; t < nt; ++t) {  // x <- x + sum_t tanh(g_t(conv_t)): each G_t holds the running sum
+        Gt[l][t] = take((size_t)rows * d);
+        int rc = gemm(C[l] + t * e, nt * e, (q + "g_" + tn[t] + ".w").c_str(), nullptr, 0, d, P(q + "g_" + tn[t] + ".b"), nullptr, 0,
+                      Gt[l][t], d, rows, d, e, 1, 0, N, st);
+        if (rc) return rc;
+        DQ_LAUNCH(act_fl_kernel<T>, dim3(rows, (d + 63) / 64), dim3(64), 0, st, Gt[l][t], d, res, d, 1, d, T(1), 0);
+        res = Gt[l][t];
+      }
+      X[l + 1] = Gt[l][nt - 1];
+    }
+    // Jastrow on sum_i x_i
+    Tape Jt;
+    T* Js = nullptr;
+    if (cfg.jastrow_n > 0) {
+      Js = take((size_t)Bc * d);
+      DQ_LAUNCH(sum_electrons_kernel<T>, dim3((Bc * d + 127) / 128), dim3(128), 0, st, (const T*)X[L], N, 1, d, Js, Bc * d);
+      int rc = tape_fwd(Js, d, cfg.jastrow_dims, cfg.jastrow_n, "J", true, 1, true, Bc, take, Jt, st);
+      if (rc) return rc;
+    }
+    // per-spin backflow MLPs: hidden layers (ssp), then the orbital head + default mult_act
+    std::vector<T*> Y(cfg.backflow_n + 1);
+    std::vector<int> yd(cfg.backflow_n + 1);
+    Y[0] = X[L]; yd[0] = d;
+    for (int i = 0; i < cfg.backflow_n; ++i) {
+      const int dout = cfg.backflow_dims[i];
+      const std::string q = std::to_string(i);
+      Y[i + 1] = take((size_t)rows * dout); yd[i + 1] = dout;
+      int rc = gemm(Y[i], yd[i], ("bfh" + q + ".up").c_str(), ("bfh" + q + ".dn").c_str(), cfg.n_up, dout, P("bfb" + q + ".up"), nullptr,
+                    0, Y[i + 1], dout, Bc, dout, yd[i], 1, 1, N, st, 0, P("bfb" + q + ".dn"));
+      if (rc) return rc;
+      DQ_LAUNCH(act_fl_kernel<T>, dim3(rows, (dout + 31) / 32), dim3(32), 0, st, Y[i + 1], dout, (const T*)nullptr, 0, 1, dout, T(1), 1);
+    }
+    T* BF = take((size_t)rows * KN); T* dBF = take((size_t)rows * KN);
+    int rc = gemm(Y.back(), yd.back(), "bf.up", "bf.dn", cfg.n_up, KN, P("bfb.up"), nullptr, 0, BF, KN, Bc, KN, yd.back(), 1, 1, N, st, 0,
+                  P("bfb.dn"));
+    if (rc) return rc;
+    if (cfg.mult_act == 1)
+      DQ_LAUNCH(act_fl_kernel<T>, dim3(rows, (KN + 127) / 128), dim3(128), 0, st, BF, KN, (const T*)nullptr, 0, 1, KN, T(1), 2);
+    T* dsign = take((size_t)Bc * K); T* dlog = take((size_t)Bc * K); T* dld = take((size_t)Bc * K);
+    const int full_det = cfg.factorized_det ? 0 : 1;
+    const int sl_wpb = slater_warps_per_block<T>(N);
+    DQ_LAUNCH(slater_kernel<T>, dim3((Bc * K + sl_wpb - 1) / sl_wpb), dim3(32 * sl_wpb), slater_smem_bytes<T>(N), st, r, R, Rb, N,
+              M, cfg.n_up, K, 1, Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)BF, KN,
+              dsign, dlog, (T*)nullptr, (T*)nullptr, env_rep, full_det, (const T*)nullptr, (const T*)nullptr, 0, 1);
+    FinalizeCfg fc;
+    fc.N = N; fc.M = M; fc.n_up = cfg.n_up; fc.K = K; fc.S = 1; fc.cusp_kind = cfg.cusp_kind;
+    fc.cusp_same_scale = cfg.cusp_same_scale; fc.cusp_anti_scale = cfg.cusp_anti_scale; fc.ecp_terms = 0;
+    fc.nuc_cusp_kind = cfg.nuc_cusp_kind;
+    DQ_LAUNCH(finalize_kernel<T>, dim3(Bc), dim3(128), finalize_smem_bytes<T>(N, K), st, fc, r, R, Rb, (const T*)dsign,
+              (const T*)dlog, (const T*)nullptr, (const T*)nullptr, P("cusp.alpha"), (const T*)d_zval, (const T*)nullptr,
+              (const int*)d_ecp_mask, Bc, sign, logp, (T*)nullptr, (T*)nullptr, (T*)nullptr,
+              cfg.conf_linear ? P("conf.w") : (const T*)nullptr, cfg.jastrow_n > 0 ? (const T*)Jt.a.back() : (const T*)nullptr,
+              cfg.nuc_cusp_kind ? P("cusp.nuc") : (const T*)nullptr, PhArgs<T>());
+    // ---- reverse ---------------------------------------------------------------------------------------------------
+    DQ_LAUNCH(finalize_bwd_kernel<T>, dim3((Bc + 127) / 128), dim3(128), 0, st, r, N, cfg.n_up, K, Bc, (const T*)dsign,
+              (const T*)dlog, wts, 0 /*fixed cusp exponent: no gradient*/, (T)cfg.cusp_same_scale, (T)cfg.cusp_anti_scale,
+              P("cusp.alpha"), dld, (T*)nullptr, R, Rb, M, cfg.nuc_cusp_kind, cfg.nuc_cusp_kind ? P("cusp.nuc") : (const T*)nullptr,
+              cfg.nuc_cusp_kind ? G + off("cusp.nuc") : (T*)nullptr, cfg.conf_linear ? P("conf.w") : (const T*)nullptr,
+              cfg.conf_linear ? G + off("conf.w") : (T*)nullptr);
+    {
+      const size_t pw = slater_bwd_smem_per_warp<T>(N);
+      int wpb = (int)((96 * 1024) / pw);
+      wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
+      DQ_LAUNCH(slater_bwd_kernel<T>, dim3((Bc * K + wpb - 1) / wpb), dim3(32 * wpb), pw * wpb, st, r, R, Rb, N, M, cfg.n_up, K,
+                Bc * K, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)BF, KN, (const T*)dld, dBF,
+                G + off("env.pi_up"), G + off("env.pi_dn"), G + off("env.zeta_up"), G + off("env.zeta_dn"), env_rep, full_det);
+    }
+    // scratch for the reverse sweep
+    const int hm = std::max(gnn_hmax(), d), hn = std::max(gnn_hnode_max(), e), em = gnn_emax();
+    T* dXa = take((size_t)rows * d); T* dXb = take((size_t)rows * d);
+    T* sr0 = take((size_t)rows * std::max(hm, hn)); T* sr1 = take((size_t)rows * std::max(hm, hn));
+    T* dCb = take((size_t)rows * nt * e); T* dCt = take((size_t)rows * e);
+    T* dWb[3] = {take((size_t)pairs * e), take((size_t)pairs * e), take((size_t)pairs * e)};
+    T* sp0 = take((size_t)pairs * em); T* sp1 = take((size_t)pairs * em);
+    T* dHb[2] = {take((size_t)rows * e), take((size_t)rows * e)};
+    // orbital head
+    if (cfg.mult_act == 1) {
+      const size_t n = (size_t)rows * KN;
+      DQ_LAUNCH(act_bwd_kernel<T>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, dBF, (const T*)BF, 2, n);
+    }
+    bgrad(dBF, KN, rows, KN, G + off("bfb.up"), st, 0, cfg.n_up);
+    bgrad(dBF, KN, rows, KN, G + off("bfb.dn"), st, cfg.n_up, N);
+    wgrad(Y.back(), yd.back(), dBF, KN, rows, yd.back(), KN, G + off("bf.up"), 0, cfg.n_up, st);
+    wgrad(Y.back(), yd.back(), dBF, KN, rows, yd.back(), KN, G + off("bf.dn"), cfg.n_up, N, st);
+    T* cur = cfg.backflow_n > 0 ? sr0 : dXa;
+    gemm_raw(dBF, KN, PT("bf.up"), PT("bf.dn"), cfg.n_up, yd.back(), nullptr, 0, cur, yd.back(), Bc, yd.back(), KN, 1, st);
+    for (int i = cfg.backflow_n - 1; i >= 0; --i) {
+      const int dout = yd[i + 1], din = yd[i];
+      const std::string q = std::to_string(i);
+      const size_t n = (size_t)rows * dout;
+      DQ_LAUNCH(act_bwd_kernel<T>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, cur, (const T*)Y[i + 1], 1, n);
+      bgrad(cur, dout, rows, dout, G + off("bfb" + q + ".up"), st, 0, cfg.n_up);
+      bgrad(cur, dout, rows, dout, G + off("bfb" + q + ".dn"), st, cfg.n_up, N);
+      wgrad(Y[i], din, cur, dout, rows, din, dout, G + off("bfh" + q + ".up"), 0, cfg.n_up, st);
+      wgrad(Y[i], din, cur, dout, rows, din, dout, G + off("bfh" + q + ".dn"), cfg.n_up, N, st);
+      T* nxt = i == 0 ? dXa : (cur == sr0 ? sr1 : sr0);
+      gemm_raw(cur, dout, PT("bfh" + q + ".up"), PT("bfh" + q + ".dn"), cfg.n_up, din, nullptr, 0, nxt, din, Bc, din, dout, 1, st);
+      cur = nxt;
+    }
+    T* dXn = dXa;  // gradient w.r.t. X_L
+    T* dXc = dXb;
+    if (cfg.jastrow_n > 0) {  // d log|psi| / d jastrow = w_b
+      T* dJ = take((size_t)Bc);  // [Bc] scalars
+      T* js0 = take((size_t)Bc * d); T* js1 = take((size_t)Bc * d); T* dJs = take((size_t)Bc * d);
+      DQ_CHECK(cudaMemcpyAsync(dJ, wts, sizeof(T) * Bc, cudaMemcpyDeviceToDevice, st));
+      tape_bwd(Jt, dJ, "J", true, 1, true, Bc, js0, js1, dJs, false, G, st);
+      const size_t n = (size_t)rows * d;
+      DQ_LAUNCH(bcast_add_kernel<T>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, (const T*)dJs, N, d, dXn, n);
+    }
+    for (int l = L - 1; l >= 0; --l) {
+      const std::string q = "G" + std::to_string(l) + ".";
+      const size_t nd = (size_t)rows * d;
+      // X_{l+1} = X_l + sum_t tanh(z_t): tanh outputs are the differences of the running sums
+      DQ_CHECK(cudaMemcpyAsync(dXc, dXn, sizeof(T) * nd, cudaMemcpyDeviceToDevice, st));  // residual
+      for (int t = 0; t < nt; ++t) {
+        const T* prev = t == 0 ? X[l] : Gt[l][t - 1];
+        DQ_LAUNCH(tanh_bwd_kernel<T>, dim3((unsigned)((nd + 255) / 256)), dim3(256), 0, st, (const T*)dXn, (const T*)Gt[l][t], prev, sr0, nd);
+        bgrad(sr0, d, rows, d, G + off(q + "g_" + tn[t] + ".b"), st);
+        // conv_t is a column slice of C: copy it out for the weight gradient
+        const size_t ne_ = (size_t)rows * e;
+        DQ_LAUNCH(slice_cols_kernel<T>, dim3((unsigned)((ne_ + 255) / 256)), dim3(256), 0, st, (const T*)C[l], nt * e, t * e, e, dCt, ne_);
+        wgrad(dCt, e, sr0, d, rows, e, d, G + off(q + "g_" + tn[t] + ".w"), 0, 0, st);
+        gemm_raw(sr0, d, PT(q + "g_" + tn[t] + ".w"), nullptr, 0, e, nullptr, 0, dCb + t * e, nt * e, rows, e, d, 0, st);
+      }
+      DQ_CHECK(cudaMemsetAsync(dHb[0], 0, sizeof(T) * (size_t)rows * e, st));
+      DQ_CHECK(cudaMemsetAsync(dHb[1], 0, sizeof(T) * (size_t)rows * e, st));
+      DQ_LAUNCH(gnn_conv_bwd_kernel<T>, dim3(rows), dim3(64), 0, st, (const T*)dCb, (const T*)Wt[l][0].a.back(),
+                (const T*)Wt[l][1].a.back(), (const T*)(nt == 3 ? Wt[l][2].a.back() : nullptr), (const T*)Ht[l][0].a.back(),
+                (const T*)Ht[l][1].a.back(), nt == 3 ? P(q + "hne") : (const T*)nullptr, N, Mne, cfg.n_up, e, dWb[0], dWb[1], dWb[2],
+                dHb[0], dHb[1], nt == 3 ? G + off(q + "hne") : (T*)nullptr);
+      for (int t = 0; t < nt; ++t)
+        tape_bwd(Wt[l][t], dWb[t], q + "w_" + tn[t] + ".", false, 0, false, pairs, sp0, sp1, nullptr, false, G, st);
+      for (int t = 0; t < 2; ++t)
+        tape_bwd(Ht[l][t], dHb[t], q + "h_" + tn[t] + ".", true, 0, false, rows, sr0, sr1, dXc, true, G, st);
+      T* tmp = dXn; dXn = dXc; dXc = tmp;
+    }
+    DQ_LAUNCH(embed_table_bwd_kernel<T>, dim3((d + 63) / 64, 64), dim3(64), 0, st, (const T*)dXn, n_types, N, cfg.n_up, d, rows,
+              G + off("emb.table"));
+    return 0;
+  }
   size_t vjp_per_walker_elems_ferminet() const {
     const size_t L = cfg.n_layers, de = cfg.edge_dim, d0 = 4 * M, dm = (size_t)d > d0 ? d : d0, em = de > 4 ? de : 4;
     const size_t rowsN = N, rowsE = (size_t)N * N;
@@ -1377,8 +1615,8 @@ struct Engine : EngineBase {
 
   int vjp_params(const void* r_, const void* R_, int Rb, int B, const void* weights, void* sign, void* logp,
                  void* grad_params, void* ws, int64_t wsb, cudaStream_t st) override {
-    if (cfg.kind != DQMC_PSIFORMER && cfg.kind != DQMC_TRANSPSIFORMER && cfg.kind != DQMC_FERMINET) {
-      err = "dqmc_wf_vjp_params: only the Psiformer / TransPsiformer / FermiNet ansatzes have a reverse pass so far";
+    if (gnn && (cfg.gnn_concat || cfg.gnn_features || cfg.gnn_deep_edges)) {
+      err = "dqmc_wf_vjp_params: conv-GNN reverse pass covers the featurewise / hk.Embed variant (tests/conf/ansatz.yaml) only";
       return 2;
     }
     if (cfg.backflow_add) { err = "dqmc_wf_vjp_params: additive backflow branch has no reverse pass"; return 2; }
@@ -1388,10 +1626,11 @@ struct Engine : EngineBase {
     if (B == 0) return 0;  // empty batch: zero gradient
     // walkers per chunk: activations of every layer stay resident for the reverse pass (64 buffers, 256 B alignment each)
     const bool fermi = cfg.kind == DQMC_FERMINET;
-    int64_t Bc = (wsb - 64 * 256) / (int64_t)(sizeof(T) * (fermi ? vjp_per_walker_elems_ferminet() : vjp_per_walker_elems()));
+    const int64_t per_w = gnn ? vjp_per_walker_elems_paulinet() : (fermi ? vjp_per_walker_elems_ferminet() : vjp_per_walker_elems());
+    int64_t Bc = (wsb - 256 * 256) / (int64_t)(sizeof(T) * per_w);
     if (Bc > B) Bc = B;
     if (Bc < 1) { err = "workspace too small for a single walker (vjp)"; return 3; }
-    if (!fermi)
+    if (!fermi && !gnn)
     DQ_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_bwd_smem_bytes<T>(N, dh, Mn)));
     DQ_CHECK(cudaFuncSetAttribute(slater_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(slater_bwd_smem_per_warp<T>(N) * 4)));
@@ -1399,7 +1638,8 @@ struct Engine : EngineBase {
       const int nb = (int)std::min<int64_t>(Bc, B - b0);
       const T* rc_ = r + (size_t)b0 * 3 * N;
       const T* Rc_ = R + (Rb ? (size_t)b0 * 3 * M : 0);
-      int rc = fermi ? vjp_chunk_ferminet(rc_, Rc_, Rb, nb, (const T*)weights + b0, (T*)sign + b0, (T*)logp + b0, (T*)grad_params, ws, st)
+      int rc = gnn ? vjp_chunk_paulinet(rc_, Rc_, Rb, nb, (const T*)weights + b0, (T*)sign + b0, (T*)logp + b0, (T*)grad_params, ws, st)
+             : fermi ? vjp_chunk_ferminet(rc_, Rc_, Rb, nb, (const T*)weights + b0, (T*)sign + b0, (T*)logp + b0, (T*)grad_params, ws, st)
                      : vjp_chunk(rc_, Rc_, Rb, nb, (const T*)weights + b0, (T*)sign + b0, (T*)logp + b0, (T*)grad_params, ws, st);
       if (rc) return rc;
     }

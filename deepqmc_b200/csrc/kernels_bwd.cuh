@@ -52,14 +52,19 @@ __global__ void gemm_tn_kernel(const T* __restrict__ A, int lda, const T* __rest
 }
 
 // db[n] += sum_rows dZ[row][n]
+// (rows are (b, i) with i = row % Nel; Nel > 0: only electrons lo <= i < hi count -- per-spin biases)
 template <class T>
-__global__ void colsum_kernel(const T* __restrict__ dZ, int ld, int rows, int Nc, int rows_per_block, T* __restrict__ db) {
+__global__ void colsum_kernel(const T* __restrict__ dZ, int ld, int rows, int Nc, int rows_per_block, T* __restrict__ db,
+                              int Nel, int lo, int hi) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= Nc) return;
   const int r_begin = blockIdx.y * rows_per_block;
   const int r_end = r_begin + rows_per_block < rows ? r_begin + rows_per_block : rows;
   T acc = T(0);
-  for (int r = r_begin; r < r_end; ++r) acc += dZ[(size_t)r * ld + n];
+  for (int r = r_begin; r < r_end; ++r) {
+    if (Nel > 0) { const int i = r % Nel; if (i < lo || i >= hi) continue; }
+    acc += dZ[(size_t)r * ld + n];
+  }
   atomic_add(db + n, acc);
 }
 
@@ -219,7 +224,9 @@ __global__ void finalize_bwd_kernel(const T* __restrict__ r, int N, int n_up, in
                                     const T* __restrict__ weights, int cusp_kind, T same_scale, T anti_scale,
                                     const T* __restrict__ cusp_alpha, T* __restrict__ dlogdet, T* __restrict__ dalpha,
                                     const T* __restrict__ R, int R_batched, int M, int nuc_cusp_kind,
-                                    const T* __restrict__ nuc_cusp /*[1 + M]: alpha, charges*/, T* __restrict__ dnuc_alpha) {
+                                    const T* __restrict__ nuc_cusp /*[1 + M]: alpha, charges*/, T* __restrict__ dnuc_alpha,
+                                    const T* __restrict__ conf_w /*[K] hk.Linear determinant weights or null (SumPool)*/,
+                                    T* __restrict__ dconf_w) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const T w = weights[b];
@@ -229,8 +236,12 @@ __global__ void finalize_bwd_kernel(const T* __restrict__ r, int N, int n_up, in
   for (int k = 1; k < K; ++k) shift = dl[k] > shift ? dl[k] : shift;
   if ((shift - shift) != T(0)) shift = T(0);
   T psi = T(0);
-  for (int k = 0; k < K; ++k) psi += ds[k] * m_exp(dl[k] - shift);
-  for (int k = 0; k < K; ++k) dlogdet[(size_t)b * K + k] = w * ds[k] * m_exp(dl[k] - shift) / psi;
+  for (int k = 0; k < K; ++k) psi += (conf_w ? conf_w[k] : T(1)) * ds[k] * m_exp(dl[k] - shift);
+  for (int k = 0; k < K; ++k) {
+    const T xk = ds[k] * m_exp(dl[k] - shift) / psi;  // d log|psi| / d c_k;  times c_k: d log|psi| / d logdet_k
+    dlogdet[(size_t)b * K + k] = w * (conf_w ? conf_w[k] : T(1)) * xk;
+    if (conf_w && dconf_w) atomic_add(dconf_w + k, w * xk);
+  }
   if (cusp_kind == 1 && dalpha) {
     const T as_ = cusp_alpha[0], aa_ = cusp_alpha[1];
     T gs = T(0), ga = T(0);
@@ -277,7 +288,8 @@ __global__ void slater_bwd_kernel(const T* __restrict__ r, const T* __restrict__
                                   const T* __restrict__ zeta_up, const T* __restrict__ zeta_dn,
                                   const T* __restrict__ BF, int ldb, const T* __restrict__ dlogdet, T* __restrict__ dBF,
                                   T* __restrict__ dpi_up, T* __restrict__ dpi_dn, T* __restrict__ dzeta_up,
-                                  T* __restrict__ dzeta_dn, int rep) {
+                                  T* __restrict__ dzeta_dn, int rep, int full_det) {
+  // full_det == 0: spin-factorised determinants = block-diagonal A (off-diagonal spin blocks zero, as in slater_kernel)
   DQMC_DYN_SMEM(smem_raw);
   const int NP = N + 1, N2 = 2 * N + 1;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -300,6 +312,7 @@ __global__ void slater_bwd_kernel(const T* __restrict__ r, const T* __restrict__
       const T rho = m_sqrt(Num<T>::eps() + dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
       for (int et = 0; et < rep; ++et) e += pi[m * rep + et] * m_exp(-m_abs(ze[m * rep + et]) * rho);
     }
+    if (!full_det && ((i < n_up) != (mu < n_up))) e = T(0);
     const T bf0 = BF[((size_t)b * N + i) * ldb + k * N + mu];
     env[i * NP + mu] = e;
     bfv[i * NP + mu] = bf0;
@@ -345,8 +358,10 @@ __global__ void slater_bwd_kernel(const T* __restrict__ r, const T* __restrict__
   const T dl = dlogdet[(size_t)b * K + k];
   for (int idx = lane; idx < N * N; idx += 32) {
     const int i = idx / N, mu = idx - i * N;
-    const T G = dl * aug[mu * N2 + N + i];
+    const bool blocked = !full_det && ((i < n_up) != (mu < n_up));
+    const T G = blocked ? T(0) : dl * aug[mu * N2 + N + i];
     dBF[((size_t)b * N + i) * ldb + k * N + mu] = G * env[i * NP + mu];
+    if (blocked) continue;
     const T gb = G * bfv[i * NP + mu];  // d / d env[i][mu]
     const bool up = i < n_up;
     const T* pi = (up ? pi_up : pi_dn) + (size_t)(k * N + mu) * M * rep;
@@ -386,4 +401,129 @@ __global__ void embed_feat_kernel(const T* __restrict__ r, const T* __restrict__
   if (m == 0) f[F - 1] = i < n_up ? T(1) : T(-1);
 }
 
+
+// ==========================================================================================
+// conv-GNN ("PauliNet" test ansatz, tests/conf/ansatz.yaml) reverse pass, plain-forward VALUE layouts:
+//   edge features E[b][i][jj][4] (receiver i, sender jj < N electron / jj >= N nucleus), filters W_t[b][i][jj][e],
+//   node transforms H_t[b][j][e], convolutions C[b][i][t e + f] for t = same, anti, ne.
+// ==========================================================================================
+template <class T>
+__global__ void gnn_edge_val_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M, int Mne,
+                                    T* __restrict__ E, int total) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int NS = N + Mne;
+  const int jj = idx % NS, i = (idx / NS) % N, b = idx / (NS * N);
+  T* out = E + (size_t)idx * 4;
+  out[0] = out[1] = out[2] = out[3] = T(0);
+  if (jj == i) return;
+  const T* ri = r + ((size_t)b * N + i) * 3;
+  const T* pj = jj >= N ? R + (R_batched ? (size_t)b * M * 3 : 0) + (size_t)(jj - N) * 3 : r + ((size_t)b * N + jj) * 3;
+  const T d0 = ri[0] - pj[0], d1 = ri[1] - pj[1], d2 = ri[2] - pj[2];
+  out[0] = m_sqrt(Num<T>::eps() + d0 * d0 + d1 * d1 + d2 * d2);
+  out[1] = d0; out[2] = d1; out[3] = d2;
+}
+
+// C[b][i][t e + f] = sum_senders W_t[b][i][jj][f] * H_t(sender)[f]   (update_features.py:196-209, no normalisation)
+template <class T>
+__global__ void gnn_conv_val_kernel(const T* __restrict__ Wsame, const T* __restrict__ Wanti, const T* __restrict__ Wne,
+                                    const T* __restrict__ Hs, const T* __restrict__ Ha, const T* __restrict__ Hne, int N,
+                                    int M, int n_up, int e, T* __restrict__ C) {
+  const int bi = blockIdx.x, b = bi / N, i = bi - b * N;
+  const int NS = N + M, nt = M > 0 ? 3 : 2;
+  for (int f = threadIdx.x; f < e; f += blockDim.x) {
+    T as = T(0), aa = T(0), an = T(0);
+    for (int j = 0; j < N; ++j) {
+      if (j == i) continue;
+      const bool same = (i < n_up) == (j < n_up);
+      const size_t p = ((size_t)bi * NS + j) * e + f;
+      const T v = (same ? Wsame : Wanti)[p] * (same ? Hs : Ha)[((size_t)b * N + j) * e + f];
+      if (same) as += v; else aa += v;
+    }
+    for (int m = 0; m < M; ++m) an += Wne[((size_t)bi * NS + N + m) * e + f] * Hne[m * e + f];
+    T* c = C + (size_t)bi * nt * e;
+    c[f] = as; c[e + f] = aa;
+    if (nt == 3) c[2 * e + f] = an;
+  }
+}
+
+// Backward of gnn_conv_val_kernel.  dW_t is written for EVERY pair (zero where the pair is not of type t), dH_t / dHne
+// are accumulated atomically (callers zero them).  Block per (walker, receiver).
+template <class T>
+__global__ void gnn_conv_bwd_kernel(const T* __restrict__ dC, const T* __restrict__ Wsame, const T* __restrict__ Wanti,
+                                    const T* __restrict__ Wne, const T* __restrict__ Hs, const T* __restrict__ Ha,
+                                    const T* __restrict__ Hne, int N, int M, int n_up, int e, T* __restrict__ dWsame,
+                                    T* __restrict__ dWanti, T* __restrict__ dWne, T* __restrict__ dHs, T* __restrict__ dHa,
+                                    T* __restrict__ dHne) {
+  const int bi = blockIdx.x, b = bi / N, i = bi - b * N;
+  const int NS = N + M, nt = M > 0 ? 3 : 2;
+  for (int f = threadIdx.x; f < e; f += blockDim.x) {
+    const T* dc = dC + (size_t)bi * nt * e;
+    const T gs = dc[f], ga = dc[e + f], gn = nt == 3 ? dc[2 * e + f] : T(0);
+    for (int jj = 0; jj < NS; ++jj) {
+      const size_t p = ((size_t)bi * NS + jj) * e + f;
+      T ws = T(0), wa = T(0), wn = T(0);
+      if (jj < N && jj != i) {
+        const size_t hj = ((size_t)b * N + jj) * e + f;
+        if ((i < n_up) == (jj < n_up)) { ws = gs * Hs[hj]; atomic_add(dHs + hj, gs * Wsame[p]); }
+        else { wa = ga * Ha[hj]; atomic_add(dHa + hj, ga * Wanti[p]); }
+      } else if (jj >= N) {
+        wn = gn * Hne[(jj - N) * e + f];
+        atomic_add(dHne + (jj - N) * e + f, gn * Wne[p]);
+      }
+      dWsame[p] = ws; dWanti[p] = wa;
+      if (nt == 3) dWne[p] = wn;
+    }
+  }
+}
+
+// In-place backward of an activation from its stored OUTPUT y: dZ = dY f'(z).  kind 0 tanh (1 - y^2); 1 ssp = softplus + log(1/2)
+// (sigmoid(z) = 1 - exp(-y) / 2); 2 the backflow's 1 + 2 tanh(z / 4) ((1 - t^2) / 2, t = (y - 1) / 2).
+template <class T>
+__global__ void act_bwd_kernel(T* __restrict__ dY, const T* __restrict__ Y, int kind, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const T y = Y[i];
+  T d;
+  if (kind == 0) d = T(1) - y * y;
+  else if (kind == 1) d = T(1) - T(0.5) * m_exp(-y);
+  else { const T t = T(0.5) * (y - T(1)); d = T(0.5) * (T(1) - t * t); }
+  dY[i] *= d;
+}
+
+// hk.Embed lookup backward: dTable[type(i)][f] += sum_b dX[b][i][f]
+template <class T>
+__global__ void embed_table_bwd_kernel(const T* __restrict__ dX, int n_types, int N, int n_up, int d, int rows,
+                                       T* __restrict__ dTable) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= d) return;
+  T a0 = T(0), a1 = T(0);
+  for (int row = blockIdx.y; row < rows; row += gridDim.y) {
+    const int i = row % N;
+    const T v = dX[(size_t)row * d + f];
+    if (n_types > 1 && i >= n_up) a1 += v; else a0 += v;
+  }
+  atomic_add(dTable + f, a0);
+  if (n_types > 1) atomic_add(dTable + d + f, a1);
+}
+
+// dX[b][i][f] += dJ[b][f]   (backward of the sum over electrons feeding the Jastrow, wf/omni.py:35-37)
+template <class T>
+__global__ void bcast_add_kernel(const T* __restrict__ dJ, int N, int d, T* __restrict__ dX, size_t total) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const size_t row = idx / d;
+  dX[idx] += dJ[(row / N) * d + (idx - row * d)];
+}
+
+// dst[row][c] = src[row][off + c]   (column slice of a row-major matrix)
+template <class T>
+__global__ void slice_cols_kernel(const T* __restrict__ src, int lds, int off, int cols, T* __restrict__ dst, size_t total) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const size_t row = idx / cols;
+  dst[idx] = src[row * lds + off + (idx - row * cols)];
+}
+
 }  // namespace dq
+

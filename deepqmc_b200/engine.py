@@ -187,6 +187,80 @@ def _unpack_psiformer_grads(spec: AnsatzSpec, entries: dict, flat) -> dict:
     return out
 
 
+def _unpack_paulinet_grads(spec: AnsatzSpec, entries: dict, flat, params: dict) -> dict:
+    """Engine-layout gradient vector -> Haiku-named tree for the conv-GNN test ansatz (inverse of _pack_haiku_params for
+    spec.kind == 'paulinet', featurewise / hk.Embed variant).  The walker-independent h_ne(nuclear embedding) rows were
+    evaluated on the host at upload; their cotangents G<l>.hne are pulled back through that small tanh MLP here."""
+    def e(name):
+        off, rows, cols = entries[name]
+        return flat[off:off + rows * cols].reshape(rows, cols)
+
+    N, K, M, d, n_up = spec.n_elec, spec.n_determinants, spec.n_nuc, spec.embedding_dim, spec.n_up
+    nl = spec.gnn_subnet_layers
+    out = {PN.GNN + 'electron_embedding/ElectronicEmbedding:embeddings': e('emb.table')}
+    types = PN.EDGE_TYPES if spec.gnn_conv_ne else PN.EDGE_TYPES[:2]
+    dxn = None
+    for l in range(spec.n_layers):
+        c, lp = PN.conv_prefix(l), PN.layer_prefix(l)
+        for t in types:
+            for i in range(nl):
+                out[c + f'w_{t}/linear_{i}:w'] = e(f'G{l}.w_{t}.{i}.w')
+                if t != 'ne':
+                    out[c + f'h_{t}/linear_{i}:w'] = e(f'G{l}.h_{t}.{i}.w')
+                    out[c + f'h_{t}/linear_{i}:b'] = e(f'G{l}.h_{t}.{i}.b')[0]
+            out[lp + f'g_conv_{t}/linear_0:w'] = e(f'G{l}.g_{t}.w')
+            out[lp + f'g_conv_{t}/linear_0:b'] = e(f'G{l}.g_{t}.b')[0]
+        if spec.gnn_conv_ne:  # host: hne = tanh MLP(xn) -> gradients of the nuclear table and of h_ne
+            leaves = {k: torch.as_tensor(np.asarray(params[k], dtype=np.float64)).requires_grad_(True)
+                      for k in [PN.GNN + 'nuclei_embedding/~/embed:embeddings']
+                      + [c + f'h_ne/linear_{i}:{wb}' for i in range(nl) for wb in 'wb']}
+            hn = leaves[PN.GNN + 'nuclei_embedding/~/embed:embeddings']
+            for i in range(nl):
+                hn = torch.tanh(hn @ leaves[c + f'h_ne/linear_{i}:w'] + leaves[c + f'h_ne/linear_{i}:b'])
+            (hn * e(f'G{l}.hne').detach().cpu().double()).sum().backward()
+            for k, v in leaves.items():
+                g = v.grad.to(device=flat.device, dtype=flat.dtype)
+                if k.endswith('embed:embeddings'):
+                    dxn = g if dxn is None else dxn + g
+                else:
+                    out[k] = g
+    if dxn is not None:
+        out[PN.GNN + 'nuclei_embedding/~/embed:embeddings'] = dxn
+    for i in range(spec.jastrow_layers):
+        out[PN.JASTROW + f'linear_{i}:w'] = e(f'J{i}.w')
+        if i < spec.jastrow_layers - 1:
+            out[PN.JASTROW + f'linear_{i}:b'] = e(f'J{i}.b')[0]
+    for tag, pre, n_spin, off in (('up', PN.BF_UP, n_up, 0), ('dn', PN.BF_DN, spec.n_down, 0 if spec.full_determinant else n_up)):
+        base = pre.rsplit('linear_0', 1)[0]
+        nb = spec.backflow_layers
+        for i in range(nb - 1):
+            shp = np.asarray(params[base + f'linear_{i}:w']).shape
+            out[base + f'linear_{i}:w'] = e(f'bfh{i}.{tag}')[:shp[0], :shp[1]]
+            if spec.backflow_bias:
+                out[base + f'linear_{i}:b'] = e(f'bfb{i}.{tag}')[0, :shp[1]]
+        shp = np.asarray(params[base + f'linear_{nb - 1}:w']).shape
+        n_orb = N if spec.full_determinant else n_spin
+        cols = torch.as_tensor((np.arange(K)[:, None] * N + off + np.arange(n_orb)[None, :]).ravel(), device=flat.device)
+        out[base + f'linear_{nb - 1}:w'] = e(f'bf.{tag}')[:shp[0]][:, cols]
+        if spec.backflow_bias:
+            out[base + f'linear_{nb - 1}:b'] = e(f'bfb.{tag}')[0, cols]
+    if spec.env_per_shell:  # packed [K N][M rep] (both spins share the parameters) -> pi[K N, n_env], zetas[n_env]
+        rep = paulinet_env_rep(spec)
+        idx, seen = [], {}
+        for c_ in spec.env_centers:
+            sh = seen.get(c_, 0)
+            seen[c_] = sh + 1
+            idx.append(c_ * rep + sh)
+        idx = torch.as_tensor(idx, device=flat.device)
+        dpi = e('env.pi_up') + e('env.pi_dn')
+        dze = e('env.zeta_up') + e('env.zeta_dn')
+        out[f'{PN.ENV}:pi'] = dpi[:, idx]
+        out[f'{PN.ENV}:zetas'] = dze[:, idx].sum(0)
+    if spec.conf_coeff == 'linear':
+        out[PN.CONF + ':w'] = e('conf.w').reshape(spec.n_determinants, 1)
+    return out
+
+
 def _unpack_ferminet_grads(spec: AnsatzSpec, entries: dict, flat) -> dict:
     """Engine-layout gradient vector -> Haiku-named tree for the FermiNet (inverse of _pack_haiku_params)."""
     def e(name):
@@ -448,8 +522,11 @@ class Engine:
         rc = self.lib.dqmc_wf_vjp_params(self.h, r.data_ptr(), R.data_ptr(), Rb, B, w.data_ptr(), sign.data_ptr(), log.data_ptr(),
                                          flat.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
         self._check(rc, 'dqmc_wf_vjp_params')
-        unpack = _unpack_ferminet_grads if self.spec.kind == 'ferminet' else _unpack_psiformer_grads
-        grads = unpack(self.spec, self.entries, flat)
+        if self.spec.kind == 'paulinet':
+            grads = _unpack_paulinet_grads(self.spec, self.entries, flat, self._params)
+        else:
+            unpack = _unpack_ferminet_grads if self.spec.kind == 'ferminet' else _unpack_psiformer_grads
+            grads = unpack(self.spec, self.entries, flat)
         if self.spec.cusp_nuclei != 'none' and self.spec.cusp_nuclei_trainable:
             grads[f'{PN.NUC_CUSP}:nuc_alpha'] = flat[self.entries['cusp.nuc'][0]]
         if self.spec.kind == 'transpsiformer':
