@@ -1430,51 +1430,91 @@ struct Engine : EngineBase {
     size_t jw = d;
     for (int i = 0; i < cfg.jastrow_n; ++i) jw += cfg.jastrow_dims[i];
     // every buffer vjp_chunk_paulinet takes, with a factor 2 of head-room (these networks are tiny)
-    return 2 * ((size_t)N * ((L + 1) * d + L * (2 * nl * hn + 3 * e + 3 * (size_t)d) + cfg.backflow_n * hm + 2 * (size_t)KN +
-                             6 * (size_t)d + 4 * hn + 3 * e + 4 * hm) +
-                pairs * (4 + L * 3 * nl * em + 3 * e + 2 * em) + 3 * jw + 6 * (size_t)d + (size_t)K * 4 + 64);
+    const size_t xm = std::max<size_t>(d, 4 * (size_t)M), fmax = 3 * xm + 3 * e;
+    return 2 * ((size_t)N * ((L + 1) * xm + L * (2 * nl * hn + 3 * e + 3 * (size_t)d + fmax) + cfg.backflow_n * hm + 2 * (size_t)KN +
+                             6 * xm + 4 * hn + 3 * e + 4 * hm + 4 * xm + fmax) +
+                pairs * (4 + L * (4 * nl * em + e) + 6 * e + 2 * em) + 3 * jw + 6 * (size_t)d + (size_t)K * 4 + 64);
   }
   int vjp_chunk_paulinet(const T* r, const T* R, int Rb, int Bc, const T* wts, T* sign, T* logp, T* G, void* wsbase,
                          cudaStream_t st) {
     const int L = cfg.n_layers, rows = Bc * N, e = cfg.edge_dim, nl = cfg.gnn_sub_n > 0 ? cfg.gnn_sub_n : 1;
     const int Mne = cfg.gnn_conv_ne ? M : 0, NS = N + Mne, nt = cfg.gnn_conv_ne ? 3 : 2, pairs = Bc * N * NS;
     const int n_types = cfg.n_elec_types > 0 ? cfg.n_elec_types : 1;
+    const bool deep = cfg.gnn_deep_edges != 0;
+    const T isq2 = (T)0.70710678118654752440;
     const char* tn[3] = {"same", "anti", "ne"};
     char* p = (char*)wsbase;
     auto take = [&](size_t n) { T* q = (T*)p; p += align_up(sizeof(T) * n); return q; };
     // ---- forward, everything kept --------------------------------------------------------------------------------
-    std::vector<T*> X(L + 1), C(L);
+    std::vector<T*> X(L + 1), C(L), Fc(L), E(L);
+    std::vector<int> xd(L + 1), ed(L);
     std::vector<std::array<T*, 3>> Gt(L);
     std::vector<std::array<Tape, 3>> Wt(L);
     std::vector<std::array<Tape, 2>> Ht(L);
-    X[0] = take((size_t)rows * d);
-    DQ_LAUNCH(gnn_embed_kernel<T>, dim3((rows * d + 127) / 128), dim3(128), 0, st, P("emb.table"), n_types, N, cfg.n_up, 1, d, X[0], rows);
-    T* E = take((size_t)pairs * 4);
-    DQ_LAUNCH(gnn_edge_val_kernel<T>, dim3((pairs + 127) / 128), dim3(128), 0, st, r, R, Rb, N, M, Mne, E, pairs);
+    std::vector<Tape> Ut(L);
+    xd[0] = cfg.gnn_features ? 4 * M : d;
+    X[0] = take((size_t)rows * xd[0]);
+    if (cfg.gnn_features)  // raw nucleus-electron features [|d|, d]: no parameters
+      DQ_LAUNCH(embed_kernel<T>, dim3(rows), dim3(128), sizeof(T) * 5 * xd[0], st, r, R, Rb, N, M, cfg.n_up, 1, 0, 0, (const T*)nullptr,
+                xd[0], X[0], rows, 1, (const T*)nullptr);
+    else
+      DQ_LAUNCH(gnn_embed_kernel<T>, dim3((rows * d + 127) / 128), dim3(128), 0, st, P("emb.table"), n_types, N, cfg.n_up, 1, d, X[0], rows);
+    E[0] = take((size_t)pairs * 4);
+    ed[0] = 4;
+    DQ_LAUNCH(gnn_edge_val_kernel<T>, dim3((pairs + 127) / 128), dim3(128), 0, st, r, R, Rb, N, M, Mne, E[0], pairs);
     for (int l = 0; l < L; ++l) {
       const std::string q = "G" + std::to_string(l) + ".";
       for (int t = 0; t < nt; ++t) {
-        int rc = tape_fwd(E, 4, cfg.gnn_w_dims[l], nl, q + "w_" + tn[t] + ".", false, 0, false, pairs, take, Wt[l][t], st);
+        int rc = tape_fwd(E[l], ed[l], cfg.gnn_w_dims[l], nl, q + "w_" + tn[t] + ".", cfg.gnn_w_bias != 0, 0, false, pairs, take, Wt[l][t], st);
         if (rc) return rc;
       }
       for (int t = 0; t < 2; ++t) {
-        int rc = tape_fwd(X[l], d, cfg.gnn_h_dims[l], nl, q + "h_" + tn[t] + ".", true, 0, false, rows, take, Ht[l][t], st);
+        int rc = tape_fwd(X[l], xd[l], cfg.gnn_h_dims[l], nl, q + "h_" + tn[t] + ".", true, 0, false, rows, take, Ht[l][t], st);
         if (rc) return rc;
       }
       C[l] = take((size_t)rows * nt * e);
       DQ_LAUNCH(gnn_conv_val_kernel<T>, dim3(rows), dim3(64), 0, st, (const T*)Wt[l][0].a.back(), (const T*)Wt[l][1].a.back(),
                 (const T*)(nt == 3 ? Wt[l][2].a.back() : nullptr), (const T*)Ht[l][0].a.back(), (const T*)Ht[l][1].a.back(),
                 nt == 3 ? P(q + "hne") : (const T*)nullptr, N, Mne, cfg.n_up, e, C[l]);
-      const T* res = X[l];
-      for (int t = 0; t < nt; ++t) {  // x <- x + sum_t tanh(g_t(conv_t)): each G_t holds the running sum
-        Gt[l][t] = take((size_t)rows * d);
-        int rc = gemm(C[l] + t * e, nt * e, (q + "g_" + tn[t] + ".w").c_str(), nullptr, 0, d, P(q + "g_" + tn[t] + ".b"), nullptr, 0,
-                      Gt[l][t], d, rows, d, e, 1, 0, N, st);
+      xd[l + 1] = d;
+      if (cfg.gnn_concat) {  // x <- [(x +) tanh(g([x, mean_up x, mean_down x, conv_*]))] (/ sqrt 2)
+        const int fin = 3 * xd[l] + nt * e;
+        Fc[l] = take((size_t)rows * fin);
+        DQ_LAUNCH(gnn_concat_kernel<T>, dim3(Bc, N), dim3(128), 0, st, (const T*)X[l], xd[l], (const T*)C[l], nt * e, N, cfg.n_up, 1, Fc[l]);
+        X[l + 1] = take((size_t)rows * d);
+        int rc = gemm(Fc[l], fin, (q + "g.w").c_str(), nullptr, 0, d, cfg.gnn_g_bias ? P(q + "g.b") : nullptr, nullptr, 0, X[l + 1], d,
+                      rows, d, fin, 1, 0, N, st);
         if (rc) return rc;
-        DQ_LAUNCH(act_fl_kernel<T>, dim3(rows, (d + 63) / 64), dim3(64), 0, st, Gt[l][t], d, res, d, 1, d, T(1), 0);
-        res = Gt[l][t];
+        const bool res = xd[l] == d;
+        DQ_LAUNCH(act_fl_kernel<T>, dim3(rows, (d + 63) / 64), dim3(64), 0, st, X[l + 1], d, res ? (const T*)X[l] : (const T*)nullptr, d, 1,
+                  d, (res && cfg.gnn_res_norm) ? isq2 : T(1), 0);
+      } else {  // featurewise: x <- x + sum_t tanh(g_t(conv_t)); each G_t holds the running sum
+        const T* res = xd[l] == d ? X[l] : nullptr;
+        for (int t = 0; t < nt; ++t) {
+          Gt[l][t] = take((size_t)rows * d);
+          int rc = gemm(C[l] + t * e, nt * e, (q + "g_" + tn[t] + ".w").c_str(), nullptr, 0, d, P(q + "g_" + tn[t] + ".b"), nullptr, 0,
+                        Gt[l][t], d, rows, d, e, 1, 0, N, st);
+          if (rc) return rc;
+          DQ_LAUNCH(act_fl_kernel<T>, dim3(rows, (d + 63) / 64), dim3(64), 0, st, Gt[l][t], d, res, d, 1, d, T(1), 0);
+          res = Gt[l][t];
+        }
+        if (cfg.gnn_res_norm) { err = "dqmc_wf_vjp_params: normalised featurewise residual not supported"; return 2; }
+        X[l + 1] = Gt[l][nt - 1];
       }
-      X[l + 1] = Gt[l][nt - 1];
+      if (deep && l < L - 1) {  // shared edge MLP u + normalised residual (electron_gnn.py:160-192)
+        int rc = tape_fwd(E[l], ed[l], cfg.gnn_u_dims[l], nl, q + "u.", true, 0, false, pairs, take, Ut[l], st);
+        if (rc) return rc;
+        ed[l + 1] = e;
+        if (ed[l] == e) {
+          E[l + 1] = take((size_t)pairs * e);
+          DQ_LAUNCH((axpby_kernel<T>), dim3((unsigned)(((size_t)pairs * e + 255) / 256)), dim3(256), 0, st, (const T*)E[l],
+                    (const T*)Ut[l].a.back(), isq2, E[l + 1], (size_t)pairs * e);
+        } else {
+          E[l + 1] = Ut[l].a.back();
+        }
+      } else if (l < L - 1) {
+        E[l + 1] = E[l]; ed[l + 1] = ed[l];
+      }
     }
     // Jastrow on sum_i x_i
     Tape Jt;
@@ -1485,7 +1525,7 @@ struct Engine : EngineBase {
       int rc = tape_fwd(Js, d, cfg.jastrow_dims, cfg.jastrow_n, "J", true, 1, true, Bc, take, Jt, st);
       if (rc) return rc;
     }
-    // per-spin backflow MLPs: hidden layers (ssp), then the orbital head + default mult_act
+    // per-spin backflow MLPs: hidden layers (ssp), then the orbital head (+ default mult_act)
     std::vector<T*> Y(cfg.backflow_n + 1);
     std::vector<int> yd(cfg.backflow_n + 1);
     Y[0] = X[L]; yd[0] = d;
@@ -1534,13 +1574,19 @@ struct Engine : EngineBase {
                 G + off("env.pi_up"), G + off("env.pi_dn"), G + off("env.zeta_up"), G + off("env.zeta_dn"), env_rep, full_det);
     }
     // scratch for the reverse sweep
-    const int hm = std::max(gnn_hmax(), d), hn = std::max(gnn_hnode_max(), e), em = gnn_emax();
-    T* dXa = take((size_t)rows * d); T* dXb = take((size_t)rows * d);
+    const int xm = std::max(d, xd[0]);
+    const int hm = std::max(gnn_hmax(), xm), hn = std::max(gnn_hnode_max(), e), em = gnn_emax();
+    const int fmax = 3 * xm + nt * e;
+    T* dXa = take((size_t)rows * xm); T* dXb = take((size_t)rows * xm);
     T* sr0 = take((size_t)rows * std::max(hm, hn)); T* sr1 = take((size_t)rows * std::max(hm, hn));
     T* dCb = take((size_t)rows * nt * e); T* dCt = take((size_t)rows * e);
+    T* dFb = cfg.gnn_concat ? take((size_t)rows * fmax) : nullptr;
     T* dWb[3] = {take((size_t)pairs * e), take((size_t)pairs * e), take((size_t)pairs * e)};
     T* sp0 = take((size_t)pairs * em); T* sp1 = take((size_t)pairs * em);
     T* dHb[2] = {take((size_t)rows * e), take((size_t)rows * e)};
+    T* dEa = deep ? take((size_t)pairs * e) : nullptr;
+    T* dEb = deep ? take((size_t)pairs * e) : nullptr;
+    T* dUb = deep ? take((size_t)pairs * e) : nullptr;
     // orbital head
     if (cfg.mult_act == 1) {
       const size_t n = (size_t)rows * KN;
@@ -1575,20 +1621,40 @@ struct Engine : EngineBase {
       const size_t n = (size_t)rows * d;
       DQ_LAUNCH(bcast_add_kernel<T>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, (const T*)dJs, N, d, dXn, n);
     }
+    T* dEn = dEa;  // gradient w.r.t. E_{l+1} (deep edge features only)
+    T* dEc = dEb;
     for (int l = L - 1; l >= 0; --l) {
       const std::string q = "G" + std::to_string(l) + ".";
       const size_t nd = (size_t)rows * d;
-      // X_{l+1} = X_l + sum_t tanh(z_t): tanh outputs are the differences of the running sums
-      DQ_CHECK(cudaMemcpyAsync(dXc, dXn, sizeof(T) * nd, cudaMemcpyDeviceToDevice, st));  // residual
-      for (int t = 0; t < nt; ++t) {
-        const T* prev = t == 0 ? X[l] : Gt[l][t - 1];
-        DQ_LAUNCH(tanh_bwd_kernel<T>, dim3((unsigned)((nd + 255) / 256)), dim3(256), 0, st, (const T*)dXn, (const T*)Gt[l][t], prev, sr0, nd);
-        bgrad(sr0, d, rows, d, G + off(q + "g_" + tn[t] + ".b"), st);
-        // conv_t is a column slice of C: copy it out for the weight gradient
-        const size_t ne_ = (size_t)rows * e;
-        DQ_LAUNCH(slice_cols_kernel<T>, dim3((unsigned)((ne_ + 255) / 256)), dim3(256), 0, st, (const T*)C[l], nt * e, t * e, e, dCt, ne_);
-        wgrad(dCt, e, sr0, d, rows, e, d, G + off(q + "g_" + tn[t] + ".w"), 0, 0, st);
-        gemm_raw(sr0, d, PT(q + "g_" + tn[t] + ".w"), nullptr, 0, e, nullptr, 0, dCb + t * e, nt * e, rows, e, d, 0, st);
+      const bool need_dx = l > 0 || !cfg.gnn_features;  // layer 0 of the raw-feature variant has nothing trainable upstream
+      if (cfg.gnn_concat) {
+        const int fin = 3 * xd[l] + nt * e;
+        const bool res = xd[l] == d;
+        const T sc = (res && cfg.gnn_res_norm) ? isq2 : T(1);
+        DQ_LAUNCH(tanh_res_bwd_kernel<T>, dim3((unsigned)((nd + 255) / 256)), dim3(256), 0, st, (const T*)dXn, (const T*)X[l + 1],
+                  (const T*)(res ? X[l] : nullptr), sc, sr0, nd);
+        if (cfg.gnn_g_bias) bgrad(sr0, d, rows, d, G + off(q + "g.b"), st);
+        wgrad(Fc[l], fin, sr0, d, rows, fin, d, G + off(q + "g.w"), 0, 0, st);
+        gemm_raw(sr0, d, PT(q + "g.w"), nullptr, 0, fin, nullptr, 0, dFb, fin, rows, fin, d, 0, st);
+        // dF -> dX_l (own row + spin means + residual) and dC (the convolution columns); F = [x, mean_up, mean_down, conv_*]
+        if (nt != 2) { err = "dqmc_wf_vjp_params: concatenate update with nucleus-electron convolutions not supported"; return 2; }
+        DQ_LAUNCH(fermi_agg_bwd_kernel<T>, dim3(Bc, N), dim3(128), 0, st, (const T*)dFb, xd[l], e, N, cfg.n_up,
+                  (const T*)(res ? dXn : nullptr), sc, dXc, (T*)nullptr);
+        const size_t nc = (size_t)rows * nt * e;
+        DQ_LAUNCH(slice_cols_kernel<T>, dim3((unsigned)((nc + 255) / 256)), dim3(256), 0, st, (const T*)dFb, fin, 3 * xd[l], nt * e, dCb, nc);
+      } else {
+        // X_{l+1} = X_l + sum_t tanh(z_t): tanh outputs are the differences of the running sums
+        if (xd[l] == d) DQ_CHECK(cudaMemcpyAsync(dXc, dXn, sizeof(T) * nd, cudaMemcpyDeviceToDevice, st));  // residual
+        else DQ_CHECK(cudaMemsetAsync(dXc, 0, sizeof(T) * (size_t)rows * xd[l], st));
+        for (int t = 0; t < nt; ++t) {
+          const T* prev = t == 0 ? (xd[l] == d ? X[l] : nullptr) : Gt[l][t - 1];
+          DQ_LAUNCH(tanh_bwd_kernel<T>, dim3((unsigned)((nd + 255) / 256)), dim3(256), 0, st, (const T*)dXn, (const T*)Gt[l][t], prev, sr0, nd);
+          bgrad(sr0, d, rows, d, G + off(q + "g_" + tn[t] + ".b"), st);
+          const size_t ne_ = (size_t)rows * e;  // conv_t is a column slice of C: copy it out for the weight gradient
+          DQ_LAUNCH(slice_cols_kernel<T>, dim3((unsigned)((ne_ + 255) / 256)), dim3(256), 0, st, (const T*)C[l], nt * e, t * e, e, dCt, ne_);
+          wgrad(dCt, e, sr0, d, rows, e, d, G + off(q + "g_" + tn[t] + ".w"), 0, 0, st);
+          gemm_raw(sr0, d, PT(q + "g_" + tn[t] + ".w"), nullptr, 0, e, nullptr, 0, dCb + t * e, nt * e, rows, e, d, 0, st);
+        }
       }
       DQ_CHECK(cudaMemsetAsync(dHb[0], 0, sizeof(T) * (size_t)rows * e, st));
       DQ_CHECK(cudaMemsetAsync(dHb[1], 0, sizeof(T) * (size_t)rows * e, st));
@@ -1596,14 +1662,27 @@ struct Engine : EngineBase {
                 (const T*)Wt[l][1].a.back(), (const T*)(nt == 3 ? Wt[l][2].a.back() : nullptr), (const T*)Ht[l][0].a.back(),
                 (const T*)Ht[l][1].a.back(), nt == 3 ? P(q + "hne") : (const T*)nullptr, N, Mne, cfg.n_up, e, dWb[0], dWb[1], dWb[2],
                 dHb[0], dHb[1], nt == 3 ? G + off(q + "hne") : (T*)nullptr);
+      // gradient w.r.t. this layer's edge features E_l (only the deep-edge variant carries it; E_0 has nothing upstream)
+      const bool need_de = deep && l > 0;
+      if (need_de) DQ_CHECK(cudaMemsetAsync(dEc, 0, sizeof(T) * (size_t)pairs * ed[l], st));
       for (int t = 0; t < nt; ++t)
-        tape_bwd(Wt[l][t], dWb[t], q + "w_" + tn[t] + ".", false, 0, false, pairs, sp0, sp1, nullptr, false, G, st);
+        tape_bwd(Wt[l][t], dWb[t], q + "w_" + tn[t] + ".", cfg.gnn_w_bias != 0, 0, false, pairs, sp0, sp1, need_de ? dEc : nullptr, true, G, st);
       for (int t = 0; t < 2; ++t)
-        tape_bwd(Ht[l][t], dHb[t], q + "h_" + tn[t] + ".", true, 0, false, rows, sr0, sr1, dXc, true, G, st);
+        tape_bwd(Ht[l][t], dHb[t], q + "h_" + tn[t] + ".", true, 0, false, rows, sr0, sr1, need_dx ? dXc : nullptr, true, G, st);
+      if (deep && l < L - 1) {  // E_{l+1} = s (E_l + u(E_l))  |  u(E_l); dEn holds the gradient w.r.t. E_{l+1}
+        const bool res_e = ed[l] == e;
+        const size_t ne2 = (size_t)pairs * e;
+        DQ_LAUNCH((axpby_kernel<T>), dim3((unsigned)((ne2 + 255) / 256)), dim3(256), 0, st, (const T*)dEn, (const T*)dEn, res_e ? isq2 / T(2) : T(0.5),
+                  dUb, ne2);  // dU = s dE_{l+1}
+        tape_bwd(Ut[l], dUb, q + "u.", true, 0, false, pairs, sp0, sp1, need_de ? dEc : nullptr, true, G, st);
+        if (need_de && res_e) DQ_LAUNCH(axpy_kernel<T>, dim3((unsigned)((ne2 + 255) / 256)), dim3(256), 0, st, (const T*)dEn, isq2, dEc, ne2);
+      }
       T* tmp = dXn; dXn = dXc; dXc = tmp;
+      T* tmq = dEn; dEn = dEc; dEc = tmq;
     }
-    DQ_LAUNCH(embed_table_bwd_kernel<T>, dim3((d + 63) / 64, 64), dim3(64), 0, st, (const T*)dXn, n_types, N, cfg.n_up, d, rows,
-              G + off("emb.table"));
+    if (!cfg.gnn_features)
+      DQ_LAUNCH(embed_table_bwd_kernel<T>, dim3((d + 63) / 64, 64), dim3(64), 0, st, (const T*)dXn, n_types, N, cfg.n_up, d, rows,
+                G + off("emb.table"));
     return 0;
   }
   size_t vjp_per_walker_elems_ferminet() const {
@@ -1615,10 +1694,7 @@ struct Engine : EngineBase {
 
   int vjp_params(const void* r_, const void* R_, int Rb, int B, const void* weights, void* sign, void* logp,
                  void* grad_params, void* ws, int64_t wsb, cudaStream_t st) override {
-    if (gnn && (cfg.gnn_concat || cfg.gnn_features || cfg.gnn_deep_edges)) {
-      err = "dqmc_wf_vjp_params: conv-GNN reverse pass covers the featurewise / hk.Embed variant (tests/conf/ansatz.yaml) only";
-      return 2;
-    }
+
     if (cfg.backflow_add) { err = "dqmc_wf_vjp_params: additive backflow branch has no reverse pass"; return 2; }
     const T* r = (const T*)r_;
     const T* R = (const T*)R_;

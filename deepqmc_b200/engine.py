@@ -197,7 +197,9 @@ def _unpack_paulinet_grads(spec: AnsatzSpec, entries: dict, flat, params: dict) 
 
     N, K, M, d, n_up = spec.n_elec, spec.n_determinants, spec.n_nuc, spec.embedding_dim, spec.n_up
     nl = spec.gnn_subnet_layers
-    out = {PN.GNN + 'electron_embedding/ElectronicEmbedding:embeddings': e('emb.table')}
+    out = {}
+    if spec.gnn_embedding == 'embed':
+        out[PN.GNN + 'electron_embedding/ElectronicEmbedding:embeddings'] = e('emb.table')
     types = PN.EDGE_TYPES if spec.gnn_conv_ne else PN.EDGE_TYPES[:2]
     dxn = None
     for l in range(spec.n_layers):
@@ -205,11 +207,22 @@ def _unpack_paulinet_grads(spec: AnsatzSpec, entries: dict, flat, params: dict) 
         for t in types:
             for i in range(nl):
                 out[c + f'w_{t}/linear_{i}:w'] = e(f'G{l}.w_{t}.{i}.w')
+                if spec.gnn_update == 'concatenate':
+                    out[c + f'w_{t}/linear_{i}:b'] = e(f'G{l}.w_{t}.{i}.b')[0]
                 if t != 'ne':
                     out[c + f'h_{t}/linear_{i}:w'] = e(f'G{l}.h_{t}.{i}.w')
                     out[c + f'h_{t}/linear_{i}:b'] = e(f'G{l}.h_{t}.{i}.b')[0]
-            out[lp + f'g_conv_{t}/linear_0:w'] = e(f'G{l}.g_{t}.w')
-            out[lp + f'g_conv_{t}/linear_0:b'] = e(f'G{l}.g_{t}.b')[0]
+            if spec.gnn_update == 'featurewise':
+                out[lp + f'g_conv_{t}/linear_0:w'] = e(f'G{l}.g_{t}.w')
+                out[lp + f'g_conv_{t}/linear_0:b'] = e(f'G{l}.g_{t}.b')[0]
+        if spec.gnn_update == 'concatenate':
+            out[lp + 'g/linear_0:w'] = e(f'G{l}.g.w')
+            if spec.gnn_g_bias:
+                out[lp + 'g/linear_0:b'] = e(f'G{l}.g.b')[0]
+        if spec.gnn_deep_edges and l < spec.n_layers - 1:
+            for i in range(nl):
+                out[lp + f'u/linear_{i}:w'] = e(f'G{l}.u.{i}.w')
+                out[lp + f'u/linear_{i}:b'] = e(f'G{l}.u.{i}.b')[0]
         if spec.gnn_conv_ne:  # host: hne = tanh MLP(xn) -> gradients of the nuclear table and of h_ne
             leaves = {k: torch.as_tensor(np.asarray(params[k], dtype=np.float64)).requires_grad_(True)
                       for k in [PN.GNN + 'nuclei_embedding/~/embed:embeddings']
@@ -256,6 +269,10 @@ def _unpack_paulinet_grads(spec: AnsatzSpec, entries: dict, flat, params: dict) 
         dze = e('env.zeta_up') + e('env.zeta_dn')
         out[f'{PN.ENV}:pi'] = dpi[:, idx]
         out[f'{PN.ENV}:zetas'] = dze[:, idx].sum(0)
+    else:
+        for s_, t in (('up', 'up'), ('down', 'dn')):
+            out[f'{PN.ENV}:pi_{s_}'] = e(f'env.pi_{t}')
+            out[f'{PN.ENV}:zetas_{s_}'] = e(f'env.zeta_{t}')
     if spec.conf_coeff == 'linear':
         out[PN.CONF + ':w'] = e('conf.w').reshape(spec.n_determinants, 1)
     return out

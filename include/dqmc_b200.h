@@ -159,7 +159,7 @@ int dqmc_langevin_sweep(dqmc_handle h, void* r, void* sign, void* log, void* for
 
 /* Parameter VJP of the wave function: out_grad_params[dqmc_param_total] (compute dtype, the packed layout of
  * dqmc_param_entry) = d/dparams sum_b weights[b] log|psi(r_b)|; also returns sign/log of the batch.
- * With weights = 2 (E_loc - <E_loc>) / B this is the energy gradient (Psiformer, TransPsiformer, FermiNet, conv-GNN test ansatz).
+ * With weights = 2 (E_loc - <E_loc>) / B this is the energy gradient (all ansatz kinds; no additive backflow branch).
  * replaces: loss/loss_function.py:53-82 compute_log_psi_tangent / jax.grad through ansatz.apply,
  *           loss/energy.py:77-102 compute_mean_energy_tangent. */
 int dqmc_wf_vjp_params(dqmc_handle h, const void* r, const void* R, int32_t R_batched, int32_t n_walkers,
