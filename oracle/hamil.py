@@ -37,6 +37,15 @@ ECP_TABLES = {
         loc=[[(14.43502, 4.00000)], [(7.38188, -25.81955)], [(8.39889, 57.74008)]],
         nl=[[(7.76079, 52.13345)]],
     ),
+    # ccECP lithium ([He] core).  The coefficient of the r^0 term is known to the author to ~1e-6 only; its trailing digits
+    # are fixed by the reference's recorded local potential (tests/test_potential/test_pseudo_potentials_LiH_ccECP_.npz);
+    # the non-local potential, E_loc and walker fixtures of the same system are then reproduced independently
+    # (tests/test_reference_fixtures.py::test_lih_ccecp_fixtures).
+    ('ccECP', 3): dict(
+        n_core=2,
+        loc=[[(15.0, 1.0)], [(1.80605123393, -1.2427295785904)], [(15.0479971411, 15.0)]],
+        nl=[[(1.33024777788, 6.75286789)]],
+    ),
 }
 
 

@@ -31,6 +31,16 @@ def test_hamil_init(goldens, cls):
     np.testing.assert_array_equal(h.ecp_mask, g['pp_mask'])
 
 
+@pytest.mark.parametrize('cls', [OracleHamiltonian, lambda mol, ecp_type=None: MolecularHamiltonian(mol=mol, ecp_type=ecp_type)])
+def test_hamil_init_with_pseudopotential(goldens, cls):
+    # reference: tests/test_hamil.py 'Molecular+PP' (LiH, ccECP on Li: two core electrons removed)
+    g = goldens['hamil_init']['Molecular_PP']
+    h = cls(Molecule.from_name('LiH'), ecp_type='ccECP')
+    assert (h.n_up, h.n_down) == (g['n_up'], g['n_down'])
+    np.testing.assert_allclose(h.ns_valence, g['ns_valence'])
+    np.testing.assert_array_equal(h.ecp_mask, g['pp_mask'])
+
+
 def _lih_walker(goldens):
     # r = ne[0] because R_Li = 0 and edges are receiver - sender (reference gnn/graph.py:24)
     ne = np.asarray(goldens['edge_builder_LiH']['ne'])

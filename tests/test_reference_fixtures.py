@@ -147,3 +147,25 @@ def test_multi_nuclear_geometry_sampler_reproduces_reference_fixture(g, lih):
     for m in range(2):
         assert np.abs(states[m]['r'].numpy() - np.asarray(gs['smpl_state:elec:r'])[m]).max() < 1e-12
         assert states[m]['age'].tolist() == gs['smpl_state:elec:age'][m] and abs(states[m]['tau'].item() - gs['smpl_state:elec:tau'][m]) < 1e-12
+
+
+def test_lih_ccecp_fixtures(g):
+    """LiH with the ccECP on lithium (tests/test_hamil.py 'Molecular+PP', tests/test_potential.py LiH / ccECP): valence
+    charges and mask, the five recorded walkers, local and non-local potential and the local energy.  (The last digits of
+    one lithium coefficient were fixed with the V_loc fixture, see oracle/hamil.py; everything else is independent of it.)"""
+    mol = Molecule.from_name('LiH')
+    oh = OracleHamiltonian(mol, ecp_type='ccECP')
+    gi = g['hamil_init']['Molecular_PP']
+    assert (oh.n_up, oh.n_down) == (gi['n_up'], gi['n_down']) and oh.ns_valence.tolist() == gi['ns_valence'] and oh.ecp_mask.tolist() == gi['pp_mask']
+    rs = np.stack([J.atom_centered_initializer(k, mol.charges, oh.ns_valence, mol.coords, 1, 1) for k in J.split(J.prng_key(0), 5)])
+    assert np.abs(rs - np.asarray(g['init_sample_Molecular_PP']['rs'])).max() < 1e-14
+    r = torch.as_tensor(J.atom_centered_initializer(J.prng_key(0), mol.charges, oh.ns_valence, mol.coords, 1, 1))
+    R = torch.as_tensor(mol.coords)
+    assert abs(oh.local_potential(r, R).item() - g['potential_LiH_ccECP']['local_potential']) < 1e-9
+    spec = paulinet_spec(oh)
+    pt = wf.to_torch(J.haiku_init_conv_gnn_ansatz(spec, seed=0))
+    f = lambda x: wf.log_psi(spec, pt, x, R)
+    tw = torch.as_tensor(J.ecp_quadrature_twists(J.prng_key(0), 1, spec.n_elec))
+    assert abs(oh.nonloc_potential(r, R, f, tw).item() / g['potential_LiH_ccECP']['nonlocal_potential'] - 1) < 1e-6
+    e_loc, _ = oh.local_energy(f, r, R, phi_random=tw)
+    assert abs(e_loc.item() - g['local_energy_Molecular_PP']['E_loc']) < 2e-6

@@ -48,6 +48,10 @@ def main():
         'init_sample_Molecular': npz('test_hamil/test_init_sample_Molecular_.npz'),
         # carbon atom: plain Coulomb and ccECP potentials on the PRNGKey(0) walker (tests/test_potential.py)
         'potential_C_ccECP': npz('test_potential/test_pseudo_potentials_C_ccECP_.npz'),
+        # LiH with ccECP on lithium: walkers, potentials and E_loc (tests/test_hamil.py, tests/test_potential.py)
+        'init_sample_Molecular_PP': npz('test_hamil/test_init_sample_Molecular_PP_.npz'),
+        'potential_LiH_ccECP': npz('test_potential/test_pseudo_potentials_LiH_ccECP_.npz'),
+        'local_energy_Molecular_PP': npz('test_hamil/test_local_energy_Molecular_PP_.npz'),
         # sampler fixtures (tests/test_sampling.py): state after init(PRNGKey(0)) and after sample(PRNGKey(step)), step < 4
         'sampling': {k: npz(f'test_sampling/test_sampler_{k}_.npz') for k in
                      ('init_Metropolis', 'init_Langevin', 'sample_Metropolis', 'sample_DecorrMetropolis', 'sample_Langevin')},
