@@ -37,6 +37,13 @@ ECP_TABLES = {
         loc=[[(14.43502, 4.00000)], [(7.38188, -25.81955)], [(8.39889, 57.74008)]],
         nl=[[(7.76079, 52.13345)]],
     ),
+    # Burkatzki-Filippi-Dolg carbon (J. Chem. Phys. 126, 234105 (2007)); reproduces the reference's recorded C / bfd potentials
+    # (tests/test_potential/test_pseudo_potentials_C_bfd_.npz: local part to 1e-13).
+    ('bfd', 6): dict(
+        n_core=2,
+        loc=[[(8.35973821, 4.0)], [(3.93831258, -19.17537323)], [(4.48361888, 33.43895285)]],
+        nl=[[(5.02991637, 22.55164191)]],
+    ),
     # ccECP lithium ([He] core).  The coefficient of the r^0 term is known to the author to ~1e-6 only; its trailing digits
     # are fixed by the reference's recorded local potential (tests/test_potential/test_pseudo_potentials_LiH_ccECP_.npz);
     # the non-local potential, E_loc and walker fixtures of the same system are then reproduced independently

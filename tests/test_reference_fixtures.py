@@ -47,24 +47,25 @@ def test_electron_initializer_reproduces_reference_walkers(g):
 
 
 def test_carbon_ccecp_potentials_match_reference_fixture(g):
-    """tests/test_potential.py for C: the ccECP table restated in oracle/hamil.py (the reference reads it from pyscf)
-    reproduces the recorded local potential, and -- with the Haiku-initialised ansatz and the fold_in-derived quadrature
+    """tests/test_potential.py for C: the ccECP and bfd tables restated in oracle/hamil.py (the reference reads them from
+    pyscf) reproduce the recorded local potential, and -- with the Haiku-initialised ansatz and the fold_in-derived quadrature
     twists -- the non-local potential (the reference notes that term is 'not particularly numerically stable')."""
     mol = Molecule.from_name('C')
     oh0 = OracleHamiltonian(mol)
     r = J.atom_centered_initializer(J.prng_key(0), mol.charges, oh0.ns_valence, mol.coords, oh0.n_up, oh0.n_down)
     v = oh0.local_potential(torch.as_tensor(r), torch.as_tensor(mol.coords))
     assert abs(v.item() - g['potential_C_None']['local_potential']) < 1e-9 * abs(v.item())
-    oh = OracleHamiltonian(mol, ecp_type='ccECP')
-    assert (oh.n_up, oh.n_down) == (3, 1)
-    r = torch.as_tensor(J.atom_centered_initializer(J.prng_key(0), mol.charges, oh.ns_valence, mol.coords, oh.n_up, oh.n_down))
-    R = torch.as_tensor(mol.coords)
-    assert abs(oh.local_potential(r, R).item() - g['potential_C_ccECP']['local_potential']) < 1e-9 * 99.0
-    spec = paulinet_spec(oh)
-    pt = wf.to_torch(J.haiku_init_conv_gnn_ansatz(spec, seed=0))
-    twists = torch.as_tensor(J.ecp_quadrature_twists(J.prng_key(0), 1, spec.n_elec))
-    vnl = oh.nonloc_potential(r, R, lambda x: wf.log_psi(spec, pt, x, R), twists)
-    assert abs(vnl.item() / g['potential_C_ccECP']['nonlocal_potential'] - 1) < 1e-5
+    for ecp in ('ccECP', 'bfd'):
+        oh = OracleHamiltonian(mol, ecp_type=ecp)
+        assert (oh.n_up, oh.n_down) == (3, 1)
+        r = torch.as_tensor(J.atom_centered_initializer(J.prng_key(0), mol.charges, oh.ns_valence, mol.coords, oh.n_up, oh.n_down))
+        R = torch.as_tensor(mol.coords)
+        assert abs(oh.local_potential(r, R).item() - g[f'potential_C_{ecp}']['local_potential']) < 1e-11 * 99.0
+        spec = paulinet_spec(oh)
+        pt = wf.to_torch(J.haiku_init_conv_gnn_ansatz(spec, seed=0))
+        twists = torch.as_tensor(J.ecp_quadrature_twists(J.prng_key(0), 1, spec.n_elec))
+        vnl = oh.nonloc_potential(r, R, lambda x: wf.log_psi(spec, pt, x, R), twists)
+        assert abs(vnl.item() / g[f'potential_C_{ecp}']['nonlocal_potential'] - 1) < 1e-5
 
 
 def _wf_batch(spec, pt, R):

@@ -48,6 +48,7 @@ def main():
         'init_sample_Molecular': npz('test_hamil/test_init_sample_Molecular_.npz'),
         # carbon atom: plain Coulomb and ccECP potentials on the PRNGKey(0) walker (tests/test_potential.py)
         'potential_C_ccECP': npz('test_potential/test_pseudo_potentials_C_ccECP_.npz'),
+        'potential_C_bfd': npz('test_potential/test_pseudo_potentials_C_bfd_.npz'),
         # LiH with ccECP on lithium: walkers, potentials and E_loc (tests/test_hamil.py, tests/test_potential.py)
         'init_sample_Molecular_PP': npz('test_hamil/test_init_sample_Molecular_PP_.npz'),
         'potential_LiH_ccECP': npz('test_potential/test_pseudo_potentials_LiH_ccECP_.npz'),
