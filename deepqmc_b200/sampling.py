@@ -96,6 +96,21 @@ class AtomCenteredElectronInitializer:
         return np.concatenate([r_up, r_dn])
 
 
+class JaxCompatibleElectronInitializer:
+    """The reference's AtomCenteredElectronInitializer(ShellBasedDistribution()) driven by a numpy restatement of its
+    jax.random streams (deepqmc_b200/jaxrand.py): ``sampler.init(seed, ...)`` then returns the SAME walkers as the
+    reference's ``sampler.init(jax.random.PRNGKey(seed), ...)`` (walker b from key ``split(PRNGKey(seed), n)[b]``,
+    electron_samplers.py:84-100).  Slower than the default numpy initialiser (a few ms per walker, one-off)."""
+
+    jax_compatible = True
+
+    def walkers(self, seed, n, charges, ns_valence, R, n_up, n_down):
+        from . import jaxrand
+
+        keys = jaxrand.split(jaxrand.prng_key(int(seed)), n)
+        return np.stack([jaxrand.atom_centered_initializer(k, charges, ns_valence, R, n_up, n_down) for k in keys])
+
+
 class MetropolisSampler:
     """reference: sampling/electron_samplers.py:32-173."""
 
@@ -128,7 +143,10 @@ class MetropolisSampler:
         g = np.random.default_rng(int(rng))
         h = self.hamil
         Rn = np.asarray(R.detach().cpu() if torch.is_tensor(R) else R, dtype=np.float64)
-        r = np.stack([self.sample_initializer(g, h.mol.charges, h.ns_valence, Rn, h.n_up, h.n_down) for _ in range(n)])
+        if getattr(self.sample_initializer, 'jax_compatible', False):  # the reference's walkers for the same seed
+            r = self.sample_initializer.walkers(int(rng), n, h.mol.charges, h.ns_valence, Rn, h.n_up, h.n_down)
+        else:
+            r = np.stack([self.sample_initializer(g, h.mol.charges, h.ns_valence, Rn, h.n_up, h.n_down) for _ in range(n)])
         state = {
             'r': torch.as_tensor(r, dtype=eng.dtype, device=eng.device),
             'age': torch.zeros(n, dtype=torch.int32, device=eng.device),

@@ -117,3 +117,19 @@ def test_equilibrate_stops_when_the_criterion_is_stationary():
     smp2 = _Sampler()
     assert len(list(equilibrate(0, None, MoleculeIdxSampler(0, 3, 1), smp2, {}, crit, range(20), block_size=4, n_blocks=3,
                                 allow_early_stopping=False))) == 20
+
+
+def test_jax_compatible_initializer_gives_the_reference_walkers():
+    """sampler.init(seed) with JaxCompatibleElectronInitializer == the reference's sampler.init(PRNGKey(seed)): the recorded
+    walkers of tests/test_sampling/test_sampler_init_Metropolis_.npz (and of every n = 1 fixture) come out bit for bit."""
+    import json
+    import os
+
+    from deepqmc_b200.molecule import Molecule
+    from deepqmc_b200.sampling import JaxCompatibleElectronInitializer
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_goldens.json')))
+    mol = Molecule.from_name('LiH')
+    r = JaxCompatibleElectronInitializer().walkers(0, 10, mol.charges, mol.charges, mol.coords, 2, 2)
+    assert np.abs(r - np.asarray(g['sampling']['init_Metropolis']['r'])).max() < 1e-14
+    assert np.abs(r[:5] - np.asarray(g['init_sample_Molecular']['rs'])).max() < 1e-14
