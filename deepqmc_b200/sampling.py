@@ -96,6 +96,15 @@ class AtomCenteredElectronInitializer:
         return np.concatenate([r_up, r_dn])
 
 
+def _as_jax_key(rng):
+    """int seed -> PRNGKey(seed); a uint32[2] key (numpy) passes through (keys derived by split in combined samplers)."""
+    from . import jaxrand
+
+    if isinstance(rng, np.ndarray) and rng.dtype == np.uint32 and rng.shape == (2,):
+        return rng
+    return jaxrand.prng_key(int(rng))
+
+
 class JaxCompatibleElectronInitializer:
     """The reference's AtomCenteredElectronInitializer(ShellBasedDistribution()) driven by a numpy restatement of its
     jax.random streams (deepqmc_b200/jaxrand.py): ``sampler.init(seed, ...)`` then returns the SAME walkers as the
@@ -107,7 +116,7 @@ class JaxCompatibleElectronInitializer:
     def walkers(self, seed, n, charges, ns_valence, R, n_up, n_down):
         from . import jaxrand
 
-        keys = jaxrand.split(jaxrand.prng_key(int(seed)), n)
+        keys = jaxrand.split(_as_jax_key(seed), n)
         return np.stack([jaxrand.atom_centered_initializer(k, charges, ns_valence, R, n_up, n_down) for k in keys])
 
 
@@ -116,7 +125,8 @@ class MetropolisSampler:
 
     WALKER_STATE = ['r', 'psi', 'age']
 
-    def __init__(self, hamil, wf, *, sample_initializer=None, tau=1.0, target_acceptance=0.57, max_age=None):
+    def __init__(self, hamil, wf, *, sample_initializer=None, tau=1.0, target_acceptance=0.57, max_age=None,
+                 jax_compatible_noise=False):
         self.hamil = hamil
         self.wf = wf  # bound B200Ansatz.apply
         self.ansatz = wf.__self__
@@ -124,6 +134,23 @@ class MetropolisSampler:
         self.initial_tau, self.target_acceptance, self.max_age = tau, target_acceptance, max_age
         self.length = 1
         self._step = 0
+        # True: sample(seed, ...) draws its proposal / acceptance numbers from the reference's jax.random streams for
+        # PRNGKey(seed) (host-side restatement, deepqmc_b200/jaxrand.py) instead of the in-kernel Philox generator, i.e. the
+        # Markov chain of the reference's sampler.sample(PRNGKey(seed), ...) -- a parity mode, not the fast path
+        self.jax_compatible_noise = jax_compatible_noise
+
+    def _jax_noise(self, rng, shape_r, device, dtype):
+        """(normal[length, B, N, 3], uniform[length, B]) exactly as the reference draws them: DecorrSampler scans over
+        split(rng, length); every Metropolis / Langevin step splits its key into (proposal, acceptance)
+        (electron_samplers.py:140-147,347-353)."""
+        from . import jaxrand
+
+        key = _as_jax_key(rng)
+        subkeys = jaxrand.split(key, self.length) if self.length > 1 else [key]
+        B = shape_r[0]
+        nn = np.stack([jaxrand.normal(jaxrand.split(k, 2)[0], tuple(shape_r)) for k in subkeys])
+        nu = np.stack([jaxrand.uniform(jaxrand.split(k, 2)[1], (B,)) for k in subkeys])
+        return torch.as_tensor(nn, device=device, dtype=dtype), torch.as_tensor(nu, device=device, dtype=dtype)
 
     def phys_conf(self, R, r):
         if r.dim() == 2:
@@ -140,11 +167,12 @@ class MetropolisSampler:
 
     def init(self, rng, params, n, R):
         eng = self._engine(params)
-        g = np.random.default_rng(int(rng))
+        jaxc = getattr(self.sample_initializer, 'jax_compatible', False)
+        g = None if jaxc else np.random.default_rng(int(rng))
         h = self.hamil
         Rn = np.asarray(R.detach().cpu() if torch.is_tensor(R) else R, dtype=np.float64)
-        if getattr(self.sample_initializer, 'jax_compatible', False):  # the reference's walkers for the same seed
-            r = self.sample_initializer.walkers(int(rng), n, h.mol.charges, h.ns_valence, Rn, h.n_up, h.n_down)
+        if jaxc:  # the reference's walkers for the same seed
+            r = self.sample_initializer.walkers(rng, n, h.mol.charges, h.ns_valence, Rn, h.n_up, h.n_down)
         else:
             r = np.stack([self.sample_initializer(g, h.mol.charges, h.ns_valence, Rn, h.n_up, h.n_down) for _ in range(n)])
         state = {
@@ -156,9 +184,11 @@ class MetropolisSampler:
 
     def sample(self, rng, state, params, R, *, walker_offset=0, noise_normal=None, noise_uniform=None):
         eng = self._engine(params)
+        if self.jax_compatible_noise and noise_normal is None:
+            noise_normal, noise_uniform = self._jax_noise(rng, state['r'].shape, state['r'].device, state['r'].dtype)
         st = {'r': state['r'], 'sign': state['psi'].sign, 'log': state['psi'].log, 'age': state['age'], 'tau': state['tau']}
         stats = eng.mcmc_sweep(st, R, self.length, target_acceptance=self.target_acceptance, max_age=self.max_age,
-                               seed=int(rng), step0=self._step, walker_offset=walker_offset,
+                               seed=0 if isinstance(rng, np.ndarray) else int(rng), step0=self._step, walker_offset=walker_offset,
                                noise_normal=noise_normal, noise_uniform=noise_uniform)
         self._step += self.length
         new = {'r': st['r'], 'psi': Psi(st['sign'], st['log']), 'age': st['age'], 'tau': st['tau']}
@@ -268,10 +298,12 @@ class LangevinSampler(MetropolisSampler):
 
     def sample(self, rng, state, params, R, *, walker_offset=0, noise_normal=None, noise_uniform=None):
         eng = self._engine(params)
+        if self.jax_compatible_noise and noise_normal is None:
+            noise_normal, noise_uniform = self._jax_noise(rng, state['r'].shape, state['r'].device, state['r'].dtype)
         st = {'r': state['r'], 'sign': state['psi'].sign, 'log': state['psi'].log, 'force': state['force'],
               'age': state['age'], 'tau': state['tau']}
         stats = eng.langevin_sweep(st, R, self.length, target_acceptance=self.target_acceptance, max_age=self.max_age,
-                                   seed=int(rng), step0=self._step, walker_offset=walker_offset, noise_normal=noise_normal,
+                                   seed=0 if isinstance(rng, np.ndarray) else int(rng), step0=self._step, walker_offset=walker_offset, noise_normal=noise_normal,
                                    noise_uniform=noise_uniform)
         self._step += self.length
         new = {'r': st['r'], 'psi': Psi(st['sign'], st['log']), 'force': st['force'], 'age': st['age'], 'tau': st['tau']}
@@ -357,11 +389,21 @@ class MultiNuclearGeometrySampler:
     def init(self, rng, params, electron_batch_size, R):
         R = torch.as_tensor(np.asarray(R, dtype=np.float64)) if not torch.is_tensor(R) else R
         n_mol = len(R)
+        if self._jax():  # reference key layout: one key per molecule from split(rng, n_mol) (combined_samplers.py:128-131)
+            from . import jaxrand
+
+            seeds = list(jaxrand.split(_as_jax_key(rng), n_mol))
+        else:
+            seeds = [int(rng) * n_mol + m for m in range(n_mol)]
         return {
             'nuc': [self.nuc_sampler.init(R[m]) for m in range(n_mol)],
-            'elec': [self.elec_sampler.init(int(rng) * n_mol + m, params, electron_batch_size, R[m]) for m in range(n_mol)],
+            'elec': [self.elec_sampler.init(seeds[m], params, electron_batch_size, R[m]) for m in range(n_mol)],
             'update_nuc_counter': torch.zeros(n_mol, dtype=torch.int64),
         }
+
+    def _jax(self):
+        inner = getattr(self.elec_sampler, 'sampler', self.elec_sampler)  # through a MultiElectronicStateSampler
+        return getattr(inner, 'jax_compatible_noise', False)
 
     def _R_dev(self, elec_state, R):
         st0 = elec_state[0] if isinstance(elec_state, list) else elec_state
@@ -384,17 +426,23 @@ class MultiNuclearGeometrySampler:
         mol_idxs = [int(m) for m in np.asarray(mol_idxs).reshape(-1)]
         counter = smpl_state['update_nuc_counter']
         rs, Rs, stats = [], [], []
+        if self._jax():  # rngs_elec, rngs_nuc = split(rng, (2, n)): electron keys first (combined_samplers.py:173)
+            from . import jaxrand
+
+            elec_seeds = list(jaxrand.split(_as_jax_key(rng), 2 * len(mol_idxs))[:len(mol_idxs)])
+        else:
+            elec_seeds = [int(rng) * len(mol_idxs) + k for k in range(len(mol_idxs))]
         for k, m in enumerate(mol_idxs):
             if self.update_nuc_period is not None:
                 if int(counter[m]) == self.update_nuc_period - 1:
                     smpl_state['nuc'][m], smpl_state['elec'][m], _ = self.update_nuc(
-                        int(rng) * 104729 + k, smpl_state['nuc'][m], smpl_state['elec'][m], params)
+                        (0 if isinstance(rng, np.ndarray) else int(rng)) * 104729 + k, smpl_state['nuc'][m], smpl_state['elec'][m], params)
                     counter[m] = 0
                 else:
                     counter[m] += 1
             Rd = self._R_dev(smpl_state['elec'][m], smpl_state['nuc'][m]['R'])
             kw = {} if noise_normal is None else {'noise_normal': noise_normal[k], 'noise_uniform': noise_uniform[k]}
-            smpl_state['elec'][m], pc, st = self.elec_sampler.sample(int(rng) * len(mol_idxs) + k, smpl_state['elec'][m], params, Rd, **kw)
+            smpl_state['elec'][m], pc, st = self.elec_sampler.sample(elec_seeds[k], smpl_state['elec'][m], params, Rd, **kw)
             r = pc.r if pc.r.dim() == 4 else pc.r[None]  # [n_state, B, N, 3]
             rs.append(r)
             Rs.append(Rd[None, None].expand(*r.shape[:2], *Rd.shape))
