@@ -7,22 +7,32 @@ from . import parallel
 from .types import PhysicalConfiguration
 
 
-def compute_local_energy(rng, hamil, ansatz_apply, params, phys_conf: PhysicalConfiguration, batch_size=None):
+def compute_local_energy(rng, hamil, ansatz_apply, params, phys_conf: PhysicalConfiguration, batch_size=None,
+                         jax_compatible_rng=False):
     """reference: loss/energy.py:19-60.  phys_conf batch shape [mol, state, walker] (or [walker]);
-    params: one tree per state (list) or a single tree.  Returns (E_loc[batch_shape], stats{key: mean over walkers})."""
+    params: one tree per state (list) or a single tree.  Returns (E_loc[batch_shape], stats{key: mean over walkers}).
+    ``jax_compatible_rng``: the ECP quadrature twists follow the reference's streams for PRNGKey(rng): the key is split over
+    the batch shape (:43), every walker folds in its nucleus slot and electron index."""
     loc = hamil.local_energy(ansatz_apply)
     r, R = phys_conf.r, phys_conf.R
     if r.dim() == 3:
-        E, stats = loc(rng, params if not isinstance(params, (list, tuple)) else params[0], phys_conf)
+        E, stats = loc(rng, params if not isinstance(params, (list, tuple)) else params[0], phys_conf,
+                       jax_compatible_rng=jax_compatible_rng)
         return E, {k: v.mean(-1) for k, v in stats.items()}
     Mb, S, B = r.shape[:3]
     E = torch.empty(Mb, S, B, dtype=r.dtype, device=r.device)
     acc: dict = {}
+    keys = None
+    if jax_compatible_rng and rng is not None:
+        from . import jaxrand
+
+        keys = jaxrand.split(jaxrand.prng_key(int(rng)), Mb * S * B).reshape(Mb, S, B, 2)  # split(rng, batch_shape)
     for m in range(Mb):
         for s in range(S):
             p = params[s] if isinstance(params, (list, tuple)) else params
-            seed = None if rng is None else int(rng) * 1000003 + m * S + s
-            e, st = loc(seed, p, PhysicalConfiguration(R[m, s, 0] if R.dim() == 5 else R, r[m, s], phys_conf.mol_idx[m, s]))
+            seed = None if rng is None else (keys[m, s] if keys is not None else int(rng) * 1000003 + m * S + s)
+            kw = {'jax_compatible_rng': True} if keys is not None else {}
+            e, st = loc(seed, p, PhysicalConfiguration(R[m, s, 0] if R.dim() == 5 else R, r[m, s], phys_conf.mol_idx[m, s]), **kw)
             E[m, s] = e
             for k, v in st.items():
                 acc.setdefault(k, torch.empty(Mb, S, dtype=r.dtype, device=r.device))[m, s] = v.mean()

@@ -464,6 +464,7 @@ class Engine:
 
     def _R(self, R, B):
         R = self._prep(R)
+        assert R.dim() in (2, 3) and tuple(R.shape[-2:]) == (self.spec.n_nuc, 3), f'R must be [M, 3] or [B, M, 3], got {tuple(R.shape)}'
         batched = 1 if R.dim() == 3 else 0
         if batched:
             assert R.shape[0] == B

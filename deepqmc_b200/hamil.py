@@ -148,7 +148,10 @@ class MolecularHamiltonian:
         if ansatz is None or not hasattr(ansatz, 'engine_for'):
             raise TypeError('local_energy expects the bound .apply of a deepqmc_b200 B200Ansatz')
 
-        def loc_ene(rng, params, phys_conf: PhysicalConfiguration, ecp_twist=None, return_grad=False):
+        def loc_ene(rng, params, phys_conf: PhysicalConfiguration, ecp_twist=None, return_grad=False, jax_compatible_rng=False):
+            """``jax_compatible_rng``: derive the quadrature twists of the non-local ECP from the reference's jax.random streams
+            for ``PRNGKey(rng)`` (``rng`` may also be a uint32[2] key or, for a batch, an array of per-walker keys [B, 2]) instead
+            of the in-kernel Philox generator: fold_in(fold_in(key, j), i) -> uniform(0, pi / 5) (gaussian_type_ecp.py:224)."""
             eng = ansatz.engine_for(self, params)
             if self.nl_params is not None and len(self.pot.nuc_with_nl_pot) and rng is None and ecp_twist is None:
                 raise AssertionError('rng is required for the non-local ECP quadrature')  # gaussian_type_ecp.py:176
@@ -156,6 +159,16 @@ class MolecularHamiltonian:
             single = r.dim() == 2
             if single:
                 r, R = r[None], R
+            n_nl = 0 if self.nl_params is None else len(self.pot.nuc_with_nl_pot)
+            if jax_compatible_rng and n_nl and ecp_twist is None:
+                from . import jaxrand
+
+                keys = np.asarray(rng, dtype=np.uint32) if isinstance(rng, np.ndarray) else jaxrand.prng_key(int(rng))
+                if keys.ndim == 1:  # one key: a single sample uses it directly, a batch splits it over the walkers
+                    keys = keys[None] if single else jaxrand.split(keys, r.shape[0])
+                tw = jaxrand.ecp_quadrature_twists_batch(keys, n_nl, r.shape[1])
+                ecp_twist = torch.as_tensor(tw, dtype=r.dtype, device=r.device)
+                rng = 0
             if R.dim() == 3 and self.nl_params is not None:
                 R = R[0]
             seed = int(rng) if isinstance(rng, (int, np.integer)) else 0

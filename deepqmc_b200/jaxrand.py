@@ -23,8 +23,9 @@ def _rotl(x, d):
 def threefry2x32(key, c0, c1):
     """key: 2 uint32; c0, c1: uint32 arrays of equal shape -> two uint32 arrays."""
     with np.errstate(over='ignore'):
-        k0, k1 = U32(key[0]), U32(key[1])
-        ks = (k0, k1, U32(k0 ^ k1 ^ U32(0x1BD11BDA)))
+        key = np.asarray(key, dtype=U32)
+        k0, k1 = key[..., 0], key[..., 1]  # a single key or an array of keys [..., 2] broadcasting against the counters
+        ks = (k0, k1, (k0 ^ k1 ^ U32(0x1BD11BDA)).astype(U32))
         x0 = (np.asarray(c0, dtype=U32) + ks[0]).astype(U32)
         x1 = (np.asarray(c1, dtype=U32) + ks[1]).astype(U32)
         for r in range(5):
@@ -223,3 +224,27 @@ def ecp_quadrature_twists(key, n_nl_nuclei: int, n_elec: int, partitionable=True
         for i in range(n_elec):
             out[j, i] = uniform(fold_in(kj, i), (), np.float64, 0.0, np.pi / 5, partitionable)
     return out
+
+
+def fold_in_many(keys, data):
+    """fold_in for an array of keys [..., 2] and broadcastable integer data -> keys [..., 2]."""
+    keys = np.asarray(keys, dtype=U32)
+    data = np.asarray(data)
+    shape = np.broadcast_shapes(keys.shape[:-1], data.shape)
+    kb = np.broadcast_to(keys, shape + (2,))
+    o0, o1 = threefry2x32(kb, np.zeros(shape, dtype=U32), np.broadcast_to(data, shape).astype(U32))
+    return np.stack([o0, o1], -1)
+
+
+def ecp_quadrature_twists_batch(keys, n_nl_nuclei: int, n_elec: int):
+    """phi_random[b, j, i] for per-walker keys [B, 2] (the reference splits its key over the batch shape, loss/energy.py:43,
+    then folds in the nucleus slot j and the electron i, gaussian_type_ecp.py:224; JAX >= 0.5 bit layout)."""
+    keys = np.asarray(keys, dtype=U32).reshape(-1, 2)
+    kj = fold_in_many(keys[:, None, :], np.arange(n_nl_nuclei)[None, :])             # [B, J, 2]
+    kji = fold_in_many(kj[:, :, None, :], np.arange(n_elec)[None, None, :])           # [B, J, N, 2]
+    zero = np.zeros(kji.shape[:-1], dtype=U32)
+    b1, b2 = threefry2x32(kji, zero, zero)                                            # random_bits(key, 64, ()) per key
+    bits = (b1.astype(np.uint64) << np.uint64(32)) | b2.astype(np.uint64)
+    f = ((bits >> np.uint64(12)) | np.float64(1.0).view(np.uint64)).view(np.float64) - 1.0
+    return np.maximum(0.0, f * (np.pi / 5))
+
