@@ -220,3 +220,47 @@ def perturb_params(params, seed=1, scale=0.2):
 
 def n_params(spec):
     return int(sum(int(np.prod(s)) for s in param_shapes(spec).values()))
+
+
+# ---- exchange with a reference run ------------------------------------------------------------------------------------
+def flatten_haiku_tree(tree: dict, sep: str = ':') -> dict:
+    """{'<module path>': {'<name>': array}} (the nested dict Haiku returns from init) -> {'<module path>:<name>': array},
+    the key layout of this module and of the reference's own test helper (tests/conftest.py:39-52 flatten_pytree)."""
+    out = {}
+    for mod, leaves in tree.items():
+        if isinstance(leaves, dict):
+            for name, v in leaves.items():
+                out[f'{mod}{sep}{name}'] = np.asarray(v)
+        else:  # already flat
+            out[mod] = np.asarray(leaves)
+    return out
+
+
+def unflatten_haiku_tree(flat: dict, sep: str = ':') -> dict:
+    out: dict = {}
+    for k, v in flat.items():
+        mod, name = k.rsplit(sep, 1)
+        out.setdefault(mod, {})[name] = np.asarray(v)
+    return out
+
+
+def save_params(path: str, params: dict) -> None:
+    """np.savez of a flat or nested parameter tree with the ':'-flattened Haiku names (what
+    ``np.savez(path, **flatten_pytree(params))`` writes on the reference side)."""
+    flat = flatten_haiku_tree(params) if any(isinstance(v, dict) for v in params.values()) else params
+    np.savez(path, **{k: np.asarray(v) for k, v in flat.items()})
+
+
+def load_params(path: str, spec: AnsatzSpec | None = None) -> dict:
+    """Read such a file; with ``spec`` the names and shapes are checked against the ansatz (a missing, extra or misshapen
+    leaf raises instead of silently evaluating a different wave function)."""
+    with np.load(path) as f:
+        flat = {k: np.asarray(f[k], dtype=np.float64) for k in f.files}
+    if spec is not None:
+        want = param_shapes(spec)
+        if set(flat) != set(want):
+            raise ValueError(f'parameter names differ: missing {sorted(set(want) - set(flat))[:3]}, unexpected {sorted(set(flat) - set(want))[:3]}')
+        for k, shp in want.items():
+            if tuple(flat[k].shape) != tuple(shp):
+                raise ValueError(f'{k}: shape {flat[k].shape}, expected {tuple(shp)}')
+    return flat

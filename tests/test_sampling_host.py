@@ -133,3 +133,24 @@ def test_jax_compatible_initializer_gives_the_reference_walkers():
     r = JaxCompatibleElectronInitializer().walkers(0, 10, mol.charges, mol.charges, mol.coords, 2, 2)
     assert np.abs(r - np.asarray(g['sampling']['init_Metropolis']['r'])).max() < 1e-14
     assert np.abs(r[:5] - np.asarray(g['init_sample_Molecular']['rs'])).max() < 1e-14
+
+
+def test_parameter_exchange_with_a_reference_run(tmp_path):
+    """':'-flattened Haiku names <-> npz: nested Haiku tree in, flat tree out, shape / name checks."""
+    import pytest
+
+    from deepqmc_b200 import params as PN
+    from deepqmc_b200.hamil import MolecularHamiltonian
+    from deepqmc_b200.molecule import Molecule
+    from deepqmc_b200.spec import paulinet_spec, psiformer_spec
+
+    hamil = MolecularHamiltonian(mol=Molecule.from_name('LiH'))
+    spec = paulinet_spec(hamil)
+    flat = PN.init_params(spec, 0)
+    nested = PN.unflatten_haiku_tree(flat)
+    assert all(isinstance(v, dict) for v in nested.values()) and PN.flatten_haiku_tree(nested).keys() == flat.keys()
+    PN.save_params(str(tmp_path / 'p.npz'), nested)  # what np.savez(..., **flatten_pytree(params)) writes on the reference side
+    back = PN.load_params(str(tmp_path / 'p.npz'), spec)
+    assert back.keys() == flat.keys() and all(np.array_equal(back[k], flat[k]) for k in flat)
+    with pytest.raises(ValueError):
+        PN.load_params(str(tmp_path / 'p.npz'), psiformer_spec(hamil))  # another ansatz: names differ
