@@ -19,7 +19,7 @@ SYMBOLS = [
     'dqmc_param_entry', 'dqmc_param_total', 'dqmc_set_params', 'dqmc_workspace_bytes',
     'dqmc_wf_forward', 'dqmc_local_energy', 'dqmc_mcmc_sweep', 'dqmc_launch_count',
     'dqmc_profile_begin', 'dqmc_profile_end', 'dqmc_debug_gemm', 'dqmc_wf_vjp_params', 'dqmc_langevin_sweep',
-    'dqmc_set_pseudo_hamiltonian', 'dqmc_wf_orbitals',
+    'dqmc_set_pseudo_hamiltonian', 'dqmc_wf_orbitals', 'dqmc_mcmc_sweep_exchange',
 ]
 
 
@@ -79,6 +79,8 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dqmc_local_energy.argtypes = [vp, vp, vp, i32, i32, u64, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     lib.dqmc_mcmc_sweep.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, C.c_double, i32, u64, u64, u64,
                                     vp, vp, vp, vp, i64, vp]
+    lib.dqmc_mcmc_sweep_exchange.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, C.c_double, i32, u64, u64, u64,
+                                             vp, vp, C.c_double, C.POINTER(i32), vp, vp, vp, i64, vp]
     lib.dqmc_langevin_sweep.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, C.c_double, i32, u64, u64, u64,
                                         vp, vp, vp, vp, i64, vp]
     lib.dqmc_wf_vjp_params.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, i64, vp]

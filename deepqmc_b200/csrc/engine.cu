@@ -64,7 +64,8 @@ struct EngineBase {
                          int sliced, int backend, cudaStream_t st) = 0;
   virtual int mcmc(void* r, void* sign, void* logp, int32_t* age, void* tau, const void* R, int Rb, int B, int n_sub,
                    double target, int max_age, uint64_t seed, uint64_t step0, uint64_t woff, const void* nn,
-                   const void* nu, void* stats, void* ws, int64_t wsb, cudaStream_t st) = 0;
+                   const void* nu, void* stats, void* ws, int64_t wsb, cudaStream_t st, double p_exchange = 0.0,
+                   const int32_t* ex_flags = nullptr, const int32_t* ex_idx = nullptr) = 0;
 
   void add(const std::string& n, int rows, int cols) {
     entries.push_back({n, total, rows, cols});
@@ -1800,7 +1801,11 @@ struct Engine : EngineBase {
 
   int mcmc(void* r_, void* sign_, void* logp_, int32_t* age, void* tau_, const void* R_, int Rb, int B, int n_sub,
            double target, int max_age, uint64_t seed, uint64_t step0, uint64_t woff, const void* nn, const void* nu,
-           void* stats_, void* ws, int64_t wsb, cudaStream_t st) override {
+           void* stats_, void* ws, int64_t wsb, cudaStream_t st, double p_exchange, const int32_t* ex_flags,
+           const int32_t* ex_idx) override {
+    // p_exchange > 0 (or ex_flags given): some sub-steps are spin-exchange steps (OppositeSpinExchangeSampler,
+    // electron_samplers.py:286-330): the whole batch swaps one up / down pair per walker, plain Metropolis acceptance without
+    // max_age override and without step-size adaptation.  ex_flags[n_sub] (host) / ex_idx[n_sub][B][2] (device): injected.
     T* r = (T*)r_; T* sign = (T*)sign_; T* logp = (T*)logp_; T* tau = (T*)tau_; T* stats = (T*)stats_;
     const T* R = (const T*)R_;
     char* p = (char*)ws;
@@ -1814,13 +1819,24 @@ struct Engine : EngineBase {
     for (int s = 0; s < n_sub; ++s) {
       const T* nns = nn ? (const T*)nn + (size_t)s * ne : nullptr;
       const T* nus = nu ? (const T*)nu + (size_t)s * B : nullptr;
+      bool exchange = false;
+      if (ex_flags) exchange = ex_flags[s] != 0;
+      else if (p_exchange > 0.0) {  // one decision per sub-step for the whole batch (as the reference's lax.cond on a scalar)
+        uint32_t w4[4];
+        Philox::gen(seed ^ 0xA0761D6478BD642Full, 0, step0 + (uint64_t)s, w4);
+        exchange = Philox::u01(w4[0], w4[1]) < p_exchange;
+      }
+      if (exchange)
+        DQ_LAUNCH(exchange_propose_kernel<T>, dim3((B + 127) / 128), dim3(128), 0, st, (const T*)r, rp,
+                  ex_idx ? ex_idx + (size_t)s * 2 * B : (const int32_t*)nullptr, seed, step0 + (uint64_t)s, woff, cfg.n_up, N, B);
+      else
       DQ_LAUNCH(propose_kernel<T>, dim3((ne / 2 + 1 + 127) / 128), dim3(128), 0, st, (const T*)r, rp, (const T*)tau, nns,
                 seed, step0 + (uint64_t)s, woff * (uint64_t)(3 * N), ne);
       int rc = run_batched(rp, R, Rb, B, 1, sp, lp, nullptr, nullptr, nullptr, p, rest, st);
       if (rc) return rc;
       DQ_LAUNCH(accept_kernel<T>, dim3((B + 127) / 128), dim3(128), 0, st, r, (const T*)rp, sign, (const T*)sp, logp,
-                (const T*)lp, age, nus, seed, step0 + (uint64_t)s, woff, max_age, B, N, cnt);
-      DQ_LAUNCH(tau_kernel<T>, dim3(1), dim3(32), 0, st, tau, cnt, B, (T)target, stats);
+                (const T*)lp, age, nus, seed, step0 + (uint64_t)s, woff, exchange ? -1 : max_age, B, N, cnt);
+      DQ_LAUNCH(tau_kernel<T>, dim3(1), dim3(32), 0, st, tau, cnt, B, exchange ? T(0) : (T)target, stats);
     }
     DQ_LAUNCH(sampler_stats_kernel<T>, dim3(1), dim3(256), 0, st, (const T*)r, (const T*)logp, (const int*)age,
               (const T*)tau, B, N, stats);
@@ -1921,6 +1937,19 @@ int dqmc_mcmc_sweep(dqmc_handle h, void* r, void* sign, void* log, int32_t* age,
   return h->e->mcmc(r, sign, log, age, tau, R, R_batched, n_walkers, n_sub, target_acceptance, max_age, seed, step0,
                     walker_offset, noise_normal, noise_uniform, out_stats, workspace, workspace_bytes,
                     (cudaStream_t)stream);
+}
+int dqmc_mcmc_sweep_exchange(dqmc_handle h, void* r, void* sign, void* log, int32_t* age, void* tau, const void* R,
+                             int32_t R_batched, int32_t n_walkers, int32_t n_sub, double target_acceptance, int32_t max_age,
+                             uint64_t seed, uint64_t step0, uint64_t walker_offset, const void* noise_normal,
+                             const void* noise_uniform, double exchange_step_probability, const int32_t* exchange_flags,
+                             const int32_t* exchange_idx, void* out_stats, void* workspace, int64_t workspace_bytes,
+                             void* stream) {
+  if (!h) return 2;
+  if (n_walkers < 1) { h->e->err = "the sampler needs at least one walker"; return 2; }
+  if (h->e->cfg.n_up < 1 || h->e->cfg.n_down < 1) { h->e->err = "spin exchange needs electrons of both spins"; return 2; }
+  return h->e->mcmc(r, sign, log, age, tau, R, R_batched, n_walkers, n_sub, target_acceptance, max_age, seed, step0,
+                    walker_offset, noise_normal, noise_uniform, out_stats, workspace, workspace_bytes, (cudaStream_t)stream,
+                    exchange_step_probability, exchange_flags, exchange_idx);
 }
 int dqmc_langevin_sweep(dqmc_handle h, void* r, void* sign, void* log, void* force, int32_t* age, void* tau, const void* R,
                         int32_t R_batched, int32_t n_walkers, int32_t n_sub, double target_acceptance, int32_t max_age,

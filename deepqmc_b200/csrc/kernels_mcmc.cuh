@@ -32,6 +32,33 @@ __global__ void propose_kernel(const T* __restrict__ r, T* __restrict__ r_prop, 
   if (e0 + 1 < n_elem) r_prop[e0 + 1] = r[e0 + 1] + t * z1;
 }
 
+// Spin-exchange proposal (reference: sampling/electron_samplers.py:235-285 OppositeSpinExchangeSampler.exchange_proposal with
+// the default uniform logits): r' = r with the positions of one spin-up electron and one spin-down electron swapped.
+// idx[b][2] = (up index, down index) injected by parity tests, else drawn from Philox.  One thread per walker.
+template <class T>
+__global__ void exchange_propose_kernel(const T* __restrict__ r, T* __restrict__ r_prop, const int* __restrict__ idx,
+                                        uint64_t seed, uint64_t step, uint64_t walker_offset, int n_up, int N, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int iu, id;
+  if (idx) { iu = idx[2 * b]; id = idx[2 * b + 1]; }
+  else {
+    uint32_t w[4];
+    Philox::gen(seed ^ 0xD1B54A32D192ED03ull, walker_offset + (uint64_t)b, step, w);
+    iu = (int)(Philox::u01(w[0], w[1]) * n_up);
+    id = (int)(Philox::u01(w[2], w[3]) * (N - n_up));
+    iu = iu < n_up ? iu : n_up - 1;
+    id = id < N - n_up ? id : N - n_up - 1;
+  }
+  const T* rb = r + (size_t)b * 3 * N;
+  T* pb = r_prop + (size_t)b * 3 * N;
+  for (int e = 0; e < 3 * N; ++e) pb[e] = rb[e];
+  for (int c = 0; c < 3; ++c) {
+    pb[3 * iu + c] = rb[3 * (n_up + id) + c];
+    pb[3 * (n_up + id) + c] = rb[3 * iu + c];
+  }
+}
+
 // Accept/reject, one thread per walker.  reference: electron_samplers.py:106-138
 // (2 dlog|psi| > log u, max_age override, age bookkeeping, per-walker select of r/psi/age).
 template <class T>

@@ -568,8 +568,11 @@ class Engine:
         return sign, log, grads
 
     def mcmc_sweep(self, state, R, n_sub, target_acceptance=0.57, max_age=None, seed=0, step0=0, walker_offset=0,
-                   noise_normal=None, noise_uniform=None, max_ws_bytes=None):
-        """state: dict(r[B,N,3], sign[B], log[B], age[B] int32, tau[1]) -- updated IN PLACE."""
+                   noise_normal=None, noise_uniform=None, max_ws_bytes=None, exchange_probability=0.0, exchange_flags=None,
+                   exchange_idx=None):
+        """state: dict(r[B,N,3], sign[B], log[B], age[B] int32, tau[1]) -- updated IN PLACE.
+        exchange_probability > 0 (or injected ``exchange_flags[n_sub]`` / ``exchange_idx[n_sub, B, 2]``): spin-exchange
+        sub-steps mixed in (dqmc_mcmc_sweep_exchange; reference OppositeSpinExchangeSampler)."""
         r = state['r']
         B = r.shape[0]
         for k in ('r', 'sign', 'log', 'tau'):
@@ -596,6 +599,23 @@ class Engine:
             self._ws = torch.empty(fw + extra, dtype=torch.uint8, device=self.device)
             self._ws_ok = set()
         ws = self._ws
+        if exchange_probability > 0.0 or exchange_flags is not None:
+            flags = None
+            if exchange_flags is not None:
+                flags = (C.c_int32 * n_sub)(*[int(f) for f in exchange_flags])
+            xi = None
+            if exchange_idx is not None:
+                xi = exchange_idx.to(device=self.device, dtype=torch.int32).contiguous()
+                assert xi.shape == (n_sub, B, 2)
+            rc = self.lib.dqmc_mcmc_sweep_exchange(
+                self.h, r.data_ptr(), state['sign'].data_ptr(), state['log'].data_ptr(), state['age'].data_ptr(),
+                state['tau'].data_ptr(), R.data_ptr(), Rb, B, n_sub, float(target_acceptance if target_acceptance else 0.0),
+                -1 if max_age is None else int(max_age), seed, step0, walker_offset,
+                nn.data_ptr() if nn is not None else None, nu.data_ptr() if nu is not None else None,
+                float(exchange_probability), flags, xi.data_ptr() if xi is not None else None,
+                stats.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
+            self._check(rc, 'dqmc_mcmc_sweep_exchange')
+            return stats
         rc = self.lib.dqmc_mcmc_sweep(
             self.h, r.data_ptr(), state['sign'].data_ptr(), state['log'].data_ptr(), state['age'].data_ptr(),
             state['tau'].data_ptr(), R.data_ptr(), Rb, B, n_sub, float(target_acceptance if target_acceptance else 0.0),

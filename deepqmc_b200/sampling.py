@@ -138,6 +138,34 @@ class MetropolisSampler:
         # PRNGKey(seed) (host-side restatement, deepqmc_b200/jaxrand.py) instead of the in-kernel Philox generator, i.e. the
         # Markov chain of the reference's sampler.sample(PRNGKey(seed), ...) -- a parity mode, not the fast path
         self.jax_compatible_noise = jax_compatible_noise
+        self.exchange_step_probability = 0.0  # set by chain(..., OppositeSpinExchangeSampler(...), MetropolisSampler(...))
+
+    def _jax_noise_exchange(self, rng, shape_r, device, dtype):
+        """The reference's streams with an OppositeSpinExchangeSampler in the chain (electron_samplers.py:286-330): every step
+        splits its key three ways (exchange decision, proposal, acceptance); an exchange step draws the up / down indices from
+        categorical(split(rng_prop)) with uniform logits.  -> (normal, uniform, flags[length], idx[length, B, 2])"""
+        from . import jaxrand
+
+        key = _as_jax_key(rng)
+        subkeys = jaxrand.split(key, self.length) if self.length > 1 else [key]
+        B, n_up, n_dn = shape_r[0], self.hamil.n_up, self.hamil.n_down
+        nn, nu, flags, idx = [], [], [], []
+        for k in subkeys:
+            ke, kp, ka = jaxrand.split(k, 3)
+            ex = bool(jaxrand.uniform(ke, ()) < self.exchange_step_probability)
+            flags.append(int(ex))
+            if ex:
+                ku, kd = jaxrand.split(kp, 2)
+                up = np.argmax(jaxrand.gumbel(ku, (B, n_up)), -1)
+                dn = np.argmax(jaxrand.gumbel(kd, (B, n_dn)), -1)
+                idx.append(np.stack([up, dn], -1))
+                nn.append(np.zeros(tuple(shape_r)))
+            else:
+                idx.append(np.zeros((B, 2), dtype=np.int64))
+                nn.append(jaxrand.normal(kp, tuple(shape_r)))
+            nu.append(jaxrand.uniform(ka, (B,)))
+        return (torch.as_tensor(np.stack(nn), device=device, dtype=dtype), torch.as_tensor(np.stack(nu), device=device, dtype=dtype),
+                flags, torch.as_tensor(np.stack(idx), dtype=torch.int32, device=device))
 
     def _jax_noise(self, rng, shape_r, device, dtype):
         """(normal[length, B, N, 3], uniform[length, B]) exactly as the reference draws them: DecorrSampler scans over
@@ -182,14 +210,22 @@ class MetropolisSampler:
         }
         return self.update(state, params, torch.as_tensor(Rn, dtype=eng.dtype, device=eng.device))
 
-    def sample(self, rng, state, params, R, *, walker_offset=0, noise_normal=None, noise_uniform=None):
+    def sample(self, rng, state, params, R, *, walker_offset=0, noise_normal=None, noise_uniform=None, exchange_flags=None,
+               exchange_idx=None):
         eng = self._engine(params)
+        xkw = {}
+        if self.exchange_step_probability > 0.0:
+            xkw = {'exchange_probability': self.exchange_step_probability, 'exchange_flags': exchange_flags, 'exchange_idx': exchange_idx}
         if self.jax_compatible_noise and noise_normal is None:
-            noise_normal, noise_uniform = self._jax_noise(rng, state['r'].shape, state['r'].device, state['r'].dtype)
+            if self.exchange_step_probability > 0.0:
+                noise_normal, noise_uniform, fl, ix = self._jax_noise_exchange(rng, state['r'].shape, state['r'].device, state['r'].dtype)
+                xkw.update(exchange_flags=fl, exchange_idx=ix)
+            else:
+                noise_normal, noise_uniform = self._jax_noise(rng, state['r'].shape, state['r'].device, state['r'].dtype)
         st = {'r': state['r'], 'sign': state['psi'].sign, 'log': state['psi'].log, 'age': state['age'], 'tau': state['tau']}
         stats = eng.mcmc_sweep(st, R, self.length, target_acceptance=self.target_acceptance, max_age=self.max_age,
                                seed=0 if isinstance(rng, np.ndarray) else int(rng), step0=self._step, walker_offset=walker_offset,
-                               noise_normal=noise_normal, noise_uniform=noise_uniform)
+                               noise_normal=noise_normal, noise_uniform=noise_uniform, **xkw)
         self._step += self.length
         new = {'r': st['r'], 'psi': Psi(st['sign'], st['log']), 'age': st['age'], 'tau': st['tau']}
         return new, self.phys_conf(R, new['r']), dict(zip(STAT_NAMES, stats))
@@ -209,6 +245,18 @@ class DecorrSampler(MetropolisSampler):
         self.length = int(length)
 
 
+class OppositeSpinExchangeSampler:
+    """Link for chain(): with probability ``exchange_step_probability`` a sampling step proposes, for every walker, to swap the
+    positions of a random spin-up / spin-down electron pair instead of the Gaussian move (reference:
+    sampling/electron_samplers.py:235-330; conf/task/sampler_factory/elec_sampler/decorr_spin_exchange_metropolis.yaml).
+    Uniform pair selection (the reference's default logits); custom logits functions are not supported."""
+
+    def __init__(self, *, exchange_step_probability: float, up_logits_fn=None, down_logits_fn=None):
+        if up_logits_fn is not None or down_logits_fn is not None:
+            raise NotImplementedError('custom spin-exchange logits')
+        self.exchange_step_probability = float(exchange_step_probability)
+
+
 def chain(*samplers):
     """chain(DecorrSampler(length=30), MetropolisSampler(hamil, wf, tau=1.0)) -> a sampler that returns every 30th
     Metropolis step (reference: sampling/sampling_utils.py:31-54, conf/task/sampler_factory/elec_sampler/*.yaml).  The last
@@ -216,6 +264,10 @@ def chain(*samplers):
     last = samplers[-1]
     assert isinstance(last, MetropolisSampler) and last.hamil is not None, 'the last link must be a Metropolis / Langevin sampler'
     for link in samplers[:-1]:
+        if isinstance(link, OppositeSpinExchangeSampler):
+            assert not isinstance(last, LangevinSampler), 'spin-exchange steps are implemented for the Metropolis sampler'
+            last.exchange_step_probability = link.exchange_step_probability
+            continue
         assert isinstance(link, DecorrSampler) and link.hamil is None, 'only DecorrSampler(length=...) links can be chained in front'
         last.length = last.length * link.length
     return last

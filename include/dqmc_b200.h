@@ -147,6 +147,20 @@ int dqmc_mcmc_sweep(dqmc_handle h, void* r, void* sign, void* log, int32_t* age,
                     const void* noise_uniform, void* out_stats, void* workspace, int64_t workspace_bytes,
                     void* stream);
 
+/* dqmc_mcmc_sweep with spin-exchange steps mixed in: every sub-step is, for the whole batch, an exchange step with
+ * probability exchange_step_probability (proposal = swap the positions of one random spin-up / spin-down pair per walker,
+ * acceptance 2 dlog|psi| > log u, no max_age override, no step-size adaptation) and an ordinary Metropolis step otherwise.
+ * exchange_flags[n_sub] (HOST int32, nullable) / exchange_idx[n_sub][B][2] (device int32, nullable): injected decisions and
+ * (up, down) indices for parity tests.
+ * replaces: sampling/electron_samplers.py:235-330 OppositeSpinExchangeSampler chained in front of MetropolisSampler
+ *           (conf/task/sampler_factory/elec_sampler/decorr_spin_exchange_metropolis.yaml). */
+int dqmc_mcmc_sweep_exchange(dqmc_handle h, void* r, void* sign, void* log, int32_t* age, void* tau, const void* R,
+                             int32_t R_batched, int32_t n_walkers, int32_t n_sub, double target_acceptance, int32_t max_age,
+                             uint64_t seed, uint64_t step0, uint64_t walker_offset, const void* noise_normal,
+                             const void* noise_uniform, double exchange_step_probability, const int32_t* exchange_flags,
+                             const int32_t* exchange_idx, void* out_stats, void* workspace, int64_t workspace_bytes,
+                             void* stream);
+
 /* Metropolis-adjusted Langevin sweep: like dqmc_mcmc_sweep with the drift force[B][N][3] (= clean_force of
  * grad log|psi|, sampling_utils.py:71-101) as an extra piece of walker state; proposals r + tau F + sqrt(tau) N(0,1),
  * acceptance with the Green's-function ratio.  Every sub-step costs one forward-Laplacian pass (value + gradient).

@@ -73,3 +73,26 @@ def langevin_step(wf_and_grad_batch, R, charges, state, normal, uniform, target_
         'age': torch.where(accepted, torch.zeros_like(state['age']), state['age'] + 1), 'tau': new_tau,
     }
     return new, acceptance
+
+
+def spin_exchange_step(wf_batch, state, up_idx, down_idx, uniform, n_up):
+    """reference: electron_samplers.py:235-330 OppositeSpinExchangeSampler exchange step: swap the positions of electron
+    up_idx[b] (among the spin-up ones) and down_idx[b] (among the spin-down ones), accept with 2 dlog|psi| > log u; no max_age
+    override, step size untouched."""
+    r = state['r']
+    b = torch.arange(len(r))
+    r_prop = r.clone()
+    r_prop[b, up_idx] = r[b, n_up + down_idx]
+    r_prop[b, n_up + down_idx] = r[b, up_idx]
+    s_p, l_p = wf_batch(r_prop)
+    accepted = 2 * (l_p - state['log']) > torch.log(uniform)
+    acceptance = accepted.to(torch.float64).sum() / accepted.shape[0]
+    new = {
+        'r': torch.where(accepted[:, None, None], r_prop, r),
+        'sign': torch.where(accepted, s_p, state['sign']),
+        'log': torch.where(accepted, l_p, state['log']),
+        'age': torch.where(accepted, torch.zeros_like(state['age']), state['age'] + 1),
+        'tau': state['tau'],
+    }
+    return new, acceptance
+

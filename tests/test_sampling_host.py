@@ -154,3 +154,26 @@ def test_parameter_exchange_with_a_reference_run(tmp_path):
     assert back.keys() == flat.keys() and all(np.array_equal(back[k], flat[k]) for k in flat)
     with pytest.raises(ValueError):
         PN.load_params(str(tmp_path / 'p.npz'), psiformer_spec(hamil))  # another ansatz: names differ
+
+
+def test_chain_with_spin_exchange_link():
+    """conf/task/sampler_factory/elec_sampler/decorr_spin_exchange_metropolis.yaml: Decorr(33), spin exchange with probability
+    0.1, Metropolis -- the exchange link only sets the probability on the combined sampler."""
+    from functools import partial
+
+    import pytest
+
+    from deepqmc_b200.sampling import DecorrSampler, LangevinSampler, MetropolisSampler, OppositeSpinExchangeSampler, combine_samplers
+
+    class _Ansatz:
+        def apply(self, *a):
+            raise AssertionError('not evaluated here')
+
+    hamil, wf = object(), _Ansatz().apply
+    s = combine_samplers([DecorrSampler(length=33), OppositeSpinExchangeSampler(exchange_step_probability=0.1),
+                          partial(MetropolisSampler, tau=1.0, max_age=None)], hamil, wf)
+    assert isinstance(s, MetropolisSampler) and s.length == 33 and s.exchange_step_probability == 0.1
+    with pytest.raises(AssertionError):
+        combine_samplers([OppositeSpinExchangeSampler(exchange_step_probability=0.1), partial(LangevinSampler, tau=0.1)], hamil, wf)
+    with pytest.raises(NotImplementedError):
+        OppositeSpinExchangeSampler(exchange_step_probability=0.1, up_logits_fn=lambda r: r)
