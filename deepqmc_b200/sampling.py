@@ -309,18 +309,27 @@ class MultiElectronicStateSampler:
     def __init__(self, sampler: MetropolisSampler, n_state: int):
         self.sampler, self.n_state = sampler, n_state
 
+    def _seeds(self, rng):
+        """per-state seeds: the reference's split(rng, n_state) keys in the seed-compatible mode, integers otherwise"""
+        if isinstance(rng, np.ndarray) or getattr(self.sampler, 'jax_compatible_noise', False):
+            from . import jaxrand
+
+            return list(jaxrand.split(_as_jax_key(rng), self.n_state))
+        return [int(rng) * self.n_state + s for s in range(self.n_state)]
+
     def init(self, rng, params, electron_batch_size, R):
         assert len(params) == self.n_state
-        return [self.sampler.init(int(rng) * self.n_state + s, params[s], electron_batch_size, R)
-                for s in range(self.n_state)]
+        seeds = self._seeds(rng)
+        return [self.sampler.init(seeds[s], params[s], electron_batch_size, R) for s in range(self.n_state)]
 
     def update(self, state, params, R):
         return [self.sampler.update(state[s], params[s], R) for s in range(self.n_state)]
 
     def sample(self, rng, state, params, R, **kw):
         new, rs, stats = [], [], []
+        seeds = self._seeds(rng)
         for s in range(self.n_state):
-            st, pc, stt = self.sampler.sample(int(rng) * self.n_state + s, state[s], params[s], R, **kw)
+            st, pc, stt = self.sampler.sample(seeds[s], state[s], params[s], R, **kw)
             new.append(st); rs.append(pc.r); stats.append(stt)
         r = torch.stack(rs)
         pc = PhysicalConfiguration(R, r, torch.zeros(r.shape[:2], dtype=torch.int32, device=r.device))
@@ -509,3 +518,28 @@ class MultiNuclearGeometrySampler:
             smpl_state['elec'][m] = self.elec_sampler.update(
                 smpl_state['elec'][m], params, self._R_dev(smpl_state['elec'][m], smpl_state['nuc'][m]['R']))
         return smpl_state
+
+
+def initialize_sampling(rng, hamil, ansatz, mols, electronic_states, molecule_batch_size, *, elec_sampler, nuc_sampler=None,
+                        elec_warp_fn=None, update_nuc_period=None, elec_equilibration_steps=None):
+    """The reference's SamplerFactory (sampling/sampling_utils.py:165-233, types.py:83-93): -> (MoleculeIdxSampler,
+    MultiNuclearGeometrySampler over a MultiElectronicStateSampler).  ``elec_sampler``: a callable taking (hamil=, wf=), e.g.
+    ``partial(combine_samplers, [DecorrSampler(length=30), partial(MetropolisSampler, tau=1.0)])``."""
+    molecule_idx_sampler = MoleculeIdxSampler(rng if not isinstance(rng, np.ndarray) else int(rng[1]), len(mols), molecule_batch_size, 'once')
+    elec = elec_sampler(hamil=hamil, wf=ansatz.apply)
+    multi_state = MultiElectronicStateSampler(elec, electronic_states)
+    nuc = (IdleNucleiSampler if nuc_sampler is None else nuc_sampler)(hamil.mol.charges)
+    sampler = MultiNuclearGeometrySampler(multi_state, nuc, no_elec_warp if elec_warp_fn is None else elec_warp_fn,
+                                          update_nuc_period, elec_equilibration_steps)
+    return molecule_idx_sampler, sampler
+
+
+def initialize_sampler_state(rng, sampler, params, electron_batch_size, nuc_coords):
+    """sampler.init with this process's share of the walkers: the reference pmaps over its local devices
+    (sampling_utils.py:236-262), here there is one process per GPU (deepqmc_b200.parallel)."""
+    from . import parallel
+
+    rank, world = parallel.world()
+    assert electron_batch_size % world == 0, 'electron_batch_size must be divisible by the number of devices'  # validate_kwargs.py:45-48
+    return sampler.init(parallel.rank_seed(rng, rank) if not isinstance(rng, np.ndarray) else rng, params, electron_batch_size // world, nuc_coords)
+
