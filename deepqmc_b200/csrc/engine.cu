@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -213,6 +214,22 @@ __global__ void split_transpose_kernel(const float* __restrict__ W, int K, int N
     }                                                                              \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel, not to an engine, and engines for molecules of different
+// size share one process: the opt-in therefore only ever grows (a later, smaller engine must not lower the cap under an
+// earlier, larger one).
+template <class F>
+inline cudaError_t raise_dyn_smem(F fn, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, int> high;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  int& h = high[std::make_pair(dev, (const void*)fn)];
+  if (bytes > h) h = bytes;
+  return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h);
+}
+
 #define DQ_LAUNCH(kern, grid, block, smem, stream, ...)          \
   do {                                                           \
     auto kfn_ = kern;                                            \
@@ -372,49 +389,44 @@ struct Engine : EngineBase {
     if (attn_f32) {
       if (launch_attn_f32(nullptr, nullptr, 0, 0, 0, 0.f, 0, (int)s_attn, nullptr, true)) return 1;
     } else if (psif)
-      DQ_CHECK(cudaFuncSetAttribute(attn_fl_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_attn));
-    DQ_CHECK(cudaFuncSetAttribute(slater_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_sl));
+      DQ_CHECK(raise_dyn_smem(attn_fl_kernel<T>, (int)s_attn));
+    DQ_CHECK(raise_dyn_smem(slater_kernel<T>, (int)s_sl));
     slater_fwd2_ok = N <= 32 && slater_fwd2_smem_bytes<T>(N, M, K) <= 110 * 1024 && !std::getenv("DQMC_SLATER_GENERIC") &&
                      !std::getenv("DQMC_SLATER_FWD1");
     if (slater_fwd2_ok) {
-      DQ_CHECK(cudaFuncSetAttribute(slater_fwd2_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)slater_fwd2_smem_bytes<T>(N, M, K)));
-      DQ_CHECK(cudaFuncSetAttribute(slater_fwd2_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)slater_fwd2_smem_bytes<T>(N, M, K)));
+      DQ_CHECK(raise_dyn_smem(slater_fwd2_kernel<T, 16>, (int)slater_fwd2_smem_bytes<T>(N, M, K)));
+      DQ_CHECK(raise_dyn_smem(slater_fwd2_kernel<T, 32>, (int)slater_fwd2_smem_bytes<T>(N, M, K)));
     }
     attn_fwd_ok = psif && std::is_same<T, float>::value && dh == 64 && N <= 32 && N + Mn <= 48 && d % 4 == 0 &&
                   !std::getenv("DQMC_ATTN_GENERIC") && !std::getenv("DQMC_ATTN_FWD_OLD");
     attn_fwd_pipelined = attn_fwd_ok && !trans && std::getenv("DQMC_ATTN_FWD2");  // measured slower than the block-per-walker kernel
     if (attn_fwd_pipelined) {
       const int smem2 = 6 * 4 * N * 64 * (int)sizeof(float);
-      DQ_CHECK(cudaFuncSetAttribute(attn_fwd2_f32_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-      DQ_CHECK(cudaFuncSetAttribute(attn_fwd2_f32_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-      DQ_CHECK(cudaFuncSetAttribute(attn_fwd2_f32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      DQ_CHECK(raise_dyn_smem(attn_fwd2_f32_kernel<8>, smem2));
+      DQ_CHECK(raise_dyn_smem(attn_fwd2_f32_kernel<16>, smem2));
+      DQ_CHECK(raise_dyn_smem(attn_fwd2_f32_kernel<32>, smem2));
     }
     if (attn_fwd_ok) {
       const int smem = 4 * 2 * (N + Mn) * 64 * (int)sizeof(float);
-      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<48, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<8, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<16, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<32, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<4, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<10, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<14, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<28, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      DQ_CHECK(cudaFuncSetAttribute((attn_fwd_f32_kernel<30, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      DQ_CHECK(raise_dyn_smem((attn_fwd_f32_kernel<48, false>), smem));
+      DQ_CHECK(raise_dyn_smem((attn_fwd_f32_kernel<8, false>), smem));
+      DQ_CHECK(raise_dyn_smem((attn_fwd_f32_kernel<16, false>), smem));
+      DQ_CHECK(raise_dyn_smem((attn_fwd_f32_kernel<32, false>), smem));
+      DQ_CHECK(raise_dyn_smem((attn_fwd_f32_kernel<4, true>), smem));
+      DQ_CHECK(raise_dyn_smem((attn_fwd_f32_kernel<10, true>), smem));
+      DQ_CHECK(raise_dyn_smem((attn_fwd_f32_kernel<14, true>), smem));
+      DQ_CHECK(raise_dyn_smem((attn_fwd_f32_kernel<28, true>), smem));
+      DQ_CHECK(raise_dyn_smem((attn_fwd_f32_kernel<30, true>), smem));
     }
     embed_fwd_ok = psif && d % 4 == 0 && embed_fwd_smem_bytes<T>(M, d) <= 200 * 1024 && !std::getenv("DQMC_EMBED_GENERIC");
     if (embed_fwd_ok)
-      DQ_CHECK(cudaFuncSetAttribute(embed_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)embed_fwd_smem_bytes<T>(M, d)));
+      DQ_CHECK(raise_dyn_smem(embed_fwd_kernel<T>, (int)embed_fwd_smem_bytes<T>(M, d)));
     if (cfg.gemm_backend == DQMC_GEMM_TCGEN05) {
 #if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
       if (!std::is_same<T, float>::value) { err = "DQMC_GEMM_TCGEN05 needs dtype DQMC_F32"; return 2; }
       if (d % 32 != 0) { err = "DQMC_GEMM_TCGEN05 needs embedding_dim % 32 == 0"; return 2; }
-      DQ_CHECK(cudaFuncSetAttribute(tc::gemm3xtf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    tc::SmemLayout::total(256)));
-      DQ_CHECK(cudaFuncSetAttribute(tc::gemm3xtf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    tc::SmemLayoutT<true>::total(256)));
+      DQ_CHECK(raise_dyn_smem(tc::gemm3xtf32_kernel<false>, tc::SmemLayout::total(256)));
+      DQ_CHECK(raise_dyn_smem(tc::gemm3xtf32_kernel<true>, tc::SmemLayoutT<true>::total(256)));
       gemm_2cta = std::getenv("DQMC_GEMM_2CTA") != nullptr;
 #else
       err = "this build has no tcgen05 backend"; return 2;
@@ -687,7 +699,7 @@ struct Engine : EngineBase {
   template <int NE, int DH>
   int attn_f32_go(const float* QKV, float* O, int Bc, int S, int tb, float scale, int smem, cudaStream_t st, bool setup) {
     if (setup) {
-      DQ_CHECK(cudaFuncSetAttribute(attn_fl_f32_kernel<NE, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      DQ_CHECK(raise_dyn_smem(attn_fl_f32_kernel<NE, DH>, smem));
       return 0;
     }
     DQ_LAUNCH((attn_fl_f32_kernel<NE, DH>), dim3(Bc, H), dim3(128), smem, st, QKV, 3 * d, O, d, N, S, dh, d, scale, tb);
@@ -1708,9 +1720,8 @@ struct Engine : EngineBase {
     if (Bc > B) Bc = B;
     if (Bc < 1) { err = "workspace too small for a single walker (vjp)"; return 3; }
     if (!fermi && !gnn)
-    DQ_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_bwd_smem_bytes<T>(N, dh, Mn)));
-    DQ_CHECK(cudaFuncSetAttribute(slater_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(slater_bwd_smem_per_warp<T>(N) * 4)));
+    DQ_CHECK(raise_dyn_smem(attn_bwd_kernel<T>, (int)attn_bwd_smem_bytes<T>(N, dh, Mn)));
+    DQ_CHECK(raise_dyn_smem(slater_bwd_kernel<T>, (int)(slater_bwd_smem_per_warp<T>(N) * 4)));
     for (int b0 = 0; b0 < B; b0 += (int)Bc) {
       const int nb = (int)std::min<int64_t>(Bc, B - b0);
       const T* rc_ = r + (size_t)b0 * 3 * N;

@@ -15,7 +15,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <functional>
+#include <map>
 #include <vector>
 
 struct dim3 {
@@ -48,15 +50,24 @@ struct State {
   std::vector<long> warp_gen;          // generation per warp
   std::vector<unsigned char> dyn_smem;
   std::function<void()> body;
+  std::map<const void*, size_t> max_dyn_smem;  // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) opt-ins per kernel
 };
 inline State& S() { static thread_local State s; return s; }
+// Scheduling order of the fibers of a block.  DQMC_EMU_REVERSE=1 runs the highest thread first and walks downwards:
+// a missing __syncthreads()/__syncwarp() between a shared-memory write and a read by another thread gives the right
+// answer in at most one of the two orders, so running a test in both orders exposes the race.
+inline int sched_dir() {
+  static const int d = (std::getenv("DQMC_EMU_REVERSE") && std::getenv("DQMC_EMU_REVERSE")[0] == '1') ? -1 : 1;
+  return d;
+}
+inline int sched_next(int me, int k, int n) { return ((me + sched_dir() * k) % n + n) % n; }
 
 inline void yield() {
   State& s = S();
   int me = s.cur;
   // next runnable fiber (round robin); if none other, continue
   for (int k = 1; k <= s.nthreads; ++k) {
-    int nxt = (me + k) % s.nthreads;
+    int nxt = sched_next(me, k, s.nthreads);
     if (!s.fibers[nxt].done) {
       if (nxt == me) return;
       s.cur = nxt;
@@ -72,7 +83,7 @@ inline void fiber_entry() {
   s.fibers[me].done = true;
   // switch to next unfinished fiber or back to main
   for (int k = 1; k <= s.nthreads; ++k) {
-    int nxt = (me + k) % s.nthreads;
+    int nxt = sched_next(me, k, s.nthreads);
     if (!s.fibers[nxt].done) {
       s.cur = nxt;
       setcontext(&s.fibers[nxt].ctx);
@@ -120,14 +131,34 @@ inline T shfl_idx(T v, int src_lane) {
   std::memcpy(&out, &got, sizeof(T));
   return out;
 }
-inline void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> body) {
+// Launch limits of sm_100 that a CPU run would otherwise never notice: 1024 threads per block, grid.y/z <= 65535,
+// dynamic shared memory <= 48 KiB unless the kernel opted in (<= 227 KiB), and no write past the requested bytes.
+inline void check_limits(dim3 grid, dim3 block, size_t smem, const void* fn, const char* name) {
+  State& s = S();
+  bool ok = block.x >= 1 && block.x <= 1024 && grid.x >= 1 && grid.y >= 1 && grid.z >= 1 && grid.x <= 2147483647u &&
+            grid.y <= 65535u && grid.z <= 65535u;
+  size_t cap = 48 * 1024;
+  auto it = s.max_dyn_smem.find(fn);
+  if (it != s.max_dyn_smem.end()) cap = std::max(cap, it->second);
+  if (!ok || smem > cap || cap > 227 * 1024) {
+    std::fprintf(stderr, "cuda_emu: invalid launch of %s: grid (%u,%u,%u) block %u smem %zu (cap %zu)\n", name, grid.x, grid.y,
+                 grid.z, block.x, smem, cap);
+    std::abort();
+  }
+}
+inline void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> body, const void* fn = nullptr,
+                   const char* name = "?") {
   State& s = S();
   assert(block.y == 1 && block.z == 1 && "emulator supports 1-D blocks");
+  check_limits(grid, block, smem, fn, name);
   s.nthreads = block.x;
   s.bdim = block;
   s.gdim = grid;
   s.body = body;
-  s.dyn_smem.assign(smem + 64, 0);
+  const size_t kGuard = 64;
+  s.dyn_smem.assign(smem + 16 + kGuard, 0);
+  unsigned char* smem_base = (unsigned char*)(((uintptr_t)s.dyn_smem.data() + 15) & ~(uintptr_t)15);
+  size_t guard_len = s.dyn_smem.data() + s.dyn_smem.size() - (smem_base + smem);
   if ((int)s.fibers.size() < s.nthreads) s.fibers.resize(s.nthreads);
   s.shfl_buf.assign(s.nthreads, 0);
   int nw = (s.nthreads + 31) / 32;
@@ -152,8 +183,15 @@ inline void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> bod
           f.ctx.uc_link = nullptr;
           makecontext(&f.ctx, (void (*)())fiber_entry, 0);
         }
-        s.cur = 0;
-        swapcontext(&s.main_ctx, &s.fibers[0].ctx);
+        std::memset(smem_base + smem, 0xA5, guard_len);
+        s.cur = sched_dir() > 0 ? 0 : s.nthreads - 1;
+        swapcontext(&s.main_ctx, &s.fibers[s.cur].ctx);
+        for (size_t g = 0; g < guard_len; ++g)
+          if (smem_base[smem + g] != 0xA5) {
+            std::fprintf(stderr, "cuda_emu: %s wrote past its %zu bytes of dynamic shared memory (block %u,%u,%u)\n", name, smem,
+                         bx, by, bz);
+            std::abort();
+          }
       }
 }
 }  // namespace emu
@@ -202,8 +240,11 @@ inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
-template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
+template <class F> inline cudaError_t cudaFuncSetAttribute(F f, int, int bytes) {
+  emu::S().max_dyn_smem[(const void*)f] = (size_t)bytes;
+  return 0;
+}
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 #define DQMC_DYN_SMEM(name) unsigned char* name = (unsigned char*)(((uintptr_t)emu::S().dyn_smem.data() + 15) & ~(uintptr_t)15)
 #define DQMC_LAUNCH(kern, grid, block, smem, stream, ...) \
-  emu::launch(dim3(grid), dim3(block), smem, [=]() { kern(__VA_ARGS__); })
+  emu::launch(dim3(grid), dim3(block), smem, [=]() { kern(__VA_ARGS__); }, (const void*)(kern), #kern)
