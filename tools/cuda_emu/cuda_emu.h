@@ -230,7 +230,13 @@ typedef int cudaError_t;
 typedef void* cudaStream_t;
 enum { cudaSuccess = 0 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return 0; }
+// fresh device memory holds garbage on the GPU, fresh mmap-backed malloc memory holds zeros: poison it (0xFF = NaN in every
+// float format, -1 in every integer) so that code relying on zero-initialised cudaMalloc memory fails here as well
+inline cudaError_t cudaMalloc(void** p, size_t n) {
+  *p = std::malloc(n ? n : 1);
+  if (*p) std::memset(*p, 0xFF, n ? n : 1);
+  return 0;
+}
 inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return 0; }
