@@ -183,6 +183,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> bod
           f.ctx.uc_link = nullptr;
           makecontext(&f.ctx, (void (*)())fiber_entry, 0);
         }
+        std::memset(s.dyn_smem.data(), 0xFF, s.dyn_smem.size());  // shared memory of a fresh block holds garbage, not zeros
         std::memset(smem_base + smem, 0xA5, guard_len);
         s.cur = sched_dir() > 0 ? 0 : s.nthreads - 1;
         swapcontext(&s.main_ctx, &s.fibers[s.cur].ctx);

@@ -26,9 +26,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 # full-size / tensor-core tests: hours on the emulator, or not emulable
-TOO_BIG = {'test_full_size_properties_4096_walkers', 'test_benzene_ccecp_small_hyper_vs_oracle',
-           'test_benzene_full_psiformer_fp32_tensor_core_vs_fp64', 'test_ferminet_n2_full_fp32_tensor_core_vs_fp64',
-           'test_paulinet_256_walkers_fp32_and_sampler', 'test_engine_external_fixtures'}
+TOO_BIG = {'test_full_size_properties_4096_walkers', 'test_benzene_full_psiformer_fp32_tensor_core_vs_fp64',
+           'test_ferminet_n2_full_fp32_tensor_core_vs_fp64', 'test_engine_external_fixtures'}
 
 
 def build(out, asan=False):
