@@ -503,6 +503,8 @@ struct Engine : EngineBase {
     for (int i = 0; i < cfg.backflow_n; ++i) h = cfg.backflow_dims[i] > h ? cfg.backflow_dims[i] : h;
     return h;
   }
+  size_t fermi_dmax() const { return (size_t)(4 * M > d ? 4 * M : d); }
+  size_t fermi_emax() const { return (size_t)(cfg.edge_dim > 4 ? cfg.edge_dim : 4); }
   int gnn_dmax() const { return cfg.gnn_features && 4 * M > d ? 4 * M : d; }
   int gnn_emax() const {  // widest edge-side row (raw features, w / u hidden and output widths)
     int m = cfg.edge_dim > 4 ? cfg.edge_dim : 4;
@@ -535,8 +537,10 @@ struct Engine : EngineBase {
              pairs8 * (4 * em + 3 * e) + (size_t)S * gnn_jsum() + dets;
     }
     if (cfg.kind == DQMC_FERMINET) {
-      const size_t de = cfg.edge_dim, fin = 3 * (size_t)d + 2 * de;
-      return rows * (2 * (size_t)d + fin + BFW) + (size_t)N * rows * 2 * de + dets;
+      // layer 0 works on the raw features: 4 M electron-nucleus columns per node, 4 per edge (wider than d / edge_dim for
+      // narrow networks on many nuclei)
+      const size_t dm = fermi_dmax(), em = fermi_emax(), fin = 3 * dm + 2 * em;
+      return rows * (2 * dm + fin + BFW) + (size_t)N * rows * 2 * em + dets;
     }
     return rows * (size_t)(4 * d + 3 * d + BFW) + dets;
   }
@@ -558,9 +562,9 @@ struct Engine : EngineBase {
       w.A = w.M1 = w.QKV = nullptr;
       w.BF = take(rows * KN);
     } else if (cfg.kind == DQMC_FERMINET) {
-      const size_t de = cfg.edge_dim, fin = 3 * (size_t)d + 2 * de;
-      w.X = take(rows * d); w.O = take(rows * d); w.QKV = take(rows * fin);    // H, H2, F
-      w.A = take(rows * N * de); w.M1 = take(rows * N * de);                   // E, E2
+      const size_t dm = fermi_dmax(), em = fermi_emax(), fin = 3 * dm + 2 * em;
+      w.X = take(rows * dm); w.O = take(rows * dm); w.QKV = take(rows * fin);  // H, H2, F
+      w.A = take(rows * N * em); w.M1 = take(rows * N * em);                   // E, E2
       w.BF = take(rows * BFW);
     } else {
       w.X = take(rows * d); w.O = take(rows * d); w.A = take(rows * d); w.M1 = take(rows * d);
@@ -577,7 +581,7 @@ struct Engine : EngineBase {
     int64_t per = (int64_t)(sizeof(T) * per_walker_elems(S));
     int64_t c = (wsb - 16 * 256) / per;
     int64_t row_cap = (int64_t)2000000000 / ((int64_t)N * S * 3 * d);  // keep 32-bit row*ld products safe
-    if (cfg.kind == DQMC_FERMINET) row_cap = (int64_t)2000000000 / ((int64_t)N * N * S * (3 * d + 64));
+    if (cfg.kind == DQMC_FERMINET) row_cap = (int64_t)2000000000 / ((int64_t)N * N * S * (3 * (int64_t)fermi_dmax() + 64));
     if (gnn) row_cap = (int64_t)2000000000 / ((int64_t)N * (N + M + S) * (8 * gnn_emax() + 3 * gnn_dmax() + 3 * cfg.edge_dim + KN));
     if (c > row_cap) c = row_cap;
     if (c > B) c = B;
@@ -1721,7 +1725,13 @@ struct Engine : EngineBase {
     if (Bc < 1) { err = "workspace too small for a single walker (vjp)"; return 3; }
     if (!fermi && !gnn)
     DQ_CHECK(raise_dyn_smem(attn_bwd_kernel<T>, (int)attn_bwd_smem_bytes<T>(N, dh, Mn)));
-    DQ_CHECK(raise_dyn_smem(slater_bwd_kernel<T>, (int)(slater_bwd_smem_per_warp<T>(N) * 4)));
+    {  // the same warps-per-block rule as at the launch sites (at most 4 warps, at most 96 KiB)
+      const size_t pw = slater_bwd_smem_per_warp<T>(N);
+      int wpb = (int)((96 * 1024) / pw);
+      wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
+      if (pw * wpb > 227 * 1024) { err = "system too large for the shared-memory tiling of the reverse pass (N)"; return 2; }
+      DQ_CHECK(raise_dyn_smem(slater_bwd_kernel<T>, (int)(pw * wpb)));
+    }
     for (int b0 = 0; b0 < B; b0 += (int)Bc) {
       const int nb = (int)std::min<int64_t>(Bc, B - b0);
       const T* rc_ = r + (size_t)b0 * 3 * N;

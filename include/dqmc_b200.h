@@ -12,6 +12,8 @@
  * Empty batches: n_walkers = 0 is a no-op for dqmc_wf_forward / dqmc_local_energy and yields a zero gradient from
  * dqmc_wf_vjp_params; the samplers need at least one walker (status 2).  Status 2 = bad argument / unsupported
  * configuration, 3 = workspace too small, other non-zero = CUDA error; dqmc_last_error gives the text.
+ * Several handles (molecules of different size, electronic states, dtypes) may live in one process and be used in any
+ * order; concurrent calls on ONE handle from several host threads are not supported.
  */
 #ifndef DQMC_B200_H
 #define DQMC_B200_H

@@ -163,9 +163,14 @@ inline void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> bod
   s.shfl_buf.assign(s.nthreads, 0);
   int nw = (s.nthreads + 31) / 32;
   const size_t kStack = 256 * 1024;
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
+  // DQMC_EMU_REVERSE_BLOCKS=1 walks the grid from the last block to the first: blocks of one launch may run in any order
+  // on the GPU, so a kernel whose blocks depend on each other (without atomics) passes in one of the two orders at most.
+  static const bool rev_blocks = std::getenv("DQMC_EMU_REVERSE_BLOCKS") && std::getenv("DQMC_EMU_REVERSE_BLOCKS")[0] == '1';
+  for (unsigned iz = 0; iz < grid.z; ++iz)
+    for (unsigned iy = 0; iy < grid.y; ++iy)
+      for (unsigned ix = 0; ix < grid.x; ++ix) {
+        const unsigned bx = rev_blocks ? grid.x - 1 - ix : ix, by = rev_blocks ? grid.y - 1 - iy : iy,
+                       bz = rev_blocks ? grid.z - 1 - iz : iz;
         s.bidx = {bx, by, bz};
         s.bar_gen = 0;
         s.bar_count = 0;
