@@ -254,6 +254,7 @@ struct Engine : EngineBase {
   int* d_ph_nuc = nullptr;
   int ph_G = 0;
   double ph_rmax = 0;
+  int64_t vjp_ws_cap = 0;  // bytes of the caller's workspace during a reverse pass (extent check of the chunk buffers)
   bool ph_on = false;      // tables uploaded
   bool ph_active = false;  // set around the forward-Laplacian pass of local_energy only
   T* mos_out = nullptr;    // set by orbitals(): the tail writes the orbital matrices of the chunk here and stops
@@ -544,7 +545,9 @@ struct Engine : EngineBase {
     }
     return rows * (size_t)(4 * d + 3 * d + BFW) + dets;
   }
-  size_t chunk_bytes(int Bc, int S) const { return sizeof(T) * per_walker_elems(S) * Bc + 16 * 256; }
+  // + alignment slack: every carved buffer (at most ~30, conv-GNN trunk) is rounded up to 256 bytes
+  static constexpr int64_t kCarveSlack = 64 * 256;
+  size_t chunk_bytes(int Bc, int S) const { return sizeof(T) * per_walker_elems(S) * Bc + kCarveSlack; }
   Ws carve(void* base, int Bc, int S) const {
     Ws w;
     size_t rows = (size_t)Bc * N * S;
@@ -579,7 +582,7 @@ struct Engine : EngineBase {
   }
   int max_chunk(int64_t wsb, int S, int B) const {
     int64_t per = (int64_t)(sizeof(T) * per_walker_elems(S));
-    int64_t c = (wsb - 16 * 256) / per;
+    int64_t c = (wsb - kCarveSlack) / per;
     int64_t row_cap = (int64_t)2000000000 / ((int64_t)N * S * 3 * d);  // keep 32-bit row*ld products safe
     if (cfg.kind == DQMC_FERMINET) row_cap = (int64_t)2000000000 / ((int64_t)N * N * S * (3 * (int64_t)fermi_dmax() + 64));
     if (gnn) row_cap = (int64_t)2000000000 / ((int64_t)N * (N + M + S) * (8 * gnn_emax() + 3 * gnn_dmax() + 3 * cfg.edge_dim + KN));
@@ -592,7 +595,7 @@ struct Engine : EngineBase {
   int64_t ecp_bytes(int64_t nb) const {
     const int64_t V = nb * J * N * 12;
     return (int64_t)align_up(sizeof(T) * V * 3 * N) + 2 * (int64_t)align_up(sizeof(T) * V) +
-           (int64_t)(sizeof(T) * per_walker_elems(1)) * V + 32 * 256;
+           (int64_t)(sizeof(T) * per_walker_elems(1)) * V + kCarveSlack + 16 * 256;
   }
   int64_t ws_bytes(int B, int mode) override {
     if (mode == DQMC_MODE_VJP)
@@ -1091,6 +1094,7 @@ struct Engine : EngineBase {
                   int64_t wsb, cudaStream_t st) {
     int Bc = max_chunk(wsb, S, B);
     if (Bc < 1) { err = "workspace too small for a single walker"; return 3; }
+    if ((int64_t)carve(ws, Bc, S).bytes > wsb) { err = "internal: carved workspace exceeds the planned size"; return 3; }
     for (int b0 = 0; b0 < B; b0 += Bc) {
       int nb = std::min(Bc, B - b0);
       int rc = run_chunk(r + (size_t)b0 * 3 * N, R + (Rb ? (size_t)b0 * 3 * M : 0), Rb, nb, S, B, sign + b0, logp + b0,
@@ -1277,6 +1281,7 @@ struct Engine : EngineBase {
     }
     DQ_LAUNCH(embed_feat_kernel<T>, dim3((rows * M + 127) / 128), dim3(128), 0, st, r, R, Rb, N, M, cfg.n_up, Feat, rows);
     wgrad(Feat, F, dXn, d, rows, F, d, G + off("emb.w"), 0, 0, st);
+    if ((int64_t)(p - (char*)wsbase) > vjp_ws_cap) { err = "internal: reverse-pass buffers exceed the planned workspace"; return 3; }
     return 0;
   }
 
@@ -1387,6 +1392,7 @@ struct Engine : EngineBase {
       T* t1 = dHn; dHn = dHc; dHc = t1;
       T* t2 = dEn; dEn = dEc; dEc = t2;
     }
+    if ((int64_t)(p - (char*)wsbase) > vjp_ws_cap) { err = "internal: reverse-pass buffers exceed the planned workspace"; return 3; }
     return 0;
   }
   // ---- conv-GNN reverse pass: the reference's test ansatz (tests/conf/ansatz.yaml: hk.Embed embeddings, 'featurewise'
@@ -1700,6 +1706,7 @@ struct Engine : EngineBase {
     if (!cfg.gnn_features)
       DQ_LAUNCH(embed_table_bwd_kernel<T>, dim3((d + 63) / 64, 64), dim3(64), 0, st, (const T*)dXn, n_types, N, cfg.n_up, d, rows,
                 G + off("emb.table"));
+    if ((int64_t)(p - (char*)wsbase) > vjp_ws_cap) { err = "internal: reverse-pass buffers exceed the planned workspace"; return 3; }
     return 0;
   }
   size_t vjp_per_walker_elems_ferminet() const {
@@ -1723,6 +1730,7 @@ struct Engine : EngineBase {
     int64_t Bc = (wsb - 256 * 256) / (int64_t)(sizeof(T) * per_w);
     if (Bc > B) Bc = B;
     if (Bc < 1) { err = "workspace too small for a single walker (vjp)"; return 3; }
+    vjp_ws_cap = wsb;
     if (!fermi && !gnn)
     DQ_CHECK(raise_dyn_smem(attn_bwd_kernel<T>, (int)attn_bwd_smem_bytes<T>(N, dh, Mn)));
     {  // the same warps-per-block rule as at the launch sites (at most 4 warps, at most 96 KiB)
