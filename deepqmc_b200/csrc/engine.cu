@@ -237,6 +237,16 @@ inline cudaError_t raise_dyn_smem(F fn, int bytes) {
     ++launches;                                                  \
   } while (0)
 
+// Emulator builds (tools/cuda_emu) put a 256-byte guard behind every buffer carved from the workspace and verify the
+// guards after each chunk: a buffer that is individually too small (with a consistent total) cannot hide.
+#ifdef DQMC_EMU
+#define DQ_TAKE_GUARD() do { std::memset(p, 0xC3, 256); emu_guards.push_back((unsigned char*)p); p += 256; } while (0)
+static constexpr int64_t kGuardFactor = 8;
+#else
+#define DQ_TAKE_GUARD() do {} while (0)
+static constexpr int64_t kGuardFactor = 1;
+#endif
+
 template <class T>
 struct Engine : EngineBase {
   T* d_params = nullptr;
@@ -254,6 +264,16 @@ struct Engine : EngineBase {
   int* d_ph_nuc = nullptr;
   int ph_G = 0;
   double ph_rmax = 0;
+  mutable std::vector<unsigned char*> emu_guards;  // emulator builds only: guard zones behind the carved workspace buffers
+  int check_guards() {
+#ifdef DQMC_EMU
+    for (unsigned char* g : emu_guards)
+      for (int i = 0; i < 256; ++i)
+        if (g[i] != 0xC3) { emu_guards.clear(); err = "emulator: a workspace buffer was overrun (guard zone modified)"; return 4; }
+    emu_guards.clear();
+#endif
+    return 0;
+  }
   int64_t vjp_ws_cap = 0;  // bytes of the caller's workspace during a reverse pass (extent check of the chunk buffers)
   bool ph_on = false;      // tables uploaded
   bool ph_active = false;  // set around the forward-Laplacian pass of local_energy only
@@ -546,13 +566,14 @@ struct Engine : EngineBase {
     return rows * (size_t)(4 * d + 3 * d + BFW) + dets;
   }
   // + alignment slack: every carved buffer (at most ~30, conv-GNN trunk) is rounded up to 256 bytes
-  static constexpr int64_t kCarveSlack = 64 * 256;
+  static constexpr int64_t kCarveSlack = 64 * 256 * kGuardFactor;
+  static constexpr int64_t kVjpSlack = 256 * 256 * kGuardFactor;
   size_t chunk_bytes(int Bc, int S) const { return sizeof(T) * per_walker_elems(S) * Bc + kCarveSlack; }
   Ws carve(void* base, int Bc, int S) const {
     Ws w;
     size_t rows = (size_t)Bc * N * S;
     char* p = (char*)base;
-    auto take = [&](size_t n) { T* q = (T*)p; p += align_up(sizeof(T) * n); return q; };
+    auto take = [&](size_t n) { T* q = (T*)p; p += align_up(sizeof(T) * n); DQ_TAKE_GUARD(); return q; };
     if (gnn) {
       const size_t e = cfg.edge_dim, hm = gnn_hmax(), dm = gnn_dmax(), em = gnn_emax(), hn = gnn_hnode_max();
       const size_t pairs8 = (size_t)Bc * N * (N + (cfg.gnn_conv_ne ? M : 0)) * 8;
@@ -600,7 +621,7 @@ struct Engine : EngineBase {
   int64_t ws_bytes(int B, int mode) override {
     if (mode == DQMC_MODE_VJP)
       return (int64_t)(sizeof(T) * (gnn ? vjp_per_walker_elems_paulinet()
-                                        : cfg.kind == DQMC_FERMINET ? vjp_per_walker_elems_ferminet() : vjp_per_walker_elems())) * B + 256 * 256;
+                                        : cfg.kind == DQMC_FERMINET ? vjp_per_walker_elems_ferminet() : vjp_per_walker_elems())) * B + kVjpSlack;
     int S = mode == DQMC_MODE_FORWARD ? 1 : T3 + 2;
     int64_t need = (int64_t)chunk_bytes(B, S);
     if (mode == DQMC_MODE_LOCAL_ENERGY && J > 0) need = std::max<int64_t>(need, ecp_bytes(B));
@@ -1101,6 +1122,8 @@ struct Engine : EngineBase {
                          E ? E + b0 : nullptr, stats ? stats + b0 : nullptr, grad ? grad + (size_t)b0 * T3 : nullptr, ws,
                          st);
       if (rc) return rc;
+      rc = check_guards();
+      if (rc) return rc;
     }
     return 0;
   }
@@ -1197,7 +1220,7 @@ struct Engine : EngineBase {
   int vjp_chunk(const T* r, const T* R, int Rb, int Bc, const T* wts, T* sign, T* logp, T* G, void* wsbase, cudaStream_t st) {
     const int L = cfg.n_layers, rows = Bc * N, F = 4 * M + 1;
     char* p = (char*)wsbase;
-    auto take = [&](size_t n) { T* q = (T*)p; p += align_up(sizeof(T) * n); return q; };
+    auto take = [&](size_t n) { T* q = (T*)p; p += align_up(sizeof(T) * n); DQ_TAKE_GUARD(); return q; };
     std::vector<T*> X(L + 1), QKV(L), O(L), A(L), M1(L);
     for (int l = 0; l <= L; ++l) X[l] = take((size_t)rows * d);
     for (int l = 0; l < L; ++l) { QKV[l] = take((size_t)rows * 3 * d); O[l] = take((size_t)rows * d); A[l] = take((size_t)rows * d); M1[l] = take((size_t)rows * d); }
@@ -1293,7 +1316,7 @@ struct Engine : EngineBase {
     const int L = cfg.n_layers, rows = Bc * N, rowsE = Bc * N * N, de = cfg.edge_dim, d0 = 4 * M;
     const T isq2 = (T)0.70710678118654752440;
     char* p = (char*)wsbase;
-    auto take = [&](size_t n) { T* q = (T*)p; p += align_up(sizeof(T) * n); return q; };
+    auto take = [&](size_t n) { T* q = (T*)p; p += align_up(sizeof(T) * n); DQ_TAKE_GUARD(); return q; };
     std::vector<T*> Hs(L + 1), Es(L), Fs(L);
     std::vector<int> dH(L + 1), dEd(L);
     dH[0] = d0;
@@ -1467,7 +1490,7 @@ struct Engine : EngineBase {
     const T isq2 = (T)0.70710678118654752440;
     const char* tn[3] = {"same", "anti", "ne"};
     char* p = (char*)wsbase;
-    auto take = [&](size_t n) { T* q = (T*)p; p += align_up(sizeof(T) * n); return q; };
+    auto take = [&](size_t n) { T* q = (T*)p; p += align_up(sizeof(T) * n); DQ_TAKE_GUARD(); return q; };
     // ---- forward, everything kept --------------------------------------------------------------------------------
     std::vector<T*> X(L + 1), C(L), Fc(L), E(L);
     std::vector<int> xd(L + 1), ed(L);
@@ -1727,7 +1750,7 @@ struct Engine : EngineBase {
     // walkers per chunk: activations of every layer stay resident for the reverse pass (64 buffers, 256 B alignment each)
     const bool fermi = cfg.kind == DQMC_FERMINET;
     const int64_t per_w = gnn ? vjp_per_walker_elems_paulinet() : (fermi ? vjp_per_walker_elems_ferminet() : vjp_per_walker_elems());
-    int64_t Bc = (wsb - 256 * 256) / (int64_t)(sizeof(T) * per_w);
+    int64_t Bc = (wsb - kVjpSlack) / (int64_t)(sizeof(T) * per_w);
     if (Bc > B) Bc = B;
     if (Bc < 1) { err = "workspace too small for a single walker (vjp)"; return 3; }
     vjp_ws_cap = wsb;
@@ -1747,6 +1770,8 @@ struct Engine : EngineBase {
       int rc = gnn ? vjp_chunk_paulinet(rc_, Rc_, Rb, nb, (const T*)weights + b0, (T*)sign + b0, (T*)logp + b0, (T*)grad_params, ws, st)
              : fermi ? vjp_chunk_ferminet(rc_, Rc_, Rb, nb, (const T*)weights + b0, (T*)sign + b0, (T*)logp + b0, (T*)grad_params, ws, st)
                      : vjp_chunk(rc_, Rc_, Rb, nb, (const T*)weights + b0, (T*)sign + b0, (T*)logp + b0, (T*)grad_params, ws, st);
+      if (rc) return rc;
+      rc = check_guards();
       if (rc) return rc;
     }
     DQ_CHECK(cudaGetLastError());
