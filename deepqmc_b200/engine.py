@@ -527,7 +527,7 @@ class Engine:
 
     def vjp_params(self, r, R, weights, max_ws_bytes=None):
         """-> (sign[B], log[B], grads): grads = d/dparams sum_b weights[b] log|psi(r_b)| as a Haiku-named dict
-        (reference: loss/loss_function.py:53-82).  Psiformer, TransPsiformer, FermiNet."""
+        (reference: loss/loss_function.py:53-82).  Every ansatz kind (the additive backflow branch excepted)."""
         r = self._prep(r)
         B = r.shape[0]
         R, Rb = self._R(R, B)
