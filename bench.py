@@ -8,8 +8,10 @@ metric: walker.local-energies / second.  A "step" = one local-energy evaluation 
 of the batch (Psiformer forward + forward-Laplacian + potentials, incl. the non-local ECP
 quadrature) followed, for N > 1, by the fused statistics all-reduce.  Default workload = the
 configuration BASELINE.json's metric is quoted on: benzene (ccECP, 30 valence electrons)
-Psiformer (d=256, L=4, H=4, K=16), 4096 walkers per GPU (the engine chunks the walkers through
-its workspace, so it fits one B200); ``--workload lih_psiformer`` = BASELINE configs[1],
+Psiformer (d=256, L=4, H=4, K=16), a GLOBAL batch of 4096 walkers split over the N GPUs as the
+reference splits electron_batch_size over its devices (parallel.py:296-317; "scaling": "strong";
+``--scaling weak`` keeps 4096 walkers per GPU instead).  The engine chunks the walkers through its
+workspace, so the whole batch fits one B200.  ``--workload lih_psiformer`` = BASELINE configs[1],
 ``n2_ferminet`` = configs[2].  Synthetic walkers (atom-centred Gaussians, equilibrated by
 Metropolis sub-steps, untimed) and random-init weights.
 """
@@ -172,8 +174,7 @@ def time_oracle(wl_name, per_worker, steps, warmup, seed=0):
     ms/step, walkers per step."""
     import multiprocessing as mp
 
-    cores = os.cpu_count() or 1
-    workers = max(1, min(cores, 64))
+    workers = max(1, len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1))
     wl = WORKLOADS[wl_name]
     heavy = wl['ecp'] is not None
     n = per_worker if heavy else workers * per_worker
@@ -215,22 +216,26 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='benzene_psiformer', choices=sorted(WORKLOADS))
     ap.add_argument('--dtype', default='float32', choices=['float32', 'float64'])
-    ap.add_argument('--walkers', type=int, default=None, help='walkers per GPU (default: workload)')
+    ap.add_argument('--walkers', type=int, default=None, help='walker batch: global (strong scaling) or per GPU (weak)')
+    ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'],
+                    help='strong (default): the global batch is split over the GPUs as the reference does; weak: per-GPU batch')
     ap.add_argument('--cpu-sample', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--gemm-backend', default='tcgen05', choices=['simt', 'tcgen05'])
     ap.add_argument('--equil-sweeps', type=int, default=None)
     a = ap.parse_args()
-    a.warmup = max(a.warmup, 3) if a.impl == 'ours' else a.warmup
     wl = WORKLOADS[a.workload]
-    B = a.walkers or wl['walkers']
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
+    B_global = (a.walkers or wl['walkers']) * (world if a.scaling == 'weak' else 1)
+    if B_global % world:
+        raise SystemExit('the walker batch must be divisible by the number of GPUs (reference validate_kwargs.py:45-48)')
+    B = B_global // world  # walkers of this rank
     unit = 'walker.local-energies/s'
     metric = 'walker.local-energies/sec'
     arch = {'psiformer': 'Psiformer d256 L4 H4 K16', 'ferminet': 'FermiNet d256 L4 e32 K16',
             'paulinet': 'PauliNet test ansatz (tests/conf/ansatz.yaml) d8 L1 K2'}[wl['kind']]
-    workload_name = f"{wl['mol']} {arch}{' ' + wl['ecp'] if wl['ecp'] else ''}, {B} walkers/GPU"
+    workload_name = f"{wl['mol']} {arch}{' ' + wl['ecp'] if wl['ecp'] else ''}, {B_global} walkers"
 
     if a.impl == 'reference':
         if rank != 0:
@@ -242,7 +247,7 @@ def main():
                if heavy else 'one single-threaded process per core')
         out = {
             'impl': 'reference', 'metric': metric, 'value': val, 'unit': unit, 'n_gpus': a.gpus, 'steps': a.steps,
-            'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': a.scaling, 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': workload_name, 'note': 'CPU oracle port of the reference JAX path (JAX not installable here)'},
             'cpu_baseline': {'value': val, 'unit': unit, 'cores': cores, 'kind': 'port',
@@ -258,11 +263,15 @@ def main():
     from deepqmc_b200.types import PhysicalConfiguration
 
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device; there is no CPU fallback (use --impl reference)'
+    if world > 1:  # communicator set-up is logged (rank count, transport) so that the run shows which collective path it used
+        os.environ.setdefault('NCCL_DEBUG', 'INFO')
+        os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT')
     rank, world = parallel.init_from_env()
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    mol, hamil, r_np, PN = make_problem(wl, B, seed=1000 + rank)
+    mol, hamil, r_np, PN = make_problem(wl, B_global, seed=1000)
+    r_np = r_np[rank * B:(rank + 1) * B]  # contiguous walker block of this rank (deepqmc_b200.parallel.shard_bounds)
     backend = 1 if (a.gemm_backend == 'tcgen05' and a.dtype == 'float32' and wl['kind'] != 'paulinet') else 0  # d = 8: CUDA cores
     ansatz = B200Ansatz(hamil, wl['kind'], dtype=a.dtype, device=local, gemm_backend=backend, **wl['hyper'])
     params = PN.perturb_params(ansatz.init(0))
@@ -330,8 +339,9 @@ def main():
         parallel.energy_statistics(E, st)
         return E.cpu()
     # long steps (seconds): the pipeline is warm already, bound the e2e leg to a few steps
+    # (same number of steps as the device-timed leg unless that would take more than ~2 minutes)
     slow = total_ms / a.steps > 500.0
-    e2e_warm, e2e_steps = (1, max(1, min(a.steps, 3))) if slow else (3, a.steps)
+    e2e_warm, e2e_steps = (1, max(3, min(a.steps, int(120e3 / (total_ms / a.steps))))) if slow else (3, a.steps)
     for w in range(e2e_warm):
         e2e_step(w)
     torch.cuda.synchronize()
@@ -388,9 +398,10 @@ def main():
     out = {
         'metric': metric, 'value': value, 'unit': unit, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
         'ms_per_step': total_ms / a.steps, 'ms_per_step_min': min(per_step), 'ms_per_step_median': float(np.median(per_step)),
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'higher_is_better': True, 'scaling': a.scaling, 'vs_baseline': None,
         'dtype': 'f32' if a.dtype == 'float32' else 'f64', 'data': 'synthetic',
-        'config': {'workload': workload_name, 'global_batch': B * world, 'parallelism': f'walker-shard x{world}',
+        'config': {'workload': workload_name, 'global_batch': B * world, 'walkers_per_gpu': B,
+                   'parallelism': f'walker-shard x{world}',
                    'l2': 'flushed between timed iterations (256 MiB memset) and activations >> L2',
                    'step': 'E_loc of all walkers (+ fused stats all-reduce for N>1)',
                    'gemm_backend': 'tcgen05-3xTF32' if backend else 'cuda-core'},

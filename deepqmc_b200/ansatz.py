@@ -26,7 +26,7 @@ class B200Ansatz:
         self.dtype, self.device, self.gemm_backend = dtype, device, gemm_backend
         self._engine = None
         self._uploaded = None
-        self._engines = []  # [(params, Engine)], most recent first: one resident engine per parameter tree
+        self._engines = []  # [(params, fingerprint, Engine)], most recent first: one resident engine per parameter tree
         self.max_engines = 4  # electronic states kept resident (excited-state runs evaluate every state's
                               # wave function on every state's walkers, reference loss/overlap.py:19-49)
 
@@ -44,19 +44,46 @@ class B200Ansatz:
             return jaxrand.haiku_init_conv_gnn_ansatz(self.spec, seed)
         return PN.init_params(self.spec, seed)
 
+    @staticmethod
+    def _fingerprint(params):
+        """Cheap identity + content probe of a parameter tree: the ids of the leaves (a functional update replaces them)
+        and three sampled elements per leaf (an in-place update ``params[k] -= lr * g`` changes them).  O(#leaves)."""
+        fp = []
+        for k, v in params.items():
+            a = v if isinstance(v, np.ndarray) else np.asarray(v)
+            f = a.reshape(-1)
+            n = f.shape[0]
+            fp.append((k, id(v), float(f[0]) + float(f[n // 2]) + float(f[n - 1]) if n else 0.0))
+        return tuple(fp)
+
+    def invalidate(self, params=None):
+        """Forget the uploaded copy of ``params`` (all trees if None): the next apply / local_energy uploads again."""
+        self._engines = [(p, f, e) if (params is not None and p is not params) else (None, None, e) for p, f, e in self._engines]
+
     def engine_for(self, hamil, params) -> Engine:
-        for i, (p, e) in enumerate(self._engines):
+        """The resident engine holding ``params``.  A tree counts as uploaded if it is the same dict AND its fingerprint is
+        unchanged, so optimisers that update the leaves in place (same dict) are picked up as well."""
+        fp = None
+        for i, (p, f, e) in enumerate(self._engines):
             if p is params:
-                if i:
-                    self._engines.insert(0, self._engines.pop(i))
-                self._engine, self._uploaded = e, params
-                return e
-        if len(self._engines) < self.max_engines:
+                fp = self._fingerprint(params)
+                if f == fp:
+                    if i:
+                        self._engines.insert(0, self._engines.pop(i))
+                    self._engine, self._uploaded = e, params
+                    return e
+                self._engines.pop(i)  # same dict, new contents: re-upload into the same handle
+                self._engines.append((None, None, e))
+                break
+        free = [i for i, (p, _, _) in enumerate(self._engines) if p is None]
+        if free:
+            _, _, e = self._engines.pop(free[0])
+        elif len(self._engines) < self.max_engines:
             e = Engine(self.spec, hamil, dtype=self.dtype, device=self.device, gemm_backend=self.gemm_backend)
         else:
-            _, e = self._engines.pop()  # least recently used handle is re-targeted
+            _, _, e = self._engines.pop()  # least recently used handle is re-targeted
         e.set_params(params)
-        self._engines.insert(0, (params, e))
+        self._engines.insert(0, (params, fp or self._fingerprint(params), e))
         self._engine, self._uploaded = e, params
         return e
 

@@ -39,6 +39,13 @@ struct EngineBase {
   int64_t launches = 0;
   std::vector<ParamEntry> entries;
   int64_t total = 0;
+  // Planning pass: the host code of an entry point is walked with every CUDA call skipped, so that the number of workspace
+  // bytes a call carves is computed by the SAME code that carves them (dqmc_workspace_bytes, dqmc_debug_plan).  An engine
+  // created with device < 0 is plan-only (dry for its whole life: no CUDA context, no allocation).
+  bool dry = false;
+  bool plan_only = false;
+  mutable const char* dry_hwm = nullptr;  // highest workspace address carved during a dry pass
+  void note_hwm(const void* q) const { if (dry && (const char*)q > dry_hwm) dry_hwm = (const char*)q; }
   // optional per-launch timing of the dominant (GEMM) kernels with CUDA events on the caller's stream
   bool prof = false;
   double prof_flops = 0;
@@ -49,6 +56,8 @@ struct EngineBase {
   virtual ~EngineBase() {}
   virtual int set_params(const double* host, int64_t n, cudaStream_t st) = 0;
   virtual int64_t ws_bytes(int B, int mode) = 0;
+  virtual int64_t ws_bytes_min(int B, int mode) = 0;
+  virtual int debug_plan(int B, int mode, int64_t wsb, int64_t* planned, int64_t* carved) = 0;
   virtual int forward(const void* r, const void* R, int Rb, int B, void* sign, void* logp, void* ws, int64_t wsb,
                       cudaStream_t st) = 0;
   virtual int local_energy(const void* r, const void* R, int Rb, int B, uint64_t seed, const void* twist, void* E,
@@ -207,6 +216,7 @@ __global__ void split_transpose_kernel(const float* __restrict__ W, int K, int N
 
 #define DQ_CHECK(call)                                                             \
   do {                                                                             \
+    if (dry) break; /* planning pass: no CUDA calls */                             \
     cudaError_t e_ = (call);                                                       \
     if (e_ != cudaSuccess) {                                                       \
       err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
@@ -232,6 +242,7 @@ inline cudaError_t raise_dyn_smem(F fn, int bytes) {
 
 #define DQ_LAUNCH(kern, grid, block, smem, stream, ...)          \
   do {                                                           \
+    if (dry) break; /* planning pass */                          \
     auto kfn_ = kern;                                            \
     DQMC_LAUNCH(kfn_, grid, block, smem, stream, __VA_ARGS__);   \
     ++launches;                                                  \
@@ -239,12 +250,12 @@ inline cudaError_t raise_dyn_smem(F fn, int bytes) {
 
 // Emulator builds (tools/cuda_emu) put a 256-byte guard behind every buffer carved from the workspace and verify the
 // guards after each chunk: a buffer that is individually too small (with a consistent total) cannot hide.
+// The guard bytes are part of what carve() / the take lambdas advance by, so the PLAN (a dry pass of the same code) contains
+// them too: emulator and hardware builds plan by the same rule, there is no build-dependent slack.
 #ifdef DQMC_EMU
-#define DQ_TAKE_GUARD() do { std::memset(p, 0xC3, 256); emu_guards.push_back((unsigned char*)p); p += 256; } while (0)
-static constexpr int64_t kGuardFactor = 8;
+#define DQ_TAKE_GUARD() do { if (!dry) { std::memset(p, 0xC3, 256); emu_guards.push_back((unsigned char*)p); } p += 256; } while (0)
 #else
 #define DQ_TAKE_GUARD() do {} while (0)
-static constexpr int64_t kGuardFactor = 1;
 #endif
 
 template <class T>
@@ -456,6 +467,7 @@ struct Engine : EngineBase {
     return 0;
   }
   ~Engine() override {
+    if (plan_only) return;  // nothing was allocated, no CUDA context
     cudaFree(d_params); cudaFree(d_params_t); cudaFree(d_stage); cudaFree(d_znuc); cudaFree(d_zval); cudaFree(d_ecp_mask);
     if (d_ecp_loc) cudaFree(d_ecp_loc);
     if (d_nl_params) cudaFree(d_nl_params);
@@ -547,28 +559,18 @@ struct Engine : EngineBase {
     for (int i = 0; i < cfg.jastrow_n; ++i) j += cfg.jastrow_dims[i];
     return j;
   }
-  size_t per_walker_elems(int S) const {
-    size_t rows = (size_t)N * S;
-    size_t dets = (size_t)K * (3 + (S > 1 ? T3 : 0)) + (ph_on && S > 1 ? (size_t)N * PH_STRIDE : 0) +
-                  (cfg.backflow_add ? (size_t)N * 5 + 64 : 0);
-    if (gnn) {
-      const size_t e = cfg.edge_dim, dm = gnn_dmax(), em = gnn_emax(), hn = gnn_hnode_max();
-      const size_t pairs8 = (size_t)N * (N + (cfg.gnn_conv_ne ? M : 0)) * 8;
-      return rows * (2 * dm + 3 * (size_t)d + (3 * dm + 3 * e) + 2 * e + hn + 3 * e + 2 * (size_t)gnn_hmax() + KN) +
-             pairs8 * (4 * em + 3 * e) + (size_t)S * gnn_jsum() + dets;
-    }
-    if (cfg.kind == DQMC_FERMINET) {
-      // layer 0 works on the raw features: 4 M electron-nucleus columns per node, 4 per edge (wider than d / edge_dim for
-      // narrow networks on many nuclei)
-      const size_t dm = fermi_dmax(), em = fermi_emax(), fin = 3 * dm + 2 * em;
-      return rows * (2 * dm + fin + BFW) + (size_t)N * rows * 2 * em + dets;
-    }
-    return rows * (size_t)(4 * d + 3 * d + BFW) + dets;
+  // Workspace plan == the carve itself: chunk_bytes() runs carve() on a dummy base, so a buffer added to carve() can never
+  // be forgotten in the plan (round 1 planned dgrad for S > 1 only while carve() always took it).
+  static char* plan_base() { return (char*)(uintptr_t)0x100000; }
+  size_t chunk_bytes(int Bc, int S) const {
+    const bool was = dry;
+    const char* hw = dry_hwm;  // a size probe is not a carve of the caller's workspace
+    const_cast<Engine*>(this)->dry = true;  // no guard writes through the dummy base
+    const size_t n = carve(plan_base(), Bc, S).bytes;
+    const_cast<Engine*>(this)->dry = was;
+    dry_hwm = hw;
+    return n;
   }
-  // + alignment slack: every carved buffer (at most ~30, conv-GNN trunk) is rounded up to 256 bytes
-  static constexpr int64_t kCarveSlack = 64 * 256 * kGuardFactor;
-  static constexpr int64_t kVjpSlack = 256 * 256 * kGuardFactor;
-  size_t chunk_bytes(int Bc, int S) const { return sizeof(T) * per_walker_elems(S) * Bc + kCarveSlack; }
   Ws carve(void* base, int Bc, int S) const {
     Ws w;
     size_t rows = (size_t)Bc * N * S;
@@ -599,33 +601,115 @@ struct Engine : EngineBase {
     if (ph_on && S > 1) w.QA = take((size_t)Bc * N * PH_STRIDE);
     if (cfg.backflow_add) w.Gadd = take((size_t)Bc * N * 5);
     w.bytes = p - (char*)base;
+    note_hwm(p);
     return w;
   }
+  // largest walker chunk (<= B, <= the 32-bit row cap) whose carve fits wsb bytes
   int max_chunk(int64_t wsb, int S, int B) const {
-    int64_t per = (int64_t)(sizeof(T) * per_walker_elems(S));
-    int64_t c = (wsb - kCarveSlack) / per;
+    int64_t c = B;
     int64_t row_cap = (int64_t)2000000000 / ((int64_t)N * S * 3 * d);  // keep 32-bit row*ld products safe
     if (cfg.kind == DQMC_FERMINET) row_cap = (int64_t)2000000000 / ((int64_t)N * N * S * (3 * (int64_t)fermi_dmax() + 64));
     if (gnn) row_cap = (int64_t)2000000000 / ((int64_t)N * (N + M + S) * (8 * gnn_emax() + 3 * gnn_dmax() + 3 * cfg.edge_dim + KN));
     if (c > row_cap) c = row_cap;
-    if (c > B) c = B;
-    return (int)c;
+    if (c < 1 || (int64_t)chunk_bytes(1, S) > wsb) return 0;
+    if ((int64_t)chunk_bytes((int)c, S) <= wsb) return (int)c;
+    int64_t lo = 1, hi = c;  // chunk_bytes is monotone in the chunk size
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) / 2;
+      if ((int64_t)chunk_bytes((int)mid, S) <= wsb) lo = mid; else hi = mid;
+    }
+    return (int)lo;
   }
   // non-local ECP pass for nb walkers: virtual walkers r_virt[V][N][3], sign[V], log[V] + one
   // forward chunk over all V = nb * J * N * 12 virtual walkers
+  int64_t ecp_prefix_bytes(int64_t nb) const {
+    const int64_t V = nb * J * N * 12;
+    return (int64_t)align_up(sizeof(T) * V * 3 * N) + 2 * (int64_t)align_up(sizeof(T) * V);
+  }
+  // walkers per ECP group are bounded by the 32-bit row cap of the plain-forward chunk: the plan never asks for more
+  int64_t ecp_group_cap() const {
+    const int64_t vper = (int64_t)J * N * 12;
+    const int64_t vcap = 2000000000LL / ((int64_t)N * 3 * d);
+    return std::max<int64_t>(1, vcap / vper);
+  }
   int64_t ecp_bytes(int64_t nb) const {
     const int64_t V = nb * J * N * 12;
-    return (int64_t)align_up(sizeof(T) * V * 3 * N) + 2 * (int64_t)align_up(sizeof(T) * V) +
-           (int64_t)(sizeof(T) * per_walker_elems(1)) * V + kCarveSlack + 16 * 256;
+    return ecp_prefix_bytes(nb) + (int64_t)chunk_bytes((int)V, 1);
+  }
+  int64_t mcmc_prefix_bytes(int B) const {
+    return (int64_t)align_up(sizeof(T) * (size_t)B * 3 * N) + 2 * (int64_t)align_up(sizeof(T) * (size_t)B) + 256;
+  }
+  int64_t force_prefix_bytes(int B) const {  // value_and_force: E, 6 stats, grad
+    return (int64_t)(align_up(sizeof(T) * (size_t)B) + align_up(sizeof(T) * (size_t)6 * B) + align_up(sizeof(T) * (size_t)B * T3));
+  }
+  int64_t langevin_prefix_bytes(int B) const {
+    return 2 * (int64_t)align_up(sizeof(T) * (size_t)B * 3 * N) + 2 * (int64_t)align_up(sizeof(T) * (size_t)B) + 256;
+  }
+  // bytes one reverse-pass chunk of Bc walkers carves: a dry pass of the chunk function itself
+  int64_t vjp_chunk_bytes(int Bc) {
+    const bool was = dry;
+    const char* hw = dry_hwm;
+    const int64_t cap = vjp_ws_cap;
+    dry = true; dry_hwm = plan_base(); vjp_ws_cap = INT64_MAX;
+    if (gnn) vjp_chunk_paulinet(nullptr, nullptr, 0, Bc, nullptr, nullptr, nullptr, nullptr, plan_base(), nullptr);
+    else if (cfg.kind == DQMC_FERMINET) vjp_chunk_ferminet(nullptr, nullptr, 0, Bc, nullptr, nullptr, nullptr, nullptr, plan_base(), nullptr);
+    else vjp_chunk(nullptr, nullptr, 0, Bc, nullptr, nullptr, nullptr, nullptr, plan_base(), nullptr);
+    const int64_t n = dry_hwm - plan_base();
+    dry = was; dry_hwm = hw; vjp_ws_cap = cap;
+    return n;
   }
   int64_t ws_bytes(int B, int mode) override {
-    if (mode == DQMC_MODE_VJP)
-      return (int64_t)(sizeof(T) * (gnn ? vjp_per_walker_elems_paulinet()
-                                        : cfg.kind == DQMC_FERMINET ? vjp_per_walker_elems_ferminet() : vjp_per_walker_elems())) * B + kVjpSlack;
+    if (B < 1) B = 1;
+    if (mode == DQMC_MODE_VJP) return vjp_chunk_bytes(B);
+    if (mode == DQMC_MODE_MCMC) return mcmc_prefix_bytes(B) + (int64_t)chunk_bytes(B, 1);
+    if (mode == DQMC_MODE_LANGEVIN) return langevin_prefix_bytes(B) + force_prefix_bytes(B) + (int64_t)chunk_bytes(B, T3 + 2);
     int S = mode == DQMC_MODE_FORWARD ? 1 : T3 + 2;
     int64_t need = (int64_t)chunk_bytes(B, S);
-    if (mode == DQMC_MODE_LOCAL_ENERGY && J > 0) need = std::max<int64_t>(need, ecp_bytes(B));
+    if (mode == DQMC_MODE_LOCAL_ENERGY && J > 0) need = std::max<int64_t>(need, ecp_bytes(std::min<int64_t>(B, ecp_group_cap())));
     return need;
+  }
+  // least workspace with which a call for B walkers proceeds (walkers chunked down to one at a time)
+  int64_t ws_bytes_min(int B, int mode) override {
+    if (B < 1) B = 1;
+    const int S = T3 + 2;
+    switch (mode) {
+      case DQMC_MODE_VJP: return vjp_chunk_bytes(1);
+      case DQMC_MODE_MCMC: return mcmc_prefix_bytes(B) + (int64_t)chunk_bytes(1, 1);
+      case DQMC_MODE_LANGEVIN: return langevin_prefix_bytes(B) + force_prefix_bytes(B) + (int64_t)chunk_bytes(1, S);
+      case DQMC_MODE_LOCAL_ENERGY:
+        return std::max<int64_t>((int64_t)chunk_bytes(1, S), J > 0 ? ecp_prefix_bytes(1) + (int64_t)chunk_bytes(1, 1) : 0);
+      default: return (int64_t)chunk_bytes(1, 1);
+    }
+  }
+  // dqmc_debug_plan: walk the entry point of `mode` with a workspace of wsb bytes (<= 0: the planned size) on a dummy base
+  // and report the highest offset it carves.  Host-only (works on plan-only engines).
+  int debug_plan(int B, int mode, int64_t wsb, int64_t* planned, int64_t* carved) override {
+    const int64_t pl = ws_bytes(B, mode);
+    if (planned) *planned = pl;
+    if (wsb <= 0) wsb = pl;
+    const bool was = dry;
+    dry = true; dry_hwm = plan_base();
+    void* ws = plan_base();
+    int rc = 0;
+    switch (mode) {
+      case DQMC_MODE_FORWARD: rc = forward(nullptr, nullptr, 0, B, nullptr, nullptr, ws, wsb, nullptr); break;
+      case DQMC_MODE_LOCAL_ENERGY:
+        rc = local_energy(nullptr, nullptr, 0, B, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ws, wsb, nullptr);
+        break;
+      case DQMC_MODE_VJP: rc = vjp_params(nullptr, nullptr, 0, B, nullptr, nullptr, nullptr, nullptr, ws, wsb, nullptr); break;
+      case DQMC_MODE_MCMC:
+        rc = mcmc(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, B, 1, 0.5, -1, 0, 0, 0, nullptr, nullptr, nullptr, ws, wsb,
+                  nullptr, 0.0, nullptr, nullptr);
+        break;
+      case DQMC_MODE_LANGEVIN:
+        rc = langevin(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, B, 1, 0.5, -1, 0, 0, 0, nullptr, nullptr,
+                      nullptr, ws, wsb, nullptr);
+        break;
+      default: err = "unknown mode"; rc = 2;
+    }
+    if (carved) *carved = dry_hwm - plan_base();
+    dry = was;
+    return rc;
   }
 
   // ---- GEMM dispatch ------------------------------------------------------------------------
@@ -639,6 +723,7 @@ struct Engine : EngineBase {
   int gemm(const T* A, int lda, const char* w0, const char* w1, int zsplit, int ldw, const T* bias, const T* Res,
            int ldr, T* C, int ldc, int Mr, int Nc, int Kc, int S, int sliced, int Nel, cudaStream_t st, int act = 0,
            const T* bias1 = nullptr) {
+    if (dry) return 0;  // planning pass
     const T* W0 = P(w0);
     const T* W1 = w1 ? P(w1) : nullptr;
 #if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
@@ -1115,7 +1200,8 @@ struct Engine : EngineBase {
                   int64_t wsb, cudaStream_t st) {
     int Bc = max_chunk(wsb, S, B);
     if (Bc < 1) { err = "workspace too small for a single walker"; return 3; }
-    if ((int64_t)carve(ws, Bc, S).bytes > wsb) { err = "internal: carved workspace exceeds the planned size"; return 3; }
+    if ((int64_t)chunk_bytes(Bc, S) > wsb) { err = "internal: carved workspace exceeds the planned size"; return 3; }
+    if (dry) { carve(ws, Bc, S); return 0; }  // planning pass: record the extent of the largest chunk
     for (int b0 = 0; b0 < B; b0 += Bc) {
       int nb = std::min(Bc, B - b0);
       int rc = run_chunk(r + (size_t)b0 * 3 * N, R + (Rb ? (size_t)b0 * 3 * M : 0), Rb, nb, S, B, sign + b0, logp + b0,
@@ -1135,7 +1221,9 @@ struct Engine : EngineBase {
     T* E = (T*)p; p += align_up(sizeof(T) * (size_t)B);
     T* stt = (T*)p; p += align_up(sizeof(T) * (size_t)6 * B);
     T* grad = (T*)p; p += align_up(sizeof(T) * (size_t)B * T3);
-    rest -= (int64_t)(align_up(sizeof(T) * (size_t)B) + align_up(sizeof(T) * (size_t)6 * B) + align_up(sizeof(T) * (size_t)B * T3));
+    rest -= force_prefix_bytes(B);
+    note_hwm(p);
+    if (rest < 0) { err = "workspace too small (Langevin force buffers)"; return 3; }
     int rc = run_batched(r, R, Rb, B, T3 + 2, sign, logp, E, stt, grad, p, rest, st);
     if (rc) return rc;
     DQ_LAUNCH(langevin_force_kernel<T>, dim3((B * N + 127) / 128), dim3(128), 0, st, (const T*)grad, r, R, Rb, (const T*)d_znuc, tau,
@@ -1155,6 +1243,8 @@ struct Engine : EngineBase {
     T* lp = (T*)p; p += align_up(sizeof(T) * (size_t)B);
     int* cnt = (int*)p; p += 256;
     int64_t rest = wsb - (p - (char*)ws);
+    note_hwm(p);
+    if (rest < 0) { err = "workspace too small (Langevin proposal buffers)"; return 3; }
     DQ_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int), st));
     const int ne = B * 3 * N;
     for (int s = 0; s < n_sub; ++s) {
@@ -1184,10 +1274,6 @@ struct Engine : EngineBase {
 
   // ---- parameter VJP of the plain forward (Psiformer): SURVEY.md 8(f) N1 ------------------------
   const T* PT(const std::string& n) const { return d_params_t + off(n); }
-  size_t vjp_per_walker_elems() const {
-    const size_t L = cfg.n_layers, F = 4 * M + 1;
-    return (size_t)N * ((7 * L + 1) * d + 9 * (size_t)d + 2 * (size_t)KN + F) + (size_t)K * 4;
-  }
   // C = (Res) + A @ W with a raw weight pointer (CUDA-core kernel; used by the reverse pass with transposed weights)
   int gemm_raw(const T* A, int lda, const T* W0, const T* W1, int zsplit, int ldw, const T* Res, int ldr, T* C, int ldc,
                int Mr, int Nc, int Kc, int sliced, cudaStream_t st) {
@@ -1304,6 +1390,7 @@ struct Engine : EngineBase {
     }
     DQ_LAUNCH(embed_feat_kernel<T>, dim3((rows * M + 127) / 128), dim3(128), 0, st, r, R, Rb, N, M, cfg.n_up, Feat, rows);
     wgrad(Feat, F, dXn, d, rows, F, d, G + off("emb.w"), 0, 0, st);
+    note_hwm(p);
     if ((int64_t)(p - (char*)wsbase) > vjp_ws_cap) { err = "internal: reverse-pass buffers exceed the planned workspace"; return 3; }
     return 0;
   }
@@ -1415,6 +1502,7 @@ struct Engine : EngineBase {
       T* t1 = dHn; dHn = dHc; dHc = t1;
       T* t2 = dEn; dEn = dEc; dEc = t2;
     }
+    note_hwm(p);
     if ((int64_t)(p - (char*)wsbase) > vjp_ws_cap) { err = "internal: reverse-pass buffers exceed the planned workspace"; return 3; }
     return 0;
   }
@@ -1469,17 +1557,6 @@ struct Engine : EngineBase {
       }
     }
     return 0;
-  }
-  size_t vjp_per_walker_elems_paulinet() const {
-    const size_t L = cfg.n_layers, e = cfg.edge_dim, NS = N + (cfg.gnn_conv_ne ? M : 0), pairs = (size_t)N * NS;
-    const size_t nl = cfg.gnn_sub_n > 0 ? cfg.gnn_sub_n : 1, em = gnn_emax(), hn = gnn_hnode_max(), hm = gnn_hmax();
-    size_t jw = d;
-    for (int i = 0; i < cfg.jastrow_n; ++i) jw += cfg.jastrow_dims[i];
-    // every buffer vjp_chunk_paulinet takes, with a factor 2 of head-room (these networks are tiny)
-    const size_t xm = std::max<size_t>(d, 4 * (size_t)M), fmax = 3 * xm + 3 * e;
-    return 2 * ((size_t)N * ((L + 1) * xm + L * (2 * nl * hn + 3 * e + 3 * (size_t)d + fmax) + cfg.backflow_n * hm + 2 * (size_t)KN +
-                             6 * xm + 4 * hn + 3 * e + 4 * hm + 4 * xm + fmax) +
-                pairs * (4 + L * (4 * nl * em + e) + 6 * e + 2 * em) + 3 * jw + 6 * (size_t)d + (size_t)K * 4 + 64);
   }
   int vjp_chunk_paulinet(const T* r, const T* R, int Rb, int Bc, const T* wts, T* sign, T* logp, T* G, void* wsbase,
                          cudaStream_t st) {
@@ -1729,14 +1806,9 @@ struct Engine : EngineBase {
     if (!cfg.gnn_features)
       DQ_LAUNCH(embed_table_bwd_kernel<T>, dim3((d + 63) / 64, 64), dim3(64), 0, st, (const T*)dXn, n_types, N, cfg.n_up, d, rows,
                 G + off("emb.table"));
+    note_hwm(p);
     if ((int64_t)(p - (char*)wsbase) > vjp_ws_cap) { err = "internal: reverse-pass buffers exceed the planned workspace"; return 3; }
     return 0;
-  }
-  size_t vjp_per_walker_elems_ferminet() const {
-    const size_t L = cfg.n_layers, de = cfg.edge_dim, d0 = 4 * M, dm = (size_t)d > d0 ? d : d0, em = de > 4 ? de : 4;
-    const size_t rowsN = N, rowsE = (size_t)N * N;
-    return rowsN * (d0 + L * d + L * (3 * dm + 2 * em) + 2 * (size_t)KN + 3 * (size_t)d + 3 * dm + 2 * em) + rowsE * (4 + L * de + 3 * de) +
-           (size_t)K * 4;
   }
 
   int vjp_params(const void* r_, const void* R_, int Rb, int B, const void* weights, void* sign, void* logp,
@@ -1749,10 +1821,17 @@ struct Engine : EngineBase {
     if (B == 0) return 0;  // empty batch: zero gradient
     // walkers per chunk: activations of every layer stay resident for the reverse pass (64 buffers, 256 B alignment each)
     const bool fermi = cfg.kind == DQMC_FERMINET;
-    const int64_t per_w = gnn ? vjp_per_walker_elems_paulinet() : (fermi ? vjp_per_walker_elems_ferminet() : vjp_per_walker_elems());
-    int64_t Bc = (wsb - kVjpSlack) / (int64_t)(sizeof(T) * per_w);
-    if (Bc > B) Bc = B;
-    if (Bc < 1) { err = "workspace too small for a single walker (vjp)"; return 3; }
+    // largest chunk whose buffers (measured by a dry pass of the chunk function) fit the caller's workspace
+    int64_t Bc = B;
+    if (vjp_chunk_bytes(1) > wsb) { err = "workspace too small for a single walker (vjp)"; return 3; }
+    if (vjp_chunk_bytes((int)Bc) > wsb) {
+      int64_t lo = 1, hi = Bc;
+      while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) / 2;
+        if (vjp_chunk_bytes((int)mid) <= wsb) lo = mid; else hi = mid;
+      }
+      Bc = lo;
+    }
     vjp_ws_cap = wsb;
     if (!fermi && !gnn)
     DQ_CHECK(raise_dyn_smem(attn_bwd_kernel<T>, (int)attn_bwd_smem_bytes<T>(N, dh, Mn)));
@@ -1773,6 +1852,7 @@ struct Engine : EngineBase {
       if (rc) return rc;
       rc = check_guards();
       if (rc) return rc;
+      if (dry) break;  // planning pass: the first chunk is the largest
     }
     DQ_CHECK(cudaGetLastError());
     return 0;
@@ -1816,18 +1896,17 @@ struct Engine : EngineBase {
     if (J > 0) {
       // non-local ECP: virtual walkers (12 quadrature points x electrons x ECP nuclei)
       const int64_t vper = (int64_t)J * N * 12;
-      int64_t Be = B;
+      int64_t Be = std::min<int64_t>(B, ecp_group_cap());
       if (ecp_bytes(Be) > wsb) {  // largest walker group whose virtual walkers fit the workspace
-        int64_t lo = 0, hi = B;
+        int64_t lo = 0, hi = Be;
         while (hi - lo > 1) {
           int64_t mid = (lo + hi) / 2;
           if (ecp_bytes(mid) <= wsb) lo = mid; else hi = mid;
         }
         Be = lo;
       }
-      if (Be < 1) { err = "workspace too small for the non-local ECP pass"; return 3; }
-      const int64_t vcap = 2000000000LL / ((int64_t)N * 3 * d);  // keep 32-bit row counts safe
-      if (Be * vper > vcap) Be = std::max<int64_t>(1, vcap / vper);
+      if (Be < 1) Be = 1;  // one walker's virtual walkers do not fit at once: the plain-forward pass chunks them
+      if (ecp_prefix_bytes(Be) + (int64_t)chunk_bytes(1, 1) > wsb) { err = "workspace too small for the non-local ECP pass"; return 3; }
       for (int b0 = 0; b0 < B; b0 += (int)Be) {
         int nb = (int)std::min<int64_t>(Be, B - b0);
         int64_t V = (int64_t)nb * vper;
@@ -1835,6 +1914,7 @@ struct Engine : EngineBase {
         T* rv = (T*)p; p += align_up(sizeof(T) * V * 3 * N);
         T* sv = (T*)p; p += align_up(sizeof(T) * V);
         T* lv = (T*)p; p += align_up(sizeof(T) * V);
+        note_hwm(p);
         const T* rb = r + (size_t)b0 * 3 * N;
         const T* Rbp = R + (Rb ? (size_t)b0 * 3 * M : 0);
         const T* tw = twist ? (const T*)twist + (size_t)b0 * J * N : nullptr;
@@ -1847,6 +1927,7 @@ struct Engine : EngineBase {
                   (const int*)d_nl_nuc, (const T*)d_nl_params, cfg.ecp_nl_lmax_p1, cfg.ecp_nl_terms,
                   (const T*)sign + b0, (const T*)logp + b0, (const T*)sv, (const T*)lv, nb, B, (T*)E + b0,
                   (T*)stats + b0);
+        if (dry) break;  // planning pass: the first group is the largest
       }
     }
     DQ_CHECK(cudaGetLastError());
@@ -1868,6 +1949,8 @@ struct Engine : EngineBase {
     T* lp = (T*)p; p += align_up(sizeof(T) * (size_t)B);
     int* cnt = (int*)p; p += 256;
     int64_t rest = wsb - (p - (char*)ws);
+    note_hwm(p);
+    if (rest < 0) { err = "workspace too small (proposal buffers)"; return 3; }
     DQ_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int), st));
     const int ne = B * 3 * N;
     for (int s = 0; s < n_sub; ++s) {
@@ -1906,6 +1989,14 @@ struct dqmc_engine {
   dq::EngineBase* e;
 };
 
+#define DQ_NEED_DEVICE(h)                                                                        \
+  do {                                                                                            \
+    if ((h)->e->plan_only) {                                                                      \
+      (h)->e->err = "plan-only engine (created with device < 0): no compute entry points";        \
+      return 2;                                                                                   \
+    }                                                                                             \
+  } while (0)
+
 extern "C" {
 
 const char* dqmc_version(void) { return "dqmc_b200 0.1 (sm_100a)"; }
@@ -1914,12 +2005,13 @@ int dqmc_create(const dqmc_config* cfg, int device, dqmc_handle* out) {
   if (!cfg || !out) return 2;
   dq::EngineBase* e = nullptr;
   int rc = 0;
+  const bool plan = device < 0;  // plan-only engine: workspace planning without a CUDA device (dqmc_debug_plan)
   if (cfg->dtype == DQMC_F64) {
     auto* x = new dq::Engine<double>();
-    x->cfg = *cfg; x->device = device; rc = x->init(); e = x;
+    x->cfg = *cfg; x->device = device; x->dry = x->plan_only = plan; rc = x->init(); e = x;
   } else if (cfg->dtype == DQMC_F32) {
     auto* x = new dq::Engine<float>();
-    x->cfg = *cfg; x->device = device; rc = x->init(); e = x;
+    x->cfg = *cfg; x->device = device; x->dry = x->plan_only = plan; rc = x->init(); e = x;
   } else {
     return 2;
   }
@@ -1954,14 +2046,19 @@ int dqmc_param_entry(dqmc_handle h, int idx, char* name, int name_len, int64_t* 
 }
 int dqmc_set_params(dqmc_handle h, const double* host_params, int64_t n, void* stream) {
   if (!h) return 2;
+  DQ_NEED_DEVICE(h);
   return h->e->set_params(host_params, n, (cudaStream_t)stream);
 }
 int64_t dqmc_workspace_bytes(dqmc_handle h, int32_t n_walkers, int32_t mode) {
   return h ? h->e->ws_bytes(n_walkers, mode) : -1;
 }
+int64_t dqmc_workspace_bytes_min(dqmc_handle h, int32_t n_walkers, int32_t mode) {
+  return h ? h->e->ws_bytes_min(n_walkers, mode) : -1;
+}
 int dqmc_wf_forward(dqmc_handle h, const void* r, const void* R, int32_t R_batched, int32_t n_walkers, void* out_sign,
                     void* out_log, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!h) return 2;
+  DQ_NEED_DEVICE(h);
   if (n_walkers < 0) { h->e->err = "negative walker count"; return 2; }
   if (n_walkers == 0) return 0;  // empty batch: nothing to evaluate
   return h->e->forward(r, R, R_batched, n_walkers, out_sign, out_log, workspace, workspace_bytes, (cudaStream_t)stream);
@@ -1969,6 +2066,7 @@ int dqmc_wf_forward(dqmc_handle h, const void* r, const void* R, int32_t R_batch
 int dqmc_wf_orbitals(dqmc_handle h, const void* r, const void* R, int32_t R_batched, int32_t n_walkers, void* out_orbitals,
                      void* workspace, int64_t workspace_bytes, void* stream) {
   if (!h) return 2;
+  DQ_NEED_DEVICE(h);
   if (n_walkers < 0) { h->e->err = "negative walker count"; return 2; }
   if (n_walkers == 0) return 0;
   return h->e->orbitals(r, R, R_batched, n_walkers, out_orbitals, workspace, workspace_bytes, (cudaStream_t)stream);
@@ -1977,6 +2075,7 @@ int dqmc_local_energy(dqmc_handle h, const void* r, const void* R, int32_t R_bat
                       const void* ecp_twist, void* out_E, void* out_stats, void* out_sign, void* out_log,
                       void* out_grad, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!h) return 2;
+  DQ_NEED_DEVICE(h);
   if (n_walkers < 0) { h->e->err = "negative walker count"; return 2; }
   if (n_walkers == 0) return 0;  // empty batch: nothing to evaluate
   return h->e->local_energy(r, R, R_batched, n_walkers, seed, ecp_twist, out_E, out_stats, out_sign, out_log, out_grad,
@@ -1987,6 +2086,7 @@ int dqmc_mcmc_sweep(dqmc_handle h, void* r, void* sign, void* log, int32_t* age,
                     uint64_t seed, uint64_t step0, uint64_t walker_offset, const void* noise_normal,
                     const void* noise_uniform, void* out_stats, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!h) return 2;
+  DQ_NEED_DEVICE(h);
   if (n_walkers < 1) { h->e->err = "the sampler needs at least one walker"; return 2; }
   return h->e->mcmc(r, sign, log, age, tau, R, R_batched, n_walkers, n_sub, target_acceptance, max_age, seed, step0,
                     walker_offset, noise_normal, noise_uniform, out_stats, workspace, workspace_bytes,
@@ -1999,6 +2099,7 @@ int dqmc_mcmc_sweep_exchange(dqmc_handle h, void* r, void* sign, void* log, int3
                              const int32_t* exchange_idx, void* out_stats, void* workspace, int64_t workspace_bytes,
                              void* stream) {
   if (!h) return 2;
+  DQ_NEED_DEVICE(h);
   if (n_walkers < 1) { h->e->err = "the sampler needs at least one walker"; return 2; }
   if (h->e->cfg.n_up < 1 || h->e->cfg.n_down < 1) { h->e->err = "spin exchange needs electrons of both spins"; return 2; }
   return h->e->mcmc(r, sign, log, age, tau, R, R_batched, n_walkers, n_sub, target_acceptance, max_age, seed, step0,
@@ -2010,6 +2111,7 @@ int dqmc_langevin_sweep(dqmc_handle h, void* r, void* sign, void* log, void* for
                         uint64_t seed, uint64_t step0, uint64_t walker_offset, const void* noise_normal,
                         const void* noise_uniform, void* out_stats, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!h) return 2;
+  DQ_NEED_DEVICE(h);
   if (n_walkers < 1) { h->e->err = "the sampler needs at least one walker"; return 2; }
   return h->e->langevin(r, sign, log, force, age, tau, R, R_batched, n_walkers, n_sub, target_acceptance, max_age, seed, step0,
                         walker_offset, noise_normal, noise_uniform, out_stats, workspace, workspace_bytes, (cudaStream_t)stream);
@@ -2018,6 +2120,7 @@ int dqmc_wf_vjp_params(dqmc_handle h, const void* r, const void* R, int32_t R_ba
                        void* out_sign, void* out_log, void* out_grad_params, void* workspace, int64_t workspace_bytes,
                        void* stream) {
   if (!h) return 2;
+  DQ_NEED_DEVICE(h);
   if (n_walkers < 0) { h->e->err = "negative walker count"; return 2; }
   return h->e->vjp_params(r, R, R_batched, n_walkers, weights, out_sign, out_log, out_grad_params, workspace, workspace_bytes,
                           (cudaStream_t)stream);
@@ -2025,14 +2128,21 @@ int dqmc_wf_vjp_params(dqmc_handle h, const void* r, const void* R, int32_t R_ba
 int dqmc_set_pseudo_hamiltonian(dqmc_handle h, int32_t n_tab, int32_t n_grid, double r_max, const double* tables,
                                 const int32_t* tab_of_nuc) {
   if (!h) return 2;
-  cudaSetDevice(h->e->device);
+  if (!h->e->plan_only) cudaSetDevice(h->e->device);
   return h->e->set_ph(n_tab, n_grid, r_max, tables, tab_of_nuc);
+}
+int dqmc_debug_plan(dqmc_handle h, int32_t n_walkers, int32_t mode, int64_t workspace_bytes, int64_t* planned_bytes,
+                    int64_t* carved_bytes) {
+  if (!h) return 2;
+  if (n_walkers < 1) { h->e->err = "dqmc_debug_plan needs at least one walker"; return 2; }
+  return h->e->debug_plan(n_walkers, mode, workspace_bytes, planned_bytes, carved_bytes);
 }
 int64_t dqmc_launch_count(dqmc_handle h) { return h ? h->e->launches : -1; }
 
 int dqmc_debug_gemm(dqmc_handle h, const char* weight, const char* bias, const void* A, const void* Res, void* C,
                     int32_t rows, int32_t S, int32_t sliced, int32_t backend, void* stream) {
   if (!h) return 2;
+  DQ_NEED_DEVICE(h);
   return h->e->debug_gemm(weight, bias, A, Res, C, rows, S, sliced, backend, (cudaStream_t)stream);
 }
 

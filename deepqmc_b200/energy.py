@@ -95,7 +95,11 @@ def compute_mean_energy_tangent(local_energy, weight, gradient_mask, ansatz, par
     (loss/energy.py:77-102 with loss/loss_function.py:53-82); here the same per-walker factors are the cotangent of
     ONE reverse pass through the CUDA engine (dqmc_wf_vjp_params).  Returns {haiku name: gradient} summed over all
     ranks (all-reduce of the packed gradient, reference optimizer.py:142 pmean)."""
-    E = local_energy.reshape(-1)
+    if local_energy.dim() != 1:
+        # the reference subtracts the mean per (molecule, state) row (loss/energy.py:88, axis=-1); one call = one row here
+        raise ValueError('compute_mean_energy_tangent takes the local energies of ONE (molecule, electronic state) batch [B]; '
+                         'loop over the leading axes with that state\'s parameters (as overlap.compute_mean_overlap_tangent does)')
+    E = local_energy
     w = torch.ones_like(E) if weight is None else weight.reshape(-1)
     mask = torch.ones_like(E, dtype=torch.bool) if gradient_mask is None else gradient_mask.reshape(-1)
     stats = parallel.energy_statistics(E * w)

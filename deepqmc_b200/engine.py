@@ -14,7 +14,7 @@ from . import _lib
 from . import params as PN
 from .spec import AnsatzSpec
 
-MODE_FORWARD, MODE_LOCAL_ENERGY, MODE_VJP = 0, 1, 2
+MODE_FORWARD, MODE_LOCAL_ENERGY, MODE_VJP, MODE_MCMC, MODE_LANGEVIN = 0, 1, 2, 3, 4
 _TORCH_DTYPE = {0: torch.float64, 1: torch.float32}
 
 
@@ -304,16 +304,22 @@ class Engine:
     """One engine per (ansatz spec, Hamiltonian constants, dtype, device)."""
 
     def __init__(self, spec: AnsatzSpec, hamil, dtype: str = 'float64', device: int | None = None,
-                 gemm_backend: int = 0, _lib_path: str | None = None):
+                 gemm_backend: int = 0, _lib_path: str | None = None, plan_only: bool = False):
+        """``plan_only``: a handle created with device = -1 -- no CUDA context; only the parameter table, the workspace
+        sizes and ``debug_plan`` work (tests/test_plan.py checks the workspace planner on the CPU with it)."""
         self._host = _lib_path is not None  # emulator build: "device" pointers are host pointers
         self.lib = _lib.load(_lib_path)
-        if not self._host and not torch.cuda.is_available():
+        self.plan_only = plan_only
+        if not self._host and not plan_only and not torch.cuda.is_available():
             raise RuntimeError('deepqmc_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
         self.spec, self.hamil = spec, hamil
         self.dtype_code = {'float64': 0, 'float32': 1}[dtype]
         self.dtype = _TORCH_DTYPE[self.dtype_code]
-        self.device_index = 0 if self._host else (torch.cuda.current_device() if device is None else device)
-        self.device = torch.device('cpu') if self._host else torch.device('cuda', self.device_index)
+        if plan_only:
+            self.device_index, self.device = -1, torch.device('cpu')
+        else:
+            self.device_index = 0 if self._host else (torch.cuda.current_device() if device is None else device)
+            self.device = torch.device('cpu') if self._host else torch.device('cuda', self.device_index)
         cfg = _lib.DqmcConfig()
         cfg.kind = {'psiformer': 0, 'ferminet': 1, 'transpsiformer': 2, 'paulinet': 3}[spec.kind]
         cfg.dtype, cfg.gemm_backend = self.dtype_code, gemm_backend
@@ -405,8 +411,8 @@ class Engine:
         self.n_packed = self.lib.dqmc_param_total(h)
         self._ws = None
         self._ws_ok = set()  # (n_walkers, mode, cap) requests the current workspace is known to satisfy
-        self._mcmc_fw = {}
         self._params_version = None
+        self._nuc_R_dev = None
 
     # ------------------------------------------------------------------------------------
     def _check(self, rc, what):
@@ -422,7 +428,7 @@ class Engine:
         if self.spec.kind == 'transpsiformer':
             R = self.hamil.mol.coords if R is None else R
             R = np.asarray(R.detach().cpu() if torch.is_tensor(R) else R, dtype=np.float64)
-            self._nuc_R, self._nuc_key = R, None
+            self._nuc_R, self._nuc_R_dev = R, None
         self._params = params
         packed = _pack_haiku_params(self.spec, params, R)
         if self.spec.cusp_nuclei != 'none':  # NuclearCuspAsymptotic: alpha (trainable or fixed) + the nuclear charges
@@ -441,16 +447,18 @@ class Engine:
             torch.cuda.current_stream(self.device).synchronize()
 
     def workspace(self, n_walkers: int, mode: int, max_bytes: int | None = None):
+        """The engine's scratch buffer for one call of the entry point ``mode`` names: dqmc_workspace_bytes (a dry pass of the
+        code that carves it), capped at ``max_bytes`` / 60 % of the free HBM -- the engine then chunks the walkers -- but
+        never below dqmc_workspace_bytes_min."""
         key = (n_walkers, mode, max_bytes)
         if self._ws is not None and key in self._ws_ok:  # hot path: no driver queries per call
             return self._ws
         need = self.lib.dqmc_workspace_bytes(self.h, n_walkers, mode)
         if max_bytes is None and not self._host:
-            # never ask for more than ~60 % of the free HBM: the engine chunks the walkers internally
             free = torch.cuda.mem_get_info(self.device)[0] + (self._ws.numel() if self._ws is not None else 0)
             max_bytes = int(0.6 * free)
         if max_bytes is not None:
-            need = min(need, max(max_bytes, self.lib.dqmc_workspace_bytes(self.h, 1, mode)))
+            need = min(need, max(max_bytes, self.lib.dqmc_workspace_bytes_min(self.h, n_walkers, mode)))
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
@@ -471,12 +479,13 @@ class Engine:
         if self.spec.kind == 'transpsiformer':
             if batched:
                 raise NotImplementedError('TransPsiformer engine: one geometry per call (unbatched R)')
-            key = (R.data_ptr(), R._version)
-            if key != self._nuc_key:  # geometry may have changed: the nuclear stream depends on it
+            # the nuclear stream depends on the geometry: compare the CONTENTS with the geometry it was evaluated for (never a
+            # pointer / version key: temporaries of different geometries reuse addresses in the caching allocator)
+            if self._nuc_R_dev is None or self._nuc_R_dev.device != R.device or not torch.equal(R.double(), self._nuc_R_dev):
                 Rh = R.detach().cpu().double().numpy()
                 if not np.allclose(Rh, self._nuc_R, rtol=0, atol=1e-12):
                     self.set_params(self._params, Rh)
-                self._nuc_key = key
+                self._nuc_R_dev = R.detach().double().clone()
         return R, batched
 
     # ------------------------------------------------------------------------------------
@@ -582,23 +591,7 @@ class Engine:
         nn = self._prep(noise_normal) if noise_normal is not None else None
         nu = self._prep(noise_uniform) if noise_uniform is not None else None
         stats = torch.zeros(7, dtype=self.dtype, device=self.device)
-        # proposal buffers (r', sign', log', counter) + the forward-pass workspace
-        extra = (B * (r.shape[1] * 3 + 2)) * r.element_size() + 8192
-        fkey = (B, max_ws_bytes)
-        fw = self._mcmc_fw.get(fkey)
-        if fw is None:  # decided once per batch size (cudaMemGetInfo is a slow driver query)
-            fw = self.lib.dqmc_workspace_bytes(self.h, B, MODE_FORWARD)
-            if max_ws_bytes is not None:
-                fw = min(fw, max(max_ws_bytes, self.lib.dqmc_workspace_bytes(self.h, 1, MODE_FORWARD)))
-            elif not self._host:
-                free = torch.cuda.mem_get_info(self.device)[0] + (self._ws.numel() if self._ws is not None else 0)
-                fw = min(fw, max(int(0.6 * free), self.lib.dqmc_workspace_bytes(self.h, 1, MODE_FORWARD)))
-            self._mcmc_fw[fkey] = fw
-        if self._ws is None or self._ws.numel() < fw + extra:
-            self._ws = None
-            self._ws = torch.empty(fw + extra, dtype=torch.uint8, device=self.device)
-            self._ws_ok = set()
-        ws = self._ws
+        ws = self.workspace(B, MODE_MCMC, max_ws_bytes)  # proposal buffers + the plain-forward chunk
         if exchange_probability > 0.0 or exchange_flags is not None:
             flags = None
             if exchange_flags is not None:
@@ -638,16 +631,7 @@ class Engine:
         nn = self._prep(noise_normal) if noise_normal is not None else None
         nu = self._prep(noise_uniform) if noise_uniform is not None else None
         stats = torch.zeros(7, dtype=self.dtype, device=self.device)
-        extra = (B * (2 * N * 3 + 2 + 7 + 3 * N)) * r.element_size() + 16384
-        need = self.lib.dqmc_workspace_bytes(self.h, B, MODE_LOCAL_ENERGY) + extra
-        if not self._host:
-            free = torch.cuda.mem_get_info(self.device)[0] + (self._ws.numel() if self._ws is not None else 0)
-            need = min(need, max(int(0.6 * free), self.lib.dqmc_workspace_bytes(self.h, 1, MODE_LOCAL_ENERGY) + extra))
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = None
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-            self._ws_ok = set()
-        ws = self._ws
+        ws = self.workspace(B, MODE_LANGEVIN)  # proposal / force buffers + the forward-Laplacian chunk
         rc = self.lib.dqmc_langevin_sweep(
             self.h, r.data_ptr(), state['sign'].data_ptr(), state['log'].data_ptr(), state['force'].data_ptr(),
             state['age'].data_ptr(), state['tau'].data_ptr(), R.data_ptr(), Rb, B, n_sub,
@@ -670,6 +654,20 @@ class Engine:
                                       backend, self._stream())
         self._check(rc, 'dqmc_debug_gemm')
         return Cout
+
+    def debug_plan(self, n_walkers: int, mode: int, workspace_bytes: int = 0):
+        """-> (planned, carved): dqmc_workspace_bytes and the highest offset the entry point of ``mode`` carves when given
+        ``workspace_bytes`` (0: the planned size); host-only."""
+        pl, cv = C.c_int64(), C.c_int64()
+        rc = self.lib.dqmc_debug_plan(self.h, n_walkers, mode, workspace_bytes, C.byref(pl), C.byref(cv))
+        self._check(rc, 'dqmc_debug_plan')
+        return pl.value, cv.value
+
+    def workspace_bytes(self, n_walkers: int, mode: int) -> int:
+        return self.lib.dqmc_workspace_bytes(self.h, n_walkers, mode)
+
+    def workspace_bytes_min(self, n_walkers: int, mode: int) -> int:
+        return self.lib.dqmc_workspace_bytes_min(self.h, n_walkers, mode)
 
     def profile_begin(self):
         self.lib.dqmc_profile_begin(self.h)

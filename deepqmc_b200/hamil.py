@@ -170,8 +170,19 @@ class MolecularHamiltonian:
                 ecp_twist = torch.as_tensor(tw, dtype=r.dtype, device=r.device)
                 rng = 0
             if R.dim() == 3 and self.nl_params is not None:
+                if not bool((R == R[:1]).all()):
+                    raise ValueError('Gaussian-type ECP: one nuclear geometry per call (all rows of a batched R must be equal)')
                 R = R[0]
-            seed = int(rng) if isinstance(rng, (int, np.integer)) else 0
+            if rng is None:
+                seed = 0
+            elif isinstance(rng, (int, np.integer)):
+                seed = int(rng)
+            elif isinstance(rng, np.ndarray) and rng.dtype == np.uint32 and rng.size == 2:
+                seed = (int(rng.reshape(-1)[0]) << 32) | int(rng.reshape(-1)[1])  # a JAX key keys the Philox stream
+            elif torch.is_tensor(rng) and rng.numel() == 1 and not rng.is_floating_point():
+                seed = int(rng.item())
+            else:
+                raise TypeError(f'rng must be an int seed, a uint32[2] key or None, got {type(rng).__name__}')
             E, stats, sign, log, grad = eng.local_energy(r, R, seed=seed, ecp_twist=ecp_twist, want_grad=return_grad)
             sd = {k: (stats[i, 0] if single else stats[i]) for i, k in enumerate(STAT_KEYS)}
             out = (E[0] if single else E, sd)

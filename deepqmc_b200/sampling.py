@@ -105,6 +105,25 @@ def _as_jax_key(rng):
     return jaxrand.prng_key(int(rng))
 
 
+def _rank_key(key):
+    """This rank's key of a uint32[2] JAX key: the reference pmaps its samplers over per-device keys split(rng, device_count)
+    (sampling_utils.py:236-262, parallel.py:126-133); with one process per GPU that is split(key, world)[rank]."""
+    from . import jaxrand, parallel
+
+    rank, world = parallel.world()
+    return key if world == 1 else jaxrand.split(key, world)[rank]
+
+
+def _default_offset(walker_offset, n_local):
+    """Global index of this rank's first walker: keys the in-kernel Philox streams, so ranks that are handed the SAME integer
+    seed still draw independent noise (contiguous walker blocks, deepqmc_b200.parallel.shard_bounds)."""
+    if walker_offset is not None:
+        return walker_offset
+    from . import parallel
+
+    return parallel.world()[0] * n_local
+
+
 class JaxCompatibleElectronInitializer:
     """The reference's AtomCenteredElectronInitializer(ShellBasedDistribution()) driven by a numpy restatement of its
     jax.random streams (deepqmc_b200/jaxrand.py): ``sampler.init(seed, ...)`` then returns the SAME walkers as the
@@ -146,7 +165,7 @@ class MetropolisSampler:
         categorical(split(rng_prop)) with uniform logits.  -> (normal, uniform, flags[length], idx[length, B, 2])"""
         from . import jaxrand
 
-        key = _as_jax_key(rng)
+        key = _rank_key(_as_jax_key(rng))
         subkeys = jaxrand.split(key, self.length) if self.length > 1 else [key]
         B, n_up, n_dn = shape_r[0], self.hamil.n_up, self.hamil.n_down
         nn, nu, flags, idx = [], [], [], []
@@ -173,7 +192,7 @@ class MetropolisSampler:
         (electron_samplers.py:140-147,347-353)."""
         from . import jaxrand
 
-        key = _as_jax_key(rng)
+        key = _rank_key(_as_jax_key(rng))
         subkeys = jaxrand.split(key, self.length) if self.length > 1 else [key]
         B = shape_r[0]
         nn = np.stack([jaxrand.normal(jaxrand.split(k, 2)[0], tuple(shape_r)) for k in subkeys])
@@ -210,9 +229,12 @@ class MetropolisSampler:
         }
         return self.update(state, params, torch.as_tensor(Rn, dtype=eng.dtype, device=eng.device))
 
-    def sample(self, rng, state, params, R, *, walker_offset=0, noise_normal=None, noise_uniform=None, exchange_flags=None,
+    def sample(self, rng, state, params, R, *, walker_offset=None, noise_normal=None, noise_uniform=None, exchange_flags=None,
                exchange_idx=None):
+        """``rng`` may be the same on every rank: the Philox streams are keyed by the global walker index (``walker_offset``
+        defaults to rank * local batch), a uint32[2] key is split per rank as the reference's pmap does."""
         eng = self._engine(params)
+        walker_offset = _default_offset(walker_offset, state['r'].shape[0])
         xkw = {}
         if self.exchange_step_probability > 0.0:
             xkw = {'exchange_probability': self.exchange_step_probability, 'exchange_flags': exchange_flags, 'exchange_idx': exchange_idx}
@@ -357,8 +379,9 @@ class LangevinSampler(MetropolisSampler):
         eng.langevin_sweep(st, R, 0)
         return {**state, 'psi': Psi(st['sign'], st['log']), 'force': st['force']}
 
-    def sample(self, rng, state, params, R, *, walker_offset=0, noise_normal=None, noise_uniform=None):
+    def sample(self, rng, state, params, R, *, walker_offset=None, noise_normal=None, noise_uniform=None):
         eng = self._engine(params)
+        walker_offset = _default_offset(walker_offset, state['r'].shape[0])
         if self.jax_compatible_noise and noise_normal is None:
             noise_normal, noise_uniform = self._jax_noise(rng, state['r'].shape, state['r'].device, state['r'].dtype)
         st = {'r': state['r'], 'sign': state['psi'].sign, 'log': state['psi'].log, 'force': state['force'],
@@ -471,7 +494,9 @@ class MultiNuclearGeometrySampler:
         return R.to(device=st0['r'].device, dtype=st0['r'].dtype)
 
     def update_nuc(self, rng, nuc_state, elec_state, params):
-        """One molecule: propose new nuclei, warp the electrons along, refresh psi, re-equilibrate (:130-160)."""
+        """One molecule: propose new nuclei, warp the electrons along, refresh psi, re-equilibrate (:130-160).  ``rng`` must be
+        the same on every rank (the reference aligns it with align_rng_key_across_devices): the nuclear move is then identical
+        everywhere, while the electron re-equilibration still draws per-rank noise through the walker offset."""
         nuc_state, dR, stats = self.nuc_sampler.sample(int(rng), nuc_state)
         R = nuc_state['R']
         elec_state = self.warp_elec_fn(int(rng) + 1, R, dR, elec_state)
@@ -541,5 +566,7 @@ def initialize_sampler_state(rng, sampler, params, electron_batch_size, nuc_coor
 
     rank, world = parallel.world()
     assert electron_batch_size % world == 0, 'electron_batch_size must be divisible by the number of devices'  # validate_kwargs.py:45-48
-    return sampler.init(parallel.rank_seed(rng, rank) if not isinstance(rng, np.ndarray) else rng, params, electron_batch_size // world, nuc_coords)
+    # per-rank walkers: integer seeds are offset by the rank (train.py:134), uint32[2] keys are split over the ranks
+    seed = _rank_key(rng) if isinstance(rng, np.ndarray) else parallel.rank_seed(rng, rank)
+    return sampler.init(seed, params, electron_batch_size // world, nuc_coords)
 

@@ -30,7 +30,7 @@ extern "C" {
 enum { DQMC_PSIFORMER = 0, DQMC_FERMINET = 1, DQMC_TRANSPSIFORMER = 2, DQMC_PAULINET = 3 };
 enum { DQMC_F64 = 0, DQMC_F32 = 1 };
 enum { DQMC_GEMM_SIMT = 0, DQMC_GEMM_TCGEN05 = 1 };
-enum { DQMC_MODE_FORWARD = 0, DQMC_MODE_LOCAL_ENERGY = 1, DQMC_MODE_VJP = 2 };
+enum { DQMC_MODE_FORWARD = 0, DQMC_MODE_LOCAL_ENERGY = 1, DQMC_MODE_VJP = 2, DQMC_MODE_MCMC = 3, DQMC_MODE_LANGEVIN = 4 };
 
 /* Ansatz + Hamiltonian constants that fix the kernel shapes.
  * reference: src/deepqmc/conf/ansatz/psiformer.yaml, ferminet.yaml;
@@ -90,7 +90,9 @@ typedef struct dqmc_config {
 
 typedef struct dqmc_engine* dqmc_handle;
 
-/* Build / tear down an engine bound to one CUDA device.
+/* Build / tear down an engine bound to one CUDA device.  device < 0 builds a PLAN-ONLY engine: no CUDA context and no
+ * allocation; only the parameter-table queries, dqmc_workspace_bytes and dqmc_debug_plan work on it (every compute entry
+ * point returns status 2).
  * replaces: app.py:82-105 instantiate_ansatz + hamil.py:97-154 MolecularHamiltonian.__init__ */
 int dqmc_create(const dqmc_config* cfg, int device, dqmc_handle* out);
 int dqmc_destroy(dqmc_handle h);
@@ -105,10 +107,14 @@ int dqmc_param_entry(dqmc_handle h, int idx, char* name, int name_len, int64_t* 
 int64_t dqmc_param_total(dqmc_handle h);
 int dqmc_set_params(dqmc_handle h, const double* host_params, int64_t n, void* stream);
 
-/* Workspace the caller must provide for n_walkers in one call (bytes). The engine chunks
- * walkers internally if given less (>= dqmc_workspace_bytes(h, 1, mode) required).
+/* Workspace the caller must provide for n_walkers in one call of the entry point `mode` names (bytes; DQMC_MODE_MCMC =
+ * dqmc_mcmc_sweep(_exchange), DQMC_MODE_LANGEVIN = dqmc_langevin_sweep, proposal buffers included).  The engine chunks
+ * walkers internally if given less (>= dqmc_workspace_bytes_min(h, n_walkers, mode) required).  The figure is computed by a dry pass of
+ * the code that carves the workspace, so plan and use cannot drift apart.
  * replaces: XLA buffer assignment / loss/energy.py:44-48 local_energy_batch_size chunking. */
 int64_t dqmc_workspace_bytes(dqmc_handle h, int32_t n_walkers, int32_t mode);
+/* The least workspace with which a call for n_walkers proceeds at all (walkers processed one at a time). */
+int64_t dqmc_workspace_bytes_min(dqmc_handle h, int32_t n_walkers, int32_t mode);
 
 /* psi(r) for a batch of walkers.  r[B][N][3], R[M][3] (R_batched = 0) or R[B][M][3].
  * replaces: vmap(ansatz.apply)(params, phys_conf) -> Psi(sign, log)
@@ -193,6 +199,14 @@ int dqmc_wf_vjp_params(dqmc_handle h, const void* r, const void* R, int32_t R_ba
  *           :71-112 load_PH_functions (RegularGridInterpolator tables). */
 int dqmc_set_pseudo_hamiltonian(dqmc_handle h, int32_t n_tab, int32_t n_grid, double r_max, const double* tables,
                                 const int32_t* tab_of_nuc);
+
+/* Self-test hook (host only, also on plan-only engines): *planned_bytes = dqmc_workspace_bytes(h, n_walkers, mode);
+ * *carved_bytes = the highest workspace offset the entry point of `mode` carves when it is given workspace_bytes bytes
+ * (<= 0: the planned size) -- found by walking that entry point's host code with every CUDA call skipped.
+ * Status 3 if that workspace is too small for one walker.  tests/test_plan.py sweeps ansatz kind x mode x batch size x
+ * dtype and asserts carved <= given.  No reference analogue (XLA assigns buffers itself). */
+int dqmc_debug_plan(dqmc_handle h, int32_t n_walkers, int32_t mode, int64_t workspace_bytes, int64_t* planned_bytes,
+                    int64_t* carved_bytes);
 
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches claim). */
 int64_t dqmc_launch_count(dqmc_handle h);
