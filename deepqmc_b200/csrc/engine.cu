@@ -58,6 +58,7 @@ struct EngineBase {
   virtual int64_t ws_bytes(int B, int mode) = 0;
   virtual int64_t ws_bytes_min(int B, int mode) = 0;
   virtual int debug_plan(int B, int mode, int64_t wsb, int64_t* planned, int64_t* carved) = 0;
+  virtual int stats_pack(const void* E, const void* stats, int B, double* out, cudaStream_t st) = 0;
   virtual int forward(const void* r, const void* R, int Rb, int B, void* sign, void* logp, void* ws, int64_t wsb,
                       cudaStream_t st) = 0;
   virtual int local_energy(const void* r, const void* R, int Rb, int B, uint64_t seed, const void* twist, void* E,
@@ -1858,6 +1859,12 @@ struct Engine : EngineBase {
     return 0;
   }
 
+  int stats_pack(const void* E, const void* stats, int B, double* out, cudaStream_t st) override {
+    DQ_LAUNCH(stats_pack_kernel<T>, dim3(1), dim3(1024), 0, st, (const T*)E, (const T*)stats, B, out);
+    DQ_CHECK(cudaGetLastError());
+    return 0;
+  }
+
   // orbital matrices out[B][K][N][N] (electron i, orbital mu) of a plain forward
   int orbitals(const void* r_, const void* R_, int Rb, int B, void* out, void* ws, int64_t wsb, cudaStream_t st) override {
     const T* r = (const T*)r_;
@@ -2136,6 +2143,12 @@ int dqmc_debug_plan(dqmc_handle h, int32_t n_walkers, int32_t mode, int64_t work
   if (!h) return 2;
   if (n_walkers < 1) { h->e->err = "dqmc_debug_plan needs at least one walker"; return 2; }
   return h->e->debug_plan(n_walkers, mode, workspace_bytes, planned_bytes, carved_bytes);
+}
+int dqmc_stats_pack(dqmc_handle h, const void* E_loc, const void* stats, int32_t n_walkers, double* out11, void* stream) {
+  if (!h) return 2;
+  DQ_NEED_DEVICE(h);
+  if (n_walkers < 1 || !E_loc || !out11) { h->e->err = "dqmc_stats_pack: bad arguments"; return 2; }
+  return h->e->stats_pack(E_loc, stats, n_walkers, out11, (cudaStream_t)stream);
 }
 int64_t dqmc_launch_count(dqmc_handle h) { return h ? h->e->launches : -1; }
 

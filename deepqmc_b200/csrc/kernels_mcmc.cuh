@@ -262,6 +262,48 @@ __global__ void sampler_stats_kernel(const T* __restrict__ r, const T* __restric
   }
 }
 
+// Per-rank part of the step statistics (reference: loss/energy.py:63-74 mean energy over all devices,
+// observable.py:474-479): out[0] = sum E, [1] = sum E^2, [2] = B, [3..8] = sums of the six hamil stats,
+// [9] = max E, [10] = -min E, accumulated in fp64.  Single block; the caller all-gathers the 11 doubles.
+template <class T>
+__global__ void stats_pack_kernel(const T* __restrict__ E, const T* __restrict__ stats, int B, double* __restrict__ out) {
+  __shared__ double sh[32][9];
+  __shared__ double shm[32][2];
+  double acc[9];
+  for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+  double mx = -1e300, mn = 1e300;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const double e = (double)E[b];
+    acc[0] += e; acc[1] += e * e; acc[2] += 1.0;
+    if (stats)
+      for (int k = 0; k < 6; ++k) acc[3 + k] += (double)stats[(size_t)k * B + b];
+    mx = e > mx ? e : mx;
+    mn = e < mn ? e : mn;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  for (int off = 16; off > 0; off >>= 1) {
+    for (int k = 0; k < 9; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+    const double omx = __shfl_xor_sync(0xffffffffu, mx, off), omn = __shfl_xor_sync(0xffffffffu, mn, off);
+    mx = omx > mx ? omx : mx;
+    mn = omn < mn ? omn : mn;
+  }
+  if (lane == 0) {
+    for (int k = 0; k < 9; ++k) sh[warp][k] = acc[k];
+    shm[warp][0] = mx; shm[warp][1] = mn;
+  }
+  __syncthreads();
+  if (threadIdx.x < 11) {
+    const int k = threadIdx.x;
+    double v = k < 9 ? 0.0 : (k == 9 ? -1e300 : 1e300);
+    for (int w = 0; w < nw; ++w) {
+      if (k < 9) v += sh[w][k];
+      else if (k == 9) v = shm[w][0] > v ? shm[w][0] : v;
+      else v = shm[w][1] < v ? shm[w][1] : v;
+    }
+    out[k] = k == 10 ? -v : v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Non-local ECP: 12-point icosahedron quadrature, rotated onto r_i - R_I with a random twist
 // about the local z axis.  reference: src/deepqmc/ecp/ecp_utils.py:24-60,

@@ -655,6 +655,15 @@ class Engine:
         self._check(rc, 'dqmc_debug_gemm')
         return Cout
 
+    def stats_pack(self, E, stats=None):
+        """-> float64[11] on the device: sum E, sum E^2, B, sums of the six stats rows, max E, -min E (one launch)."""
+        out = torch.empty(11, dtype=torch.float64, device=self.device)
+        assert E.dtype == self.dtype and E.is_contiguous() and (stats is None or (stats.is_contiguous() and stats.shape == (6, E.shape[0])))
+        rc = self.lib.dqmc_stats_pack(self.h, E.data_ptr(), stats.data_ptr() if stats is not None else None, E.shape[0],
+                                      out.data_ptr(), self._stream())
+        self._check(rc, 'dqmc_stats_pack')
+        return out
+
     def debug_plan(self, n_walkers: int, mode: int, workspace_bytes: int = 0):
         """-> (planned, carved): dqmc_workspace_bytes and the highest offset the entry point of ``mode`` carves when given
         ``workspace_bytes`` (0: the planned size); host-only."""

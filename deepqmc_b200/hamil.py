@@ -15,6 +15,13 @@ import torch
 from .molecule import Molecule
 from .types import PhysicalConfiguration
 
+class StatsDict(dict):
+    """The six per-walker statistics of hamil.py:172-180 by name; ``raw`` = the engine's [6, B] array they are rows of."""
+
+    raw = None
+    engine = None
+
+
 STAT_KEYS = ('hamil/V_el', 'hamil/E_kin', 'hamil/V_loc', 'hamil/V_nl', 'hamil/lap', 'hamil/quantum_force')
 
 # Gaussian-type ECP tables (the reference reads them from pyscf: gaussian_type_ecp.py:57).
@@ -184,7 +191,8 @@ class MolecularHamiltonian:
             else:
                 raise TypeError(f'rng must be an int seed, a uint32[2] key or None, got {type(rng).__name__}')
             E, stats, sign, log, grad = eng.local_energy(r, R, seed=seed, ecp_twist=ecp_twist, want_grad=return_grad)
-            sd = {k: (stats[i, 0] if single else stats[i]) for i, k in enumerate(STAT_KEYS)}
+            sd = StatsDict({k: (stats[i, 0] if single else stats[i]) for i, k in enumerate(STAT_KEYS)})
+            sd.raw, sd.engine = (None if single else stats), eng  # lets parallel.energy_statistics reduce in one launch
             out = (E[0] if single else E, sd)
             return out + (grad,) if return_grad else out
 

@@ -3,8 +3,8 @@
 reference: src/deepqmc/parallel.py (pmap axis 'device_axis', pmean / all_gather helpers,
 scatter of walkers :296-317, per-device RNG :126-133); loss/energy.py:63-74 (mean energy =
 all-device mean); loss/loss_function.py:187-188 (all_gather of E_loc).  Here: contiguous blocks
-of B/world walkers per rank, parameters replicated, ONE fused all-reduce of the packed
-statistics vector per step and (optionally) one all-gather of E_loc, over torch.distributed
+of B/world walkers per rank, parameters replicated, ONE all-gather of an 11-double packed
+statistics vector per step (sums, count, max, -min; reduced locally) and (optionally) one all-gather of E_loc, over torch.distributed
 (NCCL on GPUs, gloo in the CPU tests).  The walker update itself has no collective
 (electron_samplers.py:121-126: acceptance and tau are per device).
 """
@@ -53,23 +53,34 @@ def rank_seed(seed: int, rank: int | None = None) -> int:
 
 
 def energy_statistics(E_loc: torch.Tensor, stats: dict | None = None):
-    """Global mean / variance / min / max of E_loc and means of the 6 hamil stats with ONE
-    all-reduce(sum) of a packed fp64 vector plus one all-reduce(max) of a 2-vector
+    """Global mean / variance / min / max of E_loc and means of the 6 hamil stats with ONE collective per step: every
+    rank packs {sum E, sum E^2, n, 6 stat sums, max, -min} into 11 doubles (one launch of the engine's stats kernel
+    when the statistics come from it), one all_gather moves them, the reduction over ranks is local.
     (reference: loss/energy.py:63-74, observable.py:474-479)."""
-    E = E_loc.double()
     keys = sorted(stats) if stats else []
-    packed = torch.stack([E.sum(), (E * E).sum(), torch.tensor(float(E.numel()), device=E.device, dtype=torch.float64)]
-                         + [stats[k].double().sum() for k in keys])
-    mm = torch.stack([E.max(), -E.min()])
+    raw, eng = getattr(stats, 'raw', None), getattr(stats, 'engine', None)
+    if E_loc.is_cuda and eng is not None and raw is not None and E_loc.dim() == 1 and E_loc.is_contiguous():
+        packed = eng.stats_pack(E_loc, raw)  # hamil.STAT_KEYS order
+        from .hamil import STAT_KEYS
+
+        order, i_max = [3 + STAT_KEYS.index(k) for k in keys], 9
+    else:  # CPU tensors (gloo tests) or statistics that did not come from the engine
+        E = E_loc.double()
+        packed = torch.stack([E.sum(), (E * E).sum(), torch.tensor(float(E.numel()), device=E.device, dtype=torch.float64)]
+                             + [stats[k].double().sum() for k in keys]
+                             + [E.max(), -E.min()])
+        order, i_max = [3 + i for i in range(len(keys))], 3 + len(keys)
     if world()[1] > 1:
-        dist.all_reduce(packed, op=dist.ReduceOp.SUM)
-        dist.all_reduce(mm, op=dist.ReduceOp.MAX)
+        flat = torch.empty(world()[1] * packed.numel(), dtype=packed.dtype, device=packed.device)
+        dist.all_gather_into_tensor(flat, packed)
+        allp = flat.view(world()[1], packed.numel())
+        packed = torch.cat([allp[:, :i_max].sum(0), allp[:, i_max:].max(0).values])
     n = packed[2]
     mean = packed[0] / n
-    out = {'energy/mean': mean, 'energy/var': packed[1] / n - mean * mean, 'energy/max': mm[0], 'energy/min': -mm[1],
+    out = {'energy/mean': mean, 'energy/var': packed[1] / n - mean * mean, 'energy/max': packed[i_max], 'energy/min': -packed[i_max + 1],
            'energy/count': n}
-    for i, k in enumerate(keys):
-        out[k] = packed[3 + i] / n
+    for i, k in zip(order, keys):
+        out[k] = packed[i] / n
     return out
 
 

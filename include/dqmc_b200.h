@@ -200,6 +200,13 @@ int dqmc_wf_vjp_params(dqmc_handle h, const void* r, const void* R, int32_t R_ba
 int dqmc_set_pseudo_hamiltonian(dqmc_handle h, int32_t n_tab, int32_t n_grid, double r_max, const double* tables,
                                 const int32_t* tab_of_nuc);
 
+/* This rank's contribution to the per-step statistics in ONE launch: out11[0] = sum E_loc, [1] = sum E_loc^2,
+ * [2] = n_walkers, [3..8] = sums of the six rows of `stats` (dqmc_local_energy's out_stats[6][B]; nullable),
+ * [9] = max E_loc, [10] = -min E_loc, fp64 on the device.  The caller exchanges the 11 doubles with one all-gather
+ * (deepqmc_b200/parallel.py) -- the only per-step collective of the data-parallel path.
+ * replaces: loss/energy.py:63-74 (pmean of the mean energy), observable.py:474-479, parallel.py:239-245. */
+int dqmc_stats_pack(dqmc_handle h, const void* E_loc, const void* stats, int32_t n_walkers, double* out11, void* stream);
+
 /* Self-test hook (host only, also on plan-only engines): *planned_bytes = dqmc_workspace_bytes(h, n_walkers, mode);
  * *carved_bytes = the highest workspace offset the entry point of `mode` carves when it is given workspace_bytes bytes
  * (<= 0: the planned size) -- found by walking that entry point's host code with every CUDA call skipped.
