@@ -18,8 +18,9 @@
 #include "kernels_trunk.cuh"
 #include "kernels_gnn.cuh"
 #include "kernels_bwd.cuh"
-#if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
+#if !defined(DQMC_NO_TCGEN05)
 #include "gemm_tcgen05.cuh"
+#include "fused_tc.cuh"
 #endif
 
 namespace dq {
@@ -59,6 +60,7 @@ struct EngineBase {
   virtual int64_t ws_bytes_min(int B, int mode) = 0;
   virtual int debug_plan(int B, int mode, int64_t wsb, int64_t* planned, int64_t* carved) = 0;
   virtual int stats_pack(const void* E, const void* stats, int B, double* out, cudaStream_t st) = 0;
+  virtual int debug_mlp_block(int layer, const void* O, const void* X, void* Out, int rows, cudaStream_t st) = 0;
   virtual int forward(const void* r, const void* R, int Rb, int B, void* sign, void* logp, void* ws, int64_t wsb,
                       cudaStream_t st) = 0;
   virtual int local_energy(const void* r, const void* R, int Rb, int B, uint64_t seed, const void* twist, void* E,
@@ -206,14 +208,25 @@ __global__ void split_transpose_kernel(const float* __restrict__ W, int K, int N
   if (idx >= K * N) return;
   int n = idx / K, k = idx % K;
   float w = W[(size_t)k * N + n];
-#ifndef DQMC_EMU
   float h = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
-#else
-  float h = w;
-#endif
   hi[idx] = h;
   lo[idx] = w - h;
 }
+
+#if !defined(DQMC_NO_TCGEN05)
+// W[K][N] (row-major) -> (W 2^e)^T as IEEE halves, hi / lo planes [N][K]: hi = rn(w'), lo = rn(w' - hi)
+__global__ void split_transpose_f16_kernel(const float* __restrict__ W, int K, int N, float scale, uint16_t* __restrict__ hi,
+                                           uint16_t* __restrict__ lo) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * N) return;
+  int n = idx / K, k = idx % K;
+  const float w = W[(size_t)k * N + n] * scale;
+  const uint32_t h = tc::pack_half2_rn(w, 0.f) & 0xFFFFu;
+  const uint32_t l = tc::pack_half2_rn(w - tc::half_bits_to_float(h), 0.f) & 0xFFFFu;
+  hi[idx] = (uint16_t)h;
+  lo[idx] = (uint16_t)l;
+}
+#endif
 
 #define DQ_CHECK(call)                                                             \
   do {                                                                             \
@@ -305,12 +318,20 @@ struct Engine : EngineBase {
   int Mn = 0, env_rep = 1;
   size_t max_smem = 0;
   int n_sms = 148;
-#if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
-  struct TcWeight { float* hi = nullptr; float* lo = nullptr; CUtensorMap mh, ml, mh2, ml2; int N = 0, K = 0, BN = 0; };
+#if !defined(DQMC_NO_TCGEN05)
+  struct TcWeight {
+    float* hi = nullptr; float* lo = nullptr; CUtensorMap mh, ml, mh2, ml2; int N = 0, K = 0, BN = 0;
+    // "3xFP16" operands of the plain-forward kernels: (W 2^e)^T as halves, hi / lo planes [N][K]; maps with BN-row boxes
+    // (row GEMM) and with all-N-row boxes (fused MLP block, N <= 256)
+    uint16_t* h16 = nullptr; CUtensorMap m16h, m16l, m16h_all, m16l_all; float wscale = 1.f; bool f16 = false, f16_all = false;
+  };
   bool gemm_2cta = false;  // CTA-pair (cta_group::2) variant of the dense-layer GEMM
+  bool f16_on = true;      // plain forwards (S = 1) on kind::f16 with hi / lo half operands; DQMC_TC_F16=0: stay on 3xTF32
+  bool fuse_mlp = true;    // W_o + residual -> W1 + tanh -> W2 + tanh + residual in one launch (S = 1); DQMC_TC_FUSE_MLP=0 disables
+  static constexpr float kActScale = 16.f;  // 2^4: |activation| < 4094 representable, absolute floor 2^-29
   std::map<std::string, TcWeight> tcw;
   bool use_tc() const { return std::is_same<T, float>::value && cfg.gemm_backend == DQMC_GEMM_TCGEN05; }
-  int prepare_tc_weight(const std::string& name, const float* W, int Kc, int Nc, cudaStream_t st) {
+  int prepare_tc_weight(const std::string& name, const float* W, int Kc, int Nc, cudaStream_t st, double wmax) {
     TcWeight& w = tcw[name];
     if (!w.hi) {
       DQ_CHECK(cudaMalloc((void**)&w.hi, sizeof(float) * (size_t)Kc * Nc));
@@ -321,8 +342,33 @@ struct Engine : EngineBase {
         err = "cuTensorMapEncodeTiled failed for " + name;
         return 4;
       }
+      if (Kc % 64 == 0) {
+        DQ_CHECK(cudaMalloc((void**)&w.h16, sizeof(uint16_t) * 2 * (size_t)Kc * Nc));
+        const uint16_t* lo16 = w.h16 + (size_t)Kc * Nc;
+        if (tc::make_kmajor_map(&w.m16h, w.h16, 2, Nc, Kc, 64, w.BN) || tc::make_kmajor_map(&w.m16l, lo16, 2, Nc, Kc, 64, w.BN)) {
+          err = "cuTensorMapEncodeTiled (half planes) failed for " + name;
+          return 4;
+        }
+        w.f16 = true;
+        if (Nc <= 256 && Nc % 16 == 0) {
+          if (tc::make_kmajor_map(&w.m16h_all, w.h16, 2, Nc, Kc, 64, Nc) || tc::make_kmajor_map(&w.m16l_all, lo16, 2, Nc, Kc, 64, Nc)) {
+            err = "cuTensorMapEncodeTiled (whole-N half planes) failed for " + name;
+            return 4;
+          }
+          w.f16_all = true;
+        }
+      }
     }
     DQ_LAUNCH(split_transpose_kernel, dim3((Kc * Nc + 255) / 256), dim3(256), 0, st, W, Kc, Nc, w.hi, w.lo);
+    if (w.f16) {
+      // power-of-two weight scale: the largest |w| of the matrix (of the spin pair for the per-spin heads) lands in [512, 1024)
+      int e = 0;
+      if (wmax > 0) { std::frexp(wmax, &e); e = 10 - e; }
+      e = e > 24 ? 24 : (e < -24 ? -24 : e);
+      w.wscale = std::ldexp(1.f, e);
+      DQ_LAUNCH(split_transpose_f16_kernel, dim3((Kc * Nc + 255) / 256), dim3(256), 0, st, W, Kc, Nc, w.wscale, w.h16,
+                w.h16 + (size_t)Kc * Nc);
+    }
     return 0;
   }
 #else
@@ -455,12 +501,18 @@ struct Engine : EngineBase {
     if (embed_fwd_ok)
       DQ_CHECK(raise_dyn_smem(embed_fwd_kernel<T>, (int)embed_fwd_smem_bytes<T>(M, d)));
     if (cfg.gemm_backend == DQMC_GEMM_TCGEN05) {
-#if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
+#if !defined(DQMC_NO_TCGEN05)
       if (!std::is_same<T, float>::value) { err = "DQMC_GEMM_TCGEN05 needs dtype DQMC_F32"; return 2; }
       if (d % 32 != 0) { err = "DQMC_GEMM_TCGEN05 needs embedding_dim % 32 == 0"; return 2; }
-      DQ_CHECK(raise_dyn_smem(tc::gemm3xtf32_kernel<false>, tc::SmemLayout::total(256)));
-      DQ_CHECK(raise_dyn_smem(tc::gemm3xtf32_kernel<true>, tc::SmemLayoutT<true>::total(256)));
+      DQ_CHECK(raise_dyn_smem((tc::gemm3xtf32_kernel<false, false>), tc::SmemLayout::total(256)));
+      DQ_CHECK(raise_dyn_smem((tc::gemm3xtf32_kernel<false, true>), tc::SmemLayout::total(256)));
+      DQ_CHECK(raise_dyn_smem(tc::mlp_block_f16_kernel, tc::MlpSmem::total()));
+#ifndef DQMC_EMU
+      DQ_CHECK(raise_dyn_smem((tc::gemm3xtf32_kernel<true, false>), tc::SmemLayoutT<true>::total(256)));
       gemm_2cta = std::getenv("DQMC_GEMM_2CTA") != nullptr;
+#endif
+      if (const char* ev = std::getenv("DQMC_TC_F16")) f16_on = std::atoi(ev) != 0;
+      if (const char* ev = std::getenv("DQMC_TC_FUSE_MLP")) fuse_mlp = std::atoi(ev) != 0;
 #else
       err = "this build has no tcgen05 backend"; return 2;
 #endif
@@ -475,6 +527,13 @@ struct Engine : EngineBase {
     if (d_nl_nuc) cudaFree(d_nl_nuc);
     if (d_ph_tabs) cudaFree(d_ph_tabs);
     if (d_ph_nuc) cudaFree(d_ph_nuc);
+#if !defined(DQMC_NO_TCGEN05)
+    for (auto& kv : tcw) {
+      if (kv.second.hi) cudaFree(kv.second.hi);
+      if (kv.second.lo) cudaFree(kv.second.lo);
+      if (kv.second.h16) cudaFree(kv.second.h16);
+    }
+#endif
   }
   const T* P(const std::string& n) const { return d_params + off(n); }
 
@@ -508,12 +567,24 @@ struct Engine : EngineBase {
       if (e.rows >= 1 && e.cols >= 1)
         DQ_LAUNCH(transpose_kernel<T>, dim3((e.rows * e.cols + 255) / 256), dim3(256), 0, st, (const T*)(d_params + e.offset),
                   e.rows, e.cols, d_params_t + e.offset);
-#if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
+#if !defined(DQMC_NO_TCGEN05)
     if (use_tc()) {
+      // largest |w| per matrix (the two spin heads of a per-spin layer share one scale: they are used in one launch)
+      std::map<std::string, double> wmax;
+      auto group = [](const std::string& n) {
+        const size_t k = n.size();
+        return (k > 3 && (n.compare(k - 3, 3, ".up") == 0 || n.compare(k - 3, 3, ".dn") == 0)) ? n.substr(0, k - 3) : n;
+      };
+      for (auto& e : entries) {
+        double m = 0;
+        for (int64_t i = 0; i < (int64_t)e.rows * e.cols; ++i) m = std::max(m, std::fabs(host[e.offset + i]));
+        double& g = wmax[group(e.name)];
+        g = std::max(g, m);
+      }
       for (auto& e : entries) {
         bool is_w = e.name.find(".w") != std::string::npos || e.name.rfind("bf.", 0) == 0;
         if (!is_w || e.name == "emb.w" || e.rows % 32 != 0 || e.cols < 64) continue;
-        int rc = prepare_tc_weight(e.name, (const float*)(d_params + e.offset), e.rows, e.cols, st);
+        int rc = prepare_tc_weight(e.name, (const float*)(d_params + e.offset), e.rows, e.cols, st, wmax[group(e.name)]);
         if (rc) return rc;
       }
     }
@@ -727,7 +798,7 @@ struct Engine : EngineBase {
     if (dry) return 0;  // planning pass
     const T* W0 = P(w0);
     const T* W1 = w1 ? P(w1) : nullptr;
-#if !defined(DQMC_EMU) && !defined(DQMC_NO_TCGEN05)
+#if !defined(DQMC_NO_TCGEN05)
     if constexpr (std::is_same<T, float>::value) {
       if (use_tc() && !bias1 && Kc % 32 == 0 && lda % 4 == 0 && ldc % 4 == 0 && tcw.count(w0) && (!w1 || tcw.count(w1))) {
         const TcWeight& t0 = tcw.at(w0);
@@ -737,9 +808,14 @@ struct Engine : EngineBase {
         p.K = Kc; p.S = S; p.sliced = sliced; p.Nel = Nel; p.z_split = zsplit; p.BN = t0.BN; p.err_flag = nullptr;
         p.act = act;
         p.rpt = (act && S > 1) ? (128 / S) * S : tc::kBM;
+        p.a_scale = 1.f; p.unscale = 1.f;
+        // plain forwards: half operands (hi / lo), kind::f16 -- twice the MMA rate, half the shared-memory bytes per k
+        const bool f16 = S == 1 && f16_on && Kc % 64 == 0 && t0.f16 && t1.f16 && t0.wscale == t1.wscale && !gemm_2cta;
+        if (f16) { p.a_scale = kActScale; p.unscale = 1.f / (kActScale * t0.wscale); }
         int MT = (Mr + p.rpt - 1) / p.rpt, NT = (Nc + p.BN - 1) / p.BN;
         int n_tiles = (sliced ? Nel : 1) * MT * NT;
         int grid = n_tiles < n_sms ? n_tiles : n_sms;
+#ifndef DQMC_EMU
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (prof) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
         if (gemm_2cta && n_sms >= 2) {
@@ -755,17 +831,24 @@ struct Engine : EngineBase {
           at[0].id = cudaLaunchAttributeClusterDimension;
           at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
           lc.attrs = at; lc.numAttrs = 1;
-          DQ_CHECK(cudaLaunchKernelEx(&lc, tc::gemm3xtf32_kernel<true>, t0.mh2, t0.ml2, t1.mh2, t1.ml2, p));
-        } else {
-          tc::gemm3xtf32_kernel<false><<<grid, tc::kThreads, tc::SmemLayout::total(p.BN), st>>>(t0.mh, t0.ml, t1.mh, t1.ml, p);
-        }
-        ++launches;
+          DQ_CHECK(cudaLaunchKernelEx(&lc, tc::gemm3xtf32_kernel<true, false>, t0.mh2, t0.ml2, t1.mh2, t1.ml2, p));
+          ++launches;
+        } else
+#endif
+        if (f16)
+          DQ_LAUNCH((tc::gemm3xtf32_kernel<false, true>), dim3(grid), dim3(tc::kThreads), tc::SmemLayout::total(p.BN), st, t0.m16h,
+                    t0.m16l, t1.m16h, t1.m16l, p);
+        else
+          DQ_LAUNCH((tc::gemm3xtf32_kernel<false, false>), dim3(grid), dim3(tc::kThreads), tc::SmemLayout::total(p.BN), st, t0.mh,
+                    t0.ml, t1.mh, t1.ml, p);
+#ifndef DQMC_EMU
         if (prof) {
           cudaEventRecord(e1, st);
           prof_ev.push_back(e0); prof_ev.push_back(e1);
           prof_flops += 2.0 * (double)Mr * (sliced ? Nel : 1) * (double)Nc * (double)Kc;
           ++prof_n;
         }
+#endif
         return 0;
       }
     }
@@ -790,6 +873,63 @@ struct Engine : EngineBase {
       ++prof_n;
     }
 #endif
+    return 0;
+  }
+
+  // Fused MLP block of a plain forward: Out = A + tanh(tanh(A W1 + b1) W2 + b2), A = X + O Wo  (one launch; fused_tc.cuh)
+  bool can_fuse_mlp(int S, const std::string& pfx) const {
+#if !defined(DQMC_NO_TCGEN05)
+    if (S != 1 || !use_tc() || !f16_on || !fuse_mlp || (d != 128 && d != 256)) return false;
+    for (const char* n : {"wo", "w1", "w2"}) {
+      auto it = tcw.find(pfx + n);
+      if (it == tcw.end() || !it->second.f16_all) return false;
+    }
+    return true;
+#else
+    return false;
+#endif
+  }
+  int mlp_block(const std::string& pfx, const T* O, const T* X, T* Out, int rows, cudaStream_t st) {
+    if (dry) return 0;
+#if !defined(DQMC_NO_TCGEN05)
+    if constexpr (std::is_same<T, float>::value) {
+      const TcWeight& wo = tcw.at(pfx + "wo");
+      const TcWeight& w1 = tcw.at(pfx + "w1");
+      const TcWeight& w2 = tcw.at(pfx + "w2");
+      tc::MlpParams p;
+      p.O = O; p.ldo = d; p.X = X; p.ldx = d; p.Out = Out; p.ldout = d; p.b1 = P(pfx + "b1"); p.b2 = P(pfx + "b2");
+      p.M = rows; p.d = d; p.a_scale = kActScale;
+      p.us0 = 1.f / (kActScale * wo.wscale); p.us1 = 1.f / (kActScale * w1.wscale); p.us2 = 1.f / (kActScale * w2.wscale);
+      p.err_flag = nullptr;
+      const int MT = (rows + 127) / 128;
+      const int grid = MT < n_sms ? MT : n_sms;
+#ifndef DQMC_EMU
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (prof) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+#endif
+      DQ_LAUNCH(tc::mlp_block_f16_kernel, dim3(grid), dim3(tc::kMlpThreads), tc::MlpSmem::total(), st, wo.m16h_all, wo.m16l_all,
+                w1.m16h_all, w1.m16l_all, w2.m16h_all, w2.m16l_all, p);
+#ifndef DQMC_EMU
+      if (prof) {
+        cudaEventRecord(e1, st);
+        prof_ev.push_back(e0); prof_ev.push_back(e1);
+        prof_flops += 3 * 2.0 * (double)rows * (double)d * (double)d;
+        ++prof_n;
+      }
+#endif
+      return 0;
+    }
+#endif
+    err = "internal: fused MLP block without the tensor-core backend";
+    return 5;
+  }
+
+  int debug_mlp_block(int layer, const void* O, const void* X, void* Out, int rows, cudaStream_t st) override {
+    const std::string pfx = "L" + std::to_string(layer) + ".";
+    if (!can_fuse_mlp(1, pfx)) { err = "fused MLP block not available for this configuration"; return 2; }
+    int rc = mlp_block(pfx, (const T*)O, (const T*)X, (T*)Out, rows, st);
+    if (rc) return rc;
+    DQ_CHECK(cudaGetLastError());
     return 0;
   }
 
@@ -1104,6 +1244,13 @@ struct Engine : EngineBase {
           DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh, tb, Mn), st, (const T*)w.QKV,
                     3 * d, O, d, N, S, dh, d, scale, tb, kn, vn, Mn);
         }
+      }
+      if (can_fuse_mlp(S, p)) {
+        // plain forward: attention projection + residual and both MLP layers in ONE launch, result in place of O
+        int rc = mlp_block(p, O, X, O, rows, st);
+        if (rc) return rc;
+        T* tmp = X; X = O; O = tmp;
+        continue;
       }
       gemm(O, d, (p + "wo").c_str(), nullptr, 0, d, nullptr, X, d, w.A, d, rows, d, d, S, 0, N, st);
       if (can_fuse_act(S)) {
@@ -2157,6 +2304,12 @@ int dqmc_debug_gemm(dqmc_handle h, const char* weight, const char* bias, const v
   if (!h) return 2;
   DQ_NEED_DEVICE(h);
   return h->e->debug_gemm(weight, bias, A, Res, C, rows, S, sliced, backend, (cudaStream_t)stream);
+}
+
+int dqmc_debug_mlp_block(dqmc_handle h, int32_t layer, const void* O, const void* X, void* Out, int32_t rows, void* stream) {
+  if (!h) return 2;
+  DQ_NEED_DEVICE(h);
+  return h->e->debug_mlp_block(layer, O, X, Out, rows, (cudaStream_t)stream);
 }
 
 int dqmc_profile_begin(dqmc_handle h) {

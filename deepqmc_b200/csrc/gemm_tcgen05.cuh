@@ -6,6 +6,15 @@
 //   i.e. the accuracy class the reference demands (jax_default_matmul_precision='highest',
 //   NVIDIA_TF32_OVERRIDE=0: src/deepqmc/__init__.py:9-34) at 1/3 of the TF32 tensor peak.
 //
+// F16 = true (plain forwards, S = 1): the same kernel with IEEE-half operands -- "3xFP16":
+//   a 2^ea = a_hi + a_lo, w 2^ew = w_hi + w_lo with *_hi = rn_half(.), *_lo = rn_half(. - *_hi): 22 significant bits,
+//   products exact in the fp32 accumulator, power-of-two scales undone in the epilogue (exact).  kind::f16 runs at twice
+//   the kind::tf32 rate and a 128-byte swizzle row holds 64 k-values instead of 32, so a shared-memory stage covers twice
+//   the K extent.  Halves below 2^-14 are subnormal (absolute spacing 2^-24): the scales keep O(1) activations and the
+//   weights of a layer far above that, the absolute floor is ~2^-25 / 2^ea per activation.  Only plain forwards use it
+//   (values bounded by construction: residual stream, tanh outputs, attention averages); the forward-Laplacian rows
+//   (derivative slots of unbounded dynamic range) stay on 3xTF32.
+//
 // Persistent warp-specialised kernel, one CTA per SM, tile = 128 rows x BN columns x K:
 //   warps 0-3  epilogue      : TMEM -> registers (tcgen05.ld) -> +bias/+residual -> global
 //   warps 4-7  A producers   : global fp32 rows -> split hi/lo -> 128B-swizzled K-major smem
@@ -15,10 +24,9 @@
 // epilogue of tile i overlaps the main loop of tile i+1.  W^T (N x K, K contiguous) is split into
 // hi/lo once per parameter upload (engine.cu).
 #pragma once
-#include <cuda.h>
-#include <cuda_runtime.h>
-
 #include <cstdint>
+
+#include "tc_ptx.cuh"
 
 namespace dq {
 namespace tc {
@@ -42,133 +50,9 @@ struct Params {
   int act;           // 0: none, 1: tanh with forward-Laplacian propagation fused into the epilogue
   int rpt;           // rows per tile (<= 128): G*S for act = 1 so that slot groups never straddle tiles
   int* err_flag;     // device int: set to non-zero if a barrier wait times out
+  float a_scale;     // F16: activations are multiplied by this power of two before the split ...
+  float unscale;     // ... and the accumulator by 2^-(ea + ew) in the epilogue
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// Bounded wait: a protocol bug must not hang the GPU box -> flag + trap after ~2 s.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
-  uint32_t done = 0;
-  const long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (clock64() - t0 > 4000000000LL) {
-      if (err_flag) atomicExch(err_flag, 1);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int x, int y) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
-      : "memory");
-}
-// ---- CTA-pair (cta_group::2) helpers: instruction forms as in CUTLASS' cute/arch/copy_sm100_tma.hpp
-// (SM100_TMA_2SM_LOAD_2D), cutlass/arch/barrier.h (ClusterBarrier::arrive, umma_arrive_multicast_2x1SM) ----
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `p` (a shared-memory object of THIS CTA) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// TMA load of one CTA's half of a CTA-pair operand; completes on the mbarrier at cluster address `bar_cluster`
-__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t bar_cluster, void* dst, int x, int y) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(x), "r"(y)
-      : "memory");
-}
-__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// commit the MMAs issued so far; the arrival lands on the barrier at the same offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
-  asm volatile(
-      "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
-      ::"r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) = 1024B/16
-// | version=1 [46,48) | layout_type=SWIZZLE_128B(2) [61,64)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): c_format=F32 (1) [4,6),
-// a_format=b_format=TF32 (2) [7,10),[10,13), a/b K-major (0), n>>3 [17,23), m>>4 [24,29)
-__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // tanh for the plain-forward epilogue: odd polynomial below |x| = 0.15, 1 - 2 / (1 + e^{2x})
 // (ex2.approx + fast division) above; absolute error <= ~3e-7.  The forward-Laplacian epilogue
@@ -176,9 +60,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ float tanh_fwd(float x) {
   const float x2 = x * x;
   const float poly = x + x * x2 * (-0.33333333333f + x2 * (0.13333333333f + x2 * (-0.05396825397f)));
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
-  const float big = 1.f - __fdividef(2.f, 1.f + e);
+  const float e = ex2_approx(x * 2.8853900817779268f);
+  const float big = 1.f - fast_div(2.f, 1.f + e);
   return fabsf(x) < 0.15f ? poly : big;
 }
 
@@ -208,14 +91,14 @@ struct SmemLayoutT {
 };
 using SmemLayout = SmemLayoutT<false>;
 
-template <bool TWO>
+template <bool TWO, bool F16 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_constant__ CUtensorMap map_lo0,
                   const __grid_constant__ CUtensorMap map_hi1, const __grid_constant__ CUtensorMap map_lo1, Params p) {
   // 1024-byte aligned dynamic shared memory (SWIZZLE_128B atoms).  No integer round-up of the
   // pointer: that would drop the shared address space and turn every access into a generic LD/ST.
-  extern __shared__ __align__(1024) unsigned char smem[];
-  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  DQMC_TC_SMEM(smem);
+  if ((smem_u32(smem) & 1023u) != 0u) tc_trap();
   using SmemLayout = SmemLayoutT<TWO>;
   constexpr int kStages = SmemLayout::kSt;
   const int BN = p.BN;
@@ -231,7 +114,10 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
   const int RPT = p.rpt;
   const int MT = (p.M + RPT - 1) / RPT, NT = (p.N + BN - 1) / BN;
   const int Z = p.sliced ? p.Nel : 1;
+  static_assert(!(TWO && F16), "the half-precision variant is single-CTA");
+  // k-blocks of 32 floats as the producers see them; F16: two of them (64 halves = one 128-byte swizzle row) per stage
   const int KB = p.K / kBK;
+  constexpr int kSub = F16 ? 2 : 1;
   // work distribution: single CTA: tile = (z, mt, nt); pair: the two CTAs of a cluster take the M tiles 2 mt2 + rank
   // of a pair tile (z, mt2, nt) -- an M tile index >= MT simply has no valid rows
   const uint32_t crank = TWO ? cluster_ctarank() : 0u;
@@ -244,7 +130,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_a[s], kPer);
+      mbar_init(&full_a[s], kPer * kSub);
       mbar_init(&full_w[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -255,13 +141,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
     fence_barrier_init();
   }
   if (warp == 9) {  // TMEM allocation (whole warp), address lands in shared memory
-    if constexpr (TWO) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(kTmemCols));
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(kTmemCols));
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
+    if constexpr (TWO) tmem_alloc_2sm(tmem_base_slot, kTmemCols);
+    else tmem_alloc(tmem_base_slot, kTmemCols);
   }
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&map_hi0); tma_prefetch_desc(&map_lo0);
@@ -279,14 +160,19 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
     // 32 pw + 4 j + (lane >> 3), 16-byte chunk (lane & 7): every LDG covers 4 full 128-byte lines.
     const int pw = warp - 4;
     const int chunk = lane & 7, rsub = lane >> 3;
-    uint32_t it = 0;  // running k-block counter (ring position)
+    // F16: rows of one instruction differ in bit 2 within each half-warp, which keeps the 8-byte stores below conflict-free
+    // (the 128B swizzle XORs the 16-byte chunk index with row & 7; a half row of 64 bytes is written per row and instruction)
+    auto trow_of = [&](int j) {
+      return F16 ? pw * 32 + (j >> 1) * 8 + 4 * (rsub & 1) + (rsub >> 1) + 2 * (j & 1) : pw * 32 + 4 * j + rsub;
+    };
+    uint32_t it = 0;  // running counter of 32-float k-blocks (ring position = it / kSub)
     const uint32_t full_a_leader = TWO ? mapa_u32(full_a, 0) : 0u;  // cluster address of the leader's full_a[0]
     for (int tile = tile0; tile < n_tiles; tile += tstep) {
       const int mt = TWO ? 2 * ((tile / NT) % MTX) + (int)crank : (tile / NT) % MT, z = tile / (NT * MTX);
       const float* rowp[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int lrow = pw * 32 + 4 * j + rsub;
+        const int lrow = trow_of(j);
         const int m = mt * RPT + lrow;
         rowp[j] = (lrow < RPT && m < p.M) ? p.A + phys_row(p, m, z) * p.lda + chunk * 4 : nullptr;
       }
@@ -301,22 +187,35 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
         }
       };
       auto process = [&](const float4(&buf)[8]) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&empty[s], ph ^ 1, p.err_flag);
+        const int s = (it / kSub) % kStages;
+        const uint32_t ph = ((it / kSub) / kStages) & 1;
+        const int half = F16 ? (int)(it & 1u) : 0;  // F16: which 64-byte half of the stage's 128-byte rows
+        if (half == 0) mbar_wait(&empty[s], ph ^ 1, p.err_flag);
         unsigned char* ah = smem + SmemLayout::a_hi(s, BN);
         unsigned char* al = smem + SmemLayout::a_lo(s, BN);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int trow = pw * 32 + 4 * j + rsub;
-          float4 v = buf[j], h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-          const int off = (trow >> 3) * 1024 + (trow & 7) * 128 + ((chunk ^ (trow & 7)) << 4);
-          *(float4*)(ah + off) = h;
-          *(float4*)(al + off) = l;
+          const int trow = trow_of(j);
+          if constexpr (F16) {
+            const float sc = p.a_scale;
+            const float x0 = buf[j].x * sc, x1 = buf[j].y * sc, x2 = buf[j].z * sc, x3 = buf[j].w * sc;
+            const uint32_t h01 = pack_half2_rn(x0, x1), h23 = pack_half2_rn(x2, x3);
+            const uint32_t l01 = pack_half2_rn(x0 - half_bits_to_float(h01 & 0xFFFFu), x1 - half_bits_to_float(h01 >> 16));
+            const uint32_t l23 = pack_half2_rn(x2 - half_bits_to_float(h23 & 0xFFFFu), x3 - half_bits_to_float(h23 >> 16));
+            const int c16 = half * 4 + (chunk >> 1);
+            const int off = (trow >> 3) * 1024 + (trow & 7) * 128 + ((c16 ^ (trow & 7)) << 4) + (chunk & 1) * 8;
+            *(uint2*)(ah + off) = make_uint2(h01, h23);
+            *(uint2*)(al + off) = make_uint2(l01, l23);
+          } else {
+            float4 v = buf[j], h, l;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+            const int off = (trow >> 3) * 1024 + (trow & 7) * 128 + ((chunk ^ (trow & 7)) << 4);
+            *(float4*)(ah + off) = h;
+            *(float4*)(al + off) = l;
+          }
         }
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
         if (TWO && !leader) mbar_arrive_cluster(full_a_leader + 8u * (uint32_t)s);
@@ -342,7 +241,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
         const bool second = p.sliced && z >= p.z_split;
         const CUtensorMap* mh = second ? &map_hi1 : &map_hi0;
         const CUtensorMap* ml = second ? &map_lo1 : &map_lo0;
-        for (int kb = 0; kb < KB; ++kb, ++it) {
+        for (int kb = 0; kb < KB / kSub; ++kb, ++it) {  // one stage = kSub k-blocks = 128 bytes of K per operand row
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&empty[s], ph ^ 1, p.err_flag);
@@ -354,15 +253,15 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
             tma_load_2d_2sm(ml, full_w_leader + 8u * (uint32_t)s, smem + SmemLayout::w_lo(s, BN), kb * kBK, y);
           } else {
             mbar_expect_tx(&full_w[s], 2u * BN * 128u);
-            tma_load_2d(mh, &full_w[s], smem + SmemLayout::w_hi(s, BN), kb * kBK, nt * BN);
-            tma_load_2d(ml, &full_w[s], smem + SmemLayout::w_lo(s, BN), kb * kBK, nt * BN);
+            tma_load_2d(mh, &full_w[s], smem + SmemLayout::w_hi(s, BN), kb * kBK * kSub, nt * BN);
+            tma_load_2d(ml, &full_w[s], smem + SmemLayout::w_lo(s, BN), kb * kBK * kSub, nt * BN);
           }
         }
       }
     }
   } else if (warp == 9) {
     // ===================== MMA issuer ========================================================
-    const uint32_t idesc = make_idesc(TWO ? 2 * kBM : kBM, BN);
+    const uint32_t idesc = F16 ? make_idesc_f16(kBM, BN) : make_idesc(TWO ? 2 * kBM : kBM, BN);
     uint32_t it = 0, tcount = 0;
     for (int tile = tile0; tile < n_tiles && leader; tile += tstep, ++tcount) {  // pair: only the leader issues
       const int acc = tcount & 1;
@@ -370,7 +269,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
       mbar_wait(&tmem_empty[acc], aph ^ 1, p.err_flag);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
-      for (int kb = 0; kb < KB; ++kb, ++it) {
+      const int KS = KB / kSub;
+      for (int kb = 0; kb < KS; ++kb, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
         mbar_wait(&full_a[s], ph, p.err_flag);
@@ -382,7 +282,11 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             const uint32_t ko = k * kUmmaK * 4;  // byte offset inside the 128B swizzle row
-            if constexpr (TWO) {
+            if constexpr (F16) {  // 32 bytes = 16 halves per instruction, same descriptor stepping
+              umma_f16(d_tmem, make_desc(ah + ko), make_desc(wl + ko), idesc, (kb | k) ? 1u : 0u);
+              umma_f16(d_tmem, make_desc(al + ko), make_desc(wh + ko), idesc, 1u);
+              umma_f16(d_tmem, make_desc(ah + ko), make_desc(wh + ko), idesc, 1u);
+            } else if constexpr (TWO) {
               umma_tf32_2sm(d_tmem, make_desc(ah + ko), make_desc(wl + ko), idesc, (kb | k) ? 1u : 0u);
               umma_tf32_2sm(d_tmem, make_desc(al + ko), make_desc(wh + ko), idesc, 1u);
               umma_tf32_2sm(d_tmem, make_desc(ah + ko), make_desc(wh + ko), idesc, 1u);
@@ -394,10 +298,10 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
           }
           if constexpr (TWO) {
             umma_commit_2sm(&empty[s]);                         // frees the stage in BOTH CTAs when the MMAs retire
-            if (kb == KB - 1) umma_commit_2sm(&tmem_full[acc]);  // accumulator complete (both epilogues)
+            if (kb == KS - 1) umma_commit_2sm(&tmem_full[acc]);  // accumulator complete (both epilogues)
           } else {
             umma_commit(&empty[s]);                         // frees the smem stage when the MMAs retire
-            if (kb == KB - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
+            if (kb == KS - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
           }
         }
         __syncwarp();
@@ -448,12 +352,12 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
       const int rows_here = (p.M - mt * RPT) < RPT ? (p.M - mt * RPT) : RPT;
       const int ngrp = S > 1 ? rows_here / S : rows_here;  // whole slot groups in this tile (S == 1: rows)
       if (p.act) {  // bias of this tile's columns -> shared (latency overlaps the wait for the accumulator)
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // every epilogue warp is done with the previous tile's bias
+        named_bar_sync(1, 128);  // every epilogue warp is done with the previous tile's bias
         for (int i = etid; i < BN; i += 128) {
           const int cc = nt * BN + i;
           sbias[i] = (p.bias && cc < p.N) ? __ldg(p.bias + cc) : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        named_bar_sync(1, 128);
       }
       const int nchunk = BN / 32;
       const bool vec_ok = (p.N % 4) == 0;
@@ -494,6 +398,11 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
           else mbar_arrive(&tmem_empty[acc]);
         }
         if (!chunk_on) continue;
+        if constexpr (F16) {  // undo the power-of-two operand scales (exact)
+          const float us = p.unscale;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * us);
+        }
         const bool act_rows = p.act && S == 1;  // plain forward: every row is a value row -> tanh in registers
         if (act_rows) {
 #pragma unroll
@@ -507,7 +416,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
         if (p.act && !act_rows) {
           // ---- tanh + forward-Laplacian propagation (reference: hkext.py:104-113 MLP activation; rule
           // y_t = y' z_t, y_L = y' z_L + y'' sum_t z_t^2).  Tiles hold whole slot groups (rpt = G*S).
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          named_bar_sync(1, 128);
           // phase A (work spread evenly over the 128 epilogue threads, no divergence):
           // per (group, column): y = tanh(z0 + b) written over the value row, y', y'', sum_t z_t^2
           {
@@ -537,7 +446,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
               }
             }
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          named_bar_sync(1, 128);
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
             if (inf[jj] < 0) continue;
@@ -557,7 +466,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
             o.x += res[jj].x; o.y += res[jj].y; o.z += res[jj].z; o.w += res[jj].w;
             if (col < p.N) *(float4*)(Cp + (size_t)(inf[jj] >> 16) * p.ldc + col) = o;
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");  // stage / side buffers reused by the next chunk
+          named_bar_sync(1, 128);  // stage / side buffers reused by the next chunk
           continue;
         }
         __syncwarp();
@@ -593,40 +502,15 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
   if constexpr (TWO) cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer can still reach into it
   if (warp == 9) {
     tc_fence_after();
-    if constexpr (TWO)
-      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
-    else
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    if constexpr (TWO) tmem_dealloc_2sm(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
 // ---- host side -----------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-inline EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && ptr)
-      fn = (EncodeTiledFn)ptr;
-  }
-  return fn;
-}
-
 // W^T split tensors: [Nrows][K] fp32, K contiguous.  Box = 32 fp32 (128 B) x BN rows, 128B swizzle.
 inline int make_weight_map(CUtensorMap* map, const float* wt, int Nrows, int K, int BN) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return 1;
-  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)Nrows};
-  cuuint64_t gstr[1] = {(cuuint64_t)K * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)BN};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wt, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : 2;
+  return make_kmajor_map(map, wt, 4, Nrows, K, kBK, BN);
 }
 
 inline int pick_bn(int N) { return N > 128 ? 256 : (N > 64 ? 128 : 64); }

@@ -678,6 +678,14 @@ class Engine:
     def workspace_bytes_min(self, n_walkers: int, mode: int) -> int:
         return self.lib.dqmc_workspace_bytes_min(self.h, n_walkers, mode)
 
+    def debug_mlp_block(self, layer, O, X):
+        """One launch of the fused plain-forward MLP block of `layer` -> X' [rows, d] (self-test hook)."""
+        O, X = self._prep(O), self._prep(X)
+        out = torch.empty_like(O)
+        rc = self.lib.dqmc_debug_mlp_block(self.h, layer, O.data_ptr(), X.data_ptr(), out.data_ptr(), O.shape[0], self._stream())
+        self._check(rc, 'dqmc_debug_mlp_block')
+        return out
+
     def profile_begin(self):
         self.lib.dqmc_profile_begin(self.h)
 

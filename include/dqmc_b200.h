@@ -227,6 +227,12 @@ int64_t dqmc_launch_count(dqmc_handle h);
 int dqmc_debug_gemm(dqmc_handle h, const char* weight, const char* bias, const void* A, const void* Res, void* C,
                     int32_t rows, int32_t S, int32_t sliced, int32_t backend, void* stream);
 
+/* Self-test hook: ONE launch of the fused plain-forward MLP block of layer `layer` (Psiformer kinds, fp32 tensor-core
+ * backend, embedding_dim 128 | 256):  Out = A + tanh(tanh(A W1 + b1) W2 + b2),  A = X + O Wo,  O / X / Out [rows][d] device
+ * arrays (Out may alias O).  Status 2 if the configuration has no fused block.
+ * reference: gnn/update_features.py:241-286 (attention output projection + residual, MLP + residual), hkext.py:22-137. */
+int dqmc_debug_mlp_block(dqmc_handle h, int32_t layer, const void* O, const void* X, void* Out, int32_t rows, void* stream);
+
 /* Measurement aid (bench.py roofline): between begin/end every dense-layer GEMM launch is
  * bracketed by CUDA events on the caller's stream; end() returns their summed duration [ms],
  * the algorithmic flops they performed (2*M*N*K each) and their count.  No reference analogue

@@ -130,3 +130,61 @@ def test_cta_pair_variant_matches_single_cta(monkeypatch):
     E1, _ = hamil.local_energy(a1.apply)(None, params, pc)
     E2, _ = hamil2.local_energy(a2.apply)(None, params, pc)
     assert torch.allclose(E1, E2, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize('rows', [5, 128, 1000, 148 * 128 * 2 + 77])
+def test_fused_mlp_block_matches_fp64(rows):
+    """One launch of the fused plain-forward MLP block (fused_tc.cuh: A = X + O Wo, M1 = tanh(A W1 + b1), X' = A + tanh(M1 W2 + b2),
+    half hi / lo operands on kind::f16, intermediates in TMEM / shared memory) against fp64; several tiles per CTA for the
+    largest row count (barrier phases wrap), a ragged last tile, and in-place use (Out aliases O) as the engine calls it."""
+    hamil, a, params, eng = _engine(1)
+    g = torch.Generator(device='cpu').manual_seed(rows)
+    O = torch.randn(rows, 256, generator=g).to(DEV)
+    X = (3 * torch.randn(rows, 256, generator=g)).to(DEV)
+    flat = torch.as_tensor(eng._flat, device=DEV)
+
+    def W(name):
+        off, K, Nc = eng.entries[name]
+        return flat[off:off + K * Nc].reshape(K, Nc).float().double()
+
+    out = eng.debug_mlp_block(2, O, X)
+    torch.cuda.synchronize()
+    A = X.double() + O.double() @ W('L2.wo')
+    M1 = torch.tanh(A @ W('L2.w1') + W('L2.b1')[0])
+    ref = A + torch.tanh(M1 @ W('L2.w2') + W('L2.b2')[0])
+    err = (out.double() - ref).abs().max().item()
+    assert err < 1e-5, err  # fp32 class: |X'| ~ 10, tanh approximation 3e-7, products 2^-22 relative
+    # the unfused tensor-core layers (3xTF32 / half GEMMs + epilogues) agree as well
+    A32 = eng.debug_gemm('L2.wo', O, Res=X, S=1, backend=1)
+    assert (A32.double() - A).abs().max().item() < 1e-5
+
+
+def test_plain_forward_half_operands_vs_3xtf32(monkeypatch):
+    """The S = 1 path with half hi / lo operands + the fused MLP block against the same engine forced back to the 3xTF32
+    row GEMMs (DQMC_TC_F16=0, read at handle creation): log|psi| of 256 walkers agrees at fp32 round-off level, and both
+    agree with the fp64 CUDA-core engine; large activations (|x| up to ~1e3) stay in range of the scaled halves."""
+    hamil, a1, params, e1 = _engine(1)
+    monkeypatch.setenv('DQMC_TC_F16', '0')
+    _, a0, _, e0 = _engine(1)
+    monkeypatch.delenv('DQMC_TC_F16')
+    e0.set_params(params)
+    a64 = B200Ansatz(hamil, 'psiformer', dtype='float64')
+    e64 = a64.engine_for(hamil, params)
+    mol = hamil.mol
+    rng = np.random.default_rng(3)
+    B = 256
+    r = torch.as_tensor(mol.coords[rng.integers(0, 2, size=(B, 4))] + rng.normal(size=(B, 4, 3)), device=DEV)
+    R = torch.as_tensor(mol.coords, device=DEV)
+    s1, l1 = e1.wf_forward(r.float(), R.float())
+    s0, l0 = e0.wf_forward(r.float(), R.float())
+    s64, l64 = e64.wf_forward(r, R)
+    assert torch.equal(s1, s0) and torch.equal(s1.double(), s64)
+    d10, d1, d0 = (l1 - l0).abs().max().item(), (l1.double() - l64).abs().max().item(), (l0.double() - l64).abs().max().item()
+    assert d10 < 1e-3 and d1 < 1e-3 and d0 < 1e-3, (d10, d1, d0)
+    assert d1 < 3 * d0 + 2e-5, (d1, d0)  # the half-operand path is not less accurate than 3xTF32
+    A = (torch.randn(300, 256, device=DEV) * 1e3)
+    off, K, Nc = e1.entries['L0.wqkv']
+    Wq = torch.as_tensor(e1._flat, device=DEV)[off:off + K * Nc].reshape(K, Nc).float().double()
+    C = e1.debug_gemm('L0.wqkv', A, S=1, backend=1)
+    ref = A.double() @ Wq
+    assert ((C.double() - ref).abs() / (A.double().abs() @ Wq.abs())).max().item() < 2e-6

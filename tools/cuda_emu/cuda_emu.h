@@ -156,8 +156,8 @@ inline void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> bod
   s.gdim = grid;
   s.body = body;
   const size_t kGuard = 64;
-  s.dyn_smem.assign(smem + 16 + kGuard, 0);
-  unsigned char* smem_base = (unsigned char*)(((uintptr_t)s.dyn_smem.data() + 15) & ~(uintptr_t)15);
+  s.dyn_smem.assign(smem + 1024 + kGuard, 0);  // 1024-byte aligned base (SWIZZLE_128B atoms of the tensor-core kernels)
+  unsigned char* smem_base = (unsigned char*)(((uintptr_t)s.dyn_smem.data() + 1023) & ~(uintptr_t)1023);
   size_t guard_len = s.dyn_smem.data() + s.dyn_smem.size() - (smem_base + smem);
   if ((int)s.fibers.size() < s.nthreads) s.fibers.resize(s.nthreads);
   s.shfl_buf.assign(s.nthreads, 0);
@@ -203,6 +203,12 @@ inline void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> bod
 }  // namespace emu
 
 struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 
@@ -257,6 +263,6 @@ template <class F> inline cudaError_t cudaFuncSetAttribute(F f, int, int bytes) 
   return 0;
 }
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
-#define DQMC_DYN_SMEM(name) unsigned char* name = (unsigned char*)(((uintptr_t)emu::S().dyn_smem.data() + 15) & ~(uintptr_t)15)
+#define DQMC_DYN_SMEM(name) unsigned char* name = (unsigned char*)(((uintptr_t)emu::S().dyn_smem.data() + 1023) & ~(uintptr_t)1023)
 #define DQMC_LAUNCH(kern, grid, block, smem, stream, ...) \
   emu::launch(dim3(grid), dim3(block), smem, [=]() { kern(__VA_ARGS__); }, (const void*)(kern), #kern)

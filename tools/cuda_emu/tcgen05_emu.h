@@ -36,6 +36,7 @@ struct CUtensorMap {
   uint32_t swizzle;         // 0 none, 3 = 128B
 };
 #define __grid_constant__
+#define DQMC_TC_SMEM(name) unsigned char* name = dq::tc::emu_tc::smem_base()
 
 namespace dq {
 namespace tc {
@@ -240,8 +241,25 @@ __device__ __forceinline__ float half_bits_to_float(uint32_t h16) { return emu_t
 __device__ __forceinline__ void tc_trap() { std::fprintf(stderr, "tcgen05_emu: trap\n"); std::abort(); }
 __device__ __forceinline__ long long tc_clock() { return 0; }
 
-// 2-CTA (cta_group::2) forms are not modelled: the CTA-pair kernel variant is excluded from emulator builds
+// 2-CTA (cta_group::2) forms are not modelled: the CTA-pair kernel variant is never launched in emulator builds
+inline void no_pair() { std::fprintf(stderr, "tcgen05_emu: cta_group::2 is not modelled\n"); std::abort(); }
 __device__ __forceinline__ uint32_t cluster_ctarank() { return 0; }
+__device__ __forceinline__ void cluster_sync_all() { no_pair(); }
+__device__ __forceinline__ uint32_t mapa_u32(const void*, uint32_t) { no_pair(); return 0; }
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t) { no_pair(); }
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap*, uint32_t, void*, int, int) { no_pair(); }
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t, uint64_t, uint64_t, uint32_t, uint32_t) { no_pair(); }
+__device__ __forceinline__ void umma_commit_2sm(uint64_t*) { no_pair(); }
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t*, uint32_t) { no_pair(); }
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t, uint32_t) { no_pair(); }
+
+inline int make_kmajor_map(CUtensorMap* map, const void* base, int elem_bytes, int rows, int K, int box_k, int box_rows) {
+  if (box_k * elem_bytes != 128 || (elem_bytes != 4 && elem_bytes != 2)) return 3;
+  if (box_rows > 256 || box_rows < 1) return 2;  // boxDim <= 256 per dimension
+  map->base = base; map->dim0 = (uint64_t)K; map->dim1 = (uint64_t)rows; map->stride1_bytes = (uint64_t)K * elem_bytes;
+  map->box0 = (uint32_t)box_k; map->box1 = (uint32_t)box_rows; map->elem_bytes = (uint32_t)elem_bytes; map->swizzle = 3;
+  return 0;
+}
 
 }  // namespace tc
 }  // namespace dq
