@@ -18,6 +18,7 @@
 #include "kernels_trunk.cuh"
 #include "kernels_gnn.cuh"
 #include "kernels_bwd.cuh"
+#include "attn_mma.cuh"
 #if !defined(DQMC_NO_TCGEN05)
 #include "gemm_tcgen05.cuh"
 #include "fused_tc.cuh"
@@ -308,6 +309,7 @@ struct Engine : EngineBase {
   bool embed_fwd_ok = false;
   bool attn_fwd_ok = false;
   bool attn_fwd_pipelined = false;
+  bool attn_mma_ok = false;  // plain-forward attention on mma.sync (attn_mma.cuh)
   bool slater_fwd2_ok = false;
   int N, M, d, K, KN, H, dh, T3;
   int BFW = 0;      // row width of the backflow buffer: K N, or 2 K N with multiplicative + additive heads
@@ -497,6 +499,8 @@ struct Engine : EngineBase {
       DQ_CHECK(raise_dyn_smem((attn_fwd_f32_kernel<28, true>), smem));
       DQ_CHECK(raise_dyn_smem((attn_fwd_f32_kernel<30, true>), smem));
     }
+    attn_mma_ok = psif && std::is_same<T, float>::value && dh == 64 && N + Mn <= 48 && d % 4 == 0 && !std::getenv("DQMC_ATTN_GENERIC") &&
+                  !(std::getenv("DQMC_ATTN_MMA") && std::atoi(std::getenv("DQMC_ATTN_MMA")) == 0);
     embed_fwd_ok = psif && d % 4 == 0 && embed_fwd_smem_bytes<T>(M, d) <= 200 * 1024 && !std::getenv("DQMC_EMBED_GENERIC");
     if (embed_fwd_ok)
       DQ_CHECK(raise_dyn_smem(embed_fwd_kernel<T>, (int)embed_fwd_smem_bytes<T>(M, d)));
@@ -1197,7 +1201,25 @@ struct Engine : EngineBase {
         const T* kn = Mn > 0 ? P(p + "kn") : nullptr;
         const T* vn = Mn > 0 ? P(p + "vn") : nullptr;
         if constexpr (std::is_same<T, float>::value) {
-          if (S == 1 && attn_fwd_ok && attn_fwd_pipelined) {
+          if (S == 1 && attn_mma_ok) {
+            // tensor-core attention: a warp per (walker, head, 16-query tile), fragments straight from global memory
+            const int n_pairs = Bc * H, tasks = n_pairs * ((N + 15) / 16);
+            int nblk = (tasks + 3) / 4;
+            if (nblk > n_sms * 8) nblk = n_sms * 8;
+            const dim3 grid(nblk), block(128);
+#define DQ_ATTN_MMA(NK_)                                                                                                     \
+  DQ_LAUNCH(attn_fwd_mma_kernel<NK_>, grid, block, 0, st, (const float*)w.QKV, 3 * d, (float*)O, d, N, H, d, (float)scale, \
+            n_pairs, (const float*)kn, (const float*)vn, Mn)
+            switch ((N + Mn + 7) / 8) {
+              case 1: DQ_ATTN_MMA(1); break;
+              case 2: DQ_ATTN_MMA(2); break;
+              case 3: DQ_ATTN_MMA(3); break;
+              case 4: DQ_ATTN_MMA(4); break;
+              case 5: DQ_ATTN_MMA(5); break;
+              default: DQ_ATTN_MMA(6); break;
+            }
+#undef DQ_ATTN_MMA
+          } else if (S == 1 && attn_fwd_ok && attn_fwd_pipelined) {
             // persistent blocks (one per SM), 6 warps each, K / V of the next pair prefetched by cp.async
             const int n_pairs = Bc * H, wpb = 6;
             const int smem = wpb * 4 * N * 64 * (int)sizeof(float);

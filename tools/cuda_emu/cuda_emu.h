@@ -203,6 +203,8 @@ inline void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> bod
 }  // namespace emu
 
 struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) float2 { float x, y; };
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct alignas(8) uint2 { unsigned x, y; };
 inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 struct alignas(16) uint4 { unsigned x, y, z, w; };
@@ -236,6 +238,47 @@ template <class T> inline T __shfl_down_sync(unsigned, T v, int d) {
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+
+// ---- warp-level mma.sync.m16n8k16 (f16 inputs, f32 accumulate): functional model with the PTX fragment layouts ------------
+// A (16x16, row): a0 = (g, 2t..2t+1), a1 = (g+8, 2t..), a2 = (g, 2t+8..), a3 = (g+8, 2t+8..);  B (16x8, col): b0 = (k 2t..2t+1, n g),
+// b1 = (k 2t+8.., n g);  C/D (16x8): c0 = (g, 2t), c1 = (g, 2t+1), c2 = (g+8, 2t), c3 = (g+8, 2t+1);  g = lane / 4, t = lane % 4.
+namespace emu {
+inline float h2f(uint16_t h) {
+  const uint32_t s = (h >> 15) & 1u, e = (h >> 10) & 31u, m = h & 1023u;
+  float v;
+  if (e == 0) v = std::ldexp((float)m, -24);
+  else if (e == 31) v = m ? NAN : INFINITY;
+  else v = std::ldexp((float)(m | 1024u), (int)e - 25);
+  return s ? -v : v;
+}
+inline void mma_m16n8k16_f16(float* d, const uint32_t* a, const uint32_t* b, const float* c) {
+  static thread_local std::vector<uint32_t> abuf, bbuf;
+  State& s = S();
+  if ((int)abuf.size() < s.nthreads * 4) { abuf.assign(s.nthreads * 4, 0); bbuf.assign(s.nthreads * 2, 0); }
+  const int lin = s.fibers[s.cur].lin, w = lin / 32, lane = lin & 31;
+  for (int i = 0; i < 4; ++i) abuf[lin * 4 + i] = a[i];
+  for (int i = 0; i < 2; ++i) bbuf[lin * 2 + i] = b[i];
+  syncwarp();
+  auto A = [&](int r, int k) {  // element (row r, col k) of the 16x16 A tile
+    const int gl = r & 7, t = (k & 7) >> 1, reg = (r >> 3) + 2 * (k >> 3);
+    const uint32_t v = abuf[(w * 32 + gl * 4 + t) * 4 + reg];
+    return h2f((uint16_t)((k & 1) ? v >> 16 : v & 0xFFFFu));
+  };
+  auto B = [&](int k, int n) {  // element (k, n) of the 16x8 B tile
+    const int t = (k & 7) >> 1, reg = k >> 3;
+    const uint32_t v = bbuf[(w * 32 + n * 4 + t) * 2 + reg];
+    return h2f((uint16_t)((k & 1) ? v >> 16 : v & 0xFFFFu));
+  };
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = 0; i < 4; ++i) {
+    const int r = g + 8 * (i >> 1), n = 2 * t + (i & 1);
+    double acc = (double)c[i];
+    for (int k = 0; k < 16; ++k) acc += (double)A(r, k) * (double)B(k, n);
+    d[i] = (float)acc;
+  }
+  syncwarp();
+}
+}  // namespace emu
 
 // ---- tiny runtime shim ---------------------------------------------------------------
 typedef int cudaError_t;
