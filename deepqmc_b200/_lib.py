@@ -20,7 +20,7 @@ SYMBOLS = [
     'dqmc_wf_forward', 'dqmc_local_energy', 'dqmc_mcmc_sweep', 'dqmc_launch_count',
     'dqmc_profile_begin', 'dqmc_profile_end', 'dqmc_debug_gemm', 'dqmc_wf_vjp_params', 'dqmc_langevin_sweep',
     'dqmc_set_pseudo_hamiltonian', 'dqmc_wf_orbitals', 'dqmc_mcmc_sweep_exchange',
-    'dqmc_workspace_bytes_min', 'dqmc_debug_plan', 'dqmc_stats_pack', 'dqmc_debug_mlp_block',
+    'dqmc_workspace_bytes_min', 'dqmc_debug_plan', 'dqmc_stats_pack', 'dqmc_debug_mlp_block', 'dqmc_debug_trunk',
 ]
 
 
@@ -80,6 +80,7 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dqmc_debug_plan.argtypes = [vp, i32, i32, i64, C.POINTER(i64), C.POINTER(i64)]
     lib.dqmc_stats_pack.argtypes = [vp, vp, vp, i32, vp, vp]
     lib.dqmc_debug_mlp_block.argtypes = [vp, i32, vp, vp, vp, i32, vp]
+    lib.dqmc_debug_trunk.argtypes = [vp, vp, vp, i32, vp]
     lib.dqmc_wf_forward.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, i64, vp]
     lib.dqmc_wf_orbitals.argtypes = [vp, vp, vp, i32, i32, vp, vp, i64, vp]
     lib.dqmc_local_energy.argtypes = [vp, vp, vp, i32, i32, u64, vp, vp, vp, vp, vp, vp, vp, i64, vp]

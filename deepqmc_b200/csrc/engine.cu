@@ -22,6 +22,7 @@
 #if !defined(DQMC_NO_TCGEN05)
 #include "gemm_tcgen05.cuh"
 #include "fused_tc.cuh"
+#include "trunk_tc.cuh"
 #endif
 
 namespace dq {
@@ -62,6 +63,7 @@ struct EngineBase {
   virtual int debug_plan(int B, int mode, int64_t wsb, int64_t* planned, int64_t* carved) = 0;
   virtual int stats_pack(const void* E, const void* stats, int B, double* out, cudaStream_t st) = 0;
   virtual int debug_mlp_block(int layer, const void* O, const void* X, void* Out, int rows, cudaStream_t st) = 0;
+  virtual int debug_trunk(const void* X0, void* Out, int rows, cudaStream_t st) = 0;
   virtual int forward(const void* r, const void* R, int Rb, int B, void* sign, void* logp, void* ws, int64_t wsb,
                       cudaStream_t st) = 0;
   virtual int local_energy(const void* r, const void* R, int Rb, int B, uint64_t seed, const void* twist, void* E,
@@ -202,16 +204,22 @@ __global__ void convert_kernel(const double* __restrict__ src, T* __restrict__ d
   if (i < n) dst[i] = (T)src[i];
 }
 
-// W[K][N] (row-major) -> W^T hi/lo [N][K]: hi = top 19 bits (exact TF32), lo = w - hi
+// W[K][N] (row-major) -> W^T hi/lo [N][K]: hi = rna_tf32(w), lo = rna_tf32(w - hi)
 __global__ void split_transpose_kernel(const float* __restrict__ W, int K, int N, float* __restrict__ hi,
                                        float* __restrict__ lo) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= K * N) return;
   int n = idx / K, k = idx % K;
   float w = W[(size_t)k * N + n];
+#if !defined(DQMC_NO_TCGEN05)
+  float h = tc::tf32_rna(w);
+  hi[idx] = h;
+  lo[idx] = tc::tf32_rna(w - h);
+#else
   float h = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
   hi[idx] = h;
   lo[idx] = w - h;
+#endif
 }
 
 #if !defined(DQMC_NO_TCGEN05)
@@ -326,7 +334,11 @@ struct Engine : EngineBase {
     // "3xFP16" operands of the plain-forward kernels: (W 2^e)^T as halves, hi / lo planes [N][K]; maps with BN-row boxes
     // (row GEMM) and with all-N-row boxes (fused MLP block, N <= 256)
     uint16_t* h16 = nullptr; CUtensorMap m16h, m16l, m16h_all, m16l_all; float wscale = 1.f; bool f16 = false, f16_all = false;
+    CUtensorMap m16h_128, m16l_128; bool f16_128 = false;  // 128-row boxes: weight slots of the whole-trunk kernel (trunk_tc.cuh)
   };
+  bool fuse_trunk = true;  // all layers of a plain forward in one persistent launch (trunk_tc.cuh); DQMC_TC_TRUNK=0 disables
+  CUtensorMap* d_trunk_maps = nullptr;       // [L][4][2]
+  unsigned char* d_trunk_scratch = nullptr;  // n_sms x 384 KB Q / K / V planes
   bool gemm_2cta = false;  // CTA-pair (cta_group::2) variant of the dense-layer GEMM
   bool f16_on = true;      // plain forwards (S = 1) on kind::f16 with hi / lo half operands; DQMC_TC_F16=0: stay on 3xTF32
   bool fuse_mlp = true;    // W_o + residual -> W1 + tanh -> W2 + tanh + residual in one launch (S = 1); DQMC_TC_FUSE_MLP=0 disables
@@ -359,6 +371,9 @@ struct Engine : EngineBase {
           }
           w.f16_all = true;
         }
+        if (Kc == 256 && Nc % 128 == 0 &&
+            !tc::make_kmajor_map(&w.m16h_128, w.h16, 2, Nc, Kc, 64, 128) && !tc::make_kmajor_map(&w.m16l_128, lo16, 2, Nc, Kc, 64, 128))
+          w.f16_128 = true;
       }
     }
     DQ_LAUNCH(split_transpose_kernel, dim3((Kc * Nc + 255) / 256), dim3(256), 0, st, W, Kc, Nc, w.hi, w.lo);
@@ -511,12 +526,18 @@ struct Engine : EngineBase {
       DQ_CHECK(raise_dyn_smem((tc::gemm3xtf32_kernel<false, false>), tc::SmemLayout::total(256)));
       DQ_CHECK(raise_dyn_smem((tc::gemm3xtf32_kernel<false, true>), tc::SmemLayout::total(256)));
       DQ_CHECK(raise_dyn_smem(tc::mlp_block_f16_kernel, tc::MlpSmem::total()));
+      DQ_CHECK(raise_dyn_smem(tc::trunk_f16_kernel, tc::TrSmem::total()));
 #ifndef DQMC_EMU
       DQ_CHECK(raise_dyn_smem((tc::gemm3xtf32_kernel<true, false>), tc::SmemLayoutT<true>::total(256)));
       gemm_2cta = std::getenv("DQMC_GEMM_2CTA") != nullptr;
 #endif
       if (const char* ev = std::getenv("DQMC_TC_F16")) f16_on = std::atoi(ev) != 0;
       if (const char* ev = std::getenv("DQMC_TC_FUSE_MLP")) fuse_mlp = std::atoi(ev) != 0;
+      if (const char* ev = std::getenv("DQMC_TC_TRUNK")) fuse_trunk = std::atoi(ev) != 0;
+      if (psif && !trans && d == 256 && H == 4 && N <= 32 && cfg.n_layers <= tc::kTrMaxLayers) {
+        DQ_CHECK(cudaMalloc((void**)&d_trunk_maps, sizeof(CUtensorMap) * 8 * cfg.n_layers));
+        DQ_CHECK(cudaMalloc((void**)&d_trunk_scratch, (size_t)n_sms * tc::kTrScratchPerCta));
+      }
 #else
       err = "this build has no tcgen05 backend"; return 2;
 #endif
@@ -537,6 +558,8 @@ struct Engine : EngineBase {
       if (kv.second.lo) cudaFree(kv.second.lo);
       if (kv.second.h16) cudaFree(kv.second.h16);
     }
+    if (d_trunk_maps) cudaFree(d_trunk_maps);
+    if (d_trunk_scratch) cudaFree(d_trunk_scratch);
 #endif
   }
   const T* P(const std::string& n) const { return d_params + off(n); }
@@ -590,6 +613,20 @@ struct Engine : EngineBase {
         if (!is_w || e.name == "emb.w" || e.rows % 32 != 0 || e.cols < 64) continue;
         int rc = prepare_tc_weight(e.name, (const float*)(d_params + e.offset), e.rows, e.cols, st, wmax[group(e.name)]);
         if (rc) return rc;
+      }
+      if (d_trunk_maps && trunk_weights_ok()) {
+        std::vector<CUtensorMap> hm((size_t)8 * cfg.n_layers);
+        for (int l = 0; l < cfg.n_layers; ++l) {
+          const std::string pfx = "L" + std::to_string(l) + ".";
+          int g = 0;
+          for (const char* n : {"wqkv", "wo", "w1", "w2"}) {
+            const TcWeight& w = tcw.at(pfx + n);
+            hm[(size_t)8 * l + 2 * g] = w.m16h_128;
+            hm[(size_t)8 * l + 2 * g + 1] = w.m16l_128;
+            ++g;
+          }
+        }
+        DQ_CHECK(cudaMemcpy(d_trunk_maps, hm.data(), sizeof(CUtensorMap) * hm.size(), cudaMemcpyHostToDevice));
       }
     }
 #endif
@@ -937,6 +974,73 @@ struct Engine : EngineBase {
     return 0;
   }
 
+  // Whole trunk of a plain forward in one launch (trunk_tc.cuh): needs the shipped Psiformer shape (d = 256, 4 heads of 64)
+  bool trunk_weights_ok() const {
+#if !defined(DQMC_NO_TCGEN05)
+    for (int l = 0; l < cfg.n_layers; ++l)
+      for (const char* n : {"wqkv", "wo", "w1", "w2"}) {
+        auto it = tcw.find("L" + std::to_string(l) + "." + n);
+        if (it == tcw.end() || !it->second.f16_128) return false;
+      }
+    return true;
+#else
+    return false;
+#endif
+  }
+  bool can_trunk(int S) const {
+#if !defined(DQMC_NO_TCGEN05)
+    return S == 1 && use_tc() && f16_on && fuse_trunk && d_trunk_maps && d_trunk_scratch && cfg.n_layers >= 1 && trunk_weights_ok();
+#else
+    return false;
+#endif
+  }
+  int trunk_block(const T* X0, T* Out, int rows, cudaStream_t st) {
+    if (dry) return 0;
+#if !defined(DQMC_NO_TCGEN05)
+    if constexpr (std::is_same<T, float>::value) {
+      tc::TrunkParams p;
+      p.X0 = X0; p.ldx = d; p.Out = Out; p.ldout = d; p.maps = d_trunk_maps; p.scratch = d_trunk_scratch;
+      int np2 = 1;
+      while (np2 < N) np2 *= 2;  // walker slot of the tile: electrons rounded up to a power of two (<= 32)
+      p.walkers = rows / N; p.N = N; p.NP = np2; p.L = cfg.n_layers; p.a_scale = kActScale;
+      p.attn_scale = (float)(1.0 / std::sqrt((double)dh)); p.err_flag = nullptr;
+      for (int l = 0; l < cfg.n_layers; ++l) {
+        const std::string pfx = "L" + std::to_string(l) + ".";
+        p.b1[l] = P(pfx + "b1"); p.b2[l] = P(pfx + "b2");
+        int g = 0;
+        for (const char* n : {"wqkv", "wo", "w1", "w2"}) p.us[l][g++] = 1.f / (kActScale * tcw.at(pfx + n).wscale);
+      }
+      const int G = 128 / np2, MT = (p.walkers + G - 1) / G;
+      const int grid = MT < n_sms ? MT : n_sms;
+#ifndef DQMC_EMU
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (prof) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+#endif
+      DQ_LAUNCH(tc::trunk_f16_kernel, dim3(grid), dim3(tc::kTrThreads), tc::TrSmem::total(), st, p);
+#ifndef DQMC_EMU
+      if (prof) {
+        cudaEventRecord(e1, st);
+        prof_ev.push_back(e0); prof_ev.push_back(e1);
+        // dense layers 12 d^2 and attention 4 N d (scores + weighted sum) multiply-adds per row and layer
+        prof_flops += (double)cfg.n_layers * 2.0 * (double)rows * (6.0 * d * d + 2.0 * N * d);
+        ++prof_n;
+      }
+#endif
+      return 0;
+    }
+#endif
+    err = "internal: fused trunk without the tensor-core backend";
+    return 5;
+  }
+  int debug_trunk(const void* X0, void* Out, int rows, cudaStream_t st) override {
+    if (!can_trunk(1)) { err = "fused trunk not available for this configuration"; return 2; }
+    if (rows % N != 0) { err = "debug_trunk: rows must be a multiple of the electron count"; return 2; }
+    int rc = trunk_block((const T*)X0, (T*)Out, rows, st);
+    if (rc) return rc;
+    DQ_CHECK(cudaGetLastError());
+    return 0;
+  }
+
   int debug_gemm(const char* wname, const char* bname, const void* A, const void* Res, void* C, int Mr, int S,
                  int sliced, int backend, cudaStream_t st) override {
     int64_t o = off(wname);
@@ -1193,6 +1297,11 @@ struct Engine : EngineBase {
     T* X = w.X;
     T* O = w.O;
     const T scale = (T)(1.0 / std::sqrt((double)dh));
+    if (can_trunk(S)) {  // plain forward: every layer in one persistent tensor-core launch
+      int rc = trunk_block(X, O, rows, st);
+      if (rc) return rc;
+      return tail(r, R, Rb, Bc, S, Bstat, sign, logp, E, stats, grad, w, O, st, nullptr, qa);
+    }
     for (int l = 0; l < cfg.n_layers; ++l) {
       std::string p = "L" + std::to_string(l) + ".";
       gemm(X, d, (p + "wqkv").c_str(), nullptr, 0, 3 * d, nullptr, nullptr, 0, w.QKV, 3 * d, rows, 3 * d, d, S, 0, N, st);
@@ -2332,6 +2441,11 @@ int dqmc_debug_mlp_block(dqmc_handle h, int32_t layer, const void* O, const void
   if (!h) return 2;
   DQ_NEED_DEVICE(h);
   return h->e->debug_mlp_block(layer, O, X, Out, rows, (cudaStream_t)stream);
+}
+int dqmc_debug_trunk(dqmc_handle h, const void* X0, void* Out, int32_t rows, void* stream) {
+  if (!h) return 2;
+  DQ_NEED_DEVICE(h);
+  return h->e->debug_trunk(X0, Out, rows, (cudaStream_t)stream);
 }
 
 int dqmc_profile_begin(dqmc_handle h) {

@@ -1,7 +1,7 @@
 // fp32-accurate dense-layer GEMM on the 5th-gen tensor cores (sm_100a): 3xTF32 split
 //   C[row(m), :] = (Res) + A[row(m), :] @ W + (bias on value rows),  A, W, C fp32 in HBM.
 //
-//   a = a_hi + a_lo, w = w_hi + w_lo with *_hi = top 19 bits (exactly representable in TF32);
+//   a = a_hi + a_lo, w = w_hi + w_lo with *_hi = rna_tf32(.), *_lo = rna_tf32(. - *_hi) (both exactly representable in TF32);
 //   acc(fp32, TMEM) = a_hi w_lo + a_lo w_hi + a_hi w_hi        -> ~2^-21 relative per product,
 //   i.e. the accuracy class the reference demands (jax_default_matmul_precision='highest',
 //   NVIDIA_TF32_OVERRIDE=0: src/deepqmc/__init__.py:9-34) at 1/3 of the TF32 tensor peak.
@@ -208,10 +208,10 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
             *(uint2*)(al + off) = make_uint2(l01, l23);
           } else {
             float4 v = buf[j], h, l;
-            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+            h.x = tf32_rna(v.x); l.x = tf32_rna(v.x - h.x);
+            h.y = tf32_rna(v.y); l.y = tf32_rna(v.y - h.y);
+            h.z = tf32_rna(v.z); l.z = tf32_rna(v.z - h.z);
+            h.w = tf32_rna(v.w); l.w = tf32_rna(v.w - h.w);
             const int off = (trow >> 3) * 1024 + (trow & 7) * 128 + ((chunk ^ (trow & 7)) << 4);
             *(float4*)(ah + off) = h;
             *(float4*)(al + off) = l;

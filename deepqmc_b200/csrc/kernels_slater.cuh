@@ -563,6 +563,23 @@ __device__ __forceinline__ float env_exp(float x) {
 #endif
 }
 __device__ __forceinline__ double env_exp(double x) { return ::exp(x); }
+// Envelope terms of the plain-forward kernel with the exponent pre-scaled ONCE per (orbital, nucleus): zs = -|zeta| log2(e)
+// (fp32) and exp(-|zeta| rho) = ex2.approx(zs rho): one multiply + one MUFU per term instead of the 6-instruction
+// Cody-Waite form above (the kernel is issue-bound: 173 k terms per benzene walker).  Error: the rounded product x = zs rho
+// is off by <= 2^-23 |x| (scale and product rounding), i.e. the term by <= |x| 2^-23 e^{-|x|} ln 2 <= 3e-8 of a unit
+// coefficient for every x -- large exponents only occur in terms that are themselves tiny -- plus the 2 ulp of ex2.approx.
+__device__ __forceinline__ float env_scale(float z) { return z * 1.4426950408889634f; }
+__device__ __forceinline__ double env_scale(double z) { return z; }
+__device__ __forceinline__ float env_exp_scaled(float xs) {
+#ifndef DQMC_EMU
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(xs));
+  return y;
+#else
+  return ::exp2f(xs);
+#endif
+}
+__device__ __forceinline__ double env_exp_scaled(double x) { return ::exp(x); }
 
 // log|det| = sum of log|pivot|: fp32 keeps a running mantissa product and an integer exponent sum
 // (one logf at the end instead of one per pivot); pivots outside the normal range take the plain path.
@@ -671,12 +688,12 @@ slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batch
             bf[j] = i0 + j < ie ? bfp[(size_t)(i0 + j) * ldb] : T(0);
           }
           for (int mt = 0; mt < M * rep; ++mt) {
-            const T p = pi[mt], z = -m_abs(ze[mt]);
+            const T p = pi[mt], z = env_scale(-m_abs(ze[mt]));
             const int m = rep == 1 ? mt : mt / rep;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int ii = i0 + j < ie ? i0 + j : ie - 1;
-              e[j] += p * env_exp(z * rho[ii * M + m]);
+              e[j] += p * env_exp_scaled(z * rho[ii * M + m]);
             }
           }
           const bool off_block = !full_det && ((sb == 0) != (mu < n_up));  // spin-factorised determinants

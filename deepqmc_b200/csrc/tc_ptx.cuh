@@ -166,6 +166,30 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+// kind::f16 with the A operand in TENSOR MEMORY (cute::SM100_MMA_F16BF16_TS): A[m][k] = half (k % 2) of the 32-bit cell
+// (lane m, column a_taddr + k / 2); 16 k per instruction = 8 columns.  B as usual (K-major shared-memory descriptor).
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// bulk copy global -> shared (TMA, no tensor map): size multiple of 16 bytes, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// generic-proxy writes (any state space) ordered before later async-proxy accesses (TMA reads of data written with st.global)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // TMEM allocation by one whole warp: the base address lands in shared memory
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols));
@@ -200,6 +224,14 @@ __device__ __forceinline__ float half_bits_to_float(uint32_t h16) {
   return f;
 }
 __device__ __forceinline__ void tc_trap() { __trap(); }
+// fp32 -> nearest TF32 value (ties away from zero), returned as an fp32 with the low 13 mantissa bits clear.  The 3xTF32 split
+// uses it for BOTH parts: hi = rna(x), lo = rna(x - hi), so the representation error is <= 2^-23 |x| and unbiased (the tensor
+// core would otherwise truncate lo to its top 11 bits: <= 2^-21 |x|, always towards zero).
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 
 // ---- host side: tensor maps of K-major operand matrices [rows][K] (K contiguous), box = box_k x box_rows elements with the
 // inner extent box_k * elem_bytes = 128 bytes, 128-byte swizzle ---------------------------------------------------------

@@ -686,6 +686,14 @@ class Engine:
         self._check(rc, 'dqmc_debug_mlp_block')
         return out
 
+    def debug_trunk(self, X0):
+        """One launch of the whole-trunk kernel: all attention layers applied to the embedding rows -> [rows, d] (self-test hook)."""
+        X0 = self._prep(X0)
+        out = torch.empty_like(X0)
+        rc = self.lib.dqmc_debug_trunk(self.h, X0.data_ptr(), out.data_ptr(), X0.shape[0], self._stream())
+        self._check(rc, 'dqmc_debug_trunk')
+        return out
+
     def profile_begin(self):
         self.lib.dqmc_profile_begin(self.h)
 

@@ -233,6 +233,13 @@ int dqmc_debug_gemm(dqmc_handle h, const char* weight, const char* bias, const v
  * reference: gnn/update_features.py:241-286 (attention output projection + residual, MLP + residual), hkext.py:22-137. */
 int dqmc_debug_mlp_block(dqmc_handle h, int32_t layer, const void* O, const void* X, void* Out, int32_t rows, void* stream);
 
+/* Self-test hook: ONE launch of the whole-trunk kernel of a plain forward (deepqmc_b200/csrc/trunk_tc.cuh; fp32 engines with the
+ * tcgen05 backend and the shipped Psiformer shape: embedding_dim 256, 4 heads of 64, N <= 32 electrons): every attention layer
+ * (QKV projection, softmax attention, output projection + residual, tanh-MLP + residual) applied to the embedding rows
+ * X0 [rows][256] (rows = walkers x electrons, walker-major), result Out [rows][256].  Status 2 if the configuration has none.
+ * reference: gnn/electron_gnn.py:403-432 (layer loop), gnn/update_features.py:241-286, hkext.py:22-137, :215-253. */
+int dqmc_debug_trunk(dqmc_handle h, const void* X0, void* Out, int32_t rows, void* stream);
+
 /* Measurement aid (bench.py roofline): between begin/end every dense-layer GEMM launch is
  * bracketed by CUDA events on the caller's stream; end() returns their summed duration [ms],
  * the algorithmic flops they performed (2*M*N*K each) and their count.  No reference analogue

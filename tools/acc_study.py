@@ -29,7 +29,7 @@ s64, l64 = e64.wf_forward(r, R)
 E64 = None
 nE = 8
 if name == 'benzene':
-    E64, st64 = e64.local_energy(r[:nE], R, seed=7)
+    E64 = e64.local_energy(r[:nE], R, seed=7)[0]
 
 
 def run(tag, backend, env):
@@ -43,7 +43,7 @@ def run(tag, backend, env):
     q = torch.quantile(d, torch.tensor([0.5, 0.9, 0.99], device=d.device, dtype=d.dtype))
     msg = f'{tag:34s} |dlog|: median {q[0].item():.2e} p90 {q[1].item():.2e} p99 {q[2].item():.2e} max {d.max().item():.2e} sign mismatches {(s.double() != s64).sum().item()}'
     if E64 is not None:
-        E, st = e.local_energy(r[:nE].float(), R.float(), seed=7)
+        E = e.local_energy(r[:nE].float(), R.float(), seed=7)[0]
         rel = ((E.double() - E64).abs() / E64.abs().clamp(min=1.0))
         msg += f' | E_loc rel err max {rel.max().item():.2e} median {rel.median().item():.2e}'
     print(msg, flush=True)

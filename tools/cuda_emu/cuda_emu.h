@@ -227,6 +227,8 @@ template <class T> inline T __ldg(const T* p) { return *p; }
 #define gridDim (emu::S().gdim)
 inline void __syncthreads() { emu::syncthreads(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::syncwarp(); }
+inline void __threadfence_block() {}
+inline void __threadfence() {}
 template <class T> inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl_idx(v, src); }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) {
   return emu::shfl_idx(v, (emu::S().fibers[emu::S().cur].lin & 31) ^ m);

@@ -102,13 +102,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   b.tx += bytes; --b.pending; mb_check(b);
 }
 inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) { emu_tc::MBar& b = mb(bar); b.tx -= bytes; mb_check(b); }
+inline std::vector<long>& wait_trace() { static thread_local std::vector<long> v(2048, -1); return v; }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
   long spins = 0;
+  wait_trace()[threadIdx.x] = (long)smem_u32(bar) * 2 + (parity & 1);
   while ((uint32_t)mb(bar).phase == (parity & 1u)) {
     emu::yield();
     if (++spins > 2000000) {
       if (err_flag) *err_flag = 1;
-      std::fprintf(stderr, "tcgen05_emu: mbarrier wait timed out (thread %d): protocol dead-lock\n", (int)threadIdx.x);
+      std::fprintf(stderr, "tcgen05_emu: mbarrier wait timed out (thread %d, barrier at shared offset %u, parity %u, phase %d pending %d tx %ld): protocol dead-lock\n",
+                   (int)threadIdx.x, smem_u32(bar), parity, mb(bar).phase, mb(bar).pending, mb(bar).tx);
+      for (int i = 0; i < (int)blockDim.x; i += 32)  // where every warp's lane 0 waited last (shared offset, parity)
+        std::fprintf(stderr, "  warp %d lane0: last mbarrier wait at offset %ld parity %ld\n", i / 32, wait_trace()[i] / 2, wait_trace()[i] & 1);
       std::abort();
     }
   }
@@ -208,6 +213,46 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   umma_any(tmem_d, adesc, bdesc, idesc, acc, true);
 }
+// A operand in tensor memory: A[m][k] = half (k % 2) of cell (lane m, column a_col + k / 2)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  const int N = (int)((idesc >> 17) & 63u) << 3, M = (int)((idesc >> 24) & 31u) << 4;
+  if (M != 128 || N < 16 || N > 256 || (N & 15)) { std::fprintf(stderr, "tcgen05_emu: unsupported TS MMA shape %dx%d\n", M, N); std::abort(); }
+  if (((idesc >> 7) & 7u) != 0 || ((idesc >> 10) & 7u) != 0) { std::fprintf(stderr, "tcgen05_emu: TS MMA expects f16 formats\n"); std::abort(); }
+  if (((bdesc >> 61) & 7u) != 2) { std::fprintf(stderr, "tcgen05_emu: only SWIZZLE_128B descriptors\n"); std::abort(); }
+  const uint32_t b0 = (uint32_t)(bdesc & 0x3FFF) << 4, sbob = (uint32_t)((bdesc >> 32) & 0x3FFF) << 4;
+  const uint32_t col0 = tmem_d & 0xFFFFu, acol = tmem_a & 0xFFFFu;
+  if ((tmem_d >> 16) != 0 || (tmem_a >> 16) != 0 || col0 + N > 512 || acol + 8 > 512) { std::fprintf(stderr, "tcgen05_emu: TS MMA operand outside TMEM\n"); std::abort(); }
+  if (!(acol + 8 <= col0 || col0 + (uint32_t)N <= acol)) { std::fprintf(stderr, "tcgen05_emu: TS MMA A and D overlap\n"); std::abort(); }
+  auto& T = emu_tc::st().tmem;
+  std::vector<float> Bt((size_t)N * 16);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t a = emu_tc::swz128(b0 + (uint32_t)(n >> 3) * sbob + (uint32_t)(n & 7) * 128u + (uint32_t)k * 2u);
+      uint16_t h; std::memcpy(&h, emu_tc::sptr(a), 2);
+      Bt[(size_t)n * 16 + k] = emu_tc::half_to_float(h);
+    }
+  for (int m = 0; m < M; ++m) {
+    float ar[16];
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t cell = T[(size_t)m * 512 + acol + k / 2];
+      ar[k] = emu_tc::half_to_float((uint16_t)((k & 1) ? cell >> 16 : cell & 0xFFFFu));
+    }
+    for (int n = 0; n < N; ++n) {
+      double s = 0.0;
+      for (int k = 0; k < 16; ++k) s += (double)ar[k] * (double)Bt[(size_t)n * 16 + k];
+      uint32_t& cell = T[(size_t)m * 512 + col0 + n];
+      float d; std::memcpy(&d, &cell, 4);
+      d = acc ? (float)((double)d + s) : (float)s;
+      std::memcpy(&cell, &d, 4);
+    }
+  }
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  if ((bytes & 15u) || ((uintptr_t)src & 15u) || (smem_u32(dst) & 15u)) { std::fprintf(stderr, "tcgen05_emu: bulk copy alignment\n"); std::abort(); }
+  std::memcpy(dst, src, bytes);
+  mbar_complete_tx(bar, bytes);
+}
+__device__ __forceinline__ void fence_proxy_async_all() {}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) { mbar_arrive(bar); }
 
 // ---- TMEM ------------------------------------------------------------------------------------------------------------------
@@ -228,6 +273,7 @@ inline uint32_t* tmem_cell(uint32_t taddr, int i) {
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) { for (int i = 0; i < 32; ++i) v[i] = *tmem_cell(taddr, i); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) { for (int i = 0; i < 32; ++i) *tmem_cell(taddr, i) = v[i]; }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) { for (int i = 0; i < 16; ++i) *tmem_cell(taddr, i) = v[i]; }
 __device__ __forceinline__ void tmem_ld_wait() {}
 __device__ __forceinline__ void tmem_st_wait() {}
 
@@ -240,6 +286,15 @@ __device__ __forceinline__ uint32_t pack_half2_rn(float lo, float hi) {  // cvt.
 __device__ __forceinline__ float half_bits_to_float(uint32_t h16) { return emu_tc::half_to_float((uint16_t)h16); }
 __device__ __forceinline__ void tc_trap() { std::fprintf(stderr, "tcgen05_emu: trap\n"); std::abort(); }
 __device__ __forceinline__ long long tc_clock() { return 0; }
+__device__ __forceinline__ float tf32_rna(float x) {  // cvt.rna.tf32.f32: nearest, ties away from zero
+  uint32_t b;
+  std::memcpy(&b, &x, 4);
+  if (((b >> 23) & 255u) != 255u) b += 0x1000u;
+  b &= 0xFFFFE000u;
+  float y;
+  std::memcpy(&y, &b, 4);
+  return y;
+}
 
 // 2-CTA (cta_group::2) forms are not modelled: the CTA-pair kernel variant is never launched in emulator builds
 inline void no_pair() { std::fprintf(stderr, "tcgen05_emu: cta_group::2 is not modelled\n"); std::abort(); }
