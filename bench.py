@@ -35,6 +35,10 @@ WORKLOADS = {
     'n2_ferminet': dict(mol='N2', ecp=None, walkers=4096, hyper={}, kind='ferminet'),
     'benzene_psiformer': dict(mol='benzene', ecp='ccECP', walkers=4096, hyper={}, kind='psiformer'),
     'lih_paulinet': dict(mol='LiH', ecp=None, walkers=256, hyper={}, kind='paulinet'),  # BASELINE configs[0]
+    # BASELINE configs[4]: excited-state penalty run, 2 electronic states, 2048 walkers per state
+    # (conf/task/train_excited_psiformer.yaml:25, conf/ansatz/transpsiformer.yaml, conf/hamil/mol/cyclobutadiene_square.yaml)
+    'cyclobutadiene_transpsiformer': dict(mol='cyclobutadiene_square', ecp=None, walkers=2048, hyper={}, kind='transpsiformer',
+                                          states=2),
 }
 
 
@@ -115,14 +119,15 @@ _ORACLE = {}
 def _oracle_init(wl_name, seed):
     """Pool initialiser: one single-threaded oracle per worker process."""
     torch.set_num_threads(1)
-    from deepqmc_b200.spec import ferminet_spec, paulinet_spec, psiformer_spec
+    from deepqmc_b200.spec import ferminet_spec, paulinet_spec, psiformer_spec, transpsiformer_spec
     from oracle import wf
     from oracle.hamil import OracleHamiltonian
 
     wl = WORKLOADS[wl_name]
     mol, hamil, r, PN = make_problem(wl, 1, seed)
     oh = OracleHamiltonian(mol, ecp_type=wl['ecp'])
-    spec = {'psiformer': psiformer_spec, 'ferminet': ferminet_spec, 'paulinet': paulinet_spec}[wl['kind']](oh, **wl['hyper'])
+    spec = {'psiformer': psiformer_spec, 'ferminet': ferminet_spec, 'paulinet': paulinet_spec,
+            'transpsiformer': transpsiformer_spec}[wl['kind']](oh, **wl['hyper'])
     pt = wf.to_torch(PN.perturb_params(PN.init_params(spec, 0)))
     J = 0 if oh.nl_params is None else len(np.unique(np.nonzero(oh.nl_params)[0]))
     _ORACLE.update(wl=wl, oh=oh, spec=spec, pt=pt, R=torch.as_tensor(mol.coords), J=J, wf=wf)
@@ -234,8 +239,11 @@ def main():
     unit = 'walker.local-energies/s'
     metric = 'walker.local-energies/sec'
     arch = {'psiformer': 'Psiformer d256 L4 H4 K16', 'ferminet': 'FermiNet d256 L4 e32 K16',
+            'transpsiformer': 'TransPsiformer d256 L4 H4 K16',
             'paulinet': 'PauliNet test ansatz (tests/conf/ansatz.yaml) d8 L1 K2'}[wl['kind']]
-    workload_name = f"{wl['mol']} {arch}{' ' + wl['ecp'] if wl['ecp'] else ''}, {B_global} walkers"
+    n_states = wl.get('states', 1)
+    workload_name = f"{wl['mol']} {arch}{' ' + wl['ecp'] if wl['ecp'] else ''}, {B_global} walkers" + (
+        f' per state x {n_states} electronic states (energies + pairwise overlap penalty)' if n_states > 1 else '')
 
     if a.impl == 'reference':
         if rank != 0:
@@ -270,33 +278,51 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    mol, hamil, r_np, PN = make_problem(wl, B_global, seed=1000)
-    r_np = r_np[rank * B:(rank + 1) * B]  # contiguous walker block of this rank (deepqmc_b200.parallel.shard_bounds)
+    mol, hamil, r_np, PN = make_problem(wl, B_global * n_states, seed=1000)
+    r_np = r_np.reshape(n_states, B_global, *r_np.shape[1:])[:, rank * B:(rank + 1) * B]  # contiguous walker block of this rank
     backend = 1 if (a.gemm_backend == 'tcgen05' and a.dtype == 'float32' and wl['kind'] != 'paulinet') else 0  # d = 8: CUDA cores
     ansatz = B200Ansatz(hamil, wl['kind'], dtype=a.dtype, device=local, gemm_backend=backend, **wl['hyper'])
-    params = PN.perturb_params(ansatz.init(0))
+    # one parameter tree per electronic state (excited-state runs: reference wf/base.py:27-44 stacks them on a state axis)
+    params_all = [PN.perturb_params(ansatz.init(st), seed=st) for st in range(n_states)]
+    params = params_all[0]
     tdt = torch.float32 if a.dtype == 'float32' else torch.float64
     N, M = hamil.n_up + hamil.n_down, hamil.n_nuc
     n_ecp = len(hamil.pot.nuc_with_nl_pot)
     R = torch.as_tensor(mol.coords, dtype=tdt, device=dev)
-    r = torch.as_tensor(r_np, dtype=tdt, device=dev)
-    eng = ansatz.engine_for(hamil, params)
-    # equilibrate the synthetic walkers (untimed): 20 sweeps x 10 Metropolis sub-steps
-    sign, log = eng.wf_forward(r, R)
-    state = dict(r=r.clone(), sign=sign, log=log, age=torch.zeros(B, dtype=torch.int32, device=dev),
-                 tau=torch.tensor([0.5], dtype=tdt, device=dev))
     heavy = wl['ecp'] is not None
     n_equil = a.equil_sweeps if a.equil_sweeps is not None else (5 if heavy else 20)
-    for it in range(n_equil):
-        eng.mcmc_sweep(state, R, 10, seed=parallel.rank_seed(7), step0=10 * it, walker_offset=rank * B)
-    r = state['r'].clone()
-    pc = PhysicalConfiguration(R, r, torch.zeros(B, device=dev))
+    r_states = []
+    for st in range(n_states):  # equilibrate the synthetic walkers of every state (untimed): sweeps x 10 Metropolis sub-steps
+        r = torch.as_tensor(r_np[st], dtype=tdt, device=dev)
+        eng = ansatz.engine_for(hamil, params_all[st])
+        sign, log = eng.wf_forward(r, R)
+        state = dict(r=r.clone(), sign=sign, log=log, age=torch.zeros(B, dtype=torch.int32, device=dev),
+                     tau=torch.tensor([0.5], dtype=tdt, device=dev))
+        for it in range(n_equil):
+            eng.mcmc_sweep(state, R, 10, seed=parallel.rank_seed(7 + st), step0=10 * it, walker_offset=rank * B)
+        r_states.append(state['r'].clone())
+    r = r_states[0]
+    eng = ansatz.engine_for(hamil, params)
+    pcs = [PhysicalConfiguration(R, rs, torch.zeros(B, device=dev)) for rs in r_states]
+    pc = pcs[0]
     loc_ene = hamil.local_energy(ansatz.apply)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def step(seed):
-        E, st = loc_ene(seed, params, pc)
-        return parallel.energy_statistics(E, st), E
+    def step(seed, pcs_=None):
+        pcs_ = pcs_ or pcs
+        Es, sts = [], []
+        for st in range(n_states):
+            E, stt = loc_ene(seed, params_all[st], pcs_[st])
+            Es.append(E); sts.append(stt)
+        if n_states > 1:  # pairwise overlap penalty: every state's wave function on every state's walkers (loss/overlap.py:19-150)
+            from deepqmc_b200.overlap import compute_mean_overlap, compute_psi_ratio
+
+            pc_all = PhysicalConfiguration(R, torch.stack([p_.r for p_ in pcs_]), torch.zeros(n_states, B, device=dev))
+            ratio, _ = compute_psi_ratio(ansatz, params_all, pc_all)
+            compute_mean_overlap(ratio)
+            E = torch.cat(Es)
+            return parallel.energy_statistics(E, {k: torch.cat([s_[k] for s_ in sts]) for k in sts[0]}), E
+        return parallel.energy_statistics(Es[0], sts[0]), Es[0]
 
     clocks = ClockSampler(local)
     if rank == 0:
@@ -327,16 +353,15 @@ def main():
     if world > 1:
         torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
     total_ms = ms.item()
-    value = B * world * a.steps / (total_ms / 1e3)
+    value = n_states * B * world * a.steps / (total_ms / 1e3)
 
     # ---- e2e: host buffers through the plugin API, H2D + D2H inside the timed region ----------
-    r_host = r.cpu().pin_memory()
+    r_host = [rs.cpu().pin_memory() for rs in r_states]
     R_host = R.cpu().pin_memory()
     def e2e_step(seed):
-        pc_h = PhysicalConfiguration(R_host.to(dev, non_blocking=True), r_host.to(dev, non_blocking=True),
-                                     torch.zeros(B, device=dev))
-        E, st = loc_ene(seed, params, pc_h)
-        parallel.energy_statistics(E, st)
+        Rd = R_host.to(dev, non_blocking=True)
+        pcs_h = [PhysicalConfiguration(Rd, rh.to(dev, non_blocking=True), torch.zeros(B, device=dev)) for rh in r_host]
+        _, E = step(seed, pcs_h)
         return E.cpu()
     # long steps (seconds): the pipeline is warm already, bound the e2e leg to a few steps
     # (same number of steps as the device-timed leg unless that would take more than ~2 minutes)
@@ -354,8 +379,8 @@ def main():
     te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
-    e2e_val = B * world * e2e_steps / te.item()
-    esz = r_host.element_size()
+    e2e_val = n_states * B * world * e2e_steps / te.item()
+    esz = r_host[0].element_size()
 
     # ---- roofline of the dominant kernel (dense-layer GEMMs), timed live with CUDA events ------
     roof = None
@@ -363,7 +388,8 @@ def main():
         n_prof = 1 if slow else 3
         eng.profile_begin()
         for s in range(n_prof):
-            loc_ene(s, params, pc)  # rank-local: no collective here (the other ranks are already done)
+            for st in range(n_states):
+                loc_ene(s, params_all[st], pcs[st])  # rank-local: no collective here (the other ranks are already done)
         gemm_ms, gemm_flops, n_gemm = eng.profile_end()
         peaks = {}
         try:
@@ -400,13 +426,13 @@ def main():
         'ms_per_step': total_ms / a.steps, 'ms_per_step_min': min(per_step), 'ms_per_step_median': float(np.median(per_step)),
         'higher_is_better': True, 'scaling': a.scaling, 'vs_baseline': None,
         'dtype': 'f32' if a.dtype == 'float32' else 'f64', 'data': 'synthetic',
-        'config': {'workload': workload_name, 'global_batch': B * world, 'walkers_per_gpu': B,
+        'config': {'workload': workload_name, 'global_batch': B * world, 'walkers_per_gpu': B, 'electronic_states': n_states,
                    'parallelism': f'walker-shard x{world}',
                    'l2': 'flushed between timed iterations (256 MiB memset) and activations >> L2',
                    'step': 'E_loc of all walkers (+ fused stats all-reduce for N>1)',
                    'gemm_backend': 'tcgen05-3xTF32' if backend else 'cuda-core'},
-        'clocks': clk, 'e2e': {'value': e2e_val, 'unit': unit, 'h2d_bytes_per_step': (B * N * 3 + M * 3) * esz,
-                               'd2h_bytes_per_step': B * esz, 'steps': e2e_steps},
+        'clocks': clk, 'e2e': {'value': e2e_val, 'unit': unit, 'h2d_bytes_per_step': (n_states * B * N * 3 + M * 3) * esz,
+                               'd2h_bytes_per_step': n_states * B * esz, 'steps': e2e_steps},
         'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu,
         'energy_mean': float(stats['energy/mean']), 'wall_s_timed_region': t_wall,
     }

@@ -339,6 +339,7 @@ struct Engine : EngineBase {
   bool fuse_trunk = true;  // all layers of a plain forward in one persistent launch (trunk_tc.cuh); DQMC_TC_TRUNK=0 disables
   CUtensorMap* d_trunk_maps = nullptr;       // [L][4][2]
   unsigned char* d_trunk_scratch = nullptr;  // n_sms x 384 KB Q / K / V planes
+  long long* d_trunk_trace = nullptr;        // DQMC_TRUNK_TRACE: 64 clock stamps of one tile (development aid)
   bool gemm_2cta = false;  // CTA-pair (cta_group::2) variant of the dense-layer GEMM
   bool f16_on = true;      // plain forwards (S = 1) on kind::f16 with hi / lo half operands; DQMC_TC_F16=0: stay on 3xTF32
   bool fuse_mlp = true;    // W_o + residual -> W1 + tanh -> W2 + tanh + residual in one launch (S = 1); DQMC_TC_FUSE_MLP=0 disables
@@ -537,6 +538,10 @@ struct Engine : EngineBase {
       if (psif && !trans && d == 256 && H == 4 && N <= 32 && cfg.n_layers <= tc::kTrMaxLayers) {
         DQ_CHECK(cudaMalloc((void**)&d_trunk_maps, sizeof(CUtensorMap) * 8 * cfg.n_layers));
         DQ_CHECK(cudaMalloc((void**)&d_trunk_scratch, (size_t)n_sms * tc::kTrScratchPerCta));
+        if (std::getenv("DQMC_TRUNK_TRACE")) {
+          DQ_CHECK(cudaMalloc((void**)&d_trunk_trace, sizeof(long long) * 64));
+          DQ_CHECK(cudaMemset(d_trunk_trace, 0, sizeof(long long) * 64));
+        }
       }
 #else
       err = "this build has no tcgen05 backend"; return 2;
@@ -1003,7 +1008,7 @@ struct Engine : EngineBase {
       int np2 = 1;
       while (np2 < N) np2 *= 2;  // walker slot of the tile: electrons rounded up to a power of two (<= 32)
       p.walkers = rows / N; p.N = N; p.NP = np2; p.L = cfg.n_layers; p.a_scale = kActScale;
-      p.attn_scale = (float)(1.0 / std::sqrt((double)dh)); p.err_flag = nullptr;
+      p.attn_scale = (float)(1.0 / std::sqrt((double)dh)); p.err_flag = nullptr; p.trace = d_trunk_trace;
       for (int l = 0; l < cfg.n_layers; ++l) {
         const std::string pfx = "L" + std::to_string(l) + ".";
         p.b1[l] = P(pfx + "b1"); p.b2[l] = P(pfx + "b2");
@@ -1038,6 +1043,16 @@ struct Engine : EngineBase {
     int rc = trunk_block((const T*)X0, (T*)Out, rows, st);
     if (rc) return rc;
     DQ_CHECK(cudaGetLastError());
+#ifndef DQMC_EMU
+    if (d_trunk_trace) {  // print the stamps relative to the first one
+      long long h[64];
+      DQ_CHECK(cudaStreamSynchronize(st));
+      DQ_CHECK(cudaMemcpy(h, d_trunk_trace, sizeof(h), cudaMemcpyDeviceToHost));
+      std::fprintf(stderr, "trunk trace (clocks since the start of layer 1 of the traced tile):");
+      for (int i = 0; i < 37; ++i) std::fprintf(stderr, " [%d]%lld", i, h[i] ? h[i] - h[0] : -1LL);
+      std::fprintf(stderr, "\n");
+    }
+#endif
     return 0;
   }
 

@@ -58,6 +58,18 @@ __device__ __forceinline__ float mlp_tanh(float x) {
   return fabsf(x) < 0.15f ? poly : big;
 }
 
+// (x0, x1) -> packed hi halves and packed lo halves, x = hi + lo to 22 significant bits.  hi is formed in fp32 by Veltkamp's
+// splitting (c = 8193 x, hi = c - (c - x): x rounded to 11 bits, three full-rate instructions) instead of converting the packed
+// half back (F2F conversions issue at a fraction of the FMA rate and made up a fifth of the whole-trunk kernel's stall samples);
+// x - hi is exact, both packs are then plain cvt.rn.f16x2.  Values below the normal half range (2^-14 after scaling) keep
+// the absolute floor of 2^-25 that the split has anyway.
+__device__ __forceinline__ void split_half2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const float c0 = __fmul_rn(x0, 8193.f), c1 = __fmul_rn(x1, 8193.f);
+  const float h0 = __fsub_rn(c0, __fsub_rn(c0, x0)), h1 = __fsub_rn(c1, __fsub_rn(c1, x1));
+  hi = pack_half2_rn(h0, h1);
+  lo = pack_half2_rn(__fsub_rn(x0, h0), __fsub_rn(x1, h1));
+}
+
 // 32 consecutive columns [c0, c0 + 32) of tile row `row` (values v, already scaled by a_scale) -> hi / lo halves in the
 // K-major operand buffer: k-block c0 / 64, 16-byte chunks 4 (c0 / 32 % 2) .. +3 of the row's 128-byte line.
 __device__ __forceinline__ void store_operand_chunk(unsigned char* smem, int row, int c0, const float* v) {
@@ -69,9 +81,7 @@ __device__ __forceinline__ void store_operand_chunk(unsigned char* smem, int row
     uint32_t h[4], l[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float x0 = v[8 * q + 2 * e], x1 = v[8 * q + 2 * e + 1];
-      h[e] = pack_half2_rn(x0, x1);
-      l[e] = pack_half2_rn(x0 - half_bits_to_float(h[e] & 0xFFFFu), x1 - half_bits_to_float(h[e] >> 16));
+      split_half2(v[8 * q + 2 * e], v[8 * q + 2 * e + 1], h[e], l[e]);
     }
     const int off = ((cbase + q) ^ (row & 7)) << 4;
     *(uint4*)(ph + off) = make_uint4(h[0], h[1], h[2], h[3]);

@@ -115,6 +115,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// K-major operand WITHOUT swizzle (canonical "interleaved" layout, cute UMMA Major-K ((8,n),2):((1,SBO),LBO) in 16-byte
+// units): core matrices of 8 rows x 16 bytes are contiguous (128 B); leading byte offset = distance of the two 16-byte
+// k-chunks of an instruction (128 B here: chunk-major inside an 8-row group), stride byte offset = distance of 8-row groups.
+__device__ __forceinline__ uint64_t make_desc_ns(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(128 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
 // kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): c_format=F32 (1) [4,6),
 // a_format=b_format=TF32 (2) [7,10),[10,13), a/b K-major (0), n>>3 [17,23), m>>4 [24,29)
 __device__ __forceinline__ uint32_t make_idesc(int M, int N) {

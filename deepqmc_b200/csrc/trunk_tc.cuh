@@ -30,8 +30,9 @@
 //   warps 0-7  workers: tile load, QKV drain, softmax, attention-output and the three MLP epilogues.  Warp w owns TMEM lanes /
 //                       tile rows 32 (w % 4) .. +31 and the column half w / 4.
 //   warp  8    TMA    : weight slots of every GEMM in issue order, Q / K / V^T images of every head.
-//   warp  9    MMA    : tcgen05.mma kind::f16, M = 128; QKV as six N = 128 sub-chunks alternating between the two halves of
-//                       the accumulator (the drain of one overlaps the MMAs of the next), Wo / W1 / W2 with N = 256.
+//   warp  9    MMA    : tcgen05.mma kind::f16, M = 128, N = 128 throughout: QKV as six sub-chunks and Wo / W1 / W2 as two
+//                       output halves each, alternating between the two halves of the accumulator -- the drain / epilogue
+//                       of one half (by the workers of that column half) overlaps the MMAs of the next.
 // TMEM (512 columns): [0, 256) residual stream X, then A;  [256, 512) accumulator; during attention [256, 384) S -> P,
 //                     [384, 448) / [448, 512) O_h (alternating).
 #pragma once
@@ -62,6 +63,7 @@ struct TrunkParams {
   float a_scale;                 // power of two applied to activations before the hi / lo split
   float attn_scale;              // 1 / sqrt(dh)
   int* err_flag;
+  long long* trace;              // development aid (DQMC_TRUNK_TRACE): clock64 stamps of block 0, one steady-state tile, layer 1
 };
 
 struct TrSmem {
@@ -72,21 +74,21 @@ struct TrSmem {
   static __host__ __device__ int total() { return bars() + 512; }
 };
 
-__device__ __forceinline__ void tr_split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  hi = pack_half2_rn(x0, x1);
-  lo = pack_half2_rn(x0 - half_bits_to_float(hi & 0xFFFFu), x1 - half_bits_to_float(hi >> 16));
-}
+__device__ __forceinline__ void tr_split2(float x0, float x1, uint32_t& hi, uint32_t& lo) { split_half2(x0, x1, hi, lo); }
 
-// 32 columns (c0 .. c0 + 31 of a 64-wide head) of tile row `row` -> K-major operand image planes [128 rows][128 B] in GLOBAL
-// memory (hi at img, lo at img + 16 KB), same swizzle as the shared-memory operand buffer
+// 32 columns (c0 .. c0 + 31 of a 64-wide head) of tile row `row` -> K-major operand image planes [128 rows][64 halves] in GLOBAL
+// memory (hi at img, lo at img + 16 KB) in the UNSWIZZLED canonical layout: 16-byte chunk c of row r at
+// (r / 8) 1024 + c 128 + (r % 8) 16 (core matrices of 8 rows x 16 bytes, leading byte offset 128, stride byte offset 1024).
+// A warp (lane = row) then writes 4 complete 128-byte lines per store instruction; with the swizzled row-major image every
+// instruction touched 32 lines, which made the Q / K drains 3x slower than the tensor pipe that feeds them.
 __device__ __forceinline__ void image_store32(unsigned char* img, int row, int c0, const float* x) {
-  unsigned char* ph = img + (row >> 3) * 1024 + (row & 7) * 128;
+  unsigned char* ph = img + (row >> 3) * 1024 + (row & 7) * 16;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) tr_split2(x[8 * q + 2 * e], x[8 * q + 2 * e + 1], h[e], l[e]);
-    const int off = (((c0 >> 3) + q) ^ (row & 7)) << 4;
+    const int off = ((c0 >> 3) + q) * 128;
     *(uint4*)(ph + off) = make_uint4(h[0], h[1], h[2], h[3]);
     *(uint4*)(ph + 16384 + off) = make_uint4(l[0], l[1], l[2], l[3]);
   }
@@ -94,16 +96,38 @@ __device__ __forceinline__ void image_store32(unsigned char* img, int row, int c
 // V^T image: element (row = head column c, k = key = tile row): two k-blocks of 64 keys, [64 rows][128 B] = 8 KB each per
 // plane (hi at img, lo at img + 16 KB)
 __device__ __forceinline__ void image_store_vt32(unsigned char* img, int key, int c0, const float* x) {
-  unsigned char* base = img + (key >> 6) * 8192 + ((key & 7) << 1);
+  // lanes come in (even key, odd key) pairs: the even lane stores the packed pair for the even columns, the odd lane for
+  // the odd ones -- 32-bit stores, one shuffle per column
+  const bool odd = key & 1;
+  unsigned char* base = img + (key >> 6) * 8192 + ((key & 6) << 1);
   const int kc = (key & 63) >> 3;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int c = c0 + i;
-    const uint32_t h = pack_half2_rn(x[i], 0.f) & 0xFFFFu;
-    const uint32_t l = pack_half2_rn(x[i] - half_bits_to_float(h), 0.f) & 0xFFFFu;
+  for (int i = 0; i < 32; i += 2) {
+    const float mine = odd ? x[i + 1] : x[i], give = odd ? x[i] : x[i + 1];
+    const float got = __shfl_xor_sync(0xffffffffu, give, 1);  // the partner's value of MY column
+    uint32_t h, l;
+    split_half2(odd ? got : mine, odd ? mine : got, h, l);     // (even key, odd key)
+    const int c = c0 + i + (odd ? 1 : 0);
     const int off = (c >> 3) * 1024 + (c & 7) * 128 + ((kc ^ (c & 7)) << 4);
-    *(uint16_t*)(base + off) = (uint16_t)h;
-    *(uint16_t*)(base + 16384 + off) = (uint16_t)l;
+    *(uint32_t*)(base + off) = h;
+    *(uint32_t*)(base + 16384 + off) = l;
+  }
+}
+
+// 32 scaled values -> 16 packed hi pairs (v[0..15]) and 16 packed lo pairs (v[16..31])
+__device__ __forceinline__ void pack_operand32(const float* a, uint32_t* v) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) split_half2(a[2 * i], a[2 * i + 1], v[i], v[16 + i]);
+}
+// ... and those 32 words into the swizzled K-major operand buffer (columns c0 .. c0 + 31 of tile row `row`)
+__device__ __forceinline__ void store_operand_packed(unsigned char* smem, int row, int c0, const uint32_t* v) {
+  const int kb = c0 >> 6, cbase = ((c0 >> 5) & 1) * 4;
+  unsigned char* ph = smem + TrSmem::abuf(kb, 0) + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int off = ((cbase + q) ^ (row & 7)) << 4;
+    *(uint4*)(ph + off) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    *(uint4*)(ph + 16384 + off) = make_uint4(v[16 + 4 * q], v[16 + 4 * q + 1], v[16 + 4 * q + 2], v[16 + 4 * q + 3]);
   }
 }
 
@@ -185,29 +209,31 @@ trunk_f16_kernel(TrunkParams p) {
             mbar_expect_tx(v_full, 32768u);
             bulk_load(smem + TrSmem::wring(4), img + 65536, 32768u, v_full);
           }
-          // ... and back: slots 0-3 once the last S is done, slots 4-5 once the last P V is done (ring position is 0 here)
+          // ... and back: slots 0-3 once the last S is done, slots 4-5 once the last P V is done (ring position is 0 here).
+          // Wo, W1, W2: output halves [0, 128) and [128, 256) one after the other (the epilogue of a half overlaps the MMAs
+          // of the next half / GEMM)
           for (int g = 1; g < 4; ++g)
-            for (int kb = 0; kb < 4; ++kb)
-              for (int plane = 0; plane < 2; ++plane)
-                for (int q = 0; q < 2; ++q) {
-                  if (g == 1 && kb == 0 && plane == 0 && q == 0) { mbar_wait(qk_free, n_qkf & 1, p.err_flag); ++n_qkf; }
-                  if (g == 1 && kb == 1 && plane == 0 && q == 0) { mbar_wait(v_free, n_vf & 1, p.err_flag); ++n_vf; }
-                  weight_slot(lm + 2 * g + plane, kb * 64, 128 * q);
+            for (int hb = 0; hb < 2; ++hb)
+              for (int kb = 0; kb < 4; ++kb)
+                for (int plane = 0; plane < 2; ++plane) {
+                  if (g == 1 && hb == 0 && kb == 0 && plane == 0) { mbar_wait(qk_free, n_qkf & 1, p.err_flag); ++n_qkf; }
+                  if (g == 1 && hb == 0 && kb == 2 && plane == 0) { mbar_wait(v_free, n_vf & 1, p.err_flag); ++n_vf; }
+                  weight_slot(lm + 2 * g + plane, kb * 64, 128 * hb);
                 }
         }
     }
   } else if (warp == 9) {
     // ===================== MMA issuer ============================================================================
-    const uint32_t idesc64 = make_idesc_f16(128, 64), idesc128 = make_idesc_f16(128, 128), idesc256 = make_idesc_f16(128, 256);
+    const uint32_t idesc64 = make_idesc_f16(128, 64), idesc128 = make_idesc_f16(128, 128);
     uint32_t it = 0, n_af = 0, n_of = 0, n_free0 = 0, n_free1 = 0, n_qk = 0, n_v = 0, n_p = 0, n_ofr0 = 0, n_ofr1 = 0;
     for (int tile = blockIdx.x; tile < MT; tile += gridDim.x)
       for (int l = 0; l < L; ++l) {
         // ---- QKV: sub-chunk j -> accumulator half j & 1
         for (int j = 0; j < 6; ++j) {
           const int b = j & 1;
-          if (j == 0) {
-            for (int kb = 0; kb < 4; ++kb) mbar_wait(&afull[kb], n_af & 1, p.err_flag);
-            ++n_af;
+          if (j == 0) {  // the operand comes from an epilogue that also read accumulator half 0 (its k-blocks 0, 1)
+            mbar_wait(&afull[0], n_af & 1, p.err_flag);
+            mbar_wait(&afull[1], n_af & 1, p.err_flag);
           }
           if (j >= 2) {
             if (b == 0) { mbar_wait(&accfree[0], n_free0 & 1, p.err_flag); ++n_free0; }
@@ -216,6 +242,11 @@ trunk_f16_kernel(TrunkParams p) {
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + 256u + 128u * (uint32_t)b;
           for (int kb = 0; kb < 4; ++kb) {
+            if (j == 0 && kb >= 2) {  // k-blocks 2, 3 of the operand (written by the other column half of the workers)
+              mbar_wait(&afull[kb], n_af & 1, p.err_flag);
+              if (kb == 3) ++n_af;
+              tc_fence_after();
+            }
             const uint32_t ah = smem_u32(smem + TrSmem::abuf(kb, 0)), al = smem_u32(smem + TrSmem::abuf(kb, 1));
             for (int plane = 0; plane < 2; ++plane, ++it) {
               const int s = it % kTrSlots;
@@ -253,10 +284,10 @@ trunk_f16_kernel(TrunkParams p) {
             const uint32_t kh = smem_u32(smem + TrSmem::wring(2)), kl = smem_u32(smem + TrSmem::wring(3));
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint32_t ko = k * 32;
-              umma_f16(tmem_base + 256u, make_desc(ql + ko), make_desc(kh + ko), idesc128, k ? 1u : 0u);
-              umma_f16(tmem_base + 256u, make_desc(qh + ko), make_desc(kh + ko), idesc128, 1u);
-              umma_f16(tmem_base + 256u, make_desc(qh + ko), make_desc(kl + ko), idesc128, 1u);
+              const uint32_t ko = k * 256;  // unswizzled images: a k-step of 16 halves = 2 chunks of 128 bytes
+              umma_f16(tmem_base + 256u, make_desc_ns(ql + ko), make_desc_ns(kh + ko), idesc128, k ? 1u : 0u);
+              umma_f16(tmem_base + 256u, make_desc_ns(qh + ko), make_desc_ns(kh + ko), idesc128, 1u);
+              umma_f16(tmem_base + 256u, make_desc_ns(qh + ko), make_desc_ns(kl + ko), idesc128, 1u);
             }
             umma_commit(s_full);
             umma_commit(qk_free);
@@ -285,46 +316,53 @@ trunk_f16_kernel(TrunkParams p) {
           }
           __syncwarp();
         }
-        // ---- Wo (operand = attention output), W1, W2: N = 256 into the whole accumulator
+        // ---- Wo (operand = attention output), W1, W2: two N = 128 halves each -> accumulator halves 0, 1.  The workers of a
+        // column half run its epilogue as soon as that half is complete, i.e. under the MMAs of the other half / next GEMM.
         mbar_wait(&o_free[0], n_ofr0 & 1, p.err_flag); ++n_ofr0;  // heads 2, 3: buffers read (every completion is consumed)
         mbar_wait(&o_free[1], n_ofr1 & 1, p.err_flag); ++n_ofr1;
-        for (int g = 0; g < 3; ++g) {
-          const uint32_t d_tmem = tmem_base + 256u;
-          if (g == 0) {
-            for (int kb = 0; kb < 4; ++kb) mbar_wait(&ofull[kb], n_of & 1, p.err_flag);
-            ++n_of;
-          } else {
-            for (int kb = 0; kb < 4; ++kb) mbar_wait(&afull[kb], n_af & 1, p.err_flag);
-            ++n_af;
-          }
-          tc_fence_after();
-          for (int kb = 0; kb < 4; ++kb) {
-            const uint32_t ah = smem_u32(smem + TrSmem::abuf(kb, 0)), al = smem_u32(smem + TrSmem::abuf(kb, 1));
-            for (int plane = 0; plane < 2; ++plane, it += 2) {
-              const int s = it % kTrSlots;  // even: slots s, s + 1 are contiguous = 256 W^T rows
-              mbar_wait(&wfull[s], (it / kTrSlots) & 1, p.err_flag);
-              mbar_wait(&wfull[s + 1], (it / kTrSlots) & 1, p.err_flag);
-              tc_fence_after();
-              if (lane == 0) {
-                const uint32_t w = smem_u32(smem + TrSmem::wring(s));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint32_t ko = k * 32;
-                  if (plane == 0) {
-                    umma_f16(d_tmem, make_desc(al + ko), make_desc(w + ko), idesc256, (kb | k) ? 1u : 0u);
-                    umma_f16(d_tmem, make_desc(ah + ko), make_desc(w + ko), idesc256, 1u);
-                  } else {
-                    umma_f16(d_tmem, make_desc(ah + ko), make_desc(w + ko), idesc256, 1u);
-                  }
+        for (int g = 0; g < 3; ++g)
+          for (int hb = 0; hb < 2; ++hb) {
+            const uint32_t d_tmem = tmem_base + 256u + 128u * (uint32_t)hb;
+            if (hb == 0 && g > 0) {  // accumulator half 0 has been read once operand k-blocks 0 AND 1 are written
+              mbar_wait(&afull[0], n_af & 1, p.err_flag);
+              mbar_wait(&afull[1], n_af & 1, p.err_flag);
+            }
+            tc_fence_after();
+            for (int kb = 0; kb < 4; ++kb) {
+              if (hb == 0) {
+                if (g == 0) {
+                  mbar_wait(&ofull[kb], n_of & 1, p.err_flag);
+                  if (kb == 3) ++n_of;
+                } else if (kb >= 2) {
+                  mbar_wait(&afull[kb], n_af & 1, p.err_flag);
+                  if (kb == 3) ++n_af;
                 }
-                umma_commit(&wempty[s]);
-                umma_commit(&wempty[s + 1]);
-                if (kb == 3 && plane == 1) umma_commit(&accfull[0]);
+                tc_fence_after();
               }
-              __syncwarp();
+              const uint32_t ah = smem_u32(smem + TrSmem::abuf(kb, 0)), al = smem_u32(smem + TrSmem::abuf(kb, 1));
+              for (int plane = 0; plane < 2; ++plane, ++it) {
+                const int s = it % kTrSlots;
+                mbar_wait(&wfull[s], (it / kTrSlots) & 1, p.err_flag);
+                tc_fence_after();
+                if (lane == 0) {
+                  const uint32_t w = smem_u32(smem + TrSmem::wring(s));
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint32_t ko = k * 32;
+                    if (plane == 0) {
+                      umma_f16(d_tmem, make_desc(al + ko), make_desc(w + ko), idesc128, (kb | k) ? 1u : 0u);
+                      umma_f16(d_tmem, make_desc(ah + ko), make_desc(w + ko), idesc128, 1u);
+                    } else {
+                      umma_f16(d_tmem, make_desc(ah + ko), make_desc(w + ko), idesc128, 1u);
+                    }
+                  }
+                  umma_commit(&wempty[s]);
+                  if (kb == 3 && plane == 1) umma_commit(&accfull[hb]);
+                }
+                __syncwarp();
+              }
             }
           }
-        }
       }
   } else {
     // ===================== workers: warps 0-7 ======================================================================
@@ -332,9 +370,12 @@ trunk_f16_kernel(TrunkParams p) {
     const int trow = 32 * q4 + lane;
     const uint32_t tlane = (uint32_t)(32 * q4) << 16;
     const int c_lo = 4 * half, c_hi = 4 * half + 4;  // this thread's 32-column chunks
-    const int slot = trow / NP, el = trow - slot * NP;  // walker slot of the tile, electron
+    const int lnp = 31 - __clz(NP);                      // NP is a power of two
+    const int slot = trow >> lnp, el = trow & (NP - 1);  // walker slot of the tile, electron
     uint32_t n_acc0 = 0, n_acc1 = 0, n_s = 0, n_o0 = 0, n_o1 = 0;
     for (int tile = blockIdx.x; tile < MT; tile += gridDim.x) {
+      const bool tr_on = p.trace && blockIdx.x == 0 && tile == (int)(2 * gridDim.x) && threadIdx.x == 0;
+#define TR_STAMP(i) do { if (tr_on && l == 1) p.trace[i] = clock64(); } while (0)
       const int walker = tile * G + slot;
       const bool valid = el < N && walker < p.walkers;
       const size_t row = (size_t)walker * N + el;  // global row (valid rows only)
@@ -362,11 +403,13 @@ trunk_f16_kernel(TrunkParams p) {
       for (int l = 0; l < L; ++l) {
         const bool last = l == L - 1;
         // ---- QKV drain: sub-chunk j (W^T rows 128 j ..) -> matrix j / 2, heads 2 (j % 2) + {0, 1}; this thread: head .. + half
+        TR_STAMP(0);
         for (int j = 0; j < 6; ++j) {
           const int b = j & 1;
           if (b == 0) { mbar_wait(&accfull[0], n_acc0 & 1, p.err_flag); ++n_acc0; }
           else { mbar_wait(&accfull[1], n_acc1 & 1, p.err_flag); ++n_acc1; }
           tc_fence_after();
+          TR_STAMP(1 + 2 * j);
           uint32_t v0[32], v1[32];
           tmem_ld32(tmem_base + tlane + (uint32_t)(256 + 128 * b + 64 * half), v0);
           tmem_ld32(tmem_base + tlane + (uint32_t)(256 + 128 * b + 64 * half + 32), v1);
@@ -382,11 +425,13 @@ trunk_f16_kernel(TrunkParams p) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v1[i]) * sc;
           if (j < 4) image_store32(img, trow, 32, x); else image_store_vt32(img, trow, 32, x);
+          TR_STAMP(2 + 2 * j);
         }
         fence_proxy_async_all();  // the images are read back through the async proxy (bulk copies)
         __threadfence_block();
         named_bar_sync(1, 256);   // images complete; everybody is past the previous layer's last epilogue
         if (threadIdx.x == 0) mbar_arrive(scr_full);
+        TR_STAMP(13);
         if (threadIdx.x < 256) {
           sb1[threadIdx.x] = __ldg(p.b1[l] + threadIdx.x);
           sb2[threadIdx.x] = __ldg(p.b2[l] + threadIdx.x);
@@ -398,6 +443,7 @@ trunk_f16_kernel(TrunkParams p) {
           if (h < 4) {
             mbar_wait(s_full, n_s & 1, p.err_flag); ++n_s;
             tc_fence_after();
+            TR_STAMP(14 + 4 * h);
             uint32_t sv[32];
             tmem_ld32(tmem_base + tlane + (uint32_t)(256 + 32 * q4), sv);  // keys = tile rows 32 q4 .. +31
             tmem_ld_wait();
@@ -407,8 +453,8 @@ trunk_f16_kernel(TrunkParams p) {
             float e[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-              const int key = 32 * q4 + c, ks = key / NP;
-              const bool on = ks == slot && key - ks * NP < N;  // keys of this row's walker
+              const int key = 32 * q4 + c;
+              const bool on = (key >> lnp) == slot && (key & (NP - 1)) < N;  // keys of this row's walker
               e[c] = on ? __uint_as_float(sv[c]) * cs : -3.0e38f;
               mx = fmaxf(mx, e[c]);
             }
@@ -438,12 +484,14 @@ trunk_f16_kernel(TrunkParams p) {
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(p_full);
+            TR_STAMP(15 + 4 * h);
           }
           if (h > 0) {
             const int ho = h - 1, ob = ho & 1;
             if (ob == 0) { mbar_wait(&o_full[0], n_o0 & 1, p.err_flag); ++n_o0; }
             else { mbar_wait(&o_full[1], n_o1 & 1, p.err_flag); ++n_o1; }
             tc_fence_after();
+            TR_STAMP(16 + 4 * ho);
             uint32_t ov[32];
             tmem_ld32(tmem_base + tlane + (uint32_t)(384 + 64 * ob + 32 * half), ov);
             tmem_ld_wait();
@@ -456,6 +504,7 @@ trunk_f16_kernel(TrunkParams p) {
             store_operand_chunk(smem, trow, 64 * ho + 32 * half, a);
             fence_proxy_async();
             mbar_arrive(&ofull[ho]);
+            TR_STAMP(17 + 4 * ho);
           }
         }
         named_bar_sync(1, 256);  // biases of this layer are in shared memory
@@ -475,9 +524,47 @@ trunk_f16_kernel(TrunkParams p) {
           std::fclose(f);
         }
 #endif
+        // The three GEMMs run as two output halves each.  Column half 0 finishes first and its workers start at once, but the
+        // operand buffer still feeds the MMAs of half 1: they PARK their result (already scaled / split / packed) in place of
+        // the accumulator columns they have just read and move it to shared memory when half 1 is complete.  Half 1 writes
+        // directly.  Either way the epilogue of one half runs under the MMAs of the other.
+        auto emit = [&](int c, const float* a) {  // a: 32 scaled operand values of chunk c
+          uint32_t v[32];
+          pack_operand32(a, v);
+          if (half == 0) {
+            tmem_st32(tmem_base + tlane + (uint32_t)(256 + c * 32), v);
+          } else {
+            store_operand_packed(smem, trow, c * 32, v);
+            if (c & 1) {
+              tmem_st_wait();
+              fence_proxy_async();
+              tc_fence_before();
+              mbar_arrive(&afull[c >> 1]);
+            }
+          }
+        };
+        auto unpark = [&]() {  // half 0: the whole GEMM has read the operand buffer -> move the parked chunks over
+          tmem_st_wait();
+          mbar_wait(&accfull[1], n_acc1 & 1, p.err_flag); ++n_acc1;
+          tc_fence_after();
+          for (int c = c_lo; c < c_hi; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + tlane + (uint32_t)(256 + c * 32), v);
+            tmem_ld_wait();
+            store_operand_packed(smem, trow, c * 32, v);
+            if (c & 1) {
+              fence_proxy_async();
+              tc_fence_before();
+              mbar_arrive(&afull[c >> 1]);
+            }
+          }
+        };
         // ---- epilogue 1: A = X + O Wo -> TMEM [0, 256) and the operand buffer
-        mbar_wait(&accfull[0], n_acc0 & 1, p.err_flag); ++n_acc0;
+        TR_STAMP(30);
+        if (half == 0) { mbar_wait(&accfull[0], n_acc0 & 1, p.err_flag); ++n_acc0; }
+        else { mbar_wait(&accfull[1], n_acc1 & 1, p.err_flag); ++n_acc1; ++n_acc0; }
         tc_fence_after();
+        TR_STAMP(31);
         for (int c = c_lo; c < c_hi; ++c) {
           uint32_t v[32], r[32];
           tmem_ld32(tmem_base + tlane + (uint32_t)(256 + c * 32), v);
@@ -491,17 +578,15 @@ trunk_f16_kernel(TrunkParams p) {
           tmem_st32(tmem_base + tlane + (uint32_t)(c * 32), v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) a[i] *= p.a_scale;
-          store_operand_chunk(smem, trow, c * 32, a);
-          if (c & 1) {
-            tmem_st_wait();
-            fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(&afull[c >> 1]);
-          }
+          emit(c, a);
         }
+        if (half == 0) unpark();
         // ---- epilogue 2: M1 = tanh(A W1 + b1) -> operand buffer
-        mbar_wait(&accfull[0], n_acc0 & 1, p.err_flag); ++n_acc0;
+        TR_STAMP(32);
+        if (half == 0) { mbar_wait(&accfull[0], n_acc0 & 1, p.err_flag); ++n_acc0; }
+        else { mbar_wait(&accfull[1], n_acc1 & 1, p.err_flag); ++n_acc1; ++n_acc0; }
         tc_fence_after();
+        TR_STAMP(33);
         for (int c = c_lo; c < c_hi; ++c) {
           uint32_t v[32];
           tmem_ld32(tmem_base + tlane + (uint32_t)(256 + c * 32), v);
@@ -509,16 +594,15 @@ trunk_f16_kernel(TrunkParams p) {
           float a[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) a[i] = mlp_tanh(__uint_as_float(v[i]) * p.us[l][2] + sb1[c * 32 + i]) * p.a_scale;
-          store_operand_chunk(smem, trow, c * 32, a);
-          if (c & 1) {
-            fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(&afull[c >> 1]);
-          }
+          emit(c, a);
         }
+        if (half == 0) unpark();
         // ---- epilogue 3: X' = A + tanh(M1 W2 + b2) -> next layer's residual stream + operand, or the output rows
-        mbar_wait(&accfull[0], n_acc0 & 1, p.err_flag); ++n_acc0;
+        TR_STAMP(34);
+        if (half == 0) { mbar_wait(&accfull[0], n_acc0 & 1, p.err_flag); ++n_acc0; }
+        else { mbar_wait(&accfull[1], n_acc1 & 1, p.err_flag); ++n_acc1; ++n_acc0; }
         tc_fence_after();
+        TR_STAMP(35);
         for (int c = c_lo; c < c_hi; ++c) {
           uint32_t v[32], r[32];
           tmem_ld32(tmem_base + tlane + (uint32_t)(256 + c * 32), v);
@@ -540,17 +624,20 @@ trunk_f16_kernel(TrunkParams p) {
             tmem_st32(tmem_base + tlane + (uint32_t)(c * 32), v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) a[i] *= p.a_scale;
-            store_operand_chunk(smem, trow, c * 32, a);
-            if (c & 1) {
-              tmem_st_wait();
-              fence_proxy_async();
-              tc_fence_before();
-              mbar_arrive(&afull[c >> 1]);
-            }
+            emit(c, a);
           }
         }
+        if (half == 0) {
+          if (last) {  // nothing parked, but the next tile's load must not touch the operand buffer before W2 has read all of it
+            mbar_wait(&accfull[1], n_acc1 & 1, p.err_flag); ++n_acc1;
+          } else {
+            unpark();
+          }
+        }
+        TR_STAMP(36);
         if (last) tc_fence_before();  // the next tile's load overwrites TMEM [0, 256) / the operand buffer from the same threads
       }
+#undef TR_STAMP
     }
   }
   tc_fence_before();

@@ -266,6 +266,46 @@ def test_benzene_ccecp_small_hyper_vs_oracle():
     assert abs(E[0].item() - e) <= 1e-7 * max(1, abs(e))
 
 
+def test_benzene_full_size_one_walker_vs_oracle():
+    """BASELINE configs[3] at FULL size (benzene, ccECP, Psiformer d = 256, L = 4, H = 4, K = 16): ONE walker against the
+    ORACLE (autograd Hessian over the 90 coordinates, all 2160 quadrature forwards; about a minute of host time):
+      * fp64 engine: log|psi| to 1e-10, E_loc and all six statistics to 1e-8 (relative to max(1, |value|));
+      * fp32 production engine (tcgen05 backend: whole-trunk kernel for the quadrature forwards, 3xTF32 forward-Laplacian
+        rows): E_loc to 2e-4 of its natural scale max(1, |E|, |lap| / 2, |grad|^2 / 2) -- E_kin = -(lap + |grad|^2) / 2 is a
+        difference of those two terms, fp32 round-off is relative to them, not to their difference -- and V_nl to 2e-4 of
+        max(1, |V_nl|)."""
+    mol, hamil, oh, a64, params, r, R = make('benzene', ecp='ccECP', B=1)
+    # a typical walker, not a freshly drawn one (whose Laplacian next to a nucleus is ~1e6): 40 Metropolis sub-steps first
+    eng = a64.engine_for(hamil, params)
+    sg, lg = eng.wf_forward(r, R)
+    state = dict(r=r.clone(), sign=sg, log=lg, age=torch.zeros(1, dtype=torch.int32, device=DEV),
+                 tau=torch.tensor([0.3], dtype=torch.float64, device=DEV))
+    for it in range(4):
+        eng.mcmc_sweep(state, R, 10, seed=3, step0=10 * it)
+    r = state['r'].clone()
+    tw = torch.as_tensor(np.random.default_rng(5).uniform(0, np.pi / 5, size=(1, 6, 30)), device=DEV)
+    pc = PhysicalConfiguration(R, r, torch.zeros(1, device=DEV))
+    psi = a64.apply(params, pc)
+    E64, s64 = hamil.local_energy(a64.apply)(None, params, pc, ecp_twist=tw)
+    (s, l, e, st), = oracle_eval(a64, oh, params, r, R, twist=tw)
+    assert psi.sign[0].item() == s
+    assert abs(psi.log[0].item() - l) <= 1e-10 * max(1, abs(l)), (psi.log[0].item(), l)
+    assert abs(E64[0].item() - e) <= 1e-8 * max(1, abs(e)), (E64[0].item(), e)
+    for k in STAT_KEYS:
+        assert abs(s64[k][0].item() - st[k]) <= 1e-8 * max(1, abs(st[k])), (k, s64[k][0].item(), st[k])
+    a32 = B200Ansatz(hamil, 'psiformer', dtype='float32', gemm_backend=1)
+    pc32 = PhysicalConfiguration(R.float(), r.float(), torch.zeros(1, device=DEV))
+    E32, s32 = hamil.local_energy(a32.apply)(None, params, pc32, ecp_twist=tw.float())
+    psi32 = a32.apply(params, pc32)
+    assert psi32.sign[0].item() == s
+    assert abs(psi32.log[0].item() - l) <= 2e-4 * max(1, abs(l))
+    scale = max(1.0, abs(e), 0.5 * abs(st['hamil/lap']), 0.5 * st['hamil/quantum_force'])
+    assert abs(E32[0].item() - e) <= 2e-4 * scale, (E32[0].item(), e, scale)
+    assert abs(s32['hamil/V_nl'][0].item() - st['hamil/V_nl']) <= 2e-4 * max(1, abs(st['hamil/V_nl'])), (
+        s32['hamil/V_nl'][0].item(), st['hamil/V_nl'])
+    assert abs(s32['hamil/V_loc'][0].item() - st['hamil/V_loc']) <= 1e-5 * max(1, abs(st['hamil/V_loc']))
+
+
 def test_benzene_full_psiformer_fp32_tensor_core_vs_fp64():
     """Full-width benzene Psiformer (d=256, L=4, K=16): fp32 tensor-core engine against the fp64
     CUDA-core engine on the same walkers and quadrature twists (the oracle is too slow here)."""
@@ -404,32 +444,44 @@ def test_paulinet_256_walkers_fp32_and_sampler():
     assert ((E32.double() - E64).abs() <= 2e-4 * scale).float().mean().item() > 0.99
 
 
-def test_excited_state_overlap_two_states_vs_oracle():
-    """BASELINE configs[4] shape (two electronic states, TransPsiformer): Psi_i(r ~ Psi_j^2) blocks, sample-wise
-    ratios and the symmetrised mean overlap (reference loss/overlap.py:19-150) against the oracle."""
+@pytest.mark.parametrize('mol_name,nb', [('LiH', 6), ('cyclobutadiene_square', 2)])
+def test_excited_state_overlap_two_states_vs_oracle(mol_name, nb):
+    """BASELINE configs[4] (two electronic states, TransPsiformer; LiH and the cyclobutadiene geometry of
+    conf/hamil/mol/cyclobutadiene_square.yaml, reduced widths): Psi_i(r ~ Psi_j^2) blocks, sample-wise ratios and the
+    symmetrised mean overlap (reference loss/overlap.py:19-150) against the oracle, plus every state's E_loc on its own
+    walkers (what the excited-state loss sums, loss/loss_function.py)."""
     from deepqmc_b200.overlap import compute_mean_overlap, compute_psi_ratio
     from deepqmc_b200.sampling import MetropolisSampler, MultiElectronicStateSampler
     from oracle import wf
+    from oracle.hamil import OracleHamiltonian
 
     hyper = dict(embedding_dim=32, n_layers=1, n_heads=2, n_determinants=2)
-    mol = Molecule.from_name('LiH')
+    mol = Molecule.from_name(mol_name)
     hamil = MolecularHamiltonian(mol=mol)
     ansatz = B200Ansatz(hamil, 'transpsiformer', dtype='float64', **hyper)
     params = [PN.perturb_params(ansatz.init(s), seed=10 + s) for s in range(2)]
     R = torch.as_tensor(mol.coords, device=DEV)
     smp = MultiElectronicStateSampler(MetropolisSampler(hamil, ansatz.apply, tau=0.3), 2)
-    state = smp.init(5, params, 6, R)
+    state = smp.init(5, params, nb, R)
     state, pc, stats = smp.sample(6, state, params, R)
-    assert pc.r.shape == (2, 6, 4, 3) and stats['sampling/acceptance'].shape == (2,)
+    Nel = hamil.n_up + hamil.n_down
+    assert pc.r.shape == (2, nb, Nel, 3) and stats['sampling/acceptance'].shape == (2,)
+    if mol_name != 'LiH':  # E_loc of each state on its own walkers against the oracle
+        oh = OracleHamiltonian(mol)
+        for st_i in range(2):
+            pcs = PhysicalConfiguration(R, pc.r[st_i], torch.zeros(nb, device=DEV))
+            E, _ = hamil.local_energy(ansatz.apply)(None, params[st_i], pcs)
+            (s_, l_, e_, _), = oracle_eval(ansatz, oh, params[st_i], pc.r[st_i][:1], R)
+            assert abs(E[0].item() - e_) <= 1e-8 * max(1, abs(e_)), (st_i, E[0].item(), e_)
     ratio, _ = compute_psi_ratio(ansatz, params, pc)
     pts = [wf.to_torch(p) for p in params]
     Rc = R.cpu()
-    ref = torch.zeros(2, 2, 6, dtype=torch.float64)
-    logs = torch.zeros(2, 2, 6, dtype=torch.float64)
-    signs = torch.zeros(2, 2, 6, dtype=torch.float64)
+    ref = torch.zeros(2, 2, nb, dtype=torch.float64)
+    logs = torch.zeros(2, 2, nb, dtype=torch.float64)
+    signs = torch.zeros(2, 2, nb, dtype=torch.float64)
     for i in range(2):
         for j in range(2):
-            for b in range(6):
+            for b in range(nb):
                 s, l = wf.log_psi(ansatz.spec, pts[i], pc.r[j, b].cpu(), Rc)
                 signs[i, j, b], logs[i, j, b] = s, l
     mean_log = logs.mean(dim=(-1, -2))  # per wave function over the samples of all states (loss/overlap.py:93-95)
@@ -437,7 +489,7 @@ def test_excited_state_overlap_two_states_vs_oracle():
         for j in range(2):
             ref[i, j] = signs[i, j] * signs[j, j] * torch.exp((logs[i, j] - mean_log[i]) - (logs[j, j] - mean_log[j]))
     assert torch.allclose(ratio.cpu(), ref, rtol=1e-8, atol=1e-10)
-    assert torch.allclose(ratio[0, 0].cpu(), torch.ones(6, dtype=torch.float64)) and torch.allclose(ratio[1, 1].cpu(), torch.ones(6, dtype=torch.float64))
+    assert torch.allclose(ratio[0, 0].cpu(), torch.ones(nb, dtype=torch.float64)) and torch.allclose(ratio[1, 1].cpu(), torch.ones(nb, dtype=torch.float64))
     loss, ostats = compute_mean_overlap(ratio)
     S = ostats['overlap/pairwise/mean'].cpu()
     x = ref.mean(-1)

@@ -228,6 +228,10 @@ template <class T> inline T __ldg(const T* p) { return *p; }
 inline void __syncthreads() { emu::syncthreads(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::syncwarp(); }
 inline void __threadfence_block() {}
+inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+inline long long clock64() { return 0; }
+inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 inline void __threadfence() {}
 template <class T> inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl_idx(v, src); }
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) {
@@ -289,6 +293,7 @@ enum { cudaSuccess = 0 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 // fresh device memory holds garbage on the GPU, fresh mmap-backed malloc memory holds zeros: poison it (0xFF = NaN in every
 // float format, -1 in every integer) so that code relying on zero-initialised cudaMalloc memory fails here as well
+inline cudaError_t cudaMemset(void* p, int v, size_t n) { std::memset(p, v, n); return 0; }
 inline cudaError_t cudaMalloc(void** p, size_t n) {
   *p = std::malloc(n ? n : 1);
   if (*p) std::memset(*p, 0xFF, n ? n : 1);

@@ -164,6 +164,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+__device__ __forceinline__ uint64_t make_desc_ns(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(128 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
 __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -177,25 +185,30 @@ inline void umma_any(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t i
   if ((f16 && (afmt != 0 || bfmt != 0)) || (!f16 && (afmt != 2 || bfmt != 2))) {
     std::fprintf(stderr, "tcgen05_emu: instruction descriptor formats do not match the MMA kind\n"); std::abort();
   }
-  if (((adesc >> 61) & 7u) != 2 || ((bdesc >> 61) & 7u) != 2) { std::fprintf(stderr, "tcgen05_emu: only SWIZZLE_128B descriptors\n"); std::abort(); }
+  const uint32_t lta = (uint32_t)((adesc >> 61) & 7u), ltb = (uint32_t)((bdesc >> 61) & 7u);
+  if ((lta != 2 && lta != 0) || (ltb != 2 && ltb != 0)) { std::fprintf(stderr, "tcgen05_emu: only SWIZZLE_128B / unswizzled descriptors\n"); std::abort(); }
   const uint32_t a0 = (uint32_t)(adesc & 0x3FFF) << 4, b0 = (uint32_t)(bdesc & 0x3FFF) << 4;
   const uint32_t sboa = (uint32_t)((adesc >> 32) & 0x3FFF) << 4, sbob = (uint32_t)((bdesc >> 32) & 0x3FFF) << 4;
+  const uint32_t lboa = (uint32_t)((adesc >> 16) & 0x3FFF) << 4, lbob = (uint32_t)((bdesc >> 16) & 0x3FFF) << 4;
   const uint32_t lane0 = tmem_d >> 16, col0 = tmem_d & 0xFFFFu;
   if (lane0 != 0 || col0 + N > 512) { std::fprintf(stderr, "tcgen05_emu: accumulator outside TMEM\n"); std::abort(); }
   const int KE = f16 ? 16 : 8;  // 32 bytes of K per instruction
-  auto rd = [&](uint32_t base, uint32_t sbo, int r, int k) -> float {
+  auto rd = [&](uint32_t base, uint32_t sbo, uint32_t lbo, uint32_t lt, int r, int k) -> float {
     const uint32_t eb = f16 ? 2u : 4u;
-    const uint32_t a = emu_tc::swz128(base + (uint32_t)(r >> 3) * sbo + (uint32_t)(r & 7) * 128u + (uint32_t)k * eb);
+    // unswizzled: 16-byte chunk c of row r at (r / 8) SBO + c LBO + (r % 8) 16
+    const uint32_t kbyte = (uint32_t)k * eb;
+    const uint32_t a = lt == 2 ? emu_tc::swz128(base + (uint32_t)(r >> 3) * sbo + (uint32_t)(r & 7) * 128u + kbyte)
+                               : base + (uint32_t)(r >> 3) * sbo + (kbyte >> 4) * lbo + (uint32_t)(r & 7) * 16u + (kbyte & 15u);
     if (f16) { uint16_t h; std::memcpy(&h, emu_tc::sptr(a), 2); return emu_tc::half_to_float(h); }
     uint32_t w; std::memcpy(&w, emu_tc::sptr(a), 4); w &= 0xFFFFE000u;
     float v; std::memcpy(&v, &w, 4); return v;
   };
   std::vector<float> Bt((size_t)N * KE);
-  for (int n = 0; n < N; ++n) for (int k = 0; k < KE; ++k) Bt[(size_t)n * KE + k] = rd(b0, sbob, n, k);
+  for (int n = 0; n < N; ++n) for (int k = 0; k < KE; ++k) Bt[(size_t)n * KE + k] = rd(b0, sbob, lbob, ltb, n, k);
   auto& T = emu_tc::st().tmem;
   for (int m = 0; m < M; ++m) {
     float ar[16];
-    for (int k = 0; k < KE; ++k) ar[k] = rd(a0, sboa, m, k);
+    for (int k = 0; k < KE; ++k) ar[k] = rd(a0, sboa, lboa, lta, m, k);
     for (int n = 0; n < N; ++n) {
       double s = 0.0;
       for (int k = 0; k < KE; ++k) s += (double)ar[k] * (double)Bt[(size_t)n * KE + k];
