@@ -31,17 +31,11 @@ class B200Ansatz:
                               # wave function on every state's walkers, reference loss/overlap.py:19-49)
 
     # -- reference: Ansatz.init(rng, phys_conf) -> Params (types.py:119-131)
-    def init(self, rng, phys_conf: PhysicalConfiguration | None = None, haiku_compatible: bool = False):
-        """``haiku_compatible`` (conv-GNN test ansatz only): the parameters the reference's ``ansatz.init(PRNGKey(rng), phys_conf)``
-        creates -- haiku's initialisers fed by the restated jax.random streams in parameter-creation order
-        (deepqmc_b200/jaxrand.py); with them the reference's recorded psi / gradient / E_loc fixtures are reproduced."""
+    def init(self, rng, phys_conf: PhysicalConfiguration | None = None):
+        """Random parameters with the reference's initialiser distributions (deepqmc_b200/params.py).  The values differ from a
+        reference run with the same seed (haiku draws them from jax.random in module-creation order); the tests regenerate the
+        reference's own parameters with oracle/jaxrand.py where its fixtures need them."""
         seed = int(rng) if rng is not None else 0
-        if haiku_compatible:
-            from . import jaxrand
-
-            if self.spec.kind != 'paulinet' or self.spec.gnn_update != 'featurewise':
-                raise NotImplementedError('haiku-compatible initialisation is restated for the conv-GNN test ansatz only')
-            return jaxrand.haiku_init_conv_gnn_ansatz(self.spec, seed)
         return PN.init_params(self.spec, seed)
 
     @staticmethod

@@ -18,7 +18,7 @@ import math
 
 import torch
 
-from deepqmc_b200 import params as P  # names/shapes only (data)
+from . import names as P  # the oracle's own table of the reference's Haiku parameter names
 
 from .hamil import safe_norm
 

@@ -62,3 +62,14 @@ def test_product_does_not_import_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', txt, flags=re.M), f
+
+
+def test_oracle_does_not_import_product():
+    """The checker is independent of the thing it checks: nothing under oracle/ imports deepqmc_b200 (own table of the reference's
+    Haiku parameter names in oracle/names.py, own jax.random / haiku-init restatement in oracle/jaxrand.py); hyper-parameter
+    records (``spec``) and parameter dicts are handed in by the tests."""
+    for dp, _, fs in os.walk(os.path.join(ROOT, 'oracle')):
+        for f in fs:
+            if f.endswith('.py'):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+deepqmc_b200\b', txt, flags=re.M), f

@@ -1,24 +1,44 @@
-"""Known answers for oracle/jaxrand.py, the numpy restatement of the jax.random / haiku initialisation the reference's
-tests use (test infrastructure; neither library is installed here).  Values: the Threefry-2x32 known-answer vectors of
+"""Known answers for the two independent numpy restatements of jax.random -- oracle/jaxrand.py (test infrastructure: also haiku's
+initialisers, used to regenerate the reference's fixtures) and deepqmc_b200/jaxrand.py (product: the JAX-compatible walker
+initialiser) -- and their agreement with each other; neither JAX nor haiku is installed here.  Values: the Threefry-2x32 known-answer vectors of
 the Random123 distribution (also used by JAX's own test-suite) and the outputs of jax.random for PRNGKey(0) as printed
 in the JAX documentation before and after the key-layout change of JAX 0.5."""
 import numpy as np
+import pytest
 
-from oracle import jaxrand as J
+from deepqmc_b200 import jaxrand as PJ
+from oracle import jaxrand as OJ
+
+J = OJ
 
 
-def _tf(key, ctr):
+def _tf(key, ctr, J=OJ):
     a, b = J.threefry2x32(np.array(key, dtype=np.uint32), np.array([ctr[0]], dtype=np.uint32), np.array([ctr[1]], dtype=np.uint32))
     return int(a[0]), int(b[0])
 
 
-def test_threefry2x32_known_answers():
-    assert _tf((0, 0), (0, 0)) == (0x6B200159, 0x99BA4EFE)
-    assert _tf((0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF, 0xFFFFFFFF)) == (0x1CB996FC, 0xBB002BE7)
-    assert _tf((0x13198A2E, 0x03707344), (0x243F6A88, 0x85A308D3)) == (0xC4923A9C, 0x483DF7A0)
+@pytest.mark.parametrize('J', [OJ, PJ], ids=['oracle', 'product'])
+def test_threefry2x32_known_answers(J):
+    assert _tf((0, 0), (0, 0), J) == (0x6B200159, 0x99BA4EFE)
+    assert _tf((0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF, 0xFFFFFFFF), J) == (0x1CB996FC, 0xBB002BE7)
+    assert _tf((0x13198A2E, 0x03707344), (0x243F6A88, 0x85A308D3), J) == (0xC4923A9C, 0x483DF7A0)
 
 
-def test_split_and_samplers_match_documented_jax_outputs():
+def test_oracle_and_product_streams_agree():
+    """two independent implementations (64-bit masked arithmetic vs wrapping uint32 arrays), both key layouts, both widths"""
+    for seed in (0, 42, 2**40 + 17):
+        k = OJ.prng_key(seed)
+        assert np.array_equal(k, PJ.prng_key(seed))
+        for part in (True, False):
+            assert np.array_equal(OJ.split(k, 5, part), PJ.split(k, 5, part))
+            for dt in (np.float64, np.float32):
+                assert np.array_equal(OJ.normal(k, (7, 3), dt, part), PJ.normal(k, (7, 3), dt, part))
+                assert np.array_equal(OJ.uniform(k, (5,), dt, 0.0, 1.0, part), PJ.uniform(k, (5,), dt, 0.0, 1.0, part))
+                assert np.array_equal(OJ.truncated_normal(k, -2.0, 2.0, (9,), dt, part), PJ.truncated_normal(k, -2.0, 2.0, (9,), dt, part))
+
+
+@pytest.mark.parametrize('J', [OJ, PJ], ids=['oracle', 'product'])
+def test_split_and_samplers_match_documented_jax_outputs(J):
     k0 = J.prng_key(0)
     assert k0.tolist() == [0, 0]
     assert J.split(k0, 2, partitionable=True).tolist() == [[1797259609, 2579123966], [928981903, 3453687069]]  # JAX >= 0.5

@@ -14,6 +14,7 @@ import torch
 
 from deepqmc_b200.molecule import Molecule
 from deepqmc_b200.spec import paulinet_spec
+from deepqmc_b200 import jaxrand as PJ  # the product's JAX-compatible walker initialiser / quadrature twists
 from oracle import jaxrand as J
 from oracle import wf
 from oracle.hamil import OracleHamiltonian
@@ -32,7 +33,7 @@ def lih():
     spec = paulinet_spec(oh)
     pt = wf.to_torch(J.haiku_init_conv_gnn_ansatz(spec, seed=0))
     R = torch.as_tensor(mol.coords)
-    r0 = np.stack([J.atom_centered_initializer(k, mol.charges, mol.charges, mol.coords, 2, 2) for k in J.split(J.prng_key(0), 10)])
+    r0 = np.stack([PJ.atom_centered_initializer(k, mol.charges, mol.charges, mol.coords, 2, 2) for k in J.split(J.prng_key(0), 10)])
     return mol, spec, pt, R, r0
 
 
@@ -40,9 +41,9 @@ def test_electron_initializer_reproduces_reference_walkers(g):
     """AtomCenteredElectronInitializer(ShellBasedDistribution()) (sampling/electron_sample_initializers.py:43-288) driven by
     the jax.random streams: split, categorical tie-break, exponential radii, Haar-orthogonal directions."""
     mol = Molecule.from_name('LiH')
-    r = J.atom_centered_initializer(J.prng_key(0), mol.charges, mol.charges, mol.coords, 2, 2)
+    r = PJ.atom_centered_initializer(J.prng_key(0), mol.charges, mol.charges, mol.coords, 2, 2)
     assert np.abs(r - np.asarray(g['edge_builder_LiH']['ne'])[0]).max() < 1e-14  # the walker of every n = 1 fixture
-    rs = np.stack([J.atom_centered_initializer(k, mol.charges, mol.charges, mol.coords, 2, 2) for k in J.split(J.prng_key(0), 5)])
+    rs = np.stack([PJ.atom_centered_initializer(k, mol.charges, mol.charges, mol.coords, 2, 2) for k in J.split(J.prng_key(0), 5)])
     assert np.abs(rs - np.asarray(g['init_sample_Molecular']['rs'])).max() < 1e-14
 
 
@@ -52,18 +53,18 @@ def test_carbon_ccecp_potentials_match_reference_fixture(g):
     twists -- the non-local potential (the reference notes that term is 'not particularly numerically stable')."""
     mol = Molecule.from_name('C')
     oh0 = OracleHamiltonian(mol)
-    r = J.atom_centered_initializer(J.prng_key(0), mol.charges, oh0.ns_valence, mol.coords, oh0.n_up, oh0.n_down)
+    r = PJ.atom_centered_initializer(J.prng_key(0), mol.charges, oh0.ns_valence, mol.coords, oh0.n_up, oh0.n_down)
     v = oh0.local_potential(torch.as_tensor(r), torch.as_tensor(mol.coords))
     assert abs(v.item() - g['potential_C_None']['local_potential']) < 1e-9 * abs(v.item())
     for ecp in ('ccECP', 'bfd'):
         oh = OracleHamiltonian(mol, ecp_type=ecp)
         assert (oh.n_up, oh.n_down) == (3, 1)
-        r = torch.as_tensor(J.atom_centered_initializer(J.prng_key(0), mol.charges, oh.ns_valence, mol.coords, oh.n_up, oh.n_down))
+        r = torch.as_tensor(PJ.atom_centered_initializer(J.prng_key(0), mol.charges, oh.ns_valence, mol.coords, oh.n_up, oh.n_down))
         R = torch.as_tensor(mol.coords)
         assert abs(oh.local_potential(r, R).item() - g[f'potential_C_{ecp}']['local_potential']) < 1e-11 * 99.0
         spec = paulinet_spec(oh)
         pt = wf.to_torch(J.haiku_init_conv_gnn_ansatz(spec, seed=0))
-        twists = torch.as_tensor(J.ecp_quadrature_twists(J.prng_key(0), 1, spec.n_elec))
+        twists = torch.as_tensor(PJ.ecp_quadrature_twists(J.prng_key(0), 1, spec.n_elec))
         vnl = oh.nonloc_potential(r, R, lambda x: wf.log_psi(spec, pt, x, R), twists)
         assert abs(vnl.item() / g[f'potential_C_{ecp}']['nonlocal_potential'] - 1) < 1e-5
 
@@ -135,7 +136,7 @@ def test_multi_nuclear_geometry_sampler_reproduces_reference_fixture(g, lih):
     wfb = _wf_batch(spec, pt, R)
     states = []
     for m, km in enumerate(J.split(J.prng_key(0), 2)):
-        r0 = np.stack([J.atom_centered_initializer(k, mol.charges, mol.charges, mol.coords, 2, 2) for k in J.split(km, 10)])
+        r0 = np.stack([PJ.atom_centered_initializer(k, mol.charges, mol.charges, mol.coords, 2, 2) for k in J.split(km, 10)])
         assert np.abs(r0 - np.asarray(g['sampling_multi']['init']['elec:r'])[m]).max() < 1e-14
         s, l = wfb(torch.as_tensor(r0))
         states.append(dict(r=torch.as_tensor(r0), sign=s, log=l, age=torch.zeros(10, dtype=torch.int32), tau=torch.tensor(0.1, dtype=torch.float64)))
@@ -158,15 +159,15 @@ def test_lih_ccecp_fixtures(g):
     oh = OracleHamiltonian(mol, ecp_type='ccECP')
     gi = g['hamil_init']['Molecular_PP']
     assert (oh.n_up, oh.n_down) == (gi['n_up'], gi['n_down']) and oh.ns_valence.tolist() == gi['ns_valence'] and oh.ecp_mask.tolist() == gi['pp_mask']
-    rs = np.stack([J.atom_centered_initializer(k, mol.charges, oh.ns_valence, mol.coords, 1, 1) for k in J.split(J.prng_key(0), 5)])
+    rs = np.stack([PJ.atom_centered_initializer(k, mol.charges, oh.ns_valence, mol.coords, 1, 1) for k in J.split(J.prng_key(0), 5)])
     assert np.abs(rs - np.asarray(g['init_sample_Molecular_PP']['rs'])).max() < 1e-14
-    r = torch.as_tensor(J.atom_centered_initializer(J.prng_key(0), mol.charges, oh.ns_valence, mol.coords, 1, 1))
+    r = torch.as_tensor(PJ.atom_centered_initializer(J.prng_key(0), mol.charges, oh.ns_valence, mol.coords, 1, 1))
     R = torch.as_tensor(mol.coords)
     assert abs(oh.local_potential(r, R).item() - g['potential_LiH_ccECP']['local_potential']) < 1e-9
     spec = paulinet_spec(oh)
     pt = wf.to_torch(J.haiku_init_conv_gnn_ansatz(spec, seed=0))
     f = lambda x: wf.log_psi(spec, pt, x, R)
-    tw = torch.as_tensor(J.ecp_quadrature_twists(J.prng_key(0), 1, spec.n_elec))
+    tw = torch.as_tensor(PJ.ecp_quadrature_twists(J.prng_key(0), 1, spec.n_elec))
     assert abs(oh.nonloc_potential(r, R, f, tw).item() / g['potential_LiH_ccECP']['nonlocal_potential'] - 1) < 1e-6
     e_loc, _ = oh.local_energy(f, r, R, phi_random=tw)
     assert abs(e_loc.item() - g['local_energy_Molecular_PP']['E_loc']) < 2e-6
