@@ -35,6 +35,11 @@ WORKLOADS = {
     'n2_ferminet': dict(mol='N2', ecp=None, walkers=4096, hyper={}, kind='ferminet'),
     'benzene_psiformer': dict(mol='benzene', ecp='ccECP', walkers=4096, hyper={}, kind='psiformer'),
     'lih_paulinet': dict(mol='LiH', ecp=None, walkers=256, hyper={}, kind='paulinet'),  # BASELINE configs[0]
+    # the one step rate the reference publishes for this path: evaluation of the LiH Psiformer with 2048
+    # walkers, a step = DecorrSampler(30) Metropolis sub-steps + E_loc, 2.16 it/s on an RTX 3090
+    # (doc/examples/ground_state_lih.ipynb:227,238; sampling/electron_samplers.py:347-357)
+    'lih_eval_step': dict(mol='LiH', ecp=None, walkers=2048, hyper={}, kind='psiformer', mcmc_substeps=30,
+                          published_it_per_s=2.16),
     # BASELINE configs[4]: excited-state penalty run, 2 electronic states, 2048 walkers per state
     # (conf/task/train_excited_psiformer.yaml:25, conf/ansatz/transpsiformer.yaml, conf/hamil/mol/cyclobutadiene_square.yaml)
     'cyclobutadiene_transpsiformer': dict(mol='cyclobutadiene_square', ecp=None, walkers=2048, hyper={}, kind='transpsiformer',
@@ -105,12 +110,13 @@ class ClockSampler:
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from one
 # `ncu --set full` capture of the same command (profiles/, B200_PROFILING.md); None = not captured.
 TRAFFIC = {
-    # profiles/r01_ncu_full_fwd_kernels_v1.csv, launch 1: QKV row GEMM of one non-local-ECP forward chunk
-    # (518400 rows x K=256 -> N=768): dram read 0.5326 GB + write 1.5352 GB; algorithmic bytes of that launch
-    # = 518400 * (256 + 768) * 4 + weights 0.79 MB = 2.124 GB
-    'benzene_psiformer': {'bytes_per_launch': 2.0678e9, 'algorithmic_bytes_per_launch': 2.1241e9,
-                          'launch': 'QKV GEMM, 518400 rows x 256 -> 768 (8 walkers x 2160 quadrature forwards x 30 electrons)',
-                          'source': 'profiles/r01_ncu_full_fwd_kernels_v1.csv'},
+    # profiles/r02_ncu_trunk_f16_kernel.csv (ncu --set full of tools/prof_fwd.py 2 17760): one whole-trunk launch over
+    # 17760 plain-forward walkers x 30 electrons = 532800 rows: dram read 0.690 GB + write 3.074 GB.  Algorithmic bytes of
+    # that launch = rows x 256 x 4 B in + the same out + 6.3 MB of weights = 1.097 GB: the extra 2.5 GB of writes are
+    # evictions of the per-CTA Q/K/V operand scratch (57 MB, re-written every tile and layer) from L2.
+    'benzene_psiformer': {'bytes_per_launch': 3.7636e9, 'algorithmic_bytes_per_launch': 1.0975e9,
+                          'launch': 'trunk_f16_kernel, 532800 rows (17760 quadrature-forward walkers x 30 electrons), 4 layers',
+                          'source': 'profiles/r02_ncu_trunk_f16_kernel.csv'},
 }
 
 _ORACLE = {}
@@ -308,8 +314,21 @@ def main():
     loc_ene = hamil.local_energy(ansatz.apply)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    n_sub = wl.get('mcmc_substeps', 0)
+    smp_state = None
+    if n_sub:  # evaluation step: the walkers are decorrelated by n_sub Metropolis sub-steps before every E_loc (one state)
+        sign0, log0 = eng.wf_forward(r, R)
+        smp_state = dict(r=r.clone(), sign=sign0, log=log0, age=torch.zeros(B, dtype=torch.int32, device=dev),
+                         tau=torch.tensor([0.5], dtype=tdt, device=dev))
+
     def step(seed, pcs_=None):
         pcs_ = pcs_ or pcs
+        if n_sub:
+            if pcs_ is not pcs:  # e2e leg: host walkers -> sampler state (psi re-evaluated), as a restart from a checkpoint would
+                smp_state['r'].copy_(pcs_[0].r)
+                smp_state['sign'], smp_state['log'] = eng.wf_forward(smp_state['r'], R)
+            eng.mcmc_sweep(smp_state, R, n_sub, seed=parallel.rank_seed(11), step0=n_sub * (1000 + seed), walker_offset=rank * B)
+            pcs_ = [PhysicalConfiguration(R, smp_state['r'], torch.zeros(B, device=dev))]
         Es, sts = [], []
         for st in range(n_states):
             E, stt = loc_ene(seed, params_all[st], pcs_[st])
@@ -390,19 +409,35 @@ def main():
         for s in range(n_prof):
             for st in range(n_states):
                 loc_ene(s, params_all[st], pcs[st])  # rank-local: no collective here (the other ranks are already done)
-        gemm_ms, gemm_flops, n_gemm = eng.profile_end()
+        cls = eng.profile_end_classes()  # {class: (ms, algorithmic flops, launches)} of the tensor-core kernels, timed live
+        gemm_ms = sum(v[0] for v in cls.values())
+        n_gemm = sum(v[2] for v in cls.values())
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
         peak = peaks.get('bf16_tflops_sustained', 1590.0 * 0.88)
-        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-        roof = {'bound': 'tensor', 'kernel': 'dense-layer row GEMM (' + ('tcgen05 3xTF32 gemm3xtf32_kernel' if backend else 'CUDA-core gemm_kernel') + ')', 'achieved': achieved,
+        dom = max(cls, key=lambda k: cls[k][0])  # the class the step spends most time in
+        dms, dfl, dn = cls[dom]
+        achieved = dfl / (dms * 1e-3) / 1e12 if dms > 0 else 0.0
+        names = {'row_gemm': 'dense-layer row GEMM (' + ('tc::gemm3xtf32_kernel, tcgen05 3xTF32' if backend else 'CUDA-core gemm_kernel') + ')',
+                 'mlp_block': 'fused MLP block (tc::mlp_block_f16_kernel, tcgen05 3xFP16)',
+                 'trunk': 'whole-trunk kernel (tc::trunk_f16_kernel: all layers, dense GEMMs + attention, tcgen05 3xFP16, '
+                          'one persistent launch per forward chunk)'}
+        traffic = TRAFFIC.get(a.workload) if dom == 'trunk' else None
+        step_ms = total_ms / a.steps
+        roof = {'bound': 'tensor', 'kernel': names[dom], 'achieved': achieved,
                 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback',
-                'traffic': (TRAFFIC.get(a.workload) or {}).get('bytes_per_launch'), 'traffic_detail': TRAFFIC.get(a.workload),
-                'gemm_share_of_step': (gemm_ms / n_prof) / (total_ms / a.steps),
+                'scheme_ceiling_frac': 1.0 / 3.0,  # fp32-class accuracy = 3 half-precision products per multiply-add
+                'traffic': (traffic or {}).get('bytes_per_launch'), 'traffic_detail': traffic,
+                'kernel_share_of_step': (dms / n_prof) / step_ms,
+                'kernel_launches_per_step': dn // n_prof,
+                'classes': {k: {'ms_per_step': v[0] / n_prof, 'share_of_step': (v[0] / n_prof) / step_ms,
+                                'tflops': (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else None), 'launches_per_step': v[2] // n_prof}
+                            for k, v in cls.items()},
+                'gemm_share_of_step': (gemm_ms / n_prof) / step_ms,
                 'gemm_launches_per_step': n_gemm // n_prof,
                 'algorithmic_flops_per_eloc': algorithmic_flops_per_eloc(N, M, n_ecp=n_ecp) if wl['kind'] == 'psiformer' else None,
                 'whole_step_tflops': (algorithmic_flops_per_eloc(N, M, n_ecp=n_ecp) * B * a.steps / (total_ms / 1e3) / 1e12
@@ -429,13 +464,19 @@ def main():
         'config': {'workload': workload_name, 'global_batch': B * world, 'walkers_per_gpu': B, 'electronic_states': n_states,
                    'parallelism': f'walker-shard x{world}',
                    'l2': 'flushed between timed iterations (256 MiB memset) and activations >> L2',
-                   'step': 'E_loc of all walkers (+ fused stats all-reduce for N>1)',
-                   'gemm_backend': 'tcgen05-3xTF32' if backend else 'cuda-core'},
+                   'step': (f'{n_sub} Metropolis sub-steps (all-electron proposals, in-kernel Philox) + ' if n_sub else '')
+                           + 'E_loc of all walkers (+ fused stats all-reduce for N>1)',
+                   'gemm_backend': 'tcgen05 (3xFP16 whole-trunk kernel for plain forwards, 3xTF32 row GEMMs for the forward-Laplacian rows)' if backend else 'cuda-core'},
         'clocks': clk, 'e2e': {'value': e2e_val, 'unit': unit, 'h2d_bytes_per_step': (n_states * B * N * 3 + M * 3) * esz,
                                'd2h_bytes_per_step': n_states * B * esz, 'steps': e2e_steps},
         'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu,
         'energy_mean': float(stats['energy/mean']), 'wall_s_timed_region': t_wall,
     }
+    if n_sub:  # the reference's published proxy is a step RATE (it/s, other hardware: RTX 3090)
+        out['it_per_s'] = 1e3 / (total_ms / a.steps)
+        out['published_reference'] = {'it_per_s': wl['published_it_per_s'], 'hardware': '1x RTX 3090 (JAX, fp32)',
+                                      'source': 'doc/examples/ground_state_lih.ipynb:227,238 (BASELINE.md 1)'}
+        out['vs_baseline'] = out['it_per_s'] / wl['published_it_per_s']
     print(json.dumps(out))
     return 0
 

@@ -21,6 +21,7 @@ SYMBOLS = [
     'dqmc_profile_begin', 'dqmc_profile_end', 'dqmc_debug_gemm', 'dqmc_wf_vjp_params', 'dqmc_langevin_sweep',
     'dqmc_set_pseudo_hamiltonian', 'dqmc_wf_orbitals', 'dqmc_mcmc_sweep_exchange',
     'dqmc_workspace_bytes_min', 'dqmc_debug_plan', 'dqmc_stats_pack', 'dqmc_debug_mlp_block', 'dqmc_debug_trunk',
+    'dqmc_profile_end_classes',
 ]
 
 
@@ -97,5 +98,6 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dqmc_profile_begin.argtypes = [vp]
     lib.dqmc_debug_gemm.argtypes = [vp, C.c_char_p, C.c_char_p, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.dqmc_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
+    lib.dqmc_profile_end_classes.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
     _cache[path] = lib
     return lib

@@ -53,8 +53,18 @@ struct EngineBase {
   bool prof = false;
   double prof_flops = 0;
   int64_t prof_n = 0;
+  // per kernel class: 0 row GEMM (one dense layer per launch), 1 fused MLP block, 2 whole trunk (all layers in one launch)
+  double prof_cls_flops[3] = {0, 0, 0};
+  int64_t prof_cls_n[3] = {0, 0, 0};
+  std::vector<int> prof_cls;
 #ifndef DQMC_EMU
   std::vector<cudaEvent_t> prof_ev;
+  void prof_note(cudaEvent_t e0, cudaEvent_t e1, double flops, int cls) {
+    prof_ev.push_back(e0); prof_ev.push_back(e1);
+    prof_cls.push_back(cls);
+    prof_flops += flops; prof_cls_flops[cls] += flops;
+    ++prof_n; ++prof_cls_n[cls];
+  }
 #endif
   virtual ~EngineBase() {}
   virtual int set_params(const double* host, int64_t n, cudaStream_t st) = 0;
@@ -890,9 +900,7 @@ struct Engine : EngineBase {
 #ifndef DQMC_EMU
         if (prof) {
           cudaEventRecord(e1, st);
-          prof_ev.push_back(e0); prof_ev.push_back(e1);
-          prof_flops += 2.0 * (double)Mr * (sliced ? Nel : 1) * (double)Nc * (double)Kc;
-          ++prof_n;
+          prof_note(e0, e1, 2.0 * (double)Mr * (sliced ? Nel : 1) * (double)Nc * (double)Kc, 0);
         }
 #endif
         return 0;
@@ -914,9 +922,7 @@ struct Engine : EngineBase {
 #ifndef DQMC_EMU
     if (prof) {
       cudaEventRecord(e1, st);
-      prof_ev.push_back(e0); prof_ev.push_back(e1);
-      prof_flops += 2.0 * (double)Mr * (sliced ? Nel : 1) * (double)Nc * (double)Kc;
-      ++prof_n;
+      prof_note(e0, e1, 2.0 * (double)Mr * (sliced ? Nel : 1) * (double)Nc * (double)Kc, 0);
     }
 #endif
     return 0;
@@ -958,9 +964,7 @@ struct Engine : EngineBase {
 #ifndef DQMC_EMU
       if (prof) {
         cudaEventRecord(e1, st);
-        prof_ev.push_back(e0); prof_ev.push_back(e1);
-        prof_flops += 3 * 2.0 * (double)rows * (double)d * (double)d;
-        ++prof_n;
+        prof_note(e0, e1, 3 * 2.0 * (double)rows * (double)d * (double)d, 1);
       }
 #endif
       return 0;
@@ -1009,6 +1013,8 @@ struct Engine : EngineBase {
       while (np2 < N) np2 *= 2;  // walker slot of the tile: electrons rounded up to a power of two (<= 32)
       p.walkers = rows / N; p.N = N; p.NP = np2; p.L = cfg.n_layers; p.a_scale = kActScale;
       p.attn_scale = (float)(1.0 / std::sqrt((double)dh)); p.err_flag = nullptr; p.trace = d_trunk_trace;
+      p.ablate = 0;
+      if (const char* ev = std::getenv("DQMC_TRUNK_ABLATE")) p.ablate = std::atoi(ev);
       for (int l = 0; l < cfg.n_layers; ++l) {
         const std::string pfx = "L" + std::to_string(l) + ".";
         p.b1[l] = P(pfx + "b1"); p.b2[l] = P(pfx + "b2");
@@ -1025,10 +1031,8 @@ struct Engine : EngineBase {
 #ifndef DQMC_EMU
       if (prof) {
         cudaEventRecord(e1, st);
-        prof_ev.push_back(e0); prof_ev.push_back(e1);
-        // dense layers 12 d^2 and attention 4 N d (scores + weighted sum) multiply-adds per row and layer
-        prof_flops += (double)cfg.n_layers * 2.0 * (double)rows * (6.0 * d * d + 2.0 * N * d);
-        ++prof_n;
+        // dense layers 12 d^2 and attention 4 N d (scores + weighted sum) flops per row and layer
+        prof_note(e0, e1, (double)cfg.n_layers * 2.0 * (double)rows * (6.0 * d * d + 2.0 * N * d), 2);
       }
 #endif
       return 0;
@@ -2466,25 +2470,40 @@ int dqmc_debug_trunk(dqmc_handle h, const void* X0, void* Out, int32_t rows, voi
 int dqmc_profile_begin(dqmc_handle h) {
   if (!h) return 2;
   h->e->prof = true; h->e->prof_flops = 0; h->e->prof_n = 0;
+  for (int c = 0; c < 3; ++c) { h->e->prof_cls_flops[c] = 0; h->e->prof_cls_n[c] = 0; }
+  h->e->prof_cls.clear();
   return 0;
 }
-int dqmc_profile_end(dqmc_handle h, double* gemm_ms, double* gemm_flops, int64_t* n_gemm) {
+int dqmc_profile_end_classes(dqmc_handle h, double* ms3, double* flops3, int64_t* n3) {
   if (!h) return 2;
-  double ms = 0;
+  double ms[3] = {0, 0, 0};
 #ifndef DQMC_EMU
   for (size_t i = 0; i + 1 < h->e->prof_ev.size(); i += 2) {
     cudaEventSynchronize(h->e->prof_ev[i + 1]);
     float t = 0;
     cudaEventElapsedTime(&t, h->e->prof_ev[i], h->e->prof_ev[i + 1]);
-    ms += t;
+    ms[h->e->prof_cls[i / 2]] += t;
     cudaEventDestroy(h->e->prof_ev[i]); cudaEventDestroy(h->e->prof_ev[i + 1]);
   }
   h->e->prof_ev.clear();
 #endif
+  h->e->prof_cls.clear();
   h->e->prof = false;
-  if (gemm_ms) *gemm_ms = ms;
-  if (gemm_flops) *gemm_flops = h->e->prof_flops;
-  if (n_gemm) *n_gemm = h->e->prof_n;
+  for (int c = 0; c < 3; ++c) {
+    if (ms3) ms3[c] = ms[c];
+    if (flops3) flops3[c] = h->e->prof_cls_flops[c];
+    if (n3) n3[c] = h->e->prof_cls_n[c];
+  }
+  return 0;
+}
+int dqmc_profile_end(dqmc_handle h, double* gemm_ms, double* gemm_flops, int64_t* n_gemm) {
+  double ms[3], fl[3];
+  int64_t n[3];
+  const int rc = dqmc_profile_end_classes(h, ms, fl, n);
+  if (rc) return rc;
+  if (gemm_ms) *gemm_ms = ms[0] + ms[1] + ms[2];
+  if (gemm_flops) *gemm_flops = fl[0] + fl[1] + fl[2];
+  if (n_gemm) *n_gemm = n[0] + n[1] + n[2];
   return 0;
 }
 

@@ -64,6 +64,8 @@ struct TrunkParams {
   float attn_scale;              // 1 / sqrt(dh)
   int* err_flag;
   long long* trace;              // development aid (DQMC_TRUNK_TRACE): clock64 stamps of block 0, one steady-state tile, layer 1
+  int ablate;                    // development aid (DQMC_TRUNK_ABLATE, results are garbage): 1 no weight loads, 2 no MMAs,
+                                 // 4 no Q/K/V image stores, 8 no image loads
 };
 
 struct TrSmem {
@@ -187,8 +189,12 @@ trunk_f16_kernel(TrunkParams p) {
       auto weight_slot = [&](const CUtensorMap* map, int x, int y) {
         const int s = it % kTrSlots;
         mbar_wait(&wempty[s], ((it / kTrSlots) & 1) ^ 1, p.err_flag);
-        mbar_expect_tx(&wfull[s], 16384u);
-        tma_load_2d(map, &wfull[s], smem + TrSmem::wring(s), x, y);
+        if (p.ablate & 1) {
+          mbar_arrive(&wfull[s]);
+        } else {
+          mbar_expect_tx(&wfull[s], 16384u);
+          tma_load_2d(map, &wfull[s], smem + TrSmem::wring(s), x, y);
+        }
         ++it;
       };
       for (int tile = blockIdx.x; tile < MT; tile += gridDim.x)
@@ -203,11 +209,19 @@ trunk_f16_kernel(TrunkParams p) {
           for (int h = 0; h < 4; ++h) {
             const unsigned char* img = scratch + (size_t)h * kTrHeadImage;
             if (h > 0) { mbar_wait(qk_free, n_qkf & 1, p.err_flag); ++n_qkf; }
-            mbar_expect_tx(qk_full, 65536u);
-            bulk_load(smem + TrSmem::wring(0), img, 65536u, qk_full);
+            if (p.ablate & 8) {
+              mbar_arrive(qk_full);
+            } else {
+              mbar_expect_tx(qk_full, 65536u);
+              bulk_load(smem + TrSmem::wring(0), img, 65536u, qk_full);
+            }
             if (h > 0) { mbar_wait(v_free, n_vf & 1, p.err_flag); ++n_vf; }
-            mbar_expect_tx(v_full, 32768u);
-            bulk_load(smem + TrSmem::wring(4), img + 65536, 32768u, v_full);
+            if (p.ablate & 8) {
+              mbar_arrive(v_full);
+            } else {
+              mbar_expect_tx(v_full, 32768u);
+              bulk_load(smem + TrSmem::wring(4), img + 65536, 32768u, v_full);
+            }
           }
           // ... and back: slots 0-3 once the last S is done, slots 4-5 once the last P V is done (ring position is 0 here).
           // Wo, W1, W2: output halves [0, 128) and [128, 256) one after the other (the epilogue of a half overlaps the MMAs
@@ -225,6 +239,7 @@ trunk_f16_kernel(TrunkParams p) {
   } else if (warp == 9) {
     // ===================== MMA issuer ============================================================================
     const uint32_t idesc64 = make_idesc_f16(128, 64), idesc128 = make_idesc_f16(128, 128);
+    const bool mma_on = !(p.ablate & 2);
     uint32_t it = 0, n_af = 0, n_of = 0, n_free0 = 0, n_free1 = 0, n_qk = 0, n_v = 0, n_p = 0, n_ofr0 = 0, n_ofr1 = 0;
     for (int tile = blockIdx.x; tile < MT; tile += gridDim.x)
       for (int l = 0; l < L; ++l) {
@@ -257,6 +272,7 @@ trunk_f16_kernel(TrunkParams p) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   const uint32_t ko = k * 32;
+                  if (!mma_on) continue;
                   if (plane == 0) {
                     umma_f16(d_tmem, make_desc(al + ko), make_desc(w + ko), idesc128, (kb | k) ? 1u : 0u);
                     umma_f16(d_tmem, make_desc(ah + ko), make_desc(w + ko), idesc128, 1u);
@@ -285,6 +301,7 @@ trunk_f16_kernel(TrunkParams p) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint32_t ko = k * 256;  // unswizzled images: a k-step of 16 halves = 2 chunks of 128 bytes
+              if (!mma_on) continue;
               umma_f16(tmem_base + 256u, make_desc_ns(ql + ko), make_desc_ns(kh + ko), idesc128, k ? 1u : 0u);
               umma_f16(tmem_base + 256u, make_desc_ns(qh + ko), make_desc_ns(kh + ko), idesc128, 1u);
               umma_f16(tmem_base + 256u, make_desc_ns(qh + ko), make_desc_ns(kl + ko), idesc128, 1u);
@@ -307,6 +324,7 @@ trunk_f16_kernel(TrunkParams p) {
             for (int k = 0; k < 8; ++k) {  // 16 keys per step; k-block of 64 keys = 8 KB of the image plane
               const uint32_t bo = (uint32_t)(k >> 2) * 8192u + (uint32_t)(k & 3) * 32u;
               const uint32_t a_hi = tmem_base + 256u + 8u * (uint32_t)k, a_lo = a_hi + 64u;
+              if (!mma_on) continue;
               umma_f16_ts(d_o, a_lo, make_desc(vh + bo), idesc64, k ? 1u : 0u);
               umma_f16_ts(d_o, a_hi, make_desc(vh + bo), idesc64, 1u);
               umma_f16_ts(d_o, a_hi, make_desc(vl + bo), idesc64, 1u);
@@ -349,6 +367,7 @@ trunk_f16_kernel(TrunkParams p) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
                     const uint32_t ko = k * 32;
+                    if (!mma_on) continue;
                     if (plane == 0) {
                       umma_f16(d_tmem, make_desc(al + ko), make_desc(w + ko), idesc128, (kb | k) ? 1u : 0u);
                       umma_f16(d_tmem, make_desc(ah + ko), make_desc(w + ko), idesc128, 1u);
@@ -421,9 +440,12 @@ trunk_f16_kernel(TrunkParams p) {
           float x[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v0[i]) * sc;
+          const bool img_on = !(p.ablate & 4);
+          if (!img_on) {} else
           if (j < 4) image_store32(img, trow, 0, x); else image_store_vt32(img, trow, 0, x);
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v1[i]) * sc;
+          if (!img_on) {} else
           if (j < 4) image_store32(img, trow, 32, x); else image_store_vt32(img, trow, 32, x);
           TR_STAMP(2 + 2 * j);
         }

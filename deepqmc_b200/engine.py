@@ -702,6 +702,14 @@ class Engine:
         self.lib.dqmc_profile_end(self.h, C.byref(ms), C.byref(fl), C.byref(n))
         return ms.value, fl.value, n.value
 
+    PROFILE_CLASSES = ('row_gemm', 'mlp_block', 'trunk')
+
+    def profile_end_classes(self):
+        """{class: (ms, algorithmic flops, launches)} for the three tensor-core kernel classes."""
+        ms, fl, n = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_int64 * 3)()
+        self.lib.dqmc_profile_end_classes(self.h, ms, fl, n)
+        return {k: (ms[i], fl[i], n[i]) for i, k in enumerate(self.PROFILE_CLASSES)}
+
     @property
     def launch_count(self):
         return self.lib.dqmc_launch_count(self.h)

@@ -246,6 +246,9 @@ int dqmc_debug_trunk(dqmc_handle h, const void* X0, void* Out, int32_t rows, voi
  * (the reference ships no profiler hooks). */
 int dqmc_profile_begin(dqmc_handle h);
 int dqmc_profile_end(dqmc_handle h, double* gemm_ms, double* gemm_flops, int64_t* n_gemm);
+/* Same, split by kernel class (arrays of 3): [0] row GEMM (one dense layer per launch), [1] fused MLP block,
+ * [2] whole-trunk kernel (all layers incl. attention in one launch). */
+int dqmc_profile_end_classes(dqmc_handle h, double* ms3, double* flops3, int64_t* n3);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,9 @@ KEEP = ['ID', 'Kernel Name', 'Grid Size', 'Block Size', 'gpu__time_duration.sum'
         'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
         'lts__t_sector_hit_rate.pct', 'l1tex__m_xbar2l1tex_read_bytes.sum', 'l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__memory_throughput.avg.pct_of_peak_sustained_elapsed',
-        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+        'TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'sm__cycles_elapsed.max',
+        'lts__t_sectors_srcunit_tex_op_read.sum', 'lts__t_sectors_srcunit_tex_op_write.sum', 'l1tex__m_xbar2l1tex_read_bytes.sum.per_second', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'smsp__inst_executed.sum', 'sm__cycles_active.avg', 'launch__registers_per_thread', 'launch__occupancy_limit_registers',
         'launch__occupancy_limit_shared_mem', 'launch__waves_per_multiprocessor',
