@@ -347,6 +347,7 @@ struct Engine : EngineBase {
     CUtensorMap m16h_128, m16l_128; bool f16_128 = false;  // 128-row boxes: weight slots of the whole-trunk kernel (trunk_tc.cuh)
   };
   bool fuse_trunk = true;  // all layers of a plain forward in one persistent launch (trunk_tc.cuh); DQMC_TC_TRUNK=0 disables
+  bool trunk_ts = true;    // ... with the A operand of its dense GEMMs in tensor memory (DQMC_TC_TRUNK_TS=0: shared memory)
   CUtensorMap* d_trunk_maps = nullptr;       // [L][4][2]
   unsigned char* d_trunk_scratch = nullptr;  // n_sms x 384 KB Q / K / V planes
   long long* d_trunk_trace = nullptr;        // DQMC_TRUNK_TRACE: 64 clock stamps of one tile (development aid)
@@ -537,7 +538,8 @@ struct Engine : EngineBase {
       DQ_CHECK(raise_dyn_smem((tc::gemm3xtf32_kernel<false, false>), tc::SmemLayout::total(256)));
       DQ_CHECK(raise_dyn_smem((tc::gemm3xtf32_kernel<false, true>), tc::SmemLayout::total(256)));
       DQ_CHECK(raise_dyn_smem(tc::mlp_block_f16_kernel, tc::MlpSmem::total()));
-      DQ_CHECK(raise_dyn_smem(tc::trunk_f16_kernel, tc::TrSmem::total()));
+      DQ_CHECK(raise_dyn_smem(tc::trunk_f16_kernel<false>, tc::TrSmem::total()));
+      DQ_CHECK(raise_dyn_smem(tc::trunk_f16_kernel<true>, tc::TrSmem::total()));
 #ifndef DQMC_EMU
       DQ_CHECK(raise_dyn_smem((tc::gemm3xtf32_kernel<true, false>), tc::SmemLayoutT<true>::total(256)));
       gemm_2cta = std::getenv("DQMC_GEMM_2CTA") != nullptr;
@@ -545,6 +547,7 @@ struct Engine : EngineBase {
       if (const char* ev = std::getenv("DQMC_TC_F16")) f16_on = std::atoi(ev) != 0;
       if (const char* ev = std::getenv("DQMC_TC_FUSE_MLP")) fuse_mlp = std::atoi(ev) != 0;
       if (const char* ev = std::getenv("DQMC_TC_TRUNK")) fuse_trunk = std::atoi(ev) != 0;
+      if (const char* ev = std::getenv("DQMC_TC_TRUNK_TS")) trunk_ts = std::atoi(ev) != 0;
       if (psif && !trans && d == 256 && H == 4 && N <= 32 && cfg.n_layers <= tc::kTrMaxLayers) {
         DQ_CHECK(cudaMalloc((void**)&d_trunk_maps, sizeof(CUtensorMap) * 8 * cfg.n_layers));
         DQ_CHECK(cudaMalloc((void**)&d_trunk_scratch, (size_t)n_sms * tc::kTrScratchPerCta));
@@ -1027,7 +1030,9 @@ struct Engine : EngineBase {
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       if (prof) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
 #endif
-      DQ_LAUNCH(tc::trunk_f16_kernel, dim3(grid), dim3(tc::kTrThreads), tc::TrSmem::total(), st, p);
+      // DQMC_TC_TRUNK_TS=0: A operand of the dense GEMMs from shared memory (SS form) instead of tensor memory
+      if (trunk_ts) DQ_LAUNCH(tc::trunk_f16_kernel<true>, dim3(grid), dim3(tc::kTrThreads), tc::TrSmem::total(), st, p);
+      else DQ_LAUNCH(tc::trunk_f16_kernel<false>, dim3(grid), dim3(tc::kTrThreads), tc::TrSmem::total(), st, p);
 #ifndef DQMC_EMU
       if (prof) {
         cudaEventRecord(e1, st);

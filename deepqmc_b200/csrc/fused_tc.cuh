@@ -132,7 +132,7 @@ mlp_block_f16_kernel(const __grid_constant__ CUtensorMap wo_hi, const __grid_con
 
   if (warp == 8) {
     // ===================== weight planes: Wo, W1, W2 of every tile, k-block by k-block, hi then lo ==========
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < MT; tile += gridDim.x) {
         for (int g = 0; g < 3; ++g) {
@@ -169,7 +169,7 @@ mlp_block_f16_kernel(const __grid_constant__ CUtensorMap wo_hi, const __grid_con
             const uint32_t ph = (it / kMlpStages) & 1;
             mbar_wait(&wfull[s], ph, p.err_flag);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
               const uint32_t w = smem_u32(smem + MlpSmem::wring(s));
 #pragma unroll
               for (int k = 0; k < 4; ++k) {

@@ -233,7 +233,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
     }
   } else if (warp == 8) {
     // ===================== W producer: TMA of the pre-split weight tiles ====================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0;
       const uint32_t full_w_leader = TWO ? mapa_u32(full_w, 0) : 0u;
       for (int tile = tile0; tile < n_tiles; tile += tstep) {
@@ -276,7 +276,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_hi0, const __grid_cons
         mbar_wait(&full_a[s], ph, p.err_flag);
         mbar_wait(&full_w[s], ph, p.err_flag);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t ah = smem_u32(smem + SmemLayout::a_hi(s, BN)), al = smem_u32(smem + SmemLayout::a_lo(s, BN));
           const uint32_t wh = smem_u32(smem + SmemLayout::w_hi(s, BN)), wl = smem_u32(smem + SmemLayout::w_lo(s, BN));
 #pragma unroll

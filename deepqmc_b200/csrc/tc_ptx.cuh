@@ -31,6 +31,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // Bounded wait: a protocol bug must not hang the GPU box -> flag + trap after ~2 s.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
   uint32_t done = 0;
+  asm volatile(  // fast path: no clock read when the phase has completed already (the common case on the MMA issue path)
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  if (done) return;
   const long long t0 = clock64();
   while (true) {
     asm volatile(
@@ -46,6 +54,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
       __trap();
     }
   }
+}
+// One elected lane of a fully converged warp (elect.sync).  The MMA / TMA issue code sits under `if (elect_one())`: the
+// compiler then knows that exactly one thread runs it and feeds the uniform-datapath instructions (UTCHMMA, UTMALDG, UTCBAR)
+// from uniform registers directly; under `if (lane == 0)` it wraps every one of them in an ELECT / R2UR.BROADCAST / BRA.U.ANY
+// loop (~20 instructions per MMA: the issue rate, not the tensor pipe, then bounds the kernel).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

@@ -133,6 +133,35 @@ __device__ __forceinline__ void store_operand_packed(unsigned char* smem, int ro
   }
 }
 
+// ---- TS variant: the A operand of the dense GEMMs lives in TENSOR MEMORY (columns [0, 128) hi halves, [128, 256) lo halves,
+// two K values per 32-bit cell), the residual stream moves to the shared memory the operand buffer occupied.  An M = 128,
+// N = 128, K = 16 kind::f16 instruction with both operands in shared memory fetches 8 KB per instruction; measured on the SS
+// kernel it retires one such instruction per 128 clocks (the tensor pipe itself needs 64: ncu shows it 50 % active while the
+// MMAs run back to back), i.e. operand fetch at ~64 B / clock bounds it.  With A in tensor memory only the weight slice (4 KB)
+// comes from shared memory.
+// residual rows in shared memory: [128 rows][256 fp32], 16-byte chunk q of row r at r 1024 + ((q & ~7) | ((q ^ r) & 7)) 16:
+// a warp (lane = row) reading the same logical chunk of 32 consecutive rows is conflict-free (8 lanes of a phase -> 8 bank groups)
+__device__ __forceinline__ float4* resid_chunk(unsigned char* smem, int row, int q) {
+  return (float4*)(smem + row * 1024 + (((q & ~7) | ((q ^ row) & 7)) << 4));
+}
+__device__ __forceinline__ void resid_load32(unsigned char* smem, int row, int c0, float* x) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 v = *resid_chunk(smem, row, (c0 >> 2) + i);
+    x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void resid_store32(unsigned char* smem, int row, int c0, const float* x) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) *resid_chunk(smem, row, (c0 >> 2) + i) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+}
+// 32 packed words (16 hi pairs, 16 lo pairs of columns c0 .. c0 + 31) -> operand cells of this thread's TMEM lane
+__device__ __forceinline__ void store_operand_tmem(uint32_t tlane_base, int c0, const uint32_t* v) {
+  tmem_st16(tlane_base + (uint32_t)(c0 >> 1), v);
+  tmem_st16(tlane_base + 128u + (uint32_t)(c0 >> 1), v + 16);
+}
+
+template <bool TS>
 __global__ void __launch_bounds__(kTrThreads, 1)
 trunk_f16_kernel(TrunkParams p) {
   DQMC_TC_SMEM(smem);
@@ -184,7 +213,7 @@ trunk_f16_kernel(TrunkParams p) {
 
   if (warp == 8) {
     // ===================== weight slots in issue order + the attention operand images ===========================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t it = 0, n_scr = 0, n_qkf = 0, n_vf = 0;
       auto weight_slot = [&](const CUtensorMap* map, int x, int y) {
         const int s = it % kTrSlots;
@@ -237,9 +266,48 @@ trunk_f16_kernel(TrunkParams p) {
         }
     }
   } else if (warp == 9) {
-    // ===================== MMA issuer ============================================================================
+    // ===================== MMA issuer: ONE elected thread runs the whole loop (waits included) =====================
+    if (elect_one()) {
     const uint32_t idesc64 = make_idesc_f16(128, 64), idesc128 = make_idesc_f16(128, 128);
     const bool mma_on = !(p.ablate & 2);
+    // one k-block (64 K values) of a dense GEMM: ring slots it (hi plane of W^T) and it + 1 (lo plane) -> 12 instructions
+    // (A_lo W_hi + A_hi W_hi + A_hi W_lo per 16-wide k-step) issued after ONE pair of waits; the last k-block also commits the
+    // accumulator barrier
+    // tcgen05.commit costs ~150 clocks of tensor-pipe idle time per commit EVENT (tools/microbench/umma_rate.cu: 74.8 clocks per
+    // instruction without commits, 87.4 with one every 12 instructions, 99 with one every 6): one event per k-block (both ring
+    // slots + the accumulator barrier back to back).  Releasing the slots one k-block late (commit behind the NEXT k-block's
+    // instructions) was measured slower: the 3-k-block ring then starves the weight stream.
+    auto dense_kblock = [&](int kb, uint32_t d_tmem, uint32_t it0, uint64_t* accbar) {
+      const int s0 = it0 % kTrSlots, s1 = (it0 + 1) % kTrSlots;
+      mbar_wait(&wfull[s0], (it0 / kTrSlots) & 1, p.err_flag);
+      mbar_wait(&wfull[s1], ((it0 + 1) / kTrSlots) & 1, p.err_flag);
+      tc_fence_after();
+      {
+        const uint64_t whd = make_desc(smem_u32(smem + TrSmem::wring(s0))), wld = make_desc(smem_u32(smem + TrSmem::wring(s1)));
+        if (mma_on) {
+          if constexpr (TS) {
+            const uint32_t ta = tmem_base + (uint32_t)(kb * 32);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // a k-step = 32 bytes of the 128-byte swizzle row = +2 in the descriptor's address field
+              umma_f16_ts(d_tmem, ta + 128u + 8u * k, whd + 2u * k, idesc128, (kb | k) ? 1u : 0u);
+              umma_f16_ts(d_tmem, ta + 8u * k, whd + 2u * k, idesc128, 1u);
+              umma_f16_ts(d_tmem, ta + 8u * k, wld + 2u * k, idesc128, 1u);
+            }
+          } else {
+            const uint64_t ahd = make_desc(smem_u32(smem + TrSmem::abuf(kb, 0))), ald = make_desc(smem_u32(smem + TrSmem::abuf(kb, 1)));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_f16(d_tmem, ald + 2u * k, whd + 2u * k, idesc128, (kb | k) ? 1u : 0u);
+              umma_f16(d_tmem, ahd + 2u * k, whd + 2u * k, idesc128, 1u);
+              umma_f16(d_tmem, ahd + 2u * k, wld + 2u * k, idesc128, 1u);
+            }
+          }
+        }
+        umma_commit(&wempty[s0]);
+        umma_commit(&wempty[s1]);
+        if (kb == 3) umma_commit(accbar);
+      }
+    };
     uint32_t it = 0, n_af = 0, n_of = 0, n_free0 = 0, n_free1 = 0, n_qk = 0, n_v = 0, n_p = 0, n_ofr0 = 0, n_ofr1 = 0;
     for (int tile = blockIdx.x; tile < MT; tile += gridDim.x)
       for (int l = 0; l < L; ++l) {
@@ -262,29 +330,8 @@ trunk_f16_kernel(TrunkParams p) {
               if (kb == 3) ++n_af;
               tc_fence_after();
             }
-            const uint32_t ah = smem_u32(smem + TrSmem::abuf(kb, 0)), al = smem_u32(smem + TrSmem::abuf(kb, 1));
-            for (int plane = 0; plane < 2; ++plane, ++it) {
-              const int s = it % kTrSlots;
-              mbar_wait(&wfull[s], (it / kTrSlots) & 1, p.err_flag);
-              tc_fence_after();
-              if (lane == 0) {
-                const uint32_t w = smem_u32(smem + TrSmem::wring(s));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint32_t ko = k * 32;
-                  if (!mma_on) continue;
-                  if (plane == 0) {
-                    umma_f16(d_tmem, make_desc(al + ko), make_desc(w + ko), idesc128, (kb | k) ? 1u : 0u);
-                    umma_f16(d_tmem, make_desc(ah + ko), make_desc(w + ko), idesc128, 1u);
-                  } else {
-                    umma_f16(d_tmem, make_desc(ah + ko), make_desc(w + ko), idesc128, 1u);
-                  }
-                }
-                umma_commit(&wempty[s]);
-                if (kb == 3 && plane == 1) umma_commit(&accfull[b]);
-              }
-              __syncwarp();
-            }
+            dense_kblock(kb, d_tmem, it, &accfull[b]);
+            it += 2;
           }
         }
         // the last two drains (sub-chunks 4, 5) free both halves of the accumulator: it now hosts S / P / O
@@ -295,7 +342,7 @@ trunk_f16_kernel(TrunkParams p) {
           const int ob = h & 1;
           mbar_wait(qk_full, n_qk & 1, p.err_flag); ++n_qk;
           tc_fence_after();
-          if (lane == 0) {  // S = Q K^T -> TMEM [256, 384)
+          {  // S = Q K^T -> TMEM [256, 384)
             const uint32_t qh = smem_u32(smem + TrSmem::wring(0)), ql = smem_u32(smem + TrSmem::wring(1));
             const uint32_t kh = smem_u32(smem + TrSmem::wring(2)), kl = smem_u32(smem + TrSmem::wring(3));
 #pragma unroll
@@ -309,7 +356,6 @@ trunk_f16_kernel(TrunkParams p) {
             umma_commit(s_full);
             umma_commit(qk_free);
           }
-          __syncwarp();
           mbar_wait(p_full, n_p & 1, p.err_flag); ++n_p;
           mbar_wait(v_full, n_v & 1, p.err_flag); ++n_v;
           if (h >= 2) {  // the O buffer of head h - 2 has been read
@@ -317,7 +363,7 @@ trunk_f16_kernel(TrunkParams p) {
             else { mbar_wait(&o_free[1], n_ofr1 & 1, p.err_flag); ++n_ofr1; }
           }
           tc_fence_after();
-          if (lane == 0) {  // O_h = P V_h: A = P from TMEM (hi columns [256, 320), lo [320, 384)), B = V_h^T image
+          {  // O_h = P V_h: A = P from TMEM (hi columns [256, 320), lo [320, 384)), B = V_h^T image
             const uint32_t d_o = tmem_base + 384u + 64u * (uint32_t)ob;
             const uint32_t vh = smem_u32(smem + TrSmem::wring(4)), vl = smem_u32(smem + TrSmem::wring(5));
 #pragma unroll
@@ -332,7 +378,6 @@ trunk_f16_kernel(TrunkParams p) {
             umma_commit(&o_full[ob]);
             umma_commit(v_free);
           }
-          __syncwarp();
         }
         // ---- Wo (operand = attention output), W1, W2: two N = 128 halves each -> accumulator halves 0, 1.  The workers of a
         // column half run its epilogue as soon as that half is complete, i.e. under the MMAs of the other half / next GEMM.
@@ -357,32 +402,12 @@ trunk_f16_kernel(TrunkParams p) {
                 }
                 tc_fence_after();
               }
-              const uint32_t ah = smem_u32(smem + TrSmem::abuf(kb, 0)), al = smem_u32(smem + TrSmem::abuf(kb, 1));
-              for (int plane = 0; plane < 2; ++plane, ++it) {
-                const int s = it % kTrSlots;
-                mbar_wait(&wfull[s], (it / kTrSlots) & 1, p.err_flag);
-                tc_fence_after();
-                if (lane == 0) {
-                  const uint32_t w = smem_u32(smem + TrSmem::wring(s));
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const uint32_t ko = k * 32;
-                    if (!mma_on) continue;
-                    if (plane == 0) {
-                      umma_f16(d_tmem, make_desc(al + ko), make_desc(w + ko), idesc128, (kb | k) ? 1u : 0u);
-                      umma_f16(d_tmem, make_desc(ah + ko), make_desc(w + ko), idesc128, 1u);
-                    } else {
-                      umma_f16(d_tmem, make_desc(ah + ko), make_desc(w + ko), idesc128, 1u);
-                    }
-                  }
-                  umma_commit(&wempty[s]);
-                  if (kb == 3 && plane == 1) umma_commit(&accfull[hb]);
-                }
-                __syncwarp();
-              }
+              dense_kblock(kb, d_tmem, it, &accfull[hb]);
+              it += 2;
             }
           }
       }
+    }  // elected thread
   } else {
     // ===================== workers: warps 0-7 ======================================================================
     const int q4 = warp & 3, half = warp >> 2;
@@ -407,16 +432,29 @@ trunk_f16_kernel(TrunkParams p) {
           a[4 * i] = x.x; a[4 * i + 1] = x.y; a[4 * i + 2] = x.z; a[4 * i + 3] = x.w;
         }
         uint32_t v[32];
+        if constexpr (TS) {
+          resid_store32(smem, trow, c * 32, a);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(a[i]);
-        tmem_st32(tmem_base + tlane + (uint32_t)(c * 32), v);
+          for (int i = 0; i < 32; ++i) a[i] *= p.a_scale;
+          pack_operand32(a, v);
+          store_operand_tmem(tmem_base + tlane, c * 32, v);
+          if (c & 1) {
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&afull[c >> 1]);
+          }
+        } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) a[i] *= p.a_scale;
-        store_operand_chunk(smem, trow, c * 32, a);
-        if (c & 1) {
-          tmem_st_wait();
-          fence_proxy_async();
-          mbar_arrive(&afull[c >> 1]);
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(a[i]);
+          tmem_st32(tmem_base + tlane + (uint32_t)(c * 32), v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] *= p.a_scale;
+          store_operand_chunk(smem, trow, c * 32, a);
+          if (c & 1) {
+            tmem_st_wait();
+            fence_proxy_async();
+            mbar_arrive(&afull[c >> 1]);
+          }
         }
       }
       for (int l = 0; l < L; ++l) {
@@ -523,15 +561,23 @@ trunk_f16_kernel(TrunkParams p) {
             float a[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(ov[i]) * uo;
-            store_operand_chunk(smem, trow, 64 * ho + 32 * half, a);
-            fence_proxy_async();
+            if constexpr (TS) {
+              uint32_t pv[32];
+              pack_operand32(a, pv);
+              store_operand_tmem(tmem_base + tlane, 64 * ho + 32 * half, pv);
+              tmem_st_wait();
+              tc_fence_before();
+            } else {
+              store_operand_chunk(smem, trow, 64 * ho + 32 * half, a);
+              fence_proxy_async();
+            }
             mbar_arrive(&ofull[ho]);
             TR_STAMP(17 + 4 * ho);
           }
         }
         named_bar_sync(1, 256);  // biases of this layer are in shared memory
 #ifdef DQMC_EMU_DEBUG_TRUNK
-        if (threadIdx.x == 0 && tile == 0 && l == 0) {  // development aid: attention output operand of the first tile / layer
+        if (!TS && threadIdx.x == 0 && tile == 0 && l == 0) {  // development aid: attention output operand of the first tile / layer
           FILE* f = std::fopen("/tmp/trunk_dbg_O.bin", "wb");
           for (int r = 0; r < 128; ++r)
             for (int c = 0; c < 256; ++c) {
@@ -556,10 +602,11 @@ trunk_f16_kernel(TrunkParams p) {
           if (half == 0) {
             tmem_st32(tmem_base + tlane + (uint32_t)(256 + c * 32), v);
           } else {
-            store_operand_packed(smem, trow, c * 32, v);
+            if constexpr (TS) store_operand_tmem(tmem_base + tlane, c * 32, v);
+            else store_operand_packed(smem, trow, c * 32, v);
             if (c & 1) {
               tmem_st_wait();
-              fence_proxy_async();
+              if constexpr (!TS) fence_proxy_async();
               tc_fence_before();
               mbar_arrive(&afull[c >> 1]);
             }
@@ -573,9 +620,11 @@ trunk_f16_kernel(TrunkParams p) {
             uint32_t v[32];
             tmem_ld32(tmem_base + tlane + (uint32_t)(256 + c * 32), v);
             tmem_ld_wait();
-            store_operand_packed(smem, trow, c * 32, v);
+            if constexpr (TS) store_operand_tmem(tmem_base + tlane, c * 32, v);
+            else store_operand_packed(smem, trow, c * 32, v);
             if (c & 1) {
-              fence_proxy_async();
+              if constexpr (TS) tmem_st_wait();
+              else fence_proxy_async();
               tc_fence_before();
               mbar_arrive(&afull[c >> 1]);
             }
@@ -588,16 +637,25 @@ trunk_f16_kernel(TrunkParams p) {
         tc_fence_after();
         TR_STAMP(31);
         for (int c = c_lo; c < c_hi; ++c) {
-          uint32_t v[32], r[32];
-          tmem_ld32(tmem_base + tlane + (uint32_t)(256 + c * 32), v);
-          tmem_ld32(tmem_base + tlane + (uint32_t)(c * 32), r);
-          tmem_ld_wait();
+          uint32_t v[32];
           float a[32];
+          tmem_ld32(tmem_base + tlane + (uint32_t)(256 + c * 32), v);
+          if constexpr (TS) {
+            resid_load32(smem, trow, c * 32, a);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(r[i]) + __uint_as_float(v[i]) * p.us[l][1];
+            for (int i = 0; i < 32; ++i) a[i] += __uint_as_float(v[i]) * p.us[l][1];
+            resid_store32(smem, trow, c * 32, a);
+          } else {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + tlane + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(a[i]);
-          tmem_st32(tmem_base + tlane + (uint32_t)(c * 32), v);
+            for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(r[i]) + __uint_as_float(v[i]) * p.us[l][1];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(a[i]);
+            tmem_st32(tmem_base + tlane + (uint32_t)(c * 32), v);
+          }
 #pragma unroll
           for (int i = 0; i < 32; ++i) a[i] *= p.a_scale;
           emit(c, a);
@@ -626,14 +684,21 @@ trunk_f16_kernel(TrunkParams p) {
         tc_fence_after();
         TR_STAMP(35);
         for (int c = c_lo; c < c_hi; ++c) {
-          uint32_t v[32], r[32];
-          tmem_ld32(tmem_base + tlane + (uint32_t)(256 + c * 32), v);
-          tmem_ld32(tmem_base + tlane + (uint32_t)(c * 32), r);
-          tmem_ld_wait();
+          uint32_t v[32];
           float a[32];
+          tmem_ld32(tmem_base + tlane + (uint32_t)(256 + c * 32), v);
+          if constexpr (TS) {
+            resid_load32(smem, trow, c * 32, a);
+            tmem_ld_wait();
+          } else {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + tlane + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            a[i] = __uint_as_float(r[i]) + mlp_tanh(__uint_as_float(v[i]) * p.us[l][3] + sb2[c * 32 + i]);
+            for (int i = 0; i < 32; ++i) a[i] = __uint_as_float(r[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) a[i] += mlp_tanh(__uint_as_float(v[i]) * p.us[l][3] + sb2[c * 32 + i]);
           if (last) {
             if (valid) {
               float* op = p.Out + row * p.ldout + c * 32;
@@ -641,9 +706,13 @@ trunk_f16_kernel(TrunkParams p) {
               for (int i = 0; i < 8; ++i) *(float4*)(op + 4 * i) = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
             }
           } else {
+            if constexpr (TS) {
+              resid_store32(smem, trow, c * 32, a);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(a[i]);
-            tmem_st32(tmem_base + tlane + (uint32_t)(c * 32), v);
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(a[i]);
+              tmem_st32(tmem_base + tlane + (uint32_t)(c * 32), v);
+            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) a[i] *= p.a_scale;
             emit(c, a);

@@ -292,6 +292,7 @@ __device__ __forceinline__ void tmem_st_wait() {}
 
 // ---- scalar helpers with a PTX counterpart ---------------------------------------------------------------------------------
 __device__ __forceinline__ float ex2_approx(float x) { return std::exp2(x); }
+__device__ __forceinline__ bool elect_one() { return (threadIdx.x & 31) == 0; }
 __device__ __forceinline__ float fast_div(float a, float b) { return a / b; }
 __device__ __forceinline__ uint32_t pack_half2_rn(float lo, float hi) {  // cvt.rn.f16x2.f32: low half <- lo
   return (uint32_t)emu_tc::float_to_half_rn(lo) | ((uint32_t)emu_tc::float_to_half_rn(hi) << 16);
