@@ -346,6 +346,11 @@ struct Engine : EngineBase {
     uint16_t* h16 = nullptr; CUtensorMap m16h, m16l, m16h_all, m16l_all; float wscale = 1.f; bool f16 = false, f16_all = false;
     CUtensorMap m16h_128, m16l_128; bool f16_128 = false;  // 128-row boxes: weight slots of the whole-trunk kernel (trunk_tc.cuh)
   };
+  // non-local ECP group in flight: envelope table of its base walkers [nb][N][K N] (null outside the quadrature forwards),
+  // index of the current chunk's first virtual walker, virtual walkers per base walker (J N 12)
+  const T* ecp_env = nullptr;
+  int64_t ecp_v0 = 0;
+  int ecp_vper = 0;
   bool fuse_trunk = true;  // all layers of a plain forward in one persistent launch (trunk_tc.cuh); DQMC_TC_TRUNK=0 disables
   bool trunk_ts = true;    // ... with the A operand of its dense GEMMs in tensor memory (DQMC_TC_TRUNK_TS=0: shared memory)
   CUtensorMap* d_trunk_maps = nullptr;       // [L][4][2]
@@ -755,7 +760,8 @@ struct Engine : EngineBase {
   // forward chunk over all V = nb * J * N * 12 virtual walkers
   int64_t ecp_prefix_bytes(int64_t nb) const {
     const int64_t V = nb * J * N * 12;
-    return (int64_t)align_up(sizeof(T) * V * 3 * N) + 2 * (int64_t)align_up(sizeof(T) * V);
+    return (int64_t)align_up(sizeof(T) * V * 3 * N) + 2 * (int64_t)align_up(sizeof(T) * V) +
+           (int64_t)align_up(sizeof(T) * nb * N * K * N);  // + envelope table of the group's base walkers
   }
   // walkers per ECP group are bounded by the 32-bit row cap of the plain-forward chunk: the plan never asks for more
   int64_t ecp_group_cap() const {
@@ -1472,11 +1478,11 @@ struct Engine : EngineBase {
       if (N <= 16)
         DQ_LAUNCH((slater_fwd2_kernel<T, 16>), dim3(grid), dim3(nthr), slater_fwd2_smem_bytes<T>(N, M, K), st, r, R, Rb, N,
                   M, cfg.n_up, K, Bc, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF,
-                  KN, w.dsign, w.dlog, env_rep, full_det);
+                  KN, w.dsign, w.dlog, env_rep, full_det, ecp_env, (long long)ecp_v0, ecp_vper);
       else
         DQ_LAUNCH((slater_fwd2_kernel<T, 32>), dim3(grid), dim3(nthr), slater_fwd2_smem_bytes<T>(N, M, K), st, r, R, Rb, N,
                   M, cfg.n_up, K, Bc, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF,
-                  KN, w.dsign, w.dlog, env_rep, full_det);
+                  KN, w.dsign, w.dlog, env_rep, full_det, ecp_env, (long long)ecp_v0, ecp_vper);
     } else if (S == 1 && N <= 32 && !gadd && !std::getenv("DQMC_SLATER_GENERIC")) {
       const int wpb = K < 8 ? K : 8;
       DQ_LAUNCH(slater_fwd_reg_kernel<T>, dim3(Bc), dim3(32 * wpb), sizeof(T) * N * M, st, r, R, Rb, N, M, cfg.n_up, K,
@@ -1507,6 +1513,7 @@ struct Engine : EngineBase {
     if (dry) { carve(ws, Bc, S); return 0; }  // planning pass: record the extent of the largest chunk
     for (int b0 = 0; b0 < B; b0 += Bc) {
       int nb = std::min(Bc, B - b0);
+      ecp_v0 = b0;  // index of the chunk's first walker in the caller's batch (quadrature forwards: virtual-walker index)
       int rc = run_chunk(r + (size_t)b0 * 3 * N, R + (Rb ? (size_t)b0 * 3 * M : 0), Rb, nb, S, B, sign + b0, logp + b0,
                          E ? E + b0 : nullptr, stats ? stats + b0 : nullptr, grad ? grad + (size_t)b0 * T3 : nullptr, ws,
                          st);
@@ -2223,6 +2230,7 @@ struct Engine : EngineBase {
         T* rv = (T*)p; p += align_up(sizeof(T) * V * 3 * N);
         T* sv = (T*)p; p += align_up(sizeof(T) * V);
         T* lv = (T*)p; p += align_up(sizeof(T) * V);
+        T* envt = (T*)p; p += align_up(sizeof(T) * (size_t)nb * N * K * N);
         note_hwm(p);
         const T* rb = r + (size_t)b0 * 3 * N;
         const T* Rbp = R + (Rb ? (size_t)b0 * 3 * M : 0);
@@ -2230,7 +2238,15 @@ struct Engine : EngineBase {
         DQ_LAUNCH(ecp_points_kernel<T>, dim3(nb * J * N), dim3(64), 0, st, rb, Rbp, Rb, N, M, J, (const int*)d_nl_nuc, tw,
                   seed, (uint64_t)b0, rv);
         if (Rb) { err = "non-local ECP with per-walker nuclei is not supported"; return 2; }
+        const bool use_table = slater_fwd2_ok && N <= 32 && !dry && !std::getenv("DQMC_ECP_ENV_TABLE_OFF");
+        if (use_table) {  // the quadrature forwards take the unmoved electrons' envelopes from the base walkers' table
+          DQ_LAUNCH(env_table_kernel<T>, dim3(nb), dim3(256), sizeof(T) * N * M, st, rb, R, N, M, cfg.n_up, K * N,
+                    P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), cfg.n_env_per_nuc > 1 ? cfg.n_env_per_nuc : 1,
+                    envt);
+          ecp_env = envt; ecp_vper = (int)vper;
+        }
         rc = run_batched(rv, R, 0, (int)V, 1, sv, lv, nullptr, nullptr, nullptr, p, wsb - (p - (char*)ws), st);
+        ecp_env = nullptr;
         if (rc) return rc;
         DQ_LAUNCH(ecp_accumulate_kernel<T>, dim3((nb + 3) / 4), dim3(128), 0, st, rb, Rbp, Rb, N, M, J,
                   (const int*)d_nl_nuc, (const T*)d_nl_params, cfg.ecp_nl_lmax_p1, cfg.ecp_nl_terms,

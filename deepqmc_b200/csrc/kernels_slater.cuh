@@ -647,24 +647,77 @@ __device__ __forceinline__ int warp_argmax_abs(double v, bool excluded, int lane
   return bi;
 }
 
+// 8 consecutive, 8-element-aligned values from shared memory with 16-byte vector loads
+__device__ __forceinline__ void load8(const float* p, float* x) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+__device__ __forceinline__ void load8(const double* p, double* x) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double2 a = *reinterpret_cast<const double2*>(p + 2 * i);
+    x[2 * i] = a.x; x[2 * i + 1] = a.y;
+  }
+}
+
 template <class T, int NM>
 __global__ void __launch_bounds__(256, 3)
 slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M, int n_up, int K,
                    int B, const T* __restrict__ pi_up, const T* __restrict__ pi_dn, const T* __restrict__ zeta_up,
                    const T* __restrict__ zeta_dn, const T* __restrict__ BF, int ldb, T* __restrict__ det_sign,
-                   T* __restrict__ det_log, int rep, int full_det) {
+                   T* __restrict__ det_log, int rep, int full_det, const T* __restrict__ env_base, long long v0, int vper) {
   DQMC_DYN_SMEM(smem_raw);
   const int NP = N | 1, KN = K * N;
   T* As = reinterpret_cast<T*>(smem_raw);  // [K][N][NP]
-  T* rho = As + (size_t)KN * NP;           // [N][M]
+  // electron-nucleus distances, one panel per spin: rho[sb][m][il], il = electron index inside the spin block, padded to a
+  // multiple of 8 (the padding repeats the block's last electron) -> the 8 electrons of an envelope step are ONE aligned
+  // 32-byte (fp32) / 64-byte (fp64) segment, read with vector loads instead of 8 indexed scalar loads
+  const int n_dn = N - n_up;
+  const int NS = (((n_up > n_dn ? n_up : n_dn) + 7) >> 3) << 3;
+  T* rho = As + (((size_t)KN * NP + 3) & ~(size_t)3);  // 16-byte aligned
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, wib = tid >> 5, nw = nt >> 5;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const T* rb = r + (size_t)b * N * 3;
     const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
     __syncthreads();  // previous walker's determinants are in registers / written
-    for (int idx = tid; idx < N * M; idx += nt) {
-      const int i = idx / M, m = idx - i * M;
+    if (env_base) {
+      // Quadrature forward of the non-local ECP: walker v0 + b is base walker (v0 + b) / vper with ONE electron moved
+      // (ecp_points_kernel: v = ((w J + j) N + i) 12 + q).  The envelopes depend on the electron's own position only, so
+      // all rows but the moved one come from the base walker's table env_base[w][i][k N + mu] (env_table_kernel): 12 M
+      // instead of N M exponentials per orbital (the envelope sums were 3/4 of this kernel's MUFU-bound first phase).
+      const long long v = v0 + b;
+      const int bw = (int)(v / vper), imv = (int)((v / 12) % N);
+      for (int m = tid; m < M; m += nt) {
+        const T dx0 = rb[3 * imv] - Rb[3 * m], dx1 = rb[3 * imv + 1] - Rb[3 * m + 1], dx2 = rb[3 * imv + 2] - Rb[3 * m + 2];
+        rho[m] = m_sqrt(Num<T>::eps() + dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
+      }
+      __syncthreads();
+      const int sbm = imv >= n_up;
+      for (int o = tid; o < KN; o += nt) {
+        const int k = o / N, mu = o - k * N;
+        const T* pi = (sbm ? pi_dn : pi_up) + (size_t)o * M * rep;
+        const T* ze = (sbm ? zeta_dn : zeta_up) + (size_t)o * M * rep;
+        T enew = T(0);
+        for (int m = 0; m < M; ++m)
+          for (int t = 0; t < rep; ++t) enew += pi[m * rep + t] * env_exp_scaled(env_scale(-m_abs(ze[m * rep + t])) * rho[m]);
+        const T* eb = env_base + (size_t)bw * N * KN + o;
+        const T* bfp = BF + (size_t)b * N * ldb + o;
+        T* arow = As + (size_t)k * N * NP + mu;
+        const bool mu_up = mu < n_up;
+#pragma unroll 6
+        for (int i = 0; i < N; ++i) {
+          const T e = i == imv ? enew : eb[(size_t)i * KN];
+          const bool off_block = !full_det && ((i < n_up) != mu_up);
+          arow[i * NP] = off_block ? T(0) : e * bfp[(size_t)i * ldb];
+        }
+      }
+    } else {
+    for (int idx = tid; idx < 2 * M * NS; idx += nt) {
+      const int sb = idx / (M * NS), rem = idx - sb * M * NS, m = rem / NS, il = rem - m * NS;
+      const int nsp = sb ? n_dn : n_up;
+      if (nsp == 0) continue;
+      const int i = (sb ? n_up : 0) + (il < nsp ? il : nsp - 1);
       const T dx0 = rb[3 * i] - Rb[3 * m], dx1 = rb[3 * i + 1] - Rb[3 * m + 1], dx2 = rb[3 * i + 2] - Rb[3 * m + 2];
       rho[idx] = m_sqrt(Num<T>::eps() + dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
     }
@@ -676,33 +729,47 @@ slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batch
       T* arow = As + (size_t)k * N * NP + mu;
 #pragma unroll 1
       for (int sb = 0; sb < 2; ++sb) {
-        const int ib = sb ? n_up : 0, ie = sb ? N : n_up;
+        const int ib = sb ? n_up : 0, nsp = sb ? n_dn : n_up;
         const T* pi = (sb ? pi_dn : pi_up) + (size_t)o * M * rep;
         const T* ze = (sb ? zeta_dn : zeta_up) + (size_t)o * M * rep;
+        const T* rs = rho + (size_t)sb * M * NS;
+        const bool off_block = !full_det && ((sb == 0) != (mu < n_up));  // spin-factorised determinants
 #pragma unroll 1
-        for (int i0 = ib; i0 < ie; i0 += 8) {
+        for (int il0 = 0; il0 < nsp; il0 += 8) {
           T e[8], bf[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             e[j] = T(0);
-            bf[j] = i0 + j < ie ? bfp[(size_t)(i0 + j) * ldb] : T(0);
+            bf[j] = il0 + j < nsp ? bfp[(size_t)(ib + il0 + j) * ldb] : T(0);
           }
-          for (int mt = 0; mt < M * rep; ++mt) {
-            const T p = pi[mt], z = env_scale(-m_abs(ze[mt]));
-            const int m = rep == 1 ? mt : mt / rep;
+          const T* rp = rs + il0;
+          if (rep == 1) {
+#pragma unroll 4
+            for (int m = 0; m < M; ++m) {
+              const T p = pi[m], z = env_scale(-m_abs(ze[m]));
+              T r8[8];
+              load8(rp + m * NS, r8);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int ii = i0 + j < ie ? i0 + j : ie - 1;
-              e[j] += p * env_exp_scaled(z * rho[ii * M + m]);
+              for (int j = 0; j < 8; ++j) e[j] += p * env_exp_scaled(z * r8[j]);
+            }
+          } else {
+            for (int m = 0; m < M; ++m) {
+              T r8[8];
+              load8(rp + m * NS, r8);
+              for (int t = 0; t < rep; ++t) {
+                const T p = pi[m * rep + t], z = env_scale(-m_abs(ze[m * rep + t]));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) e[j] += p * env_exp_scaled(z * r8[j]);
+              }
             }
           }
-          const bool off_block = !full_det && ((sb == 0) != (mu < n_up));  // spin-factorised determinants
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (i0 + j < ie) arow[(i0 + j) * NP] = off_block ? T(0) : e[j] * bf[j];
+            if (il0 + j < nsp) arow[(ib + il0 + j) * NP] = off_block ? T(0) : e[j] * bf[j];
         }
       }
     }
+    }  // full envelope evaluation
     __syncthreads();
     // ---- phase 2 ---------------------------------------------------------------------------
     for (int k = wib; k < K; k += nw) {
@@ -744,6 +811,34 @@ slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batch
   }
 }
 
+// Envelope table of the base walkers of a non-local-ECP group: out[w][i][o] = sum_m pi_{o m} exp(-|zeta_{o m}| |r_i - R_m|),
+// o = k N + mu (spin of electron i selects the parameter set).  One block per walker; thread <-> orbital, so the quadrature
+// forwards read it coalesced.  reference: wf/env.py (ExponentialEnvelopes), used through ecp/gaussian_type_ecp.py:161-255.
+template <class T>
+__global__ void env_table_kernel(const T* __restrict__ r, const T* __restrict__ R, int N, int M, int n_up, int KN,
+                                 const T* __restrict__ pi_up, const T* __restrict__ pi_dn, const T* __restrict__ zeta_up,
+                                 const T* __restrict__ zeta_dn, int rep, T* __restrict__ out) {
+  DQMC_DYN_SMEM(smem_raw);
+  T* rho = reinterpret_cast<T*>(smem_raw);  // [N][M]
+  const int w = blockIdx.x;
+  const T* rb = r + (size_t)w * N * 3;
+  for (int idx = threadIdx.x; idx < N * M; idx += blockDim.x) {
+    const int i = idx / M, m = idx - i * M;
+    const T dx0 = rb[3 * i] - R[3 * m], dx1 = rb[3 * i + 1] - R[3 * m + 1], dx2 = rb[3 * i + 2] - R[3 * m + 2];
+    rho[idx] = m_sqrt(Num<T>::eps() + dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < KN; o += blockDim.x)
+    for (int i = 0; i < N; ++i) {
+      const T* pi = (i < n_up ? pi_up : pi_dn) + (size_t)o * M * rep;
+      const T* ze = (i < n_up ? zeta_up : zeta_dn) + (size_t)o * M * rep;
+      T e = T(0);
+      for (int m = 0; m < M; ++m)
+        for (int t = 0; t < rep; ++t) e += pi[m * rep + t] * env_exp_scaled(env_scale(-m_abs(ze[m * rep + t])) * rho[i * M + m]);
+      out[((size_t)w * N + i) * KN + o] = e;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Molecular orbitals  A[b][k][i][mu] = envelope_{k mu}(r_i) * backflow[b][i][k N + mu]  -- what Ansatz.apply returns
 // with return_mos = True (reference wf/nn_wave_function.py:131-142; used by pretraining/pretraining.py:73-78).  BF already
@@ -780,7 +875,8 @@ __global__ void orbitals_kernel(const T* __restrict__ r, const T* __restrict__ R
 
 template <class T>
 inline size_t slater_fwd2_smem_bytes(int N, int M, int K) {
-  return sizeof(T) * ((size_t)K * N * (N | 1) + (size_t)N * M);
+  // A matrices (16-byte rounded) + the two per-spin distance panels [M][NS <= round8(N)]
+  return sizeof(T) * ((((size_t)K * N * (N | 1) + 3) & ~(size_t)3) + 2 * (size_t)M * (((size_t)N + 7) & ~(size_t)7));
 }
 
 // ------------------------------------------------------------------------------------------

@@ -203,6 +203,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem, std::function<void()> bod
 }  // namespace emu
 
 struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) double2 { double x, y; };
 struct alignas(8) float2 { float x, y; };
 inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct alignas(8) uint2 { unsigned x, y; };
