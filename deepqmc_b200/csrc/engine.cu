@@ -349,6 +349,7 @@ struct Engine : EngineBase {
   // non-local ECP group in flight: envelope table of its base walkers [nb][N][K N] (null outside the quadrature forwards),
   // index of the current chunk's first virtual walker, virtual walkers per base walker (J N 12)
   const T* ecp_env = nullptr;
+  const T* ecp_emb = nullptr;  // ... and their embedding rows [nb][N][d] (whole-trunk kernel only)
   int64_t ecp_v0 = 0;
   int ecp_vper = 0;
   bool fuse_trunk = true;  // all layers of a plain forward in one persistent launch (trunk_tc.cuh); DQMC_TC_TRUNK=0 disables
@@ -761,7 +762,8 @@ struct Engine : EngineBase {
   int64_t ecp_prefix_bytes(int64_t nb) const {
     const int64_t V = nb * J * N * 12;
     return (int64_t)align_up(sizeof(T) * V * 3 * N) + 2 * (int64_t)align_up(sizeof(T) * V) +
-           (int64_t)align_up(sizeof(T) * nb * N * K * N);  // + envelope table of the group's base walkers
+           (int64_t)align_up(sizeof(T) * nb * N * K * N) +  // + envelope table of the group's base walkers
+           (int64_t)align_up(sizeof(T) * nb * N * d);        // + their embedding rows
   }
   // walkers per ECP group are bounded by the 32-bit row cap of the plain-forward chunk: the plan never asks for more
   int64_t ecp_group_cap() const {
@@ -1012,12 +1014,13 @@ struct Engine : EngineBase {
     return false;
 #endif
   }
-  int trunk_block(const T* X0, T* Out, int rows, cudaStream_t st) {
+  int trunk_block(const T* X0, T* Out, int rows, cudaStream_t st, const T* Xbase = nullptr) {
     if (dry) return 0;
 #if !defined(DQMC_NO_TCGEN05)
     if constexpr (std::is_same<T, float>::value) {
       tc::TrunkParams p;
       p.X0 = X0; p.ldx = d; p.Out = Out; p.ldout = d; p.maps = d_trunk_maps; p.scratch = d_trunk_scratch;
+      p.Xbase = Xbase; p.v0 = Xbase ? (long long)ecp_v0 : 0; p.vper = Xbase ? ecp_vper : 0;
       int np2 = 1;
       while (np2 < N) np2 *= 2;  // walker slot of the tile: electrons rounded up to a power of two (<= 32)
       p.walkers = rows / N; p.N = N; p.NP = np2; p.L = cfg.n_layers; p.a_scale = kActScale;
@@ -1312,13 +1315,21 @@ struct Engine : EngineBase {
       return tail(r, R, Rb, Bc, S, Bstat, sign, logp, E, stats, grad, w, Xf, st, nullptr, qa);
     }
     const int F = 4 * M + 1;
-    if (S == 1 && embed_fwd_ok) {
+    const bool compact = S == 1 && embed_fwd_ok && ecp_emb && can_trunk(S);
+    if (compact) {
+      // quadrature forwards of the non-local ECP: only the moved electron's embedding row is new, the whole-trunk kernel
+      // takes the other rows from the base walkers' table
+      int epb = (Bc / (2 * n_sms)) / 32 * 32;
+      epb = epb < 32 ? 32 : (epb > 512 ? 512 : epb);
+      DQ_LAUNCH(embed_fwd_kernel<T>, dim3((Bc + epb - 1) / epb), dim3(256), embed_fwd_smem_bytes<T>(M, d), st, r, R, Rb, N,
+                M, cfg.n_up, 1, P("emb.w"), d, w.X, Bc, epb, (long long)ecp_v0, ecp_vper);
+    } else if (S == 1 && embed_fwd_ok) {
       // plain forwards (Metropolis, ECP quadrature): register-tiled projection, W staged per block
       const int tot = Bc * N;
       int epb = (tot / (2 * n_sms)) / 32 * 32;
       epb = epb < 32 ? 32 : (epb > 512 ? 512 : epb);
       DQ_LAUNCH(embed_fwd_kernel<T>, dim3((tot + epb - 1) / epb), dim3(256), embed_fwd_smem_bytes<T>(M, d), st, r, R, Rb, N,
-                M, cfg.n_up, 1, P("emb.w"), d, w.X, tot, epb);
+                M, cfg.n_up, 1, P("emb.w"), d, w.X, tot, epb, 0LL, 0);
     } else {
       const int epb = S == 1 ? 8 : 1;  // plain forwards: several electrons per block (tiny per-electron work)
       DQ_LAUNCH(embed_kernel<T>, dim3((Bc * N + epb - 1) / epb), dim3(128), sizeof(T) * 5 * F, st, r, R, Rb, N, M,
@@ -1328,7 +1339,7 @@ struct Engine : EngineBase {
     T* O = w.O;
     const T scale = (T)(1.0 / std::sqrt((double)dh));
     if (can_trunk(S)) {  // plain forward: every layer in one persistent tensor-core launch
-      int rc = trunk_block(X, O, rows, st);
+      int rc = trunk_block(X, O, rows, st, compact ? ecp_emb : nullptr);
       if (rc) return rc;
       return tail(r, R, Rb, Bc, S, Bstat, sign, logp, E, stats, grad, w, O, st, nullptr, qa);
     }
@@ -2231,6 +2242,7 @@ struct Engine : EngineBase {
         T* sv = (T*)p; p += align_up(sizeof(T) * V);
         T* lv = (T*)p; p += align_up(sizeof(T) * V);
         T* envt = (T*)p; p += align_up(sizeof(T) * (size_t)nb * N * K * N);
+        T* embt = (T*)p; p += align_up(sizeof(T) * (size_t)nb * N * d);
         note_hwm(p);
         const T* rb = r + (size_t)b0 * 3 * N;
         const T* Rbp = R + (Rb ? (size_t)b0 * 3 * M : 0);
@@ -2244,9 +2256,14 @@ struct Engine : EngineBase {
                     P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), cfg.n_env_per_nuc > 1 ? cfg.n_env_per_nuc : 1,
                     envt);
           ecp_env = envt; ecp_vper = (int)vper;
+          if (embed_fwd_ok && can_trunk(1) && !std::getenv("DQMC_ECP_EMB_TABLE_OFF")) {
+            DQ_LAUNCH(embed_fwd_kernel<T>, dim3((nb * N + 31) / 32), dim3(256), embed_fwd_smem_bytes<T>(M, d), st, rb, R, 0, N, M,
+                      cfg.n_up, 1, P("emb.w"), d, embt, nb * N, 32, 0LL, 0);
+            ecp_emb = embt;
+          }
         }
         rc = run_batched(rv, R, 0, (int)V, 1, sv, lv, nullptr, nullptr, nullptr, p, wsb - (p - (char*)ws), st);
-        ecp_env = nullptr;
+        ecp_env = nullptr; ecp_emb = nullptr;
         if (rc) return rc;
         DQ_LAUNCH(ecp_accumulate_kernel<T>, dim3((nb + 3) / 4), dim3(128), 0, st, rb, Rbp, Rb, N, M, J,
                   (const int*)d_nl_nuc, (const T*)d_nl_params, cfg.ecp_nl_lmax_p1, cfg.ecp_nl_terms,

@@ -127,7 +127,10 @@ __global__ void embed_kernel(const T* __restrict__ r, const T* __restrict__ R, i
 template <class T>
 __global__ void __launch_bounds__(256)
 embed_fwd_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched, int N, int M, int n_up,
-                 int log_rescale, const T* __restrict__ W, int d, T* __restrict__ X, int total, int epb) {
+                 int log_rescale, const T* __restrict__ W, int d, T* __restrict__ X, int total, int epb,
+                 long long v0 = 0, int vper = 0) {
+  // vper > 0: compact mode of the non-local-ECP quadrature forwards -- row t is the MOVED electron (v / 12) % N of virtual
+  // walker v = v0 + t (ecp_points_kernel layout); the other electrons' rows are those of the base walker (see trunk_tc.cuh)
   DQMC_DYN_SMEM(smem_raw);
   const int F = 4 * M + 1;
   T* Ws = reinterpret_cast<T*>(smem_raw);  // [F][d]
@@ -144,8 +147,8 @@ embed_fwd_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched
       const int bi = e0 + el;
       T f0 = T(0), g0 = T(0), g1 = T(0), g2 = T(0);
       if (bi < e_end) {
-        const int b = bi / N;
-        const T* ri = r + (size_t)bi * 3;
+        const int b = vper > 0 ? bi : bi / N;
+        const T* ri = r + (vper > 0 ? ((size_t)bi * N + (size_t)(((v0 + bi) / 12) % N)) : (size_t)bi) * 3;
         const T* Rb = R + (R_batched ? (size_t)b * M * 3 : 0);
         const T dx0 = ri[0] - Rb[3 * m], dx1 = ri[1] - Rb[3 * m + 1], dx2 = ri[2] - Rb[3 * m + 2];
         const T rho = m_sqrt(Num<T>::eps() + dx0 * dx0 + dx1 * dx1 + dx2 * dx2);
@@ -161,7 +164,8 @@ embed_fwd_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batched
     }
     if (tid < 32) {
       const int bi = e0 + tid;
-      ft[(F - 1) * 32 + tid] = (bi < e_end && (bi % N) < n_up) ? T(1) : T(-1);
+      const int el_i = vper > 0 ? (int)(((v0 + bi) / 12) % N) : bi % N;
+      ft[(F - 1) * 32 + tid] = (bi < e_end && el_i < n_up) ? T(1) : T(-1);
     }
     __syncthreads();
     for (int f0 = 4 * tf; f0 < d; f0 += 256) {

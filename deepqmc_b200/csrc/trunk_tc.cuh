@@ -52,7 +52,10 @@ constexpr int kTrHeadImage = 96 * 1024;             // per head: Q hi, Q lo, K h
 constexpr int kTrScratchPerCta = 4 * kTrHeadImage;  // 4 heads
 
 struct TrunkParams {
-  const float* X0; int ldx;      // embedding rows [rows][256]
+  const float* X0; int ldx;      // embedding rows [rows][256]  (vper > 0: [walkers][256], the moved electron's row only)
+  const float* Xbase;            // vper > 0 (non-local-ECP quadrature forwards): embedding rows of the group's base walkers
+  long long v0; int vper;        //   [base][N][256]; walker w of this launch is virtual walker v0 + w = base (v0 + w) / vper
+                                 //   with electron ((v0 + w) / 12) % N moved (ecp_points_kernel layout)
   float* Out; int ldout;         // trunk output rows [rows][256]
   const CUtensorMap* maps;       // device array [L][4][2]: (Wqkv, Wo, W1, W2) x (hi, lo); boxes of 64 halves x 128 rows
   const float* b1[kTrMaxLayers];
@@ -423,12 +426,17 @@ trunk_f16_kernel(TrunkParams p) {
       const int walker = tile * G + slot;
       const bool valid = el < N && walker < p.walkers;
       const size_t row = (size_t)walker * N + el;  // global row (valid rows only)
+      const float* xrow = p.X0 + row * p.ldx;
+      if (p.vper > 0 && valid) {
+        const long long v = p.v0 + walker;
+        xrow = el == (int)((v / 12) % N) ? p.X0 + (size_t)walker * p.ldx : p.Xbase + ((size_t)(v / p.vper) * N + el) * p.ldx;
+      }
       // ---- tile load: embedding rows -> residual stream in TMEM [0, 256) and the operand buffer
       for (int c = c_lo; c < c_hi; ++c) {
         float a[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 x = valid ? __ldg((const float4*)(p.X0 + row * p.ldx + c * 32 + 4 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 x = valid ? __ldg((const float4*)(xrow + c * 32 + 4 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
           a[4 * i] = x.x; a[4 * i + 1] = x.y; a[4 * i + 2] = x.z; a[4 * i + 3] = x.w;
         }
         uint32_t v[32];
