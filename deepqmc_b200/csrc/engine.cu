@@ -508,7 +508,10 @@ struct Engine : EngineBase {
     slater_fwd2_ok = N <= 32 && slater_fwd2_smem_bytes<T>(N, M, K) <= 110 * 1024 && !std::getenv("DQMC_SLATER_GENERIC") &&
                      !std::getenv("DQMC_SLATER_FWD1");
     if (slater_fwd2_ok) {
+      DQ_CHECK(raise_dyn_smem(slater_fwd2_kernel<T, 14>, (int)slater_fwd2_smem_bytes<T>(N, M, K)));
       DQ_CHECK(raise_dyn_smem(slater_fwd2_kernel<T, 16>, (int)slater_fwd2_smem_bytes<T>(N, M, K)));
+      DQ_CHECK(raise_dyn_smem(slater_fwd2_kernel<T, 28>, (int)slater_fwd2_smem_bytes<T>(N, M, K)));
+      DQ_CHECK(raise_dyn_smem(slater_fwd2_kernel<T, 30>, (int)slater_fwd2_smem_bytes<T>(N, M, K)));
       DQ_CHECK(raise_dyn_smem(slater_fwd2_kernel<T, 32>, (int)slater_fwd2_smem_bytes<T>(N, M, K)));
     }
     attn_fwd_ok = psif && std::is_same<T, float>::value && dh == 64 && N <= 32 && N + Mn <= 48 && d % 4 == 0 &&
@@ -1486,14 +1489,18 @@ struct Engine : EngineBase {
     } else if (S == 1 && N <= 32 && slater_fwd2_ok && !gadd) {
       const int nthr = 32 * K < 256 ? 32 * K : 256;
       const int grid = Bc < 3 * n_sms ? Bc : 3 * n_sms;
-      if (N <= 16)
-        DQ_LAUNCH((slater_fwd2_kernel<T, 16>), dim3(grid), dim3(nthr), slater_fwd2_smem_bytes<T>(N, M, K), st, r, R, Rb, N,
-                  M, cfg.n_up, K, Bc, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF,
-                  KN, w.dsign, w.dlog, env_rep, full_det, ecp_env, (long long)ecp_v0, ecp_vper);
-      else
-        DQ_LAUNCH((slater_fwd2_kernel<T, 32>), dim3(grid), dim3(nthr), slater_fwd2_smem_bytes<T>(N, M, K), st, r, R, Rb, N,
-                  M, cfg.n_up, K, Bc, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF,
-                  KN, w.dsign, w.dlog, env_rep, full_det, ecp_env, (long long)ecp_v0, ecp_vper);
+      // register-resident LU: the row array is sized to the electron count where an exact instance exists (every padded
+      // column costs a shuffle + FMA per elimination step)
+#define DQ_SL_FWD2(NMV)                                                                                                        \
+  DQ_LAUNCH((slater_fwd2_kernel<T, NMV>), dim3(grid), dim3(nthr), slater_fwd2_smem_bytes<T>(N, M, K), st, r, R, Rb, N, M,      \
+            cfg.n_up, K, Bc, P("env.pi_up"), P("env.pi_dn"), P("env.zeta_up"), P("env.zeta_dn"), (const T*)w.BF, KN, w.dsign, \
+            w.dlog, env_rep, full_det, ecp_env, (long long)ecp_v0, ecp_vper)
+      if (N == 14) DQ_SL_FWD2(14);
+      else if (N <= 16) DQ_SL_FWD2(16);
+      else if (N == 28) DQ_SL_FWD2(28);
+      else if (N == 30) DQ_SL_FWD2(30);
+      else DQ_SL_FWD2(32);
+#undef DQ_SL_FWD2
     } else if (S == 1 && N <= 32 && !gadd && !std::getenv("DQMC_SLATER_GENERIC")) {
       const int wpb = K < 8 ? K : 8;
       DQ_LAUNCH(slater_fwd_reg_kernel<T>, dim3(Bc), dim3(32 * wpb), sizeof(T) * N * M, st, r, R, Rb, N, M, cfg.n_up, K,

@@ -705,12 +705,22 @@ slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batch
         const T* bfp = BF + (size_t)b * N * ldb + o;
         T* arow = As + (size_t)k * N * NP + mu;
         const bool mu_up = mu < n_up;
-#pragma unroll 6
-        for (int i = 0; i < N; ++i) {
-          const T e = i == imv ? enew : eb[(size_t)i * KN];
-          const bool off_block = !full_det && ((i < n_up) != mu_up);
-          arow[i * NP] = off_block ? T(0) : e * bfp[(size_t)i * ldb];
+        // rows of the two spin blocks; a block that is structurally zero (spin-factorised determinants) is only cleared
+        const T* ep = eb;
+        const T* bp = bfp;
+        T* ap = arow;
+#pragma unroll 1
+        for (int sb = 0; sb < 2; ++sb) {
+          const int cnt = sb ? N - n_up : n_up;
+          if (!full_det && ((sb == 0) != mu_up)) {
+            for (int i = 0; i < cnt; ++i, ap += NP) *ap = T(0);
+            ep += (size_t)cnt * KN; bp += (size_t)cnt * ldb;
+          } else {
+#pragma unroll 5
+            for (int i = 0; i < cnt; ++i, ep += KN, bp += ldb, ap += NP) *ap = *ep * *bp;
+          }
         }
+        if (full_det || ((imv < n_up) == mu_up)) arow[imv * NP] = enew * bfp[(size_t)imv * ldb];  // the moved electron's row
       }
     } else {
     for (int idx = tid; idx < 2 * M * NS; idx += nt) {
@@ -782,8 +792,8 @@ slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batch
         a[mu] = v;
       }
       LogProd<T> logdet;
-      T sgn = T(1);
-      unsigned used = 0u;  // rows already chosen as pivots (warp-uniform)
+      bool neg = false, zero = false;  // sign of the pivot product / an exactly singular pivot (warp-uniform)
+      unsigned used = N < 32 ? ~((1u << N) - 1u) : 0u;  // rows already chosen as pivots (warp-uniform); padding lanes never are
       int inv = 0;         // inversion count of the pivot order
 #pragma unroll
       for (int c = 0; c < NM; ++c) {
@@ -793,7 +803,8 @@ slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batch
           used |= 1u << prow;
           const T pv = __shfl_sync(0xffffffffu, a[c], prow);
           logdet.mul(m_abs(pv));
-          sgn = pv < T(0) ? -sgn : (pv == T(0) ? T(0) : sgn);
+          neg ^= pv < T(0);
+          zero |= pv == T(0);
           const bool elim = !((used >> lane) & 1u);
           const T f = (elim && pv != T(0)) ? a[c] * pivot_rcp(pv) : T(0);  // exactly singular: (sign 0, log -inf) like slogdet
 #pragma unroll
@@ -805,7 +816,7 @@ slater_fwd2_kernel(const T* __restrict__ r, const T* __restrict__ R, int R_batch
       }
       if (lane == 0) {
         det_log[(size_t)b * K + k] = logdet.value();
-        det_sign[(size_t)b * K + k] = (inv & 1) ? -sgn : sgn;
+        det_sign[(size_t)b * K + k] = zero ? T(0) : ((neg != ((inv & 1) != 0)) ? T(-1) : T(1));
       }
     }
   }
