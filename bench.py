@@ -110,13 +110,14 @@ class ClockSampler:
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from one
 # `ncu --set full` capture of the same command (profiles/, B200_PROFILING.md); None = not captured.
 TRAFFIC = {
-    # profiles/r02_ncu_trunk_f16_kernel.csv (ncu --set full of tools/prof_fwd.py 2 17760): one whole-trunk launch over
-    # 17760 plain-forward walkers x 30 electrons = 532800 rows: dram read 0.690 GB + write 3.074 GB.  Algorithmic bytes of
-    # that launch = rows x 256 x 4 B in + the same out + 6.3 MB of weights = 1.097 GB: the extra 2.5 GB of writes are
-    # evictions of the per-CTA Q/K/V operand scratch (57 MB, re-written every tile and layer) from L2.
-    'benzene_psiformer': {'bytes_per_launch': 3.7636e9, 'algorithmic_bytes_per_launch': 1.0975e9,
-                          'launch': 'trunk_f16_kernel, 532800 rows (17760 quadrature-forward walkers x 30 electrons), 4 layers',
-                          'source': 'profiles/r02_ncu_trunk_f16_kernel.csv'},
+    # profiles/r02_ncu_trunk_f16_kernel_ts.csv (ncu --set full of `tools/prof_fwd.py 2 17760`): one whole-trunk launch over
+    # 17760 plain-forward walkers x 30 electrons = 532800 rows: dram read 0.705 GB + write 2.368 GB.  Algorithmic bytes of
+    # that launch = rows x 256 x 4 B in + the same out + 6.3 MB of weights = 1.097 GB: the extra ~1.8 GB of writes are
+    # evictions of the per-CTA Q/K/V operand scratch (57 MB, re-written every tile and layer) from L2.  (The quadrature
+    # forwards of the ECP pass read even less: the unmoved electrons' embedding rows come from the base walkers' table.)
+    'benzene_psiformer': {'bytes_per_launch': 3.0727e9, 'algorithmic_bytes_per_launch': 1.0975e9,
+                          'launch': 'trunk_f16_kernel<TS>, 532800 rows (17760 plain-forward walkers x 30 electrons), 4 layers',
+                          'source': 'profiles/r02_ncu_trunk_f16_kernel_ts.csv'},
 }
 
 _ORACLE = {}

@@ -323,6 +323,7 @@ struct Engine : EngineBase {
   bool ph_active = false;  // set around the forward-Laplacian pass of local_energy only
   T* mos_out = nullptr;    // set by orbitals(): the tail writes the orbital matrices of the chunk here and stops
   int attn_tb = 1, attn_tb1 = 1;
+  int attn_fl_threads = 128;  // block size of the fp32 forward-Laplacian attention (large molecules: one block per SM fits -> more warps)
   bool attn_f32 = false;
   bool embed_fwd_ok = false;
   bool attn_fwd_ok = false;
@@ -496,6 +497,7 @@ struct Engine : EngineBase {
     attn_f32 = psif && !trans && std::is_same<T, float>::value && dh % 16 == 0 && !std::getenv("DQMC_ATTN_GENERIC");
     if (attn_f32) attn_tb = attn_f32_pick_tb(N, dh, T3, 32 * 1024);  // ~7 blocks/SM for small molecules
     if (const char* ev = std::getenv("DQMC_ATTN_TB")) { int x = std::atoi(ev); if (x >= 1 && x <= T3) attn_tb = x; }
+    if (const char* ev = std::getenv("DQMC_ATTN_NT")) { int x = std::atoi(ev); if (x >= 32 && x <= 1024 && x % 32 == 0) attn_fl_threads = x; }
     size_t s_attn = !psif ? 0 : attn_f32 ? attn_f32_smem_bytes(N, dh, attn_tb) : attn_smem_bytes<T>(N, dh, attn_tb, Mn);
     size_t s_sl = slater_smem_bytes<T>(N);
     max_smem = s_attn > s_sl ? s_attn : s_sl;
@@ -1100,7 +1102,7 @@ struct Engine : EngineBase {
       DQ_CHECK(raise_dyn_smem(attn_fl_f32_kernel<NE, DH>, smem));
       return 0;
     }
-    DQ_LAUNCH((attn_fl_f32_kernel<NE, DH>), dim3(Bc, H), dim3(128), smem, st, QKV, 3 * d, O, d, N, S, dh, d, scale, tb);
+    DQ_LAUNCH((attn_fl_f32_kernel<NE, DH>), dim3(Bc, H), dim3(attn_fl_threads), smem, st, QKV, 3 * d, O, d, N, S, dh, d, scale, tb);
     return 0;
   }
   int launch_attn_f32(const float* QKV, float* O, int Bc, int S, int tb, float scale, int, int smem, cudaStream_t st,
