@@ -323,6 +323,7 @@ struct Engine : EngineBase {
   bool ph_active = false;  // set around the forward-Laplacian pass of local_energy only
   T* mos_out = nullptr;    // set by orbitals(): the tail writes the orbital matrices of the chunk here and stops
   int attn_tb = 1, attn_tb1 = 1;
+  bool attn_fl_mma = false;   // fp32 forward-Laplacian attention: tangent chunks as warp-level 3xTF32 mma.sync products
   int attn_fl_threads = 128;  // block size of the fp32 forward-Laplacian attention (large molecules: one block per SM fits -> more warps)
   bool attn_f32 = false;
   bool embed_fwd_ok = false;
@@ -499,6 +500,13 @@ struct Engine : EngineBase {
     if (const char* ev = std::getenv("DQMC_ATTN_TB")) { int x = std::atoi(ev); if (x >= 1 && x <= T3) attn_tb = x; }
     if (const char* ev = std::getenv("DQMC_ATTN_NT")) { int x = std::atoi(ev); if (x >= 32 && x <= 1024 && x % 32 == 0) attn_fl_threads = x; }
     size_t s_attn = !psif ? 0 : attn_f32 ? attn_f32_smem_bytes(N, dh, attn_tb) : attn_smem_bytes<T>(N, dh, attn_tb, Mn);
+    // few resident blocks per SM (large molecules: the tangent chunk fills the shared memory) -> more warps per block
+    // (benzene, one 170 KB block per SM: 128 threads 707 ms per 512-walker step, 512 threads 684 ms)
+    if (!std::getenv("DQMC_ATTN_NT")) attn_fl_threads = s_attn > 110 * 1024 ? 512 : (s_attn > 56 * 1024 ? 256 : 128);
+    // 16 x 8 tiles: worthwhile from about 20 electrons (benzene, N = 30: 686 -> 648 ms per 512-walker step; LiH, N = 4, where
+    // 7/8 of every tile is padding: 6.9 -> 15.7 ms, so small molecules keep the SIMT variant)
+    attn_fl_mma = attn_f32 && N >= 20 && N <= 32 && dh % 16 == 0;
+    if (const char* ev = std::getenv("DQMC_ATTN_FL_MMA")) attn_fl_mma = attn_f32 && N <= 32 && dh % 16 == 0 && std::atoi(ev) != 0;
     size_t s_sl = slater_smem_bytes<T>(N);
     max_smem = s_attn > s_sl ? s_attn : s_sl;
     if (max_smem > 227 * 1024) { err = "system too large for the shared-memory tiling (N)"; return 2; }
@@ -1099,10 +1107,14 @@ struct Engine : EngineBase {
   template <int NE, int DH>
   int attn_f32_go(const float* QKV, float* O, int Bc, int S, int tb, float scale, int smem, cudaStream_t st, bool setup) {
     if (setup) {
-      DQ_CHECK(raise_dyn_smem(attn_fl_f32_kernel<NE, DH>, smem));
+      DQ_CHECK(raise_dyn_smem((attn_fl_f32_kernel<NE, DH, false>), smem));
+      DQ_CHECK(raise_dyn_smem((attn_fl_f32_kernel<NE, DH, true>), smem));
       return 0;
     }
-    DQ_LAUNCH((attn_fl_f32_kernel<NE, DH>), dim3(Bc, H), dim3(attn_fl_threads), smem, st, QKV, 3 * d, O, d, N, S, dh, d, scale, tb);
+    if (attn_fl_mma && S > 1)  // tangent chunks on the tensor cores (8 warp tasks per phase: 256 threads)
+      DQ_LAUNCH((attn_fl_f32_kernel<NE, DH, true>), dim3(Bc, H), dim3(256), smem, st, QKV, 3 * d, O, d, N, S, dh, d, scale, tb);
+    else
+      DQ_LAUNCH((attn_fl_f32_kernel<NE, DH, false>), dim3(Bc, H), dim3(attn_fl_threads), smem, st, QKV, 3 * d, O, d, N, S, dh, d, scale, tb);
     return 0;
   }
   int launch_attn_f32(const float* QKV, float* O, int Bc, int S, int tb, float scale, int, int smem, cudaStream_t st,
@@ -1414,12 +1426,12 @@ struct Engine : EngineBase {
                                 (int)attn_f32_smem_bytes(N, dh, tb), st, false))
               return 1;
           } else {
-            DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh, tb, Mn), st, (const T*)w.QKV,
-                      3 * d, O, d, N, S, dh, d, scale, tb, kn, vn, Mn);
+            DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(S > 1 ? attn_fl_threads : 128), attn_smem_bytes<T>(N, dh, tb, Mn), st,
+                      (const T*)w.QKV, 3 * d, O, d, N, S, dh, d, scale, tb, kn, vn, Mn);
           }
         } else {
-          DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(128), attn_smem_bytes<T>(N, dh, tb, Mn), st, (const T*)w.QKV,
-                    3 * d, O, d, N, S, dh, d, scale, tb, kn, vn, Mn);
+          DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(S > 1 ? attn_fl_threads : 128), attn_smem_bytes<T>(N, dh, tb, Mn), st,
+                    (const T*)w.QKV, 3 * d, O, d, N, S, dh, d, scale, tb, kn, vn, Mn);
         }
       }
       if (can_fuse_mlp(S, p)) {

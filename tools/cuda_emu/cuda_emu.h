@@ -285,6 +285,27 @@ inline void mma_m16n8k16_f16(float* d, const uint32_t* a, const uint32_t* b, con
   }
   syncwarp();
 }
+// mma.sync.m16n8k8 .tf32: A a0 (g, t) a1 (g + 8, t) a2 (g, t + 4) a3 (g + 8, t + 4); B b0 (k = t, n = g) b1 (k = t + 4, n = g)
+inline void mma_m16n8k8_tf32(float* d, const uint32_t* a, const uint32_t* b, const float* c) {
+  static thread_local std::vector<uint32_t> abuf, bbuf;
+  State& s = S();
+  if ((int)abuf.size() < s.nthreads * 4) { abuf.assign(s.nthreads * 4, 0); bbuf.assign(s.nthreads * 2, 0); }
+  const int lin = s.fibers[s.cur].lin, w = lin / 32, lane = lin & 31;
+  for (int i = 0; i < 4; ++i) abuf[lin * 4 + i] = a[i];
+  for (int i = 0; i < 2; ++i) bbuf[lin * 2 + i] = b[i];
+  syncwarp();
+  auto f = [](uint32_t u) { u &= 0xFFFFE000u; float x; std::memcpy(&x, &u, 4); return x; };
+  auto A = [&](int r, int k) { return f(abuf[(w * 32 + (r & 7) * 4 + (k & 3)) * 4 + (r >> 3) + 2 * (k >> 2)]); };
+  auto B = [&](int k, int n) { return f(bbuf[(w * 32 + n * 4 + (k & 3)) * 2 + (k >> 2)]); };
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = 0; i < 4; ++i) {
+    const int r = g + 8 * (i >> 1), n = 2 * t + (i & 1);
+    double acc = (double)c[i];
+    for (int k = 0; k < 8; ++k) acc += (double)A(r, k) * (double)B(k, n);
+    d[i] = (float)acc;
+  }
+  syncwarp();
+}
 }  // namespace emu
 
 // ---- tiny runtime shim ---------------------------------------------------------------
