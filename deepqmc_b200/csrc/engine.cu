@@ -323,6 +323,7 @@ struct Engine : EngineBase {
   bool ph_active = false;  // set around the forward-Laplacian pass of local_energy only
   T* mos_out = nullptr;    // set by orbitals(): the tail writes the orbital matrices of the chunk here and stops
   int attn_tb = 1, attn_tb1 = 1;
+  bool attn_gen_mma = false;  // ... same for the generic kernel (TransPsiformer: extra key / value tokens)
   bool attn_fl_mma = false;   // fp32 forward-Laplacian attention: tangent chunks as warp-level 3xTF32 mma.sync products
   int attn_fl_threads = 128;  // block size of the fp32 forward-Laplacian attention (large molecules: one block per SM fits -> more warps)
   bool attn_f32 = false;
@@ -507,13 +508,27 @@ struct Engine : EngineBase {
     // 7/8 of every tile is padding: 6.9 -> 15.7 ms, so small molecules keep the SIMT variant)
     attn_fl_mma = attn_f32 && N >= 20 && N <= 32 && dh % 16 == 0;
     if (const char* ev = std::getenv("DQMC_ATTN_FL_MMA")) attn_fl_mma = attn_f32 && N <= 32 && dh % 16 == 0 && std::atoi(ev) != 0;
+    if (attn_fl_mma && !std::getenv("DQMC_ATTN_TB")) {  // two resident blocks of 8 warps per SM
+      attn_tb = attn_f32_pick_tb(N, dh, T3, 110 * 1024);
+      s_attn = attn_f32_smem_bytes(N, dh, attn_tb);
+    }
+    // generic kernel (extra key / value tokens: TransPsiformer) in fp32: same tensor-core products, row pitch dh + 4
+    attn_gen_mma = psif && !attn_f32 && std::is_same<T, float>::value && N >= 20 && dh % 16 == 0 && !std::getenv("DQMC_ATTN_GENERIC");
+    if (const char* ev = std::getenv("DQMC_ATTN_FL_MMA"))
+      attn_gen_mma = psif && !attn_f32 && std::is_same<T, float>::value && dh % 16 == 0 && std::atoi(ev) != 0;
+    if (attn_gen_mma) {
+      if (!std::getenv("DQMC_ATTN_TB")) attn_tb = attn_pick_tb<T>(N, dh, T3, 110 * 1024, Mn, 4);
+      s_attn = attn_smem_bytes<T>(N, dh, attn_tb, Mn, 4);
+    }
     size_t s_sl = slater_smem_bytes<T>(N);
     max_smem = s_attn > s_sl ? s_attn : s_sl;
     if (max_smem > 227 * 1024) { err = "system too large for the shared-memory tiling (N)"; return 2; }
     if (attn_f32) {
       if (launch_attn_f32(nullptr, nullptr, 0, 0, 0, 0.f, 0, (int)s_attn, nullptr, true)) return 1;
-    } else if (psif)
+    } else if (psif) {
       DQ_CHECK(raise_dyn_smem(attn_fl_kernel<T>, (int)s_attn));
+      if constexpr (std::is_same<T, float>::value) DQ_CHECK(raise_dyn_smem((attn_fl_kernel<T, true>), (int)s_attn));
+    }
     DQ_CHECK(raise_dyn_smem(slater_kernel<T>, (int)s_sl));
     slater_fwd2_ok = N <= 32 && slater_fwd2_smem_bytes<T>(N, M, K) <= 110 * 1024 && !std::getenv("DQMC_SLATER_GENERIC") &&
                      !std::getenv("DQMC_SLATER_FWD1");
@@ -1117,6 +1132,19 @@ struct Engine : EngineBase {
       DQ_LAUNCH((attn_fl_f32_kernel<NE, DH, false>), dim3(Bc, H), dim3(attn_fl_threads), smem, st, QKV, 3 * d, O, d, N, S, dh, d, scale, tb);
     return 0;
   }
+  // generic forward-Laplacian attention (any dtype, extra key / value tokens); fp32 with tangents: tensor-core variant
+  int launch_attn_generic(const T* QKV, T* O, int Bc, int S, int tb, T scale, const T* kn, const T* vn, cudaStream_t st) {
+    if constexpr (std::is_same<T, float>::value) {
+      if (attn_gen_mma && S > 1) {
+        DQ_LAUNCH((attn_fl_kernel<T, true>), dim3(Bc, H), dim3(256), attn_smem_bytes<T>(N, dh, tb, Mn, 4), st, QKV, 3 * d, O, d, N, S,
+                  dh, d, scale, tb, kn, vn, Mn);
+        return 0;
+      }
+    }
+    DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(S > 1 ? attn_fl_threads : 128), attn_smem_bytes<T>(N, dh, tb, Mn), st, QKV, 3 * d,
+              O, d, N, S, dh, d, scale, tb, kn, vn, Mn);
+    return 0;
+  }
   int launch_attn_f32(const float* QKV, float* O, int Bc, int S, int tb, float scale, int, int smem, cudaStream_t st,
                       bool setup) {
     if (dh == 64) {
@@ -1426,12 +1454,12 @@ struct Engine : EngineBase {
                                 (int)attn_f32_smem_bytes(N, dh, tb), st, false))
               return 1;
           } else {
-            DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(S > 1 ? attn_fl_threads : 128), attn_smem_bytes<T>(N, dh, tb, Mn), st,
-                      (const T*)w.QKV, 3 * d, O, d, N, S, dh, d, scale, tb, kn, vn, Mn);
+            int rc = launch_attn_generic((const T*)w.QKV, O, Bc, S, tb, scale, kn, vn, st);
+            if (rc) return rc;
           }
         } else {
-          DQ_LAUNCH(attn_fl_kernel<T>, dim3(Bc, H), dim3(S > 1 ? attn_fl_threads : 128), attn_smem_bytes<T>(N, dh, tb, Mn), st,
-                    (const T*)w.QKV, 3 * d, O, d, N, S, dh, d, scale, tb, kn, vn, Mn);
+          int rc = launch_attn_generic((const T*)w.QKV, O, Bc, S, tb, scale, kn, vn, st);
+          if (rc) return rc;
         }
       }
       if (can_fuse_mlp(S, p)) {

@@ -339,6 +339,177 @@ __global__ void tanh_fl_kernel(T* __restrict__ Z, int ldz, const T* __restrict__
   }
 }
 
+// ---- warp-level tensor-core products for the tangent chunks (MMA variant below): mma.sync m16n8k8 on TF32 operands split
+// hi + lo in registers ("3xTF32": a_lo b_hi + a_hi b_lo + a_hi b_hi accumulated in fp32, 2^-21-class products; the tangent
+// rows have no bounded range, so the 8-bit exponent of TF32 is kept instead of scaled halves).  Fragment layouts (PTX ISA,
+// m16n8k8 .tf32, g = lane / 4, t = lane % 4): A a0 (g, t) a1 (g + 8, t) a2 (g, t + 4) a3 (g + 8, t + 4); B b0 (k = t, n = g)
+// b1 (k = t + 4, n = g); C c0 (g, 2 t) c1 (g, 2 t + 1) c2 (g + 8, 2 t) c3 (g + 8, 2 t + 1).
+struct TfA { uint32_t hi[4], lo[4]; };
+struct TfB { uint32_t hi[2], lo[2]; };
+#ifdef DQMC_EMU
+__device__ __forceinline__ uint32_t tf32_rna_bits(float x) {
+  uint32_t u; std::memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) != 0x7F800000u) u += 0x1000u;  // round to nearest, ties away
+  return u & 0xFFFFE000u;
+}
+__device__ __forceinline__ void mma1688(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  float c[4] = {d[0], d[1], d[2], d[3]};
+  emu::mma_m16n8k8_tf32(d, a, b, c);
+}
+#else
+__device__ __forceinline__ uint32_t tf32_rna_bits(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma1688(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+#endif
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = tf32_rna_bits(x);
+  lo = tf32_rna_bits(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma3(float (&d)[4], const TfA& a, const TfB& b) {
+  mma1688(d, a.lo, b.hi);
+  mma1688(d, a.hi, b.lo);
+  mma1688(d, a.hi, b.hi);
+}
+
+// Scores of a tangent chunk: st[t][i][j] = c (q^t_i . k_j + q_i . k^t_j), qk[i][j] += sum_t q^t_i . k^t_j for the N queries
+// and NK >= N keys (keys j >= N are walker-independent extra tokens: k^t_j = 0).  Rows of q / k / qt / kt have pitch PQ
+// floats (PQ % 32 == 4: conflict-free fragment loads), qt / kt are [tc][N][PQ], st is [tc][N][NK], qk [N][NK].
+// A warp task owns one 16-query x 8-key tile for all tangents of the chunk (single writer of every running sum).
+__device__ __forceinline__ void attn_fl_mma_scores(const float* q, const float* k, const float* qt, const float* kt, float* st,
+                                                   float* qk, int N, int NK, int PQ, int dh, int tc, float scale, int tid, int nt) {
+  const int wid = tid >> 5, nw = nt >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  const int mtiles = (N + 15) >> 4, ntiles = (NK + 7) >> 3;
+  for (int task = wid; task < mtiles * ntiles; task += nw) {
+    const int mt = task / ntiles, nt8 = task - mt * ntiles;
+    const int i0 = mt * 16 + g, i1 = i0 + 8, jn = nt8 * 8 + g;
+    const int i0c = i0 < N ? i0 : N - 1, i1c = i1 < N ? i1 : N - 1, jc = jn < NK ? jn : NK - 1;
+    const bool tang = nt8 * 8 < N;          // the tile holds electron keys (k^t != 0 for j < N)
+    const bool jt = jn < N;                 // this lane's key carries tangents
+    const int jtc = jt ? jn : N - 1;
+    const float* q0 = q + i0c * PQ;
+    const float* q1 = q + i1c * PQ;
+    const float* kj = k + jc * PQ;
+    float cacc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < tc; ++t) {
+      const float* qt0 = qt + (size_t)(t * N + i0c) * PQ;
+      const float* qt1 = qt + (size_t)(t * N + i1c) * PQ;
+      const float* ktj = kt + (size_t)(t * N + jtc) * PQ;
+      float sacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+      for (int e = tq; e < dh; e += 8) {
+        TfA aqt;
+        TfB bk;
+        tf32_split(qt0[e], aqt.hi[0], aqt.lo[0]); tf32_split(qt1[e], aqt.hi[1], aqt.lo[1]);
+        tf32_split(qt0[e + 4], aqt.hi[2], aqt.lo[2]); tf32_split(qt1[e + 4], aqt.hi[3], aqt.lo[3]);
+        tf32_split(kj[e], bk.hi[0], bk.lo[0]); tf32_split(kj[e + 4], bk.hi[1], bk.lo[1]);
+        mma3(sacc, aqt, bk);
+        if (tang) {  // warp-uniform
+          TfA aq;
+          TfB bkt;
+          tf32_split(q0[e], aq.hi[0], aq.lo[0]); tf32_split(q1[e], aq.hi[1], aq.lo[1]);
+          tf32_split(q0[e + 4], aq.hi[2], aq.lo[2]); tf32_split(q1[e + 4], aq.hi[3], aq.lo[3]);
+          tf32_split(jt ? ktj[e] : 0.f, bkt.hi[0], bkt.lo[0]); tf32_split(jt ? ktj[e + 4] : 0.f, bkt.hi[1], bkt.lo[1]);
+          mma3(sacc, aq, bkt);
+          mma3(cacc, aqt, bkt);
+        }
+      }
+      const int j0 = nt8 * 8 + 2 * tq;
+      float* s0 = st + ((size_t)t * N + i0) * NK;
+      float* s1 = st + ((size_t)t * N + i1) * NK;
+      if (i0 < N) {
+        if (j0 < NK) s0[j0] = scale * sacc[0];
+        if (j0 + 1 < NK) s0[j0 + 1] = scale * sacc[1];
+      }
+      if (i1 < N) {
+        if (j0 < NK) s1[j0] = scale * sacc[2];
+        if (j0 + 1 < NK) s1[j0 + 1] = scale * sacc[3];
+      }
+    }
+    if (tang) {
+      const int j0 = nt8 * 8 + 2 * tq;
+      if (i0 < N) {
+        if (j0 < N) qk[i0 * NK + j0] += cacc[0];
+        if (j0 + 1 < N) qk[i0 * NK + j0 + 1] += cacc[1];
+      }
+      if (i1 < N) {
+        if (j0 < N) qk[i1 * NK + j0] += cacc[2];
+        if (j0 + 1 < N) qk[i1 * NK + j0 + 1] += cacc[3];
+      }
+    }
+  }
+}
+// Outputs of a tangent chunk: o^t_i = sum_j p^t_ij v_j + p_ij v^t_j (written to Ot + t * ldt, row i at i * ldrow, dh columns),
+// olap[i][:] += 2 sum_t sum_j p^t_ij v^t_j; pt is [tc][N][NK] (p^t, in the st buffer), p [N][NK], v [NK][PQ], vt [tc][N][PQ]
+// (v^t_j = 0 for j >= N).  A warp task owns 16 queries x 16 columns for all tangents of the chunk.
+__device__ __forceinline__ void attn_fl_mma_outputs(const float* pt, const float* p, const float* v, const float* vt, float* olap,
+                                                    float* Ot, size_t ldt, size_t ldrow, int N, int NK, int PQ, int dh, int tc,
+                                                    int tid, int nt) {
+  const int wid = tid >> 5, nw = nt >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  const int mtiles = (N + 15) >> 4, n_eg = dh >> 4;
+  for (int task = wid; task < mtiles * n_eg; task += nw) {
+    const int mt = task / n_eg, eg = task - mt * n_eg;
+    const int i0 = mt * 16 + g, i1 = i0 + 8;
+    const int i0c = i0 < N ? i0 : N - 1, i1c = i1 < N ? i1 : N - 1;
+    float c2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (int t = 0; t < tc; ++t) {
+      float oa[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      const float* pt0 = pt + ((size_t)t * N + i0c) * NK;
+      const float* pt1 = pt + ((size_t)t * N + i1c) * NK;
+      const float* pr0 = p + i0c * NK;
+      const float* pr1 = p + i1c * NK;
+      for (int jb = 0; jb < NK; jb += 8) {
+        const int j0 = jb + tq, j1 = j0 + 4;
+        const bool v0 = j0 < NK, v1 = j1 < NK;  // keys beyond NK contribute nothing (A = 0, B read from a valid row)
+        const int j0c = v0 ? j0 : NK - 1, j1c = v1 ? j1 : NK - 1;
+        const bool tang = jb < N;               // warp-uniform: the k-step holds electron keys
+        const bool t0v = j0 < N, t1v = j1 < N;
+        const int j0t = t0v ? j0 : N - 1, j1t = t1v ? j1 : N - 1;
+        TfA apt, ap;
+        tf32_split(v0 ? pt0[j0c] : 0.f, apt.hi[0], apt.lo[0]); tf32_split(v0 ? pt1[j0c] : 0.f, apt.hi[1], apt.lo[1]);
+        tf32_split(v1 ? pt0[j1c] : 0.f, apt.hi[2], apt.lo[2]); tf32_split(v1 ? pt1[j1c] : 0.f, apt.hi[3], apt.lo[3]);
+        if (tang) {
+          tf32_split(v0 ? pr0[j0c] : 0.f, ap.hi[0], ap.lo[0]); tf32_split(v0 ? pr1[j0c] : 0.f, ap.hi[1], ap.lo[1]);
+          tf32_split(v1 ? pr0[j1c] : 0.f, ap.hi[2], ap.lo[2]); tf32_split(v1 ? pr1[j1c] : 0.f, ap.hi[3], ap.lo[3]);
+        }
+#pragma unroll
+        for (int nn = 0; nn < 2; ++nn) {
+          const int e = eg * 16 + nn * 8 + g;
+          TfB bv;
+          tf32_split(v[j0c * PQ + e], bv.hi[0], bv.lo[0]); tf32_split(v[j1c * PQ + e], bv.hi[1], bv.lo[1]);
+          mma3(oa[nn], apt, bv);
+          if (tang) {
+            TfB bvt;
+            tf32_split(t0v ? vt[(size_t)(t * N + j0t) * PQ + e] : 0.f, bvt.hi[0], bvt.lo[0]);
+            tf32_split(t1v ? vt[(size_t)(t * N + j1t) * PQ + e] : 0.f, bvt.hi[1], bvt.lo[1]);
+            mma3(oa[nn], ap, bvt);
+            mma3(c2[nn], apt, bvt);
+          }
+        }
+      }
+#pragma unroll
+      for (int nn = 0; nn < 2; ++nn) {
+        const int e0 = eg * 16 + nn * 8 + 2 * tq;
+        if (i0 < N) *(float2*)(Ot + (size_t)t * ldt + (size_t)i0 * ldrow + e0) = make_float2(oa[nn][0], oa[nn][1]);
+        if (i1 < N) *(float2*)(Ot + (size_t)t * ldt + (size_t)i1 * ldrow + e0) = make_float2(oa[nn][2], oa[nn][3]);
+      }
+    }
+#pragma unroll
+    for (int nn = 0; nn < 2; ++nn) {
+      const int e0 = eg * 16 + nn * 8 + 2 * tq;
+      if (i0 < N) { olap[i0 * dh + e0] += 2.f * c2[nn][0]; olap[i0 * dh + e0 + 1] += 2.f * c2[nn][1]; }
+      if (i1 < N) { olap[i1 * dh + e0] += 2.f * c2[nn][2]; olap[i1 * dh + e0 + 1] += 2.f * c2[nn][3]; }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Self-attention with forward-Laplacian propagation, one block per (walker, head).
 // value algebra: hk.MultiHeadAttention (restated in reference src/deepqmc/hkext.py:215-253,
@@ -350,7 +521,9 @@ __global__ void tanh_fl_kernel(T* __restrict__ Z, int ldz, const T* __restrict__
 //   o^t  = p^t v + p v^t ;  o^L = (lap p) v + 2 sum_t p^t v^t + p v^L
 // QKV: [rows][ldq] with q at col h*dh, k at dmodel + h*dh, v at 2*dmodel + h*dh.
 // ------------------------------------------------------------------------------------------
-template <class T>
+// MMA (float only, dh % 16 == 0): the tangent-chunk contractions as warp-level 3xTF32 tensor-core products
+// (attn_fl_mma_scores / attn_fl_mma_outputs above); the shared-memory rows then have pitch dh + 4.
+template <class T, bool MMA = false>
 __global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict__ O, int ldo, int N, int S, int dh,
                                int dmodel, T scale, int TB, const T* __restrict__ Kn, const T* __restrict__ Vn, int Mn) {
   // Tangent slots are processed in chunks of TB so that every phase has (TB x N x NK) or (N x dh)
@@ -361,7 +534,7 @@ __global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict
   // tangents, so every derivative term with k^t_j, v^t_j, k^L_j, v^L_j vanishes for j >= N.
   DQMC_DYN_SMEM(smem_raw);
   const int NK = N + Mn;
-  const int dhp = dh + 1, NN = N * NK;
+  const int dhp = dh + (MMA ? 4 : 1), NN = N * NK;
   T* q = reinterpret_cast<T*>(smem_raw);   // [N][dhp]
   T* k = q + N * dhp;                      // [NK][dhp]
   T* v = k + NK * dhp;                     // [NK][dhp]
@@ -431,6 +604,9 @@ __global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict
     __syncthreads();  // previous chunk done with qt/kt/vt/st
     load3(1 + t0, tc, qt, kt, vt);
     __syncthreads();
+    if constexpr (MMA && std::is_same<T, float>::value) {
+      attn_fl_mma_scores(q, k, qt, kt, st, qk, N, NK, dhp, dh, tc, scale, tid, nt);
+    } else {
     for (int idx = tid; idx < tc * NN; idx += nt) {
       int j = idx % NK, i = (idx / NK) % N, t = idx / NN;
       const T* qti = qt + (t * N + i) * dhp;
@@ -454,6 +630,7 @@ __global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict
       }
       qk[idx] += c;
     }
+    }  // SIMT scores
     __syncthreads();
     for (int idx = tid; idx < tc * N; idx += nt) {  // (t, i)
       const T* pr = p + (idx % N) * NK;
@@ -474,6 +651,10 @@ __global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict
       u[idx] += uu;
     }
     __syncthreads();
+    if constexpr (MMA && std::is_same<T, float>::value) {
+      attn_fl_mma_outputs(st, p, v, vt, olap, O + (row0 + 1 + t0) * ldo + h * dh, (size_t)ldo, (size_t)S * ldo, N, NK, dhp, dh, tc,
+                          tid, nt);
+    } else
     for (int idx = tid; idx < N * dh; idx += nt) {
       int i = idx / dh, e = idx % dh;
       T c2 = T(0);
@@ -532,16 +713,16 @@ __global__ void attn_fl_kernel(const T* __restrict__ QKV, int ldq, T* __restrict
 }
 
 template <class T>
-inline size_t attn_smem_bytes(int N, int dh, int TB, int Mn = 0) {
+inline size_t attn_smem_bytes(int N, int dh, int TB, int Mn = 0, int pad = 1) {
   const size_t NK = N + Mn;
-  return sizeof(T) * ((size_t)N * (dh + 1) + 2 * NK * (dh + 1) + (size_t)3 * TB * N * (dh + 1) +
+  return sizeof(T) * ((size_t)N * (dh + pad) + 2 * NK * (dh + pad) + (size_t)3 * TB * N * (dh + pad) +
                       (size_t)N * NK * (3 + TB) + (size_t)N * dh + (size_t)TB * N + N);
 }
 // largest tangent chunk whose working set fits `budget` bytes of shared memory
 template <class T>
-inline int attn_pick_tb(int N, int dh, int T3, size_t budget, int Mn = 0) {
+inline int attn_pick_tb(int N, int dh, int T3, size_t budget, int Mn = 0, int pad = 1) {
   int tb = T3 > 0 ? T3 : 1;
-  while (tb > 1 && attn_smem_bytes<T>(N, dh, tb, Mn) > budget) --tb;
+  while (tb > 1 && attn_smem_bytes<T>(N, dh, tb, Mn, pad) > budget) --tb;
   return tb;
 }
 
@@ -556,46 +737,6 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
 }
 __device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
   acc.x += s * v.x; acc.y += s * v.y; acc.z += s * v.z; acc.w += s * v.w;
-}
-
-// ---- warp-level tensor-core products for the tangent chunks (MMA variant below): mma.sync m16n8k8 on TF32 operands split
-// hi + lo in registers ("3xTF32": a_lo b_hi + a_hi b_lo + a_hi b_hi accumulated in fp32, 2^-21-class products; the tangent
-// rows have no bounded range, so the 8-bit exponent of TF32 is kept instead of scaled halves).  Fragment layouts (PTX ISA,
-// m16n8k8 .tf32, g = lane / 4, t = lane % 4): A a0 (g, t) a1 (g + 8, t) a2 (g, t + 4) a3 (g + 8, t + 4); B b0 (k = t, n = g)
-// b1 (k = t + 4, n = g); C c0 (g, 2 t) c1 (g, 2 t + 1) c2 (g + 8, 2 t) c3 (g + 8, 2 t + 1).
-struct TfA { uint32_t hi[4], lo[4]; };
-struct TfB { uint32_t hi[2], lo[2]; };
-#ifdef DQMC_EMU
-__device__ __forceinline__ uint32_t tf32_rna_bits(float x) {
-  uint32_t u; std::memcpy(&u, &x, 4);
-  if ((u & 0x7F800000u) != 0x7F800000u) u += 0x1000u;  // round to nearest, ties away
-  return u & 0xFFFFE000u;
-}
-__device__ __forceinline__ void mma1688(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  float c[4] = {d[0], d[1], d[2], d[3]};
-  emu::mma_m16n8k8_tf32(d, a, b, c);
-}
-#else
-__device__ __forceinline__ uint32_t tf32_rna_bits(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ void mma1688(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-#endif
-__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
-  hi = tf32_rna_bits(x);
-  lo = tf32_rna_bits(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma3(float (&d)[4], const TfA& a, const TfB& b) {
-  mma1688(d, a.lo, b.hi);
-  mma1688(d, a.hi, b.lo);
-  mma1688(d, a.hi, b.hi);
 }
 
 // NE / DH: compile-time electron count / head dim (0 = use the runtime value): with constants the
@@ -681,55 +822,7 @@ __global__ void attn_fl_f32_kernel(const float* __restrict__ QKV, int ldq, float
     load3(1 + t0, tc, qt, kt, vt);
     __syncthreads();
     if constexpr (MMA) {
-      // ---- scores of the chunk on the tensor cores: st[t][i][j] = c (q^t_i . k_j + q_i . k^t_j), qk[i][j] += q^t_i . k^t_j
-      const int wid = tid >> 5, nw = nt >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
-      for (int task = wid; task < 8; task += nw) {
-        const int mt = task >> 2, nt8 = task & 3;
-        const int i0 = mt * 16 + g, i1 = i0 + 8, jn = nt8 * 8 + g;
-        const int i0c = i0 < N ? i0 : N - 1, i1c = i1 < N ? i1 : N - 1, jc = jn < N ? jn : N - 1;
-        const float* q0 = q + i0c * PQ;
-        const float* q1 = q + i1c * PQ;
-        const float* kj = k + jc * PQ;
-        float cacc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int t = 0; t < tc; ++t) {
-          const float* qt0 = qt + (size_t)(t * N + i0c) * PQ;
-          const float* qt1 = qt + (size_t)(t * N + i1c) * PQ;
-          const float* ktj = kt + (size_t)(t * N + jc) * PQ;
-          float sacc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-          for (int e = tq; e < dh; e += 8) {
-            TfA aqt, aq;
-            TfB bk, bkt;
-            tf32_split(qt0[e], aqt.hi[0], aqt.lo[0]); tf32_split(qt1[e], aqt.hi[1], aqt.lo[1]);
-            tf32_split(qt0[e + 4], aqt.hi[2], aqt.lo[2]); tf32_split(qt1[e + 4], aqt.hi[3], aqt.lo[3]);
-            tf32_split(q0[e], aq.hi[0], aq.lo[0]); tf32_split(q1[e], aq.hi[1], aq.lo[1]);
-            tf32_split(q0[e + 4], aq.hi[2], aq.lo[2]); tf32_split(q1[e + 4], aq.hi[3], aq.lo[3]);
-            tf32_split(kj[e], bk.hi[0], bk.lo[0]); tf32_split(kj[e + 4], bk.hi[1], bk.lo[1]);
-            tf32_split(ktj[e], bkt.hi[0], bkt.lo[0]); tf32_split(ktj[e + 4], bkt.hi[1], bkt.lo[1]);
-            mma3(sacc, aqt, bk);
-            mma3(sacc, aq, bkt);
-            mma3(cacc, aqt, bkt);
-          }
-          const int j0 = nt8 * 8 + 2 * tq;
-          if (i0 < N) {
-            if (j0 < N) st[((size_t)t * N + i0) * N + j0] = scale * sacc[0];
-            if (j0 + 1 < N) st[((size_t)t * N + i0) * N + j0 + 1] = scale * sacc[1];
-          }
-          if (i1 < N) {
-            if (j0 < N) st[((size_t)t * N + i1) * N + j0] = scale * sacc[2];
-            if (j0 + 1 < N) st[((size_t)t * N + i1) * N + j0 + 1] = scale * sacc[3];
-          }
-        }
-        const int j0 = nt8 * 8 + 2 * tq;
-        if (i0 < N) {
-          if (j0 < N) qk[i0 * N + j0] += cacc[0];
-          if (j0 + 1 < N) qk[i0 * N + j0 + 1] += cacc[1];
-        }
-        if (i1 < N) {
-          if (j0 < N) qk[i1 * N + j0] += cacc[2];
-          if (j0 + 1 < N) qk[i1 * N + j0 + 1] += cacc[3];
-        }
-      }
+      attn_fl_mma_scores(q, k, qt, kt, st, qk, N, N, PQ, dh, tc, scale, tid, nt);
     } else {
     // ---- (t,i) x 4 lanes: a_j = q^t_i . k_j,  c_j = q^t_i . k^t_j ----------------------------
     {
@@ -806,55 +899,7 @@ __global__ void attn_fl_f32_kernel(const float* __restrict__ QKV, int ldq, float
     }
     __syncthreads();
     if constexpr (MMA) {
-      // ---- outputs of the chunk on the tensor cores: o^t = p^t v + p v^t, olap += 2 sum_t p^t v^t
-      const int wid = tid >> 5, nw = nt >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
-      const int n_eg = dh / 16;  // column groups of 16 (two 8-column tiles)
-      for (int task = wid; task < 2 * n_eg; task += nw) {
-        const int mt = task / n_eg, eg = task - mt * n_eg;
-        const int i0 = mt * 16 + g, i1 = i0 + 8;
-        const int i0c = i0 < N ? i0 : N - 1, i1c = i1 < N ? i1 : N - 1;
-        float c2[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-        for (int t = 0; t < tc; ++t) {
-          float oa[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-          const float* pt0 = st + ((size_t)t * N + i0c) * N;
-          const float* pt1 = st + ((size_t)t * N + i1c) * N;
-          const float* pr0 = p + i0c * N;
-          const float* pr1 = p + i1c * N;
-          for (int jb = 0; jb < N; jb += 8) {
-            const int j0 = jb + tq, j1 = j0 + 4;
-            const bool v0 = j0 < N, v1 = j1 < N;  // keys beyond N contribute nothing (A = 0, B read from a valid row)
-            const int j0c = v0 ? j0 : N - 1, j1c = v1 ? j1 : N - 1;
-            TfA apt, ap;
-            tf32_split(v0 ? pt0[j0c] : 0.f, apt.hi[0], apt.lo[0]); tf32_split(v0 ? pt1[j0c] : 0.f, apt.hi[1], apt.lo[1]);
-            tf32_split(v1 ? pt0[j1c] : 0.f, apt.hi[2], apt.lo[2]); tf32_split(v1 ? pt1[j1c] : 0.f, apt.hi[3], apt.lo[3]);
-            tf32_split(v0 ? pr0[j0c] : 0.f, ap.hi[0], ap.lo[0]); tf32_split(v0 ? pr1[j0c] : 0.f, ap.hi[1], ap.lo[1]);
-            tf32_split(v1 ? pr0[j1c] : 0.f, ap.hi[2], ap.lo[2]); tf32_split(v1 ? pr1[j1c] : 0.f, ap.hi[3], ap.lo[3]);
-#pragma unroll
-            for (int nn = 0; nn < 2; ++nn) {
-              const int e = eg * 16 + nn * 8 + g;
-              TfB bv, bvt;
-              tf32_split(v[j0c * PQ + e], bv.hi[0], bv.lo[0]); tf32_split(v[j1c * PQ + e], bv.hi[1], bv.lo[1]);
-              tf32_split(vt[(size_t)(t * N + j0c) * PQ + e], bvt.hi[0], bvt.lo[0]);
-              tf32_split(vt[(size_t)(t * N + j1c) * PQ + e], bvt.hi[1], bvt.lo[1]);
-              mma3(oa[nn], apt, bv);
-              mma3(oa[nn], ap, bvt);
-              mma3(c2[nn], apt, bvt);
-            }
-          }
-#pragma unroll
-          for (int nn = 0; nn < 2; ++nn) {
-            const int e0 = eg * 16 + nn * 8 + 2 * tq;
-            if (i0 < N) *(float2*)(O + (row0 + (size_t)i0 * S + 1 + t0 + t) * ldo + h * dh + e0) = make_float2(oa[nn][0], oa[nn][1]);
-            if (i1 < N) *(float2*)(O + (row0 + (size_t)i1 * S + 1 + t0 + t) * ldo + h * dh + e0) = make_float2(oa[nn][2], oa[nn][3]);
-          }
-        }
-#pragma unroll
-        for (int nn = 0; nn < 2; ++nn) {
-          const int e0 = eg * 16 + nn * 8 + 2 * tq;
-          if (i0 < N) { olap[i0 * dh + e0] += 2.f * c2[nn][0]; olap[i0 * dh + e0 + 1] += 2.f * c2[nn][1]; }
-          if (i1 < N) { olap[i1 * dh + e0] += 2.f * c2[nn][2]; olap[i1 * dh + e0 + 1] += 2.f * c2[nn][3]; }
-        }
-      }
+      attn_fl_mma_outputs(st, p, v, vt, olap, O + (row0 + 1 + t0) * ldo + h * dh, (size_t)ldo, (size_t)S * ldo, N, N, PQ, dh, tc, tid, nt);
     } else
     for (int idx = tid; idx < N * d4; idx += nt) {
       int i = idx / d4, e4 = idx % d4;
