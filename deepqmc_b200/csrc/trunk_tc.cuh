@@ -185,7 +185,8 @@ trunk_f16_kernel(TrunkParams p) {
   uint64_t* p_full = s_full + 1;                // P written back by all 256 workers
   uint64_t* o_full = p_full + 1;                // [2] O_h complete in TMEM (commit)
   uint64_t* o_free = o_full + 2;                // [2] O_h buffer read by all 256 workers
-  uint32_t* tmem_slot = (uint32_t*)(o_free + 2);
+  uint64_t* scr_qk = o_free + 2;                // Q / K images of the tile are in the scratch buffer (V^T: scr_full)
+  uint32_t* tmem_slot = (uint32_t*)(scr_qk + 1);
   float* sb1 = (float*)(smem + TrSmem::bias());
   float* sb2 = sb1 + 256;
 
@@ -202,7 +203,7 @@ trunk_f16_kernel(TrunkParams p) {
       mbar_init(&accfull[b], 1); mbar_init(&accfree[b], 256);
       mbar_init(&o_full[b], 1); mbar_init(&o_free[b], 256);
     }
-    mbar_init(scr_full, 1); mbar_init(qk_full, 1); mbar_init(v_full, 1); mbar_init(qk_free, 1); mbar_init(v_free, 1);
+    mbar_init(scr_full, 1); mbar_init(scr_qk, 1); mbar_init(qk_full, 1); mbar_init(v_full, 1); mbar_init(qk_free, 1); mbar_init(v_free, 1);
     mbar_init(s_full, 1); mbar_init(p_full, 256);
     fence_barrier_init();
   }
@@ -220,7 +221,7 @@ trunk_f16_kernel(TrunkParams p) {
       uint32_t it = 0, n_scr = 0, n_qkf = 0, n_vf = 0;
       auto weight_slot = [&](const CUtensorMap* map, int x, int y) {
         const int s = it % kTrSlots;
-        mbar_wait(&wempty[s], ((it / kTrSlots) & 1) ^ 1, p.err_flag);
+        mbar_wait(&wempty[s & ~1], ((it / kTrSlots) & 1) ^ 1, p.err_flag);  // one release barrier per k-block (slot pair)
         if (p.ablate & 1) {
           mbar_arrive(&wfull[s]);
         } else {
@@ -236,8 +237,10 @@ trunk_f16_kernel(TrunkParams p) {
             for (int kb = 0; kb < 4; ++kb)
               for (int plane = 0; plane < 2; ++plane) weight_slot(lm + plane, kb * 64, 128 * j);
           // the ring is handed to the attention: every weight slot issued so far has been consumed, the images are written
-          for (uint32_t k = it - kTrSlots; k != it; ++k) mbar_wait(&wempty[k % kTrSlots], (k / kTrSlots) & 1, p.err_flag);
-          mbar_wait(scr_full, n_scr & 1, p.err_flag); ++n_scr;
+          for (uint32_t k = it - kTrSlots; k != it; k += 2) mbar_wait(&wempty[k % kTrSlots], (k / kTrSlots) & 1, p.err_flag);
+          // Q / K images first (drains of sub-chunks 0-3); the V^T drains (4, 5) still run while head 0's Q / K load, S and
+          // softmax proceed
+          mbar_wait(scr_qk, n_scr & 1, p.err_flag);
           for (int h = 0; h < 4; ++h) {
             const unsigned char* img = scratch + (size_t)h * kTrHeadImage;
             if (h > 0) { mbar_wait(qk_free, n_qkf & 1, p.err_flag); ++n_qkf; }
@@ -248,6 +251,7 @@ trunk_f16_kernel(TrunkParams p) {
               bulk_load(smem + TrSmem::wring(0), img, 65536u, qk_full);
             }
             if (h > 0) { mbar_wait(v_free, n_vf & 1, p.err_flag); ++n_vf; }
+            else { mbar_wait(scr_full, n_scr & 1, p.err_flag); ++n_scr; }
             if (p.ablate & 8) {
               mbar_arrive(v_full);
             } else {
@@ -306,8 +310,7 @@ trunk_f16_kernel(TrunkParams p) {
             }
           }
         }
-        umma_commit(&wempty[s0]);
-        umma_commit(&wempty[s1]);
+        umma_commit(&wempty[s0]);  // s0 is even: the barrier of the slot pair (s0, s0 + 1)
         if (kb == 3) umma_commit(accbar);
       }
     };
@@ -494,6 +497,12 @@ trunk_f16_kernel(TrunkParams p) {
           if (!img_on) {} else
           if (j < 4) image_store32(img, trow, 32, x); else image_store_vt32(img, trow, 32, x);
           TR_STAMP(2 + 2 * j);
+          if (j == 3) {  // Q and K images complete
+            fence_proxy_async_all();
+            __threadfence_block();
+            named_bar_sync(1, 256);
+            if (threadIdx.x == 0) mbar_arrive(scr_qk);
+          }
         }
         fence_proxy_async_all();  // the images are read back through the async proxy (bulk copies)
         __threadfence_block();

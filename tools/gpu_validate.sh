@@ -23,7 +23,7 @@ for wl in lih_psiformer lih_eval_step n2_ferminet cyclobutadiene_transpsiformer;
   echo "rc=$?"; cut -c1-330 gpurun_out/bench_$wl.json; tail -2 gpurun_out/bench_$wl.err
 done
 echo "== ncu launch list (benzene, 32 walkers, one step)"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 600 --csv --log-file gpurun_out/launches_benzene32.csv python bench.py --walkers 32 --steps 1 --warmup 3 --no-cpu-baseline --equil-sweeps 0 > gpurun_out/ncu_bz32.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 300 --csv --log-file gpurun_out/launches_benzene32.csv python bench.py --walkers 32 --steps 1 --warmup 3 --no-cpu-baseline --equil-sweeps 0 > gpurun_out/ncu_bz32.log 2>&1
 echo "rc=$?"
 if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
   echo "== torchrun N=2 default bench"
