@@ -466,7 +466,7 @@ def main():
                    'parallelism': f'walker-shard x{world}',
                    'l2': 'flushed between timed iterations (256 MiB memset) and activations >> L2',
                    'step': (f'{n_sub} Metropolis sub-steps (all-electron proposals, in-kernel Philox) + ' if n_sub else '')
-                           + 'E_loc of all walkers (+ fused stats all-reduce for N>1)',
+                           + 'E_loc of all walkers (+ one all_gather of the packed statistics for N>1)',
                    'gemm_backend': 'tcgen05 (3xFP16 whole-trunk kernel for plain forwards, 3xTF32 row GEMMs for the forward-Laplacian rows)' if backend else 'cuda-core'},
         'clocks': clk, 'e2e': {'value': e2e_val, 'unit': unit, 'h2d_bytes_per_step': (n_states * B * N * 3 + M * 3) * esz,
                                'd2h_bytes_per_step': n_states * B * esz, 'steps': e2e_steps},
