@@ -957,7 +957,7 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
       T dx0 = rb[3 * i] - rb[3 * j], dx1 = rb[3 * i + 1] - rb[3 * j + 1], dx2 = rb[3 * i + 2] - rb[3 * j + 2];
       T d2 = dx0 * dx0 + dx1 * dx1 + dx2 * dx2;
       T rho2 = Num<T>::eps() + d2, rho = m_sqrt(rho2);
-      vel += T(0.5) / rho;
+      vel += T(0.5) / rho;  // (dead for S == 1: only sign / log are written, the compiler drops it there)
       if (c.cusp_kind != 0) {
         bool same = (i < c.n_up) == (j < c.n_up);
         T al = same ? as_ : aa_;
@@ -980,12 +980,13 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
       }
     }
     // electron-nucleus attraction (plain norm) + local ECP (+ nuclear cusp factor on the plain distances,
-    // reference wf/nn_wave_function.py:129,169-170)
-    for (int m = 0; m < M; ++m) {
+    // reference wf/nn_wave_function.py:129,169-170).  Plain forwards (S == 1: Metropolis, ECP quadrature) write sign / log only:
+    // the potentials are skipped there (N M (1 + 3 ecp_terms) exponentials per walker that nobody reads)
+    for (int m = 0; m < M && (S > 1 || c.nuc_cusp_kind != 0); ++m) {
       T dx0 = rb[3 * i] - Rb[3 * m], dx1 = rb[3 * i + 1] - Rb[3 * m + 1], dx2 = rb[3 * i + 2] - Rb[3 * m + 2];
       T d2 = dx0 * dx0 + dx1 * dx1 + dx2 * dx2;
       T dist = m_sqrt(d2);
-      vloc -= z_val[m] / dist;
+      if (S > 1) vloc -= z_val[m] / dist;
       if (c.nuc_cusp_kind != 0) {
         const T al = nuc_cusp[0], zn = nuc_cusp[1 + m];
         const T sc = zn * (c.nuc_cusp_kind == 1 ? al * al : T(1) / (al * al));
@@ -1004,6 +1005,7 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
           cusp_l += fpp + T(2) * fp / dist;
         }
       }
+      if (S == 1) continue;
       if (ph.tabs && ph.tab_of_nuc[m] >= 0)  // local pseudo-Hamiltonian term r V_loc(r) / r (pseudo_hamiltonian.py:180-196)
         vloc += ph_interp(ph.tabs + (size_t)ph.tab_of_nuc[m] * 2 * ph.G, ph.G, ph.rmax, dist) / dist;
       if (c.ecp_terms > 0 && ecp_mask[m]) {
@@ -1020,7 +1022,7 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
       grad[3 * i] = g0; grad[3 * i + 1] = g1; grad[3 * i + 2] = g2;
     }
   }
-  for (int idx = tid; idx < M * M; idx += nt) {
+  for (int idx = tid; idx < M * M && S > 1; idx += nt) {
     int I = idx / M, J = idx % M;
     if (I < J) {
       T dx0 = Rb[3 * I] - Rb[3 * J], dx1 = Rb[3 * I + 1] - Rb[3 * J + 1], dx2 = Rb[3 * I + 2] - Rb[3 * J + 2];
@@ -1028,9 +1030,11 @@ __global__ void finalize_kernel(FinalizeCfg c, const T* __restrict__ r, const T*
     }
   }
   block_sum2(cusp_v, cusp_l, scratch);
-  block_sum2(vel, vloc, scratch);
-  T dummy = T(0);
-  block_sum2(enuc, dummy, scratch);
+  if (S > 1) {  // block-uniform
+    block_sum2(vel, vloc, scratch);
+    T dummy = T(0);
+    block_sum2(enuc, dummy, scratch);
+  }
   const T* jr = jastrow ? jastrow + (size_t)b * S : nullptr;
   if (tid == 0) {
     out_sign[b] = misc[1];
