@@ -51,3 +51,43 @@ def test_oracle_psiformer_trunk_equals_torch_multi_head_attention(mol_name, hype
         x = att + m
     assert x.shape == x_oracle.shape == (N, d)
     assert (x - x_oracle).abs().max().item() < 1e-11 * max(1.0, x_oracle.abs().max().item())
+
+
+@pytest.mark.parametrize('mol_name,hyper', [('LiH', dict(embedding_dim=32, n_layers=2, n_heads=4)),
+                                            ('cyclobutadiene_square', dict(embedding_dim=64, n_layers=3, n_heads=4))])
+def test_oracle_transpsiformer_trunk_equals_torch_masked_multi_head_attention(mol_name, hyper):
+    """Joint attention over [nuclei; electrons] tokens with the nuclei masked from attending electrons (reference
+    gnn/update_features.py:385-451) == torch's multi-head attention with the corresponding boolean attn_mask."""
+    from deepqmc_b200.spec import transpsiformer_spec
+
+    mol = Molecule.from_name(mol_name)
+    hamil = MolecularHamiltonian(mol=mol)
+    spec = transpsiformer_spec(hamil, n_determinants=2, **hyper)
+    pt = wf.to_torch(PN.perturb_params(PN.init_params(spec, 0)))
+    rng = np.random.default_rng(4)
+    N, M, d, H = spec.n_elec, spec.n_nuc, spec.embedding_dim, spec.n_heads
+    r = torch.as_tensor(mol.coords[rng.integers(0, len(mol.coords), size=N)] + rng.normal(size=(N, 3)))
+    R = torch.as_tensor(mol.coords)
+    xe_oracle, xn_oracle = wf.transpsiformer_embeddings(spec, pt, r, R)
+
+    def W(name):
+        return torch.as_tensor(pt[name], dtype=torch.float64)
+
+    feats, _ = wf.ne_features(r, R, True)
+    spins = torch.cat([torch.ones(spec.n_up), -torch.ones(spec.n_down)]).double()[:, None]
+    xe = torch.cat([feats, spins], 1) @ W(P.GNN + 'electron_embedding/linear:w')
+    h = torch.cat([wf.nuclei_embedding(spec, pt, R), xe], 0)  # token order of the reference: nuclei first
+    not_allowed = torch.zeros(M + N, M + N, dtype=torch.bool)
+    not_allowed[:M, M:] = True  # a nucleus never attends an electron
+    for l in range(spec.n_layers):
+        a = P.comb_prefix(l)
+        in_proj = torch.cat([W(a + f'multi_head_attention/{n}:w').T for n in ('query', 'key', 'value')], 0)
+        out, _ = F.multi_head_attention_forward(
+            h[:, None, :], h[:, None, :], h[:, None, :], d, H, in_proj, None, None, None, False, 0.0,
+            W(a + 'multi_head_attention/linear:w').T, None, training=False, need_weights=False, attn_mask=not_allowed)
+        att = h + out[:, 0, :]
+        m = torch.tanh(att @ W(a + 'mlp/linear_0:w') + W(a + 'mlp/linear_0:b'))
+        m = torch.tanh(m @ W(a + 'mlp/linear_1:w') + W(a + 'mlp/linear_1:b'))
+        h = att + m
+    scale = max(1.0, xe_oracle.abs().max().item())
+    assert (h[M:] - xe_oracle).abs().max().item() < 1e-11 * scale and (h[:M] - xn_oracle).abs().max().item() < 1e-11 * scale
